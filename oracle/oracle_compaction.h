@@ -1,0 +1,60 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_codec.h).
+//
+// CPU restatement of the compaction hot loop: SST iterators -> MergingIterator (binary heap) ->
+// CompactionIterator (rule A + seqno zeroing) -> DocDBCompactionFeed (MVCC retention) ->
+// TableBuilder. One thread per compaction, like the reference (rocksdb/util/options.cc:258).
+#pragma once
+#include "oracle_sst.h"
+#include <functional>
+
+namespace orc {
+
+// docdb/docdb_compaction_context.h:57-111,178-196 flattened.
+struct RetentionParams {
+  bool enabled = true;                       // false = no compaction_context_factory (plain RocksDB)
+  uint64_t primary_cutoff_ht = kHtMin;       // HistoryCutoff::primary_cutoff_ht (HybridTime repr)
+  uint64_t cotables_cutoff_ht = kHtInvalid;  // invalid = not set
+  int64_t table_ttl_ns = kMaxTtlNs;          // MonoDelta; kMaxTtl = no table TTL
+  bool retain_delete_markers_in_major_compaction = false;
+  uint64_t other_min_ht = kHtMax;            // CompactionHybridTimeConstraints::other_min; kMax = "major"
+  std::string lower_bound, upper_bound;      // KeyBounds (empty = unbounded)
+};
+
+struct CompactionParams {
+  bool bottommost_level = true;              // Compaction::bottommost_level()
+  uint64_t last_sequence = kMaxSequenceNumber;  // VersionSet::LastSequence() => earliest_snapshot_
+  std::string largest_user_key;              // Compaction::GetLargestUserKey(); computed if !has_largest
+  bool has_largest_user_key = false;
+  RetentionParams retention;
+};
+
+struct CompactionStats {
+  uint64_t num_input_records = 0, num_output_records = 0;
+  uint64_t num_dropped_hidden = 0;      // rule A (compaction_iterator.cc:388-400)
+  uint64_t num_dropped_obsolete = 0;    // kTypeDeletion at bottommost
+  uint64_t num_dropped_feed = 0;        // dropped by DocDBCompactionFeed
+  uint64_t total_input_raw_key_bytes = 0, total_input_raw_value_bytes = 0;
+  uint64_t total_output_raw_key_bytes = 0, total_output_raw_value_bytes = 0;
+};
+
+// rocksdb/db/compaction_context.h:25-35.
+struct CompactionFeed {
+  virtual ~CompactionFeed() {}
+  virtual void Feed(Slice internal_key, Slice value) = 0;
+  virtual void Flush() = 0;
+};
+
+struct SstInput { Slice meta, data; uint64_t hybrid_time_filter = kHtInvalid; };
+
+// Runs the whole loop (rocksdb/db/compaction_job.cc:664-895). `sink` receives every surviving
+// (internal key, value) in output order.
+void RunCompaction(const std::vector<SstInput>& inputs, const CompactionParams& params,
+                   CompactionFeed* sink, CompactionStats* stats, bool verify_checksums = true);
+
+// Same, but over already-decoded sorted runs (used by the retention golden tests, which the
+// reference drives through mock tables / tiny SSTs).
+struct KvRun { std::vector<std::pair<std::string, std::string>> kv; };
+void RunCompactionOnRuns(const std::vector<KvRun>& runs, const CompactionParams& params,
+                         CompactionFeed* sink, CompactionStats* stats);
+
+}  // namespace orc

@@ -1,0 +1,379 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/liboracle.so (the CPU restatement of the reference compaction path) for
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  Nothing under
+yugabyte-db_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+HT_MIN = 0
+HT_MAX = 2**64 - 1
+HT_INVALID = 2**64 - 2
+MAX_TTL_NS = 2**63 - 1
+MAX_SEQ = (1 << 56) - 1
+YB_EPOCH_US = 1500000000 * 1000000
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _DIR])
+
+
+class TableOptions(C.Structure):
+    _fields_ = [("block_size", C.c_uint32), ("block_restart_interval", C.c_int32),
+                ("key_encoding", C.c_int32), ("block_size_deviation", C.c_int32),
+                ("index_block_size", C.c_uint32), ("min_keys_per_index_block", C.c_uint32)]
+
+    def __init__(self, block_size=32768, restart=16, key_encoding=1, deviation=10,
+                 index_block_size=32768, min_keys_per_index_block=100):
+        super().__init__(block_size, restart, key_encoding, deviation, index_block_size,
+                         min_keys_per_index_block)
+
+
+class CompactionParams(C.Structure):
+    _fields_ = [("bottommost_level", C.c_int32), ("last_sequence", C.c_uint64),
+                ("largest_user_key", C.c_char_p), ("largest_user_key_len", C.c_uint64),
+                ("has_largest_user_key", C.c_int32), ("retention_enabled", C.c_int32),
+                ("primary_cutoff_ht", C.c_uint64), ("cotables_cutoff_ht", C.c_uint64),
+                ("table_ttl_ns", C.c_int64), ("retain_delete_markers", C.c_int32),
+                ("other_min_ht", C.c_uint64),
+                ("lower_bound", C.c_char_p), ("lower_len", C.c_uint64),
+                ("upper_bound", C.c_char_p), ("upper_len", C.c_uint64)]
+
+    def __init__(self, bottommost=True, last_sequence=MAX_SEQ, largest_user_key=None,
+                 retention=True, cutoff_ht=HT_MIN, cotables_cutoff_ht=HT_INVALID,
+                 table_ttl_ns=MAX_TTL_NS, retain_delete_markers=False, other_min_ht=HT_MAX,
+                 lower=b"", upper=b""):
+        super().__init__()
+        self.bottommost_level = int(bottommost)
+        self.last_sequence = last_sequence
+        self._luk = largest_user_key
+        self.largest_user_key = largest_user_key
+        self.largest_user_key_len = len(largest_user_key) if largest_user_key is not None else 0
+        self.has_largest_user_key = int(largest_user_key is not None)
+        self.retention_enabled = int(retention)
+        self.primary_cutoff_ht = cutoff_ht
+        self.cotables_cutoff_ht = cotables_cutoff_ht
+        self.table_ttl_ns = table_ttl_ns
+        self.retain_delete_markers = int(retain_delete_markers)
+        self.other_min_ht = other_min_ht
+        self._lo, self._up = lower, upper
+        self.lower_bound, self.lower_len = lower, len(lower)
+        self.upper_bound, self.upper_len = upper, len(upper)
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in
+                ("num_input_records", "num_output_records", "num_dropped_hidden",
+                 "num_dropped_obsolete", "num_dropped_feed", "in_key_bytes", "in_val_bytes",
+                 "out_key_bytes", "out_val_bytes", "kv_hash")] + [("seconds", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class GenConfig(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("num_rows", C.c_uint64), ("cols", C.c_uint32),
+                ("versions", C.c_uint32), ("num_files", C.c_uint32), ("value_len", C.c_uint32),
+                ("base_micros", C.c_uint64), ("tombstone_per_1024", C.c_uint32),
+                ("tombstone_newest", C.c_uint32), ("row_offset", C.c_uint64),
+                ("hash_rows_total", C.c_uint64)]
+
+    def __init__(self, seed=1, num_rows=1000, cols=1, versions=1, num_files=2, value_len=256,
+                 base_micros=1790000000 * 1000000, tombstone_per_1024=0, tombstone_newest=0,
+                 row_offset=0, hash_rows_total=0):
+        super().__init__(seed, num_rows, cols, versions, num_files, value_len, base_micros,
+                         tombstone_per_1024, tombstone_newest, row_offset, hash_rows_total)
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_DIR, "liboracle.so")
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path)
+    vp, u64, u8p = C.c_void_p, C.c_uint64, C.POINTER(C.c_uint8)
+    L.orc_last_error.restype = C.c_char_p
+    L.orc_encode_doc_ht.argtypes = [u64, C.c_uint32, C.c_char_p]
+    L.orc_decode_doc_ht.argtypes = [C.c_char_p, u64, C.POINTER(u64), C.POINTER(C.c_uint32)]
+    L.orc_signed_varint.argtypes = [C.c_int64, C.c_char_p]
+    L.orc_unsigned_varint.argtypes = [u64, C.c_char_p]
+    L.orc_decode_signed_varint.argtypes = [C.c_char_p, u64, C.POINTER(C.c_int64)]
+    L.orc_crc32c.argtypes = [C.c_char_p, u64]
+    L.orc_crc32c.restype = C.c_uint32
+    L.orc_crc32c_mask.argtypes = [C.c_uint32]
+    L.orc_crc32c_mask.restype = C.c_uint32
+    L.orc_subdockey_ends.argtypes = [C.c_char_p, u64, C.POINTER(u64), C.c_int]
+    L.orc_shortest_separator.argtypes = [C.c_char_p, u64, C.c_char_p, u64, C.c_char_p, u64]
+    L.orc_sst_build.argtypes = [u64, vp, vp, vp, vp, C.POINTER(TableOptions)]
+    L.orc_sst_build.restype = vp
+    L.orc_sst_from_bytes.argtypes = [C.c_char_p, u64, C.c_char_p, u64]
+    L.orc_sst_from_bytes.restype = vp
+    L.orc_sst_free.argtypes = [vp]
+    for f in ("data_size", "meta_size", "num_entries", "raw_key_bytes", "raw_val_bytes", "num_blocks"):
+        getattr(L, "orc_sst_" + f).argtypes = [vp]
+        getattr(L, "orc_sst_" + f).restype = u64
+    L.orc_sst_data.argtypes = [vp]
+    L.orc_sst_data.restype = vp
+    L.orc_sst_meta.argtypes = [vp]
+    L.orc_sst_meta.restype = vp
+    L.orc_sst_block_handles.argtypes = [vp, vp, vp]
+    L.orc_sst_key_encoding.argtypes = [vp]
+    L.orc_sst_read_all.argtypes = [vp, C.c_int]
+    L.orc_sst_read_all.restype = vp
+    L.orc_compact.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(u64), C.POINTER(CompactionParams),
+                              C.POINTER(TableOptions), C.c_int, C.c_int]
+    L.orc_compact.restype = vp
+    L.orc_compact_runs.argtypes = [C.c_int, vp, vp, vp, vp, vp, C.POINTER(CompactionParams)]
+    L.orc_compact_runs.restype = vp
+    L.orc_result_free.argtypes = [vp]
+    L.orc_result_error.argtypes = [vp]
+    L.orc_result_error.restype = C.c_char_p
+    L.orc_result_stats.argtypes = [vp]
+    L.orc_result_stats.restype = C.POINTER(Stats)
+    L.orc_result_sst.argtypes = [vp]
+    L.orc_result_sst.restype = vp
+    for f in ("num_kv", "keys_size", "vals_size"):
+        getattr(L, "orc_result_" + f).argtypes = [vp]
+        getattr(L, "orc_result_" + f).restype = u64
+    for f in ("keys", "vals", "koff", "voff"):
+        getattr(L, "orc_result_" + f).argtypes = [vp]
+        getattr(L, "orc_result_" + f).restype = vp
+    L.orc_gen_sst.argtypes = [C.POINTER(GenConfig), C.c_uint32, C.POINTER(TableOptions)]
+    L.orc_gen_sst.restype = vp
+    L.orc_gen_ssts.argtypes = [C.POINTER(GenConfig), C.POINTER(TableOptions), C.POINTER(vp), C.c_int]
+    _LIB = L
+    return L
+
+
+# ------------------------------------------------------------------------------------------------
+def encode_doc_ht(micros, logical=0, write_id=0):
+    buf = C.create_string_buffer(32)
+    n = lib().orc_encode_doc_ht((micros << 12) + logical, write_id, buf)
+    return buf.raw[:n]
+
+
+def encode_doc_ht_repr(ht_repr, write_id=0):
+    buf = C.create_string_buffer(32)
+    n = lib().orc_encode_doc_ht(ht_repr, write_id, buf)
+    return buf.raw[:n]
+
+
+def decode_doc_ht(b):
+    ht, wid = C.c_uint64(), C.c_uint32()
+    if lib().orc_decode_doc_ht(b, len(b), C.byref(ht), C.byref(wid)) != 0:
+        raise ValueError(lib().orc_last_error().decode())
+    return ht.value >> 12, ht.value & 0xfff, wid.value
+
+
+def signed_varint(v):
+    buf = C.create_string_buffer(16)
+    n = lib().orc_signed_varint(v, buf)
+    return buf.raw[:n]
+
+
+def unsigned_varint(v):
+    buf = C.create_string_buffer(16)
+    n = lib().orc_unsigned_varint(v, buf)
+    return buf.raw[:n]
+
+
+def crc32c(b):
+    return lib().orc_crc32c(b, len(b))
+
+
+def subdockey_ends(key):
+    ends = (C.c_uint64 * 32)()
+    n = lib().orc_subdockey_ends(key, len(key), ends, 32)
+    if n < 0:
+        raise ValueError(lib().orc_last_error().decode())
+    return list(ends[:n])
+
+
+def ht_from_micros(micros, logical=0):
+    return (micros << 12) + logical
+
+
+def ikey(user_key, seq, vtype=1):
+    return user_key + int((seq << 8) | vtype).to_bytes(8, "little")
+
+
+def _flat(items):
+    offs = np.zeros(len(items) + 1, dtype=np.uint64)
+    if items:
+        offs[1:] = np.cumsum([len(x) for x in items], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(items), dtype=np.uint8) if items else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(blob), offs
+
+
+class Sst:
+    """Owns an orc_sst handle."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("oracle: " + lib().orc_last_error().decode())
+        self.h = handle
+        self._own = True
+
+    @classmethod
+    def borrowed(cls, handle):
+        s = cls.__new__(cls)
+        s.h = handle
+        s._own = False
+        return s
+
+    def __del__(self):
+        if getattr(self, "_own", False) and self.h and _LIB is not None:
+            _LIB.orc_sst_free(self.h)
+            self.h = None
+
+    @classmethod
+    def build(cls, kvs, opts=None):
+        """kvs: list of (internal_key, value) in internal-key order."""
+        opts = opts or TableOptions()
+        kb, ko = _flat([k for k, _ in kvs])
+        vb, vo = _flat([v for _, v in kvs])
+        return cls(lib().orc_sst_build(len(kvs), kb.ctypes.data, ko.ctypes.data, vb.ctypes.data,
+                                       vo.ctypes.data, C.byref(opts)))
+
+    @classmethod
+    def from_bytes(cls, meta, data):
+        return cls(lib().orc_sst_from_bytes(meta, len(meta), data, len(data)))
+
+    @classmethod
+    def generate(cls, cfg, file_index, opts=None):
+        opts = opts or TableOptions()
+        return cls(lib().orc_gen_sst(C.byref(cfg), file_index, C.byref(opts)))
+
+    @classmethod
+    def generate_all(cls, cfg, opts=None, max_threads=None):
+        opts = opts or TableOptions()
+        arr = (C.c_void_p * cfg.num_files)()
+        rc = lib().orc_gen_ssts(C.byref(cfg), C.byref(opts), arr, max_threads or os.cpu_count() or 1)
+        if rc != 0:
+            raise RuntimeError("oracle: " + lib().orc_last_error().decode())
+        return [cls(arr[i]) for i in range(cfg.num_files)]
+
+    # zero-copy numpy views (valid while self is alive)
+    def data_view(self):
+        n = lib().orc_sst_data_size(self.h)
+        return np.ctypeslib.as_array(C.cast(lib().orc_sst_data(self.h), C.POINTER(C.c_uint8)), (n,)) if n else np.zeros(0, np.uint8)
+
+    def meta_view(self):
+        n = lib().orc_sst_meta_size(self.h)
+        return np.ctypeslib.as_array(C.cast(lib().orc_sst_meta(self.h), C.POINTER(C.c_uint8)), (n,)) if n else np.zeros(0, np.uint8)
+
+    @property
+    def data(self):
+        return self.data_view().tobytes()
+
+    @property
+    def meta(self):
+        return self.meta_view().tobytes()
+
+    @property
+    def num_entries(self):
+        return lib().orc_sst_num_entries(self.h)
+
+    @property
+    def raw_bytes(self):
+        return lib().orc_sst_raw_key_bytes(self.h) + lib().orc_sst_raw_val_bytes(self.h)
+
+    def block_handles(self):
+        n = lib().orc_sst_num_blocks(self.h)
+        off = np.zeros(n, np.uint64)
+        sz = np.zeros(n, np.uint64)
+        lib().orc_sst_block_handles(self.h, off.ctypes.data, sz.ctypes.data)
+        return off, sz
+
+    @property
+    def key_encoding(self):
+        return lib().orc_sst_key_encoding(self.h)
+
+    def read_all(self, verify=True):
+        r = Result(lib().orc_sst_read_all(self.h, int(verify)))
+        return r.kv_list()
+
+
+class Result:
+    def __init__(self, handle):
+        self.h = handle
+        err = lib().orc_result_error(handle)
+        if err:
+            msg = err.decode()
+            lib().orc_result_free(handle)
+            self.h = None
+            raise RuntimeError("oracle: " + msg)
+
+    def __del__(self):
+        if getattr(self, "h", None) and _LIB is not None:
+            _LIB.orc_result_free(self.h)
+            self.h = None
+
+    @property
+    def stats(self):
+        return lib().orc_result_stats(self.h).contents
+
+    def sst(self):
+        h = lib().orc_result_sst(self.h)
+        if not h:
+            return None
+        s = Sst.borrowed(h)
+        s._keepalive = self
+        return s
+
+    def flat(self):
+        L = lib()
+        n = L.orc_result_num_kv(self.h)
+        ks, vs = L.orc_result_keys_size(self.h), L.orc_result_vals_size(self.h)
+
+        def arr(ptr, count, ty):
+            if count == 0:
+                return np.zeros(0, ty)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(ty))), (count,)).copy()
+        keys = arr(L.orc_result_keys(self.h), ks, np.uint8)
+        vals = arr(L.orc_result_vals(self.h), vs, np.uint8)
+        koff = arr(L.orc_result_koff(self.h), n + 1, np.uint64)
+        voff = arr(L.orc_result_voff(self.h), n + 1, np.uint64)
+        return keys, koff, vals, voff
+
+    def kv_list(self):
+        keys, koff, vals, voff = self.flat()
+        kb, vb = keys.tobytes(), vals.tobytes()
+        return [(kb[int(koff[i]):int(koff[i + 1])], vb[int(voff[i]):int(voff[i + 1])])
+                for i in range(len(koff) - 1)]
+
+
+COLLECT_KV = 1
+BUILD_SST = 2
+NO_HASH = 4
+
+
+def compact(ssts, params=None, opts=None, mode=COLLECT_KV | BUILD_SST, verify=True, ht_filters=None):
+    params = params or CompactionParams()
+    opts = opts or TableOptions()
+    arr = (C.c_void_p * len(ssts))(*[s.h for s in ssts])
+    filt = None
+    if ht_filters is not None:
+        filt = (C.c_uint64 * len(ssts))(*ht_filters)
+    return Result(lib().orc_compact(len(ssts), arr, filt, C.byref(params), C.byref(opts), mode, int(verify)))
+
+
+def compact_runs(runs, params=None):
+    """runs: list of sorted lists of (internal_key, value)."""
+    params = params or CompactionParams()
+    flat = [kv for r in runs for kv in r]
+    starts = np.zeros(len(runs) + 1, np.uint64)
+    starts[1:] = np.cumsum([len(r) for r in runs])
+    kb, ko = _flat([k for k, _ in flat])
+    vb, vo = _flat([v for _, v in flat])
+    return Result(lib().orc_compact_runs(len(runs), starts.ctypes.data, kb.ctypes.data, ko.ctypes.data,
+                                         vb.ctypes.data, vo.ctypes.data, C.byref(params)))
