@@ -1,0 +1,214 @@
+/*
+ * ybgpu_compaction.h — C ABI of the B200-native DocDB compaction engine.
+ *
+ * This is the drop-in boundary for the one hot path this repository replaces: the loop inside
+ * rocksdb::CompactionJob::ProcessKeyValueCompaction (reference
+ * src/yb/rocksdb/db/compaction_job.cc:664-895) together with everything that loop pulls through
+ * per entry — MergingIterator/BlockIter (table/merger.cc:406-430, table/block.cc:348-447),
+ * CompactionIterator (db/compaction_iterator.cc:139-483), DocDBCompactionFeed::Feed
+ * (docdb/docdb_compaction_context.cc:941-1311) and BlockBasedTableBuilder::Add
+ * (table/block_based_table_builder.cc:498-541).
+ *
+ * Plain pointers and sizes only; no C++/torch types.  Every entry point returns a ybgpu_status
+ * (mapped 1:1 onto yb::Status codes by the C++ adapter) and fills the job's
+ * error string on failure.  There is no CPU fallback: if no CUDA device is usable, create fails
+ * with YBGPU_RUNTIME_ERROR.
+ *
+ * Threading: a job handle is used by one thread at a time (the reference runs one
+ * PriorityThreadPool worker per CompactionJob, db_impl.cc:397-403); different jobs may run
+ * concurrently on the same or different devices.
+ */
+#ifndef YBGPU_COMPACTION_H_
+#define YBGPU_COMPACTION_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* yb::Status::Code subset (src/yb/util/status.h) used on this path. */
+typedef enum ybgpu_status {
+  YBGPU_OK = 0,
+  YBGPU_NOT_FOUND = 1,
+  YBGPU_CORRUPTION = 2,           /* bad block / entry / key encoding */
+  YBGPU_NOT_SUPPORTED = 3,        /* e.g. compressed block, packed row without schema provider */
+  YBGPU_INVALID_ARGUMENT = 4,
+  YBGPU_IO_ERROR = 5,
+  YBGPU_RUNTIME_ERROR = 9,        /* CUDA failure, out of device memory */
+  YBGPU_SHUTDOWN_IN_PROGRESS = 19, /* shutting_down flag observed (compaction_job.cc:820-824) */
+  YBGPU_ILLEGAL_STATE = 10
+} ybgpu_status;
+
+/* rocksdb::KeyValueEncodingFormat (rocksdb/types.h:50-56); per input file from the table
+ * property kDataBlockKeyValueEncodingFormat (block_based_table_reader.cc:759-765). */
+enum { YBGPU_KEY_ENCODING_SHARED_PREFIX = 1, YBGPU_KEY_ENCODING_THREE_SHARED_PARTS = 2 };
+
+#define YBGPU_HT_MIN      0ull
+#define YBGPU_HT_MAX      0xffffffffffffffffull
+#define YBGPU_HT_INVALID  0xfffffffffffffffeull   /* HybridTime::kInvalid (common/hybrid_time.h:58) */
+#define YBGPU_TTL_MAX_NS  0x7fffffffffffffffll    /* ValueControlFields::kMaxTtl = MonoDelta::kMax */
+#define YBGPU_MAX_SEQUENCE 0x00ffffffffffffffull  /* kMaxSequenceNumber (db/dbformat.h:75) */
+
+/* Everything CompactionJob / DocDBCompactionContext know when the loop starts. */
+typedef struct ybgpu_job_options {
+  int32_t device;                    /* CUDA device ordinal */
+
+  /* --- rocksdb::Compaction / CompactionIterator inputs --- */
+  int32_t bottommost_level;          /* Compaction::bottommost_level() (db/compaction.cc:168-200) */
+  uint64_t last_sequence;            /* VersionSet::LastSequence(): earliest_snapshot_ when there are
+                                        no snapshots (compaction_iterator.cc:56-65) */
+  const uint8_t* largest_user_key;   /* Compaction::GetLargestUserKey() (db/compaction.cc:318);  */
+  uint64_t largest_user_key_len;     /* NULL/has=0 => engine derives it from the inputs          */
+  int32_t has_largest_user_key;
+
+  /* --- DocDB retention (docdb/docdb_compaction_context.h:57-111,178-196) ---
+   * retention_enabled = 0 reproduces a DB without compaction_context_factory (plain RocksDB). */
+  int32_t retention_enabled;
+  uint64_t history_cutoff_ht;        /* HistoryCutoff::primary_cutoff_ht (HybridTime repr) */
+  uint64_t cotables_cutoff_ht;       /* HistoryCutoff::cotables_cutoff_ht or YBGPU_HT_INVALID */
+  int64_t table_ttl_ns;              /* HistoryRetentionDirective::table_ttl, YBGPU_TTL_MAX_NS = none */
+  int32_t retain_delete_markers_in_major_compaction;
+  uint64_t other_min_ht;             /* CompactionHybridTimeConstraints::other_min; HT_MAX = "major" */
+  const uint8_t* key_bounds_lower;   /* docdb::KeyBounds (docdb/key_bounds.h); len 0 = unbounded */
+  uint64_t key_bounds_lower_len;
+  const uint8_t* key_bounds_upper;
+  uint64_t key_bounds_upper_len;
+
+  /* --- output table (rocksdb::BlockBasedTableOptions, table.h:107-217) --- */
+  uint32_t block_size;               /* 32 KB in DocDB (dockv/packed_row.cc:39) */
+  int32_t block_restart_interval;    /* 16 (docdb_rocksdb_util.cc:74,188) */
+  int32_t block_size_deviation;      /* 10 (table.h:144) */
+  int32_t output_key_encoding;       /* YBGPU_KEY_ENCODING_* */
+  uint32_t index_block_size;         /* 32 KB */
+  uint32_t min_keys_per_index_block; /* 100 */
+
+  int32_t verify_checksums;          /* verify input block CRC32C (version_set.cc:3788-3849) */
+} ybgpu_job_options;
+
+void ybgpu_job_options_init(ybgpu_job_options* o);   /* reference defaults */
+
+/* rocksdb::BlockHandle (table/format.cc:59-74): offset/size of a data block inside the input's
+ * data file (<n>.sst.sblock.0), excluding the 5-byte trailer. */
+typedef struct ybgpu_block_handle {
+  uint64_t offset;
+  uint64_t size;
+} ybgpu_block_handle;
+
+/* CompactionJobStats / CompactionIteratorStats fields filled by the loop
+ * (compaction_job.cc:851-861,897-920; compaction_iterator.h). */
+typedef struct ybgpu_job_stats {
+  uint64_t num_input_records;
+  uint64_t num_output_records;
+  uint64_t num_record_drop_hidden;     /* rule A, compaction_iterator.cc:388-400 */
+  uint64_t num_record_drop_obsolete;   /* kTypeDeletion at bottommost, :401-420 */
+  uint64_t num_record_drop_feed;       /* dropped by the fused DocDB retention predicate */
+  uint64_t total_input_raw_key_bytes;
+  uint64_t total_input_raw_value_bytes;
+  uint64_t total_output_raw_key_bytes;
+  uint64_t total_output_raw_value_bytes;
+  uint64_t num_output_data_blocks;
+  uint64_t output_data_file_size;      /* bytes of <n>.sst.sblock.0 */
+  uint64_t output_meta_file_size;      /* bytes of <n>.sst */
+  uint64_t smallest_seqno, largest_seqno;   /* FileMetaData seqno bounds of the output */
+  double gpu_seconds;                  /* device time of all kernels (CUDA events) */
+  uint32_t gpu_kernel_launches;        /* kernels launched by run() */
+  uint64_t h2d_bytes, d2h_bytes;       /* bytes copied by add_input / fetch calls */
+} ybgpu_job_stats;
+
+typedef struct ybgpu_job ybgpu_job;
+
+/* Replaces: CompactionJob ctor + Prepare() parameter capture (db/compaction_job.h:77-104). */
+ybgpu_status ybgpu_job_create(const ybgpu_job_options* options, ybgpu_job** job);
+void ybgpu_job_destroy(ybgpu_job* job);
+const char* ybgpu_job_error(const ybgpu_job* job);       /* message of the last failure */
+const char* ybgpu_last_error(void);                      /* for failures of create itself */
+
+/* Replaces: VersionSet::MakeInputIterator's per-file TableCache::NewIterator
+ * (db/version_set.cc:3788-3849). `data_file` is the whole data file in HOST memory (copied to
+ * HBM here); `handles` are the data-block handles in key order as read from the file's index.
+ * `hybrid_time_filter` is the file's global HybridTime filter (docdb_rocksdb_util.cc:494-571) or
+ * YBGPU_HT_INVALID.  Inputs may be added in any order; order does not affect the output. */
+ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint64_t data_file_len,
+                                 const ybgpu_block_handle* handles, uint64_t num_handles,
+                                 int32_t key_encoding, uint64_t hybrid_time_filter);
+
+/* Same, but `data_file_dev` already lives in device memory of the job's device (used by the
+ * bench's HBM-resident measurement and by callers that stage files themselves). Not copied, not
+ * owned; must stay valid until destroy. */
+ybgpu_status ybgpu_job_add_input_device(ybgpu_job* job, const uint8_t* data_file_dev, uint64_t data_file_len,
+                                        const ybgpu_block_handle* handles, uint64_t num_handles,
+                                        int32_t key_encoding, uint64_t hybrid_time_filter);
+
+/* Convenience: parse a split SST's metadata file (<n>.sst: footer, metaindex, properties,
+ * multi-level index; table/format.cc:118-153, table/index_reader.h:215-256) on the host and call
+ * add_input with the handles / encoding found there. */
+ybgpu_status ybgpu_job_add_input_sst(ybgpu_job* job, const uint8_t* meta_file, uint64_t meta_file_len,
+                                     const uint8_t* data_file, uint64_t data_file_len,
+                                     uint64_t hybrid_time_filter);
+
+/* Replaces: CompactionJob::Run() -> ProcessKeyValueCompaction. Runs decode, merge, the fused
+ * CompactionIterator + DocDB retention predicate and output encoding on the GPU. `shutting_down`
+ * (may be NULL) is polled between kernel phases like compaction_job.cc:771. */
+ybgpu_status ybgpu_job_run(ybgpu_job* job, const volatile int32_t* shutting_down);
+
+ybgpu_status ybgpu_job_get_stats(const ybgpu_job* job, ybgpu_job_stats* stats);
+
+/* --- results ---------------------------------------------------------------------------------
+ * (a) The surviving KV stream in output order, the form CompactionFeed::Feed /
+ *     TableBuilder::Add (table/table_builder.h:93-136) consume.  Sizes first, then one copy. */
+ybgpu_status ybgpu_job_kv_stream_sizes(const ybgpu_job* job, uint64_t* num_entries,
+                                       uint64_t* key_bytes, uint64_t* value_bytes);
+/* key_offsets / value_offsets have num_entries + 1 elements. */
+ybgpu_status ybgpu_job_fetch_kv_stream(ybgpu_job* job, uint8_t* keys, uint64_t* key_offsets,
+                                       uint8_t* values, uint64_t* value_offsets);
+/* Calls emit(ctx, key, klen, value, vlen) for every surviving entry in order; a non-zero return
+ * aborts with that status (the reference aborts its loop on the first non-OK Feed,
+ * compaction_job.cc:797-800). */
+typedef int (*ybgpu_emit_fn)(void* ctx, const uint8_t* key, uint64_t key_len, const uint8_t* value,
+                             uint64_t value_len);
+ybgpu_status ybgpu_job_emit_kv_stream(ybgpu_job* job, ybgpu_emit_fn emit, void* ctx);
+
+/* (b) The finished output SST, split the way the reference writes it
+ *     (block_based_table_builder.cc:762-903, db/filename.cc:44-45): data blocks + trailers for
+ *     <n>.sst.sblock.0 and index/properties/metaindex/footer for <n>.sst. */
+ybgpu_status ybgpu_job_output_sizes(const ybgpu_job* job, uint64_t* data_file_len, uint64_t* meta_file_len);
+ybgpu_status ybgpu_job_fetch_output(ybgpu_job* job, uint8_t* data_file, uint64_t data_cap,
+                                    uint8_t* meta_file, uint64_t meta_cap);
+
+/* FileMetaData boundaries of the output (db/version_edit.h:101-165): smallest / largest internal
+ * key. Buffers must hold the longest key (use 4096). */
+ybgpu_status ybgpu_job_output_boundaries(const ybgpu_job* job, uint8_t* smallest, uint64_t* smallest_len,
+                                         uint8_t* largest, uint64_t* largest_len);
+
+/* Device-side checksum of the surviving KV stream: order-sensitive 64-bit hash over
+ * (key_len, key, value_len, value) per entry, combined per entry position. Used by the parity
+ * tests at sizes where copying the stream back is pointless. */
+ybgpu_status ybgpu_job_kv_stream_digest(ybgpu_job* job, uint64_t* digest);
+
+/* --- host-side table builder --------------------------------------------------------------------
+ * rocksdb::TableBuilder shape (table/table_builder.h:93-136) over the product's split-SST writer:
+ * what TableFactory::NewTableBuilder (rocksdb/table.h:394-397) returns when the engine's KV
+ * stream is consumed entry by entry (e.g. after a host-only CompactionFeed such as the packed-row
+ * repacker). Keys are internal keys in InternalKeyComparator order. */
+typedef struct ybgpu_table_builder ybgpu_table_builder;
+ybgpu_status ybgpu_table_builder_create(const ybgpu_job_options* table_options, ybgpu_table_builder** b);
+ybgpu_status ybgpu_table_builder_add(ybgpu_table_builder* b, const uint8_t* key, uint64_t key_len,
+                                     const uint8_t* value, uint64_t value_len);          /* Add() */
+ybgpu_status ybgpu_table_builder_finish(ybgpu_table_builder* b);                         /* Finish() */
+uint64_t ybgpu_table_builder_num_entries(const ybgpu_table_builder* b);                  /* NumEntries() */
+uint64_t ybgpu_table_builder_total_file_size(const ybgpu_table_builder* b);              /* TotalFileSize() */
+uint64_t ybgpu_table_builder_base_file_size(const ybgpu_table_builder* b);               /* BaseFileSize() */
+ybgpu_status ybgpu_table_builder_files(const ybgpu_table_builder* b, const uint8_t** data_file, uint64_t* data_len,
+                                       const uint8_t** meta_file, uint64_t* meta_len);
+void ybgpu_table_builder_destroy(ybgpu_table_builder* b);                                /* Abandon() / dtor */
+
+/* Library / device probe. */
+int32_t ybgpu_device_count(void);
+const char* ybgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* YBGPU_COMPACTION_H_ */

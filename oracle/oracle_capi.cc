@@ -169,11 +169,18 @@ orc_result* orc_sst_read_all(const orc_sst* s, int verify) {
 
 // ---- compaction ------------------------------------------------------------------------------
 struct ResultSink : CompactionFeed {
-  orc_result* res; TableBuilder* builder; bool collect; uint64_t h = 1469598103934665603ull;
-  void Mix(const uint8_t* p, size_t n) { for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; } }
+  // kv_hash: order-sensitive digest matching ybgpu_job_kv_stream_digest: per entry FNV-1a-64 over
+  // (klen u32 LE, key, vlen u32 LE, value), finalised together with the entry index, summed.
+  orc_result* res; TableBuilder* builder; bool collect; uint64_t h = 0; uint64_t index = 0;
+  static uint64_t Fnv(uint64_t x, const uint8_t* p, size_t n) { for (size_t i = 0; i < n; i++) { x ^= p[i]; x *= 1099511628211ull; } return x; }
+  static uint64_t Fin(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; }
   void Feed(Slice k, Slice v) override {
     uint32_t kl = static_cast<uint32_t>(k.n), vl = static_cast<uint32_t>(v.n);
-    Mix(reinterpret_cast<uint8_t*>(&kl), 4); Mix(k.p, k.n); Mix(reinterpret_cast<uint8_t*>(&vl), 4); Mix(v.p, v.n);
+    uint64_t e = 1469598103934665603ull;
+    e = Fnv(e, reinterpret_cast<uint8_t*>(&kl), 4); e = Fnv(e, k.p, k.n);
+    e = Fnv(e, reinterpret_cast<uint8_t*>(&vl), 4); e = Fnv(e, v.p, v.n);
+    h += Fin(e + index * 0x9e3779b97f4a7c15ull);
+    index++;
     if (collect) {
       res->keys.append(reinterpret_cast<const char*>(k.p), k.n); res->vals.append(reinterpret_cast<const char*>(v.p), v.n);
       res->koff.push_back(res->keys.size()); res->voff.push_back(res->vals.size());

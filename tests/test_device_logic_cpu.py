@@ -1,0 +1,60 @@
+"""The per-entry device logic (dev_logic.cuh: key compare, row grouping, CompactionIterator rules,
+feed_step) compiled for the CPU by tests/host_harness, against the oracle. Same inputs the GPU
+parity tests use, so logic bugs surface without a GPU."""
+import pytest
+
+import dockv_util as dk
+import harness_py as hh
+import oracle_py as o
+import workloads as w
+
+
+def both(runs, **kw):
+    p = o.CompactionParams(**kw)
+    exp = o.compact_runs(runs, p).kv_list()
+    got = hh.compact_runs(runs, p)
+    return got, exp
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_docdb_runs(seed):
+    runs = w.random_docdb_runs(seed, n_runs=1 + seed % 5, n_rows=25 + 5 * seed)
+    for kw in w.param_grid():
+        got, exp = both(runs, **kw)
+        assert got == exp, kw
+
+
+def test_plain_rocksdb_mode():
+    seq = 0
+    runs = []
+    for i in range(2):
+        c = []
+        for k in range(2000):
+            seq += 1
+            c.append((o.ikey(str(i * 1000 + k).encode(), seq), str(i * 2000 + k).encode()))
+        runs.append(w.sort_run(c))
+    got, exp = both(runs, retention=False, bottommost=True, last_sequence=seq + 1)
+    assert got == exp and len(got) == 3000
+    got, exp = both(runs, retention=False, bottommost=False, last_sequence=seq + 1)
+    assert got == exp
+
+
+def test_key_bounds_and_obsolete_prefix():
+    runs = w.random_docdb_runs(99, n_runs=3, n_rows=60)
+    keys = sorted(k[:-8] for r in runs for k, _ in r)
+    lo, up = keys[len(keys) // 4], keys[3 * len(keys) // 4]
+    got, exp = both(runs, cutoff_ht=o.ht_from_micros(w.BASE_US + 50), lower=lo, upper=up)
+    assert got == exp and 0 < len(got) < len(keys)
+
+
+def test_group_prefix_len():
+    L = hh.lib()
+    d = dk.doc_key(["a", 5], hash_code=7, hashed=["h"])
+    k = dk.sub_doc_key(d, [dk.kcol(2), "x"], micros=o.YB_EPOCH_US + 5)
+    assert L.hh_group_prefix_len(k, len(k), 1) == len(d)
+    assert L.hh_group_prefix_len(k, len(k), 0) == len(k)
+    d2 = dk.doc_key(["only-range"])
+    k2 = dk.sub_doc_key(d2, [], micros=o.YB_EPOCH_US + 5)
+    assert L.hh_group_prefix_len(k2, len(k2), 1) == len(d2)
+    co = dk.sub_doc_key(dk.doc_key(["r"], colocation=5), [dk.kcol(1)], micros=o.YB_EPOCH_US)
+    assert L.hh_group_prefix_len(co, len(co), 1) == -14      # DEV_ERR_COTABLE (loud, not silent)

@@ -1,0 +1,181 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on the same inputs.
+Bit-exact KV stream (integer/byte work), stats, and output SST bytes."""
+import importlib
+
+import numpy as np
+import pytest
+
+import dockv_util as dk
+import oracle_py as o
+import workloads as w
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    m = importlib.import_module("yugabyte-db_b200")
+    assert m.device_count() >= 1, "GPU tests need a CUDA device"
+    return m
+
+
+def gpu_compact(pkg, ssts, ht_filters=None, **kw):
+    job = pkg.GpuCompactionJob(**kw)
+    for i, s in enumerate(ssts):
+        job.add_input_sst(s.meta_view(), s.data_view(), ht_filter=(ht_filters[i] if ht_filters else pkg.HT_INVALID))
+    job.run()
+    return job
+
+
+def okw(kw):
+    """binding kwargs -> oracle CompactionParams kwargs"""
+    m = dict(kw)
+    m.pop("block_size", None)
+    return m
+
+
+def check(pkg, ssts, block_size=4096, ht_filters=None, **kw):
+    exp = o.compact(ssts, o.CompactionParams(**okw(kw)), o.TableOptions(block_size=block_size), ht_filters=ht_filters)
+    job = gpu_compact(pkg, ssts, ht_filters=ht_filters, block_size=block_size, **kw)
+    st = job.stats()
+    assert job.kv_list() == exp.kv_list()
+    es = exp.stats
+    assert st.num_input_records == es.num_input_records
+    assert st.num_output_records == es.num_output_records
+    assert st.num_record_drop_hidden == es.num_dropped_hidden
+    assert st.num_record_drop_obsolete == es.num_dropped_obsolete
+    assert st.num_record_drop_feed == es.num_dropped_feed
+    assert st.total_input_raw_key_bytes == es.in_key_bytes and st.total_input_raw_value_bytes == es.in_val_bytes
+    assert st.total_output_raw_key_bytes == es.out_key_bytes and st.total_output_raw_value_bytes == es.out_val_bytes
+    assert job.digest() == es.kv_hash
+    data, meta = job.fetch_output()
+    ref = exp.sst()
+    if ref is None:
+        assert data.size == 0 and meta.size == 0
+    else:
+        assert data.tobytes() == ref.data
+        assert meta.tobytes() == ref.meta
+    assert st.gpu_kernel_launches > 0
+    return job, exp
+
+
+def runs_to_ssts(runs, block_size=1024):
+    return [o.Sst.build(r, o.TableOptions(block_size=block_size)) for r in runs if r]
+
+
+def test_config1_two_sst_minor_10k(pkg):
+    """BASELINE config 1: 2 SSTs x 10k entries, 5k overlapping user keys (mirrors
+    rocksdb/db/compaction_job_test.cc:193-231), minor compaction, cutoff = min."""
+    base = o.YB_EPOCH_US + 10**9
+    runs = []
+    seq = 1 << 50
+    for f in range(2):
+        kvs = []
+        for k in range(10000):
+            row = f * 5000 + k
+            d = dk.doc_key([("%024d" % row)], hash_code=(row * 65536) // 15000, hashed=[])
+            uk = dk.sub_doc_key(d, [dk.kcol(1)], micros=base + 1000)
+            seq += 1
+            kvs.append((o.ikey(uk, seq), b"S" + bytes([(row + j) % 251 + 1 for j in range(255)])))
+        runs.append(w.sort_run(kvs))
+    ssts = [o.Sst.build(r, o.TableOptions(block_size=32768)) for r in runs]
+    job, exp = check(pkg, ssts, block_size=32768, bottommost=False, cutoff_ht=o.HT_MIN, other_min_ht=o.HT_MIN)
+    assert job.stats().num_output_records == 15000
+    assert job.stats().num_record_drop_hidden == 5000
+
+
+def test_plain_rocksdb_compaction_job_test_simple(pkg):
+    # compaction_job_test.cc:339-347 through real SSTs, no DocDB context
+    seq = 0
+    runs = []
+    for i in range(2):
+        c = []
+        for k in range(10000):
+            seq += 1
+            c.append((o.ikey(str(i * 5000 + k).encode(), seq), str(i * 10000 + k).encode()))
+        runs.append(w.sort_run(c))
+    ssts = runs_to_ssts(runs, 4096)
+    job, exp = check(pkg, ssts, retention=False, bottommost=True, last_sequence=seq + 1)
+    kv = dict(job.kv_list())
+    assert kv[o.ikey(b"9999", 15000)] == b"14999"          # largest user key keeps its seqno
+    assert o.ikey(b"0", 0) in kv
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomized_docdb(pkg, seed):
+    runs = w.random_docdb_runs(seed, n_runs=1 + seed % 6, n_rows=150 + 40 * seed)
+    ssts = runs_to_ssts(runs, 512 if seed % 2 else 2048)
+    for kw in w.param_grid():
+        check(pkg, ssts, block_size=1024, **kw)
+
+
+def test_golden_first_row_regression(pkg):
+    # docdb/docdb-test-wrapper.cc:99-133
+    d = dk.doc_key(["mydockey", dk.INT_KEY1])
+    e = [(dk.sub_doc_key(d, [], micros=4000), dk.OBJECT), (dk.sub_doc_key(d, [], micros=1000), dk.OBJECT),
+         (dk.sub_doc_key(d, ["subkey1"], micros=3000), dk.vstr("value3")),
+         (dk.sub_doc_key(d, ["subkey1"], micros=2000), dk.vstr("value2")),
+         (dk.sub_doc_key(d, ["subkey1"], micros=1000), dk.vstr("value1"))]
+    run = w.sort_run([(o.ikey(k, (1 << 50) + i), v) for i, (k, v) in enumerate(e)])
+    job, _ = check(pkg, runs_to_ssts([run]), cutoff_ht=o.ht_from_micros(3500))
+    assert [k[:-8] for k, _ in job.kv_list()] == [e[0][0], e[1][0], e[2][0]]
+
+
+def test_generated_shapes_and_mvcc_heavy(pkg):
+    # config-4 shape scaled: 20 versions per key, cutoff above 19 of them
+    cfg = o.GenConfig(seed=2, num_rows=5000, cols=1, versions=20, num_files=8, value_len=64)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=8192))
+    cutoff = o.ht_from_micros(cfg.base_micros + 18 * 1000 + 500)
+    job, exp = check(pkg, ssts, block_size=8192, cutoff_ht=cutoff)
+    assert job.stats().num_output_records == 5000 * 2
+
+
+def test_config2_shape_scaled_8way(pkg):
+    cfg = o.GenConfig(seed=7, num_rows=200000, cols=1, versions=1, num_files=8, value_len=256)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=32768))
+    job, exp = check(pkg, ssts, block_size=32768)
+    assert job.stats().num_output_records == 200000
+
+
+def test_hybrid_time_filter(pkg):
+    cfg = o.GenConfig(seed=5, num_rows=800, cols=2, versions=6, num_files=3, value_len=32)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=2048))
+    filt = [o.ht_from_micros(cfg.base_micros + 3500), o.HT_INVALID, o.ht_from_micros(cfg.base_micros + 1500)]
+    check(pkg, ssts, block_size=2048, ht_filters=filt, cutoff_ht=o.ht_from_micros(cfg.base_micros + 2500))
+
+
+def test_edge_cases(pkg):
+    # single entry, single file
+    d = dk.doc_key(["only"])
+    one = [(o.ikey(dk.sub_doc_key(d, [dk.kcol(1)], micros=o.YB_EPOCH_US + 1), 1 << 50), dk.vstr("x"))]
+    check(pkg, runs_to_ssts([one]))
+    # everything dropped -> empty output, no files
+    tomb = [(o.ikey(dk.sub_doc_key(d, [dk.kcol(1)], micros=o.YB_EPOCH_US + 1), 1 << 50), dk.TOMBSTONE)]
+    job, _ = check(pkg, runs_to_ssts([tomb]), cutoff_ht=o.ht_from_micros(o.YB_EPOCH_US + 100))
+    assert job.stats().num_output_records == 0
+    # empty values, long keys (> 128 bytes), ragged sizes
+    long_rows = []
+    for i in range(300):
+        dd = dk.doc_key(["L" * (5 + (i * 7) % 200) + "%05d" % i])
+        long_rows.append((o.ikey(dk.sub_doc_key(dd, [dk.kcol(1)], micros=o.YB_EPOCH_US + i), (1 << 50) + i),
+                          b"" if i % 3 == 0 else dk.vstr("v" * (i % 50))))
+    check(pkg, runs_to_ssts([w.sort_run(long_rows)], 256))
+
+
+def test_errors_are_loud(pkg):
+    d = dk.doc_key(["r"], colocation=7)
+    run = [(o.ikey(dk.sub_doc_key(d, [dk.kcol(1)], micros=o.YB_EPOCH_US + 1), 1 << 50), dk.vstr("x"))]
+    job = pkg.GpuCompactionJob()
+    s = runs_to_ssts([run])[0]
+    job.add_input_sst(s.meta_view(), s.data_view())
+    with pytest.raises(pkg.YbGpuError) as e:
+        job.run()
+    assert e.value.status_name == "NotSupported"
+    # corrupted block checksum
+    s2 = runs_to_ssts([[(o.ikey(b"Sabc\x00\x00!#" + o.encode_doc_ht(o.YB_EPOCH_US), 5), b"Sv")]])[0]
+    data = s2.data_view().copy()
+    data[3] ^= 0xff
+    job = pkg.GpuCompactionJob()
+    with pytest.raises(pkg.YbGpuError) as e:
+        job.add_input_sst(s2.meta_view(), data)
+    assert e.value.status_name == "Corruption"

@@ -1,0 +1,84 @@
+"""Shared randomized DocDB-shaped workloads for the parity tests (CPU device-logic harness and GPU)."""
+import random
+
+import dockv_util as dk
+import oracle_py as o
+
+BASE_US = o.YB_EPOCH_US + 100_000_000
+
+
+def sort_run(kvs):
+    kvs.sort(key=lambda kv: (kv[0][:-8], -int.from_bytes(kv[0][-8:], "little")))
+    return kvs
+
+
+def random_docdb_runs(seed, n_runs=4, n_rows=40, deep=True, ttl=True, dup_rate=0.1, n_ht=12):
+    """Rows with nested subkeys, tombstones, TTLs, merge (TTL) rows, intent doc HTs, and exact
+    duplicate user keys across runs (rule A). Returns list of sorted runs of (ikey, value)."""
+    rng = random.Random(seed)
+    runs = [[] for _ in range(n_runs)]
+    seq = [(1 << 50) + (r << 30) for r in range(n_runs)]
+    used = set()
+
+    def put(user_key, value):
+        r = rng.randrange(n_runs)
+        seq[r] += 1
+        runs[r].append((o.ikey(user_key, seq[r]), value))
+        if rng.random() < dup_rate:
+            r2 = rng.randrange(n_runs)
+            if r2 != r:
+                seq[r2] += 1
+                runs[r2].append((o.ikey(user_key, seq[r2]), dk.vstr("dup%d" % rng.randrange(100))))
+
+    def rand_value():
+        x = rng.random()
+        if x < 0.15:
+            return dk.TOMBSTONE
+        v = dk.vstr("v" + "x" * rng.randrange(0, 40) + str(rng.randrange(1000)))
+        if x < 0.2:
+            v = dk.OBJECT
+        if ttl and rng.random() < 0.15:
+            v = dk.with_ttl(v, rng.choice([0, 1, 50, 5000, 10**7]))
+        if rng.random() < 0.08:
+            v = dk.with_intent_ht(v, BASE_US + rng.randrange(n_ht * 10), 0, rng.randrange(4))
+        if ttl and rng.random() < 0.05:
+            v = dk.ttl_merge_row(rng.choice([1, 100, 10**6]))
+        return v
+
+    for row in range(n_rows):
+        style = rng.random()
+        if style < 0.5:
+            d = dk.doc_key([rng.choice(["r", "row", "k"]) + str(row), rng.randrange(5)],
+                           hash_code=rng.randrange(65536), hashed=["h%d" % row])
+        else:
+            d = dk.doc_key(["plain%04d" % row] + ([rng.randrange(-5, 5)] if rng.random() < 0.5 else []))
+        paths = [[]] if rng.random() < 0.5 else []
+        for c in range(rng.randrange(1, 5)):
+            p = [dk.kcol(c + 1) if rng.random() < 0.7 else "sub%d" % c]
+            paths.append(p)
+            if deep and rng.random() < 0.4:
+                for j in range(rng.randrange(1, 3)):
+                    paths.append(p + ["leaf%d" % j])
+                    if rng.random() < 0.3:
+                        paths.append(p + ["leaf%d" % j, dk.kint64(j)])
+        for p in paths:
+            for _ in range(rng.randrange(1, 5)):
+                ht = (BASE_US + rng.randrange(n_ht) * 10, rng.randrange(2), rng.randrange(3))
+                uk = dk.sub_doc_key(d, p, ht=ht)
+                if uk in used:
+                    continue
+                used.add(uk)
+                put(uk, rand_value())
+    return [sort_run(r) for r in runs]
+
+
+def param_grid():
+    cut = [o.HT_MIN, o.ht_from_micros(BASE_US + 35), o.ht_from_micros(BASE_US + 75, 1), o.ht_from_micros(BASE_US + 10**6)]
+    out = []
+    for c in cut:
+        for major in (True, False):
+            out.append(dict(bottommost=major, cutoff_ht=c, other_min_ht=o.HT_MAX if major else o.HT_MIN))
+    out.append(dict(bottommost=True, cutoff_ht=cut[2], other_min_ht=o.HT_MAX, retain_delete_markers=True))
+    out.append(dict(bottommost=True, cutoff_ht=cut[3], other_min_ht=o.ht_from_micros(BASE_US + 50), table_ttl_ns=20 * 10**3))
+    out.append(dict(bottommost=False, cutoff_ht=cut[1], other_min_ht=o.HT_MIN, table_ttl_ns=10**9))
+    return out

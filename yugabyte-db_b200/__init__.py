@@ -1,0 +1,10 @@
+"""yugabyte-db_b200 — B200-native DocDB compaction engine.
+
+Python is only the test / bench binding over the C ABI in include/ybgpu_compaction.h (the product
+is libybgpu.so: hand-written sm_100a CUDA + a C++ host layer). Importing this package never
+falls back to a CPU implementation: if libybgpu.so is missing the import fails loudly.
+"""
+from .binding import (  # noqa: F401
+    GpuCompactionJob, JobOptions, JobStats, BlockHandle, YbGpuError, lib, device_count,
+    HT_MIN, HT_MAX, HT_INVALID, TTL_MAX_NS, MAX_SEQUENCE, LIB_PATH, HostTableBuilder,
+)

@@ -1,0 +1,262 @@
+"""ctypes binding of libybgpu.so (include/ybgpu_compaction.h)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libybgpu.so")
+
+HT_MIN = 0
+HT_MAX = 2**64 - 1
+HT_INVALID = 2**64 - 2
+TTL_MAX_NS = 2**63 - 1
+MAX_SEQUENCE = (1 << 56) - 1
+
+STATUS_NAMES = {0: "OK", 1: "NotFound", 2: "Corruption", 3: "NotSupported", 4: "InvalidArgument", 5: "IOError",
+                9: "RuntimeError", 10: "IllegalState", 19: "ShutdownInProgress"}
+
+
+class YbGpuError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), msg))
+        self.status = status
+        self.status_name = STATUS_NAMES.get(status, str(status))
+
+
+class JobOptions(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("bottommost_level", C.c_int32), ("last_sequence", C.c_uint64),
+        ("largest_user_key", C.c_char_p), ("largest_user_key_len", C.c_uint64), ("has_largest_user_key", C.c_int32),
+        ("retention_enabled", C.c_int32), ("history_cutoff_ht", C.c_uint64), ("cotables_cutoff_ht", C.c_uint64),
+        ("table_ttl_ns", C.c_int64), ("retain_delete_markers_in_major_compaction", C.c_int32),
+        ("other_min_ht", C.c_uint64),
+        ("key_bounds_lower", C.c_char_p), ("key_bounds_lower_len", C.c_uint64),
+        ("key_bounds_upper", C.c_char_p), ("key_bounds_upper_len", C.c_uint64),
+        ("block_size", C.c_uint32), ("block_restart_interval", C.c_int32), ("block_size_deviation", C.c_int32),
+        ("output_key_encoding", C.c_int32), ("index_block_size", C.c_uint32), ("min_keys_per_index_block", C.c_uint32),
+        ("verify_checksums", C.c_int32),
+    ]
+
+
+class BlockHandle(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("size", C.c_uint64)]
+
+
+class JobStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "num_input_records", "num_output_records", "num_record_drop_hidden", "num_record_drop_obsolete",
+        "num_record_drop_feed", "total_input_raw_key_bytes", "total_input_raw_value_bytes",
+        "total_output_raw_key_bytes", "total_output_raw_value_bytes", "num_output_data_blocks",
+        "output_data_file_size", "output_meta_file_size", "smallest_seqno", "largest_seqno")] + [
+        ("gpu_seconds", C.c_double), ("gpu_kernel_launches", C.c_uint32), ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_LIB = None
+
+
+def lib():
+    """Loads libybgpu.so; raises (never falls back) when the CUDA library is not built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libybgpu.so is not built (run __graft_entry__.build()); "
+                          "there is no CPU fallback for the compaction engine")
+    L = C.CDLL(LIB_PATH)
+    vp, u64 = C.c_void_p, C.c_uint64
+    L.ybgpu_job_options_init.argtypes = [C.POINTER(JobOptions)]
+    L.ybgpu_job_create.argtypes = [C.POINTER(JobOptions), C.POINTER(vp)]
+    L.ybgpu_job_destroy.argtypes = [vp]
+    L.ybgpu_job_error.argtypes = [vp]
+    L.ybgpu_job_error.restype = C.c_char_p
+    L.ybgpu_last_error.restype = C.c_char_p
+    L.ybgpu_job_add_input.argtypes = [vp, vp, u64, vp, u64, C.c_int32, u64]
+    L.ybgpu_job_add_input_device.argtypes = [vp, vp, u64, vp, u64, C.c_int32, u64]
+    L.ybgpu_job_add_input_sst.argtypes = [vp, vp, u64, vp, u64, u64]
+    L.ybgpu_job_run.argtypes = [vp, vp]
+    L.ybgpu_job_get_stats.argtypes = [vp, C.POINTER(JobStats)]
+    L.ybgpu_job_kv_stream_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.ybgpu_job_fetch_kv_stream.argtypes = [vp, vp, vp, vp, vp]
+    L.ybgpu_job_output_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.ybgpu_job_fetch_output.argtypes = [vp, vp, u64, vp, u64]
+    L.ybgpu_job_output_boundaries.argtypes = [vp, vp, C.POINTER(u64), vp, C.POINTER(u64)]
+    L.ybgpu_job_kv_stream_digest.argtypes = [vp, C.POINTER(u64)]
+    L.ybgpu_device_count.restype = C.c_int32
+    L.ybgpu_version.restype = C.c_char_p
+    _LIB = L
+    return L
+
+
+def device_count():
+    return lib().ybgpu_device_count()
+
+
+def _np_ptr(a):
+    return a.ctypes.data if a.size else None
+
+
+class GpuCompactionJob:
+    """One rocksdb::CompactionJob::Run on the GPU (compaction_job.cc:521-589)."""
+
+    def __init__(self, device=0, bottommost=True, last_sequence=MAX_SEQUENCE, largest_user_key=None,
+                 retention=True, cutoff_ht=HT_MIN, cotables_cutoff_ht=HT_INVALID, table_ttl_ns=TTL_MAX_NS,
+                 retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
+                 restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
+                 min_keys_per_index_block=100, verify_checksums=True):
+        L = lib()
+        o = JobOptions()
+        L.ybgpu_job_options_init(C.byref(o))
+        o.device = device
+        o.bottommost_level = int(bottommost)
+        o.last_sequence = last_sequence
+        if largest_user_key is not None:
+            o.largest_user_key, o.largest_user_key_len, o.has_largest_user_key = largest_user_key, len(largest_user_key), 1
+        o.retention_enabled = int(retention)
+        o.history_cutoff_ht = cutoff_ht
+        o.cotables_cutoff_ht = cotables_cutoff_ht
+        o.table_ttl_ns = table_ttl_ns
+        o.retain_delete_markers_in_major_compaction = int(retain_delete_markers)
+        o.other_min_ht = other_min_ht
+        o.key_bounds_lower, o.key_bounds_lower_len = lower, len(lower)
+        o.key_bounds_upper, o.key_bounds_upper_len = upper, len(upper)
+        o.block_size, o.block_restart_interval, o.block_size_deviation = block_size, restart_interval, deviation
+        o.output_key_encoding = output_key_encoding
+        o.index_block_size, o.min_keys_per_index_block = index_block_size, min_keys_per_index_block
+        o.verify_checksums = int(verify_checksums)
+        self._keep = (largest_user_key, lower, upper)
+        h = C.c_void_p()
+        st = L.ybgpu_job_create(C.byref(o), C.byref(h))
+        if st != 0:
+            raise YbGpuError(st, L.ybgpu_last_error().decode())
+        self.h = h
+        self._inputs = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ybgpu_job_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != 0:
+            raise YbGpuError(st, lib().ybgpu_job_error(self.h).decode())
+
+    def add_input(self, data, offsets, sizes, key_encoding=1, ht_filter=HT_INVALID):
+        """data: numpy uint8 array (host) of the data file; offsets/sizes: block handles."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        hs = np.zeros((len(offsets), 2), dtype=np.uint64)
+        hs[:, 0] = offsets
+        hs[:, 1] = sizes
+        self._check(lib().ybgpu_job_add_input(self.h, _np_ptr(data), data.size, _np_ptr(hs), len(offsets), key_encoding, ht_filter))
+
+    def add_input_device(self, dev_ptr, length, offsets, sizes, key_encoding=1, ht_filter=HT_INVALID):
+        hs = np.zeros((len(offsets), 2), dtype=np.uint64)
+        hs[:, 0] = offsets
+        hs[:, 1] = sizes
+        self._check(lib().ybgpu_job_add_input_device(self.h, dev_ptr, length, _np_ptr(hs), len(offsets), key_encoding, ht_filter))
+
+    def add_input_sst(self, meta, data, ht_filter=HT_INVALID):
+        meta = np.ascontiguousarray(meta, dtype=np.uint8)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        self._inputs.append((meta, data))
+        self._check(lib().ybgpu_job_add_input_sst(self.h, _np_ptr(meta), meta.size, _np_ptr(data), data.size, ht_filter))
+
+    def run(self):
+        self._check(lib().ybgpu_job_run(self.h, None))
+        return self.stats()
+
+    def stats(self):
+        s = JobStats()
+        self._check(lib().ybgpu_job_get_stats(self.h, C.byref(s)))
+        return s
+
+    def kv_stream_sizes(self):
+        n, kb, vb = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(lib().ybgpu_job_kv_stream_sizes(self.h, C.byref(n), C.byref(kb), C.byref(vb)))
+        return n.value, kb.value, vb.value
+
+    def fetch_kv_stream(self):
+        n, kb, vb = self.kv_stream_sizes()
+        keys = np.zeros(kb + 1, np.uint8)
+        vals = np.zeros(vb + 1, np.uint8)
+        koff = np.zeros(n + 1, np.uint64)
+        voff = np.zeros(n + 1, np.uint64)
+        self._check(lib().ybgpu_job_fetch_kv_stream(self.h, keys.ctypes.data, koff.ctypes.data, vals.ctypes.data, voff.ctypes.data))
+        return keys[:kb], koff, vals[:vb], voff
+
+    def kv_list(self):
+        keys, koff, vals, voff = self.fetch_kv_stream()
+        kb, vb = keys.tobytes(), vals.tobytes()
+        return [(kb[int(koff[i]):int(koff[i + 1])], vb[int(voff[i]):int(voff[i + 1])]) for i in range(len(koff) - 1)]
+
+    def fetch_output(self):
+        dl, ml = C.c_uint64(), C.c_uint64()
+        self._check(lib().ybgpu_job_output_sizes(self.h, C.byref(dl), C.byref(ml)))
+        data = np.zeros(dl.value + 1, np.uint8)
+        meta = np.zeros(ml.value + 1, np.uint8)
+        self._check(lib().ybgpu_job_fetch_output(self.h, data.ctypes.data, dl.value, meta.ctypes.data, ml.value))
+        return data[:dl.value], meta[:ml.value]
+
+    def boundaries(self):
+        a, b = C.create_string_buffer(4096), C.create_string_buffer(4096)
+        al, bl = C.c_uint64(), C.c_uint64()
+        self._check(lib().ybgpu_job_output_boundaries(self.h, a, C.byref(al), b, C.byref(bl)))
+        return a.raw[:al.value], b.raw[:bl.value]
+
+    def digest(self):
+        d = C.c_uint64()
+        self._check(lib().ybgpu_job_kv_stream_digest(self.h, C.byref(d)))
+        return d.value
+
+
+class HostTableBuilder:
+    """rocksdb::TableBuilder-shaped host writer (ybgpu_table_builder_*)."""
+
+    def __init__(self, block_size=32768, restart_interval=16, deviation=10, index_block_size=32768,
+                 min_keys_per_index_block=100, key_encoding=1):
+        L = lib()
+        L.ybgpu_table_builder_create.argtypes = [C.POINTER(JobOptions), C.POINTER(C.c_void_p)]
+        L.ybgpu_table_builder_add.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+        L.ybgpu_table_builder_finish.argtypes = [C.c_void_p]
+        L.ybgpu_table_builder_destroy.argtypes = [C.c_void_p]
+        L.ybgpu_table_builder_num_entries.argtypes = [C.c_void_p]
+        L.ybgpu_table_builder_num_entries.restype = C.c_uint64
+        L.ybgpu_table_builder_files.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                                C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        o = JobOptions()
+        L.ybgpu_job_options_init(C.byref(o))
+        o.block_size, o.block_restart_interval, o.block_size_deviation = block_size, restart_interval, deviation
+        o.index_block_size, o.min_keys_per_index_block, o.output_key_encoding = index_block_size, min_keys_per_index_block, key_encoding
+        self.h = C.c_void_p()
+        st = L.ybgpu_table_builder_create(C.byref(o), C.byref(self.h))
+        if st != 0:
+            raise YbGpuError(st, L.ybgpu_last_error().decode())
+
+    def add(self, key, value):
+        st = lib().ybgpu_table_builder_add(self.h, key, len(key), value, len(value))
+        if st != 0:
+            raise YbGpuError(st, "table builder add")
+
+    def finish(self):
+        L = lib()
+        st = L.ybgpu_table_builder_finish(self.h)
+        if st != 0:
+            raise YbGpuError(st, "table builder finish")
+        d, m, dl, ml = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        L.ybgpu_table_builder_files(self.h, C.byref(d), C.byref(dl), C.byref(m), C.byref(ml))
+        return C.string_at(d, dl.value), C.string_at(m, ml.value)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ybgpu_table_builder_destroy(self.h)
+            self.h = None

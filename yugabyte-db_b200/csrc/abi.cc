@@ -1,0 +1,265 @@
+// abi.cc — extern "C" surface declared in include/ybgpu_compaction.h.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "host_sst.h"
+
+using ybgpu::Engine;
+
+struct ybgpu_job {
+  std::unique_ptr<Engine> engine;
+  // host copies of the results (filled lazily)
+  bool have_kv = false;
+  std::vector<uint8_t> keys, vals;
+  std::vector<uint64_t> koff, voff;
+  bool have_sst = false;
+  std::string data_file, meta_file;
+  uint64_t num_blocks = 0;
+  std::string error;
+};
+
+static thread_local std::string g_last_error;
+
+static ybgpu_status JobFail(ybgpu_job* j, ybgpu_status s, const std::string& msg) {
+  j->error = msg;
+  return s;
+}
+static ybgpu_status Sync(ybgpu_job* j, ybgpu_status s) {
+  if (s != YBGPU_OK) j->error = j->engine->error();
+  return s;
+}
+
+extern "C" {
+
+void ybgpu_job_options_init(ybgpu_job_options* o) {
+  memset(o, 0, sizeof(*o));
+  o->bottommost_level = 1;
+  o->last_sequence = YBGPU_MAX_SEQUENCE;
+  o->retention_enabled = 1;
+  o->history_cutoff_ht = YBGPU_HT_MIN;
+  o->cotables_cutoff_ht = YBGPU_HT_INVALID;
+  o->table_ttl_ns = YBGPU_TTL_MAX_NS;
+  o->other_min_ht = YBGPU_HT_MAX;
+  o->block_size = 32 * 1024;
+  o->block_restart_interval = 16;
+  o->block_size_deviation = 10;
+  o->output_key_encoding = YBGPU_KEY_ENCODING_SHARED_PREFIX;
+  o->index_block_size = 32 * 1024;
+  o->min_keys_per_index_block = 100;
+  o->verify_checksums = 1;
+}
+
+ybgpu_status ybgpu_job_create(const ybgpu_job_options* options, ybgpu_job** job) {
+  if (!options || !job) { g_last_error = "null argument"; return YBGPU_INVALID_ARGUMENT; }
+  std::unique_ptr<ybgpu_job> j(new ybgpu_job);
+  j->engine.reset(new Engine(*options));
+  ybgpu_status s = j->engine->Init();
+  if (s != YBGPU_OK) { g_last_error = j->engine->error(); return s; }
+  *job = j.release();
+  return YBGPU_OK;
+}
+
+void ybgpu_job_destroy(ybgpu_job* job) { delete job; }
+const char* ybgpu_job_error(const ybgpu_job* job) { return job ? job->error.c_str() : "null job"; }
+const char* ybgpu_last_error(void) { return g_last_error.c_str(); }
+
+static bool VerifyBlocks(const uint8_t* data, uint64_t len, const ybgpu_block_handle* h, uint64_t n, uint64_t* bad) {
+  for (uint64_t i = 0; i < n; i++) {
+    if (h[i].offset + h[i].size + 5 > len) { *bad = i; return false; }
+    const uint8_t* p = data + h[i].offset;
+    uint32_t stored; memcpy(&stored, p + h[i].size + 1, 4);
+    uint32_t actual = ybgpu::host::Crc32cMask(ybgpu::host::Crc32c(p, h[i].size + 1));
+    if (stored != actual) { *bad = i; return false; }
+  }
+  return true;
+}
+
+ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint64_t data_file_len,
+                                 const ybgpu_block_handle* handles, uint64_t num_handles, int32_t key_encoding,
+                                 uint64_t hybrid_time_filter) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  if (job->engine->options().verify_checksums) {
+    // ReadBlock's CRC32C check (table/format.cc:352-395). Done on the host while the file is
+    // still in host memory, as the reference does; a device-side CRC kernel is planned.
+    uint64_t bad = 0;
+    if (!VerifyBlocks(data_file, data_file_len, handles, num_handles, &bad))
+      return JobFail(job, YBGPU_CORRUPTION, "block checksum mismatch in input block " + std::to_string(bad));
+  }
+  return Sync(job, job->engine->AddInput(data_file, data_file_len, handles, num_handles, key_encoding, hybrid_time_filter, false));
+}
+
+ybgpu_status ybgpu_job_add_input_device(ybgpu_job* job, const uint8_t* data_file_dev, uint64_t data_file_len,
+                                        const ybgpu_block_handle* handles, uint64_t num_handles, int32_t key_encoding,
+                                        uint64_t hybrid_time_filter) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  return Sync(job, job->engine->AddInput(data_file_dev, data_file_len, handles, num_handles, key_encoding, hybrid_time_filter, true));
+}
+
+ybgpu_status ybgpu_job_add_input_sst(ybgpu_job* job, const uint8_t* meta_file, uint64_t meta_file_len,
+                                     const uint8_t* data_file, uint64_t data_file_len, uint64_t hybrid_time_filter) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  ybgpu::host::SstMeta m;
+  std::string err = ybgpu::host::ParseSplitSstMeta(meta_file, meta_file_len, &m);
+  if (!err.empty()) return JobFail(job, YBGPU_CORRUPTION, err);
+  std::vector<ybgpu_block_handle> h(m.data_blocks.size());
+  for (size_t i = 0; i < h.size(); i++) { h[i].offset = m.data_blocks[i].offset; h[i].size = m.data_blocks[i].size; }
+  return ybgpu_job_add_input(job, data_file, data_file_len, h.data(), h.size(), m.key_encoding, hybrid_time_filter);
+}
+
+ybgpu_status ybgpu_job_run(ybgpu_job* job, const volatile int32_t* shutting_down) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  return Sync(job, job->engine->Run(shutting_down));
+}
+
+ybgpu_status ybgpu_job_get_stats(const ybgpu_job* job, ybgpu_job_stats* stats) {
+  if (!job || !stats) return YBGPU_INVALID_ARGUMENT;
+  *stats = const_cast<ybgpu_job*>(job)->engine->stats();
+  stats->num_output_data_blocks = job->num_blocks;
+  stats->output_data_file_size = job->data_file.size();
+  stats->output_meta_file_size = job->meta_file.size();
+  return YBGPU_OK;
+}
+
+ybgpu_status ybgpu_job_kv_stream_sizes(const ybgpu_job* job, uint64_t* n, uint64_t* kb, uint64_t* vb) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  return Sync(const_cast<ybgpu_job*>(job), job->engine->KvStreamSizes(n, kb, vb));
+}
+
+ybgpu_status ybgpu_job_fetch_kv_stream(ybgpu_job* job, uint8_t* keys, uint64_t* koff, uint8_t* vals, uint64_t* voff) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  return Sync(job, job->engine->FetchKvStream(keys, koff, vals, voff));
+}
+
+static ybgpu_status EnsureHostKv(ybgpu_job* job) {
+  if (job->have_kv) return YBGPU_OK;
+  uint64_t n, kb, vb;
+  ybgpu_status s = Sync(job, job->engine->KvStreamSizes(&n, &kb, &vb));
+  if (s != YBGPU_OK) return s;
+  job->keys.resize(kb + 1); job->vals.resize(vb + 1); job->koff.resize(n + 1); job->voff.resize(n + 1);
+  s = Sync(job, job->engine->FetchKvStream(job->keys.data(), job->koff.data(), job->vals.data(), job->voff.data()));
+  if (s == YBGPU_OK) job->have_kv = true;
+  return s;
+}
+
+ybgpu_status ybgpu_job_emit_kv_stream(ybgpu_job* job, ybgpu_emit_fn emit, void* ctx) {
+  if (!job || !emit) return YBGPU_INVALID_ARGUMENT;
+  ybgpu_status s = EnsureHostKv(job);
+  if (s != YBGPU_OK) return s;
+  const uint64_t n = job->koff.size() - 1;
+  for (uint64_t i = 0; i < n; i++) {
+    int rc = emit(ctx, job->keys.data() + job->koff[i], job->koff[i + 1] - job->koff[i],
+                  job->vals.data() + job->voff[i], job->voff[i + 1] - job->voff[i]);
+    if (rc != 0) return JobFail(job, static_cast<ybgpu_status>(rc), "emit callback failed");
+  }
+  return YBGPU_OK;
+}
+
+static ybgpu_status EnsureSst(ybgpu_job* job) {
+  if (job->have_sst) return YBGPU_OK;
+  ybgpu_status s = EnsureHostKv(job);
+  if (s != YBGPU_OK) return s;
+  try {
+    const ybgpu_job_options& o = job->engine->options();
+    ybgpu::host::TableOptions t;
+    t.block_size = o.block_size; t.block_restart_interval = o.block_restart_interval;
+    t.block_size_deviation = o.block_size_deviation; t.index_block_size = o.index_block_size;
+    t.min_keys_per_index_block = o.min_keys_per_index_block; t.key_encoding = o.output_key_encoding;
+    ybgpu::host::SplitSstWriter w(t);
+    const uint64_t n = job->koff.size() - 1;
+    for (uint64_t i = 0; i < n; i++)
+      w.Add(job->keys.data() + job->koff[i], job->koff[i + 1] - job->koff[i], job->vals.data() + job->voff[i],
+            job->voff[i + 1] - job->voff[i]);
+    if (n) {   // the reference never opens an output file for an empty result (compaction_job.cc:156-160)
+      w.Finish();
+      job->data_file = w.data_file(); job->meta_file = w.meta_file(); job->num_blocks = w.NumDataBlocks();
+    }
+    job->have_sst = true;
+  } catch (const std::exception& e) {
+    return JobFail(job, YBGPU_NOT_SUPPORTED, e.what());
+  }
+  return YBGPU_OK;
+}
+
+ybgpu_status ybgpu_job_output_sizes(const ybgpu_job* job, uint64_t* data_len, uint64_t* meta_len) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  ybgpu_status s = EnsureSst(const_cast<ybgpu_job*>(job));
+  if (s != YBGPU_OK) return s;
+  *data_len = job->data_file.size(); *meta_len = job->meta_file.size();
+  return YBGPU_OK;
+}
+
+ybgpu_status ybgpu_job_fetch_output(ybgpu_job* job, uint8_t* data_file, uint64_t data_cap, uint8_t* meta_file, uint64_t meta_cap) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  ybgpu_status s = EnsureSst(job);
+  if (s != YBGPU_OK) return s;
+  if (data_cap < job->data_file.size() || meta_cap < job->meta_file.size()) return JobFail(job, YBGPU_INVALID_ARGUMENT, "output buffer too small");
+  memcpy(data_file, job->data_file.data(), job->data_file.size());
+  memcpy(meta_file, job->meta_file.data(), job->meta_file.size());
+  return YBGPU_OK;
+}
+
+ybgpu_status ybgpu_job_output_boundaries(const ybgpu_job* job, uint8_t* smallest, uint64_t* smallest_len, uint8_t* largest, uint64_t* largest_len) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  ybgpu_job* j = const_cast<ybgpu_job*>(job);
+  ybgpu_status s = EnsureHostKv(j);
+  if (s != YBGPU_OK) return s;
+  const uint64_t n = j->koff.size() - 1;
+  if (n == 0) { *smallest_len = 0; *largest_len = 0; return YBGPU_OK; }
+  *smallest_len = j->koff[1] - j->koff[0];
+  memcpy(smallest, j->keys.data(), *smallest_len);
+  *largest_len = j->koff[n] - j->koff[n - 1];
+  memcpy(largest, j->keys.data() + j->koff[n - 1], *largest_len);
+  return YBGPU_OK;
+}
+
+ybgpu_status ybgpu_job_kv_stream_digest(ybgpu_job* job, uint64_t* digest) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  return Sync(job, job->engine->Digest(digest));
+}
+
+struct ybgpu_table_builder {
+  std::unique_ptr<ybgpu::host::SplitSstWriter> w;
+  bool finished = false;
+};
+
+ybgpu_status ybgpu_table_builder_create(const ybgpu_job_options* o, ybgpu_table_builder** b) {
+  if (!o || !b) return YBGPU_INVALID_ARGUMENT;
+  try {
+    ybgpu::host::TableOptions t;
+    t.block_size = o->block_size; t.block_restart_interval = o->block_restart_interval;
+    t.block_size_deviation = o->block_size_deviation; t.index_block_size = o->index_block_size;
+    t.min_keys_per_index_block = o->min_keys_per_index_block; t.key_encoding = o->output_key_encoding;
+    std::unique_ptr<ybgpu_table_builder> tb(new ybgpu_table_builder);
+    tb->w.reset(new ybgpu::host::SplitSstWriter(t));
+    *b = tb.release();
+    return YBGPU_OK;
+  } catch (const std::exception& e) { g_last_error = e.what(); return YBGPU_NOT_SUPPORTED; }
+}
+ybgpu_status ybgpu_table_builder_add(ybgpu_table_builder* b, const uint8_t* key, uint64_t klen, const uint8_t* val, uint64_t vlen) {
+  if (!b || b->finished || klen < 8) return YBGPU_INVALID_ARGUMENT;
+  b->w->Add(key, klen, val, vlen);
+  return YBGPU_OK;
+}
+ybgpu_status ybgpu_table_builder_finish(ybgpu_table_builder* b) {
+  if (!b || b->finished) return YBGPU_INVALID_ARGUMENT;
+  b->w->Finish(); b->finished = true;
+  return YBGPU_OK;
+}
+uint64_t ybgpu_table_builder_num_entries(const ybgpu_table_builder* b) { return b->w->NumEntries(); }
+uint64_t ybgpu_table_builder_total_file_size(const ybgpu_table_builder* b) { return b->w->TotalFileSize(); }
+uint64_t ybgpu_table_builder_base_file_size(const ybgpu_table_builder* b) { return b->w->meta_file().size(); }
+ybgpu_status ybgpu_table_builder_files(const ybgpu_table_builder* b, const uint8_t** d, uint64_t* dl, const uint8_t** m, uint64_t* ml) {
+  if (!b || !b->finished) return YBGPU_ILLEGAL_STATE;
+  *d = reinterpret_cast<const uint8_t*>(b->w->data_file().data()); *dl = b->w->data_file().size();
+  *m = reinterpret_cast<const uint8_t*>(b->w->meta_file().data()); *ml = b->w->meta_file().size();
+  return YBGPU_OK;
+}
+void ybgpu_table_builder_destroy(ybgpu_table_builder* b) { delete b; }
+
+int32_t ybgpu_device_count(void);   // engine.cu
+const char* ybgpu_version(void) { return "ybgpu-compaction 0.1 (sm_100a)"; }
+
+}  // extern "C"

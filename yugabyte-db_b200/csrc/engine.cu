@@ -1,0 +1,1171 @@
+// engine.cu — B200 (sm_100a) DocDB compaction engine: kernels + host orchestration.
+//
+// Pipeline (one ybgpu_job = one rocksdb::CompactionJob::Run, reference
+// src/yb/rocksdb/db/compaction_job.cc:664-895):
+//
+//   K1  k_prepass   per data block: entry count, max key length, raw sizes        (BlockIter walk,
+//   K1' k_decode    per restart interval: delta-decode keys -> fixed-stride records  table/block.cc:348-447)
+//   K2  k_sample_*  DocKey-aligned multiway partition of the k sorted runs into tiles
+//   K3  k_merge_filter  per tile: rank-based k-way merge in shared memory (MergingIterator,
+//                   table/merger.cc), CompactionIterator rule A + seqno zeroing
+//                   (db/compaction_iterator.cc:388-400,467-483) and the DocDB retention
+//                   predicate (docdb/docdb_compaction_context.cc:941-1311) per row group
+//   K4  k_emit_*    scan survivors, gather keys + values into the output KV stream
+//
+// All byte/integer work, HBM-bound: no tensor cores. See DESIGN.md for the data layout and the
+// per-kernel algorithmic bytes.
+#include "engine.h"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace ybgpu {
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      return Fail(YBGPU_RUNTIME_ERROR, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    }                                                                                       \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Device-side views
+struct RunView {
+  const uint8_t* data;          // data file bytes (HBM)
+  const uint64_t* blk_off;      // per data block
+  const uint32_t* blk_size;
+  uint32_t* blk_count;          // entries per block (K1), then exclusive prefix (blk_base)
+  uint8_t* rec;                 // n_entries * S key records (K1')
+  uint64_t* val_off;            // value offset inside `data` per entry
+  uint32_t nb;
+  uint32_t n_entries;
+  uint32_t restart_interval;    // entries per restart interval in this file
+  uint32_t gid_base;            // global entry id of entry 0
+  uint64_t ht_filter;
+};
+
+struct JobDev {                 // device-global job state
+  int error;                    // first DevError
+  uint32_t error_where;         // block / tile index
+  uint32_t max_ikey_len;        // K1
+  uint32_t restart_interval[MAX_RUNS];
+  unsigned long long in_key_bytes, in_val_bytes;
+  unsigned long long n_counted, n_hidden, n_obsolete, n_feed_dropped, n_kept, out_key_bytes, out_val_bytes;
+  unsigned long long min_seq, max_seq;
+  uint32_t n_rewrites;
+  uint32_t n_tiles;
+  unsigned long long digest;
+};
+
+struct JobParams {
+  int S;                        // record stride
+  int k;                        // number of runs
+  int bottommost;
+  uint64_t last_sequence;
+  uint32_t largest_len; uint8_t largest[1024];   // Compaction::GetLargestUserKey
+  uint32_t tile_cap;            // records per tile
+  uint32_t H;                   // target rank step between tile boundaries
+  uint32_t M;                   // sample stride
+  RetentionDev R;
+};
+
+struct Desc {                   // one per input entry in merged order
+  uint32_t gid;
+  uint32_t vlen_out;
+  uint16_t klen;                // internal key length
+  uint8_t flags;                // ENT_*
+  uint8_t run;
+  uint32_t rewrite_slot;
+};
+
+__device__ __forceinline__ void dev_fail(JobDev* J, int code, uint32_t where) {
+  if (atomicCAS(&J->error, 0, code) == 0) J->error_where = where;
+}
+
+__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* p) {
+  return static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8) | (static_cast<uint32_t>(p[2]) << 16) |
+         (static_cast<uint32_t>(p[3]) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: one warp per data block, one lane per restart interval. Walks entry headers only.
+__global__ void __launch_bounds__(256) k_prepass(RunView run, int run_idx, JobDev* J) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long key_bytes = 0, val_bytes = 0;
+  uint32_t max_klen = 0;
+  for (uint32_t b = warp; b < run.nb; b += nwarps) {
+    const uint8_t* blk = run.data + run.blk_off[b];
+    const uint32_t size = run.blk_size[b];
+    uint32_t count = 0;
+    bool bad = false;
+    uint32_t num_restarts = 0, restarts_off = 0;
+    if (size < 4) bad = true;
+    else {
+      num_restarts = ldg_u32_unaligned(blk + size - 4);
+      if (num_restarts == 0 || static_cast<uint64_t>(num_restarts) * 4 + 4 > size) bad = true;
+      else restarts_off = size - 4 - 4 * num_restarts;
+    }
+    if (bad) { if (lane == 0) dev_fail(J, DEV_ERR_BAD_BLOCK, b); continue; }
+    if (blk[size] != 0) { if (lane == 0) dev_fail(J, DEV_ERR_COMPRESSED, b); continue; }   // trailer type byte
+    for (uint32_t r = lane; r < num_restarts; r += 32) {
+      uint32_t p = ldg_u32_unaligned(blk + restarts_off + 4 * r);
+      const uint32_t end = (r + 1 < num_restarts) ? ldg_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
+      if (p > end || end > restarts_off) { dev_fail(J, DEV_ERR_BAD_BLOCK, b); break; }
+      uint32_t n = 0, klen = 0;
+      while (p < end) {
+        uint32_t shared, non_shared, vlen;
+        int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
+        if (!h || shared > klen || (n == 0 && shared != 0) ||
+            static_cast<uint64_t>(p) + h + non_shared + vlen > end) { dev_fail(J, DEV_ERR_BAD_ENTRY, b); n = 0; break; }
+        klen = shared + non_shared;
+        if (klen < 8) { dev_fail(J, DEV_ERR_SHORT_KEY, b); break; }
+        max_klen = max(max_klen, klen);
+        key_bytes += klen; val_bytes += vlen;
+        p += h + non_shared + vlen;
+        n++;
+      }
+      count += n;
+      // every interval but the last of a block must be full (BlockBuilder restarts every
+      // block_restart_interval entries, table/block_builder.cc:357-361)
+      uint32_t expect = __ldcg(&J->restart_interval[run_idx]);
+      if (r + 1 < num_restarts) {
+        if (expect == 0) { uint32_t old = atomicCAS(&J->restart_interval[run_idx], 0u, n); expect = old ? old : n; }
+        if (expect != n) dev_fail(J, DEV_ERR_IRREGULAR_RESTARTS, b);
+      } else if (expect != 0 && n > expect) {
+        dev_fail(J, DEV_ERR_IRREGULAR_RESTARTS, b);
+      }
+    }
+    for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (lane == 0) run.blk_count[b] = count;
+  }
+  for (int o = 16; o; o >>= 1) {
+    key_bytes += __shfl_xor_sync(0xffffffffu, key_bytes, o);
+    val_bytes += __shfl_xor_sync(0xffffffffu, val_bytes, o);
+    max_klen = max(max_klen, __shfl_xor_sync(0xffffffffu, max_klen, o));
+  }
+  if (lane == 0 && (key_bytes | val_bytes | max_klen)) {
+    atomicAdd(&J->in_key_bytes, key_bytes);
+    atomicAdd(&J->in_val_bytes, val_bytes);
+    atomicMax(&J->max_ikey_len, max_klen);
+  }
+}
+
+// Exclusive scan of a u32 array with one CTA (n up to a few million: nb per file).
+__global__ void __launch_bounds__(1024) k_scan_u32_single(uint32_t* a, uint32_t n, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < n ? a[i] : 0;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = warp_sums[lane];
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t excl = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
+    if (i < n) a[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// K1': decode. One warp per data block, one lane per restart interval; each lane rebuilds its
+// interval's keys serially (the delta chain is inherently serial inside an interval) and writes
+// one record per entry.
+template <int KMAX>
+__global__ void __launch_bounds__(128) k_decode(RunView run, int S, JobDev* J) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  __align__(16) uint8_t keybuf[KMAX];
+  const uint32_t ri = run.restart_interval ? run.restart_interval : 1;
+  for (uint32_t b = warp; b < run.nb; b += nwarps) {
+    const uint64_t boff = run.blk_off[b];
+    const uint8_t* blk = run.data + boff;
+    const uint32_t size = run.blk_size[b];
+    const uint32_t num_restarts = ldg_u32_unaligned(blk + size - 4);
+    const uint32_t restarts_off = size - 4 - 4 * num_restarts;
+    const uint32_t base = run.blk_count[b];            // exclusive prefix after the scan
+    for (uint32_t r = lane; r < num_restarts; r += 32) {
+      uint32_t p = ldg_u32_unaligned(blk + restarts_off + 4 * r);
+      const uint32_t end = (r + 1 < num_restarts) ? ldg_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
+      uint32_t idx = base + r * ri;
+      while (p < end) {
+        uint32_t shared, non_shared, vlen;
+        int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
+        if (!h) break;                                  // validated by k_prepass
+        p += h;
+        const uint32_t klen = shared + non_shared;
+        if (klen > KMAX) { dev_fail(J, DEV_ERR_KEY_TOO_LONG, b); break; }
+        for (uint32_t i = 0; i < non_shared; i++) keybuf[shared + i] = blk[p + i];
+        p += non_shared;
+        const uint32_t ulen = klen - 8;
+        uint8_t* rec = run.rec + static_cast<size_t>(idx) * S;
+        const int key_words = (S - 16) >> 2;
+        for (int w = 0; w < key_words; w++) {
+          uint32_t v = 0;
+          const int valid = static_cast<int>(ulen) - 4 * w;
+          if (valid > 0) {
+            v = *reinterpret_cast<const uint32_t*>(keybuf + 4 * w);
+            if (valid < 4) v &= (1u << (8 * valid)) - 1;
+          }
+          reinterpret_cast<uint32_t*>(rec)[w] = v;
+        }
+        uint64_t suffix = 0;
+        for (int i = 7; i >= 0; i--) suffix = (suffix << 8) | keybuf[ulen + i];
+        uint8_t flags = 0;
+        if (run.ht_filter != 0xfffffffffffffffeull) {
+          // HybridTimeFilteringIterator::Satisfied (docdb_rocksdb_util.cc:525-540)
+          uint32_t htl = doc_ht_len_from_end(keybuf, ulen);
+          uint64_t ht;
+          if (htl && doc_ht_decode(keybuf + ulen - htl, htl, &ht) && ht > run.ht_filter) flags |= REC_F_HT_FILTERED;
+        }
+        const uint8_t vfirst = vlen ? blk[p] : 0;
+        uint4 tr;
+        tr.x = static_cast<uint32_t>(suffix); tr.y = static_cast<uint32_t>(suffix >> 32);
+        tr.z = ulen | (static_cast<uint32_t>(vfirst) << 16) | (static_cast<uint32_t>(flags) << 24);
+        tr.w = vlen;
+        *reinterpret_cast<uint4*>(rec + S - 16) = tr;
+        run.val_off[idx] = boff + p;
+        p += vlen;
+        idx++;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: partition. Sample s of run r is record s*M of that run; its splitter is the row-group prefix
+// of that record. pos[s_global * k + r2] = lower bound of the splitter in run r2.
+struct PartView {
+  const RunView* runs;          // device array [k]
+  const uint32_t* sample_base;  // [k+1] prefix of samples per run
+  uint32_t* pos;                // [n_samples * k]
+  unsigned long long* bucket_min;   // [n_buckets]  (rank << 28 | sample)
+  uint32_t n_samples;
+  uint32_t n_buckets;
+};
+
+__global__ void __launch_bounds__(256) k_sample_pos(PartView P, const JobParams* prm, JobDev* J) {
+  const int S = prm->S, k = prm->k;
+  const uint64_t total = static_cast<uint64_t>(P.n_samples) * k;
+  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t s = static_cast<uint32_t>(t / k), r2 = static_cast<uint32_t>(t % k);
+    // which run owns sample s
+    int r = 0;
+    while (r + 1 < k && P.sample_base[r + 1] <= s) r++;
+    const uint32_t idx = (s - P.sample_base[r]) * prm->M;
+    const uint8_t* srec = P.runs[r].rec + static_cast<size_t>(idx) * S;
+    const int g = group_prefix_len(srec, rec_ulen(srec, S), prm->R.enabled != 0);
+    if (g < 0) { dev_fail(J, -g, s); continue; }
+    const RunView& q = P.runs[r2];
+    uint32_t lo = 0, hi = q.n_entries;
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      const uint8_t* c = q.rec + static_cast<size_t>(mid) * S;
+      // first record whose user key >= prefix
+      if (cmp_prefix_vs_key(srec, g, c, rec_ulen(c, S)) > 0) lo = mid + 1; else hi = mid;
+    }
+    P.pos[static_cast<size_t>(s) * k + r2] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sample_bucket(PartView P, const JobParams* prm) {
+  const int k = prm->k;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_samples; s += gridDim.x * blockDim.x) {
+    unsigned long long rank = 0;
+    for (int r = 0; r < k; r++) rank += P.pos[static_cast<size_t>(s) * k + r];
+    if (rank == 0) continue;                       // implicit first boundary
+    uint32_t b = static_cast<uint32_t>(rank / prm->H);
+    atomicMin(&P.bucket_min[b], (rank << 28) | s);
+  }
+}
+
+// Compact non-empty buckets into the tile boundary list. tile_lo[t*k + r] = start of tile t in
+// run r; tile t ends where tile t+1 starts (last: run ends). Single CTA.
+__global__ void __launch_bounds__(1024) k_build_tiles(PartView P, const JobParams* prm, uint32_t* tile_lo,
+                                                      unsigned long long* tile_rank, JobDev* J) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  const int k = prm->k;
+  if (threadIdx.x == 0) carry = 1;                 // tile 0 = implicit boundary at all-zero
+  if (threadIdx.x < k) tile_lo[threadIdx.x] = 0;
+  if (threadIdx.x == 0) tile_rank[0] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < P.n_buckets; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    unsigned long long v = i < P.n_buckets ? P.bucket_min[i] : ~0ull;
+    uint32_t f = v != ~0ull;
+    uint32_t x = f;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = warp_sums[lane];
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    if (f) {
+      uint32_t t = carry + (wid ? warp_sums[wid - 1] : 0) + x - 1;
+      uint32_t s = static_cast<uint32_t>(v & ((1u << 28) - 1));
+      for (int r = 0; r < k; r++) tile_lo[static_cast<size_t>(t) * k + r] = P.pos[static_cast<size_t>(s) * k + r];
+      tile_rank[t] = v >> 28;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) J->n_tiles = carry;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: merge + filter, one CTA per tile.
+struct MergeView {
+  const RunView* runs;            // [k]
+  const uint32_t* tile_lo;        // [n_tiles * k]
+  const unsigned long long* tile_rank;   // [n_tiles] rank (merged position) of the tile's first entry
+  Desc* desc;                     // [N]
+  ValueRewrite* rewrites;         // [rewrite_cap]
+  uint32_t rewrite_cap;
+  uint32_t n_tiles;
+};
+
+constexpr int MERGE_THREADS = 256;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+  // scan of one value per thread; all threads must call. Returns exclusive prefix.
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  __syncthreads();
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  uint32_t excl = (wid ? warp_sums[wid - 1] : 0) + x - v;
+  if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
+  return excl;
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, const JobParams* prm, JobDev* J) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int S = prm->S, k = prm->k;
+  const uint32_t cap = prm->tile_cap;
+  uint8_t* recs = smem;                                             // cap * S
+  uint16_t* order = reinterpret_cast<uint16_t*>(recs + static_cast<size_t>(cap) * S);   // sorted pos -> local idx
+  uint16_t* glen = order + cap;                                     // local idx -> group prefix len
+  uint16_t* gstart = glen + cap;                                    // group -> first sorted pos (cap + 1)
+  uint16_t* pvis = gstart + cap + 2;                                // sorted pos -> previous visible sorted pos
+  uint8_t* res = reinterpret_cast<uint8_t*>(pvis + cap);            // sorted pos -> ENT_* flags
+  uint32_t* seg_lo = reinterpret_cast<uint32_t*>(res + ((cap + 15) & ~15u));   // [k]
+  uint32_t* seg_start = seg_lo + MAX_RUNS;                          // [k+1]
+  uint32_t* rw_slot = seg_start + MAX_RUNS + 1;                     // sorted pos -> rewrite slot (cap)
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t sh_T, sh_ngroups, sh_any_filtered;
+  __shared__ int sh_err;
+  __shared__ unsigned long long sh_stats[8];
+
+  const uint32_t tile = blockIdx.x;
+  if (threadIdx.x < 8) sh_stats[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int r = 0; r < k; r++) {
+      uint32_t lo = V.tile_lo[static_cast<size_t>(tile) * k + r];
+      uint32_t hi = (tile + 1 < V.n_tiles) ? V.tile_lo[static_cast<size_t>(tile + 1) * k + r] : V.runs[r].n_entries;
+      seg_lo[r] = lo; seg_start[r] = acc; acc += hi - lo;
+    }
+    seg_start[k] = acc;
+    sh_T = acc;
+    sh_any_filtered = 0;
+  }
+  __syncthreads();
+  const uint32_t T = sh_T;
+  if (T == 0) return;
+  if (T > cap) { if (threadIdx.x == 0) dev_fail(J, DEV_ERR_TILE_OVERFLOW, tile); return; }
+
+  // (a) stage the k segments: contiguous 16-byte vector loads from HBM
+  for (int r = 0; r < k; r++) {
+    const uint32_t n = seg_start[r + 1] - seg_start[r];
+    const uint4* src = reinterpret_cast<const uint4*>(V.runs[r].rec + static_cast<size_t>(seg_lo[r]) * S);
+    uint4* dst = reinterpret_cast<uint4*>(recs + static_cast<size_t>(seg_start[r]) * S);
+    const uint32_t nvec = n * (S >> 4);
+    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  // (b) rank every record among the other segments (rank-based k-way merge) and parse its group
+  for (uint32_t li = threadIdx.x; li < T; li += blockDim.x) {
+    int r = 0;
+    while (seg_start[r + 1] <= li) r++;
+    const uint32_t p = li - seg_start[r];
+    const uint8_t* e = recs + static_cast<size_t>(li) * S;
+    if (p > 0 && cmp_records(e - S, e, S) >= 0) dev_fail(J, DEV_ERR_UNSORTED, tile);
+    uint32_t rank = p;
+    for (int r2 = 0; r2 < k; r2++) {
+      if (r2 == r) continue;
+      const uint32_t b2 = seg_start[r2];
+      uint32_t lo = 0, hi = seg_start[r2 + 1] - b2;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const int c = cmp_records(recs + static_cast<size_t>(b2 + mid) * S, e, S);
+        const bool less = (r2 < r) ? (c <= 0) : (c < 0);
+        if (less) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    order[rank] = static_cast<uint16_t>(li);
+    const int g = group_prefix_len(e, rec_ulen(e, S), prm->R.enabled != 0);
+    if (g < 0) { dev_fail(J, -g, tile); glen[li] = 0; } else glen[li] = static_cast<uint16_t>(g);
+    if (rec_flags(e, S) & REC_F_HT_FILTERED) sh_any_filtered = 1;
+  }
+  if (threadIdx.x == 0) sh_err = *reinterpret_cast<volatile int*>(&J->error);
+  __syncthreads();
+  if (sh_err) return;
+
+  // previous-visible map (identity - 1 unless HybridTime-filtered entries exist)
+  if (sh_any_filtered) {
+    if (threadIdx.x == 0) {
+      uint32_t last = 0xffff;
+      for (uint32_t i = 0; i < T; i++) {
+        pvis[i] = static_cast<uint16_t>(last);
+        if (!(rec_flags(recs + static_cast<size_t>(order[i]) * S, S) & REC_F_HT_FILTERED)) last = i;
+      }
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) pvis[i] = static_cast<uint16_t>(i ? i - 1 : 0xffff);
+  }
+  __syncthreads();
+
+  // (c) CompactionIterator per sorted position + group starts
+  const uint32_t items = (T + blockDim.x - 1) / blockDim.x;          // consecutive items per thread
+  uint32_t my_groups = 0;
+  unsigned long long st_counted = 0, st_hidden = 0, st_obsolete = 0;
+  for (uint32_t j = 0; j < items; j++) {
+    const uint32_t i = threadIdx.x * items + j;
+    if (i >= T) break;
+    const uint32_t li = order[i];
+    const uint8_t* e = recs + static_cast<size_t>(li) * S;
+    uint8_t f = 0;
+    if (!(rec_flags(e, S) & REC_F_HT_FILTERED)) {
+      f |= ENT_COUNTED; st_counted++;
+      const uint64_t suffix = rec_suffix(e, S);
+      const uint32_t type = static_cast<uint32_t>(suffix & 0xff);
+      const uint64_t seq = suffix >> 8;
+      if (type != 0 && type != 1) dev_fail(J, DEV_ERR_UNSUPPORTED_VALUE, tile);     // merge / single delete
+      const uint32_t ulen = rec_ulen(e, S);
+      bool first_occ = true;
+      if (pvis[i] != 0xffff) {
+        const uint8_t* pe = recs + static_cast<size_t>(order[pvis[i]]) * S;
+        first_occ = cmp_user_keys(pe, rec_ulen(pe, S), e, ulen) != 0;
+      }
+      if (!first_occ) { f |= ENT_DROP_HIDDEN; st_hidden++; }                       // rule A
+      else if (type == 0 && prm->bottommost && seq <= prm->last_sequence) { f |= ENT_DROP_OBSOLETE; st_obsolete++; }
+      else {
+        f |= ENT_KEEP;
+        if (prm->bottommost && seq < prm->last_sequence) {                         // PrepareOutput
+          bool is_largest = ulen == prm->largest_len;
+          for (uint32_t q = 0; is_largest && q < ulen; q++) is_largest = e[q] == prm->largest[q];
+          if (!is_largest) f |= ENT_ZERO_SEQ;
+        }
+      }
+    }
+    res[i] = f;
+    bool gs = i == 0;
+    if (!gs) {
+      const uint32_t lp = order[i - 1];
+      const uint32_t g = glen[li];
+      gs = glen[lp] != g || common_prefix_len(e, g, recs + static_cast<size_t>(lp) * S, g) < g;
+    }
+    if (gs) my_groups++;
+  }
+  uint32_t ngroups;
+  uint32_t gbase = block_exclusive_scan(my_groups, warp_sums, &ngroups);
+  for (uint32_t j = 0; j < items; j++) {
+    const uint32_t i = threadIdx.x * items + j;
+    if (i >= T) break;
+    bool gs = i == 0;
+    if (!gs) {
+      const uint32_t li = order[i], lp = order[i - 1];
+      const uint32_t g = glen[li];
+      gs = glen[lp] != g || common_prefix_len(recs + static_cast<size_t>(li) * S, g, recs + static_cast<size_t>(lp) * S, g) < g;
+    }
+    if (gs) gstart[gbase++] = static_cast<uint16_t>(i);
+  }
+  if (threadIdx.x == 0) { gstart[ngroups] = static_cast<uint16_t>(T); sh_ngroups = ngroups; }
+  __syncthreads();
+
+  // (d) DocDB retention predicate: one thread per row group, serial inside the group
+  unsigned long long st_feed = 0;
+  for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) rw_slot[i] = 0xffffffffu;
+  __syncthreads();
+  if (prm->R.enabled) {
+    for (uint32_t g = threadIdx.x; g < sh_ngroups; g += blockDim.x) {
+      FeedState st;
+      feed_state_reset(&st);
+      const uint32_t i0 = gstart[g], i1 = gstart[g + 1];
+      for (uint32_t i = i0; i < i1; i++) {
+        uint8_t f = res[i];
+        if (!(f & ENT_KEEP)) continue;
+        const uint32_t li = order[i];
+        const uint8_t* e = recs + static_cast<size_t>(li) * S;
+        int r = 0;
+        while (seg_start[r + 1] <= li) r++;
+        const uint32_t idx = seg_lo[r] + (li - seg_start[r]);
+        const uint32_t vlen = rec_vlen(e, S);
+        const uint8_t vfirst = rec_vfirst(e, S);
+        const uint8_t* val = nullptr;
+        if (vlen && has_control_fields(vfirst)) val = V.runs[r].data + V.runs[r].val_off[idx];
+        ValueRewrite rw;
+        int d = feed_step(&st, prm->R, e, rec_ulen(e, S), vfirst, val, vlen, &rw);
+        if (d < 0) { dev_fail(J, -d, tile); break; }
+        if (d == 0) { res[i] = f & ~ENT_KEEP & ~ENT_ZERO_SEQ; st_feed++; continue; }
+        f |= static_cast<uint8_t>(d);
+        if (d & ENT_VAL_REENCODE) {
+          uint32_t slot = atomicAdd(&J->n_rewrites, 1u);
+          if (slot < V.rewrite_cap) { V.rewrites[slot] = rw; rw_slot[i] = slot; }
+          else dev_fail(J, DEV_ERR_UNSUPPORTED_VALUE, tile);
+        }
+        res[i] = f;
+      }
+    }
+  }
+  __syncthreads();
+
+  // (e) descriptors in merged order
+  const unsigned long long rank0 = V.tile_rank[tile];
+  unsigned long long st_kept = 0, st_kbytes = 0, st_vbytes = 0, mn = ~0ull, mx = 0;
+  for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
+    const uint32_t li = order[i];
+    const uint8_t* e = recs + static_cast<size_t>(li) * S;
+    int r = 0;
+    while (seg_start[r + 1] <= li) r++;
+    const uint32_t idx = seg_lo[r] + (li - seg_start[r]);
+    const uint8_t f = res[i];
+    Desc d;
+    d.gid = V.runs[r].gid_base + idx;
+    d.klen = static_cast<uint16_t>(rec_ulen(e, S) + 8);
+    d.flags = f; d.run = static_cast<uint8_t>(r);
+    d.rewrite_slot = rw_slot[i];
+    uint32_t vout = rec_vlen(e, S);
+    if (f & ENT_VAL_TOMBSTONE) vout = 1;
+    else if (f & ENT_VAL_REENCODE) { const ValueRewrite& rw = V.rewrites[rw_slot[i]]; vout = vout - rw.skip + rw.prefix_len; }
+    d.vlen_out = vout;
+    V.desc[rank0 + i] = d;
+    if (f & ENT_KEEP) {
+      st_kept++; st_kbytes += d.klen; st_vbytes += vout;
+      const unsigned long long seq = (f & ENT_ZERO_SEQ) ? 0ull : (rec_suffix(e, S) >> 8);
+      mn = min(mn, seq); mx = max(mx, seq);
+    }
+  }
+  // block-reduce stats
+  unsigned long long vals[7] = {st_counted, st_hidden, st_obsolete, st_feed, st_kept, st_kbytes, st_vbytes};
+  for (int q = 0; q < 7; q++) {
+    unsigned long long v = vals[q];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh_stats[q], v);
+  }
+  for (int o = 16; o; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if ((threadIdx.x & 31) == 0) { if (mn != ~0ull) atomicMin(&J->min_seq, mn); if (mx) atomicMax(&J->max_seq, mx); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (sh_stats[0]) atomicAdd(&J->n_counted, sh_stats[0]);
+    if (sh_stats[1]) atomicAdd(&J->n_hidden, sh_stats[1]);
+    if (sh_stats[2]) atomicAdd(&J->n_obsolete, sh_stats[2]);
+    if (sh_stats[3]) atomicAdd(&J->n_feed_dropped, sh_stats[3]);
+    if (sh_stats[4]) atomicAdd(&J->n_kept, sh_stats[4]);
+    if (sh_stats[5]) atomicAdd(&J->out_key_bytes, sh_stats[5]);
+    if (sh_stats[6]) atomicAdd(&J->out_val_bytes, sh_stats[6]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: emit. Chunked three-quantity scan (count, key bytes, value bytes) over the descriptors,
+// then gather.
+constexpr int EMIT_CHUNK = 2048;
+constexpr int EMIT_THREADS = 256;
+
+struct Sums3 { unsigned long long n, kb, vb; };
+
+__global__ void __launch_bounds__(EMIT_THREADS) k_emit_sums(const Desc* desc, uint64_t N, Sums3* partial) {
+  __shared__ unsigned long long sh[3];
+  if (threadIdx.x < 3) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * EMIT_CHUNK;
+  unsigned long long n = 0, kb = 0, vb = 0;
+  for (uint32_t j = threadIdx.x; j < EMIT_CHUNK; j += blockDim.x) {
+    uint64_t i = base + j;
+    if (i < N) { Desc d = desc[i]; if (d.flags & ENT_KEEP) { n++; kb += d.klen; vb += d.vlen_out; } }
+  }
+  for (int o = 16; o; o >>= 1) { n += __shfl_xor_sync(0xffffffffu, n, o); kb += __shfl_xor_sync(0xffffffffu, kb, o); vb += __shfl_xor_sync(0xffffffffu, vb, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], n); atomicAdd(&sh[1], kb); atomicAdd(&sh[2], vb); }
+  __syncthreads();
+  if (threadIdx.x == 0) { partial[blockIdx.x].n = sh[0]; partial[blockIdx.x].kb = sh[1]; partial[blockIdx.x].vb = sh[2]; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(Sums3* partial, uint32_t n) {
+  // single CTA exclusive scan of three u64 sequences
+  __shared__ unsigned long long ws[3][32];
+  __shared__ unsigned long long carry[3];
+  if (threadIdx.x < 3) carry[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    unsigned long long v[3] = {0, 0, 0};
+    if (i < n) { v[0] = partial[i].n; v[1] = partial[i].kb; v[2] = partial[i].vb; }
+    unsigned long long x[3] = {v[0], v[1], v[2]};
+    for (int q = 0; q < 3; q++) {
+      for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x[q], o); if (lane >= o) x[q] += y; }
+      if (lane == 31) ws[q][wid] = x[q];
+    }
+    __syncthreads();
+    if (wid == 0) {
+      for (int q = 0; q < 3; q++) {
+        unsigned long long w = ws[q][lane];
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        ws[q][lane] = w;
+      }
+    }
+    __syncthreads();
+    if (i < n) {
+      partial[i].n = carry[0] + (wid ? ws[0][wid - 1] : 0) + x[0] - v[0];
+      partial[i].kb = carry[1] + (wid ? ws[1][wid - 1] : 0) + x[1] - v[1];
+      partial[i].vb = carry[2] + (wid ? ws[2][wid - 1] : 0) + x[2] - v[2];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) carry[threadIdx.x] += ws[threadIdx.x][31];
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+  // dst-aligned 4-byte stores; source words assembled with a funnel shift. Reads at most 3 bytes
+  // beyond src+n and 3 before src (buffers are padded by 16 bytes on both sides of the payload).
+  uint32_t head = (4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3;
+  if (head > n) head = n;
+  if (lane < static_cast<int>(head)) dst[lane] = src[lane];
+  dst += head; src += head; n -= head;
+  const uint32_t nw = n >> 2;
+  const uint32_t sh = reinterpret_cast<uintptr_t>(src) & 3;
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src - sh);
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+  for (uint32_t w = lane; w < nw; w += 32) {
+    uint32_t lo = __ldg(s32 + w);
+    if (sh) { uint32_t hi = __ldg(s32 + w + 1); lo = __funnelshift_r(lo, hi, sh * 8); }
+    d32[w] = lo;
+  }
+  const uint32_t tail = n & 3;
+  if (lane < static_cast<int>(tail)) dst[nw * 4 + lane] = src[nw * 4 + lane];
+}
+
+struct EmitView {
+  const RunView* runs;
+  const Desc* desc;
+  const Sums3* partial;
+  const ValueRewrite* rewrites;
+  uint8_t* out_keys; uint64_t* out_koff;
+  uint8_t* out_vals; uint64_t* out_voff;
+  uint64_t N;
+};
+
+__global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitView E, int S, JobDev* J) {
+  __shared__ uint32_t s_n[EMIT_CHUNK + 1];
+  __shared__ uint32_t s_kb[EMIT_CHUNK + 1];
+  __shared__ uint32_t s_vb[EMIT_CHUNK + 1];
+  __shared__ uint32_t warp_sums[32];
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * EMIT_CHUNK;
+  const Sums3 off = E.partial[blockIdx.x];
+  // local exclusive scans: each thread owns EMIT_CHUNK / EMIT_THREADS consecutive descriptors
+  constexpr int PER = EMIT_CHUNK / EMIT_THREADS;
+  uint32_t n = 0, kb = 0, vb = 0;
+  uint32_t ln[PER], lk[PER], lv[PER];
+  for (int j = 0; j < PER; j++) {
+    uint64_t i = base + threadIdx.x * PER + j;
+    ln[j] = n; lk[j] = kb; lv[j] = vb;
+    if (i < E.N) { Desc d = E.desc[i]; if (d.flags & ENT_KEEP) { n++; kb += d.klen; vb += d.vlen_out; } }
+  }
+  uint32_t bn = block_exclusive_scan(n, warp_sums, nullptr);
+  uint32_t bk = block_exclusive_scan(kb, warp_sums, nullptr);
+  uint32_t bv = block_exclusive_scan(vb, warp_sums, nullptr);
+  for (int j = 0; j < PER; j++) {
+    uint32_t q = threadIdx.x * PER + j;
+    s_n[q] = bn + ln[j]; s_kb[q] = bk + lk[j]; s_vb[q] = bv + lv[j];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t q = wid; q < EMIT_CHUNK; q += EMIT_THREADS / 32) {
+    const uint64_t i = base + q;
+    if (i >= E.N) break;
+    const Desc d = E.desc[i];
+    if (!(d.flags & ENT_KEEP)) continue;
+    const RunView& run = E.runs[d.run];
+    const uint32_t idx = d.gid - run.gid_base;
+    const uint8_t* rec = run.rec + static_cast<size_t>(idx) * S;
+    const uint64_t j = off.n + s_n[q];
+    const uint64_t ko = off.kb + s_kb[q], vo = off.vb + s_vb[q];
+    if (lane == 0) { E.out_koff[j] = ko; E.out_voff[j] = vo; }
+    // key: user key bytes + 8-byte suffix
+    const uint32_t ulen = d.klen - 8u;
+    uint8_t* kd = E.out_keys + ko;
+    for (uint32_t b = lane; b < ulen; b += 32) kd[b] = rec[b];
+    if (lane < 8) {
+      uint64_t suffix = rec_suffix(rec, S);
+      if (d.flags & ENT_ZERO_SEQ) suffix &= 0xff;
+      kd[ulen + lane] = static_cast<uint8_t>(suffix >> (8 * lane));
+    }
+    // value
+    uint8_t* vd = E.out_vals + vo;
+    const uint8_t* vs = run.data + run.val_off[idx];
+    if (d.flags & ENT_VAL_TOMBSTONE) {
+      if (lane == 0) vd[0] = 'X';
+    } else if (d.flags & ENT_VAL_REENCODE) {
+      const ValueRewrite& rw = E.rewrites[d.rewrite_slot];
+      if (lane < rw.prefix_len) vd[lane] = rw.prefix[lane];
+      const uint32_t rest = d.vlen_out - rw.prefix_len;
+      for (uint32_t b = lane; b < rest; b += 32) vd[rw.prefix_len + b] = vs[rw.skip + b];
+    } else {
+      warp_copy(vd, vs, d.vlen_out, lane);
+    }
+  }
+  (void)J;
+}
+
+// Order-sensitive digest of the emitted KV stream (test aid): per entry FNV-1a-64 over
+// (klen u32, key, vlen u32, value), finalised with the entry index, summed mod 2^64.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x;
+}
+__global__ void __launch_bounds__(256) k_digest(const uint8_t* keys, const uint64_t* koff, const uint8_t* vals,
+                                                const uint64_t* voff, uint64_t n, JobDev* J) {
+  unsigned long long acc = 0;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    unsigned long long h = 1469598103934665603ull;
+    const uint32_t kl = static_cast<uint32_t>(koff[i + 1] - koff[i]), vl = static_cast<uint32_t>(voff[i + 1] - voff[i]);
+    for (int b = 0; b < 4; b++) { h ^= (kl >> (8 * b)) & 0xff; h *= 1099511628211ull; }
+    const uint8_t* p = keys + koff[i];
+    for (uint32_t b = 0; b < kl; b++) { h ^= p[b]; h *= 1099511628211ull; }
+    for (int b = 0; b < 4; b++) { h ^= (vl >> (8 * b)) & 0xff; h *= 1099511628211ull; }
+    p = vals + voff[i];
+    for (uint32_t b = 0; b < vl; b++) { h ^= p[b]; h *= 1099511628211ull; }
+    acc += mix64(h + i * 0x9e3779b97f4a7c15ull);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&J->digest, acc);
+}
+
+// =============================================================================================
+// Host orchestration
+// =============================================================================================
+static const char* DevErrorName(int e) {
+  switch (e) {
+    case DEV_ERR_BAD_BLOCK: return "bad block contents";
+    case DEV_ERR_BAD_ENTRY: return "bad entry in block";
+    case DEV_ERR_COMPRESSED: return "compressed block (only kNoCompression inputs are supported)";
+    case DEV_ERR_KEY_TOO_LONG: return "key longer than the engine limit";
+    case DEV_ERR_IRREGULAR_RESTARTS: return "data block restart intervals are not uniform";
+    case DEV_ERR_BAD_KEY: return "cannot decode DocKey/SubDocKey components";
+    case DEV_ERR_UNSUPPORTED_KEY: return "key component type not supported on the GPU path";
+    case DEV_ERR_TILE_OVERFLOW: return "row group larger than a merge tile";
+    case DEV_ERR_BAD_HT: return "bad DocHybridTime at the end of a key";
+    case DEV_ERR_BAD_VALUE: return "cannot decode value control fields";
+    case DEV_ERR_STACK_DEPTH: return "too many subkey levels";
+    case DEV_ERR_UNSUPPORTED_VALUE: return "record type needs a host callback (packed row / merge / single delete)";
+    case DEV_ERR_BAD_CRC: return "block checksum mismatch";
+    case DEV_ERR_COTABLE: return "cotable/colocated keys are not supported yet";
+    case DEV_ERR_SHORT_KEY: return "internal key shorter than 8 bytes";
+    case DEV_ERR_UNSORTED: return "input file is not sorted";
+    default: return "unknown device error";
+  }
+}
+
+static ybgpu_status DevErrorStatus(int e) {
+  switch (e) {
+    case DEV_ERR_COMPRESSED: case DEV_ERR_UNSUPPORTED_KEY: case DEV_ERR_UNSUPPORTED_VALUE:
+    case DEV_ERR_TILE_OVERFLOW: case DEV_ERR_COTABLE: case DEV_ERR_KEY_TOO_LONG: case DEV_ERR_STACK_DEPTH:
+    case DEV_ERR_IRREGULAR_RESTARTS:
+      return YBGPU_NOT_SUPPORTED;
+    default: return YBGPU_CORRUPTION;
+  }
+}
+
+struct Engine::Impl {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<void*> allocs;
+  JobDev* dJ = nullptr;
+  JobParams* dP = nullptr;
+  RunView* dRuns = nullptr;
+  std::vector<RunView> runs;
+  std::vector<bool> owns_data;
+  // outputs
+  uint8_t* out_keys = nullptr; uint64_t* out_koff = nullptr;
+  uint8_t* out_vals = nullptr; uint64_t* out_voff = nullptr;
+  uint64_t n_out = 0, out_key_bytes = 0, out_val_bytes = 0;
+  JobDev hJ{};
+};
+
+Engine::Engine(const ybgpu_job_options& o) : opt_(o), impl_(new Impl) {
+  if (o.largest_user_key && o.has_largest_user_key) largest_.assign(o.largest_user_key, o.largest_user_key + o.largest_user_key_len);
+  if (o.key_bounds_lower_len) lower_.assign(o.key_bounds_lower, o.key_bounds_lower + o.key_bounds_lower_len);
+  if (o.key_bounds_upper_len) upper_.assign(o.key_bounds_upper, o.key_bounds_upper + o.key_bounds_upper_len);
+  opt_.largest_user_key = nullptr; opt_.key_bounds_lower = nullptr; opt_.key_bounds_upper = nullptr;
+  memset(&stats_, 0, sizeof(stats_));
+}
+
+Engine::~Engine() {
+  if (impl_) {
+    cudaSetDevice(opt_.device);
+    for (void* p : impl_->allocs) cudaFree(p);
+    if (impl_->ev0) cudaEventDestroy(impl_->ev0);
+    if (impl_->ev1) cudaEventDestroy(impl_->ev1);
+    if (impl_->stream) cudaStreamDestroy(impl_->stream);
+    delete impl_;
+  }
+}
+
+ybgpu_status Engine::Fail(ybgpu_status s, const std::string& msg) { error_ = msg; return s; }
+
+template <typename T>
+static cudaError_t DevAlloc(std::vector<void*>* allocs, T** out, size_t count) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16) + 32);
+  if (e == cudaSuccess) { allocs->push_back(p); *out = reinterpret_cast<T*>(p); }
+  return e;
+}
+
+ybgpu_status Engine::Init() {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return Fail(YBGPU_RUNTIME_ERROR, std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+                                         " (this engine has no CPU fallback)");
+  if (opt_.device < 0 || opt_.device >= ndev) return Fail(YBGPU_INVALID_ARGUMENT, "bad device ordinal");
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&impl_->ev0));
+  CUDA_TRY(cudaEventCreate(&impl_->ev1));
+  CUDA_TRY(DevAlloc(&impl_->allocs, &impl_->dJ, 1));
+  CUDA_TRY(DevAlloc(&impl_->allocs, &impl_->dP, 1));
+  CUDA_TRY(DevAlloc(&impl_->allocs, &impl_->dRuns, MAX_RUNS));
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_block_handle* handles, uint64_t nh,
+                              int key_encoding, uint64_t ht_filter, bool on_device) {
+  if (ran_) return Fail(YBGPU_ILLEGAL_STATE, "add_input after run");
+  if (impl_->runs.size() >= MAX_RUNS) return Fail(YBGPU_NOT_SUPPORTED, "too many input files");
+  if (key_encoding != YBGPU_KEY_ENCODING_SHARED_PREFIX)
+    return Fail(YBGPU_NOT_SUPPORTED, "only kKeyDeltaEncodingSharedPrefix inputs are decoded on the GPU so far");
+  if (nh >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "too many data blocks in one file");
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  for (uint64_t i = 0; i < nh; i++) {
+    if (handles[i].offset + handles[i].size + 5 > len) return Fail(YBGPU_CORRUPTION, "block handle outside the data file");
+    if (handles[i].size >= (1ull << 31)) return Fail(YBGPU_NOT_SUPPORTED, "data block too large");
+  }
+  RunView rv{};
+  if (on_device) {
+    rv.data = data;
+  } else {
+    uint8_t* d = nullptr;
+    CUDA_TRY(DevAlloc(&impl_->allocs, &d, len + 64));
+    // 16 bytes of zero padding on both sides so word-granular copies may over-read
+    CUDA_TRY(cudaMemsetAsync(d, 0, 16, impl_->stream));
+    CUDA_TRY(cudaMemcpyAsync(d + 16, data, len, cudaMemcpyHostToDevice, impl_->stream));
+    CUDA_TRY(cudaMemsetAsync(d + 16 + len, 0, 16, impl_->stream));
+    rv.data = d + 16;
+    stats_.h2d_bytes += len;
+  }
+  std::vector<uint64_t> off(nh); std::vector<uint32_t> sz(nh);
+  for (uint64_t i = 0; i < nh; i++) { off[i] = handles[i].offset; sz[i] = static_cast<uint32_t>(handles[i].size); }
+  uint64_t* doff = nullptr; uint32_t* dsz = nullptr; uint32_t* dcnt = nullptr;
+  CUDA_TRY(DevAlloc(&impl_->allocs, &doff, nh)); CUDA_TRY(DevAlloc(&impl_->allocs, &dsz, nh));
+  CUDA_TRY(DevAlloc(&impl_->allocs, &dcnt, nh + 1));
+  CUDA_TRY(cudaMemcpyAsync(doff, off.data(), nh * 8, cudaMemcpyHostToDevice, impl_->stream));
+  CUDA_TRY(cudaMemcpyAsync(dsz, sz.data(), nh * 4, cudaMemcpyHostToDevice, impl_->stream));
+  CUDA_TRY(cudaStreamSynchronize(impl_->stream));   // host vectors go out of scope
+  rv.blk_off = doff; rv.blk_size = dsz; rv.blk_count = dcnt; rv.nb = static_cast<uint32_t>(nh);
+  rv.ht_filter = ht_filter;
+  impl_->runs.push_back(rv);
+  return YBGPU_OK;
+}
+
+static int GridFor(uint64_t work_items, int threads, int sms) {
+  uint64_t blocks = (work_items + threads - 1) / threads;
+  uint64_t cap = static_cast<uint64_t>(sms) * 16;
+  return static_cast<int>(std::max<uint64_t>(1, std::min(blocks, cap)));
+}
+
+ybgpu_status Engine::CheckDeviceError(const char* phase) {
+  Impl& I = *impl_;
+  CUDA_TRY(cudaMemcpyAsync(&I.hJ, I.dJ, sizeof(JobDev), cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  if (I.hJ.error) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s (%s, at block/tile %u)", DevErrorName(I.hJ.error), phase, I.hJ.error_where);
+    return Fail(DevErrorStatus(I.hJ.error), buf);
+  }
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
+  if (ran_) return Fail(YBGPU_ILLEGAL_STATE, "job already ran");
+  Impl& I = *impl_;
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, opt_.device));
+  const int sms = prop.multiProcessorCount;
+  const int k = static_cast<int>(I.runs.size());
+  auto shutdown = [&]() { return shutting_down && *shutting_down; };
+  uint32_t launches = 0;
+
+  CUDA_TRY(cudaMemsetAsync(I.dJ, 0, sizeof(JobDev), I.stream));
+  {
+    JobDev init{}; init.min_seq = ~0ull;
+    CUDA_TRY(cudaMemcpyAsync(I.dJ, &init, sizeof(init), cudaMemcpyHostToDevice, I.stream));
+  }
+  CUDA_TRY(cudaEventRecord(I.ev0, I.stream));
+
+  // ---- K1: prepass + scan per file
+  std::vector<uint32_t*> dtotals(k);
+  for (int r = 0; r < k; r++) {
+    RunView& rv = I.runs[r];
+    CUDA_TRY(DevAlloc(&I.allocs, &dtotals[r], 1));
+    if (rv.nb) {
+      k_prepass<<<GridFor(static_cast<uint64_t>(rv.nb) * 32, 256, sms), 256, 0, I.stream>>>(rv, r, I.dJ);
+      k_scan_u32_single<<<1, 1024, 0, I.stream>>>(rv.blk_count, rv.nb, dtotals[r]);
+      launches += 2;
+    } else {
+      CUDA_TRY(cudaMemsetAsync(dtotals[r], 0, 4, I.stream));
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (ybgpu_status s = CheckDeviceError("block scan")) return s;
+  if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
+  uint64_t N = 0;
+  for (int r = 0; r < k; r++) {
+    uint32_t n;
+    CUDA_TRY(cudaMemcpy(&n, dtotals[r], 4, cudaMemcpyDeviceToHost));
+    I.runs[r].n_entries = n;
+    I.runs[r].restart_interval = I.hJ.restart_interval[r];
+    if (N + n >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "more than 2^32 entries in one job: shard the compaction");
+    I.runs[r].gid_base = static_cast<uint32_t>(N);
+    N += n;
+  }
+  stats_.total_input_raw_key_bytes = I.hJ.in_key_bytes;
+  stats_.total_input_raw_value_bytes = I.hJ.in_val_bytes;
+  const uint32_t max_ikey = I.hJ.max_ikey_len;
+  if (max_ikey > 1008 + 8) return Fail(YBGPU_NOT_SUPPORTED, "user keys longer than 1008 bytes are not supported");
+  const int S = N ? static_cast<int>(((max_ikey - 8 + 16) + 15) & ~15u) : 32;   // user key + 16-byte trailer
+  const int Sfinal = std::max(S, 32);
+
+  // ---- K1': decode
+  for (int r = 0; r < k; r++) {
+    RunView& rv = I.runs[r];
+    CUDA_TRY(DevAlloc(&I.allocs, &rv.rec, static_cast<size_t>(rv.n_entries) * Sfinal + 16));
+    CUDA_TRY(DevAlloc(&I.allocs, &rv.val_off, static_cast<size_t>(rv.n_entries) + 1));
+    if (rv.nb == 0) continue;
+    int grid = GridFor(static_cast<uint64_t>(rv.nb) * 32, 128, sms);
+    if (max_ikey <= 128) k_decode<128><<<grid, 128, 0, I.stream>>>(rv, Sfinal, I.dJ);
+    else if (max_ikey <= 320) k_decode<320><<<grid, 128, 0, I.stream>>>(rv, Sfinal, I.dJ);
+    else k_decode<1024><<<grid, 128, 0, I.stream>>>(rv, Sfinal, I.dJ);
+    launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+
+  // ---- job parameters
+  JobParams hp{};
+  hp.S = Sfinal; hp.k = k; hp.bottommost = opt_.bottommost_level; hp.last_sequence = opt_.last_sequence;
+  // smem budget: ~110 KB per CTA (records + per-record side arrays) so two CTAs fit one SM
+  uint32_t cap = (110u * 1024u - 1024u) / (Sfinal + 14);
+  cap = std::min(cap, 4096u) & ~1u;
+  hp.tile_cap = cap;
+  hp.H = std::max(1u, cap / 2);
+  hp.M = std::max(1u, hp.H / std::max(1, k));
+  hp.R.enabled = opt_.retention_enabled;
+  hp.R.cutoff_ht = opt_.history_cutoff_ht;
+  hp.R.table_ttl_ns = opt_.table_ttl_ns;
+  hp.R.cutoff_enc.n = static_cast<uint8_t>(doc_ht_encode(opt_.history_cutoff_ht, 0xffffffffu, hp.R.cutoff_enc.b));
+  const uint64_t min_other = opt_.retain_delete_markers_in_major_compaction ? 0 : opt_.other_min_ht;
+  hp.R.min_other_enc.n = static_cast<uint8_t>(doc_ht_encode(min_other, 0, hp.R.min_other_enc.b));
+  hp.R.ht_min_enc.n = static_cast<uint8_t>(doc_ht_encode(0, 0, hp.R.ht_min_enc.b));
+  if (lower_.size() > 255 || upper_.size() > 255) return Fail(YBGPU_NOT_SUPPORTED, "key bounds longer than 255 bytes");
+  hp.R.lower_len = static_cast<uint32_t>(lower_.size()); memcpy(hp.R.lower, lower_.data(), lower_.size());
+  hp.R.upper_len = static_cast<uint32_t>(upper_.size()); memcpy(hp.R.upper, upper_.data(), upper_.size());
+  if (opt_.cotables_cutoff_ht != YBGPU_HT_INVALID && opt_.retention_enabled) {
+    // only consulted for 'y' keys, which the GPU path rejects for now (DEV_ERR_COTABLE)
+  }
+
+  // Compaction::GetLargestUserKey: given by the caller or the max over the runs' last records.
+  if (!opt_.has_largest_user_key) {
+    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    std::vector<uint8_t> best; bool any = false;
+    std::vector<uint8_t> tmp(Sfinal);
+    for (int r = 0; r < k; r++) {
+      if (!I.runs[r].n_entries) continue;
+      CUDA_TRY(cudaMemcpy(tmp.data(), I.runs[r].rec + static_cast<size_t>(I.runs[r].n_entries - 1) * Sfinal, Sfinal, cudaMemcpyDeviceToHost));
+      uint32_t ulen = rec_ulen(tmp.data(), Sfinal);
+      std::vector<uint8_t> key(tmp.begin(), tmp.begin() + ulen);
+      if (!any || std::lexicographical_compare(best.begin(), best.end(), key.begin(), key.end())) { best = key; any = true; }
+    }
+    largest_ = best;
+  }
+  if (largest_.size() > sizeof(hp.largest)) return Fail(YBGPU_NOT_SUPPORTED, "largest user key too long");
+  hp.largest_len = static_cast<uint32_t>(largest_.size());
+  memcpy(hp.largest, largest_.data(), largest_.size());
+  CUDA_TRY(cudaMemcpyAsync(I.dP, &hp, sizeof(hp), cudaMemcpyHostToDevice, I.stream));
+  if (ybgpu_status s = CheckDeviceError("decode")) return s;
+  if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
+
+  if (N == 0) {
+    ran_ = true;
+    CUDA_TRY(DevAlloc(&I.allocs, &I.out_koff, 1)); CUDA_TRY(DevAlloc(&I.allocs, &I.out_voff, 1));
+    CUDA_TRY(cudaMemset(I.out_koff, 0, 8)); CUDA_TRY(cudaMemset(I.out_voff, 0, 8));
+    CUDA_TRY(DevAlloc(&I.allocs, &I.out_keys, 1)); CUDA_TRY(DevAlloc(&I.allocs, &I.out_vals, 1));
+    stats_.gpu_kernel_launches = launches;
+    return YBGPU_OK;
+  }
+
+  // ---- K2: partition
+  std::vector<uint32_t> sample_base(k + 1, 0);
+  for (int r = 0; r < k; r++) sample_base[r + 1] = sample_base[r] + (I.runs[r].n_entries + hp.M - 1) / hp.M;
+  const uint32_t n_samples = sample_base[k];
+  if (n_samples >= (1u << 28)) return Fail(YBGPU_NOT_SUPPORTED, "too many partition samples");
+  const uint32_t n_buckets = static_cast<uint32_t>(N / hp.H) + 2;
+  PartView pv{};
+  uint32_t* d_sample_base = nullptr; uint32_t* d_tile_lo = nullptr; unsigned long long* d_tile_rank = nullptr;
+  CUDA_TRY(DevAlloc(&I.allocs, &d_sample_base, k + 1));
+  CUDA_TRY(DevAlloc(&I.allocs, &pv.pos, static_cast<size_t>(n_samples) * k));
+  CUDA_TRY(DevAlloc(&I.allocs, &pv.bucket_min, n_buckets));
+  CUDA_TRY(DevAlloc(&I.allocs, &d_tile_lo, static_cast<size_t>(n_buckets + 1) * k));
+  CUDA_TRY(DevAlloc(&I.allocs, &d_tile_rank, n_buckets + 1));
+  CUDA_TRY(cudaMemcpyAsync(d_sample_base, sample_base.data(), 4 * (k + 1), cudaMemcpyHostToDevice, I.stream));
+  CUDA_TRY(cudaMemsetAsync(pv.bucket_min, 0xff, static_cast<size_t>(n_buckets) * 8, I.stream));
+  pv.runs = I.dRuns; pv.sample_base = d_sample_base; pv.n_samples = n_samples; pv.n_buckets = n_buckets;
+  k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ);
+  k_sample_bucket<<<GridFor(n_samples, 256, sms), 256, 0, I.stream>>>(pv, I.dP);
+  k_build_tiles<<<1, 1024, 0, I.stream>>>(pv, I.dP, d_tile_lo, d_tile_rank, I.dJ);
+  launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  if (ybgpu_status s = CheckDeviceError("partition")) return s;
+  const uint32_t n_tiles = I.hJ.n_tiles;
+
+  // ---- K3: merge + filter
+  Desc* d_desc = nullptr; ValueRewrite* d_rw = nullptr;
+  const uint32_t rewrite_cap = static_cast<uint32_t>(std::min<uint64_t>(N, 1u << 26));
+  CUDA_TRY(DevAlloc(&I.allocs, &d_desc, N));
+  CUDA_TRY(DevAlloc(&I.allocs, &d_rw, rewrite_cap));
+  MergeView mv{};
+  mv.runs = I.dRuns; mv.tile_lo = d_tile_lo; mv.tile_rank = d_tile_rank; mv.desc = d_desc;
+  mv.rewrites = d_rw; mv.rewrite_cap = rewrite_cap; mv.n_tiles = n_tiles;
+  const size_t smem = static_cast<size_t>(cap) * Sfinal + (cap * 4 + 4) * 2 + ((cap + 15) & ~15u) +
+                      (2 * MAX_RUNS + 1) * 4 + static_cast<size_t>(cap) * 4 + 64;
+  CUDA_TRY(cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  k_merge_filter<<<n_tiles, MERGE_THREADS, smem, I.stream>>>(mv, I.dP, I.dJ);
+  launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (ybgpu_status s = CheckDeviceError("merge")) return s;
+  if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
+
+  // ---- K4: emit
+  I.n_out = I.hJ.n_kept; I.out_key_bytes = I.hJ.out_key_bytes; I.out_val_bytes = I.hJ.out_val_bytes;
+  const uint32_t n_chunks = static_cast<uint32_t>((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
+  Sums3* d_partial = nullptr;
+  CUDA_TRY(DevAlloc(&I.allocs, &d_partial, n_chunks + 1));
+  CUDA_TRY(DevAlloc(&I.allocs, &I.out_keys, I.out_key_bytes + 16));
+  CUDA_TRY(DevAlloc(&I.allocs, &I.out_vals, I.out_val_bytes + 16));
+  CUDA_TRY(DevAlloc(&I.allocs, &I.out_koff, I.n_out + 1));
+  CUDA_TRY(DevAlloc(&I.allocs, &I.out_voff, I.n_out + 1));
+  k_emit_sums<<<n_chunks, EMIT_THREADS, 0, I.stream>>>(d_desc, N, d_partial);
+  k_scan_sums<<<1, 1024, 0, I.stream>>>(d_partial, n_chunks);
+  EmitView ev{};
+  ev.runs = I.dRuns; ev.desc = d_desc; ev.partial = d_partial; ev.rewrites = d_rw;
+  ev.out_keys = I.out_keys; ev.out_koff = I.out_koff; ev.out_vals = I.out_vals; ev.out_voff = I.out_voff; ev.N = N;
+  k_emit<<<n_chunks, EMIT_THREADS, 0, I.stream>>>(ev, Sfinal, I.dJ);
+  launches += 3;
+  CUDA_TRY(cudaMemcpyAsync(I.out_koff + I.n_out, &I.out_key_bytes, 8, cudaMemcpyHostToDevice, I.stream));
+  CUDA_TRY(cudaMemcpyAsync(I.out_voff + I.n_out, &I.out_val_bytes, 8, cudaMemcpyHostToDevice, I.stream));
+  CUDA_TRY(cudaEventRecord(I.ev1, I.stream));
+  CUDA_TRY(cudaGetLastError());
+  if (ybgpu_status s = CheckDeviceError("emit")) return s;
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, I.ev0, I.ev1));
+
+  stats_.num_input_records = I.hJ.n_counted;
+  stats_.num_output_records = I.hJ.n_kept;
+  stats_.num_record_drop_hidden = I.hJ.n_hidden;
+  stats_.num_record_drop_obsolete = I.hJ.n_obsolete;
+  stats_.num_record_drop_feed = I.hJ.n_feed_dropped;
+  stats_.total_output_raw_key_bytes = I.hJ.out_key_bytes;
+  stats_.total_output_raw_value_bytes = I.hJ.out_val_bytes;
+  stats_.smallest_seqno = I.hJ.n_kept ? I.hJ.min_seq : 0;
+  stats_.largest_seqno = I.hJ.max_seq;
+  stats_.gpu_seconds = ms / 1e3;
+  stats_.gpu_kernel_launches = launches;
+  record_stride_ = Sfinal; num_tiles_ = n_tiles;
+  ran_ = true;
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::KvStreamSizes(uint64_t* n, uint64_t* kb, uint64_t* vb) const {
+  if (!ran_) return const_cast<Engine*>(this)->Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  *n = impl_->n_out; *kb = impl_->out_key_bytes; *vb = impl_->out_val_bytes;
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::FetchKvStream(uint8_t* keys, uint64_t* koff, uint8_t* vals, uint64_t* voff) {
+  if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  Impl& I = *impl_;
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  if (I.out_key_bytes) CUDA_TRY(cudaMemcpyAsync(keys, I.out_keys, I.out_key_bytes, cudaMemcpyDeviceToHost, I.stream));
+  if (I.out_val_bytes) CUDA_TRY(cudaMemcpyAsync(vals, I.out_vals, I.out_val_bytes, cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaMemcpyAsync(koff, I.out_koff, (I.n_out + 1) * 8, cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaMemcpyAsync(voff, I.out_voff, (I.n_out + 1) * 8, cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  stats_.d2h_bytes += I.out_key_bytes + I.out_val_bytes + (I.n_out + 1) * 16;
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::Digest(uint64_t* digest) {
+  if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  Impl& I = *impl_;
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  CUDA_TRY(cudaMemsetAsync(&I.dJ->digest, 0, 8, I.stream));
+  if (I.n_out) k_digest<<<GridFor(I.n_out, 256, 148), 256, 0, I.stream>>>(I.out_keys, I.out_koff, I.out_vals, I.out_voff, I.n_out, I.dJ);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(&I.hJ, I.dJ, sizeof(JobDev), cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  *digest = I.hJ.digest;
+  return YBGPU_OK;
+}
+
+}  // namespace ybgpu
+
+extern "C" int32_t ybgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}

@@ -1,0 +1,45 @@
+// engine.h — host-side interface of the CUDA engine (implementation: engine.cu).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/ybgpu_compaction.h"
+#include "dev_logic.cuh"
+
+namespace ybgpu {
+
+constexpr int MAX_RUNS = 64;   // input files per job (configs use 2..32)
+
+class Engine {
+ public:
+  explicit Engine(const ybgpu_job_options& o);
+  ~Engine();
+  ybgpu_status Init();
+  ybgpu_status AddInput(const uint8_t* data, uint64_t len, const ybgpu_block_handle* handles, uint64_t nh,
+                        int key_encoding, uint64_t ht_filter, bool on_device);
+  ybgpu_status Run(const volatile int32_t* shutting_down);
+  ybgpu_status KvStreamSizes(uint64_t* n, uint64_t* kb, uint64_t* vb) const;
+  ybgpu_status FetchKvStream(uint8_t* keys, uint64_t* koff, uint8_t* vals, uint64_t* voff);
+  ybgpu_status Digest(uint64_t* digest);
+  const ybgpu_job_options& options() const { return opt_; }
+  ybgpu_job_stats& stats() { return stats_; }
+  const std::string& error() const { return error_; }
+  ybgpu_status Fail(ybgpu_status s, const std::string& msg);
+  bool ran() const { return ran_; }
+  int record_stride() const { return record_stride_; }
+  uint32_t num_tiles() const { return num_tiles_; }
+
+ private:
+  ybgpu_status CheckDeviceError(const char* phase);
+  struct Impl;
+  ybgpu_job_options opt_;
+  Impl* impl_;
+  std::vector<uint8_t> largest_, lower_, upper_;
+  ybgpu_job_stats stats_;
+  std::string error_;
+  bool ran_ = false;
+  int record_stride_ = 0;
+  uint32_t num_tiles_ = 0;
+};
+
+}  // namespace ybgpu

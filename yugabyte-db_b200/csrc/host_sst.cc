@@ -1,0 +1,398 @@
+// host_sst.cc — see host_sst.h.
+#include "host_sst.h"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+
+#if defined(__SSE4_2__)
+#include <nmmintrin.h>
+#endif
+
+namespace ybgpu {
+namespace host {
+
+namespace {
+
+constexpr size_t kTrailer = 5;                                   // table/format.h:208
+constexpr size_t kFooterLen = 53;                                // table/format.h:170
+constexpr uint64_t kMagic = 0x88e241b785f4cff7ull;               // block_based_table_builder.cc:195
+
+uint32_t g_tab[256];
+bool g_tab_ready = [] {
+  for (uint32_t i = 0; i < 256; i++) {
+    uint32_t c = i;
+    for (int j = 0; j < 8; j++) c = (c >> 1) ^ ((c & 1) ? 0x82F63B78u : 0);
+    g_tab[i] = c;
+  }
+  return true;
+}();
+
+inline void AppendVarint(std::string* s, uint64_t v) {
+  while (v > 0x7f) { s->push_back(static_cast<char>(0x80 | (v & 0x7f))); v >>= 7; }
+  s->push_back(static_cast<char>(v));
+}
+inline size_t VarintLen(uint64_t v) { size_t n = 1; while (v > 0x7f) { v >>= 7; n++; } return n; }
+inline void AppendU32(std::string* s, uint32_t v) { s->append(reinterpret_cast<const char*>(&v), 4); }
+inline void AppendU64(std::string* s, uint64_t v) { s->append(reinterpret_cast<const char*>(&v), 8); }
+inline uint32_t LoadU32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+bool ReadVarint(const uint8_t** p, const uint8_t* end, uint64_t* out) {
+  uint64_t v = 0;
+  for (int shift = 0; shift < 64 && *p < end; shift += 7) {
+    uint8_t b = *(*p)++;
+    v |= static_cast<uint64_t>(b & 0x7f) << shift;
+    if (!(b & 0x80)) { *out = v; return true; }
+  }
+  return false;
+}
+
+// Minimal forward reader of a shared-prefix block (index / metaindex / properties blocks always
+// use kKeyDeltaEncodingSharedPrefix, table/format.h:46-51, meta_blocks.cc:46-50).
+struct BlockCursor {
+  const uint8_t* p; const uint8_t* end; std::string key; const uint8_t* val = nullptr; size_t vlen = 0;
+  BlockCursor(const uint8_t* data, size_t n) {
+    if (n < 4) throw std::runtime_error("bad block contents");
+    uint32_t nr = LoadU32(data + n - 4);
+    if (static_cast<uint64_t>(nr) * 4 + 4 > n) throw std::runtime_error("bad block contents");
+    p = data; end = data + n - 4 - 4 * static_cast<size_t>(nr);
+  }
+  bool Next() {
+    if (p >= end) return false;
+    uint64_t shared, non_shared, vl;
+    if (!ReadVarint(&p, end, &shared) || !ReadVarint(&p, end, &non_shared) || !ReadVarint(&p, end, &vl) ||
+        shared > key.size() || static_cast<uint64_t>(end - p) < non_shared + vl)
+      throw std::runtime_error("bad entry in block");
+    key.resize(shared);
+    key.append(reinterpret_cast<const char*>(p), non_shared);
+    val = p + non_shared; vlen = vl;
+    p += non_shared + vl;
+    return true;
+  }
+};
+
+const uint8_t* BlockAt(const uint8_t* file, uint64_t len, const Handle& h) {
+  if (h.offset + h.size + kTrailer > len) throw std::runtime_error("block handle outside file");
+  if (file[h.offset + h.size] != 0) throw std::runtime_error("compressed meta block not supported");
+  return file + h.offset;
+}
+
+Handle ReadHandle(const uint8_t** p, const uint8_t* end) {
+  Handle h;
+  if (!ReadVarint(p, end, &h.offset) || !ReadVarint(p, end, &h.size)) throw std::runtime_error("bad block handle");
+  return h;
+}
+
+}  // namespace
+
+uint32_t Crc32c(const uint8_t* p, size_t n, uint32_t init) {
+  uint32_t c = ~init;
+#if defined(__SSE4_2__)
+  uint64_t c64 = c;
+  for (; n >= 8; n -= 8, p += 8) { uint64_t v; memcpy(&v, p, 8); c64 = _mm_crc32_u64(c64, v); }
+  c = static_cast<uint32_t>(c64);
+  for (; n; n--, p++) c = _mm_crc32_u8(c, *p);
+#else
+  for (; n; n--, p++) c = g_tab[(c ^ *p) & 0xff] ^ (c >> 8);
+#endif
+  return ~c;
+}
+
+std::string ParseSplitSstMeta(const uint8_t* meta, uint64_t len, SstMeta* out) {
+  try {
+    if (len < kFooterLen) return "file is too short to be an sstable";
+    const uint8_t* f = meta + len - kFooterLen;
+    uint64_t magic = static_cast<uint64_t>(LoadU32(f + kFooterLen - 8)) | (static_cast<uint64_t>(LoadU32(f + kFooterLen - 4)) << 32);
+    if (magic != kMagic) return "bad table magic number";
+    const uint8_t* p = f + 1;
+    Handle metaindex = ReadHandle(&p, f + 41);
+    Handle index = ReadHandle(&p, f + 41);
+    BlockCursor mi(BlockAt(meta, len, metaindex), metaindex.size);
+    while (mi.Next()) {
+      if (mi.key == "rocksdb.properties") {
+        const uint8_t* vp = mi.val;
+        Handle ph = ReadHandle(&vp, mi.val + mi.vlen);
+        BlockCursor props(BlockAt(meta, len, ph), ph.size);
+        while (props.Next()) out->properties[props.key] = std::string(reinterpret_cast<const char*>(props.val), props.vlen);
+      }
+    }
+    auto e = out->properties.find("rocksdb.block.based.table.data.block.key.value.encoding.format");
+    out->key_encoding = (e == out->properties.end() || e->second.empty()) ? 1 : static_cast<uint8_t>(e->second[0]);
+    auto l = out->properties.find("rocksdb.block.based.table.index.num.levels");
+    out->index_levels = (l == out->properties.end() || l->second.size() < 4)
+                            ? 1 : static_cast<int>(LoadU32(reinterpret_cast<const uint8_t*>(l->second.data())));
+    std::vector<Handle> level{index};
+    for (int lv = 0; lv < out->index_levels; lv++) {
+      std::vector<Handle> next;
+      for (const Handle& h : level) {
+        BlockCursor c(BlockAt(meta, len, h), h.size);
+        while (c.Next()) { const uint8_t* vp = c.val; next.push_back(ReadHandle(&vp, c.val + c.vlen)); }
+      }
+      level.swap(next);
+    }
+    out->data_blocks.swap(level);
+    return std::string();
+  } catch (const std::exception& ex) {
+    return ex.what();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+BlockEncoder::BlockEncoder(int restart_interval, int key_encoding) : interval_(restart_interval), encoding_(key_encoding) {
+  restarts_.push_back(0);
+}
+
+void BlockEncoder::Reset() {
+  body_.clear(); last_key_.clear(); restarts_.assign(1, 0); in_interval_ = 0; finished_ = false;
+}
+
+size_t BlockEncoder::SizeAfter(size_t klen, size_t vlen) const {   // block_builder.cc:94-108
+  size_t e = SizeEstimate() + klen + vlen;
+  if (in_interval_ >= interval_) e += 4;
+  return e + 4 + VarintLen(klen) + VarintLen(vlen);
+}
+
+void BlockEncoder::Add(const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen) {
+  size_t shared = 0;
+  if (in_interval_ >= interval_) {
+    restarts_.push_back(static_cast<uint32_t>(body_.size()));
+    in_interval_ = 0;
+  } else {
+    const size_t lim = std::min(last_key_.size(), klen);
+    const uint8_t* prev = reinterpret_cast<const uint8_t*>(last_key_.data());
+    while (shared < lim && prev[shared] == key[shared]) shared++;
+  }
+  AppendVarint(&body_, shared);
+  AppendVarint(&body_, klen - shared);
+  AppendVarint(&body_, vlen);
+  body_.append(reinterpret_cast<const char*>(key + shared), klen - shared);
+  body_.append(reinterpret_cast<const char*>(val), vlen);
+  last_key_.assign(reinterpret_cast<const char*>(key), klen);
+  in_interval_++;
+}
+
+const std::string& BlockEncoder::Finish() {
+  for (uint32_t r : restarts_) AppendU32(&body_, r);
+  AppendU32(&body_, static_cast<uint32_t>(restarts_.size()));
+  finished_ = true;
+  return body_;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Separator shortening (util/comparator.cc:53-93, db/dbformat.cc:139-172).
+static void ShortenUserSeparator(std::string* start, const uint8_t* limit, size_t llen) {
+  const size_t lim = std::min(start->size(), llen);
+  size_t d = 0;
+  while (d < lim && static_cast<uint8_t>((*start)[d]) == limit[d]) d++;
+  if (d >= lim) return;
+  const uint8_t a = static_cast<uint8_t>((*start)[d]), b = limit[d];
+  if (a > b) return;
+  if (d == llen - 1 && a + 1 == b) {
+    ++d;
+    while (d < start->size() && static_cast<uint8_t>((*start)[d]) == 0xff) ++d;
+    if (d == start->size()) return;
+  }
+  (*start)[d] = static_cast<char>(static_cast<uint8_t>((*start)[d]) + 1);
+  start->resize(d + 1);
+}
+
+static int CompareBytes(const std::string& a, const std::string& b) {
+  const size_t m = std::min(a.size(), b.size());
+  int r = m ? memcmp(a.data(), b.data(), m) : 0;
+  if (r == 0) r = a.size() < b.size() ? -1 : (a.size() > b.size() ? 1 : 0);
+  return r;
+}
+
+static const uint64_t kSeekSuffix = (((1ull << 56) - 1) << 8) | 7;   // kMaxSequenceNumber, kValueTypeForSeek
+
+static void InternalSeparator(std::string* key, const uint8_t* limit, size_t llen) {
+  std::string user(key->data(), key->size() - 8), tmp = user;
+  ShortenUserSeparator(&tmp, limit, llen - 8);
+  if (tmp.size() < user.size() && CompareBytes(user, tmp) < 0) { AppendU64(&tmp, kSeekSuffix); key->swap(tmp); }
+}
+
+static void InternalSuccessor(std::string* key) {
+  std::string user(key->data(), key->size() - 8), tmp = user;
+  for (size_t i = 0; i < tmp.size(); i++) {
+    if (static_cast<uint8_t>(tmp[i]) != 0xff) { tmp[i] = static_cast<char>(static_cast<uint8_t>(tmp[i]) + 1); tmp.resize(i + 1); break; }
+  }
+  if (tmp.size() < user.size() && CompareBytes(user, tmp) < 0) { AppendU64(&tmp, kSeekSuffix); key->swap(tmp); }
+}
+
+// Multi-level index. Level L collects one entry per finished block of level L-1 (level 0: per
+// data block). A level's block is cut by the size policy evaluated after each added entry
+// (index_builder.cc:170-196); the finished block's own entry is added to level L+1 on the next
+// flush round, after which a full level-L+1 block is written BEFORE the pending level-L block
+// (index_builder.cc:228-249). The explicit per-level state below replays exactly that order.
+class IndexWriter {
+ public:
+  explicit IndexWriter(const TableOptions& o) : o_(o) { levels_.emplace_back(new Level(o)); }
+
+  void AddDataBlock(std::string* last_key, const uint8_t* next_key, size_t next_len, bool has_next, const Handle& h) {
+    if (!has_next) InternalSuccessor(last_key); else InternalSeparator(last_key, next_key, next_len);
+    AddEntry(0, *last_key, has_next ? std::string(reinterpret_cast<const char*>(next_key), next_len) : std::string(), has_next, h);
+  }
+  bool ShouldFlush(size_t lv = 0) const {
+    const Level& L = *levels_[lv];
+    return L.ready.on || (L.to_parent.on && !L.to_parent.has_next) || (lv + 1 < levels_.size() && ShouldFlush(lv + 1));
+  }
+  // One flush step: true => *contents must be written, its handle reported via the next call.
+  bool FlushNext(std::string* contents, const Handle& last_written, bool last_written_set, size_t lv = 0) {
+    Level& L = *levels_[lv];
+    if (L.parent_just_flushed) { L.parent_last = last_written; L.parent_last_set = last_written_set; L.parent_just_flushed = false; }
+    if (L.flushing) {
+      if (L.to_parent.on) {
+        AddEntry(lv + 1, L.to_parent.last_key, L.to_parent.next_first, L.to_parent.has_next, last_written);
+        L.to_parent.on = false;
+      }
+      if (lv + 1 < levels_.size() && ShouldFlush(lv + 1)) {
+        bool r = FlushNext(contents, L.parent_last, L.parent_last_set, lv + 1);
+        L.parent_just_flushed = true;
+        return r;
+      }
+    }
+    L.flushing = true;
+    if (L.ready.on) {
+      Emit(&L, contents);
+      if (lv + 1 == levels_.size() && L.ready.has_next) levels_.emplace_back(new Level(o_));
+      if (lv + 1 < levels_.size()) L.to_parent = L.ready;
+      L.ready.on = false;
+      return true;
+    }
+    if (!last_written_set) { Emit(&L, contents); return true; }   // empty table: empty index block
+    return false;
+  }
+  size_t EstimatedSize() const {
+    size_t s = 0;
+    for (auto& l : levels_) s += l->bytes;
+    return s - kTrailer;
+  }
+  int NumLevels() const { return static_cast<int>(levels_.size()); }
+
+ private:
+  struct Pending { bool on = false; std::string last_key, next_first; bool has_next = false; };
+  struct Level {
+    explicit Level(const TableOptions& o) : enc(o.index_block_restart_interval, 1) {}
+    BlockEncoder enc;
+    Pending ready, to_parent;
+    Handle parent_last; bool parent_last_set = false, parent_just_flushed = false, flushing = false;
+    size_t bytes = 0;
+  };
+  void AddEntry(size_t lv, const std::string& key, const std::string& next_first, bool has_next, const Handle& h) {
+    while (lv >= levels_.size()) levels_.emplace_back(new Level(o_));
+    Level& L = *levels_[lv];
+    std::string enc;
+    AppendVarint(&enc, h.offset); AppendVarint(&enc, h.size);
+    L.enc.Add(reinterpret_cast<const uint8_t*>(key.data()), key.size(), reinterpret_cast<const uint8_t*>(enc.data()), enc.size());
+    const size_t cur = L.enc.SizeEstimate();
+    const bool almost = L.enc.SizeAfter(key.size(), enc.size()) > o_.index_block_size && o_.block_size_deviation > 0 &&
+                        cur * 100 > static_cast<size_t>(o_.index_block_size) * (100 - o_.block_size_deviation);
+    const bool cut = (cur >= o_.index_block_size || almost) && L.enc.NumKeysForPolicy() >= o_.min_keys_per_index_block;
+    if (cut || !has_next) { L.ready.on = true; L.ready.last_key = key; L.ready.has_next = has_next; L.ready.next_first = next_first; }
+  }
+  void Emit(Level* L, std::string* contents) {
+    *contents = L->enc.Finish();
+    L->enc.Reset();
+    L->bytes += contents->size() + kTrailer;
+  }
+  TableOptions o_;
+  std::vector<std::unique_ptr<Level>> levels_;
+};
+
+// ---------------------------------------------------------------------------------------------
+SplitSstWriter::SplitSstWriter(const TableOptions& o)
+    : o_(o), block_(o.block_restart_interval, o.key_encoding), index_(new IndexWriter(o)) {
+  if (o.key_encoding != 1) throw std::runtime_error("host writer: only kKeyDeltaEncodingSharedPrefix output");
+}
+SplitSstWriter::~SplitSstWriter() {}
+
+void SplitSstWriter::AppendBlock(const std::string& c, std::string* file, Handle* h) {
+  h->offset = file->size(); h->size = c.size();
+  file->append(c);
+  const uint8_t type = 0;
+  uint32_t crc = Crc32c(&type, 1, Crc32c(reinterpret_cast<const uint8_t*>(c.data()), c.size()));
+  file->push_back(static_cast<char>(type));
+  AppendU32(file, Crc32cMask(crc));
+}
+
+void SplitSstWriter::Add(const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen) {
+  // FlushBlockBySizePolicy::Update (flush_block_policy.cc:45-76), min_keys_per_block = 1
+  if (!block_.empty()) {
+    const size_t cur = block_.SizeEstimate();
+    const bool almost = block_.SizeAfter(klen, vlen) > o_.block_size && o_.block_size_deviation > 0 &&
+                        cur * 100 > static_cast<size_t>(o_.block_size) * (100 - o_.block_size_deviation);
+    if ((cur >= o_.block_size || almost) && block_.NumKeysForPolicy() >= 1) CutDataBlock(key, klen, true);
+  }
+  last_key_.assign(reinterpret_cast<const char*>(key), klen);
+  block_.Add(key, klen, val, vlen);
+  num_entries_++; raw_key_ += klen; raw_val_ += vlen;
+  const uint8_t t = key[klen - 8];
+  if (t == 0 || t == 7) deleted_keys_++;
+}
+
+void SplitSstWriter::CutDataBlock(const uint8_t* next_key, size_t next_len, bool has_next) {
+  if (!block_.empty()) {
+    AppendBlock(block_.Finish(), &data_, &pending_);
+    block_.Reset();
+    data_size_ += pending_.size + kTrailer;
+  }
+  num_data_blocks_++;
+  index_->AddDataBlock(&last_key_, next_key, next_len, has_next, pending_);
+  while (index_->ShouldFlush()) {
+    std::string contents;
+    if (!index_->FlushNext(&contents, last_index_, last_index_set_)) throw std::runtime_error("index flush failed");
+    AppendBlock(contents, &meta_, &last_index_);
+    last_index_set_ = true;
+    num_index_blocks_++;
+  }
+}
+
+void SplitSstWriter::Finish() {
+  if (!block_.empty()) CutDataBlock(nullptr, 0, false);
+  std::string top;
+  const bool have_top = index_->FlushNext(&top, last_index_, last_index_set_);
+  if (have_top) num_index_blocks_++;
+  std::map<std::string, std::string> props;
+  auto num = [&](const char* name, uint64_t v) { std::string s; AppendVarint(&s, v); props[name] = s; };
+  num("rocksdb.raw.key.size", raw_key_);
+  num("rocksdb.raw.value.size", raw_val_);
+  num("rocksdb.data.size", data_size_);
+  num("rocksdb.data.index.size", index_->EstimatedSize() + kTrailer);
+  num("rocksdb.filter.index.size", 0);
+  num("rocksdb.num.entries", num_entries_);
+  num("rocksdb.num.data.blocks", num_data_blocks_);
+  num("rocksdb.num.filter.blocks", 0);
+  num("rocksdb.num.data.index.blocks", num_index_blocks_);
+  num("rocksdb.filter.size", 0);
+  num("rocksdb.format.version", 0);
+  num("rocksdb.fixed.key.length", 0);
+  num("rocksdb.deleted.keys", deleted_keys_);
+  { std::string v; AppendU32(&v, 2); props["rocksdb.block.based.table.index.type"] = v; }   // kMultiLevelBinarySearch
+  props["rocksdb.block.based.table.whole.key.filtering"] = "1";
+  props["rocksdb.block.based.table.prefix.filtering"] = "0";
+  { std::string v; AppendU32(&v, static_cast<uint32_t>(index_->NumLevels())); props["rocksdb.block.based.table.index.num.levels"] = v; }
+  props["rocksdb.block.based.table.data.block.key.value.encoding.format"] = std::string(1, static_cast<char>(o_.key_encoding));
+  BlockEncoder pb(1, 1);
+  for (auto& kv : props)
+    pb.Add(reinterpret_cast<const uint8_t*>(kv.first.data()), kv.first.size(), reinterpret_cast<const uint8_t*>(kv.second.data()), kv.second.size());
+  Handle ph;
+  AppendBlock(pb.Finish(), &meta_, &ph);
+  BlockEncoder mb(1, 1);
+  { std::string k = "rocksdb.properties", v; AppendVarint(&v, ph.offset); AppendVarint(&v, ph.size);
+    mb.Add(reinterpret_cast<const uint8_t*>(k.data()), k.size(), reinterpret_cast<const uint8_t*>(v.data()), v.size()); }
+  Handle mh;
+  AppendBlock(mb.Finish(), &meta_, &mh);
+  if (have_top) { AppendBlock(top, &meta_, &last_index_); last_index_set_ = true; }
+  std::string f;
+  f.push_back(1);   // kCRC32c
+  AppendVarint(&f, mh.offset); AppendVarint(&f, mh.size);
+  AppendVarint(&f, last_index_.offset); AppendVarint(&f, last_index_.size);
+  f.resize(kFooterLen - 12);
+  AppendU32(&f, 2);
+  AppendU32(&f, static_cast<uint32_t>(kMagic & 0xffffffffu));
+  AppendU32(&f, static_cast<uint32_t>(kMagic >> 32));
+  meta_.append(f);
+}
+
+}  // namespace host
+}  // namespace ybgpu

@@ -1,0 +1,92 @@
+// host_sst.h — host-side (CPU) pieces of the product around the GPU engine:
+//   * reading a split SST's metadata file to find the data-block handles
+//     (reference: rocksdb/table/format.cc:118-153, table/block_based_table_reader.cc:759-765,
+//      table/index_reader.h:215-256) — small, latency-bound host work the reference also does on
+//      the CPU before a compaction starts (VersionSet::MakeInputIterator);
+//   * the SST writer that turns the GPU's surviving KV stream (or, later, its finished data
+//     blocks) into <n>.sst.sblock.0 + <n>.sst, mirroring rocksdb::BlockBasedTableBuilder
+//     (table/block_based_table_builder.cc:498-903) and rocksdb::TableBuilder's interface
+//     (table/table_builder.h:93-136).
+// None of this is a CPU fallback for the GPU path: the merge / filter / decode never run here.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace ybgpu {
+namespace host {
+
+struct Handle { uint64_t offset = 0, size = 0; };
+
+uint32_t Crc32c(const uint8_t* p, size_t n, uint32_t init = 0);   // rocksdb/util/crc32c.h Extend
+inline uint32_t Crc32cMask(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xa282ead8u; }
+
+struct SstMeta {
+  std::vector<Handle> data_blocks;   // key order
+  int key_encoding = 1;
+  int index_levels = 1;
+  std::map<std::string, std::string> properties;
+};
+// Returns empty string on success, else an error message.
+std::string ParseSplitSstMeta(const uint8_t* meta, uint64_t len, SstMeta* out);
+
+struct TableOptions {
+  uint32_t block_size = 32 * 1024;
+  int block_restart_interval = 16;
+  int index_block_restart_interval = 1;
+  int block_size_deviation = 10;
+  uint32_t index_block_size = 32 * 1024;
+  uint32_t min_keys_per_index_block = 100;
+  int key_encoding = 1;
+};
+
+// Append-only encoder of one block (rocksdb::BlockBuilder, table/block_builder.cc:347-412).
+class BlockEncoder {
+ public:
+  BlockEncoder(int restart_interval, int key_encoding);
+  void Add(const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen);
+  const std::string& Finish();
+  void Reset();
+  bool empty() const { return body_.empty(); }
+  size_t SizeEstimate() const { return body_.size() + (finished_ ? 0 : restarts_.size() * 4 + 4); }
+  size_t SizeAfter(size_t klen, size_t vlen) const;
+  size_t NumKeysForPolicy() const { return restarts_.size() * interval_ + in_interval_; }
+ private:
+  int interval_, encoding_;
+  std::string body_, last_key_;
+  std::vector<uint32_t> restarts_;
+  int in_interval_ = 0;
+  bool finished_ = false;
+};
+
+class IndexWriter;   // multi-level index (table/index_builder.cc:143-289)
+
+// rocksdb::TableBuilder shape: Add / Finish / NumEntries / TotalFileSize / status.
+class SplitSstWriter {
+ public:
+  explicit SplitSstWriter(const TableOptions& o);
+  ~SplitSstWriter();
+  void Add(const uint8_t* ikey, size_t klen, const uint8_t* val, size_t vlen);
+  void Finish();
+  uint64_t NumEntries() const { return num_entries_; }
+  uint64_t TotalFileSize() const { return data_.size() + meta_.size(); }
+  uint64_t NumDataBlocks() const { return num_data_blocks_; }
+  const std::string& data_file() const { return data_; }
+  const std::string& meta_file() const { return meta_; }
+ private:
+  void CutDataBlock(const uint8_t* next_key, size_t next_len, bool has_next);
+  void AppendBlock(const std::string& contents, std::string* file, Handle* h);
+  TableOptions o_;
+  BlockEncoder block_;
+  std::unique_ptr<IndexWriter> index_;
+  std::string data_, meta_, last_key_;
+  Handle pending_, last_index_;
+  bool last_index_set_ = false;
+  uint64_t num_entries_ = 0, raw_key_ = 0, raw_val_ = 0, data_size_ = 0, num_data_blocks_ = 0,
+           num_index_blocks_ = 0, deleted_keys_ = 0;
+};
+
+}  // namespace host
+}  // namespace ybgpu
