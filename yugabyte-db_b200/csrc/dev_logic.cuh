@@ -271,7 +271,7 @@ YB_HD int encht_cmp(const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb
 // ----------------------------------------------------------------------------------------------
 // dockv/primitive_value.cc:1232-1626 KeyEntryValue::DecodeKey(slice, nullptr): number of bytes of
 // one key entry (type byte + payload) at p, or a negative DevError.
-YB_HD_NOINLINE int key_entry_size(const uint8_t* p, int n, int depth = 0) {
+YB_HD_NOINLINE int key_entry_size_flat(const uint8_t* p, int n) {   // everything except frozen containers
   if (n <= 0) return -DEV_ERR_BAD_KEY;
   const uint8_t t = p[0];
   int fixed = -1;
@@ -313,23 +313,41 @@ YB_HD_NOINLINE int key_entry_size(const uint8_t* p, int n, int depth = 0) {
       for (int j = 0; j < 4; j++) { int64_t v; int k = fast_varint_decode(p + i, n - i, &v); if (!k) return -DEV_ERR_BAD_KEY; i += k; }
       return i;
     }
-    case '<': case '>': {                                   // frozen: nested entries until group end
-      if (depth > 4) return -DEV_ERR_UNSUPPORTED_KEY;
-      const uint8_t endm = t == '>' ? '}' : '!';
-      int i = 1;
-      while (i < n) {
-        if (p[i] == endm) return i + 1;
-        int k = key_entry_size(p + i, n - i, depth + 1);
-        if (k < 0) return k;
-        i += k;
-      }
-      return -DEV_ERR_BAD_KEY;
-    }
+    case '<': case '>':
+      return -1000;                                         // frozen container: handled by key_entry_size
     case 'B': case 'f': case 'E': case 'd': case 'o': case 'p':
       return -DEV_ERR_UNSUPPORTED_KEY;                      // varint / decimal / bson comparable encodings
     default:
       return -DEV_ERR_BAD_KEY;
   }
+}
+
+// Full KeyEntryValue::DecodeKey size including frozen containers ('<' ... '!' / '>' ... '}'),
+// which nest (primitive_value.cc:1287-1313). Iterative (no recursion: device stack is static).
+YB_HD_NOINLINE int key_entry_size(const uint8_t* p, int n) {
+  int k = key_entry_size_flat(p, n);
+  if (k != -1000) return k;
+  uint8_t endm[4];
+  int depth = 0, i = 0;
+  endm[depth++] = p[0] == '>' ? '}' : '!';
+  i = 1;
+  while (i < n) {
+    if (p[i] == endm[depth - 1]) {
+      i++;
+      if (--depth == 0) return i;
+      continue;
+    }
+    k = key_entry_size_flat(p + i, n - i);
+    if (k == -1000) {
+      if (depth >= 4) return -DEV_ERR_UNSUPPORTED_KEY;
+      endm[depth++] = p[i] == '>' ? '}' : '!';
+      i++;
+      continue;
+    }
+    if (k < 0) return k;
+    i += k;
+  }
+  return -DEV_ERR_BAD_KEY;   // "Reached end of slice looking for frozen group end marker"
 }
 
 YB_HD bool is_special_key_entry_type(uint8_t t) {   // value_type.h:280-284

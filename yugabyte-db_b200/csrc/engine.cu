@@ -148,11 +148,8 @@ __global__ void __launch_bounds__(256) k_prepass(RunView run, int run_idx, JobDe
     val_bytes += __shfl_xor_sync(0xffffffffu, val_bytes, o);
     max_klen = max(max_klen, __shfl_xor_sync(0xffffffffu, max_klen, o));
   }
-  if (lane == 0 && (key_bytes | val_bytes | max_klen)) {
-    atomicAdd(&J->in_key_bytes, key_bytes);
-    atomicAdd(&J->in_val_bytes, val_bytes);
-    atomicMax(&J->max_ikey_len, max_klen);
-  }
+  (void)key_bytes; (void)val_bytes;
+  if (lane == 0 && max_klen) atomicMax(&J->max_ikey_len, max_klen);
 }
 
 // Exclusive scan of a u32 array with one CTA (n up to a few million: nb per file).
@@ -385,10 +382,10 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t sh_T, sh_ngroups, sh_any_filtered;
   __shared__ int sh_err;
-  __shared__ unsigned long long sh_stats[8];
+  __shared__ unsigned long long sh_stats[9];
 
   const uint32_t tile = blockIdx.x;
-  if (threadIdx.x < 8) sh_stats[threadIdx.x] = 0;
+  if (threadIdx.x < 9) sh_stats[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     uint32_t acc = 0;
     for (int r = 0; r < k; r++) {
@@ -461,7 +458,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
   // (c) CompactionIterator per sorted position + group starts
   const uint32_t items = (T + blockDim.x - 1) / blockDim.x;          // consecutive items per thread
   uint32_t my_groups = 0;
-  unsigned long long st_counted = 0, st_hidden = 0, st_obsolete = 0;
+  unsigned long long st_counted = 0, st_hidden = 0, st_obsolete = 0, st_in_k = 0, st_in_v = 0;
   for (uint32_t j = 0; j < items; j++) {
     const uint32_t i = threadIdx.x * items + j;
     if (i >= T) break;
@@ -470,6 +467,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
     uint8_t f = 0;
     if (!(rec_flags(e, S) & REC_F_HT_FILTERED)) {
       f |= ENT_COUNTED; st_counted++;
+      st_in_k += rec_ulen(e, S) + 8; st_in_v += rec_vlen(e, S);
       const uint64_t suffix = rec_suffix(e, S);
       const uint32_t type = static_cast<uint32_t>(suffix & 0xff);
       const uint64_t seq = suffix >> 8;
@@ -580,8 +578,8 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
     }
   }
   // block-reduce stats
-  unsigned long long vals[7] = {st_counted, st_hidden, st_obsolete, st_feed, st_kept, st_kbytes, st_vbytes};
-  for (int q = 0; q < 7; q++) {
+  unsigned long long vals[9] = {st_counted, st_hidden, st_obsolete, st_feed, st_kept, st_kbytes, st_vbytes, st_in_k, st_in_v};
+  for (int q = 0; q < 9; q++) {
     unsigned long long v = vals[q];
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh_stats[q], v);
@@ -597,6 +595,8 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
     if (sh_stats[4]) atomicAdd(&J->n_kept, sh_stats[4]);
     if (sh_stats[5]) atomicAdd(&J->out_key_bytes, sh_stats[5]);
     if (sh_stats[6]) atomicAdd(&J->out_val_bytes, sh_stats[6]);
+    if (sh_stats[7]) atomicAdd(&J->in_key_bytes, sh_stats[7]);
+    if (sh_stats[8]) atomicAdd(&J->in_val_bytes, sh_stats[8]);
   }
 }
 
@@ -974,8 +974,6 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     I.runs[r].gid_base = static_cast<uint32_t>(N);
     N += n;
   }
-  stats_.total_input_raw_key_bytes = I.hJ.in_key_bytes;
-  stats_.total_input_raw_value_bytes = I.hJ.in_val_bytes;
   const uint32_t max_ikey = I.hJ.max_ikey_len;
   if (max_ikey > 1008 + 8) return Fail(YBGPU_NOT_SUPPORTED, "user keys longer than 1008 bytes are not supported");
   const int S = N ? static_cast<int>(((max_ikey - 8 + 16) + 15) & ~15u) : 32;   // user key + 16-byte trailer
@@ -1119,6 +1117,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   stats_.num_record_drop_hidden = I.hJ.n_hidden;
   stats_.num_record_drop_obsolete = I.hJ.n_obsolete;
   stats_.num_record_drop_feed = I.hJ.n_feed_dropped;
+  stats_.total_input_raw_key_bytes = I.hJ.in_key_bytes;
+  stats_.total_input_raw_value_bytes = I.hJ.in_val_bytes;
   stats_.total_output_raw_key_bytes = I.hJ.out_key_bytes;
   stats_.total_output_raw_value_bytes = I.hJ.out_val_bytes;
   stats_.smallest_seqno = I.hJ.n_kept ? I.hJ.min_seq : 0;
