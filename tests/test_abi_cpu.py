@@ -66,3 +66,14 @@ def test_host_table_builder_docdb_shape(pkg):
         b.add(k, v)
     data, meta = b.finish()
     assert data == ref.data and meta == ref.meta
+
+
+def test_product_generator_matches_oracle_generator(pkg):
+    """bench.py's inputs come from the product's generator; the oracle has an independent one.
+    Same spec => same bytes."""
+    kw = dict(seed=21, num_rows=4000, cols=2, versions=3, num_files=4, value_len=100, tombstone_per_1024=50)
+    a = pkg.generate_ssts(pkg.GenConfig(**kw), block_size=4096)
+    b = o.Sst.generate_all(o.GenConfig(**kw), o.TableOptions(block_size=4096))
+    for x, y in zip(a, b):
+        assert x.data_view().tobytes() == y.data and x.meta_view().tobytes() == y.meta
+        assert x.num_entries == y.num_entries and x.raw_bytes == y.raw_bytes

@@ -35,7 +35,7 @@ class JobOptions(C.Structure):
         ("key_bounds_upper", C.c_char_p), ("key_bounds_upper_len", C.c_uint64),
         ("block_size", C.c_uint32), ("block_restart_interval", C.c_int32), ("block_size_deviation", C.c_int32),
         ("output_key_encoding", C.c_int32), ("index_block_size", C.c_uint32), ("min_keys_per_index_block", C.c_uint32),
-        ("verify_checksums", C.c_int32),
+        ("verify_checksums", C.c_int32), ("cuda_stream", C.c_void_p),
     ]
 
 
@@ -50,10 +50,29 @@ class JobStats(C.Structure):
         "total_output_raw_key_bytes", "total_output_raw_value_bytes", "num_output_data_blocks",
         "output_data_file_size", "output_meta_file_size", "smallest_seqno", "largest_seqno")] + [
         ("gpu_seconds", C.c_double), ("gpu_kernel_launches", C.c_uint32), ("h2d_bytes", C.c_uint64),
-        ("d2h_bytes", C.c_uint64)]
+        ("d2h_bytes", C.c_uint64), ("phase_seconds", C.c_double * 8), ("phase_launches", C.c_uint32 * 8)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["phase_seconds"] = list(self.phase_seconds)
+        d["phase_launches"] = list(self.phase_launches)
+        return d
+
+
+PHASE_NAMES = ["block_scan", "decode", "partition", "merge_filter", "emit"]
+
+
+class GenConfig(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("num_rows", C.c_uint64), ("cols", C.c_uint32), ("versions", C.c_uint32),
+                ("num_files", C.c_uint32), ("value_len", C.c_uint32), ("base_micros", C.c_uint64),
+                ("tombstone_per_1024", C.c_uint32), ("tombstone_newest", C.c_uint32), ("row_offset", C.c_uint64),
+                ("hash_rows_total", C.c_uint64)]
+
+    def __init__(self, seed=1, num_rows=1000, cols=1, versions=1, num_files=2, value_len=256,
+                 base_micros=1790000000 * 1000000, tombstone_per_1024=0, tombstone_newest=0, row_offset=0,
+                 hash_rows_total=0):
+        super().__init__(seed, num_rows, cols, versions, num_files, value_len, base_micros, tombstone_per_1024,
+                         tombstone_newest, row_offset, hash_rows_total)
 
 
 _LIB = None
@@ -86,6 +105,17 @@ def lib():
     L.ybgpu_job_fetch_output.argtypes = [vp, vp, u64, vp, u64]
     L.ybgpu_job_output_boundaries.argtypes = [vp, vp, C.POINTER(u64), vp, C.POINTER(u64)]
     L.ybgpu_job_kv_stream_digest.argtypes = [vp, C.POINTER(u64)]
+    L.ybgpu_gen_ssts.argtypes = [C.POINTER(GenConfig), C.POINTER(JobOptions), C.POINTER(vp), C.c_int32]
+    L.ybgpu_gen_sst.argtypes = [C.POINTER(GenConfig), C.c_uint32, C.POINTER(JobOptions), C.POINTER(vp)]
+    L.ybgpu_sst_free.argtypes = [vp]
+    L.ybgpu_sst_data.argtypes = [vp, C.POINTER(u64)]
+    L.ybgpu_sst_data.restype = vp
+    L.ybgpu_sst_meta.argtypes = [vp, C.POINTER(u64)]
+    L.ybgpu_sst_meta.restype = vp
+    L.ybgpu_sst_num_entries.argtypes = [vp]
+    L.ybgpu_sst_num_entries.restype = u64
+    L.ybgpu_sst_raw_bytes.argtypes = [vp]
+    L.ybgpu_sst_raw_bytes.restype = u64
     L.ybgpu_device_count.restype = C.c_int32
     L.ybgpu_version.restype = C.c_char_p
     _LIB = L
@@ -107,7 +137,7 @@ class GpuCompactionJob:
                  retention=True, cutoff_ht=HT_MIN, cotables_cutoff_ht=HT_INVALID, table_ttl_ns=TTL_MAX_NS,
                  retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
                  restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
-                 min_keys_per_index_block=100, verify_checksums=True):
+                 min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None):
         L = lib()
         o = JobOptions()
         L.ybgpu_job_options_init(C.byref(o))
@@ -128,6 +158,7 @@ class GpuCompactionJob:
         o.output_key_encoding = output_key_encoding
         o.index_block_size, o.min_keys_per_index_block = index_block_size, min_keys_per_index_block
         o.verify_checksums = int(verify_checksums)
+        o.cuda_stream = cuda_stream
         self._keep = (largest_user_key, lower, upper)
         h = C.c_void_p()
         st = L.ybgpu_job_create(C.byref(o), C.byref(h))
@@ -260,3 +291,48 @@ class HostTableBuilder:
         if getattr(self, "h", None):
             lib().ybgpu_table_builder_destroy(self.h)
             self.h = None
+
+
+class GeneratedSst:
+    """A synthetic split SST made by the product's generator (ybgpu_gen_ssts)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    def __del__(self):
+        if getattr(self, "h", None) and _LIB is not None:
+            _LIB.ybgpu_sst_free(self.h)
+            self.h = None
+
+    def _view(self, fn):
+        n = C.c_uint64()
+        p = fn(self.h, C.byref(n))
+        if n.value == 0:
+            return np.zeros(0, np.uint8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (n.value,))
+
+    def data_view(self):
+        return self._view(lib().ybgpu_sst_data)
+
+    def meta_view(self):
+        return self._view(lib().ybgpu_sst_meta)
+
+    @property
+    def num_entries(self):
+        return lib().ybgpu_sst_num_entries(self.h)
+
+    @property
+    def raw_bytes(self):
+        return lib().ybgpu_sst_raw_bytes(self.h)
+
+
+def generate_ssts(cfg, block_size=32768, restart_interval=16, max_threads=None):
+    L = lib()
+    o = JobOptions()
+    L.ybgpu_job_options_init(C.byref(o))
+    o.block_size, o.block_restart_interval = block_size, restart_interval
+    arr = (C.c_void_p * cfg.num_files)()
+    st = L.ybgpu_gen_ssts(C.byref(cfg), C.byref(o), arr, max_threads or os.cpu_count() or 1)
+    if st != 0:
+        raise YbGpuError(st, "synthetic SST generation failed")
+    return [GeneratedSst(arr[i]) for i in range(cfg.num_files)]

@@ -259,6 +259,21 @@ ybgpu_status ybgpu_table_builder_files(const ybgpu_table_builder* b, const uint8
 }
 void ybgpu_table_builder_destroy(ybgpu_table_builder* b) { delete b; }
 
+ybgpu_status ybgpu_sst_meta_handles(const uint8_t* meta, uint64_t len, ybgpu_block_handle* handles, uint64_t cap,
+                                    uint64_t* n, int32_t* enc) {
+  if (!meta || !n) return YBGPU_INVALID_ARGUMENT;
+  ybgpu::host::SstMeta m;
+  std::string err = ybgpu::host::ParseSplitSstMeta(meta, len, &m);
+  if (!err.empty()) { g_last_error = err; return YBGPU_CORRUPTION; }
+  *n = m.data_blocks.size();
+  if (enc) *enc = m.key_encoding;
+  if (handles) {
+    if (cap < m.data_blocks.size()) return YBGPU_INVALID_ARGUMENT;
+    for (size_t i = 0; i < m.data_blocks.size(); i++) { handles[i].offset = m.data_blocks[i].offset; handles[i].size = m.data_blocks[i].size; }
+  }
+  return YBGPU_OK;
+}
+
 int32_t ybgpu_device_count(void);   // engine.cu
 const char* ybgpu_version(void) { return "ybgpu-compaction 0.1 (sm_100a)"; }
 

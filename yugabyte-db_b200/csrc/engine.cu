@@ -814,6 +814,7 @@ static ybgpu_status DevErrorStatus(int e) {
 struct Engine::Impl {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t phase_ev[8] = {};
   std::vector<void*> allocs;
   JobDev* dJ = nullptr;
   JobParams* dP = nullptr;
@@ -838,20 +839,23 @@ Engine::Engine(const ybgpu_job_options& o) : opt_(o), impl_(new Impl) {
 Engine::~Engine() {
   if (impl_) {
     cudaSetDevice(opt_.device);
-    for (void* p : impl_->allocs) cudaFree(p);
+    for (void* p : impl_->allocs) cudaFreeAsync(p, impl_->stream);
     if (impl_->ev0) cudaEventDestroy(impl_->ev0);
     if (impl_->ev1) cudaEventDestroy(impl_->ev1);
-    if (impl_->stream) cudaStreamDestroy(impl_->stream);
+    for (auto& e : impl_->phase_ev) if (e) cudaEventDestroy(e);
     delete impl_;
   }
 }
 
 ybgpu_status Engine::Fail(ybgpu_status s, const std::string& msg) { error_ = msg; return s; }
 
+// Stream-ordered allocation from the device's default memory pool (release threshold raised to
+// "never" in Init), so steady-state jobs reuse HBM instead of paying cudaMalloc/cudaFree.
+static thread_local cudaStream_t g_alloc_stream = nullptr;
 template <typename T>
 static cudaError_t DevAlloc(std::vector<void*>* allocs, T** out, size_t count) {
   void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16) + 32);
+  cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count * sizeof(T), 16) + 32, g_alloc_stream);
   if (e == cudaSuccess) { allocs->push_back(p); *out = reinterpret_cast<T*>(p); }
   return e;
 }
@@ -864,9 +868,17 @@ ybgpu_status Engine::Init() {
                                          " (this engine has no CPU fallback)");
   if (opt_.device < 0 || opt_.device >= ndev) return Fail(YBGPU_INVALID_ARGUMENT, "bad device ordinal");
   CUDA_TRY(cudaSetDevice(opt_.device));
-  CUDA_TRY(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking));
+  impl_->stream = reinterpret_cast<cudaStream_t>(opt_.cuda_stream);   // NULL = legacy default stream
+  g_alloc_stream = impl_->stream;
+  {
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, opt_.device));
+    uint64_t thr = ~0ull;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
   CUDA_TRY(cudaEventCreate(&impl_->ev0));
   CUDA_TRY(cudaEventCreate(&impl_->ev1));
+  for (auto& e : impl_->phase_ev) CUDA_TRY(cudaEventCreate(&e));
   CUDA_TRY(DevAlloc(&impl_->allocs, &impl_->dJ, 1));
   CUDA_TRY(DevAlloc(&impl_->allocs, &impl_->dP, 1));
   CUDA_TRY(DevAlloc(&impl_->allocs, &impl_->dRuns, MAX_RUNS));
@@ -881,6 +893,7 @@ ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_blo
     return Fail(YBGPU_NOT_SUPPORTED, "only kKeyDeltaEncodingSharedPrefix inputs are decoded on the GPU so far");
   if (nh >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "too many data blocks in one file");
   CUDA_TRY(cudaSetDevice(opt_.device));
+  g_alloc_stream = impl_->stream;
   for (uint64_t i = 0; i < nh; i++) {
     if (handles[i].offset + handles[i].size + 5 > len) return Fail(YBGPU_CORRUPTION, "block handle outside the data file");
     if (handles[i].size >= (1ull << 31)) return Fail(YBGPU_NOT_SUPPORTED, "data block too large");
@@ -934,6 +947,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   if (ran_) return Fail(YBGPU_ILLEGAL_STATE, "job already ran");
   Impl& I = *impl_;
   CUDA_TRY(cudaSetDevice(opt_.device));
+  g_alloc_stream = I.stream;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, opt_.device));
   const int sms = prop.multiProcessorCount;
@@ -947,6 +961,12 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(cudaMemcpyAsync(I.dJ, &init, sizeof(init), cudaMemcpyHostToDevice, I.stream));
   }
   CUDA_TRY(cudaEventRecord(I.ev0, I.stream));
+  uint32_t phase_launch_mark[8] = {};
+  int phase = 0;
+  auto end_phase = [&]() -> cudaError_t {
+    phase_launch_mark[phase] = launches;
+    return cudaEventRecord(I.phase_ev[phase++], I.stream);
+  };
 
   // ---- K1: prepass + scan per file
   std::vector<uint32_t*> dtotals(k);
@@ -962,12 +982,14 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     }
   }
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(end_phase());
   if (ybgpu_status s = CheckDeviceError("block scan")) return s;
   if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
   uint64_t N = 0;
   for (int r = 0; r < k; r++) {
     uint32_t n;
-    CUDA_TRY(cudaMemcpy(&n, dtotals[r], 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(&n, dtotals[r], 4, cudaMemcpyDeviceToHost, I.stream));
+    CUDA_TRY(cudaStreamSynchronize(I.stream));
     I.runs[r].n_entries = n;
     I.runs[r].restart_interval = I.hJ.restart_interval[r];
     if (N + n >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "more than 2^32 entries in one job: shard the compaction");
@@ -992,6 +1014,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(end_phase());
   CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
 
   // ---- job parameters
@@ -1024,7 +1047,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     std::vector<uint8_t> tmp(Sfinal);
     for (int r = 0; r < k; r++) {
       if (!I.runs[r].n_entries) continue;
-      CUDA_TRY(cudaMemcpy(tmp.data(), I.runs[r].rec + static_cast<size_t>(I.runs[r].n_entries - 1) * Sfinal, Sfinal, cudaMemcpyDeviceToHost));
+      CUDA_TRY(cudaMemcpyAsync(tmp.data(), I.runs[r].rec + static_cast<size_t>(I.runs[r].n_entries - 1) * Sfinal, Sfinal, cudaMemcpyDeviceToHost, I.stream));
+      CUDA_TRY(cudaStreamSynchronize(I.stream));
       uint32_t ulen = rec_ulen(tmp.data(), Sfinal);
       std::vector<uint8_t> key(tmp.begin(), tmp.begin() + ulen);
       if (!any || std::lexicographical_compare(best.begin(), best.end(), key.begin(), key.end())) { best = key; any = true; }
@@ -1041,7 +1065,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   if (N == 0) {
     ran_ = true;
     CUDA_TRY(DevAlloc(&I.allocs, &I.out_koff, 1)); CUDA_TRY(DevAlloc(&I.allocs, &I.out_voff, 1));
-    CUDA_TRY(cudaMemset(I.out_koff, 0, 8)); CUDA_TRY(cudaMemset(I.out_voff, 0, 8));
+    CUDA_TRY(cudaMemsetAsync(I.out_koff, 0, 8, I.stream)); CUDA_TRY(cudaMemsetAsync(I.out_voff, 0, 8, I.stream));
     CUDA_TRY(DevAlloc(&I.allocs, &I.out_keys, 1)); CUDA_TRY(DevAlloc(&I.allocs, &I.out_vals, 1));
     stats_.gpu_kernel_launches = launches;
     return YBGPU_OK;
@@ -1068,6 +1092,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   k_build_tiles<<<1, 1024, 0, I.stream>>>(pv, I.dP, d_tile_lo, d_tile_rank, I.dJ);
   launches += 3;
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(end_phase());
   if (ybgpu_status s = CheckDeviceError("partition")) return s;
   const uint32_t n_tiles = I.hJ.n_tiles;
 
@@ -1085,6 +1110,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   k_merge_filter<<<n_tiles, MERGE_THREADS, smem, I.stream>>>(mv, I.dP, I.dJ);
   launches++;
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(end_phase());
   if (ybgpu_status s = CheckDeviceError("merge")) return s;
   if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
 
@@ -1106,11 +1132,18 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   launches += 3;
   CUDA_TRY(cudaMemcpyAsync(I.out_koff + I.n_out, &I.out_key_bytes, 8, cudaMemcpyHostToDevice, I.stream));
   CUDA_TRY(cudaMemcpyAsync(I.out_voff + I.n_out, &I.out_val_bytes, 8, cudaMemcpyHostToDevice, I.stream));
+  CUDA_TRY(end_phase());
   CUDA_TRY(cudaEventRecord(I.ev1, I.stream));
   CUDA_TRY(cudaGetLastError());
   if (ybgpu_status s = CheckDeviceError("emit")) return s;
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, I.ev0, I.ev1));
+  for (int ph = 0; ph < phase; ph++) {
+    float pms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&pms, ph ? I.phase_ev[ph - 1] : I.ev0, I.phase_ev[ph]));
+    stats_.phase_seconds[ph] = pms / 1e3;
+    stats_.phase_launches[ph] = phase_launch_mark[ph] - (ph ? phase_launch_mark[ph - 1] : 0);
+  }
 
   stats_.num_input_records = I.hJ.n_counted;
   stats_.num_output_records = I.hJ.n_kept;
