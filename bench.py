@@ -294,7 +294,7 @@ def main():
         "decode": in_bytes,                     # must read every input entry once
         "partition": 0.0,
         "merge_filter": 0.0,
-        "emit": out_bytes * 2.0,                # read each survivor once, write it once
+        "encode": out_bytes * 2.0,              # read each survivor once, write it once
     }
     names = pkg.PHASE_NAMES
     dom = max(range(5), key=lambda i: phases[i])

@@ -117,7 +117,8 @@ typedef struct ybgpu_job_stats {
   uint32_t gpu_kernel_launches;        /* kernels launched by run() */
   uint64_t h2d_bytes, d2h_bytes;       /* bytes copied by add_input / fetch calls */
   /* device time per phase (CUDA events on the job's stream), seconds:
-   * 0 block scan (K1), 1 decode (K1'), 2 partition (K2), 3 merge+filter (K3), 4 emit/encode (K4) */
+   * 0 checksum verify + block scan (K1), 1 decode (K1'), 2 partition (K2), 3 merge+filter (K3),
+   * 4 survivor scan + block encode + CRC (K4/K5) */
   double phase_seconds[8];
   uint32_t phase_launches[8];
 } ybgpu_job_stats;

@@ -176,6 +176,44 @@ def test_errors_are_loud(pkg):
     data = s2.data_view().copy()
     data[3] ^= 0xff
     job = pkg.GpuCompactionJob()
+    job.add_input_sst(s2.meta_view(), data)
     with pytest.raises(pkg.YbGpuError) as e:
-        job.add_input_sst(s2.meta_view(), data)
+        job.run()                       # input CRC32C is verified on the GPU
     assert e.value.status_name == "Corruption"
+    job = pkg.GpuCompactionJob(verify_checksums=False)
+    job.add_input_sst(s2.meta_view(), data)
+    job.run()                           # like ReadOptions::verify_checksums = false
+
+
+def test_gpu_block_encoder_cut_rules(pkg):
+    """Block cuts (flush_block_policy.cc:45-76) under many block sizes / entry-size mixes, including
+    blocks longer than a chain segment and deviation = 0."""
+    import random
+    rng = random.Random(17)
+    rows = []
+    for i in range(30000):
+        d = dk.doc_key(["k%07d" % i])
+        vlen = rng.choice([0, 1, 3, 20, 100, 300, 2000]) if i % 7 else rng.randrange(0, 5000)
+        rows.append((o.ikey(dk.sub_doc_key(d, [dk.kcol(1 + i % 3)], micros=o.YB_EPOCH_US + i), (1 << 50) + i),
+                     b"S" + bytes(rng.randrange(256) for _ in range(vlen))))
+    run = w.sort_run(rows)
+    sst = o.Sst.build(run, o.TableOptions(block_size=4096))
+    for bs, dev, ri in ((256, 10, 16), (4096, 10, 16), (32768, 10, 16), (1 << 20, 10, 16), (4096, 0, 16), (4096, 10, 4), (2048, 50, 1)):
+        exp = o.compact([sst], o.CompactionParams(), o.TableOptions(block_size=bs, deviation=dev, restart=ri))
+        job = pkg.GpuCompactionJob(block_size=bs, deviation=dev, restart_interval=ri)
+        job.add_input_sst(sst.meta_view(), sst.data_view())
+        job.run()
+        data, meta = job.fetch_output()
+        assert data.tobytes() == exp.sst().data, (bs, dev, ri)
+        assert meta.tobytes() == exp.sst().meta, (bs, dev, ri)
+    # blocks far longer than a chain segment (4096 entries): tiny entries, 1 MB blocks
+    tiny = w.sort_run([(o.ikey(dk.sub_doc_key(dk.doc_key(["t%06d" % i]), [], micros=o.YB_EPOCH_US + 5), (1 << 50) + i), b"")
+                       for i in range(40000)])
+    sst = o.Sst.build(tiny, o.TableOptions(block_size=4096))
+    for bs in (1 << 20, 1 << 17):
+        exp = o.compact([sst], o.CompactionParams(), o.TableOptions(block_size=bs))
+        job = pkg.GpuCompactionJob(block_size=bs)
+        job.add_input_sst(sst.meta_view(), sst.data_view())
+        job.run()
+        data, meta = job.fetch_output()
+        assert data.tobytes() == exp.sst().data and meta.tobytes() == exp.sst().meta

@@ -59,7 +59,7 @@ class JobStats(C.Structure):
         return d
 
 
-PHASE_NAMES = ["block_scan", "decode", "partition", "merge_filter", "emit"]
+PHASE_NAMES = ["block_scan", "decode", "partition", "merge_filter", "encode"]
 
 
 class GenConfig(C.Structure):

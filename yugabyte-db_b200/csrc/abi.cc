@@ -66,28 +66,10 @@ void ybgpu_job_destroy(ybgpu_job* job) { delete job; }
 const char* ybgpu_job_error(const ybgpu_job* job) { return job ? job->error.c_str() : "null job"; }
 const char* ybgpu_last_error(void) { return g_last_error.c_str(); }
 
-static bool VerifyBlocks(const uint8_t* data, uint64_t len, const ybgpu_block_handle* h, uint64_t n, uint64_t* bad) {
-  for (uint64_t i = 0; i < n; i++) {
-    if (h[i].offset + h[i].size + 5 > len) { *bad = i; return false; }
-    const uint8_t* p = data + h[i].offset;
-    uint32_t stored; memcpy(&stored, p + h[i].size + 1, 4);
-    uint32_t actual = ybgpu::host::Crc32cMask(ybgpu::host::Crc32c(p, h[i].size + 1));
-    if (stored != actual) { *bad = i; return false; }
-  }
-  return true;
-}
-
 ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint64_t data_file_len,
                                  const ybgpu_block_handle* handles, uint64_t num_handles, int32_t key_encoding,
                                  uint64_t hybrid_time_filter) {
   if (!job) return YBGPU_INVALID_ARGUMENT;
-  if (job->engine->options().verify_checksums) {
-    // ReadBlock's CRC32C check (table/format.cc:352-395). Done on the host while the file is
-    // still in host memory, as the reference does; a device-side CRC kernel is planned.
-    uint64_t bad = 0;
-    if (!VerifyBlocks(data_file, data_file_len, handles, num_handles, &bad))
-      return JobFail(job, YBGPU_CORRUPTION, "block checksum mismatch in input block " + std::to_string(bad));
-  }
   return Sync(job, job->engine->AddInput(data_file, data_file_len, handles, num_handles, key_encoding, hybrid_time_filter, false));
 }
 
@@ -157,28 +139,48 @@ ybgpu_status ybgpu_job_emit_kv_stream(ybgpu_job* job, ybgpu_emit_fn emit, void* 
   return YBGPU_OK;
 }
 
+// Output SST: the data file comes finished from the GPU (K5); the host writes the metadata file
+// from per-block boundary keys and handles (index blocks, properties, metaindex, footer).
 static ybgpu_status EnsureSst(ybgpu_job* job) {
   if (job->have_sst) return YBGPU_OK;
-  ybgpu_status s = EnsureHostKv(job);
+  Engine& e = *job->engine;
+  uint64_t data_len = 0; uint32_t nb = 0, stride = 0;
+  ybgpu_status s = Sync(job, e.OutputInfo(&data_len, &nb, &stride));
   if (s != YBGPU_OK) return s;
   try {
-    const ybgpu_job_options& o = job->engine->options();
-    ybgpu::host::TableOptions t;
-    t.block_size = o.block_size; t.block_restart_interval = o.block_restart_interval;
-    t.block_size_deviation = o.block_size_deviation; t.index_block_size = o.index_block_size;
-    t.min_keys_per_index_block = o.min_keys_per_index_block; t.key_encoding = o.output_key_encoding;
-    ybgpu::host::SplitSstWriter w(t);
-    const uint64_t n = job->koff.size() - 1;
-    for (uint64_t i = 0; i < n; i++)
-      w.Add(job->keys.data() + job->koff[i], job->koff[i + 1] - job->koff[i], job->vals.data() + job->voff[i],
-            job->voff[i + 1] - job->voff[i]);
-    if (n) {   // the reference never opens an output file for an empty result (compaction_job.cc:156-160)
-      w.Finish();
-      job->data_file = w.data_file(); job->meta_file = w.meta_file(); job->num_blocks = w.NumDataBlocks();
+    job->data_file.resize(data_len);
+    std::vector<uint64_t> off(static_cast<size_t>(nb) + 1);
+    std::vector<uint8_t> bnd(static_cast<size_t>(nb) * 2 * stride);
+    s = Sync(job, e.FetchOutput(reinterpret_cast<uint8_t*>(&job->data_file[0]), off.data(), bnd.data()));
+    if (s != YBGPU_OK) return s;
+    if (nb) {   // the reference never opens an output file for an empty result (compaction_job.cc:156-160)
+      const ybgpu_job_options& o = e.options();
+      ybgpu::host::TableOptions t;
+      t.block_size = o.block_size; t.block_restart_interval = o.block_restart_interval;
+      t.block_size_deviation = o.block_size_deviation; t.index_block_size = o.index_block_size;
+      t.min_keys_per_index_block = o.min_keys_per_index_block; t.key_encoding = o.output_key_encoding;
+      ybgpu::host::MetaFileWriter w(t);
+      std::string last;
+      for (uint32_t b = 0; b < nb; b++) {
+        const uint8_t* lk = bnd.data() + static_cast<size_t>(2 * b) * stride;
+        const uint8_t* nk = lk + stride;
+        const size_t ll = lk[0] | (lk[1] << 8), nl = nk[0] | (nk[1] << 8);
+        last.assign(reinterpret_cast<const char*>(lk + 2), ll);
+        ybgpu::host::Handle h; h.offset = off[b]; h.size = off[b + 1] - off[b] - 5;
+        w.AddDataBlock(&last, nk + 2, nl, b + 1 < nb, h);
+      }
+      const ybgpu_job_stats& st = e.stats();
+      ybgpu::host::MetaProps mp;
+      mp.raw_key_size = st.total_output_raw_key_bytes; mp.raw_value_size = st.total_output_raw_value_bytes;
+      mp.data_size = data_len; mp.num_entries = st.num_output_records; mp.num_data_blocks = nb;
+      mp.deleted_keys = e.kept_deletions();
+      w.Finish(mp);
+      job->meta_file = w.meta_file();
     }
+    job->num_blocks = nb;
     job->have_sst = true;
-  } catch (const std::exception& e) {
-    return JobFail(job, YBGPU_NOT_SUPPORTED, e.what());
+  } catch (const std::exception& ex) {
+    return JobFail(job, YBGPU_NOT_SUPPORTED, ex.what());
   }
   return YBGPU_OK;
 }

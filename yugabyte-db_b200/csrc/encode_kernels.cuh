@@ -1,0 +1,528 @@
+// encode_kernels.cuh — K5: the output side of the compaction on the GPU.
+//
+// Turns the surviving entries (dense, in output order) into the data file of a split SST exactly
+// as rocksdb::BlockBasedTableBuilder would (table/block_based_table_builder.cc:498-707):
+//   * BlockBuilder entry encoding, restart every `ri` entries (table/block_builder.cc:347-412);
+//   * FlushBlockBySizePolicy block cuts (table/flush_block_policy.cc:45-76) — a sequential rule
+//     (each cut depends on where the block started), resolved in parallel by computing, for every
+//     entry s, next[s] = first entry of the following block if a block started at s, and then
+//     following that chain with two levels of segment "exit" tables;
+//   * 5-byte trailers with masked CRC32C over block + type (:669-698), CRC computed by a
+//     warp-parallel slicing-by-4 kernel combined with GF(2) shifts (also used to verify inputs).
+//
+// Included by engine.cu only.
+#pragma once
+
+namespace ybgpu {
+
+constexpr int SEG = 4096;          // entries per chain segment
+constexpr int GROUP_SEGS = 64;     // segments per group
+
+struct EncView {
+  const RunView* runs;
+  const Desc* kept;                // dense survivors [n]
+  const ValueRewrite* rewrites;
+  uint32_t* nr;                    // [n] encoded size of entry as a non-restart entry
+  uint16_t* shared;                // [n] bytes shared with the previous survivor's internal key
+  uint16_t* D;                     // [n] extra bytes if the entry is a restart point
+  unsigned long long* P;           // [n+1] exclusive prefix of nr
+  unsigned long long* QQ;          // [n] inclusive prefix of D within the entry's residue class mod ri
+  uint32_t* next;                  // [n]
+  uint32_t* exit1;                 // [n] first chain element >= end of s's segment
+  uint32_t n;
+  uint32_t ri;                     // block_restart_interval
+  uint32_t ri_shift;               // log2(ri)
+  uint32_t block_size;
+  uint32_t deviation;
+};
+
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint32_t varint_len(uint32_t v) { return v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5; }
+
+// Compact the merged-order descriptors into the dense survivor list.
+__global__ void __launch_bounds__(EMIT_THREADS) k_compact_desc(const Desc* desc, uint64_t N, const Sums3* partial, Desc* kept) {
+  __shared__ uint32_t warp_sums[32];
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * EMIT_CHUNK;
+  constexpr int PER = EMIT_CHUNK / EMIT_THREADS;
+  uint32_t n = 0;
+  Desc d[PER];
+  for (int j = 0; j < PER; j++) {
+    uint64_t i = base + threadIdx.x * PER + j;
+    d[j].flags = 0;
+    if (i < N) { d[j] = desc[i]; if (d[j].flags & ENT_KEEP) n++; }
+  }
+  uint32_t off = block_exclusive_scan(n, warp_sums, nullptr);
+  uint64_t o = partial[blockIdx.x].n + off;
+  for (int j = 0; j < PER; j++) if (d[j].flags & ENT_KEEP) kept[o++] = d[j];
+}
+
+__device__ __forceinline__ const uint8_t* kept_rec(const EncView& E, const Desc& d, int S) {
+  const RunView& run = E.runs[d.run];
+  return run.rec + static_cast<size_t>(d.gid - run.gid_base) * S;
+}
+
+// Internal-key byte i of a survivor (user key bytes, then the 8-byte suffix, zeroed seq if flagged).
+__device__ __forceinline__ uint64_t kept_suffix(const uint8_t* rec, const Desc& d, int S) {
+  uint64_t s = rec_suffix(rec, S);
+  return (d.flags & ENT_ZERO_SEQ) ? (s & 0xff) : s;
+}
+
+// Per survivor: shared prefix with the previous survivor's internal key, encoded sizes.
+__global__ void __launch_bounds__(256) k_entry_sizes(EncView E, int S) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < E.n; j += gridDim.x * blockDim.x) {
+    const Desc d = E.kept[j];
+    const uint8_t* rec = kept_rec(E, d, S);
+    const uint32_t klen = d.klen, ulen = klen - 8u;
+    uint32_t shared = 0;
+    if (j > 0) {
+      const Desc pd = E.kept[j - 1];
+      const uint8_t* prec = kept_rec(E, pd, S);
+      const uint32_t pul = pd.klen - 8u;
+      const uint32_t m = min(ulen, pul);
+      shared = common_prefix_len(rec, m, prec, m);
+      if (shared == m) {
+        // one user key is a prefix of the other: the comparison continues into the suffix bytes
+        // of the shorter key (internal keys are compared as plain byte strings here,
+        // block_builder.cc:363-365)
+        uint8_t a[8], b[8];
+        const uint64_t sa = kept_suffix(rec, d, S), sb = kept_suffix(prec, pd, S);
+        for (int q = 0; q < 8; q++) { a[q] = static_cast<uint8_t>(sa >> (8 * q)); b[q] = static_cast<uint8_t>(sb >> (8 * q)); }
+        const uint32_t minlen = min(klen, static_cast<uint32_t>(pd.klen));
+        while (shared < minlen) {
+          const uint8_t x = shared < ulen ? rec[shared] : a[shared - ulen];
+          const uint8_t y = shared < pul ? prec[shared] : b[shared - pul];
+          if (x != y) break;
+          shared++;
+        }
+      }
+    }
+    const uint32_t vlen = d.vlen_out;
+    const uint32_t nr = varint_len(shared) + varint_len(klen - shared) + varint_len(vlen) + (klen - shared) + vlen;
+    const uint32_t rs = 1 + varint_len(klen) + varint_len(vlen) + klen + vlen;
+    E.nr[j] = nr; E.shared[j] = static_cast<uint16_t>(shared); E.D[j] = static_cast<uint16_t>(rs - nr);
+  }
+}
+
+// ---- scans: P = exclusive prefix of nr (u64); QQ = per-residue-class inclusive prefix of D ------
+constexpr int SCAN_CHUNK = 4096;
+__global__ void __launch_bounds__(256) k_p_sums(const uint32_t* nr, uint32_t n, unsigned long long* partial) {
+  __shared__ unsigned long long sh;
+  if (threadIdx.x == 0) sh = 0;
+  __syncthreads();
+  unsigned long long s = 0;
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_CHUNK;
+  for (uint32_t j = threadIdx.x; j < SCAN_CHUNK; j += 256) { uint64_t i = base + j; if (i < n) s += nr[i]; }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sh, s);
+  __syncthreads();
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh;
+}
+__global__ void __launch_bounds__(1024) k_scan_u64_single(unsigned long long* a, uint32_t n, unsigned long long* total) {
+  __shared__ unsigned long long ws[32];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    unsigned long long v = i < n ? a[i] : 0, x = v;
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) ws[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long w = ws[lane];
+      for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      ws[lane] = w;
+    }
+    __syncthreads();
+    if (i < n) a[i] = carry + (wid ? ws[wid - 1] : 0) + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += ws[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_p_final(const uint32_t* nr, uint32_t n, const unsigned long long* partial, unsigned long long* P) {
+  __shared__ uint32_t warp_sums[32];
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_CHUNK;
+  constexpr int PER = SCAN_CHUNK / 256;
+  uint32_t v[PER], s = 0;
+  for (int j = 0; j < PER; j++) { uint64_t i = base + threadIdx.x * PER + j; v[j] = i < n ? nr[i] : 0; s += v[j]; }
+  uint32_t off = block_exclusive_scan(s, warp_sums, nullptr);
+  unsigned long long run = partial[blockIdx.x] + off;
+  for (int j = 0; j < PER; j++) {
+    uint64_t i = base + threadIdx.x * PER + j;
+    if (i < n) P[i] = run;
+    run += v[j];
+    if (i + 1 == n) P[n] = run;
+  }
+}
+
+// QQ: rows of ri entries; thread = (row chunk of QROWS rows, column).
+constexpr int QROWS = 128;
+__global__ void __launch_bounds__(256) k_qq_sums(const uint16_t* D, uint32_t n, uint32_t ri, unsigned long long* partial /*[ri][nchunks]*/, uint32_t nchunks) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t chunk = t / ri, col = t % ri;
+  if (chunk >= nchunks) return;
+  unsigned long long s = 0;
+  for (int r = 0; r < QROWS; r++) {
+    uint64_t i = (static_cast<uint64_t>(chunk) * QROWS + r) * ri + col;
+    if (i < n) s += D[i];
+  }
+  partial[static_cast<size_t>(col) * nchunks + chunk] = s;
+}
+__global__ void __launch_bounds__(256) k_qq_final(const uint16_t* D, uint32_t n, uint32_t ri, const unsigned long long* partial, uint32_t nchunks, unsigned long long* QQ) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t chunk = t / ri, col = t % ri;
+  if (chunk >= nchunks) return;
+  unsigned long long s = partial[static_cast<size_t>(col) * nchunks + chunk];
+  for (int r = 0; r < QROWS; r++) {
+    uint64_t i = (static_cast<uint64_t>(chunk) * QROWS + r) * ri + col;
+    if (i < n) { s += D[i]; QQ[i] = s; }
+  }
+}
+
+// BlockBuilder::CurrentSizeEstimate after entries s..j of a block that started at s.
+__device__ __forceinline__ unsigned long long blk_cur(const EncView& E, uint32_t s, uint32_t j) {
+  const uint32_t t = (j - s) >> E.ri_shift;
+  return (E.P[j + 1] - E.P[s]) + (E.QQ[s + (t << E.ri_shift)] - E.QQ[s] + E.D[s]) + 4ull * (t + 1) + 4ull;
+}
+
+// next[s]: first entry of the block after the one starting at s (flush_block_policy.cc:45-76).
+__global__ void __launch_bounds__(256) k_next(EncView E) {
+  const unsigned long long BS = E.block_size;
+  const unsigned long long thresh = BS * (100 - E.deviation);       // cur*100 > thresh
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < E.n; s += gridDim.x * blockDim.x) {
+    // smallest m in (s, n] such that the block [s, m) satisfies cur*100 > thresh (or m == n)
+    uint32_t lo = s + 1, hi = E.n;
+    if (E.deviation == 0) {
+      // only rule 1 (cur >= BS)
+      while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (blk_cur(E, s, mid - 1) >= BS) hi = mid; else lo = mid + 1; }
+      E.next[s] = lo;
+      continue;
+    }
+    while (lo < hi) {
+      uint32_t mid = lo + ((hi - lo) >> 1);
+      if (blk_cur(E, s, mid - 1) * 100 > thresh) hi = mid; else lo = mid + 1;
+    }
+    uint32_t m = lo;
+    while (m < E.n) {
+      const unsigned long long cur = blk_cur(E, s, m - 1);
+      if (cur >= BS) break;
+      const Desc d = E.kept[m];
+      const unsigned long long est = cur + d.klen + d.vlen_out + ((((m - s) & (E.ri - 1)) == 0) ? 4 : 0) + 4 +
+                                     varint_len(d.klen) + varint_len(d.vlen_out);
+      if (est > BS && cur * 100 > thresh) break;
+      m++;
+    }
+    E.next[s] = m;
+  }
+}
+
+// exit1[s] = first chain element at or beyond the end of s's segment. One thread per segment,
+// right to left (exit1 of later entries is already known).
+__global__ void __launch_bounds__(128) k_seg_exit(EncView E) {
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t b = static_cast<uint64_t>(seg) * SEG;
+  if (b >= E.n) return;
+  const uint32_t e = static_cast<uint32_t>(umin64(b + SEG, E.n));
+  for (uint32_t s = e; s-- > static_cast<uint32_t>(b);) {
+    const uint32_t nx = E.next[s];
+    E.exit1[s] = nx >= e ? nx : E.exit1[nx];
+  }
+}
+
+// gexit[g][q]: for a chain element at offset q inside the FIRST segment of group g, the first
+// chain element at or beyond the end of the group.
+__global__ void __launch_bounds__(256) k_group_exit(EncView E, uint32_t* gexit, uint32_t ngroups) {
+  const uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+  const uint32_t g = static_cast<uint32_t>(t / SEG), q = static_cast<uint32_t>(t % SEG);
+  if (g >= ngroups) return;
+  const uint64_t gb = static_cast<uint64_t>(g) * SEG * GROUP_SEGS;
+  const uint64_t ge = umin64(gb + static_cast<uint64_t>(SEG) * GROUP_SEGS, E.n);
+  uint64_t s = gb + q;
+  if (s >= E.n) { gexit[t] = E.n; return; }
+  while (s < ge) s = E.exit1[s];
+  gexit[t] = static_cast<uint32_t>(s);
+}
+
+// Serial walk over groups (one thread): group_first[g] = first chain element inside group g or
+// 0xffffffff.
+__global__ void k_chain_groups(EncView E, const uint32_t* gexit, uint32_t ngroups, uint32_t* group_first) {
+  if (threadIdx.x || blockIdx.x) return;
+  for (uint32_t g = 0; g < ngroups; g++) group_first[g] = 0xffffffffu;
+  uint64_t s = 0;
+  const uint64_t GS = static_cast<uint64_t>(SEG) * GROUP_SEGS;
+  while (s < E.n) {
+    const uint32_t g = static_cast<uint32_t>(s / GS);
+    if (group_first[g] == 0xffffffffu) group_first[g] = static_cast<uint32_t>(s);
+    const uint64_t q = s - g * GS;
+    if (q < SEG) s = gexit[static_cast<uint64_t>(g) * SEG + q];
+    else s = E.exit1[s];          // a block longer than a segment straddled the group boundary
+  }
+}
+
+// Per group: walk segment exits from the group's first chain element, recording each segment's
+// first chain element.
+__global__ void __launch_bounds__(128) k_group_fill(EncView E, const uint32_t* group_first, uint32_t ngroups, uint32_t* seg_first, uint32_t nsegs) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngroups) return;
+  const uint32_t s0 = static_cast<uint32_t>(g) * GROUP_SEGS, s1 = min(s0 + GROUP_SEGS, nsegs);
+  for (uint32_t q = s0; q < s1; q++) seg_first[q] = 0xffffffffu;
+  uint64_t s = group_first[g];
+  if (s == 0xffffffffu) return;
+  const uint64_t ge = umin64((static_cast<uint64_t>(g) + 1) * SEG * GROUP_SEGS, E.n);
+  while (s < ge) {
+    const uint32_t seg = static_cast<uint32_t>(s / SEG);
+    if (seg_first[seg] == 0xffffffffu) seg_first[seg] = static_cast<uint32_t>(s);
+    s = E.exit1[s];
+  }
+}
+
+// Per segment: follow next[] from the segment's first chain element, marking block starts.
+__global__ void __launch_bounds__(128) k_mark_starts(EncView E, const uint32_t* seg_first, uint32_t nsegs, uint8_t* is_start) {
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= nsegs) return;
+  uint64_t s = seg_first[seg];
+  if (s == 0xffffffffu) return;
+  const uint64_t e = umin64((static_cast<uint64_t>(seg) + 1) * SEG, E.n);
+  while (s < e) { is_start[s] = 1; s = E.next[s]; }
+}
+
+// Block ids: scan of is_start in chunks (reusing the three-phase pattern with u32 partials).
+__global__ void __launch_bounds__(256) k_start_sums(const uint8_t* is_start, uint32_t n, uint32_t* partial) {
+  __shared__ uint32_t sh;
+  if (threadIdx.x == 0) sh = 0;
+  __syncthreads();
+  uint32_t s = 0;
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_CHUNK;
+  for (uint32_t j = threadIdx.x; j < SCAN_CHUNK; j += 256) { uint64_t i = base + j; if (i < n) s += is_start[i]; }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sh, s);
+  __syncthreads();
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh;
+}
+__global__ void __launch_bounds__(256) k_block_first(const uint8_t* is_start, uint32_t n, const uint32_t* partial, uint32_t* block_first) {
+  __shared__ uint32_t warp_sums[32];
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_CHUNK;
+  constexpr int PER = SCAN_CHUNK / 256;
+  uint32_t s = 0;
+  uint8_t f[PER];
+  for (int j = 0; j < PER; j++) { uint64_t i = base + threadIdx.x * PER + j; f[j] = i < n ? is_start[i] : 0; s += f[j]; }
+  uint32_t off = partial[blockIdx.x] + block_exclusive_scan(s, warp_sums, nullptr);
+  for (int j = 0; j < PER; j++) if (f[j]) block_first[off++] = static_cast<uint32_t>(base + threadIdx.x * PER + j);
+}
+
+// Block sizes (contents incl. restart array) -> later scanned into file offsets (+5 per trailer).
+__global__ void __launch_bounds__(256) k_block_sizes(EncView E, const uint32_t* block_first, uint32_t nblocks, unsigned long long* block_off) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nblocks; b += gridDim.x * blockDim.x) {
+    const uint32_t s = block_first[b], e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
+    block_off[b] = blk_cur(E, s, e - 1) + 5;      // contents + trailer
+  }
+}
+
+__device__ __forceinline__ int put_varint(uint8_t* p, uint32_t v) {
+  int n = 0;
+  while (v >= 128) { p[n++] = static_cast<uint8_t>(v | 128); v >>= 7; }
+  p[n++] = static_cast<uint8_t>(v);
+  return n;
+}
+
+// Encode: one CTA per output block, warps take entries round-robin.
+__global__ void __launch_bounds__(128) k_encode_blocks(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
+                                                      const unsigned long long* block_off, uint8_t* out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const uint32_t s = block_first[b], e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
+    uint8_t* blk = out + block_off[b];
+    const unsigned long long Ps = E.P[s];
+    const unsigned long long Qs = E.QQ[s] - E.D[s];
+    for (uint32_t j = s + wid; j < e; j += nw) {
+      const uint32_t t = (j - s) >> E.ri_shift;
+      const bool restart = ((j - s) & (E.ri - 1)) == 0;
+      // offset of entry j = bytes of entries s..j-1
+      unsigned long long off = E.P[j] - Ps;
+      if (j > s) { const uint32_t tp = (j - 1 - s) >> E.ri_shift; off += E.QQ[s + (tp << E.ri_shift)] - Qs; }
+      const Desc d = E.kept[j];
+      const uint8_t* rec = kept_rec(E, d, S);
+      const uint32_t klen = d.klen, ulen = klen - 8u, vlen = d.vlen_out;
+      const uint32_t shared = restart ? 0u : E.shared[j];
+      uint8_t hdr[16];
+      int hl = put_varint(hdr, shared);
+      hl += put_varint(hdr + hl, klen - shared);
+      hl += put_varint(hdr + hl, vlen);
+      uint8_t* p = blk + off;
+      if (lane < hl) p[lane] = hdr[lane];
+      p += hl;
+      // key delta: internal key bytes [shared, klen)
+      const uint64_t suffix = kept_suffix(rec, d, S);
+      for (uint32_t q = shared + lane; q < klen; q += 32)
+        p[q - shared] = q < ulen ? rec[q] : static_cast<uint8_t>(suffix >> (8 * (q - ulen)));
+      p += klen - shared;
+      // value
+      const RunView& run = E.runs[d.run];
+      const uint8_t* vs = run.data + run.val_off[d.gid - run.gid_base];
+      if (d.flags & ENT_VAL_TOMBSTONE) { if (lane == 0) p[0] = 'X'; }
+      else if (d.flags & ENT_VAL_REENCODE) {
+        const ValueRewrite& rw = E.rewrites[d.rewrite_slot];
+        if (lane < rw.prefix_len) p[lane] = rw.prefix[lane];
+        const uint32_t rest = vlen - rw.prefix_len;
+        for (uint32_t q = lane; q < rest; q += 32) p[rw.prefix_len + q] = vs[rw.skip + q];
+      } else warp_copy(p, vs, vlen, lane);
+      if (restart && lane == 0) {
+        // restart array entry t lives after all entries; its position needs the block's entry bytes
+        const uint32_t tl = (e - 1 - s) >> E.ri_shift;
+        const unsigned long long body = (E.P[e] - Ps) + (E.QQ[s + (tl << E.ri_shift)] - Qs);
+        uint8_t* r = blk + body + 4ull * t;
+        const uint32_t o32 = static_cast<uint32_t>(off);
+        r[0] = static_cast<uint8_t>(o32); r[1] = static_cast<uint8_t>(o32 >> 8); r[2] = static_cast<uint8_t>(o32 >> 16); r[3] = static_cast<uint8_t>(o32 >> 24);
+        if (j == s) {
+          const uint32_t nres = tl + 1;
+          uint8_t* q = blk + body + 4ull * nres;
+          q[0] = static_cast<uint8_t>(nres); q[1] = static_cast<uint8_t>(nres >> 8); q[2] = static_cast<uint8_t>(nres >> 16); q[3] = static_cast<uint8_t>(nres >> 24);
+          q[4] = 0;   // trailer type byte: kNoCompression
+        }
+      }
+    }
+  }
+}
+
+// ---- CRC32C -------------------------------------------------------------------------------------
+// Reflected polynomial 0x82F63B78 (rocksdb/util/crc32c.cc). Each lane runs slicing-by-4 over its
+// word range of the block, the 32 partial CRCs are combined with
+//   crc(A || B) = x^(8|B|) * crc(A) + crc(B)   (mod P, reflected; zlib's crc32_combine identity).
+__device__ uint32_t g_crc_tab[4][256];
+__device__ uint32_t g_crc_x2n[32];      // x^(2^k) mod P
+
+__global__ void k_crc_init() {
+  const uint32_t i = threadIdx.x;
+  uint32_t c = i;
+  for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? 0x82F63B78u : 0u);
+  g_crc_tab[0][i] = c;
+  __syncthreads();
+  for (int t = 1; t < 4; t++) {
+    uint32_t prev = g_crc_tab[t - 1][i];
+    g_crc_tab[t][i] = (prev >> 8) ^ g_crc_tab[0][prev & 0xff];
+    __syncthreads();
+  }
+  if (i == 0) {
+    auto mul = [](uint32_t a, uint32_t b) {
+      uint32_t m = 1u << 31, p = 0;
+      for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+        m >>= 1;
+        b = (b & 1) ? (b >> 1) ^ 0x82F63B78u : b >> 1;
+      }
+      return p;
+    };
+    uint32_t p = 1u << 30;                      // x^1
+    g_crc_x2n[0] = p;
+    for (int n = 1; n < 32; n++) { p = mul(p, p); g_crc_x2n[n] = p; }
+  }
+}
+
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {
+  uint32_t m = 1u << 31, p = 0;
+  for (;;) {
+    if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+    m >>= 1;
+    b = (b & 1) ? (b >> 1) ^ 0x82F63B78u : b >> 1;
+  }
+  return p;
+}
+// x^(8 * nbytes) mod P
+__device__ __forceinline__ uint32_t crc_xpow_bytes(uint64_t nbytes, const uint32_t* x2n) {
+  uint32_t p = 1u << 31;                         // x^0
+  uint32_t k = 3;
+  while (nbytes) {
+    if (nbytes & 1) p = crc_mulmod(x2n[k & 31], p);
+    nbytes >>= 1; k++;
+  }
+  return p;
+}
+
+// CRC32C of [p, p+len) computed by one warp. Returns the finalized CRC in every lane.
+__device__ uint32_t warp_crc32c(const uint8_t* p, uint64_t len, int lane, const uint32_t (*tab)[256], const uint32_t* x2n) {
+  // head bytes up to 4-byte alignment, body words split evenly over lanes, tail bytes
+  uint32_t head = static_cast<uint32_t>((4 - (reinterpret_cast<uintptr_t>(p) & 3)) & 3);
+  if (head > len) head = static_cast<uint32_t>(len);
+  const uint64_t nwords = (len - head) >> 2;
+  const uint32_t tail = static_cast<uint32_t>((len - head) & 3);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p + head);
+  const uint64_t per = (nwords + 31) / 32;
+  const uint64_t w0 = umin64(per * lane, nwords), w1 = umin64(w0 + per, nwords);
+  uint32_t acc = 0;
+  if (w1 > w0) {
+    uint32_t c = 0xffffffffu;
+    for (uint64_t i = w0; i < w1; i++) {
+      c ^= __ldg(w + i);
+      c = tab[3][c & 0xff] ^ tab[2][(c >> 8) & 0xff] ^ tab[1][(c >> 16) & 0xff] ^ tab[0][c >> 24];
+    }
+    c = ~c;
+    const uint64_t after = (nwords - w1) * 4 + tail;
+    acc = after ? crc_mulmod(crc_xpow_bytes(after, x2n), c) : c;
+  }
+  if (lane == 0 && head) {
+    uint32_t c = 0xffffffffu;
+    for (uint32_t i = 0; i < head; i++) c = tab[0][(c ^ p[i]) & 0xff] ^ (c >> 8);
+    c = ~c;
+    const uint64_t after = len - head;
+    acc ^= after ? crc_mulmod(crc_xpow_bytes(after, x2n), c) : c;
+  }
+  if (lane == 31 && tail) {
+    uint32_t c = 0xffffffffu;
+    const uint8_t* q = p + len - tail;
+    for (uint32_t i = 0; i < tail; i++) c = tab[0][(c ^ q[i]) & 0xff] ^ (c >> 8);
+    acc ^= ~c;
+  }
+  for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+__device__ __forceinline__ uint32_t crc_mask(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xa282ead8u; }
+
+// mode 0: write trailers of freshly encoded blocks. mode 1: verify stored trailers (inputs).
+__global__ void __launch_bounds__(256) k_crc_blocks(uint8_t* file, const unsigned long long* off, const uint32_t* size32,
+                                                    const unsigned long long* size_from_next, uint32_t nblocks, int mode, JobDev* J) {
+  __shared__ uint32_t tab[4][256];
+  __shared__ uint32_t x2n[32];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+  if (threadIdx.x < 32) x2n[threadIdx.x] = g_crc_x2n[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t b = warp; b < nblocks; b += nwarps) {
+    const unsigned long long o = off[b];
+    // contents length (without the 5-byte trailer)
+    const uint64_t len = size32 ? size32[b] : (size_from_next[b + 1] - o - 5);
+    uint8_t* p = file + o;
+    const uint32_t crc = crc_mask(warp_crc32c(p, len + 1, lane, tab, x2n));   // block + type byte
+    if (mode == 0) {
+      if (lane < 4) p[len + 1 + lane] = static_cast<uint8_t>(crc >> (8 * lane));
+    } else {
+      const uint32_t stored = ldg_u32_unaligned(p + len + 1);
+      if (lane == 0 && stored != crc) dev_fail(J, DEV_ERR_BAD_CRC, b);
+    }
+  }
+}
+
+// Boundary keys for the host-side index: for every block its last internal key and the first key
+// of the next block, fixed stride KB bytes each: [u16 len][bytes].
+__global__ void __launch_bounds__(256) k_boundary_keys(EncView E, int S, const uint32_t* block_first, uint32_t nblocks, uint8_t* out, uint32_t KB) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nblocks * 2; t += gridDim.x * blockDim.x) {
+    const uint32_t b = t >> 1, which = t & 1;
+    const uint32_t e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
+    uint8_t* o = out + static_cast<size_t>(t) * KB;
+    const uint32_t j = which ? e : e - 1;
+    if (j >= E.n) { o[0] = 0; o[1] = 0; continue; }
+    const Desc d = E.kept[j];
+    const uint8_t* rec = kept_rec(E, d, S);
+    const uint32_t ulen = d.klen - 8u;
+    o[0] = static_cast<uint8_t>(d.klen); o[1] = static_cast<uint8_t>(d.klen >> 8);
+    for (uint32_t q = 0; q < ulen; q++) o[2 + q] = rec[q];
+    const uint64_t suffix = kept_suffix(rec, d, S);
+    for (int q = 0; q < 8; q++) o[2 + ulen + q] = static_cast<uint8_t>(suffix >> (8 * q));
+  }
+}
+
+}  // namespace ybgpu

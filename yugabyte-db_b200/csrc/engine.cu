@@ -54,7 +54,7 @@ struct JobDev {                 // device-global job state
   uint32_t restart_interval[MAX_RUNS];
   unsigned long long in_key_bytes, in_val_bytes;
   unsigned long long n_counted, n_hidden, n_obsolete, n_feed_dropped, n_kept, out_key_bytes, out_val_bytes;
-  unsigned long long min_seq, max_seq;
+  unsigned long long min_seq, max_seq, n_kept_deletions;
   uint32_t n_rewrites;
   uint32_t n_tiles;
   unsigned long long digest;
@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
     V.desc[rank0 + i] = d;
     if (f & ENT_KEEP) {
       st_kept++; st_kbytes += d.klen; st_vbytes += vout;
+      if ((rec_suffix(e, S) & 0xff) != 1) atomicAdd(&J->n_kept_deletions, 1ull);
       const unsigned long long seq = (f & ENT_ZERO_SEQ) ? 0ull : (rec_suffix(e, S) >> 8);
       mn = min(mn, seq); mx = max(mx, seq);
     }
@@ -776,6 +777,10 @@ __global__ void __launch_bounds__(256) k_digest(const uint8_t* keys, const uint6
   if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&J->digest, acc);
 }
 
+}  // namespace ybgpu
+#include "encode_kernels.cuh"
+namespace ybgpu {
+
 // =============================================================================================
 // Host orchestration
 // =============================================================================================
@@ -826,6 +831,15 @@ struct Engine::Impl {
   uint8_t* out_vals = nullptr; uint64_t* out_voff = nullptr;
   uint64_t n_out = 0, out_key_bytes = 0, out_val_bytes = 0;
   JobDev hJ{};
+  // K4/K5 state kept for lazy result fetches
+  Desc* d_desc = nullptr; Sums3* d_partial = nullptr; ValueRewrite* d_rw = nullptr;
+  uint64_t N = 0; int S = 0; uint32_t n_chunks = 0;
+  bool kv_emitted = false;
+  Desc* d_kept = nullptr;
+  uint8_t* out_file = nullptr; uint64_t out_file_len = 0;
+  uint32_t n_blocks = 0; unsigned long long* d_block_off = nullptr; uint32_t* d_block_first = nullptr;
+  uint8_t* d_boundary = nullptr; uint32_t boundary_stride = 0;
+  EncView enc{};
 };
 
 Engine::Engine(const ybgpu_job_options& o) : opt_(o), impl_(new Impl) {
@@ -960,6 +974,10 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     JobDev init{}; init.min_seq = ~0ull;
     CUDA_TRY(cudaMemcpyAsync(I.dJ, &init, sizeof(init), cudaMemcpyHostToDevice, I.stream));
   }
+  {
+    static bool crc_ready[64] = {};
+    if (!crc_ready[opt_.device & 63]) { k_crc_init<<<1, 256, 0, I.stream>>>(); crc_ready[opt_.device & 63] = true; }
+  }
   CUDA_TRY(cudaEventRecord(I.ev0, I.stream));
   uint32_t phase_launch_mark[8] = {};
   int phase = 0;
@@ -974,6 +992,12 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     RunView& rv = I.runs[r];
     CUDA_TRY(DevAlloc(&I.allocs, &dtotals[r], 1));
     if (rv.nb) {
+      if (opt_.verify_checksums) {
+        // ReadBlock's checksum verification (table/format.cc:352-395) for every input block
+        k_crc_blocks<<<GridFor(static_cast<uint64_t>(rv.nb) * 32, 256, sms), 256, 0, I.stream>>>(
+            const_cast<uint8_t*>(rv.data), reinterpret_cast<const unsigned long long*>(rv.blk_off), rv.blk_size, nullptr, rv.nb, 1, I.dJ);
+        launches++;
+      }
       k_prepass<<<GridFor(static_cast<uint64_t>(rv.nb) * 32, 256, sms), 256, 0, I.stream>>>(rv, r, I.dJ);
       k_scan_u32_single<<<1, 1024, 0, I.stream>>>(rv.blk_count, rv.nb, dtotals[r]);
       launches += 2;
@@ -1064,9 +1088,6 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
 
   if (N == 0) {
     ran_ = true;
-    CUDA_TRY(DevAlloc(&I.allocs, &I.out_koff, 1)); CUDA_TRY(DevAlloc(&I.allocs, &I.out_voff, 1));
-    CUDA_TRY(cudaMemsetAsync(I.out_koff, 0, 8, I.stream)); CUDA_TRY(cudaMemsetAsync(I.out_voff, 0, 8, I.stream));
-    CUDA_TRY(DevAlloc(&I.allocs, &I.out_keys, 1)); CUDA_TRY(DevAlloc(&I.allocs, &I.out_vals, 1));
     stats_.gpu_kernel_launches = launches;
     return YBGPU_OK;
   }
@@ -1114,28 +1135,96 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   if (ybgpu_status s = CheckDeviceError("merge")) return s;
   if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
 
-  // ---- K4: emit
+  // ---- K4: survivor scan + dense list; K5: block encode
   I.n_out = I.hJ.n_kept; I.out_key_bytes = I.hJ.out_key_bytes; I.out_val_bytes = I.hJ.out_val_bytes;
   const uint32_t n_chunks = static_cast<uint32_t>((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
   Sums3* d_partial = nullptr;
   CUDA_TRY(DevAlloc(&I.allocs, &d_partial, n_chunks + 1));
-  CUDA_TRY(DevAlloc(&I.allocs, &I.out_keys, I.out_key_bytes + 16));
-  CUDA_TRY(DevAlloc(&I.allocs, &I.out_vals, I.out_val_bytes + 16));
-  CUDA_TRY(DevAlloc(&I.allocs, &I.out_koff, I.n_out + 1));
-  CUDA_TRY(DevAlloc(&I.allocs, &I.out_voff, I.n_out + 1));
   k_emit_sums<<<n_chunks, EMIT_THREADS, 0, I.stream>>>(d_desc, N, d_partial);
   k_scan_sums<<<1, 1024, 0, I.stream>>>(d_partial, n_chunks);
-  EmitView ev{};
-  ev.runs = I.dRuns; ev.desc = d_desc; ev.partial = d_partial; ev.rewrites = d_rw;
-  ev.out_keys = I.out_keys; ev.out_koff = I.out_koff; ev.out_vals = I.out_vals; ev.out_voff = I.out_voff; ev.N = N;
-  k_emit<<<n_chunks, EMIT_THREADS, 0, I.stream>>>(ev, Sfinal, I.dJ);
-  launches += 3;
-  CUDA_TRY(cudaMemcpyAsync(I.out_koff + I.n_out, &I.out_key_bytes, 8, cudaMemcpyHostToDevice, I.stream));
-  CUDA_TRY(cudaMemcpyAsync(I.out_voff + I.n_out, &I.out_val_bytes, 8, cudaMemcpyHostToDevice, I.stream));
+  launches += 2;
+  I.d_desc = d_desc; I.d_partial = d_partial; I.d_rw = d_rw; I.N = N; I.S = Sfinal; I.n_chunks = n_chunks;
+  if (I.n_out >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "too many output entries");
+  const uint32_t n = static_cast<uint32_t>(I.n_out);
+  if (n) {
+    const uint32_t ri = static_cast<uint32_t>(opt_.block_restart_interval);
+    if (ri == 0 || (ri & (ri - 1)) || ri > 64)
+      return Fail(YBGPU_NOT_SUPPORTED, "block_restart_interval must be a power of two <= 64 for the GPU block encoder");
+    if (opt_.output_key_encoding != YBGPU_KEY_ENCODING_SHARED_PREFIX)
+      return Fail(YBGPU_NOT_SUPPORTED, "only kKeyDeltaEncodingSharedPrefix output is encoded on the GPU so far");
+    CUDA_TRY(DevAlloc(&I.allocs, &I.d_kept, n));
+    k_compact_desc<<<n_chunks, EMIT_THREADS, 0, I.stream>>>(d_desc, N, d_partial, I.d_kept);
+    EncView& E = I.enc;
+    E.runs = I.dRuns; E.kept = I.d_kept; E.rewrites = d_rw; E.n = n; E.ri = ri;
+    E.ri_shift = 0; while ((1u << E.ri_shift) < ri) E.ri_shift++;
+    E.block_size = opt_.block_size; E.deviation = static_cast<uint32_t>(std::max(0, opt_.block_size_deviation));
+    CUDA_TRY(DevAlloc(&I.allocs, &E.nr, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.shared, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.D, n));
+    CUDA_TRY(DevAlloc(&I.allocs, &E.P, static_cast<size_t>(n) + 1)); CUDA_TRY(DevAlloc(&I.allocs, &E.QQ, n));
+    CUDA_TRY(DevAlloc(&I.allocs, &E.next, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.exit1, n));
+    k_entry_sizes<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E, Sfinal);
+    // P
+    const uint32_t pc = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    unsigned long long* d_pp = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_pp, pc + 1));
+    k_p_sums<<<pc, 256, 0, I.stream>>>(E.nr, n, d_pp);
+    k_scan_u64_single<<<1, 1024, 0, I.stream>>>(d_pp, pc, nullptr);
+    k_p_final<<<pc, 256, 0, I.stream>>>(E.nr, n, d_pp, E.P);
+    // QQ
+    const uint32_t rows = (n + ri - 1) / ri;
+    const uint32_t qchunks = (rows + QROWS - 1) / QROWS;
+    unsigned long long* d_qp = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_qp, static_cast<size_t>(qchunks) * ri + 1));
+    const uint32_t qthreads = qchunks * ri;
+    k_qq_sums<<<(qthreads + 255) / 256, 256, 0, I.stream>>>(E.D, n, ri, d_qp, qchunks);
+    for (uint32_t c = 0; c < ri; c++) k_scan_u64_single<<<1, 1024, 0, I.stream>>>(d_qp + static_cast<size_t>(c) * qchunks, qchunks, nullptr);
+    k_qq_final<<<(qthreads + 255) / 256, 256, 0, I.stream>>>(E.D, n, ri, d_qp, qchunks, E.QQ);
+    launches += 7 + ri;
+    // block cuts
+    k_next<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E);
+    const uint32_t nsegs = (n + SEG - 1) / SEG;
+    const uint32_t ngroups = (nsegs + GROUP_SEGS - 1) / GROUP_SEGS;
+    uint32_t *d_gexit = nullptr, *d_group_first = nullptr, *d_seg_first = nullptr, *d_spart = nullptr, *d_nblocks = nullptr;
+    uint8_t* d_is_start = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_gexit, static_cast<size_t>(ngroups) * SEG));
+    CUDA_TRY(DevAlloc(&I.allocs, &d_group_first, ngroups)); CUDA_TRY(DevAlloc(&I.allocs, &d_seg_first, nsegs));
+    CUDA_TRY(DevAlloc(&I.allocs, &d_is_start, n)); CUDA_TRY(DevAlloc(&I.allocs, &d_spart, pc + 1)); CUDA_TRY(DevAlloc(&I.allocs, &d_nblocks, 1));
+    CUDA_TRY(cudaMemsetAsync(d_is_start, 0, n, I.stream));
+    k_seg_exit<<<(nsegs + 127) / 128, 128, 0, I.stream>>>(E);
+    k_group_exit<<<static_cast<uint32_t>((static_cast<uint64_t>(ngroups) * SEG + 255) / 256), 256, 0, I.stream>>>(E, d_gexit, ngroups);
+    k_chain_groups<<<1, 32, 0, I.stream>>>(E, d_gexit, ngroups, d_group_first);
+    k_group_fill<<<(ngroups + 127) / 128, 128, 0, I.stream>>>(E, d_group_first, ngroups, d_seg_first, nsegs);
+    k_mark_starts<<<(nsegs + 127) / 128, 128, 0, I.stream>>>(E, d_seg_first, nsegs, d_is_start);
+    k_start_sums<<<pc, 256, 0, I.stream>>>(d_is_start, n, d_spart);
+    k_scan_u32_single<<<1, 1024, 0, I.stream>>>(d_spart, pc, d_nblocks);
+    launches += 8;
+    uint32_t nblocks = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nblocks, d_nblocks, 4, cudaMemcpyDeviceToHost, I.stream));
+    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    I.n_blocks = nblocks;
+    CUDA_TRY(DevAlloc(&I.allocs, &I.d_block_first, static_cast<size_t>(nblocks) + 1));
+    CUDA_TRY(DevAlloc(&I.allocs, &I.d_block_off, static_cast<size_t>(nblocks) + 1));
+    unsigned long long* d_total = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_total, 1));
+    k_block_first<<<pc, 256, 0, I.stream>>>(d_is_start, n, d_spart, I.d_block_first);
+    k_block_sizes<<<GridFor(nblocks, 256, sms), 256, 0, I.stream>>>(E, I.d_block_first, nblocks, I.d_block_off);
+    k_scan_u64_single<<<1, 1024, 0, I.stream>>>(I.d_block_off, nblocks, d_total);
+    unsigned long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, I.stream));
+    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    CUDA_TRY(cudaMemcpyAsync(I.d_block_off + nblocks, &total, 8, cudaMemcpyHostToDevice, I.stream));
+    I.out_file_len = total;
+    CUDA_TRY(DevAlloc(&I.allocs, &I.out_file, total + 64));
+    k_encode_blocks<<<std::min<uint32_t>(nblocks, sms * 8), 128, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
+    k_crc_blocks<<<GridFor(static_cast<uint64_t>(nblocks) * 32, 256, sms), 256, 0, I.stream>>>(I.out_file, I.d_block_off, nullptr, I.d_block_off, nblocks, 0, I.dJ);
+    I.boundary_stride = static_cast<uint32_t>((max_ikey + 2 + 7) & ~7u);
+    CUDA_TRY(DevAlloc(&I.allocs, &I.d_boundary, static_cast<size_t>(nblocks) * 2 * I.boundary_stride));
+    k_boundary_keys<<<GridFor(static_cast<uint64_t>(nblocks) * 2, 256, sms), 256, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_boundary, I.boundary_stride);
+    launches += 6;
+  }
   CUDA_TRY(end_phase());
   CUDA_TRY(cudaEventRecord(I.ev1, I.stream));
   CUDA_TRY(cudaGetLastError());
-  if (ybgpu_status s = CheckDeviceError("emit")) return s;
+  if (ybgpu_status s = CheckDeviceError("encode")) return s;
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, I.ev0, I.ev1));
   for (int ph = 0; ph < phase; ph++) {
@@ -1156,6 +1245,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   stats_.total_output_raw_value_bytes = I.hJ.out_val_bytes;
   stats_.smallest_seqno = I.hJ.n_kept ? I.hJ.min_seq : 0;
   stats_.largest_seqno = I.hJ.max_seq;
+  stats_.num_output_data_blocks = I.n_blocks;
+  stats_.output_data_file_size = I.out_file_len;
   stats_.gpu_seconds = ms / 1e3;
   stats_.gpu_kernel_launches = launches;
   record_stride_ = Sfinal; num_tiles_ = n_tiles;
@@ -1169,10 +1260,35 @@ ybgpu_status Engine::KvStreamSizes(uint64_t* n, uint64_t* kb, uint64_t* vb) cons
   return YBGPU_OK;
 }
 
+// The flat KV stream (what CompactionFeed::Feed consumers want) is materialised on demand.
+ybgpu_status Engine::EnsureKvStream() {
+  Impl& I = *impl_;
+  if (I.kv_emitted) return YBGPU_OK;
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  g_alloc_stream = I.stream;
+  CUDA_TRY(DevAlloc(&I.allocs, &I.out_keys, I.out_key_bytes + 16));
+  CUDA_TRY(DevAlloc(&I.allocs, &I.out_vals, I.out_val_bytes + 16));
+  CUDA_TRY(DevAlloc(&I.allocs, &I.out_koff, I.n_out + 1));
+  CUDA_TRY(DevAlloc(&I.allocs, &I.out_voff, I.n_out + 1));
+  if (I.N) {
+    EmitView ev{};
+    ev.runs = I.dRuns; ev.desc = I.d_desc; ev.partial = I.d_partial; ev.rewrites = I.d_rw;
+    ev.out_keys = I.out_keys; ev.out_koff = I.out_koff; ev.out_vals = I.out_vals; ev.out_voff = I.out_voff; ev.N = I.N;
+    k_emit<<<I.n_chunks, EMIT_THREADS, 0, I.stream>>>(ev, I.S, I.dJ);
+    stats_.gpu_kernel_launches++;
+  }
+  CUDA_TRY(cudaMemcpyAsync(I.out_koff + I.n_out, &I.out_key_bytes, 8, cudaMemcpyHostToDevice, I.stream));
+  CUDA_TRY(cudaMemcpyAsync(I.out_voff + I.n_out, &I.out_val_bytes, 8, cudaMemcpyHostToDevice, I.stream));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  I.kv_emitted = true;
+  return YBGPU_OK;
+}
+
 ybgpu_status Engine::FetchKvStream(uint8_t* keys, uint64_t* koff, uint8_t* vals, uint64_t* voff) {
   if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  if (ybgpu_status s = EnsureKvStream()) return s;
   Impl& I = *impl_;
-  CUDA_TRY(cudaSetDevice(opt_.device));
   if (I.out_key_bytes) CUDA_TRY(cudaMemcpyAsync(keys, I.out_keys, I.out_key_bytes, cudaMemcpyDeviceToHost, I.stream));
   if (I.out_val_bytes) CUDA_TRY(cudaMemcpyAsync(vals, I.out_vals, I.out_val_bytes, cudaMemcpyDeviceToHost, I.stream));
   CUDA_TRY(cudaMemcpyAsync(koff, I.out_koff, (I.n_out + 1) * 8, cudaMemcpyDeviceToHost, I.stream));
@@ -1182,8 +1298,33 @@ ybgpu_status Engine::FetchKvStream(uint8_t* keys, uint64_t* koff, uint8_t* vals,
   return YBGPU_OK;
 }
 
+// Finished data file (<n>.sst.sblock.0) + what the host needs to write <n>.sst.
+ybgpu_status Engine::OutputInfo(uint64_t* data_len, uint32_t* n_blocks, uint32_t* boundary_stride) const {
+  if (!ran_) return const_cast<Engine*>(this)->Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  *data_len = impl_->out_file_len; *n_blocks = impl_->n_blocks; *boundary_stride = impl_->boundary_stride;
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::FetchOutput(uint8_t* data_file, uint64_t* block_off /*n_blocks+1*/, uint8_t* boundary /*2*n_blocks*stride*/) {
+  if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  Impl& I = *impl_;
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  if (I.out_file_len && data_file) CUDA_TRY(cudaMemcpyAsync(data_file, I.out_file, I.out_file_len, cudaMemcpyDeviceToHost, I.stream));
+  if (I.n_blocks) {
+    if (block_off) CUDA_TRY(cudaMemcpyAsync(block_off, I.d_block_off, (static_cast<size_t>(I.n_blocks) + 1) * 8, cudaMemcpyDeviceToHost, I.stream));
+    if (boundary) CUDA_TRY(cudaMemcpyAsync(boundary, I.d_boundary, static_cast<size_t>(I.n_blocks) * 2 * I.boundary_stride, cudaMemcpyDeviceToHost, I.stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  stats_.d2h_bytes += (data_file ? I.out_file_len : 0) + (block_off ? (static_cast<size_t>(I.n_blocks) + 1) * 8 : 0) +
+                      (boundary ? static_cast<size_t>(I.n_blocks) * 2 * I.boundary_stride : 0);
+  return YBGPU_OK;
+}
+
+uint64_t Engine::kept_deletions() const { return impl_->hJ.n_kept_deletions; }
+
 ybgpu_status Engine::Digest(uint64_t* digest) {
   if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  if (ybgpu_status s = EnsureKvStream()) return s;
   Impl& I = *impl_;
   CUDA_TRY(cudaSetDevice(opt_.device));
   CUDA_TRY(cudaMemsetAsync(&I.dJ->digest, 0, 8, I.stream));

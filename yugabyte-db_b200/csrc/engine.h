@@ -21,6 +21,9 @@ class Engine {
   ybgpu_status KvStreamSizes(uint64_t* n, uint64_t* kb, uint64_t* vb) const;
   ybgpu_status FetchKvStream(uint8_t* keys, uint64_t* koff, uint8_t* vals, uint64_t* voff);
   ybgpu_status Digest(uint64_t* digest);
+  ybgpu_status OutputInfo(uint64_t* data_len, uint32_t* n_blocks, uint32_t* boundary_stride) const;
+  ybgpu_status FetchOutput(uint8_t* data_file, uint64_t* block_off, uint8_t* boundary);
+  uint64_t kept_deletions() const;
   const ybgpu_job_options& options() const { return opt_; }
   ybgpu_job_stats& stats() { return stats_; }
   const std::string& error() const { return error_; }
@@ -31,6 +34,7 @@ class Engine {
 
  private:
   ybgpu_status CheckDeviceError(const char* phase);
+  ybgpu_status EnsureKvStream();
   struct Impl;
   ybgpu_job_options opt_;
   Impl* impl_;

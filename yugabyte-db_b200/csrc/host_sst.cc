@@ -300,13 +300,7 @@ class IndexWriter {
 };
 
 // ---------------------------------------------------------------------------------------------
-SplitSstWriter::SplitSstWriter(const TableOptions& o)
-    : o_(o), block_(o.block_restart_interval, o.key_encoding), index_(new IndexWriter(o)) {
-  if (o.key_encoding != 1) throw std::runtime_error("host writer: only kKeyDeltaEncodingSharedPrefix output");
-}
-SplitSstWriter::~SplitSstWriter() {}
-
-void SplitSstWriter::AppendBlock(const std::string& c, std::string* file, Handle* h) {
+static void AppendBlockTo(const std::string& c, std::string* file, Handle* h) {
   h->offset = file->size(); h->size = c.size();
   file->append(c);
   const uint8_t type = 0;
@@ -314,6 +308,74 @@ void SplitSstWriter::AppendBlock(const std::string& c, std::string* file, Handle
   file->push_back(static_cast<char>(type));
   AppendU32(file, Crc32cMask(crc));
 }
+
+MetaFileWriter::MetaFileWriter(const TableOptions& o) : o_(o), index_(new IndexWriter(o)) {}
+MetaFileWriter::~MetaFileWriter() {}
+void MetaFileWriter::AppendBlock(const std::string& c, Handle* h) { AppendBlockTo(c, &meta_, h); }
+
+void MetaFileWriter::AddDataBlock(std::string* last_key, const uint8_t* next_key, size_t next_len, bool has_next, const Handle& h) {
+  index_->AddDataBlock(last_key, next_key, next_len, has_next, h);
+  while (index_->ShouldFlush()) {
+    std::string contents;
+    if (!index_->FlushNext(&contents, last_index_, last_index_set_)) throw std::runtime_error("index flush failed");
+    AppendBlock(contents, &last_index_);
+    last_index_set_ = true;
+    num_index_blocks_++;
+  }
+}
+
+void MetaFileWriter::Finish(const MetaProps& mp) {
+  std::string top;
+  const bool have_top = index_->FlushNext(&top, last_index_, last_index_set_);
+  if (have_top) num_index_blocks_++;
+  std::map<std::string, std::string> props;
+  auto num = [&](const char* name, uint64_t v) { std::string s; AppendVarint(&s, v); props[name] = s; };
+  num("rocksdb.raw.key.size", mp.raw_key_size);
+  num("rocksdb.raw.value.size", mp.raw_value_size);
+  num("rocksdb.data.size", mp.data_size);
+  num("rocksdb.data.index.size", index_->EstimatedSize() + kTrailer);
+  num("rocksdb.filter.index.size", 0);
+  num("rocksdb.num.entries", mp.num_entries);
+  num("rocksdb.num.data.blocks", mp.num_data_blocks);
+  num("rocksdb.num.filter.blocks", 0);
+  num("rocksdb.num.data.index.blocks", num_index_blocks_);
+  num("rocksdb.filter.size", 0);
+  num("rocksdb.format.version", 0);
+  num("rocksdb.fixed.key.length", 0);
+  num("rocksdb.deleted.keys", mp.deleted_keys);
+  { std::string v; AppendU32(&v, 2); props["rocksdb.block.based.table.index.type"] = v; }   // kMultiLevelBinarySearch
+  props["rocksdb.block.based.table.whole.key.filtering"] = "1";
+  props["rocksdb.block.based.table.prefix.filtering"] = "0";
+  { std::string v; AppendU32(&v, static_cast<uint32_t>(index_->NumLevels())); props["rocksdb.block.based.table.index.num.levels"] = v; }
+  props["rocksdb.block.based.table.data.block.key.value.encoding.format"] = std::string(1, static_cast<char>(o_.key_encoding));
+  BlockEncoder pb(1, 1);
+  for (auto& kv : props)
+    pb.Add(reinterpret_cast<const uint8_t*>(kv.first.data()), kv.first.size(), reinterpret_cast<const uint8_t*>(kv.second.data()), kv.second.size());
+  Handle ph;
+  AppendBlock(pb.Finish(), &ph);
+  BlockEncoder mb(1, 1);
+  { std::string k = "rocksdb.properties", v; AppendVarint(&v, ph.offset); AppendVarint(&v, ph.size);
+    mb.Add(reinterpret_cast<const uint8_t*>(k.data()), k.size(), reinterpret_cast<const uint8_t*>(v.data()), v.size()); }
+  Handle mh;
+  AppendBlock(mb.Finish(), &mh);
+  if (have_top) { AppendBlock(top, &last_index_); last_index_set_ = true; }
+  std::string f;
+  f.push_back(1);   // kCRC32c
+  AppendVarint(&f, mh.offset); AppendVarint(&f, mh.size);
+  AppendVarint(&f, last_index_.offset); AppendVarint(&f, last_index_.size);
+  f.resize(kFooterLen - 12);
+  AppendU32(&f, 2);
+  AppendU32(&f, static_cast<uint32_t>(kMagic & 0xffffffffu));
+  AppendU32(&f, static_cast<uint32_t>(kMagic >> 32));
+  meta_.append(f);
+}
+
+// ---------------------------------------------------------------------------------------------
+SplitSstWriter::SplitSstWriter(const TableOptions& o)
+    : o_(o), block_(o.block_restart_interval, o.key_encoding), metaw_(o) {
+  if (o.key_encoding != 1) throw std::runtime_error("host writer: only kKeyDeltaEncodingSharedPrefix output");
+}
+SplitSstWriter::~SplitSstWriter() {}
 
 void SplitSstWriter::Add(const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen) {
   // FlushBlockBySizePolicy::Update (flush_block_policy.cc:45-76), min_keys_per_block = 1
@@ -332,66 +394,20 @@ void SplitSstWriter::Add(const uint8_t* key, size_t klen, const uint8_t* val, si
 
 void SplitSstWriter::CutDataBlock(const uint8_t* next_key, size_t next_len, bool has_next) {
   if (!block_.empty()) {
-    AppendBlock(block_.Finish(), &data_, &pending_);
+    AppendBlockTo(block_.Finish(), &data_, &pending_);
     block_.Reset();
     data_size_ += pending_.size + kTrailer;
   }
   num_data_blocks_++;
-  index_->AddDataBlock(&last_key_, next_key, next_len, has_next, pending_);
-  while (index_->ShouldFlush()) {
-    std::string contents;
-    if (!index_->FlushNext(&contents, last_index_, last_index_set_)) throw std::runtime_error("index flush failed");
-    AppendBlock(contents, &meta_, &last_index_);
-    last_index_set_ = true;
-    num_index_blocks_++;
-  }
+  metaw_.AddDataBlock(&last_key_, next_key, next_len, has_next, pending_);
 }
 
 void SplitSstWriter::Finish() {
   if (!block_.empty()) CutDataBlock(nullptr, 0, false);
-  std::string top;
-  const bool have_top = index_->FlushNext(&top, last_index_, last_index_set_);
-  if (have_top) num_index_blocks_++;
-  std::map<std::string, std::string> props;
-  auto num = [&](const char* name, uint64_t v) { std::string s; AppendVarint(&s, v); props[name] = s; };
-  num("rocksdb.raw.key.size", raw_key_);
-  num("rocksdb.raw.value.size", raw_val_);
-  num("rocksdb.data.size", data_size_);
-  num("rocksdb.data.index.size", index_->EstimatedSize() + kTrailer);
-  num("rocksdb.filter.index.size", 0);
-  num("rocksdb.num.entries", num_entries_);
-  num("rocksdb.num.data.blocks", num_data_blocks_);
-  num("rocksdb.num.filter.blocks", 0);
-  num("rocksdb.num.data.index.blocks", num_index_blocks_);
-  num("rocksdb.filter.size", 0);
-  num("rocksdb.format.version", 0);
-  num("rocksdb.fixed.key.length", 0);
-  num("rocksdb.deleted.keys", deleted_keys_);
-  { std::string v; AppendU32(&v, 2); props["rocksdb.block.based.table.index.type"] = v; }   // kMultiLevelBinarySearch
-  props["rocksdb.block.based.table.whole.key.filtering"] = "1";
-  props["rocksdb.block.based.table.prefix.filtering"] = "0";
-  { std::string v; AppendU32(&v, static_cast<uint32_t>(index_->NumLevels())); props["rocksdb.block.based.table.index.num.levels"] = v; }
-  props["rocksdb.block.based.table.data.block.key.value.encoding.format"] = std::string(1, static_cast<char>(o_.key_encoding));
-  BlockEncoder pb(1, 1);
-  for (auto& kv : props)
-    pb.Add(reinterpret_cast<const uint8_t*>(kv.first.data()), kv.first.size(), reinterpret_cast<const uint8_t*>(kv.second.data()), kv.second.size());
-  Handle ph;
-  AppendBlock(pb.Finish(), &meta_, &ph);
-  BlockEncoder mb(1, 1);
-  { std::string k = "rocksdb.properties", v; AppendVarint(&v, ph.offset); AppendVarint(&v, ph.size);
-    mb.Add(reinterpret_cast<const uint8_t*>(k.data()), k.size(), reinterpret_cast<const uint8_t*>(v.data()), v.size()); }
-  Handle mh;
-  AppendBlock(mb.Finish(), &meta_, &mh);
-  if (have_top) { AppendBlock(top, &meta_, &last_index_); last_index_set_ = true; }
-  std::string f;
-  f.push_back(1);   // kCRC32c
-  AppendVarint(&f, mh.offset); AppendVarint(&f, mh.size);
-  AppendVarint(&f, last_index_.offset); AppendVarint(&f, last_index_.size);
-  f.resize(kFooterLen - 12);
-  AppendU32(&f, 2);
-  AppendU32(&f, static_cast<uint32_t>(kMagic & 0xffffffffu));
-  AppendU32(&f, static_cast<uint32_t>(kMagic >> 32));
-  meta_.append(f);
+  MetaProps mp;
+  mp.raw_key_size = raw_key_; mp.raw_value_size = raw_val_; mp.data_size = data_size_; mp.num_entries = num_entries_;
+  mp.num_data_blocks = num_data_blocks_; mp.deleted_keys = deleted_keys_;
+  metaw_.Finish(mp);
 }
 
 }  // namespace host

@@ -63,6 +63,31 @@ class BlockEncoder {
 
 class IndexWriter;   // multi-level index (table/index_builder.cc:143-289)
 
+// Writer of the metadata file (<n>.sst) alone: index blocks as data blocks are reported, then
+// properties, metaindex and footer (block_based_table_builder.cc:543-592,762-903). Used directly
+// when the data file was encoded on the GPU.
+struct MetaProps {
+  uint64_t raw_key_size = 0, raw_value_size = 0, data_size = 0, num_entries = 0, num_data_blocks = 0, deleted_keys = 0;
+};
+class MetaFileWriter {
+ public:
+  explicit MetaFileWriter(const TableOptions& o);
+  ~MetaFileWriter();
+  // `last_key` = last internal key of the block (modified in place into the separator),
+  // `next_key` = first key of the next block (has_next = false for the last block).
+  void AddDataBlock(std::string* last_key, const uint8_t* next_key, size_t next_len, bool has_next, const Handle& h);
+  void Finish(const MetaProps& p);
+  const std::string& meta_file() const { return meta_; }
+ private:
+  void AppendBlock(const std::string& contents, Handle* h);
+  TableOptions o_;
+  std::unique_ptr<IndexWriter> index_;
+  std::string meta_;
+  Handle last_index_;
+  bool last_index_set_ = false;
+  uint64_t num_index_blocks_ = 0;
+};
+
 // rocksdb::TableBuilder shape: Add / Finish / NumEntries / TotalFileSize / status.
 class SplitSstWriter {
  public:
@@ -71,21 +96,18 @@ class SplitSstWriter {
   void Add(const uint8_t* ikey, size_t klen, const uint8_t* val, size_t vlen);
   void Finish();
   uint64_t NumEntries() const { return num_entries_; }
-  uint64_t TotalFileSize() const { return data_.size() + meta_.size(); }
+  uint64_t TotalFileSize() const { return data_.size() + metaw_.meta_file().size(); }
   uint64_t NumDataBlocks() const { return num_data_blocks_; }
   const std::string& data_file() const { return data_; }
-  const std::string& meta_file() const { return meta_; }
+  const std::string& meta_file() const { return metaw_.meta_file(); }
  private:
   void CutDataBlock(const uint8_t* next_key, size_t next_len, bool has_next);
-  void AppendBlock(const std::string& contents, std::string* file, Handle* h);
   TableOptions o_;
   BlockEncoder block_;
-  std::unique_ptr<IndexWriter> index_;
-  std::string data_, meta_, last_key_;
-  Handle pending_, last_index_;
-  bool last_index_set_ = false;
-  uint64_t num_entries_ = 0, raw_key_ = 0, raw_val_ = 0, data_size_ = 0, num_data_blocks_ = 0,
-           num_index_blocks_ = 0, deleted_keys_ = 0;
+  MetaFileWriter metaw_;
+  std::string data_, last_key_;
+  Handle pending_;
+  uint64_t num_entries_ = 0, raw_key_ = 0, raw_val_ = 0, data_size_ = 0, num_data_blocks_ = 0, deleted_keys_ = 0;
 };
 
 }  // namespace host
