@@ -174,7 +174,7 @@ def test_errors_are_loud(pkg):
     # corrupted block checksum
     s2 = runs_to_ssts([[(o.ikey(b"Sabc\x00\x00!#" + o.encode_doc_ht(o.YB_EPOCH_US), 5), b"Sv")]])[0]
     data = s2.data_view().copy()
-    data[3] ^= 0xff
+    data[-1] ^= 0xff                    # damage the stored CRC, contents stay decodable
     job = pkg.GpuCompactionJob()
     job.add_input_sst(s2.meta_view(), data)
     with pytest.raises(pkg.YbGpuError) as e:
