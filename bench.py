@@ -252,12 +252,16 @@ def main():
             rc = cudart.cudaHostRegister(v.ctypes.data, v.size, 0)
             pinned.append((v, int(rc) == 0))
 
+        # pinned host buffers for the output files, reused by every step
+        out_data = torch.empty(file_bytes + (64 << 20), dtype=torch.uint8, pin_memory=True).numpy()
+        out_meta = torch.empty(max(64 << 20, file_bytes // 100), dtype=torch.uint8, pin_memory=True).numpy()
+
         def step_e2e():
             job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=bool(args.verify), cuda_stream=stream_ptr)
             for s, (off, sz) in zip(ssts, handles):
                 job.add_input(s.data_view(), off, sz)
             job.run()
-            data, meta = job.fetch_output()
+            data, meta = job.fetch_output(out_data, out_meta)
             st = job.stats().as_dict()
             job.close()
             return st, data.size + meta.size

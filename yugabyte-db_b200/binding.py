@@ -230,13 +230,19 @@ class GpuCompactionJob:
         kb, vb = keys.tobytes(), vals.tobytes()
         return [(kb[int(koff[i]):int(koff[i + 1])], vb[int(voff[i]):int(voff[i + 1])]) for i in range(len(koff) - 1)]
 
-    def fetch_output(self):
+    def output_sizes(self):
         dl, ml = C.c_uint64(), C.c_uint64()
         self._check(lib().ybgpu_job_output_sizes(self.h, C.byref(dl), C.byref(ml)))
-        data = np.zeros(dl.value + 1, np.uint8)
-        meta = np.zeros(ml.value + 1, np.uint8)
-        self._check(lib().ybgpu_job_fetch_output(self.h, data.ctypes.data, dl.value, meta.ctypes.data, ml.value))
-        return data[:dl.value], meta[:ml.value]
+        return dl.value, ml.value
+
+    def fetch_output(self, data_buf=None, meta_buf=None):
+        """Copies <n>.sst.sblock.0 and <n>.sst into the given uint8 numpy buffers (allocated here when
+        None). Returns views trimmed to the file sizes."""
+        dl, ml = self.output_sizes()
+        data = data_buf if data_buf is not None else np.empty(dl + 1, np.uint8)
+        meta = meta_buf if meta_buf is not None else np.empty(ml + 1, np.uint8)
+        self._check(lib().ybgpu_job_fetch_output(self.h, data.ctypes.data, data.size, meta.ctypes.data, meta.size))
+        return data[:dl], meta[:ml]
 
     def boundaries(self):
         a, b = C.create_string_buffer(4096), C.create_string_buffer(4096)

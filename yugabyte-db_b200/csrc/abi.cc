@@ -16,7 +16,8 @@ struct ybgpu_job {
   std::vector<uint8_t> keys, vals;
   std::vector<uint64_t> koff, voff;
   bool have_sst = false;
-  std::string data_file, meta_file;
+  std::string meta_file;
+  uint64_t data_len = 0;
   uint64_t num_blocks = 0;
   std::string error;
 };
@@ -100,7 +101,7 @@ ybgpu_status ybgpu_job_get_stats(const ybgpu_job* job, ybgpu_job_stats* stats) {
   if (!job || !stats) return YBGPU_INVALID_ARGUMENT;
   *stats = const_cast<ybgpu_job*>(job)->engine->stats();
   stats->num_output_data_blocks = job->num_blocks;
-  stats->output_data_file_size = job->data_file.size();
+  stats->output_data_file_size = job->data_len;
   stats->output_meta_file_size = job->meta_file.size();
   return YBGPU_OK;
 }
@@ -148,10 +149,10 @@ static ybgpu_status EnsureSst(ybgpu_job* job) {
   ybgpu_status s = Sync(job, e.OutputInfo(&data_len, &nb, &stride));
   if (s != YBGPU_OK) return s;
   try {
-    job->data_file.resize(data_len);
+    job->data_len = data_len;
     std::vector<uint64_t> off(static_cast<size_t>(nb) + 1);
     std::vector<uint8_t> bnd(static_cast<size_t>(nb) * 2 * stride);
-    s = Sync(job, e.FetchOutput(reinterpret_cast<uint8_t*>(&job->data_file[0]), off.data(), bnd.data()));
+    s = Sync(job, e.FetchOutput(nullptr, off.data(), bnd.data()));   // the data file itself goes straight to the caller
     if (s != YBGPU_OK) return s;
     if (nb) {   // the reference never opens an output file for an empty result (compaction_job.cc:156-160)
       const ybgpu_job_options& o = e.options();
@@ -189,7 +190,7 @@ ybgpu_status ybgpu_job_output_sizes(const ybgpu_job* job, uint64_t* data_len, ui
   if (!job) return YBGPU_INVALID_ARGUMENT;
   ybgpu_status s = EnsureSst(const_cast<ybgpu_job*>(job));
   if (s != YBGPU_OK) return s;
-  *data_len = job->data_file.size(); *meta_len = job->meta_file.size();
+  *data_len = job->data_len; *meta_len = job->meta_file.size();
   return YBGPU_OK;
 }
 
@@ -197,8 +198,11 @@ ybgpu_status ybgpu_job_fetch_output(ybgpu_job* job, uint8_t* data_file, uint64_t
   if (!job) return YBGPU_INVALID_ARGUMENT;
   ybgpu_status s = EnsureSst(job);
   if (s != YBGPU_OK) return s;
-  if (data_cap < job->data_file.size() || meta_cap < job->meta_file.size()) return JobFail(job, YBGPU_INVALID_ARGUMENT, "output buffer too small");
-  memcpy(data_file, job->data_file.data(), job->data_file.size());
+  if (data_cap < job->data_len || meta_cap < job->meta_file.size()) return JobFail(job, YBGPU_INVALID_ARGUMENT, "output buffer too small");
+  if (job->data_len) {
+    s = Sync(job, job->engine->FetchOutput(data_file, nullptr, nullptr));   // D2H directly into the caller's buffer
+    if (s != YBGPU_OK) return s;
+  }
   memcpy(meta_file, job->meta_file.data(), job->meta_file.size());
   return YBGPU_OK;
 }

@@ -219,17 +219,26 @@ __global__ void __launch_bounds__(256) k_next(EncView E) {
   }
 }
 
-// exit1[s] = first chain element at or beyond the end of s's segment. One thread per segment,
-// right to left (exit1 of later entries is already known).
-__global__ void __launch_bounds__(128) k_seg_exit(EncView E) {
-  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t b = static_cast<uint64_t>(seg) * SEG;
+// exit1[s] = first chain element at or beyond the end of s's segment. One CTA per segment:
+// pointer jumping in shared memory (every update replaces a chain element by a later element of
+// the same chain, so unsynchronised reads of neighbours are harmless).
+__global__ void __launch_bounds__(256) k_seg_exit(EncView E) {
+  __shared__ uint32_t ex[SEG];
+  const uint64_t b = static_cast<uint64_t>(blockIdx.x) * SEG;
   if (b >= E.n) return;
   const uint32_t e = static_cast<uint32_t>(umin64(b + SEG, E.n));
-  for (uint32_t s = e; s-- > static_cast<uint32_t>(b);) {
-    const uint32_t nx = E.next[s];
-    E.exit1[s] = nx >= e ? nx : E.exit1[nx];
+  const uint32_t cnt = e - static_cast<uint32_t>(b);
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) ex[i] = E.next[b + i];
+  __syncthreads();
+  for (;;) {
+    int changed = 0;
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const uint32_t v = reinterpret_cast<volatile uint32_t*>(ex)[i];
+      if (v < e) { reinterpret_cast<volatile uint32_t*>(ex)[i] = reinterpret_cast<volatile uint32_t*>(ex)[v - static_cast<uint32_t>(b)]; changed = 1; }
+    }
+    if (!__syncthreads_or(changed)) break;
   }
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) E.exit1[b + i] = ex[i];
 }
 
 // gexit[g][q]: for a chain element at offset q inside the FIRST segment of group g, the first
@@ -455,7 +464,7 @@ __device__ uint32_t warp_crc32c(const uint8_t* p, uint64_t len, int lane, const 
   if (w1 > w0) {
     uint32_t c = 0xffffffffu;
     for (uint64_t i = w0; i < w1; i++) {
-      c ^= __ldg(w + i);
+      c ^= w[i];
       c = tab[3][c & 0xff] ^ tab[2][(c >> 8) & 0xff] ^ tab[1][(c >> 16) & 0xff] ^ tab[0][c >> 24];
     }
     c = ~c;
@@ -503,6 +512,163 @@ __global__ void __launch_bounds__(256) k_crc_blocks(uint8_t* file, const unsigne
       const uint32_t stored = ldg_u32_unaligned(p + len + 1);
       if (lane == 0 && stored != crc) dev_fail(J, DEV_ERR_BAD_CRC, b);
     }
+  }
+}
+
+// ---- fused encoder (v2): one CTA per output block -------------------------------------------
+// Phase A  one thread per entry: header + key delta (few bytes) straight to HBM, value copy job
+//          into a shared-memory table.
+// Phase B  the value bytes (the bulk) are moved as 16-byte destination-aligned vector stores;
+//          every thread takes (entry, 16-B chunk) items from a flat list, sources are read as two
+//          aligned 16-B loads and funnel-shifted into place.
+// Phase C  restart array, count, trailer type byte.
+// Phase D  CRC32C of the block while it is still hot in L1/L2 (no second pass over HBM), trailer.
+constexpr int ENC_THREADS = 256;
+constexpr int ENC_EMAX = 512;      // entries per pass through the shared-memory table
+
+__device__ __forceinline__ void copy_chunk16(uint8_t* dst_chunk, const uint8_t* src) {
+  // dst_chunk 16-byte aligned; src arbitrary. Reads [src & ~15, (src & ~15) + 32).
+  const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15);
+  const uint4* sa = reinterpret_cast<const uint4*>(src - sh);
+  const uint4 a = __ldg(sa);
+  if (sh == 0) { *reinterpret_cast<uint4*>(dst_chunk) = a; return; }
+  const uint4 b = __ldg(sa + 1);
+  uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+  const uint32_t q = sh >> 2, bits = (sh & 3) * 8;
+  if (q & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
+  if (q & 2) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
+  uint4 o;
+  o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
+  o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
+  *reinterpret_cast<uint4*>(dst_chunk) = o;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
+                                                                const unsigned long long* block_off, uint8_t* out) {
+  __shared__ uint32_t tab[4][256];
+  __shared__ uint32_t x2n[32];
+  __shared__ unsigned long long t_dst[ENC_EMAX];     // absolute destination address of the value
+  __shared__ unsigned long long t_src[ENC_EMAX];     // source address of the value
+  __shared__ uint32_t t_len[ENC_EMAX];               // bytes to copy (0 = value written in phase A)
+  __shared__ uint32_t t_chunk[ENC_EMAX + 1];         // exclusive prefix of 16-B chunk counts
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t warp_crc[ENC_THREADS / 32];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+  if (threadIdx.x < 32) x2n[threadIdx.x] = g_crc_x2n[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int NW = ENC_THREADS / 32;
+
+  for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const uint32_t s = block_first[b], e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
+    const unsigned long long boff = block_off[b];
+    const unsigned long long blen = block_off[b + 1] - boff - 5;     // contents length
+    uint8_t* blk = out + boff;
+    const unsigned long long Ps = E.P[s];
+    const unsigned long long Qs = E.QQ[s] - E.D[s];
+    const uint32_t tl = (e - 1 - s) >> E.ri_shift;
+    const unsigned long long body = (E.P[e] - Ps) + (E.QQ[s + (tl << E.ri_shift)] - Qs);
+
+    for (uint32_t p0 = s; p0 < e; p0 += ENC_EMAX) {
+      const uint32_t pn = min(static_cast<uint32_t>(ENC_EMAX), e - p0);
+      // ---- phase A
+      for (uint32_t q = threadIdx.x; q < pn; q += blockDim.x) {
+        const uint32_t j = p0 + q;
+        const bool restart = ((j - s) & (E.ri - 1)) == 0;
+        unsigned long long off = E.P[j] - Ps;
+        if (j > s) { const uint32_t tp = (j - 1 - s) >> E.ri_shift; off += E.QQ[s + (tp << E.ri_shift)] - Qs; }
+        const Desc d = E.kept[j];
+        const uint8_t* rec = kept_rec(E, d, S);
+        const uint32_t klen = d.klen, ulen = klen - 8u, vlen = d.vlen_out;
+        const uint32_t shared = restart ? 0u : E.shared[j];
+        uint8_t* p = blk + off;
+        p += put_varint(p, shared);
+        p += put_varint(p, klen - shared);
+        p += put_varint(p, vlen);
+        const uint64_t suffix = kept_suffix(rec, d, S);
+        for (uint32_t i = shared; i < klen; i++) *p++ = i < ulen ? rec[i] : static_cast<uint8_t>(suffix >> (8 * (i - ulen)));
+        const RunView& run = E.runs[d.run];
+        const uint8_t* vs = run.data + run.val_off[d.gid - run.gid_base];
+        uint32_t copy_len = vlen;
+        if (d.flags & ENT_VAL_TOMBSTONE) { p[0] = 'X'; copy_len = 0; }
+        else if (d.flags & ENT_VAL_REENCODE) {
+          const ValueRewrite& rw = E.rewrites[d.rewrite_slot];
+          for (uint32_t i = 0; i < rw.prefix_len; i++) p[i] = rw.prefix[i];
+          const uint32_t rest = vlen - rw.prefix_len;
+          for (uint32_t i = 0; i < rest; i++) p[rw.prefix_len + i] = vs[rw.skip + i];
+          copy_len = 0;
+        }
+        t_dst[q] = reinterpret_cast<unsigned long long>(p);
+        t_src[q] = reinterpret_cast<unsigned long long>(vs);
+        t_len[q] = copy_len;
+        if (restart) {
+          const uint32_t t = (j - s) >> E.ri_shift;
+          uint8_t* r = blk + body + 4ull * t;
+          const uint32_t o32 = static_cast<uint32_t>(off);
+          r[0] = static_cast<uint8_t>(o32); r[1] = static_cast<uint8_t>(o32 >> 8); r[2] = static_cast<uint8_t>(o32 >> 16); r[3] = static_cast<uint8_t>(o32 >> 24);
+        }
+      }
+      __syncthreads();
+      // chunk counts -> exclusive prefix (pn <= ENC_EMAX = 2 * blockDim)
+      uint32_t c0 = 0, c1 = 0;
+      {
+        const uint32_t q0 = threadIdx.x * 2, q1 = q0 + 1;
+        if (q0 < pn && t_len[q0]) { const unsigned long long d0 = t_dst[q0]; c0 = static_cast<uint32_t>((((d0 + t_len[q0] + 15) & ~15ull) - (d0 & ~15ull)) >> 4); }
+        if (q1 < pn && t_len[q1]) { const unsigned long long d0 = t_dst[q1]; c1 = static_cast<uint32_t>((((d0 + t_len[q1] + 15) & ~15ull) - (d0 & ~15ull)) >> 4); }
+      }
+      uint32_t total_chunks;
+      const uint32_t base = block_exclusive_scan(c0 + c1, warp_sums, &total_chunks);
+      {
+        const uint32_t q0 = threadIdx.x * 2;
+        if (q0 < ENC_EMAX) { t_chunk[q0] = base; if (q0 + 1 <= ENC_EMAX) t_chunk[q0 + 1] = base + c0; }
+        if (threadIdx.x == blockDim.x - 1) t_chunk[ENC_EMAX] = base + c0 + c1;
+      }
+      __syncthreads();
+      // ---- phase B
+      for (uint32_t it = threadIdx.x; it < total_chunks; it += blockDim.x) {
+        uint32_t lo = 0, hi = pn;                     // last q with t_chunk[q] <= it
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (t_chunk[mid] <= it) lo = mid; else hi = mid; }
+        const uint32_t q = lo;
+        const unsigned long long d0 = t_dst[q], d1 = d0 + t_len[q];
+        const unsigned long long A = (d0 & ~15ull) + 16ull * (it - t_chunk[q]);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(t_src[q]) + static_cast<long long>(A - d0);
+        if (A >= d0 && A + 16 <= d1) {
+          copy_chunk16(reinterpret_cast<uint8_t*>(A), src);
+        } else {
+          const unsigned long long lo_a = A > d0 ? A : d0, hi_a = (A + 16 < d1) ? A + 16 : d1;
+          for (unsigned long long a = lo_a; a < hi_a; a++) *reinterpret_cast<uint8_t*>(a) = src[a - A];
+        }
+      }
+      __syncthreads();
+    }
+    // ---- phase C
+    if (threadIdx.x == 0) {
+      const uint32_t nres = tl + 1;
+      uint8_t* q = blk + body + 4ull * nres;
+      q[0] = static_cast<uint8_t>(nres); q[1] = static_cast<uint8_t>(nres >> 8); q[2] = static_cast<uint8_t>(nres >> 16); q[3] = static_cast<uint8_t>(nres >> 24);
+      q[4] = 0;   // kNoCompression
+    }
+    __syncthreads();
+    // ---- phase D: CRC over contents + type byte, split over the warps
+    const unsigned long long L = blen + 1;
+    const unsigned long long per = (L + NW - 1) / NW;
+    const unsigned long long a0 = umin64(per * wid, L), a1 = umin64(a0 + per, L);
+    uint32_t c = 0;
+    if (a1 > a0) {
+      c = warp_crc32c(blk + a0, a1 - a0, lane, tab, x2n);
+      const unsigned long long after = L - a1;
+      if (after) c = crc_mulmod(crc_xpow_bytes(after, x2n), c);
+    }
+    if (lane == 0) warp_crc[wid] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t crc = 0;
+      for (int w = 0; w < NW; w++) crc ^= warp_crc[w];
+      crc = crc_mask(crc);
+      uint8_t* t = blk + blen + 1;
+      t[0] = static_cast<uint8_t>(crc); t[1] = static_cast<uint8_t>(crc >> 8); t[2] = static_cast<uint8_t>(crc >> 16); t[3] = static_cast<uint8_t>(crc >> 24);
+    }
+    __syncthreads();
   }
 }
 

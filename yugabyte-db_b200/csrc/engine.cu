@@ -369,9 +369,10 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, const JobParams* prm, JobDev* J) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int S = prm->S, k = prm->k;
+  const int SS = S + 8;                       // smem record stride: +8 B so that consecutive records start in different banks
   const uint32_t cap = prm->tile_cap;
-  uint8_t* recs = smem;                                             // cap * S
-  uint16_t* order = reinterpret_cast<uint16_t*>(recs + static_cast<size_t>(cap) * S);   // sorted pos -> local idx
+  uint8_t* recs = smem;                                             // cap * SS
+  uint16_t* order = reinterpret_cast<uint16_t*>(recs + static_cast<size_t>(SS) * cap);   // sorted pos -> local idx
   uint16_t* glen = order + cap;                                     // local idx -> group prefix len
   uint16_t* gstart = glen + cap;                                    // group -> first sorted pos (cap + 1)
   uint16_t* pvis = gstart + cap + 2;                                // sorted pos -> previous visible sorted pos
@@ -379,9 +380,11 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
   uint32_t* seg_lo = reinterpret_cast<uint32_t*>(res + ((cap + 15) & ~15u));   // [k]
   uint32_t* seg_start = seg_lo + MAX_RUNS;                          // [k+1]
   uint32_t* rw_slot = seg_start + MAX_RUNS + 1;                     // sorted pos -> rewrite slot (cap)
+  unsigned long long* pfx = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(rw_slot + cap) + 7) & ~static_cast<uintptr_t>(7));   // local idx -> sort prefix (cap)
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t sh_T, sh_ngroups, sh_any_filtered;
   __shared__ int sh_err;
+  __shared__ uint32_t sh_c0;
   __shared__ unsigned long long sh_stats[9];
 
   const uint32_t tile = blockIdx.x;
@@ -402,13 +405,42 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
   if (T == 0) return;
   if (T > cap) { if (threadIdx.x == 0) dev_fail(J, DEV_ERR_TILE_OVERFLOW, tile); return; }
 
-  // (a) stage the k segments: contiguous 16-byte vector loads from HBM
+  // (a) stage the k segments: contiguous 16-byte vector loads from HBM, re-strided to SS in smem
   for (int r = 0; r < k; r++) {
     const uint32_t n = seg_start[r + 1] - seg_start[r];
     const uint4* src = reinterpret_cast<const uint4*>(V.runs[r].rec + static_cast<size_t>(seg_lo[r]) * S);
-    uint4* dst = reinterpret_cast<uint4*>(recs + static_cast<size_t>(seg_start[r]) * S);
-    const uint32_t nvec = n * (S >> 4);
-    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
+    uint8_t* dst = recs + static_cast<size_t>(SS) * seg_start[r];
+    const uint32_t vpr = S >> 4;                      // 16-byte vectors per record
+    const uint32_t nvec = n * vpr;
+    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const uint4 v = __ldg(src + i);
+      const uint32_t rec_i = i / vpr, q = i - rec_i * vpr;
+      uint2* d = reinterpret_cast<uint2*>(dst + static_cast<size_t>(rec_i) * SS + 16 * q);
+      d[0] = make_uint2(v.x, v.y); d[1] = make_uint2(v.z, v.w);
+    }
+  }
+  __syncthreads();
+
+  // tile-common key prefix -> 8-byte sort prefixes (most comparisons are decided by one u64)
+  if (threadIdx.x == 0) {
+    const uint8_t* mn = nullptr; const uint8_t* mx = nullptr;
+    for (int r = 0; r < k; r++) {
+      const uint32_t n = seg_start[r + 1] - seg_start[r];
+      if (!n) continue;
+      const uint8_t* f = recs + static_cast<size_t>(SS) * seg_start[r];
+      const uint8_t* l = recs + static_cast<size_t>(SS) * (seg_start[r + 1] - 1);
+      if (!mn || cmp_user_keys(f, rec_ulen(f, S), mn, rec_ulen(mn, S)) < 0) mn = f;
+      if (!mx || cmp_user_keys(l, rec_ulen(l, S), mx, rec_ulen(mx, S)) > 0) mx = l;
+    }
+    uint32_t c = common_prefix_len(mn, rec_ulen(mn, S), mx, rec_ulen(mx, S)) & ~7u;
+    if (c + 8 > static_cast<uint32_t>(S - 16)) c = (S - 16 >= 8) ? static_cast<uint32_t>(S - 24) & ~7u : 0;
+    sh_c0 = c;
+  }
+  __syncthreads();
+  {
+    const uint32_t c0 = sh_c0;
+    for (uint32_t li = threadIdx.x; li < T; li += blockDim.x)
+      pfx[li] = bswap64(ld_u64_aligned(recs + static_cast<size_t>(SS) * li + c0));
   }
   __syncthreads();
 
@@ -417,8 +449,9 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
     int r = 0;
     while (seg_start[r + 1] <= li) r++;
     const uint32_t p = li - seg_start[r];
-    const uint8_t* e = recs + static_cast<size_t>(li) * S;
-    if (p > 0 && cmp_records(e - S, e, S) >= 0) dev_fail(J, DEV_ERR_UNSORTED, tile);
+    const uint8_t* e = recs + static_cast<size_t>(SS) * (li);
+    if (p > 0 && cmp_records(e - SS, e, S) >= 0) dev_fail(J, DEV_ERR_UNSORTED, tile);
+    const unsigned long long pe = pfx[li];
     uint32_t rank = p;
     for (int r2 = 0; r2 < k; r2++) {
       if (r2 == r) continue;
@@ -426,8 +459,13 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
       uint32_t lo = 0, hi = seg_start[r2 + 1] - b2;
       while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        const int c = cmp_records(recs + static_cast<size_t>(b2 + mid) * S, e, S);
-        const bool less = (r2 < r) ? (c <= 0) : (c < 0);
+        const unsigned long long pm = pfx[b2 + mid];
+        bool less;
+        if (pm != pe) less = pm < pe;
+        else {
+          const int c = cmp_records(recs + static_cast<size_t>(SS) * (b2 + mid), e, S);
+          less = (r2 < r) ? (c <= 0) : (c < 0);
+        }
         if (less) lo = mid + 1; else hi = mid;
       }
       rank += lo;
@@ -447,7 +485,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
       uint32_t last = 0xffff;
       for (uint32_t i = 0; i < T; i++) {
         pvis[i] = static_cast<uint16_t>(last);
-        if (!(rec_flags(recs + static_cast<size_t>(order[i]) * S, S) & REC_F_HT_FILTERED)) last = i;
+        if (!(rec_flags(recs + static_cast<size_t>(SS) * (order[i]), S) & REC_F_HT_FILTERED)) last = i;
       }
     }
   } else {
@@ -463,7 +501,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
     const uint32_t i = threadIdx.x * items + j;
     if (i >= T) break;
     const uint32_t li = order[i];
-    const uint8_t* e = recs + static_cast<size_t>(li) * S;
+    const uint8_t* e = recs + static_cast<size_t>(SS) * (li);
     uint8_t f = 0;
     if (!(rec_flags(e, S) & REC_F_HT_FILTERED)) {
       f |= ENT_COUNTED; st_counted++;
@@ -475,7 +513,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
       const uint32_t ulen = rec_ulen(e, S);
       bool first_occ = true;
       if (pvis[i] != 0xffff) {
-        const uint8_t* pe = recs + static_cast<size_t>(order[pvis[i]]) * S;
+        const uint8_t* pe = recs + static_cast<size_t>(SS) * (order[pvis[i]]);
         first_occ = cmp_user_keys(pe, rec_ulen(pe, S), e, ulen) != 0;
       }
       if (!first_occ) { f |= ENT_DROP_HIDDEN; st_hidden++; }                       // rule A
@@ -494,7 +532,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
     if (!gs) {
       const uint32_t lp = order[i - 1];
       const uint32_t g = glen[li];
-      gs = glen[lp] != g || common_prefix_len(e, g, recs + static_cast<size_t>(lp) * S, g) < g;
+      gs = glen[lp] != g || common_prefix_len(e, g, recs + static_cast<size_t>(SS) * (lp), g) < g;
     }
     if (gs) my_groups++;
   }
@@ -507,7 +545,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
     if (!gs) {
       const uint32_t li = order[i], lp = order[i - 1];
       const uint32_t g = glen[li];
-      gs = glen[lp] != g || common_prefix_len(recs + static_cast<size_t>(li) * S, g, recs + static_cast<size_t>(lp) * S, g) < g;
+      gs = glen[lp] != g || common_prefix_len(recs + static_cast<size_t>(SS) * (li), g, recs + static_cast<size_t>(SS) * (lp), g) < g;
     }
     if (gs) gstart[gbase++] = static_cast<uint16_t>(i);
   }
@@ -527,7 +565,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
         uint8_t f = res[i];
         if (!(f & ENT_KEEP)) continue;
         const uint32_t li = order[i];
-        const uint8_t* e = recs + static_cast<size_t>(li) * S;
+        const uint8_t* e = recs + static_cast<size_t>(SS) * (li);
         int r = 0;
         while (seg_start[r + 1] <= li) r++;
         const uint32_t idx = seg_lo[r] + (li - seg_start[r]);
@@ -556,7 +594,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
   unsigned long long st_kept = 0, st_kbytes = 0, st_vbytes = 0, mn = ~0ull, mx = 0;
   for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
     const uint32_t li = order[i];
-    const uint8_t* e = recs + static_cast<size_t>(li) * S;
+    const uint8_t* e = recs + static_cast<size_t>(SS) * (li);
     int r = 0;
     while (seg_start[r + 1] <= li) r++;
     const uint32_t idx = seg_lo[r] + (li - seg_start[r]);
@@ -1045,7 +1083,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   JobParams hp{};
   hp.S = Sfinal; hp.k = k; hp.bottommost = opt_.bottommost_level; hp.last_sequence = opt_.last_sequence;
   // smem budget: ~110 KB per CTA (records + per-record side arrays) so two CTAs fit one SM
-  uint32_t cap = (110u * 1024u - 1024u) / (Sfinal + 14);
+  uint32_t cap = (110u * 1024u - 1024u) / (Sfinal + 8 + 14 + 8);
   cap = std::min(cap, 4096u) & ~1u;
   hp.tile_cap = cap;
   hp.H = std::max(1u, cap / 2);
@@ -1125,8 +1163,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   MergeView mv{};
   mv.runs = I.dRuns; mv.tile_lo = d_tile_lo; mv.tile_rank = d_tile_rank; mv.desc = d_desc;
   mv.rewrites = d_rw; mv.rewrite_cap = rewrite_cap; mv.n_tiles = n_tiles;
-  const size_t smem = static_cast<size_t>(cap) * Sfinal + (cap * 4 + 4) * 2 + ((cap + 15) & ~15u) +
-                      (2 * MAX_RUNS + 1) * 4 + static_cast<size_t>(cap) * 4 + 64;
+  const size_t smem = static_cast<size_t>(cap) * (Sfinal + 8) + (cap * 4 + 4) * 2 + ((cap + 15) & ~15u) +
+                      (2 * MAX_RUNS + 1) * 4 + static_cast<size_t>(cap) * 4 + static_cast<size_t>(cap) * 8 + 64;
   CUDA_TRY(cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   k_merge_filter<<<n_tiles, MERGE_THREADS, smem, I.stream>>>(mv, I.dP, I.dJ);
   launches++;
@@ -1189,7 +1227,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(DevAlloc(&I.allocs, &d_group_first, ngroups)); CUDA_TRY(DevAlloc(&I.allocs, &d_seg_first, nsegs));
     CUDA_TRY(DevAlloc(&I.allocs, &d_is_start, n)); CUDA_TRY(DevAlloc(&I.allocs, &d_spart, pc + 1)); CUDA_TRY(DevAlloc(&I.allocs, &d_nblocks, 1));
     CUDA_TRY(cudaMemsetAsync(d_is_start, 0, n, I.stream));
-    k_seg_exit<<<(nsegs + 127) / 128, 128, 0, I.stream>>>(E);
+    k_seg_exit<<<nsegs, 256, 0, I.stream>>>(E);
     k_group_exit<<<static_cast<uint32_t>((static_cast<uint64_t>(ngroups) * SEG + 255) / 256), 256, 0, I.stream>>>(E, d_gexit, ngroups);
     k_chain_groups<<<1, 32, 0, I.stream>>>(E, d_gexit, ngroups, d_group_first);
     k_group_fill<<<(ngroups + 127) / 128, 128, 0, I.stream>>>(E, d_group_first, ngroups, d_seg_first, nsegs);
@@ -1214,12 +1252,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(cudaMemcpyAsync(I.d_block_off + nblocks, &total, 8, cudaMemcpyHostToDevice, I.stream));
     I.out_file_len = total;
     CUDA_TRY(DevAlloc(&I.allocs, &I.out_file, total + 64));
-    k_encode_blocks<<<std::min<uint32_t>(nblocks, sms * 8), 128, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
-    k_crc_blocks<<<GridFor(static_cast<uint64_t>(nblocks) * 32, 256, sms), 256, 0, I.stream>>>(I.out_file, I.d_block_off, nullptr, I.d_block_off, nblocks, 0, I.dJ);
+    k_encode_fused<<<std::min<uint32_t>(nblocks, sms * 16), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
     I.boundary_stride = static_cast<uint32_t>((max_ikey + 2 + 7) & ~7u);
     CUDA_TRY(DevAlloc(&I.allocs, &I.d_boundary, static_cast<size_t>(nblocks) * 2 * I.boundary_stride));
     k_boundary_keys<<<GridFor(static_cast<uint64_t>(nblocks) * 2, 256, sms), 256, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_boundary, I.boundary_stride);
-    launches += 6;
+    launches += 5;
   }
   CUDA_TRY(end_phase());
   CUDA_TRY(cudaEventRecord(I.ev1, I.stream));
