@@ -402,6 +402,8 @@ __global__ void __launch_bounds__(128) k_encode_blocks(EncView E, int S, const u
 //   crc(A || B) = x^(8|B|) * crc(A) + crc(B)   (mod P, reflected; zlib's crc32_combine identity).
 __device__ uint32_t g_crc_tab[4][256];
 __device__ uint32_t g_crc_x2n[32];      // x^(2^k) mod P
+constexpr uint32_t CRC_XPOW_TABLE = 1u << 16;
+__device__ uint32_t g_crc_xpow8[CRC_XPOW_TABLE + 1];   // x^(8m) mod P for m = 0..65536 bytes
 
 __global__ void k_crc_init() {
   const uint32_t i = threadIdx.x;
@@ -450,6 +452,17 @@ __device__ __forceinline__ uint32_t crc_xpow_bytes(uint64_t nbytes, const uint32
   return p;
 }
 
+__global__ void k_crc_init_xpow() {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m <= CRC_XPOW_TABLE) g_crc_xpow8[m] = crc_xpow_bytes(m, g_crc_x2n);
+}
+// crc * x^(8 nbytes): table lookup + one modular multiplication for the common distances.
+__device__ __forceinline__ uint32_t crc_shift(uint32_t crc, uint64_t nbytes, const uint32_t* x2n) {
+  if (nbytes == 0) return crc;
+  const uint32_t m = nbytes <= CRC_XPOW_TABLE ? __ldg(&g_crc_xpow8[nbytes]) : crc_xpow_bytes(nbytes, x2n);
+  return crc_mulmod(m, crc);
+}
+
 // CRC32C of [p, p+len) computed by one warp. Returns the finalized CRC in every lane.
 __device__ uint32_t warp_crc32c(const uint8_t* p, uint64_t len, int lane, const uint32_t (*tab)[256], const uint32_t* x2n) {
   // head bytes up to 4-byte alignment, body words split evenly over lanes, tail bytes
@@ -469,14 +482,14 @@ __device__ uint32_t warp_crc32c(const uint8_t* p, uint64_t len, int lane, const 
     }
     c = ~c;
     const uint64_t after = (nwords - w1) * 4 + tail;
-    acc = after ? crc_mulmod(crc_xpow_bytes(after, x2n), c) : c;
+    acc = crc_shift(c, after, x2n);
   }
   if (lane == 0 && head) {
     uint32_t c = 0xffffffffu;
     for (uint32_t i = 0; i < head; i++) c = tab[0][(c ^ p[i]) & 0xff] ^ (c >> 8);
     c = ~c;
     const uint64_t after = len - head;
-    acc ^= after ? crc_mulmod(crc_xpow_bytes(after, x2n), c) : c;
+    acc ^= crc_shift(c, after, x2n);
   }
   if (lane == 31 && tail) {
     uint32_t c = 0xffffffffu;
@@ -525,6 +538,25 @@ __global__ void __launch_bounds__(256) k_crc_blocks(uint8_t* file, const unsigne
 // Phase D  CRC32C of the block while it is still hot in L1/L2 (no second pass over HBM), trailer.
 constexpr int ENC_THREADS = 256;
 constexpr int ENC_EMAX = 512;      // entries per pass through the shared-memory table
+constexpr int ENC_ITEMS = 4096;    // direct item->entry map size (64 KB of values per pass)
+
+// 16 bytes starting at an arbitrary address: two aligned 16-byte loads + funnel shift. Reads
+// [src & ~15, (src & ~15) + 32).
+__device__ __forceinline__ uint4 load_unaligned16(const uint8_t* src) {
+  const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15);
+  const uint4* sa = reinterpret_cast<const uint4*>(src - sh);
+  const uint4 a = __ldg(sa);
+  if (sh == 0) return a;
+  const uint4 b = __ldg(sa + 1);
+  uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+  const uint32_t q = sh >> 2, bits = (sh & 3) * 8;
+  if (q & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
+  if (q & 2) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
+  uint4 o;
+  o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
+  o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
+  return o;
+}
 
 __device__ __forceinline__ void copy_chunk16(uint8_t* dst_chunk, const uint8_t* src) {
   // dst_chunk 16-byte aligned; src arbitrary. Reads [src & ~15, (src & ~15) + 32).
@@ -544,13 +576,14 @@ __device__ __forceinline__ void copy_chunk16(uint8_t* dst_chunk, const uint8_t* 
 }
 
 __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
-                                                                const unsigned long long* block_off, uint8_t* out) {
+                                                                const unsigned long long* block_off, uint8_t* out, unsigned long long min_total) {
   __shared__ uint32_t tab[4][256];
   __shared__ uint32_t x2n[32];
   __shared__ unsigned long long t_dst[ENC_EMAX];     // absolute destination address of the value
   __shared__ unsigned long long t_src[ENC_EMAX];     // source address of the value
   __shared__ uint32_t t_len[ENC_EMAX];               // bytes to copy (0 = value written in phase A)
   __shared__ uint32_t t_chunk[ENC_EMAX + 1];         // exclusive prefix of 16-B chunk counts
+  __shared__ uint16_t t_item[ENC_ITEMS];             // chunk item -> entry (when the pass has <= ENC_ITEMS items)
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t warp_crc[ENC_THREADS / 32];
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
@@ -562,6 +595,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
   for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
     const uint32_t s = block_first[b], e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
     const unsigned long long boff = block_off[b];
+    if (block_off[b + 1] - boff <= min_total) continue;              // handled by k_encode_smem
     const unsigned long long blen = block_off[b + 1] - boff - 5;     // contents length
     uint8_t* blk = out + boff;
     const unsigned long long Ps = E.P[s];
@@ -624,11 +658,22 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
         if (threadIdx.x == blockDim.x - 1) t_chunk[ENC_EMAX] = base + c0 + c1;
       }
       __syncthreads();
+      const bool direct = total_chunks <= ENC_ITEMS;
+      if (direct) {
+        const uint32_t q0 = threadIdx.x * 2;
+        for (uint32_t q = q0; q < q0 + 2 && q < pn; q++)
+          for (uint32_t it = t_chunk[q]; it < t_chunk[q + 1]; it++) t_item[it] = static_cast<uint16_t>(q);
+        __syncthreads();
+      }
       // ---- phase B
       for (uint32_t it = threadIdx.x; it < total_chunks; it += blockDim.x) {
-        uint32_t lo = 0, hi = pn;                     // last q with t_chunk[q] <= it
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (t_chunk[mid] <= it) lo = mid; else hi = mid; }
-        const uint32_t q = lo;
+        uint32_t q;
+        if (direct) q = t_item[it];
+        else {
+          uint32_t lo = 0, hi = pn;                   // last q with t_chunk[q] <= it
+          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (t_chunk[mid] <= it) lo = mid; else hi = mid; }
+          q = lo;
+        }
         const unsigned long long d0 = t_dst[q], d1 = d0 + t_len[q];
         const unsigned long long A = (d0 & ~15ull) + 16ull * (it - t_chunk[q]);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(t_src[q]) + static_cast<long long>(A - d0);
@@ -657,7 +702,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
     if (a1 > a0) {
       c = warp_crc32c(blk + a0, a1 - a0, lane, tab, x2n);
       const unsigned long long after = L - a1;
-      if (after) c = crc_mulmod(crc_xpow_bytes(after, x2n), c);
+      c = crc_shift(c, after, x2n);
     }
     if (lane == 0) warp_crc[wid] = c;
     __syncthreads();
@@ -667,6 +712,210 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
       crc = crc_mask(crc);
       uint8_t* t = blk + blen + 1;
       t[0] = static_cast<uint8_t>(crc); t[1] = static_cast<uint8_t>(crc >> 8); t[2] = static_cast<uint8_t>(crc >> 16); t[3] = static_cast<uint8_t>(crc >> 24);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- shared-memory block assembler (v3): the whole block image is built in shared memory --------
+// All byte-granular scatter (headers, key deltas, value edges, restart array) lands in shared
+// memory; HBM sees only 16-byte vector loads of the source values and 16-byte vector stores of
+// the finished image; the CRC is computed from the shared-memory image. Blocks larger than
+// ENC_SMEM_CAP are left to k_encode_fused (only_big = 1).
+constexpr uint32_t ENC_SMEM_CAP = 40 * 1024;       // bytes of block image (contents + trailer) per CTA
+
+__global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_smem(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
+                                                               const unsigned long long* block_off, uint8_t* out) {
+  extern __shared__ __align__(16) uint8_t img_raw[];    // ENC_SMEM_CAP + 32
+  __shared__ uint32_t tab[4][256];
+  __shared__ uint32_t x2n[32];
+  __shared__ uint32_t warp_crc[ENC_THREADS / 32];
+  __shared__ uint32_t warp_sums[32];
+  __shared__ unsigned long long t_src[ENC_EMAX];
+  __shared__ uint32_t t_dsto[ENC_EMAX];
+  __shared__ uint32_t t_len[ENC_EMAX];
+  __shared__ uint32_t t_chunk[ENC_EMAX + 1];
+  __shared__ uint16_t t_item[ENC_ITEMS];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+  if (threadIdx.x < 32) x2n[threadIdx.x] = g_crc_x2n[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const unsigned long long boff = block_off[b];
+    const unsigned long long btot = block_off[b + 1] - boff;         // contents + 5-byte trailer
+    if (btot > ENC_SMEM_CAP) continue;                               // uniform for the CTA
+    const uint32_t blen = static_cast<uint32_t>(btot - 5);
+    const uint32_t s = block_first[b], e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
+    uint8_t* gdst = out + boff;
+    // image[0] corresponds to gdst[0]; shifted so that image and destination agree mod 16
+    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gdst) & 15);
+    uint8_t* img = img_raw + mis;
+    const unsigned long long Ps = E.P[s];
+    const unsigned long long Qs = E.QQ[s] - E.D[s];
+    const uint32_t tl = (e - 1 - s) >> E.ri_shift;
+    const uint32_t body = static_cast<uint32_t>((E.P[e] - Ps) + (E.QQ[s + (tl << E.ri_shift)] - Qs));
+
+    for (uint32_t p0 = s; p0 < e; p0 += ENC_EMAX) {
+      const uint32_t pn = min(static_cast<uint32_t>(ENC_EMAX), e - p0);
+      // ---- phase A: one thread per entry. Header + key delta bytes into the image, value copy job
+      // into the table. All metadata loads of all entries are in flight together.
+      for (uint32_t q = threadIdx.x; q < pn; q += blockDim.x) {
+        const uint32_t j = p0 + q;
+        const bool restart = ((j - s) & (E.ri - 1)) == 0;
+        uint32_t off = static_cast<uint32_t>(E.P[j] - Ps);
+        if (j > s) { const uint32_t tp = (j - 1 - s) >> E.ri_shift; off += static_cast<uint32_t>(E.QQ[s + (tp << E.ri_shift)] - Qs); }
+        const Desc d = E.kept[j];
+        const uint8_t* rec = kept_rec(E, d, S);
+        const uint32_t klen = d.klen, ulen = klen - 8u, vlen = d.vlen_out;
+        const uint32_t shared = restart ? 0u : E.shared[j];
+        const RunView& run = E.runs[d.run];
+        const uint8_t* vs = run.data + run.val_off[d.gid - run.gid_base];
+        uint8_t* p = img + off;
+        p += put_varint(p, shared);
+        p += put_varint(p, klen - shared);
+        p += put_varint(p, vlen);
+        const uint64_t suffix = kept_suffix(rec, d, S);
+        {
+          // key bytes [shared, klen): read the record as aligned 8-byte words
+          uint32_t i = shared;
+          while (i < klen) {
+            if (i < ulen) {
+              const uint64_t wv = ld_u64_aligned(rec + (i & ~7u));
+              const uint32_t lim = min(ulen, (i & ~7u) + 8);
+              for (; i < lim; i++) *p++ = static_cast<uint8_t>(wv >> (8 * (i & 7)));
+            } else { *p++ = static_cast<uint8_t>(suffix >> (8 * (i - ulen))); i++; }
+          }
+        }
+        uint32_t copy_len = vlen;
+        if (d.flags & ENT_VAL_TOMBSTONE) { p[0] = 'X'; copy_len = 0; }
+        else if (d.flags & ENT_VAL_REENCODE) {
+          const ValueRewrite& rw = E.rewrites[d.rewrite_slot];
+          for (uint32_t i = 0; i < rw.prefix_len; i++) p[i] = rw.prefix[i];
+          const uint32_t rest = vlen - rw.prefix_len;
+          for (uint32_t i = 0; i < rest; i++) p[rw.prefix_len + i] = vs[rw.skip + i];
+          copy_len = 0;
+        }
+        t_dsto[q] = static_cast<uint32_t>(p - img);
+        t_src[q] = reinterpret_cast<unsigned long long>(vs);
+        t_len[q] = copy_len;
+        if (restart) {
+          const uint32_t t = (j - s) >> E.ri_shift;
+          uint8_t* r = img + body + 4 * t;
+          r[0] = static_cast<uint8_t>(off); r[1] = static_cast<uint8_t>(off >> 8); r[2] = static_cast<uint8_t>(off >> 16); r[3] = static_cast<uint8_t>(off >> 24);
+        }
+      }
+      __syncthreads();
+      // items = destination-aligned 16-byte chunks of every value (image and HBM agree mod 16)
+      uint32_t c0 = 0, c1 = 0;
+      {
+        const uint32_t q0 = threadIdx.x * 2, q1 = q0 + 1;
+        if (q0 < pn && t_len[q0]) { const uint32_t d0 = t_dsto[q0] + mis; c0 = (((d0 + t_len[q0] + 15) & ~15u) - (d0 & ~15u)) >> 4; }
+        if (q1 < pn && t_len[q1]) { const uint32_t d0 = t_dsto[q1] + mis; c1 = (((d0 + t_len[q1] + 15) & ~15u) - (d0 & ~15u)) >> 4; }
+      }
+      uint32_t total_items;
+      const uint32_t ibase = block_exclusive_scan(c0 + c1, warp_sums, &total_items);
+      {
+        const uint32_t q0 = threadIdx.x * 2;
+        t_chunk[q0] = ibase; t_chunk[q0 + 1] = ibase + c0;
+        if (threadIdx.x == blockDim.x - 1) t_chunk[ENC_EMAX] = ibase + c0 + c1;
+      }
+      __syncthreads();
+      const bool direct = total_items <= ENC_ITEMS;
+      if (direct) {
+        const uint32_t q0 = threadIdx.x * 2;
+        for (uint32_t q = q0; q < q0 + 2 && q < pn; q++)
+          for (uint32_t it = t_chunk[q]; it < t_chunk[q + 1]; it++) t_item[it] = static_cast<uint16_t>(q);
+        __syncthreads();
+      }
+      // ---- phase B: value bytes, one 16-byte source vector per item
+      for (uint32_t it = threadIdx.x; it < total_items; it += blockDim.x) {
+        uint32_t q;
+        if (direct) q = t_item[it];
+        else {
+          uint32_t lo = 0, hi = pn;
+          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (t_chunk[mid] <= it) lo = mid; else hi = mid; }
+          q = lo;
+        }
+        // offsets below are relative to img_raw (16-byte aligned): r = image offset + mis
+        const uint32_t d0 = t_dsto[q] + mis, d1 = d0 + t_len[q];
+        const uint32_t A = (d0 & ~15u) + 16u * (it - t_chunk[q]);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(t_src[q]) + (static_cast<int>(A) - static_cast<int>(d0));
+        const uint4 x = load_unaligned16(src);
+        if (A >= d0 && A + 16 <= d1) {
+          *reinterpret_cast<uint4*>(img_raw + A) = x;
+        } else {
+          const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int bb = 0; bb < 16; bb++) {
+            const uint32_t a = A + bb;
+            if (a >= d0 && a < d1) img_raw[a] = static_cast<uint8_t>(w[bb >> 2] >> (8 * (bb & 3)));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const uint32_t nres = tl + 1;
+      uint8_t* q = img + body + 4 * nres;
+      q[0] = static_cast<uint8_t>(nres); q[1] = static_cast<uint8_t>(nres >> 8); q[2] = static_cast<uint8_t>(nres >> 16); q[3] = static_cast<uint8_t>(nres >> 24);
+      q[4] = 0;   // kNoCompression
+    }
+    __syncthreads();
+    // ---- CRC32C over image[0, blen] from shared memory: thread t takes an odd-sized word range so
+    // that the 32 lanes of a warp read different banks
+    {
+      const uint32_t L = blen + 1;
+      const uint32_t head = (4 - ((mis) & 3)) & 3;                  // bytes before the first aligned word of img
+      const uint32_t hb = head < L ? head : L;
+      const uint32_t nwords = (L - hb) >> 2, tail = (L - hb) & 3;
+      uint32_t W = (nwords + ENC_THREADS - 1) / ENC_THREADS;
+      W |= 1;                                                       // odd stride in words
+      const uint32_t w0 = min(W * threadIdx.x, nwords), w1 = min(w0 + W, nwords);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + hb);
+      uint32_t acc = 0;
+      if (w1 > w0) {
+        uint32_t c = 0xffffffffu;
+        for (uint32_t i = w0; i < w1; i++) {
+          c ^= wp[i];
+          c = tab[3][c & 0xff] ^ tab[2][(c >> 8) & 0xff] ^ tab[1][(c >> 16) & 0xff] ^ tab[0][c >> 24];
+        }
+        acc = crc_shift(~c, static_cast<uint64_t>(nwords - w1) * 4 + tail, x2n);
+      }
+      if (threadIdx.x == 0 && hb) {
+        uint32_t c = 0xffffffffu;
+        for (uint32_t i = 0; i < hb; i++) c = tab[0][(c ^ img[i]) & 0xff] ^ (c >> 8);
+        acc ^= crc_shift(~c, L - hb, x2n);
+      }
+      if (threadIdx.x == ENC_THREADS - 1 && tail) {
+        uint32_t c = 0xffffffffu;
+        for (uint32_t i = 0; i < tail; i++) c = tab[0][(c ^ img[L - tail + i]) & 0xff] ^ (c >> 8);
+        acc ^= ~c;
+      }
+      for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) warp_crc[wid] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t crc = 0;
+      for (int w = 0; w < ENC_THREADS / 32; w++) crc ^= warp_crc[w];
+      crc = crc_mask(crc);
+      uint8_t* t = img + blen + 1;
+      t[0] = static_cast<uint8_t>(crc); t[1] = static_cast<uint8_t>(crc >> 8); t[2] = static_cast<uint8_t>(crc >> 16); t[3] = static_cast<uint8_t>(crc >> 24);
+    }
+    __syncthreads();
+    // ---- image -> HBM: 16-byte vector stores (image and destination agree mod 16)
+    {
+      const uint32_t total = static_cast<uint32_t>(btot);
+      const uint32_t head = (16 - mis) & 15;
+      const uint32_t hb = head < total ? head : total;
+      if (threadIdx.x < hb) gdst[threadIdx.x] = img[threadIdx.x];
+      const uint32_t nvec = (total - hb) >> 4;
+      const uint4* sv = reinterpret_cast<const uint4*>(img + hb);
+      uint4* dv = reinterpret_cast<uint4*>(gdst + hb);
+      for (uint32_t v = threadIdx.x; v < nvec; v += blockDim.x) dv[v] = sv[v];
+      const uint32_t done = hb + nvec * 16;
+      if (threadIdx.x < total - done) gdst[done + threadIdx.x] = img[done + threadIdx.x];
     }
     __syncthreads();
   }

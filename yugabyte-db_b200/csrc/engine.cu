@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
   uint32_t* seg_start = seg_lo + MAX_RUNS;                          // [k+1]
   uint32_t* rw_slot = seg_start + MAX_RUNS + 1;                     // sorted pos -> rewrite slot (cap)
   unsigned long long* pfx = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(rw_slot + cap) + 7) & ~static_cast<uintptr_t>(7));   // local idx -> sort prefix (cap)
+  unsigned long long* pfx2 = pfx + cap;             // second 8 bytes of the 16-byte sort prefix
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t sh_T, sh_ngroups, sh_any_filtered;
   __shared__ int sh_err;
@@ -433,14 +434,17 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
       if (!mx || cmp_user_keys(l, rec_ulen(l, S), mx, rec_ulen(mx, S)) > 0) mx = l;
     }
     uint32_t c = common_prefix_len(mn, rec_ulen(mn, S), mx, rec_ulen(mx, S)) & ~7u;
-    if (c + 8 > static_cast<uint32_t>(S - 16)) c = (S - 16 >= 8) ? static_cast<uint32_t>(S - 24) & ~7u : 0;
+    if (c + 16 > static_cast<uint32_t>(S - 16)) c = (S - 16 >= 16) ? static_cast<uint32_t>(S - 32) & ~7u : 0;
     sh_c0 = c;
   }
   __syncthreads();
   {
     const uint32_t c0 = sh_c0;
     for (uint32_t li = threadIdx.x; li < T; li += blockDim.x)
+    {
       pfx[li] = bswap64(ld_u64_aligned(recs + static_cast<size_t>(SS) * li + c0));
+      pfx2[li] = bswap64(ld_u64_aligned(recs + static_cast<size_t>(SS) * li + c0 + 8));
+    }
   }
   __syncthreads();
 
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
     const uint32_t p = li - seg_start[r];
     const uint8_t* e = recs + static_cast<size_t>(SS) * (li);
     if (p > 0 && cmp_records(e - SS, e, S) >= 0) dev_fail(J, DEV_ERR_UNSORTED, tile);
-    const unsigned long long pe = pfx[li];
+    const unsigned long long pe = pfx[li], pe2 = pfx2[li];
     uint32_t rank = p;
     for (int r2 = 0; r2 < k; r2++) {
       if (r2 == r) continue;
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
         const unsigned long long pm = pfx[b2 + mid];
         bool less;
         if (pm != pe) less = pm < pe;
+        else if (pfx2[b2 + mid] != pe2) less = pfx2[b2 + mid] < pe2;
         else {
           const int c = cmp_records(recs + static_cast<size_t>(SS) * (b2 + mid), e, S);
           less = (r2 < r) ? (c <= 0) : (c < 0);
@@ -1014,7 +1019,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   }
   {
     static bool crc_ready[64] = {};
-    if (!crc_ready[opt_.device & 63]) { k_crc_init<<<1, 256, 0, I.stream>>>(); crc_ready[opt_.device & 63] = true; }
+    if (!crc_ready[opt_.device & 63]) {
+      k_crc_init<<<1, 256, 0, I.stream>>>();
+      k_crc_init_xpow<<<(CRC_XPOW_TABLE + 256) / 256, 256, 0, I.stream>>>();
+      crc_ready[opt_.device & 63] = true;
+    }
   }
   CUDA_TRY(cudaEventRecord(I.ev0, I.stream));
   uint32_t phase_launch_mark[8] = {};
@@ -1083,7 +1092,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   JobParams hp{};
   hp.S = Sfinal; hp.k = k; hp.bottommost = opt_.bottommost_level; hp.last_sequence = opt_.last_sequence;
   // smem budget: ~110 KB per CTA (records + per-record side arrays) so two CTAs fit one SM
-  uint32_t cap = (110u * 1024u - 1024u) / (Sfinal + 8 + 14 + 8);
+  uint32_t cap = (110u * 1024u - 1024u) / (Sfinal + 8 + 14 + 16);
   cap = std::min(cap, 4096u) & ~1u;
   hp.tile_cap = cap;
   hp.H = std::max(1u, cap / 2);
@@ -1164,7 +1173,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   mv.runs = I.dRuns; mv.tile_lo = d_tile_lo; mv.tile_rank = d_tile_rank; mv.desc = d_desc;
   mv.rewrites = d_rw; mv.rewrite_cap = rewrite_cap; mv.n_tiles = n_tiles;
   const size_t smem = static_cast<size_t>(cap) * (Sfinal + 8) + (cap * 4 + 4) * 2 + ((cap + 15) & ~15u) +
-                      (2 * MAX_RUNS + 1) * 4 + static_cast<size_t>(cap) * 4 + static_cast<size_t>(cap) * 8 + 64;
+                      (2 * MAX_RUNS + 1) * 4 + static_cast<size_t>(cap) * 4 + static_cast<size_t>(cap) * 16 + 64;
   CUDA_TRY(cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   k_merge_filter<<<n_tiles, MERGE_THREADS, smem, I.stream>>>(mv, I.dP, I.dJ);
   launches++;
@@ -1252,11 +1261,17 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(cudaMemcpyAsync(I.d_block_off + nblocks, &total, 8, cudaMemcpyHostToDevice, I.stream));
     I.out_file_len = total;
     CUDA_TRY(DevAlloc(&I.allocs, &I.out_file, total + 64));
-    k_encode_fused<<<std::min<uint32_t>(nblocks, sms * 16), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
+    {
+      const size_t esm = ENC_SMEM_CAP + 32;
+      CUDA_TRY(cudaFuncSetAttribute(k_encode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esm)));
+      k_encode_smem<<<std::min<uint32_t>(nblocks, sms * 8), ENC_THREADS, esm, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
+      // blocks whose image does not fit shared memory (huge values)
+      k_encode_fused<<<std::min<uint32_t>(nblocks, sms * 4), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file, ENC_SMEM_CAP);
+    }
     I.boundary_stride = static_cast<uint32_t>((max_ikey + 2 + 7) & ~7u);
     CUDA_TRY(DevAlloc(&I.allocs, &I.d_boundary, static_cast<size_t>(nblocks) * 2 * I.boundary_stride));
     k_boundary_keys<<<GridFor(static_cast<uint64_t>(nblocks) * 2, 256, sms), 256, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_boundary, I.boundary_stride);
-    launches += 5;
+    launches += 6;
   }
   CUDA_TRY(end_phase());
   CUDA_TRY(cudaEventRecord(I.ev1, I.stream));
