@@ -1,0 +1,43 @@
+"""The C++ host adapter (rocksdb::CompactionJob / TableBuilder shaped classes over the C ABI)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "adapter_cpp_test")
+
+
+def build_bin():
+    import __graft_entry__ as g
+    g.build()
+    lib_dir = os.path.join(ROOT, "yugabyte-db_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", BIN, os.path.join(ROOT, "tests", "adapter_cpp_test.cc"),
+                           "-L" + lib_dir, "-lybgpu", "-Wl,-rpath," + lib_dir, "-L/usr/local/cuda/lib64",
+                           "-Wl,-rpath,/usr/local/cuda/lib64"])
+
+
+def test_adapter_compiles_and_fails_loudly_without_gpu():
+    build_bin()
+    out = subprocess.check_output([BIN, "cpu"], text=True)
+    assert out.strip().endswith("OK")
+
+
+@pytest.mark.gpu
+def test_adapter_runs_compaction(tmp_path):
+    import oracle_py as o
+    build_bin()
+    cfg = o.GenConfig(seed=8, num_rows=3000, cols=2, versions=3, num_files=3, value_len=80)
+    ssts = o.Sst.generate_all(cfg)
+    args = [BIN, "gpu"]
+    for i, s in enumerate(ssts):
+        b, d = tmp_path / ("%d.sst" % i), tmp_path / ("%d.sst.sblock.0" % i)
+        b.write_bytes(s.meta)
+        d.write_bytes(s.data)
+        args += [str(b), str(d)]
+    out = subprocess.check_output(args, text=True)
+    assert "OK in=18000" in out
+    exp = o.compact(ssts, o.CompactionParams())
+    assert (tmp_path / "0.sst.out.data").read_bytes() == exp.sst().data
+    assert (tmp_path / "0.sst.out.base").read_bytes() == exp.sst().meta

@@ -1,0 +1,249 @@
+// gpu_compaction_job.h — C++ host adapter above the C ABI (include/ybgpu_compaction.h).
+//
+// Mirrors the reference's operator surface for this path so that the call sites in
+// rocksdb::DBImpl (db/db_impl.cc:2548-2592, 4019-4035) change by one type name:
+//
+//     CompactionJob job(...);  job.Prepare();  mutex_.Unlock();  job.Run();  mutex_.Lock();  job.Install(...)
+//
+// Names, argument meaning and error behaviour follow rocksdb/db/compaction_job.h:75-194,
+// rocksdb/db/compaction_context.h:25-72 and rocksdb/table/table_builder.h:93-136. The types below
+// (Slice, Status, CompactionFeed, ...) are minimal stand-ins with the reference's member names so
+// that this header compiles stand-alone (tests/test_adapter_cpp.py); inside the reference tree the
+// real yb/rocksdb headers are included instead.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../../include/ybgpu_compaction.h"
+
+namespace ybgpu_adapter {
+
+#ifndef YBGPU_ADAPTER_USE_REFERENCE_TYPES
+struct Slice {   // yb/util/slice.h
+  const uint8_t* data_ = nullptr; size_t size_ = 0;
+  Slice() {}
+  Slice(const uint8_t* d, size_t n) : data_(d), size_(n) {}
+  Slice(const std::string& s) : data_(reinterpret_cast<const uint8_t*>(s.data())), size_(s.size()) {}
+  const uint8_t* data() const { return data_; }
+  size_t size() const { return size_; }
+  bool empty() const { return size_ == 0; }
+};
+
+class Status {   // yb/util/status.h (codes used on this path)
+ public:
+  enum Code { kOk = 0, kNotFound = 1, kCorruption = 2, kNotSupported = 3, kInvalidArgument = 4, kIOError = 5,
+              kRuntimeError = 9, kIllegalState = 10, kShutdownInProgress = 19 };
+  Status() {}
+  Status(Code c, std::string m) : code_(c), msg_(std::move(m)) {}
+  static Status OK() { return Status(); }
+  bool ok() const { return code_ == kOk; }
+  bool IsShutdownInProgress() const { return code_ == kShutdownInProgress; }
+  bool IsCorruption() const { return code_ == kCorruption; }
+  Code code() const { return code_; }
+  const std::string& message() const { return msg_; }
+  std::string ToString() const { return ok() ? "OK" : msg_; }
+ private:
+  Code code_ = kOk; std::string msg_;
+};
+
+// rocksdb/db/compaction_context.h:25-35
+class CompactionFeed {
+ public:
+  virtual ~CompactionFeed() = default;
+  virtual Status Feed(const Slice& key, const Slice& value) = 0;
+  virtual Status Flush() = 0;
+};
+
+// rocksdb/table/table_builder.h:93-136 (the members the compaction loop uses)
+class TableBuilder {
+ public:
+  virtual ~TableBuilder() = default;
+  virtual void Add(const Slice& key, const Slice& value) = 0;
+  virtual Status status() const = 0;
+  virtual Status Finish() = 0;
+  virtual void Abandon() = 0;
+  virtual uint64_t NumEntries() const = 0;
+  virtual uint64_t TotalFileSize() const = 0;
+  virtual uint64_t BaseFileSize() const = 0;
+};
+#endif
+
+inline Status ToStatus(ybgpu_status s, const char* msg) {
+  return s == YBGPU_OK ? Status::OK() : Status(static_cast<Status::Code>(s), msg ? msg : "");
+}
+
+// docdb::HistoryRetentionDirective + CompactionHybridTimeConstraints (docdb/docdb_compaction_context.h:57-111,
+// 178-196) flattened the way DocDBCompactionContext consumes them (docdb_compaction_context.cc:655-669).
+struct DocDBRetention {
+  bool enabled = true;                       // false: no compaction_context_factory on this DB
+  uint64_t primary_cutoff_ht = YBGPU_HT_MIN;
+  uint64_t cotables_cutoff_ht = YBGPU_HT_INVALID;
+  int64_t table_ttl_ns = YBGPU_TTL_MAX_NS;
+  bool retain_delete_markers_in_major_compaction = false;
+  uint64_t other_min_ht = YBGPU_HT_MAX;
+  std::string key_bounds_lower, key_bounds_upper;
+};
+
+// One L0 input file, as VersionSet::MakeInputIterator sees it (db/version_set.cc:3788-3849).
+struct InputFile {
+  Slice base_file;            // <n>.sst (metadata file) bytes
+  Slice data_file;            // <n>.sst.sblock.0 bytes
+  uint64_t hybrid_time_filter = YBGPU_HT_INVALID;   // FdWithBoundaries::user_filter_data (:3824)
+};
+
+// TableBuilder over the product's host writer (what TableFactory::NewTableBuilder returns when the
+// KV stream is consumed by a host-side CompactionFeed chain).
+class GpuSideTableBuilder : public TableBuilder {
+ public:
+  explicit GpuSideTableBuilder(const ybgpu_job_options& table_options) {
+    st_ = ToStatus(ybgpu_table_builder_create(&table_options, &b_), ybgpu_last_error());
+  }
+  ~GpuSideTableBuilder() override { if (b_) ybgpu_table_builder_destroy(b_); }
+  void Add(const Slice& key, const Slice& value) override {
+    if (st_.ok()) st_ = ToStatus(ybgpu_table_builder_add(b_, key.data(), key.size(), value.data(), value.size()), "Add");
+  }
+  Status status() const override { return st_; }
+  Status Finish() override { if (st_.ok()) st_ = ToStatus(ybgpu_table_builder_finish(b_), "Finish"); return st_; }
+  void Abandon() override {}
+  uint64_t NumEntries() const override { return ybgpu_table_builder_num_entries(b_); }
+  uint64_t TotalFileSize() const override { return ybgpu_table_builder_total_file_size(b_); }
+  uint64_t BaseFileSize() const override { return ybgpu_table_builder_base_file_size(b_); }
+  Status Files(Slice* data_file, Slice* base_file) const {
+    const uint8_t *d, *m; uint64_t dl, ml;
+    Status s = ToStatus(ybgpu_table_builder_files(b_, &d, &dl, &m, &ml), "files");
+    if (s.ok()) { *data_file = Slice(d, dl); *base_file = Slice(m, ml); }
+    return s;
+  }
+ private:
+  ybgpu_table_builder* b_ = nullptr;
+  Status st_;
+};
+
+// rocksdb::CompactionJob shape (db/compaction_job.h:75-194).
+class GpuCompactionJob {
+ public:
+  struct Params {                       // what the CompactionJob ctor + Compaction* provide
+    int device = 0;
+    bool bottommost_level = true;       // Compaction::bottommost_level()
+    uint64_t last_sequence = YBGPU_MAX_SEQUENCE;   // versions_->LastSequence()
+    std::string largest_user_key;       // Compaction::GetLargestUserKey(); empty + !has => derived
+    bool has_largest_user_key = false;
+    DocDBRetention retention;
+    uint32_t block_size = 32 * 1024;    // BlockBasedTableOptions
+    int block_restart_interval = 16;
+    int block_size_deviation = 10;
+    uint32_t index_block_size = 32 * 1024;
+    uint32_t min_keys_per_index_block = 100;
+    bool verify_checksums = true;
+    const volatile int32_t* shutting_down = nullptr;   // std::atomic<bool>* shutting_down_ in the reference
+  };
+
+  explicit GpuCompactionJob(const Params& p) : p_(p) {}
+  ~GpuCompactionJob() { if (job_) ybgpu_job_destroy(job_); }
+  GpuCompactionJob(const GpuCompactionJob&) = delete;
+  GpuCompactionJob& operator=(const GpuCompactionJob&) = delete;
+
+  // REQUIRED: mutex held (same contract as CompactionJob::Prepare). Captures parameters only.
+  Status Prepare(const std::vector<InputFile>& inputs) {
+    ybgpu_job_options o;
+    ybgpu_job_options_init(&o);
+    o.device = p_.device;
+    o.bottommost_level = p_.bottommost_level;
+    o.last_sequence = p_.last_sequence;
+    o.largest_user_key = reinterpret_cast<const uint8_t*>(p_.largest_user_key.data());
+    o.largest_user_key_len = p_.largest_user_key.size();
+    o.has_largest_user_key = p_.has_largest_user_key;
+    o.retention_enabled = p_.retention.enabled;
+    o.history_cutoff_ht = p_.retention.primary_cutoff_ht;
+    o.cotables_cutoff_ht = p_.retention.cotables_cutoff_ht;
+    o.table_ttl_ns = p_.retention.table_ttl_ns;
+    o.retain_delete_markers_in_major_compaction = p_.retention.retain_delete_markers_in_major_compaction;
+    o.other_min_ht = p_.retention.other_min_ht;
+    o.key_bounds_lower = reinterpret_cast<const uint8_t*>(p_.retention.key_bounds_lower.data());
+    o.key_bounds_lower_len = p_.retention.key_bounds_lower.size();
+    o.key_bounds_upper = reinterpret_cast<const uint8_t*>(p_.retention.key_bounds_upper.data());
+    o.key_bounds_upper_len = p_.retention.key_bounds_upper.size();
+    o.block_size = p_.block_size; o.block_restart_interval = p_.block_restart_interval;
+    o.block_size_deviation = p_.block_size_deviation; o.index_block_size = p_.index_block_size;
+    o.min_keys_per_index_block = p_.min_keys_per_index_block; o.verify_checksums = p_.verify_checksums;
+    ybgpu_status s = ybgpu_job_create(&o, &job_);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_last_error());
+    inputs_ = inputs;
+    return Status::OK();
+  }
+
+  // REQUIRED: mutex NOT held. Replaces ProcessKeyValueCompaction; on success the output files are
+  // available through output_data_file()/output_base_file() and stats().
+  Status Run() {
+    for (const InputFile& f : inputs_) {
+      ybgpu_status s = ybgpu_job_add_input_sst(job_, f.base_file.data(), f.base_file.size(), f.data_file.data(),
+                                               f.data_file.size(), f.hybrid_time_filter);
+      if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
+    }
+    ybgpu_status s = ybgpu_job_run(job_, p_.shutting_down);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
+    uint64_t dl = 0, ml = 0;
+    s = ybgpu_job_output_sizes(job_, &dl, &ml);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
+    data_.resize(dl); base_.resize(ml);
+    s = ybgpu_job_fetch_output(job_, reinterpret_cast<uint8_t*>(&data_[0]), dl, reinterpret_cast<uint8_t*>(&base_[0]), ml);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
+    ybgpu_job_get_stats(job_, &stats_);
+    return Status::OK();
+  }
+
+  // Variant for DBs whose CompactionFeed chain must see every surviving entry on the host (e.g. the
+  // packed-row repacker): the GPU still does decode + merge + retention, the host feed gets the
+  // stream in order (compaction_job.cc:797-800 semantics: first non-OK aborts).
+  Status RunIntoFeed(CompactionFeed* feed) {
+    for (const InputFile& f : inputs_) {
+      ybgpu_status s = ybgpu_job_add_input_sst(job_, f.base_file.data(), f.base_file.size(), f.data_file.data(),
+                                               f.data_file.size(), f.hybrid_time_filter);
+      if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
+    }
+    ybgpu_status s = ybgpu_job_run(job_, p_.shutting_down);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
+    struct Ctx { CompactionFeed* feed; Status st; } ctx{feed, Status::OK()};
+    s = ybgpu_job_emit_kv_stream(job_, [](void* c, const uint8_t* k, uint64_t kl, const uint8_t* v, uint64_t vl) -> int {
+      Ctx* x = static_cast<Ctx*>(c);
+      x->st = x->feed->Feed(Slice(k, kl), Slice(v, vl));
+      return x->st.ok() ? 0 : static_cast<int>(x->st.code());
+    }, &ctx);
+    if (!ctx.st.ok()) return ctx.st;
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
+    ybgpu_job_get_stats(job_, &stats_);
+    return feed->Flush();
+  }
+
+  // REQUIRED: mutex held. In the reference this adds the output FileMetaData to a VersionEdit
+  // (compaction_job.cc:1098-1141); here it hands the caller what that edit needs.
+  struct OutputMeta { std::string smallest_key, largest_key; uint64_t smallest_seqno = 0, largest_seqno = 0, num_entries = 0; };
+  Status Install(OutputMeta* meta) {
+    uint8_t a[4096], b[4096]; uint64_t al = 0, bl = 0;
+    ybgpu_status s = ybgpu_job_output_boundaries(job_, a, &al, b, &bl);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
+    meta->smallest_key.assign(reinterpret_cast<char*>(a), al);
+    meta->largest_key.assign(reinterpret_cast<char*>(b), bl);
+    meta->smallest_seqno = stats_.smallest_seqno; meta->largest_seqno = stats_.largest_seqno;
+    meta->num_entries = stats_.num_output_records;
+    return Status::OK();
+  }
+
+  const std::string& output_data_file() const { return data_; }    // <n>.sst.sblock.0
+  const std::string& output_base_file() const { return base_; }    // <n>.sst
+  const ybgpu_job_stats& stats() const { return stats_; }
+
+ private:
+  Params p_;
+  ybgpu_job* job_ = nullptr;
+  std::vector<InputFile> inputs_;
+  std::string data_, base_;
+  ybgpu_job_stats stats_{};
+};
+
+}  // namespace ybgpu_adapter
