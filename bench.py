@@ -335,23 +335,9 @@ def main():
 
 
 def read_handles(pkg, sst):
-    """Data-block handles of a generated SST, via the product's host meta reader (exposed through
-    the table-reader probe of the C ABI)."""
-    import ctypes as C
-    import numpy as np
-    L = pkg.lib()
-    L.ybgpu_sst_meta_handles.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
-    meta = sst.meta_view()
-    n = C.c_uint64()
-    enc = C.c_int32()
-    st = L.ybgpu_sst_meta_handles(meta.ctypes.data, meta.size, None, 0, C.byref(n), C.byref(enc))
-    if st != 0:
-        raise RuntimeError("cannot parse SST meta file")
-    hs = np.zeros((n.value, 2), dtype=np.uint64)
-    st = L.ybgpu_sst_meta_handles(meta.ctypes.data, meta.size, hs.ctypes.data, n.value, C.byref(n), C.byref(enc))
-    if st != 0:
-        raise RuntimeError("cannot parse SST meta file")
-    return hs[:, 0].copy(), hs[:, 1].copy()
+    """Data-block handles of a generated SST, via the product's host meta reader."""
+    off, sz, _ = pkg.sst_block_handles(sst.meta_view())
+    return off, sz
 
 
 if __name__ == "__main__":

@@ -85,6 +85,12 @@ typedef struct ybgpu_job_options {
   uint32_t min_keys_per_index_block; /* 100 */
 
   int32_t verify_checksums;          /* verify input block CRC32C (version_set.cc:3788-3849) */
+
+  /* --- key-range sharding of one oversized compaction (the GPU analogue of
+   * subcompaction boundaries, rocksdb/db/compaction_job.cc:409-519,771-788): only entries with
+   * range_lower <= user_key < range_upper take part; the others are invisible (not counted). */
+  const uint8_t* range_lower; uint64_t range_lower_len;   /* len 0 = unbounded */
+  const uint8_t* range_upper; uint64_t range_upper_len;
   void* cuda_stream;                 /* cudaStream_t to launch on; NULL = the legacy default stream */
 } ybgpu_job_options;
 
@@ -237,6 +243,12 @@ uint64_t ybgpu_sst_raw_bytes(const ybgpu_sst* s);
  * block_based_table_reader.cc:759-765 + index walk). Call with handles=NULL to get the count. */
 ybgpu_status ybgpu_sst_meta_handles(const uint8_t* meta_file, uint64_t meta_file_len, ybgpu_block_handle* handles,
                                     uint64_t cap, uint64_t* num_handles, int32_t* key_encoding);
+
+/* Index keys of the data blocks (the separators BlockBasedTableBuilder stored: >= last key of the
+ * block, < first key of the next), concatenated into `keys` with num_handles+1 offsets. Used to
+ * slice a file by key range (key-range sharding). Call with keys=NULL to get the sizes. */
+ybgpu_status ybgpu_sst_meta_separators(const uint8_t* meta_file, uint64_t meta_file_len, uint8_t* keys, uint64_t keys_cap,
+                                       uint64_t* key_offsets, uint64_t* num_keys, uint64_t* keys_bytes);
 
 /* Library / device probe. */
 int32_t ybgpu_device_count(void);

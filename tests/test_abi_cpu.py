@@ -77,3 +77,17 @@ def test_product_generator_matches_oracle_generator(pkg):
     for x, y in zip(a, b):
         assert x.data_view().tobytes() == y.data and x.meta_view().tobytes() == y.meta
         assert x.num_entries == y.num_entries and x.raw_bytes == y.raw_bytes
+
+
+def test_meta_reader_handles_and_separators(pkg):
+    cfg = o.GenConfig(seed=6, num_rows=5000, cols=1, versions=2, num_files=1, value_len=50)
+    sst = o.Sst.generate(cfg, 0, o.TableOptions(block_size=1024, index_block_size=512, min_keys_per_index_block=4))
+    off, sz, enc = pkg.sst_block_handles(sst.meta_view())
+    eo, es = sst.block_handles()
+    assert enc == 1 and list(off) == list(eo) and list(sz) == list(es)
+    seps = pkg.sst_separators(sst.meta_view())
+    assert len(seps) == len(off)
+    kvs = sst.read_all()
+    # separator i is >= every key of block i and < first key of block i+1 (index_builder.cc:61-90)
+    assert seps == sorted(seps, key=lambda k: (k[:-8], -int.from_bytes(k[-8:], "little")))
+    assert seps[-1][:-8] >= kvs[-1][0][:-8]

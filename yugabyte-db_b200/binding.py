@@ -35,7 +35,10 @@ class JobOptions(C.Structure):
         ("key_bounds_upper", C.c_char_p), ("key_bounds_upper_len", C.c_uint64),
         ("block_size", C.c_uint32), ("block_restart_interval", C.c_int32), ("block_size_deviation", C.c_int32),
         ("output_key_encoding", C.c_int32), ("index_block_size", C.c_uint32), ("min_keys_per_index_block", C.c_uint32),
-        ("verify_checksums", C.c_int32), ("cuda_stream", C.c_void_p),
+        ("verify_checksums", C.c_int32),
+        ("range_lower", C.c_char_p), ("range_lower_len", C.c_uint64),
+        ("range_upper", C.c_char_p), ("range_upper_len", C.c_uint64),
+        ("cuda_stream", C.c_void_p),
     ]
 
 
@@ -137,7 +140,7 @@ class GpuCompactionJob:
                  retention=True, cutoff_ht=HT_MIN, cotables_cutoff_ht=HT_INVALID, table_ttl_ns=TTL_MAX_NS,
                  retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
                  restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
-                 min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None):
+                 min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b""):
         L = lib()
         o = JobOptions()
         L.ybgpu_job_options_init(C.byref(o))
@@ -159,6 +162,9 @@ class GpuCompactionJob:
         o.index_block_size, o.min_keys_per_index_block = index_block_size, min_keys_per_index_block
         o.verify_checksums = int(verify_checksums)
         o.cuda_stream = cuda_stream
+        o.range_lower, o.range_lower_len = range_lower, len(range_lower)
+        o.range_upper, o.range_upper_len = range_upper, len(range_upper)
+        self._keep2 = (range_lower, range_upper)
         self._keep = (largest_user_key, lower, upper)
         h = C.c_void_p()
         st = L.ybgpu_job_create(C.byref(o), C.byref(h))
@@ -342,3 +348,33 @@ def generate_ssts(cfg, block_size=32768, restart_interval=16, max_threads=None):
     if st != 0:
         raise YbGpuError(st, "synthetic SST generation failed")
     return [GeneratedSst(arr[i]) for i in range(cfg.num_files)]
+
+
+def sst_block_handles(meta):
+    """(offsets, sizes, key_encoding) of the data blocks of a split SST, from its metadata file."""
+    L = lib()
+    L.ybgpu_sst_meta_handles.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+    meta = np.ascontiguousarray(meta, dtype=np.uint8)
+    n, enc = C.c_uint64(), C.c_int32()
+    if L.ybgpu_sst_meta_handles(meta.ctypes.data, meta.size, None, 0, C.byref(n), C.byref(enc)) != 0:
+        raise YbGpuError(2, L.ybgpu_last_error().decode())
+    hs = np.zeros((n.value, 2), dtype=np.uint64)
+    if n.value and L.ybgpu_sst_meta_handles(meta.ctypes.data, meta.size, hs.ctypes.data, n.value, C.byref(n), C.byref(enc)) != 0:
+        raise YbGpuError(2, L.ybgpu_last_error().decode())
+    return hs[:, 0].copy(), hs[:, 1].copy(), enc.value
+
+
+def sst_separators(meta):
+    """Index (separator) internal keys of the data blocks, as a list of bytes."""
+    L = lib()
+    L.ybgpu_sst_meta_separators.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    meta = np.ascontiguousarray(meta, dtype=np.uint8)
+    n, nb = C.c_uint64(), C.c_uint64()
+    if L.ybgpu_sst_meta_separators(meta.ctypes.data, meta.size, None, 0, None, C.byref(n), C.byref(nb)) != 0:
+        raise YbGpuError(2, L.ybgpu_last_error().decode())
+    keys = np.zeros(nb.value + 1, np.uint8)
+    offs = np.zeros(n.value + 1, np.uint64)
+    if L.ybgpu_sst_meta_separators(meta.ctypes.data, meta.size, keys.ctypes.data, keys.size, offs.ctypes.data, C.byref(n), C.byref(nb)) != 0:
+        raise YbGpuError(2, L.ybgpu_last_error().decode())
+    kb = keys.tobytes()
+    return [kb[int(offs[i]):int(offs[i + 1])] for i in range(n.value)]

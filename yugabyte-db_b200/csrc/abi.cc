@@ -280,6 +280,24 @@ ybgpu_status ybgpu_sst_meta_handles(const uint8_t* meta, uint64_t len, ybgpu_blo
   return YBGPU_OK;
 }
 
+ybgpu_status ybgpu_sst_meta_separators(const uint8_t* meta, uint64_t len, uint8_t* keys, uint64_t cap, uint64_t* offs,
+                                       uint64_t* n, uint64_t* bytes) {
+  if (!meta || !n || !bytes) return YBGPU_INVALID_ARGUMENT;
+  ybgpu::host::SstMeta m;
+  std::string err = ybgpu::host::ParseSplitSstMeta(meta, len, &m);
+  if (!err.empty()) { g_last_error = err; return YBGPU_CORRUPTION; }
+  uint64_t total = 0;
+  for (auto& k : m.separators) total += k.size();
+  *n = m.separators.size(); *bytes = total;
+  if (keys && offs) {
+    if (cap < total) return YBGPU_INVALID_ARGUMENT;
+    uint64_t o = 0;
+    for (size_t i = 0; i < m.separators.size(); i++) { offs[i] = o; memcpy(keys + o, m.separators[i].data(), m.separators[i].size()); o += m.separators[i].size(); }
+    offs[m.separators.size()] = o;
+  }
+  return YBGPU_OK;
+}
+
 int32_t ybgpu_device_count(void);   // engine.cu
 const char* ybgpu_version(void) { return "ybgpu-compaction 0.1 (sm_100a)"; }
 

@@ -29,7 +29,7 @@
 namespace ybgpu {
 
 enum : uint8_t {
-  REC_F_HT_FILTERED = 0x80,   // invisible: file's HybridTime filter (docdb_rocksdb_util.cc:525-540)
+  REC_F_HT_FILTERED = 0x80,   // invisible: file's HybridTime filter (docdb_rocksdb_util.cc:525-540) or outside the job's key range
 };
 
 enum DevError : int {
@@ -408,6 +408,16 @@ YB_HD int group_prefix_len(const uint8_t* key, int ulen, bool retention) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// memcmp-with-length comparison of a raw (unpadded) byte string with another.
+YB_HD int cmp_raw(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb) {
+  const uint32_t m = la < lb ? la : lb;
+  for (uint32_t i = 0; i < m; i++) if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+
+// Key range of a range-sharded job: [lower, upper).
+struct RangeDev { uint32_t lower_len, upper_len; uint8_t lower[256], upper[256]; };
+
 // Retention parameters, precomputed on the host (docdb_compaction_context.cc:655-669).
 struct RetentionDev {
   int enabled;

@@ -70,6 +70,7 @@ struct JobParams {
   uint32_t H;                   // target rank step between tile boundaries
   uint32_t M;                   // sample stride
   RetentionDev R;
+  RangeDev range;
 };
 
 struct Desc {                   // one per input entry in merged order
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(1024) k_scan_u32_single(uint32_t* a, uint32_t 
 // interval's keys serially (the delta chain is inherently serial inside an interval) and writes
 // one record per entry.
 template <int KMAX>
-__global__ void __launch_bounds__(128) k_decode(RunView run, int S, JobDev* J) {
+__global__ void __launch_bounds__(128) k_decode(RunView run, int S, const RangeDev* range, JobDev* J) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -231,6 +232,10 @@ __global__ void __launch_bounds__(128) k_decode(RunView run, int S, JobDev* J) {
           uint32_t htl = doc_ht_len_from_end(keybuf, ulen);
           uint64_t ht;
           if (htl && doc_ht_decode(keybuf + ulen - htl, htl, &ht) && ht > run.ht_filter) flags |= REC_F_HT_FILTERED;
+        }
+        if (range && (range->lower_len | range->upper_len)) {
+          if (range->lower_len && cmp_raw(keybuf, ulen, range->lower, range->lower_len) < 0) flags |= REC_F_HT_FILTERED;
+          if (range->upper_len && cmp_raw(keybuf, ulen, range->upper, range->upper_len) >= 0) flags |= REC_F_HT_FILTERED;
         }
         const uint8_t vfirst = vlen ? blk[p] : 0;
         uint4 tr;
@@ -889,6 +894,9 @@ Engine::Engine(const ybgpu_job_options& o) : opt_(o), impl_(new Impl) {
   if (o.largest_user_key && o.has_largest_user_key) largest_.assign(o.largest_user_key, o.largest_user_key + o.largest_user_key_len);
   if (o.key_bounds_lower_len) lower_.assign(o.key_bounds_lower, o.key_bounds_lower + o.key_bounds_lower_len);
   if (o.key_bounds_upper_len) upper_.assign(o.key_bounds_upper, o.key_bounds_upper + o.key_bounds_upper_len);
+  if (o.range_lower_len) range_lower_.assign(o.range_lower, o.range_lower + o.range_lower_len);
+  if (o.range_upper_len) range_upper_.assign(o.range_upper, o.range_upper + o.range_upper_len);
+  opt_.range_lower = nullptr; opt_.range_upper = nullptr;
   opt_.largest_user_key = nullptr; opt_.key_bounds_lower = nullptr; opt_.key_bounds_upper = nullptr;
   memset(&stats_, 0, sizeof(stats_));
 }
@@ -1073,15 +1081,24 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   const int Sfinal = std::max(S, 32);
 
   // ---- K1': decode
+  RangeDev* d_range = nullptr;
+  if (!range_lower_.empty() || !range_upper_.empty()) {
+    if (range_lower_.size() > 255 || range_upper_.size() > 255) return Fail(YBGPU_NOT_SUPPORTED, "range bounds longer than 255 bytes");
+    RangeDev hr{};
+    hr.lower_len = static_cast<uint32_t>(range_lower_.size()); memcpy(hr.lower, range_lower_.data(), range_lower_.size());
+    hr.upper_len = static_cast<uint32_t>(range_upper_.size()); memcpy(hr.upper, range_upper_.data(), range_upper_.size());
+    CUDA_TRY(DevAlloc(&I.allocs, &d_range, 1));
+    CUDA_TRY(cudaMemcpyAsync(d_range, &hr, sizeof(hr), cudaMemcpyHostToDevice, I.stream));
+  }
   for (int r = 0; r < k; r++) {
     RunView& rv = I.runs[r];
     CUDA_TRY(DevAlloc(&I.allocs, &rv.rec, static_cast<size_t>(rv.n_entries) * Sfinal + 16));
     CUDA_TRY(DevAlloc(&I.allocs, &rv.val_off, static_cast<size_t>(rv.n_entries) + 1));
     if (rv.nb == 0) continue;
     int grid = GridFor(static_cast<uint64_t>(rv.nb) * 32, 128, sms);
-    if (max_ikey <= 128) k_decode<128><<<grid, 128, 0, I.stream>>>(rv, Sfinal, I.dJ);
-    else if (max_ikey <= 320) k_decode<320><<<grid, 128, 0, I.stream>>>(rv, Sfinal, I.dJ);
-    else k_decode<1024><<<grid, 128, 0, I.stream>>>(rv, Sfinal, I.dJ);
+    if (max_ikey <= 128) k_decode<128><<<grid, 128, 0, I.stream>>>(rv, Sfinal, d_range, I.dJ);
+    else if (max_ikey <= 320) k_decode<320><<<grid, 128, 0, I.stream>>>(rv, Sfinal, d_range, I.dJ);
+    else k_decode<1024><<<grid, 128, 0, I.stream>>>(rv, Sfinal, d_range, I.dJ);
     launches++;
   }
   CUDA_TRY(cudaGetLastError());

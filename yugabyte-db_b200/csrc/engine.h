@@ -38,7 +38,7 @@ class Engine {
   struct Impl;
   ybgpu_job_options opt_;
   Impl* impl_;
-  std::vector<uint8_t> largest_, lower_, upper_;
+  std::vector<uint8_t> largest_, lower_, upper_, range_lower_, range_upper_;
   ybgpu_job_stats stats_;
   std::string error_;
   bool ran_ = false;

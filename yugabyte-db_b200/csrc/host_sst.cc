@@ -124,9 +124,13 @@ std::string ParseSplitSstMeta(const uint8_t* meta, uint64_t len, SstMeta* out) {
     std::vector<Handle> level{index};
     for (int lv = 0; lv < out->index_levels; lv++) {
       std::vector<Handle> next;
+      const bool last_level = lv + 1 == out->index_levels;
       for (const Handle& h : level) {
         BlockCursor c(BlockAt(meta, len, h), h.size);
-        while (c.Next()) { const uint8_t* vp = c.val; next.push_back(ReadHandle(&vp, c.val + c.vlen)); }
+        while (c.Next()) {
+          const uint8_t* vp = c.val; next.push_back(ReadHandle(&vp, c.val + c.vlen));
+          if (last_level) out->separators.push_back(c.key);
+        }
       }
       level.swap(next);
     }

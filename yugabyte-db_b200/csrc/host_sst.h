@@ -25,6 +25,7 @@ inline uint32_t Crc32cMask(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xa282
 
 struct SstMeta {
   std::vector<Handle> data_blocks;   // key order
+  std::vector<std::string> separators;   // index key of every data block (>= its last key, < next block's first key)
   int key_encoding = 1;
   int index_levels = 1;
   std::map<std::string, std::string> properties;
