@@ -209,17 +209,28 @@ def main():
         dev_files.append(t)
     stream_ptr = torch.cuda.current_stream().cuda_stream
 
+    host_ms = {"create": 0.0, "add_inputs": 0.0, "run": 0.0, "close": 0.0}
+
     def step_resident():
+        t0 = time.perf_counter()
         job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=False, cuda_stream=stream_ptr)
+        t1 = time.perf_counter()
         for t, s, (off, sz) in zip(dev_files, ssts, handles):
             job.add_input_device(t.data_ptr() + 16, s.data_view().size, off, sz)
+        t2 = time.perf_counter()
         st = job.run()
+        t3 = time.perf_counter()
         d = st.as_dict()
         job.close()
+        t4 = time.perf_counter()
+        for k, v in zip(("create", "add_inputs", "run", "close"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            host_ms[k] += v * 1e3
         return d
 
     for _ in range(args.warmup):
         step_resident()
+    for k in host_ms:
+        host_ms[k] = 0.0
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -324,6 +335,7 @@ def main():
                                   "achieved": round(pipeline_achieved, 1), "frac": round(pipeline_achieved / hbm_peak, 4)},
                      "phase_ms": {names[i]: round(phases[i] * 1e3, 3) for i in range(5)}},
         "setup": {"generate_s": round(gen_s, 1)},
+        "host_ms_per_step": {k: round(v / args.steps, 3) for k, v in host_ms.items()},
     }
     if e2e:
         line["e2e"] = e2e

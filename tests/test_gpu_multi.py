@@ -46,10 +46,10 @@ def _ranges_worker(rank, world, port, q):
 
 
 def test_key_range_sharded_compaction_two_gpus():
-    import torch
-    import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
+    pkg = importlib.import_module("yugabyte-db_b200")
+    if pkg.device_count() < 2:                     # checked without importing torch (cold import is slow)
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]

@@ -539,6 +539,8 @@ __global__ void __launch_bounds__(256) k_crc_blocks(uint8_t* file, const unsigne
 constexpr int ENC_THREADS = 256;
 constexpr int ENC_EMAX = 512;      // entries per pass through the shared-memory table
 constexpr int ENC_ITEMS = 4096;    // direct item->entry map size (64 KB of values per pass)
+constexpr int ENC_EM_S = 256;          // entries per pass in k_encode_smem (= ENC_THREADS)
+constexpr int ENC_ITEMS_SMEM = 2560;   // same for k_encode_smem (a 36 KB image has at most ~2400 value chunks)
 
 // 16 bytes starting at an arbitrary address: two aligned 16-byte loads + funnel shift. Reads
 // [src & ~15, (src & ~15) + 32).
@@ -722,20 +724,20 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
 // memory; HBM sees only 16-byte vector loads of the source values and 16-byte vector stores of
 // the finished image; the CRC is computed from the shared-memory image. Blocks larger than
 // ENC_SMEM_CAP are left to k_encode_fused (only_big = 1).
-constexpr uint32_t ENC_SMEM_CAP = 40 * 1024;       // bytes of block image (contents + trailer) per CTA
+constexpr uint32_t ENC_SMEM_CAP = 36 * 1024;       // bytes of block image (contents + trailer) per CTA
 
-__global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_smem(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
+__global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
                                                                const unsigned long long* block_off, uint8_t* out) {
   extern __shared__ __align__(16) uint8_t img_raw[];    // ENC_SMEM_CAP + 32
   __shared__ uint32_t tab[4][256];
   __shared__ uint32_t x2n[32];
   __shared__ uint32_t warp_crc[ENC_THREADS / 32];
   __shared__ uint32_t warp_sums[32];
-  __shared__ unsigned long long t_src[ENC_EMAX];
-  __shared__ uint32_t t_dsto[ENC_EMAX];
-  __shared__ uint32_t t_len[ENC_EMAX];
-  __shared__ uint32_t t_chunk[ENC_EMAX + 1];
-  __shared__ uint16_t t_item[ENC_ITEMS];
+  __shared__ unsigned long long t_src[ENC_EM_S];
+  __shared__ uint32_t t_dsto[ENC_EM_S];
+  __shared__ uint32_t t_len[ENC_EM_S];
+  __shared__ uint32_t t_chunk[ENC_EM_S + 1];
+  __shared__ uint16_t t_item[ENC_ITEMS_SMEM];
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
   if (threadIdx.x < 32) x2n[threadIdx.x] = g_crc_x2n[threadIdx.x];
   __syncthreads();
@@ -756,8 +758,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_smem(EncView E, int S
     const uint32_t tl = (e - 1 - s) >> E.ri_shift;
     const uint32_t body = static_cast<uint32_t>((E.P[e] - Ps) + (E.QQ[s + (tl << E.ri_shift)] - Qs));
 
-    for (uint32_t p0 = s; p0 < e; p0 += ENC_EMAX) {
-      const uint32_t pn = min(static_cast<uint32_t>(ENC_EMAX), e - p0);
+    for (uint32_t p0 = s; p0 < e; p0 += ENC_EM_S) {
+      const uint32_t pn = min(static_cast<uint32_t>(ENC_EM_S), e - p0);
       // ---- phase A: one thread per entry. Header + key delta bytes into the image, value copy job
       // into the table. All metadata loads of all entries are in flight together.
       for (uint32_t q = threadIdx.x; q < pn; q += blockDim.x) {
@@ -807,25 +809,20 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_smem(EncView E, int S
       }
       __syncthreads();
       // items = destination-aligned 16-byte chunks of every value (image and HBM agree mod 16)
-      uint32_t c0 = 0, c1 = 0;
+      uint32_t c0 = 0;
       {
-        const uint32_t q0 = threadIdx.x * 2, q1 = q0 + 1;
+        const uint32_t q0 = threadIdx.x;
         if (q0 < pn && t_len[q0]) { const uint32_t d0 = t_dsto[q0] + mis; c0 = (((d0 + t_len[q0] + 15) & ~15u) - (d0 & ~15u)) >> 4; }
-        if (q1 < pn && t_len[q1]) { const uint32_t d0 = t_dsto[q1] + mis; c1 = (((d0 + t_len[q1] + 15) & ~15u) - (d0 & ~15u)) >> 4; }
       }
       uint32_t total_items;
-      const uint32_t ibase = block_exclusive_scan(c0 + c1, warp_sums, &total_items);
-      {
-        const uint32_t q0 = threadIdx.x * 2;
-        t_chunk[q0] = ibase; t_chunk[q0 + 1] = ibase + c0;
-        if (threadIdx.x == blockDim.x - 1) t_chunk[ENC_EMAX] = ibase + c0 + c1;
-      }
+      const uint32_t ibase = block_exclusive_scan(c0, warp_sums, &total_items);
+      t_chunk[threadIdx.x] = ibase;
+      if (threadIdx.x == blockDim.x - 1) t_chunk[ENC_EM_S] = ibase + c0;
       __syncthreads();
-      const bool direct = total_items <= ENC_ITEMS;
+      const bool direct = total_items <= ENC_ITEMS_SMEM;
       if (direct) {
-        const uint32_t q0 = threadIdx.x * 2;
-        for (uint32_t q = q0; q < q0 + 2 && q < pn; q++)
-          for (uint32_t it = t_chunk[q]; it < t_chunk[q + 1]; it++) t_item[it] = static_cast<uint16_t>(q);
+        const uint32_t q = threadIdx.x;
+        if (q < pn) for (uint32_t it = t_chunk[q]; it < t_chunk[q + 1]; it++) t_item[it] = static_cast<uint16_t>(q);
         __syncthreads();
       }
       // ---- phase B: value bytes, one 16-byte source vector per item

@@ -351,6 +351,8 @@ struct MergeView {
 };
 
 constexpr int MERGE_THREADS = 256;
+constexpr int RANK_C = 8;        // coarse stride of the two-level rank search
+constexpr int RANK_KMAX = 16;    // two-level search used for k <= RANK_KMAX runs
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
   // scan of one value per thread; all threads must call. Returns exclusive prefix.
@@ -387,6 +389,8 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
   uint32_t* rw_slot = seg_start + MAX_RUNS + 1;                     // sorted pos -> rewrite slot (cap)
   unsigned long long* pfx = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(rw_slot + cap) + 7) & ~static_cast<uintptr_t>(7));   // local idx -> sort prefix (cap)
   unsigned long long* pfx2 = pfx + cap;             // second 8 bytes of the 16-byte sort prefix
+  uint32_t* cbase = reinterpret_cast<uint32_t*>(pfx2 + cap);   // [k+1] coarse index base per segment
+  uint16_t* crank = reinterpret_cast<uint16_t*>(cbase + MAX_RUNS + 1);   // [(cap/RANK_C + k) * RANK_KMAX] coarse ranks
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t sh_T, sh_ngroups, sh_any_filtered;
   __shared__ int sh_err;
@@ -453,32 +457,62 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, 
   }
   __syncthreads();
 
-  // (b) rank every record among the other segments (rank-based k-way merge) and parse its group
+  // (b) rank every record among the other segments (rank-based k-way merge) and parse its group.
+  // Two levels: every RANK_C-th record of a segment is ranked by a full binary search; the others
+  // only search between the ranks of their two coarse neighbours (ranks are monotone inside a
+  // segment), which cuts the probes by ~40 %.
+  const bool two_level = k <= RANK_KMAX;
+  auto search = [&](const uint8_t* e, unsigned long long pe, unsigned long long pe2, int r, int r2, uint32_t lo, uint32_t hi) {
+    const uint32_t b2 = seg_start[r2];
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      const unsigned long long pm = pfx[b2 + mid];
+      bool less;
+      if (pm != pe) less = pm < pe;
+      else if (pfx2[b2 + mid] != pe2) less = pfx2[b2 + mid] < pe2;
+      else {
+        const int c = cmp_records(recs + static_cast<size_t>(SS) * (b2 + mid), e, S);
+        less = (r2 < r) ? (c <= 0) : (c < 0);
+      }
+      if (less) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  if (two_level) {
+    // coarse index of record p of segment r: cbase[r] + p / RANK_C
+    if (threadIdx.x == 0) { uint32_t acc = 0; for (int r = 0; r < k; r++) { cbase[r] = acc; acc += (seg_start[r + 1] - seg_start[r] + RANK_C - 1) / RANK_C; } cbase[k] = acc; }
+    __syncthreads();
+    const uint32_t ncoarse = cbase[k];
+    for (uint32_t t = threadIdx.x; t < ncoarse * k; t += blockDim.x) {
+      const uint32_t ci = t / k; const int r2 = static_cast<int>(t - ci * k);
+      int r = 0;
+      while (cbase[r + 1] <= ci) r++;
+      if (r2 == r) continue;
+      const uint32_t p = (ci - cbase[r]) * RANK_C;
+      const uint32_t li = seg_start[r] + p;
+      crank[ci * RANK_KMAX + r2] = static_cast<uint16_t>(search(recs + static_cast<size_t>(SS) * li, pfx[li], pfx2[li], r, r2, 0, seg_start[r2 + 1] - seg_start[r2]));
+    }
+    __syncthreads();
+  }
   for (uint32_t li = threadIdx.x; li < T; li += blockDim.x) {
     int r = 0;
     while (seg_start[r + 1] <= li) r++;
     const uint32_t p = li - seg_start[r];
-    const uint8_t* e = recs + static_cast<size_t>(SS) * (li);
+    const uint8_t* e = recs + static_cast<size_t>(SS) * li;
     if (p > 0 && cmp_records(e - SS, e, S) >= 0) dev_fail(J, DEV_ERR_UNSORTED, tile);
     const unsigned long long pe = pfx[li], pe2 = pfx2[li];
     uint32_t rank = p;
+    const uint32_t nseg = seg_start[r + 1] - seg_start[r];
+    const uint32_t ci = two_level ? cbase[r] + p / RANK_C : 0;
+    const bool is_coarse = two_level && (p % RANK_C) == 0;
+    const bool has_next_coarse = two_level && (p / RANK_C + 1) * RANK_C < nseg;
     for (int r2 = 0; r2 < k; r2++) {
       if (r2 == r) continue;
-      const uint32_t b2 = seg_start[r2];
-      uint32_t lo = 0, hi = seg_start[r2 + 1] - b2;
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        const unsigned long long pm = pfx[b2 + mid];
-        bool less;
-        if (pm != pe) less = pm < pe;
-        else if (pfx2[b2 + mid] != pe2) less = pfx2[b2 + mid] < pe2;
-        else {
-          const int c = cmp_records(recs + static_cast<size_t>(SS) * (b2 + mid), e, S);
-          less = (r2 < r) ? (c <= 0) : (c < 0);
-        }
-        if (less) lo = mid + 1; else hi = mid;
-      }
-      rank += lo;
+      const uint32_t n2 = seg_start[r2 + 1] - seg_start[r2];
+      if (is_coarse) { rank += crank[ci * RANK_KMAX + r2]; continue; }
+      uint32_t lo = 0, hi = n2;
+      if (two_level) { lo = crank[ci * RANK_KMAX + r2]; if (has_next_coarse) hi = crank[(ci + 1) * RANK_KMAX + r2]; }
+      rank += search(e, pe, pe2, r, r2, lo, hi);
     }
     order[rank] = static_cast<uint16_t>(li);
     const int g = group_prefix_len(e, rec_ulen(e, S), prm->R.enabled != 0);
@@ -1109,7 +1143,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   JobParams hp{};
   hp.S = Sfinal; hp.k = k; hp.bottommost = opt_.bottommost_level; hp.last_sequence = opt_.last_sequence;
   // smem budget: ~110 KB per CTA (records + per-record side arrays) so two CTAs fit one SM
-  uint32_t cap = (110u * 1024u - 1024u) / (Sfinal + 8 + 14 + 16);
+  uint32_t cap = (110u * 1024u - 2048u) / (Sfinal + 8 + 14 + 16 + 4);
   cap = std::min(cap, 4096u) & ~1u;
   hp.tile_cap = cap;
   hp.H = std::max(1u, cap / 2);
@@ -1190,7 +1224,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   mv.runs = I.dRuns; mv.tile_lo = d_tile_lo; mv.tile_rank = d_tile_rank; mv.desc = d_desc;
   mv.rewrites = d_rw; mv.rewrite_cap = rewrite_cap; mv.n_tiles = n_tiles;
   const size_t smem = static_cast<size_t>(cap) * (Sfinal + 8) + (cap * 4 + 4) * 2 + ((cap + 15) & ~15u) +
-                      (2 * MAX_RUNS + 1) * 4 + static_cast<size_t>(cap) * 4 + static_cast<size_t>(cap) * 16 + 64;
+                      (2 * MAX_RUNS + 1) * 4 + static_cast<size_t>(cap) * 4 + static_cast<size_t>(cap) * 16 + (MAX_RUNS + 1) * 4 +
+                      (static_cast<size_t>(cap) / RANK_C + RANK_KMAX + 1) * RANK_KMAX * 2 + 64;
   CUDA_TRY(cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   k_merge_filter<<<n_tiles, MERGE_THREADS, smem, I.stream>>>(mv, I.dP, I.dJ);
   launches++;
