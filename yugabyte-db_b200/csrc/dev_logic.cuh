@@ -295,7 +295,25 @@ YB_HD_NOINLINE int key_entry_size_flat(const uint8_t* p, int n) {   // everythin
       int i = 1;
       if (i >= n) return -DEV_ERR_BAD_KEY;                  // "Encoded string is empty"
       for (;;) {
-        while (i < n && p[i] != endb) i++;
+        // find the next terminator byte: bytewise to 8-byte alignment, then 8 bytes at a time
+        while (i < n && p[i] != endb && (reinterpret_cast<uintptr_t>(p + i) & 7)) i++;
+        if (i < n && p[i] != endb) {
+          while (i + 8 <= n) {
+            uint64_t w = ld_u64_aligned(p + i);
+            if (endb) w = ~w;
+            const uint64_t z = (w - 0x0101010101010101ull) & ~w & 0x8080808080808080ull;
+            if (z) {
+#if defined(__CUDA_ARCH__)
+              i += (__ffsll(static_cast<long long>(z)) - 1) >> 3;
+#else
+              i += __builtin_ctzll(z) >> 3;
+#endif
+              break;
+            }
+            i += 8;
+          }
+          while (i < n && p[i] != endb) i++;
+        }
         if (i >= n - 1) return -DEV_ERR_BAD_KEY;            // not terminated / single terminator byte
         if (p[i + 1] == endb) return i + 2;
         if (p[i + 1] != (endb ^ 1)) return -DEV_ERR_BAD_KEY;

@@ -779,11 +779,17 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
         p += put_varint(p, vlen);
         const uint64_t suffix = kept_suffix(rec, d, S);
         {
-          // key bytes [shared, klen): read the record as aligned 8-byte words
+          // key bytes [shared, klen): the (at most 4) aligned 8-byte record words that hold the
+          // non-shared user-key bytes are fetched together, longer deltas fall back to a loop
+          const uint32_t wfirst = shared >> 3;
+          uint64_t kw[4];
+#pragma unroll
+          for (int t = 0; t < 4; t++) kw[t] = (8 * (wfirst + t) < ulen) ? ld_u64_aligned(rec + 8 * (wfirst + t)) : 0;
           uint32_t i = shared;
           while (i < klen) {
             if (i < ulen) {
-              const uint64_t wv = ld_u64_aligned(rec + (i & ~7u));
+              const uint32_t wi = (i >> 3) - wfirst;
+              const uint64_t wv = wi < 4 ? (wi == 0 ? kw[0] : wi == 1 ? kw[1] : wi == 2 ? kw[2] : kw[3]) : ld_u64_aligned(rec + (i & ~7u));
               const uint32_t lim = min(ulen, (i & ~7u) + 8);
               for (; i < lim; i++) *p++ = static_cast<uint8_t>(wv >> (8 * (i & 7)));
             } else { *p++ = static_cast<uint8_t>(suffix >> (8 * (i - ulen))); i++; }
@@ -812,7 +818,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
       uint32_t c0 = 0;
       {
         const uint32_t q0 = threadIdx.x;
-        if (q0 < pn && t_len[q0]) { const uint32_t d0 = t_dsto[q0] + mis; c0 = (((d0 + t_len[q0] + 15) & ~15u) - (d0 & ~15u)) >> 4; }
+        // number of 16-byte destination-aligned chunks lying entirely inside the value
+        if (q0 < pn && t_len[q0]) {
+          const uint32_t d0 = t_dsto[q0] + mis, d1 = d0 + t_len[q0];
+          const uint32_t fa = (d0 + 15) & ~15u, fb = d1 & ~15u;
+          c0 = fb > fa ? (fb - fa) >> 4 : 0;
+        }
       }
       uint32_t total_items;
       const uint32_t ibase = block_exclusive_scan(c0, warp_sums, &total_items);
@@ -826,6 +837,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
         __syncthreads();
       }
       // ---- phase B: value bytes, one 16-byte source vector per item
+#pragma unroll 4
       for (uint32_t it = threadIdx.x; it < total_items; it += blockDim.x) {
         uint32_t q;
         if (direct) q = t_item[it];
@@ -835,19 +847,29 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
           q = lo;
         }
         // offsets below are relative to img_raw (16-byte aligned): r = image offset + mis
-        const uint32_t d0 = t_dsto[q] + mis, d1 = d0 + t_len[q];
-        const uint32_t A = (d0 & ~15u) + 16u * (it - t_chunk[q]);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(t_src[q]) + (static_cast<int>(A) - static_cast<int>(d0));
-        const uint4 x = load_unaligned16(src);
-        if (A >= d0 && A + 16 <= d1) {
-          *reinterpret_cast<uint4*>(img_raw + A) = x;
-        } else {
+        const uint32_t d0 = t_dsto[q] + mis;
+        const uint32_t A = ((d0 + 15) & ~15u) + 16u * (it - t_chunk[q]);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(t_src[q]) + (A - d0);
+        *reinterpret_cast<uint4*>(img_raw + A) = load_unaligned16(src);
+      }
+      // value edges (bytes before the first / after the last full chunk): two small jobs per entry
+      for (uint32_t t = threadIdx.x; t < 2 * pn; t += blockDim.x) {
+        const uint32_t q = t >> 1;
+        const uint32_t len = t_len[q];
+        if (!len) continue;
+        const uint32_t d0 = t_dsto[q] + mis, d1 = d0 + len;
+        const uint32_t fa = (d0 + 15) & ~15u, fb = d1 & ~15u;
+        uint32_t lo, hi;                           // byte range [lo, hi) of this edge, in img_raw offsets
+        if (fb > fa) { if (t & 1) { lo = fb; hi = d1; } else { lo = d0; hi = fa; } }
+        else { if (t & 1) continue; lo = d0; hi = d1; }          // short value: one job copies it all
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(t_src[q]) + (lo - d0);
+        while (lo < hi) {
+          const uint4 x = load_unaligned16(src);
           const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+          const uint32_t nb = min(16u, hi - lo);
 #pragma unroll
-          for (int bb = 0; bb < 16; bb++) {
-            const uint32_t a = A + bb;
-            if (a >= d0 && a < d1) img_raw[a] = static_cast<uint8_t>(w[bb >> 2] >> (8 * (bb & 3)));
-          }
+          for (int bb = 0; bb < 16; bb++) if (bb < static_cast<int>(nb)) img_raw[lo + bb] = static_cast<uint8_t>(w[bb >> 2] >> (8 * (bb & 3)));
+          lo += nb; src += nb;
         }
       }
       __syncthreads();
@@ -866,9 +888,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
       const uint32_t head = (4 - ((mis) & 3)) & 3;                  // bytes before the first aligned word of img
       const uint32_t hb = head < L ? head : L;
       const uint32_t nwords = (L - hb) >> 2, tail = (L - hb) & 3;
-      uint32_t W = (nwords + ENC_THREADS - 1) / ENC_THREADS;
+      constexpr uint32_t CRC_T = 64;                                // fewer, longer ranges: one GF(2) shift per range
+      uint32_t W = (nwords + CRC_T - 1) / CRC_T;
       W |= 1;                                                       // odd stride in words
-      const uint32_t w0 = min(W * threadIdx.x, nwords), w1 = min(w0 + W, nwords);
+      const uint32_t w0 = threadIdx.x < CRC_T ? min(W * threadIdx.x, nwords) : nwords, w1 = min(w0 + W, nwords);
       const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + hb);
       uint32_t acc = 0;
       if (w1 > w0) {

@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
 
 namespace ybgpu {
 
@@ -251,6 +253,98 @@ __global__ void __launch_bounds__(128) k_decode(RunView run, int S, const RangeD
   }
 }
 
+// K1' (single launch): all files at once. A warp takes DEC_WB consecutive data blocks of one file
+// and spreads their restart intervals over its 32 lanes (a 32 KB block of 300-byte entries has only
+// ~7 intervals, so one block per warp would leave most lanes idle).
+constexpr int DEC_WB = 4;
+template <int KMAX>
+__global__ void __launch_bounds__(128) k_decode_all(const RunView* runs, const uint32_t* run_group_base /*[k+1]*/, int k, int S,
+                                                   const RangeDev* range, JobDev* J) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  __align__(16) uint8_t keybuf[KMAX];
+  const uint32_t total_groups = run_group_base[k];
+  for (uint32_t g = warp; g < total_groups; g += nwarps) {
+    int ri_ = 0;
+    while (run_group_base[ri_ + 1] <= g) ri_++;
+    const RunView& run = runs[ri_];
+    const uint32_t b0 = (g - run_group_base[ri_]) * DEC_WB;
+    const uint32_t nbk = min(static_cast<uint32_t>(DEC_WB), run.nb - b0);
+    // restart counts of the group's blocks (lanes 0..nbk-1 read them), exclusive prefix by shuffles
+    uint32_t nres = 0;
+    if (lane < static_cast<int>(nbk)) {
+      const uint8_t* blk = run.data + run.blk_off[b0 + lane];
+      nres = ldg_u32_unaligned(blk + run.blk_size[b0 + lane] - 4);
+    }
+    uint32_t pre[DEC_WB + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int q = 0; q < DEC_WB; q++) pre[q + 1] = pre[q] + __shfl_sync(0xffffffffu, nres, q);
+    const uint32_t total_int = pre[DEC_WB];
+    const uint32_t ri = run.restart_interval ? run.restart_interval : 1;
+    for (uint32_t t = lane; t < total_int; t += 32) {
+      int q = 0;
+#pragma unroll
+      for (int z = 1; z < DEC_WB; z++) if (t >= pre[z]) q = z;
+      const uint32_t b = b0 + q, r = t - pre[q];
+      const uint64_t boff = run.blk_off[b];
+      const uint8_t* blk = run.data + boff;
+      const uint32_t size = run.blk_size[b];
+      const uint32_t num_restarts = pre[q + 1] - pre[q];
+      const uint32_t restarts_off = size - 4 - 4 * num_restarts;
+      uint32_t p = ldg_u32_unaligned(blk + restarts_off + 4 * r);
+      const uint32_t end = (r + 1 < num_restarts) ? ldg_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
+      uint32_t idx = run.blk_count[b] + r * ri;
+      while (p < end) {
+        uint32_t shared, non_shared, vlen;
+        int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
+        if (!h) break;                                  // validated by k_prepass
+        p += h;
+        const uint32_t klen = shared + non_shared;
+        if (klen > KMAX) { dev_fail(J, DEV_ERR_KEY_TOO_LONG, b); break; }
+        for (uint32_t i = 0; i < non_shared; i++) keybuf[shared + i] = blk[p + i];
+        p += non_shared;
+        const uint32_t ulen = klen - 8;
+        uint8_t* rec = run.rec + static_cast<size_t>(idx) * S;
+        const int key_vecs = (S - 16) >> 4;
+        for (int w = 0; w < key_vecs; w++) {
+          uint4 v = *reinterpret_cast<const uint4*>(keybuf + 16 * w);
+          const int valid = static_cast<int>(ulen) - 16 * w;
+          uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int vb = valid - 4 * c;
+            if (vb <= 0) vw[c] = 0; else if (vb < 4) vw[c] &= (1u << (8 * vb)) - 1;
+          }
+          reinterpret_cast<uint4*>(rec)[w] = v;
+        }
+        uint64_t suffix = 0;
+        for (int i = 7; i >= 0; i--) suffix = (suffix << 8) | keybuf[ulen + i];
+        uint8_t flags = 0;
+        if (run.ht_filter != 0xfffffffffffffffeull) {
+          uint32_t htl = doc_ht_len_from_end(keybuf, ulen);
+          uint64_t ht;
+          if (htl && doc_ht_decode(keybuf + ulen - htl, htl, &ht) && ht > run.ht_filter) flags |= REC_F_HT_FILTERED;
+        }
+        if (range && (range->lower_len | range->upper_len)) {
+          if (range->lower_len && cmp_raw(keybuf, ulen, range->lower, range->lower_len) < 0) flags |= REC_F_HT_FILTERED;
+          if (range->upper_len && cmp_raw(keybuf, ulen, range->upper, range->upper_len) >= 0) flags |= REC_F_HT_FILTERED;
+        }
+        const uint8_t vfirst = vlen ? blk[p] : 0;
+        uint4 tr;
+        tr.x = static_cast<uint32_t>(suffix); tr.y = static_cast<uint32_t>(suffix >> 32);
+        tr.z = ulen | (static_cast<uint32_t>(vfirst) << 16) | (static_cast<uint32_t>(flags) << 24);
+        tr.w = vlen;
+        *reinterpret_cast<uint4*>(rec + S - 16) = tr;
+        run.val_off[idx] = boff + p;
+        p += vlen;
+        idx++;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: partition. Sample s of run r is record s*M of that run; its splitter is the row-group prefix
 // of that record. pos[s_global * k + r2] = lower bound of the splitter in run r2.
@@ -373,7 +467,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
   return excl;
 }
 
-__global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge_filter(MergeView V, const JobParams* prm, JobDev* J) {
+__global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, const JobParams* prm, JobDev* J) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int S = prm->S, k = prm->k;
   const int SS = S + 8;                       // smem record stride: +8 B so that consecutive records start in different banks
@@ -1070,6 +1164,16 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   CUDA_TRY(cudaEventRecord(I.ev0, I.stream));
   uint32_t phase_launch_mark[8] = {};
   int phase = 0;
+  const bool trace = getenv("YBGPU_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(I.stream);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ybgpu trace] %-14s %8.3f ms (host wall, after stream sync)\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
+  tick("setup");
   auto end_phase = [&]() -> cudaError_t {
     phase_launch_mark[phase] = launches;
     return cudaEventRecord(I.phase_ev[phase++], I.stream);
@@ -1097,6 +1201,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(end_phase());
   if (ybgpu_status s = CheckDeviceError("block scan")) return s;
+  tick("block scan");
   if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
   uint64_t N = 0;
   for (int r = 0; r < k; r++) {
@@ -1124,15 +1229,22 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(DevAlloc(&I.allocs, &d_range, 1));
     CUDA_TRY(cudaMemcpyAsync(d_range, &hr, sizeof(hr), cudaMemcpyHostToDevice, I.stream));
   }
+  std::vector<uint32_t> group_base(k + 1, 0);
   for (int r = 0; r < k; r++) {
     RunView& rv = I.runs[r];
     CUDA_TRY(DevAlloc(&I.allocs, &rv.rec, static_cast<size_t>(rv.n_entries) * Sfinal + 16));
     CUDA_TRY(DevAlloc(&I.allocs, &rv.val_off, static_cast<size_t>(rv.n_entries) + 1));
-    if (rv.nb == 0) continue;
-    int grid = GridFor(static_cast<uint64_t>(rv.nb) * 32, 128, sms);
-    if (max_ikey <= 128) k_decode<128><<<grid, 128, 0, I.stream>>>(rv, Sfinal, d_range, I.dJ);
-    else if (max_ikey <= 320) k_decode<320><<<grid, 128, 0, I.stream>>>(rv, Sfinal, d_range, I.dJ);
-    else k_decode<1024><<<grid, 128, 0, I.stream>>>(rv, Sfinal, d_range, I.dJ);
+    group_base[r + 1] = group_base[r] + (rv.nb + DEC_WB - 1) / DEC_WB;
+  }
+  CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+  if (group_base[k]) {
+    uint32_t* d_group_base = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_group_base, k + 1));
+    CUDA_TRY(cudaMemcpyAsync(d_group_base, group_base.data(), 4 * (k + 1), cudaMemcpyHostToDevice, I.stream));
+    const int grid = GridFor(static_cast<uint64_t>(group_base[k]) * 32, 128, sms);
+    if (max_ikey <= 128) k_decode_all<128><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
+    else if (max_ikey <= 320) k_decode_all<320><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
+    else k_decode_all<1024><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
     launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -1142,8 +1254,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   // ---- job parameters
   JobParams hp{};
   hp.S = Sfinal; hp.k = k; hp.bottommost = opt_.bottommost_level; hp.last_sequence = opt_.last_sequence;
-  // smem budget: ~110 KB per CTA (records + per-record side arrays) so two CTAs fit one SM
-  uint32_t cap = (110u * 1024u - 2048u) / (Sfinal + 8 + 14 + 16 + 4);
+  // smem budget: ~74 KB per CTA (records + per-record side arrays) so three CTAs fit one SM
+  uint32_t cap = (74u * 1024u - 2048u) / (Sfinal + 8 + 14 + 16 + 4);
   cap = std::min(cap, 4096u) & ~1u;
   hp.tile_cap = cap;
   hp.H = std::max(1u, cap / 2);
@@ -1182,6 +1294,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   memcpy(hp.largest, largest_.data(), largest_.size());
   CUDA_TRY(cudaMemcpyAsync(I.dP, &hp, sizeof(hp), cudaMemcpyHostToDevice, I.stream));
   if (ybgpu_status s = CheckDeviceError("decode")) return s;
+  tick("decode");
   if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
 
   if (N == 0) {
@@ -1213,6 +1326,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(end_phase());
   if (ybgpu_status s = CheckDeviceError("partition")) return s;
+  tick("partition");
   const uint32_t n_tiles = I.hJ.n_tiles;
 
   // ---- K3: merge + filter
@@ -1232,6 +1346,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(end_phase());
   if (ybgpu_status s = CheckDeviceError("merge")) return s;
+  tick("merge");
   if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
 
   // ---- K4: survivor scan + dense list; K5: block encode
@@ -1329,6 +1444,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   CUDA_TRY(cudaEventRecord(I.ev1, I.stream));
   CUDA_TRY(cudaGetLastError());
   if (ybgpu_status s = CheckDeviceError("encode")) return s;
+  tick("encode");
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, I.ev0, I.ev1));
   for (int ph = 0; ph < phase; ph++) {
