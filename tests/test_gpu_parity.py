@@ -217,3 +217,16 @@ def test_gpu_block_encoder_cut_rules(pkg):
         job.run()
         data, meta = job.fetch_output()
         assert data.tobytes() == exp.sst().data and meta.tobytes() == exp.sst().meta
+
+
+def test_three_shared_parts_inputs(pkg):
+    """kKeyDeltaEncodingThreeSharedParts (YCQL's data-block encoding, block_builder.cc:248-333) inputs,
+    mixed with shared-prefix inputs in one job."""
+    cfg = o.GenConfig(seed=19, num_rows=6000, cols=3, versions=4, num_files=4, value_len=48, tombstone_per_1024=50)
+    ssts = [o.Sst.generate(cfg, f, o.TableOptions(block_size=2048, key_encoding=2 if f != 2 else 1)) for f in range(4)]
+    assert [s.key_encoding for s in ssts] == [2, 2, 1, 2]
+    check(pkg, ssts, block_size=4096, cutoff_ht=o.ht_from_micros(cfg.base_micros + 2500))
+    runs = w.random_docdb_runs(4, n_runs=3, n_rows=200)
+    ssts = [o.Sst.build(r, o.TableOptions(block_size=512, key_encoding=2)) for r in runs]
+    for kw in w.param_grid()[:4]:
+        check(pkg, ssts, block_size=1024, **kw)

@@ -531,6 +531,74 @@ YB_HD int parse_entry_header(const uint8_t* p, uint32_t avail, uint32_t* shared,
   return static_cast<int>(i);
 }
 
+// rocksdb/table/block_internal.h:51-162 DecodeEntryThreeSharedParts for
+// kKeyDeltaEncodingThreeSharedParts. Returns the header length (0 on error).
+struct TspHeader {
+  uint32_t shared_prefix, ns1, ns2, last_size, vlen;
+  int64_t d1, d2;            // non_shared_{1,2}_size_delta
+  uint64_t last_inc;         // 0 or 0x100 (seq + 1)
+  bool something_shared;
+};
+YB_HD int tsp_get_varint(const uint8_t* p, uint32_t avail, uint64_t* out) {
+  uint64_t r = 0; uint32_t i = 0;
+  for (int shift = 0; shift <= 63 && i < avail; shift += 7) {
+    const uint64_t b = p[i++];
+    if (b & 128) r |= (b & 127) << shift; else { r |= b << shift; *out = r; return static_cast<int>(i); }
+  }
+  return 0;
+}
+YB_HD int parse_entry_header_tsp(const uint8_t* p, uint32_t avail, TspHeader* h) {
+  if (avail < 2) return 0;
+  uint64_t e1; int n = tsp_get_varint(p, avail, &e1);
+  if (!n) return 0;
+  uint32_t i = static_cast<uint32_t>(n);
+  h->vlen = static_cast<uint32_t>(e1 >> 2);
+  h->last_inc = (e1 & 2) << 7;
+  h->shared_prefix = 0; h->ns1 = 0; h->ns2 = 0; h->last_size = 0; h->d1 = 0; h->d2 = 0;
+  uint64_t v;
+  if (e1 & 1) {
+    n = tsp_get_varint(p + i, avail - i, &v); if (!n) return 0; i += n;
+    h->shared_prefix = static_cast<uint32_t>(v); h->last_size = 8; h->something_shared = true; h->ns1 = 1; h->ns2 = 1;
+    return static_cast<int>(i);
+  }
+  if (i >= avail) return 0;
+  const uint8_t e2 = p[i++];
+  if ((e2 & 1) == 0) {
+    h->something_shared = false;
+    if (e2 == 0) { n = tsp_get_varint(p + i, avail - i, &v); if (!n) return 0; i += n; h->ns1 = static_cast<uint32_t>(v); }
+    else h->ns1 = e2 >> 1;
+    return static_cast<int>(i);
+  }
+  h->something_shared = true;
+  if ((e2 & 2) == 0) {
+    h->last_size = 8; h->d2 = (e2 >> 2) & 1; h->ns1 = (e2 >> 3) & 7; h->ns2 = (e2 >> 6) & 3;
+  } else {
+    h->last_size = (e2 & 4) ? 8 : 0;
+    n = tsp_get_varint(p + i, avail - i, &v); if (!n) return 0; i += n; h->ns1 = static_cast<uint32_t>(v);
+    if (e2 & 8) { n = fast_varint_decode(p + i, static_cast<int>(avail - i), &h->d1); if (!n) return 0; i += n; }
+    if (e2 & 16) { n = tsp_get_varint(p + i, avail - i, &v); if (!n) return 0; i += n; h->ns2 = static_cast<uint32_t>(v); }
+    if (e2 & 32) { n = fast_varint_decode(p + i, static_cast<int>(avail - i), &h->d2); if (!n) return 0; i += n; }
+  }
+  n = tsp_get_varint(p + i, avail - i, &v); if (!n) return 0; i += n;
+  h->shared_prefix = static_cast<uint32_t>(v);
+  return static_cast<int>(i);
+}
+// Key length and the source offset of the shared middle (rocksdb/table/block.cc:313-343): returns
+// false on corruption. prev_len = length of the previous key.
+YB_HD bool tsp_key_layout(const TspHeader& h, uint32_t prev_len, uint32_t* klen, uint32_t* mid_src, uint32_t* mid_len) {
+  if (!h.something_shared) { *klen = h.ns1; *mid_src = 0; *mid_len = 0; return true; }
+  const int64_t prev_mid_start = static_cast<int64_t>(h.shared_prefix) + h.ns1 - h.d1;
+  const int64_t prev_ns2 = static_cast<int64_t>(h.ns2) - h.d2;
+  const int64_t except_mid = prev_mid_start + prev_ns2 + h.last_size;
+  if (prev_mid_start < 0 || prev_ns2 < 0 || static_cast<int64_t>(prev_len) < except_mid) return false;
+  const uint32_t mid = prev_len - static_cast<uint32_t>(except_mid);
+  if (h.shared_prefix + mid + h.last_size == 0) return false;
+  if (h.shared_prefix > prev_len) return false;
+  *mid_src = static_cast<uint32_t>(prev_mid_start); *mid_len = mid;
+  *klen = h.shared_prefix + h.ns1 + mid + h.ns2 + h.last_size;
+  return true;
+}
+
 YB_HD int encode_control_fields(const ControlFields& cf, uint8_t* out) {   // value.cc:118-132
   int i = 0;
   if (cf.merge_flags) { out[i++] = 'k'; i += fast_uvarint_encode(cf.merge_flags, out + i); }

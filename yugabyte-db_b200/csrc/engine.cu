@@ -46,6 +46,7 @@ struct RunView {
   uint32_t n_entries;
   uint32_t restart_interval;    // entries per restart interval in this file
   uint32_t gid_base;            // global entry id of entry 0
+  uint32_t key_encoding;        // rocksdb::KeyValueEncodingFormat of this file's data blocks
   uint64_t ht_filter;
 };
 
@@ -122,6 +123,18 @@ __global__ void __launch_bounds__(256) k_prepass(RunView run, int run_idx, JobDe
       uint32_t n = 0, klen = 0;
       while (p < end) {
         uint32_t shared, non_shared, vlen;
+        if (run.key_encoding == 2) {
+          TspHeader th; uint32_t nk, ms, ml;
+          int h = parse_entry_header_tsp(blk + p, end - p, &th);
+          if (!h || (n == 0 && th.something_shared) || !tsp_key_layout(th, klen, &nk, &ms, &ml) ||
+              static_cast<uint64_t>(p) + h + th.ns1 + th.ns2 + th.vlen > end) { dev_fail(J, DEV_ERR_BAD_ENTRY, b); n = 0; break; }
+          klen = nk;
+          if (klen < 8) { dev_fail(J, DEV_ERR_SHORT_KEY, b); break; }
+          max_klen = max(max_klen, klen);
+          p += h + th.ns1 + th.ns2 + th.vlen;
+          n++;
+          continue;
+        }
         int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
         if (!h || shared > klen || (n == 0 && shared != 0) ||
             static_cast<uint64_t>(p) + h + non_shared + vlen > end) { dev_fail(J, DEV_ERR_BAD_ENTRY, b); n = 0; break; }
@@ -296,15 +309,41 @@ __global__ void __launch_bounds__(128) k_decode_all(const RunView* runs, const u
       uint32_t p = ldg_u32_unaligned(blk + restarts_off + 4 * r);
       const uint32_t end = (r + 1 < num_restarts) ? ldg_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
       uint32_t idx = run.blk_count[b] + r * ri;
+      uint32_t prev_klen = 0;
       while (p < end) {
-        uint32_t shared, non_shared, vlen;
-        int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
-        if (!h) break;                                  // validated by k_prepass
-        p += h;
-        const uint32_t klen = shared + non_shared;
-        if (klen > KMAX) { dev_fail(J, DEV_ERR_KEY_TOO_LONG, b); break; }
-        for (uint32_t i = 0; i < non_shared; i++) keybuf[shared + i] = blk[p + i];
-        p += non_shared;
+        uint32_t shared, non_shared, vlen, klen;
+        if (run.key_encoding == 2) {
+          // kKeyDeltaEncodingThreeSharedParts (table/block.cc:294-343, db/dbformat.h:413-470)
+          TspHeader th; uint32_t ms, ml;
+          int h = parse_entry_header_tsp(blk + p, end - p, &th);
+          if (!h || !tsp_key_layout(th, prev_klen, &klen, &ms, &ml)) break;      // validated by k_prepass
+          p += h;
+          if (klen > KMAX) { dev_fail(J, DEV_ERR_KEY_TOO_LONG, b); break; }
+          if (!th.something_shared) {
+            for (uint32_t i = 0; i < th.ns1; i++) keybuf[i] = blk[p + i];
+          } else {
+            __align__(16) uint8_t tmp[KMAX];
+            uint64_t last = 0;
+            if (th.last_size) { for (int i = 7; i >= 0; i--) last = (last << 8) | keybuf[prev_klen - 8 + i]; last += th.last_inc; }
+            uint32_t n2 = th.shared_prefix;
+            for (uint32_t i = 0; i < th.ns1; i++) tmp[n2++] = blk[p + i];
+            for (uint32_t i = 0; i < ml; i++) tmp[n2++] = keybuf[ms + i];
+            for (uint32_t i = 0; i < th.ns2; i++) tmp[n2++] = blk[p + th.ns1 + i];
+            if (th.last_size) for (int i = 0; i < 8; i++) tmp[n2++] = static_cast<uint8_t>(last >> (8 * i));
+            for (uint32_t i = th.shared_prefix; i < klen; i++) keybuf[i] = tmp[i];
+          }
+          p += th.ns1 + th.ns2;
+          vlen = th.vlen;
+        } else {
+          int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
+          if (!h) break;                                  // validated by k_prepass
+          p += h;
+          klen = shared + non_shared;
+          if (klen > KMAX) { dev_fail(J, DEV_ERR_KEY_TOO_LONG, b); break; }
+          for (uint32_t i = 0; i < non_shared; i++) keybuf[shared + i] = blk[p + i];
+          p += non_shared;
+        }
+        prev_klen = klen;
         const uint32_t ulen = klen - 8;
         uint8_t* rec = run.rec + static_cast<size_t>(idx) * S;
         const int key_vecs = (S - 16) >> 4;
@@ -1082,8 +1121,8 @@ ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_blo
                               int key_encoding, uint64_t ht_filter, bool on_device) {
   if (ran_) return Fail(YBGPU_ILLEGAL_STATE, "add_input after run");
   if (impl_->runs.size() >= MAX_RUNS) return Fail(YBGPU_NOT_SUPPORTED, "too many input files");
-  if (key_encoding != YBGPU_KEY_ENCODING_SHARED_PREFIX)
-    return Fail(YBGPU_NOT_SUPPORTED, "only kKeyDeltaEncodingSharedPrefix inputs are decoded on the GPU so far");
+  if (key_encoding != YBGPU_KEY_ENCODING_SHARED_PREFIX && key_encoding != YBGPU_KEY_ENCODING_THREE_SHARED_PARTS)
+    return Fail(YBGPU_INVALID_ARGUMENT, "unknown data block key encoding");
   if (nh >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "too many data blocks in one file");
   CUDA_TRY(cudaSetDevice(opt_.device));
   g_alloc_stream = impl_->stream;
@@ -1114,6 +1153,7 @@ ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_blo
   CUDA_TRY(cudaStreamSynchronize(impl_->stream));   // host vectors go out of scope
   rv.blk_off = doff; rv.blk_size = dsz; rv.blk_count = dcnt; rv.nb = static_cast<uint32_t>(nh);
   rv.ht_filter = ht_filter;
+  rv.key_encoding = static_cast<uint32_t>(key_encoding);
   impl_->runs.push_back(rv);
   return YBGPU_OK;
 }
