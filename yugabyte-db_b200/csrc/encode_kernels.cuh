@@ -337,65 +337,6 @@ __device__ __forceinline__ int put_varint(uint8_t* p, uint32_t v) {
   return n;
 }
 
-// Encode: one CTA per output block, warps take entries round-robin.
-__global__ void __launch_bounds__(128) k_encode_blocks(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
-                                                      const unsigned long long* block_off, uint8_t* out) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
-    const uint32_t s = block_first[b], e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
-    uint8_t* blk = out + block_off[b];
-    const unsigned long long Ps = E.P[s];
-    const unsigned long long Qs = E.QQ[s] - E.D[s];
-    for (uint32_t j = s + wid; j < e; j += nw) {
-      const uint32_t t = (j - s) >> E.ri_shift;
-      const bool restart = ((j - s) & (E.ri - 1)) == 0;
-      // offset of entry j = bytes of entries s..j-1
-      unsigned long long off = E.P[j] - Ps;
-      if (j > s) { const uint32_t tp = (j - 1 - s) >> E.ri_shift; off += E.QQ[s + (tp << E.ri_shift)] - Qs; }
-      const Desc d = E.kept[j];
-      const uint8_t* rec = kept_rec(E, d, S);
-      const uint32_t klen = d.klen, ulen = klen - 8u, vlen = d.vlen_out;
-      const uint32_t shared = restart ? 0u : E.shared[j];
-      uint8_t hdr[16];
-      int hl = put_varint(hdr, shared);
-      hl += put_varint(hdr + hl, klen - shared);
-      hl += put_varint(hdr + hl, vlen);
-      uint8_t* p = blk + off;
-      if (lane < hl) p[lane] = hdr[lane];
-      p += hl;
-      // key delta: internal key bytes [shared, klen)
-      const uint64_t suffix = kept_suffix(rec, d, S);
-      for (uint32_t q = shared + lane; q < klen; q += 32)
-        p[q - shared] = q < ulen ? rec[q] : static_cast<uint8_t>(suffix >> (8 * (q - ulen)));
-      p += klen - shared;
-      // value
-      const RunView& run = E.runs[d.run];
-      const uint8_t* vs = run.data + run.val_off[d.gid - run.gid_base];
-      if (d.flags & ENT_VAL_TOMBSTONE) { if (lane == 0) p[0] = 'X'; }
-      else if (d.flags & ENT_VAL_REENCODE) {
-        const ValueRewrite& rw = E.rewrites[d.rewrite_slot];
-        if (lane < rw.prefix_len) p[lane] = rw.prefix[lane];
-        const uint32_t rest = vlen - rw.prefix_len;
-        for (uint32_t q = lane; q < rest; q += 32) p[rw.prefix_len + q] = vs[rw.skip + q];
-      } else warp_copy(p, vs, vlen, lane);
-      if (restart && lane == 0) {
-        // restart array entry t lives after all entries; its position needs the block's entry bytes
-        const uint32_t tl = (e - 1 - s) >> E.ri_shift;
-        const unsigned long long body = (E.P[e] - Ps) + (E.QQ[s + (tl << E.ri_shift)] - Qs);
-        uint8_t* r = blk + body + 4ull * t;
-        const uint32_t o32 = static_cast<uint32_t>(off);
-        r[0] = static_cast<uint8_t>(o32); r[1] = static_cast<uint8_t>(o32 >> 8); r[2] = static_cast<uint8_t>(o32 >> 16); r[3] = static_cast<uint8_t>(o32 >> 24);
-        if (j == s) {
-          const uint32_t nres = tl + 1;
-          uint8_t* q = blk + body + 4ull * nres;
-          q[0] = static_cast<uint8_t>(nres); q[1] = static_cast<uint8_t>(nres >> 8); q[2] = static_cast<uint8_t>(nres >> 16); q[3] = static_cast<uint8_t>(nres >> 24);
-          q[4] = 0;   // trailer type byte: kNoCompression
-        }
-      }
-    }
-  }
-}
-
 // ---- CRC32C -------------------------------------------------------------------------------------
 // Reflected polynomial 0x82F63B78 (rocksdb/util/crc32c.cc). Each lane runs slicing-by-4 over its
 // word range of the block, the 32 partial CRCs are combined with

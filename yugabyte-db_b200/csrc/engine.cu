@@ -197,75 +197,6 @@ __global__ void __launch_bounds__(1024) k_scan_u32_single(uint32_t* a, uint32_t 
   if (threadIdx.x == 0) *total = carry;
 }
 
-// K1': decode. One warp per data block, one lane per restart interval; each lane rebuilds its
-// interval's keys serially (the delta chain is inherently serial inside an interval) and writes
-// one record per entry.
-template <int KMAX>
-__global__ void __launch_bounds__(128) k_decode(RunView run, int S, const RangeDev* range, JobDev* J) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  __align__(16) uint8_t keybuf[KMAX];
-  const uint32_t ri = run.restart_interval ? run.restart_interval : 1;
-  for (uint32_t b = warp; b < run.nb; b += nwarps) {
-    const uint64_t boff = run.blk_off[b];
-    const uint8_t* blk = run.data + boff;
-    const uint32_t size = run.blk_size[b];
-    const uint32_t num_restarts = ldg_u32_unaligned(blk + size - 4);
-    const uint32_t restarts_off = size - 4 - 4 * num_restarts;
-    const uint32_t base = run.blk_count[b];            // exclusive prefix after the scan
-    for (uint32_t r = lane; r < num_restarts; r += 32) {
-      uint32_t p = ldg_u32_unaligned(blk + restarts_off + 4 * r);
-      const uint32_t end = (r + 1 < num_restarts) ? ldg_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
-      uint32_t idx = base + r * ri;
-      while (p < end) {
-        uint32_t shared, non_shared, vlen;
-        int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
-        if (!h) break;                                  // validated by k_prepass
-        p += h;
-        const uint32_t klen = shared + non_shared;
-        if (klen > KMAX) { dev_fail(J, DEV_ERR_KEY_TOO_LONG, b); break; }
-        for (uint32_t i = 0; i < non_shared; i++) keybuf[shared + i] = blk[p + i];
-        p += non_shared;
-        const uint32_t ulen = klen - 8;
-        uint8_t* rec = run.rec + static_cast<size_t>(idx) * S;
-        const int key_words = (S - 16) >> 2;
-        for (int w = 0; w < key_words; w++) {
-          uint32_t v = 0;
-          const int valid = static_cast<int>(ulen) - 4 * w;
-          if (valid > 0) {
-            v = *reinterpret_cast<const uint32_t*>(keybuf + 4 * w);
-            if (valid < 4) v &= (1u << (8 * valid)) - 1;
-          }
-          reinterpret_cast<uint32_t*>(rec)[w] = v;
-        }
-        uint64_t suffix = 0;
-        for (int i = 7; i >= 0; i--) suffix = (suffix << 8) | keybuf[ulen + i];
-        uint8_t flags = 0;
-        if (run.ht_filter != 0xfffffffffffffffeull) {
-          // HybridTimeFilteringIterator::Satisfied (docdb_rocksdb_util.cc:525-540)
-          uint32_t htl = doc_ht_len_from_end(keybuf, ulen);
-          uint64_t ht;
-          if (htl && doc_ht_decode(keybuf + ulen - htl, htl, &ht) && ht > run.ht_filter) flags |= REC_F_HT_FILTERED;
-        }
-        if (range && (range->lower_len | range->upper_len)) {
-          if (range->lower_len && cmp_raw(keybuf, ulen, range->lower, range->lower_len) < 0) flags |= REC_F_HT_FILTERED;
-          if (range->upper_len && cmp_raw(keybuf, ulen, range->upper, range->upper_len) >= 0) flags |= REC_F_HT_FILTERED;
-        }
-        const uint8_t vfirst = vlen ? blk[p] : 0;
-        uint4 tr;
-        tr.x = static_cast<uint32_t>(suffix); tr.y = static_cast<uint32_t>(suffix >> 32);
-        tr.z = ulen | (static_cast<uint32_t>(vfirst) << 16) | (static_cast<uint32_t>(flags) << 24);
-        tr.w = vlen;
-        *reinterpret_cast<uint4*>(rec + S - 16) = tr;
-        run.val_off[idx] = boff + p;
-        p += vlen;
-        idx++;
-      }
-    }
-  }
-}
-
 // K1' (single launch): all files at once. A warp takes DEC_WB consecutive data blocks of one file
 // and spreads their restart intervals over its 32 lanes (a 32 KB block of 300-byte entries has only
 // ~7 intervals, so one block per warp would leave most lanes idle).
