@@ -18,7 +18,7 @@ def lib():
         L = C.CDLL(os.path.join(_DIR, "libhostharness.so"))
         vp, u64 = C.c_void_p, C.c_uint64
         L.hh_compact.argtypes = [C.c_int, vp, vp, vp, vp, vp, C.c_int, u64, C.c_int64, C.c_int, u64, C.c_int, u64,
-                                 C.c_char_p, u64, C.c_char_p, u64, C.c_char_p, u64]
+                                 C.c_char_p, u64, C.c_char_p, u64, C.c_char_p, u64, u64]
         for f in ("hh_keys", "hh_vals", "hh_koff", "hh_voff"):
             getattr(L, f).restype = vp
         L.hh_num.restype = u64
@@ -43,7 +43,8 @@ def compact_runs(runs, params):
     rc = L.hh_compact(len(runs), starts.ctypes.data, kb.ctypes.data, ko.ctypes.data, vb.ctypes.data, vo.ctypes.data,
                       params.retention_enabled, params.primary_cutoff_ht, params.table_ttl_ns,
                       params.retain_delete_markers, params.other_min_ht, params.bottommost_level,
-                      params.last_sequence, luk, len(luk), params._lo, len(params._lo), params._up, len(params._up))
+                      params.last_sequence, luk, len(luk), params._lo, len(params._lo), params._up, len(params._up),
+                      params.cotables_cutoff_ht)
     if rc != 0:
         raise RuntimeError("device logic error %d" % rc)
     n = L.hh_num()

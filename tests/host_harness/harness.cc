@@ -23,7 +23,7 @@ extern "C" {
 int hh_compact(int n_runs, const uint64_t* run_start, const uint8_t* keys, const uint64_t* koff, const uint8_t* vals,
                const uint64_t* voff, int retention, uint64_t cutoff_ht, int64_t table_ttl_ns, int retain_markers,
                uint64_t other_min_ht, int bottommost, uint64_t last_sequence, const uint8_t* largest, uint64_t largest_len,
-               const uint8_t* lower, uint64_t lower_len, const uint8_t* upper, uint64_t upper_len) {
+               const uint8_t* lower, uint64_t lower_len, const uint8_t* upper, uint64_t upper_len, uint64_t cotables_cutoff_ht) {
   delete g_out; g_out = new Out;
   const uint64_t n = run_start[n_runs];
   size_t max_ulen = 0;
@@ -54,6 +54,8 @@ int hh_compact(int n_runs, const uint64_t* run_start, const uint8_t* keys, const
   R.cutoff_enc.n = static_cast<uint8_t>(doc_ht_encode(cutoff_ht, 0xffffffffu, R.cutoff_enc.b));
   R.min_other_enc.n = static_cast<uint8_t>(doc_ht_encode(retain_markers ? 0 : other_min_ht, 0, R.min_other_enc.b));
   R.ht_min_enc.n = static_cast<uint8_t>(doc_ht_encode(0, 0, R.ht_min_enc.b));
+  R.has_cotables_cutoff = cotables_cutoff_ht != 0xfffffffffffffffeull; R.cotables_cutoff_ht = cotables_cutoff_ht;
+  if (R.has_cotables_cutoff) R.cotables_cutoff_enc.n = static_cast<uint8_t>(doc_ht_encode(cotables_cutoff_ht, 0xffffffffu, R.cotables_cutoff_enc.b));
   R.lower_len = static_cast<uint32_t>(lower_len); memcpy(R.lower, lower, lower_len);
   R.upper_len = static_cast<uint32_t>(upper_len); memcpy(R.upper, upper, upper_len);
 
@@ -67,7 +69,32 @@ int hh_compact(int n_runs, const uint64_t* run_start, const uint8_t* keys, const
     const int g = group_prefix_len(e, ulen, retention != 0);
     if (g < 0) return -g;
     const bool new_group = !prev_group || g != prev_g || common_prefix_len(e, g, prev_group, g) < static_cast<uint32_t>(g);
-    if (new_group) { feed_state_reset(&st); prev_group = e; prev_g = g; }
+    if (new_group) {
+      feed_state_reset(&st); prev_group = e; prev_g = g;
+      // cotable / colocated rows: seed slot 0 from the table's tombstone entries, as the tile kernel does
+      if (retention && ulen && (e[0] == 'y' || e[0] == '0')) {
+        const int id = dockey_id_size(e, ulen);
+        if (id > 0 && static_cast<uint32_t>(id) < ulen && e[id] != '!') {
+          FeedState ts; feed_state_reset(&ts);
+          const uint8_t* prev_t = nullptr; bool any = false;
+          for (uint64_t x = 0; x < n; x++) {
+            const uint8_t* c = base + size_t(order[x]) * S;
+            const uint32_t cl = rec_ulen(c, S);
+            if (cl < static_cast<uint32_t>(id) + 1 || memcmp(c, e, id) != 0 || c[id] != '!') continue;
+            if (prev_t && cmp_user_keys(prev_t, rec_ulen(prev_t, S), c, cl) == 0) { continue; }
+            prev_t = c;
+            const uint64_t sfx = rec_suffix(c, S);
+            if ((sfx & 0xff) == 0 && bottommost && (sfx >> 8) <= last_sequence) continue;
+            ValueRewrite rw2{};
+            const uint32_t vl = rec_vlen(c, S);
+            int d2 = feed_step(&ts, R, c, cl, rec_vfirst(c, S), has_control_fields(rec_vfirst(c, S)) ? vals + voff[order[x]] : nullptr, vl, &rw2);
+            if (d2 < 0) return -d2;
+            any = true;
+          }
+          if (any && ts.n_ow >= 1 && ts.n_ends == 1) feed_state_seed(&st, e, id, ts.ow[0]);
+        }
+      }
+    }
     const bool first_occ = !prev_rec || cmp_user_keys(prev_rec, rec_ulen(prev_rec, S), e, ulen) != 0;
     prev_rec = e;
     if (!first_occ) continue;

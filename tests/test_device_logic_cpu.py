@@ -56,5 +56,20 @@ def test_group_prefix_len():
     d2 = dk.doc_key(["only-range"])
     k2 = dk.sub_doc_key(d2, [], micros=o.YB_EPOCH_US + 5)
     assert L.hh_group_prefix_len(k2, len(k2), 1) == len(d2)
-    co = dk.sub_doc_key(dk.doc_key(["r"], colocation=5), [dk.kcol(1)], micros=o.YB_EPOCH_US)
-    assert L.hh_group_prefix_len(co, len(co), 1) == -14      # DEV_ERR_COTABLE (loud, not silent)
+    cd = dk.doc_key(["r"], colocation=5)
+    co = dk.sub_doc_key(cd, [dk.kcol(1)], micros=o.YB_EPOCH_US)
+    assert L.hh_group_prefix_len(co, len(co), 1) == len(cd)
+    tt = dk.table_tombstone_key(colocation=5, micros=o.YB_EPOCH_US)
+    assert L.hh_group_prefix_len(tt, len(tt), 1) == 6         # id + '!'
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_cotables_and_colocated_tables(seed):
+    runs = w.random_cotable_runs(seed, n_runs=1 + seed % 4, colocated=seed % 2 == 0)
+    for kw in w.param_grid():
+        got, exp = both(runs, **kw)
+        assert got == exp, kw
+    if seed % 2:        # cotables cutoff (master sys catalog): 'y' keys use their own history cutoff
+        kw = dict(bottommost=True, cutoff_ht=o.ht_from_micros(w.BASE_US + 35), cotables_cutoff_ht=o.ht_from_micros(w.BASE_US + 85))
+        got, exp = both(runs, **kw)
+        assert got == exp

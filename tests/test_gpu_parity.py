@@ -163,8 +163,9 @@ def test_edge_cases(pkg):
 
 
 def test_errors_are_loud(pkg):
-    d = dk.doc_key(["r"], colocation=7)
-    run = [(o.ikey(dk.sub_doc_key(d, [dk.kcol(1)], micros=o.YB_EPOCH_US + 1), 1 << 50), dk.vstr("x"))]
+    # packed rows need the tablet's SchemaPackingProvider: NotSupported, never silently mishandled
+    d = dk.doc_key(["r"])
+    run = [(o.ikey(dk.sub_doc_key(d, [], micros=o.YB_EPOCH_US + 1), 1 << 50), b"z\x01packed")]
     job = pkg.GpuCompactionJob()
     s = runs_to_ssts([run])[0]
     job.add_input_sst(s.meta_view(), s.data_view())
@@ -230,3 +231,16 @@ def test_three_shared_parts_inputs(pkg):
     ssts = [o.Sst.build(r, o.TableOptions(block_size=512, key_encoding=2)) for r in runs]
     for kw in w.param_grid()[:4]:
         check(pkg, ssts, block_size=1024, **kw)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cotables_and_colocated_tables(pkg, seed):
+    """Table tombstones (id ! # HT) shadow every older row of their table across row groups and
+    tiles (slot 0 of the overwrite stack, docdb_compaction_context.cc:999-1024)."""
+    runs = w.random_cotable_runs(seed, n_runs=1 + seed % 4, n_tables=6, rows_per_table=60, colocated=seed % 2 == 0)
+    ssts = runs_to_ssts(runs, 512)
+    for kw in w.param_grid()[:6]:
+        check(pkg, ssts, block_size=1024, **kw)
+    if seed % 2:
+        check(pkg, ssts, block_size=1024, bottommost=True, cutoff_ht=o.ht_from_micros(w.BASE_US + 35),
+              cotables_cutoff_ht=o.ht_from_micros(w.BASE_US + 85))

@@ -82,3 +82,40 @@ def param_grid():
     out.append(dict(bottommost=True, cutoff_ht=cut[3], other_min_ht=o.ht_from_micros(BASE_US + 50), table_ttl_ns=20 * 10**3))
     out.append(dict(bottommost=False, cutoff_ht=cut[1], other_min_ht=o.HT_MIN, table_ttl_ns=10**9))
     return out
+
+
+def random_cotable_runs(seed, n_runs=3, n_tables=4, rows_per_table=12, colocated=True, n_ht=12):
+    """Colocated ('0' + u32 id) or cotable ('y' + 16-byte uuid) tables with optional table tombstones
+    (id ! # HT) at several hybrid times, mixed with plain rows of an id-less table."""
+    rng = random.Random(seed)
+    runs = [[] for _ in range(n_runs)]
+    seq = [(1 << 50) + (r << 30) for r in range(n_runs)]
+
+    def put(user_key, value):
+        r = rng.randrange(n_runs)
+        seq[r] += 1
+        runs[r].append((o.ikey(user_key, seq[r]), value))
+    used = set()
+    for t in range(n_tables):
+        kw = dict(colocation=1000 + t) if colocated else dict(cotable=bytes([(t * 37 + j) % 251 + 1 for j in range(16)]))
+        n_tomb = rng.choice([0, 1, 2, 3])
+        for _ in range(n_tomb):
+            k = dk.table_tombstone_key(micros=BASE_US + rng.randrange(n_ht) * 10, **kw)
+            if k not in used:
+                used.add(k)
+                put(k, dk.TOMBSTONE)
+        for row in range(rows_per_table):
+            d = dk.doc_key(["r%03d" % row], **kw) if rng.random() < 0.5 else dk.doc_key([row], hash_code=rng.randrange(65536), hashed=["h%d" % row], **kw)
+            for c in range(rng.randrange(1, 4)):
+                for _ in range(rng.randrange(1, 4)):
+                    uk = dk.sub_doc_key(d, [dk.kcol(c + 1)], ht=(BASE_US + rng.randrange(n_ht) * 10, rng.randrange(2), 0))
+                    if uk in used:
+                        continue
+                    used.add(uk)
+                    put(uk, dk.TOMBSTONE if rng.random() < 0.15 else dk.vstr("v%d" % rng.randrange(1000)))
+    for row in range(10):
+        uk = dk.sub_doc_key(dk.doc_key(["plain%d" % row]), [dk.kcol(1)], ht=(BASE_US + rng.randrange(n_ht) * 10, 0, 0))
+        if uk not in used:
+            used.add(uk)
+            put(uk, dk.vstr("p"))
+    return [sort_run(r) for r in runs]

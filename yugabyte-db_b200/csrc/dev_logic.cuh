@@ -419,7 +419,7 @@ YB_HD int group_prefix_len(const uint8_t* key, int ulen, bool retention) {
   if (t == 6) return -DEV_ERR_UNSUPPORTED_KEY;       // vector index metadata: tablet-side filter
   int id = dockey_id_size(key, ulen);
   if (id < 0) return id;
-  if (id > 0) return -DEV_ERR_COTABLE;
+  if (id > 0 && id < ulen && key[id] == '!') return id + 1;    // table tombstone: id ! # HT (doc_key.cc:973-982)
   int body = dockey_body_size(key + id, ulen - id);
   if (body < 0) return body;
   return id + body;
@@ -442,6 +442,9 @@ struct RetentionDev {
   uint64_t cutoff_ht;               // primary_cutoff_ht
   int64_t table_ttl_ns;
   EncHt cutoff_enc;                 // (cutoff, kMaxWriteId)
+  int has_cotables_cutoff;          // HistoryCutoff::cotables_cutoff_ht set (master's sys catalog)
+  uint64_t cotables_cutoff_ht;
+  EncHt cotables_cutoff_enc;
   EncHt min_other_enc;              // (retain_delete_markers ? kMin : other_min, kMinWriteId)
   EncHt ht_min_enc;                 // DocHybridTime::kMin
   uint32_t lower_len, upper_len;    // key bounds
@@ -479,6 +482,13 @@ struct FeedState {
 };
 
 YB_HD void feed_state_reset(FeedState* s) { s->prev_key = nullptr; s->prev_len = 0; s->n_ends = 0; s->n_ow = 0; s->within_merge_block = false; }
+// State of the reference feed when it reaches a row of cotable / colocation id `id` after that
+// table's tombstone entries (id ! # HT) were processed: prev_key_ = the id bytes, one component
+// end, and slot 0 of the overwrite stack = the table-level overwrite (docdb_compaction_context.cc:
+// 999-1024: slot 0 survives row changes, only new_stack_size == 1 entries replace it).
+YB_HD void feed_state_seed(FeedState* s, const uint8_t* key, uint32_t id_len, const Overwrite& ow0) {
+  s->prev_key = key; s->prev_len = id_len; s->n_ends = 1; s->ends[0] = id_len; s->n_ow = 1; s->ow[0] = ow0; s->within_merge_block = false;
+}
 
 // dockv/value.cc:77-115 DecodeControlFields over the head of a value. `v`/`n` is the value (the
 // caller guarantees at least min(n, 64) readable bytes). Returns the control-field byte count or
@@ -704,9 +714,10 @@ YB_HD_NOINLINE int feed_step(FeedState* st, const RetentionDev& R, const uint8_t
   if (st->n_ow) popped = st->ow[st->n_ow - 1].exp;
   if (st->n_ow == new_stack) st->n_ow--;                                              // :1087
   if (same != st->ends[st->n_ends - 1]) st->within_merge_block = false;               // :1092
-  // :1103-1114 — cotables cutoff only applies to 'y' keys, which group_prefix_len rejects for now.
-  const EncHt& chosen = R.cutoff_enc;
-  const uint64_t chosen_ht = R.cutoff_ht;
+  // :1103-1114 — cotables on the master use their own cutoff
+  const bool use_cot = key_type == 'y' && R.has_cotables_cutoff;
+  const EncHt& chosen = use_cot ? R.cotables_cutoff_enc : R.cutoff_enc;
+  const uint64_t chosen_ht = use_cot ? R.cotables_cutoff_ht : R.cutoff_ht;
   // LastExpiration() after the possible pop.
   Expiration cur_last; cur_last.ttl_ns = kMaxTtlNs; cur_last.write_ht = 0;
   if (st->n_ow) cur_last = st->ow[st->n_ow - 1].exp;

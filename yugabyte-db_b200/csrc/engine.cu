@@ -415,6 +415,8 @@ struct MergeView {
 };
 
 constexpr int MERGE_THREADS = 256;
+constexpr int COT_MAX = 8;       // distinct cotable / colocation ids per tile
+constexpr int COT_TOMB_MAX = 16; // table-tombstone entries replayed per id
 constexpr int RANK_C = 8;        // coarse stride of the two-level rank search
 constexpr int RANK_KMAX = 16;    // two-level search used for k <= RANK_KMAX runs
 
@@ -459,6 +461,10 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   __shared__ uint32_t sh_T, sh_ngroups, sh_any_filtered;
   __shared__ int sh_err;
   __shared__ uint32_t sh_c0;
+  __shared__ Overwrite sh_cot_ow[COT_MAX];       // table-level overwrite (slot 0) per distinct cotable id in the tile
+  __shared__ uint16_t sh_cot_li[COT_MAX];        // a record of the tile that carries the id bytes
+  __shared__ uint16_t sh_cot_len[COT_MAX];
+  __shared__ uint32_t sh_ncot;
   __shared__ unsigned long long sh_stats[9];
 
   const uint32_t tile = blockIdx.x;
@@ -663,12 +669,101 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   // (d) DocDB retention predicate: one thread per row group, serial inside the group
   unsigned long long st_feed = 0;
   for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) rw_slot[i] = 0xffffffffu;
+  if (threadIdx.x == 0) sh_ncot = 0;
+  __syncthreads();
+  // (d0) cotable / colocated tables: slot 0 of the overwrite stack (the table tombstone's time)
+  // carries over all rows of a table. The table-tombstone entries `id ! # HT` sort before every
+  // row of the table; they are looked up in the runs (binary search) and replayed, so that tiles
+  // stay independent. Only tiles that contain 'y' / '0' keys pay for this.
+  if (prm->R.enabled && threadIdx.x == 0) {
+    for (uint32_t g = 0; g < sh_ngroups; g++) {
+      const uint32_t li = order[gstart[g]];
+      const uint8_t* e = recs + static_cast<size_t>(SS) * li;
+      const uint32_t ulen = rec_ulen(e, S);
+      if (ulen == 0 || (e[0] != 'y' && e[0] != '0')) continue;
+      const int id = dockey_id_size(e, ulen);
+      if (id <= 0 || static_cast<uint32_t>(id) >= ulen || e[id] == '!') continue;   // tombstone groups start fresh
+      bool known = false;
+      for (uint32_t c = 0; c < sh_ncot && !known; c++) {
+        const uint8_t* o = recs + static_cast<size_t>(SS) * sh_cot_li[c];
+        known = (sh_cot_len[c] & 0x7fff) == id && common_prefix_len(o, id, e, id) >= static_cast<uint32_t>(id);
+      }
+      if (known) continue;
+      if (sh_ncot >= COT_MAX) { dev_fail(J, DEV_ERR_COTABLE, tile); break; }
+      // collect the table-tombstone entries of this id from all runs
+      const uint8_t* tomb[COT_TOMB_MAX]; int tomb_run[COT_TOMB_MAX]; uint32_t tomb_idx[COT_TOMB_MAX]; int nt = 0;
+      __align__(8) uint8_t pfxkey[24];
+      for (int q = 0; q < 24; q++) pfxkey[q] = q < id ? e[q] : (q == id ? '!' : 0);
+      bool overflow = false;
+      for (int r = 0; r < k && !overflow; r++) {
+        const RunView& run = V.runs[r];
+        uint32_t lo = 0, hi = run.n_entries;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          const uint8_t* c = run.rec + static_cast<size_t>(mid) * S;
+          if (cmp_prefix_vs_key(pfxkey, id + 1, c, rec_ulen(c, S)) > 0) lo = mid + 1; else hi = mid;
+        }
+        for (uint32_t x = lo; x < run.n_entries; x++) {
+          const uint8_t* c = run.rec + static_cast<size_t>(x) * S;
+          const uint32_t cl = rec_ulen(c, S);
+          if (cl < static_cast<uint32_t>(id) + 1 || common_prefix_len(c, id + 1, pfxkey, id + 1) < static_cast<uint32_t>(id) + 1) break;
+          if (rec_flags(c, S) & REC_F_HT_FILTERED) continue;
+          if (nt >= COT_TOMB_MAX) { overflow = true; break; }
+          tomb[nt] = c; tomb_run[nt] = r; tomb_idx[nt] = x; nt++;
+        }
+      }
+      if (overflow) { dev_fail(J, DEV_ERR_COTABLE, tile); break; }
+      for (int a = 1; a < nt; a++)                      // insertion sort by internal key
+        for (int b = a; b > 0 && cmp_records(tomb[b], tomb[b - 1], S) < 0; b--) {
+          const uint8_t* tp = tomb[b]; tomb[b] = tomb[b - 1]; tomb[b - 1] = tp;
+          int tr = tomb_run[b]; tomb_run[b] = tomb_run[b - 1]; tomb_run[b - 1] = tr;
+          uint32_t ti = tomb_idx[b]; tomb_idx[b] = tomb_idx[b - 1]; tomb_idx[b - 1] = ti;
+        }
+      FeedState st;
+      feed_state_reset(&st);
+      for (int a = 0; a < nt; a++) {
+        const uint8_t* c = tomb[a];
+        if (a > 0 && cmp_user_keys(tomb[a - 1], rec_ulen(tomb[a - 1], S), c, rec_ulen(c, S)) == 0) continue;   // rule A
+        const uint64_t suffix = rec_suffix(c, S);
+        if ((suffix & 0xff) == 0 && prm->bottommost && (suffix >> 8) <= prm->last_sequence) continue;          // obsolete deletion
+        const uint32_t vlen = rec_vlen(c, S);
+        const uint8_t vfirst = rec_vfirst(c, S);
+        const uint8_t* val = nullptr;
+        if (vlen && has_control_fields(vfirst)) val = V.runs[tomb_run[a]].data + V.runs[tomb_run[a]].val_off[tomb_idx[a]];
+        ValueRewrite rw;
+        int d = feed_step(&st, prm->R, c, rec_ulen(c, S), vfirst, val, vlen, &rw);
+        if (d < 0) { dev_fail(J, -d, tile); break; }
+      }
+      const uint32_t c = sh_ncot;
+      sh_cot_li[c] = static_cast<uint16_t>(li); sh_cot_len[c] = static_cast<uint16_t>(id);
+      if (st.n_ow >= 1 && st.n_ends == 1) sh_cot_ow[c] = st.ow[0];
+      else { sh_cot_ow[c].ht = prm->R.ht_min_enc; sh_cot_ow[c].exp.ttl_ns = kMaxTtlNs; sh_cot_ow[c].exp.write_ht = 0; sh_cot_len[c] = static_cast<uint16_t>(0x8000 | id); }
+      sh_ncot = c + 1;
+    }
+  }
   __syncthreads();
   if (prm->R.enabled) {
     for (uint32_t g = threadIdx.x; g < sh_ngroups; g += blockDim.x) {
       FeedState st;
       feed_state_reset(&st);
       const uint32_t i0 = gstart[g], i1 = gstart[g + 1];
+      if (sh_ncot) {
+        const uint8_t* e0 = recs + static_cast<size_t>(SS) * order[i0];
+        const uint32_t ul0 = rec_ulen(e0, S);
+        if (ul0 && (e0[0] == 'y' || e0[0] == '0')) {
+          const int id = dockey_id_size(e0, ul0);
+          if (id > 0 && static_cast<uint32_t>(id) < ul0 && e0[id] != '!') {
+            for (uint32_t c = 0; c < sh_ncot; c++) {
+              const uint32_t clen = sh_cot_len[c] & 0x7fff;
+              const uint8_t* o = recs + static_cast<size_t>(SS) * sh_cot_li[c];
+              if (clen == static_cast<uint32_t>(id) && common_prefix_len(o, id, e0, id) >= static_cast<uint32_t>(id)) {
+                if (!(sh_cot_len[c] & 0x8000)) feed_state_seed(&st, e0, id, sh_cot_ow[c]);   // 0x8000: no tombstones => fresh
+                break;
+              }
+            }
+          }
+        }
+      }
       for (uint32_t i = i0; i < i1; i++) {
         uint8_t f = res[i];
         if (!(f & ENT_KEEP)) continue;
@@ -1241,9 +1336,9 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   if (lower_.size() > 255 || upper_.size() > 255) return Fail(YBGPU_NOT_SUPPORTED, "key bounds longer than 255 bytes");
   hp.R.lower_len = static_cast<uint32_t>(lower_.size()); memcpy(hp.R.lower, lower_.data(), lower_.size());
   hp.R.upper_len = static_cast<uint32_t>(upper_.size()); memcpy(hp.R.upper, upper_.data(), upper_.size());
-  if (opt_.cotables_cutoff_ht != YBGPU_HT_INVALID && opt_.retention_enabled) {
-    // only consulted for 'y' keys, which the GPU path rejects for now (DEV_ERR_COTABLE)
-  }
+  hp.R.has_cotables_cutoff = opt_.cotables_cutoff_ht != YBGPU_HT_INVALID;
+  hp.R.cotables_cutoff_ht = opt_.cotables_cutoff_ht;
+  if (hp.R.has_cotables_cutoff) hp.R.cotables_cutoff_enc.n = static_cast<uint8_t>(doc_ht_encode(opt_.cotables_cutoff_ht, 0xffffffffu, hp.R.cotables_cutoff_enc.b));
 
   // Compaction::GetLargestUserKey: given by the caller or the max over the runs' last records.
   if (!opt_.has_largest_user_key) {
