@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", type=int, default=1, help="verify input block checksums (reference default: on)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "mvcc"],
+                    help="config2 = BASELINE configs[1] (the bench line); mvcc = configs[3] shape (20 versions/key, "
+                         "history cutoff drops 90 %), scaled to --rows entries, for profiles/ only")
     return ap.parse_args()
 
 
@@ -188,8 +191,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- inputs: this rank's tablet (distinct key range per rank) ----
-    cfg = pkg.GenConfig(seed=2 + rank, num_rows=args.rows, cols=1, versions=1, num_files=NUM_FILES, value_len=VALUE_LEN,
-                        row_offset=rank * args.rows, hash_rows_total=args.rows * world)
+    versions = 20 if args.workload == "mvcc" else 1
+    nrows = args.rows // versions
+    cfg = pkg.GenConfig(seed=2 + rank, num_rows=nrows, cols=1, versions=versions, num_files=NUM_FILES, value_len=VALUE_LEN,
+                        row_offset=rank * nrows, hash_rows_total=nrows * world)
+    job_kw = {}
+    if args.workload == "mvcc":
+        # versions 0..18 are at or below the cutoff (only the newest of them survives), version 19 is above
+        job_kw["cutoff_ht"] = ((cfg.base_micros + 18 * 1000 + 500) << 12)
     t0 = time.perf_counter()
     ssts = pkg.generate_ssts(cfg, max_threads=NUM_FILES)
     gen_s = time.perf_counter() - t0
@@ -213,7 +222,7 @@ def main():
 
     def step_resident():
         t0 = time.perf_counter()
-        job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=False, cuda_stream=stream_ptr)
+        job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=False, cuda_stream=stream_ptr, **job_kw)
         t1 = time.perf_counter()
         for t, s, (off, sz) in zip(dev_files, ssts, handles):
             job.add_input_device(t.data_ptr() + 16, s.data_view().size, off, sz)
@@ -268,7 +277,7 @@ def main():
         out_meta = torch.empty(max(64 << 20, file_bytes // 100), dtype=torch.uint8, pin_memory=True).numpy()
 
         def step_e2e():
-            job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=bool(args.verify), cuda_stream=stream_ptr)
+            job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=bool(args.verify), cuda_stream=stream_ptr, **job_kw)
             for s, (off, sz) in zip(ssts, handles):
                 job.add_input(s.data_view(), off, sz)
             job.run()
@@ -321,7 +330,10 @@ def main():
         "metric": "compaction GB/s (input bytes merged)", "value": round(value, 3), "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_s / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.rows == DEFAULT_ROWS else WORKLOAD + " (scaled to %d entries)" % args.rows,
+        "config": {"workload": (WORKLOAD if args.rows == DEFAULT_ROWS else WORKLOAD + " (scaled to %d entries)" % args.rows)
+                   if args.workload == "config2" else
+                   "MVCC-heavy: 20 versions/key, history_cutoff drops 90%%, %d live keys, 1 GPU (8 input files)" % nrows,
+                   "output_entries_per_gpu": int(stats[-1]["num_output_records"]),
                    "entries_per_gpu": int(n_entries), "input_raw_bytes_per_gpu": int(in_bytes),
                    "input_file_bytes_per_gpu": int(file_bytes), "tablets": world,
                    "parallelism": "tablet-per-GPU, no collective", "l2": "inputs (%.1f GB) far larger than the 126 MB L2" % (file_bytes / 1e9)},

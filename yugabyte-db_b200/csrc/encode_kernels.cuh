@@ -34,6 +34,7 @@ struct EncView {
   uint32_t ri_shift;               // log2(ri)
   uint32_t block_size;
   uint32_t deviation;
+  uint32_t guess;                  // ~0.85 x expected entries per block: first probe of k_next's galloping search
 };
 
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
@@ -200,6 +201,17 @@ __global__ void __launch_bounds__(256) k_next(EncView E) {
       while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (blk_cur(E, s, mid - 1) >= BS) hi = mid; else lo = mid + 1; }
       E.next[s] = lo;
       continue;
+    }
+    {
+      // gallop: the answer is almost always within [guess, 2*guess] entries of s
+      uint32_t step = E.guess;
+      uint32_t probe = s + step < hi ? s + step : hi;
+      while (probe < hi && !(blk_cur(E, s, probe - 1) * 100 > thresh)) {
+        lo = probe + 1;
+        step <<= 1;
+        probe = (hi - probe > step) ? probe + step : hi;
+      }
+      if (probe < hi) hi = probe;
     }
     while (lo < hi) {
       uint32_t mid = lo + ((hi - lo) >> 1);

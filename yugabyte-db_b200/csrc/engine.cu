@@ -764,6 +764,26 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
           }
         }
       }
+      // Fast path: every visible entry of the row is newer than the history cutoff and is a plain
+      // value of an ordinary table key. Feed forwards such entries verbatim
+      // (docdb_compaction_context.cc:1117-1130) and the row's overwrite stack is never consulted, so
+      // the state machine can be skipped (subkey decoding errors of such rows are not diagnosed).
+      {
+        bool all_above = !(prm->R.lower_len | prm->R.upper_len);
+        for (uint32_t i = i0; i < i1 && all_above; i++) {
+          if (!(res[i] & ENT_KEEP)) continue;
+          const uint8_t* e = recs + static_cast<size_t>(SS) * (order[i]);
+          const uint32_t ulen = rec_ulen(e, S);
+          const uint8_t b0 = ulen ? e[0] : 10;
+          const uint32_t htl = doc_ht_len_from_end(e, ulen);
+          const uint8_t vf = rec_vfirst(e, S);
+          if (b0 == 10 || b0 == 6 || b0 == 7 || b0 == 'y' || b0 == '0' || !htl ||
+              encht_cmp(e + ulen - htl, htl, prm->R.cutoff_enc.b, prm->R.cutoff_enc.n) <= 0 ||
+              (rec_vlen(e, S) && (has_control_fields(vf) || vf == 'z' || vf == '|')))
+            all_above = false;
+        }
+        if (all_above) continue;
+      }
       for (uint32_t i = i0; i < i1; i++) {
         uint8_t f = res[i];
         if (!(f & ENT_KEEP)) continue;
@@ -1438,6 +1458,10 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     E.runs = I.dRuns; E.kept = I.d_kept; E.rewrites = d_rw; E.n = n; E.ri = ri;
     E.ri_shift = 0; while ((1u << E.ri_shift) < ri) E.ri_shift++;
     E.block_size = opt_.block_size; E.deviation = static_cast<uint32_t>(std::max(0, opt_.block_size_deviation));
+    {
+      const double avg = static_cast<double>(I.out_key_bytes + I.out_val_bytes) / n + 3.0;
+      E.guess = static_cast<uint32_t>(std::max(1.0, 0.85 * opt_.block_size / avg));
+    }
     CUDA_TRY(DevAlloc(&I.allocs, &E.nr, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.shared, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.D, n));
     CUDA_TRY(DevAlloc(&I.allocs, &E.P, static_cast<size_t>(n) + 1)); CUDA_TRY(DevAlloc(&I.allocs, &E.QQ, n));
     CUDA_TRY(DevAlloc(&I.allocs, &E.next, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.exit1, n));
