@@ -415,6 +415,8 @@ struct MergeView {
 };
 
 constexpr int MERGE_THREADS = 256;
+constexpr uint32_t RW_PRE_DROPPED = 0xfffffffeu;   // rw_slot marker: dropped as an overwritten older version
+constexpr int COT_CAND_MAX = 16; // first row groups of id runs per tile (>= distinct ids)
 constexpr int COT_MAX = 8;       // distinct cotable / colocation ids per tile
 constexpr int COT_TOMB_MAX = 16; // table-tombstone entries replayed per id
 constexpr int RANK_C = 8;        // coarse stride of the two-level rank search
@@ -464,6 +466,8 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   __shared__ Overwrite sh_cot_ow[COT_MAX];       // table-level overwrite (slot 0) per distinct cotable id in the tile
   __shared__ uint16_t sh_cot_li[COT_MAX];        // a record of the tile that carries the id bytes
   __shared__ uint16_t sh_cot_len[COT_MAX];
+  __shared__ uint16_t sh_cand[COT_CAND_MAX];
+  __shared__ uint32_t sh_ncand;
   __shared__ uint32_t sh_ncot;
   __shared__ unsigned long long sh_stats[9];
 
@@ -668,21 +672,61 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
 
   // (d) DocDB retention predicate: one thread per row group, serial inside the group
   unsigned long long st_feed = 0;
-  for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) rw_slot[i] = 0xffffffffu;
-  if (threadIdx.x == 0) sh_ncot = 0;
+  for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
+    uint32_t mark = 0xffffffffu;
+    // Older versions of one SubDocKey: when the entry fed just before this one has the same key
+    // up to the hybrid time, is at or below the history cutoff and neither is a TTL merge record,
+    // Feed has (at least) that entry's time on top of the overwrite stack and drops this one at
+    // docdb_compaction_context.cc:1067-1074 without touching its state. Decided here by all
+    // threads so that the serial walk of a row group only visits entries that can survive.
+    if (i > 0 && prm->R.enabled && (res[i] & ENT_KEEP) && (res[i - 1] & ENT_KEEP)) {
+      const uint8_t* e = recs + static_cast<size_t>(SS) * order[i];
+      const uint8_t* p = recs + static_cast<size_t>(SS) * order[i - 1];
+      const uint32_t ul = rec_ulen(e, S), pl = rec_ulen(p, S);
+      const uint32_t hl = doc_ht_len_from_end(e, ul), hp = doc_ht_len_from_end(p, pl);
+      if (hl && hp && ul - hl == pl - hp &&
+          !(rec_vlen(e, S) && rec_vfirst(e, S) == 'k') && !(rec_vlen(p, S) && rec_vfirst(p, S) == 'k')) {
+        const EncHt& chosen = (e[0] == 'y' && prm->R.has_cotables_cutoff) ? prm->R.cotables_cutoff_enc : prm->R.cutoff_enc;
+        if (encht_cmp(p + pl - hp, hp, chosen.b, chosen.n) <= 0 && common_prefix_len(e, ul - hl, p, ul - hl) >= ul - hl)
+          mark = RW_PRE_DROPPED;
+      }
+    }
+    rw_slot[i] = mark;
+  }
+  if (threadIdx.x == 0) { sh_ncot = 0; sh_ncand = 0; }
   __syncthreads();
   // (d0) cotable / colocated tables: slot 0 of the overwrite stack (the table tombstone's time)
   // carries over all rows of a table. The table-tombstone entries `id ! # HT` sort before every
   // row of the table; they are looked up in the runs (binary search) and replayed, so that tiles
   // stay independent. Only tiles that contain 'y' / '0' keys pay for this.
-  if (prm->R.enabled && threadIdx.x == 0) {
-    for (uint32_t g = 0; g < sh_ngroups; g++) {
-      const uint32_t li = order[gstart[g]];
-      const uint8_t* e = recs + static_cast<size_t>(SS) * li;
+  // Candidate groups (first row group of each id run) are found by all threads; thread 0 then
+  // replays the tombstones of the few distinct ids.
+  if (prm->R.enabled) {
+    for (uint32_t g = threadIdx.x; g < sh_ngroups; g += blockDim.x) {
+      const uint8_t* e = recs + static_cast<size_t>(SS) * order[gstart[g]];
       const uint32_t ulen = rec_ulen(e, S);
       if (ulen == 0 || (e[0] != 'y' && e[0] != '0')) continue;
       const int id = dockey_id_size(e, ulen);
       if (id <= 0 || static_cast<uint32_t>(id) >= ulen || e[id] == '!') continue;   // tombstone groups start fresh
+      if (g > 0) {
+        const uint8_t* p = recs + static_cast<size_t>(SS) * order[gstart[g - 1]];
+        const uint32_t pl = rec_ulen(p, S);
+        if (pl > static_cast<uint32_t>(id) && p[id] != '!' && common_prefix_len(p, id, e, id) >= static_cast<uint32_t>(id)) continue;
+      }
+      const uint32_t slot = atomicAdd(&sh_ncand, 1u);
+      if (slot < COT_CAND_MAX) sh_cand[slot] = static_cast<uint16_t>(g);
+    }
+  }
+  __syncthreads();
+  if (prm->R.enabled && threadIdx.x == 0 && sh_ncand) {
+    if (sh_ncand > COT_CAND_MAX) dev_fail(J, DEV_ERR_COTABLE, tile);
+    const uint32_t ncand = sh_ncand < COT_CAND_MAX ? sh_ncand : COT_CAND_MAX;
+    for (uint32_t q = 0; q < ncand; q++) {
+      const uint32_t g = sh_cand[q];
+      const uint32_t li = order[gstart[g]];
+      const uint8_t* e = recs + static_cast<size_t>(SS) * li;
+      const uint32_t ulen = rec_ulen(e, S);
+      const int id = dockey_id_size(e, ulen);
       bool known = false;
       for (uint32_t c = 0; c < sh_ncot && !known; c++) {
         const uint8_t* o = recs + static_cast<size_t>(SS) * sh_cot_li[c];
@@ -787,6 +831,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
       for (uint32_t i = i0; i < i1; i++) {
         uint8_t f = res[i];
         if (!(f & ENT_KEEP)) continue;
+        if (rw_slot[i] == RW_PRE_DROPPED) { rw_slot[i] = 0xffffffffu; res[i] = f & ~ENT_KEEP & ~ENT_ZERO_SEQ; st_feed++; continue; }
         const uint32_t li = order[i];
         const uint8_t* e = recs + static_cast<size_t>(SS) * (li);
         int r = 0;
@@ -1225,11 +1270,14 @@ ybgpu_status Engine::CheckDeviceError(const char* phase) {
 ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   if (ran_) return Fail(YBGPU_ILLEGAL_STATE, "job already ran");
   Impl& I = *impl_;
+  const bool trace = getenv("YBGPU_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
   CUDA_TRY(cudaSetDevice(opt_.device));
   g_alloc_stream = I.stream;
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, opt_.device));
-  const int sms = prop.multiProcessorCount;
+  // cudaGetDeviceProperties costs milliseconds per call; one attribute, cached per device.
+  static int sm_count[64] = {};
+  if (!sm_count[opt_.device & 63]) CUDA_TRY(cudaDeviceGetAttribute(&sm_count[opt_.device & 63], cudaDevAttrMultiProcessorCount, opt_.device));
+  const int sms = sm_count[opt_.device & 63];
   const int k = static_cast<int>(I.runs.size());
   auto shutdown = [&]() { return shutting_down && *shutting_down; };
   uint32_t launches = 0;
@@ -1250,8 +1298,6 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   CUDA_TRY(cudaEventRecord(I.ev0, I.stream));
   uint32_t phase_launch_mark[8] = {};
   int phase = 0;
-  const bool trace = getenv("YBGPU_TRACE") != nullptr;
-  auto t_prev = std::chrono::steady_clock::now();
   auto tick = [&](const char* what) {
     if (!trace) return;
     cudaStreamSynchronize(I.stream);
@@ -1267,9 +1313,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
 
   // ---- K1: prepass + scan per file
   std::vector<uint32_t*> dtotals(k);
+  uint32_t* d_totals = nullptr;
+  CUDA_TRY(DevAlloc(&I.allocs, &d_totals, static_cast<size_t>(k) + 1));
   for (int r = 0; r < k; r++) {
     RunView& rv = I.runs[r];
-    CUDA_TRY(DevAlloc(&I.allocs, &dtotals[r], 1));
+    dtotals[r] = d_totals + r;
     if (rv.nb) {
       if (opt_.verify_checksums) {
         // ReadBlock's checksum verification (table/format.cc:352-395) for every input block
@@ -1290,10 +1338,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   tick("block scan");
   if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
   uint64_t N = 0;
+  std::vector<uint32_t> h_totals(k + 1, 0);
+  CUDA_TRY(cudaMemcpyAsync(h_totals.data(), d_totals, 4 * static_cast<size_t>(k), cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
   for (int r = 0; r < k; r++) {
-    uint32_t n;
-    CUDA_TRY(cudaMemcpyAsync(&n, dtotals[r], 4, cudaMemcpyDeviceToHost, I.stream));
-    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    const uint32_t n = h_totals[r];
     I.runs[r].n_entries = n;
     I.runs[r].restart_interval = I.hJ.restart_interval[r];
     if (N + n >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "more than 2^32 entries in one job: shard the compaction");
@@ -1364,13 +1413,17 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   if (!opt_.has_largest_user_key) {
     CUDA_TRY(cudaStreamSynchronize(I.stream));
     std::vector<uint8_t> best; bool any = false;
-    std::vector<uint8_t> tmp(Sfinal);
+    std::vector<uint8_t> lastrec(static_cast<size_t>(Sfinal) * k);
     for (int r = 0; r < k; r++) {
       if (!I.runs[r].n_entries) continue;
-      CUDA_TRY(cudaMemcpyAsync(tmp.data(), I.runs[r].rec + static_cast<size_t>(I.runs[r].n_entries - 1) * Sfinal, Sfinal, cudaMemcpyDeviceToHost, I.stream));
-      CUDA_TRY(cudaStreamSynchronize(I.stream));
-      uint32_t ulen = rec_ulen(tmp.data(), Sfinal);
-      std::vector<uint8_t> key(tmp.begin(), tmp.begin() + ulen);
+      CUDA_TRY(cudaMemcpyAsync(lastrec.data() + static_cast<size_t>(r) * Sfinal, I.runs[r].rec + static_cast<size_t>(I.runs[r].n_entries - 1) * Sfinal, Sfinal, cudaMemcpyDeviceToHost, I.stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    for (int r = 0; r < k; r++) {
+      if (!I.runs[r].n_entries) continue;
+      const uint8_t* tmp = lastrec.data() + static_cast<size_t>(r) * Sfinal;
+      uint32_t ulen = rec_ulen(tmp, Sfinal);
+      std::vector<uint8_t> key(tmp, tmp + ulen);
       if (!any || std::lexicographical_compare(best.begin(), best.end(), key.begin(), key.end())) { best = key; any = true; }
     }
     largest_ = best;
