@@ -20,7 +20,7 @@
 
 #if defined(__CUDACC__)
 #define YB_HD __host__ __device__ __forceinline__
-#define YB_HD_NOINLINE __host__ __device__ inline
+#define YB_HD_NOINLINE __host__ __device__ __noinline__ inline
 #else
 #define YB_HD inline
 #define YB_HD_NOINLINE inline

@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(256) k_p_sums(const uint32_t* nr, uint32_t n, 
   __syncthreads();
   if (threadIdx.x == 0) partial[blockIdx.x] = sh;
 }
-__global__ void __launch_bounds__(1024) k_scan_u64_single(unsigned long long* a, uint32_t n, unsigned long long* total) {
+// One CTA scans one array; blockIdx.x selects the array at a + blockIdx.x * stride.
+__global__ void __launch_bounds__(1024) k_scan_u64_single(unsigned long long* a, uint32_t n, unsigned long long* total, size_t stride = 0) {
+  a += blockIdx.x * stride;
   __shared__ unsigned long long ws[32];
   __shared__ unsigned long long carry;
   if (threadIdx.x == 0) carry = 0;
@@ -335,11 +337,17 @@ __global__ void __launch_bounds__(256) k_block_first(const uint8_t* is_start, ui
 }
 
 // Block sizes (contents incl. restart array) -> later scanned into file offsets (+5 per trailer).
-__global__ void __launch_bounds__(256) k_block_sizes(EncView E, const uint32_t* block_first, uint32_t nblocks, unsigned long long* block_off) {
+__global__ void __launch_bounds__(256) k_block_sizes(EncView E, const uint32_t* block_first, uint32_t nblocks, unsigned long long* block_off,
+                                                     unsigned long long* max_size) {
+  unsigned long long mx = 0;
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nblocks; b += gridDim.x * blockDim.x) {
     const uint32_t s = block_first[b], e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
-    block_off[b] = blk_cur(E, s, e - 1) + 5;      // contents + trailer
+    const unsigned long long sz = blk_cur(E, s, e - 1) + 5;      // contents + trailer
+    block_off[b] = sz;
+    mx = sz > mx ? sz : mx;
   }
+  for (int o = 16; o; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, mx, o); mx = y > mx ? y : mx; }
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_size, mx);
 }
 
 __device__ __forceinline__ int put_varint(uint8_t* p, uint32_t v) {
@@ -357,6 +365,12 @@ __device__ uint32_t g_crc_tab[4][256];
 __device__ uint32_t g_crc_x2n[32];      // x^(2^k) mod P
 constexpr uint32_t CRC_XPOW_TABLE = 1u << 16;
 __device__ uint32_t g_crc_xpow8[CRC_XPOW_TABLE + 1];   // x^(8m) mod P for m = 0..65536 bytes
+// Strided CRC (k_encode_smem): multiplying the register by x^(8 * 1024) (256 words further from the
+// end of the message) is a fixed GF(2)-linear map and so costs the same four lookups as the
+// ordinary one-word step; g_crc_stride[3 - b][x] = (x << 8b) * x^(8 * 1024) mod P.
+constexpr uint32_t CRC_STRIDE_WORDS = 256;
+__device__ uint32_t g_crc_stride[4][256];
+__device__ uint32_t g_crc_c16[16];                     // x^(8 * 64 * g) mod P
 
 __global__ void k_crc_init() {
   const uint32_t i = threadIdx.x;
@@ -408,6 +422,12 @@ __device__ __forceinline__ uint32_t crc_xpow_bytes(uint64_t nbytes, const uint32
 __global__ void k_crc_init_xpow() {
   const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m <= CRC_XPOW_TABLE) g_crc_xpow8[m] = crc_xpow_bytes(m, g_crc_x2n);
+  if (m < 1024) {
+    const uint32_t xp = crc_xpow_bytes(4 * CRC_STRIDE_WORDS, g_crc_x2n);
+    const uint32_t r = m >> 8, x = m & 255;
+    g_crc_stride[r][x] = crc_mulmod(xp, x << (8 * (3 - r)));
+  }
+  if (m < 16) g_crc_c16[m] = crc_xpow_bytes(64 * m, g_crc_x2n);
 }
 // crc * x^(8 nbytes): table lookup + one modular multiplication for the common distances.
 __device__ __forceinline__ uint32_t crc_shift(uint32_t crc, uint64_t nbytes, const uint32_t* x2n) {
@@ -493,7 +513,7 @@ constexpr int ENC_THREADS = 256;
 constexpr int ENC_EMAX = 512;      // entries per pass through the shared-memory table
 constexpr int ENC_ITEMS = 4096;    // direct item->entry map size (64 KB of values per pass)
 constexpr int ENC_EM_S = 256;          // entries per pass in k_encode_smem (= ENC_THREADS)
-constexpr int ENC_ITEMS_SMEM = 2560;   // same for k_encode_smem (a 36 KB image has at most ~2400 value chunks)
+constexpr int ENC_ITEMS_SMEM = 1024;   // items (runs of up to 4 value chunks) per pass in k_encode_smem: a 36 KB image has < 850
 
 // 16 bytes starting at an arbitrary address: two aligned 16-byte loads + funnel shift. Reads
 // [src & ~15, (src & ~15) + 32).
@@ -679,37 +699,134 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
 // ENC_SMEM_CAP are left to k_encode_fused (only_big = 1).
 constexpr uint32_t ENC_SMEM_CAP = 36 * 1024;       // bytes of block image (contents + trailer) per CTA
 
+// Bytes [sh, sh + 16) of the 32-byte pair (a, b).
+__device__ __forceinline__ uint4 shift16(const uint4& a, const uint4& b, uint32_t sh) {
+  uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+  const uint32_t q = sh >> 2, bits = (sh & 3) * 8;
+  if (q & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
+  if (q & 2) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
+  uint4 o;
+  o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
+  o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
+  return o;
+}
+
+// Bytes [from, to) of a 16-byte-aligned record in global memory into shared memory (any
+// alignment): the record is fetched as 16-byte vectors (all in flight together), the 4-byte
+// shared stores are funnel-shifted out of registers; single bytes only at the two ends.
+// Reads record bytes up to ((to + 3) & ~3) + 4 at most (inside the record stride).
+__device__ __forceinline__ void copy_rec_to_smem(uint8_t* dst, const uint8_t* rec, uint32_t from, uint32_t to) {
+  uint32_t n = to - from;
+  while (n && (reinterpret_cast<uintptr_t>(dst) & 3)) { *dst++ = __ldg(rec + from); from++; n--; }
+  const uint32_t nw = n >> 2;
+  if (nw) {
+    const uint32_t w1 = from >> 2, bits = (from & 3) * 8;
+    const uint32_t wend = w1 + nw + (bits ? 1 : 0);            // source words [w1, wend)
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+    const uint4* rv = reinterpret_cast<const uint4*>(rec);
+    uint32_t prev = 0;
+    for (uint32_t c = w1 >> 2; c * 4 < wend; c++) {
+      const uint4 v = __ldg(rv + c);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const uint32_t j = c * 4 + t;
+        if (bits) { if (j > w1 && j - 1 - w1 < nw) dw[j - 1 - w1] = __funnelshift_r(prev, w[t], bits); }
+        else if (j >= w1 && j - w1 < nw) dw[j - w1] = w[t];
+        prev = w[t];
+      }
+    }
+  }
+  for (uint32_t i = nw * 4; i < n; i++) dst[i] = __ldg(rec + from + i);
+}
+
+// n bytes from global memory (read-only path, any alignment) into shared memory (any alignment):
+// 4-byte shared stores fed by funnel-shifted aligned loads, single bytes only at the two ends.
+__device__ __forceinline__ void copy_global_to_smem(uint8_t* dst, const uint8_t* src, uint32_t n) {
+  while (n && (reinterpret_cast<uintptr_t>(dst) & 3)) { *dst++ = __ldg(src++); n--; }
+  const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3);
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - sh);
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+  const uint32_t nw = n >> 2;
+  if (sh == 0) {
+#pragma unroll 4
+    for (uint32_t i = 0; i < nw; i++) dw[i] = __ldg(sw + i);
+  } else if (nw) {
+    const uint32_t bits = sh * 8;
+    uint32_t lo = __ldg(sw);
+#pragma unroll 4
+    for (uint32_t i = 0; i < nw; i++) {
+      const uint32_t hi = __ldg(sw + i + 1);      // holds at least one byte of [src, src + n)
+      dw[i] = __funnelshift_r(lo, hi, bits);
+      lo = hi;
+    }
+  }
+  for (uint32_t i = nw * 4; i < n; i++) dst[i] = __ldg(src + i);
+}
+
+struct EncBlkHdr { unsigned long long boff; uint32_t btot, s, e; };
+struct EncBlkSums { unsigned long long Ps, Qs; uint32_t body, tl; };
+__device__ __forceinline__ EncBlkHdr enc_load_hdr(const EncView& E, const uint32_t* block_first, const unsigned long long* block_off,
+                                                  uint32_t b, uint32_t nblocks) {
+  EncBlkHdr h;
+  h.boff = block_off[b];
+  const unsigned long long t = block_off[b + 1] - h.boff;
+  h.btot = t > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(t);
+  h.s = block_first[b];
+  h.e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
+  return h;
+}
+__device__ __forceinline__ EncBlkSums enc_load_sums(const EncView& E, const EncBlkHdr& h) {
+  EncBlkSums u;
+  u.Ps = E.P[h.s];
+  u.Qs = E.QQ[h.s] - E.D[h.s];
+  u.tl = (h.e - 1 - h.s) >> E.ri_shift;
+  u.body = static_cast<uint32_t>((E.P[h.e] - u.Ps) + (E.QQ[h.s + (u.tl << E.ri_shift)] - u.Qs));
+  return u;
+}
+
 __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
                                                                const unsigned long long* block_off, uint8_t* out) {
   extern __shared__ __align__(16) uint8_t img_raw[];    // ENC_SMEM_CAP + 32
-  __shared__ uint32_t tab[4][256];
-  __shared__ uint32_t x2n[32];
-  __shared__ uint32_t warp_crc[ENC_THREADS / 32];
+  __shared__ uint32_t tab0[256];
+  __shared__ uint32_t stab[4][256];
   __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t warp_crc[ENC_THREADS / 32];
   __shared__ unsigned long long t_src[ENC_EM_S];
   __shared__ uint32_t t_dsto[ENC_EM_S];
   __shared__ uint32_t t_len[ENC_EM_S];
   __shared__ uint32_t t_chunk[ENC_EM_S + 1];
   __shared__ uint16_t t_item[ENC_ITEMS_SMEM];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
-  if (threadIdx.x < 32) x2n[threadIdx.x] = g_crc_x2n[threadIdx.x];
+  static_assert(ENC_EM_S == ENC_THREADS && CRC_STRIDE_WORDS == ENC_THREADS, "one CRC lane per thread");
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&stab[0][0])[i] = (&g_crc_stride[0][0])[i];
+  tab0[threadIdx.x] = g_crc_tab[0][threadIdx.x];
+  // x^(32 (t + 1)): moves this thread's strided partial to its distance from the end of the message
+  const uint32_t crc_kc = g_crc_xpow8[4 * (threadIdx.x + 1)];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-  for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
-    const unsigned long long boff = block_off[b];
-    const unsigned long long btot = block_off[b + 1] - boff;         // contents + 5-byte trailer
-    if (btot > ENC_SMEM_CAP) continue;                               // uniform for the CTA
-    const uint32_t blen = static_cast<uint32_t>(btot - 5);
-    const uint32_t s = block_first[b], e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
-    uint8_t* gdst = out + boff;
+  uint32_t b = blockIdx.x;
+  EncBlkHdr nh{}; EncBlkSums ns{};
+  if (b < nblocks) { nh = enc_load_hdr(E, block_first, block_off, b, nblocks); ns = enc_load_sums(E, nh); }
+  for (; b < nblocks; b += gridDim.x) {
+    const EncBlkHdr h = nh; const EncBlkSums u = ns;
+    const uint32_t nb = b + gridDim.x;
+    // the next block's parameters are fetched while this one is assembled
+    if (nb < nblocks) nh = enc_load_hdr(E, block_first, block_off, nb, nblocks);
+    if (h.btot > ENC_SMEM_CAP) {                                     // uniform for the CTA; k_encode_fused takes it
+      if (nb < nblocks) ns = enc_load_sums(E, nh);
+      continue;
+    }
+    const uint32_t blen = h.btot - 5;
+    const uint32_t s = h.s, e = h.e;
+    uint8_t* gdst = out + h.boff;
     // image[0] corresponds to gdst[0]; shifted so that image and destination agree mod 16
     const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gdst) & 15);
     uint8_t* img = img_raw + mis;
-    const unsigned long long Ps = E.P[s];
-    const unsigned long long Qs = E.QQ[s] - E.D[s];
-    const uint32_t tl = (e - 1 - s) >> E.ri_shift;
-    const uint32_t body = static_cast<uint32_t>((E.P[e] - Ps) + (E.QQ[s + (tl << E.ri_shift)] - Qs));
+    if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(img_raw)[threadIdx.x] = 0;    // leading zeros do not change a CRC register of 0
+    const unsigned long long Ps = u.Ps, Qs = u.Qs;
+    const uint32_t tl = u.tl, body = u.body;
+    __syncthreads();
 
     for (uint32_t p0 = s; p0 < e; p0 += ENC_EM_S) {
       const uint32_t pn = min(static_cast<uint32_t>(ENC_EM_S), e - p0);
@@ -731,23 +848,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
         p += put_varint(p, klen - shared);
         p += put_varint(p, vlen);
         const uint64_t suffix = kept_suffix(rec, d, S);
-        {
-          // key bytes [shared, klen): the (at most 4) aligned 8-byte record words that hold the
-          // non-shared user-key bytes are fetched together, longer deltas fall back to a loop
-          const uint32_t wfirst = shared >> 3;
-          uint64_t kw[4];
-#pragma unroll
-          for (int t = 0; t < 4; t++) kw[t] = (8 * (wfirst + t) < ulen) ? ld_u64_aligned(rec + 8 * (wfirst + t)) : 0;
-          uint32_t i = shared;
-          while (i < klen) {
-            if (i < ulen) {
-              const uint32_t wi = (i >> 3) - wfirst;
-              const uint64_t wv = wi < 4 ? (wi == 0 ? kw[0] : wi == 1 ? kw[1] : wi == 2 ? kw[2] : kw[3]) : ld_u64_aligned(rec + (i & ~7u));
-              const uint32_t lim = min(ulen, (i & ~7u) + 8);
-              for (; i < lim; i++) *p++ = static_cast<uint8_t>(wv >> (8 * (i & 7)));
-            } else { *p++ = static_cast<uint8_t>(suffix >> (8 * (i - ulen))); i++; }
-          }
-        }
+        if (shared < ulen) { copy_rec_to_smem(p, rec, shared, ulen); p += ulen - shared; }
+        for (uint32_t i = shared > ulen ? shared - ulen : 0; i < 8; i++) *p++ = static_cast<uint8_t>(suffix >> (8 * i));
         uint32_t copy_len = vlen;
         if (d.flags & ENT_VAL_TOMBSTONE) { p[0] = 'X'; copy_len = 0; }
         else if (d.flags & ENT_VAL_REENCODE) {
@@ -778,6 +880,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
           c0 = fb > fa ? (fb - fa) >> 4 : 0;
         }
       }
+      c0 = (c0 + 3) >> 2;                        // one item = up to four consecutive chunks of one value
       uint32_t total_items;
       const uint32_t ibase = block_exclusive_scan(c0, warp_sums, &total_items);
       t_chunk[threadIdx.x] = ibase;
@@ -789,8 +892,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
         if (q < pn) for (uint32_t it = t_chunk[q]; it < t_chunk[q + 1]; it++) t_item[it] = static_cast<uint16_t>(q);
         __syncthreads();
       }
-      // ---- phase B: value bytes, one 16-byte source vector per item
-#pragma unroll 4
+      // ---- phase B: value bytes. An item covers up to four destination-aligned 16-byte chunks and
+      // needs at most five aligned source vectors, all fetched before the first store.
+#pragma unroll 2
       for (uint32_t it = threadIdx.x; it < total_items; it += blockDim.x) {
         uint32_t q;
         if (direct) q = t_item[it];
@@ -800,10 +904,19 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
           q = lo;
         }
         // offsets below are relative to img_raw (16-byte aligned): r = image offset + mis
-        const uint32_t d0 = t_dsto[q] + mis;
-        const uint32_t A = ((d0 + 15) & ~15u) + 16u * (it - t_chunk[q]);
+        const uint32_t d0 = t_dsto[q] + mis, d1 = d0 + t_len[q];
+        const uint32_t A = ((d0 + 15) & ~15u) + 64u * (it - t_chunk[q]);
+        const uint32_t nch = min(4u, ((d1 & ~15u) - A) >> 4);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(t_src[q]) + (A - d0);
-        *reinterpret_cast<uint4*>(img_raw + A) = load_unaligned16(src);
+        const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15);
+        const uint4* sa = reinterpret_cast<const uint4*>(src - sh);
+        const uint32_t nld = nch + (sh ? 1 : 0);
+        uint4 v[5];
+#pragma unroll
+        for (int t = 0; t < 5; t++) v[t] = (static_cast<uint32_t>(t) < nld) ? __ldg(sa + t) : make_uint4(0, 0, 0, 0);
+        uint4* dv = reinterpret_cast<uint4*>(img_raw + A);
+#pragma unroll
+        for (int t = 0; t < 4; t++) if (static_cast<uint32_t>(t) < nch) dv[t] = sh ? shift16(v[t], v[t + 1], sh) : v[t];
       }
       // value edges (bytes before the first / after the last full chunk): two small jobs per entry
       for (uint32_t t = threadIdx.x; t < 2 * pn; t += blockDim.x) {
@@ -819,14 +932,15 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
         while (lo < hi) {
           const uint4 x = load_unaligned16(src);
           const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-          const uint32_t nb = min(16u, hi - lo);
+          const uint32_t nbytes = min(16u, hi - lo);
 #pragma unroll
-          for (int bb = 0; bb < 16; bb++) if (bb < static_cast<int>(nb)) img_raw[lo + bb] = static_cast<uint8_t>(w[bb >> 2] >> (8 * (bb & 3)));
-          lo += nb; src += nb;
+          for (int bb = 0; bb < 16; bb++) if (bb < static_cast<int>(nbytes)) img_raw[lo + bb] = static_cast<uint8_t>(w[bb >> 2] >> (8 * (bb & 3)));
+          lo += nbytes; src += nbytes;
         }
       }
       __syncthreads();
     }
+    if (nb < nblocks) ns = enc_load_sums(E, nh);
     if (threadIdx.x == 0) {
       const uint32_t nres = tl + 1;
       uint8_t* q = img + body + 4 * nres;
@@ -834,52 +948,48 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
       q[4] = 0;   // kNoCompression
     }
     __syncthreads();
-    // ---- CRC32C over image[0, blen] from shared memory: thread t takes an odd-sized word range so
-    // that the 32 lanes of a warp read different banks
+    // ---- CRC32C over image[0, blen] from shared memory. The words of img_raw (zeros in front of
+    // the image) are numbered from the END of the message; thread t owns the words at distance
+    // t, t + 256, ... and folds them with the x^(8*1024) map, so consecutive lanes read consecutive
+    // words and no per-thread polynomial shift is needed:
+    //   R = sum_t T^(t+1) ( sum_j S^j w[t + 256 j] ),  T = one-word step, S = T^256.
+    const uint32_t L = blen + 1;                                    // contents + type byte
+    const uint32_t nwords = (mis + L) >> 2, tailb = (mis + L) & 3;
     {
-      const uint32_t L = blen + 1;
-      const uint32_t head = (4 - ((mis) & 3)) & 3;                  // bytes before the first aligned word of img
-      const uint32_t hb = head < L ? head : L;
-      const uint32_t nwords = (L - hb) >> 2, tail = (L - hb) & 3;
-      constexpr uint32_t CRC_T = 64;                                // fewer, longer ranges: one GF(2) shift per range
-      uint32_t W = (nwords + CRC_T - 1) / CRC_T;
-      W |= 1;                                                       // odd stride in words
-      const uint32_t w0 = threadIdx.x < CRC_T ? min(W * threadIdx.x, nwords) : nwords, w1 = min(w0 + W, nwords);
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + hb);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(img_raw);
+      // the 0xffffffff initial register == the first four message bytes complemented
+      const uint32_t wi0 = mis >> 2, sh0 = (mis & 3) * 8;
+      const uint32_t m0 = 0xffffffffu << sh0, m1 = sh0 ? 0xffffffffu >> (32 - sh0) : 0u;
       uint32_t acc = 0;
-      if (w1 > w0) {
-        uint32_t c = 0xffffffffu;
-        for (uint32_t i = w0; i < w1; i++) {
-          c ^= wp[i];
-          c = tab[3][c & 0xff] ^ tab[2][(c >> 8) & 0xff] ^ tab[1][(c >> 16) & 0xff] ^ tab[0][c >> 24];
+      if (nwords > threadIdx.x) {
+        const uint32_t last = nwords - 1 - threadIdx.x;             // index of this thread's word nearest the end
+        uint32_t i = last & (CRC_STRIDE_WORDS - 1);                 // its farthest word
+        acc = wp[i];
+        if (i == wi0) acc ^= m0; else if (i == wi0 + 1) acc ^= m1;
+        for (i += CRC_STRIDE_WORDS; i <= last; i += CRC_STRIDE_WORDS) {
+          acc = stab[3][acc & 0xff] ^ stab[2][(acc >> 8) & 0xff] ^ stab[1][(acc >> 16) & 0xff] ^ stab[0][acc >> 24];
+          acc ^= wp[i];
         }
-        acc = crc_shift(~c, static_cast<uint64_t>(nwords - w1) * 4 + tail, x2n);
       }
-      if (threadIdx.x == 0 && hb) {
-        uint32_t c = 0xffffffffu;
-        for (uint32_t i = 0; i < hb; i++) c = tab[0][(c ^ img[i]) & 0xff] ^ (c >> 8);
-        acc ^= crc_shift(~c, L - hb, x2n);
-      }
-      if (threadIdx.x == ENC_THREADS - 1 && tail) {
-        uint32_t c = 0xffffffffu;
-        for (uint32_t i = 0; i < tail; i++) c = tab[0][(c ^ img[L - tail + i]) & 0xff] ^ (c >> 8);
-        acc ^= ~c;
-      }
-      for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) warp_crc[wid] = acc;
+      uint32_t r = acc ? crc_mulmod(crc_kc, acc) : 0u;              // * T^(t + 1)
+      for (int o = 16; o; o >>= 1) r ^= __shfl_xor_sync(0xffffffffu, r, o);
+      if (lane == 0) warp_crc[wid] = r;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      uint32_t crc = 0;
-      for (int w = 0; w < ENC_THREADS / 32; w++) crc ^= warp_crc[w];
-      crc = crc_mask(crc);
+      uint32_t r = 0;
+#pragma unroll
+      for (int w = 0; w < ENC_THREADS / 32; w++) r ^= warp_crc[w];
+      const uint8_t* tp = img_raw + 4 * nwords;
+      for (uint32_t i = 0; i < tailb; i++) r = tab0[(r ^ tp[i]) & 0xff] ^ (r >> 8);
+      const uint32_t crc = crc_mask(~r);
       uint8_t* t = img + blen + 1;
       t[0] = static_cast<uint8_t>(crc); t[1] = static_cast<uint8_t>(crc >> 8); t[2] = static_cast<uint8_t>(crc >> 16); t[3] = static_cast<uint8_t>(crc >> 24);
     }
     __syncthreads();
     // ---- image -> HBM: 16-byte vector stores (image and destination agree mod 16)
     {
-      const uint32_t total = static_cast<uint32_t>(btot);
+      const uint32_t total = h.btot;
       const uint32_t head = (16 - mis) & 15;
       const uint32_t hb = head < total ? head : total;
       if (threadIdx.x < hb) gdst[threadIdx.x] = img[threadIdx.x];

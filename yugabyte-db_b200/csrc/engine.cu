@@ -412,6 +412,8 @@ struct MergeView {
   ValueRewrite* rewrites;         // [rewrite_cap]
   uint32_t rewrite_cap;
   uint32_t n_tiles;
+  int32_t S, k;                   // record stride / number of runs / tile capacity: kernel-parameter constants
+  uint32_t cap;
 };
 
 constexpr int MERGE_THREADS = 256;
@@ -421,6 +423,31 @@ constexpr int COT_MAX = 8;       // distinct cotable / colocation ids per tile
 constexpr int COT_TOMB_MAX = 16; // table-tombstone entries replayed per id
 constexpr int RANK_C = 8;        // coarse stride of the two-level rank search
 constexpr int RANK_KMAX = 16;    // two-level search used for k <= RANK_KMAX runs
+
+// Shared-memory layout of a merge tile. Every array base is FIXED + cap * K with compile-time FIXED
+// and K (cap is a multiple of 16, so all alignments hold by construction): a base costs one
+// multiply-add wherever it is needed instead of a chain of dependent pointer computations.
+namespace tile_layout {
+constexpr uint32_t SEG_LO = 0;                                  // u32 [MAX_RUNS]
+constexpr uint32_t SEG_START = SEG_LO + 4 * MAX_RUNS;           // u32 [MAX_RUNS + 1]
+constexpr uint32_t CBASE = SEG_START + 4 * (MAX_RUNS + 2);      // u32 [MAX_RUNS + 1] coarse index base per segment
+constexpr uint32_t CRANK = CBASE + 4 * (MAX_RUNS + 2);          // u16 [(cap / RANK_C + RANK_KMAX + 1) * RANK_KMAX] coarse ranks
+constexpr uint32_t CRANK_FIXED = 2 * (RANK_KMAX + 1) * RANK_KMAX;
+constexpr uint32_t CRANK_PER = 2 * RANK_KMAX / RANK_C;          // bytes per record
+constexpr uint32_t A0 = (CRANK + CRANK_FIXED + 15) & ~15u;
+constexpr uint32_t ORDER_K = CRANK_PER;      // u16 sorted pos -> local idx
+constexpr uint32_t GLEN_K = ORDER_K + 2;     // u16 local idx -> group prefix len
+constexpr uint32_t GSTART_K = GLEN_K + 2;    // u16 group -> first sorted pos (cap + 2 entries; +16 bytes below)
+constexpr uint32_t A1 = A0 + 16;
+constexpr uint32_t PVIS_K = GSTART_K + 2;    // u16 sorted pos -> previous visible sorted pos
+constexpr uint32_t RES_K = PVIS_K + 2;       // u8 sorted pos -> ENT_* flags
+constexpr uint32_t RW_K = RES_K + 1;         // u32 sorted pos -> rewrite slot
+constexpr uint32_t PFX_K = RW_K + 4;         // u64 local idx -> sort prefix
+constexpr uint32_t PFX2_K = PFX_K + 8;       // u64 second 8 bytes of the 16-byte sort prefix
+constexpr uint32_t RECS_K = PFX2_K + 8;      // records, SS bytes each
+static_assert(RANK_KMAX % RANK_C == 0 && (PFX_K % 1) == 0, "layout");
+__host__ __device__ constexpr uint32_t bytes(uint32_t S, uint32_t cap) { return A1 + (RECS_K + S + 8) * cap; }
+}  // namespace tile_layout
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
   // scan of one value per thread; all threads must call. Returns exclusive prefix.
@@ -443,22 +470,23 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 
 __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, const JobParams* prm, JobDev* J) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int S = prm->S, k = prm->k;
+  const int S = V.S, k = V.k;
   const int SS = S + 8;                       // smem record stride: +8 B so that consecutive records start in different banks
-  const uint32_t cap = prm->tile_cap;
-  uint8_t* recs = smem;                                             // cap * SS
-  uint16_t* order = reinterpret_cast<uint16_t*>(recs + static_cast<size_t>(SS) * cap);   // sorted pos -> local idx
-  uint16_t* glen = order + cap;                                     // local idx -> group prefix len
-  uint16_t* gstart = glen + cap;                                    // group -> first sorted pos (cap + 1)
-  uint16_t* pvis = gstart + cap + 2;                                // sorted pos -> previous visible sorted pos
-  uint8_t* res = reinterpret_cast<uint8_t*>(pvis + cap);            // sorted pos -> ENT_* flags
-  uint32_t* seg_lo = reinterpret_cast<uint32_t*>(res + ((cap + 15) & ~15u));   // [k]
-  uint32_t* seg_start = seg_lo + MAX_RUNS;                          // [k+1]
-  uint32_t* rw_slot = seg_start + MAX_RUNS + 1;                     // sorted pos -> rewrite slot (cap)
-  unsigned long long* pfx = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(rw_slot + cap) + 7) & ~static_cast<uintptr_t>(7));   // local idx -> sort prefix (cap)
-  unsigned long long* pfx2 = pfx + cap;             // second 8 bytes of the 16-byte sort prefix
-  uint32_t* cbase = reinterpret_cast<uint32_t*>(pfx2 + cap);   // [k+1] coarse index base per segment
-  uint16_t* crank = reinterpret_cast<uint16_t*>(cbase + MAX_RUNS + 1);   // [(cap/RANK_C + k) * RANK_KMAX] coarse ranks
+  const uint32_t cap = V.cap;
+  namespace L = tile_layout;
+  uint32_t* seg_lo = reinterpret_cast<uint32_t*>(smem + L::SEG_LO);
+  uint32_t* seg_start = reinterpret_cast<uint32_t*>(smem + L::SEG_START);
+  uint32_t* cbase = reinterpret_cast<uint32_t*>(smem + L::CBASE);
+  uint16_t* crank = reinterpret_cast<uint16_t*>(smem + L::CRANK);
+  uint16_t* order = reinterpret_cast<uint16_t*>(smem + L::A0 + L::ORDER_K * cap);
+  uint16_t* glen = reinterpret_cast<uint16_t*>(smem + L::A0 + L::GLEN_K * cap);
+  uint16_t* gstart = reinterpret_cast<uint16_t*>(smem + L::A0 + L::GSTART_K * cap);
+  uint16_t* pvis = reinterpret_cast<uint16_t*>(smem + L::A1 + L::PVIS_K * cap);
+  uint8_t* res = smem + L::A1 + L::RES_K * cap;
+  uint32_t* rw_slot = reinterpret_cast<uint32_t*>(smem + L::A1 + L::RW_K * cap);
+  unsigned long long* pfx = reinterpret_cast<unsigned long long*>(smem + L::A1 + L::PFX_K * cap);
+  unsigned long long* pfx2 = reinterpret_cast<unsigned long long*>(smem + L::A1 + L::PFX2_K * cap);
+  uint8_t* recs = smem + L::A1 + L::RECS_K * cap;                   // cap * SS
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t sh_T, sh_ngroups, sh_any_filtered;
   __shared__ int sh_err;
@@ -1390,8 +1418,9 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   JobParams hp{};
   hp.S = Sfinal; hp.k = k; hp.bottommost = opt_.bottommost_level; hp.last_sequence = opt_.last_sequence;
   // smem budget: ~74 KB per CTA (records + per-record side arrays) so three CTAs fit one SM
-  uint32_t cap = (74u * 1024u - 2048u) / (Sfinal + 8 + 14 + 16 + 4);
-  cap = std::min(cap, 4096u) & ~1u;
+  uint32_t cap = (74u * 1024u - tile_layout::A1 - 64u) / (Sfinal + 8 + tile_layout::RECS_K);
+  cap = std::min(cap, 4096u) & ~15u;
+  if (cap < 16) return Fail(YBGPU_NOT_SUPPORTED, "record stride too large for a merge tile");
   hp.tile_cap = cap;
   hp.H = std::max(1u, cap / 2);
   hp.M = std::max(1u, hp.H / std::max(1, k));
@@ -1476,9 +1505,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   MergeView mv{};
   mv.runs = I.dRuns; mv.tile_lo = d_tile_lo; mv.tile_rank = d_tile_rank; mv.desc = d_desc;
   mv.rewrites = d_rw; mv.rewrite_cap = rewrite_cap; mv.n_tiles = n_tiles;
-  const size_t smem = static_cast<size_t>(cap) * (Sfinal + 8) + (cap * 4 + 4) * 2 + ((cap + 15) & ~15u) +
-                      (2 * MAX_RUNS + 1) * 4 + static_cast<size_t>(cap) * 4 + static_cast<size_t>(cap) * 16 + (MAX_RUNS + 1) * 4 +
-                      (static_cast<size_t>(cap) / RANK_C + RANK_KMAX + 1) * RANK_KMAX * 2 + 64;
+  mv.S = Sfinal; mv.k = k; mv.cap = cap;
+  const size_t smem = tile_layout::bytes(Sfinal, cap);
   CUDA_TRY(cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   k_merge_filter<<<n_tiles, MERGE_THREADS, smem, I.stream>>>(mv, I.dP, I.dJ);
   launches++;
@@ -1533,9 +1561,9 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(DevAlloc(&I.allocs, &d_qp, static_cast<size_t>(qchunks) * ri + 1));
     const uint32_t qthreads = qchunks * ri;
     k_qq_sums<<<(qthreads + 255) / 256, 256, 0, I.stream>>>(E.D, n, ri, d_qp, qchunks);
-    for (uint32_t c = 0; c < ri; c++) k_scan_u64_single<<<1, 1024, 0, I.stream>>>(d_qp + static_cast<size_t>(c) * qchunks, qchunks, nullptr);
+    k_scan_u64_single<<<ri, 1024, 0, I.stream>>>(d_qp, qchunks, nullptr, qchunks);   // one residue class per CTA
     k_qq_final<<<(qthreads + 255) / 256, 256, 0, I.stream>>>(E.D, n, ri, d_qp, qchunks, E.QQ);
-    launches += 7 + ri;
+    launches += 8;
     // block cuts
     k_next<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E);
     const uint32_t nsegs = (n + SEG - 1) / SEG;
@@ -1560,14 +1588,16 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     I.n_blocks = nblocks;
     CUDA_TRY(DevAlloc(&I.allocs, &I.d_block_first, static_cast<size_t>(nblocks) + 1));
     CUDA_TRY(DevAlloc(&I.allocs, &I.d_block_off, static_cast<size_t>(nblocks) + 1));
-    unsigned long long* d_total = nullptr;
-    CUDA_TRY(DevAlloc(&I.allocs, &d_total, 1));
+    unsigned long long* d_total = nullptr;                // [0] file length, [1] largest block (contents + trailer)
+    CUDA_TRY(DevAlloc(&I.allocs, &d_total, 2));
+    CUDA_TRY(cudaMemsetAsync(d_total, 0, 16, I.stream));
     k_block_first<<<pc, 256, 0, I.stream>>>(d_is_start, n, d_spart, I.d_block_first);
-    k_block_sizes<<<GridFor(nblocks, 256, sms), 256, 0, I.stream>>>(E, I.d_block_first, nblocks, I.d_block_off);
+    k_block_sizes<<<GridFor(nblocks, 256, sms), 256, 0, I.stream>>>(E, I.d_block_first, nblocks, I.d_block_off, d_total + 1);
     k_scan_u64_single<<<1, 1024, 0, I.stream>>>(I.d_block_off, nblocks, d_total);
-    unsigned long long total = 0;
-    CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, I.stream));
+    unsigned long long total_and_max[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(total_and_max, d_total, 16, cudaMemcpyDeviceToHost, I.stream));
     CUDA_TRY(cudaStreamSynchronize(I.stream));
+    const unsigned long long total = total_and_max[0];
     CUDA_TRY(cudaMemcpyAsync(I.d_block_off + nblocks, &total, 8, cudaMemcpyHostToDevice, I.stream));
     I.out_file_len = total;
     CUDA_TRY(DevAlloc(&I.allocs, &I.out_file, total + 64));
@@ -1575,13 +1605,17 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       const size_t esm = ENC_SMEM_CAP + 32;
       CUDA_TRY(cudaFuncSetAttribute(k_encode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esm)));
       k_encode_smem<<<std::min<uint32_t>(nblocks, sms * 8), ENC_THREADS, esm, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
+      launches++;
       // blocks whose image does not fit shared memory (huge values)
-      k_encode_fused<<<std::min<uint32_t>(nblocks, sms * 4), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file, ENC_SMEM_CAP);
+      if (total_and_max[1] > ENC_SMEM_CAP) {
+        k_encode_fused<<<std::min<uint32_t>(nblocks, sms * 4), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file, ENC_SMEM_CAP);
+        launches++;
+      }
     }
     I.boundary_stride = static_cast<uint32_t>((max_ikey + 2 + 7) & ~7u);
     CUDA_TRY(DevAlloc(&I.allocs, &I.d_boundary, static_cast<size_t>(nblocks) * 2 * I.boundary_stride));
     k_boundary_keys<<<GridFor(static_cast<uint64_t>(nblocks) * 2, 256, sms), 256, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_boundary, I.boundary_stride);
-    launches += 6;
+    launches += 4;
   }
   CUDA_TRY(end_phase());
   CUDA_TRY(cudaEventRecord(I.ev1, I.stream));
