@@ -40,21 +40,36 @@ struct EncView {
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint32_t varint_len(uint32_t v) { return v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5; }
 
-// Compact the merged-order descriptors into the dense survivor list.
+// Compact the merged-order descriptors into the dense survivor list. Every warp owns a contiguous
+// slice of the chunk and walks it 32 descriptors at a time (coalesced 16-byte loads); positions
+// come from ballots, the warp bases from a count pass over the same (cache-resident) slice.
 __global__ void __launch_bounds__(EMIT_THREADS) k_compact_desc(const Desc* desc, uint64_t N, const Sums3* partial, Desc* kept) {
-  __shared__ uint32_t warp_sums[32];
-  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * EMIT_CHUNK;
-  constexpr int PER = EMIT_CHUNK / EMIT_THREADS;
-  uint32_t n = 0;
-  Desc d[PER];
-  for (int j = 0; j < PER; j++) {
-    uint64_t i = base + threadIdx.x * PER + j;
-    d[j].flags = 0;
-    if (i < N) { d[j] = desc[i]; if (d[j].flags & ENT_KEEP) n++; }
+  constexpr int NW = EMIT_THREADS / 32, PER_WARP = EMIT_CHUNK / NW;
+  static_assert(sizeof(Desc) == 16 && PER_WARP % 32 == 0, "descriptor layout");
+  __shared__ uint32_t wcount[NW];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * EMIT_CHUNK + static_cast<uint64_t>(wid) * PER_WARP;
+  const uint4* dv = reinterpret_cast<const uint4*>(desc);
+  uint32_t cnt = 0;
+  for (int r = 0; r < PER_WARP; r += 32) {
+    const uint64_t i = base + r + lane;
+    // flags live in byte 2 of the third word (gid, vlen_out, klen | flags << 16 | run << 24, rewrite_slot)
+    const bool keep = i < N && ((__ldg(reinterpret_cast<const uint32_t*>(desc + i) + 2) >> 16) & ENT_KEEP);
+    cnt += __popc(__ballot_sync(0xffffffffu, keep));
   }
-  uint32_t off = block_exclusive_scan(n, warp_sums, nullptr);
-  uint64_t o = partial[blockIdx.x].n + off;
-  for (int j = 0; j < PER; j++) if (d[j].flags & ENT_KEEP) kept[o++] = d[j];
+  if (lane == 0) wcount[wid] = cnt;
+  __syncthreads();
+  uint64_t o = partial[blockIdx.x].n;
+  for (int w = 0; w < wid; w++) o += wcount[w];
+  for (int r = 0; r < PER_WARP; r += 32) {
+    const uint64_t i = base + r + lane;
+    uint4 d = make_uint4(0, 0, 0, 0);
+    if (i < N) d = __ldg(dv + i);
+    const bool keep = ((d.z >> 16) & ENT_KEEP) != 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) reinterpret_cast<uint4*>(kept)[o + __popc(m & ((1u << lane) - 1))] = d;
+    o += __popc(m);
+  }
 }
 
 __device__ __forceinline__ const uint8_t* kept_rec(const EncView& E, const Desc& d, int S) {

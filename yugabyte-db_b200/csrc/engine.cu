@@ -96,13 +96,18 @@ __device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* p) {
 
 // ---------------------------------------------------------------------------------------------
 // K1: one warp per data block, one lane per restart interval. Walks entry headers only.
-__global__ void __launch_bounds__(256) k_prepass(RunView run, int run_idx, JobDev* J) {
+__global__ void __launch_bounds__(256) k_prepass(const RunView* runs, const uint32_t* blk_base /*[k+1]*/, int k, JobDev* J) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   unsigned long long key_bytes = 0, val_bytes = 0;
   uint32_t max_klen = 0;
-  for (uint32_t b = warp; b < run.nb; b += nwarps) {
+  const uint32_t total_blocks = blk_base[k];
+  for (uint32_t gb = warp; gb < total_blocks; gb += nwarps) {
+    int run_idx = 0;
+    while (blk_base[run_idx + 1] <= gb) run_idx++;
+    const RunView& run = runs[run_idx];
+    const uint32_t b = gb - blk_base[run_idx];
     const uint8_t* blk = run.data + run.blk_off[b];
     const uint32_t size = run.blk_size[b];
     uint32_t count = 0;
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(256) k_prepass(RunView run, int run_idx, JobDe
 }
 
 // Exclusive scan of a u32 array with one CTA (n up to a few million: nb per file).
-__global__ void __launch_bounds__(1024) k_scan_u32_single(uint32_t* a, uint32_t n, uint32_t* total) {
+__device__ __forceinline__ void scan_u32_cta(uint32_t* a, uint32_t n, uint32_t* total) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry;
   if (threadIdx.x == 0) carry = 0;
@@ -195,6 +200,11 @@ __global__ void __launch_bounds__(1024) k_scan_u32_single(uint32_t* a, uint32_t 
     __syncthreads();
   }
   if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(1024) k_scan_u32_single(uint32_t* a, uint32_t n, uint32_t* total) { scan_u32_cta(a, n, total); }
+// Per-run exclusive scan of the per-block entry counts: CTA r scans run r.
+__global__ void __launch_bounds__(1024) k_scan_blk_counts(const RunView* runs, uint32_t* totals) {
+  scan_u32_cta(runs[blockIdx.x].blk_count, runs[blockIdx.x].nb, totals + blockIdx.x);
 }
 
 // K1' (single launch): all files at once. A warp takes DEC_WB consecutive data blocks of one file
@@ -1340,25 +1350,30 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   };
 
   // ---- K1: prepass + scan per file
-  std::vector<uint32_t*> dtotals(k);
   uint32_t* d_totals = nullptr;
   CUDA_TRY(DevAlloc(&I.allocs, &d_totals, static_cast<size_t>(k) + 1));
-  for (int r = 0; r < k; r++) {
-    RunView& rv = I.runs[r];
-    dtotals[r] = d_totals + r;
-    if (rv.nb) {
-      if (opt_.verify_checksums) {
-        // ReadBlock's checksum verification (table/format.cc:352-395) for every input block
+  {
+    std::vector<uint32_t> blk_base(k + 1, 0);
+    for (int r = 0; r < k; r++) blk_base[r + 1] = blk_base[r] + I.runs[r].nb;
+    uint32_t* d_blk_base = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_blk_base, static_cast<size_t>(k) + 1));
+    CUDA_TRY(cudaMemcpyAsync(d_blk_base, blk_base.data(), 4 * (static_cast<size_t>(k) + 1), cudaMemcpyHostToDevice, I.stream));
+    CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+    if (opt_.verify_checksums) {
+      // ReadBlock's checksum verification (table/format.cc:352-395) for every input block
+      for (int r = 0; r < k; r++) {
+        RunView& rv = I.runs[r];
+        if (!rv.nb) continue;
         k_crc_blocks<<<GridFor(static_cast<uint64_t>(rv.nb) * 32, 256, sms), 256, 0, I.stream>>>(
             const_cast<uint8_t*>(rv.data), reinterpret_cast<const unsigned long long*>(rv.blk_off), rv.blk_size, nullptr, rv.nb, 1, I.dJ);
         launches++;
       }
-      k_prepass<<<GridFor(static_cast<uint64_t>(rv.nb) * 32, 256, sms), 256, 0, I.stream>>>(rv, r, I.dJ);
-      k_scan_u32_single<<<1, 1024, 0, I.stream>>>(rv.blk_count, rv.nb, dtotals[r]);
-      launches += 2;
-    } else {
-      CUDA_TRY(cudaMemsetAsync(dtotals[r], 0, 4, I.stream));
     }
+    if (blk_base[k]) {
+      k_prepass<<<GridFor(static_cast<uint64_t>(blk_base[k]) * 32, 256, sms), 256, 0, I.stream>>>(I.dRuns, d_blk_base, k, I.dJ);
+      launches++;
+    }
+    if (k) { k_scan_blk_counts<<<k, 1024, 0, I.stream>>>(I.dRuns, d_totals); launches++; }
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(end_phase());
