@@ -68,6 +68,29 @@ def test_host_table_builder_docdb_shape(pkg):
     assert data == ref.data and meta == ref.meta
 
 
+@pytest.mark.parametrize("shape", ["random", "docdb", "counter"])
+def test_host_table_builder_three_shared_parts(pkg, shape):
+    """kKeyDeltaEncodingThreeSharedParts through the host writer (the planner is the code the GPU
+    encoder runs, compiled for the host) against the oracle's ThreeSharedPartsEncoder."""
+    if shape == "random":
+        kvs = _rand_kvs(random.Random(5), 4000, klen=(1, 60))
+    elif shape == "docdb":
+        cfg = o.GenConfig(seed=6, num_rows=2500, cols=3, versions=3, num_files=1, value_len=60, tombstone_per_1024=40)
+        kvs = o.Sst.generate(cfg, 0, o.TableOptions(block_size=4096)).read_all()
+    else:
+        # same user-key length, consecutive sequence numbers / equal suffixes: last-component reuse and "+1"
+        kvs = [(o.ikey(b"row%07d" % (i // 3) + bytes([65 + i % 3]), 1000 + (i if i % 5 else 0)), b"x" * (i % 9)) for i in range(6000)]
+    topt = dict(block_size=2048, index_block_size=1024, min_keys_per_index_block=8)
+    ref = o.Sst.build(kvs, o.TableOptions(key_encoding=2, **topt))
+    b = pkg.HostTableBuilder(key_encoding=2, **topt)
+    for k, v in kvs:
+        b.add(k, v)
+    data, meta = b.finish()
+    assert data == ref.data
+    assert meta == ref.meta
+    assert [kv for kv in ref.read_all()] == kvs
+
+
 def test_product_generator_matches_oracle_generator(pkg):
     """bench.py's inputs come from the product's generator; the oracle has an independent one.
     Same spec => same bytes."""

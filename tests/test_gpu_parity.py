@@ -31,11 +31,13 @@ def okw(kw):
     """binding kwargs -> oracle CompactionParams kwargs"""
     m = dict(kw)
     m.pop("block_size", None)
+    m.pop("output_key_encoding", None)
     return m
 
 
 def check(pkg, ssts, block_size=4096, ht_filters=None, **kw):
-    exp = o.compact(ssts, o.CompactionParams(**okw(kw)), o.TableOptions(block_size=block_size), ht_filters=ht_filters)
+    topt = o.TableOptions(block_size=block_size, key_encoding=kw.get("output_key_encoding", 1))
+    exp = o.compact(ssts, o.CompactionParams(**okw(kw)), topt, ht_filters=ht_filters)
     job = gpu_compact(pkg, ssts, ht_filters=ht_filters, block_size=block_size, **kw)
     st = job.stats()
     assert job.kv_list() == exp.kv_list()
@@ -231,6 +233,36 @@ def test_three_shared_parts_inputs(pkg):
     ssts = [o.Sst.build(r, o.TableOptions(block_size=512, key_encoding=2)) for r in runs]
     for kw in w.param_grid()[:4]:
         check(pkg, ssts, block_size=1024, **kw)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_three_shared_parts_output(pkg, seed):
+    """Output encoded as kKeyDeltaEncodingThreeSharedParts on the GPU (ThreeSharedPartsEncoder,
+    block_builder.cc:265-333: shared prefix + shared middle + reused / incremented last component),
+    byte-identical files; inputs in either encoding."""
+    if seed == 0:
+        # config-2 shaped rows: consecutive columns of a row differ in one byte + the sequence number
+        cfg = o.GenConfig(seed=23, num_rows=3000, cols=4, versions=3, num_files=3, value_len=40, tombstone_per_1024=30)
+        ssts = [o.Sst.generate(cfg, f, o.TableOptions(block_size=2048, key_encoding=1 + f % 2)) for f in range(3)]
+        check(pkg, ssts, block_size=4096, output_key_encoding=2)
+        check(pkg, ssts, block_size=32768, output_key_encoding=2, cutoff_ht=o.ht_from_micros(cfg.base_micros + 1500))
+    else:
+        runs = w.random_docdb_runs(40 + seed, n_runs=1 + seed, n_rows=120 + 50 * seed)
+        ssts = [o.Sst.build(r, o.TableOptions(block_size=1024, key_encoding=1 + (i + seed) % 2)) for i, r in enumerate(runs) if r]
+        for kw in w.param_grid()[:5]:
+            check(pkg, ssts, block_size=1024 if seed % 2 else 4096, output_key_encoding=2, **kw)
+    # plain RocksDB keys (no DocDB structure): sequence numbers zeroed at the bottommost level make
+    # the last component reusable, increasing ones exercise the "+0x100" path
+    seq = 0
+    runs = []
+    for i in range(2):
+        c = []
+        for k in range(3000):
+            seq += 1
+            c.append((o.ikey(b"user%06d" % (i * 1500 + k), seq), b"v" * (k % 7)))
+        runs.append(w.sort_run(c))
+    ssts = runs_to_ssts(runs, 4096)
+    check(pkg, ssts, block_size=2048, retention=False, bottommost=bool(seed % 2), last_sequence=seq + 1, output_key_encoding=2)
 
 
 @pytest.mark.parametrize("seed", range(6))

@@ -609,6 +609,102 @@ YB_HD bool tsp_key_layout(const TspHeader& h, uint32_t prev_len, uint32_t* klen,
   return true;
 }
 
+// ---- kKeyDeltaEncodingThreeSharedParts, encoder side -------------------------------------------
+// (table/block_builder.cc:119-246,265-333; table/block_builder_internal.h:101-239.) Keys are given
+// as (user key bytes, user key length, 8-byte suffix) so that a rewritten suffix (zeroed sequence
+// number) never has to be materialised.
+struct IKeyRef { const uint8_t* u; uint32_t ulen; uint64_t suffix; };
+YB_HD uint8_t ikey_byte(const IKeyRef& k, uint32_t i) {
+  return i < k.ulen ? k.u[i] : static_cast<uint8_t>(k.suffix >> (8 * (i - k.ulen)));
+}
+YB_HD int put_varint32_hd(uint8_t* p, uint32_t v) {
+  int n = 0;
+  while (v >= 128) { p[n++] = static_cast<uint8_t>(v | 128); v >>= 7; }
+  p[n++] = static_cast<uint8_t>(v);
+  return n;
+}
+YB_HD int put_varint64_hd(uint8_t* p, uint64_t v) {
+  int n = 0;
+  while (v >= 128) { p[n++] = static_cast<uint8_t>(v | 128); v >>= 7; }
+  p[n++] = static_cast<uint8_t>(v);
+  return n;
+}
+// FindMaxSharedSubstringAtTheSamePos (block_builder.cc:119-141): only runs ended by a mismatch count.
+YB_HD void tsp_max_shared_same_pos(const IKeyRef& l, uint32_t lo, const IKeyRef& r, uint32_t ro, uint32_t n,
+                                   uint32_t* best_off, uint32_t* best) {
+  uint32_t b = 0, bo = 0, cur = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (ikey_byte(l, lo + i) == ikey_byte(r, ro + i)) cur++;
+    else { if (cur > b) { b = cur; bo = i - cur; } cur = 0; }
+  }
+  *best_off = bo; *best = b;
+}
+struct TspPlan {
+  uint32_t shared;        // shared prefix
+  uint32_t ns1, ns2;      // non-shared bytes stored: key[shared, shared+ns1) and key[klen-last_reuse-ns2, klen-last_reuse)
+  uint32_t last_reuse;    // 0 or 8
+  uint32_t hdr_len;
+  uint8_t hdr[28];
+};
+// Plans the entry for `key` following `prev` (restart => no delta encoding; `shared` = common
+// prefix of the two internal keys as plain byte strings, ignored on restarts).
+YB_HD_NOINLINE void tsp_plan(const IKeyRef& prev, const IKeyRef& key, uint32_t vlen, bool restart, uint32_t shared, TspPlan* out) {
+  const uint32_t pn = prev.ulen + 8, kn = key.ulen + 8;
+  uint32_t prev_ns1 = pn, ns1 = kn, mid = 0, prev_ns2 = 0, ns2 = 0, last_reuse = 0;
+  bool last_inc = false;
+  if (restart) shared = 0;
+  else {
+    const uint32_t min_len = pn < kn ? pn : kn;
+    if (min_len >= shared + 8) {                                     // CalculateLastInternalComponentReuse :222-246
+      if (key.suffix == prev.suffix + 0x100) { last_inc = true; last_reuse = 8; }
+      else if (key.suffix == prev.suffix) last_reuse = 8;
+    }
+    // FindMaxSharedMiddle :163-220 over prev[shared, pn - last_reuse) and key[shared, kn - last_reuse)
+    const uint32_t ln = pn - shared - last_reuse, rn = kn - shared - last_reuse;
+    uint32_t mo, ml; bool from_left = true; uint32_t min2;
+    if (ln == rn) { min2 = rn; tsp_max_shared_same_pos(prev, shared, key, shared, min2, &mo, &ml); }
+    else {
+      uint32_t lso, rso;
+      if (ln > rn) { min2 = rn; lso = shared + ln - min2; rso = shared; }
+      else { min2 = ln; lso = shared; rso = shared + rn - min2; }
+      tsp_max_shared_same_pos(prev, shared, key, shared, min2, &mo, &ml);
+      uint32_t mo2, ml2;
+      tsp_max_shared_same_pos(prev, lso, key, rso, min2, &mo2, &ml2);
+      if (ml2 > ml) { from_left = false; mo = mo2; ml = ml2; }
+    }
+    if (ml == 0) { prev_ns1 = ln; ns1 = rn; }
+    else if (from_left) { prev_ns1 = mo; ns1 = mo; mid = ml; prev_ns2 = ln - mo - ml; ns2 = rn - mo - ml; }
+    else {
+      const uint32_t mid_plus_ns2 = min2 - mo, t2 = mid_plus_ns2 - ml;
+      prev_ns1 = ln - mid_plus_ns2; ns1 = rn - mid_plus_ns2; mid = ml; prev_ns2 = t2; ns2 = t2;
+    }
+  }
+  (void)mid;
+  // EncodeThreeSharedPartsSizes (block_builder_internal.h:101-239)
+  const int64_t d1 = static_cast<int64_t>(ns1) - static_cast<int64_t>(prev_ns1);
+  const int64_t d2 = static_cast<int64_t>(ns2) - static_cast<int64_t>(prev_ns2);
+  const bool frequent = last_reuse > 0 && ns1 == 1 && ns2 == 1 && d1 == 0 && d2 == 0;
+  uint8_t* h = out->hdr; int n = 0;
+  n += put_varint64_hd(h + n, (static_cast<uint64_t>(vlen) << 2) | (static_cast<uint64_t>(last_inc) << 1) | (frequent ? 1u : 0u));
+  if (frequent) n += put_varint32_hd(h + n, shared);
+  else if (ns1 < kn) {                                               // something is reused
+    if (last_reuse > 0 && d1 == 0 && (d2 == 0 || d2 == 1) && ns1 < 8 && ns2 < 4) {
+      h[n++] = static_cast<uint8_t>(0b01 | ((d2 == 1) << 2) | (ns1 << 3) | (ns2 << 6));
+    } else {
+      h[n++] = static_cast<uint8_t>(0b11 | ((last_reuse > 0) << 2) | ((d1 != 0) << 3) | ((ns2 != 0) << 4) | ((d2 != 0) << 5));
+      n += put_varint32_hd(h + n, ns1);
+      if (d1 != 0) n += fast_varint_encode(d1, h + n);
+      if (ns2 != 0) n += put_varint32_hd(h + n, ns2);
+      if (d2 != 0) n += fast_varint_encode(d2, h + n);
+    }
+    n += put_varint32_hd(h + n, shared);
+  } else {
+    if (kn < 128 && kn > 0) h[n++] = static_cast<uint8_t>(kn << 1);
+    else { h[n++] = 0; n += put_varint32_hd(h + n, kn); }
+  }
+  out->shared = shared; out->ns1 = ns1; out->ns2 = ns2; out->last_reuse = last_reuse; out->hdr_len = static_cast<uint32_t>(n);
+}
+
 YB_HD int encode_control_fields(const ControlFields& cf, uint8_t* out) {   // value.cc:118-132
   int i = 0;
   if (cf.merge_flags) { out[i++] = 'k'; i += fast_uvarint_encode(cf.merge_flags, out + i); }

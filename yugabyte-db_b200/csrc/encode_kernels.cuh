@@ -24,7 +24,8 @@ struct EncView {
   const ValueRewrite* rewrites;
   uint32_t* nr;                    // [n] encoded size of entry as a non-restart entry
   uint16_t* shared;                // [n] bytes shared with the previous survivor's internal key
-  uint16_t* D;                     // [n] extra bytes if the entry is a restart point
+  int16_t* D;                      // [n] size difference if the entry is a restart point (negative values possible with
+                                   //     three_shared_parts; all sums below are modulo 2^64, differences come out right)
   unsigned long long* P;           // [n+1] exclusive prefix of nr
   unsigned long long* QQ;          // [n] inclusive prefix of D within the entry's residue class mod ri
   uint32_t* next;                  // [n]
@@ -35,6 +36,7 @@ struct EncView {
   uint32_t block_size;
   uint32_t deviation;
   uint32_t guess;                  // ~0.85 x expected entries per block: first probe of k_next's galloping search
+  int key_encoding;                // 1 = shared_prefix, 2 = three_shared_parts (rocksdb/types.h:50-56)
 };
 
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
@@ -113,9 +115,26 @@ __global__ void __launch_bounds__(256) k_entry_sizes(EncView E, int S) {
       }
     }
     const uint32_t vlen = d.vlen_out;
-    const uint32_t nr = varint_len(shared) + varint_len(klen - shared) + varint_len(vlen) + (klen - shared) + vlen;
-    const uint32_t rs = 1 + varint_len(klen) + varint_len(vlen) + klen + vlen;
-    E.nr[j] = nr; E.shared[j] = static_cast<uint16_t>(shared); E.D[j] = static_cast<uint16_t>(rs - nr);
+    uint32_t nr, rs;
+    if (E.key_encoding == 2) {
+      // three_shared_parts: restart entries carry (value_size << 2) and the key size, then the whole key
+      const uint64_t v4 = static_cast<uint64_t>(vlen) << 2;
+      rs = (v4 < (1ull << 28) ? varint_len(static_cast<uint32_t>(v4)) : 5u) + ((klen < 128) ? 1u : 1u + varint_len(klen)) + klen + vlen;
+      nr = rs;
+      if (j > 0) {
+        const Desc pd = E.kept[j - 1];
+        const uint8_t* prec = kept_rec(E, pd, S);
+        const IKeyRef pk{prec, pd.klen - 8u, kept_suffix(prec, pd, S)}, kk{rec, ulen, kept_suffix(rec, d, S)};
+        TspPlan pl;
+        tsp_plan(pk, kk, vlen, false, shared, &pl);
+        nr = pl.hdr_len + pl.ns1 + pl.ns2 + vlen;
+      }
+    } else {
+      nr = varint_len(shared) + varint_len(klen - shared) + varint_len(vlen) + (klen - shared) + vlen;
+      rs = 1 + varint_len(klen) + varint_len(vlen) + klen + vlen;
+    }
+    E.nr[j] = nr; E.shared[j] = static_cast<uint16_t>(shared);
+    E.D[j] = static_cast<int16_t>(static_cast<int32_t>(rs) - static_cast<int32_t>(nr));
   }
 }
 
@@ -178,32 +197,32 @@ __global__ void __launch_bounds__(256) k_p_final(const uint32_t* nr, uint32_t n,
 
 // QQ: rows of ri entries; thread = (row chunk of QROWS rows, column).
 constexpr int QROWS = 128;
-__global__ void __launch_bounds__(256) k_qq_sums(const uint16_t* D, uint32_t n, uint32_t ri, unsigned long long* partial /*[ri][nchunks]*/, uint32_t nchunks) {
+__global__ void __launch_bounds__(256) k_qq_sums(const int16_t* D, uint32_t n, uint32_t ri, unsigned long long* partial /*[ri][nchunks]*/, uint32_t nchunks) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t chunk = t / ri, col = t % ri;
   if (chunk >= nchunks) return;
   unsigned long long s = 0;
   for (int r = 0; r < QROWS; r++) {
     uint64_t i = (static_cast<uint64_t>(chunk) * QROWS + r) * ri + col;
-    if (i < n) s += D[i];
+    if (i < n) s += static_cast<unsigned long long>(static_cast<long long>(D[i]));
   }
   partial[static_cast<size_t>(col) * nchunks + chunk] = s;
 }
-__global__ void __launch_bounds__(256) k_qq_final(const uint16_t* D, uint32_t n, uint32_t ri, const unsigned long long* partial, uint32_t nchunks, unsigned long long* QQ) {
+__global__ void __launch_bounds__(256) k_qq_final(const int16_t* D, uint32_t n, uint32_t ri, const unsigned long long* partial, uint32_t nchunks, unsigned long long* QQ) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t chunk = t / ri, col = t % ri;
   if (chunk >= nchunks) return;
   unsigned long long s = partial[static_cast<size_t>(col) * nchunks + chunk];
   for (int r = 0; r < QROWS; r++) {
     uint64_t i = (static_cast<uint64_t>(chunk) * QROWS + r) * ri + col;
-    if (i < n) { s += D[i]; QQ[i] = s; }
+    if (i < n) { s += static_cast<unsigned long long>(static_cast<long long>(D[i])); QQ[i] = s; }
   }
 }
 
 // BlockBuilder::CurrentSizeEstimate after entries s..j of a block that started at s.
 __device__ __forceinline__ unsigned long long blk_cur(const EncView& E, uint32_t s, uint32_t j) {
   const uint32_t t = (j - s) >> E.ri_shift;
-  return (E.P[j + 1] - E.P[s]) + (E.QQ[s + (t << E.ri_shift)] - E.QQ[s] + E.D[s]) + 4ull * (t + 1) + 4ull;
+  return (E.P[j + 1] - E.P[s]) + (E.QQ[s + (t << E.ri_shift)] - E.QQ[s] + static_cast<unsigned long long>(static_cast<long long>(E.D[s]))) + 4ull * (t + 1) + 4ull;
 }
 
 // next[s]: first entry of the block after the one starting at s (flush_block_policy.cc:45-76).
@@ -516,6 +535,111 @@ __global__ void __launch_bounds__(256) k_crc_blocks(uint8_t* file, const unsigne
   }
 }
 
+// Bytes [sh, sh + 16) of the 32-byte pair (a, b).
+__device__ __forceinline__ uint4 shift16(const uint4& a, const uint4& b, uint32_t sh) {
+  uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+  const uint32_t q = sh >> 2, bits = (sh & 3) * 8;
+  if (q & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
+  if (q & 2) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
+  uint4 o;
+  o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
+  o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
+  return o;
+}
+
+// Bytes [from, to) of a 16-byte-aligned record in global memory into shared memory (any
+// alignment): the record is fetched as 16-byte vectors (all in flight together), the 4-byte
+// shared stores are funnel-shifted out of registers; single bytes only at the two ends.
+// Reads record bytes up to ((to + 3) & ~3) + 4 at most (inside the record stride).
+__device__ __forceinline__ void copy_rec_to_smem(uint8_t* dst, const uint8_t* rec, uint32_t from, uint32_t to) {
+  uint32_t n = to - from;
+  while (n && (reinterpret_cast<uintptr_t>(dst) & 3)) { *dst++ = __ldg(rec + from); from++; n--; }
+  const uint32_t nw = n >> 2;
+  if (nw) {
+    const uint32_t w1 = from >> 2, bits = (from & 3) * 8;
+    const uint32_t wend = w1 + nw + (bits ? 1 : 0);            // source words [w1, wend)
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+    const uint4* rv = reinterpret_cast<const uint4*>(rec);
+    uint32_t prev = 0;
+    for (uint32_t c = w1 >> 2; c * 4 < wend; c++) {
+      const uint4 v = __ldg(rv + c);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const uint32_t j = c * 4 + t;
+        if (bits) { if (j > w1 && j - 1 - w1 < nw) dw[j - 1 - w1] = __funnelshift_r(prev, w[t], bits); }
+        else if (j >= w1 && j - w1 < nw) dw[j - w1] = w[t];
+        prev = w[t];
+      }
+    }
+  }
+  for (uint32_t i = nw * 4; i < n; i++) dst[i] = __ldg(rec + from + i);
+}
+
+// n bytes from global memory (read-only path, any alignment) into shared memory (any alignment):
+// 4-byte shared stores fed by funnel-shifted aligned loads, single bytes only at the two ends.
+__device__ __forceinline__ void copy_global_to_smem(uint8_t* dst, const uint8_t* src, uint32_t n) {
+  while (n && (reinterpret_cast<uintptr_t>(dst) & 3)) { *dst++ = __ldg(src++); n--; }
+  const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3);
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - sh);
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+  const uint32_t nw = n >> 2;
+  if (sh == 0) {
+#pragma unroll 4
+    for (uint32_t i = 0; i < nw; i++) dw[i] = __ldg(sw + i);
+  } else if (nw) {
+    const uint32_t bits = sh * 8;
+    uint32_t lo = __ldg(sw);
+#pragma unroll 4
+    for (uint32_t i = 0; i < nw; i++) {
+      const uint32_t hi = __ldg(sw + i + 1);      // holds at least one byte of [src, src + n)
+      dw[i] = __funnelshift_r(lo, hi, bits);
+      lo = hi;
+    }
+  }
+  for (uint32_t i = nw * 4; i < n; i++) dst[i] = __ldg(src + i);
+}
+
+// Internal-key bytes [from, to) of a survivor (user key from the record, then the 8-byte suffix).
+__device__ __forceinline__ uint8_t* copy_ikey(uint8_t* p, const uint8_t* rec, uint32_t ulen, uint64_t suffix, uint32_t from, uint32_t to) {
+  if (from < ulen && from < to) {
+    const uint32_t e = to < ulen ? to : ulen;
+    copy_rec_to_smem(p, rec, from, e);
+    p += e - from; from = e;
+  }
+  for (uint32_t i = from; i < to; i++) *p++ = static_cast<uint8_t>(suffix >> (8 * (i - ulen)));
+  return p;
+}
+
+// Entry header + key delta of survivor j at p, either key encoding (BlockBuilder::Add,
+// table/block_builder.cc:347-412). Returns the position of the value.
+__device__ __forceinline__ uint8_t* emit_entry_key(const EncView& E, int S, uint32_t j, const Desc& d, const uint8_t* rec, uint64_t suffix,
+                                                   bool restart, uint8_t* p) {
+  const uint32_t klen = d.klen, ulen = klen - 8u, vlen = d.vlen_out;
+  if (E.key_encoding != 2) {
+    const uint32_t shared = restart ? 0u : E.shared[j];
+    p += put_varint(p, shared);
+    p += put_varint(p, klen - shared);
+    p += put_varint(p, vlen);
+    return copy_ikey(p, rec, ulen, suffix, shared, klen);
+  }
+  TspPlan pl;
+  const IKeyRef kk{rec, ulen, suffix};
+  if (restart) {
+    const IKeyRef none{nullptr, 0, 0};
+    tsp_plan(none, kk, vlen, true, 0, &pl);
+  } else {
+    const Desc pd = E.kept[j - 1];
+    const uint8_t* prec = kept_rec(E, pd, S);
+    const IKeyRef pk{prec, pd.klen - 8u, kept_suffix(prec, pd, S)};
+    tsp_plan(pk, kk, vlen, false, E.shared[j], &pl);
+  }
+  for (uint32_t i = 0; i < pl.hdr_len; i++) *p++ = pl.hdr[i];
+  p = copy_ikey(p, rec, ulen, suffix, pl.shared, pl.shared + pl.ns1);
+  const uint32_t b2 = klen - pl.last_reuse - pl.ns2;
+  return copy_ikey(p, rec, ulen, suffix, b2, b2 + pl.ns2);
+}
+
 // ---- fused encoder (v2): one CTA per output block -------------------------------------------
 // Phase A  one thread per entry: header + key delta (few bytes) straight to HBM, value copy job
 //          into a shared-memory table.
@@ -589,7 +713,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
     const unsigned long long blen = block_off[b + 1] - boff - 5;     // contents length
     uint8_t* blk = out + boff;
     const unsigned long long Ps = E.P[s];
-    const unsigned long long Qs = E.QQ[s] - E.D[s];
+    const unsigned long long Qs = E.QQ[s] - static_cast<unsigned long long>(static_cast<long long>(E.D[s]));
     const uint32_t tl = (e - 1 - s) >> E.ri_shift;
     const unsigned long long body = (E.P[e] - Ps) + (E.QQ[s + (tl << E.ri_shift)] - Qs);
 
@@ -603,14 +727,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
         if (j > s) { const uint32_t tp = (j - 1 - s) >> E.ri_shift; off += E.QQ[s + (tp << E.ri_shift)] - Qs; }
         const Desc d = E.kept[j];
         const uint8_t* rec = kept_rec(E, d, S);
-        const uint32_t klen = d.klen, ulen = klen - 8u, vlen = d.vlen_out;
-        const uint32_t shared = restart ? 0u : E.shared[j];
-        uint8_t* p = blk + off;
-        p += put_varint(p, shared);
-        p += put_varint(p, klen - shared);
-        p += put_varint(p, vlen);
-        const uint64_t suffix = kept_suffix(rec, d, S);
-        for (uint32_t i = shared; i < klen; i++) *p++ = i < ulen ? rec[i] : static_cast<uint8_t>(suffix >> (8 * (i - ulen)));
+        const uint32_t vlen = d.vlen_out;
+        uint8_t* p = emit_entry_key(E, S, j, d, rec, kept_suffix(rec, d, S), restart, blk + off);
         const RunView& run = E.runs[d.run];
         const uint8_t* vs = run.data + run.val_off[d.gid - run.gid_base];
         uint32_t copy_len = vlen;
@@ -714,71 +832,6 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
 // ENC_SMEM_CAP are left to k_encode_fused (only_big = 1).
 constexpr uint32_t ENC_SMEM_CAP = 36 * 1024;       // bytes of block image (contents + trailer) per CTA
 
-// Bytes [sh, sh + 16) of the 32-byte pair (a, b).
-__device__ __forceinline__ uint4 shift16(const uint4& a, const uint4& b, uint32_t sh) {
-  uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
-  const uint32_t q = sh >> 2, bits = (sh & 3) * 8;
-  if (q & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
-  if (q & 2) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
-  uint4 o;
-  o.x = __funnelshift_r(w0, w1, bits); o.y = __funnelshift_r(w1, w2, bits);
-  o.z = __funnelshift_r(w2, w3, bits); o.w = __funnelshift_r(w3, w4, bits);
-  return o;
-}
-
-// Bytes [from, to) of a 16-byte-aligned record in global memory into shared memory (any
-// alignment): the record is fetched as 16-byte vectors (all in flight together), the 4-byte
-// shared stores are funnel-shifted out of registers; single bytes only at the two ends.
-// Reads record bytes up to ((to + 3) & ~3) + 4 at most (inside the record stride).
-__device__ __forceinline__ void copy_rec_to_smem(uint8_t* dst, const uint8_t* rec, uint32_t from, uint32_t to) {
-  uint32_t n = to - from;
-  while (n && (reinterpret_cast<uintptr_t>(dst) & 3)) { *dst++ = __ldg(rec + from); from++; n--; }
-  const uint32_t nw = n >> 2;
-  if (nw) {
-    const uint32_t w1 = from >> 2, bits = (from & 3) * 8;
-    const uint32_t wend = w1 + nw + (bits ? 1 : 0);            // source words [w1, wend)
-    uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
-    const uint4* rv = reinterpret_cast<const uint4*>(rec);
-    uint32_t prev = 0;
-    for (uint32_t c = w1 >> 2; c * 4 < wend; c++) {
-      const uint4 v = __ldg(rv + c);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const uint32_t j = c * 4 + t;
-        if (bits) { if (j > w1 && j - 1 - w1 < nw) dw[j - 1 - w1] = __funnelshift_r(prev, w[t], bits); }
-        else if (j >= w1 && j - w1 < nw) dw[j - w1] = w[t];
-        prev = w[t];
-      }
-    }
-  }
-  for (uint32_t i = nw * 4; i < n; i++) dst[i] = __ldg(rec + from + i);
-}
-
-// n bytes from global memory (read-only path, any alignment) into shared memory (any alignment):
-// 4-byte shared stores fed by funnel-shifted aligned loads, single bytes only at the two ends.
-__device__ __forceinline__ void copy_global_to_smem(uint8_t* dst, const uint8_t* src, uint32_t n) {
-  while (n && (reinterpret_cast<uintptr_t>(dst) & 3)) { *dst++ = __ldg(src++); n--; }
-  const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3);
-  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - sh);
-  uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
-  const uint32_t nw = n >> 2;
-  if (sh == 0) {
-#pragma unroll 4
-    for (uint32_t i = 0; i < nw; i++) dw[i] = __ldg(sw + i);
-  } else if (nw) {
-    const uint32_t bits = sh * 8;
-    uint32_t lo = __ldg(sw);
-#pragma unroll 4
-    for (uint32_t i = 0; i < nw; i++) {
-      const uint32_t hi = __ldg(sw + i + 1);      // holds at least one byte of [src, src + n)
-      dw[i] = __funnelshift_r(lo, hi, bits);
-      lo = hi;
-    }
-  }
-  for (uint32_t i = nw * 4; i < n; i++) dst[i] = __ldg(src + i);
-}
-
 struct EncBlkHdr { unsigned long long boff; uint32_t btot, s, e; };
 struct EncBlkSums { unsigned long long Ps, Qs; uint32_t body, tl; };
 __device__ __forceinline__ EncBlkHdr enc_load_hdr(const EncView& E, const uint32_t* block_first, const unsigned long long* block_off,
@@ -794,7 +847,7 @@ __device__ __forceinline__ EncBlkHdr enc_load_hdr(const EncView& E, const uint32
 __device__ __forceinline__ EncBlkSums enc_load_sums(const EncView& E, const EncBlkHdr& h) {
   EncBlkSums u;
   u.Ps = E.P[h.s];
-  u.Qs = E.QQ[h.s] - E.D[h.s];
+  u.Qs = E.QQ[h.s] - static_cast<unsigned long long>(static_cast<long long>(E.D[h.s]));
   u.tl = (h.e - 1 - h.s) >> E.ri_shift;
   u.body = static_cast<uint32_t>((E.P[h.e] - u.Ps) + (E.QQ[h.s + (u.tl << E.ri_shift)] - u.Qs));
   return u;
@@ -854,17 +907,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
         if (j > s) { const uint32_t tp = (j - 1 - s) >> E.ri_shift; off += static_cast<uint32_t>(E.QQ[s + (tp << E.ri_shift)] - Qs); }
         const Desc d = E.kept[j];
         const uint8_t* rec = kept_rec(E, d, S);
-        const uint32_t klen = d.klen, ulen = klen - 8u, vlen = d.vlen_out;
-        const uint32_t shared = restart ? 0u : E.shared[j];
+        const uint32_t vlen = d.vlen_out;
         const RunView& run = E.runs[d.run];
         const uint8_t* vs = run.data + run.val_off[d.gid - run.gid_base];
-        uint8_t* p = img + off;
-        p += put_varint(p, shared);
-        p += put_varint(p, klen - shared);
-        p += put_varint(p, vlen);
-        const uint64_t suffix = kept_suffix(rec, d, S);
-        if (shared < ulen) { copy_rec_to_smem(p, rec, shared, ulen); p += ulen - shared; }
-        for (uint32_t i = shared > ulen ? shared - ulen : 0; i < 8; i++) *p++ = static_cast<uint8_t>(suffix >> (8 * i));
+        uint8_t* p = emit_entry_key(E, S, j, d, rec, kept_suffix(rec, d, S), restart, img + off);
         uint32_t copy_len = vlen;
         if (d.flags & ENT_VAL_TOMBSTONE) { p[0] = 'X'; copy_len = 0; }
         else if (d.flags & ENT_VAL_REENCODE) {

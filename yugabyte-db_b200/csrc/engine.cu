@@ -1546,13 +1546,14 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     const uint32_t ri = static_cast<uint32_t>(opt_.block_restart_interval);
     if (ri == 0 || (ri & (ri - 1)) || ri > 64)
       return Fail(YBGPU_NOT_SUPPORTED, "block_restart_interval must be a power of two <= 64 for the GPU block encoder");
-    if (opt_.output_key_encoding != YBGPU_KEY_ENCODING_SHARED_PREFIX)
-      return Fail(YBGPU_NOT_SUPPORTED, "only kKeyDeltaEncodingSharedPrefix output is encoded on the GPU so far");
+    if (opt_.output_key_encoding != YBGPU_KEY_ENCODING_SHARED_PREFIX && opt_.output_key_encoding != YBGPU_KEY_ENCODING_THREE_SHARED_PARTS)
+      return Fail(YBGPU_INVALID_ARGUMENT, "unknown output_key_encoding");
     CUDA_TRY(DevAlloc(&I.allocs, &I.d_kept, n));
     k_compact_desc<<<n_chunks, EMIT_THREADS, 0, I.stream>>>(d_desc, N, d_partial, I.d_kept);
     EncView& E = I.enc;
     E.runs = I.dRuns; E.kept = I.d_kept; E.rewrites = d_rw; E.n = n; E.ri = ri;
     E.ri_shift = 0; while ((1u << E.ri_shift) < ri) E.ri_shift++;
+    E.key_encoding = opt_.output_key_encoding;
     E.block_size = opt_.block_size; E.deviation = static_cast<uint32_t>(std::max(0, opt_.block_size_deviation));
     {
       const double avg = static_cast<double>(I.out_key_bytes + I.out_val_bytes) / n + 3.0;

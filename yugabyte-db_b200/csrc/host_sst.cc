@@ -1,5 +1,6 @@
 // host_sst.cc — see host_sst.h.
 #include "host_sst.h"
+#include "dev_logic.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -166,10 +167,28 @@ void BlockEncoder::Add(const uint8_t* key, size_t klen, const uint8_t* val, size
     const uint8_t* prev = reinterpret_cast<const uint8_t*>(last_key_.data());
     while (shared < lim && prev[shared] == key[shared]) shared++;
   }
-  AppendVarint(&body_, shared);
-  AppendVarint(&body_, klen - shared);
-  AppendVarint(&body_, vlen);
-  body_.append(reinterpret_cast<const char*>(key + shared), klen - shared);
+  if (encoding_ == 2 && klen >= 8) {
+    // kKeyDeltaEncodingThreeSharedParts (block_builder.cc:265-333): same planner as the GPU encoder
+    const bool restart = in_interval_ == 0;
+    auto ref = [](const uint8_t* k, size_t n) {
+      uint64_t suf = 0;
+      for (int i = 7; i >= 0; i--) suf = (suf << 8) | k[n - 8 + i];
+      return IKeyRef{k, static_cast<uint32_t>(n - 8), suf};
+    };
+    const IKeyRef kk = ref(key, klen);
+    const IKeyRef pk = (restart || last_key_.size() < 8) ? IKeyRef{nullptr, 0, 0}
+                                                         : ref(reinterpret_cast<const uint8_t*>(last_key_.data()), last_key_.size());
+    TspPlan pl;
+    tsp_plan(pk, kk, static_cast<uint32_t>(vlen), restart, static_cast<uint32_t>(shared), &pl);
+    body_.append(reinterpret_cast<const char*>(pl.hdr), pl.hdr_len);
+    body_.append(reinterpret_cast<const char*>(key + pl.shared), pl.ns1);
+    body_.append(reinterpret_cast<const char*>(key + klen - pl.last_reuse - pl.ns2), pl.ns2);
+  } else {
+    AppendVarint(&body_, shared);
+    AppendVarint(&body_, klen - shared);
+    AppendVarint(&body_, vlen);
+    body_.append(reinterpret_cast<const char*>(key + shared), klen - shared);
+  }
   body_.append(reinterpret_cast<const char*>(val), vlen);
   last_key_.assign(reinterpret_cast<const char*>(key), klen);
   in_interval_++;
@@ -377,7 +396,7 @@ void MetaFileWriter::Finish(const MetaProps& mp) {
 // ---------------------------------------------------------------------------------------------
 SplitSstWriter::SplitSstWriter(const TableOptions& o)
     : o_(o), block_(o.block_restart_interval, o.key_encoding), metaw_(o) {
-  if (o.key_encoding != 1) throw std::runtime_error("host writer: only kKeyDeltaEncodingSharedPrefix output");
+  if (o.key_encoding != 1 && o.key_encoding != 2) throw std::runtime_error("host writer: unknown key-value encoding format");
 }
 SplitSstWriter::~SplitSstWriter() {}
 
