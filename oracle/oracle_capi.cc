@@ -16,6 +16,7 @@ struct orc_sst { std::string data, meta; uint64_t num_entries = 0, raw_key = 0, 
 struct orc_table_options {
   uint32_t block_size; int32_t block_restart_interval; int32_t key_encoding; int32_t block_size_deviation;
   uint32_t index_block_size; uint32_t min_keys_per_index_block;
+  int32_t filter_policy; uint32_t filter_block_size;
 };
 
 struct orc_compaction_params {
@@ -58,6 +59,8 @@ static TableOptions ToOpts(const orc_table_options* o) {
     if (o->block_size_deviation >= 0) t.block_size_deviation = o->block_size_deviation;
     if (o->index_block_size) t.index_block_size = o->index_block_size;
     if (o->min_keys_per_index_block) t.min_keys_per_index_block = o->min_keys_per_index_block;
+    t.filter_policy = o->filter_policy;
+    if (o->filter_block_size) t.filter_block_size = o->filter_block_size;
   }
   return t;
 }
@@ -377,6 +380,40 @@ int orc_gen_ssts(const orc_gen_config* cfg, const orc_table_options* o, orc_sst*
     });
   for (auto& t : th) t.join();
   return failed ? -1 : 0;
+}
+
+// Metadata dump for tests: [u32 n_props]{[u32 klen][key][u32 vlen][val]} [u32 n_filters]{[u32 klen][index key][u32 flen][filter block]}.
+// Returns the size needed; fills out when cap suffices.
+uint64_t orc_sst_meta_dump(const orc_sst* s, uint8_t* out, uint64_t cap) {
+  try {
+    TableReader r; r.Open(Slice(s->meta), Slice(s->data), true);
+    std::string b;
+    auto put = [&](const std::string& x) { PutFixed32(&b, static_cast<uint32_t>(x.size())); b.append(x); };
+    PutFixed32(&b, static_cast<uint32_t>(r.properties.size()));
+    for (auto& kv : r.properties) { put(kv.first); put(kv.second); }
+    PutFixed32(&b, static_cast<uint32_t>(r.filter_blocks.size()));
+    for (auto& f : r.filter_blocks) { put(f.first); put(TableReader::ReadBlock(r.meta, f.second, true).str()); }
+    if (cap >= b.size()) memcpy(out, b.data(), b.size());
+    return b.size();
+  } catch (const std::exception& e) { g_err = e.what(); return 0; }
+}
+
+// ---- bloom filter helpers (tests) -------------------------------------------------------------
+uint32_t orc_bloom_hash(const uint8_t* key, uint64_t n) { return BloomHash(Slice(key, n)); }
+uint64_t orc_docdb_filter_prefix(const uint8_t* key, uint64_t n) { return DocKeyV3FilterPrefix(Slice(key, n)); }
+// Builds one fixed-size filter block from `count` keys ([len u32][bytes] records); returns its size
+// (contents without trailer) and copies at most cap bytes to out. params[0..2] = max_keys, num_lines, num_probes.
+uint64_t orc_fixed_size_filter(uint64_t total_bits, const uint8_t* keys, uint64_t count, uint8_t* out, uint64_t cap, uint64_t* params) {
+  FixedSizeFilterBits f(total_bits, 0.01);
+  const uint8_t* p = keys;
+  for (uint64_t i = 0; i < count; i++) { uint32_t n; memcpy(&n, p, 4); f.AddKey(Slice(p + 4, n)); p += 4 + n; }
+  if (params) { params[0] = f.max_keys(); params[1] = f.num_lines(); params[2] = f.num_probes(); }
+  std::string s = f.Finish();
+  memcpy(out, s.data(), std::min<uint64_t>(cap, s.size()));
+  return s.size();
+}
+int orc_filter_may_match(const uint8_t* filter, uint64_t flen, const uint8_t* key, uint64_t klen) {
+  return FixedSizeFilterBits::MayMatch(Slice(filter, flen), Slice(key, klen)) ? 1 : 0;
 }
 
 }  // extern "C"

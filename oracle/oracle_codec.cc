@@ -299,6 +299,15 @@ size_t DocKeyEncodedSize(Slice s, int part) {
   }
   if (hash_present) ConsumePrimitiveValues(&s);
   if (s.empty()) return s.p - begin;
+  if (part == 2) {
+    // MaxRangeComponentsToDecode (doc_key.cc:523-538): none after hashed components, else one
+    if (!hash_present) {
+      if (s[0] == kt::kGroupEnd) s.remove_prefix(1);
+      else if (IsSpecialKeyEntryType(s[0])) throw Corruption("Expected a primitive value type");
+      else SkipKeyEntry(&s);
+    }
+    return s.p - begin;
+  }
   ConsumePrimitiveValues(&s);   // range group
   return s.p - begin;
 }

@@ -149,7 +149,8 @@ constexpr uint8_t kTombstone = 'X', kPackedRowV1 = 'z', kPackedRowV2 = '|', kObj
 // entry (type byte + payload). Throws Corruption / NotSupported.
 void SkipKeyEntry(Slice* s);
 // dockv/doc_key.cc:417-422,543-590 DocKey::EncodedSize(slice, part): part 0 = kUpToId,
-// 1 = kWholeDocKey.
+// 1 = kWholeDocKey, 2 = kUpToHashOrFirstRange (hashed components, or the first range component
+// of a key without a hash code).
 size_t DocKeyEncodedSize(Slice s, int part);
 // dockv/doc_key.cc:963-996 SubDocKey::DecodeDocKeyAndSubKeyEnds (incremental on *out).
 void DecodeDocKeyAndSubKeyEnds(Slice key, std::vector<size_t>* out);

@@ -25,15 +25,27 @@ def build():
     subprocess.check_call(["make", "-s", "-C", _DIR])
 
 
+def varint(b):
+    """Decode one varint64 from the start of b."""
+    v = shift = 0
+    for c in b:
+        v |= (c & 0x7f) << shift
+        shift += 7
+        if not c & 0x80:
+            break
+    return v
+
+
 class TableOptions(C.Structure):
     _fields_ = [("block_size", C.c_uint32), ("block_restart_interval", C.c_int32),
                 ("key_encoding", C.c_int32), ("block_size_deviation", C.c_int32),
-                ("index_block_size", C.c_uint32), ("min_keys_per_index_block", C.c_uint32)]
+                ("index_block_size", C.c_uint32), ("min_keys_per_index_block", C.c_uint32),
+                ("filter_policy", C.c_int32), ("filter_block_size", C.c_uint32)]
 
     def __init__(self, block_size=32768, restart=16, key_encoding=1, deviation=10,
-                 index_block_size=32768, min_keys_per_index_block=100):
+                 index_block_size=32768, min_keys_per_index_block=100, filter_policy=0, filter_block_size=65536):
         super().__init__(block_size, restart, key_encoding, deviation, index_block_size,
-                         min_keys_per_index_block)
+                         min_keys_per_index_block, filter_policy, filter_block_size)
 
 
 class CompactionParams(C.Structure):
@@ -301,6 +313,34 @@ class Sst:
     def read_all(self, verify=True):
         r = Result(lib().orc_sst_read_all(self.h, int(verify)))
         return r.kv_list()
+
+    def _meta_dump(self):
+        L = lib()
+        L.orc_sst_meta_dump.restype = C.c_uint64
+        L.orc_sst_meta_dump.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+        n = L.orc_sst_meta_dump(self.h, None, 0)
+        buf = C.create_string_buffer(int(n))
+        L.orc_sst_meta_dump(self.h, buf, n)
+        raw, pos, out = buf.raw, 0, []
+        for _ in range(2):
+            cnt = int.from_bytes(raw[pos:pos + 4], "little"); pos += 4
+            items = []
+            for _ in range(cnt):
+                pair = []
+                for _ in range(2):
+                    ln = int.from_bytes(raw[pos:pos + 4], "little"); pos += 4
+                    pair.append(raw[pos:pos + ln]); pos += ln
+                items.append(tuple(pair))
+            out.append(items)
+        return out
+
+    def properties(self):
+        """Properties block of the metadata file: {name: raw value bytes}."""
+        return {k.decode(): v for k, v in self._meta_dump()[0]}
+
+    def filter_blocks(self):
+        """[(filter index key, filter block contents)] in index order."""
+        return self._meta_dump()[1]
 
 
 class Result:

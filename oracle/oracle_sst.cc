@@ -1,5 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_codec.h).
 #include "oracle_sst.h"
+#include <cmath>
+#include <cstring>
 
 namespace orc {
 
@@ -370,10 +372,95 @@ class MultiLevelIndexBuilder {
 };
 
 // ---------------------------------------------------------------------------------------------
+// util/hash.cc:32-75. The tail bytes are added as SIGNED chars (a disk-format quirk kept on purpose).
+uint32_t LevelDbHash(const uint8_t* data, size_t n, uint32_t seed) {
+  const uint32_t m = 0xc6a4a793u, r = 24;
+  const uint8_t* limit = data + n;
+  uint32_t h = static_cast<uint32_t>(seed ^ (n * m));
+  while (data + 4 <= limit) {
+    h += DecodeFixed32(data); data += 4;
+    h *= m; h ^= (h >> 16);
+  }
+  switch (limit - data) {
+    case 3: h += static_cast<uint32_t>(static_cast<int32_t>(static_cast<int8_t>(data[2])) << 16);  // fallthrough
+    case 2: h += static_cast<uint32_t>(static_cast<int32_t>(static_cast<int8_t>(data[1])) << 8);   // fallthrough
+    case 1: h += static_cast<uint32_t>(static_cast<int32_t>(static_cast<int8_t>(data[0])));
+            h *= m; h ^= (h >> r);
+            break;
+  }
+  return h;
+}
+
+static constexpr size_t kCacheLine = 64;      // port/port_posix.h:179
+
+FixedSizeFilterBits::FixedSizeFilterBits(size_t total_bits, double error_rate) {
+  const double kLog2 = std::log(2.0);
+  num_lines_ = (total_bits + kCacheLine * 8 - 1) / (kCacheLine * 8);
+  if (num_lines_ % 2 == 0) {                       // bloom.cc:395-403
+    if (num_lines_ * kCacheLine < 4096) num_lines_++; else num_lines_--;
+  }
+  total_bits_ = num_lines_ * kCacheLine * 8;
+  const double minus_log_error_rate = -std::log(error_rate);
+  num_probes_ = static_cast<size_t>(minus_log_error_rate / kLog2);
+  num_probes_ = std::max<size_t>(num_probes_, 1);
+  num_probes_ = std::min<size_t>(num_probes_, 255);
+  const double max_keys = total_bits_ * kLog2 * kLog2 / minus_log_error_rate;
+  max_keys_ = static_cast<size_t>(max_keys);
+  data_.assign(total_bits_ / 8 + 5, '\0');
+}
+
+void FixedSizeFilterBits::AddKey(Slice key) {
+  ++keys_added_;
+  uint32_t h = BloomHash(key);
+  const uint32_t delta = (h >> 17) | (h << 15);
+  const size_t b = (h % num_lines_) * (kCacheLine * 8);
+  for (size_t i = 0; i < num_probes_; ++i) {
+    const size_t bitpos = b + (h % (kCacheLine * 8));
+    data_[bitpos / 8] = static_cast<char>(data_[bitpos / 8] | (1 << (bitpos % 8)));
+    h += delta;
+  }
+}
+
+std::string FixedSizeFilterBits::Finish() {
+  data_[total_bits_ / 8] = static_cast<char>(num_probes_);
+  uint32_t nl = static_cast<uint32_t>(num_lines_);
+  memcpy(&data_[total_bits_ / 8 + 1], &nl, 4);
+  return data_;
+}
+
+bool FixedSizeFilterBits::MayMatch(Slice filter, Slice key) {      // bloom.cc:159-197,~330-360
+  if (filter.n <= 5) return false;
+  const size_t len = filter.n - 5;
+  const size_t num_probes = filter.p[len];
+  const uint32_t num_lines = DecodeFixed32(filter.p + len + 1);
+  if (num_lines == 0 || len % num_lines != 0) return true;
+  uint32_t h = BloomHash(key);
+  const uint32_t delta = (h >> 17) | (h << 15);
+  const size_t b = (h % num_lines) * (kCacheLine * 8);
+  for (size_t i = 0; i < num_probes; ++i) {
+    const size_t bitpos = b + (h % (kCacheLine * 8));
+    if ((filter.p[bitpos / 8] & (1 << (bitpos % 8))) == 0) return false;
+    h += delta;
+  }
+  return true;
+}
+
+size_t DocKeyV3FilterPrefix(Slice user_key) {
+  try { return DocKeyEncodedSize(user_key, 2); } catch (const std::exception&) { return 0; }
+}
+
+// ---------------------------------------------------------------------------------------------
 TableBuilder::TableBuilder(const TableOptions& o)
     : o_(o), data_block_(o.block_restart_interval, o.key_encoding, o.use_delta_encoding),
       policy_{o.block_size, static_cast<uint64_t>(o.block_size_deviation), 1, &data_block_},
-      index_(new MultiLevelIndexBuilder(o)) {}
+      index_(new MultiLevelIndexBuilder(o)) {
+  if (o.filter_policy) {
+    // block_based_table_builder.cc:398-415,465-467: the filter builder is started right away; the
+    // filter index is a plain binary-search index over bytewise-compared filter keys.
+    filter_.reset(new FixedSizeFilterBits(static_cast<size_t>(o.filter_block_size) * 8, 0.01));
+    filter_index_.reset(new BlockBuilder(o.index_block_restart_interval, kSharedPrefix));
+  }
+}
 TableBuilder::~TableBuilder() {}
 
 void TableBuilder::WriteRawBlock(Slice c, std::string* file, BlockHandle* h) {
@@ -385,8 +472,31 @@ void TableBuilder::WriteRawBlock(Slice c, std::string* file, BlockHandle* h) {
   PutFixed32(file, Crc32cMask(crc));
 }
 
+// block_based_table_builder.cc:594-620.
+void TableBuilder::FlushFilterBlock(const Slice* next_block_first_filter_key) {
+  std::string contents = filter_->Finish();
+  WriteRawBlock(Slice(contents), &meta_, &filter_pending_);
+  props_.filter_size += contents.size() + kBlockTrailerSize;
+  ++props_.num_filter_blocks;
+  if (next_block_first_filter_key) filter_.reset(new FixedSizeFilterBits(static_cast<size_t>(o_.filter_block_size) * 8, 0.01));
+  // ShortenedIndexBuilder::AddIndexEntry with BytewiseComparator (index_builder.cc:60-86)
+  if (!next_block_first_filter_key) BytewiseFindShortSuccessor(&last_filter_key_);
+  else BytewiseFindShortestSeparator(&last_filter_key_, *next_block_first_filter_key);
+  std::string enc; PutVarint64(&enc, filter_pending_.offset); PutVarint64(&enc, filter_pending_.size);
+  filter_index_->Add(Slice(last_filter_key_), Slice(enc));
+}
+
 void TableBuilder::Add(Slice key, Slice value) {
   if (policy_.Update(key, value)) FlushDataBlock(key, true);
+  if (filter_) {                                                   // block_based_table_builder.cc:514-528
+    Slice user_key(key.p, key.n - 8);
+    Slice filter_key(user_key.p, DocKeyV3FilterPrefix(user_key));
+    if (!filter_key.empty() && (props_.num_entries == 0 || Slice(last_filter_key_).compare(filter_key) != 0)) {
+      if (filter_->IsFull()) FlushFilterBlock(&filter_key);
+      filter_->AddKey(filter_key);
+      last_filter_key_ = filter_key.str();
+    }
+  }
   last_key_.assign(reinterpret_cast<const char*>(key.p), key.n);
   data_block_.Add(key, value);
   props_.num_entries++;
@@ -418,6 +528,7 @@ void TableBuilder::FlushDataBlock(Slice next_first_key, bool has_next) {
 
 void TableBuilder::Finish() {
   if (!data_block_.empty()) FlushDataBlock(Slice(), false);
+  if (filter_) FlushFilterBlock(nullptr);
   closed_ = true;
   std::string top_index;
   bool have_top = index_->FlushNextBlock(&top_index, last_index_handle_, last_index_handle_set_);
@@ -448,6 +559,15 @@ void TableBuilder::Finish() {
   { std::string v; PutFixed32(&v, index_->NumLevels()); p["rocksdb.block.based.table.index.num.levels"] = v; }
   { std::string v(1, static_cast<char>(o_.key_encoding));
     p["rocksdb.block.based.table.data.block.key.value.encoding.format"] = v; }
+  // Filter index block: written before the properties block (block_based_table_builder.cc:795-830).
+  BlockHandle filter_index_handle;
+  if (filter_) {
+    Slice fi = filter_index_->Finish();
+    WriteRawBlock(fi, &meta_, &filter_index_handle);
+    props_.filter_index_size = filter_index_->CurrentSizeEstimate() + kBlockTrailerSize;
+    p["rocksdb.filter.index.size"].clear(); PutVarint64(&p["rocksdb.filter.index.size"], props_.filter_index_size);
+    p["rocksdb.filter.policy"] = "DocKeyV3Filter";
+  }
   BlockBuilder pb(1, kSharedPrefix);
   for (auto& kv : p) pb.Add(Slice(kv.first), Slice(kv.second));
   BlockHandle props_handle;
@@ -456,6 +576,11 @@ void TableBuilder::Finish() {
   // Metaindex block.
   BlockBuilder mb(1, kSharedPrefix);
   { std::string enc; PutVarint64(&enc, props_handle.offset); PutVarint64(&enc, props_handle.size);
+    // MetaIndexBuilder keeps a sorted map (meta_blocks.cc:71-83): "fixedsizefilter." < "rocksdb."
+    if (filter_) {
+      std::string fe; PutVarint64(&fe, filter_index_handle.offset); PutVarint64(&fe, filter_index_handle.size);
+      mb.Add(Slice(std::string("fixedsizefilter.DocKeyV3Filter")), Slice(fe));
+    }
     mb.Add(Slice(std::string("rocksdb.properties")), Slice(enc)); }
   BlockHandle metaindex_handle;
   WriteRawBlock(mb.Finish(), &meta_, &metaindex_handle);
@@ -514,6 +639,11 @@ void TableReader::Open(Slice meta_file, Slice data_file, bool verify) {
         BlockHandle ph = DecodeHandle(&v);
         BlockIter pit(ReadBlock(meta, ph, verify), kSharedPrefix);
         for (pit.SeekToFirst(); pit.Valid(); pit.Next()) properties[pit.key().str()] = pit.value().str();
+      } else if (it.key().str().rfind("fixedsizefilter.", 0) == 0) {
+        Slice v = it.value();
+        BlockHandle fh = DecodeHandle(&v);
+        BlockIter fit(ReadBlock(meta, fh, verify), kSharedPrefix);
+        for (fit.SeekToFirst(); fit.Valid(); fit.Next()) { Slice hv = fit.value(); filter_blocks.emplace_back(fit.key().str(), DecodeHandle(&hv)); }
       }
     }
   }

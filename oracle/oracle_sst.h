@@ -45,7 +45,38 @@ struct TableOptions {
   int key_encoding = kSharedPrefix;
   bool use_delta_encoding = true;
   bool multi_level_index = true;            // docdb_rocksdb_util.cc:772-773
+  // 0 = no filter policy; 1 = DocDbAwareV3FilterPolicy ("DocKeyV3Filter", docdb_filter_policy.h:71-80):
+  // fixed-size bloom blocks of filter_block_size bytes, error rate 0.01 (filter_policy.h:179-180),
+  // keyed by the DocKey up to its hashed components / first range component
+  // (docdb_rocksdb_util.cc:761-763, docdb_filter_policy.cc:103-108).
+  int filter_policy = 0;
+  uint32_t filter_block_size = 64 * 1024;   // db_filter_block_size_bytes (docdb_rocksdb_util.cc:132)
 };
+
+// util/hash.cc:32-75 (the LevelDB hash) and util/hash.h:40-42.
+uint32_t LevelDbHash(const uint8_t* data, size_t n, uint32_t seed);
+inline uint32_t BloomHash(Slice key) { return LevelDbHash(key.p, key.n, 0xbc9f1d34u); }
+
+// util/bloom.cc:384-455 FixedSizeFilterBitsBuilder + :43-61 AddHash; reader side :159-197,
+// FullFilterBitsReader::HashMayMatch.
+class FixedSizeFilterBits {
+ public:
+  FixedSizeFilterBits(size_t total_bits, double error_rate);
+  void AddKey(Slice key);
+  bool IsFull() const { return keys_added_ >= max_keys_; }
+  std::string Finish();                       // filter data + num_probes byte + fixed32 num_lines
+  size_t max_keys() const { return max_keys_; }
+  size_t num_lines() const { return num_lines_; }
+  size_t num_probes() const { return num_probes_; }
+  static bool MayMatch(Slice filter, Slice key);
+ private:
+  std::string data_;
+  size_t max_keys_, keys_added_ = 0, total_bits_, num_lines_, num_probes_;
+};
+
+// FilterPolicy::KeyTransformer of DocDbAwareV3FilterPolicy (docdb_filter_policy.cc:27-47,103-108):
+// length of the filter key inside `user_key`, 0 when the key does not decode as a DocKey.
+size_t DocKeyV3FilterPrefix(Slice user_key);
 
 // table/block_builder.cc:63-412.
 class BlockBuilder {
@@ -148,6 +179,11 @@ class TableBuilder {
   std::string last_key_;
   std::string data_, meta_;
   TableProps props_;
+  void FlushFilterBlock(const Slice* next_block_first_filter_key);
+  std::unique_ptr<FixedSizeFilterBits> filter_;
+  std::unique_ptr<BlockBuilder> filter_index_;
+  std::string last_filter_key_;
+  BlockHandle filter_pending_;
   BlockHandle pending_, last_index_handle_;
   bool last_index_handle_set_ = false;
   std::vector<BlockHandle> data_handles_;
@@ -162,6 +198,9 @@ struct TableReader {
   int num_index_levels = 1;
   std::map<std::string, std::string> properties;
   std::vector<BlockHandle> data_blocks;      // in file order, from walking the index
+  // fixed-size bloom filter: (index key, block handle) of every filter block, from the filter index
+  // found under "fixedsizefilter.<policy>" in the metaindex (block_based_table_reader.cc:805-830)
+  std::vector<std::pair<std::string, BlockHandle>> filter_blocks;
   void Open(Slice meta_file, Slice data_file, bool verify_checksums = true);
   // Returns block contents (without trailer); verifies CRC if asked.
   static Slice ReadBlock(Slice file, BlockHandle h, bool verify);

@@ -613,10 +613,11 @@ __device__ __forceinline__ uint8_t* copy_ikey(uint8_t* p, const uint8_t* rec, ui
 
 // Entry header + key delta of survivor j at p, either key encoding (BlockBuilder::Add,
 // table/block_builder.cc:347-412). Returns the position of the value.
+template <int ENC>
 __device__ __forceinline__ uint8_t* emit_entry_key(const EncView& E, int S, uint32_t j, const Desc& d, const uint8_t* rec, uint64_t suffix,
                                                    bool restart, uint8_t* p) {
   const uint32_t klen = d.klen, ulen = klen - 8u, vlen = d.vlen_out;
-  if (E.key_encoding != 2) {
+  if (ENC != 2) {
     const uint32_t shared = restart ? 0u : E.shared[j];
     p += put_varint(p, shared);
     p += put_varint(p, klen - shared);
@@ -689,6 +690,7 @@ __device__ __forceinline__ void copy_chunk16(uint8_t* dst_chunk, const uint8_t* 
   *reinterpret_cast<uint4*>(dst_chunk) = o;
 }
 
+template <int ENC>
 __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
                                                                 const unsigned long long* block_off, uint8_t* out, unsigned long long min_total) {
   __shared__ uint32_t tab[4][256];
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) k_encode_fused(EncView E, int 
         const Desc d = E.kept[j];
         const uint8_t* rec = kept_rec(E, d, S);
         const uint32_t vlen = d.vlen_out;
-        uint8_t* p = emit_entry_key(E, S, j, d, rec, kept_suffix(rec, d, S), restart, blk + off);
+        uint8_t* p = emit_entry_key<ENC>(E, S, j, d, rec, kept_suffix(rec, d, S), restart, blk + off);
         const RunView& run = E.runs[d.run];
         const uint8_t* vs = run.data + run.val_off[d.gid - run.gid_base];
         uint32_t copy_len = vlen;
@@ -853,6 +855,7 @@ __device__ __forceinline__ EncBlkSums enc_load_sums(const EncView& E, const EncB
   return u;
 }
 
+template <int ENC>
 __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
                                                                const unsigned long long* block_off, uint8_t* out) {
   extern __shared__ __align__(16) uint8_t img_raw[];    // ENC_SMEM_CAP + 32
@@ -910,7 +913,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
         const uint32_t vlen = d.vlen_out;
         const RunView& run = E.runs[d.run];
         const uint8_t* vs = run.data + run.val_off[d.gid - run.gid_base];
-        uint8_t* p = emit_entry_key(E, S, j, d, rec, kept_suffix(rec, d, S), restart, img + off);
+        uint8_t* p = emit_entry_key<ENC>(E, S, j, d, rec, kept_suffix(rec, d, S), restart, img + off);
         uint32_t copy_len = vlen;
         if (d.flags & ENT_VAL_TOMBSTONE) { p[0] = 'X'; copy_len = 0; }
         else if (d.flags & ENT_VAL_REENCODE) {

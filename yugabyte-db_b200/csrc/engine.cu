@@ -1619,12 +1619,15 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(DevAlloc(&I.allocs, &I.out_file, total + 64));
     {
       const size_t esm = ENC_SMEM_CAP + 32;
-      CUDA_TRY(cudaFuncSetAttribute(k_encode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esm)));
-      k_encode_smem<<<std::min<uint32_t>(nblocks, sms * 8), ENC_THREADS, esm, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
+      const bool tsp = E.key_encoding == YBGPU_KEY_ENCODING_THREE_SHARED_PARTS;
+      auto smem_kernel = tsp ? k_encode_smem<2> : k_encode_smem<1>;
+      auto fused_kernel = tsp ? k_encode_fused<2> : k_encode_fused<1>;
+      CUDA_TRY(cudaFuncSetAttribute(smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esm)));
+      smem_kernel<<<std::min<uint32_t>(nblocks, sms * 8), ENC_THREADS, esm, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
       launches++;
       // blocks whose image does not fit shared memory (huge values)
       if (total_and_max[1] > ENC_SMEM_CAP) {
-        k_encode_fused<<<std::min<uint32_t>(nblocks, sms * 4), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file, ENC_SMEM_CAP);
+        fused_kernel<<<std::min<uint32_t>(nblocks, sms * 4), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file, ENC_SMEM_CAP);
         launches++;
       }
     }
