@@ -44,6 +44,7 @@ typedef enum ybgpu_status {
 /* rocksdb::KeyValueEncodingFormat (rocksdb/types.h:50-56); per input file from the table
  * property kDataBlockKeyValueEncodingFormat (block_based_table_reader.cc:759-765). */
 enum { YBGPU_KEY_ENCODING_SHARED_PREFIX = 1, YBGPU_KEY_ENCODING_THREE_SHARED_PARTS = 2 };
+enum { YBGPU_FILTER_NONE = 0, YBGPU_FILTER_DOCKEY_V3 = 1 };
 
 #define YBGPU_HT_MIN      0ull
 #define YBGPU_HT_MAX      0xffffffffffffffffull
@@ -92,6 +93,14 @@ typedef struct ybgpu_job_options {
   const uint8_t* range_lower; uint64_t range_lower_len;   /* len 0 = unbounded */
   const uint8_t* range_upper; uint64_t range_upper_len;
   void* cuda_stream;                 /* cudaStream_t to launch on; NULL = the legacy default stream */
+
+  /* --- bloom filter of the output (BlockBasedTableOptions::filter_policy, table.h:118-125) ---
+   * YBGPU_FILTER_DOCKEY_V3 = docdb::DocDbAwareV3FilterPolicy (docdb_rocksdb_util.cc:761-763): fixed-size
+   * filter blocks of filter_block_size bytes (db_filter_block_size_bytes, 64 KB), 1 % error rate, keyed
+   * by the DocKey up to its hashed components / first range component; written into the metadata file
+   * with a filter index (block_based_table_builder.cc:514-528,594-620,795-830). */
+  int32_t filter_policy;             /* YBGPU_FILTER_* ; default none */
+  uint32_t filter_block_size;        /* bytes; 65536 */
 } ybgpu_job_options;
 
 void ybgpu_job_options_init(ybgpu_job_options* o);   /* reference defaults */

@@ -39,6 +39,7 @@ class JobOptions(C.Structure):
         ("range_lower", C.c_char_p), ("range_lower_len", C.c_uint64),
         ("range_upper", C.c_char_p), ("range_upper_len", C.c_uint64),
         ("cuda_stream", C.c_void_p),
+        ("filter_policy", C.c_int32), ("filter_block_size", C.c_uint32),
     ]
 
 
@@ -140,7 +141,8 @@ class GpuCompactionJob:
                  retention=True, cutoff_ht=HT_MIN, cotables_cutoff_ht=HT_INVALID, table_ttl_ns=TTL_MAX_NS,
                  retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
                  restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
-                 min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b""):
+                 min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b"",
+                 filter_policy=0, filter_block_size=65536):
         L = lib()
         o = JobOptions()
         L.ybgpu_job_options_init(C.byref(o))
@@ -161,6 +163,7 @@ class GpuCompactionJob:
         o.output_key_encoding = output_key_encoding
         o.index_block_size, o.min_keys_per_index_block = index_block_size, min_keys_per_index_block
         o.verify_checksums = int(verify_checksums)
+        o.filter_policy, o.filter_block_size = filter_policy, filter_block_size
         o.cuda_stream = cuda_stream
         o.range_lower, o.range_lower_len = range_lower, len(range_lower)
         o.range_upper, o.range_upper_len = range_upper, len(range_upper)
@@ -266,7 +269,7 @@ class HostTableBuilder:
     """rocksdb::TableBuilder-shaped host writer (ybgpu_table_builder_*)."""
 
     def __init__(self, block_size=32768, restart_interval=16, deviation=10, index_block_size=32768,
-                 min_keys_per_index_block=100, key_encoding=1):
+                 min_keys_per_index_block=100, key_encoding=1, filter_policy=0, filter_block_size=65536):
         L = lib()
         L.ybgpu_table_builder_create.argtypes = [C.POINTER(JobOptions), C.POINTER(C.c_void_p)]
         L.ybgpu_table_builder_add.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
@@ -280,6 +283,7 @@ class HostTableBuilder:
         L.ybgpu_job_options_init(C.byref(o))
         o.block_size, o.block_restart_interval, o.block_size_deviation = block_size, restart_interval, deviation
         o.index_block_size, o.min_keys_per_index_block, o.output_key_encoding = index_block_size, min_keys_per_index_block, key_encoding
+        o.filter_policy, o.filter_block_size = filter_policy, filter_block_size
         self.h = C.c_void_p()
         st = L.ybgpu_table_builder_create(C.byref(o), C.byref(self.h))
         if st != 0:

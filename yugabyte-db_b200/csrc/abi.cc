@@ -51,6 +51,8 @@ void ybgpu_job_options_init(ybgpu_job_options* o) {
   o->index_block_size = 32 * 1024;
   o->min_keys_per_index_block = 100;
   o->verify_checksums = 1;
+  o->filter_policy = YBGPU_FILTER_NONE;
+  o->filter_block_size = 64 * 1024;
 }
 
 ybgpu_status ybgpu_job_create(const ybgpu_job_options* options, ybgpu_job** job) {
@@ -160,6 +162,7 @@ static ybgpu_status EnsureSst(ybgpu_job* job) {
       t.block_size = o.block_size; t.block_restart_interval = o.block_restart_interval;
       t.block_size_deviation = o.block_size_deviation; t.index_block_size = o.index_block_size;
       t.min_keys_per_index_block = o.min_keys_per_index_block; t.key_encoding = o.output_key_encoding;
+      t.filter_policy = o.filter_policy; if (o.filter_block_size) t.filter_block_size = o.filter_block_size;
       ybgpu::host::MetaFileWriter w(t);
       std::string last;
       for (uint32_t b = 0; b < nb; b++) {
@@ -238,6 +241,7 @@ ybgpu_status ybgpu_table_builder_create(const ybgpu_job_options* o, ybgpu_table_
     t.block_size = o->block_size; t.block_restart_interval = o->block_restart_interval;
     t.block_size_deviation = o->block_size_deviation; t.index_block_size = o->index_block_size;
     t.min_keys_per_index_block = o->min_keys_per_index_block; t.key_encoding = o->output_key_encoding;
+    t.filter_policy = o->filter_policy; if (o->filter_block_size) t.filter_block_size = o->filter_block_size;
     std::unique_ptr<ybgpu_table_builder> tb(new ybgpu_table_builder);
     tb->w.reset(new ybgpu::host::SplitSstWriter(t));
     *b = tb.release();

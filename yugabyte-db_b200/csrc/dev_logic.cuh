@@ -609,6 +609,50 @@ YB_HD bool tsp_key_layout(const TspHeader& h, uint32_t prev_len, uint32_t* klen,
   return true;
 }
 
+// ---- bloom filter (rocksdb/util/hash.cc:32-75, util/bloom.cc:43-61,384-455; docdb_filter_policy.cc) ----
+// The LevelDB hash; tail bytes are added as signed chars (on-disk quirk the reference keeps).
+YB_HD uint32_t leveldb_hash(const uint8_t* data, uint32_t n, uint32_t seed) {
+  const uint32_t m = 0xc6a4a793u;
+  uint32_t h = seed ^ (n * m);
+  uint32_t i = 0;
+  for (; i + 4 <= n; i += 4) {
+    h += ld_u32_unaligned(data + i);
+    h *= m; h ^= (h >> 16);
+  }
+  const uint32_t rest = n - i;
+  if (rest == 3) h += static_cast<uint32_t>(static_cast<int32_t>(static_cast<int8_t>(data[i + 2])) << 16);
+  if (rest >= 2) h += static_cast<uint32_t>(static_cast<int32_t>(static_cast<int8_t>(data[i + 1])) << 8);
+  if (rest >= 1) { h += static_cast<uint32_t>(static_cast<int32_t>(static_cast<int8_t>(data[i]))); h *= m; h ^= (h >> 24); }
+  return h;
+}
+constexpr uint32_t kBloomSeed = 0xbc9f1d34u;
+constexpr uint32_t kBloomLineBits = 64 * 8;      // CACHE_LINE_SIZE * 8 (port/port_posix.h:179)
+
+// Geometry of one fixed-size filter block (FixedSizeFilterBitsBuilder ctor, bloom.cc:389-422); the
+// host computes it (double arithmetic as in the reference) and hands the integers to the device.
+struct BloomGeometry { uint32_t num_lines, num_probes, max_keys, block_bytes; };
+
+// DocDbAwareV3FilterPolicy's key transformer: DocKey::EncodedSize(key, kUpToHashOrFirstRange)
+// (doc_key.cc:417-422,523-590,1229-1310): cotable/colocation id, then either the hash code and the
+// hashed components or, for range-partitioned keys, the first range component. 0 = not a DocKey
+// (such keys are never added to the filter, docdb_filter_policy.cc:36-39).
+YB_HD int docdb_filter_prefix_len(const uint8_t* key, int ulen) {
+  const int id = dockey_id_size(key, ulen);
+  if (id < 0) return 0;
+  int i = id;
+  bool hash_present = false;
+  if (i < ulen && key[i] != '!') {
+    if (is_special_key_entry_type(key[i])) return 0;
+    if (key[i] == 'G') { if (ulen - i < 3) return 0; i += 3; hash_present = true; }
+  }
+  if (hash_present) { const int k = consume_primitive_group(key + i, ulen - i); if (k < 0) return 0; i += k; }
+  if (i >= ulen || hash_present) return i;
+  if (key[i] == '!') return i + 1;
+  if (is_special_key_entry_type(key[i])) return 0;
+  const int k = key_entry_size(key + i, ulen - i);
+  return k < 0 ? 0 : i + k;
+}
+
 // ---- kKeyDeltaEncodingThreeSharedParts, encoder side -------------------------------------------
 // (table/block_builder.cc:119-246,265-333; table/block_builder_internal.h:101-239.) Keys are given
 // as (user key bytes, user key length, 8-byte suffix) so that a rewritten suffix (zeroed sequence

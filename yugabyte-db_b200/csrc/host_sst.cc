@@ -3,6 +3,7 @@
 #include "dev_logic.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 
@@ -332,7 +333,36 @@ static void AppendBlockTo(const std::string& c, std::string* file, Handle* h) {
   AppendU32(file, Crc32cMask(crc));
 }
 
-MetaFileWriter::MetaFileWriter(const TableOptions& o) : o_(o), index_(new IndexWriter(o)) {}
+FilterGeometry ComputeFilterGeometry(uint32_t block_bytes) {
+  // same double arithmetic, in the same order, as FixedSizeFilterBitsBuilder's ctor (bloom.cc:389-415)
+  FilterGeometry g;
+  const double kLog2 = std::log(2.0), error_rate = 0.01;
+  const size_t total_bits_in = static_cast<size_t>(block_bytes) * 8;
+  size_t num_lines = (total_bits_in + 64 * 8 - 1) / (64 * 8);
+  if (num_lines % 2 == 0) { if (num_lines * 64 < 4096) num_lines++; else num_lines--; }
+  const size_t total_bits = num_lines * 64 * 8;
+  const double minus_log_error_rate = -std::log(error_rate);
+  size_t num_probes = static_cast<size_t>(minus_log_error_rate / kLog2);
+  num_probes = std::max<size_t>(num_probes, 1);
+  num_probes = std::min<size_t>(num_probes, 255);
+  const double max_keys = total_bits * kLog2 * kLog2 / minus_log_error_rate;
+  g.num_lines = static_cast<uint32_t>(num_lines); g.num_probes = static_cast<uint32_t>(num_probes);
+  g.max_keys = static_cast<uint32_t>(static_cast<size_t>(max_keys));
+  g.filter_bytes = static_cast<uint32_t>(total_bits / 8 + 5);
+  return g;
+}
+
+// util/comparator.cc:53-93 BytewiseComparator::FindShortSuccessor
+static void ShortSuccessor(std::string* key) {
+  for (size_t i = 0; i < key->size(); i++) {
+    const uint8_t b = static_cast<uint8_t>((*key)[i]);
+    if (b != 0xff) { (*key)[i] = static_cast<char>(b + 1); key->resize(i + 1); return; }
+  }
+}
+
+MetaFileWriter::MetaFileWriter(const TableOptions& o) : o_(o), index_(new IndexWriter(o)) {
+  if (o.filter_policy) filter_index_.reset(new BlockEncoder(o.index_block_restart_interval, 1));
+}
 MetaFileWriter::~MetaFileWriter() {}
 void MetaFileWriter::AppendBlock(const std::string& c, Handle* h) { AppendBlockTo(c, &meta_, h); }
 
@@ -345,6 +375,19 @@ void MetaFileWriter::AddDataBlock(std::string* last_key, const uint8_t* next_key
     last_index_set_ = true;
     num_index_blocks_++;
   }
+}
+
+void MetaFileWriter::AddFilterBlock(const uint8_t* contents, size_t len, std::string* last_filter_key, const uint8_t* next_key, size_t next_len,
+                                    bool has_next) {
+  Handle h;
+  AppendBlock(std::string(reinterpret_cast<const char*>(contents), len), &h);
+  filter_size_ += len + kTrailer;
+  num_filter_blocks_++;
+  // ShortenedIndexBuilder::AddIndexEntry with BytewiseComparator (index_builder.cc:60-86)
+  if (has_next) ShortenUserSeparator(last_filter_key, next_key, next_len); else ShortSuccessor(last_filter_key);
+  std::string enc; AppendVarint(&enc, h.offset); AppendVarint(&enc, h.size);
+  filter_index_->Add(reinterpret_cast<const uint8_t*>(last_filter_key->data()), last_filter_key->size(),
+                     reinterpret_cast<const uint8_t*>(enc.data()), enc.size());
 }
 
 void MetaFileWriter::Finish(const MetaProps& mp) {
@@ -371,12 +414,26 @@ void MetaFileWriter::Finish(const MetaProps& mp) {
   props["rocksdb.block.based.table.prefix.filtering"] = "0";
   { std::string v; AppendU32(&v, static_cast<uint32_t>(index_->NumLevels())); props["rocksdb.block.based.table.index.num.levels"] = v; }
   props["rocksdb.block.based.table.data.block.key.value.encoding.format"] = std::string(1, static_cast<char>(o_.key_encoding));
+  Handle filter_index_handle;
+  if (filter_index_) {
+    // filter index block, then its metaindex entry (block_based_table_builder.cc:795-830)
+    const std::string& fi = filter_index_->Finish();
+    AppendBlock(fi, &filter_index_handle);
+    num("rocksdb.filter.index.size", filter_index_->SizeEstimate() + kTrailer);
+    num("rocksdb.num.filter.blocks", num_filter_blocks_);
+    num("rocksdb.filter.size", filter_size_);
+    props["rocksdb.filter.policy"] = "DocKeyV3Filter";
+  }
   BlockEncoder pb(1, 1);
   for (auto& kv : props)
     pb.Add(reinterpret_cast<const uint8_t*>(kv.first.data()), kv.first.size(), reinterpret_cast<const uint8_t*>(kv.second.data()), kv.second.size());
   Handle ph;
   AppendBlock(pb.Finish(), &ph);
   BlockEncoder mb(1, 1);
+  if (filter_index_) {   // MetaIndexBuilder sorts its keys: "fixedsizefilter." < "rocksdb." (meta_blocks.cc:71-83)
+    std::string k = "fixedsizefilter.DocKeyV3Filter", v; AppendVarint(&v, filter_index_handle.offset); AppendVarint(&v, filter_index_handle.size);
+    mb.Add(reinterpret_cast<const uint8_t*>(k.data()), k.size(), reinterpret_cast<const uint8_t*>(v.data()), v.size());
+  }
   { std::string k = "rocksdb.properties", v; AppendVarint(&v, ph.offset); AppendVarint(&v, ph.size);
     mb.Add(reinterpret_cast<const uint8_t*>(k.data()), k.size(), reinterpret_cast<const uint8_t*>(v.data()), v.size()); }
   Handle mh;
@@ -397,6 +454,7 @@ void MetaFileWriter::Finish(const MetaProps& mp) {
 SplitSstWriter::SplitSstWriter(const TableOptions& o)
     : o_(o), block_(o.block_restart_interval, o.key_encoding), metaw_(o) {
   if (o.key_encoding != 1 && o.key_encoding != 2) throw std::runtime_error("host writer: unknown key-value encoding format");
+  if (o.filter_policy) { fg_ = ComputeFilterGeometry(o.filter_block_size); filter_bits_.assign(fg_.filter_bytes, '\0'); }
 }
 SplitSstWriter::~SplitSstWriter() {}
 
@@ -407,6 +465,22 @@ void SplitSstWriter::Add(const uint8_t* key, size_t klen, const uint8_t* val, si
     const bool almost = block_.SizeAfter(klen, vlen) > o_.block_size && o_.block_size_deviation > 0 &&
                         cur * 100 > static_cast<size_t>(o_.block_size) * (100 - o_.block_size_deviation);
     if ((cur >= o_.block_size || almost) && block_.NumKeysForPolicy() >= 1) CutDataBlock(key, klen, true);
+  }
+  if (o_.filter_policy && klen >= 8) {                                  // block_based_table_builder.cc:514-528
+    const int fl = docdb_filter_prefix_len(key, static_cast<int>(klen - 8));
+    if (fl > 0 && (num_entries_ == 0 || last_filter_key_.size() != static_cast<size_t>(fl) || memcmp(last_filter_key_.data(), key, fl) != 0)) {
+      if (filter_keys_ >= fg_.max_keys) FlushFilter(key, fl, true);
+      filter_keys_++;
+      uint32_t h = leveldb_hash(key, static_cast<uint32_t>(fl), kBloomSeed);   // AddHash, bloom.cc:43-61
+      const uint32_t delta = (h >> 17) | (h << 15);
+      const size_t b = static_cast<size_t>(h % fg_.num_lines) * kBloomLineBits;
+      for (uint32_t i = 0; i < fg_.num_probes; i++) {
+        const size_t bitpos = b + (h % kBloomLineBits);
+        filter_bits_[bitpos / 8] = static_cast<char>(filter_bits_[bitpos / 8] | (1 << (bitpos % 8)));
+        h += delta;
+      }
+      last_filter_key_.assign(reinterpret_cast<const char*>(key), fl);
+    }
   }
   last_key_.assign(reinterpret_cast<const char*>(key), klen);
   block_.Add(key, klen, val, vlen);
@@ -425,8 +499,18 @@ void SplitSstWriter::CutDataBlock(const uint8_t* next_key, size_t next_len, bool
   metaw_.AddDataBlock(&last_key_, next_key, next_len, has_next, pending_);
 }
 
+void SplitSstWriter::FlushFilter(const uint8_t* next_key, size_t next_len, bool has_next) {
+  const size_t bits_bytes = fg_.filter_bytes - 5;
+  filter_bits_[bits_bytes] = static_cast<char>(fg_.num_probes);
+  memcpy(&filter_bits_[bits_bytes + 1], &fg_.num_lines, 4);
+  metaw_.AddFilterBlock(reinterpret_cast<const uint8_t*>(filter_bits_.data()), filter_bits_.size(), &last_filter_key_, next_key, next_len, has_next);
+  filter_bits_.assign(fg_.filter_bytes, '\0');
+  filter_keys_ = 0;
+}
+
 void SplitSstWriter::Finish() {
   if (!block_.empty()) CutDataBlock(nullptr, 0, false);
+  if (o_.filter_policy) FlushFilter(nullptr, 0, false);
   MetaProps mp;
   mp.raw_key_size = raw_key_; mp.raw_value_size = raw_val_; mp.data_size = data_size_; mp.num_entries = num_entries_;
   mp.num_data_blocks = num_data_blocks_; mp.deleted_keys = deleted_keys_;

@@ -41,7 +41,13 @@ struct TableOptions {
   uint32_t index_block_size = 32 * 1024;
   uint32_t min_keys_per_index_block = 100;
   int key_encoding = 1;
+  int filter_policy = 0;             // 1 = DocKeyV3Filter fixed-size bloom blocks (docdb_filter_policy.h:71-80)
+  uint32_t filter_block_size = 64 * 1024;
 };
+
+// FixedSizeFilterBitsBuilder geometry (util/bloom.cc:389-422) for filter blocks of `block_bytes`.
+struct FilterGeometry { uint32_t num_lines = 0, num_probes = 0, max_keys = 0, filter_bytes = 0; };   // filter_bytes incl. 5 metadata bytes
+FilterGeometry ComputeFilterGeometry(uint32_t block_bytes);
 
 // Append-only encoder of one block (rocksdb::BlockBuilder, table/block_builder.cc:347-412).
 class BlockEncoder {
@@ -77,11 +83,17 @@ class MetaFileWriter {
   // `last_key` = last internal key of the block (modified in place into the separator),
   // `next_key` = first key of the next block (has_next = false for the last block).
   void AddDataBlock(std::string* last_key, const uint8_t* next_key, size_t next_len, bool has_next, const Handle& h);
+  // A finished filter block (bits + 5 metadata bytes): BlockBasedTableBuilder::FlushFilterBlock
+  // (block_based_table_builder.cc:594-620). `last_filter_key` = last key added to this block,
+  // `next_key` = first key of the next filter block (has_next = false for the final flush).
+  void AddFilterBlock(const uint8_t* contents, size_t len, std::string* last_filter_key, const uint8_t* next_key, size_t next_len, bool has_next);
   void Finish(const MetaProps& p);
   const std::string& meta_file() const { return meta_; }
  private:
   void AppendBlock(const std::string& contents, Handle* h);
   TableOptions o_;
+  std::unique_ptr<BlockEncoder> filter_index_;
+  uint64_t filter_size_ = 0, num_filter_blocks_ = 0;
   std::unique_ptr<IndexWriter> index_;
   std::string meta_;
   Handle last_index_;
@@ -109,6 +121,11 @@ class SplitSstWriter {
   std::string data_, last_key_;
   Handle pending_;
   uint64_t num_entries_ = 0, raw_key_ = 0, raw_val_ = 0, data_size_ = 0, num_data_blocks_ = 0, deleted_keys_ = 0;
+  // host-side filter builder (the TableBuilder-shaped path; the compaction job builds filters on the GPU)
+  void FlushFilter(const uint8_t* next_key, size_t next_len, bool has_next);
+  FilterGeometry fg_;
+  std::string filter_bits_, last_filter_key_;
+  uint64_t filter_keys_ = 0;
 };
 
 }  // namespace host
