@@ -32,11 +32,14 @@ def okw(kw):
     m = dict(kw)
     m.pop("block_size", None)
     m.pop("output_key_encoding", None)
+    m.pop("filter_policy", None)
+    m.pop("filter_block_size", None)
     return m
 
 
 def check(pkg, ssts, block_size=4096, ht_filters=None, **kw):
-    topt = o.TableOptions(block_size=block_size, key_encoding=kw.get("output_key_encoding", 1))
+    topt = o.TableOptions(block_size=block_size, key_encoding=kw.get("output_key_encoding", 1),
+                          filter_policy=kw.get("filter_policy", 0), filter_block_size=kw.get("filter_block_size", 65536))
     exp = o.compact(ssts, o.CompactionParams(**okw(kw)), topt, ht_filters=ht_filters)
     job = gpu_compact(pkg, ssts, ht_filters=ht_filters, block_size=block_size, **kw)
     st = job.stats()
@@ -263,6 +266,37 @@ def test_three_shared_parts_output(pkg, seed):
         runs.append(w.sort_run(c))
     ssts = runs_to_ssts(runs, 4096)
     check(pkg, ssts, block_size=2048, retention=False, bottommost=bool(seed % 2), last_sequence=seq + 1, output_key_encoding=2)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_bloom_filter_blocks(pkg, seed):
+    """DocKeyV3Filter fixed-size bloom filter blocks built on the GPU (hash, bit setting, block cuts every
+    max_keys distinct filter keys) and placed by the host among the index blocks: metadata file
+    byte-identical to the oracle's BlockBasedTableBuilder restatement."""
+    if seed == 0:
+        cfg = o.GenConfig(seed=31, num_rows=6000, cols=2, versions=3, num_files=4, value_len=40, tombstone_per_1024=30)
+        ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=4096))
+        for fbs in (256, 2048, 65536):
+            check(pkg, ssts, block_size=2048, filter_policy=1, filter_block_size=fbs)
+        check(pkg, ssts, block_size=32768, filter_policy=1, filter_block_size=512, cutoff_ht=o.ht_from_micros(cfg.base_micros + 1500))
+    elif seed == 1:
+        # cotables / colocated tables: table tombstones and rows share the id prefix; range-only keys
+        runs = w.random_cotable_runs(5, n_runs=3, n_tables=5, rows_per_table=80, colocated=True)
+        ssts = runs_to_ssts(runs, 512)
+        for kw in w.param_grid()[:3]:
+            check(pkg, ssts, block_size=1024, filter_policy=1, filter_block_size=128, **kw)
+    else:
+        runs = w.random_docdb_runs(60 + seed, n_runs=2 + seed, n_rows=200 + 100 * seed)
+        ssts = runs_to_ssts(runs, 1024)
+        for kw in w.param_grid()[:4]:
+            check(pkg, ssts, block_size=1024, filter_policy=1, filter_block_size=128 * seed, output_key_encoding=seed - 1, **kw)
+    # keys that are not DocKeys never enter the filter; an empty filter block is still written
+    seq = 0
+    c = []
+    for k in range(500):
+        seq += 1
+        c.append((o.ikey(b"\x7fplain%05d" % k, seq), b"v%d" % k))
+    check(pkg, runs_to_ssts([w.sort_run(c)], 1024), block_size=1024, retention=False, filter_policy=1, filter_block_size=256)
 
 
 @pytest.mark.parametrize("seed", range(6))

@@ -164,8 +164,34 @@ static ybgpu_status EnsureSst(ybgpu_job* job) {
       t.min_keys_per_index_block = o.min_keys_per_index_block; t.key_encoding = o.output_key_encoding;
       t.filter_policy = o.filter_policy; if (o.filter_block_size) t.filter_block_size = o.filter_block_size;
       ybgpu::host::MetaFileWriter w(t);
+      // Filter blocks come finished from the GPU too. In the metadata file they are interleaved with
+      // the index blocks in the order BlockBasedTableBuilder::Add produces them: filter block f is
+      // written when the first key of block f+1 is added, i.e. at output entry first_entry[f+1], after
+      // a data block cut at the same entry (block_based_table_builder.cc:508-528).
+      uint32_t nfb = 0, fbytes = 0, fstride = 0;
+      std::vector<uint8_t> filters, fkeys; std::vector<uint32_t> ffirst, bfirst;
+      if (o.filter_policy != YBGPU_FILTER_NONE) {
+        s = Sync(job, e.FilterInfo(&nfb, &fbytes, &fstride));
+        if (s != YBGPU_OK) return s;
+        filters.resize(static_cast<size_t>(nfb) * fbytes); fkeys.resize(static_cast<size_t>(nfb) * 2 * fstride);
+        ffirst.resize(nfb); bfirst.resize(nb);
+        s = Sync(job, e.FetchFilter(filters.data(), fkeys.data(), ffirst.data(), bfirst.data()));
+        if (s != YBGPU_OK) return s;
+      }
+      uint32_t f = 0;
+      std::string flast;
+      auto flush_filter = [&](bool has_next) {
+        const uint8_t* lk = fkeys.data() + static_cast<size_t>(2 * f + 1) * fstride;       // last key of block f
+        flast.assign(reinterpret_cast<const char*>(lk + 2), lk[0] | (lk[1] << 8));
+        const uint8_t* nk = has_next ? fkeys.data() + static_cast<size_t>(2 * (f + 1)) * fstride : nullptr;   // first key of block f+1
+        w.AddFilterBlock(filters.data() + static_cast<size_t>(f) * fbytes, fbytes, &flast, nk ? nk + 2 : nullptr, nk ? (nk[0] | (nk[1] << 8)) : 0, has_next);
+        f++;
+      };
       std::string last;
       for (uint32_t b = 0; b < nb; b++) {
+        // data block b is cut when entry bfirst[b+1] arrives; filter flushes of earlier entries come first
+        // (the last data block is cut by Finish(), after every Add — hence after every such flush)
+        while (nfb && f + 1 < nfb && (b + 1 >= nb || ffirst[f + 1] < bfirst[b + 1])) flush_filter(true);
         const uint8_t* lk = bnd.data() + static_cast<size_t>(2 * b) * stride;
         const uint8_t* nk = lk + stride;
         const size_t ll = lk[0] | (lk[1] << 8), nl = nk[0] | (nk[1] << 8);
@@ -173,6 +199,7 @@ static ybgpu_status EnsureSst(ybgpu_job* job) {
         ybgpu::host::Handle h; h.offset = off[b]; h.size = off[b + 1] - off[b] - 5;
         w.AddDataBlock(&last, nk + 2, nl, b + 1 < nb, h);
       }
+      if (nfb) flush_filter(false);                       // Finish(): the final filter block
       const ybgpu_job_stats& st = e.stats();
       ybgpu::host::MetaProps mp;
       mp.raw_key_size = st.total_output_raw_key_bytes; mp.raw_value_size = st.total_output_raw_value_bytes;

@@ -630,7 +630,7 @@ constexpr uint32_t kBloomLineBits = 64 * 8;      // CACHE_LINE_SIZE * 8 (port/po
 
 // Geometry of one fixed-size filter block (FixedSizeFilterBitsBuilder ctor, bloom.cc:389-422); the
 // host computes it (double arithmetic as in the reference) and hands the integers to the device.
-struct BloomGeometry { uint32_t num_lines, num_probes, max_keys, block_bytes; };
+struct BloomGeometry { uint32_t num_lines, num_probes, max_keys, block_bytes, dev_stride; };   // dev_stride: 8-aligned pitch of a block on the device
 
 // DocDbAwareV3FilterPolicy's key transformer: DocKey::EncodedSize(key, kUpToHashOrFirstRange)
 // (doc_key.cc:417-422,523-590,1229-1310): cotable/colocation id, then either the hash code and the

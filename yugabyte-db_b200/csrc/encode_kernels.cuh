@@ -37,6 +37,7 @@ struct EncView {
   uint32_t deviation;
   uint32_t guess;                  // ~0.85 x expected entries per block: first probe of k_next's galloping search
   int key_encoding;                // 1 = shared_prefix, 2 = three_shared_parts (rocksdb/types.h:50-56)
+  uint16_t* fk_len;                // [n] bloom filter key length of the entry (0 = none), nullptr = no filter policy
 };
 
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) k_entry_sizes(EncView E, int S) {
       nr = varint_len(shared) + varint_len(klen - shared) + varint_len(vlen) + (klen - shared) + vlen;
       rs = 1 + varint_len(klen) + varint_len(vlen) + klen + vlen;
     }
+    if (E.fk_len) E.fk_len[j] = static_cast<uint16_t>(docdb_filter_prefix_len(rec, static_cast<int>(ulen)));
     E.nr[j] = nr; E.shared[j] = static_cast<uint16_t>(shared);
     E.D[j] = static_cast<int16_t>(static_cast<int32_t>(rs) - static_cast<int32_t>(nr));
   }
@@ -1065,6 +1067,77 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
       if (threadIdx.x < total - done) gdst[done + threadIdx.x] = img[done + threadIdx.x];
     }
     __syncthreads();
+  }
+}
+
+// ---- bloom filter blocks (block_based_table_builder.cc:514-528,594-620; util/bloom.cc:43-61,384-455) ----
+// is_new[j] = the entry's filter key is non-empty and differs from the last non-empty filter key
+// before it ("no need to insert duplicate keys"). Equal keys are adjacent, so the previous entry
+// decides — through the already computed shared-prefix length — unless entries without a filter
+// key lie in between (walked over; every such entry is walked once).
+__global__ void __launch_bounds__(256) k_filter_new(EncView E, int S, uint8_t* is_new) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < E.n; j += gridDim.x * blockDim.x) {
+    const uint32_t fl = E.fk_len[j];
+    uint8_t nw = 0;
+    if (fl) {
+      nw = 1;
+      if (j > 0) {
+        if (E.fk_len[j - 1]) nw = !(E.fk_len[j - 1] == fl && E.shared[j] >= fl);
+        else {
+          uint32_t i = j - 1;
+          while (i > 0 && !E.fk_len[i]) i--;
+          if (E.fk_len[i] == fl) {
+            const Desc d = E.kept[j], pd = E.kept[i];
+            nw = common_prefix_len(kept_rec(E, d, S), fl, kept_rec(E, pd, S), fl) < fl;
+          }
+        }
+      }
+    }
+    is_new[j] = nw;
+  }
+}
+
+// One thread per distinct filter key (new_entry[ord] = survivor that introduces it): hash it and set
+// its bits in filter block ord / max_keys. All probes of a key fall into one 64-byte line.
+__global__ void __launch_bounds__(256) k_filter_build(EncView E, int S, const uint32_t* new_entry, uint32_t n_keys, BloomGeometry g, uint8_t* filters) {
+  for (uint32_t ord = blockIdx.x * blockDim.x + threadIdx.x; ord < n_keys; ord += gridDim.x * blockDim.x) {
+    const uint32_t j = new_entry[ord];
+    const Desc d = E.kept[j];
+    const uint8_t* rec = kept_rec(E, d, S);
+    uint32_t h = leveldb_hash(rec, E.fk_len[j], kBloomSeed);
+    const uint32_t delta = (h >> 17) | (h << 15);
+    uint32_t* line = reinterpret_cast<uint32_t*>(filters + static_cast<size_t>(ord / g.max_keys) * g.dev_stride) + (h % g.num_lines) * (kBloomLineBits / 32);
+    for (uint32_t i = 0; i < g.num_probes; i++) {
+      const uint32_t bit = h % kBloomLineBits;
+      atomicOr(line + (bit >> 5), 1u << (bit & 31));
+      h += delta;
+    }
+  }
+}
+
+// Per filter block: metadata bytes, and for the host-side filter index the last key added to the
+// block and the first key of the block ([u16 len][bytes], stride KB each).
+__global__ void __launch_bounds__(256) k_filter_finish(EncView E, int S, const uint32_t* new_entry, uint32_t n_keys, BloomGeometry g, uint32_t nfb,
+                                                       uint8_t* filters, uint8_t* keys_out, uint32_t KB, uint32_t* first_entry) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nfb * 2; t += gridDim.x * blockDim.x) {
+    const uint32_t f = t >> 1, which = t & 1;
+    uint8_t* o = keys_out + static_cast<size_t>(t) * KB;
+    const uint32_t lo = f * g.max_keys;
+    if (lo >= n_keys) { o[0] = 0; o[1] = 0; if (!which) first_entry[f] = 0; }
+    else {
+      const uint32_t hi = min(n_keys, lo + g.max_keys);
+      const uint32_t j = new_entry[which ? hi - 1 : lo];
+      if (!which) first_entry[f] = j;
+      const uint32_t fl = E.fk_len[j];
+      const uint8_t* rec = kept_rec(E, E.kept[j], S);
+      o[0] = static_cast<uint8_t>(fl); o[1] = static_cast<uint8_t>(fl >> 8);
+      for (uint32_t q = 0; q < fl; q++) o[2 + q] = rec[q];
+    }
+    if (!which) {
+      uint8_t* meta = filters + static_cast<size_t>(f) * g.dev_stride + (g.block_bytes - 5);
+      meta[0] = static_cast<uint8_t>(g.num_probes);
+      for (int q = 0; q < 4; q++) meta[1 + q] = static_cast<uint8_t>(g.num_lines >> (8 * q));
+    }
   }
 }
 

@@ -15,6 +15,7 @@
 // All byte/integer work, HBM-bound: no tensor cores. See DESIGN.md for the data layout and the
 // per-kernel algorithmic bytes.
 #include "engine.h"
+#include "host_sst.h"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -1184,6 +1185,9 @@ struct Engine::Impl {
   uint32_t n_blocks = 0; unsigned long long* d_block_off = nullptr; uint32_t* d_block_first = nullptr;
   uint8_t* d_boundary = nullptr; uint32_t boundary_stride = 0;
   EncView enc{};
+  // bloom filter blocks
+  uint32_t n_filter_blocks = 0, filter_block_bytes = 0, filter_key_stride = 0;
+  uint8_t* d_filters = nullptr; uint8_t* d_filter_keys = nullptr; uint32_t* d_filter_first = nullptr;
 };
 
 Engine::Engine(const ybgpu_job_options& o) : opt_(o), impl_(new Impl) {
@@ -1562,6 +1566,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(DevAlloc(&I.allocs, &E.nr, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.shared, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.D, n));
     CUDA_TRY(DevAlloc(&I.allocs, &E.P, static_cast<size_t>(n) + 1)); CUDA_TRY(DevAlloc(&I.allocs, &E.QQ, n));
     CUDA_TRY(DevAlloc(&I.allocs, &E.next, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.exit1, n));
+    E.fk_len = nullptr;
+    if (opt_.filter_policy != YBGPU_FILTER_NONE) {
+      if (opt_.filter_policy != YBGPU_FILTER_DOCKEY_V3) return Fail(YBGPU_INVALID_ARGUMENT, "unknown filter_policy");
+      CUDA_TRY(DevAlloc(&I.allocs, &E.fk_len, n));
+    }
     k_entry_sizes<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E, Sfinal);
     // P
     const uint32_t pc = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
@@ -1630,6 +1639,34 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
         fused_kernel<<<std::min<uint32_t>(nblocks, sms * 4), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file, ENC_SMEM_CAP);
         launches++;
       }
+    }
+    if (E.fk_len) {
+      // ---- bloom filter blocks: distinct filter keys -> ordinals -> 64 KB blocks of max_keys keys each
+      const host::FilterGeometry hg = host::ComputeFilterGeometry(opt_.filter_block_size ? opt_.filter_block_size : 65536u);
+      BloomGeometry g{hg.num_lines, hg.num_probes, hg.max_keys, hg.filter_bytes, (hg.filter_bytes + 7u) & ~7u};
+      if (g.max_keys == 0) return Fail(YBGPU_INVALID_ARGUMENT, "filter_block_size too small");
+      uint8_t* d_is_new = nullptr; uint32_t* d_npart = nullptr; uint32_t* d_nkeys = nullptr; uint32_t* d_new_entry = nullptr;
+      CUDA_TRY(DevAlloc(&I.allocs, &d_is_new, n)); CUDA_TRY(DevAlloc(&I.allocs, &d_npart, pc + 1)); CUDA_TRY(DevAlloc(&I.allocs, &d_nkeys, 1));
+      k_filter_new<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E, Sfinal, d_is_new);
+      k_start_sums<<<pc, 256, 0, I.stream>>>(d_is_new, n, d_npart);
+      k_scan_u32_single<<<1, 1024, 0, I.stream>>>(d_npart, pc, d_nkeys);
+      uint32_t n_keys = 0;
+      CUDA_TRY(cudaMemcpyAsync(&n_keys, d_nkeys, 4, cudaMemcpyDeviceToHost, I.stream));
+      CUDA_TRY(cudaStreamSynchronize(I.stream));
+      // a (possibly empty) block is always flushed at Finish (block_based_table_builder.cc:768-770)
+      const uint32_t nfb = std::max<uint32_t>(1, (n_keys + g.max_keys - 1) / g.max_keys);
+      I.n_filter_blocks = nfb; I.filter_block_bytes = g.block_bytes;
+      I.filter_key_stride = static_cast<uint32_t>((max_ikey + 2 + 7) & ~7u);
+      CUDA_TRY(DevAlloc(&I.allocs, &d_new_entry, static_cast<size_t>(n_keys) + 1));
+      CUDA_TRY(DevAlloc(&I.allocs, &I.d_filters, static_cast<size_t>(nfb) * g.dev_stride + 16));
+      CUDA_TRY(DevAlloc(&I.allocs, &I.d_filter_keys, static_cast<size_t>(nfb) * 2 * I.filter_key_stride));
+      CUDA_TRY(DevAlloc(&I.allocs, &I.d_filter_first, nfb));
+      CUDA_TRY(cudaMemsetAsync(I.d_filters, 0, static_cast<size_t>(nfb) * g.dev_stride, I.stream));
+      k_block_first<<<pc, 256, 0, I.stream>>>(d_is_new, n, d_npart, d_new_entry);
+      if (n_keys) k_filter_build<<<GridFor(n_keys, 256, sms), 256, 0, I.stream>>>(E, Sfinal, d_new_entry, n_keys, g, I.d_filters);
+      k_filter_finish<<<GridFor(static_cast<uint64_t>(nfb) * 2, 256, sms), 256, 0, I.stream>>>(E, Sfinal, d_new_entry, n_keys, g, nfb, I.d_filters,
+                                                                                              I.d_filter_keys, I.filter_key_stride, I.d_filter_first);
+      launches += 5 + (n_keys ? 1 : 0);
     }
     I.boundary_stride = static_cast<uint32_t>((max_ikey + 2 + 7) & ~7u);
     CUDA_TRY(DevAlloc(&I.allocs, &I.d_boundary, static_cast<size_t>(nblocks) * 2 * I.boundary_stride));
@@ -1737,6 +1774,29 @@ ybgpu_status Engine::FetchOutput(uint8_t* data_file, uint64_t* block_off /*n_blo
 }
 
 uint64_t Engine::kept_deletions() const { return impl_->hJ.n_kept_deletions; }
+
+ybgpu_status Engine::FilterInfo(uint32_t* n_filter_blocks, uint32_t* block_bytes, uint32_t* key_stride) const {
+  if (!ran_) return const_cast<Engine*>(this)->Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  *n_filter_blocks = impl_->n_filter_blocks; *block_bytes = impl_->filter_block_bytes; *key_stride = impl_->filter_key_stride;
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::FetchFilter(uint8_t* filters, uint8_t* keys, uint32_t* first_entry, uint32_t* block_first) {
+  if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  Impl& I = *impl_;
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  const size_t fb = static_cast<size_t>(I.n_filter_blocks) * I.filter_block_bytes, kb = static_cast<size_t>(I.n_filter_blocks) * 2 * I.filter_key_stride;
+  if (I.n_filter_blocks) {
+    CUDA_TRY(cudaMemcpy2DAsync(filters, I.filter_block_bytes, I.d_filters, (I.filter_block_bytes + 7u) & ~7u, I.filter_block_bytes, I.n_filter_blocks,
+                               cudaMemcpyDeviceToHost, I.stream));
+    CUDA_TRY(cudaMemcpyAsync(keys, I.d_filter_keys, kb, cudaMemcpyDeviceToHost, I.stream));
+    CUDA_TRY(cudaMemcpyAsync(first_entry, I.d_filter_first, static_cast<size_t>(I.n_filter_blocks) * 4, cudaMemcpyDeviceToHost, I.stream));
+  }
+  if (I.n_blocks) CUDA_TRY(cudaMemcpyAsync(block_first, I.d_block_first, static_cast<size_t>(I.n_blocks) * 4, cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  stats_.d2h_bytes += fb + kb + static_cast<size_t>(I.n_filter_blocks) * 4 + static_cast<size_t>(I.n_blocks) * 4;
+  return YBGPU_OK;
+}
 
 ybgpu_status Engine::Digest(uint64_t* digest) {
   if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");

@@ -24,6 +24,12 @@ class Engine {
   ybgpu_status OutputInfo(uint64_t* data_len, uint32_t* n_blocks, uint32_t* boundary_stride) const;
   ybgpu_status FetchOutput(uint8_t* data_file, uint64_t* block_off, uint8_t* boundary);
   uint64_t kept_deletions() const;
+  // Bloom filter blocks of the output (filter_policy != none): number of blocks, bytes per block
+  // (bits + 5 metadata bytes), stride of the boundary key records.
+  ybgpu_status FilterInfo(uint32_t* n_filter_blocks, uint32_t* block_bytes, uint32_t* key_stride) const;
+  // filters: n*block_bytes; keys: per block [first key][last key] records ([u16 len][bytes], key_stride each);
+  // first_entry[f]: output entry whose filter key opens block f; block_first[b]: first entry of data block b.
+  ybgpu_status FetchFilter(uint8_t* filters, uint8_t* keys, uint32_t* first_entry, uint32_t* block_first);
   const ybgpu_job_options& options() const { return opt_; }
   ybgpu_job_stats& stats() { return stats_; }
   const std::string& error() const { return error_; }
