@@ -615,9 +615,10 @@ YB_HD uint32_t leveldb_hash(const uint8_t* data, uint32_t n, uint32_t seed) {
   const uint32_t m = 0xc6a4a793u;
   uint32_t h = seed ^ (n * m);
   uint32_t i = 0;
-  for (; i + 4 <= n; i += 4) {
-    h += ld_u32_unaligned(data + i);
-    h *= m; h ^= (h >> 16);
+  if ((reinterpret_cast<uintptr_t>(data) & 3) == 0) {          // records start 16-byte aligned: whole-word loads
+    for (; i + 4 <= n; i += 4) { h += *reinterpret_cast<const uint32_t*>(data + i); h *= m; h ^= (h >> 16); }
+  } else {
+    for (; i + 4 <= n; i += 4) { h += ld_u32_unaligned(data + i); h *= m; h ^= (h >> 16); }
   }
   const uint32_t rest = n - i;
   if (rest == 3) h += static_cast<uint32_t>(static_cast<int32_t>(static_cast<int8_t>(data[i + 2])) << 16);

@@ -1115,6 +1115,43 @@ __global__ void __launch_bounds__(256) k_filter_build(EncView E, int S, const ui
   }
 }
 
+// Same, one CTA per filter block with the bits assembled in shared memory (a 64 KB block fits):
+// shared-memory atomics instead of ~6 scattered global atomics per key, then one coalesced write.
+constexpr uint32_t FILTER_SMEM_MAX = 96 * 1024;
+__global__ void __launch_bounds__(1024) k_filter_build_smem(EncView E, int S, const uint32_t* new_entry, uint32_t n_keys, BloomGeometry g, uint32_t nfb,
+                                                            uint32_t parts, uint8_t* filters) {
+  // `parts` CTAs share one filter block (each takes a slice of its keys); the zero-initialised
+  // global block receives the non-zero words of every partial image by atomicOr.
+  extern __shared__ __align__(16) uint32_t fbits[];
+  const uint32_t words = g.dev_stride / 4;
+  for (uint32_t t = blockIdx.x; t < nfb * parts; t += gridDim.x) {
+    const uint32_t f = t / parts, part = t - f * parts;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) fbits[i] = 0;
+    __syncthreads();
+    const uint32_t lo = f * g.max_keys, hi = min(n_keys, lo + g.max_keys);
+    const uint32_t per = (hi - lo + parts - 1) / parts;
+    const uint32_t plo = min(hi, lo + part * per), phi = min(hi, plo + per);
+    for (uint32_t ord = plo + threadIdx.x; ord < phi; ord += blockDim.x) {
+      const uint32_t j = new_entry[ord];
+      const Desc d = E.kept[j];
+      const uint8_t* rec = kept_rec(E, d, S);
+      uint32_t h = leveldb_hash(rec, E.fk_len[j], kBloomSeed);
+      const uint32_t delta = (h >> 17) | (h << 15);
+      uint32_t* line = fbits + (h % g.num_lines) * (kBloomLineBits / 32);
+      for (uint32_t i = 0; i < g.num_probes; i++) {
+        const uint32_t bit = h % kBloomLineBits;
+        atomicOr(line + (bit >> 5), 1u << (bit & 31));
+        h += delta;
+      }
+    }
+    __syncthreads();
+    uint32_t* out = reinterpret_cast<uint32_t*>(filters + static_cast<size_t>(f) * g.dev_stride);
+    if (parts == 1) { for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) out[i] = fbits[i]; }
+    else { for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) if (fbits[i]) atomicOr(out + i, fbits[i]); }
+    __syncthreads();
+  }
+}
+
 // Per filter block: metadata bytes, and for the host-side filter index the last key added to the
 // block and the first key of the block ([u16 len][bytes], stride KB each).
 __global__ void __launch_bounds__(256) k_filter_finish(EncView E, int S, const uint32_t* new_entry, uint32_t n_keys, BloomGeometry g, uint32_t nfb,

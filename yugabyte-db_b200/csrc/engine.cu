@@ -1663,7 +1663,14 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       CUDA_TRY(DevAlloc(&I.allocs, &I.d_filter_first, nfb));
       CUDA_TRY(cudaMemsetAsync(I.d_filters, 0, static_cast<size_t>(nfb) * g.dev_stride, I.stream));
       k_block_first<<<pc, 256, 0, I.stream>>>(d_is_new, n, d_npart, d_new_entry);
-      if (n_keys) k_filter_build<<<GridFor(n_keys, 256, sms), 256, 0, I.stream>>>(E, Sfinal, d_new_entry, n_keys, g, I.d_filters);
+      if (n_keys && g.dev_stride <= FILTER_SMEM_MAX) {
+        CUDA_TRY(cudaFuncSetAttribute(k_filter_build_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.dev_stride)));
+        const uint32_t resident = std::max<uint32_t>(1, std::min<uint32_t>(2, (200u * 1024u) / (g.dev_stride + 1024u))) * sms;   // CTAs that fit at once
+        const uint32_t parts = std::max<uint32_t>(1, std::min<uint32_t>(8, resident / nfb));
+        k_filter_build_smem<<<std::min<uint32_t>(nfb * parts, resident * 4), 1024, g.dev_stride, I.stream>>>(E, Sfinal, d_new_entry, n_keys, g, nfb, parts, I.d_filters);
+      } else if (n_keys) {
+        k_filter_build<<<GridFor(n_keys, 256, sms), 256, 0, I.stream>>>(E, Sfinal, d_new_entry, n_keys, g, I.d_filters);
+      }
       k_filter_finish<<<GridFor(static_cast<uint64_t>(nfb) * 2, 256, sms), 256, 0, I.stream>>>(E, Sfinal, d_new_entry, n_keys, g, nfb, I.d_filters,
                                                                                               I.d_filter_keys, I.filter_key_stride, I.d_filter_first);
       launches += 5 + (n_keys ? 1 : 0);
