@@ -139,6 +139,9 @@ class GpuCompactionJob {
     int block_size_deviation = 10;
     uint32_t index_block_size = 32 * 1024;
     uint32_t min_keys_per_index_block = 100;
+    int output_key_encoding = YBGPU_KEY_ENCODING_SHARED_PREFIX;   // data_block_key_value_encoding_format
+    int filter_policy = YBGPU_FILTER_NONE;     // YBGPU_FILTER_DOCKEY_V3 for DocDB tables (docdb_rocksdb_util.cc:761-763)
+    uint32_t filter_block_size = 64 * 1024;    // db_filter_block_size_bytes
     bool verify_checksums = true;
     const volatile int32_t* shutting_down = nullptr;   // std::atomic<bool>* shutting_down_ in the reference
   };
@@ -171,6 +174,7 @@ class GpuCompactionJob {
     o.block_size = p_.block_size; o.block_restart_interval = p_.block_restart_interval;
     o.block_size_deviation = p_.block_size_deviation; o.index_block_size = p_.index_block_size;
     o.min_keys_per_index_block = p_.min_keys_per_index_block; o.verify_checksums = p_.verify_checksums;
+    o.output_key_encoding = p_.output_key_encoding; o.filter_policy = p_.filter_policy; o.filter_block_size = p_.filter_block_size;
     ybgpu_status s = ybgpu_job_create(&o, &job_);
     if (s != YBGPU_OK) return ToStatus(s, ybgpu_last_error());
     inputs_ = inputs;
