@@ -261,6 +261,7 @@ def main():
     launches = sum(s["gpu_kernel_launches"] for s in stats)
     out_bytes = stats[-1]["total_output_raw_key_bytes"] + stats[-1]["total_output_raw_value_bytes"]
     phases = [sum(s["phase_seconds"][i] for s in stats) / args.steps for i in range(5)]
+    enc_kernel_s = sum(s["phase_seconds"][5] for s in stats) / args.steps      # k_encode_smem alone (CUDA events around its launch)
     gpu_s = sum(s["gpu_seconds"] for s in stats) / args.steps
 
     # ---- e2e arm: host (pinned) files in, host files out ----
@@ -322,9 +323,28 @@ def main():
         "encode": out_bytes * 2.0,              # read each survivor once, write it once
     }
     names = pkg.PHASE_NAMES
+    # The dominant KERNEL: decode and merge phases are one kernel each; the encode phase is ~25 launches of
+    # which the block assembler k_encode_smem is timed separately.
+    kernel_s = {"k_decode_all": phases[1], "k_merge_filter": phases[3], "k_encode_smem": enc_kernel_s}
+    kernel_alg = {"k_decode_all": float(in_bytes),                  # must read every input entry once
+                  "k_merge_filter": float(in_bytes + out_bytes),    # charged the whole path (it moves only keys)
+                  "k_encode_smem": out_bytes * 2.0}                 # read each survivor once, write it once
+    dom_kernel = max(kernel_s, key=lambda k: kernel_s[k])
     dom = max(range(5), key=lambda i: phases[i])
-    dom_bytes = alg_bytes[names[dom]] if alg_bytes[names[dom]] else (in_bytes + out_bytes)
-    achieved = dom_bytes / phases[dom] / 1e9 if phases[dom] > 0 else 0.0
+    dom_bytes = kernel_alg[dom_kernel]
+    achieved = dom_bytes / kernel_s[dom_kernel] / 1e9 if kernel_s[dom_kernel] > 0 else 0.0
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture of this same command
+    traffic = None
+    try:
+        if args.workload == "config2" and args.rows == DEFAULT_ROWS:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_100m.json")))["kernels"]
+            for name, kd in prof.items():
+                if name.startswith(dom_kernel):
+                    def gb(x):
+                        v = float(x["value"]); return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[x["unit"]]
+                    traffic = int(gb(kd["dram__bytes_read.sum"]) + gb(kd["dram__bytes_write.sum"]))
+    except Exception:
+        traffic = None
     pipeline_achieved = (in_bytes + out_bytes) / gpu_s / 1e9 if gpu_s > 0 else 0.0
     value = in_bytes * world * args.steps / total_s / 1e9
     line = {
@@ -343,9 +363,10 @@ def main():
         "mkeys_per_s": round(n_entries * world * args.steps / total_s / 1e6, 2),
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_kind,
-                     "kernel_ms": round(phases[dom] * 1e3, 3),
+        "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                     "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_kind,
+                     "kernel_ms": round(kernel_s[dom_kernel] * 1e3, 3), "algorithmic_bytes_per_launch": int(dom_bytes),
+                     "kernels_ms": {k: round(v * 1e3, 3) for k, v in kernel_s.items()},
                      "pipeline": {"algorithmic_bytes": int(in_bytes + out_bytes), "gpu_ms": round(gpu_s * 1e3, 3),
                                   "achieved": round(pipeline_achieved, 1), "frac": round(pipeline_achieved / hbm_peak, 4)},
                      "phase_ms": {names[i]: round(phases[i] * 1e3, 3) for i in range(5)}},

@@ -133,7 +133,8 @@ typedef struct ybgpu_job_stats {
   uint64_t h2d_bytes, d2h_bytes;       /* bytes copied by add_input / fetch calls */
   /* device time per phase (CUDA events on the job's stream), seconds:
    * 0 checksum verify + block scan (K1), 1 decode (K1'), 2 partition (K2), 3 merge+filter (K3),
-   * 4 survivor scan + block encode + CRC (K4/K5) */
+   * 4 survivor scan + block encode + CRC + bloom filter blocks (K4/K5/K6),
+   * 5 the block-assembler kernel alone (k_encode_smem, one launch; part of phase 4) */
   double phase_seconds[8];
   uint32_t phase_launches[8];
 } ybgpu_job_stats;

@@ -407,6 +407,7 @@ __device__ uint32_t g_crc_xpow8[CRC_XPOW_TABLE + 1];   // x^(8m) mod P for m = 0
 constexpr uint32_t CRC_STRIDE_WORDS = 256;
 __device__ uint32_t g_crc_stride[4][256];
 __device__ uint32_t g_crc_c16[16];                     // x^(8 * 64 * g) mod P
+__device__ uint32_t g_crc_s16[4][256];                 // the same for a stride of 16 words: (x << 8b) * x^(8 * 64) mod P
 
 __global__ void k_crc_init() {
   const uint32_t i = threadIdx.x;
@@ -464,6 +465,11 @@ __global__ void k_crc_init_xpow() {
     g_crc_stride[r][x] = crc_mulmod(xp, x << (8 * (3 - r)));
   }
   if (m < 16) g_crc_c16[m] = crc_xpow_bytes(64 * m, g_crc_x2n);
+  if (m < 1024) {
+    const uint32_t xp = crc_xpow_bytes(4 * 16, g_crc_x2n);
+    const uint32_t r = m >> 8, x = m & 255;
+    g_crc_s16[r][x] = crc_mulmod(xp, x << (8 * (3 - r)));
+  }
 }
 // crc * x^(8 nbytes): table lookup + one modular multiplication for the common distances.
 __device__ __forceinline__ uint32_t crc_shift(uint32_t crc, uint64_t nbytes, const uint32_t* x2n) {
@@ -863,8 +869,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
   extern __shared__ __align__(16) uint8_t img_raw[];    // ENC_SMEM_CAP + 32
   __shared__ uint32_t tab0[256];
   __shared__ uint32_t stab[4][256];
+  __shared__ uint32_t warp_crc[2];
   __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t warp_crc[ENC_THREADS / 32];
   __shared__ unsigned long long t_src[ENC_EM_S];
   __shared__ uint32_t t_dsto[ENC_EM_S];
   __shared__ uint32_t t_len[ENC_EM_S];
@@ -873,8 +879,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
   static_assert(ENC_EM_S == ENC_THREADS && CRC_STRIDE_WORDS == ENC_THREADS, "one CRC lane per thread");
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&stab[0][0])[i] = (&g_crc_stride[0][0])[i];
   tab0[threadIdx.x] = g_crc_tab[0][threadIdx.x];
-  // x^(32 (t + 1)): moves this thread's strided partial to its distance from the end of the message
-  const uint32_t crc_kc = g_crc_xpow8[4 * (threadIdx.x + 1)];
+  // x^(32 * 4g): moves the fold of partials 4g .. 4g+3 to its distance from the end of the message
+  const uint32_t crc_kc = g_crc_xpow8[16 * (threadIdx.x & 63)];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
@@ -1037,15 +1043,27 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
           acc ^= wp[i];
         }
       }
-      uint32_t r = acc ? crc_mulmod(crc_kc, acc) : 0u;              // * T^(t + 1)
+      t_len[threadIdx.x] = acc;                                       // partial A_t (t_len is free by now)
+    }
+    __syncthreads();
+    // R = sum_t T^(t+1) A_t. 64 threads take four consecutive partials each: four ordinary word steps
+    // (byte table), then ONE multiplication by x^(32 * 4g) per thread — two warps instead of eight pay
+    // for the bit-serial modular multiplication.
+    if (threadIdx.x < 64) {
+      uint32_t r = 0;
+#pragma unroll
+      for (int tp = 3; tp >= 0; tp--) {
+        r ^= t_len[4 * threadIdx.x + tp];
+#pragma unroll
+        for (int q = 0; q < 4; q++) r = tab0[r & 0xff] ^ (r >> 8);
+      }
+      if (r) r = crc_mulmod(crc_kc, r);
       for (int o = 16; o; o >>= 1) r ^= __shfl_xor_sync(0xffffffffu, r, o);
       if (lane == 0) warp_crc[wid] = r;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      uint32_t r = 0;
-#pragma unroll
-      for (int w = 0; w < ENC_THREADS / 32; w++) r ^= warp_crc[w];
+      uint32_t r = warp_crc[0] ^ warp_crc[1];
       const uint8_t* tp = img_raw + 4 * nwords;
       for (uint32_t i = 0; i < tailb; i++) r = tab0[(r ^ tp[i]) & 0xff] ^ (r >> 8);
       const uint32_t crc = crc_mask(~r);
