@@ -428,6 +428,7 @@ struct MergeView {
 };
 
 constexpr int MERGE_THREADS = 256;
+constexpr uint8_t ENT_GROUP_START = 128;           // tile-local: first entry of a row group (never leaves the merge kernel)
 constexpr uint32_t RW_PRE_DROPPED = 0xfffffffeu;   // rw_slot marker: dropped as an overwritten older version
 constexpr int COT_CAND_MAX = 16; // first row groups of id runs per tile (>= distinct ids)
 constexpr int COT_MAX = 8;       // distinct cotable / colocation ids per tile
@@ -535,9 +536,11 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
     uint8_t* dst = recs + static_cast<size_t>(SS) * seg_start[r];
     const uint32_t vpr = S >> 4;                      // 16-byte vectors per record
     const uint32_t nvec = n * vpr;
+    const bool vpr_pow2 = (vpr & (vpr - 1)) == 0;
+    const uint32_t vpr_shift = 31 - __clz(vpr);
     for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
       const uint4 v = __ldg(src + i);
-      const uint32_t rec_i = i / vpr, q = i - rec_i * vpr;
+      const uint32_t rec_i = vpr_pow2 ? i >> vpr_shift : i / vpr, q = i - rec_i * vpr;
       uint2* d = reinterpret_cast<uint2*>(dst + static_cast<size_t>(rec_i) * SS + 16 * q);
       d[0] = make_uint2(v.x, v.y); d[1] = make_uint2(v.z, v.w);
     }
@@ -684,27 +687,21 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
         }
       }
     }
-    res[i] = f;
     bool gs = i == 0;
     if (!gs) {
       const uint32_t lp = order[i - 1];
       const uint32_t g = glen[li];
       gs = glen[lp] != g || common_prefix_len(e, g, recs + static_cast<size_t>(SS) * (lp), g) < g;
     }
-    if (gs) my_groups++;
+    if (gs) { my_groups++; f |= ENT_GROUP_START; }
+    res[i] = f;
   }
   uint32_t ngroups;
   uint32_t gbase = block_exclusive_scan(my_groups, warp_sums, &ngroups);
   for (uint32_t j = 0; j < items; j++) {
     const uint32_t i = threadIdx.x * items + j;
     if (i >= T) break;
-    bool gs = i == 0;
-    if (!gs) {
-      const uint32_t li = order[i], lp = order[i - 1];
-      const uint32_t g = glen[li];
-      gs = glen[lp] != g || common_prefix_len(recs + static_cast<size_t>(SS) * (li), g, recs + static_cast<size_t>(SS) * (lp), g) < g;
-    }
-    if (gs) gstart[gbase++] = static_cast<uint16_t>(i);
+    if (res[i] & ENT_GROUP_START) gstart[gbase++] = static_cast<uint16_t>(i);
   }
   if (threadIdx.x == 0) { gstart[ngroups] = static_cast<uint16_t>(T); sh_ngroups = ngroups; }
   __syncthreads();
@@ -909,7 +906,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
     Desc d;
     d.gid = V.runs[r].gid_base + idx;
     d.klen = static_cast<uint16_t>(rec_ulen(e, S) + 8);
-    d.flags = f; d.run = static_cast<uint8_t>(r);
+    d.flags = f & static_cast<uint8_t>(~ENT_GROUP_START); d.run = static_cast<uint8_t>(r);
     d.rewrite_slot = rw_slot[i];
     uint32_t vout = rec_vlen(e, S);
     if (f & ENT_VAL_TOMBSTONE) vout = 1;
@@ -927,7 +924,11 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   unsigned long long vals[9] = {st_counted, st_hidden, st_obsolete, st_feed, st_kept, st_kbytes, st_vbytes, st_in_k, st_in_v};
   for (int q = 0; q < 9; q++) {
     unsigned long long v = vals[q];
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (__any_sync(0xffffffffu, (v >> 26) != 0)) {       // giant values: 64-bit butterfly
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    } else {
+      v = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(v));   // one instruction per warp
+    }
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh_stats[q], v);
   }
   for (int o = 16; o; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
