@@ -278,18 +278,29 @@ def main():
         out_data = torch.empty(file_bytes + (64 << 20), dtype=torch.uint8, pin_memory=True).numpy()
         out_meta = torch.empty(max(64 << 20, file_bytes // 100), dtype=torch.uint8, pin_memory=True).numpy()
 
+        e2e_ms = {"add_inputs_h2d": 0.0, "run": 0.0, "fetch_output_d2h": 0.0, "close": 0.0}
+
         def step_e2e():
+            t0 = time.perf_counter()
             job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=bool(args.verify), cuda_stream=stream_ptr, **job_kw)
             for s, (off, sz) in zip(ssts, handles):
                 job.add_input(s.data_view(), off, sz)
+            t1 = time.perf_counter()
             job.run()
+            t2 = time.perf_counter()
             data, meta = job.fetch_output(out_data, out_meta)
+            t3 = time.perf_counter()
             st = job.stats().as_dict()
             job.close()
+            t4 = time.perf_counter()
+            for k, v in zip(e2e_ms, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                e2e_ms[k] += v * 1e3
             return st, data.size + meta.size
 
         for _ in range(min(args.warmup, 1) if args.rows >= 50_000_000 else args.warmup):
             step_e2e()
+        for k in e2e_ms:
+            e2e_ms[k] = 0.0
         barrier()
         t0 = time.perf_counter()
         res = [step_e2e() for _ in range(args.steps)]
@@ -302,7 +313,8 @@ def main():
         e2e = {"value": round(in_bytes * world * args.steps / e2e_s / 1e9, 4), "unit": "GB/s",
                "h2d_bytes_per_step": int(res[-1][0]["h2d_bytes"]), "d2h_bytes_per_step": int(res[-1][0]["d2h_bytes"]),
                "ms_per_step": round(e2e_s / args.steps * 1e3, 2), "pinned_inputs": all(ok for _, ok in pinned),
-               "output_file_bytes": int(res[-1][1]), "verify_checksums": bool(args.verify)}
+               "output_file_bytes": int(res[-1][1]), "verify_checksums": bool(args.verify),
+               "host_ms_per_step": {k: round(v / args.steps, 2) for k, v in e2e_ms.items()}}
         for v, ok in pinned:
             if ok:
                 cudart.cudaHostUnregister(v.ctypes.data)

@@ -138,6 +138,17 @@ int hh_group_prefix_len(const uint8_t* key, int ulen, int retention) {
   memcpy(p, key, ulen);
   return group_prefix_len(p, ulen, retention != 0);
 }
+// Bloom filter key length two ways: out[0] = by-product of the row-group walk (what the merge kernel
+// stores), out[1] = docdb_filter_prefix_len (what the host writer uses). Returns the group prefix length.
+int hh_filter_len_pair(const uint8_t* key, int ulen, int retention, int* out) {
+  std::vector<uint8_t> buf(ulen + 32, 0); uint8_t* p = buf.data(); p += (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+  memcpy(p, key, ulen);
+  int f = -1;
+  const int g = group_prefix_len(p, ulen, retention != 0, &f);
+  out[0] = f; out[1] = docdb_filter_prefix_len(p, ulen);
+  return g;
+}
+uint32_t hh_bloom_hash(const uint8_t* key, uint32_t n) { return leveldb_hash(key, n, kBloomSeed); }
 int hh_doc_ht_encode(uint64_t ht, uint32_t wid, uint8_t* out) { return doc_ht_encode(ht, wid, out); }
 int hh_parse_entry_header(const uint8_t* p, uint32_t avail, uint32_t* a, uint32_t* b, uint32_t* c) { return parse_entry_header(p, avail, a, b, c); }
 

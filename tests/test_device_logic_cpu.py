@@ -73,3 +73,37 @@ def test_cotables_and_colocated_tables(seed):
         kw = dict(bottommost=True, cutoff_ht=o.ht_from_micros(w.BASE_US + 35), cotables_cutoff_ht=o.ht_from_micros(w.BASE_US + 85))
         got, exp = both(runs, **kw)
         assert got == exp
+
+
+def test_bloom_filter_key_and_hash_match_the_oracle():
+    """The device-side DocKeyV3 key transformer (both the stand-alone walk and the by-product of the
+    row-group walk the merge kernel stores) and the LevelDB hash against the oracle restatement."""
+    import ctypes as C
+    import random
+    import test_oracle_bloom as ob
+    L = hh.lib()
+    L.hh_filter_len_pair.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.hh_bloom_hash.argtypes = [C.c_char_p, C.c_uint32]
+    L.hh_bloom_hash.restype = C.c_uint32
+    keys = []
+    for seed in range(6):
+        for run in w.random_docdb_runs(seed, n_runs=2, n_rows=80):
+            keys += [k[:-8] for k, _ in run]
+        for run in w.random_cotable_runs(seed, n_runs=2, n_tables=4, rows_per_table=20, colocated=bool(seed % 2)):
+            keys += [k[:-8] for k, _ in run]
+    keys += [dk.sub_doc_key(dk.doc_key(["r1", dk.kint64(5)]), [dk.kcol(1)], micros=o.YB_EPOCH_US + 1),
+             dk.sub_doc_key(dk.doc_key([], hash_code=7, hashed=["h"]), [], micros=o.YB_EPOCH_US + 1),
+             dk.sub_doc_key(dk.doc_key([]), [dk.kcol(2)], micros=o.YB_EPOCH_US + 1)]
+    assert len(keys) > 2000
+    pair = (C.c_int * 2)()
+    rng = random.Random(3)
+    for k in keys:
+        g = L.hh_filter_len_pair(k, len(k), 1, pair)
+        want = len(ob.filter_key(k))
+        assert pair[1] == want
+        if g >= 0:
+            assert pair[0] == want
+        L.hh_filter_len_pair(k, len(k), 0, pair)             # plain mode: stand-alone walk
+        assert pair[0] == want
+        fk = k[:want] + bytes(rng.randrange(256) for _ in range(rng.randrange(4)))
+        assert L.hh_bloom_hash(fk, len(fk)) == ob.bloom_hash(fk)

@@ -247,6 +247,12 @@ class GpuCompactionJob:
     def fetch_output(self, data_buf=None, meta_buf=None):
         """Copies <n>.sst.sblock.0 and <n>.sst into the given uint8 numpy buffers (allocated here when
         None). Returns views trimmed to the file sizes."""
+        if data_buf is not None and meta_buf is not None:
+            # caller-provided (pinned) buffers: one call, the metadata file is built on the host while the
+            # data file is in flight
+            self._check(lib().ybgpu_job_fetch_output(self.h, data_buf.ctypes.data, data_buf.size, meta_buf.ctypes.data, meta_buf.size))
+            dl, ml = self.output_sizes()
+            return data_buf[:dl], meta_buf[:ml]
         dl, ml = self.output_sizes()
         data = data_buf if data_buf is not None else np.empty(dl + 1, np.uint8)
         meta = meta_buf if meta_buf is not None else np.empty(ml + 1, np.uint8)

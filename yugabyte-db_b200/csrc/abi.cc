@@ -1,4 +1,7 @@
 // abi.cc — extern "C" surface declared in include/ybgpu_compaction.h.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -16,6 +19,15 @@ struct ybgpu_job {
   std::vector<uint8_t> keys, vals;
   std::vector<uint64_t> koff, voff;
   bool have_sst = false;
+  // small per-block results of the GPU the host builds the metadata file from (fetched before the
+  // big data-file copy is queued, so that they do not wait behind it on the copy engine)
+  struct SstParts {
+    bool fetched = false;
+    uint64_t data_len = 0; uint32_t nb = 0, stride = 0;
+    std::vector<uint64_t> off; std::vector<uint8_t> bnd;
+    uint32_t nfb = 0, fbytes = 0, fstride = 0;
+    std::vector<uint8_t> filters, fkeys; std::vector<uint32_t> ffirst, bfirst;
+  } parts;
   std::string meta_file;
   uint64_t data_len = 0;
   uint64_t num_blocks = 0;
@@ -144,18 +156,47 @@ ybgpu_status ybgpu_job_emit_kv_stream(ybgpu_job* job, ybgpu_emit_fn emit, void* 
 
 // Output SST: the data file comes finished from the GPU (K5); the host writes the metadata file
 // from per-block boundary keys and handles (index blocks, properties, metaindex, footer).
+static ybgpu_status FetchSstParts(ybgpu_job* job) {
+  ybgpu_job::SstParts& P = job->parts;
+  if (P.fetched) return YBGPU_OK;
+  Engine& e = *job->engine;
+  ybgpu_status s = Sync(job, e.OutputInfo(&P.data_len, &P.nb, &P.stride));
+  if (s != YBGPU_OK) return s;
+  P.off.resize(static_cast<size_t>(P.nb) + 1);
+  P.bnd.resize(static_cast<size_t>(P.nb) * 2 * P.stride);
+  s = Sync(job, e.FetchOutput(nullptr, P.off.data(), P.bnd.data()));   // the data file itself goes straight to the caller
+  if (s != YBGPU_OK) return s;
+  if (P.nb && e.options().filter_policy != YBGPU_FILTER_NONE) {
+    s = Sync(job, e.FilterInfo(&P.nfb, &P.fbytes, &P.fstride));
+    if (s != YBGPU_OK) return s;
+    P.filters.resize(static_cast<size_t>(P.nfb) * P.fbytes); P.fkeys.resize(static_cast<size_t>(P.nfb) * 2 * P.fstride);
+    P.ffirst.resize(P.nfb); P.bfirst.resize(P.nb);
+    s = Sync(job, e.FetchFilter(P.filters.data(), P.fkeys.data(), P.ffirst.data(), P.bfirst.data()));
+    if (s != YBGPU_OK) return s;
+  }
+  P.fetched = true;
+  return YBGPU_OK;
+}
+
 static ybgpu_status EnsureSst(ybgpu_job* job) {
   if (job->have_sst) return YBGPU_OK;
   Engine& e = *job->engine;
-  uint64_t data_len = 0; uint32_t nb = 0, stride = 0;
-  ybgpu_status s = Sync(job, e.OutputInfo(&data_len, &nb, &stride));
+  const bool trace = getenv("YBGPU_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (!trace) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ybgpu trace] sst/%-12s %8.3f ms (host wall)\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
+  ybgpu_status s = FetchSstParts(job);
   if (s != YBGPU_OK) return s;
+  tick("fetch parts");
+  ybgpu_job::SstParts& P = job->parts;
+  const uint64_t data_len = P.data_len; const uint32_t nb = P.nb, stride = P.stride;
+  const std::vector<uint64_t>& off = P.off; const std::vector<uint8_t>& bnd = P.bnd;
   try {
     job->data_len = data_len;
-    std::vector<uint64_t> off(static_cast<size_t>(nb) + 1);
-    std::vector<uint8_t> bnd(static_cast<size_t>(nb) * 2 * stride);
-    s = Sync(job, e.FetchOutput(nullptr, off.data(), bnd.data()));   // the data file itself goes straight to the caller
-    if (s != YBGPU_OK) return s;
     if (nb) {   // the reference never opens an output file for an empty result (compaction_job.cc:156-160)
       const ybgpu_job_options& o = e.options();
       ybgpu::host::TableOptions t;
@@ -168,16 +209,9 @@ static ybgpu_status EnsureSst(ybgpu_job* job) {
       // the index blocks in the order BlockBasedTableBuilder::Add produces them: filter block f is
       // written when the first key of block f+1 is added, i.e. at output entry first_entry[f+1], after
       // a data block cut at the same entry (block_based_table_builder.cc:508-528).
-      uint32_t nfb = 0, fbytes = 0, fstride = 0;
-      std::vector<uint8_t> filters, fkeys; std::vector<uint32_t> ffirst, bfirst;
-      if (o.filter_policy != YBGPU_FILTER_NONE) {
-        s = Sync(job, e.FilterInfo(&nfb, &fbytes, &fstride));
-        if (s != YBGPU_OK) return s;
-        filters.resize(static_cast<size_t>(nfb) * fbytes); fkeys.resize(static_cast<size_t>(nfb) * 2 * fstride);
-        ffirst.resize(nfb); bfirst.resize(nb);
-        s = Sync(job, e.FetchFilter(filters.data(), fkeys.data(), ffirst.data(), bfirst.data()));
-        if (s != YBGPU_OK) return s;
-      }
+      const uint32_t nfb = P.nfb, fbytes = P.fbytes, fstride = P.fstride;
+      const std::vector<uint8_t>& filters = P.filters; const std::vector<uint8_t>& fkeys = P.fkeys;
+      const std::vector<uint32_t>& ffirst = P.ffirst; const std::vector<uint32_t>& bfirst = P.bfirst;
       uint32_t f = 0;
       std::string flast;
       auto flush_filter = [&](bool has_next) {
@@ -205,8 +239,10 @@ static ybgpu_status EnsureSst(ybgpu_job* job) {
       mp.raw_key_size = st.total_output_raw_key_bytes; mp.raw_value_size = st.total_output_raw_value_bytes;
       mp.data_size = data_len; mp.num_entries = st.num_output_records; mp.num_data_blocks = nb;
       mp.deleted_keys = e.kept_deletions();
+      tick("index+filter");
       w.Finish(mp);
       job->meta_file = w.meta_file();
+      tick("finish");
     }
     job->num_blocks = nb;
     job->have_sst = true;
@@ -226,13 +262,21 @@ ybgpu_status ybgpu_job_output_sizes(const ybgpu_job* job, uint64_t* data_len, ui
 
 ybgpu_status ybgpu_job_fetch_output(ybgpu_job* job, uint8_t* data_file, uint64_t data_cap, uint8_t* meta_file, uint64_t meta_cap) {
   if (!job) return YBGPU_INVALID_ARGUMENT;
-  ybgpu_status s = EnsureSst(job);
+  // The data file goes D2H straight into the caller's buffer on a copy stream; the host builds the
+  // metadata file (index blocks, filter index, properties) while that DMA runs.
+  uint64_t data_len = 0; uint32_t nb = 0, stride = 0;
+  ybgpu_status s = Sync(job, job->engine->OutputInfo(&data_len, &nb, &stride));
   if (s != YBGPU_OK) return s;
-  if (data_cap < job->data_len || meta_cap < job->meta_file.size()) return JobFail(job, YBGPU_INVALID_ARGUMENT, "output buffer too small");
-  if (job->data_len) {
-    s = Sync(job, job->engine->FetchOutput(data_file, nullptr, nullptr));   // D2H directly into the caller's buffer
-    if (s != YBGPU_OK) return s;
-  }
+  if (data_cap < data_len) return JobFail(job, YBGPU_INVALID_ARGUMENT, "output buffer too small");
+  s = FetchSstParts(job);                 // small D2H copies first: they must not queue behind the data file
+  if (s != YBGPU_OK) return s;
+  s = Sync(job, job->engine->BeginFetchDataFile(data_file));
+  if (s != YBGPU_OK) return s;
+  s = EnsureSst(job);
+  ybgpu_status s2 = Sync(job, job->engine->EndFetchDataFile());
+  if (s != YBGPU_OK) return s;
+  if (s2 != YBGPU_OK) return s2;
+  if (meta_cap < job->meta_file.size()) return JobFail(job, YBGPU_INVALID_ARGUMENT, "output buffer too small");
   memcpy(meta_file, job->meta_file.data(), job->meta_file.size());
   return YBGPU_OK;
 }

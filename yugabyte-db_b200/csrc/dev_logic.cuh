@@ -393,7 +393,10 @@ YB_HD int dockey_id_size(const uint8_t* p, int n) {
 }
 
 // DocKey::EncodedSize(kWholeDocKey) of the bytes after the id prefix (doc_key.cc:543-590).
-YB_HD int dockey_body_size(const uint8_t* p, int n) {
+YB_HD int dockey_body_size(const uint8_t* p, int n, int* filter_end = nullptr) {
+  // *filter_end (when asked for): end of the part DocDbAwareV3FilterPolicy keys the bloom filter by —
+  // hashed components, or the first range component of a key without hash code
+  // (DocKeyPart::kUpToHashOrFirstRange, doc_key.cc:523-538) — a by-product of this walk.
   int i = 0;
   bool hash_present = false;
   if (n > 0 && p[0] != '!') {
@@ -401,7 +404,12 @@ YB_HD int dockey_body_size(const uint8_t* p, int n) {
     if (p[0] == 'G') { if (n < 3) return -DEV_ERR_BAD_KEY; i = 3; hash_present = true; }
   }
   if (hash_present) { int k = consume_primitive_group(p + i, n - i); if (k < 0) return k; i += k; }
+  if (filter_end) *filter_end = i;
   if (i >= n) return i;
+  if (filter_end && !hash_present) {
+    if (p[i] == '!') *filter_end = i + 1;
+    else if (!is_special_key_entry_type(p[i])) { const int k1 = key_entry_size(p + i, n - i); *filter_end = k1 < 0 ? 0 : i + k1; }
+  }
   int k = consume_primitive_group(p + i, n - i);
   if (k < 0) return k;
   return i + k;
@@ -411,22 +419,25 @@ YB_HD int dockey_body_size(const uint8_t* p, int n) {
 // state is independent of every other group (docdb_compaction_context.cc:999-1003: state resets
 // when fewer than 2 components are shared). Plain mode (no retention): the whole user key.
 // Returns <0 DevError.
-YB_HD int group_prefix_len(const uint8_t* key, int ulen, bool retention) {
-  if (!retention) return ulen;
+YB_HD int docdb_filter_prefix_len(const uint8_t* key, int ulen);
+// filter_len (optional): the bloom filter key length of the same key (== docdb_filter_prefix_len), taken
+// from the same DocKey walk where possible.
+YB_HD int group_prefix_len(const uint8_t* key, int ulen, bool retention, int* filter_len = nullptr) {
+  if (!retention) { if (filter_len) *filter_len = docdb_filter_prefix_len(key, ulen); return ulen; }
   if (ulen == 0) return -DEV_ERR_BAD_KEY;
   const uint8_t t = key[0];
-  if (t == 10) return ulen;                          // obsolete intent: dropped, any grouping is fine
+  if (t == 10) { if (filter_len) *filter_len = docdb_filter_prefix_len(key, ulen); return ulen; }   // obsolete intent: dropped, any grouping is fine
   if (t == 6) return -DEV_ERR_UNSUPPORTED_KEY;       // vector index metadata: tablet-side filter
   int id = dockey_id_size(key, ulen);
   if (id < 0) return id;
-  if (id > 0 && id < ulen && key[id] == '!') return id + 1;    // table tombstone: id ! # HT (doc_key.cc:973-982)
-  int body = dockey_body_size(key + id, ulen - id);
+  if (id > 0 && id < ulen && key[id] == '!') { if (filter_len) *filter_len = id + 1; return id + 1; }   // table tombstone: id ! # HT (doc_key.cc:973-982)
+  int fe = 0;
+  int body = dockey_body_size(key + id, ulen - id, filter_len ? &fe : nullptr);
   if (body < 0) return body;
+  if (filter_len) *filter_len = id + fe;
   return id + body;
 }
 
-// ----------------------------------------------------------------------------------------------
-// memcmp-with-length comparison of a raw (unpadded) byte string with another.
 YB_HD int cmp_raw(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb) {
   const uint32_t m = la < lb ? la : lb;
   for (uint32_t i = 0; i < m; i++) if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;

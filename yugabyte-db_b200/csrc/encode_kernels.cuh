@@ -38,6 +38,7 @@ struct EncView {
   uint32_t guess;                  // ~0.85 x expected entries per block: first probe of k_next's galloping search
   int key_encoding;                // 1 = shared_prefix, 2 = three_shared_parts (rocksdb/types.h:50-56)
   uint16_t* fk_len;                // [n] bloom filter key length of the entry (0 = none), nullptr = no filter policy
+  const uint16_t* fk_src;          // [N] the same by input entry id, written by the merge kernel's DocKey walk
 };
 
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) k_entry_sizes(EncView E, int S) {
       nr = varint_len(shared) + varint_len(klen - shared) + varint_len(vlen) + (klen - shared) + vlen;
       rs = 1 + varint_len(klen) + varint_len(vlen) + klen + vlen;
     }
-    if (E.fk_len) E.fk_len[j] = static_cast<uint16_t>(docdb_filter_prefix_len(rec, static_cast<int>(ulen)));
+    if (E.fk_len) E.fk_len[j] = E.fk_src ? E.fk_src[d.gid] : static_cast<uint16_t>(docdb_filter_prefix_len(rec, static_cast<int>(ulen)));
     E.nr[j] = nr; E.shared[j] = static_cast<uint16_t>(shared);
     E.D[j] = static_cast<int16_t>(static_cast<int32_t>(rs) - static_cast<int32_t>(nr));
   }

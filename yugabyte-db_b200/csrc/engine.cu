@@ -374,43 +374,62 @@ __global__ void __launch_bounds__(256) k_sample_bucket(PartView P, const JobPara
   }
 }
 
-// Compact non-empty buckets into the tile boundary list. tile_lo[t*k + r] = start of tile t in
-// run r; tile t ends where tile t+1 starts (last: run ends). Single CTA.
-__global__ void __launch_bounds__(1024) k_build_tiles(PartView P, const JobParams* prm, uint32_t* tile_lo,
-                                                      unsigned long long* tile_rank, JobDev* J) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  const int k = prm->k;
-  if (threadIdx.x == 0) carry = 1;                 // tile 0 = implicit boundary at all-zero
-  if (threadIdx.x < k) tile_lo[threadIdx.x] = 0;
-  if (threadIdx.x == 0) tile_rank[0] = 0;
-  __syncthreads();
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+  // scan of one value per thread; all threads must call. Returns exclusive prefix.
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < P.n_buckets; base += 1024) {
-    uint32_t i = base + threadIdx.x;
-    unsigned long long v = i < P.n_buckets ? P.bucket_min[i] : ~0ull;
-    uint32_t f = v != ~0ull;
-    uint32_t x = f;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-      uint32_t w = warp_sums[lane];
-      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-      warp_sums[lane] = w;
-    }
-    __syncthreads();
-    if (f) {
-      uint32_t t = carry + (wid ? warp_sums[wid - 1] : 0) + x - 1;
-      uint32_t s = static_cast<uint32_t>(v & ((1u << 28) - 1));
-      for (int r = 0; r < k; r++) tile_lo[static_cast<size_t>(t) * k + r] = P.pos[static_cast<size_t>(s) * k + r];
-      tile_rank[t] = v >> 28;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += warp_sums[31];
-    __syncthreads();
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  __syncthreads();
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+    warp_sums[lane] = w;
   }
-  if (threadIdx.x == 0) J->n_tiles = carry;
+  __syncthreads();
+  uint32_t excl = (wid ? warp_sums[wid - 1] : 0) + x - v;
+  if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
+  return excl;
+}
+
+// Compact non-empty buckets into the tile boundary list. tile_lo[t*k + r] = start of tile t in
+// run r; tile t ends where tile t+1 starts (last: run ends). Chunked: counts per chunk, a scan of
+// the chunk counts (k_scan_u32_single), then every chunk places its tiles.
+constexpr int TILE_CHUNK = 2048;
+__global__ void __launch_bounds__(256) k_bucket_counts(PartView P, uint32_t* partial) {
+  __shared__ uint32_t sh;
+  if (threadIdx.x == 0) sh = 0;
+  __syncthreads();
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * TILE_CHUNK;
+  uint32_t c = 0;
+  for (uint32_t j = threadIdx.x; j < TILE_CHUNK; j += 256) { const uint64_t i = base + j; if (i < P.n_buckets && P.bucket_min[i] != ~0ull) c++; }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh, c);
+  __syncthreads();
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh;
+}
+__global__ void __launch_bounds__(256) k_build_tiles(PartView P, const JobParams* prm, const uint32_t* partial /*exclusive*/, const uint32_t* total,
+                                                     uint32_t* tile_lo, unsigned long long* tile_rank, JobDev* J) {
+  __shared__ uint32_t warp_sums[32];
+  const int k = prm->k;
+  if (blockIdx.x == 0) {                           // tile 0 = implicit boundary at all-zero
+    if (threadIdx.x < k) tile_lo[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { tile_rank[0] = 0; J->n_tiles = *total + 1; }
+  }
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * TILE_CHUNK;
+  constexpr int PER = TILE_CHUNK / 256;
+  unsigned long long v[PER];
+  uint32_t c = 0;
+  for (int j = 0; j < PER; j++) { const uint64_t i = base + threadIdx.x * PER + j; v[j] = i < P.n_buckets ? P.bucket_min[i] : ~0ull; c += v[j] != ~0ull; }
+  uint32_t t = 1 + partial[blockIdx.x] + block_exclusive_scan(c, warp_sums, nullptr);
+  for (int j = 0; j < PER; j++) {
+    if (v[j] == ~0ull) continue;
+    const uint32_t s = static_cast<uint32_t>(v[j] & ((1u << 28) - 1));
+    for (int r = 0; r < k; r++) tile_lo[static_cast<size_t>(t) * k + r] = P.pos[static_cast<size_t>(s) * k + r];
+    tile_rank[t] = v[j] >> 28;
+    t++;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -423,6 +442,7 @@ struct MergeView {
   ValueRewrite* rewrites;         // [rewrite_cap]
   uint32_t rewrite_cap;
   uint32_t n_tiles;
+  uint16_t* fk16;                 // [N] by input entry id: bloom filter key length (nullptr = no filter policy)
   int32_t S, k;                   // record stride / number of runs / tile capacity: kernel-parameter constants
   uint32_t cap;
 };
@@ -461,24 +481,6 @@ static_assert(RANK_KMAX % RANK_C == 0 && (PFX_K % 1) == 0, "layout");
 __host__ __device__ constexpr uint32_t bytes(uint32_t S, uint32_t cap) { return A1 + (RECS_K + S + 8) * cap; }
 }  // namespace tile_layout
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
-  // scan of one value per thread; all threads must call. Returns exclusive prefix.
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t x = v;
-  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-  __syncthreads();
-  if (lane == 31) warp_sums[wid] = x;
-  __syncthreads();
-  if (wid == 0) {
-    uint32_t w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-    warp_sums[lane] = w;
-  }
-  __syncthreads();
-  uint32_t excl = (wid ? warp_sums[wid - 1] : 0) + x - v;
-  if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
-  return excl;
-}
 
 __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, const JobParams* prm, JobDev* J) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -631,8 +633,10 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
       rank += search(e, pe, pe2, r, r2, lo, hi);
     }
     order[rank] = static_cast<uint16_t>(li);
-    const int g = group_prefix_len(e, rec_ulen(e, S), prm->R.enabled != 0);
+    int fk = 0;
+    const int g = group_prefix_len(e, rec_ulen(e, S), prm->R.enabled != 0, V.fk16 ? &fk : nullptr);
     if (g < 0) { dev_fail(J, -g, tile); glen[li] = 0; } else glen[li] = static_cast<uint16_t>(g);
+    if (V.fk16) V.fk16[V.runs[r].gid_base + seg_lo[r] + p] = static_cast<uint16_t>(g < 0 ? 0 : fk);
     if (rec_flags(e, S) & REC_F_HT_FILTERED) sh_any_filtered = 1;
   }
   if (threadIdx.x == 0) sh_err = *reinterpret_cast<volatile int*>(&J->error);
@@ -1174,6 +1178,7 @@ struct Engine::Impl {
   RunView* dRuns = nullptr;
   std::vector<RunView> runs;
   std::vector<bool> owns_data;
+  std::vector<std::vector<uint64_t>> keep_off; std::vector<std::vector<uint32_t>> keep_sz;   // sources of async H2D copies
   // outputs
   uint8_t* out_keys = nullptr; uint64_t* out_koff = nullptr;
   uint8_t* out_vals = nullptr; uint64_t* out_voff = nullptr;
@@ -1188,6 +1193,7 @@ struct Engine::Impl {
   uint32_t n_blocks = 0; unsigned long long* d_block_off = nullptr; uint32_t* d_block_first = nullptr;
   uint8_t* d_boundary = nullptr; uint32_t boundary_stride = 0;
   EncView enc{};
+  cudaStream_t copy_stream = nullptr; cudaEvent_t copy_ev = nullptr; bool copy_pending = false;
   // bloom filter blocks
   uint32_t n_filter_blocks = 0, filter_block_bytes = 0, filter_key_stride = 0;
   uint8_t* d_filters = nullptr; uint8_t* d_filter_keys = nullptr; uint32_t* d_filter_first = nullptr;
@@ -1210,6 +1216,9 @@ Engine::~Engine() {
     for (void* p : impl_->allocs) cudaFreeAsync(p, impl_->stream);
     if (impl_->ev0) cudaEventDestroy(impl_->ev0);
     if (impl_->ev1) cudaEventDestroy(impl_->ev1);
+    if (impl_->copy_pending) cudaStreamSynchronize(impl_->copy_stream);
+    if (impl_->copy_stream) cudaStreamDestroy(impl_->copy_stream);
+    if (impl_->copy_ev) cudaEventDestroy(impl_->copy_ev);
     for (auto& e : impl_->enc_ev) if (e) cudaEventDestroy(e);
     for (auto& e : impl_->phase_ev) if (e) cudaEventDestroy(e);
     delete impl_;
@@ -1281,14 +1290,16 @@ ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_blo
     rv.data = d + 16;
     stats_.h2d_bytes += len;
   }
-  std::vector<uint64_t> off(nh); std::vector<uint32_t> sz(nh);
+  // handle arrays stay alive in the job so that no stream synchronisation is needed here: the H2D
+  // copies of all input files queue back to back and Run() simply follows them on the stream
+  impl_->keep_off.emplace_back(nh); impl_->keep_sz.emplace_back(nh);
+  std::vector<uint64_t>& off = impl_->keep_off.back(); std::vector<uint32_t>& sz = impl_->keep_sz.back();
   for (uint64_t i = 0; i < nh; i++) { off[i] = handles[i].offset; sz[i] = static_cast<uint32_t>(handles[i].size); }
   uint64_t* doff = nullptr; uint32_t* dsz = nullptr; uint32_t* dcnt = nullptr;
   CUDA_TRY(DevAlloc(&impl_->allocs, &doff, nh)); CUDA_TRY(DevAlloc(&impl_->allocs, &dsz, nh));
   CUDA_TRY(DevAlloc(&impl_->allocs, &dcnt, nh + 1));
   CUDA_TRY(cudaMemcpyAsync(doff, off.data(), nh * 8, cudaMemcpyHostToDevice, impl_->stream));
   CUDA_TRY(cudaMemcpyAsync(dsz, sz.data(), nh * 4, cudaMemcpyHostToDevice, impl_->stream));
-  CUDA_TRY(cudaStreamSynchronize(impl_->stream));   // host vectors go out of scope
   rv.blk_off = doff; rv.blk_size = dsz; rv.blk_count = dcnt; rv.nb = static_cast<uint32_t>(nh);
   rv.ht_filter = ht_filter;
   rv.key_encoding = static_cast<uint32_t>(key_encoding);
@@ -1513,8 +1524,15 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   pv.runs = I.dRuns; pv.sample_base = d_sample_base; pv.n_samples = n_samples; pv.n_buckets = n_buckets;
   k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ);
   k_sample_bucket<<<GridFor(n_samples, 256, sms), 256, 0, I.stream>>>(pv, I.dP);
-  k_build_tiles<<<1, 1024, 0, I.stream>>>(pv, I.dP, d_tile_lo, d_tile_rank, I.dJ);
-  launches += 3;
+  {
+    const uint32_t tchunks = (n_buckets + TILE_CHUNK - 1) / TILE_CHUNK;
+    uint32_t* d_tpart = nullptr; uint32_t* d_ttotal = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_tpart, tchunks + 1)); CUDA_TRY(DevAlloc(&I.allocs, &d_ttotal, 1));
+    k_bucket_counts<<<tchunks, 256, 0, I.stream>>>(pv, d_tpart);
+    k_scan_u32_single<<<1, 1024, 0, I.stream>>>(d_tpart, tchunks, d_ttotal);
+    k_build_tiles<<<tchunks, 256, 0, I.stream>>>(pv, I.dP, d_tpart, d_ttotal, d_tile_lo, d_tile_rank, I.dJ);
+  }
+  launches += 5;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(end_phase());
   if (ybgpu_status s = CheckDeviceError("partition")) return s;
@@ -1529,6 +1547,9 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   MergeView mv{};
   mv.runs = I.dRuns; mv.tile_lo = d_tile_lo; mv.tile_rank = d_tile_rank; mv.desc = d_desc;
   mv.rewrites = d_rw; mv.rewrite_cap = rewrite_cap; mv.n_tiles = n_tiles;
+  uint16_t* d_fk16 = nullptr;
+  if (opt_.filter_policy != YBGPU_FILTER_NONE) CUDA_TRY(DevAlloc(&I.allocs, &d_fk16, N));
+  mv.fk16 = d_fk16;
   mv.S = Sfinal; mv.k = k; mv.cap = cap;
   const size_t smem = tile_layout::bytes(Sfinal, cap);
   CUDA_TRY(cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1571,10 +1592,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(DevAlloc(&I.allocs, &E.nr, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.shared, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.D, n));
     CUDA_TRY(DevAlloc(&I.allocs, &E.P, static_cast<size_t>(n) + 1)); CUDA_TRY(DevAlloc(&I.allocs, &E.QQ, n));
     CUDA_TRY(DevAlloc(&I.allocs, &E.next, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.exit1, n));
-    E.fk_len = nullptr;
+    E.fk_len = nullptr; E.fk_src = nullptr;
     if (opt_.filter_policy != YBGPU_FILTER_NONE) {
       if (opt_.filter_policy != YBGPU_FILTER_DOCKEY_V3) return Fail(YBGPU_INVALID_ARGUMENT, "unknown filter_policy");
       CUDA_TRY(DevAlloc(&I.allocs, &E.fk_len, n));
+      E.fk_src = d_fk16;
     }
     k_entry_sizes<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E, Sfinal);
     // P
@@ -1790,6 +1812,31 @@ ybgpu_status Engine::FetchOutput(uint8_t* data_file, uint64_t* block_off /*n_blo
   CUDA_TRY(cudaStreamSynchronize(I.stream));
   stats_.d2h_bytes += (data_file ? I.out_file_len : 0) + (block_off ? (static_cast<size_t>(I.n_blocks) + 1) * 8 : 0) +
                       (boundary ? static_cast<size_t>(I.n_blocks) * 2 * I.boundary_stride : 0);
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::BeginFetchDataFile(uint8_t* data_file) {
+  if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  Impl& I = *impl_;
+  if (!I.out_file_len) return YBGPU_OK;
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  if (!I.copy_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&I.copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&I.copy_ev, cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventRecord(I.copy_ev, I.stream));
+  CUDA_TRY(cudaStreamWaitEvent(I.copy_stream, I.copy_ev, 0));
+  CUDA_TRY(cudaMemcpyAsync(data_file, I.out_file, I.out_file_len, cudaMemcpyDeviceToHost, I.copy_stream));
+  I.copy_pending = true;
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::EndFetchDataFile() {
+  Impl& I = *impl_;
+  if (!I.copy_pending) return YBGPU_OK;
+  I.copy_pending = false;
+  CUDA_TRY(cudaStreamSynchronize(I.copy_stream));
+  stats_.d2h_bytes += I.out_file_len;
   return YBGPU_OK;
 }
 

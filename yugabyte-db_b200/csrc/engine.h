@@ -23,6 +23,10 @@ class Engine {
   ybgpu_status Digest(uint64_t* digest);
   ybgpu_status OutputInfo(uint64_t* data_len, uint32_t* n_blocks, uint32_t* boundary_stride) const;
   ybgpu_status FetchOutput(uint8_t* data_file, uint64_t* block_off, uint8_t* boundary);
+  // The finished data file, copied on a second stream so that the caller can build the metadata file
+  // on the host while the DMA runs.
+  ybgpu_status BeginFetchDataFile(uint8_t* data_file);
+  ybgpu_status EndFetchDataFile();
   uint64_t kept_deletions() const;
   // Bloom filter blocks of the output (filter_policy != none): number of blocks, bytes per block
   // (bits + 5 metadata bytes), stride of the boundary key records.
