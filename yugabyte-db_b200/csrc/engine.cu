@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(1024) k_scan_blk_counts(const RunView* runs, u
 // ~7 intervals, so one block per warp would leave most lanes idle).
 constexpr int DEC_WB = 4;
 template <int KMAX>
-__global__ void __launch_bounds__(128) k_decode_all(const RunView* runs, const uint32_t* run_group_base /*[k+1]*/, int k, int S,
+__global__ void __launch_bounds__(128, 16) k_decode_all(const RunView* runs, const uint32_t* run_group_base /*[k+1]*/, int k, int S,
                                                    const RangeDev* range, JobDev* J) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
