@@ -158,7 +158,9 @@ ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint6
 
 /* Same, but `data_file_dev` already lives in device memory of the job's device (used by the
  * bench's HBM-resident measurement and by callers that stage files themselves). Not copied, not
- * owned; must stay valid until destroy. */
+ * owned; must stay valid until destroy. The kernels fetch 16-byte vectors around entry boundaries:
+ * 16 readable bytes before data_file_dev and 48 after data_file_dev + data_file_len are required
+ * (ybgpu_job_add_input pads its own device copy the same way). */
 ybgpu_status ybgpu_job_add_input_device(ybgpu_job* job, const uint8_t* data_file_dev, uint64_t data_file_len,
                                         const ybgpu_block_handle* handles, uint64_t num_handles,
                                         int32_t key_encoding, uint64_t hybrid_time_filter);

@@ -326,6 +326,126 @@ __global__ void __launch_bounds__(128, 16) k_decode_all(const RunView* runs, con
   }
 }
 
+// K1' fast path: shared-prefix inputs whose internal keys fit NVI 16-byte vectors, no per-file
+// HybridTime filter, no key range. The previous internal key lives in registers (NVI uint4); an
+// entry is decoded with at most NVI unaligned 16-byte fetches of its key delta, byte masks merge it
+// over the shared prefix, and the record's key vectors are stored straight from the registers — no
+// per-thread key buffer in local memory, no byte loops.
+__device__ __forceinline__ uint32_t low_bytes_mask(int n) {   // 0xff in the first n bytes of a word, n in (-inf, +inf)
+  return n <= 0 ? 0u : (n >= 4 ? 0xffffffffu : ((1u << (8 * n)) - 1u));
+}
+__device__ __forceinline__ uint4 low_bytes_mask16(int n) {    // same for a 16-byte vector
+  return make_uint4(low_bytes_mask(n), low_bytes_mask(n - 4), low_bytes_mask(n - 8), low_bytes_mask(n - 12));
+}
+__device__ __forceinline__ uint4 ldg_unaligned16(const uint8_t* src) {   // reads [src & ~15, (src & ~15) + 32)
+  const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15);
+  const uint4* sa = reinterpret_cast<const uint4*>(src - sh);
+  const uint4 a = __ldg(sa);
+  if (sh == 0) return a;
+  const uint4 b = __ldg(sa + 1);
+  uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+  const uint32_t q = sh >> 2, bits = (sh & 3) * 8;
+  if (q & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
+  if (q & 2) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
+  return make_uint4(__funnelshift_r(w0, w1, bits), __funnelshift_r(w1, w2, bits), __funnelshift_r(w2, w3, bits), __funnelshift_r(w3, w4, bits));
+}
+template <int NVI>
+__global__ void __launch_bounds__(128, 10) k_decode_fast(const RunView* runs, const uint32_t* run_group_base /*[k+1]*/, int k, int S, JobDev* J) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t total_groups = run_group_base[k];
+  const int key_vecs = (S - 16) >> 4;                       // user-key vectors of a record (<= NVI)
+  for (uint32_t g = warp; g < total_groups; g += nwarps) {
+    int ri_ = 0;
+    while (run_group_base[ri_ + 1] <= g) ri_++;
+    const RunView& run = runs[ri_];
+    const uint32_t b0 = (g - run_group_base[ri_]) * DEC_WB;
+    const uint32_t nbk = min(static_cast<uint32_t>(DEC_WB), run.nb - b0);
+    uint32_t nres = 0;
+    if (lane < static_cast<int>(nbk)) {
+      const uint8_t* blk = run.data + run.blk_off[b0 + lane];
+      nres = ldg_u32_unaligned(blk + run.blk_size[b0 + lane] - 4);
+    }
+    uint32_t pre[DEC_WB + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int q = 0; q < DEC_WB; q++) pre[q + 1] = pre[q] + __shfl_sync(0xffffffffu, nres, q);
+    const uint32_t total_int = pre[DEC_WB];
+    const uint32_t ri = run.restart_interval ? run.restart_interval : 1;
+    for (uint32_t t = lane; t < total_int; t += 32) {
+      int q = 0;
+#pragma unroll
+      for (int z = 1; z < DEC_WB; z++) if (t >= pre[z]) q = z;
+      const uint32_t b = b0 + q, r = t - pre[q];
+      const uint64_t boff = run.blk_off[b];
+      const uint8_t* blk = run.data + boff;
+      const uint32_t size = run.blk_size[b];
+      const uint32_t num_restarts = pre[q + 1] - pre[q];
+      const uint32_t restarts_off = size - 4 - 4 * num_restarts;
+      uint32_t p = ldg_u32_unaligned(blk + restarts_off + 4 * r);
+      const uint32_t end = (r + 1 < num_restarts) ? ldg_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
+      uint32_t idx = run.blk_count[b] + r * ri;
+      uint4 kv[NVI];                                          // previous internal key, zero beyond its length
+#pragma unroll
+      for (int w = 0; w < NVI; w++) kv[w] = make_uint4(0, 0, 0, 0);
+      while (p < end) {
+        uint32_t shared, non_shared, vlen;
+        const int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
+        if (!h) break;                                        // validated by k_prepass
+        p += h;
+        const uint32_t klen = shared + non_shared;
+        if (klen > 16 * NVI || klen < 8) { dev_fail(J, DEV_ERR_KEY_TOO_LONG, b); break; }
+        const uint32_t ulen = klen - 8;
+        // new internal key: bytes [0, shared) kept, [shared, klen) from the block, zero beyond
+#pragma unroll
+        for (int w = 0; w < NVI; w++) {
+          const int lo = 16 * w;
+          if (lo + 16 <= static_cast<int>(shared)) continue;
+          if (lo >= static_cast<int>(klen)) { kv[w] = make_uint4(0, 0, 0, 0); continue; }
+          const uint4 nw = ldg_unaligned16(blk + p + lo - static_cast<int>(shared));
+          const uint4 keep = low_bytes_mask16(static_cast<int>(shared) - lo);
+          const uint4 valid = low_bytes_mask16(static_cast<int>(klen) - lo);
+          kv[w].x = (kv[w].x & keep.x) | (nw.x & ~keep.x & valid.x);
+          kv[w].y = (kv[w].y & keep.y) | (nw.y & ~keep.y & valid.y);
+          kv[w].z = (kv[w].z & keep.z) | (nw.z & ~keep.z & valid.z);
+          kv[w].w = (kv[w].w & keep.w) | (nw.w & ~keep.w & valid.w);
+        }
+        p += non_shared;
+        // suffix = internal-key bytes [ulen, ulen + 8): a 16-byte window starting at vector ulen / 16
+        uint4 va = kv[0], vb = NVI > 1 ? kv[1] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int w = 1; w < NVI; w++) if (static_cast<int>(ulen >> 4) == w) { va = kv[w]; vb = (w + 1 < NVI) ? kv[w + 1] : make_uint4(0, 0, 0, 0); }
+        uint32_t s0, s1;
+        {
+          uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w, w4 = vb.x, w5 = vb.y;
+          const uint32_t sh = ulen & 15, qq = sh >> 2, bits = (sh & 3) * 8;
+          if (qq & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+          if (qq & 2) { w0 = w2; w1 = w3; w2 = w4; }
+          s0 = __funnelshift_r(w0, w1, bits); s1 = __funnelshift_r(w1, w2, bits);
+        }
+        uint8_t* rec = run.rec + static_cast<size_t>(idx) * S;
+#pragma unroll
+        for (int w = 0; w < NVI; w++) {
+          if (w < key_vecs) {
+            const uint4 m = low_bytes_mask16(static_cast<int>(ulen) - 16 * w);
+            reinterpret_cast<uint4*>(rec)[w] = make_uint4(kv[w].x & m.x, kv[w].y & m.y, kv[w].z & m.z, kv[w].w & m.w);
+          }
+        }
+        const uint8_t vfirst = vlen ? blk[p] : 0;
+        uint4 tr;
+        tr.x = s0; tr.y = s1;
+        tr.z = ulen | (static_cast<uint32_t>(vfirst) << 16);
+        tr.w = vlen;
+        *reinterpret_cast<uint4*>(rec + S - 16) = tr;
+        run.val_off[idx] = boff + p;
+        p += vlen;
+        idx++;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: partition. Sample s of run r is record s*M of that run; its splitter is the row-group prefix
 // of that record. pos[s_global * k + r2] = lower bound of the splitter in run r2.
@@ -1440,7 +1560,14 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(DevAlloc(&I.allocs, &d_group_base, k + 1));
     CUDA_TRY(cudaMemcpyAsync(d_group_base, group_base.data(), 4 * (k + 1), cudaMemcpyHostToDevice, I.stream));
     const int grid = GridFor(static_cast<uint64_t>(group_base[k]) * 32, 128, sms);
-    if (max_ikey <= 128) k_decode_all<128><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
+    // fast path: shared-prefix inputs, internal keys of at most 64 bytes, no HybridTime filter / key range
+    bool fast = d_range == nullptr && max_ikey <= 64;
+    for (int r = 0; r < k; r++) fast = fast && I.runs[r].key_encoding == 1 && I.runs[r].ht_filter == 0xfffffffffffffffeull;
+    if (fast && getenv("YBGPU_NO_FAST_DECODE") == nullptr) {
+      if (max_ikey <= 32) k_decode_fast<2><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
+      else if (max_ikey <= 48) k_decode_fast<3><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
+      else k_decode_fast<4><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
+    } else if (max_ikey <= 128) k_decode_all<128><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
     else if (max_ikey <= 320) k_decode_all<320><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
     else k_decode_all<1024><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
     launches++;
@@ -1617,6 +1744,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     k_qq_final<<<(qthreads + 255) / 256, 256, 0, I.stream>>>(E.D, n, ri, d_qp, qchunks, E.QQ);
     launches += 8;
     // block cuts
+    k_next_coarse<<<GridFor((n + NEXT_COARSE - 1) / NEXT_COARSE, 256, sms), 256, 0, I.stream>>>(E);
     k_next<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E);
     const uint32_t nsegs = (n + SEG - 1) / SEG;
     const uint32_t ngroups = (nsegs + GROUP_SEGS - 1) / GROUP_SEGS;
@@ -1633,7 +1761,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     k_mark_starts<<<(nsegs + 127) / 128, 128, 0, I.stream>>>(E, d_seg_first, nsegs, d_is_start);
     k_start_sums<<<pc, 256, 0, I.stream>>>(d_is_start, n, d_spart);
     k_scan_u32_single<<<1, 1024, 0, I.stream>>>(d_spart, pc, d_nblocks);
-    launches += 8;
+    launches += 9;
     uint32_t nblocks = 0;
     CUDA_TRY(cudaMemcpyAsync(&nblocks, d_nblocks, 4, cudaMemcpyDeviceToHost, I.stream));
     CUDA_TRY(cudaStreamSynchronize(I.stream));
