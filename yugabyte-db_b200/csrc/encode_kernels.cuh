@@ -229,77 +229,46 @@ __device__ __forceinline__ unsigned long long blk_cur(const EncView& E, uint32_t
 }
 
 // next[s]: first entry of the block after the one starting at s (flush_block_policy.cc:45-76).
-// Step 1 (crossing): smallest m in (s, n] such that the block [s, m) satisfies cur*100 > thresh (or
-// cur >= BS when deviation == 0), or n. Step 2 (exact rule): walk forward while the policy keeps
-// the block open. The crossing is found from a guess of its distance (blocks that start next to
-// each other end next to each other): a short linear walk around the guess, with a galloping +
-// binary search as fallback.
-__device__ __forceinline__ bool blk_crossed(const EncView& E, uint32_t s, uint32_t m, unsigned long long BS, unsigned long long thresh) {
-  const unsigned long long cur = blk_cur(E, s, m - 1);
-  return E.deviation == 0 ? cur >= BS : cur * 100 > thresh;
-}
-__device__ __forceinline__ uint32_t blk_crossing(const EncView& E, uint32_t s, uint32_t dist_guess, unsigned long long BS, unsigned long long thresh) {
-  uint32_t lo = s + 1, hi = E.n;
-  uint32_t m = static_cast<uint32_t>(umin64(static_cast<uint64_t>(s) + (dist_guess ? dist_guess : 1), E.n));
-  if (m < lo) m = lo;
-  if (m < hi || blk_crossed(E, s, m, BS, thresh)) {
-    if (blk_crossed(E, s, m, BS, thresh)) {
-      hi = m;                                            // answer in [lo, m]
-      for (int t = 0; t < 6 && hi > lo; t++) { if (blk_crossed(E, s, hi - 1, BS, thresh)) hi--; else return hi; }
-      if (hi == lo) return lo;
-    } else {
-      lo = m + 1;                                        // answer in (m, n]
-      uint32_t step = 1;
-      for (int t = 0; t < 6 && lo < hi; t++) { if (blk_crossed(E, s, lo, BS, thresh)) return lo; lo++; }
-      // gallop
-      uint32_t probe = lo;
-      while (probe < hi && !blk_crossed(E, s, probe, BS, thresh)) { lo = probe + 1; step <<= 1; probe = (hi - probe > step) ? probe + step : hi; }
-      if (probe < hi) hi = probe;
-    }
-  } else {
-    return E.n;                                          // not even the whole tail crosses
-  }
-  while (lo < hi) {
-    const uint32_t mid = lo + ((hi - lo) >> 1);
-    if (blk_crossed(E, s, mid, BS, thresh)) hi = mid; else lo = mid + 1;
-  }
-  return lo;
-}
-__device__ __forceinline__ uint32_t blk_next(const EncView& E, uint32_t s, uint32_t dist_guess) {
+// (A two-level variant — every 32nd start searched fully, the others guided by their neighbour's block
+// length — measured slower on B200 than this single pass from a static guess and was dropped.)
+__global__ void __launch_bounds__(256) k_next(EncView E) {
   const unsigned long long BS = E.block_size;
   const unsigned long long thresh = BS * (100 - E.deviation);       // cur*100 > thresh
-  uint32_t m = blk_crossing(E, s, dist_guess, BS, thresh);
-  if (E.deviation == 0) return m;                                    // only rule 1 (cur >= BS)
-  while (m < E.n) {
-    const unsigned long long cur = blk_cur(E, s, m - 1);
-    if (cur >= BS) break;
-    const Desc d = E.kept[m];
-    const unsigned long long est = cur + d.klen + d.vlen_out + ((((m - s) & (E.ri - 1)) == 0) ? 4 : 0) + 4 +
-                                   varint_len(d.klen) + varint_len(d.vlen_out);
-    if (est > BS && cur * 100 > thresh) break;
-    m++;
-  }
-  return m;
-}
-constexpr uint32_t NEXT_COARSE = 32;
-// every NEXT_COARSE-th start from the static guess ...
-__global__ void __launch_bounds__(256) k_next_coarse(EncView E) {
-  const uint32_t nc = (E.n + NEXT_COARSE - 1) / NEXT_COARSE;
-  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
-    const uint32_t s = c * NEXT_COARSE;
-    E.next[s] = blk_next(E, s, E.guess);
-  }
-}
-// ... the others from their coarse neighbour's block length
-__global__ void __launch_bounds__(256) k_next(EncView E) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < E.n; s += gridDim.x * blockDim.x) {
-    const uint32_t s0 = s & ~(NEXT_COARSE - 1);
-    if (s == s0) continue;
-    const unsigned long long BS = E.block_size, thresh = BS * (100 - E.deviation);
-    // distance from s0 to its threshold crossing (the exact rule may add a little on top)
-    const uint32_t n0 = E.next[s0];
-    E.next[s] = blk_next(E, s, n0 > s ? n0 - s0 : 1);
-    (void)BS; (void)thresh;
+    // smallest m in (s, n] such that the block [s, m) satisfies cur*100 > thresh (or m == n)
+    uint32_t lo = s + 1, hi = E.n;
+    if (E.deviation == 0) {
+      // only rule 1 (cur >= BS)
+      while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (blk_cur(E, s, mid - 1) >= BS) hi = mid; else lo = mid + 1; }
+      E.next[s] = lo;
+      continue;
+    }
+    {
+      // gallop: the answer is almost always within [guess, 2*guess] entries of s
+      uint32_t step = E.guess;
+      uint32_t probe = s + step < hi ? s + step : hi;
+      while (probe < hi && !(blk_cur(E, s, probe - 1) * 100 > thresh)) {
+        lo = probe + 1;
+        step <<= 1;
+        probe = (hi - probe > step) ? probe + step : hi;
+      }
+      if (probe < hi) hi = probe;
+    }
+    while (lo < hi) {
+      uint32_t mid = lo + ((hi - lo) >> 1);
+      if (blk_cur(E, s, mid - 1) * 100 > thresh) hi = mid; else lo = mid + 1;
+    }
+    uint32_t m = lo;
+    while (m < E.n) {
+      const unsigned long long cur = blk_cur(E, s, m - 1);
+      if (cur >= BS) break;
+      const Desc d = E.kept[m];
+      const unsigned long long est = cur + d.klen + d.vlen_out + ((((m - s) & (E.ri - 1)) == 0) ? 4 : 0) + 4 +
+                                     varint_len(d.klen) + varint_len(d.vlen_out);
+      if (est > BS && cur * 100 > thresh) break;
+      m++;
+    }
+    E.next[s] = m;
   }
 }
 

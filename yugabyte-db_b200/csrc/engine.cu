@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(1024) k_scan_blk_counts(const RunView* runs, u
 // ~7 intervals, so one block per warp would leave most lanes idle).
 constexpr int DEC_WB = 4;
 template <int KMAX>
-__global__ void __launch_bounds__(128, 16) k_decode_all(const RunView* runs, const uint32_t* run_group_base /*[k+1]*/, int k, int S,
+__global__ void __launch_bounds__(128) k_decode_all(const RunView* runs, const uint32_t* run_group_base /*[k+1]*/, int k, int S,
                                                    const RangeDev* range, JobDev* J) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1675,7 +1675,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   mv.runs = I.dRuns; mv.tile_lo = d_tile_lo; mv.tile_rank = d_tile_rank; mv.desc = d_desc;
   mv.rewrites = d_rw; mv.rewrite_cap = rewrite_cap; mv.n_tiles = n_tiles;
   uint16_t* d_fk16 = nullptr;
-  if (opt_.filter_policy != YBGPU_FILTER_NONE) CUDA_TRY(DevAlloc(&I.allocs, &d_fk16, N));
+  if (opt_.filter_policy != YBGPU_FILTER_NONE && getenv("YBGPU_NO_FK16") == nullptr) CUDA_TRY(DevAlloc(&I.allocs, &d_fk16, N));
   mv.fk16 = d_fk16;
   mv.S = Sfinal; mv.k = k; mv.cap = cap;
   const size_t smem = tile_layout::bytes(Sfinal, cap);
@@ -1744,7 +1744,6 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     k_qq_final<<<(qthreads + 255) / 256, 256, 0, I.stream>>>(E.D, n, ri, d_qp, qchunks, E.QQ);
     launches += 8;
     // block cuts
-    k_next_coarse<<<GridFor((n + NEXT_COARSE - 1) / NEXT_COARSE, 256, sms), 256, 0, I.stream>>>(E);
     k_next<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E);
     const uint32_t nsegs = (n + SEG - 1) / SEG;
     const uint32_t ngroups = (nsegs + GROUP_SEGS - 1) / GROUP_SEGS;
@@ -1761,7 +1760,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     k_mark_starts<<<(nsegs + 127) / 128, 128, 0, I.stream>>>(E, d_seg_first, nsegs, d_is_start);
     k_start_sums<<<pc, 256, 0, I.stream>>>(d_is_start, n, d_spart);
     k_scan_u32_single<<<1, 1024, 0, I.stream>>>(d_spart, pc, d_nblocks);
-    launches += 9;
+    launches += 8;
     uint32_t nblocks = 0;
     CUDA_TRY(cudaMemcpyAsync(&nblocks, d_nblocks, 4, cudaMemcpyDeviceToHost, I.stream));
     CUDA_TRY(cudaStreamSynchronize(I.stream));
