@@ -173,7 +173,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "many_tablets_all_cores": many,
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -194,7 +194,31 @@ def cpu_baseline(args):
             "mkeys_per_s": round(rows / dt / 1e6, 3)}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, torchrun
+    notices) is rerouted to stderr; the JSON goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    quiet_stdout()
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -420,7 +444,7 @@ def main():
         line["e2e"] = e2e
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
 
