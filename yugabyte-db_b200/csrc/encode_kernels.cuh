@@ -409,8 +409,7 @@ __device__ uint32_t g_crc_xpow8[CRC_XPOW_TABLE + 1];   // x^(8m) mod P for m = 0
 // ordinary one-word step; g_crc_stride[3 - b][x] = (x << 8b) * x^(8 * 1024) mod P.
 constexpr uint32_t CRC_STRIDE_WORDS = 256;
 __device__ uint32_t g_crc_stride[4][256];
-__device__ uint32_t g_crc_c16[16];                     // x^(8 * 64 * g) mod P
-__device__ uint32_t g_crc_s16[4][256];                 // the same for a stride of 16 words: (x << 8b) * x^(8 * 64) mod P
+__device__ uint32_t g_crc_s32[4][256];                 // the same for a stride of 32 words (one warp): (x << 8b) * x^(8 * 128) mod P
 
 __global__ void k_crc_init() {
   const uint32_t i = threadIdx.x;
@@ -467,11 +466,10 @@ __global__ void k_crc_init_xpow() {
     const uint32_t r = m >> 8, x = m & 255;
     g_crc_stride[r][x] = crc_mulmod(xp, x << (8 * (3 - r)));
   }
-  if (m < 16) g_crc_c16[m] = crc_xpow_bytes(64 * m, g_crc_x2n);
   if (m < 1024) {
-    const uint32_t xp = crc_xpow_bytes(4 * 16, g_crc_x2n);
+    const uint32_t xp = crc_xpow_bytes(4 * 32, g_crc_x2n);
     const uint32_t r = m >> 8, x = m & 255;
-    g_crc_s16[r][x] = crc_mulmod(xp, x << (8 * (3 - r)));
+    g_crc_s32[r][x] = crc_mulmod(xp, x << (8 * (3 - r)));
   }
 }
 // crc * x^(8 nbytes): table lookup + one modular multiplication for the common distances.
@@ -521,22 +519,68 @@ __device__ uint32_t warp_crc32c(const uint8_t* p, uint64_t len, int lane, const 
 
 __device__ __forceinline__ uint32_t crc_mask(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xa282ead8u; }
 
+// CRC32C of [p, p+len) in global memory by one warp with COALESCED reads: the words are numbered from
+// the end, lane l folds the words at distance l, l+32, ... with the map "multiply by x^(8*128)"
+// (s32, four lookups per word like an ordinary step), then multiplies its partial by x^(32(l+1)) (kc)
+// and the lanes XOR. Leading bytes up to word alignment seed the register (folded into word 0),
+// trailing bytes are stepped at the end. Returns the finalized CRC in every lane.
+__device__ uint32_t warp_crc32c_strided(const uint8_t* p, uint64_t len, int lane, const uint32_t* tab0, const uint32_t (*s32)[256], uint32_t kc) {
+  uint32_t head = static_cast<uint32_t>((4 - (reinterpret_cast<uintptr_t>(p) & 3)) & 3);
+  if (head > len) head = static_cast<uint32_t>(len);
+  uint32_t c1 = 0xffffffffu;
+  for (uint32_t i = 0; i < head; i++) c1 = tab0[(c1 ^ p[i]) & 0xff] ^ (c1 >> 8);
+  const uint64_t nwords = (len - head) >> 2;
+  const uint32_t tail = static_cast<uint32_t>((len - head) & 3);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p + head);
+  uint32_t acc = 0;
+  if (nwords > static_cast<uint64_t>(lane)) {
+    const uint64_t last = nwords - 1 - lane;
+    uint64_t i = last & 31;
+    acc = __ldg(w + i);
+    if (i == 0) acc ^= c1;
+    i += 32;
+    // eight independent loads in flight per lane, then the dependent fold
+    for (; i + 7 * 32 <= last; i += 8 * 32) {
+      uint32_t nx[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) nx[u] = __ldg(w + i + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        acc = s32[3][acc & 0xff] ^ s32[2][(acc >> 8) & 0xff] ^ s32[1][(acc >> 16) & 0xff] ^ s32[0][acc >> 24];
+        acc ^= nx[u];
+      }
+    }
+    for (; i <= last; i += 32) {
+      const uint32_t nx = __ldg(w + i);
+      acc = s32[3][acc & 0xff] ^ s32[2][(acc >> 8) & 0xff] ^ s32[1][(acc >> 16) & 0xff] ^ s32[0][acc >> 24];
+      acc ^= nx;
+    }
+  }
+  uint32_t r = acc ? crc_mulmod(kc, acc) : 0u;
+  for (int o = 16; o; o >>= 1) r ^= __shfl_xor_sync(0xffffffffu, r, o);
+  if (nwords == 0) r = c1;
+  const uint8_t* q = p + len - tail;
+  for (uint32_t i = 0; i < tail; i++) r = tab0[(r ^ q[i]) & 0xff] ^ (r >> 8);
+  return ~r;
+}
+
 // mode 0: write trailers of freshly encoded blocks. mode 1: verify stored trailers (inputs).
 __global__ void __launch_bounds__(256) k_crc_blocks(uint8_t* file, const unsigned long long* off, const uint32_t* size32,
                                                     const unsigned long long* size_from_next, uint32_t nblocks, int mode, JobDev* J) {
-  __shared__ uint32_t tab[4][256];
-  __shared__ uint32_t x2n[32];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
-  if (threadIdx.x < 32) x2n[threadIdx.x] = g_crc_x2n[threadIdx.x];
+  __shared__ uint32_t tab0[256];
+  __shared__ uint32_t s32[4][256];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&s32[0][0])[i] = (&g_crc_s32[0][0])[i];
+  tab0[threadIdx.x] = g_crc_tab[0][threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const uint32_t kc = g_crc_xpow8[4 * (lane + 1)];                 // x^(32 (lane + 1))
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t b = warp; b < nblocks; b += nwarps) {
     const unsigned long long o = off[b];
     // contents length (without the 5-byte trailer)
     const uint64_t len = size32 ? size32[b] : (size_from_next[b + 1] - o - 5);
     uint8_t* p = file + o;
-    const uint32_t crc = crc_mask(warp_crc32c(p, len + 1, lane, tab, x2n));   // block + type byte
+    const uint32_t crc = crc_mask(warp_crc32c_strided(p, len + 1, lane, tab0, s32, kc));   // block + type byte
     if (mode == 0) {
       if (lane < 4) p[len + 1 + lane] = static_cast<uint8_t>(crc >> (8 * lane));
     } else {
@@ -585,30 +629,6 @@ __device__ __forceinline__ void copy_rec_to_smem(uint8_t* dst, const uint8_t* re
     }
   }
   for (uint32_t i = nw * 4; i < n; i++) dst[i] = __ldg(rec + from + i);
-}
-
-// n bytes from global memory (read-only path, any alignment) into shared memory (any alignment):
-// 4-byte shared stores fed by funnel-shifted aligned loads, single bytes only at the two ends.
-__device__ __forceinline__ void copy_global_to_smem(uint8_t* dst, const uint8_t* src, uint32_t n) {
-  while (n && (reinterpret_cast<uintptr_t>(dst) & 3)) { *dst++ = __ldg(src++); n--; }
-  const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3);
-  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - sh);
-  uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
-  const uint32_t nw = n >> 2;
-  if (sh == 0) {
-#pragma unroll 4
-    for (uint32_t i = 0; i < nw; i++) dw[i] = __ldg(sw + i);
-  } else if (nw) {
-    const uint32_t bits = sh * 8;
-    uint32_t lo = __ldg(sw);
-#pragma unroll 4
-    for (uint32_t i = 0; i < nw; i++) {
-      const uint32_t hi = __ldg(sw + i + 1);      // holds at least one byte of [src, src + n)
-      dw[i] = __funnelshift_r(lo, hi, bits);
-      lo = hi;
-    }
-  }
-  for (uint32_t i = nw * 4; i < n; i++) dst[i] = __ldg(src + i);
 }
 
 // Internal-key bytes [from, to) of a survivor (user key from the record, then the 8-byte suffix).
