@@ -13,7 +13,11 @@ JSON line (one, rank 0): metric = GB/s of input bytes merged (raw key+value byte
 entries, as rocksdb.raw.key.size + rocksdb.raw.value.size count them).
   value     inputs already resident in HBM; whole job device pipeline, wall clock between syncs.
   e2e       same job through the C ABI with HOST (pinned) input files and HOST output files:
-            H2D of every input file and D2H of the result inside the timed region.
+            H2D of every input file and D2H of the result inside the timed region. Headline mode:
+            ybgpu_compact_files with --subcompactions key ranges (the reference's max_subcompactions
+            feature, compaction_job.cc:409-552), pipelined so that H2D / kernels / D2H of different
+            ranges overlap; one output SST per range. e2e.single_job is the same measurement with one
+            job and one output file (H2D, run and D2H back to back).
   roofline  dominant kernel, algorithmic bytes / its CUDA-event time.
   cpu_baseline  the oracle (CPU restatement of the reference loop) on a bounded sample, 1 thread
             like the reference (max_subcompactions = 1).
@@ -48,6 +52,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", type=int, default=1, help="verify input block checksums (reference default: on)")
+    ap.add_argument("--subcompactions", type=int, default=16,
+                    help="e2e arm: key-range subcompactions per job (DBOptions::max_subcompactions; 1 = one job, one output file)")
+    ap.add_argument("--in-flight", type=int, default=3, help="e2e arm: subcompactions in flight (host threads / private streams)")
     ap.add_argument("--workload", default="config2", choices=["config2", "mvcc"],
                     help="config2 = BASELINE configs[1] (the bench line); mvcc = configs[3] shape (20 versions/key, "
                          "history cutoff drops 90 %), scaled to --rows entries, for profiles/ only")
@@ -352,24 +359,48 @@ def main():
                 e2e_ms[k] += v * 1e3
             return st, data.size + meta.size
 
-        for _ in range(min(args.warmup, 1) if args.rows >= 50_000_000 else args.warmup):
-            step_e2e()
-        for k in e2e_ms:
-            e2e_ms[k] = 0.0
-        barrier()
-        t0 = time.perf_counter()
-        res = [step_e2e() for _ in range(args.steps)]
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-        e2e = {"value": round(in_bytes * world * args.steps / e2e_s / 1e9, 4), "unit": "GB/s",
-               "h2d_bytes_per_step": int(res[-1][0]["h2d_bytes"]), "d2h_bytes_per_step": int(res[-1][0]["d2h_bytes"]),
-               "ms_per_step": round(e2e_s / args.steps * 1e3, 2), "pinned_inputs": all(ok for _, ok in pinned),
-               "output_file_bytes": int(res[-1][1]), "verify_checksums": bool(args.verify),
-               "host_ms_per_step": {k: round(v / args.steps, 2) for k, v in e2e_ms.items()}}
+        def timed(step_fn):
+            for _ in range(min(args.warmup, 2) if args.rows >= 50_000_000 else args.warmup):
+                step_fn()
+            for k in e2e_ms:
+                e2e_ms[k] = 0.0
+            barrier()
+            t0 = time.perf_counter()
+            res = [step_fn() for _ in range(args.steps)]
+            barrier()
+            dt = time.perf_counter() - t0
+            te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return float(te.item()), res
+
+        e2e_s, res = timed(step_e2e)
+        single = {"value": round(in_bytes * world * args.steps / e2e_s / 1e9, 4), "unit": "GB/s",
+                  "h2d_bytes_per_step": int(res[-1][0]["h2d_bytes"]), "d2h_bytes_per_step": int(res[-1][0]["d2h_bytes"]),
+                  "ms_per_step": round(e2e_s / args.steps * 1e3, 2), "output_file_bytes": int(res[-1][1]),
+                  "host_ms_per_step": {k: round(v / args.steps, 2) for k, v in e2e_ms.items()}}
+        e2e = dict(single, pinned_inputs=all(ok for _, ok in pinned), verify_checksums=bool(args.verify),
+                   mode="one job, one output file")
+        if args.subcompactions > 1:
+            files = [(s.meta_view(), s.data_view()) for s in ssts]
+
+            def step_sub():
+                r = pkg.compact_files(files, max_subcompactions=args.subcompactions, max_in_flight=args.in_flight,
+                                      data_arena=out_data, meta_arena=out_meta, device=local_rank,
+                                      verify_checksums=bool(args.verify), **job_kw)
+                return r.total.as_dict(), sum(o_.data_len + o_.meta_len for o_ in r.outputs), len(r.outputs)
+
+            sub_s, sres = timed(step_sub)
+            assert sres[-1][0]["num_input_records"] == n_entries, "subcompactions must see every input entry once"
+            e2e = {"value": round(in_bytes * world * args.steps / sub_s / 1e9, 4), "unit": "GB/s",
+                   "h2d_bytes_per_step": int(sres[-1][0]["h2d_bytes"]), "d2h_bytes_per_step": int(sres[-1][0]["d2h_bytes"]),
+                   "ms_per_step": round(sub_s / args.steps * 1e3, 2), "pinned_inputs": all(ok for _, ok in pinned),
+                   "output_file_bytes": int(sres[-1][1]), "verify_checksums": bool(args.verify),
+                   "mode": "ybgpu_compact_files: %d key-range subcompactions (max_subcompactions=%d), %d in flight on private "
+                           "streams, one output SST per range" % (sres[-1][2], args.subcompactions, args.in_flight),
+                   "output_files": int(sres[-1][2]),
+                   "gpu_ms_per_step": round(sres[-1][0]["gpu_seconds"] * 1e3, 2),
+                   "single_job": single}
         for v, ok in pinned:
             if ok:
                 cudart.cudaHostUnregister(v.ctypes.data)

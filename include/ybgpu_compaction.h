@@ -51,6 +51,7 @@ enum { YBGPU_FILTER_NONE = 0, YBGPU_FILTER_DOCKEY_V3 = 1 };
 #define YBGPU_HT_INVALID  0xfffffffffffffffeull   /* HybridTime::kInvalid (common/hybrid_time.h:58) */
 #define YBGPU_TTL_MAX_NS  0x7fffffffffffffffll    /* ValueControlFields::kMaxTtl = MonoDelta::kMax */
 #define YBGPU_MAX_SEQUENCE 0x00ffffffffffffffull  /* kMaxSequenceNumber (db/dbformat.h:75) */
+#define YBGPU_STREAM_PRIVATE ((void*)(intptr_t)-1) /* ybgpu_job_options::cuda_stream: job-owned stream */
 
 /* Everything CompactionJob / DocDBCompactionContext know when the loop starts. */
 typedef struct ybgpu_job_options {
@@ -92,7 +93,9 @@ typedef struct ybgpu_job_options {
    * range_lower <= user_key < range_upper take part; the others are invisible (not counted). */
   const uint8_t* range_lower; uint64_t range_lower_len;   /* len 0 = unbounded */
   const uint8_t* range_upper; uint64_t range_upper_len;
-  void* cuda_stream;                 /* cudaStream_t to launch on; NULL = the legacy default stream */
+  void* cuda_stream;                 /* cudaStream_t to launch on; NULL = the legacy default stream;
+                                        YBGPU_STREAM_PRIVATE = a non-blocking stream owned by the job
+                                        (what concurrent jobs on one device should use) */
 
   /* --- bloom filter of the output (BlockBasedTableOptions::filter_policy, table.h:118-125) ---
    * YBGPU_FILTER_DOCKEY_V3 = docdb::DocDbAwareV3FilterPolicy (docdb_rocksdb_util.cc:761-763): fixed-size
@@ -205,6 +208,58 @@ ybgpu_status ybgpu_job_fetch_output(ybgpu_job* job, uint8_t* data_file, uint64_t
  * key. Buffers must hold the longest key (use 4096). */
 ybgpu_status ybgpu_job_output_boundaries(const ybgpu_job* job, uint8_t* smallest, uint64_t* smallest_len,
                                          uint8_t* largest, uint64_t* largest_len);
+
+/* --- subcompactions ------------------------------------------------------------------------------
+ * Replaces: CompactionJob::GenSubcompactionBoundaries + the per-subcompaction threads of
+ * CompactionJob::Run (rocksdb/db/compaction_job.cc:409-519,532-552; DBOptions::max_subcompactions,
+ * rocksdb/options.h). One compaction is cut into key ranges on row boundaries; every range is an
+ * ordinary job over the data blocks of each input that can hold its keys, bounded by
+ * range_lower/range_upper like SubcompactionState::start/end (compaction_job.cc:721-729,779-783), and writes
+ * its own output SST — the reference installs every sub-output in range order too
+ * (compaction_job.cc:1128-1131). Ranges run on `max_in_flight` host threads with a private stream
+ * each, so that the host->device copy of one range, the kernels of another and the device->host copy
+ * of a third overlap (PCIe is full duplex); device memory in use is bounded by max_in_flight ranges
+ * instead of the whole compaction. */
+typedef struct ybgpu_input_file {
+  const uint8_t* meta_file; uint64_t meta_file_len;     /* <n>.sst */
+  const uint8_t* data_file; uint64_t data_file_len;     /* <n>.sst.sblock.0 (host memory; pinned = async DMA) */
+  uint64_t hybrid_time_filter;                          /* YBGPU_HT_INVALID = none */
+} ybgpu_input_file;
+
+#define YBGPU_MAX_SPLITTER_LEN 255
+typedef struct ybgpu_sub_output {
+  uint64_t data_offset, data_len;    /* <n>.sst.sblock.0 of this range inside the caller's data arena; len 0 = no output file */
+  uint64_t meta_offset, meta_len;    /* <n>.sst inside the caller's metadata arena */
+  ybgpu_job_stats stats;
+  uint32_t range_lower_len, range_upper_len;            /* [lower, upper) user keys; len 0 = unbounded */
+  uint8_t range_lower[256], range_upper[256];
+  uint32_t smallest_key_len, largest_key_len;           /* FileMetaData::smallest / largest (internal keys) */
+  uint8_t smallest_key[1032], largest_key[1032];
+} ybgpu_sub_output;
+
+/* Splitter user keys for at most `max_subcompactions` ranges, chosen from the inputs' index
+ * separators weighted by block size and cut back to the row prefix (the DocKey when
+ * docdb_keys != 0, the whole user key otherwise), so that no row — the unit of DocDB's retention
+ * state — straddles two ranges. splitters: (max_subcompactions - 1) slots of 256 bytes. */
+ybgpu_status ybgpu_plan_subcompactions(const ybgpu_input_file* files, uint32_t num_files, uint32_t max_subcompactions,
+                                       int32_t docdb_keys, uint8_t* splitters, uint32_t* splitter_lens,
+                                       uint32_t* num_splitters);
+
+/* Runs the whole compaction as pipelined subcompactions. options->range_* must be empty and
+ * options->cuda_stream is ignored (every range gets a private stream). If
+ * options->has_largest_user_key == 0 the key (Compaction::GetLargestUserKey) is read from the last
+ * data block of every input on the host. outputs: max_subcompactions slots, filled in range order;
+ * *num_outputs = number of ranges. err (optional) receives the message of the first failure. */
+ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_input_file* files, uint32_t num_files,
+                                 uint32_t max_subcompactions, uint32_t max_in_flight,
+                                 uint8_t* data_arena, uint64_t data_arena_cap, uint8_t* meta_arena, uint64_t meta_arena_cap,
+                                 const volatile int32_t* shutting_down, ybgpu_sub_output* outputs, uint32_t* num_outputs,
+                                 ybgpu_job_stats* total, char* err, uint64_t err_cap);
+
+/* Last internal key of a split SST (its last data block is decoded on the host): what
+ * FileMetaData::largest holds for the file. key must hold 1032 bytes. */
+ybgpu_status ybgpu_sst_last_key(const uint8_t* meta_file, uint64_t meta_file_len, const uint8_t* data_file,
+                                uint64_t data_file_len, uint8_t* key, uint32_t* key_len);
 
 /* Device-side checksum of the surviving KV stream: order-sensitive 64-bit hash over
  * (key_len, key, value_len, value) per entry, combined per entry position. Used by the parity

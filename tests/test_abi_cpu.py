@@ -131,3 +131,41 @@ def test_meta_reader_handles_and_separators(pkg):
     # separator i is >= every key of block i and < first key of block i+1 (index_builder.cc:61-90)
     assert seps == sorted(seps, key=lambda k: (k[:-8], -int.from_bytes(k[-8:], "little")))
     assert seps[-1][:-8] >= kvs[-1][0][:-8]
+
+
+@pytest.mark.parametrize("enc", [1, 2])
+def test_sst_last_key_both_encodings(pkg, enc):
+    """FileMetaData::largest of an input, read on the host from its last data block (the seqno-zeroing
+    exception key of a compaction cut into subcompactions: db/compaction.cc:318)."""
+    cfg = o.GenConfig(seed=8, num_rows=1500, cols=2, versions=3, num_files=3, value_len=40, tombstone_per_1024=60)
+    for s in o.Sst.generate_all(cfg, o.TableOptions(block_size=1024)):
+        kvs = s.read_all()
+        sst = o.Sst.build(kvs, o.TableOptions(block_size=700, key_encoding=enc))
+        assert pkg.sst_last_key(sst.meta_view(), sst.data_view()) == kvs[-1][0]
+    one = o.Sst.build([(o.ikey(b"only", 9), b"v")], o.TableOptions(key_encoding=enc))
+    assert pkg.sst_last_key(one.meta_view(), one.data_view()) == o.ikey(b"only", 9)
+
+
+def test_plan_subcompactions_row_aligned_and_balanced(pkg):
+    """GenSubcompactionBoundaries analogue (compaction_job.cc:409-519): splitters are complete DocKeys
+    (no row straddles two ranges), strictly increasing, and the ranges carry similar numbers of entries."""
+    cfg = o.GenConfig(seed=17, num_rows=6000, cols=3, versions=4, num_files=5, value_len=60)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=2048))
+    files = [(s.meta_view(), s.data_view()) for s in ssts]
+    sp = pkg.plan_subcompactions(files, 6)
+    assert 3 <= len(sp) <= 5 and sp == sorted(set(sp))
+    users = sorted(k[:-8] for s in ssts for k, _ in s.read_all())
+    rows = {u[:32] for u in users}                      # the generator's DocKeys are 32 bytes
+    for s in sp:
+        assert len(s) == 32 and s[-2:] == b"!!"         # hashed group end + range group end: a complete DocKey
+        assert all(not (r != s and r.startswith(s)) for r in rows)
+    import bisect
+    cuts = [0] + [bisect.bisect_left(users, s) for s in sp] + [len(users)]
+    sizes = [b - a for a, b in zip(cuts, cuts[1:])]
+    assert min(sizes) > 0.4 * len(users) / len(sizes) and max(sizes) < 2.0 * len(users) / len(sizes)
+    # plain RocksDB keys: the whole user key is the row
+    kvs = [(o.ikey(b"key%06d" % i, 100 + i), b"v" * 30) for i in range(20000)]
+    plain = o.Sst.build(kvs, o.TableOptions(block_size=1024))
+    sp2 = pkg.plan_subcompactions([(plain.meta_view(), plain.data_view())], 4, docdb_keys=False)
+    assert len(sp2) == 3 and sp2 == sorted(sp2)
+    assert pkg.plan_subcompactions(files, 1) == []

@@ -43,7 +43,10 @@ def check(pkg, ssts, block_size=4096, ht_filters=None, **kw):
     exp = o.compact(ssts, o.CompactionParams(**okw(kw)), topt, ht_filters=ht_filters)
     job = gpu_compact(pkg, ssts, ht_filters=ht_filters, block_size=block_size, **kw)
     st = job.stats()
-    assert job.kv_list() == exp.kv_list()
+    # FileMetaData::smallest / largest come from the block encoder's boundary records (no KV stream)
+    ekv = exp.kv_list()
+    assert job.boundaries() == ((ekv[0][0], ekv[-1][0]) if ekv else (b"", b""))
+    assert job.kv_list() == ekv
     es = exp.stats
     assert st.num_input_records == es.num_input_records
     assert st.num_output_records == es.num_output_records
@@ -310,3 +313,71 @@ def test_cotables_and_colocated_tables(pkg, seed):
     if seed % 2:
         check(pkg, ssts, block_size=1024, bottommost=True, cutoff_ht=o.ht_from_micros(w.BASE_US + 35),
               cotables_cutoff_ht=o.ht_from_micros(w.BASE_US + 85))
+
+
+@pytest.mark.parametrize("enc,in_flight", [(1, 3), (2, 1)])
+def test_subcompactions_pipelined(pkg, enc, in_flight):
+    """ybgpu_compact_files: one compaction cut into key ranges on row boundaries, ranges pipelined on
+    private streams (compaction_job.cc:409-519,532-552). Every range's output SST is byte-identical to
+    the oracle's compaction of the same key range, the outputs concatenate to the single-job KV stream,
+    the seqno-zeroing exception key is the compaction's (not the range's) largest user key, and
+    FileMetaData boundaries come back per output."""
+    cfg = o.GenConfig(seed=23, num_rows=9000, cols=2, versions=4, num_files=6, value_len=90, tombstone_per_1024=50)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=4096))
+    cutoff = o.ht_from_micros(cfg.base_micros + 2500)
+    topt = o.TableOptions(block_size=4096, key_encoding=enc, filter_policy=1, filter_block_size=4096)
+    exp = o.compact(ssts, o.CompactionParams(cutoff_ht=cutoff), topt)
+    files = [(s.meta_view(), s.data_view()) for s in ssts]
+    res = pkg.compact_files(files, max_subcompactions=5, max_in_flight=in_flight, cutoff_ht=cutoff, block_size=4096,
+                            output_key_encoding=enc, filter_policy=1, filter_block_size=4096)
+    assert 3 <= len(res.outputs) <= 5
+    all_kvs = [s.read_all() for s in ssts]
+    largest = max(kvs[-1][0][:-8] for kvs in all_kvs)
+    got = []
+    for out in res.outputs:
+        lo, hi = out.lower, out.upper
+        part = [[kv for kv in kvs if (not lo or kv[0][:-8] >= lo) and (not hi or kv[0][:-8] < hi)] for kvs in all_kvs]
+        part_ssts = [o.Sst.build(p, o.TableOptions(block_size=4096)) for p in part if p]
+        ref = o.compact(part_ssts, o.CompactionParams(cutoff_ht=cutoff, largest_user_key=largest), topt)
+        assert out.stats.num_input_records == ref.stats.num_input_records
+        assert out.stats.num_output_records == ref.stats.num_output_records
+        rs = ref.sst()
+        if rs is None:
+            assert out.data_len == 0
+            continue
+        data = res.data_arena[out.data_offset:out.data_offset + out.data_len].tobytes()
+        meta = res.meta_arena[out.meta_offset:out.meta_offset + out.meta_len].tobytes()
+        assert data == rs.data and meta == rs.meta
+        kvs = ref.kv_list()
+        assert (out.smallest, out.largest) == (kvs[0][0], kvs[-1][0])
+        got += kvs
+    assert got == exp.kv_list()
+    assert res.total.num_input_records == exp.stats.num_input_records
+    assert res.total.num_output_records == exp.stats.num_output_records
+    assert [o_.lower for o_ in res.outputs[1:]] == [o_.upper for o_ in res.outputs[:-1]]
+
+
+def test_concurrent_jobs_on_private_streams(pkg):
+    """Jobs of different tablets run concurrently on one device (one PriorityThreadPool worker per
+    CompactionJob, db_impl.cc:397-403): each on its own stream, results unchanged."""
+    import threading
+    cfgs = [o.GenConfig(seed=40 + i, num_rows=3000 + 500 * i, cols=2, versions=3, num_files=3, value_len=70, tombstone_per_1024=30) for i in range(4)]
+    tablets = [o.Sst.generate_all(c, o.TableOptions(block_size=4096)) for c in cfgs]
+    cutoffs = [o.ht_from_micros(c.base_micros + 1500) for c in cfgs]
+    exps = [o.compact(t, o.CompactionParams(cutoff_ht=c), o.TableOptions(block_size=4096)) for t, c in zip(tablets, cutoffs)]
+    results = [None] * len(tablets)
+
+    def work(i):
+        for _ in range(3):
+            job = gpu_compact(pkg, tablets[i], cutoff_ht=cutoffs[i], block_size=4096, cuda_stream=pkg.STREAM_PRIVATE)
+            data, meta = job.fetch_output()
+            results[i] = (data.tobytes(), meta.tobytes(), job.stats().num_input_records)
+            job.close()
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(tablets))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for r, e in zip(results, exps):
+        assert r is not None and r[0] == e.sst().data and r[1] == e.sst().meta and r[2] == e.stats.num_input_records

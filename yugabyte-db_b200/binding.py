@@ -134,6 +134,43 @@ def _np_ptr(a):
     return a.ctypes.data if a.size else None
 
 
+STREAM_PRIVATE = 2**64 - 1      # YBGPU_STREAM_PRIVATE: a non-blocking stream owned by the job
+
+
+def make_options(device=0, bottommost=True, last_sequence=MAX_SEQUENCE, largest_user_key=None,
+                 retention=True, cutoff_ht=HT_MIN, cotables_cutoff_ht=HT_INVALID, table_ttl_ns=TTL_MAX_NS,
+                 retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
+                 restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
+                 min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b"",
+                 filter_policy=0, filter_block_size=65536):
+    """ybgpu_job_options from keyword arguments; returns (options, objects to keep alive)."""
+    L = lib()
+    o = JobOptions()
+    L.ybgpu_job_options_init(C.byref(o))
+    o.device = device
+    o.bottommost_level = int(bottommost)
+    o.last_sequence = last_sequence
+    if largest_user_key is not None:
+        o.largest_user_key, o.largest_user_key_len, o.has_largest_user_key = largest_user_key, len(largest_user_key), 1
+    o.retention_enabled = int(retention)
+    o.history_cutoff_ht = cutoff_ht
+    o.cotables_cutoff_ht = cotables_cutoff_ht
+    o.table_ttl_ns = table_ttl_ns
+    o.retain_delete_markers_in_major_compaction = int(retain_delete_markers)
+    o.other_min_ht = other_min_ht
+    o.key_bounds_lower, o.key_bounds_lower_len = lower, len(lower)
+    o.key_bounds_upper, o.key_bounds_upper_len = upper, len(upper)
+    o.block_size, o.block_restart_interval, o.block_size_deviation = block_size, restart_interval, deviation
+    o.output_key_encoding = output_key_encoding
+    o.index_block_size, o.min_keys_per_index_block = index_block_size, min_keys_per_index_block
+    o.verify_checksums = int(verify_checksums)
+    o.filter_policy, o.filter_block_size = filter_policy, filter_block_size
+    o.cuda_stream = cuda_stream
+    o.range_lower, o.range_lower_len = range_lower, len(range_lower)
+    o.range_upper, o.range_upper_len = range_upper, len(range_upper)
+    return o, (largest_user_key, lower, upper, range_lower, range_upper)
+
+
 class GpuCompactionJob:
     """One rocksdb::CompactionJob::Run on the GPU (compaction_job.cc:521-589)."""
 
@@ -144,31 +181,11 @@ class GpuCompactionJob:
                  min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b"",
                  filter_policy=0, filter_block_size=65536):
         L = lib()
-        o = JobOptions()
-        L.ybgpu_job_options_init(C.byref(o))
-        o.device = device
-        o.bottommost_level = int(bottommost)
-        o.last_sequence = last_sequence
-        if largest_user_key is not None:
-            o.largest_user_key, o.largest_user_key_len, o.has_largest_user_key = largest_user_key, len(largest_user_key), 1
-        o.retention_enabled = int(retention)
-        o.history_cutoff_ht = cutoff_ht
-        o.cotables_cutoff_ht = cotables_cutoff_ht
-        o.table_ttl_ns = table_ttl_ns
-        o.retain_delete_markers_in_major_compaction = int(retain_delete_markers)
-        o.other_min_ht = other_min_ht
-        o.key_bounds_lower, o.key_bounds_lower_len = lower, len(lower)
-        o.key_bounds_upper, o.key_bounds_upper_len = upper, len(upper)
-        o.block_size, o.block_restart_interval, o.block_size_deviation = block_size, restart_interval, deviation
-        o.output_key_encoding = output_key_encoding
-        o.index_block_size, o.min_keys_per_index_block = index_block_size, min_keys_per_index_block
-        o.verify_checksums = int(verify_checksums)
-        o.filter_policy, o.filter_block_size = filter_policy, filter_block_size
-        o.cuda_stream = cuda_stream
-        o.range_lower, o.range_lower_len = range_lower, len(range_lower)
-        o.range_upper, o.range_upper_len = range_upper, len(range_upper)
-        self._keep2 = (range_lower, range_upper)
-        self._keep = (largest_user_key, lower, upper)
+        o, self._keep = make_options(device, bottommost, last_sequence, largest_user_key, retention, cutoff_ht,
+                                     cotables_cutoff_ht, table_ttl_ns, retain_delete_markers, other_min_ht, lower, upper,
+                                     block_size, restart_interval, deviation, output_key_encoding, index_block_size,
+                                     min_keys_per_index_block, verify_checksums, cuda_stream, range_lower, range_upper,
+                                     filter_policy, filter_block_size)
         h = C.c_void_p()
         st = L.ybgpu_job_create(C.byref(o), C.byref(h))
         if st != 0:
@@ -388,3 +405,108 @@ def sst_separators(meta):
         raise YbGpuError(2, L.ybgpu_last_error().decode())
     kb = keys.tobytes()
     return [kb[int(offs[i]):int(offs[i + 1])] for i in range(n.value)]
+
+
+class InputFile(C.Structure):
+    _fields_ = [("meta_file", C.c_void_p), ("meta_file_len", C.c_uint64), ("data_file", C.c_void_p),
+                ("data_file_len", C.c_uint64), ("hybrid_time_filter", C.c_uint64)]
+
+
+class SubOutput(C.Structure):
+    _fields_ = [("data_offset", C.c_uint64), ("data_len", C.c_uint64), ("meta_offset", C.c_uint64), ("meta_len", C.c_uint64),
+                ("stats", JobStats), ("range_lower_len", C.c_uint32), ("range_upper_len", C.c_uint32),
+                ("range_lower", C.c_uint8 * 256), ("range_upper", C.c_uint8 * 256),
+                ("smallest_key_len", C.c_uint32), ("largest_key_len", C.c_uint32),
+                ("smallest_key", C.c_uint8 * 1032), ("largest_key", C.c_uint8 * 1032)]
+
+    @property
+    def lower(self):
+        return bytes(self.range_lower[:self.range_lower_len])
+
+    @property
+    def upper(self):
+        return bytes(self.range_upper[:self.range_upper_len])
+
+    @property
+    def smallest(self):
+        return bytes(self.smallest_key[:self.smallest_key_len])
+
+    @property
+    def largest(self):
+        return bytes(self.largest_key[:self.largest_key_len])
+
+
+def _input_files(ssts, ht_filters=None):
+    """ssts: list of (meta ndarray, data ndarray). Returns (ctypes array, keepalive)."""
+    arr = (InputFile * len(ssts))()
+    keep = []
+    for i, (meta, data) in enumerate(ssts):
+        meta = np.ascontiguousarray(meta, dtype=np.uint8)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        keep += [meta, data]
+        arr[i] = InputFile(meta.ctypes.data, meta.size, data.ctypes.data, data.size,
+                           ht_filters[i] if ht_filters else HT_INVALID)
+    return arr, keep
+
+
+def plan_subcompactions(ssts, max_subcompactions, docdb_keys=True):
+    """Splitter user keys (row aligned) for at most max_subcompactions key ranges."""
+    L = lib()
+    L.ybgpu_plan_subcompactions.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+    arr, keep = _input_files(ssts)
+    buf = np.zeros((max(1, max_subcompactions), 256), np.uint8)
+    lens = np.zeros(max(1, max_subcompactions), np.uint32)
+    n = C.c_uint32()
+    st = L.ybgpu_plan_subcompactions(arr, len(ssts), max_subcompactions, int(docdb_keys), buf.ctypes.data, lens.ctypes.data, C.byref(n))
+    if st != 0:
+        raise YbGpuError(st, "plan_subcompactions")
+    return [buf[i, :lens[i]].tobytes() for i in range(n.value)]
+
+
+def sst_last_key(meta, data):
+    """Last internal key of a split SST (FileMetaData::largest), read on the host."""
+    L = lib()
+    L.ybgpu_sst_last_key.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]
+    meta = np.ascontiguousarray(meta, dtype=np.uint8)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    out = np.zeros(1032, np.uint8)
+    n = C.c_uint32()
+    st = L.ybgpu_sst_last_key(meta.ctypes.data, meta.size, data.ctypes.data, data.size, out.ctypes.data, C.byref(n))
+    if st != 0:
+        raise YbGpuError(st, "sst_last_key")
+    return out[:n.value].tobytes()
+
+
+class SubcompactionResult:
+    def __init__(self, outputs, total, data_arena, meta_arena):
+        self.outputs, self.total, self.data_arena, self.meta_arena = outputs, total, data_arena, meta_arena
+
+    def files(self):
+        """[(data bytes view, meta bytes view)] of the non-empty outputs, in range order."""
+        return [(self.data_arena[o.data_offset:o.data_offset + o.data_len], self.meta_arena[o.meta_offset:o.meta_offset + o.meta_len])
+                for o in self.outputs if o.data_len]
+
+
+def compact_files(ssts, max_subcompactions=8, max_in_flight=3, data_arena=None, meta_arena=None, ht_filters=None, **job_kwargs):
+    """ybgpu_compact_files: one compaction as pipelined key-range subcompactions (one output SST per
+    range, in range order). ssts: list of (meta ndarray, data ndarray) in host memory."""
+    L = lib()
+    L.ybgpu_compact_files.argtypes = [C.POINTER(JobOptions), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                                      C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(JobStats),
+                                      C.c_char_p, C.c_uint64]
+    o, keep_o = make_options(**job_kwargs)
+    arr, keep = _input_files(ssts, ht_filters)
+    in_bytes = sum(int(d.size) for _, d in ssts)
+    if data_arena is None:
+        data_arena = np.empty(in_bytes + (in_bytes >> 4) + (1 << 20) + 4096 * max_subcompactions, np.uint8)
+    if meta_arena is None:
+        meta_arena = np.empty((in_bytes >> 5) + (4 << 20) + 4096 * max_subcompactions, np.uint8)
+    outs = (SubOutput * max(1, max_subcompactions))()
+    n = C.c_uint32()
+    total = JobStats()
+    err = C.create_string_buffer(512)
+    st = L.ybgpu_compact_files(C.byref(o), arr, len(ssts), max_subcompactions, max_in_flight, data_arena.ctypes.data, data_arena.size,
+                               meta_arena.ctypes.data, meta_arena.size, None, outs, C.byref(n), C.byref(total), err, 512)
+    if st != 0:
+        raise YbGpuError(st, err.value.decode(errors="replace"))
+    return SubcompactionResult([outs[i] for i in range(n.value)], total, data_arena, meta_arena)

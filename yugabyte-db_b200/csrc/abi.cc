@@ -284,14 +284,18 @@ ybgpu_status ybgpu_job_fetch_output(ybgpu_job* job, uint8_t* data_file, uint64_t
 ybgpu_status ybgpu_job_output_boundaries(const ybgpu_job* job, uint8_t* smallest, uint64_t* smallest_len, uint8_t* largest, uint64_t* largest_len) {
   if (!job) return YBGPU_INVALID_ARGUMENT;
   ybgpu_job* j = const_cast<ybgpu_job*>(job);
-  ybgpu_status s = EnsureHostKv(j);
+  // two boundary-key records kept by the block encoder; the KV stream is not materialised for this
+  uint64_t data_len = 0; uint32_t nb = 0, stride = 0;
+  ybgpu_status s = Sync(j, j->engine->OutputInfo(&data_len, &nb, &stride));
   if (s != YBGPU_OK) return s;
-  const uint64_t n = j->koff.size() - 1;
-  if (n == 0) { *smallest_len = 0; *largest_len = 0; return YBGPU_OK; }
-  *smallest_len = j->koff[1] - j->koff[0];
-  memcpy(smallest, j->keys.data(), *smallest_len);
-  *largest_len = j->koff[n] - j->koff[n - 1];
-  memcpy(largest, j->keys.data() + j->koff[n - 1], *largest_len);
+  *smallest_len = 0; *largest_len = 0;
+  if (nb == 0) return YBGPU_OK;
+  std::vector<uint8_t> a(stride), b(stride);
+  s = Sync(j, j->engine->FetchFileBoundaries(a.data(), b.data()));
+  if (s != YBGPU_OK) return s;
+  *smallest_len = a[0] | (a[1] << 8); *largest_len = b[0] | (b[1] << 8);
+  memcpy(smallest, a.data() + 2, *smallest_len);
+  memcpy(largest, b.data() + 2, *largest_len);
   return YBGPU_OK;
 }
 

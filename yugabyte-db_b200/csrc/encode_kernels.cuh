@@ -1222,11 +1222,11 @@ __global__ void __launch_bounds__(256) k_filter_finish(EncView E, int S, const u
 // Boundary keys for the host-side index: for every block its last internal key and the first key
 // of the next block, fixed stride KB bytes each: [u16 len][bytes].
 __global__ void __launch_bounds__(256) k_boundary_keys(EncView E, int S, const uint32_t* block_first, uint32_t nblocks, uint8_t* out, uint32_t KB) {
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nblocks * 2; t += gridDim.x * blockDim.x) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nblocks * 2 + 1; t += gridDim.x * blockDim.x) {
     const uint32_t b = t >> 1, which = t & 1;
     const uint32_t e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
     uint8_t* o = out + static_cast<size_t>(t) * KB;
-    const uint32_t j = which ? e : e - 1;
+    const uint32_t j = b == nblocks ? 0u : (which ? e : e - 1);      // the extra slot: the first key of the file
     if (j >= E.n) { o[0] = 0; o[1] = 0; continue; }
     const Desc d = E.kept[j];
     const uint8_t* rec = kept_rec(E, d, S);

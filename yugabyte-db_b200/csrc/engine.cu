@@ -23,6 +23,7 @@
 #include <cstring>
 #include <chrono>
 #include <cstdlib>
+#include <mutex>
 
 namespace ybgpu {
 
@@ -1288,6 +1289,7 @@ static ybgpu_status DevErrorStatus(int e) {
 
 struct Engine::Impl {
   cudaStream_t stream = nullptr;
+  bool owns_stream = false;            // cuda_stream == YBGPU_STREAM_PRIVATE: created in Init, destroyed with the job
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t phase_ev[8] = {};
   cudaEvent_t enc_ev[2] = {};          // around the block-assembler launch (the dominant kernel of the encode phase)
@@ -1333,14 +1335,15 @@ Engine::Engine(const ybgpu_job_options& o) : opt_(o), impl_(new Impl) {
 Engine::~Engine() {
   if (impl_) {
     cudaSetDevice(opt_.device);
+    if (impl_->copy_pending) cudaStreamSynchronize(impl_->copy_stream);   // before the output buffer returns to the pool
     for (void* p : impl_->allocs) cudaFreeAsync(p, impl_->stream);
     if (impl_->ev0) cudaEventDestroy(impl_->ev0);
     if (impl_->ev1) cudaEventDestroy(impl_->ev1);
-    if (impl_->copy_pending) cudaStreamSynchronize(impl_->copy_stream);
     if (impl_->copy_stream) cudaStreamDestroy(impl_->copy_stream);
     if (impl_->copy_ev) cudaEventDestroy(impl_->copy_ev);
     for (auto& e : impl_->enc_ev) if (e) cudaEventDestroy(e);
     for (auto& e : impl_->phase_ev) if (e) cudaEventDestroy(e);
+    if (impl_->owns_stream && impl_->stream) cudaStreamDestroy(impl_->stream);   // the queued frees complete first
     delete impl_;
   }
 }
@@ -1366,7 +1369,14 @@ ybgpu_status Engine::Init() {
                                          " (this engine has no CPU fallback)");
   if (opt_.device < 0 || opt_.device >= ndev) return Fail(YBGPU_INVALID_ARGUMENT, "bad device ordinal");
   CUDA_TRY(cudaSetDevice(opt_.device));
-  impl_->stream = reinterpret_cast<cudaStream_t>(opt_.cuda_stream);   // NULL = legacy default stream
+  if (opt_.cuda_stream == YBGPU_STREAM_PRIVATE) {
+    // jobs that run concurrently on one device (subcompactions, several tablets) must not meet on the
+    // legacy default stream: each gets its own non-blocking stream
+    CUDA_TRY(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking));
+    impl_->owns_stream = true;
+  } else {
+    impl_->stream = reinterpret_cast<cudaStream_t>(opt_.cuda_stream);   // NULL = legacy default stream
+  }
   g_alloc_stream = impl_->stream;
   {
     cudaMemPool_t pool;
@@ -1452,9 +1462,24 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   auto t_prev = std::chrono::steady_clock::now();
   CUDA_TRY(cudaSetDevice(opt_.device));
   g_alloc_stream = I.stream;
-  // cudaGetDeviceProperties costs milliseconds per call; one attribute, cached per device.
+  // Per-device one-time state (SM count, CRC tables in device memory), shared by every job of the
+  // process; jobs may run concurrently on different host threads, so it is built under a lock and
+  // the table kernels are complete before any job proceeds.
+  static std::mutex dev_init_mu;
   static int sm_count[64] = {};
-  if (!sm_count[opt_.device & 63]) CUDA_TRY(cudaDeviceGetAttribute(&sm_count[opt_.device & 63], cudaDevAttrMultiProcessorCount, opt_.device));
+  static bool crc_ready[64] = {};
+  {
+    std::lock_guard<std::mutex> lock(dev_init_mu);
+    // cudaGetDeviceProperties costs milliseconds per call; one attribute, cached per device.
+    if (!sm_count[opt_.device & 63]) CUDA_TRY(cudaDeviceGetAttribute(&sm_count[opt_.device & 63], cudaDevAttrMultiProcessorCount, opt_.device));
+    if (!crc_ready[opt_.device & 63]) {
+      k_crc_init<<<1, 256, 0, I.stream>>>();
+      k_crc_init_xpow<<<(CRC_XPOW_TABLE + 256) / 256, 256, 0, I.stream>>>();
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(I.stream));
+      crc_ready[opt_.device & 63] = true;
+    }
+  }
   const int sms = sm_count[opt_.device & 63];
   const int k = static_cast<int>(I.runs.size());
   auto shutdown = [&]() { return shutting_down && *shutting_down; };
@@ -1464,14 +1489,6 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   {
     JobDev init{}; init.min_seq = ~0ull;
     CUDA_TRY(cudaMemcpyAsync(I.dJ, &init, sizeof(init), cudaMemcpyHostToDevice, I.stream));
-  }
-  {
-    static bool crc_ready[64] = {};
-    if (!crc_ready[opt_.device & 63]) {
-      k_crc_init<<<1, 256, 0, I.stream>>>();
-      k_crc_init_xpow<<<(CRC_XPOW_TABLE + 256) / 256, 256, 0, I.stream>>>();
-      crc_ready[opt_.device & 63] = true;
-    }
   }
   CUDA_TRY(cudaEventRecord(I.ev0, I.stream));
   uint32_t phase_launch_mark[8] = {};
@@ -1833,8 +1850,9 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       launches += 5 + (n_keys ? 1 : 0);
     }
     I.boundary_stride = static_cast<uint32_t>((max_ikey + 2 + 7) & ~7u);
-    CUDA_TRY(DevAlloc(&I.allocs, &I.d_boundary, static_cast<size_t>(nblocks) * 2 * I.boundary_stride));
-    k_boundary_keys<<<GridFor(static_cast<uint64_t>(nblocks) * 2, 256, sms), 256, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_boundary, I.boundary_stride);
+    // slot 2*nblocks (one past the per-block pairs): the first key of the file (FileMetaData::smallest)
+    CUDA_TRY(DevAlloc(&I.allocs, &I.d_boundary, (static_cast<size_t>(nblocks) * 2 + 1) * I.boundary_stride));
+    k_boundary_keys<<<GridFor(static_cast<uint64_t>(nblocks) * 2 + 1, 256, sms), 256, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_boundary, I.boundary_stride);
     launches += 4;
   }
   CUDA_TRY(end_phase());
@@ -1968,6 +1986,21 @@ ybgpu_status Engine::EndFetchDataFile() {
 }
 
 uint64_t Engine::kept_deletions() const { return impl_->hJ.n_kept_deletions; }
+
+// FileMetaData::smallest / largest of the output (db/version_edit.h:101-165): records of
+// [u16 key length][internal key], boundary_stride bytes each (zero length: no output).
+ybgpu_status Engine::FetchFileBoundaries(uint8_t* smallest, uint8_t* largest) {
+  if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  Impl& I = *impl_;
+  smallest[0] = smallest[1] = 0; largest[0] = largest[1] = 0;
+  if (!I.n_blocks) return YBGPU_OK;
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  CUDA_TRY(cudaMemcpyAsync(smallest, I.d_boundary + static_cast<size_t>(I.n_blocks) * 2 * I.boundary_stride, I.boundary_stride, cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaMemcpyAsync(largest, I.d_boundary + static_cast<size_t>(I.n_blocks - 1) * 2 * I.boundary_stride, I.boundary_stride, cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  stats_.d2h_bytes += 2ull * I.boundary_stride;
+  return YBGPU_OK;
+}
 
 ybgpu_status Engine::FilterInfo(uint32_t* n_filter_blocks, uint32_t* block_bytes, uint32_t* key_stride) const {
   if (!ran_) return const_cast<Engine*>(this)->Fail(YBGPU_ILLEGAL_STATE, "job has not run");

@@ -28,6 +28,8 @@ class Engine {
   ybgpu_status BeginFetchDataFile(uint8_t* data_file);
   ybgpu_status EndFetchDataFile();
   uint64_t kept_deletions() const;
+  // smallest / largest internal key of the output as [u16 length][key] records (boundary stride of OutputInfo)
+  ybgpu_status FetchFileBoundaries(uint8_t* smallest, uint8_t* largest);
   // Bloom filter blocks of the output (filter_policy != none): number of blocks, bytes per block
   // (bits + 5 metadata bytes), stride of the boundary key records.
   ybgpu_status FilterInfo(uint32_t* n_filter_blocks, uint32_t* block_bytes, uint32_t* key_stride) const;

@@ -1,0 +1,361 @@
+// subcompaction.cc — one compaction run as pipelined key-range subcompactions.
+//
+// Host-side replacement of CompactionJob::GenSubcompactionBoundaries and of the per-subcompaction
+// threads of CompactionJob::Run (reference rocksdb/db/compaction_job.cc:409-519,532-552): the
+// compaction is cut into key ranges on row boundaries, every range is an ordinary GPU job
+// (ybgpu_job_*) over the data blocks of each input that can hold its keys, and the ranges run on a
+// few host threads with a private CUDA stream each. While one range's inputs travel host->device,
+// another range's kernels run and a third range's output travels device->host: PCIe is full duplex,
+// so the end-to-end time of a large compaction approaches max(H2D, D2H) instead of their sum, and
+// the device memory in use is bounded by `max_in_flight` ranges instead of the whole compaction.
+// Everything here is host orchestration above the C ABI; no compaction logic runs on the CPU.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ybgpu_compaction.h"
+#include "dev_logic.cuh"
+#include "host_sst.h"
+
+namespace {
+
+using ybgpu::host::SstMeta;
+
+struct ParsedInput {
+  SstMeta meta;
+  std::vector<std::string> useps;      // user-key part of every block's index separator
+};
+
+std::string UserPart(const std::string& ikey) { return ikey.size() >= 8 ? ikey.substr(0, ikey.size() - 8) : ikey; }
+
+bool ParseInputs(const ybgpu_input_file* files, uint32_t n, std::vector<ParsedInput>* out, std::string* err) {
+  out->resize(n);
+  for (uint32_t f = 0; f < n; f++) {
+    std::string e = ybgpu::host::ParseSplitSstMeta(files[f].meta_file, files[f].meta_file_len, &(*out)[f].meta);
+    if (!e.empty()) { *err = "input " + std::to_string(f) + ": " + e; return false; }
+    ParsedInput& p = (*out)[f];
+    if (p.meta.separators.size() != p.meta.data_blocks.size()) { *err = "index entries do not match data blocks"; return false; }
+    p.useps.reserve(p.meta.separators.size());
+    for (const std::string& k : p.meta.separators) p.useps.push_back(UserPart(k));
+    for (const auto& h : p.meta.data_blocks)
+      if (h.offset + h.size + 5 > files[f].data_file_len) { *err = "block handle outside the data file"; return false; }
+  }
+  return true;
+}
+
+// Weighted quantiles of the index separators, cut back to the row prefix. A splitter s must never
+// fall inside a row (all entries of one DocKey): s = DocKey prefix of a separator is a complete
+// DocKey by construction, and no other complete DocKey can be a proper prefix of it (the DocKey
+// grammar is prefix-free), so every row lies entirely on one side. Separators whose DocKey does
+// not parse (FindShortestSeparator may have shortened them) are skipped.
+std::vector<std::string> PlanSplitters(const std::vector<ParsedInput>& in, uint32_t n_ranges, bool docdb_keys) {
+  std::vector<std::string> out;
+  if (n_ranges <= 1) return out;
+  struct Sample { const std::string* key; uint64_t w; };
+  std::vector<Sample> samples;
+  uint64_t total = 0;
+  for (const ParsedInput& p : in)
+    for (size_t i = 0; i < p.useps.size(); i++) {
+      samples.push_back({&p.useps[i], p.meta.data_blocks[i].size + 5});
+      total += p.meta.data_blocks[i].size + 5;
+    }
+  if (samples.empty()) return out;
+  std::sort(samples.begin(), samples.end(), [](const Sample& a, const Sample& b) { return *a.key < *b.key; });
+  const double target = static_cast<double>(total) / n_ranges;
+  double acc = 0, next = target;
+  for (const Sample& s : samples) {
+    acc += static_cast<double>(s.w);
+    if (acc < next || out.size() + 1 >= n_ranges) continue;
+    const std::string& k = *s.key;
+    int plen = static_cast<int>(k.size());
+    if (docdb_keys) {
+      // group_prefix_len scans with aligned 8-byte loads: give it an aligned, padded copy
+      alignas(8) uint8_t buf[1040];
+      if (k.size() > 1024) continue;
+      memset(buf, 0, sizeof(buf));
+      memcpy(buf, k.data(), k.size());
+      plen = ybgpu::group_prefix_len(buf, static_cast<int>(k.size()), true);
+      if (plen <= 0) continue;
+    }
+    if (plen == 0 || plen > YBGPU_MAX_SPLITTER_LEN) continue;
+    std::string cut = k.substr(0, plen);
+    if (!out.empty() && !(out.back() < cut)) continue;
+    out.push_back(cut);
+    next = target * static_cast<double>(out.size() + 1);
+  }
+  return out;
+}
+
+// Blocks [a, b) of one input that can hold user keys in [lo, hi): block i holds keys in
+// (sep[i-1], sep[i]] (the separator is >= the block's last key and < the next block's first key).
+void BlocksForRange(const std::vector<std::string>& useps, const std::string& lo, const std::string& hi, size_t* a, size_t* b) {
+  const size_t nb = useps.size();
+  *a = lo.empty() ? 0 : static_cast<size_t>(std::lower_bound(useps.begin(), useps.end(), lo) - useps.begin());
+  if (hi.empty()) { *b = nb; return; }
+  const size_t c = static_cast<size_t>(std::lower_bound(useps.begin(), useps.end(), hi) - useps.begin());
+  *b = std::max(*a, std::min(nb, c + 1));
+}
+
+// Last internal key of one data block (BlockIter::SeekToLast: from the last restart point forward;
+// table/block.cc:248-262,348-447 and block_internal.h:51-162 for three_shared_parts).
+bool LastKeyOfBlock(const uint8_t* blk, uint64_t size, int key_encoding, std::string* key) {
+  using namespace ybgpu;
+  if (size < 8) return false;
+  uint32_t num_restarts; memcpy(&num_restarts, blk + size - 4, 4);
+  if (num_restarts == 0 || static_cast<uint64_t>(num_restarts) * 4 + 4 > size) return false;
+  const uint32_t restarts_off = static_cast<uint32_t>(size - 4 - 4ull * num_restarts);
+  uint32_t p; memcpy(&p, blk + restarts_off + 4ull * (num_restarts - 1), 4);
+  if (p >= restarts_off) return false;
+  std::string cur;
+  bool first = true;
+  while (p < restarts_off) {
+    const uint32_t avail = restarts_off - p;
+    if (key_encoding == YBGPU_KEY_ENCODING_THREE_SHARED_PARTS) {
+      TspHeader th; uint32_t klen, ms, ml;
+      const int h = parse_entry_header_tsp(blk + p, avail, &th);
+      if (!h || (first && th.something_shared) || !tsp_key_layout(th, static_cast<uint32_t>(cur.size()), &klen, &ms, &ml)) return false;
+      if (static_cast<uint64_t>(p) + h + th.ns1 + th.ns2 + th.vlen > restarts_off) return false;
+      p += h;
+      std::string nk;
+      if (!th.something_shared) {
+        nk.assign(reinterpret_cast<const char*>(blk + p), th.ns1);
+      } else {
+        uint64_t last = 0;
+        if (th.last_size) {
+          if (cur.size() < 8) return false;
+          memcpy(&last, cur.data() + cur.size() - 8, 8);
+          last += th.last_inc;
+        }
+        nk.assign(cur, 0, th.shared_prefix);
+        nk.append(reinterpret_cast<const char*>(blk + p), th.ns1);
+        nk.append(cur, ms, ml);
+        nk.append(reinterpret_cast<const char*>(blk + p + th.ns1), th.ns2);
+        if (th.last_size) nk.append(reinterpret_cast<const char*>(&last), 8);
+      }
+      if (nk.size() != klen) return false;
+      cur.swap(nk);
+      p += th.ns1 + th.ns2 + th.vlen;
+    } else {
+      uint32_t shared, non_shared, vlen;
+      const int h = parse_entry_header(blk + p, avail, &shared, &non_shared, &vlen);
+      if (!h || shared > cur.size() || (first && shared != 0)) return false;
+      if (static_cast<uint64_t>(p) + h + non_shared + vlen > restarts_off) return false;
+      p += h;
+      cur.resize(shared);
+      cur.append(reinterpret_cast<const char*>(blk + p), non_shared);
+      p += non_shared + vlen;
+    }
+    first = false;
+  }
+  if (cur.size() < 8) return false;
+  *key = cur;
+  return true;
+}
+
+bool LastKeyOfFile(const ybgpu_input_file& f, const SstMeta& m, std::string* key) {
+  if (m.data_blocks.empty()) { key->clear(); return true; }
+  const auto& h = m.data_blocks.back();
+  if (h.offset + h.size + 5 > f.data_file_len) return false;
+  if (f.data_file[h.offset + h.size] != 0) return false;            // compressed block: not supported
+  return LastKeyOfBlock(f.data_file + h.offset, h.size, m.key_encoding, key);
+}
+
+void AddStats(ybgpu_job_stats* t, const ybgpu_job_stats& s, bool first_output) {
+  t->num_input_records += s.num_input_records; t->num_output_records += s.num_output_records;
+  t->num_record_drop_hidden += s.num_record_drop_hidden; t->num_record_drop_obsolete += s.num_record_drop_obsolete;
+  t->num_record_drop_feed += s.num_record_drop_feed;
+  t->total_input_raw_key_bytes += s.total_input_raw_key_bytes; t->total_input_raw_value_bytes += s.total_input_raw_value_bytes;
+  t->total_output_raw_key_bytes += s.total_output_raw_key_bytes; t->total_output_raw_value_bytes += s.total_output_raw_value_bytes;
+  t->num_output_data_blocks += s.num_output_data_blocks;
+  t->output_data_file_size += s.output_data_file_size; t->output_meta_file_size += s.output_meta_file_size;
+  if (s.num_output_records) {
+    t->smallest_seqno = first_output ? s.smallest_seqno : std::min(t->smallest_seqno, s.smallest_seqno);
+    t->largest_seqno = std::max(t->largest_seqno, s.largest_seqno);
+  }
+  t->gpu_seconds += s.gpu_seconds; t->gpu_kernel_launches += s.gpu_kernel_launches;
+  t->h2d_bytes += s.h2d_bytes; t->d2h_bytes += s.d2h_bytes;
+  for (int i = 0; i < 8; i++) { t->phase_seconds[i] += s.phase_seconds[i]; t->phase_launches[i] += s.phase_launches[i]; }
+}
+
+}  // namespace
+
+extern "C" {
+
+ybgpu_status ybgpu_sst_last_key(const uint8_t* meta_file, uint64_t meta_file_len, const uint8_t* data_file,
+                                uint64_t data_file_len, uint8_t* key, uint32_t* key_len) {
+  if (!meta_file || !data_file || !key || !key_len) return YBGPU_INVALID_ARGUMENT;
+  SstMeta m;
+  if (!ybgpu::host::ParseSplitSstMeta(meta_file, meta_file_len, &m).empty()) return YBGPU_CORRUPTION;
+  ybgpu_input_file f{meta_file, meta_file_len, data_file, data_file_len, YBGPU_HT_INVALID};
+  std::string k;
+  if (!LastKeyOfFile(f, m, &k) || k.size() > 1032) return YBGPU_CORRUPTION;
+  memcpy(key, k.data(), k.size());
+  *key_len = static_cast<uint32_t>(k.size());
+  return YBGPU_OK;
+}
+
+ybgpu_status ybgpu_plan_subcompactions(const ybgpu_input_file* files, uint32_t num_files, uint32_t max_subcompactions,
+                                       int32_t docdb_keys, uint8_t* splitters, uint32_t* splitter_lens,
+                                       uint32_t* num_splitters) {
+  if (!files || !splitters || !splitter_lens || !num_splitters) return YBGPU_INVALID_ARGUMENT;
+  std::vector<ParsedInput> in;
+  std::string err;
+  if (!ParseInputs(files, num_files, &in, &err)) return YBGPU_CORRUPTION;
+  const std::vector<std::string> sp = PlanSplitters(in, max_subcompactions, docdb_keys != 0);
+  for (size_t i = 0; i < sp.size(); i++) {
+    memcpy(splitters + 256 * i, sp[i].data(), sp[i].size());
+    splitter_lens[i] = static_cast<uint32_t>(sp[i].size());
+  }
+  *num_splitters = static_cast<uint32_t>(sp.size());
+  return YBGPU_OK;
+}
+
+ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_input_file* files, uint32_t num_files,
+                                 uint32_t max_subcompactions, uint32_t max_in_flight,
+                                 uint8_t* data_arena, uint64_t data_arena_cap, uint8_t* meta_arena, uint64_t meta_arena_cap,
+                                 const volatile int32_t* shutting_down, ybgpu_sub_output* outputs, uint32_t* num_outputs,
+                                 ybgpu_job_stats* total, char* err, uint64_t err_cap) {
+  auto fail = [&](ybgpu_status s, const std::string& msg) {
+    if (err && err_cap) snprintf(err, err_cap, "%s", msg.c_str());
+    return s;
+  };
+  if (!options || !files || !outputs || !num_outputs || !data_arena || !meta_arena) return fail(YBGPU_INVALID_ARGUMENT, "null argument");
+  if (options->range_lower_len || options->range_upper_len) return fail(YBGPU_INVALID_ARGUMENT, "range bounds are set by the subcompaction planner");
+  if (max_subcompactions == 0) max_subcompactions = 1;
+  if (max_in_flight == 0) max_in_flight = 3;
+  std::vector<ParsedInput> in;
+  std::string perr;
+  if (!ParseInputs(files, num_files, &in, &perr)) return fail(YBGPU_CORRUPTION, perr);
+
+  // Compaction::GetLargestUserKey (db/compaction.cc:318): the seqno-zeroing exception key is a
+  // property of the whole compaction, not of a range.
+  std::string largest_user;
+  bool have_largest = options->has_largest_user_key != 0;
+  if (have_largest) {
+    largest_user.assign(reinterpret_cast<const char*>(options->largest_user_key), options->largest_user_key_len);
+  } else {
+    for (uint32_t f = 0; f < num_files; f++) {
+      std::string k;
+      if (!LastKeyOfFile(files[f], in[f].meta, &k)) return fail(YBGPU_CORRUPTION, "cannot read the last key of input " + std::to_string(f));
+      if (k.empty()) continue;
+      std::string u = UserPart(k);
+      if (!have_largest || largest_user < u) { largest_user = u; have_largest = true; }
+    }
+  }
+
+  const std::vector<std::string> splitters = PlanSplitters(in, max_subcompactions, options->retention_enabled != 0);
+  const uint32_t n_ranges = static_cast<uint32_t>(splitters.size()) + 1;
+  *num_outputs = n_ranges;
+  for (uint32_t r = 0; r < n_ranges; r++) {
+    ybgpu_sub_output& o = outputs[r];
+    memset(&o, 0, sizeof(o));
+    if (r > 0) { o.range_lower_len = static_cast<uint32_t>(splitters[r - 1].size()); memcpy(o.range_lower, splitters[r - 1].data(), splitters[r - 1].size()); }
+    if (r + 1 < n_ranges) { o.range_upper_len = static_cast<uint32_t>(splitters[r].size()); memcpy(o.range_upper, splitters[r].data(), splitters[r].size()); }
+  }
+
+  std::atomic<uint32_t> next_range{0};
+  std::atomic<uint64_t> data_used{0}, meta_used{0};
+  std::atomic<bool> failed{false};
+  std::mutex err_mu;
+  ybgpu_status first_status = YBGPU_OK;
+  std::string first_error;
+  auto record_failure = [&](ybgpu_status s, const std::string& msg) {
+    std::lock_guard<std::mutex> lock(err_mu);
+    if (!failed.exchange(true)) { first_status = s; first_error = msg; }
+  };
+
+  auto run_range = [&](uint32_t r) {
+    ybgpu_sub_output& out = outputs[r];
+    const std::string lo(reinterpret_cast<const char*>(out.range_lower), out.range_lower_len);
+    const std::string hi(reinterpret_cast<const char*>(out.range_upper), out.range_upper_len);
+    ybgpu_job_options o = *options;
+    o.cuda_stream = YBGPU_STREAM_PRIVATE;
+    o.range_lower = out.range_lower; o.range_lower_len = out.range_lower_len;
+    o.range_upper = out.range_upper; o.range_upper_len = out.range_upper_len;
+    o.has_largest_user_key = have_largest ? 1 : 0;
+    o.largest_user_key = reinterpret_cast<const uint8_t*>(largest_user.data());
+    o.largest_user_key_len = largest_user.size();
+    ybgpu_job* job = nullptr;
+    ybgpu_status s = ybgpu_job_create(&o, &job);
+    if (s != YBGPU_OK) { record_failure(s, std::string("create: ") + ybgpu_last_error()); return; }
+    auto job_fail = [&](ybgpu_status st, const char* what) {
+      record_failure(st, std::string(what) + " (range " + std::to_string(r) + "): " + ybgpu_job_error(job));
+      ybgpu_job_destroy(job);
+    };
+    uint32_t added = 0;
+    std::vector<ybgpu_block_handle> h;
+    for (uint32_t f = 0; f < num_files; f++) {
+      size_t a, b;
+      BlocksForRange(in[f].useps, lo, hi, &a, &b);
+      if (b <= a) continue;
+      const auto& blocks = in[f].meta.data_blocks;
+      const uint64_t start = blocks[a].offset;
+      const uint64_t end = blocks[b - 1].offset + blocks[b - 1].size + 5;
+      h.resize(b - a);
+      for (size_t i = a; i < b; i++) { h[i - a].offset = blocks[i].offset - start; h[i - a].size = blocks[i].size; }
+      s = ybgpu_job_add_input(job, files[f].data_file + start, end - start, h.data(), h.size(), in[f].meta.key_encoding, files[f].hybrid_time_filter);
+      if (s != YBGPU_OK) { job_fail(s, "add_input"); return; }
+      added++;
+    }
+    if (added) {
+      s = ybgpu_job_run(job, shutting_down);
+      if (s != YBGPU_OK) { job_fail(s, "run"); return; }
+      uint64_t dl = 0, ml = 0;
+      s = ybgpu_job_output_sizes(job, &dl, &ml);
+      if (s != YBGPU_OK) { job_fail(s, "output_sizes"); return; }
+      if (dl) {
+        // 4 KB aligned slices of the caller's arenas, handed out in completion order
+        const uint64_t doff = data_used.fetch_add((dl + 4095) & ~4095ull);
+        const uint64_t moff = meta_used.fetch_add((ml + 4095) & ~4095ull);
+        if (doff + dl > data_arena_cap || moff + ml > meta_arena_cap) { job_fail(YBGPU_INVALID_ARGUMENT, "output arena too small"); return; }
+        s = ybgpu_job_fetch_output(job, data_arena + doff, dl, meta_arena + moff, ml);
+        if (s != YBGPU_OK) { job_fail(s, "fetch_output"); return; }
+        out.data_offset = doff; out.data_len = dl; out.meta_offset = moff; out.meta_len = ml;
+        uint64_t sl = 0, ll = 0;
+        uint8_t sk[4096], lk[4096];
+        s = ybgpu_job_output_boundaries(job, sk, &sl, lk, &ll);
+        if (s != YBGPU_OK) { job_fail(s, "output_boundaries"); return; }
+        out.smallest_key_len = static_cast<uint32_t>(std::min<uint64_t>(sl, sizeof(out.smallest_key)));
+        out.largest_key_len = static_cast<uint32_t>(std::min<uint64_t>(ll, sizeof(out.largest_key)));
+        memcpy(out.smallest_key, sk, out.smallest_key_len);
+        memcpy(out.largest_key, lk, out.largest_key_len);
+      }
+      ybgpu_job_get_stats(job, &out.stats);
+    }
+    ybgpu_job_destroy(job);
+  };
+
+  auto worker = [&]() {
+    for (;;) {
+      if (failed.load()) return;
+      const uint32_t r = next_range.fetch_add(1);
+      if (r >= n_ranges) return;
+      run_range(r);
+    }
+  };
+  const uint32_t n_threads = std::min(max_in_flight, n_ranges);
+  if (n_threads <= 1) {
+    worker();
+  } else {
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < n_threads; t++) pool.emplace_back(worker);
+    for (std::thread& t : pool) t.join();
+  }
+  if (failed.load()) return fail(first_status, first_error);
+  if (total) {
+    memset(total, 0, sizeof(*total));
+    bool first_output = true;
+    for (uint32_t r = 0; r < n_ranges; r++) {
+      AddStats(total, outputs[r].stats, first_output);
+      if (outputs[r].stats.num_output_records) first_output = false;
+    }
+  }
+  return YBGPU_OK;
+}
+
+}  // extern "C"
