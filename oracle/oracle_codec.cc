@@ -171,6 +171,44 @@ size_t DocHtEncodedSizeFromEnd(Slice key) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// util/varint.cc:159-205 VarInt::DecodeFromComparable, the num_decoded_bytes it reports: sign bit
+// (after `num_reserved_bits` reserved bits), then a unary count of bytes, then the magnitude;
+// negative numbers are stored complemented.
+size_t VarIntComparableSize(Slice slice, size_t num_reserved_bits) {
+  const size_t len = slice.n;
+  if (len == 0) throw Corruption("Cannot decode varint from empty slice");
+  const bool negative = (slice[0] & (0x80 >> num_reserved_bits)) == 0;
+  std::vector<uint8_t> buffer(slice.p, slice.p + slice.n);
+  if (negative) for (auto& b : buffer) b = static_cast<uint8_t>(~b);
+  if (num_reserved_bits) buffer[0] |= static_cast<uint8_t>(~((1 << (8 - num_reserved_bits)) - 1));
+  size_t idx = 0, num_ones = 0;
+  while (buffer[idx] == 0xff) {
+    ++idx;
+    if (idx >= len) throw Corruption("Encoded varint failure, no prefix termination");
+    num_ones += 8;
+  }
+  for (uint8_t temp = 0x80; buffer[idx] & temp; temp >>= 1) ++num_ones;
+  num_ones -= num_reserved_bits;
+  if (num_ones > len) throw Corruption("Not enough data in encoded varint");
+  return num_ones;
+}
+
+// util/decimal.cc:311-367 Decimal::DecodeFromComparable, the num_decoded_bytes it reports: 0x80 is
+// zero; otherwise sign from the first bit (negatives complemented), exponent as a varint with two
+// reserved bits, then mantissa digit pairs, the last of which has its low bit clear.
+size_t DecimalComparableSize(Slice slice) {
+  if (slice.empty()) throw Corruption("Cannot decode Decimal from empty slice.");
+  if (slice[0] == 128) return 1;
+  const bool positive = slice[0] >= 128;
+  std::vector<uint8_t> encoded(slice.p, slice.p + slice.n);
+  if (!positive) for (auto& b : encoded) b = static_cast<uint8_t>(~b);
+  const size_t num_exponent_bytes = VarIntComparableSize(Slice(encoded.data(), encoded.size()), 2);
+  for (size_t i = num_exponent_bytes; i < encoded.size(); i++)
+    if (!(encoded[i] & 1)) return i + 1;
+  throw Corruption("Decoded the whole slice but didn't find the ending");
+}
+
+// ---------------------------------------------------------------------------------------------
 // dockv/doc_kv_util.cc:60-101 DecodeEncodedStr<kEnd>: scan to the terminator pair (kEnd kEnd);
 // (kEnd kEnd^1) is an escaped kEnd byte.
 static void SkipEncodedStr(Slice* s, uint8_t end_byte) {
@@ -216,10 +254,12 @@ void SkipKeyEntry(Slice* s) {
       }
       throw Corruption("Reached end of slice looking for frozen group end marker");
     }
-    case kt::kDecimalDescending: case kt::kDecimal: case kt::kVarIntDescending: case kt::kVarInt:
-      // util/decimal.cc / util/varint.cc comparable encodings: not restated (not used by the
-      // configs); fail loudly rather than guess.
-      throw NotSupported("decimal/varint key components are not restated in the oracle");
+    case kt::kDecimalDescending: case kt::kDecimal:
+      // primitive_value.cc:1314-1332: both orders decode the bytes as they are (the descending
+      // form is the comparable encoding of the negated number)
+      s->remove_prefix(DecimalComparableSize(*s)); return;
+    case kt::kVarIntDescending: case kt::kVarInt:
+      s->remove_prefix(VarIntComparableSize(*s, 0)); return;        // primitive_value.cc:1334-1349
     case kt::kGinNull:
       NeedBytes(*s, 1, "gin null"); s->remove_prefix(1); return;
     case kt::kInt32Descending: case kt::kInt32: case kt::kColocationId: case kt::kUInt32Descending:

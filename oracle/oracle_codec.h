@@ -147,6 +147,8 @@ constexpr uint8_t kTombstone = 'X', kPackedRowV1 = 'z', kPackedRowV2 = '|', kObj
 
 // dockv/primitive_value.cc:1232-1626 KeyEntryValue::DecodeKey(slice, nullptr): consume one key
 // entry (type byte + payload). Throws Corruption / NotSupported.
+size_t VarIntComparableSize(Slice slice, size_t num_reserved_bits);   // util/varint.cc:159-205
+size_t DecimalComparableSize(Slice slice);                            // util/decimal.cc:339-367
 void SkipKeyEntry(Slice* s);
 // dockv/doc_key.cc:417-422,543-590 DocKey::EncodedSize(slice, part): part 0 = kUpToId,
 // 1 = kWholeDocKey, 2 = kUpToHashOrFirstRange (hashed components, or the first range component

@@ -1,6 +1,7 @@
 // Compiled by tests/test_adapter_cpp.py: exercises the C++ adapter above the C ABI.
 // argv[1] = "cpu": only checks that creation fails loudly without a GPU and the host TableBuilder works.
 // argv[1] = "gpu": runs a small compaction read from files given as argv[2..] pairs (base, data).
+// argv[1] = "gpusub": the same with max_subcompactions = 4 (one output file per key range).
 #include <cstdio>
 #include <fstream>
 #include <iterator>
@@ -33,6 +34,7 @@ int main(int argc, char** argv) {
   std::vector<InputFile> in;
   for (size_t i = 0; i + 1 < bufs.size(); i += 2) { InputFile f; f.base_file = Slice(bufs[i]); f.data_file = Slice(bufs[i + 1]); in.push_back(f); }
   GpuCompactionJob::Params p;
+  if (mode == "gpusub") p.max_subcompactions = 4;
   GpuCompactionJob job(p);
   Status s = job.Prepare(in);
   if (!s.ok()) { printf("prepare: %s\n", s.ToString().c_str()); return 1; }
@@ -41,6 +43,15 @@ int main(int argc, char** argv) {
   GpuCompactionJob::OutputMeta m;
   s = job.Install(&m);
   if (!s.ok()) { printf("install: %s\n", s.ToString().c_str()); return 1; }
+  if (mode == "gpusub") {
+    for (size_t i = 0; i < job.outputs().size(); i++) {
+      std::ofstream(std::string(argv[2]) + ".sub" + std::to_string(i) + ".base", std::ios::binary) << job.outputs()[i].base_file;
+      std::ofstream(std::string(argv[2]) + ".sub" + std::to_string(i) + ".data", std::ios::binary) << job.outputs()[i].data_file;
+    }
+    if (!job.outputs().empty() && (m.smallest_key != job.outputs().front().smallest_key || m.largest_key != job.outputs().back().largest_key)) { printf("boundaries\n"); return 1; }
+    printf("OK in=%llu out=%llu files=%zu\n", (unsigned long long)job.stats().num_input_records, (unsigned long long)m.num_entries, job.outputs().size());
+    return 0;
+  }
   std::ofstream(std::string(argv[2]) + ".out.base", std::ios::binary) << job.output_base_file();
   std::ofstream(std::string(argv[2]) + ".out.data", std::ios::binary) << job.output_data_file();
   printf("OK in=%llu out=%llu\n", (unsigned long long)job.stats().num_input_records, (unsigned long long)m.num_entries);

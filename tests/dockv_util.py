@@ -41,8 +41,58 @@ def ksyscol(cid):
     return b"J" + o.signed_varint(cid)
 
 
+def varint_comparable(v, reserved_bits=0):
+    """util/varint.cc:102-157 VarInt::EncodeToComparable: sign bit, unary byte count, big-endian magnitude;
+    negatives are complemented; `reserved_bits` leading bits are left zero for the caller."""
+    if v == 0:
+        return bytes([0x80 >> reserved_bits])
+    mag = abs(v)
+    num_bits = mag.bit_length()
+    total = num_bits + 1 + reserved_bits
+    num_bytes = (total + 6) // 7
+    x = mag | (((1 << (num_bytes + reserved_bits)) - 1) << (num_bytes * 8 - num_bytes - reserved_bits))
+    if v < 0:
+        x ^= (1 << (num_bytes * 8)) - 1
+    out = bytearray(x.to_bytes(num_bytes, "big"))
+    if reserved_bits:
+        out[0] &= (1 << (8 - reserved_bits)) - 1
+    return bytes(out)
+
+
+def decimal_comparable(digits, exponent, positive=True):
+    """util/decimal.cc:270-310 Decimal::EncodeToComparable for value 0.d1d2.. * 10^exponent."""
+    if not digits:
+        return bytes([128])
+    pairs = bytearray()
+    n = (len(digits) + 1) // 2
+    for i in range(n):
+        lo = digits[2 * i + 1] if 2 * i + 1 < len(digits) else 0
+        pairs.append((digits[2 * i] * 10 + lo) * 2 + (1 if i < n - 1 else 0))
+    out = bytearray(varint_comparable(exponent, 2) + bytes(pairs))
+    out[0] |= 0xc0
+    if not positive:
+        out = bytearray((~c) & 0xff for c in out)
+    return bytes(out)
+
+
+def kvarint(v):
+    return b"B" + varint_comparable(v)
+
+
+def kvarint_desc(v):
+    return b"f" + varint_comparable(-v)          # primitive_value.cc:869-872: the negated number
+
+
+def kdecimal(digits, exponent, positive=True):
+    return b"E" + decimal_comparable(digits, exponent, positive)
+
+
+def kdecimal_desc(digits, exponent, positive=True):
+    return b"d" + decimal_comparable(digits, exponent, not positive)   # :861-864: the negated number
+
+
 def kprim(v):
-    if isinstance(v, bytes) and v[:1] in (b"S", b"I", b"H", b"K", b"J", b"a", b"["):
+    if isinstance(v, bytes) and v[:1] in (b"S", b"I", b"H", b"K", b"J", b"a", b"[", b"B", b"f", b"E", b"d"):
         return v
     if isinstance(v, (str, bytes)):
         return kstr(v)

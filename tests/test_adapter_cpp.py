@@ -41,3 +41,29 @@ def test_adapter_runs_compaction(tmp_path):
     exp = o.compact(ssts, o.CompactionParams())
     assert (tmp_path / "0.sst.out.data").read_bytes() == exp.sst().data
     assert (tmp_path / "0.sst.out.base").read_bytes() == exp.sst().meta
+
+
+@pytest.mark.gpu
+def test_adapter_runs_subcompactions(tmp_path):
+    """GpuCompactionJob with max_subcompactions = 4: one output file per key range, in range order;
+    together they hold exactly the single-job KV stream."""
+    import oracle_py as o
+    build_bin()
+    cfg = o.GenConfig(seed=9, num_rows=6000, cols=2, versions=3, num_files=4, value_len=80, tombstone_per_1024=40)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=4096))
+    args = [BIN, "gpusub"]
+    for i, s in enumerate(ssts):
+        b, d = tmp_path / ("%d.sst" % i), tmp_path / ("%d.sst.sblock.0" % i)
+        b.write_bytes(s.meta)
+        d.write_bytes(s.data)
+        args += [str(b), str(d)]
+    out = subprocess.check_output(args, text=True)
+    assert "OK in=36000" in out
+    n_files = int(out.strip().split("files=")[1])
+    assert 2 <= n_files <= 4
+    exp = o.compact(ssts, o.CompactionParams())
+    got = []
+    for i in range(n_files):
+        part = o.Sst.from_bytes((tmp_path / ("0.sst.sub%d.base" % i)).read_bytes(), (tmp_path / ("0.sst.sub%d.data" % i)).read_bytes())
+        got += part.read_all()
+    assert got == exp.kv_list()

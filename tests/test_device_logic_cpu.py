@@ -24,6 +24,20 @@ def test_randomized_docdb_runs(seed):
         assert got == exp, kw
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_varint_and_decimal_key_components(seed):
+    """kVarInt / kDecimal key entries in DocKeys and subkeys (primitive_value.cc:1314-1349): the device
+    walk must delimit them exactly like the reference decoders, or rows and overwrite stacks break."""
+    runs = w.random_numeric_key_runs(seed, n_runs=1 + seed % 4, n_rows=30 + 5 * seed)
+    for kw in w.param_grid():
+        got, exp = both(runs, **kw)
+        assert got == exp, kw
+    L = hh.lib()
+    for k, _ in runs[0][:50]:
+        u = k[:-8]
+        assert L.hh_group_prefix_len(u, len(u), 1) == o.subdockey_ends(u)[1]
+
+
 def test_plain_rocksdb_mode():
     seq = 0
     runs = []

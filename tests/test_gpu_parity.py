@@ -117,6 +117,16 @@ def test_randomized_docdb(pkg, seed):
         check(pkg, ssts, block_size=1024, **kw)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_varint_and_decimal_key_components(pkg, seed):
+    """DocKeys / subkeys with kVarInt / kDecimal entries (YSQL numeric, YCQL varint / decimal keys;
+    primitive_value.cc:1314-1349), with the DocKeyV3 bloom filter keyed by them."""
+    runs = w.random_numeric_key_runs(10 + seed, n_runs=2 + seed, n_rows=300)
+    ssts = runs_to_ssts(runs, 1024)
+    for kw in w.param_grid()[1::3]:
+        check(pkg, ssts, block_size=1024, filter_policy=1, filter_block_size=1024, **kw)
+
+
 def test_golden_first_row_regression(pkg):
     # docdb/docdb-test-wrapper.cc:99-133
     d = dk.doc_key(["mydockey", dk.INT_KEY1])

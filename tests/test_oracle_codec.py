@@ -117,3 +117,56 @@ def test_fast_varint_known_answers(oracle):
         if prev is not None and prev[0] != v:
             assert prev[1] < e          # order preserving (fast_varint-test.cc lexicographic check)
         prev = (v, e)
+
+
+VARINT_GOLDEN = [          # util/varint-test.cc:151-190 TestComparableEncoding (exact bit strings)
+    (-37618632178637216379216387, "00000000 00000111 11100000 11100001 11110001 11011101 00000001 00110000 11011100 11111011 11101101 01011101 11111100"),
+    (-9223372036854775809, "00000000 00111111 01111111 11111111 11111111 11111111 11111111 11111111 11111111 11111110"),
+    (-(1 << 63), "00000000 00111111 01111111 11111111 11111111 11111111 11111111 11111111 11111111 11111111"),
+    (-(1 << 31) - 1, "00000111 01111111 11111111 11111111 11111110"),
+    (-(1 << 31), "00000111 01111111 11111111 11111111 11111111"),
+    (-129, "00111111 01111110"), (-128, "00111111 01111111"), (-127, "00111111 10000000"),
+    (-23, "01101000"), (0, "10000000"), (38, "10100110"),
+    ((1 << 31) - 1, "11111000 01111111 11111111 11111111 11111111"),
+    (1 << 31, "11111000 10000000 00000000 00000000 00000000"),
+    ((1 << 63) - 1, "11111111 11000000 01111111 11111111 11111111 11111111 11111111 11111111 11111111 11111111"),
+    (1 << 63, "11111111 11000000 10000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000"),
+    (8429024091289482183283928321, "11111111 11111100 00011011 00111100 01010011 01000111 10010101 11011111 00011011 00001010 01111011 11111101 01101101 00000001"),
+]
+
+# util/decimal-test.cc:27-53: test_cases with kComparableEncodingLengths; (digits, exponent, positive)
+# in the canonical form 0.d1d2... * 10^exponent the Decimal class keeps.
+DECIMAL_GOLDEN = [
+    ([9, 8, 4, 7, 2, 3, 6, 7, 7, 6], 2147483658, False, 10), ([9, 8, 4, 7, 2, 3, 6, 7, 8], 2147483657, False, 10),
+    ([1, 3, 4], 1, False, 3), ([1, 3, 3, 7], 1, False, 3), ([1, 3, 3, 4], 1, False, 3), ([1, 3, 3], 1, False, 3),
+    ([1, 3, 6], -2147483644, False, 7), ([], 0, False, 1), ([5], -1, True, 2), ([1, 1, 5], 1, True, 3),
+    ([1, 2], 1, True, 2), ([1, 2], 3, True, 2), ([1, 2], 101, True, 3), ([2, 6, 3, 8, 2], 3628, True, 6),
+]
+
+
+def test_varint_and_decimal_key_components(oracle):
+    """kVarInt / kDecimal key entries (primitive_value.cc:1314-1349): the comparable encodings are
+    self-delimiting only through their decoders (util/varint.cc:159-205, util/decimal.cc:339-367).
+    The test-side encoders are pinned by the reference's exact bit strings / encoded lengths, then the
+    oracle's component walk must find every entry's end, for both sort orders, at any position."""
+    for v, bits in VARINT_GOLDEN:
+        assert dk.varint_comparable(v) == bytes(int(b, 2) for b in bits.split()), v
+    encs = [dk.varint_comparable(v) for v, _ in VARINT_GOLDEN]
+    assert encs == sorted(encs)                                   # comparable: byte order = numeric order
+    for digits, exp, pos, length in DECIMAL_GOLDEN:
+        assert len(dk.decimal_comparable(digits, exp, pos)) == length, (digits, exp)
+    dencs = [dk.decimal_comparable(d, e, p) for d, e, p, _ in DECIMAL_GOLDEN]
+    assert dencs == sorted(dencs)
+    comps = [dk.kvarint(v) for v, _ in VARINT_GOLDEN] + [dk.kvarint_desc(v) for v, _ in VARINT_GOLDEN]
+    comps += [dk.kdecimal(d, e, p) for d, e, p, _ in DECIMAL_GOLDEN] + [dk.kdecimal_desc(d, e, p) for d, e, p, _ in DECIMAL_GOLDEN]
+    rng = random.Random(7)
+    for _ in range(300):
+        comps.append(dk.kvarint(rng.randrange(-10**rng.randrange(1, 40), 10**rng.randrange(1, 40))))
+        digits = [rng.randrange(1, 10)] + [rng.randrange(10) for _ in range(rng.randrange(0, 12))] + [rng.randrange(1, 10)]
+        comps.append(dk.kdecimal(digits, rng.randrange(-10**6, 10**6), rng.random() < 0.5))
+    for c in comps:
+        d = dk.doc_key([c, "tail"], hash_code=3, hashed=[c])
+        key = dk.sub_doc_key(d, [dk.kcol(1), c], micros=EPOCH + 5)
+        ends = oracle.subdockey_ends(key)
+        # [cotable-id end, DocKey end, subkey ends...] (SubDocKey::DecodeDocKeyAndSubKeyEnds, doc_key.cc:963-996)
+        assert ends[:4] == [0, len(d), len(d) + 2, len(d) + 2 + len(c)], c

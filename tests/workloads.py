@@ -119,3 +119,43 @@ def random_cotable_runs(seed, n_runs=3, n_tables=4, rows_per_table=12, colocated
             used.add(uk)
             put(uk, dk.vstr("p"))
     return [sort_run(r) for r in runs]
+
+
+def random_numeric_key_runs(seed, n_runs=3, n_rows=40, n_ht=12):
+    """Rows whose DocKeys / subkeys carry kVarInt / kDecimal components (YSQL numeric, YCQL varint /
+    decimal primary keys) in both sort orders; several versions per column, tombstones."""
+    rng = random.Random(seed)
+    runs = [[] for _ in range(n_runs)]
+    seq = [(1 << 50) + (r << 30) for r in range(n_runs)]
+    used = set()
+
+    def numeric():
+        x = rng.randrange(4)
+        if x == 0:
+            return dk.kvarint(rng.randrange(-10**rng.randrange(1, 30), 10**rng.randrange(1, 30)))
+        if x == 1:
+            return dk.kvarint_desc(rng.randrange(-10**6, 10**6))
+        digits = [rng.randrange(1, 10)] + [rng.randrange(10) for _ in range(rng.randrange(0, 9))] + [rng.randrange(1, 10)]
+        if rng.random() < 0.1:
+            digits = []
+        f = dk.kdecimal if x == 2 else dk.kdecimal_desc
+        return f(digits, rng.randrange(-400, 400), rng.random() < 0.6)
+
+    for row in range(n_rows):
+        if rng.random() < 0.5:
+            d = dk.doc_key([numeric()] + (["s%d" % row] if rng.random() < 0.5 else []), hash_code=rng.randrange(65536), hashed=[numeric(), "h%d" % row])
+        else:
+            d = dk.doc_key([numeric(), numeric(), row])
+        paths = [[dk.kcol(c + 1)] for c in range(rng.randrange(1, 4))]
+        if rng.random() < 0.4:
+            paths.append([dk.kcol(7), numeric()])
+        for p in paths:
+            for _ in range(rng.randrange(1, 5)):
+                uk = dk.sub_doc_key(d, p, ht=(BASE_US + rng.randrange(n_ht) * 10, rng.randrange(2), rng.randrange(3)))
+                if uk in used:
+                    continue
+                used.add(uk)
+                r = rng.randrange(n_runs)
+                seq[r] += 1
+                runs[r].append((o.ikey(uk, seq[r]), dk.TOMBSTONE if rng.random() < 0.15 else dk.vstr("v%d" % rng.randrange(1000))))
+    return [sort_run(r) for r in runs]

@@ -144,6 +144,11 @@ class GpuCompactionJob {
     uint32_t filter_block_size = 64 * 1024;    // db_filter_block_size_bytes
     bool verify_checksums = true;
     const volatile int32_t* shutting_down = nullptr;   // std::atomic<bool>* shutting_down_ in the reference
+    // DBOptions::max_subcompactions (rocksdb/options.h:1029; default 1, util/options.cc:258). > 1: the
+    // compaction is cut into key ranges on row boundaries (GenSubcompactionBoundaries,
+    // compaction_job.cc:409-519) that run pipelined on private streams, one output file per range.
+    uint32_t max_subcompactions = 1;
+    uint32_t subcompactions_in_flight = 3;
   };
 
   explicit GpuCompactionJob(const Params& p) : p_(p) {}
@@ -175,15 +180,18 @@ class GpuCompactionJob {
     o.block_size_deviation = p_.block_size_deviation; o.index_block_size = p_.index_block_size;
     o.min_keys_per_index_block = p_.min_keys_per_index_block; o.verify_checksums = p_.verify_checksums;
     o.output_key_encoding = p_.output_key_encoding; o.filter_policy = p_.filter_policy; o.filter_block_size = p_.filter_block_size;
+    options_ = o;
+    inputs_ = inputs;
+    if (p_.max_subcompactions > 1) return Status::OK();      // every range creates its own job in Run()
     ybgpu_status s = ybgpu_job_create(&o, &job_);
     if (s != YBGPU_OK) return ToStatus(s, ybgpu_last_error());
-    inputs_ = inputs;
     return Status::OK();
   }
 
   // REQUIRED: mutex NOT held. Replaces ProcessKeyValueCompaction; on success the output files are
   // available through output_data_file()/output_base_file() and stats().
   Status Run() {
+    if (p_.max_subcompactions > 1) return RunSubcompactions();
     for (const InputFile& f : inputs_) {
       ybgpu_status s = ybgpu_job_add_input_sst(job_, f.base_file.data(), f.base_file.size(), f.data_file.data(),
                                                f.data_file.size(), f.hybrid_time_filter);
@@ -200,6 +208,52 @@ class GpuCompactionJob {
     ybgpu_job_get_stats(job_, &stats_);
     return Status::OK();
   }
+
+  // CompactionJob::Run with subcompactions (compaction_job.cc:521-589): every key range becomes one
+  // output file; outputs() lists them in range order the way Install adds them (:1128-1131).
+  struct OutputFile {
+    std::string data_file, base_file;        // <n>.sst.sblock.0, <n>.sst
+    std::string smallest_key, largest_key;   // FileMetaData::smallest / largest (internal keys)
+    ybgpu_job_stats stats;
+  };
+  Status RunSubcompactions() {
+    ybgpu_job_options o = options_;
+    o.largest_user_key = reinterpret_cast<const uint8_t*>(p_.largest_user_key.data());
+    o.key_bounds_lower = reinterpret_cast<const uint8_t*>(p_.retention.key_bounds_lower.data());
+    o.key_bounds_upper = reinterpret_cast<const uint8_t*>(p_.retention.key_bounds_upper.data());
+    std::vector<ybgpu_input_file> files;
+    uint64_t in_bytes = 0;
+    for (const InputFile& f : inputs_) {
+      files.push_back({f.base_file.data(), f.base_file.size(), f.data_file.data(), f.data_file.size(), f.hybrid_time_filter});
+      in_bytes += f.data_file.size();
+    }
+    // the output of a compaction is never larger than its input plus per-file metadata
+    std::string data_arena, meta_arena;
+    data_arena.resize(in_bytes + in_bytes / 16 + (1u << 20) + 4096ull * p_.max_subcompactions);
+    meta_arena.resize(in_bytes / 32 + (4u << 20) + 4096ull * p_.max_subcompactions);
+    std::vector<ybgpu_sub_output> outs(p_.max_subcompactions);
+    uint32_t n = 0;
+    char err[512] = {0};
+    ybgpu_status s = ybgpu_compact_files(&o, files.data(), static_cast<uint32_t>(files.size()), p_.max_subcompactions,
+                                         p_.subcompactions_in_flight, reinterpret_cast<uint8_t*>(&data_arena[0]), data_arena.size(),
+                                         reinterpret_cast<uint8_t*>(&meta_arena[0]), meta_arena.size(), p_.shutting_down,
+                                         outs.data(), &n, &stats_, err, sizeof(err));
+    if (s != YBGPU_OK) return ToStatus(s, err);
+    outputs_.clear();
+    for (uint32_t i = 0; i < n; i++) {
+      const ybgpu_sub_output& so = outs[i];
+      if (!so.data_len) continue;             // nothing survived in this range: no file (compaction_job.cc:156-160)
+      OutputFile f;
+      f.data_file.assign(data_arena, so.data_offset, so.data_len);
+      f.base_file.assign(meta_arena, so.meta_offset, so.meta_len);
+      f.smallest_key.assign(reinterpret_cast<const char*>(so.smallest_key), so.smallest_key_len);
+      f.largest_key.assign(reinterpret_cast<const char*>(so.largest_key), so.largest_key_len);
+      f.stats = so.stats;
+      outputs_.push_back(std::move(f));
+    }
+    return Status::OK();
+  }
+  const std::vector<OutputFile>& outputs() const { return outputs_; }
 
   // Variant for DBs whose CompactionFeed chain must see every surviving entry on the host (e.g. the
   // packed-row repacker): the GPU still does decode + merge + retention, the host feed gets the
@@ -228,6 +282,13 @@ class GpuCompactionJob {
   // (compaction_job.cc:1098-1141); here it hands the caller what that edit needs.
   struct OutputMeta { std::string smallest_key, largest_key; uint64_t smallest_seqno = 0, largest_seqno = 0, num_entries = 0; };
   Status Install(OutputMeta* meta) {
+    if (p_.max_subcompactions > 1) {          // per-file metadata is in outputs(); this is the union
+      *meta = OutputMeta();
+      if (!outputs_.empty()) { meta->smallest_key = outputs_.front().smallest_key; meta->largest_key = outputs_.back().largest_key; }
+      meta->smallest_seqno = stats_.smallest_seqno; meta->largest_seqno = stats_.largest_seqno;
+      meta->num_entries = stats_.num_output_records;
+      return Status::OK();
+    }
     uint8_t a[4096], b[4096]; uint64_t al = 0, bl = 0;
     ybgpu_status s = ybgpu_job_output_boundaries(job_, a, &al, b, &bl);
     if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
@@ -247,6 +308,8 @@ class GpuCompactionJob {
   ybgpu_job* job_ = nullptr;
   std::vector<InputFile> inputs_;
   std::string data_, base_;
+  std::vector<OutputFile> outputs_;
+  ybgpu_job_options options_{};
   ybgpu_job_stats stats_{};
 };
 

@@ -40,7 +40,7 @@ enum DevError : int {
   DEV_ERR_KEY_TOO_LONG = 4,
   DEV_ERR_IRREGULAR_RESTARTS = 5, // restart intervals of different sizes inside one file
   DEV_ERR_BAD_KEY = 6,            // DocKey / SubDocKey component decode failed
-  DEV_ERR_UNSUPPORTED_KEY = 7,    // decimal/varint/bson components, vector-index metadata keys
+  DEV_ERR_UNSUPPORTED_KEY = 7,    // bson components, vector-index metadata keys
   DEV_ERR_TILE_OVERFLOW = 8,      // one DocKey group larger than a merge tile
   DEV_ERR_BAD_HT = 9,             // DocHybridTime at the end of a key is malformed
   DEV_ERR_BAD_VALUE = 10,         // value control fields malformed
@@ -269,6 +269,43 @@ YB_HD int encht_cmp(const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb
 }
 
 // ----------------------------------------------------------------------------------------------
+// Sizes of the comparable VarInt / Decimal encodings, which only the decoder can tell.
+// util/varint.cc:159-205 (VarInt::DecodeFromComparable): after `reserved` reserved bits comes the
+// sign bit, then a unary byte count, then the magnitude; negatives are stored complemented.
+// `flip`: the caller's view of the bytes is complemented (a negative decimal's exponent).
+YB_HD int comparable_varint_size(const uint8_t* p, int n, int reserved, bool flip) {
+  if (n <= 0) return -DEV_ERR_BAD_KEY;
+  const uint8_t fm = flip ? 0xff : 0x00;
+  const bool negative = ((p[0] ^ fm) & (0x80u >> reserved)) == 0;
+  const uint8_t m = negative ? static_cast<uint8_t>(~fm) : fm;
+  const uint8_t first_or = reserved ? static_cast<uint8_t>(~((1u << (8 - reserved)) - 1u)) : 0;
+  int idx = 0, ones = 0;
+  uint8_t c = static_cast<uint8_t>((p[0] ^ m) | first_or);
+  while (c == 0xff) {
+    if (++idx >= n) return -DEV_ERR_BAD_KEY;              // "no prefix termination"
+    ones += 8;
+    c = static_cast<uint8_t>(p[idx] ^ m);
+  }
+  for (uint8_t t = 0x80; c & t; t >>= 1) ones++;
+  ones -= reserved;
+  if (ones > n) return -DEV_ERR_BAD_KEY;                  // "Not enough data in encoded varint"
+  return ones;
+}
+// util/decimal.cc:339-367 (Decimal::DecodeFromComparable): 0x80 is zero; else the sign is the first
+// bit (negatives complemented), the exponent a varint with two reserved bits, then mantissa digit
+// pairs of which the last has its low bit clear.
+YB_HD int comparable_decimal_size(const uint8_t* p, int n) {
+  if (n <= 0) return -DEV_ERR_BAD_KEY;
+  if (p[0] == 128) return 1;
+  const bool flip = p[0] < 128;
+  const int e = comparable_varint_size(p, n, 2, flip);
+  if (e < 0) return e;
+  for (int i = e; i < n; i++)
+    if (!((flip ? ~p[i] : p[i]) & 1)) return i + 1;
+  return -DEV_ERR_BAD_KEY;                                // "didn't find the ending"
+}
+
+// ----------------------------------------------------------------------------------------------
 // dockv/primitive_value.cc:1232-1626 KeyEntryValue::DecodeKey(slice, nullptr): number of bytes of
 // one key entry (type byte + payload) at p, or a negative DevError.
 YB_HD_NOINLINE int key_entry_size_flat(const uint8_t* p, int n) {   // everything except frozen containers
@@ -333,8 +370,16 @@ YB_HD_NOINLINE int key_entry_size_flat(const uint8_t* p, int n) {   // everythin
     }
     case '<': case '>':
       return -1000;                                         // frozen container: handled by key_entry_size
-    case 'B': case 'f': case 'E': case 'd': case 'o': case 'p':
-      return -DEV_ERR_UNSUPPORTED_KEY;                      // varint / decimal / bson comparable encodings
+    case 'B': case 'f': {                                   // kVarInt / kVarIntDescending (primitive_value.cc:1334-1349)
+      const int k = comparable_varint_size(p + 1, n - 1, 0, false);
+      return k < 0 ? k : 1 + k;
+    }
+    case 'E': case 'd': {                                   // kDecimal / kDecimalDescending (:1314-1332)
+      const int k = comparable_decimal_size(p + 1, n - 1);
+      return k < 0 ? k : 1 + k;
+    }
+    case 'o': case 'p':
+      return -DEV_ERR_UNSUPPORTED_KEY;                      // bson comparable encodings
     default:
       return -DEV_ERR_BAD_KEY;
   }

@@ -35,35 +35,57 @@ std::string UserPart(const std::string& ikey) { return ikey.size() >= 8 ? ikey.s
 
 bool ParseInputs(const ybgpu_input_file* files, uint32_t n, std::vector<ParsedInput>* out, std::string* err) {
   out->resize(n);
-  for (uint32_t f = 0; f < n; f++) {
-    std::string e = ybgpu::host::ParseSplitSstMeta(files[f].meta_file, files[f].meta_file_len, &(*out)[f].meta);
-    if (!e.empty()) { *err = "input " + std::to_string(f) + ": " + e; return false; }
+  std::vector<std::string> errs(n);
+  auto parse_one = [&](uint32_t f) {
     ParsedInput& p = (*out)[f];
-    if (p.meta.separators.size() != p.meta.data_blocks.size()) { *err = "index entries do not match data blocks"; return false; }
+    std::string e = ybgpu::host::ParseSplitSstMeta(files[f].meta_file, files[f].meta_file_len, &p.meta);
+    if (!e.empty()) { errs[f] = "input " + std::to_string(f) + ": " + e; return; }
+    if (p.meta.separators.size() != p.meta.data_blocks.size()) { errs[f] = "index entries do not match data blocks"; return; }
     p.useps.reserve(p.meta.separators.size());
     for (const std::string& k : p.meta.separators) p.useps.push_back(UserPart(k));
     for (const auto& h : p.meta.data_blocks)
-      if (h.offset + h.size + 5 > files[f].data_file_len) { *err = "block handle outside the data file"; return false; }
+      if (h.offset + h.size + 5 > files[f].data_file_len) { errs[f] = "block handle outside the data file"; return; }
+  };
+  // the index of a multi-GB input has ~10^5 entries: the files are walked side by side
+  if (n > 1) {
+    std::vector<std::thread> pool;
+    for (uint32_t f = 0; f < n; f++) pool.emplace_back(parse_one, f);
+    for (std::thread& t : pool) t.join();
+  } else if (n == 1) {
+    parse_one(0);
   }
+  for (uint32_t f = 0; f < n; f++)
+    if (!errs[f].empty()) { *err = errs[f]; return false; }
   return true;
 }
 
 // Weighted quantiles of the index separators, cut back to the row prefix. A splitter s must never
-// fall inside a row (all entries of one DocKey): s = DocKey prefix of a separator is a complete
-// DocKey by construction, and no other complete DocKey can be a proper prefix of it (the DocKey
-// grammar is prefix-free), so every row lies entirely on one side. Separators whose DocKey does
-// not parse (FindShortestSeparator may have shortened them) are skipped.
+// fall inside a row (all entries of one DocKey D): that happens only if s = D + more bytes for the
+// complete DocKey D of an existing row (a string between two strings that share the prefix D has
+// the prefix D itself). The DocKey walk is a deterministic left-to-right parse, so
+//   * if it succeeds on a separator, the separator is cut to that DocKey: a complete DocKey, of
+//     which no other complete DocKey is a proper prefix;
+//   * if it fails with a malformed key (FindShortestSeparator cut the separator inside a
+//     component), the separator does not start with any complete DocKey and is used whole;
+//   * if it stops at a component it cannot size (bson), the separator is skipped.
 std::vector<std::string> PlanSplitters(const std::vector<ParsedInput>& in, uint32_t n_ranges, bool docdb_keys) {
   std::vector<std::string> out;
   if (n_ranges <= 1) return out;
   struct Sample { const std::string* key; uint64_t w; };
   std::vector<Sample> samples;
   uint64_t total = 0;
-  for (const ParsedInput& p : in)
+  // every stride-th separator of a file stands for the bytes of the blocks since the previous sample
+  // (about 2^11 samples per range are plenty; a 30 GB compaction has ~10^6 index entries)
+  size_t n_blocks = 0;
+  for (const ParsedInput& p : in) n_blocks += p.useps.size();
+  const size_t stride = std::max<size_t>(1, n_blocks / (static_cast<size_t>(n_ranges) << 11));
+  for (const ParsedInput& p : in) {
+    uint64_t w = 0;
     for (size_t i = 0; i < p.useps.size(); i++) {
-      samples.push_back({&p.useps[i], p.meta.data_blocks[i].size + 5});
-      total += p.meta.data_blocks[i].size + 5;
+      w += p.meta.data_blocks[i].size + 5;
+      if ((i + 1) % stride == 0 || i + 1 == p.useps.size()) { samples.push_back({&p.useps[i], w}); total += w; w = 0; }
     }
+  }
   if (samples.empty()) return out;
   std::sort(samples.begin(), samples.end(), [](const Sample& a, const Sample& b) { return *a.key < *b.key; });
   const double target = static_cast<double>(total) / n_ranges;
@@ -80,7 +102,8 @@ std::vector<std::string> PlanSplitters(const std::vector<ParsedInput>& in, uint3
       memset(buf, 0, sizeof(buf));
       memcpy(buf, k.data(), k.size());
       plen = ybgpu::group_prefix_len(buf, static_cast<int>(k.size()), true);
-      if (plen <= 0) continue;
+      if (plen == -ybgpu::DEV_ERR_UNSUPPORTED_KEY) continue;
+      if (plen <= 0) plen = static_cast<int>(k.size());
     }
     if (plen == 0 || plen > YBGPU_MAX_SPLITTER_LEN) continue;
     std::string cut = k.substr(0, plen);
