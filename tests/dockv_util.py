@@ -75,24 +75,30 @@ def decimal_comparable(digits, exponent, positive=True):
     return bytes(out)
 
 
+class Enc(bytes):
+    """An already encoded key entry (kprim passes it through whatever its first byte is)."""
+
+
 def kvarint(v):
-    return b"B" + varint_comparable(v)
+    return Enc(b"B" + varint_comparable(v))
 
 
 def kvarint_desc(v):
-    return b"f" + varint_comparable(-v)          # primitive_value.cc:869-872: the negated number
+    return Enc(b"f" + varint_comparable(-v))          # primitive_value.cc:869-872: the negated number
 
 
 def kdecimal(digits, exponent, positive=True):
-    return b"E" + decimal_comparable(digits, exponent, positive)
+    return Enc(b"E" + decimal_comparable(digits, exponent, positive))
 
 
 def kdecimal_desc(digits, exponent, positive=True):
-    return b"d" + decimal_comparable(digits, exponent, not positive)   # :861-864: the negated number
+    return Enc(b"d" + decimal_comparable(digits, exponent, not positive))   # :861-864: the negated number
 
 
 def kprim(v):
-    if isinstance(v, bytes) and v[:1] in (b"S", b"I", b"H", b"K", b"J", b"a", b"[", b"B", b"f", b"E", b"d"):
+    if isinstance(v, Enc):
+        return bytes(v)
+    if isinstance(v, bytes) and v[:1] in (b"S", b"I", b"H", b"K", b"J", b"a", b"["):
         return v
     if isinstance(v, (str, bytes)):
         return kstr(v)

@@ -1290,6 +1290,8 @@ static ybgpu_status DevErrorStatus(int e) {
 struct Engine::Impl {
   cudaStream_t stream = nullptr;
   bool owns_stream = false;            // cuda_stream == YBGPU_STREAM_PRIVATE: created in Init, destroyed with the job
+  uint8_t* status_host = nullptr; uint8_t* status_dev = nullptr;   // host-mapped page for small read-backs (may be null)
+  uint32_t readback_launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t phase_ev[8] = {};
   cudaEvent_t enc_ev[2] = {};          // around the block-assembler launch (the dominant kernel of the encode phase)
@@ -1321,6 +1323,41 @@ struct Engine::Impl {
   uint8_t* d_filters = nullptr; uint8_t* d_filter_keys = nullptr; uint32_t* d_filter_first = nullptr;
 };
 
+// Small device->host reads between phases (error word, counts: <= 4 KB) do not use the copy engine:
+// a one-CTA kernel stores the words into a host-mapped pinned page (a posted PCIe write from the SM)
+// and the host reads the page after the stream synchronises. Next to other jobs' multi-GB output
+// copies a DMA read-back would queue behind them on the device->host engine.
+__global__ void k_readback(uint8_t* dst_mapped, const uint8_t* src, uint32_t n) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst_mapped[i] = src[i];
+  __threadfence_system();
+}
+constexpr size_t STATUS_PAGE_BYTES = 4096;
+struct StatusPage { uint8_t* host = nullptr; uint8_t* dev = nullptr; };
+static std::mutex g_status_mu;
+static std::vector<StatusPage> g_status_free;          // process-wide: cudaHostAlloc costs ~1 ms
+static cudaError_t AcquireStatusPage(StatusPage* p) {
+  {
+    std::lock_guard<std::mutex> lock(g_status_mu);
+    if (!g_status_free.empty()) { *p = g_status_free.back(); g_status_free.pop_back(); return cudaSuccess; }
+  }
+  void* h = nullptr; void* d = nullptr;
+  cudaError_t e = cudaHostAlloc(&h, STATUS_PAGE_BYTES, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e != cudaSuccess) return e;
+  e = cudaHostGetDevicePointer(&d, h, 0);
+  if (e != cudaSuccess) { cudaFreeHost(h); return e; }
+  p->host = static_cast<uint8_t*>(h); p->dev = static_cast<uint8_t*>(d);
+  return cudaSuccess;
+}
+static void ReleaseStatusPage(const StatusPage& p) {
+  if (!p.host) return;
+  std::lock_guard<std::mutex> lock(g_status_mu);
+  g_status_free.push_back(p);
+}
+static bool ZeroCopyStatusEnabled() {
+  const char* e = getenv("YBGPU_ZC_STATUS");
+  return e ? atoi(e) != 0 : true;
+}
+
 Engine::Engine(const ybgpu_job_options& o) : opt_(o), impl_(new Impl) {
   if (o.largest_user_key && o.has_largest_user_key) largest_.assign(o.largest_user_key, o.largest_user_key + o.largest_user_key_len);
   if (o.key_bounds_lower_len) lower_.assign(o.key_bounds_lower, o.key_bounds_lower + o.key_bounds_lower_len);
@@ -1343,6 +1380,11 @@ Engine::~Engine() {
     if (impl_->copy_ev) cudaEventDestroy(impl_->copy_ev);
     for (auto& e : impl_->enc_ev) if (e) cudaEventDestroy(e);
     for (auto& e : impl_->phase_ev) if (e) cudaEventDestroy(e);
+    if (impl_->status_host) {
+      cudaStreamSynchronize(impl_->stream);              // no read-back kernel may still target the page
+      StatusPage pg; pg.host = impl_->status_host; pg.dev = impl_->status_dev;
+      ReleaseStatusPage(pg);
+    }
     if (impl_->owns_stream && impl_->stream) cudaStreamDestroy(impl_->stream);   // the queued frees complete first
     delete impl_;
   }
@@ -1359,6 +1401,24 @@ static cudaError_t DevAlloc(std::vector<void*>* allocs, T** out, size_t count) {
   cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count * sizeof(T), 16) + 32, g_alloc_stream);
   if (e == cudaSuccess) { allocs->push_back(p); *out = reinterpret_cast<T*>(p); }
   return e;
+}
+
+
+// Bulk host<->device copies are issued in chunks: a copy engine serves its queues copy by copy, so a
+// multi-GB cudaMemcpyAsync of one job would hold every small copy of the jobs running beside it
+// (status words, block counts, parameters: ~10 round trips per job) for tens of milliseconds.
+static size_t CopyChunkBytes() {
+  const char* e = getenv("YBGPU_COPY_CHUNK_MB");          // read per bulk copy (a handful per job)
+  const long mb = e ? atol(e) : 32;
+  return mb > 0 ? static_cast<size_t>(mb) << 20 : ~static_cast<size_t>(0);
+}
+static cudaError_t ChunkedCopyAsync(void* dst, const void* src, size_t len, cudaMemcpyKind kind, cudaStream_t stream) {
+  const size_t chunk = CopyChunkBytes();
+  for (size_t off = 0; off < len; off += chunk) {
+    cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, std::min(chunk, len - off), kind, stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 ybgpu_status Engine::Init() {
@@ -1383,6 +1443,11 @@ ybgpu_status Engine::Init() {
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, opt_.device));
     uint64_t thr = ~0ull;
     CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+  if (ZeroCopyStatusEnabled()) {
+    StatusPage pg;
+    CUDA_TRY(AcquireStatusPage(&pg));
+    impl_->status_host = pg.host; impl_->status_dev = pg.dev;
   }
   CUDA_TRY(cudaEventCreate(&impl_->ev0));
   CUDA_TRY(cudaEventCreate(&impl_->ev1));
@@ -1415,7 +1480,7 @@ ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_blo
     CUDA_TRY(DevAlloc(&impl_->allocs, &d, len + 64));
     // 16 bytes of zero padding on both sides so word-granular copies may over-read
     CUDA_TRY(cudaMemsetAsync(d, 0, 16, impl_->stream));
-    CUDA_TRY(cudaMemcpyAsync(d + 16, data, len, cudaMemcpyHostToDevice, impl_->stream));
+    CUDA_TRY(ChunkedCopyAsync(d + 16, data, len, cudaMemcpyHostToDevice, impl_->stream));
     CUDA_TRY(cudaMemsetAsync(d + 16 + len, 0, 16, impl_->stream));
     rv.data = d + 16;
     stats_.h2d_bytes += len;
@@ -1443,10 +1508,25 @@ static int GridFor(uint64_t work_items, int threads, int sms) {
   return static_cast<int>(std::max<uint64_t>(1, std::min(blocks, cap)));
 }
 
+// Device -> host read of a few words followed by a stream synchronisation (see k_readback).
+ybgpu_status Engine::ReadSmall(void* host_dst, const void* dev_src, size_t n) {
+  Impl& I = *impl_;
+  if (I.status_host && n <= STATUS_PAGE_BYTES) {
+    k_readback<<<1, 128, 0, I.stream>>>(I.status_dev, static_cast<const uint8_t*>(dev_src), static_cast<uint32_t>(n));
+    I.readback_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    memcpy(host_dst, I.status_host, n);
+    return YBGPU_OK;
+  }
+  CUDA_TRY(cudaMemcpyAsync(host_dst, dev_src, n, cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  return YBGPU_OK;
+}
+
 ybgpu_status Engine::CheckDeviceError(const char* phase) {
   Impl& I = *impl_;
-  CUDA_TRY(cudaMemcpyAsync(&I.hJ, I.dJ, sizeof(JobDev), cudaMemcpyDeviceToHost, I.stream));
-  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  if (ybgpu_status s = ReadSmall(&I.hJ, I.dJ, sizeof(JobDev))) return s;
   if (I.hJ.error) {
     char buf[256];
     snprintf(buf, sizeof(buf), "%s (%s, at block/tile %u)", DevErrorName(I.hJ.error), phase, I.hJ.error_where);
@@ -1539,8 +1619,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
   uint64_t N = 0;
   std::vector<uint32_t> h_totals(k + 1, 0);
-  CUDA_TRY(cudaMemcpyAsync(h_totals.data(), d_totals, 4 * static_cast<size_t>(k), cudaMemcpyDeviceToHost, I.stream));
-  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  if (k) { if (ybgpu_status s = ReadSmall(h_totals.data(), d_totals, 4 * static_cast<size_t>(k))) return s; }
   for (int r = 0; r < k; r++) {
     const uint32_t n = h_totals[r];
     I.runs[r].n_entries = n;
@@ -1779,8 +1858,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     k_scan_u32_single<<<1, 1024, 0, I.stream>>>(d_spart, pc, d_nblocks);
     launches += 8;
     uint32_t nblocks = 0;
-    CUDA_TRY(cudaMemcpyAsync(&nblocks, d_nblocks, 4, cudaMemcpyDeviceToHost, I.stream));
-    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    if (ybgpu_status s = ReadSmall(&nblocks, d_nblocks, 4)) return s;
     I.n_blocks = nblocks;
     CUDA_TRY(DevAlloc(&I.allocs, &I.d_block_first, static_cast<size_t>(nblocks) + 1));
     CUDA_TRY(DevAlloc(&I.allocs, &I.d_block_off, static_cast<size_t>(nblocks) + 1));
@@ -1791,8 +1869,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     k_block_sizes<<<GridFor(nblocks, 256, sms), 256, 0, I.stream>>>(E, I.d_block_first, nblocks, I.d_block_off, d_total + 1);
     k_scan_u64_single<<<1, 1024, 0, I.stream>>>(I.d_block_off, nblocks, d_total);
     unsigned long long total_and_max[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(total_and_max, d_total, 16, cudaMemcpyDeviceToHost, I.stream));
-    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    if (ybgpu_status s = ReadSmall(total_and_max, d_total, 16)) return s;
     const unsigned long long total = total_and_max[0];
     CUDA_TRY(cudaMemcpyAsync(I.d_block_off + nblocks, &total, 8, cudaMemcpyHostToDevice, I.stream));
     I.out_file_len = total;
@@ -1825,8 +1902,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       k_start_sums<<<pc, 256, 0, I.stream>>>(d_is_new, n, d_npart);
       k_scan_u32_single<<<1, 1024, 0, I.stream>>>(d_npart, pc, d_nkeys);
       uint32_t n_keys = 0;
-      CUDA_TRY(cudaMemcpyAsync(&n_keys, d_nkeys, 4, cudaMemcpyDeviceToHost, I.stream));
-      CUDA_TRY(cudaStreamSynchronize(I.stream));
+      if (ybgpu_status s = ReadSmall(&n_keys, d_nkeys, 4)) return s;
       // a (possibly empty) block is always flushed at Finish (block_based_table_builder.cc:768-770)
       const uint32_t nfb = std::max<uint32_t>(1, (n_keys + g.max_keys - 1) / g.max_keys);
       I.n_filter_blocks = nfb; I.filter_block_bytes = g.block_bytes;
@@ -1888,7 +1964,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   stats_.num_output_data_blocks = I.n_blocks;
   stats_.output_data_file_size = I.out_file_len;
   stats_.gpu_seconds = ms / 1e3;
-  stats_.gpu_kernel_launches = launches;
+  stats_.gpu_kernel_launches = launches + I.readback_launches;
   record_stride_ = Sfinal; num_tiles_ = n_tiles;
   ran_ = true;
   return YBGPU_OK;
@@ -1971,7 +2047,7 @@ ybgpu_status Engine::BeginFetchDataFile(uint8_t* data_file) {
   }
   CUDA_TRY(cudaEventRecord(I.copy_ev, I.stream));
   CUDA_TRY(cudaStreamWaitEvent(I.copy_stream, I.copy_ev, 0));
-  CUDA_TRY(cudaMemcpyAsync(data_file, I.out_file, I.out_file_len, cudaMemcpyDeviceToHost, I.copy_stream));
+  CUDA_TRY(ChunkedCopyAsync(data_file, I.out_file, I.out_file_len, cudaMemcpyDeviceToHost, I.copy_stream));
   I.copy_pending = true;
   return YBGPU_OK;
 }

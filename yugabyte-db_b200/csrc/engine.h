@@ -46,6 +46,7 @@ class Engine {
 
  private:
   ybgpu_status CheckDeviceError(const char* phase);
+  ybgpu_status ReadSmall(void* host_dst, const void* dev_src, size_t n);
   ybgpu_status EnsureKvStream();
   struct Impl;
   ybgpu_job_options opt_;

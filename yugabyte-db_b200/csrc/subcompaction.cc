@@ -11,6 +11,8 @@
 // Everything here is host orchestration above the C ABI; no compaction logic runs on the CPU.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -292,8 +294,14 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
     if (!failed.exchange(true)) { first_status = s; first_error = msg; }
   };
 
+  const bool trace = getenv("YBGPU_SUB_TRACE") != nullptr;      // per-range timeline on stderr (ms since the call)
+  const auto t_start = std::chrono::steady_clock::now();
+  auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+  if (trace) fprintf(stderr, "[ybgpu sub] planned %u ranges at %.1f ms\n", n_ranges, ms_now());
+
   auto run_range = [&](uint32_t r) {
     ybgpu_sub_output& out = outputs[r];
+    double t_begin = ms_now(), t_added = 0, t_ran = 0, t_sized = 0, t_fetched = 0;
     const std::string lo(reinterpret_cast<const char*>(out.range_lower), out.range_lower_len);
     const std::string hi(reinterpret_cast<const char*>(out.range_upper), out.range_upper_len);
     ybgpu_job_options o = *options;
@@ -325,12 +333,15 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
       if (s != YBGPU_OK) { job_fail(s, "add_input"); return; }
       added++;
     }
+    t_added = ms_now();
     if (added) {
       s = ybgpu_job_run(job, shutting_down);
       if (s != YBGPU_OK) { job_fail(s, "run"); return; }
+      t_ran = ms_now();
       uint64_t dl = 0, ml = 0;
       s = ybgpu_job_output_sizes(job, &dl, &ml);
       if (s != YBGPU_OK) { job_fail(s, "output_sizes"); return; }
+      t_sized = ms_now();
       if (dl) {
         // 4 KB aligned slices of the caller's arenas, handed out in completion order
         const uint64_t doff = data_used.fetch_add((dl + 4095) & ~4095ull);
@@ -348,9 +359,13 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
         memcpy(out.smallest_key, sk, out.smallest_key_len);
         memcpy(out.largest_key, lk, out.largest_key_len);
       }
+      t_fetched = ms_now();
       ybgpu_job_get_stats(job, &out.stats);
     }
     ybgpu_job_destroy(job);
+    if (trace)
+      fprintf(stderr, "[ybgpu sub] range %2u: begin %7.1f  inputs queued %7.1f  run done %7.1f  meta built %7.1f  output fetched %7.1f  destroyed %7.1f  (gpu %.1f ms, %.2f GB in)\n",
+              r, t_begin, t_added, t_ran, t_sized, t_fetched, ms_now(), out.stats.gpu_seconds * 1e3, out.stats.h2d_bytes / 1e9);
   };
 
   auto worker = [&]() {
