@@ -52,9 +52,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", type=int, default=1, help="verify input block checksums (reference default: on)")
-    ap.add_argument("--subcompactions", type=int, default=16,
+    ap.add_argument("--subcompactions", type=int, default=32,
                     help="e2e arm: key-range subcompactions per job (DBOptions::max_subcompactions; 1 = one job, one output file)")
-    ap.add_argument("--in-flight", type=int, default=4, help="e2e arm: subcompactions in flight (host threads / private streams)")
+    ap.add_argument("--in-flight", type=int, default=6, help="e2e arm: subcompactions in flight (host threads / private streams)")
     ap.add_argument("--workload", default="config2", choices=["config2", "mvcc"],
                     help="config2 = BASELINE configs[1] (the bench line); mvcc = configs[3] shape (20 versions/key, "
                          "history cutoff drops 90 %), scaled to --rows entries, for profiles/ only")
