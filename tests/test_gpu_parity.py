@@ -391,3 +391,26 @@ def test_concurrent_jobs_on_private_streams(pkg):
         t.join()
     for r, e in zip(results, exps):
         assert r is not None and r[0] == e.sst().data and r[1] == e.sst().meta and r[2] == e.stats.num_input_records
+
+
+def test_reference_golden_dumps_on_gpu(pkg):
+    """Every history compaction of tests/test_reference_dumps.py (the reference's own golden dumps:
+    docdb-test-wrapper.cc BasicTest / StaticColumnCompaction / user timestamps / cotables, docdb-ttl-test.cc
+    TTL sequences) replayed through the CUDA path: surviving set = the reference's expected dump, and
+    files / stats = the oracle's."""
+    import test_reference_dumps as t
+    replayed = []
+
+    def on_gpu(runs, kw, want):
+        job, _ = check(pkg, runs_to_ssts(runs), block_size=512, **kw)
+        assert [(k[:-8], v) for k, v in job.kv_list()] == want
+        replayed.append(len(want))
+
+    t.EXTRA_CHECK = on_gpu
+    try:
+        for name in sorted(dir(t)):
+            if name.startswith("test_") and "parser" not in name:
+                getattr(t, name)()
+    finally:
+        t.EXTRA_CHECK = None
+    assert len(replayed) >= 20
