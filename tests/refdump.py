@@ -68,8 +68,15 @@ def _doc_key(text):
 
 
 def _value(text):
-    parts = [p.strip() for p in text.split(";")]
-    body, fields = parts[0], parts[1:]
+    text = text.strip()
+    if text.startswith('"'):                                # a string may itself contain "; "
+        end = text.index('"', 1)
+        body, rest = text[:end + 1], text[end + 1:]
+    else:
+        body, _, rest = text.partition(";")
+        rest = ";" + rest if rest else ""
+    body = body.strip()
+    fields = [p.strip() for p in rest.split(";") if p.strip()]
     if body.startswith('"') and body.endswith('"'):
         v = dk.vstr(body[1:-1])
     elif body == "{}":
@@ -96,19 +103,25 @@ def _value(text):
     return prefix + v
 
 
-def parse(dump):
-    """Returns [(user_key, value)] in dump order (= RocksDB order)."""
+def parse(dump, with_files=False):
+    """Returns [(user_key, value)] in dump order (= RocksDB order); with_files=True adds the number of the
+    trailing "// file N" comment some reference dumps carry: [(user_key, value, file)]."""
     text = re.sub(r"\\\n\s*", "", dump)
     out = []
     for line in text.splitlines():
         line = line.strip()
         if not line:
             continue
+        file_no = None
+        fm = re.search(r"\s*// file (\d+)$", line)
+        if fm:
+            file_no = int(fm.group(1))
+            line = line[:fm.start()]
         m = _LINE.match(line)
         if not m:
             raise ValueError("cannot parse dump line %r" % line)
         ht = dict((k, int(v)) for k, v in re.findall(r"(physical|logical|w): (\d+)", m.group("ht")))
         key = dk.sub_doc_key(_doc_key(m.group("dk")), _entries(m.group("sub")),
                              micros=ht["physical"], logical=ht.get("logical", 0), write_id=ht.get("w", 0))
-        out.append((key, _value(m.group("val"))))
+        out.append((key, _value(m.group("val")), file_no) if with_files else (key, _value(m.group("val"))))
     return out

@@ -338,3 +338,158 @@ def test_history_retention_with_non_colocated_tables():
 def test_parser_rejects_what_it_does_not_know(bad):
     with pytest.raises(ValueError):
         rd.parse(bad)
+
+
+def test_redis_ttl_compaction():
+    """docdb-ttl-test.cc:674-881 (RedisTTLCompactionTest): value TTLs on whole documents, then TTL merge
+    records (merge flags: 1) whose TTL the compaction folds into the value below them (rewritten
+    values: docdb_compaction_context.cc:1252-1293). t[i] = 1000 + 1000 i microseconds."""
+    s = fully_compact(r'''
+SubDocKey(DocKey([], ["k0"]), [HT{ physical: 3000 }]) -> "v0"; ttl: 0.004s
+SubDocKey(DocKey([], ["k0"]), [HT{ physical: 1000 }]) -> "v1"; ttl: 0.003s
+SubDocKey(DocKey([], ["k1"]), [HT{ physical: 6000 }]) -> "v3"; ttl: 0.001s
+SubDocKey(DocKey([], ["k1"]), [HT{ physical: 4000 }]) -> "v2"; ttl: 0.008s
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 12000 }]) -> "v6"
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 8000 }]) -> "v5"; ttl: 0.005s
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 6000 }]) -> "v4"; ttl: 0.003s
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 14000 }]) -> "v9"; ttl: 0.001s
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 5000 }]) -> "v8"
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 2000 }]) -> "v7"; ttl: 0.004s
+SubDocKey(DocKey([], ["k4"]), [HT{ physical: 13000 }]) -> DEL
+SubDocKey(DocKey([], ["k5"]), [HT{ physical: 10000 }]) -> DEL
+SubDocKey(DocKey([], ["k5"]), [HT{ physical: 9000 }]) -> "v:"; ttl: 0.009s
+SubDocKey(DocKey([], ["k6"]), [HT{ physical: 9000 }]) -> "v;"; ttl: 0.009s
+SubDocKey(DocKey([], ["k6"]), [HT{ physical: 7000 }]) -> DEL
+''', 11000, r'''
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 12000 }]) -> "v6"
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 8000 }]) -> "v5"; ttl: 0.005s
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 14000 }]) -> "v9"; ttl: 0.001s
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 5000 }]) -> "v8"
+SubDocKey(DocKey([], ["k4"]), [HT{ physical: 13000 }]) -> DEL
+SubDocKey(DocKey([], ["k6"]), [HT{ physical: 9000 }]) -> "v;"; ttl: 0.009s
+''')
+    s = fully_compact(s, 15000, r'''
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 12000 }]) -> "v6"
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 14000 }]) -> "v9"; ttl: 0.001s
+SubDocKey(DocKey([], ["k6"]), [HT{ physical: 9000 }]) -> "v;"; ttl: 0.009s
+''')
+    fully_compact(s, 20000, r'''
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 12000 }]) -> "v6"
+''')
+    # "Checking TTL rows now"
+    fully_compact(r'''
+SubDocKey(DocKey([], ["k0"]), [HT{ physical: 6000 }]) -> ""; merge flags: 1; ttl: 0.006s
+SubDocKey(DocKey([], ["k0"]), [HT{ physical: 3000 }]) -> ""; merge flags: 1; ttl: 0.004s
+SubDocKey(DocKey([], ["k0"]), [HT{ physical: 1000 }]) -> "v0"; ttl: 0.003s
+SubDocKey(DocKey([], ["k1"]), [HT{ physical: 6000 }]) -> ""; merge flags: 1; ttl: 0.003s
+SubDocKey(DocKey([], ["k1"]), [HT{ physical: 4000 }]) -> "v1"; ttl: 0.008s
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 13000 }]) -> ""; merge flags: 1
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 12000 }]) -> "v6"
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 8000 }]) -> ""; merge flags: 1; ttl: 0.005s
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 6000 }]) -> "v2"; ttl: 0.003s
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 14000 }]) -> "v4"; ttl: 0.001s
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 5000 }]) -> ""; merge flags: 1
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 2000 }]) -> "v3"; ttl: 0.004s
+SubDocKey(DocKey([], ["k4"]), [HT{ physical: 13000 }]) -> DEL
+SubDocKey(DocKey([], ["k5"]), [HT{ physical: 10000 }]) -> DEL
+SubDocKey(DocKey([], ["k5"]), [HT{ physical: 9000 }]) -> "v5"; ttl: 0.009s
+SubDocKey(DocKey([], ["k6"]), [HT{ physical: 11000 }]) -> ""; merge flags: 1; ttl: 0.004s
+SubDocKey(DocKey([], ["k6"]), [HT{ physical: 9000 }]) -> "v6"; ttl: 0.009s
+SubDocKey(DocKey([], ["k6"]), [HT{ physical: 7000 }]) -> DEL
+''', 10000, r'''
+SubDocKey(DocKey([], ["k0"]), [HT{ physical: 1000 }]) -> "v0"; ttl: 0.011s
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 13000 }]) -> ""; merge flags: 1
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 12000 }]) -> "v6"
+SubDocKey(DocKey([], ["k2"]), [HT{ physical: 6000 }]) -> "v2"; ttl: 0.007s
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 14000 }]) -> "v4"; ttl: 0.001s
+SubDocKey(DocKey([], ["k3"]), [HT{ physical: 2000 }]) -> "v3"
+SubDocKey(DocKey([], ["k4"]), [HT{ physical: 13000 }]) -> DEL
+SubDocKey(DocKey([], ["k6"]), [HT{ physical: 11000 }]) -> ""; merge flags: 1; ttl: 0.004s
+SubDocKey(DocKey([], ["k6"]), [HT{ physical: 9000 }]) -> "v6"; ttl: 0.009s
+''')
+
+
+def test_redis_collection_ttl_compaction_chain():
+    """docdb-ttl-test.cc:72-672 (RedisCollectionTTLCompactionTest): 13 successive history compactions of
+    collections with init markers, collection-level TTL merge records, tombstoned and re-created
+    collections. Dumps extracted verbatim by tests/golden/extract_reference_dumps.py."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "redis_collection_ttl_compaction.json")))
+    assert len(fx["steps"]) == 13
+    state = rd.parse(fx["initial"])
+    for step in fx["steps"]:
+        state = fully_compact(state, step["cutoff_us"], step["expected"])
+
+
+COLLECTION_WITH_TTL = r'''
+            SubDocKey(DocKey([], ["c"]), [HT{ physical: 1000 }]) -> {}; ttl: 10.000s               // file 1
+            SubDocKey(DocKey([], ["c"]), ["k0"; HT{ physical: 1100 }]) -> "vv0"; ttl: 20.000s      // file 2
+            SubDocKey(DocKey([], ["c"]), ["k0"; HT{ physical: 1000 w: 1 }]) -> "v0"; ttl: 10.000s  // file 1
+            SubDocKey(DocKey([], ["c"]), ["k1"; HT{ physical: 1100 }]) -> "vv1"; ttl: 21.000s      // file 3
+            SubDocKey(DocKey([], ["c"]), ["k1"; HT{ physical: 1000 w: 2 }]) -> "v1"; ttl: 10.000s  // file 1
+            SubDocKey(DocKey([], ["c"]), ["k2"; HT{ physical: 1100 }]) -> "vv2"; ttl: 22.000s      // file 4
+            SubDocKey(DocKey([], ["c"]), ["k2"; HT{ physical: 1000 w: 3 }]) -> "v2"; ttl: 10.000s  // file 1
+            SubDocKey(DocKey([], ["c"]), ["k3"; HT{ physical: 1100 }]) -> "vv3"; ttl: 23.000s      // file 5
+            SubDocKey(DocKey([], ["c"]), ["k4"; HT{ physical: 1100 }]) -> "vv4"; ttl: 24.000s      // file 6
+            SubDocKey(DocKey([], ["c"]), ["k5"; HT{ physical: 1100 }]) -> "vv5"; ttl: 25.000s      // file 7
+'''
+
+
+def test_compaction_for_collections_with_ttl():
+    """docdb-ttl-test.cc:1090-1098 + docdb-test.h:394-425 (TestCompactionForCollectionsWithTTL): after the
+    collection's init marker and first values expire, a major compaction leaves no tombstone for them."""
+    fully_compact(COLLECTION_WITH_TTL, 1050 + 10 * 1000000, r'''
+            SubDocKey(DocKey([], ["c"]), ["k0"; HT{ physical: 1100 }]) -> "vv0"; ttl: 20.000s
+            SubDocKey(DocKey([], ["c"]), ["k1"; HT{ physical: 1100 }]) -> "vv1"; ttl: 21.000s
+            SubDocKey(DocKey([], ["c"]), ["k2"; HT{ physical: 1100 }]) -> "vv2"; ttl: 22.000s
+            SubDocKey(DocKey([], ["c"]), ["k3"; HT{ physical: 1100 }]) -> "vv3"; ttl: 23.000s
+            SubDocKey(DocKey([], ["c"]), ["k4"; HT{ physical: 1100 }]) -> "vv4"; ttl: 24.000s
+            SubDocKey(DocKey([], ["c"]), ["k5"; HT{ physical: 1100 }]) -> "vv5"; ttl: 25.000s
+''')
+
+
+def test_minor_compactions_for_collections_with_ttl():
+    """docdb-ttl-test.cc:1117-1161 (MinorCompactionsForCollectionsWithTTL): compactions of some of the
+    files ("// file N" tags of the reference dumps); expired values become delete markers because older
+    data may exist in the files left out (docdb_compaction_context.cc:1268-1277)."""
+    def minor(state, files, cutoff_us, expected_dump, new_file):
+        runs = [w.sort_run([(o.ikey(k, SEQ0 + f * 100 + i), v) for i, (k, v, ff) in enumerate(state) if ff == f]) for f in files]
+        p = o.CompactionParams(bottommost=False, cutoff_ht=us(cutoff_us), other_min_ht=o.HT_MIN)
+        want_all = rd.parse(expected_dump, with_files=True)
+        want = [(k, v) for k, v, f in want_all if f == new_file]
+        assert [(k[:-8], v) for k, v in o.compact_runs(runs, p).kv_list()] == want
+        assert [(k[:-8], v) for k, v in hh.compact_runs(runs, p)] == want
+        if EXTRA_CHECK is not None:
+            EXTRA_CHECK(runs, dict(bottommost=False, cutoff_ht=us(cutoff_us), other_min_ht=o.HT_MIN), want)
+        untouched = [e for e in state if e[2] not in files]
+        assert sorted((k, v) for k, v, f in want_all if f != new_file) == sorted((k, v) for k, v, _ in untouched)
+        return want_all
+
+    s0 = rd.parse(COLLECTION_WITH_TTL, with_files=True)
+    # MinorCompaction(cutoff, num_files_to_compact = 2, start_index = 1): files 2 and 3 -> file 8
+    s1 = minor(s0, [2, 3], 1100 + 20 * 1000000 + 1, r'''
+SubDocKey(DocKey([], ["c"]), [HT{ physical: 1000 }]) -> {}; ttl: 10.000s               // file 1
+SubDocKey(DocKey([], ["c"]), ["k0"; HT{ physical: 1100 }]) -> DEL                      // file 8
+SubDocKey(DocKey([], ["c"]), ["k0"; HT{ physical: 1000 w: 1 }]) -> "v0"; ttl: 10.000s  // file 1
+SubDocKey(DocKey([], ["c"]), ["k1"; HT{ physical: 1100 }]) -> "vv1"; ttl: 21.000s      // file 8
+SubDocKey(DocKey([], ["c"]), ["k1"; HT{ physical: 1000 w: 2 }]) -> "v1"; ttl: 10.000s  // file 1
+SubDocKey(DocKey([], ["c"]), ["k2"; HT{ physical: 1100 }]) -> "vv2"; ttl: 22.000s      // file 4
+SubDocKey(DocKey([], ["c"]), ["k2"; HT{ physical: 1000 w: 3 }]) -> "v2"; ttl: 10.000s  // file 1
+SubDocKey(DocKey([], ["c"]), ["k3"; HT{ physical: 1100 }]) -> "vv3"; ttl: 23.000s      // file 5
+SubDocKey(DocKey([], ["c"]), ["k4"; HT{ physical: 1100 }]) -> "vv4"; ttl: 24.000s      // file 6
+SubDocKey(DocKey([], ["c"]), ["k5"; HT{ physical: 1100 }]) -> "vv5"; ttl: 25.000s      // file 7
+''', 8)
+    # "Compact files 4, 5, 6, 7, 8" -> file 9
+    minor(s1, [4, 5, 6, 7, 8], 1100 + 24 * 1000000 + 1, r'''
+SubDocKey(DocKey([], ["c"]), [HT{ physical: 1000 }]) -> {}; ttl: 10.000s               // file 1
+SubDocKey(DocKey([], ["c"]), ["k0"; HT{ physical: 1100 }]) -> DEL                      // file 9
+SubDocKey(DocKey([], ["c"]), ["k0"; HT{ physical: 1000 w: 1 }]) -> "v0"; ttl: 10.000s  // file 1
+SubDocKey(DocKey([], ["c"]), ["k1"; HT{ physical: 1100 }]) -> DEL                      // file 9
+SubDocKey(DocKey([], ["c"]), ["k1"; HT{ physical: 1000 w: 2 }]) -> "v1"; ttl: 10.000s  // file 1
+SubDocKey(DocKey([], ["c"]), ["k2"; HT{ physical: 1100 }]) -> DEL                      // file 9
+SubDocKey(DocKey([], ["c"]), ["k2"; HT{ physical: 1000 w: 3 }]) -> "v2"; ttl: 10.000s  // file 1
+SubDocKey(DocKey([], ["c"]), ["k3"; HT{ physical: 1100 }]) -> DEL                      // file 9
+SubDocKey(DocKey([], ["c"]), ["k4"; HT{ physical: 1100 }]) -> DEL                      // file 9
+SubDocKey(DocKey([], ["c"]), ["k5"; HT{ physical: 1100 }]) -> "vv5"; ttl: 25.000s      // file 9
+''', 9)
