@@ -216,7 +216,8 @@ ybgpu_status ybgpu_job_output_boundaries(const ybgpu_job* job, uint8_t* smallest
  * ordinary job over the data blocks of each input that can hold its keys, bounded by
  * range_lower/range_upper like SubcompactionState::start/end (compaction_job.cc:721-729,779-783), and writes
  * its own output SST — the reference installs every sub-output in range order too
- * (compaction_job.cc:1128-1131). Ranges run on `max_in_flight` host threads with a private stream
+ * (compaction_job.cc:1128-1131). Note: with a single-level universal layout (DocDB's) the reference
+ * never forms subcompactions (db/compaction.cc:593-604); see DESIGN.md "End-to-end modes". Ranges run on `max_in_flight` host threads with a private stream
  * each, so that the host->device copy of one range, the kernels of another and the device->host copy
  * of a third overlap (PCIe is full duplex); device memory in use is bounded by max_in_flight ranges
  * instead of the whole compaction. */

@@ -183,3 +183,18 @@ def test_plan_subcompactions_row_aligned_and_balanced(pkg):
     cuts = [0] + [bisect.bisect_left(users1, s) for s in sp3] + [len(users1)]
     sizes = [b - a for a, b in zip(cuts, cuts[1:])]
     assert min(sizes) > 0.6 * len(users1) / 8 and max(sizes) < 1.5 * len(users1) / 8
+
+
+def test_compact_files_fails_loudly_without_gpu(pkg):
+    """The subcompaction entry point plans on the host but never compacts there: without a CUDA device
+    it fails like ybgpu_job_create does."""
+    if pkg.device_count() > 0:
+        pytest.skip("GPU present")
+    cfg = o.GenConfig(seed=5, num_rows=500, cols=2, versions=2, num_files=2, value_len=30)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=1024))
+    with pytest.raises(pkg.YbGpuError) as e:
+        pkg.compact_files([(s.meta_view(), s.data_view()) for s in ssts], max_subcompactions=3, max_in_flight=2)
+    assert "no CPU fallback" in str(e.value) and e.value.status_name == "RuntimeError"
+    with pytest.raises(pkg.YbGpuError) as e:      # range bounds belong to the planner
+        pkg.compact_files([(s.meta_view(), s.data_view()) for s in ssts], max_subcompactions=3, range_lower=b"x")
+    assert e.value.status_name == "InvalidArgument"
