@@ -14,10 +14,11 @@ entries, as rocksdb.raw.key.size + rocksdb.raw.value.size count them).
   value     inputs already resident in HBM; whole job device pipeline, wall clock between syncs.
   e2e       same job through the C ABI with HOST (pinned) input files and HOST output files:
             H2D of every input file and D2H of the result inside the timed region. Headline mode:
-            ybgpu_compact_files with --subcompactions key ranges (the reference's max_subcompactions
-            feature, compaction_job.cc:409-552), pipelined so that H2D / kernels / D2H of different
+            ybgpu_compact_files with --subcompactions key ranges (CompactionJob's subcompaction
+            mechanism, compaction_job.cc:409-552), pipelined so that H2D / kernels / D2H of different
             ranges overlap; one output SST per range. e2e.single_job is the same measurement with one
-            job and one output file (H2D, run and D2H back to back).
+            job and one output file (H2D, run and D2H back to back) — the shape DocDB's single-level
+            universal layout produces today (db/compaction.cc:593-604 never forms subcompactions there).
   roofline  dominant kernel, algorithmic bytes / its CUDA-event time.
   cpu_baseline  the oracle (CPU restatement of the reference loop) on a bounded sample, 1 thread
             like the reference (max_subcompactions = 1).
