@@ -122,7 +122,10 @@ class ClockSampler:
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU loop (oracle port; the reference tree itself cannot be
     compiled in this image) on the host cores. One compaction = one thread, as in the reference
-    (rocksdb/util/options.cc:258, db/compaction.cc:593-604), on a bounded sample of the workload."""
+    (rocksdb/util/options.cc:258, db/compaction.cc:593-604), on a bounded sample of the workload.
+    Two informational figures ride along: many independent tablets on all cores, and the same
+    compaction cut into key ranges with one thread per range (the CPU counterpart of the GPU arm's
+    pipelined subcompactions)."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -171,6 +174,50 @@ def run_reference(args, rank, world):
                 "sample": "%d concurrent one-thread compactions of %d entries each (independent tablets), %.1f s" % (T, small_rows, dt)}
     except Exception as e:   # never fail the arm because of the informational figure
         many = {"error": str(e)}
+    # Informational: the SAME compaction cut into key ranges, one CPU-port thread per range — what
+    # CompactionJob's subcompactions (compaction_job.cc:409-552) would give the host on a layout that forms them
+    # (DocDB's single-level universal layout never does, db/compaction.cc:593-604). This is the CPU counterpart of
+    # the GPU arm's pipelined e2e mode; the per-range input slices are cut outside the timed region.
+    subs = None
+    try:
+        import bisect
+        from concurrent.futures import ThreadPoolExecutor
+        T = max(1, min(os.cpu_count() or 1, 32))
+        rows_s = min(rows, 2_000_000)
+        cfg3 = o.GenConfig(seed=2, num_rows=rows_s, cols=1, versions=1, num_files=NUM_FILES, value_len=VALUE_LEN)
+        ssts3 = o.Sst.generate_all(cfg3, o.TableOptions())
+        b3 = sum(s.raw_bytes for s in ssts3)
+        kvs = [s.read_all() for s in ssts3]
+        uks = [[k[:-8] for k, _ in f] for f in kvs]
+        dockeys = sorted(u[:32] for u in uks[0])                      # rows of this workload are 32-byte DocKeys
+        splitters = [dockeys[len(dockeys) * i // T] for i in range(1, T)]
+        largest = max(u[-1] for u in uks if u)
+        range_ssts = []
+        for r in range(T):
+            lo = splitters[r - 1] if r > 0 else None
+            hi = splitters[r] if r < T - 1 else None
+            parts = []
+            for f, u in zip(kvs, uks):
+                a = bisect.bisect_left(u, lo) if lo is not None else 0
+                b = bisect.bisect_left(u, hi) if hi is not None else len(u)
+                if b > a:
+                    parts.append(o.Sst.build(f[a:b], o.TableOptions()))
+            range_ssts.append(parts)
+        del kvs, uks
+        p3 = o.CompactionParams(largest_user_key=largest)
+
+        def one_range(r):
+            if range_ssts[r]:
+                res = o.compact(range_ssts[r], p3, o.TableOptions(filter_policy=1), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
+                del res
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(T) as ex:
+            list(ex.map(one_range, range(T)))
+        dt = time.perf_counter() - t0
+        subs = {"value": round(b3 / dt / 1e9, 3), "unit": "GB/s", "cores": T,
+                "sample": "one compaction of %d entries cut into %d key ranges, one thread per range, %.2f s" % (rows_s, T, dt)}
+    except Exception as e:
+        subs = {"error": str(e)}
     line = {
         "impl": "reference", "metric": "compaction GB/s (input bytes merged)", "value": round(gbs, 4), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps * 1e3, 3),
@@ -180,6 +227,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "many_tablets_all_cores": many,
+        "subcompactions_all_cores": subs,
     }
     emit_json_line(line)
 
