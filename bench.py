@@ -16,7 +16,9 @@ entries, as rocksdb.raw.key.size + rocksdb.raw.value.size count them).
             H2D of every input file and D2H of the result inside the timed region. Headline mode:
             ybgpu_compact_files with --subcompactions key ranges (CompactionJob's subcompaction
             mechanism, compaction_job.cc:409-552), pipelined so that H2D / kernels / D2H of different
-            ranges overlap; one output SST per range. e2e.single_job is the same measurement with one
+            ranges overlap; one output SST per range. e2e.one_table adds ybgpu_sst_concat_meta: the range
+            outputs assembled into ONE table (data pieces appended in range order, one rebased index /
+            filter index) inside the timed region. e2e.single_job is the same measurement with one
             job and one output file (H2D, run and D2H back to back) — the shape DocDB's single-level
             universal layout produces today (db/compaction.cc:593-604 never forms subcompactions there).
   roofline  dominant kernel, algorithmic bytes / its CUDA-event time.
@@ -441,6 +443,35 @@ def main():
 
             sub_s, sres = timed(step_sub)
             assert sres[-1][0]["num_input_records"] == n_entries, "subcompactions must see every input entry once"
+
+            # One table out of the range outputs (what a single-level universal layout such as DocDB's needs): the
+            # range data files are appended in range order as they are, ybgpu_sst_concat_meta writes the one metadata
+            # file (rebased multi-level index, all filter blocks + one filter index, summed properties).
+            one_table = None
+            try:
+                if world > 1:
+                    raise RuntimeError("measured at N=1 only (an exception on one rank must not strand the others at a barrier)")
+                concat_buf = np.empty(2 * out_meta.size + (1 << 20), np.uint8)
+                concat_buf[::4096] = 0                      # touch the pages once, outside the timed region
+
+                def step_one_table():
+                    r = pkg.compact_files(files, max_subcompactions=args.subcompactions, max_in_flight=args.in_flight,
+                                          data_arena=out_data, meta_arena=out_meta, device=local_rank,
+                                          verify_checksums=bool(args.verify), **job_kw)
+                    outs = [o_ for o_ in r.outputs if o_.data_len]
+                    pieces = [(out_meta[o_.meta_offset:o_.meta_offset + o_.meta_len], o_.data_len, o_.smallest, o_.largest) for o_ in outs]
+                    meta = pkg.sst_concat_meta(pieces, out=concat_buf, filter_policy=job_kw.get("filter_policy", 0))
+                    return r.total.as_dict(), sum(o_.data_len for o_ in outs), int(meta.size), len(outs), meta
+                ot_s, ores = timed(step_one_table)
+                st_d, data_bytes, meta_bytes, n_pieces, meta = ores[-1]
+                off, sz, _ = pkg.sst_block_handles(meta)     # the product's own reader walks the merged index
+                assert len(off) == st_d["num_output_data_blocks"] and int(off[-1] + sz[-1]) + 5 == data_bytes
+                assert st_d["num_input_records"] == n_entries
+                one_table = {"value": round(in_bytes * world * args.steps / ot_s / 1e9, 4), "unit": "GB/s",
+                             "ms_per_step": round(ot_s / args.steps * 1e3, 2), "output_file_bytes": int(data_bytes + meta_bytes),
+                             "pieces": int(n_pieces), "data_blocks": int(len(off))}
+            except Exception as ex:                          # never lose the bench line to the extra figure
+                one_table = {"error": "%s: %s" % (type(ex).__name__, ex)}
             e2e = {"value": round(in_bytes * world * args.steps / sub_s / 1e9, 4), "unit": "GB/s",
                    "h2d_bytes_per_step": int(sres[-1][0]["h2d_bytes"]), "d2h_bytes_per_step": int(sres[-1][0]["d2h_bytes"]),
                    "ms_per_step": round(sub_s / args.steps * 1e3, 2), "pinned_inputs": all(ok for _, ok in pinned),
@@ -449,6 +480,7 @@ def main():
                            "streams, one output SST per range" % (sres[-1][2], args.subcompactions, args.in_flight),
                    "output_files": int(sres[-1][2]),
                    "gpu_ms_per_step": round(sres[-1][0]["gpu_seconds"] * 1e3, 2),
+                   "one_table": one_table,
                    "single_job": single}
         for v, ok in pinned:
             if ok:

@@ -257,6 +257,24 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
                                  const volatile int32_t* shutting_down, ybgpu_sub_output* outputs, uint32_t* num_outputs,
                                  ybgpu_job_stats* total, char* err, uint64_t err_cap);
 
+/* One table out of the range outputs. For layouts where a compaction must produce a single sorted run
+ * (DocDB's single-level universal compaction, db/compaction.cc:593-604), the per-range SSTs of
+ * ybgpu_compact_files — ascending, key-disjoint — concatenate into one split SST without re-encoding
+ * anything: the data file is the pieces' data files back to back (the caller appends them in order) and
+ * this call writes its metadata file: one multi-level index over all data blocks with offsets rebased
+ * (index_builder.cc:143-289), every fixed-size bloom filter block with one filter index, summed
+ * properties, footer. Key/value bytes equal the single-pass output; block cuts differ only at the piece
+ * boundaries. table_options: the options the pieces were written with. Call with meta_out = NULL to get
+ * an upper bound of the size in *meta_len (the call with a buffer returns the exact length). */
+typedef struct ybgpu_sst_piece {
+  const uint8_t* meta_file; uint64_t meta_file_len;     /* <n>.sst of the piece */
+  uint64_t data_file_len;                               /* length of its <n>.sst.sblock.0 */
+  const uint8_t* smallest_key; uint32_t smallest_key_len;   /* first / last internal key of the piece */
+  const uint8_t* largest_key; uint32_t largest_key_len;     /* (ybgpu_sub_output carries both) */
+} ybgpu_sst_piece;
+ybgpu_status ybgpu_sst_concat_meta(const ybgpu_job_options* table_options, const ybgpu_sst_piece* pieces,
+                                   uint32_t num_pieces, uint8_t* meta_out, uint64_t meta_cap, uint64_t* meta_len);
+
 /* Last internal key of a split SST (its last data block is decoded on the host): what
  * FileMetaData::largest holds for the file. key must hold 1032 bytes. */
 ybgpu_status ybgpu_sst_last_key(const uint8_t* meta_file, uint64_t meta_file_len, const uint8_t* data_file,

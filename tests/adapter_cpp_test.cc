@@ -48,6 +48,11 @@ int main(int argc, char** argv) {
       std::ofstream(std::string(argv[2]) + ".sub" + std::to_string(i) + ".base", std::ios::binary) << job.outputs()[i].base_file;
       std::ofstream(std::string(argv[2]) + ".sub" + std::to_string(i) + ".data", std::ios::binary) << job.outputs()[i].data_file;
     }
+    std::string one_data, one_base;
+    Status cs = job.ConcatenatedOutput(&one_data, &one_base);
+    if (!cs.ok()) { printf("concat: %s\n", cs.ToString().c_str()); return 1; }
+    std::ofstream(std::string(argv[2]) + ".one.base", std::ios::binary) << one_base;
+    std::ofstream(std::string(argv[2]) + ".one.data", std::ios::binary) << one_data;
     if (!job.outputs().empty() && (m.smallest_key != job.outputs().front().smallest_key || m.largest_key != job.outputs().back().largest_key)) { printf("boundaries\n"); return 1; }
     printf("OK in=%llu out=%llu files=%zu\n", (unsigned long long)job.stats().num_input_records, (unsigned long long)m.num_entries, job.outputs().size());
     return 0;

@@ -198,3 +198,64 @@ def test_compact_files_fails_loudly_without_gpu(pkg):
     with pytest.raises(pkg.YbGpuError) as e:      # range bounds belong to the planner
         pkg.compact_files([(s.meta_view(), s.data_view()) for s in ssts], max_subcompactions=3, range_lower=b"x")
     assert e.value.status_name == "InvalidArgument"
+
+
+@pytest.mark.parametrize("enc,with_filter", [(1, True), (2, True), (1, False)])
+def test_sst_concat_meta_builds_one_valid_table(pkg, enc, with_filter):
+    """ybgpu_sst_concat_meta: the key-disjoint range outputs of one compaction (here: the oracle's
+    compaction of each key range — byte-identical to what ybgpu_compact_files returns per range, see
+    test_subcompactions_pipelined) become ONE split SST. The oracle's independent reader must find every
+    key/value of the single-pass compaction in it, walk the rebased multi-level index, and every key's
+    bloom filter key must hit the filter block the filter index routes it to."""
+    import bisect
+    import test_oracle_bloom as ob
+    cfg = o.GenConfig(seed=29, num_rows=7000, cols=2, versions=3, num_files=5, value_len=70, tombstone_per_1024=40)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=2048))
+    cutoff = o.ht_from_micros(cfg.base_micros + 1500)
+    topt = dict(block_size=2048, index_block_size=512, min_keys_per_index_block=4, key_encoding=enc,
+                filter_policy=int(with_filter), filter_block_size=1024)
+    exp = o.compact(ssts, o.CompactionParams(cutoff_ht=cutoff), o.TableOptions(**topt))
+    splitters = pkg.plan_subcompactions([(s.meta_view(), s.data_view()) for s in ssts], 6)
+    assert len(splitters) >= 3
+    all_kvs = [s.read_all() for s in ssts]
+    largest = max(kvs[-1][0][:-8] for kvs in all_kvs)
+    pieces, datas = [], []
+    bounds = [b""] + splitters + [b""]
+    for lo, hi in zip(bounds, bounds[1:]):
+        part = [[kv for kv in kvs if (not lo or kv[0][:-8] >= lo) and (not hi or kv[0][:-8] < hi)] for kvs in all_kvs]
+        ref = o.compact([o.Sst.build(p, o.TableOptions(block_size=2048)) for p in part if p],
+                        o.CompactionParams(cutoff_ht=cutoff, largest_user_key=largest), o.TableOptions(**topt))
+        sst = ref.sst()
+        if sst is None:
+            continue
+        kvs = ref.kv_list()
+        pieces.append((sst.meta_view().copy(), len(sst.data), kvs[0][0], kvs[-1][0]))
+        datas.append(sst.data)
+    assert len(pieces) >= 3
+    meta = pkg.sst_concat_meta(pieces, block_size=2048, index_block_size=512, min_keys_per_index_block=4,
+                               output_key_encoding=enc, filter_policy=int(with_filter), filter_block_size=1024)
+    data = b"".join(datas)
+    whole = o.Sst.from_bytes(meta, data)
+    assert whole.read_all() == exp.kv_list()                 # checksums verified, index walked by the oracle's reader
+    props = whole.properties()
+    assert o.varint(props["rocksdb.num.entries"]) == len(exp.kv_list())
+    assert o.varint(props["rocksdb.data.size"]) == len(data)
+    assert o.varint(props["rocksdb.raw.key.size"]) == exp.stats.out_key_bytes
+    assert o.varint(props["rocksdb.raw.value.size"]) == exp.stats.out_val_bytes
+    # the product's own reader agrees on the block list
+    off, sz, e2 = pkg.sst_block_handles(np.frombuffer(meta, np.uint8))
+    assert e2 == enc and len(off) == o.varint(props["rocksdb.num.data.blocks"]) and int(off[-1] + sz[-1]) + 5 == len(data)
+    if with_filter:
+        fb = whole.filter_blocks()
+        assert len(fb) == sum(len(o.Sst.from_bytes(p[0].tobytes(), d).filter_blocks()) for p, d in zip(pieces, datas))
+        index_keys = [k for k, _ in fb]
+        assert index_keys == sorted(index_keys)
+        for k, _ in exp.kv_list()[::7]:
+            fk = ob.filter_key(k[:-8])
+            i = bisect.bisect_left(index_keys, fk)           # FixedSizeFilterBlockReader: first index entry >= key
+            assert i < len(fb) and ob.may_match(fb[i][1], fk)
+    # rejected: pieces out of order, options that do not match the pieces
+    with pytest.raises(pkg.YbGpuError):
+        pkg.sst_concat_meta(pieces[::-1], block_size=2048, output_key_encoding=enc, filter_policy=int(with_filter), filter_block_size=1024)
+    with pytest.raises(pkg.YbGpuError):
+        pkg.sst_concat_meta(pieces, block_size=2048, output_key_encoding=3 - enc, filter_policy=int(with_filter), filter_block_size=1024)

@@ -67,3 +67,6 @@ def test_adapter_runs_subcompactions(tmp_path):
         part = o.Sst.from_bytes((tmp_path / ("0.sst.sub%d.base" % i)).read_bytes(), (tmp_path / ("0.sst.sub%d.data" % i)).read_bytes())
         got += part.read_all()
     assert got == exp.kv_list()
+    # ... and as ONE table (ConcatenatedOutput): the same key/value stream behind one index
+    one = o.Sst.from_bytes((tmp_path / "0.sst.one.base").read_bytes(), (tmp_path / "0.sst.one.data").read_bytes())
+    assert one.read_all() == exp.kv_list()

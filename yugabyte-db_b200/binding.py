@@ -510,3 +510,33 @@ def compact_files(ssts, max_subcompactions=8, max_in_flight=3, data_arena=None, 
     if st != 0:
         raise YbGpuError(st, err.value.decode(errors="replace"))
     return SubcompactionResult([outs[i] for i in range(n.value)], total, data_arena, meta_arena)
+
+
+class SstPiece(C.Structure):
+    _fields_ = [("meta_file", C.c_void_p), ("meta_file_len", C.c_uint64), ("data_file_len", C.c_uint64),
+                ("smallest_key", C.c_char_p), ("smallest_key_len", C.c_uint32),
+                ("largest_key", C.c_char_p), ("largest_key_len", C.c_uint32)]
+
+
+def sst_concat_meta(pieces, out=None, **table_kwargs):
+    """ybgpu_sst_concat_meta. pieces: [(meta ndarray/bytes, data_len, smallest internal key, largest internal key)]
+    in key order. Returns the metadata file (bytes; a view of `out` when a uint8 buffer is given) of the table
+    whose data file is the pieces' data files back to back."""
+    L = lib()
+    L.ybgpu_sst_concat_meta.argtypes = [C.POINTER(JobOptions), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    o, keep_o = make_options(**table_kwargs)
+    arr = (SstPiece * len(pieces))()
+    keep = []
+    for i, (meta, data_len, smallest, largest) in enumerate(pieces):
+        meta = np.ascontiguousarray(np.frombuffer(meta, np.uint8) if isinstance(meta, (bytes, bytearray)) else meta, dtype=np.uint8)
+        keep += [meta, smallest, largest]
+        arr[i] = SstPiece(meta.ctypes.data, meta.size, int(data_len), smallest, len(smallest), largest, len(largest))
+    n = C.c_uint64()
+    st = L.ybgpu_sst_concat_meta(C.byref(o), arr, len(pieces), None, 0, C.byref(n))
+    if st != 0:
+        raise YbGpuError(st, L.ybgpu_last_error().decode())
+    buf = out if out is not None and out.size >= n.value else np.empty(n.value, np.uint8)
+    st = L.ybgpu_sst_concat_meta(C.byref(o), arr, len(pieces), buf.ctypes.data, buf.size, C.byref(n))
+    if st != 0:
+        raise YbGpuError(st, L.ybgpu_last_error().decode())
+    return buf[:n.value] if out is not None else buf[:n.value].tobytes()

@@ -377,6 +377,37 @@ ybgpu_status ybgpu_sst_meta_separators(const uint8_t* meta, uint64_t len, uint8_
   return YBGPU_OK;
 }
 
+ybgpu_status ybgpu_sst_concat_meta(const ybgpu_job_options* o, const ybgpu_sst_piece* pieces, uint32_t n, uint8_t* meta_out,
+                                   uint64_t meta_cap, uint64_t* meta_len) {
+  if (!o || !pieces || !meta_len || n == 0) { g_last_error = "null argument"; return YBGPU_INVALID_ARGUMENT; }
+  if (!meta_out) {
+    // size bound: filter blocks are copied as they are; an index entry (key delta + handle, >= ~10 bytes)
+    // grows by at most the 5 extra varint bytes of a rebased offset
+    uint64_t total = 65536;
+    for (uint32_t i = 0; i < n; i++) total += 2 * pieces[i].meta_file_len + 256;
+    *meta_len = total;
+    return YBGPU_OK;
+  }
+  ybgpu::host::TableOptions t;
+  t.block_size = o->block_size; t.block_restart_interval = o->block_restart_interval;
+  t.block_size_deviation = o->block_size_deviation; t.index_block_size = o->index_block_size;
+  t.min_keys_per_index_block = o->min_keys_per_index_block; t.key_encoding = o->output_key_encoding;
+  t.filter_policy = o->filter_policy; if (o->filter_block_size) t.filter_block_size = o->filter_block_size;
+  std::vector<ybgpu::host::SstPiece> ps(n);
+  for (uint32_t i = 0; i < n; i++) {
+    ps[i].meta = pieces[i].meta_file; ps[i].meta_len = pieces[i].meta_file_len; ps[i].data_len = pieces[i].data_file_len;
+    if (pieces[i].smallest_key) ps[i].smallest.assign(reinterpret_cast<const char*>(pieces[i].smallest_key), pieces[i].smallest_key_len);
+    if (pieces[i].largest_key) ps[i].largest.assign(reinterpret_cast<const char*>(pieces[i].largest_key), pieces[i].largest_key_len);
+  }
+  std::string out;
+  std::string err = ybgpu::host::ConcatSplitSstMeta(t, ps, &out);
+  if (!err.empty()) { g_last_error = err; return YBGPU_INVALID_ARGUMENT; }
+  *meta_len = out.size();
+  if (out.size() > meta_cap) { g_last_error = "metadata buffer too small"; return YBGPU_INVALID_ARGUMENT; }
+  memcpy(meta_out, out.data(), out.size());
+  return YBGPU_OK;
+}
+
 int32_t ybgpu_device_count(void);   // engine.cu
 const char* ybgpu_version(void) { return "ybgpu-compaction 0.1 (sm_100a)"; }
 

@@ -255,6 +255,34 @@ class GpuCompactionJob {
   }
   const std::vector<OutputFile>& outputs() const { return outputs_; }
 
+  // The range outputs as ONE table, for layouts where a compaction must leave a single sorted run (DocDB's
+  // single-level universal compaction never forms subcompactions, db/compaction.cc:593-604): the data file
+  // is the outputs' data files appended in order (nothing is re-encoded), the metadata file is rebuilt over
+  // all blocks by ybgpu_sst_concat_meta. Key/value bytes equal the single-job output.
+  Status ConcatenatedOutput(std::string* data_file, std::string* base_file) const {
+    data_file->clear(); base_file->clear();
+    if (outputs_.empty()) return Status::OK();
+    std::vector<ybgpu_sst_piece> pieces;
+    uint64_t total = 0;
+    for (const OutputFile& f : outputs_) {
+      pieces.push_back({reinterpret_cast<const uint8_t*>(f.base_file.data()), f.base_file.size(), f.data_file.size(),
+                        reinterpret_cast<const uint8_t*>(f.smallest_key.data()), static_cast<uint32_t>(f.smallest_key.size()),
+                        reinterpret_cast<const uint8_t*>(f.largest_key.data()), static_cast<uint32_t>(f.largest_key.size())});
+      total += f.data_file.size();
+    }
+    uint64_t cap = 0, len = 0;
+    ybgpu_status s = ybgpu_sst_concat_meta(&options_, pieces.data(), static_cast<uint32_t>(pieces.size()), nullptr, 0, &cap);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_last_error());
+    base_file->resize(cap);
+    s = ybgpu_sst_concat_meta(&options_, pieces.data(), static_cast<uint32_t>(pieces.size()),
+                              reinterpret_cast<uint8_t*>(&(*base_file)[0]), cap, &len);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_last_error());
+    base_file->resize(len);
+    data_file->reserve(total);
+    for (const OutputFile& f : outputs_) data_file->append(f.data_file);
+    return Status::OK();
+  }
+
   // Variant for DBs whose CompactionFeed chain must see every surviving entry on the host (e.g. the
   // packed-row repacker): the GPU still does decode + merge + retention, the host feed gets the
   // stream in order (compaction_job.cc:797-800 semantics: first non-OK aborts).

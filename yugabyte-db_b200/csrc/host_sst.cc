@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 #if defined(__SSE4_2__)
 #include <nmmintrin.h>
@@ -111,6 +112,19 @@ std::string ParseSplitSstMeta(const uint8_t* meta, uint64_t len, SstMeta* out) {
     Handle index = ReadHandle(&p, f + 41);
     BlockCursor mi(BlockAt(meta, len, metaindex), metaindex.size);
     while (mi.Next()) {
+      if (mi.key.compare(0, 16, "fixedsizefilter.") == 0) {
+        out->filter_policy_name = mi.key.substr(16);
+        const uint8_t* vp = mi.val;
+        Handle fh = ReadHandle(&vp, mi.val + mi.vlen);
+        BlockCursor fi(BlockAt(meta, len, fh), fh.size);
+        while (fi.Next()) {
+          const uint8_t* hp = fi.val;
+          Handle bh = ReadHandle(&hp, fi.val + fi.vlen);
+          BlockAt(meta, len, bh);
+          out->filter_blocks.push_back(bh);
+          out->filter_index_keys.push_back(fi.key);
+        }
+      }
       if (mi.key == "rocksdb.properties") {
         const uint8_t* vp = mi.val;
         Handle ph = ReadHandle(&vp, mi.val + mi.vlen);
@@ -256,6 +270,7 @@ class IndexWriter {
     if (!has_next) InternalSuccessor(last_key); else InternalSeparator(last_key, next_key, next_len);
     AddEntry(0, *last_key, has_next ? std::string(reinterpret_cast<const char*>(next_key), next_len) : std::string(), has_next, h);
   }
+  void AddRaw(const std::string& index_key, bool has_next, const Handle& h) { AddEntry(0, index_key, std::string(), has_next, h); }
   bool ShouldFlush(size_t lv = 0) const {
     const Level& L = *levels_[lv];
     return L.ready.on || (L.to_parent.on && !L.to_parent.has_next) || (lv + 1 < levels_.size() && ShouldFlush(lv + 1));
@@ -390,6 +405,27 @@ void MetaFileWriter::AddFilterBlock(const uint8_t* contents, size_t len, std::st
                      reinterpret_cast<const uint8_t*>(enc.data()), enc.size());
 }
 
+void MetaFileWriter::AddDataBlockRaw(const std::string& index_key, bool has_next, const Handle& h) {
+  index_->AddRaw(index_key, has_next, h);
+  while (index_->ShouldFlush()) {
+    std::string contents;
+    if (!index_->FlushNext(&contents, last_index_, last_index_set_)) throw std::runtime_error("index flush failed");
+    AppendBlock(contents, &last_index_);
+    last_index_set_ = true;
+    num_index_blocks_++;
+  }
+}
+
+void MetaFileWriter::AddFilterBlockRaw(const uint8_t* contents, size_t len, const std::string& filter_index_key) {
+  Handle h;
+  AppendBlock(std::string(reinterpret_cast<const char*>(contents), len), &h);   // + trailer (type byte, masked CRC32C)
+  filter_size_ += len + kTrailer;
+  num_filter_blocks_++;
+  std::string enc; AppendVarint(&enc, h.offset); AppendVarint(&enc, h.size);
+  filter_index_->Add(reinterpret_cast<const uint8_t*>(filter_index_key.data()), filter_index_key.size(),
+                     reinterpret_cast<const uint8_t*>(enc.data()), enc.size());
+}
+
 void MetaFileWriter::Finish(const MetaProps& mp) {
   std::string top;
   const bool have_top = index_->FlushNext(&top, last_index_, last_index_set_);
@@ -515,6 +551,99 @@ void SplitSstWriter::Finish() {
   mp.raw_key_size = raw_key_; mp.raw_value_size = raw_val_; mp.data_size = data_size_; mp.num_entries = num_entries_;
   mp.num_data_blocks = num_data_blocks_; mp.deleted_keys = deleted_keys_;
   metaw_.Finish(mp);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Concatenation of finished split SSTs with ascending, disjoint key ranges (the per-range outputs of a
+// compaction run as subcompactions) into one table: see host_sst.h. Index keys inside a piece are
+// reused; only the entry of a piece's LAST block (a short successor of its last key when the piece
+// was written: index_builder.cc:72-77) is recomputed as the separator between the piece's largest key
+// and the next piece's smallest, and likewise the index key of its last filter block.
+static uint64_t PropVarint(const SstMeta& m, const char* name) {
+  auto it = m.properties.find(name);
+  if (it == m.properties.end()) return 0;
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(it->second.data());
+  uint64_t v = 0;
+  if (!ReadVarint(&p, p + it->second.size(), &v)) return 0;
+  return v;
+}
+
+std::string ConcatSplitSstMeta(const TableOptions& o, const std::vector<SstPiece>& pieces, std::string* meta_out) {
+  try {
+    std::vector<SstMeta> metas(pieces.size());
+    {
+      // the pieces' indexes are walked side by side (a 30 GB table has ~10^6 index entries)
+      std::vector<std::string> errs(pieces.size());
+      std::vector<std::thread> pool;
+      for (size_t i = 0; i < pieces.size(); i++)
+        pool.emplace_back([&, i] { errs[i] = ParseSplitSstMeta(pieces[i].meta, pieces[i].meta_len, &metas[i]); });
+      for (std::thread& t : pool) t.join();
+      for (size_t i = 0; i < pieces.size(); i++)
+        if (!errs[i].empty()) return "piece " + std::to_string(i) + ": " + errs[i];
+    }
+    uint64_t total_meta = 0;
+    for (size_t i = 0; i < pieces.size(); i++) {
+      total_meta += pieces[i].meta_len;
+      const SstMeta& m = metas[i];
+      if (m.data_blocks.empty()) return "piece " + std::to_string(i) + " has no data blocks";
+      if (m.key_encoding != o.key_encoding) return "pieces use a different data block key encoding than the output table options";
+      if ((o.filter_policy != 0) != !m.filter_blocks.empty()) return "filter blocks of piece " + std::to_string(i) + " do not match the output table options";
+      if (o.filter_policy && m.filter_policy_name != "DocKeyV3Filter") return "unknown filter policy " + m.filter_policy_name;
+      if (pieces[i].smallest.size() < 8 || pieces[i].largest.size() < 8) return "piece boundary keys are missing";
+      if (i && CompareBytes(pieces[i - 1].largest.substr(0, pieces[i - 1].largest.size() - 8),
+                            pieces[i].smallest.substr(0, pieces[i].smallest.size() - 8)) >= 0)
+        return "pieces are not in ascending, disjoint key order";
+      const Handle& last = m.data_blocks.back();
+      if (last.offset + last.size + kTrailer > pieces[i].data_len) return "piece " + std::to_string(i) + ": data file shorter than its index says";
+    }
+    MetaFileWriter w(o);
+    w.Reserve(total_meta + total_meta / 4 + 65536);
+    MetaProps mp;
+    uint64_t base = 0;
+    for (size_t i = 0; i < pieces.size(); i++) {
+      const SstMeta& m = metas[i];
+      const bool last_piece = i + 1 == pieces.size();
+      // filter blocks of this piece first: the order of blocks inside the metadata file is free, the handles
+      // in the filter index are what readers follow
+      for (size_t f = 0; f < m.filter_blocks.size(); f++) {
+        std::string key = m.filter_index_keys[f];
+        if (f + 1 == m.filter_blocks.size() && !last_piece) {
+          const std::string& lk = pieces[i].largest; const std::string& nk = pieces[i + 1].smallest;
+          const int fl = docdb_filter_prefix_len(reinterpret_cast<const uint8_t*>(lk.data()), static_cast<int>(lk.size() - 8));
+          const int fn = docdb_filter_prefix_len(reinterpret_cast<const uint8_t*>(nk.data()), static_cast<int>(nk.size() - 8));
+          if (fl <= 0 || fn <= 0) return "a piece boundary key has no bloom filter key (not a DocKey): cannot place the filter index entry";
+          key.assign(lk.data(), fl);
+          ShortenUserSeparator(&key, reinterpret_cast<const uint8_t*>(nk.data()), static_cast<size_t>(fn));
+        }
+        w.AddFilterBlockRaw(pieces[i].meta + m.filter_blocks[f].offset, m.filter_blocks[f].size, key);
+      }
+      for (size_t b = 0; b < m.data_blocks.size(); b++) {
+        const bool last_block = b + 1 == m.data_blocks.size();
+        Handle h = m.data_blocks[b];
+        h.offset += base;
+        if (last_block && !last_piece) {
+          std::string key = pieces[i].largest;
+          InternalSeparator(&key, reinterpret_cast<const uint8_t*>(pieces[i + 1].smallest.data()), pieces[i + 1].smallest.size());
+          w.AddDataBlockRaw(key, true, h);
+        } else {
+          w.AddDataBlockRaw(m.separators[b], !(last_block && last_piece), h);
+        }
+      }
+      base += pieces[i].data_len;
+      mp.raw_key_size += PropVarint(m, "rocksdb.raw.key.size");
+      mp.raw_value_size += PropVarint(m, "rocksdb.raw.value.size");
+      mp.num_entries += PropVarint(m, "rocksdb.num.entries");
+      mp.num_data_blocks += PropVarint(m, "rocksdb.num.data.blocks");
+      mp.deleted_keys += PropVarint(m, "rocksdb.deleted.keys");
+    }
+    mp.data_size = base;
+    w.Finish(mp);
+    w.TakeMetaFile(meta_out);
+    return std::string();
+  } catch (const std::exception& ex) {
+    return ex.what();
+  }
 }
 
 }  // namespace host

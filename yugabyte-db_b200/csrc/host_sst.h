@@ -29,6 +29,11 @@ struct SstMeta {
   int key_encoding = 1;
   int index_levels = 1;
   std::map<std::string, std::string> properties;
+  // fixed-size bloom filter blocks (metaindex entry "fixedsizefilter.<policy>"): handles inside the metadata
+  // file and the keys of the filter index, in index order
+  std::string filter_policy_name;
+  std::vector<Handle> filter_blocks;
+  std::vector<std::string> filter_index_keys;
 };
 // Returns empty string on success, else an error message.
 std::string ParseSplitSstMeta(const uint8_t* meta, uint64_t len, SstMeta* out);
@@ -87,8 +92,13 @@ class MetaFileWriter {
   // (block_based_table_builder.cc:594-620). `last_filter_key` = last key added to this block,
   // `next_key` = first key of the next filter block (has_next = false for the final flush).
   void AddFilterBlock(const uint8_t* contents, size_t len, std::string* last_filter_key, const uint8_t* next_key, size_t next_len, bool has_next);
+  // Entries whose index keys are already final (re-emitting the blocks of finished files).
+  void AddDataBlockRaw(const std::string& index_key, bool has_next, const Handle& h);
+  void AddFilterBlockRaw(const uint8_t* contents, size_t len, const std::string& filter_index_key);
   void Finish(const MetaProps& p);
   const std::string& meta_file() const { return meta_; }
+  void Reserve(size_t bytes) { meta_.reserve(bytes); }
+  void TakeMetaFile(std::string* out) { out->swap(meta_); }
  private:
   void AppendBlock(const std::string& contents, Handle* h);
   TableOptions o_;
@@ -100,6 +110,18 @@ class MetaFileWriter {
   bool last_index_set_ = false;
   uint64_t num_index_blocks_ = 0;
 };
+
+// One piece of a concatenation (ConcatSplitSstMeta): a finished split SST whose keys all sort after the
+// previous piece's. smallest / largest = its first / last internal key.
+struct SstPiece {
+  const uint8_t* meta = nullptr; uint64_t meta_len = 0;
+  uint64_t data_len = 0;
+  std::string smallest, largest;
+};
+// Metadata file of the split SST whose data file is the pieces' data files back to back: one multi-level
+// index over all data blocks (offsets rebased), every filter block with one filter index, summed
+// properties. Nothing in the data files is re-encoded. Returns "" or an error message.
+std::string ConcatSplitSstMeta(const TableOptions& o, const std::vector<SstPiece>& pieces, std::string* meta_out);
 
 // rocksdb::TableBuilder shape: Add / Finish / NumEntries / TotalFileSize / status.
 class SplitSstWriter {
