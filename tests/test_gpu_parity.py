@@ -414,3 +414,26 @@ def test_reference_golden_dumps_on_gpu(pkg):
     finally:
         t.EXTRA_CHECK = None
     assert len(replayed) >= 20
+
+
+def test_subcompaction_outputs_concatenate_into_one_table(pkg):
+    """ybgpu_compact_files + ybgpu_sst_concat_meta: the GPU's range outputs, appended in range order under one
+    rebuilt index / filter index, are a single table holding exactly the single-job KV stream."""
+    cfg = o.GenConfig(seed=37, num_rows=8000, cols=2, versions=3, num_files=5, value_len=80, tombstone_per_1024=40)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=4096))
+    cutoff = o.ht_from_micros(cfg.base_micros + 1500)
+    topt = o.TableOptions(block_size=4096, filter_policy=1, filter_block_size=4096)
+    exp = o.compact(ssts, o.CompactionParams(cutoff_ht=cutoff), topt)
+    res = pkg.compact_files([(s.meta_view(), s.data_view()) for s in ssts], max_subcompactions=6, max_in_flight=3,
+                            cutoff_ht=cutoff, block_size=4096, filter_policy=1, filter_block_size=4096)
+    outs = [x for x in res.outputs if x.data_len]
+    assert len(outs) >= 3
+    pieces = [(res.meta_arena[x.meta_offset:x.meta_offset + x.meta_len], x.data_len, x.smallest, x.largest) for x in outs]
+    meta = pkg.sst_concat_meta(pieces, block_size=4096, filter_policy=1, filter_block_size=4096)
+    data = b"".join(res.data_arena[x.data_offset:x.data_offset + x.data_len].tobytes() for x in outs)
+    whole = o.Sst.from_bytes(meta, data)
+    assert whole.read_all() == exp.kv_list()
+    assert o.varint(whole.properties()["rocksdb.num.entries"]) == exp.stats.num_output_records
+    # and the table is a valid INPUT of the next compaction
+    job = gpu_compact(pkg, [whole], cutoff_ht=cutoff, block_size=4096)
+    assert job.kv_list() == exp.kv_list()
