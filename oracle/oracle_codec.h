@@ -6,7 +6,10 @@
 //
 // Every function cites the reference file:line it restates (paths relative to
 // /root/reference/src/yb/).  Nothing here is copied from the reference; it is rewritten from the
-// behaviour read there and pinned by the reference's own golden vectors (tests/test_oracle_*.py).
+// behaviour read there and pinned by the reference's own golden vectors (tests/test_oracle_*.py) and
+// by the reference's debug dumps replayed verbatim (tests/test_reference_dumps.py): parity PINNED for
+// the codecs, the merge / CompactionIterator rules and the retention predicate; see DESIGN.md §2 for the
+// pieces no reference test fixes byte-wise (metadata file layout, three_shared_parts entry bytes).
 #pragma once
 
 #include <cstdint>
