@@ -104,6 +104,13 @@ typedef struct ybgpu_job_options {
    * with a filter index (block_based_table_builder.cc:514-528,594-620,795-830). */
   int32_t filter_policy;             /* YBGPU_FILTER_* ; default none */
   uint32_t filter_block_size;        /* bytes; 65536 */
+
+  /* --- yield points (PriorityThreadPoolSuspender::PauseIfNecessary, which the reference honours at its
+   * file-write points: util/file_reader_writer.cc:343, compaction_job.cc:156-169) --- called on the job's
+   * host thread between kernel phases of ybgpu_job_run and, by ybgpu_compact_files, before every range is
+   * started; it may block for as long as the scheduler wants the compaction paused. NULL = none. */
+  void (*yield_fn)(void* ctx);
+  void* yield_ctx;
 } ybgpu_job_options;
 
 void ybgpu_job_options_init(ybgpu_job_options* o);   /* reference defaults */

@@ -259,3 +259,24 @@ def test_sst_concat_meta_builds_one_valid_table(pkg, enc, with_filter):
         pkg.sst_concat_meta(pieces[::-1], block_size=2048, output_key_encoding=enc, filter_policy=int(with_filter), filter_block_size=1024)
     with pytest.raises(pkg.YbGpuError):
         pkg.sst_concat_meta(pieces, block_size=2048, output_key_encoding=3 - enc, filter_policy=int(with_filter), filter_block_size=1024)
+
+
+def test_ctypes_structs_match_the_header(pkg, tmp_path):
+    """The Python binding mirrors the C structs by hand: sizes and the offsets of the trailing fields must
+    agree with what a C compiler makes of include/ybgpu_compaction.h (ybgpu_job_options_init memsets the
+    whole struct)."""
+    import ctypes as C
+    import subprocess
+    b = importlib.import_module("yugabyte-db_b200.binding")
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\n'
+                   'int main(void) { printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(ybgpu_job_options), sizeof(ybgpu_job_stats),'
+                   ' sizeof(ybgpu_sub_output), sizeof(ybgpu_sst_piece), sizeof(ybgpu_input_file), offsetof(ybgpu_job_options, yield_fn),'
+                   ' offsetof(ybgpu_job_options, cuda_stream), offsetof(ybgpu_sub_output, smallest_key)); return 0; }\n'
+                   % os.path.join(ROOT, "include", "ybgpu_compaction.h"))
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    want = [C.sizeof(b.JobOptions), C.sizeof(b.JobStats), C.sizeof(b.SubOutput), C.sizeof(b.SstPiece), C.sizeof(b.InputFile),
+            b.JobOptions.yield_fn.offset, b.JobOptions.cuda_stream.offset, b.SubOutput.smallest_key.offset]
+    assert got == want

@@ -437,3 +437,17 @@ def test_subcompaction_outputs_concatenate_into_one_table(pkg):
     # and the table is a valid INPUT of the next compaction
     job = gpu_compact(pkg, [whole], cutoff_ht=cutoff, block_size=4096)
     assert job.kv_list() == exp.kv_list()
+
+
+def test_yield_points(pkg):
+    """The scheduler's pause hook (PriorityThreadPoolSuspender::PauseIfNecessary in the reference) is honoured
+    between kernel phases of a job and between the ranges of a compaction run as subcompactions."""
+    cfg = o.GenConfig(seed=3, num_rows=3000, cols=2, versions=2, num_files=3, value_len=40)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=4096))
+    calls = []
+    job = gpu_compact(pkg, ssts, block_size=4096, yield_fn=lambda: calls.append(1))
+    assert len(calls) >= 3 and job.stats().num_input_records == 12000
+    calls.clear()
+    res = pkg.compact_files([(s.meta_view(), s.data_view()) for s in ssts], max_subcompactions=4, max_in_flight=2,
+                            block_size=4096, yield_fn=lambda: calls.append(1))
+    assert len(calls) >= len(res.outputs) and res.total.num_input_records == 12000

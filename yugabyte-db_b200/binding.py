@@ -40,7 +40,11 @@ class JobOptions(C.Structure):
         ("range_upper", C.c_char_p), ("range_upper_len", C.c_uint64),
         ("cuda_stream", C.c_void_p),
         ("filter_policy", C.c_int32), ("filter_block_size", C.c_uint32),
+        ("yield_fn", C.c_void_p), ("yield_ctx", C.c_void_p),
     ]
+
+
+YIELD_FN = C.CFUNCTYPE(None, C.c_void_p)
 
 
 class BlockHandle(C.Structure):
@@ -142,8 +146,9 @@ def make_options(device=0, bottommost=True, last_sequence=MAX_SEQUENCE, largest_
                  retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
                  restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
                  min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b"",
-                 filter_policy=0, filter_block_size=65536):
-    """ybgpu_job_options from keyword arguments; returns (options, objects to keep alive)."""
+                 filter_policy=0, filter_block_size=65536, yield_fn=None):
+    """ybgpu_job_options from keyword arguments; returns (options, objects to keep alive). yield_fn: a Python
+    callable() invoked at the engine's yield points (PauseIfNecessary)."""
     L = lib()
     o = JobOptions()
     L.ybgpu_job_options_init(C.byref(o))
@@ -168,7 +173,11 @@ def make_options(device=0, bottommost=True, last_sequence=MAX_SEQUENCE, largest_
     o.cuda_stream = cuda_stream
     o.range_lower, o.range_lower_len = range_lower, len(range_lower)
     o.range_upper, o.range_upper_len = range_upper, len(range_upper)
-    return o, (largest_user_key, lower, upper, range_lower, range_upper)
+    cb = None
+    if yield_fn is not None:
+        cb = YIELD_FN(lambda _ctx: yield_fn())
+        o.yield_fn = C.cast(cb, C.c_void_p)
+    return o, (largest_user_key, lower, upper, range_lower, range_upper, cb)
 
 
 class GpuCompactionJob:
@@ -179,13 +188,13 @@ class GpuCompactionJob:
                  retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
                  restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
                  min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b"",
-                 filter_policy=0, filter_block_size=65536):
+                 filter_policy=0, filter_block_size=65536, yield_fn=None):
         L = lib()
         o, self._keep = make_options(device, bottommost, last_sequence, largest_user_key, retention, cutoff_ht,
                                      cotables_cutoff_ht, table_ttl_ns, retain_delete_markers, other_min_ht, lower, upper,
                                      block_size, restart_interval, deviation, output_key_encoding, index_block_size,
                                      min_keys_per_index_block, verify_checksums, cuda_stream, range_lower, range_upper,
-                                     filter_policy, filter_block_size)
+                                     filter_policy, filter_block_size, yield_fn)
         h = C.c_void_p()
         st = L.ybgpu_job_create(C.byref(o), C.byref(h))
         if st != 0:

@@ -149,6 +149,10 @@ class GpuCompactionJob {
     // compaction_job.cc:409-519) that run pipelined on private streams, one output file per range.
     uint32_t max_subcompactions = 1;
     uint32_t subcompactions_in_flight = 3;
+    // Yield point, e.g. [](void* s) { static_cast<yb::PriorityThreadPoolSuspender*>(s)->PauseIfNecessary(); }
+    // (util/file_reader_writer.cc:343): called between kernel phases and between subcompaction ranges.
+    void (*yield_fn)(void*) = nullptr;
+    void* yield_ctx = nullptr;
   };
 
   explicit GpuCompactionJob(const Params& p) : p_(p) {}
@@ -180,6 +184,7 @@ class GpuCompactionJob {
     o.block_size_deviation = p_.block_size_deviation; o.index_block_size = p_.index_block_size;
     o.min_keys_per_index_block = p_.min_keys_per_index_block; o.verify_checksums = p_.verify_checksums;
     o.output_key_encoding = p_.output_key_encoding; o.filter_policy = p_.filter_policy; o.filter_block_size = p_.filter_block_size;
+    o.yield_fn = p_.yield_fn; o.yield_ctx = p_.yield_ctx;
     options_ = o;
     inputs_ = inputs;
     if (p_.max_subcompactions > 1) return Status::OK();      // every range creates its own job in Run()

@@ -1562,7 +1562,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   }
   const int sms = sm_count[opt_.device & 63];
   const int k = static_cast<int>(I.runs.size());
-  auto shutdown = [&]() { return shutting_down && *shutting_down; };
+  // the yield point sits where the shutdown flag is polled: between kernel phases
+  auto shutdown = [&]() {
+    if (opt_.yield_fn) opt_.yield_fn(opt_.yield_ctx);
+    return shutting_down && *shutting_down;
+  };
   uint32_t launches = 0;
 
   CUDA_TRY(cudaMemsetAsync(I.dJ, 0, sizeof(JobDev), I.stream));

@@ -371,6 +371,8 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
   auto worker = [&]() {
     for (;;) {
       if (failed.load()) return;
+      if (options->yield_fn) options->yield_fn(options->yield_ctx);      // PauseIfNecessary between ranges
+      if (shutting_down && *shutting_down) { record_failure(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction"); return; }
       const uint32_t r = next_range.fetch_add(1);
       if (r >= n_ranges) return;
       run_range(r);
