@@ -291,8 +291,8 @@ void SkipKeyEntry(Slice* s) {
     }
     case kt::kIntentTypeSet: case kt::kObsoleteIntentTypeSet: case kt::kObsoleteIntentType:
       NeedBytes(*s, 1, "TypeSet"); s->remove_prefix(1); return;
-    case kt::kBson: case kt::kBsonDescending:
-      throw NotSupported("bson key components are not restated in the oracle");
+    case kt::kBson: SkipEncodedStr(s, 0x00); return;             // dockv/doc_bson.cc:33-35: a zero-encoded string
+    case kt::kBsonDescending: SkipEncodedStr(s, 0xff); return;   // :46-48: its complement
     default:
       throw Corruption("Cannot decode value type from the key encoding format");
   }

@@ -75,6 +75,14 @@ def decimal_comparable(digits, exponent, positive=True):
     return bytes(out)
 
 
+def kbson(b):
+    return Enc(b"o" + zero_encode(b))                       # dockv/doc_bson.cc:29-31 BsonKeyToComparableBinary
+
+
+def kbson_desc(b):
+    return Enc(b"p" + bytes((~c) & 0xff for c in zero_encode(b)))
+
+
 class Enc(bytes):
     """An already encoded key entry (kprim passes it through whatever its first byte is)."""
 

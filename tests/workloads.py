@@ -122,15 +122,18 @@ def random_cotable_runs(seed, n_runs=3, n_tables=4, rows_per_table=12, colocated
 
 
 def random_numeric_key_runs(seed, n_runs=3, n_rows=40, n_ht=12):
-    """Rows whose DocKeys / subkeys carry kVarInt / kDecimal components (YSQL numeric, YCQL varint /
-    decimal primary keys) in both sort orders; several versions per column, tombstones."""
+    """Rows whose DocKeys / subkeys carry kVarInt / kDecimal / kBson components (YSQL numeric, YCQL varint /
+    decimal primary keys, bson keys) in both sort orders; several versions per column, tombstones."""
     rng = random.Random(seed)
     runs = [[] for _ in range(n_runs)]
     seq = [(1 << 50) + (r << 30) for r in range(n_runs)]
     used = set()
 
     def numeric():
-        x = rng.randrange(4)
+        x = rng.randrange(5)
+        if x == 4:                                           # kBson / kBsonDescending: (complement) zero-encoded bytes
+            raw = bytes(rng.randrange(256) for _ in range(rng.randrange(0, 12)))
+            return dk.kbson(raw) if rng.random() < 0.5 else dk.kbson_desc(raw)
         if x == 0:
             return dk.kvarint(rng.randrange(-10**rng.randrange(1, 30), 10**rng.randrange(1, 30)))
         if x == 1:

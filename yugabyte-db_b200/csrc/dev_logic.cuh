@@ -40,7 +40,7 @@ enum DevError : int {
   DEV_ERR_KEY_TOO_LONG = 4,
   DEV_ERR_IRREGULAR_RESTARTS = 5, // restart intervals of different sizes inside one file
   DEV_ERR_BAD_KEY = 6,            // DocKey / SubDocKey component decode failed
-  DEV_ERR_UNSUPPORTED_KEY = 7,    // bson components, vector-index metadata keys
+  DEV_ERR_UNSUPPORTED_KEY = 7,    // vector-index metadata keys, frozen containers nested deeper than 4
   DEV_ERR_TILE_OVERFLOW = 8,      // one DocKey group larger than a merge tile
   DEV_ERR_BAD_HT = 9,             // DocHybridTime at the end of a key is malformed
   DEV_ERR_BAD_VALUE = 10,         // value control fields malformed
@@ -326,9 +326,9 @@ YB_HD_NOINLINE int key_entry_size_flat(const uint8_t* p, int n) {   // everythin
   }
   if (fixed >= 0) return (n - 1 < fixed) ? -DEV_ERR_BAD_KEY : 1 + fixed;
   switch (t) {
-    case 'S': case '\\': case '-': case 'x': case 'y': case '_':                    // zero-terminated strings
-    case 'a': case ']': case '.': case '`': {                                       // complemented variants
-      const uint8_t endb = (t == 'a' || t == ']' || t == '.' || t == '`') ? 0xff : 0x00;
+    case 'S': case '\\': case '-': case 'x': case 'y': case '_': case 'o':          // zero-terminated strings (kBson: dockv/doc_bson.cc:33-35)
+    case 'a': case ']': case '.': case '`': case 'p': {                             // complemented variants (kBsonDescending: :46-48)
+      const uint8_t endb = (t == 'a' || t == ']' || t == '.' || t == '`' || t == 'p') ? 0xff : 0x00;
       int i = 1;
       if (i >= n) return -DEV_ERR_BAD_KEY;                  // "Encoded string is empty"
       for (;;) {
@@ -378,8 +378,6 @@ YB_HD_NOINLINE int key_entry_size_flat(const uint8_t* p, int n) {   // everythin
       const int k = comparable_decimal_size(p + 1, n - 1);
       return k < 0 ? k : 1 + k;
     }
-    case 'o': case 'p':
-      return -DEV_ERR_UNSUPPORTED_KEY;                      // bson comparable encodings
     default:
       return -DEV_ERR_BAD_KEY;
   }

@@ -69,7 +69,7 @@ bool ParseInputs(const ybgpu_input_file* files, uint32_t n, std::vector<ParsedIn
 //     which no other complete DocKey is a proper prefix;
 //   * if it fails with a malformed key (FindShortestSeparator cut the separator inside a
 //     component), the separator does not start with any complete DocKey and is used whole;
-//   * if it stops at a component it cannot size (bson), the separator is skipped.
+//   * if it stops at a key the engine does not take (vector-index metadata), the separator is skipped.
 std::vector<std::string> PlanSplitters(const std::vector<ParsedInput>& in, uint32_t n_ranges, bool docdb_keys) {
   std::vector<std::string> out;
   if (n_ranges <= 1) return out;
