@@ -19,6 +19,14 @@ int main(int argc, char** argv) {
   tb.Add(Slice(k1), Slice(std::string("v1")));
   tb.Add(Slice(k2), Slice(std::string("v2")));
   if (!tb.Finish().ok() || tb.NumEntries() != 2) { printf("table builder failed\n"); return 1; }
+  {   // compaction_job_test.cc:389-436 SeqNoTrackingWithFewDeletes: inputs 3..4 and 1..2, the one survivor zeroed => 0..4
+    InputFile f1, f2; f1.smallest_seqno = 3; f1.largest_seqno = 4; f2.smallest_seqno = 1; f2.largest_seqno = 2;
+    uint64_t lo = 99, hi = 99;
+    GpuCompactionJob::SeqnoBounds({f1, f2}, 0, 0, 1, &lo, &hi);
+    if (lo != 0 || hi != 4) { printf("seqno bounds %llu..%llu\n", (unsigned long long)lo, (unsigned long long)hi); return 1; }
+    GpuCompactionJob::SeqnoBounds({InputFile(), InputFile()}, 7, 9, 2, &lo, &hi);      // inputs' bounds unknown: survivors only
+    if (lo != 7 || hi != 9) { printf("seqno bounds (untracked inputs)\n"); return 1; }
+  }
   if (mode == "cpu") {
     if (ybgpu_device_count() == 0) {
       GpuCompactionJob job(GpuCompactionJob::Params{});

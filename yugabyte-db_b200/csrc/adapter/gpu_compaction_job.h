@@ -94,6 +94,10 @@ struct InputFile {
   Slice base_file;            // <n>.sst (metadata file) bytes
   Slice data_file;            // <n>.sst.sblock.0 bytes
   uint64_t hybrid_time_filter = YBGPU_HT_INVALID;   // FdWithBoundaries::user_filter_data (:3824)
+  // FileMetaData::smallest.seqno / largest.seqno of the input (db/version_edit.h:101-165). The reference seeds
+  // every output file's seqno bounds with the union over the inputs (compaction_job.cc:1188-1195) before the
+  // surviving entries extend them; leave the defaults when the caller does not track them.
+  uint64_t smallest_seqno = YBGPU_MAX_SEQUENCE, largest_seqno = 0;
 };
 
 // TableBuilder over the product's host writer (what TableFactory::NewTableBuilder returns when the
@@ -314,11 +318,23 @@ class GpuCompactionJob {
   // REQUIRED: mutex held. In the reference this adds the output FileMetaData to a VersionEdit
   // (compaction_job.cc:1098-1141); here it hands the caller what that edit needs.
   struct OutputMeta { std::string smallest_key, largest_key; uint64_t smallest_seqno = 0, largest_seqno = 0, num_entries = 0; };
+  // Output seqno bounds the way the reference computes them: the union of the inputs' FileMetaData bounds
+  // (UpdateBoundariesExceptKey, compaction_job.cc:1188-1195; db/version_edit.cc:133-152) extended by every
+  // surviving entry's (possibly zeroed) sequence number (SubcompactionState::Feed, :156-169) — which is what the
+  // engine reports. E.g. compaction_job_test.cc:389-436: inputs 3..4 and 1..2, one survivor rewritten to
+  // seqno 0 => output bounds 0..4.
+  static void SeqnoBounds(const std::vector<InputFile>& inputs, uint64_t kept_smallest, uint64_t kept_largest, uint64_t num_kept,
+                          uint64_t* smallest, uint64_t* largest) {
+    uint64_t lo = YBGPU_MAX_SEQUENCE, hi = 0;
+    for (const InputFile& f : inputs) { lo = f.smallest_seqno < lo ? f.smallest_seqno : lo; hi = f.largest_seqno > hi ? f.largest_seqno : hi; }
+    if (num_kept) { lo = kept_smallest < lo ? kept_smallest : lo; hi = kept_largest > hi ? kept_largest : hi; }
+    *smallest = lo == YBGPU_MAX_SEQUENCE && !num_kept ? 0 : lo; *largest = hi;
+  }
   Status Install(OutputMeta* meta) {
     if (p_.max_subcompactions > 1) {          // per-file metadata is in outputs(); this is the union
       *meta = OutputMeta();
       if (!outputs_.empty()) { meta->smallest_key = outputs_.front().smallest_key; meta->largest_key = outputs_.back().largest_key; }
-      meta->smallest_seqno = stats_.smallest_seqno; meta->largest_seqno = stats_.largest_seqno;
+      SeqnoBounds(inputs_, stats_.smallest_seqno, stats_.largest_seqno, stats_.num_output_records, &meta->smallest_seqno, &meta->largest_seqno);
       meta->num_entries = stats_.num_output_records;
       return Status::OK();
     }
@@ -327,7 +343,7 @@ class GpuCompactionJob {
     if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
     meta->smallest_key.assign(reinterpret_cast<char*>(a), al);
     meta->largest_key.assign(reinterpret_cast<char*>(b), bl);
-    meta->smallest_seqno = stats_.smallest_seqno; meta->largest_seqno = stats_.largest_seqno;
+    SeqnoBounds(inputs_, stats_.smallest_seqno, stats_.largest_seqno, stats_.num_output_records, &meta->smallest_seqno, &meta->largest_seqno);
     meta->num_entries = stats_.num_output_records;
     return Status::OK();
   }
