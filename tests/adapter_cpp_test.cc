@@ -27,6 +27,39 @@ int main(int argc, char** argv) {
     GpuCompactionJob::SeqnoBounds({InputFile(), InputFile()}, 7, 9, 2, &lo, &hi);      // inputs' bounds unknown: survivors only
     if (lo != 7 || hi != 9) { printf("seqno bounds (untracked inputs)\n"); return 1; }
   }
+  {   // ConcatFiles on host-built tables with disjoint key ranges: one index over all blocks, offsets rebased
+    ybgpu_job_options to; ybgpu_job_options_init(&to); to.block_size = 256;
+    std::vector<GpuCompactionJob::OutputFile> files;
+    uint64_t blocks = 0, total = 0;
+    for (int p = 0; p < 3; p++) {
+      GpuSideTableBuilder b(to);
+      GpuCompactionJob::OutputFile f;
+      for (int i = 0; i < 200; i++) {
+        char k[32]; snprintf(k, sizeof(k), "key%d%05d", p, i);
+        std::string ik = std::string(k) + std::string("\1\0\0\0\0\0\0\0", 8);
+        b.Add(Slice(ik), Slice(std::string(40, 'v')));
+        if (i == 0) f.smallest_key = ik;
+        f.largest_key = ik;
+      }
+      if (!b.Finish().ok()) { printf("piece build failed\n"); return 1; }
+      Slice d, m; b.Files(&d, &m);
+      f.data_file.assign(reinterpret_cast<const char*>(d.data()), d.size());
+      f.base_file.assign(reinterpret_cast<const char*>(m.data()), m.size());
+      uint64_t n = 0; int32_t enc = 0;
+      ybgpu_sst_meta_handles(m.data(), m.size(), nullptr, 0, &n, &enc);
+      blocks += n; total += d.size();
+      files.push_back(f);
+    }
+    std::string data, base;
+    Status cs = GpuCompactionJob::ConcatFiles(to, files, &data, &base);
+    if (!cs.ok()) { printf("concat: %s\n", cs.ToString().c_str()); return 1; }
+    uint64_t n = 0; int32_t enc = 0;
+    ybgpu_sst_meta_handles(reinterpret_cast<const uint8_t*>(base.data()), base.size(), nullptr, 0, &n, &enc);
+    std::vector<ybgpu_block_handle> h(n);
+    ybgpu_sst_meta_handles(reinterpret_cast<const uint8_t*>(base.data()), base.size(), h.data(), n, &n, &enc);
+    if (n != blocks || data.size() != total || h.back().offset + h.back().size + 5 != total) { printf("concat layout\n"); return 1; }
+    for (uint64_t i = 1; i < n; i++) if (h[i].offset != h[i - 1].offset + h[i - 1].size + 5) { printf("concat handles\n"); return 1; }
+  }
   if (mode == "cpu") {
     if (ybgpu_device_count() == 0) {
       GpuCompactionJob job(GpuCompactionJob::Params{});

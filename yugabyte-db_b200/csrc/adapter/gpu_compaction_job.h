@@ -269,6 +269,12 @@ class GpuCompactionJob {
   // is the outputs' data files appended in order (nothing is re-encoded), the metadata file is rebuilt over
   // all blocks by ybgpu_sst_concat_meta. Key/value bytes equal the single-job output.
   Status ConcatenatedOutput(std::string* data_file, std::string* base_file) const {
+    return ConcatFiles(options_, outputs_, data_file, base_file);
+  }
+  static Status ConcatFiles(const ybgpu_job_options& table_options, const std::vector<OutputFile>& files,
+                            std::string* data_file, std::string* base_file) {
+    const ybgpu_job_options& options_ = table_options;
+    const std::vector<OutputFile>& outputs_ = files;
     data_file->clear(); base_file->clear();
     if (outputs_.empty()) return Status::OK();
     std::vector<ybgpu_sst_piece> pieces;
