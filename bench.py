@@ -430,6 +430,25 @@ def main():
                   "h2d_bytes_per_step": int(res[-1][0]["h2d_bytes"]), "d2h_bytes_per_step": int(res[-1][0]["d2h_bytes"]),
                   "ms_per_step": round(e2e_s / args.steps * 1e3, 2), "output_file_bytes": int(res[-1][1]),
                   "host_ms_per_step": {k: round(v / args.steps, 2) for k, v in e2e_ms.items()}}
+        def verify_outputs(file_list, stride=257):
+            # host-side CRC32C check of every stride-th output data block (outside the timed regions): the full-size
+            # outputs cannot be compared with the oracle, but a wrong or torn device->host copy cannot pass this
+            try:
+                checked = bad = 0
+                for meta_v, data_v in file_list:
+                    c, b_ = pkg.sst_verify_blocks(meta_v, data_v, stride)
+                    checked += c
+                    bad += b_
+                return {"blocks_checked": int(checked), "bad_blocks": int(bad), "stride": stride}
+            except Exception as ex:
+                return {"error": "%s: %s" % (type(ex).__name__, ex)}
+
+        try:
+            dlen = int(res[-1][0]["output_data_file_size"])
+            mlen = int(res[-1][0]["output_meta_file_size"])
+            single["output_check"] = verify_outputs([(out_meta[:mlen], out_data[:dlen])])
+        except Exception as ex:
+            single["output_check"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
         e2e = dict(single, pinned_inputs=all(ok for _, ok in pinned), verify_checksums=bool(args.verify),
                    mode="one job, one output file")
         if args.subcompactions > 1:
@@ -439,9 +458,16 @@ def main():
                 r = pkg.compact_files(files, max_subcompactions=args.subcompactions, max_in_flight=args.in_flight,
                                       data_arena=out_data, meta_arena=out_meta, device=local_rank,
                                       verify_checksums=bool(args.verify), **job_kw)
+                last_sub[0] = r
                 return r.total.as_dict(), sum(o_.data_len + o_.meta_len for o_ in r.outputs), len(r.outputs)
 
+            last_sub = [None]
             sub_s, sres = timed(step_sub)
+            try:
+                sub_check = verify_outputs([(out_meta[o_.meta_offset:o_.meta_offset + o_.meta_len], out_data[o_.data_offset:o_.data_offset + o_.data_len])
+                                            for o_ in last_sub[0].outputs if o_.data_len])
+            except Exception as ex:
+                sub_check = {"error": "%s: %s" % (type(ex).__name__, ex)}
             assert sres[-1][0]["num_input_records"] == n_entries, "subcompactions must see every input entry once"
 
             # One table out of the range outputs (what a single-level universal layout such as DocDB's needs): the
@@ -478,7 +504,7 @@ def main():
                    "output_file_bytes": int(sres[-1][1]), "verify_checksums": bool(args.verify),
                    "mode": "ybgpu_compact_files: %d key-range subcompactions (max_subcompactions=%d), %d in flight on private "
                            "streams, one output SST per range" % (sres[-1][2], args.subcompactions, args.in_flight),
-                   "output_files": int(sres[-1][2]),
+                   "output_files": int(sres[-1][2]), "output_check": sub_check,
                    "gpu_ms_per_step": round(sres[-1][0]["gpu_seconds"] * 1e3, 2),
                    "one_table": one_table,
                    "single_job": single}

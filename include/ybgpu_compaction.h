@@ -282,6 +282,13 @@ typedef struct ybgpu_sst_piece {
 ybgpu_status ybgpu_sst_concat_meta(const ybgpu_job_options* table_options, const ybgpu_sst_piece* pieces,
                                    uint32_t num_pieces, uint8_t* meta_out, uint64_t meta_cap, uint64_t* meta_len);
 
+/* Host-side integrity check of a split SST: walks the index of `meta_file` and verifies the trailer of every
+ * `stride`-th data block (type byte kNoCompression + masked CRC32C over contents and type, format.cc:352-395) in
+ * `data_file`; stride 1 = every block. Used by bench.py on the full-size outputs it cannot compare with the
+ * oracle. *bad_blocks > 0 => YBGPU_CORRUPTION. */
+ybgpu_status ybgpu_sst_verify_blocks(const uint8_t* meta_file, uint64_t meta_file_len, const uint8_t* data_file,
+                                     uint64_t data_file_len, uint32_t stride, uint64_t* blocks_checked, uint64_t* bad_blocks);
+
 /* Last internal key of a split SST (its last data block is decoded on the host): what
  * FileMetaData::largest holds for the file. key must hold 1032 bytes. */
 ybgpu_status ybgpu_sst_last_key(const uint8_t* meta_file, uint64_t meta_file_len, const uint8_t* data_file,

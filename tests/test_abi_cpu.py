@@ -280,3 +280,17 @@ def test_ctypes_structs_match_the_header(pkg, tmp_path):
     want = [C.sizeof(b.JobOptions), C.sizeof(b.JobStats), C.sizeof(b.SubOutput), C.sizeof(b.SstPiece), C.sizeof(b.InputFile),
             b.JobOptions.yield_fn.offset, b.JobOptions.cuda_stream.offset, b.SubOutput.smallest_key.offset]
     assert got == want
+
+
+def test_sst_verify_blocks_detects_corruption(pkg):
+    cfg = o.GenConfig(seed=9, num_rows=3000, cols=2, versions=2, num_files=1, value_len=60)
+    sst = o.Sst.generate(cfg, 0, o.TableOptions(block_size=1024))
+    nb = len(sst.block_handles()[0])
+    assert pkg.sst_verify_blocks(sst.meta_view(), sst.data_view()) == (nb, 0)
+    assert pkg.sst_verify_blocks(sst.meta_view(), sst.data_view(), stride=7) == ((nb + 6) // 7, 0)
+    bad = sst.data_view().copy()
+    off, sz = sst.block_handles()
+    bad[int(off[3]) + 10] ^= 0x40                    # one flipped bit inside block 3
+    assert pkg.sst_verify_blocks(sst.meta_view(), bad) == (nb, 1)
+    assert pkg.sst_verify_blocks(sst.meta_view(), bad, stride=2) == ((nb + 1) // 2, 0)      # block 3 is not sampled
+    assert pkg.sst_verify_blocks(sst.meta_view(), sst.data_view()[:int(off[-1])].copy())[1] == 1   # truncated data file: last block missing

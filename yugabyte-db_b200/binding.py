@@ -549,3 +549,16 @@ def sst_concat_meta(pieces, out=None, **table_kwargs):
     if st != 0:
         raise YbGpuError(st, L.ybgpu_last_error().decode())
     return buf[:n.value] if out is not None else buf[:n.value].tobytes()
+
+
+def sst_verify_blocks(meta, data, stride=1):
+    """ybgpu_sst_verify_blocks: (blocks checked, bad blocks) — host-side CRC32C check of every stride-th data block."""
+    L = lib()
+    L.ybgpu_sst_verify_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    meta = np.ascontiguousarray(np.frombuffer(meta, np.uint8) if isinstance(meta, (bytes, bytearray)) else meta, dtype=np.uint8)
+    data = np.ascontiguousarray(np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+    n, bad = C.c_uint64(), C.c_uint64()
+    st = L.ybgpu_sst_verify_blocks(meta.ctypes.data, meta.size, data.ctypes.data, data.size, stride, C.byref(n), C.byref(bad))
+    if st not in (0, 2):
+        raise YbGpuError(st, L.ybgpu_last_error().decode())
+    return n.value, bad.value

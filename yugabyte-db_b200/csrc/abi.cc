@@ -408,6 +408,26 @@ ybgpu_status ybgpu_sst_concat_meta(const ybgpu_job_options* o, const ybgpu_sst_p
   return YBGPU_OK;
 }
 
+ybgpu_status ybgpu_sst_verify_blocks(const uint8_t* meta, uint64_t meta_len, const uint8_t* data, uint64_t data_len, uint32_t stride,
+                                     uint64_t* checked, uint64_t* bad) {
+  if (!meta || !data || !checked || !bad) return YBGPU_INVALID_ARGUMENT;
+  ybgpu::host::SstMeta m;
+  std::string err = ybgpu::host::ParseSplitSstMeta(meta, meta_len, &m);
+  if (!err.empty()) { g_last_error = err; return YBGPU_CORRUPTION; }
+  if (stride == 0) stride = 1;
+  *checked = 0; *bad = 0;
+  for (size_t i = 0; i < m.data_blocks.size(); i += stride) {
+    const ybgpu::host::Handle& h = m.data_blocks[i];
+    (*checked)++;
+    if (h.offset + h.size + 5 > data_len) { (*bad)++; continue; }
+    const uint8_t* p = data + h.offset;
+    uint32_t stored; memcpy(&stored, p + h.size + 1, 4);
+    if (p[h.size] != 0 || ybgpu::host::Crc32cMask(ybgpu::host::Crc32c(p, h.size + 1)) != stored) (*bad)++;
+  }
+  if (*bad) { g_last_error = "block checksum mismatch"; return YBGPU_CORRUPTION; }
+  return YBGPU_OK;
+}
+
 int32_t ybgpu_device_count(void);   // engine.cu
 const char* ybgpu_version(void) { return "ybgpu-compaction 0.1 (sm_100a)"; }
 
