@@ -10,7 +10,7 @@
  * (table/block_based_table_builder.cc:498-541).
  *
  * Plain pointers and sizes only; no C++/torch types.  Every entry point returns a ybgpu_status
- * (mapped 1:1 onto yb::Status codes by the C++ adapter) and fills the job's
+ * (numerically equal to yb::Status::Code, util/status_codes.h; the C++ adapter casts) and fills the job's
  * error string on failure.  There is no CPU fallback: if no CUDA device is usable, create fails
  * with YBGPU_RUNTIME_ERROR.
  *
@@ -28,17 +28,20 @@
 extern "C" {
 #endif
 
-/* yb::Status::Code subset (src/yb/util/status.h) used on this path. */
+/* yb::Status::Code values (src/yb/util/status_codes.h:14-43) used on this path; the numbers are the
+ * reference's, so the adapter's static_cast<Status::Code>(s) is exact (tests/golden/status_codes_table.json holds the
+ * table extracted from the reference header; tests/test_abi_cpu.py checks this enum against it). */
 typedef enum ybgpu_status {
   YBGPU_OK = 0,
   YBGPU_NOT_FOUND = 1,
-  YBGPU_CORRUPTION = 2,           /* bad block / entry / key encoding */
-  YBGPU_NOT_SUPPORTED = 3,        /* e.g. compressed block, packed row without schema provider */
+  YBGPU_CORRUPTION = 2,            /* bad block / entry / key encoding */
+  YBGPU_NOT_SUPPORTED = 3,         /* e.g. compressed output, packed row without schema provider */
   YBGPU_INVALID_ARGUMENT = 4,
   YBGPU_IO_ERROR = 5,
-  YBGPU_RUNTIME_ERROR = 9,        /* CUDA failure, out of device memory */
-  YBGPU_SHUTDOWN_IN_PROGRESS = 19, /* shutting_down flag observed (compaction_job.cc:820-824) */
-  YBGPU_ILLEGAL_STATE = 10
+  YBGPU_RUNTIME_ERROR = 7,         /* CUDA failure, out of device memory (status_codes.h:22) */
+  YBGPU_ILLEGAL_STATE = 9,         /* (status_codes.h:24) */
+  YBGPU_TRY_AGAIN = 25,            /* whole-subcompaction retry if no output was kept (compaction_job.cc:830-840) */
+  YBGPU_SHUTDOWN_IN_PROGRESS = 27  /* shutting_down flag observed (compaction_job.cc:820-824; status_codes.h:43) */
 } ybgpu_status;
 
 /* rocksdb::KeyValueEncodingFormat (rocksdb/types.h:50-56); per input file from the table
@@ -158,8 +161,10 @@ const char* ybgpu_job_error(const ybgpu_job* job);       /* message of the last 
 const char* ybgpu_last_error(void);                      /* for failures of create itself */
 
 /* Replaces: VersionSet::MakeInputIterator's per-file TableCache::NewIterator
- * (db/version_set.cc:3788-3849). `data_file` is the whole data file in HOST memory (copied to
- * HBM here); `handles` are the data-block handles in key order as read from the file's index.
+ * (db/version_set.cc:3788-3849). `data_file` is the whole data file in HOST memory; the copy to HBM is QUEUED
+ * here on the job's stream (asynchronous DMA when the memory is pinned), so `data_file` must stay valid and
+ * unchanged until ybgpu_job_run has returned or the job is destroyed (destroy synchronises the stream);
+ * `handles` are the data-block handles in key order as read from the file's index (copied before returning).
  * `hybrid_time_filter` is the file's global HybridTime filter (docdb_rocksdb_util.cc:494-571) or
  * YBGPU_HT_INVALID.  Inputs may be added in any order; order does not affect the output. */
 ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint64_t data_file_len,

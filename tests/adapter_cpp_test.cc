@@ -76,6 +76,46 @@ int main(int argc, char** argv) {
   for (size_t i = 0; i + 1 < bufs.size(); i += 2) { InputFile f; f.base_file = Slice(bufs[i]); f.data_file = Slice(bufs[i + 1]); in.push_back(f); }
   GpuCompactionJob::Params p;
   if (mode == "gpusub") p.max_subcompactions = 4;
+  if (mode == "gpufeed") {
+    // RunIntoFeed: the surviving stream goes entry by entry through a host CompactionFeed (compaction_context.h:25-35)
+    // into the host TableBuilder; a second job's feed fails at entry `abort_at` and the status must come back
+    // unchanged (compaction_job.cc:797-800: the first non-OK Feed aborts the loop).
+    struct BuilderFeed : CompactionFeed {
+      GpuSideTableBuilder* tb; uint64_t n = 0, abort_at = ~0ull; bool flushed = false;
+      Status Feed(const Slice& k, const Slice& v) override {
+        if (n == abort_at) return Status(Status::kIOError, "injected feed failure");
+        n++; tb->Add(k, v); return tb->status();
+      }
+      Status Flush() override { flushed = true; return Status::OK(); }
+    };
+    ybgpu_job_options to; ybgpu_job_options_init(&to);
+    GpuSideTableBuilder tb(to);
+    BuilderFeed feed; feed.tb = &tb;
+    GpuCompactionJob job(p);
+    Status s = job.Prepare(in);
+    if (!s.ok()) { printf("prepare: %s\n", s.ToString().c_str()); return 1; }
+    s = job.RunIntoFeed(&feed);
+    if (!s.ok() || !feed.flushed) { printf("RunIntoFeed: %s\n", s.ToString().c_str()); return 1; }
+    if (!tb.Finish().ok() || tb.NumEntries() != feed.n || feed.n != job.stats().num_output_records) { printf("feed count\n"); return 1; }
+    Slice d, m; tb.Files(&d, &m);
+    std::ofstream(std::string(argv[2]) + ".feed.data", std::ios::binary).write(reinterpret_cast<const char*>(d.data()), d.size());
+    std::ofstream(std::string(argv[2]) + ".feed.base", std::ios::binary).write(reinterpret_cast<const char*>(m.data()), m.size());
+    GpuSideTableBuilder tb2(to);
+    BuilderFeed bad; bad.tb = &tb2; bad.abort_at = feed.n / 2;
+    GpuCompactionJob job2(p);
+    s = job2.Prepare(in);
+    if (!s.ok()) { printf("prepare2: %s\n", s.ToString().c_str()); return 1; }
+    s = job2.RunIntoFeed(&bad);
+    if (s.ok() || s.code() != Status::kIOError || bad.n != feed.n / 2 || bad.flushed) { printf("abort semantics: %s n=%llu\n", s.ToString().c_str(), (unsigned long long)bad.n); return 1; }
+    GpuCompactionJob::Params ps = p; ps.max_subcompactions = 4;
+    GpuCompactionJob job3(ps);
+    s = job3.Prepare(in);
+    if (!s.ok()) { printf("prepare3: %s\n", s.ToString().c_str()); return 1; }
+    s = job3.RunIntoFeed(&bad);
+    if (!s.IsNotSupported()) { printf("RunIntoFeed with subcompactions must be NotSupported\n"); return 1; }
+    printf("OK in=%llu out=%llu\n", (unsigned long long)job.stats().num_input_records, (unsigned long long)feed.n);
+    return 0;
+  }
   GpuCompactionJob job(p);
   Status s = job.Prepare(in);
   if (!s.ok()) { printf("prepare: %s\n", s.ToString().c_str()); return 1; }

@@ -30,6 +30,31 @@ def test_exports_every_declared_symbol(pkg):
         assert hasattr(L, n), "libybgpu.so does not export %s" % n
 
 
+def test_status_codes_are_the_reference_numbers(pkg):
+    """ybgpu_status values must equal yb::Status::Code (util/status_codes.h) because the adapter casts them; the
+    committed table was extracted from the reference header (tests/golden/extract_status_codes.py) and, when the
+    reference tree is present (build container), is re-checked against the header itself."""
+    import json
+    tab = json.load(open(os.path.join(ROOT, "tests", "golden", "status_codes_table.json")))["codes"]
+    hdr = open(os.path.join(ROOT, "include", "ybgpu_compaction.h")).read()
+    enum = dict((n, int(v)) for n, v in re.findall(r"YBGPU_([A-Z_]+)\s*=\s*(\d+)", hdr.split("typedef enum ybgpu_status")[1].split("}")[0]))
+    want = {"OK": "Ok", "NOT_FOUND": "NotFound", "CORRUPTION": "Corruption", "NOT_SUPPORTED": "NotSupported",
+            "INVALID_ARGUMENT": "InvalidArgument", "IO_ERROR": "IOError", "RUNTIME_ERROR": "RuntimeError",
+            "ILLEGAL_STATE": "IllegalState", "TRY_AGAIN": "TryAgain", "SHUTDOWN_IN_PROGRESS": "ShutdownInProgress"}
+    assert set(enum) == set(want)
+    for k, ref_name in want.items():
+        assert enum[k] == tab[ref_name], (k, enum[k], tab[ref_name])
+    adapter = open(os.path.join(ROOT, "yugabyte-db_b200", "csrc", "adapter", "gpu_compaction_job.h")).read()
+    for name, v in re.findall(r"\bk(\w+) = (\d+)", adapter.split("enum Code {")[1].split("}")[0]):
+        assert tab[name if name != "Ok" else "Ok"] == int(v), name
+    for v, name in pkg.STATUS_NAMES.items():
+        assert tab["Ok" if name == "OK" else name] == v
+    ref = "/root/reference/src/yb/util/status_codes.h"
+    if os.path.exists(ref):
+        live = {m[0]: int(m[1]) for m in re.findall(r"YB_STATUS_CODE\((\w+),\s*\w+,\s*(\d+),", open(ref).read())}
+        assert live == tab
+
+
 def test_no_cpu_fallback_without_gpu(pkg):
     if pkg.device_count() > 0:
         pytest.skip("GPU present")

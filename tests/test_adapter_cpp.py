@@ -70,3 +70,24 @@ def test_adapter_runs_subcompactions(tmp_path):
     # ... and as ONE table (ConcatenatedOutput): the same key/value stream behind one index
     one = o.Sst.from_bytes((tmp_path / "0.sst.one.base").read_bytes(), (tmp_path / "0.sst.one.data").read_bytes())
     assert one.read_all() == exp.kv_list()
+
+
+@pytest.mark.gpu
+def test_adapter_run_into_feed(tmp_path):
+    """a8: CompactionFeed interface. RunIntoFeed pushes the surviving stream through a host feed into the host
+    TableBuilder: the files equal the oracle's (= the GPU-built ones); a failing Feed aborts with its own status."""
+    import oracle_py as o
+    build_bin()
+    cfg = o.GenConfig(seed=12, num_rows=2500, cols=2, versions=3, num_files=3, value_len=70, tombstone_per_1024=50)
+    ssts = o.Sst.generate_all(cfg)
+    args = [BIN, "gpufeed"]
+    for i, s in enumerate(ssts):
+        b, d = tmp_path / ("%d.sst" % i), tmp_path / ("%d.sst.sblock.0" % i)
+        b.write_bytes(s.meta)
+        d.write_bytes(s.data)
+        args += [str(b), str(d)]
+    out = subprocess.check_output(args, text=True)
+    assert "OK in=15000" in out, out
+    exp = o.compact(ssts, o.CompactionParams())
+    assert (tmp_path / "0.sst.feed.data").read_bytes() == exp.sst().data
+    assert (tmp_path / "0.sst.feed.base").read_bytes() == exp.sst().meta

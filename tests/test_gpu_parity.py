@@ -367,6 +367,56 @@ def test_subcompactions_pipelined(pkg, enc, in_flight):
     assert [o_.lower for o_ in res.outputs[1:]] == [o_.upper for o_ in res.outputs[:-1]]
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_subcompactions_inside_cotables(pkg, seed):
+    """Ranges that start inside a cotable / colocated table still see the table's tombstones (`id ! # HT`), which
+    sort before the range: their blocks are loaded out of range and seed slot 0 of the overwrite stack
+    (docdb_compaction_context.cc:999-1024). The range outputs must concatenate to the single-pass oracle output."""
+    runs = w.random_cotable_runs(100 + seed, n_runs=2 + seed % 3, n_tables=3, rows_per_table=150, colocated=seed % 2 == 0)
+    ssts = runs_to_ssts(runs, 512)
+    files = [(s.meta_view(), s.data_view()) for s in ssts]
+    inside = 0
+    for kw in [w.param_grid()[i] for i in (0, 2, 4, 6)]:
+        exp = o.compact(ssts, o.CompactionParams(**okw(kw)), o.TableOptions(block_size=1024))
+        res = pkg.compact_files(files, max_subcompactions=7, max_in_flight=2, block_size=1024, **kw)
+        assert len(res.outputs) >= 4
+        got = []
+        for out in res.outputs:
+            if out.lower and out.lower[:1] in (b"y", b"0") and len(out.lower) > (17 if out.lower[:1] == b"y" else 5) + 1:
+                inside += 1
+            if out.data_len:
+                got += o.Sst.from_bytes(res.meta_arena[out.meta_offset:out.meta_offset + out.meta_len].tobytes(),
+                                        res.data_arena[out.data_offset:out.data_offset + out.data_len].tobytes()).read_all()
+        assert got == exp.kv_list()
+        assert res.total.num_input_records == exp.stats.num_input_records
+        assert res.total.num_output_records == exp.stats.num_output_records
+        assert res.total.num_record_drop_feed == exp.stats.num_dropped_feed
+    assert inside >= 4, "the test must cut inside tables"
+
+
+def test_emit_kv_stream_is_the_kv_list(pkg):
+    """a8: ybgpu_job_emit_kv_stream hands the surviving stream to a CompactionFeed-shaped callback in output order;
+    a non-zero return aborts with that status (compaction_job.cc:797-800)."""
+    cfg = o.GenConfig(seed=5, num_rows=2000, cols=2, versions=3, num_files=3, value_len=60, tombstone_per_1024=60)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=4096))
+    cutoff = o.ht_from_micros(cfg.base_micros + 1500)
+    exp = o.compact(ssts, o.CompactionParams(cutoff_ht=cutoff), o.TableOptions(block_size=4096))
+    job = gpu_compact(pkg, ssts, cutoff_ht=cutoff, block_size=4096)
+    got = []
+    job.emit_kv_stream(lambda k, v: got.append((k, v)) or 0)
+    assert got == exp.kv_list() == job.kv_list()
+    seen = []
+
+    def failing(k, v):
+        if len(seen) == 100:
+            return 5            # IOError
+        seen.append(k)
+        return 0
+    with pytest.raises(pkg.YbGpuError) as e:
+        job.emit_kv_stream(failing)
+    assert e.value.status == 5 and len(seen) == 100
+
+
 def test_concurrent_jobs_on_private_streams(pkg):
     """Jobs of different tablets run concurrently on one device (one PriorityThreadPool worker per
     CompactionJob, db_impl.cc:397-403): each on its own stream, results unchanged."""

@@ -14,7 +14,7 @@ TTL_MAX_NS = 2**63 - 1
 MAX_SEQUENCE = (1 << 56) - 1
 
 STATUS_NAMES = {0: "OK", 1: "NotFound", 2: "Corruption", 3: "NotSupported", 4: "InvalidArgument", 5: "IOError",
-                9: "RuntimeError", 10: "IllegalState", 19: "ShutdownInProgress"}
+                7: "RuntimeError", 9: "IllegalState", 25: "TryAgain", 27: "ShutdownInProgress"}
 
 
 class YbGpuError(RuntimeError):
@@ -113,6 +113,7 @@ def lib():
     L.ybgpu_job_fetch_output.argtypes = [vp, vp, u64, vp, u64]
     L.ybgpu_job_output_boundaries.argtypes = [vp, vp, C.POINTER(u64), vp, C.POINTER(u64)]
     L.ybgpu_job_kv_stream_digest.argtypes = [vp, C.POINTER(u64)]
+    L.ybgpu_job_emit_kv_stream.argtypes = [vp, vp, vp]
     L.ybgpu_gen_ssts.argtypes = [C.POINTER(GenConfig), C.POINTER(JobOptions), C.POINTER(vp), C.c_int32]
     L.ybgpu_gen_sst.argtypes = [C.POINTER(GenConfig), C.c_uint32, C.POINTER(JobOptions), C.POINTER(vp)]
     L.ybgpu_sst_free.argtypes = [vp]
@@ -138,6 +139,7 @@ def _np_ptr(a):
     return a.ctypes.data if a.size else None
 
 
+EMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64)
 STREAM_PRIVATE = 2**64 - 1      # YBGPU_STREAM_PRIVATE: a non-blocking stream owned by the job
 
 
@@ -290,6 +292,14 @@ class GpuCompactionJob:
         al, bl = C.c_uint64(), C.c_uint64()
         self._check(lib().ybgpu_job_output_boundaries(self.h, a, C.byref(al), b, C.byref(bl)))
         return a.raw[:al.value], b.raw[:bl.value]
+
+    def emit_kv_stream(self, fn):
+        """ybgpu_job_emit_kv_stream: fn(key: bytes, value: bytes) -> int is called for every surviving entry in
+        output order (the CompactionFeed::Feed shape); a non-zero return aborts with that status."""
+        def tramp(_ctx, k, kl, v, vl):
+            return int(fn(C.string_at(k, kl), C.string_at(v, vl)) or 0)
+        cb = EMIT_FN(tramp)
+        self._check(lib().ybgpu_job_emit_kv_stream(self.h, C.cast(cb, C.c_void_p), None))
 
     def digest(self):
         d = C.c_uint64()

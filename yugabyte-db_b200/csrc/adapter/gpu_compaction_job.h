@@ -37,13 +37,15 @@ struct Slice {   // yb/util/slice.h
 class Status {   // yb/util/status.h (codes used on this path)
  public:
   enum Code { kOk = 0, kNotFound = 1, kCorruption = 2, kNotSupported = 3, kInvalidArgument = 4, kIOError = 5,
-              kRuntimeError = 9, kIllegalState = 10, kShutdownInProgress = 19 };
+              kRuntimeError = 7, kIllegalState = 9, kTryAgain = 25, kShutdownInProgress = 27 };   // util/status_codes.h:14-43
   Status() {}
   Status(Code c, std::string m) : code_(c), msg_(std::move(m)) {}
   static Status OK() { return Status(); }
   bool ok() const { return code_ == kOk; }
   bool IsShutdownInProgress() const { return code_ == kShutdownInProgress; }
   bool IsCorruption() const { return code_ == kCorruption; }
+  bool IsTryAgain() const { return code_ == kTryAgain; }
+  bool IsNotSupported() const { return code_ == kNotSupported; }
   Code code() const { return code_; }
   const std::string& message() const { return msg_; }
   std::string ToString() const { return ok() ? "OK" : msg_; }
@@ -302,6 +304,8 @@ class GpuCompactionJob {
   // packed-row repacker): the GPU still does decode + merge + retention, the host feed gets the
   // stream in order (compaction_job.cc:797-800 semantics: first non-OK aborts).
   Status RunIntoFeed(CompactionFeed* feed) {
+    if (p_.max_subcompactions > 1 || !job_)
+      return Status(Status::kNotSupported, "RunIntoFeed needs max_subcompactions == 1 (the host feed consumes one ordered stream)");
     for (const InputFile& f : inputs_) {
       ybgpu_status s = ybgpu_job_add_input_sst(job_, f.base_file.data(), f.base_file.size(), f.data_file.data(),
                                                f.data_file.size(), f.hybrid_time_filter);

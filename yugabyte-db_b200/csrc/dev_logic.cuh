@@ -29,7 +29,11 @@
 namespace ybgpu {
 
 enum : uint8_t {
-  REC_F_HT_FILTERED = 0x80,   // invisible: file's HybridTime filter (docdb_rocksdb_util.cc:525-540) or outside the job's key range
+  REC_F_HT_FILTERED = 0x80,   // invisible: file's HybridTime filter (docdb_rocksdb_util.cc:525-540)
+  REC_F_OUT_OF_RANGE = 0x40,  // invisible: outside the job's key range (subcompaction / key-range shard). Table tombstones
+                              // (`id ! # HT`) of the table the range starts in are loaded out of range on purpose: they
+                              // seed slot 0 of the overwrite stack (docdb_compaction_context.cc:999-1024) and nothing else
+  REC_F_INVISIBLE = 0xC0,
 };
 
 enum DevError : int {

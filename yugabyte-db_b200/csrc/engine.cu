@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(128) k_decode_all(const RunView* runs, const u
           if (htl && doc_ht_decode(keybuf + ulen - htl, htl, &ht) && ht > run.ht_filter) flags |= REC_F_HT_FILTERED;
         }
         if (range && (range->lower_len | range->upper_len)) {
-          if (range->lower_len && cmp_raw(keybuf, ulen, range->lower, range->lower_len) < 0) flags |= REC_F_HT_FILTERED;
-          if (range->upper_len && cmp_raw(keybuf, ulen, range->upper, range->upper_len) >= 0) flags |= REC_F_HT_FILTERED;
+          if (range->lower_len && cmp_raw(keybuf, ulen, range->lower, range->lower_len) < 0) flags |= REC_F_OUT_OF_RANGE;
+          if (range->upper_len && cmp_raw(keybuf, ulen, range->upper, range->upper_len) >= 0) flags |= REC_F_OUT_OF_RANGE;
         }
         const uint8_t vfirst = vlen ? blk[p] : 0;
         uint4 tr;
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
     const int g = group_prefix_len(e, rec_ulen(e, S), prm->R.enabled != 0, V.fk16 ? &fk : nullptr);
     if (g < 0) { dev_fail(J, -g, tile); glen[li] = 0; } else glen[li] = static_cast<uint16_t>(g);
     if (V.fk16) V.fk16[V.runs[r].gid_base + seg_lo[r] + p] = static_cast<uint16_t>(g < 0 ? 0 : fk);
-    if (rec_flags(e, S) & REC_F_HT_FILTERED) sh_any_filtered = 1;
+    if (rec_flags(e, S) & REC_F_INVISIBLE) sh_any_filtered = 1;
   }
   if (threadIdx.x == 0) sh_err = *reinterpret_cast<volatile int*>(&J->error);
   __syncthreads();
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
       uint32_t last = 0xffff;
       for (uint32_t i = 0; i < T; i++) {
         pvis[i] = static_cast<uint16_t>(last);
-        if (!(rec_flags(recs + static_cast<size_t>(SS) * (order[i]), S) & REC_F_HT_FILTERED)) last = i;
+        if (!(rec_flags(recs + static_cast<size_t>(SS) * (order[i]), S) & REC_F_INVISIBLE)) last = i;
       }
     }
   } else {
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
     const uint32_t li = order[i];
     const uint8_t* e = recs + static_cast<size_t>(SS) * (li);
     uint8_t f = 0;
-    if (!(rec_flags(e, S) & REC_F_HT_FILTERED)) {
+    if (!(rec_flags(e, S) & REC_F_INVISIBLE)) {
       f |= ENT_COUNTED; st_counted++;
       st_in_k += rec_ulen(e, S) + 8; st_in_v += rec_vlen(e, S);
       const uint64_t suffix = rec_suffix(e, S);
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
           const uint8_t* c = run.rec + static_cast<size_t>(x) * S;
           const uint32_t cl = rec_ulen(c, S);
           if (cl < static_cast<uint32_t>(id) + 1 || common_prefix_len(c, id + 1, pfxkey, id + 1) < static_cast<uint32_t>(id) + 1) break;
-          if (rec_flags(c, S) & REC_F_HT_FILTERED) continue;
+          if (rec_flags(c, S) & REC_F_HT_FILTERED) continue;     // out-of-range tombstones DO seed the table state
           if (nt >= COT_TOMB_MAX) { overflow = true; break; }
           tomb[nt] = c; tomb_run[nt] = r; tomb_idx[nt] = x; nt++;
         }
@@ -1373,6 +1373,8 @@ Engine::~Engine() {
   if (impl_) {
     cudaSetDevice(opt_.device);
     if (impl_->copy_pending) cudaStreamSynchronize(impl_->copy_stream);   // before the output buffer returns to the pool
+    // a job abandoned before Run() may still have input DMAs queued that read the caller's buffers
+    if (!ran_ && !impl_->runs.empty()) cudaStreamSynchronize(impl_->stream);
     for (void* p : impl_->allocs) cudaFreeAsync(p, impl_->stream);
     if (impl_->ev0) cudaEventDestroy(impl_->ev0);
     if (impl_->ev1) cudaEventDestroy(impl_->ev1);
@@ -1469,7 +1471,9 @@ ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_blo
   CUDA_TRY(cudaSetDevice(opt_.device));
   g_alloc_stream = impl_->stream;
   for (uint64_t i = 0; i < nh; i++) {
-    if (handles[i].offset + handles[i].size + 5 > len) return Fail(YBGPU_CORRUPTION, "block handle outside the data file");
+    // offset + size + 5 <= len without wrapping on corrupt (huge) handles
+    if (handles[i].offset > len || handles[i].size > len - handles[i].offset || len - handles[i].offset - handles[i].size < 5)
+      return Fail(YBGPU_CORRUPTION, "block handle outside the data file");
     if (handles[i].size >= (1ull << 31)) return Fail(YBGPU_NOT_SUPPORTED, "data block too large");
   }
   RunView rv{};

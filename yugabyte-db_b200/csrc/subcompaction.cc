@@ -46,7 +46,9 @@ bool ParseInputs(const ybgpu_input_file* files, uint32_t n, std::vector<ParsedIn
     p.useps.reserve(p.meta.separators.size());
     for (const std::string& k : p.meta.separators) p.useps.push_back(UserPart(k));
     for (const auto& h : p.meta.data_blocks)
-      if (h.offset + h.size + 5 > files[f].data_file_len) { errs[f] = "block handle outside the data file"; return; }
+      if (h.offset > files[f].data_file_len || h.size > files[f].data_file_len - h.offset || files[f].data_file_len - h.offset - h.size < 5) {
+        errs[f] = "block handle outside the data file"; return;
+      }
   };
   // the index of a multi-GB input has ~10^5 entries: the files are walked side by side
   if (n > 1) {
@@ -320,11 +322,43 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
     };
     uint32_t added = 0;
     std::vector<ybgpu_block_handle> h;
+    // A range that starts inside a cotable / colocated table ('y' + uuid or '0' + colocation id): the table's
+    // tombstone entries `id ! # HT` sort before every row of the table, i.e. before this range, yet their
+    // overwrite time (slot 0 of DocDBCompactionFeed's overwrite stack, docdb_compaction_context.cc:999-1024)
+    // shadows the rows in it. The blocks that hold them are loaded too; the engine keeps such out-of-range
+    // entries invisible (REC_F_OUT_OF_RANGE) except for seeding the table state.
+    std::string tomb_lo, tomb_hi;
+    if (options->retention_enabled && !lo.empty() && (lo[0] == 'y' || lo[0] == '0')) {
+      const int id = ybgpu::dockey_id_size(reinterpret_cast<const uint8_t*>(lo.data()), static_cast<int>(lo.size()));
+      if (id > 0 && static_cast<size_t>(id) <= lo.size()) {
+        tomb_lo = lo.substr(0, id) + '!';
+        tomb_hi = lo.substr(0, id) + '"';              // '!' + 1
+        if (!(tomb_lo < lo)) tomb_lo.clear();           // the range starts at the tombstones themselves
+      }
+    }
     for (uint32_t f = 0; f < num_files; f++) {
       size_t a, b;
       BlocksForRange(in[f].useps, lo, hi, &a, &b);
-      if (b <= a) continue;
       const auto& blocks = in[f].meta.data_blocks;
+      if (!tomb_lo.empty()) {
+        size_t ta, tb;
+        BlocksForRange(in[f].useps, tomb_lo, tomb_hi, &ta, &tb);
+        if (b <= a) { a = b = tb; }                     // no block of this file holds range keys
+        tb = std::min(tb, a);
+        if (tb > ta) {
+          if (tb == a && b > a) {
+            a = ta;                                     // contiguous with the range's blocks: one span
+          } else {
+            const uint64_t start = blocks[ta].offset;
+            const uint64_t end = blocks[tb - 1].offset + blocks[tb - 1].size + 5;
+            h.resize(tb - ta);
+            for (size_t i = ta; i < tb; i++) { h[i - ta].offset = blocks[i].offset - start; h[i - ta].size = blocks[i].size; }
+            s = ybgpu_job_add_input(job, files[f].data_file + start, end - start, h.data(), h.size(), in[f].meta.key_encoding, files[f].hybrid_time_filter);
+            if (s != YBGPU_OK) { job_fail(s, "add_input (table tombstones)"); return; }
+          }
+        }
+      }
+      if (b <= a) continue;
       const uint64_t start = blocks[a].offset;
       const uint64_t end = blocks[b - 1].offset + blocks[b - 1].size + 5;
       h.resize(b - a);
