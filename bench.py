@@ -11,19 +11,27 @@ collective, weak scaling).
 
 JSON line (one, rank 0): metric = GB/s of input bytes merged (raw key+value bytes of the input
 entries, as rocksdb.raw.key.size + rocksdb.raw.value.size count them).
-  value     inputs already resident in HBM; whole job device pipeline, wall clock between syncs.
-  e2e       same job through the C ABI with HOST (pinned) input files and HOST output files:
-            H2D of every input file and D2H of the result inside the timed region. Headline mode:
-            ybgpu_compact_files with --subcompactions key ranges (CompactionJob's subcompaction
-            mechanism, compaction_job.cc:409-552), pipelined so that H2D / kernels / D2H of different
-            ranges overlap; one output SST per range. e2e.one_table adds ybgpu_sst_concat_meta: the range
-            outputs assembled into ONE table (data pieces appended in range order, one rebased index /
-            filter index) inside the timed region. e2e.single_job is the same measurement with one
-            job and one output file (H2D, run and D2H back to back) — the shape DocDB's single-level
-            universal layout produces today (db/compaction.cc:593-604 never forms subcompactions there).
-  roofline  dominant kernel, algorithmic bytes / its CUDA-event time.
-  cpu_baseline  the oracle (CPU restatement of the reference loop) on a bounded sample, 1 thread
-            like the reference (max_subcompactions = 1).
+  value     inputs already resident in HBM, input block checksums VERIFIED (the reference default,
+            rocksdb/util/options.cc:135): whole job device pipeline, wall clock between syncs.
+            value_no_verify: the same without verification (informational).
+  e2e       same compaction through the C ABI with HOST (pinned) input files and ONE HOST output table:
+            H2D of every input file and D2H of the result inside the timed region. The compaction runs
+            as --subcompactions key ranges pipelined on private streams (ybgpu_compact_files) so that H2D /
+            kernels / D2H of different ranges overlap, and ybgpu_sst_concat_meta assembles the range
+            outputs into ONE table (data pieces appended in range order, one rebased index / filter
+            index) inside the timed region — the shape DocDB's single-level universal layout (and the
+            reference arm) writes. e2e.range_files = the same without the assembly (one SST per range);
+            e2e.single_job = one job, H2D / run / D2H back to back. e2e.pcie_ceiling_gbs = concurrent
+            bidirectional copies of the same pinned buffers, measured in this run.
+  roofline  dominant kernel, algorithmic bytes / its CUDA-event time; roofline.traffic is
+            read from the committed ncu capture under profiles/ (traffic_source says which), not measured here.
+  configs   BASELINE configs[2] (64 tablets x 4-way x 10 M: 8 tablets per GPU) and configs[3] (MVCC-heavy, the
+            largest size resident on one GPU) as sub-results with their own pipeline roofline.
+  cpu_baseline  the oracle (CPU restatement of the reference loop) on a bounded sample, 1 thread like the
+            reference (max_subcompactions = 1), plus all_cores: the reference's pool size and all hardware
+            threads running independent one-thread compactions.
+  parity_check  the GPU engine compacts the cpu_baseline sample files in this run: counters, KV hash and the
+            SHA-256 of both output files must equal the oracle's.
 """
 import argparse
 import ctypes
@@ -58,6 +66,11 @@ def parse_args():
     ap.add_argument("--subcompactions", type=int, default=32,
                     help="e2e arm: key-range subcompactions per job (DBOptions::max_subcompactions; 1 = one job, one output file)")
     ap.add_argument("--in-flight", type=int, default=6, help="e2e arm: subcompactions in flight (host threads / private streams)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE configs[2] / configs[3] sub-results")
+    ap.add_argument("--c3-tablets", type=int, default=8, help="configs[2]: tablets per GPU (64 tablets / 8 GPUs)")
+    ap.add_argument("--c3-rows", type=int, default=10_000_000, help="configs[2]: entries per tablet")
+    ap.add_argument("--c4-rows", type=int, default=200_000_000,
+                    help="configs[3] (MVCC-heavy, 20 versions/key): entries resident on one GPU (the full 1 G entries = 310 GB do not fit HBM)")
     ap.add_argument("--workload", default="config2", choices=["config2", "mvcc"],
                     help="config2 = BASELINE configs[1] (the bench line); mvcc = configs[3] shape (20 versions/key, "
                          "history cutoff drops 90 %), scaled to --rows entries, for profiles/ only")
@@ -138,104 +151,85 @@ def run_reference(args, rank, world):
     in_bytes = sum(s.raw_bytes for s in ssts)
     params = o.CompactionParams()
     times = []
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        r = o.compact(ssts, params, o.TableOptions(filter_policy=1), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
-        t1 = time.perf_counter()
-        n_out = r.stats.num_output_records
-        del r
-        if i >= args.warmup:
-            times.append(t1 - t0)
-    total = sum(times)
-    gbs = in_bytes * args.steps / total / 1e9
-    sample = "%d entries (%0.2f GB raw) of the same 8-way shape, %d output entries" % (rows, in_bytes / 1e9, n_out)
-    # Informational: what the host delivers across MANY tablets — T independent compactions of the
-    # same sample, one thread each, run concurrently. One job cannot use more than one thread in the reference
-    # (max_subcompactions = 1, rocksdb/util/options.cc:258; universal compaction with one level never forms
-    # subcompactions, db/compaction.cc:593-604), so the headline value above stays the one-thread figure.
-    many = None
-    try:
-        from concurrent.futures import ThreadPoolExecutor
-        T = max(1, min(os.cpu_count() or 1, 32))
-        small_rows = min(rows, 1_000_000)
-        if small_rows != rows:
-            cfg2 = o.GenConfig(seed=2, num_rows=small_rows, cols=1, versions=1, num_files=NUM_FILES, value_len=VALUE_LEN)
-            ssts2 = o.Sst.generate_all(cfg2, o.TableOptions())
-        else:
-            ssts2 = ssts
-        b2 = sum(s.raw_bytes for s in ssts2)
+    # N GPUs compact N tablets at once (tablet-per-GPU): the CPU counterpart is N concurrent compactions, one thread
+    # each (the reference cannot use more than one thread per compaction: max_subcompactions = 1,
+    # rocksdb/util/options.cc:258; db/compaction.cc:593-604), each on its own copy of the sample.
+    from concurrent.futures import ThreadPoolExecutor
+    conc = max(1, args.gpus)
+    n_out_box = [0]
 
-        def one(_):
-            r = o.compact(ssts2, params, o.TableOptions(filter_policy=1), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
-            del r
-        t0 = time.perf_counter()
-        with ThreadPoolExecutor(T) as ex:
-            list(ex.map(one, range(T)))
-        dt = time.perf_counter() - t0
-        many = {"value": round(T * b2 / dt / 1e9, 3), "unit": "GB/s", "cores": T,
-                "sample": "%d concurrent one-thread compactions of %d entries each (independent tablets), %.1f s" % (T, small_rows, dt)}
+    def one(_):
+        r = o.compact(ssts, params, o.TableOptions(filter_policy=1), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
+        n_out_box[0] = r.stats.num_output_records
+        del r
+    with ThreadPoolExecutor(conc) as ex:
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            list(ex.map(one, range(conc)))
+            t1 = time.perf_counter()
+            if i >= args.warmup:
+                times.append(t1 - t0)
+    n_out = n_out_box[0]
+    total = sum(times)
+    gbs = conc * in_bytes * args.steps / total / 1e9
+    sample = "%d entries (%0.2f GB raw) of the same 8-way shape, %d output entries" % (rows, in_bytes / 1e9, n_out)
+    # Informational: what the host delivers across MANY tablets (one compaction is one thread in the
+    # reference: max_subcompactions = 1, rocksdb/util/options.cc:258; universal compaction with one level never
+    # forms subcompactions, db/compaction.cc:593-604) — the CPU counterpart of N GPUs each compacting its own tablet.
+    try:
+        many = all_cores_cpu(o, args)
     except Exception as e:   # never fail the arm because of the informational figure
         many = {"error": str(e)}
-    # Informational: the SAME compaction cut into key ranges, one CPU-port thread per range — what
-    # CompactionJob's subcompactions (compaction_job.cc:409-552) would give the host on a layout that forms them
-    # (DocDB's single-level universal layout never does, db/compaction.cc:593-604). This is the CPU counterpart of
-    # the GPU arm's pipelined e2e mode; the per-range input slices are cut outside the timed region.
-    subs = None
-    try:
-        import bisect
-        from concurrent.futures import ThreadPoolExecutor
-        T = max(1, min(os.cpu_count() or 1, 32))
-        rows_s = min(rows, 2_000_000)
-        cfg3 = o.GenConfig(seed=2, num_rows=rows_s, cols=1, versions=1, num_files=NUM_FILES, value_len=VALUE_LEN)
-        ssts3 = o.Sst.generate_all(cfg3, o.TableOptions())
-        b3 = sum(s.raw_bytes for s in ssts3)
-        kvs = [s.read_all() for s in ssts3]
-        uks = [[k[:-8] for k, _ in f] for f in kvs]
-        dockeys = sorted(u[:32] for u in uks[0])                      # rows of this workload are 32-byte DocKeys
-        splitters = [dockeys[len(dockeys) * i // T] for i in range(1, T)]
-        largest = max(u[-1] for u in uks if u)
-        range_ssts = []
-        for r in range(T):
-            lo = splitters[r - 1] if r > 0 else None
-            hi = splitters[r] if r < T - 1 else None
-            parts = []
-            for f, u in zip(kvs, uks):
-                a = bisect.bisect_left(u, lo) if lo is not None else 0
-                b = bisect.bisect_left(u, hi) if hi is not None else len(u)
-                if b > a:
-                    parts.append(o.Sst.build(f[a:b], o.TableOptions()))
-            range_ssts.append(parts)
-        del kvs, uks
-        p3 = o.CompactionParams(largest_user_key=largest)
-
-        def one_range(r):
-            if range_ssts[r]:
-                res = o.compact(range_ssts[r], p3, o.TableOptions(filter_policy=1), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
-                del res
-        t0 = time.perf_counter()
-        with ThreadPoolExecutor(T) as ex:
-            list(ex.map(one_range, range(T)))
-        dt = time.perf_counter() - t0
-        subs = {"value": round(b3 / dt / 1e9, 3), "unit": "GB/s", "cores": T,
-                "sample": "one compaction of %d entries cut into %d key ranges, one thread per range, %.2f s" % (rows_s, T, dt)}
-    except Exception as e:
-        subs = {"error": str(e)}
     line = {
         "impl": "reference", "metric": "compaction GB/s (input bytes merged)", "value": round(gbs, 4), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample, "threads_per_compaction": 1},
-        "mkeys_per_s": round(rows * args.steps / total / 1e6, 3),
-        "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": sample, "threads_per_compaction": 1, "concurrent_compactions": conc,
+                   "same_config_note": "one-thread throughput is independent of the job size; the sample bounds the run time"},
+        "mkeys_per_s": round(conc * rows * args.steps / total / 1e6, 3),
+        "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": conc, "kind": "port", "sample": sample},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "many_tablets_all_cores": many,
-        "subcompactions_all_cores": subs,
+        "all_cores": many,
     }
     emit_json_line(line)
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(args):
+def all_cores_cpu(o, args, rows_each=1_000_000, min_seconds=4.0):
+    """The host's compaction rate across MANY tablets: P concurrent one-thread compactions, P = the reference's
+    compaction pool size floor(ncpu * 3.5 / 8) (docdb_rocksdb_util.cc:630-641), plus the all-hardware-threads figure.
+    Each worker loops over its own private sample until min_seconds have passed (no 0.07 s samples)."""
+    from concurrent.futures import ThreadPoolExecutor
+    ncpu = os.cpu_count() or 1
+    cfg = o.GenConfig(seed=2, num_rows=rows_each, cols=1, versions=1, num_files=NUM_FILES, value_len=VALUE_LEN)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions())
+    b = sum(s.raw_bytes for s in ssts)
+    out = {}
+    for label, T in (("pool", max(1, int(ncpu * 3.5 / 8))), ("all_threads", ncpu)):
+        done = [0] * T
+        t_end = [0.0] * T
+        t0 = time.perf_counter()
+
+        def one(i):
+            while time.perf_counter() - t0 < min_seconds:
+                r = o.compact(ssts, o.CompactionParams(), o.TableOptions(filter_policy=1), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
+                del r
+                done[i] += 1
+            t_end[i] = time.perf_counter()
+        with ThreadPoolExecutor(T) as ex:
+            list(ex.map(one, range(T)))
+        dt = max(t_end) - t0
+        out[label] = {"value": round(sum(done) * b / dt / 1e9, 3), "unit": "GB/s", "threads": T,
+                      "sample": "%d one-thread compactions of %d entries each on %d concurrent threads, %.1f s" % (sum(done), rows_each, T, dt)}
+    out["host_threads"] = ncpu
+    return out
+
+
+def cpu_baseline(args, pkg=None, device=0):
+    """The oracle (CPU restatement of the reference loop) on a bounded sample, one thread; when `pkg` is given the GPU
+    engine compacts the SAME sample files and every counter, the KV-stream hash and both output files' SHA-256 must equal
+    the oracle's (parity_check)."""
+    import hashlib
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as o
     rows = min(args.rows, args.sample_rows)
@@ -246,10 +240,45 @@ def cpu_baseline(args):
     r = o.compact(ssts, o.CompactionParams(), o.TableOptions(filter_policy=1), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
     dt = time.perf_counter() - t0
     del r
-    return {"value": round(in_bytes / dt / 1e9, 4), "unit": "GB/s", "cores": 1, "kind": "port",
+    base = {"value": round(in_bytes / dt / 1e9, 4), "unit": "GB/s", "cores": 1, "kind": "port",
             "sample": "%d entries (%0.2f GB raw) of the same 8-way shape, %.1f s on one host thread (the reference "
-                      "runs one thread per compaction)" % (rows, in_bytes / 1e9, dt),
+                      "runs one thread per compaction; one-thread throughput does not depend on the job size)" % (rows, in_bytes / 1e9, dt),
             "mkeys_per_s": round(rows / dt / 1e6, 3)}
+    parity = None
+    if pkg is not None:
+        try:
+            exp = o.compact(ssts, o.CompactionParams(), o.TableOptions(filter_policy=1), mode=o.BUILD_SST, verify=bool(args.verify))
+            job = pkg.GpuCompactionJob(device=device, verify_checksums=bool(args.verify), filter_policy=1)
+            for s_ in ssts:
+                job.add_input_sst(s_.meta_view(), s_.data_view())
+            st = job.run()
+            es = exp.stats
+            counters = {
+                "num_input_records": (st.num_input_records, es.num_input_records),
+                "num_output_records": (st.num_output_records, es.num_output_records),
+                "drop_hidden": (st.num_record_drop_hidden, es.num_dropped_hidden),
+                "drop_obsolete": (st.num_record_drop_obsolete, es.num_dropped_obsolete),
+                "drop_feed": (st.num_record_drop_feed, es.num_dropped_feed),
+                "in_key_bytes": (st.total_input_raw_key_bytes, es.in_key_bytes), "in_val_bytes": (st.total_input_raw_value_bytes, es.in_val_bytes),
+                "out_key_bytes": (st.total_output_raw_key_bytes, es.out_key_bytes), "out_val_bytes": (st.total_output_raw_value_bytes, es.out_val_bytes),
+                "kv_hash": (job.digest(), es.kv_hash),
+            }
+            data, meta = job.fetch_output()
+            ref = exp.sst()
+            sha = lambda b_: hashlib.sha256(b_).hexdigest()
+            files = {"data_sha256": (sha(data.tobytes()), sha(ref.data)), "meta_sha256": (sha(meta.tobytes()), sha(ref.meta))}
+            bad = [k for k, (a, b_) in list(counters.items()) + list(files.items()) if a != b_]
+            parity = {"entries": int(rows), "ok": not bad, "mismatch": bad, "kv_hash": "%016x" % counters["kv_hash"][0],
+                      "data_sha256": files["data_sha256"][0][:16], "meta_sha256": files["meta_sha256"][0][:16],
+                      "checked": sorted(list(counters) + list(files)), "against": "oracle (CPU port) on the cpu_baseline sample files"}
+            job.close()
+        except Exception as ex:
+            parity = {"ok": False, "error": "%s: %s" % (type(ex).__name__, ex)}
+    try:
+        base["all_cores"] = all_cores_cpu(o, args)
+    except Exception as ex:
+        base["all_cores"] = {"error": str(ex)}
+    return base, parity
 
 
 _REAL_STDOUT = None
@@ -275,6 +304,65 @@ def emit_json_line(line):
         sys.stdout.flush()
 
 
+def resident_arm(pkg, torch, ssts, handles, local_rank, stream_ptr, job_kw, verify, steps, warmup, barrier, world, dist, sample_clocks=False):
+    """`steps` whole jobs with the input files resident in HBM, timed between barriers (CUDA events + wall clock,
+    max over ranks). Returns (total seconds, per-step stats, clocks, host ms per phase)."""
+    dev_files = []
+    for s in ssts:
+        v = s.data_view()
+        t = torch.empty(v.size + 64, dtype=torch.uint8, device="cuda")
+        t[16:16 + v.size].copy_(torch.from_numpy(v))
+        dev_files.append(t)
+    host_ms = {"create": 0.0, "add_inputs": 0.0, "run": 0.0, "close": 0.0}
+
+    def step():
+        t0 = time.perf_counter()
+        job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=bool(verify), cuda_stream=stream_ptr, **job_kw)
+        t1 = time.perf_counter()
+        for t, s, (off, sz) in zip(dev_files, ssts, handles):
+            job.add_input_device(t.data_ptr() + 16, s.data_view().size, off, sz)
+        t2 = time.perf_counter()
+        st = job.run()
+        t3 = time.perf_counter()
+        d = st.as_dict()
+        job.close()
+        t4 = time.perf_counter()
+        for k, v in zip(("create", "add_inputs", "run", "close"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            host_ms[k] += v * 1e3
+        return d
+
+    for _ in range(warmup):
+        step()
+    for k in host_ms:
+        host_ms[k] = 0.0
+    clocks = ClockSampler(local_rank) if sample_clocks else None
+    barrier()
+    if clocks:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    stats = [step() for _ in range(steps)]
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clock_info = clocks.stop() if clocks else None
+    step_s = max(wall, e0.elapsed_time(e1) / 1e3)
+    tt = torch.tensor([step_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    del dev_files
+    return float(tt.item()), stats, clock_info, {k: round(v / steps, 3) for k, v in host_ms.items()}
+
+
+def pipeline_roofline(stats, in_bytes, hbm_peak, steps):
+    gpu_s = sum(s["gpu_seconds"] for s in stats) / steps
+    out_bytes = stats[-1]["total_output_raw_key_bytes"] + stats[-1]["total_output_raw_value_bytes"]
+    ach = (in_bytes + out_bytes) / gpu_s / 1e9 if gpu_s > 0 else 0.0
+    return {"algorithmic_bytes": int(in_bytes + out_bytes), "gpu_ms": round(gpu_s * 1e3, 3), "achieved": round(ach, 1),
+            "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4)}
+
+
 def main():
     quiet_stdout()
     args = parse_args()
@@ -292,16 +380,26 @@ def main():
     if not torch.cuda.is_available() or pkg.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the compaction engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # Host placement first: every buffer this rank allocates below (generated input files, pinned output arenas) and
+    # every thread it starts must sit on the NUMA node of its GPU, or the e2e arm pays the inter-socket link
+    # (profiles/h2d_d2h_ceiling.py measures the difference).
+    numa_node, numa_cpus = pkg.bind_thread_to_device(local_rank)
     if world > 1:
         # keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if rank == 0:
+            sys.stderr.write("[bench] NCCL communicator: %d ranks, backend %s, local_rank %d, NCCL %s\n" % (
+                dist.get_world_size(), dist.get_backend(), local_rank, ".".join(map(str, torch.cuda.nccl.version()))))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
 
     # ---- inputs: this rank's tablet (distinct key range per rank) ----
     versions = 20 if args.workload == "mvcc" else 1
@@ -322,60 +420,19 @@ def main():
 
     # block handles from each file's own index (host, once; not part of the hot path)
     handles = [read_handles(pkg, s) for s in ssts]
-
-    # ---- HBM-resident arm ----
-    dev_files = []
-    for s in ssts:
-        v = s.data_view()
-        t = torch.empty(v.size + 64, dtype=torch.uint8, device="cuda")
-        t[16:16 + v.size].copy_(torch.from_numpy(v))
-        dev_files.append(t)
     stream_ptr = torch.cuda.current_stream().cuda_stream
 
-    host_ms = {"create": 0.0, "add_inputs": 0.0, "run": 0.0, "close": 0.0}
-
-    def step_resident():
-        t0 = time.perf_counter()
-        job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=False, cuda_stream=stream_ptr, **job_kw)
-        t1 = time.perf_counter()
-        for t, s, (off, sz) in zip(dev_files, ssts, handles):
-            job.add_input_device(t.data_ptr() + 16, s.data_view().size, off, sz)
-        t2 = time.perf_counter()
-        st = job.run()
-        t3 = time.perf_counter()
-        d = st.as_dict()
-        job.close()
-        t4 = time.perf_counter()
-        for k, v in zip(("create", "add_inputs", "run", "close"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
-            host_ms[k] += v * 1e3
-        return d
-
-    for _ in range(args.warmup):
-        step_resident()
-    for k in host_ms:
-        host_ms[k] = 0.0
-    clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    stats = [step_resident() for _ in range(args.steps)]
-    e1.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    clock_info = clocks.stop()
-    ev_s = e0.elapsed_time(e1) / 1e3
-    step_s = max(wall, ev_s)
-    tt = torch.tensor([step_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_s = float(tt.item())
+    # ---- HBM-resident arm: checksum verification ON like the reference (verify_checksums_in_compaction = true,
+    # rocksdb/util/options.cc:135, db/version_set.cc:3791-3792); the no-verify figure rides along ----
+    total_s, stats, clock_info, host_ms = resident_arm(pkg, torch, ssts, handles, local_rank, stream_ptr, job_kw, args.verify,
+                                                       args.steps, args.warmup, barrier, world, dist, sample_clocks=True)
+    nv_steps = max(1, min(args.steps, 5))
+    nv_s, nv_stats, _, _ = resident_arm(pkg, torch, ssts, handles, local_rank, stream_ptr, job_kw, 0, nv_steps, 1, barrier, world, dist)
     launches = sum(s["gpu_kernel_launches"] for s in stats)
     out_bytes = stats[-1]["total_output_raw_key_bytes"] + stats[-1]["total_output_raw_value_bytes"]
     phases = [sum(s["phase_seconds"][i] for s in stats) / args.steps for i in range(5)]
-    enc_kernel_s = sum(s["phase_seconds"][5] for s in stats) / args.steps      # k_encode_smem alone (CUDA events around its launch)
-    gpu_s = sum(s["gpu_seconds"] for s in stats) / args.steps
+    enc_kernel_s = sum(s["phase_seconds"][5] for s in stats) / args.steps      # block assembler alone (CUDA events around its launch)
+    torch.cuda.empty_cache()
 
     # ---- e2e arm: host (pinned) files in, host files out ----
     e2e = None
@@ -390,6 +447,40 @@ def main():
         # pinned host buffers for the output files, reused by every step
         out_data = torch.empty(file_bytes + (64 << 20), dtype=torch.uint8, pin_memory=True).numpy()
         out_meta = torch.empty(max(64 << 20, file_bytes // 100), dtype=torch.uint8, pin_memory=True).numpy()
+
+        # what the link itself gives this rank: both directions at once, 32 MB chunks, the bench's own buffers
+        def pcie_ceiling():
+            n = min(int(file_bytes), 4 << 30) & ~0xfffff
+            src = torch.from_numpy(pinned[0][0])[:min(n, pinned[0][0].size)]
+            n = int(src.numel()) & ~0xfffff
+            dst = torch.from_numpy(out_data)[:n]
+            din = torch.empty(n, dtype=torch.uint8, device="cuda")
+            dout = torch.empty(n, dtype=torch.uint8, device="cuda")
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+            res = {}
+            for mode in ("h2d", "d2h", "both"):
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    for off in range(0, n, 32 << 20):
+                        if mode != "d2h":
+                            with torch.cuda.stream(s1):
+                                din[off:off + (32 << 20)].copy_(src[off:off + (32 << 20)], non_blocking=True)
+                        if mode != "h2d":
+                            with torch.cuda.stream(s2):
+                                dst[off:off + (32 << 20)].copy_(dout[off:off + (32 << 20)], non_blocking=True)
+                s1.synchronize(); s2.synchronize()
+                dt = time.perf_counter() - t0
+                te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+                res[mode] = round(world * 2 * n / float(te.item()) / 1e9, 1)      # per direction, aggregate over ranks
+            return res
+        try:
+            ceiling = pcie_ceiling()
+        except Exception as ex:
+            ceiling = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        torch.cuda.empty_cache()
 
         e2e_ms = {"add_inputs_h2d": 0.0, "run": 0.0, "fetch_output_d2h": 0.0, "close": 0.0}
 
@@ -410,14 +501,14 @@ def main():
                 e2e_ms[k] += v * 1e3
             return st, data.size + meta.size
 
-        def timed(step_fn):
+        def timed(step_fn, steps):
             for _ in range(min(args.warmup, 2) if args.rows >= 50_000_000 else args.warmup):
                 step_fn()
             for k in e2e_ms:
                 e2e_ms[k] = 0.0
             barrier()
             t0 = time.perf_counter()
-            res = [step_fn() for _ in range(args.steps)]
+            res = [step_fn() for _ in range(steps)]
             barrier()
             dt = time.perf_counter() - t0
             te = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -425,11 +516,14 @@ def main():
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             return float(te.item()), res
 
-        e2e_s, res = timed(step_e2e)
-        single = {"value": round(in_bytes * world * args.steps / e2e_s / 1e9, 4), "unit": "GB/s",
+        info_steps = max(1, min(args.steps, 5))          # the two informational modes; the headline runs args.steps
+        e2e_s, res = timed(step_e2e, info_steps)
+        single = {"value": round(in_bytes * world * info_steps / e2e_s / 1e9, 4), "unit": "GB/s", "steps": info_steps,
                   "h2d_bytes_per_step": int(res[-1][0]["h2d_bytes"]), "d2h_bytes_per_step": int(res[-1][0]["d2h_bytes"]),
-                  "ms_per_step": round(e2e_s / args.steps * 1e3, 2), "output_file_bytes": int(res[-1][1]),
-                  "host_ms_per_step": {k: round(v / args.steps, 2) for k, v in e2e_ms.items()}}
+                  "ms_per_step": round(e2e_s / info_steps * 1e3, 2), "output_file_bytes": int(res[-1][1]),
+                  "host_ms_per_step": {k: round(v / info_steps, 2) for k, v in e2e_ms.items()},
+                  "mode": "one ybgpu_job: H2D of all inputs, run, D2H of the one output file, back to back"}
+
         def verify_outputs(file_list, stride=257):
             # host-side CRC32C check of every stride-th output data block (outside the timed regions): the full-size
             # outputs cannot be compared with the oracle, but a wrong or torn device->host copy cannot pass this
@@ -449,8 +543,7 @@ def main():
             single["output_check"] = verify_outputs([(out_meta[:mlen], out_data[:dlen])])
         except Exception as ex:
             single["output_check"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
-        e2e = dict(single, pinned_inputs=all(ok for _, ok in pinned), verify_checksums=bool(args.verify),
-                   mode="one job, one output file")
+        e2e = dict(single, pinned_inputs=all(ok for _, ok in pinned), verify_checksums=bool(args.verify))
         if args.subcompactions > 1:
             files = [(s.meta_view(), s.data_view()) for s in ssts]
 
@@ -462,95 +555,185 @@ def main():
                 return r.total.as_dict(), sum(o_.data_len + o_.meta_len for o_ in r.outputs), len(r.outputs)
 
             last_sub = [None]
-            sub_s, sres = timed(step_sub)
+            sub_s, sres = timed(step_sub, info_steps)
             try:
                 sub_check = verify_outputs([(out_meta[o_.meta_offset:o_.meta_offset + o_.meta_len], out_data[o_.data_offset:o_.data_offset + o_.data_len])
                                             for o_ in last_sub[0].outputs if o_.data_len])
             except Exception as ex:
                 sub_check = {"error": "%s: %s" % (type(ex).__name__, ex)}
             assert sres[-1][0]["num_input_records"] == n_entries, "subcompactions must see every input entry once"
+            range_files = {"value": round(in_bytes * world * info_steps / sub_s / 1e9, 4), "unit": "GB/s", "steps": info_steps,
+                           "ms_per_step": round(sub_s / info_steps * 1e3, 2), "output_files": int(sres[-1][2]),
+                           "output_file_bytes": int(sres[-1][1]), "output_check": sub_check,
+                           "gpu_ms_per_step": round(sres[-1][0]["gpu_seconds"] * 1e3, 2),
+                           "mode": "ybgpu_compact_files, one output SST per key range (the shape CompactionJob gives "
+                                   "subcompactions, compaction_job.cc:1128-1131) — NOT the headline: DocDB writes one file"}
 
-            # One table out of the range outputs (what a single-level universal layout such as DocDB's needs): the
-            # range data files are appended in range order as they are, ybgpu_sst_concat_meta writes the one metadata
-            # file (rebased multi-level index, all filter blocks + one filter index, summed properties).
-            one_table = None
-            try:
-                if world > 1:
-                    raise RuntimeError("measured at N=1 only (an exception on one rank must not strand the others at a barrier)")
-                concat_buf = np.empty(2 * out_meta.size + (1 << 20), np.uint8)
-                concat_buf[::4096] = 0                      # touch the pages once, outside the timed region
+            # HEADLINE: ONE output table, the shape DocDB's single-level universal compaction (and the reference arm)
+            # writes. The key ranges run pipelined; their data pieces are appended in range order as they are and
+            # ybgpu_sst_concat_meta writes the one metadata file (rebased multi-level index, all filter blocks + one
+            # filter index, summed properties) — all inside the timed region.
+            concat_buf = np.empty(2 * out_meta.size + (1 << 20), np.uint8)
+            concat_buf[::4096] = 0                      # touch the pages once, outside the timed region
 
-                def step_one_table():
-                    r = pkg.compact_files(files, max_subcompactions=args.subcompactions, max_in_flight=args.in_flight,
-                                          data_arena=out_data, meta_arena=out_meta, device=local_rank,
-                                          verify_checksums=bool(args.verify), **job_kw)
-                    outs = [o_ for o_ in r.outputs if o_.data_len]
-                    pieces = [(out_meta[o_.meta_offset:o_.meta_offset + o_.meta_len], o_.data_len, o_.smallest, o_.largest) for o_ in outs]
-                    meta = pkg.sst_concat_meta(pieces, out=concat_buf, filter_policy=job_kw.get("filter_policy", 0))
-                    return r.total.as_dict(), sum(o_.data_len for o_ in outs), int(meta.size), len(outs), meta
-                ot_s, ores = timed(step_one_table)
-                st_d, data_bytes, meta_bytes, n_pieces, meta = ores[-1]
-                off, sz, _ = pkg.sst_block_handles(meta)     # the product's own reader walks the merged index
-                assert len(off) == st_d["num_output_data_blocks"] and int(off[-1] + sz[-1]) + 5 == data_bytes
-                assert st_d["num_input_records"] == n_entries
-                one_table = {"value": round(in_bytes * world * args.steps / ot_s / 1e9, 4), "unit": "GB/s",
-                             "ms_per_step": round(ot_s / args.steps * 1e3, 2), "output_file_bytes": int(data_bytes + meta_bytes),
-                             "pieces": int(n_pieces), "data_blocks": int(len(off))}
-            except Exception as ex:                          # never lose the bench line to the extra figure
-                one_table = {"error": "%s: %s" % (type(ex).__name__, ex)}
-            e2e = {"value": round(in_bytes * world * args.steps / sub_s / 1e9, 4), "unit": "GB/s",
-                   "h2d_bytes_per_step": int(sres[-1][0]["h2d_bytes"]), "d2h_bytes_per_step": int(sres[-1][0]["d2h_bytes"]),
-                   "ms_per_step": round(sub_s / args.steps * 1e3, 2), "pinned_inputs": all(ok for _, ok in pinned),
-                   "output_file_bytes": int(sres[-1][1]), "verify_checksums": bool(args.verify),
-                   "mode": "ybgpu_compact_files: %d key-range subcompactions (max_subcompactions=%d), %d in flight on private "
-                           "streams, one output SST per range" % (sres[-1][2], args.subcompactions, args.in_flight),
-                   "output_files": int(sres[-1][2]), "output_check": sub_check,
-                   "gpu_ms_per_step": round(sres[-1][0]["gpu_seconds"] * 1e3, 2),
-                   "one_table": one_table,
+            def step_one_table():
+                r = pkg.compact_files(files, max_subcompactions=args.subcompactions, max_in_flight=args.in_flight,
+                                      data_arena=out_data, meta_arena=out_meta, device=local_rank,
+                                      verify_checksums=bool(args.verify), **job_kw)
+                outs = [o_ for o_ in r.outputs if o_.data_len]
+                pieces = [(out_meta[o_.meta_offset:o_.meta_offset + o_.meta_len], o_.data_len, o_.smallest, o_.largest) for o_ in outs]
+                meta = pkg.sst_concat_meta(pieces, out=concat_buf, filter_policy=job_kw.get("filter_policy", 0))
+                return r.total.as_dict(), sum(o_.data_len for o_ in outs), int(meta.size), len(outs), meta
+            ot_s, ores = timed(step_one_table, args.steps)
+            st_d, data_bytes, meta_bytes, n_pieces, meta = ores[-1]
+            off, sz, _ = pkg.sst_block_handles(meta)     # the product's own reader walks the merged index
+            assert len(off) == st_d["num_output_data_blocks"] and int(off[-1] + sz[-1]) + 5 == data_bytes
+            assert st_d["num_input_records"] == n_entries
+            e2e = {"value": round(in_bytes * world * args.steps / ot_s / 1e9, 4), "unit": "GB/s", "steps": args.steps,
+                   "h2d_bytes_per_step": int(st_d["h2d_bytes"]), "d2h_bytes_per_step": int(st_d["d2h_bytes"]),
+                   "ms_per_step": round(ot_s / args.steps * 1e3, 2), "pinned_inputs": all(ok for _, ok in pinned),
+                   "output_files": 1, "output_file_bytes": int(data_bytes + meta_bytes), "verify_checksums": bool(args.verify),
+                   "mode": "ONE output table: ybgpu_compact_files (%d key ranges, %d in flight on private streams) + "
+                           "ybgpu_sst_concat_meta inside the timed region" % (n_pieces, args.in_flight),
+                   "pieces": int(n_pieces), "data_blocks": int(len(off)),
+                   "gpu_ms_per_step": round(st_d["gpu_seconds"] * 1e3, 2),
+                   "pcie_ceiling_gbs": ceiling,
+                   "range_files": range_files,
                    "single_job": single}
+            if isinstance(ceiling, dict) and "both" in ceiling and ceiling["both"]:
+                # the step moves in_bytes in and about as much out: bound = the slower direction of the duplex figure
+                e2e["frac_of_pcie_ceiling"] = round(e2e["value"] / (ceiling["both"] / 2.0), 3)
+            del concat_buf
         for v, ok in pinned:
             if ok:
                 cudart.cudaHostUnregister(v.ctypes.data)
+        del out_data, out_meta
+
+    # ---- BASELINE configs[2] and configs[3] as sub-results (the bench line itself is configs[1]) ----
+    extra = {}
+    if not args.no_extra_configs and args.workload == "config2":
+        pinned = None
+        del ssts, handles
+        torch.cuda.empty_cache()
+        try:   # configs[2]: 64 tablets x 4-way x 10 M keys across 8 GPUs = 8 tablets per GPU, one after the other
+            tabs = []
+            t0 = time.perf_counter()
+            for t in range(args.c3_tablets):
+                tid = rank * args.c3_tablets + t
+                c3 = pkg.GenConfig(seed=1000 + tid, num_rows=args.c3_rows, cols=1, versions=1, num_files=4, value_len=VALUE_LEN,
+                                   row_offset=tid * args.c3_rows, hash_rows_total=args.c3_rows * args.c3_tablets * world)
+                ts = pkg.generate_ssts(c3, max_threads=4)
+                tabs.append((ts, [read_handles(pkg, s_) for s_ in ts]))
+            c3_gen = time.perf_counter() - t0
+            c3_in = sum(s_.raw_bytes for ts, _ in tabs for s_ in ts)
+            c3_entries = sum(s_.num_entries for ts, _ in tabs for s_ in ts)
+            def to_dev(v):
+                t_ = torch.empty(v.size + 64, dtype=torch.uint8, device="cuda")
+                t_[16:16 + v.size].copy_(torch.from_numpy(v))
+                return t_
+            dev = [[to_dev(s_.data_view()) for s_ in ts] for ts, _ in tabs]
+
+            def c3_step():
+                sts = []
+                for (ts, hs), dts in zip(tabs, dev):
+                    job = pkg.GpuCompactionJob(device=local_rank, verify_checksums=bool(args.verify), cuda_stream=stream_ptr, **job_kw)
+                    for t_, s_, (off, sz) in zip(dts, ts, hs):
+                        job.add_input_device(t_.data_ptr() + 16, s_.data_view().size, off, sz)
+                    sts.append(job.run().as_dict())
+                    job.close()
+                return sts
+            c3_step()
+            c3_steps = 3
+            barrier()
+            t0 = time.perf_counter()
+            c3_stats = [c3_step() for _ in range(c3_steps)]
+            barrier()
+            dt = time.perf_counter() - t0
+            te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dt = float(te.item())
+            flat = [x for st_ in c3_stats for x in st_]
+            gpu_s = sum(x["gpu_seconds"] for x in flat) / c3_steps
+            c3_out = sum(x["total_output_raw_key_bytes"] + x["total_output_raw_value_bytes"] for x in c3_stats[-1])
+            ach = (c3_in + c3_out) / gpu_s / 1e9
+            extra["configs[2]"] = {
+                "workload": "64 tablets x 4-way compaction, 10M keys each, tablet-sharded across 8 GPUs: %d tablets x %d entries per GPU, %d GPU(s) in this run, "
+                            "inputs resident in HBM, jobs back to back on one stream" % (args.c3_tablets, args.c3_rows, world),
+                "value": round(c3_in * world * c3_steps / dt / 1e9, 2), "unit": "GB/s", "mkeys_per_s": round(c3_entries * world * c3_steps / dt / 1e6, 1),
+                "ms_per_step": round(dt / c3_steps * 1e3, 2), "steps": c3_steps, "tablets_per_gpu": args.c3_tablets,
+                "entries_per_gpu": int(c3_entries), "verify_checksums": bool(args.verify), "generate_s": round(c3_gen, 1),
+                "roofline": {"bound": "hbm", "scope": "whole pipeline", "algorithmic_bytes": int(c3_in + c3_out), "gpu_ms": round(gpu_s * 1e3, 2),
+                             "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4)}}
+            del tabs, dev
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            extra["configs[2]"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        if world == 1:
+            try:   # configs[3]: MVCC-heavy, 20 versions per key, the history cutoff drops 18 of 20 (90 %)
+                live = args.c4_rows // 20
+                c4 = pkg.GenConfig(seed=77, num_rows=live, cols=1, versions=20, num_files=NUM_FILES, value_len=VALUE_LEN)
+                t0 = time.perf_counter()
+                s4 = pkg.generate_ssts(c4, max_threads=NUM_FILES)
+                c4_gen = time.perf_counter() - t0
+                h4 = [read_handles(pkg, s_) for s_ in s4]
+                kw4 = dict(job_kw, cutoff_ht=((c4.base_micros + 18 * 1000 + 500) << 12))
+                c4_in = sum(s_.raw_bytes for s_ in s4)
+                c4_entries = sum(s_.num_entries for s_ in s4)
+                c4_steps = 3
+                c4_s, c4_stats, _, _ = resident_arm(pkg, torch, s4, h4, local_rank, stream_ptr, kw4, args.verify, c4_steps, 1, barrier, world, dist)
+                roof = pipeline_roofline(c4_stats, c4_in, hbm_peak, c4_steps)
+                extra["configs[3]"] = {
+                    "workload": "MVCC-heavy: 20 versions/key, history_cutoff drops 90%%, %d live keys (%d entries, %.1f GB raw) resident on 1 GPU; "
+                                "BASELINE names 50M live keys = 1 G entries = 310 GB, which exceeds the 180 GB of HBM" % (live, c4_entries, c4_in / 1e9),
+                    "value": round(c4_in * c4_steps / c4_s / 1e9, 2), "unit": "GB/s", "mkeys_per_s": round(c4_entries * c4_steps / c4_s / 1e6, 1),
+                    "ms_per_step": round(c4_s / c4_steps * 1e3, 2), "steps": c4_steps, "entries": int(c4_entries),
+                    "output_entries": int(c4_stats[-1]["num_output_records"]), "dropped_fraction": round(1.0 - c4_stats[-1]["num_output_records"] / c4_entries, 4),
+                    "verify_checksums": bool(args.verify), "generate_s": round(c4_gen, 1),
+                    "roofline": dict(roof, bound="hbm", scope="whole pipeline")}
+                del s4, h4
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                extra["configs[3]"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks, peak_kind = measured_peaks()
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # dominant kernel = longest phase; its algorithmic bytes (DESIGN.md "Roofline accounting")
-    alg_bytes = {
-        "block_scan": in_bytes * 0.0,           # header walk only: not the dominant phase
-        "decode": in_bytes,                     # must read every input entry once
-        "partition": 0.0,
-        "merge_filter": 0.0,
-        "encode": out_bytes * 2.0,              # read each survivor once, write it once
-    }
     names = pkg.PHASE_NAMES
-    # The dominant KERNEL: decode and merge phases are one kernel each; the encode phase is ~25 launches of
-    # which the block assembler k_encode_smem is timed separately.
-    kernel_s = {"k_decode_all": phases[1], "k_merge_filter": phases[3], "k_encode_smem": enc_kernel_s}
-    kernel_alg = {"k_decode_all": float(in_bytes),                  # must read every input entry once
+    # The dominant KERNEL: ingest (verify + decode) and merge phases are one kernel each; the encode phase is ~25
+    # launches of which the block assembler is timed separately.
+    kernel_s = {"ingest(verify+decode)": phases[0] + phases[1], "k_merge_filter": phases[3], "k_encode": enc_kernel_s}
+    kernel_alg = {"ingest(verify+decode)": float(in_bytes),         # must read every input byte once
                   "k_merge_filter": float(in_bytes + out_bytes),    # charged the whole path (it moves only keys)
-                  "k_encode_smem": out_bytes * 2.0}                 # read each survivor once, write it once
+                  "k_encode": out_bytes * 2.0}                      # read each survivor once, write it once
     dom_kernel = max(kernel_s, key=lambda k: kernel_s[k])
-    dom = max(range(5), key=lambda i: phases[i])
     dom_bytes = kernel_alg[dom_kernel]
     achieved = dom_bytes / kernel_s[dom_kernel] / 1e9 if kernel_s[dom_kernel] > 0 else 0.0
-    # DRAM traffic of that kernel from the committed `ncu --set full` capture of this same command
-    traffic = None
+    # DRAM traffic of that kernel: NOT measured in this run — read from the committed `ncu --set full` capture of this
+    # same command (profiles/), labelled so
+    traffic, traffic_src = None, None
     try:
         if args.workload == "config2" and args.rows == DEFAULT_ROWS:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_100m.json")))["kernels"]
-            for name, kd in prof.items():
-                if name.startswith(dom_kernel):
-                    def gb(x):
-                        v = float(x["value"]); return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[x["unit"]]
-                    traffic = int(gb(kd["dram__bytes_read.sum"]) + gb(kd["dram__bytes_write.sum"]))
+            for fn in ("r02_ncu_full_100m.json", "r01_ncu_full_100m.json"):
+                path = os.path.join(ROOT, "profiles", fn)
+                if not os.path.exists(path):
+                    continue
+                prof = json.load(open(path))["kernels"]
+                want = {"ingest(verify+decode)": ("k_ingest", "k_decode"), "k_merge_filter": ("k_merge_filter",), "k_encode": ("k_encode",)}[dom_kernel]
+                for name, kd in prof.items():
+                    if name.startswith(want):
+                        def gb(x):
+                            v = float(x["value"]); return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[x["unit"]]
+                        traffic = int(gb(kd["dram__bytes_read.sum"]) + gb(kd["dram__bytes_write.sum"]))
+                        traffic_src = "profiles/%s (%s), committed capture, not measured in this run" % (fn, name)
+                        break
+                if traffic is not None:
+                    break
     except Exception:
         traffic = None
-    pipeline_achieved = (in_bytes + out_bytes) / gpu_s / 1e9 if gpu_s > 0 else 0.0
     value = in_bytes * world * args.steps / total_s / 1e9
     line = {
         "metric": "compaction GB/s (input bytes merged)", "value": round(value, 3), "unit": "GB/s",
@@ -563,25 +746,33 @@ def main():
                    "entries_per_gpu": int(n_entries), "input_raw_bytes_per_gpu": int(in_bytes),
                    "input_file_bytes_per_gpu": int(file_bytes), "tablets": world,
                    "parallelism": "tablet-per-GPU, no collective",
+                   "verify_checksums": bool(args.verify),
+                   "host_placement": {"numa_node": numa_node, "cpus": numa_cpus},
                    "output": "split SST: data blocks + CRC32C, multi-level index, DocKeyV3 bloom filter blocks (64 KB), properties, footer",
                    "l2": "inputs (%.1f GB) far larger than the 126 MB L2" % (file_bytes / 1e9)},
         "mkeys_per_s": round(n_entries * world * args.steps / total_s / 1e6, 2),
         "gpu_launches": int(launches),
         "clocks": clock_info,
+        "value_no_verify": {"value": round(in_bytes * world * nv_steps / nv_s / 1e9, 3), "unit": "GB/s", "steps": nv_steps,
+                            "ms_per_step": round(nv_s / nv_steps * 1e3, 3),
+                            "note": "input block checksums NOT verified (work the reference does is skipped): informational only"},
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_kind,
+                     "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
                      "kernel_ms": round(kernel_s[dom_kernel] * 1e3, 3), "algorithmic_bytes_per_launch": int(dom_bytes),
                      "kernels_ms": {k: round(v * 1e3, 3) for k, v in kernel_s.items()},
-                     "pipeline": {"algorithmic_bytes": int(in_bytes + out_bytes), "gpu_ms": round(gpu_s * 1e3, 3),
-                                  "achieved": round(pipeline_achieved, 1), "frac": round(pipeline_achieved / hbm_peak, 4)},
+                     "pipeline": pipeline_roofline(stats, in_bytes, hbm_peak, args.steps),
                      "phase_ms": {names[i]: round(phases[i] * 1e3, 3) for i in range(5)}},
         "setup": {"generate_s": round(gen_s, 1)},
-        "host_ms_per_step": {k: round(v / args.steps, 3) for k, v in host_ms.items()},
+        "host_ms_per_step": host_ms,
     }
     if e2e:
         line["e2e"] = e2e
+    if extra:
+        line["configs"] = extra
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args)
+        base, parity = cpu_baseline(args, pkg, local_rank)
+        line["cpu_baseline"] = base
+        line["parity_check"] = parity
     emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()

@@ -355,6 +355,16 @@ ybgpu_status ybgpu_sst_meta_handles(const uint8_t* meta_file, uint64_t meta_file
 ybgpu_status ybgpu_sst_meta_separators(const uint8_t* meta_file, uint64_t meta_file_len, uint8_t* keys, uint64_t keys_cap,
                                        uint64_t* key_offsets, uint64_t* num_keys, uint64_t* keys_bytes);
 
+/* --- host placement ---------------------------------------------------------------------------------
+ * Binds the CALLING thread to the CPUs of the NUMA node the device is attached to and makes that node the
+ * thread's preferred memory node (threads created afterwards inherit both), so that staging buffers
+ * allocated / first touched / pinned by it are one PCIe hop from the GPU instead of across the inter-socket
+ * link. The reference's PriorityThreadPool workers are unbound (db_impl.cc:397-403); a device-attached worker
+ * wants this in addition. ybgpu_compact_files binds its range worker threads this way (YBGPU_NUMA_BIND=0
+ * disables). numa_node / num_cpus (optional) receive what was applied (-1 / 0: nothing to do on this host). */
+int32_t ybgpu_device_numa_node(int32_t device);
+ybgpu_status ybgpu_bind_thread_to_device(int32_t device, int32_t* numa_node, int32_t* num_cpus);
+
 /* Library / device probe. */
 int32_t ybgpu_device_count(void);
 const char* ybgpu_version(void);

@@ -135,6 +135,14 @@ def device_count():
     return lib().ybgpu_device_count()
 
 
+def bind_thread_to_device(device):
+    """ybgpu_bind_thread_to_device: CPU affinity + preferred memory node of the calling thread (and of threads it
+    creates later) = the NUMA node of `device`. Returns (numa_node, num_cpus); (-1, 0) when nothing was done."""
+    node, ncpu = C.c_int32(-1), C.c_int32(0)
+    lib().ybgpu_bind_thread_to_device(device, C.byref(node), C.byref(ncpu))
+    return node.value, ncpu.value
+
+
 def _np_ptr(a):
     return a.ctypes.data if a.size else None
 

@@ -402,7 +402,8 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
               r, t_begin, t_added, t_ran, t_sized, t_fetched, ms_now(), out.stats.gpu_seconds * 1e3, out.stats.h2d_bytes / 1e9);
   };
 
-  auto worker = [&]() {
+  auto worker = [&](bool pool_thread) {
+    if (pool_thread) ybgpu_bind_thread_to_device(options->device, nullptr, nullptr);   // never the caller's own thread
     for (;;) {
       if (failed.load()) return;
       if (options->yield_fn) options->yield_fn(options->yield_ctx);      // PauseIfNecessary between ranges
@@ -414,10 +415,10 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
   };
   const uint32_t n_threads = std::min(max_in_flight, n_ranges);
   if (n_threads <= 1) {
-    worker();
+    worker(false);
   } else {
     std::vector<std::thread> pool;
-    for (uint32_t t = 0; t < n_threads; t++) pool.emplace_back(worker);
+    for (uint32_t t = 0; t < n_threads; t++) pool.emplace_back(worker, true);
     for (std::thread& t : pool) t.join();
   }
   if (failed.load()) return fail(first_status, first_error);
