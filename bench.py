@@ -198,29 +198,29 @@ def run_reference(args, rank, world):
 def all_cores_cpu(o, args, rows_each=1_000_000, min_seconds=4.0):
     """The host's compaction rate across MANY tablets: P concurrent one-thread compactions, P = the reference's
     compaction pool size floor(ncpu * 3.5 / 8) (docdb_rocksdb_util.cc:630-641), plus the all-hardware-threads figure.
-    Each worker loops over its own private sample until min_seconds have passed (no 0.07 s samples)."""
-    from concurrent.futures import ThreadPoolExecutor
+    One PROCESS per compaction (oracle/cpu_worker.py): tablets share nothing in the reference, and threads of one
+    process would contend on the allocator. All workers start their timed loop at the same wall-clock instant and
+    run for min_seconds; the aggregate is the sum of the workers' own rates."""
     ncpu = os.cpu_count() or 1
-    cfg = o.GenConfig(seed=2, num_rows=rows_each, cols=1, versions=1, num_files=NUM_FILES, value_len=VALUE_LEN)
-    ssts = o.Sst.generate_all(cfg, o.TableOptions())
-    b = sum(s.raw_bytes for s in ssts)
+    worker = os.path.join(ROOT, "oracle", "cpu_worker.py")
     out = {}
     for label, T in (("pool", max(1, int(ncpu * 3.5 / 8))), ("all_threads", ncpu)):
-        done = [0] * T
-        t_end = [0.0] * T
-        t0 = time.perf_counter()
-
-        def one(i):
-            while time.perf_counter() - t0 < min_seconds:
-                r = o.compact(ssts, o.CompactionParams(), o.TableOptions(filter_policy=1), mode=o.BUILD_SST | o.NO_HASH, verify=bool(args.verify))
-                del r
-                done[i] += 1
-            t_end[i] = time.perf_counter()
-        with ThreadPoolExecutor(T) as ex:
-            list(ex.map(one, range(T)))
-        dt = max(t_end) - t0
-        out[label] = {"value": round(sum(done) * b / dt / 1e9, 3), "unit": "GB/s", "threads": T,
-                      "sample": "%d one-thread compactions of %d entries each on %d concurrent threads, %.1f s" % (sum(done), rows_each, T, dt)}
+        start_at = time.time() + 3.0 + 0.02 * T          # interpreter start + sample generation of every worker
+        procs = [subprocess.Popen([sys.executable, worker, "--rows", str(rows_each), "--seconds", str(min_seconds),
+                                   "--start-at", "%.3f" % start_at, "--verify", str(int(bool(args.verify)))],
+                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(T)]
+        rate, done, late = 0.0, 0, 0
+        for p_ in procs:
+            txt, _ = p_.communicate(timeout=120 + 10 * min_seconds)
+            try:
+                r = json.loads(txt.strip().splitlines()[-1])
+                rate += r["done"] * r["bytes_each"] / r["elapsed"]
+                done += r["done"]
+            except Exception:
+                late += 1
+        out[label] = {"value": round(rate / 1e9, 3), "unit": "GB/s", "processes": T,
+                      "sample": "%d one-thread compactions of %d entries each in %d concurrent processes, %.0f s each%s" % (
+                          done, rows_each, T, min_seconds, (", %d workers failed" % late) if late else "")}
     out["host_threads"] = ncpu
     return out
 
@@ -451,8 +451,8 @@ def main():
         # what the link itself gives this rank: both directions at once, 32 MB chunks, the bench's own buffers
         def pcie_ceiling():
             n = min(int(file_bytes), 4 << 30) & ~0xfffff
-            src = torch.from_numpy(pinned[0][0])[:min(n, pinned[0][0].size)]
-            n = int(src.numel()) & ~0xfffff
+            n = min(n, int(pinned[0][0].size)) & ~0xfffff
+            src = torch.from_numpy(pinned[0][0])[:n]
             dst = torch.from_numpy(out_data)[:n]
             din = torch.empty(n, dtype=torch.uint8, device="cuda")
             dout = torch.empty(n, dtype=torch.uint8, device="cuda")

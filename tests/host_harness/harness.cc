@@ -15,9 +15,15 @@ using namespace ybgpu;
 namespace {
 struct Out { std::string keys, vals; std::vector<uint64_t> koff{0}, voff{0}; int error = 0; };
 Out* g_out = nullptr;
+int g_cut_every = 0;     // > 0: emulate a merge-tile boundary before every g_cut_every-th sorted record
 }
 
 extern "C" {
+
+// Emulates tiles that start in the middle of a row group: before every n-th record (in merged order) that is not
+// the first of its group, the feed state is thrown away and rebuilt the way the tile kernel does it — reset,
+// cotable seed, replay_ancestors over the records that precede it.
+void hh_set_cut_every(int n) { g_cut_every = n; }
 
 // returns 0 or a positive DevError
 int hh_compact(int n_runs, const uint64_t* run_start, const uint8_t* keys, const uint64_t* koff, const uint8_t* vals,
@@ -59,18 +65,17 @@ int hh_compact(int n_runs, const uint64_t* run_start, const uint8_t* keys, const
   R.lower_len = static_cast<uint32_t>(lower_len); memcpy(R.lower, lower, lower_len);
   R.upper_len = static_cast<uint32_t>(upper_len); memcpy(R.upper, upper, upper_len);
 
+  // merged-order copy of the records (one "run") for replay_ancestors
+  std::vector<uint8_t> sorted_store(static_cast<size_t>(n) * S + 64, 0);
+  uint8_t* sbase = sorted_store.data();
+  sbase += (16 - (reinterpret_cast<uintptr_t>(sbase) & 15)) & 15;
+  std::vector<uint64_t> sorted_voff(n + 1, 0);
+  if (g_cut_every > 0)
+    for (uint64_t i = 0; i < n; i++) { memcpy(sbase + i * S, base + size_t(order[i]) * S, S); sorted_voff[i] = voff[order[i]]; }
+
   FeedState st; feed_state_reset(&st);
   const uint8_t* prev_group = nullptr; int prev_g = -1;
-  const uint8_t* prev_rec = nullptr;
-  for (uint64_t i = 0; i < n; i++) {
-    const uint32_t id = order[i];
-    const uint8_t* e = base + size_t(id) * S;
-    const uint32_t ulen = rec_ulen(e, S);
-    const int g = group_prefix_len(e, ulen, retention != 0);
-    if (g < 0) return -g;
-    const bool new_group = !prev_group || g != prev_g || common_prefix_len(e, g, prev_group, g) < static_cast<uint32_t>(g);
-    if (new_group) {
-      feed_state_reset(&st); prev_group = e; prev_g = g;
+  auto seed_cotable = [&](const uint8_t* e, uint32_t ulen) -> int {
       // cotable / colocated rows: seed slot 0 from the table's tombstone entries, as the tile kernel does
       if (retention && ulen && (e[0] == 'y' || e[0] == '0')) {
         const int id = dockey_id_size(e, ulen);
@@ -94,6 +99,28 @@ int hh_compact(int n_runs, const uint64_t* run_start, const uint8_t* keys, const
           if (any && ts.n_ow >= 1 && ts.n_ends == 1) feed_state_seed(&st, e, id, ts.ow[0]);
         }
       }
+    return 0;
+  };
+  const uint8_t* prev_rec = nullptr;
+  for (uint64_t i = 0; i < n; i++) {
+    const uint32_t id = order[i];
+    const uint8_t* e = base + size_t(id) * S;
+    const uint32_t ulen = rec_ulen(e, S);
+    const int g = group_prefix_len(e, ulen, retention != 0);
+    if (g < 0) return -g;
+    const bool new_group = !prev_group || g != prev_g || common_prefix_len(e, g, prev_group, g) < static_cast<uint32_t>(g);
+    if (new_group) {
+      feed_state_reset(&st); prev_group = e; prev_g = g;
+      int rc = seed_cotable(e, ulen);
+      if (rc) return rc;
+    } else if (retention && g_cut_every > 0 && i % g_cut_every == 0) {
+      // a tile boundary inside the group: rebuild the state from nothing
+      feed_state_reset(&st);
+      int rc = seed_cotable(e, ulen);
+      if (rc) return rc;
+      ReplayRun rr{sbase, static_cast<uint32_t>(i), vals, sorted_voff.data()};
+      const int d3 = replay_ancestors(&st, R, &rr, 1, S, sbase + i * S, ulen, bottommost, last_sequence);
+      if (d3 < 0) return -d3;
     }
     const bool first_occ = !prev_rec || cmp_user_keys(prev_rec, rec_ulen(prev_rec, S), e, ulen) != 0;
     prev_rec = e;

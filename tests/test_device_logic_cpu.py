@@ -121,3 +121,35 @@ def test_bloom_filter_key_and_hash_match_the_oracle():
         assert pair[0] == want
         fk = k[:want] + bytes(rng.randrange(256) for _ in range(rng.randrange(4)))
         assert L.hh_bloom_hash(fk, len(fk)) == ob.bloom_hash(fk)
+
+
+@pytest.mark.parametrize("cut", [1, 2, 3, 7])
+def test_state_rebuilt_by_ancestor_replay_inside_groups(cut):
+    """Merge tiles may start inside a row group (groups larger than a tile): the tile rebuilds Feed's state by
+    replaying the ancestors `P_i # HT` and the earlier versions of its first key (dev_logic.cuh replay_ancestors).
+    Here the state is thrown away and rebuilt before every `cut`-th record of every group — cut = 1: before EVERY
+    record — and the result must still equal the oracle's single sequential pass."""
+    L = hh.lib()
+    L.hh_set_cut_every(cut)
+    try:
+        for seed in range(6):
+            runs = w.random_docdb_runs(200 + seed, n_runs=1 + seed % 4, n_rows=20 + 5 * seed)
+            for kw in w.param_grid():
+                got, exp = both(runs, **kw)
+                assert got == exp, (seed, kw)
+        for seed in range(4):
+            runs = w.random_cotable_runs(300 + seed, n_runs=1 + seed % 3, n_tables=3, rows_per_table=10, colocated=seed % 2 == 0)
+            for kw in w.param_grid()[:8]:
+                got, exp = both(runs, **kw)
+                assert got == exp, (seed, kw)
+        for seed in range(3):
+            runs = w.random_numeric_key_runs(400 + seed, n_runs=2, n_rows=25)
+            for kw in w.param_grid()[:6]:
+                got, exp = both(runs, **kw)
+                assert got == exp, (seed, kw)
+        import test_reference_dumps as t          # TTL / merge-record chains, collections, user timestamps
+        for name in sorted(dir(t)):
+            if name.startswith("test_") and "parser" not in name:
+                getattr(t, name)()
+    finally:
+        L.hh_set_cut_every(0)

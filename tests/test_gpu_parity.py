@@ -394,6 +394,37 @@ def test_subcompactions_inside_cotables(pkg, seed):
     assert inside >= 4, "the test must cut inside tables"
 
 
+@pytest.mark.parametrize("seed,cols,versions,collection,colocated", [(0, 250, 20, 2000, False), (1, 120, 45, 1500, True), (2, 500, 100, 4000, False)])
+def test_rows_larger_than_a_merge_tile(pkg, seed, cols, versions, collection, colocated):
+    """a9 without a row-size limit: DocDBCompactionFeed carries its overwrite stack over any number of entries of one
+    DocKey (docdb_compaction_context.cc:999-1024). Rows of ~5 000 and ~50 000 entries (many columns x versions, a
+    collection under a column with its own tombstones) are cut across merge tiles; tiles that start inside the row
+    rebuild the state by replaying the ancestors of their first key. Full-file parity with the oracle."""
+    runs = w.giant_row_runs(seed, n_runs=2 + seed, cols=cols, versions=versions, collection=collection, colocated=colocated)
+    assert sum(len(r) for r in runs) > (40000 if seed == 2 else 5000)
+    ssts = runs_to_ssts(runs, 4096)
+    grid = w.param_grid()
+    for kw in ([grid[i] for i in (0, 2, 3, 4, 6, 8, 9)] if seed < 2 else [grid[2], grid[4]]):
+        check(pkg, ssts, block_size=4096, **kw)
+
+
+def test_plain_mode_user_key_with_thousands_of_versions(pkg):
+    """retention off (plain RocksDB): a row group is one user key; 6 000 versions of one key span many tiles and
+    rule A (compaction_iterator.cc:388-400) must still keep exactly the newest one."""
+    seq = 1 << 40
+    runs = [[], [], []]
+    for i in range(6000):
+        seq += 1
+        runs[i % 3].append((o.ikey(b"hot-key", seq), b"v%d" % i))
+    for j in range(300):
+        seq += 1
+        runs[j % 3].append((o.ikey(b"key%04d" % j, seq), b"x" * (j % 50)))
+    ssts = runs_to_ssts([w.sort_run(r) for r in runs], 2048)
+    job, exp = check(pkg, ssts, block_size=2048, retention=False, bottommost=True)
+    assert job.stats().num_output_records == 301
+    check(pkg, ssts, block_size=2048, retention=False, bottommost=False)
+
+
 def test_emit_kv_stream_is_the_kv_list(pkg):
     """a8: ybgpu_job_emit_kv_stream hands the surviving stream to a CompactionFeed-shaped callback in output order;
     a non-zero return aborts with that status (compaction_job.cc:797-800)."""

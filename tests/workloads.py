@@ -162,3 +162,57 @@ def random_numeric_key_runs(seed, n_runs=3, n_rows=40, n_ht=12):
                 seq[r] += 1
                 runs[r].append((o.ikey(uk, seq[r]), dk.TOMBSTONE if rng.random() < 0.15 else dk.vstr("v%d" % rng.randrange(1000))))
     return [sort_run(r) for r in runs]
+
+
+def giant_row_runs(seed, n_runs=3, cols=250, versions=20, collection=2000, small_rows=30, colocated=False, n_ht=40):
+    """Rows far larger than a merge tile: one row of cols x versions column entries with row-level markers and
+    tombstones (`DocKey # HT`), one row holding a collection of `collection` elements x 3 versions under a column
+    that itself has several versions / tombstones (`DocKey col # HT`), surrounded by small rows; optionally inside a
+    colocated table with table tombstones. The ancestors' overwrite times shadow entries thousands of records later."""
+    rng = random.Random(seed)
+    runs = [[] for _ in range(n_runs)]
+    seq = [(1 << 50) + (r << 30) for r in range(n_runs)]
+    used = set()
+    kw = dict(colocation=77) if colocated else {}
+
+    def put(uk, value):
+        if uk in used:
+            return
+        used.add(uk)
+        r = rng.randrange(n_runs)
+        seq[r] += 1
+        runs[r].append((o.ikey(uk, seq[r]), value))
+
+    def ht():
+        return (BASE_US + rng.randrange(n_ht) * 10, rng.randrange(2), rng.randrange(3))
+
+    def val():
+        x = rng.random()
+        return dk.TOMBSTONE if x < 0.12 else dk.vstr("v%d" % rng.randrange(10**6) + "y" * rng.randrange(0, 30))
+
+    if colocated:
+        for _ in range(2):
+            put(dk.table_tombstone_key(micros=BASE_US + rng.randrange(n_ht) * 10, **kw), dk.TOMBSTONE)
+    for i in range(small_rows // 2):
+        put(dk.sub_doc_key(dk.doc_key(["a%03d" % i], **kw), [dk.kcol(1)], ht=ht()), val())
+    wide = dk.doc_key(["m-wide"], hash_code=4242, hashed=["w"], **kw)
+    for _ in range(3):
+        put(dk.sub_doc_key(wide, [], ht=ht()), rng.choice([dk.OBJECT, dk.TOMBSTONE, dk.OBJECT]))
+    for c in range(cols):
+        for _ in range(versions):
+            put(dk.sub_doc_key(wide, [dk.kcol(c + 1)], ht=ht()), val())
+    coll = dk.doc_key(["n-coll"], **kw)
+    put(dk.sub_doc_key(coll, [], ht=ht()), dk.OBJECT)
+    for _ in range(4):
+        put(dk.sub_doc_key(coll, [dk.kcol(7)], ht=ht()), rng.choice([dk.OBJECT, dk.TOMBSTONE]))
+    for e in range(collection):
+        for _ in range(3):
+            put(dk.sub_doc_key(coll, [dk.kcol(7), "elem%06d" % e], ht=ht()), val())
+        if e % 97 == 0:
+            for _ in range(2):
+                put(dk.sub_doc_key(coll, [dk.kcol(7), "elem%06d" % e, dk.kint64(e)], ht=ht()), val())
+    for c in range(3):
+        put(dk.sub_doc_key(coll, [dk.kcol(8 + c)], ht=ht()), val())
+    for i in range(small_rows // 2):
+        put(dk.sub_doc_key(dk.doc_key(["z%03d" % i], **kw), [dk.kcol(1)], ht=ht()), val())
+    return [sort_run(r) for r in runs]

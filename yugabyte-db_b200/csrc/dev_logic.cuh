@@ -1002,4 +1002,136 @@ YB_HD_NOINLINE int feed_step(FeedState* st, const RetentionDev& R, const uint8_t
   return ENT_KEEP;
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Resuming DocDBCompactionFeed in the middle of a row group (merge tiles that start inside a group
+// larger than a tile). Feed's state when it reaches a key K0 = (path components..., '#', HT) is a
+// function of only those earlier entries whose component path is a PREFIX of K0's path — the
+// ancestors `P_i # HT` (row-level / collection-level markers) and the earlier versions of K0's own
+// SubDocKey: the overwrite stack is truncated to the shared components on every key change
+// (docdb_compaction_context.cc:977-1021) and entries of sibling subtrees only write their own stack
+// level or pad missing levels with the parent's value (:1078), which K0 would pad identically. All of
+// these entries sort before K0 ('#' < every key entry type that can follow a component) and each
+// level's entries are contiguous in every run, so a tile finds them with one search per run and
+// level and replays them through feed_step — tiles stay independent, no state is carried between them.
+
+// Component ends of a user key decoded from scratch: the same walk as feed_step's
+// (SubDocKey::DecodeDocKeyAndSubKeyEnds, dockv/doc_key.cc:963-996). Returns the count or <0.
+YB_HD int decode_key_ends(const uint8_t* key, uint32_t ulen, uint32_t* ends) {
+  if (ulen == 0) return -DEV_ERR_BAD_KEY;
+  const uint8_t key_type = key[0];
+  int n = 0;
+  if (key_type == 6 || key_type == 7) {
+    const int body = dockey_body_size(key, ulen);
+    if (body < 0) return body;
+    ends[n++] = body;
+    return n;
+  }
+  const int id = dockey_id_size(key, ulen);
+  if (id < 0) return id;
+  ends[n++] = id;
+  if (ulen < static_cast<uint32_t>(id) + 1) return -DEV_ERR_BAD_KEY;
+  uint32_t pos;
+  if ((key[0] == '0' || key[0] == 'y') && key[id] == '!') {
+    pos = id + 1;
+  } else {
+    const int body = dockey_body_size(key + id, ulen - id);
+    if (body < 0) return body;
+    pos = id + body;
+    ends[n++] = pos;
+  }
+  while (pos < ulen && key[pos] != '#') {
+    const int k = key_entry_size(key + pos, ulen - pos);
+    if (k < 0) return k;
+    pos += k;
+    if (n >= DEV_MAX_DEPTH) return -DEV_ERR_STACK_DEPTH;
+    ends[n++] = pos;
+  }
+  return n;
+}
+
+// (key[0, g) + extra) against the user key c: <0 / >0 as byte strings, 0 when c STARTS WITH the pattern.
+// key and c are record pointers (zero padded, 8-byte aligned).
+YB_HD int cmp_pattern(const uint8_t* key, uint32_t g, uint8_t extra, const uint8_t* c, uint32_t lc) {
+  const uint32_t m = g < lc ? g : lc;
+  const uint32_t cp = common_prefix_len(key, m, c, m);
+  if (cp < m) return key[cp] < c[cp] ? -1 : 1;
+  if (lc <= g) return 1;                               // c is a proper prefix of the pattern (or equals P): c < pattern
+  return extra < c[g] ? -1 : (extra > c[g] ? 1 : 0);
+}
+
+struct ReplayRun { const uint8_t* rec; uint32_t limit; const uint8_t* data; const uint64_t* val_off; };
+constexpr int REPLAY_MAX_RUNS = 64;
+
+// First index in [0, run.limit] whose record is >= the pattern; the answer is usually close to the limit
+// (inside the same group), so the search gallops backwards from there.
+YB_HD uint32_t replay_lower_bound(const ReplayRun& run, int S, const uint8_t* key, uint32_t g) {
+  uint32_t hi = run.limit, lo = 0, step = 1;
+  while (hi > 0) {
+    const uint32_t probe = hi > step ? hi - step : 0;
+    const uint8_t* c = run.rec + static_cast<size_t>(probe) * S;
+    if (cmp_pattern(key, g, '#', c, rec_ulen(c, S)) > 0) { lo = probe + 1; break; }   // rec[probe] < pattern
+    hi = probe;
+    if (probe == 0) break;
+    step <<= 1;
+  }
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    const uint8_t* c = run.rec + static_cast<size_t>(mid) * S;
+    if (cmp_pattern(key, g, '#', c, rec_ulen(c, S)) > 0) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Brings *st (freshly reset, or seeded with the table tombstone state of a cotable) to the state Feed has
+// when it reaches the record k0, which is the first record of a tile and lies inside a row group that
+// began in an earlier tile. runs[r].limit = index of the first record of run r that belongs to this tile
+// or a later one (everything below it sorts before k0). Returns 0 or a negative DevError.
+YB_HD_NOINLINE int replay_ancestors(FeedState* st, const RetentionDev& R, const ReplayRun* runs, int k, int S,
+                                    const uint8_t* k0, uint32_t ulen0, int bottommost, uint64_t last_sequence) {
+  if (k > REPLAY_MAX_RUNS) return -DEV_ERR_COTABLE;
+  uint32_t ends[DEV_MAX_DEPTH];
+  const int n = decode_key_ends(k0, ulen0, ends);
+  if (n < 0) return n;
+  const uint8_t t0 = k0[0];
+  const bool sub_doc_key = !(t0 == 6 || t0 == 7);
+  // level 0 of a SubDocKey is the table id: its entries are the table tombstones `id ! # HT`, which seed the rows
+  // of the table elsewhere (cotable seeding). Only when k0 is itself such a tombstone are its earlier versions
+  // replayed here: their pattern is id + '!' + '#'.
+  const bool tombstone = sub_doc_key && n == 1;
+  for (int lev = (sub_doc_key && !tombstone) ? 1 : 0; lev < n; lev++) {
+    const uint32_t g = tombstone ? ends[0] + 1 : ends[lev];
+    if (g >= ulen0) break;
+    uint32_t cur[REPLAY_MAX_RUNS];
+    for (int r = 0; r < k; r++) cur[r] = replay_lower_bound(runs[r], S, k0, g);
+    const uint8_t* prev = nullptr;
+    for (;;) {
+      int best = -1; const uint8_t* bk = nullptr;
+      for (int r = 0; r < k; r++) {
+        if (cur[r] >= runs[r].limit) continue;
+        const uint8_t* c = runs[r].rec + static_cast<size_t>(cur[r]) * S;
+        if (cmp_pattern(k0, g, '#', c, rec_ulen(c, S)) != 0) { cur[r] = runs[r].limit; continue; }   // left the level
+        if (best < 0 || cmp_records(c, bk, S) < 0) { best = r; bk = c; }
+      }
+      if (best < 0) break;
+      const uint32_t idx = cur[best]++;
+      if (rec_flags(bk, S) & REC_F_INVISIBLE) continue;
+      const uint32_t cl = rec_ulen(bk, S);
+      const bool hidden = prev && cmp_user_keys(prev, rec_ulen(prev, S), bk, cl) == 0;     // rule A
+      prev = bk;
+      if (hidden) continue;
+      const uint64_t suffix = rec_suffix(bk, S);
+      if ((suffix & 0xff) == 0 && bottommost && (suffix >> 8) <= last_sequence) continue;  // obsolete deletion
+      const uint32_t vlen = rec_vlen(bk, S);
+      const uint8_t vfirst = rec_vfirst(bk, S);
+      const uint8_t* val = nullptr;
+      if (vlen && has_control_fields(vfirst)) val = runs[best].data + runs[best].val_off[idx];
+      ValueRewrite rw;
+      const int d = feed_step(st, R, bk, cl, vfirst, val, vlen, &rw);
+      if (d < 0) return d;
+    }
+  }
+  return 0;
+}
+
 }  // namespace ybgpu

@@ -62,6 +62,7 @@ struct JobDev {                 // device-global job state
   unsigned long long min_seq, max_seq, n_kept_deletions;
   uint32_t n_rewrites;
   uint32_t n_tiles;
+  uint32_t max_tile;            // largest tile of the current partition (k_tile_check)
   unsigned long long digest;
 };
 
@@ -455,10 +456,19 @@ struct PartView {
   const uint32_t* sample_base;  // [k+1] prefix of samples per run
   uint32_t* pos;                // [n_samples * k]
   unsigned long long* bucket_min;   // [n_buckets]  (rank << 28 | sample)
+  uint8_t* smode;               // [n_samples] 1 = the sample splits INSIDE its row group (full-key splitter)
   uint32_t n_samples;
   uint32_t n_buckets;
 };
 
+// Splitters. A sample normally stands for the START of its row group (prefix splitter), so that tiles hold whole
+// groups and their retention state is self-contained. A group with more than M records in one run would pin all
+// its samples to the same position and overflow a tile; such samples — recognised locally: the previous sample of
+// the same run lies in the same group — split INSIDE the group at their own internal key instead (full-key
+// splitter). Tiles that start there rebuild Feed's state by replaying the ancestors of their first key
+// (dev_logic.cuh replay_ancestors). Candidates of one run are then < 2M records apart in that run, which bounds
+// a tile by H + 2kM records (the host halves M and repeats the partition in the rare case that exceeds a tile).
+constexpr unsigned long long TILE_CONT = 1ull << 63;   // tile_rank flag: the tile starts inside a row group
 __global__ void __launch_bounds__(256) k_sample_pos(PartView P, const JobParams* prm, JobDev* J) {
   const int S = prm->S, k = prm->k;
   const uint64_t total = static_cast<uint64_t>(P.n_samples) * k;
@@ -472,13 +482,30 @@ __global__ void __launch_bounds__(256) k_sample_pos(PartView P, const JobParams*
     const uint8_t* srec = P.runs[r].rec + static_cast<size_t>(idx) * S;
     const int g = group_prefix_len(srec, rec_ulen(srec, S), prm->R.enabled != 0);
     if (g < 0) { dev_fail(J, -g, s); continue; }
+    bool inside = false;
+    if (idx >= prm->M) {
+      const uint8_t* prec = srec - static_cast<size_t>(prm->M) * S;
+      inside = rec_ulen(prec, S) >= static_cast<uint32_t>(g) && common_prefix_len(srec, g, prec, g) >= static_cast<uint32_t>(g) &&
+               group_prefix_len(prec, rec_ulen(prec, S), prm->R.enabled != 0) == g;
+    }
+    if (r2 == 0) P.smode[s] = inside ? 1 : 0;
     const RunView& q = P.runs[r2];
     uint32_t lo = 0, hi = q.n_entries;
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      const uint8_t* c = q.rec + static_cast<size_t>(mid) * S;
-      // first record whose user key >= prefix
-      if (cmp_prefix_vs_key(srec, g, c, rec_ulen(c, S)) > 0) lo = mid + 1; else hi = mid;
+    if (inside) {
+      if (r2 == static_cast<uint32_t>(r)) lo = hi = idx;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const int c = cmp_records(q.rec + static_cast<size_t>(mid) * S, srec, S);
+        // merged order breaks ties by run index: equal records of lower runs come first
+        if (r2 < static_cast<uint32_t>(r) ? c <= 0 : c < 0) lo = mid + 1; else hi = mid;
+      }
+    } else {
+      while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        const uint8_t* c = q.rec + static_cast<size_t>(mid) * S;
+        // first record whose user key >= prefix
+        if (cmp_prefix_vs_key(srec, g, c, rec_ulen(c, S)) > 0) lo = mid + 1; else hi = mid;
+      }
     }
     P.pos[static_cast<size_t>(s) * k + r2] = lo;
   }
@@ -548,9 +575,26 @@ __global__ void __launch_bounds__(256) k_build_tiles(PartView P, const JobParams
     if (v[j] == ~0ull) continue;
     const uint32_t s = static_cast<uint32_t>(v[j] & ((1u << 28) - 1));
     for (int r = 0; r < k; r++) tile_lo[static_cast<size_t>(t) * k + r] = P.pos[static_cast<size_t>(s) * k + r];
-    tile_rank[t] = v[j] >> 28;
+    tile_rank[t] = (v[j] >> 28) | (P.smode[s] ? TILE_CONT : 0ull);
     t++;
   }
+}
+
+// Largest tile of the partition (the host repeats the partition with a smaller sample stride if it exceeds a tile).
+__global__ void __launch_bounds__(256) k_tile_check(const RunView* runs, const uint32_t* tile_lo, int k, JobDev* J) {
+  const uint32_t n_tiles = J->n_tiles;
+  uint32_t mx = 0;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+    uint32_t sz = 0;
+    for (int r = 0; r < k; r++) {
+      const uint32_t lo = tile_lo[static_cast<size_t>(t) * k + r];
+      const uint32_t hi = (t + 1 < n_tiles) ? tile_lo[static_cast<size_t>(t + 1) * k + r] : runs[r].n_entries;
+      sz += hi - lo;
+    }
+    mx = max(mx, sz);
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(&J->max_tile, mx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -603,6 +647,15 @@ __host__ __device__ constexpr uint32_t bytes(uint32_t S, uint32_t cap) { return 
 }  // namespace tile_layout
 
 
+// One thread, rare: the run table for replay_ancestors lives in this function's frame, not in the kernel's.
+__device__ __noinline__ int seed_continuation(FeedState* st, const JobParams* prm, const RunView* runs, const uint32_t* seg_lo, int k, int S,
+                                              const uint8_t* k0_smem) {
+  if (k > REPLAY_MAX_RUNS) return -DEV_ERR_COTABLE;
+  ReplayRun rr[REPLAY_MAX_RUNS];
+  for (int r = 0; r < k; r++) { rr[r].rec = runs[r].rec; rr[r].limit = seg_lo[r]; rr[r].data = runs[r].data; rr[r].val_off = runs[r].val_off; }
+  return replay_ancestors(st, prm->R, rr, k, S, k0_smem, rec_ulen(k0_smem, S), prm->bottommost, prm->last_sequence);
+}
+
 __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, const JobParams* prm, JobDev* J) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int S = V.S, k = V.k;
@@ -633,8 +686,10 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   __shared__ uint32_t sh_ncand;
   __shared__ uint32_t sh_ncot;
   __shared__ unsigned long long sh_stats[9];
+  __shared__ const uint8_t* sh_pred;             // tile that starts inside a row group: the last visible record before it
 
   const uint32_t tile = blockIdx.x;
+  const bool cont = (V.tile_rank[tile] & TILE_CONT) != 0;
   if (threadIdx.x < 9) sh_stats[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     uint32_t acc = 0;
@@ -684,6 +739,22 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
     uint32_t c = common_prefix_len(mn, rec_ulen(mn, S), mx, rec_ulen(mx, S)) & ~7u;
     if (c + 16 > static_cast<uint32_t>(S - 16)) c = (S - 16 >= 16) ? static_cast<uint32_t>(S - 32) & ~7u : 0;
     sh_c0 = c;
+    // A tile that starts inside a row group needs the record that precedes it in merged order (rule A compares
+    // with the previous visible user key): the largest visible record below the tile's start over all runs.
+    const uint8_t* pred = nullptr;
+    if (cont) {
+      for (int r = 0; r < k; r++) {
+        uint32_t j = seg_lo[r];
+        const uint8_t* c2 = nullptr;
+        while (j > 0) {
+          const uint8_t* q = V.runs[r].rec + static_cast<size_t>(j - 1) * S;
+          if (!(rec_flags(q, S) & REC_F_INVISIBLE)) { c2 = q; break; }
+          j--;
+        }
+        if (c2 && (!pred || cmp_records(c2, pred, S) >= 0)) pred = c2;     // ties: the higher run comes later
+      }
+    }
+    sh_pred = pred;
   }
   __syncthreads();
   {
@@ -800,6 +871,8 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
       if (pvis[i] != 0xffff) {
         const uint8_t* pe = recs + static_cast<size_t>(SS) * (order[pvis[i]]);
         first_occ = cmp_user_keys(pe, rec_ulen(pe, S), e, ulen) != 0;
+      } else if (cont && sh_pred) {
+        first_occ = cmp_user_keys(sh_pred, rec_ulen(sh_pred, S), e, ulen) != 0;   // previous visible record lies in an earlier tile
       }
       if (!first_occ) { f |= ENT_DROP_HIDDEN; st_hidden++; }                       // rule A
       else if (type == 0 && prm->bottommost && seq <= prm->last_sequence) { f |= ENT_DROP_OBSOLETE; st_obsolete++; }
@@ -969,12 +1042,19 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
           }
         }
       }
+      const bool continued = cont && g == 0;
+      if (continued) {
+        // The group began in an earlier tile: rebuild Feed's state at the tile's first record from the entries
+        // that determine it (its ancestors `P_i # HT` and the earlier versions of its own SubDocKey).
+        const int rc = seed_continuation(&st, prm, V.runs, seg_lo, k, S, recs + static_cast<size_t>(SS) * order[i0]);
+        if (rc < 0) { dev_fail(J, -rc, tile); continue; }
+      }
       // Fast path: every visible entry of the row is newer than the history cutoff and is a plain
       // value of an ordinary table key. Feed forwards such entries verbatim
       // (docdb_compaction_context.cc:1117-1130) and the row's overwrite stack is never consulted, so
       // the state machine can be skipped (subkey decoding errors of such rows are not diagnosed).
       {
-        bool all_above = !(prm->R.lower_len | prm->R.upper_len);
+        bool all_above = !(prm->R.lower_len | prm->R.upper_len) && !continued;
         for (uint32_t i = i0; i < i1 && all_above; i++) {
           if (!(res[i] & ENT_KEEP)) continue;
           const uint8_t* e = recs + static_cast<size_t>(SS) * (order[i]);
@@ -1019,7 +1099,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   __syncthreads();
 
   // (e) descriptors in merged order
-  const unsigned long long rank0 = V.tile_rank[tile];
+  const unsigned long long rank0 = V.tile_rank[tile] & ~TILE_CONT;
   unsigned long long st_kept = 0, st_kbytes = 0, st_vbytes = 0, mn = ~0ull, mx = 0;
   for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
     const uint32_t li = order[i];
@@ -1264,7 +1344,7 @@ static const char* DevErrorName(int e) {
     case DEV_ERR_IRREGULAR_RESTARTS: return "data block restart intervals are not uniform";
     case DEV_ERR_BAD_KEY: return "cannot decode DocKey/SubDocKey components";
     case DEV_ERR_UNSUPPORTED_KEY: return "key component type not supported on the GPU path";
-    case DEV_ERR_TILE_OVERFLOW: return "row group larger than a merge tile";
+    case DEV_ERR_TILE_OVERFLOW: return "internal error: merge tile larger than its capacity";
     case DEV_ERR_BAD_HT: return "bad DocHybridTime at the end of a key";
     case DEV_ERR_BAD_VALUE: return "cannot decode value control fields";
     case DEV_ERR_STACK_DEPTH: return "too many subkey levels";
@@ -1737,36 +1817,48 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     return YBGPU_OK;
   }
 
-  // ---- K2: partition
-  std::vector<uint32_t> sample_base(k + 1, 0);
-  for (int r = 0; r < k; r++) sample_base[r + 1] = sample_base[r] + (I.runs[r].n_entries + hp.M - 1) / hp.M;
-  const uint32_t n_samples = sample_base[k];
-  if (n_samples >= (1u << 28)) return Fail(YBGPU_NOT_SUPPORTED, "too many partition samples");
-  const uint32_t n_buckets = static_cast<uint32_t>(N / hp.H) + 2;
-  PartView pv{};
-  uint32_t* d_sample_base = nullptr; uint32_t* d_tile_lo = nullptr; unsigned long long* d_tile_rank = nullptr;
-  CUDA_TRY(DevAlloc(&I.allocs, &d_sample_base, k + 1));
-  CUDA_TRY(DevAlloc(&I.allocs, &pv.pos, static_cast<size_t>(n_samples) * k));
-  CUDA_TRY(DevAlloc(&I.allocs, &pv.bucket_min, n_buckets));
-  CUDA_TRY(DevAlloc(&I.allocs, &d_tile_lo, static_cast<size_t>(n_buckets + 1) * k));
-  CUDA_TRY(DevAlloc(&I.allocs, &d_tile_rank, n_buckets + 1));
-  CUDA_TRY(cudaMemcpyAsync(d_sample_base, sample_base.data(), 4 * (k + 1), cudaMemcpyHostToDevice, I.stream));
-  CUDA_TRY(cudaMemsetAsync(pv.bucket_min, 0xff, static_cast<size_t>(n_buckets) * 8, I.stream));
-  pv.runs = I.dRuns; pv.sample_base = d_sample_base; pv.n_samples = n_samples; pv.n_buckets = n_buckets;
-  k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ);
-  k_sample_bucket<<<GridFor(n_samples, 256, sms), 256, 0, I.stream>>>(pv, I.dP);
-  {
-    const uint32_t tchunks = (n_buckets + TILE_CHUNK - 1) / TILE_CHUNK;
-    uint32_t* d_tpart = nullptr; uint32_t* d_ttotal = nullptr;
-    CUDA_TRY(DevAlloc(&I.allocs, &d_tpart, tchunks + 1)); CUDA_TRY(DevAlloc(&I.allocs, &d_ttotal, 1));
-    k_bucket_counts<<<tchunks, 256, 0, I.stream>>>(pv, d_tpart);
-    k_scan_u32_single<<<1, 1024, 0, I.stream>>>(d_tpart, tchunks, d_ttotal);
-    k_build_tiles<<<tchunks, 256, 0, I.stream>>>(pv, I.dP, d_tpart, d_ttotal, d_tile_lo, d_tile_rank, I.dJ);
+  // ---- K2: partition (repeated with a smaller sample stride in the rare case a tile comes out larger than the
+  // merge kernel's capacity: see k_sample_pos)
+  uint32_t* d_tile_lo = nullptr; unsigned long long* d_tile_rank = nullptr;
+  for (int attempt = 0;; attempt++) {
+    std::vector<uint32_t> sample_base(k + 1, 0);
+    for (int r = 0; r < k; r++) sample_base[r + 1] = sample_base[r] + (I.runs[r].n_entries + hp.M - 1) / hp.M;
+    const uint32_t n_samples = sample_base[k];
+    if (n_samples >= (1u << 28)) return Fail(YBGPU_NOT_SUPPORTED, "too many partition samples");
+    const uint32_t n_buckets = static_cast<uint32_t>(N / hp.H) + 2;
+    PartView pv{};
+    uint32_t* d_sample_base = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_sample_base, k + 1));
+    CUDA_TRY(DevAlloc(&I.allocs, &pv.pos, static_cast<size_t>(n_samples) * k));
+    CUDA_TRY(DevAlloc(&I.allocs, &pv.smode, n_samples));
+    CUDA_TRY(DevAlloc(&I.allocs, &pv.bucket_min, n_buckets));
+    CUDA_TRY(DevAlloc(&I.allocs, &d_tile_lo, static_cast<size_t>(n_buckets + 1) * k));
+    CUDA_TRY(DevAlloc(&I.allocs, &d_tile_rank, n_buckets + 1));
+    CUDA_TRY(cudaMemcpyAsync(d_sample_base, sample_base.data(), 4 * (k + 1), cudaMemcpyHostToDevice, I.stream));
+    CUDA_TRY(cudaMemsetAsync(pv.bucket_min, 0xff, static_cast<size_t>(n_buckets) * 8, I.stream));
+    pv.runs = I.dRuns; pv.sample_base = d_sample_base; pv.n_samples = n_samples; pv.n_buckets = n_buckets;
+    k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ);
+    k_sample_bucket<<<GridFor(n_samples, 256, sms), 256, 0, I.stream>>>(pv, I.dP);
+    {
+      const uint32_t tchunks = (n_buckets + TILE_CHUNK - 1) / TILE_CHUNK;
+      uint32_t* d_tpart = nullptr; uint32_t* d_ttotal = nullptr;
+      CUDA_TRY(DevAlloc(&I.allocs, &d_tpart, tchunks + 1)); CUDA_TRY(DevAlloc(&I.allocs, &d_ttotal, 1));
+      k_bucket_counts<<<tchunks, 256, 0, I.stream>>>(pv, d_tpart);
+      k_scan_u32_single<<<1, 1024, 0, I.stream>>>(d_tpart, tchunks, d_ttotal);
+      k_build_tiles<<<tchunks, 256, 0, I.stream>>>(pv, I.dP, d_tpart, d_ttotal, d_tile_lo, d_tile_rank, I.dJ);
+      k_tile_check<<<GridFor(n_buckets + 1, 256, sms), 256, 0, I.stream>>>(I.dRuns, d_tile_lo, k, I.dJ);
+    }
+    launches += 6;
+    CUDA_TRY(cudaGetLastError());
+    if (ybgpu_status s = CheckDeviceError("partition")) return s;
+    if (I.hJ.max_tile <= cap) break;
+    if (hp.M <= 1 || attempt >= 4)
+      return Fail(YBGPU_NOT_SUPPORTED, "record stride and run count too large for a merge tile");
+    hp.M = std::max(1u, hp.M / 2);
+    CUDA_TRY(cudaMemcpyAsync(I.dP, &hp, sizeof(hp), cudaMemcpyHostToDevice, I.stream));
+    CUDA_TRY(cudaMemsetAsync(&I.dJ->max_tile, 0, sizeof(uint32_t), I.stream));
   }
-  launches += 5;
-  CUDA_TRY(cudaGetLastError());
   CUDA_TRY(end_phase());
-  if (ybgpu_status s = CheckDeviceError("partition")) return s;
   tick("partition");
   const uint32_t n_tiles = I.hJ.n_tiles;
 
