@@ -570,40 +570,39 @@ def main():
                                    "subcompactions, compaction_job.cc:1128-1131) — NOT the headline: DocDB writes one file"}
 
             # HEADLINE: ONE output table, the shape DocDB's single-level universal compaction (and the reference arm)
-            # writes. The key ranges run pipelined; their data pieces are appended in range order as they are and
-            # ybgpu_sst_concat_meta writes the one metadata file (rebased multi-level index, all filter blocks + one
-            # filter index, summed properties) — all inside the timed region.
-            concat_buf = np.empty(2 * out_meta.size + (1 << 20), np.uint8)
-            concat_buf[::4096] = 0                      # touch the pages once, outside the timed region
+            # writes. ybgpu_compact_files_one_table: the key ranges run pipelined, every range's data blocks go
+            # device->host straight to their final position in the one data file, and the one metadata file
+            # (rebased multi-level index, all filter blocks + one filter index, summed properties) is assembled in key
+            # order while later ranges still run — all inside the timed region.
+            one_meta = np.empty(2 * out_meta.size + (1 << 20), np.uint8)
+            one_meta[::4096] = 0                        # touch the pages once, outside the timed region
 
             def step_one_table():
-                r = pkg.compact_files(files, max_subcompactions=args.subcompactions, max_in_flight=args.in_flight,
-                                      data_arena=out_data, meta_arena=out_meta, device=local_rank,
-                                      verify_checksums=bool(args.verify), **job_kw)
-                outs = [o_ for o_ in r.outputs if o_.data_len]
-                pieces = [(out_meta[o_.meta_offset:o_.meta_offset + o_.meta_len], o_.data_len, o_.smallest, o_.largest) for o_ in outs]
-                meta = pkg.sst_concat_meta(pieces, out=concat_buf, filter_policy=job_kw.get("filter_policy", 0))
-                return r.total.as_dict(), sum(o_.data_len for o_ in outs), int(meta.size), len(outs), meta
+                data, meta, res_, tot = pkg.compact_files_one_table(files, max_subcompactions=args.subcompactions, max_in_flight=args.in_flight,
+                                                                    data_out=out_data, meta_out=one_meta, device=local_rank,
+                                                                    verify_checksums=bool(args.verify), **job_kw)
+                return tot.as_dict(), int(data.size), int(meta.size), int(res_.num_pieces), meta
             ot_s, ores = timed(step_one_table, args.steps)
             st_d, data_bytes, meta_bytes, n_pieces, meta = ores[-1]
             off, sz, _ = pkg.sst_block_handles(meta)     # the product's own reader walks the merged index
             assert len(off) == st_d["num_output_data_blocks"] and int(off[-1] + sz[-1]) + 5 == data_bytes
             assert st_d["num_input_records"] == n_entries
+            one_check = verify_outputs([(meta, out_data[:data_bytes])])
             e2e = {"value": round(in_bytes * world * args.steps / ot_s / 1e9, 4), "unit": "GB/s", "steps": args.steps,
                    "h2d_bytes_per_step": int(st_d["h2d_bytes"]), "d2h_bytes_per_step": int(st_d["d2h_bytes"]),
                    "ms_per_step": round(ot_s / args.steps * 1e3, 2), "pinned_inputs": all(ok for _, ok in pinned),
                    "output_files": 1, "output_file_bytes": int(data_bytes + meta_bytes), "verify_checksums": bool(args.verify),
-                   "mode": "ONE output table: ybgpu_compact_files (%d key ranges, %d in flight on private streams) + "
-                           "ybgpu_sst_concat_meta inside the timed region" % (n_pieces, args.in_flight),
-                   "pieces": int(n_pieces), "data_blocks": int(len(off)),
+                   "mode": "ONE output table: ybgpu_compact_files_one_table (%d key ranges, %d in flight on private streams, data pieces "
+                           "copied to their final offsets, metadata file assembled while later ranges run)" % (n_pieces, args.in_flight),
+                   "pieces": int(n_pieces), "data_blocks": int(len(off)), "output_check": one_check,
                    "gpu_ms_per_step": round(st_d["gpu_seconds"] * 1e3, 2),
                    "pcie_ceiling_gbs": ceiling,
                    "range_files": range_files,
                    "single_job": single}
+            del one_meta
             if isinstance(ceiling, dict) and "both" in ceiling and ceiling["both"]:
                 # the step moves in_bytes in and about as much out: bound = the slower direction of the duplex figure
                 e2e["frac_of_pcie_ceiling"] = round(e2e["value"] / (ceiling["both"] / 2.0), 3)
-            del concat_buf
         for v, ok in pinned:
             if ok:
                 cudart.cudaHostUnregister(v.ctypes.data)

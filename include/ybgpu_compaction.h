@@ -114,6 +114,14 @@ typedef struct ybgpu_job_options {
    * started; it may block for as long as the scheduler wants the compaction paused. NULL = none. */
   void (*yield_fn)(void* ctx);
   void* yield_ctx;
+
+  /* --- FileMetaData user boundary values (docdb_compaction_context.cc:684-689,754-773) --- non-zero: the engine
+   * reduces, over the first surviving entry of every DocKey, the bytewise smallest / largest encoded value of each
+   * range-group component (DocBoundaryValuesExtractor, doc_boundary_values_extractor.cc:40-64); read them with
+   * ybgpu_job_output_user_values. The caller sets it when DocDBCompactionFeed's could_change_key_range_ holds
+   * (input_min has no other data before it, docdb_compaction_context.cc:668): only then does UpdateMeta replace
+   * the union of the inputs' values. */
+  int32_t compute_user_boundary_values;
 } ybgpu_job_options;
 
 void ybgpu_job_options_init(ybgpu_job_options* o);   /* reference defaults */
@@ -221,6 +229,15 @@ ybgpu_status ybgpu_job_fetch_output(ybgpu_job* job, uint8_t* data_file, uint64_t
 ybgpu_status ybgpu_job_output_boundaries(const ybgpu_job* job, uint8_t* smallest, uint64_t* smallest_len,
                                          uint8_t* largest, uint64_t* largest_len);
 
+/* FileMetaData::smallest.user_values / largest.user_values of the output: one entry per range-group component that
+ * occurs in a surviving DocKey, tag = 10 + component index (TagForRangeComponent, doc_boundary_values_extractor.cc:
+ * 108-110), value = the encoded key component. Needs options.compute_user_boundary_values. Up to 16 components of up
+ * to 255 bytes are reported; more => YBGPU_NOT_SUPPORTED (the caller then keeps the union of the inputs' values,
+ * which is a superset range). *n = number of tags; smallest[i].tag == largest[i].tag. */
+typedef struct ybgpu_user_value { uint32_t tag; uint32_t len; uint8_t value[256]; } ybgpu_user_value;
+ybgpu_status ybgpu_job_output_user_values(ybgpu_job* job, ybgpu_user_value* smallest, ybgpu_user_value* largest,
+                                          uint32_t cap, uint32_t* n);
+
 /* --- subcompactions ------------------------------------------------------------------------------
  * Replaces: CompactionJob::GenSubcompactionBoundaries + the per-subcompaction threads of
  * CompactionJob::Run (rocksdb/db/compaction_job.cc:409-519,532-552; DBOptions::max_subcompactions,
@@ -268,6 +285,29 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
                                  uint8_t* data_arena, uint64_t data_arena_cap, uint8_t* meta_arena, uint64_t meta_arena_cap,
                                  const volatile int32_t* shutting_down, ybgpu_sub_output* outputs, uint32_t* num_outputs,
                                  ybgpu_job_stats* total, char* err, uint64_t err_cap);
+
+/* The same pipelined compaction with ONE output table — the shape DocDB's single-level universal compaction needs
+ * (one sorted run per compaction; db/compaction.cc:593-604 never forms subcompactions there) and the shape
+ * CompactionJob::Run writes without subcompactions. The key ranges still run pipelined on private streams, but
+ *   * every range's data blocks are copied device->host straight to their final position in data_out (a range's
+ *     offset is the sum of the sizes of all earlier ranges, known as soon as those have run), so the data file
+ *     <n>.sst.sblock.0 is contiguous without any host copy;
+ *   * the metadata file <n>.sst is assembled incrementally, in key order, while later ranges are still running:
+ *     one multi-level index over all data blocks (index_builder.cc:143-289), every fixed-size bloom filter block
+ *     under one filter index, summed properties — exactly what ybgpu_sst_concat_meta writes for the same pieces.
+ * Key/value bytes equal the single-job output; block cuts differ only at the range boundaries.
+ * result->smallest_key / largest_key: FileMetaData::smallest / largest of the table (internal keys). */
+typedef struct ybgpu_one_table_result {
+  uint64_t data_len, meta_len;
+  uint32_t num_ranges, num_pieces;                      /* ranges planned / ranges that produced output */
+  uint32_t smallest_key_len, largest_key_len;
+  uint8_t smallest_key[1032], largest_key[1032];
+} ybgpu_one_table_result;
+ybgpu_status ybgpu_compact_files_one_table(const ybgpu_job_options* options, const ybgpu_input_file* files, uint32_t num_files,
+                                           uint32_t max_subcompactions, uint32_t max_in_flight,
+                                           uint8_t* data_out, uint64_t data_cap, uint8_t* meta_out, uint64_t meta_cap,
+                                           const volatile int32_t* shutting_down, ybgpu_one_table_result* result,
+                                           ybgpu_job_stats* total, char* err, uint64_t err_cap);
 
 /* One table out of the range outputs. For layouts where a compaction must produce a single sorted run
  * (DocDB's single-level universal compaction, db/compaction.cc:593-604), the per-range SSTs of

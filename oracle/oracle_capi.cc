@@ -44,6 +44,7 @@ struct orc_result {
   std::string keys, vals;               // collected KV stream (if requested)
   std::vector<uint64_t> koff, voff;
   orc_stats stats{};
+  std::vector<std::pair<uint32_t, std::string>> user_values[2];   // [0] smallest, [1] largest (tag, encoded component)
   std::string error;
 };
 
@@ -201,6 +202,7 @@ static void FillStats(orc_result* res, const CompactionStats& st, uint64_t hash,
   o.in_key_bytes = st.total_input_raw_key_bytes; o.in_val_bytes = st.total_input_raw_value_bytes;
   o.out_key_bytes = st.total_output_raw_key_bytes; o.out_val_bytes = st.total_output_raw_value_bytes;
   o.kv_hash = hash; o.seconds = secs;
+  res->user_values[0] = st.smallest_user_values; res->user_values[1] = st.largest_user_values;
 }
 
 // mode bit0: collect KV stream; bit1: build output SST; bit2: hash_kv==0 -> skip hashing (baseline
@@ -276,6 +278,12 @@ const uint8_t* orc_result_vals(const orc_result* r) { return reinterpret_cast<co
 const uint64_t* orc_result_koff(const orc_result* r) { return r->koff.data(); }
 const uint64_t* orc_result_voff(const orc_result* r) { return r->voff.data(); }
 uint64_t orc_result_keys_size(const orc_result* r) { return r->keys.size(); }
+uint32_t orc_result_num_user_values(const orc_result* r, int which) { return static_cast<uint32_t>(r->user_values[which & 1].size()); }
+uint32_t orc_result_user_value(const orc_result* r, int which, uint32_t i, const uint8_t** p, uint64_t* n) {
+  const auto& v = r->user_values[which & 1][i];
+  *p = reinterpret_cast<const uint8_t*>(v.second.data()); *n = v.second.size();
+  return v.first;
+}
 uint64_t orc_result_vals_size(const orc_result* r) { return r->vals.size(); }
 
 // ---- synthetic SST generator (SURVEY.md 8d "Synthetic inputs") -------------------------------

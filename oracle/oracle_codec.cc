@@ -352,6 +352,30 @@ size_t DocKeyEncodedSize(Slice s, int part) {
   return s.p - begin;
 }
 
+void DocKeyRangeComponents(Slice key, std::vector<Slice>* out) {
+  Slice s = key;
+  s.remove_prefix(DocKeyEncodedSize(s, 0));                 // cotable / colocation id
+  bool hash_present = false;
+  if (!s.empty()) {
+    uint8_t t = s[0];
+    if (t != kt::kGroupEnd) {
+      if (IsSpecialKeyEntryType(t)) throw Corruption("Expected first value type to be primitive or GroupEnd");
+      if (t == kt::kUInt16Hash) { NeedBytes(s, 3, "16-bit hash component"); s.remove_prefix(3); hash_present = true; }
+    }
+  }
+  if (hash_present) ConsumePrimitiveValues(&s);             // hashed group: no slices (hashed_group() == nullptr)
+  if (s.empty()) return;
+  for (;;) {                                                // range group, one slice per component
+    if (s.empty()) throw Corruption("Unexpected end of key when decoding document key");
+    uint8_t t = s[0];
+    if (t == kt::kGroupEnd) return;
+    if (IsSpecialKeyEntryType(t)) throw Corruption("Expected a primitive value type");
+    const uint8_t* b = s.p;
+    SkipKeyEntry(&s);
+    out->push_back(Slice(b, s.p - b));
+  }
+}
+
 void DecodeDocKeyAndSubKeyEnds(Slice key, std::vector<size_t>* out) {
   Slice s = key;
   if (out->empty()) out->push_back(DocKeyEncodedSize(s, 0));

@@ -157,6 +157,9 @@ void SkipKeyEntry(Slice* s);
 // 1 = kWholeDocKey, 2 = kUpToHashOrFirstRange (hashed components, or the first range component
 // of a key without a hash code).
 size_t DocKeyEncodedSize(Slice s, int part);
+// DocKey::PartiallyDecode (doc_key.cc:398-406 with DecodeDocKeyCallback :280-300): the encoded range-group components of the
+// DocKey at the front of `key` (hashed components are not reported).
+void DocKeyRangeComponents(Slice key, std::vector<Slice>* out);
 // dockv/doc_key.cc:963-996 SubDocKey::DecodeDocKeyAndSubKeyEnds (incremental on *out).
 void DecodeDocKeyAndSubKeyEnds(Slice key, std::vector<size_t>* out);
 

@@ -177,7 +177,35 @@ class DocDBFeed : public CompactionFeed {
     static const Expiration kDefault;
     return ow_.empty() ? kDefault : ow_.back().exp;
   }
-  bool Forward(Slice ikey, Slice value) { next_->Feed(ikey, value); return true; }
+  // PassToNextFeed (docdb_compaction_context.cc:754-762) + UpdateBoundaryValues (:764-773): the first entry passed on
+  // for every DocKey (doc_key_serial_) contributes its range components to the per-tag minima / maxima.
+  bool Forward(Slice ikey, Slice value) {
+    if (last_passed_serial_ != doc_key_serial_) {
+      UpdateBoundaryValues(Slice(ikey.p, ikey.n - 8));
+      last_passed_serial_ = doc_key_serial_;
+    }
+    next_->Feed(ikey, value);
+    return true;
+  }
+  void UpdateBoundaryValues(Slice user_key) {
+    const uint8_t t = user_key.empty() ? kt::kInvalid : user_key[0];
+    // IsMetaKeyType (dockv/value_type.h:252-273): internal DocDB records are skipped
+    if (t == kt::kVectorIndexMetadata || t == kt::kTransactionApplyState || t == kt::kExternalTransactionId || t == kt::kTransactionId) return;
+    std::vector<Slice> comps;
+    DocKeyRangeComponents(user_key, &comps);
+    for (size_t i = 0; i < comps.size(); i++) {
+      const uint32_t tag = 10 + static_cast<uint32_t>(i);            // TagForRangeComponent
+      auto upd = [&](std::vector<std::pair<uint32_t, std::string>>* dst, int sign) {   // rocksdb/db/metadata.cc:44-57
+        for (auto& v : *dst)
+          if (v.first == tag) { if (Slice(v.second).compare(comps[i]) * sign > 0) v.second = comps[i].str(); return; }
+        dst->emplace_back(tag, comps[i].str());
+      };
+      upd(&smallest_, 1); upd(&largest_, -1);
+    }
+  }
+ public:
+  std::vector<std::pair<uint32_t, std::string>> smallest_, largest_;
+ private:
 
   bool FeedImpl(Slice internal_key, Slice value) {
     Slice key(internal_key.p, internal_key.n - 8);
@@ -313,6 +341,7 @@ class DocDBFeed : public CompactionFeed {
   std::vector<OverwriteData> ow_;
   bool within_merge_block_ = false;
   size_t doc_key_serial_ = 0;
+  size_t last_passed_serial_ = 0;
   std::string new_value_;
 };
 
@@ -391,6 +420,7 @@ static void CompactionLoop(MergingIterator* input, const CompactionParams& p, Co
   }
   feed->Flush();
   st->num_dropped_feed = feed_dropped;
+  if (docdb) { st->smallest_user_values = docdb->smallest_; st->largest_user_values = docdb->largest_; }
 }
 
 struct CountingSink : CompactionFeed {

@@ -35,6 +35,10 @@ struct CompactionStats {
   uint64_t num_dropped_feed = 0;        // dropped by DocDBCompactionFeed
   uint64_t total_input_raw_key_bytes = 0, total_input_raw_value_bytes = 0;
   uint64_t total_output_raw_key_bytes = 0, total_output_raw_value_bytes = 0;
+  // FileMetaData::smallest / largest .user_values as DocDBCompactionFeed accumulates them
+  // (docdb_compaction_context.cc:754-773 + doc_boundary_values_extractor.cc:40-64): per range-group component
+  // index of the surviving DocKeys, the bytewise smallest / largest encoded component (tag = 10 + index).
+  std::vector<std::pair<uint32_t, std::string>> smallest_user_values, largest_user_values;
 };
 
 // rocksdb/db/compaction_context.h:25-35.

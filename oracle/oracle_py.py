@@ -370,6 +370,24 @@ class Result:
         s._keepalive = self
         return s
 
+    def user_values(self):
+        """(smallest, largest): {tag: encoded key component} — FileMetaData user boundary values as
+        DocDBCompactionFeed::UpdateBoundaryValues accumulates them (tag = 10 + range component index)."""
+        L = lib()
+        L.orc_result_num_user_values.argtypes = [C.c_void_p, C.c_int]
+        L.orc_result_num_user_values.restype = C.c_uint32
+        L.orc_result_user_value.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.orc_result_user_value.restype = C.c_uint32
+        out = []
+        for which in (0, 1):
+            d = {}
+            for i in range(L.orc_result_num_user_values(self.h, which)):
+                p, n = C.c_void_p(), C.c_uint64()
+                tag = L.orc_result_user_value(self.h, which, i, C.byref(p), C.byref(n))
+                d[tag] = C.string_at(p, n.value)
+            out.append(d)
+        return tuple(out)
+
     def flat(self):
         L = lib()
         n = L.orc_result_num_kv(self.h)

@@ -520,6 +520,62 @@ def test_subcompaction_outputs_concatenate_into_one_table(pkg):
     assert job.kv_list() == exp.kv_list()
 
 
+@pytest.mark.parametrize("enc,in_flight,nsub", [(1, 3, 6), (2, 2, 9), (1, 1, 3)])
+def test_compact_files_one_table(pkg, enc, in_flight, nsub):
+    """ybgpu_compact_files_one_table: the pipelined key ranges land back to back in ONE data file and one metadata
+    file is assembled while later ranges run. The table must (i) hold exactly the single-job KV stream, (ii) equal,
+    byte for byte, what ybgpu_sst_concat_meta builds from the per-range outputs of ybgpu_compact_files, (iii) carry
+    the compaction's FileMetaData boundaries, (iv) be a valid input of the next compaction."""
+    cfg = o.GenConfig(seed=51, num_rows=9000, cols=2, versions=3, num_files=5, value_len=80, tombstone_per_1024=40)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=4096))
+    cutoff = o.ht_from_micros(cfg.base_micros + 1500)
+    kw = dict(cutoff_ht=cutoff, block_size=4096, output_key_encoding=enc, filter_policy=1, filter_block_size=4096)
+    exp = o.compact(ssts, o.CompactionParams(cutoff_ht=cutoff), o.TableOptions(block_size=4096, key_encoding=enc, filter_policy=1, filter_block_size=4096))
+    files = [(s.meta_view(), s.data_view()) for s in ssts]
+    data, meta, res, total = pkg.compact_files_one_table(files, max_subcompactions=nsub, max_in_flight=in_flight, **kw)
+    assert res.num_pieces >= 2 and res.num_ranges >= res.num_pieces
+    whole = o.Sst.from_bytes(meta.tobytes(), data.tobytes())
+    ekv = exp.kv_list()
+    assert whole.read_all() == ekv
+    assert (res.smallest, res.largest) == (ekv[0][0], ekv[-1][0])
+    assert total.num_input_records == exp.stats.num_input_records and total.num_output_records == exp.stats.num_output_records
+    assert total.output_data_file_size == data.size and total.output_meta_file_size == meta.size
+    ranges = pkg.compact_files(files, max_subcompactions=nsub, max_in_flight=in_flight, **kw)
+    outs = [x for x in ranges.outputs if x.data_len]
+    pieces = [(ranges.meta_arena[x.meta_offset:x.meta_offset + x.meta_len], x.data_len, x.smallest, x.largest) for x in outs]
+    assert meta.tobytes() == bytes(pkg.sst_concat_meta(pieces, block_size=4096, output_key_encoding=enc, filter_policy=1, filter_block_size=4096))
+    assert data.tobytes() == b"".join(ranges.data_arena[x.data_offset:x.data_offset + x.data_len].tobytes() for x in outs)
+    job = gpu_compact(pkg, [whole], cutoff_ht=cutoff, block_size=4096)
+    assert job.kv_list() == ekv
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_user_boundary_values(pkg, seed):
+    """a19: FileMetaData user boundary values. DocDBCompactionFeed::UpdateBoundaryValues keeps, per range component of
+    the DocKeys it passes on, the bytewise smallest / largest encoded value (docdb_compaction_context.cc:754-773,
+    doc_boundary_values_extractor.cc:40-64); the GPU reduces them over the first surviving entry of every row."""
+    if seed < 3:
+        runs = w.random_docdb_runs(500 + seed, n_runs=2 + seed, n_rows=120)
+    elif seed == 3:
+        runs = w.random_cotable_runs(510, n_runs=3, n_tables=4, rows_per_table=40, colocated=True)
+    else:
+        runs = w.random_numeric_key_runs(520, n_runs=3, n_rows=80)
+    ssts = runs_to_ssts(runs, 1024)
+    for kw in [w.param_grid()[i] for i in (0, 2, 4, 6)]:
+        exp = o.compact(ssts, o.CompactionParams(**okw(kw)), o.TableOptions(block_size=1024))
+        job = gpu_compact(pkg, ssts, block_size=1024, user_boundary_values=True, **kw)
+        assert job.kv_list() == exp.kv_list()
+        assert job.user_values() == exp.user_values(), kw
+    # rows larger than a merge tile: the first surviving entry of a row may be met in several tiles — same extrema
+    big = w.giant_row_runs(7, n_runs=3, cols=150, versions=12, collection=800)
+    ssts = runs_to_ssts(big, 4096)
+    if seed == 0:
+        kw = w.param_grid()[6]
+        exp = o.compact(ssts, o.CompactionParams(**okw(kw)), o.TableOptions(block_size=4096))
+        job = gpu_compact(pkg, ssts, block_size=4096, user_boundary_values=True, **kw)
+        assert job.user_values() == exp.user_values()
+
+
 def test_yield_points(pkg):
     """The scheduler's pause hook (PriorityThreadPoolSuspender::PauseIfNecessary in the reference) is honoured
     between kernel phases of a job and between the ranges of a compaction run as subcompactions."""

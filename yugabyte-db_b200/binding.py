@@ -41,10 +41,15 @@ class JobOptions(C.Structure):
         ("cuda_stream", C.c_void_p),
         ("filter_policy", C.c_int32), ("filter_block_size", C.c_uint32),
         ("yield_fn", C.c_void_p), ("yield_ctx", C.c_void_p),
+        ("compute_user_boundary_values", C.c_int32),
     ]
 
 
 YIELD_FN = C.CFUNCTYPE(None, C.c_void_p)
+
+
+class UserValue(C.Structure):
+    _fields_ = [("tag", C.c_uint32), ("len", C.c_uint32), ("value", C.c_uint8 * 256)]
 
 
 class BlockHandle(C.Structure):
@@ -156,7 +161,7 @@ def make_options(device=0, bottommost=True, last_sequence=MAX_SEQUENCE, largest_
                  retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
                  restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
                  min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b"",
-                 filter_policy=0, filter_block_size=65536, yield_fn=None):
+                 filter_policy=0, filter_block_size=65536, yield_fn=None, user_boundary_values=False):
     """ybgpu_job_options from keyword arguments; returns (options, objects to keep alive). yield_fn: a Python
     callable() invoked at the engine's yield points (PauseIfNecessary)."""
     L = lib()
@@ -183,6 +188,7 @@ def make_options(device=0, bottommost=True, last_sequence=MAX_SEQUENCE, largest_
     o.cuda_stream = cuda_stream
     o.range_lower, o.range_lower_len = range_lower, len(range_lower)
     o.range_upper, o.range_upper_len = range_upper, len(range_upper)
+    o.compute_user_boundary_values = int(bool(user_boundary_values))
     cb = None
     if yield_fn is not None:
         cb = YIELD_FN(lambda _ctx: yield_fn())
@@ -198,13 +204,13 @@ class GpuCompactionJob:
                  retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
                  restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
                  min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b"",
-                 filter_policy=0, filter_block_size=65536, yield_fn=None):
+                 filter_policy=0, filter_block_size=65536, yield_fn=None, user_boundary_values=False):
         L = lib()
         o, self._keep = make_options(device, bottommost, last_sequence, largest_user_key, retention, cutoff_ht,
                                      cotables_cutoff_ht, table_ttl_ns, retain_delete_markers, other_min_ht, lower, upper,
                                      block_size, restart_interval, deviation, output_key_encoding, index_block_size,
                                      min_keys_per_index_block, verify_checksums, cuda_stream, range_lower, range_upper,
-                                     filter_policy, filter_block_size, yield_fn)
+                                     filter_policy, filter_block_size, yield_fn, user_boundary_values)
         h = C.c_void_p()
         st = L.ybgpu_job_create(C.byref(o), C.byref(h))
         if st != 0:
@@ -308,6 +314,16 @@ class GpuCompactionJob:
             return int(fn(C.string_at(k, kl), C.string_at(v, vl)) or 0)
         cb = EMIT_FN(tramp)
         self._check(lib().ybgpu_job_emit_kv_stream(self.h, C.cast(cb, C.c_void_p), None))
+
+    def user_values(self):
+        """ybgpu_job_output_user_values -> (smallest, largest): {tag: encoded key component}."""
+        L = lib()
+        L.ybgpu_job_output_user_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        a, b = (UserValue * 32)(), (UserValue * 32)()
+        n = C.c_uint32()
+        self._check(L.ybgpu_job_output_user_values(self.h, a, b, 32, C.byref(n)))
+        return ({a[i].tag: bytes(a[i].value[:a[i].len]) for i in range(n.value)},
+                {b[i].tag: bytes(b[i].value[:b[i].len]) for i in range(n.value)})
 
     def digest(self):
         d = C.c_uint64()
@@ -537,6 +553,44 @@ def compact_files(ssts, max_subcompactions=8, max_in_flight=3, data_arena=None, 
     if st != 0:
         raise YbGpuError(st, err.value.decode(errors="replace"))
     return SubcompactionResult([outs[i] for i in range(n.value)], total, data_arena, meta_arena)
+
+
+class OneTableResult(C.Structure):
+    _fields_ = [("data_len", C.c_uint64), ("meta_len", C.c_uint64), ("num_ranges", C.c_uint32), ("num_pieces", C.c_uint32),
+                ("smallest_key_len", C.c_uint32), ("largest_key_len", C.c_uint32),
+                ("smallest_key", C.c_uint8 * 1032), ("largest_key", C.c_uint8 * 1032)]
+
+    @property
+    def smallest(self):
+        return bytes(self.smallest_key[:self.smallest_key_len])
+
+    @property
+    def largest(self):
+        return bytes(self.largest_key[:self.largest_key_len])
+
+
+def compact_files_one_table(ssts, max_subcompactions=8, max_in_flight=3, data_out=None, meta_out=None, ht_filters=None, **job_kwargs):
+    """ybgpu_compact_files_one_table: the pipelined compaction with ONE output table. Returns
+    (data view, meta view, OneTableResult, total JobStats)."""
+    L = lib()
+    L.ybgpu_compact_files_one_table.argtypes = [C.POINTER(JobOptions), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                                                C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(OneTableResult), C.POINTER(JobStats),
+                                                C.c_char_p, C.c_uint64]
+    o, keep_o = make_options(**job_kwargs)
+    arr, keep = _input_files(ssts, ht_filters)
+    in_bytes = sum(int(d.size) for _, d in ssts)
+    if data_out is None:
+        data_out = np.empty(in_bytes + (in_bytes >> 4) + (1 << 20), np.uint8)
+    if meta_out is None:
+        meta_out = np.empty((in_bytes >> 4) + (4 << 20), np.uint8)
+    res = OneTableResult()
+    total = JobStats()
+    err = C.create_string_buffer(512)
+    st = L.ybgpu_compact_files_one_table(C.byref(o), arr, len(ssts), max_subcompactions, max_in_flight, data_out.ctypes.data, data_out.size,
+                                         meta_out.ctypes.data, meta_out.size, None, C.byref(res), C.byref(total), err, 512)
+    if st != 0:
+        raise YbGpuError(st, err.value.decode(errors="replace"))
+    return data_out[:res.data_len], meta_out[:res.meta_len], res, total
 
 
 class SstPiece(C.Structure):

@@ -299,6 +299,11 @@ ybgpu_status ybgpu_job_output_boundaries(const ybgpu_job* job, uint8_t* smallest
   return YBGPU_OK;
 }
 
+ybgpu_status ybgpu_job_output_user_values(ybgpu_job* job, ybgpu_user_value* smallest, ybgpu_user_value* largest, uint32_t cap, uint32_t* n) {
+  if (!job || !smallest || !largest || !n) return YBGPU_INVALID_ARGUMENT;
+  return Sync(job, job->engine->FetchUserValues(smallest, largest, cap, n));
+}
+
 ybgpu_status ybgpu_job_kv_stream_digest(ybgpu_job* job, uint64_t* digest) {
   if (!job) return YBGPU_INVALID_ARGUMENT;
   return Sync(job, job->engine->Digest(digest));

@@ -524,6 +524,9 @@ enum : uint8_t {
   ENT_COUNTED = 16,        // counted as an input record (not HT-filtered)
   ENT_DROP_HIDDEN = 32,    // rule A
   ENT_DROP_OBSOLETE = 64,  // bottommost kTypeDeletion
+  ENT_FIRST_OF_ROW = 128,  // first surviving entry of its DocKey (within a merge tile): the entry DocDBCompactionFeed passes
+                           // to UpdateBoundaryValues (docdb_compaction_context.cc:754-773). Same bit as the merge kernel's
+                           // tile-local group-start mark, which it replaces once the row groups are laid out.
 };
 
 // Re-encoded value prefix for ENT_VAL_REENCODE: new value = prefix[0..prefix_len) + old value

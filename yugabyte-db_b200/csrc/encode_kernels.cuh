@@ -1111,6 +1111,229 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_smem(EncView E, int S
   }
 }
 
+// ---- block assembler v4: value bytes never enter shared memory, the CRC never touches them ----------------
+// Values are copied verbatim from the input files, and their RAW CRC32C is already known (RunView::val_crc, computed
+// by the ingest pass while it verified the inputs). So
+//   * the full destination-aligned 16-byte chunks of every value go global -> registers -> global (shifted into
+//     place), without a stop in shared memory;
+//   * shared memory holds only what is assembled byte by byte: entry headers, key deltas, the few value bytes
+//     around chunk boundaries, rewritten values, the restart array and the trailer — the 16-byte chunks that
+//     contain any such byte are stored from the image by the thread of the entry they begin in;
+//   * the block checksum is the GF(2)-linear combination of per-entry pieces,
+//       crc(block) = sum_e [ crc(gap_e) * x^(8 |value_e|) + crc(value_e) ] * x^(8 (L - end_e)) + crc(tail) + init term,
+//     where gap_e = header + key delta of entry e, read from the image (a few dozen bytes per entry).
+// Per 32 KB block that is ~2 modular multiplications and ~30 table look-ups per entry instead of four look-ups
+// per 4 bytes of the whole image.
+constexpr int ENC4_REP = 8;            // copies of the byte table (lane l uses copy l % 8)
+
+template <int ENC>
+__global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_v4(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
+                                                             const unsigned long long* block_off, uint8_t* out) {
+  extern __shared__ __align__(16) uint8_t img_raw[];    // ENC_SMEM_CAP + 32
+  __shared__ uint32_t tab0[256 * ENC4_REP];
+  __shared__ uint32_t warp_sums[32];
+  __shared__ unsigned long long t_src[ENC_EM_S];
+  __shared__ uint32_t t_est[ENC_EM_S];      // entry start (image offset)
+  __shared__ uint32_t t_dsto[ENC_EM_S];     // where the copied value body starts (image offset)
+  __shared__ uint32_t t_len[ENC_EM_S];      // bytes copied from the input (0: the value was written into the image)
+  __shared__ uint32_t t_end[ENC_EM_S];      // entry end (image offset)
+  __shared__ uint32_t t_vcrc[ENC_EM_S];
+  __shared__ uint32_t t_chunk[ENC_EM_S + 1];
+  __shared__ uint16_t t_item[ENC_ITEMS_SMEM];
+  __shared__ uint32_t sh_acc;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const uint32_t v = g_crc_tab[0][i];
+#pragma unroll
+    for (int c = 0; c < ENC4_REP; c++) tab0[i * ENC4_REP + c] = v;
+  }
+  const uint32_t copy = threadIdx.x & (ENC4_REP - 1);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+
+  uint32_t b = blockIdx.x;
+  EncBlkHdr nh{}; EncBlkSums ns{};
+  if (b < nblocks) { nh = enc_load_hdr(E, block_first, block_off, b, nblocks); ns = enc_load_sums(E, nh); }
+  for (; b < nblocks; b += gridDim.x) {
+    const EncBlkHdr h = nh; const EncBlkSums u = ns;
+    const uint32_t nb = b + gridDim.x;
+    if (nb < nblocks) nh = enc_load_hdr(E, block_first, block_off, nb, nblocks);
+    if (h.btot > ENC_SMEM_CAP) {                                     // uniform for the CTA; k_encode_fused takes it
+      if (nb < nblocks) ns = enc_load_sums(E, nh);
+      continue;
+    }
+    const uint32_t blen = h.btot - 5;
+    const uint32_t L = blen + 1;                                     // contents + type byte
+    const uint32_t s = h.s, e = h.e;
+    uint8_t* gdst = out + h.boff;
+    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gdst) & 15);
+    uint8_t* img = img_raw + mis;                                    // image and destination agree mod 16
+    uint8_t* gbase = gdst - mis;                                     // 16-byte aligned; chunk c <-> img_raw[16c, 16c + 16)
+    const uint32_t vlo = mis, vhi = mis + h.btot;                    // bytes of this block inside the chunk grid
+    const unsigned long long Ps = u.Ps, Qs = u.Qs;
+    const uint32_t tl = u.tl, body = u.body;
+    if (threadIdx.x == 0) sh_acc = 0;
+    // a chunk of the grid: whole chunks as one vector, the block's first / last partial chunk byte by byte
+    auto store_chunk = [&](uint32_t c) {
+      const uint32_t lo = 16 * c, hi = lo + 16;
+      if (lo >= vlo && hi <= vhi) *reinterpret_cast<uint4*>(gbase + lo) = *reinterpret_cast<const uint4*>(img_raw + lo);
+      else for (uint32_t x = max(lo, vlo); x < min(hi, vhi); x++) gbase[x] = img_raw[x];
+    };
+    __syncthreads();
+
+    uint32_t acc = 0;
+    for (uint32_t p0 = s; p0 < e; p0 += ENC_EM_S) {
+      const uint32_t pn = min(static_cast<uint32_t>(ENC_EM_S), e - p0);
+      // ---- phase A: one thread per entry: header + key delta into the image, value copy job into the table
+      for (uint32_t q = threadIdx.x; q < pn; q += blockDim.x) {
+        const uint32_t j = p0 + q;
+        const bool restart = ((j - s) & (E.ri - 1)) == 0;
+        uint32_t off = static_cast<uint32_t>(E.P[j] - Ps);
+        if (j > s) { const uint32_t tp = (j - 1 - s) >> E.ri_shift; off += static_cast<uint32_t>(E.QQ[s + (tp << E.ri_shift)] - Qs); }
+        const Desc d = E.kept[j];
+        const uint8_t* rec = kept_rec(E, d, S);
+        const uint32_t vlen = d.vlen_out;
+        const RunView& run = E.runs[d.run];
+        const uint32_t idx = d.gid - run.gid_base;
+        const uint8_t* vs = run.data + run.val_off[idx];
+        uint8_t* p = emit_entry_key<ENC>(E, S, j, d, rec, kept_suffix(rec, d, S), restart, img + off);
+        uint32_t copy_len = vlen;
+        uint32_t vcrc = 0;
+        if (d.flags & ENT_VAL_TOMBSTONE) { p[0] = 'X'; copy_len = 0; }
+        else if (d.flags & ENT_VAL_REENCODE) {
+          const ValueRewrite& rw = E.rewrites[d.rewrite_slot];
+          for (uint32_t i = 0; i < rw.prefix_len; i++) p[i] = rw.prefix[i];
+          const uint32_t rest = vlen - rw.prefix_len;
+          for (uint32_t i = 0; i < rest; i++) p[rw.prefix_len + i] = vs[rw.skip + i];
+          copy_len = 0;
+        } else if (vlen) vcrc = run.val_crc[idx];
+        t_est[q] = off + mis;
+        t_dsto[q] = static_cast<uint32_t>(p - img_raw);
+        t_end[q] = static_cast<uint32_t>(p - img_raw) + vlen;
+        t_src[q] = reinterpret_cast<unsigned long long>(vs);
+        t_len[q] = copy_len;
+        t_vcrc[q] = vcrc;
+        if (restart) {
+          const uint32_t t = (j - s) >> E.ri_shift;
+          uint8_t* r = img + body + 4 * t;
+          r[0] = static_cast<uint8_t>(off); r[1] = static_cast<uint8_t>(off >> 8); r[2] = static_cast<uint8_t>(off >> 16); r[3] = static_cast<uint8_t>(off >> 24);
+        }
+      }
+      __syncthreads();
+      // items = runs of up to four destination-aligned 16-byte chunks lying entirely inside one value
+      uint32_t c0 = 0;
+      {
+        const uint32_t q0 = threadIdx.x;
+        if (q0 < pn && t_len[q0]) {
+          const uint32_t d0 = t_dsto[q0], d1 = d0 + t_len[q0];
+          const uint32_t fa = (d0 + 15) & ~15u, fb = d1 & ~15u;
+          c0 = fb > fa ? (fb - fa) >> 4 : 0;
+        }
+      }
+      c0 = (c0 + 3) >> 2;
+      uint32_t total_items;
+      const uint32_t ibase = block_exclusive_scan(c0, warp_sums, &total_items);
+      t_chunk[threadIdx.x] = ibase;
+      if (threadIdx.x == blockDim.x - 1) t_chunk[ENC_EM_S] = ibase + c0;
+      __syncthreads();
+      const bool direct = total_items <= ENC_ITEMS_SMEM;
+      if (direct) {
+        const uint32_t q = threadIdx.x;
+        if (q < pn) for (uint32_t it = t_chunk[q]; it < t_chunk[q + 1]; it++) t_item[it] = static_cast<uint16_t>(q);
+        __syncthreads();
+      }
+      // ---- phase B: value bodies, HBM -> registers -> HBM
+#pragma unroll 2
+      for (uint32_t it = threadIdx.x; it < total_items; it += blockDim.x) {
+        uint32_t q;
+        if (direct) q = t_item[it];
+        else {
+          uint32_t lo = 0, hi = pn;
+          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (t_chunk[mid] <= it) lo = mid; else hi = mid; }
+          q = lo;
+        }
+        const uint32_t d0 = t_dsto[q], d1 = d0 + t_len[q];
+        const uint32_t A = ((d0 + 15) & ~15u) + 64u * (it - t_chunk[q]);
+        const uint32_t nch = min(4u, ((d1 & ~15u) - A) >> 4);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(t_src[q]) + (A - d0);
+        const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15);
+        const uint4* sa = reinterpret_cast<const uint4*>(src - sh);
+        const uint32_t nld = nch + (sh ? 1 : 0);
+        uint4 v[5];
+#pragma unroll
+        for (int t = 0; t < 5; t++) v[t] = (static_cast<uint32_t>(t) < nld) ? __ldg(sa + t) : make_uint4(0, 0, 0, 0);
+        uint4* dv = reinterpret_cast<uint4*>(gbase + A);
+#pragma unroll
+        for (int t = 0; t < 4; t++) if (static_cast<uint32_t>(t) < nch) dv[t] = sh ? shift16(v[t], v[t + 1], sh) : v[t];
+      }
+      // value edges (bytes before the first / after the last full chunk) into the image: two small jobs per entry
+      for (uint32_t t = threadIdx.x; t < 2 * pn; t += blockDim.x) {
+        const uint32_t q = t >> 1;
+        const uint32_t len = t_len[q];
+        if (!len) continue;
+        const uint32_t d0 = t_dsto[q], d1 = d0 + len;
+        const uint32_t fa = (d0 + 15) & ~15u, fb = d1 & ~15u;
+        uint32_t lo, hi;
+        if (fb > fa) { if (t & 1) { lo = fb; hi = d1; } else { lo = d0; hi = fa; } }
+        else { if (t & 1) continue; lo = d0; hi = d1; }
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(t_src[q]) + (lo - d0);
+        while (lo < hi) {
+          const uint4 x = load_unaligned16(src);
+          const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+          const uint32_t nbytes = min(16u, hi - lo);
+#pragma unroll
+          for (int bb = 0; bb < 16; bb++) if (bb < static_cast<int>(nbytes)) img_raw[lo + bb] = static_cast<uint8_t>(w[bb >> 2] >> (8 * (bb & 3)));
+          lo += nbytes; src += nbytes;
+        }
+      }
+      __syncthreads();
+      // ---- phase C: per entry, its share of the block checksum and the chunks it owns
+      for (uint32_t q = threadIdx.x; q < pn; q += blockDim.x) {
+        const uint32_t est = t_est[q], d0 = t_dsto[q], len = t_len[q], eend = t_end[q];
+        const uint32_t fa = (d0 + 15) & ~15u, fb = (d0 + len) & ~15u;
+        const bool full = len && fb > fa;
+        // checksum: the bytes that exist only in the image are the entry's "gap" (a rewritten value belongs to it);
+        // a short copied value (no full chunk) sits in the image as well, but its CRC is known
+        const uint32_t gap_end = len ? d0 : eend;
+        uint32_t gc = 0;
+        for (uint32_t x = est; x < gap_end; x++) gc = tab0[((gc ^ img_raw[x]) & 0xff) * ENC4_REP + copy] ^ (gc >> 8);
+        uint32_t Ee = (gc && len) ? crc_mulmod(__ldg(&g_crc_xpow8[len]), gc) : gc;
+        Ee ^= t_vcrc[q];
+        if (Ee) acc ^= crc_mulmod(__ldg(&g_crc_xpow8[(mis + L) - eend]), Ee);
+        // chunks: from the one the entry starts in up to the first full value chunk (or the end of the entry)
+        const uint32_t c_lo = est >> 4, c_hi = full ? (fa >> 4) : ((eend + 15) >> 4);
+        for (uint32_t c = c_lo; c < c_hi; c++) store_chunk(c);
+      }
+      __syncthreads();
+    }
+    if (nb < nblocks) ns = enc_load_sums(E, nh);
+    // ---- tail: restart count + type byte, checksum, trailer, the chunks behind the last entry
+    if (threadIdx.x == 0) {
+      const uint32_t nres = tl + 1;
+      uint8_t* q = img + body + 4 * nres;
+      q[0] = static_cast<uint8_t>(nres); q[1] = static_cast<uint8_t>(nres >> 8); q[2] = static_cast<uint8_t>(nres >> 16); q[3] = static_cast<uint8_t>(nres >> 24);
+      q[4] = 0;   // kNoCompression
+    }
+    acc = __reduce_xor_sync(0xffffffffu, acc);
+    if (lane == 0 && acc) atomicXor(&sh_acc, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t r = sh_acc, tc = 0;
+      for (uint32_t x = body; x < L; x++) tc = tab0[((tc ^ img[x]) & 0xff) * ENC4_REP + copy] ^ (tc >> 8);
+      r ^= tc;
+      r ^= crc_mulmod(__ldg(&g_crc_xpow8[L]), 0xffffffffu);        // the 0xffffffff initial register, L <= 36 K
+      const uint32_t crc = crc_mask(~r);
+      uint8_t* t = img + blen + 1;
+      t[0] = static_cast<uint8_t>(crc); t[1] = static_cast<uint8_t>(crc >> 8); t[2] = static_cast<uint8_t>(crc >> 16); t[3] = static_cast<uint8_t>(crc >> 24);
+    }
+    __syncthreads();
+    {
+      const uint32_t c_lo = (mis + body) >> 4, c_hi = (vhi + 15) >> 4;
+      for (uint32_t c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) store_chunk(c);
+    }
+    __syncthreads();
+  }
+}
+
 // ---- bloom filter blocks (block_based_table_builder.cc:514-528,594-620; util/bloom.cc:43-61,384-455) ----
 // is_new[j] = the entry's filter key is non-empty and differs from the last non-empty filter key
 // before it ("no need to insert duplicate keys"). Equal keys are adjacent, so the previous entry
@@ -1236,6 +1459,118 @@ __global__ void __launch_bounds__(256) k_boundary_keys(EncView E, int S, const u
     const uint64_t suffix = kept_suffix(rec, d, S);
     for (int q = 0; q < 8; q++) o[2 + ulen + q] = static_cast<uint8_t>(suffix >> (8 * q));
   }
+}
+
+
+// ---- FileMetaData user boundary values (a19) --------------------------------------------------------------------
+// DocDBCompactionFeed::UpdateBoundaryValues (docdb_compaction_context.cc:754-773) feeds the first entry it passes on
+// for every DocKey to DocBoundaryValuesExtractor::Extract (doc_boundary_values_extractor.cc:40-64): the encoded
+// range-group components of the DocKey (hashed components are not reported, internal meta records are skipped),
+// tag = 10 + component index, and keeps per tag the bytewise smallest and largest value (rocksdb/db/metadata.cc:44-57).
+// Here: the survivors that carry ENT_FIRST_OF_ROW are walked once; every thread keeps (pointer, length) of its best
+// candidates per component, warps and CTAs reduce them by comparing the bytes behind the pointers, the last kernel
+// copies the winners out.
+constexpr int BV_MAXC = 16;            // range components reported (tags 10 .. 25)
+constexpr int BV_MAXLEN = 255;         // longest component value copied out
+struct BvCand { const uint8_t* p; uint32_t len; uint32_t valid; };
+struct BvOut { uint32_t n_comps; uint32_t overflow; uint32_t len[2][BV_MAXC]; uint8_t val[2][BV_MAXC][BV_MAXLEN + 1]; };
+
+__device__ __forceinline__ int bv_cmp(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb) {
+  const uint32_t m = la < lb ? la : lb;
+  for (uint32_t i = 0; i < m; i++) { const uint8_t x = a[i], y = b[i]; if (x != y) return x < y ? -1 : 1; }
+  return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+// which = 0: keep the smaller, 1: keep the larger
+__device__ __forceinline__ void bv_take(BvCand* best, const uint8_t* p, uint32_t len, int which) {
+  if (!best->valid) { best->p = p; best->len = len; best->valid = 1; return; }
+  const int c = bv_cmp(p, len, best->p, best->len);
+  if (which == 0 ? c < 0 : c > 0) { best->p = p; best->len = len; }
+}
+
+__global__ void __launch_bounds__(256) k_boundary_values(EncView E, int S, BvCand* cand /*[grid][2][BV_MAXC]*/, BvOut* out) {
+  BvCand best[2][BV_MAXC];
+#pragma unroll
+  for (int w = 0; w < 2; w++)
+    for (int c = 0; c < BV_MAXC; c++) { best[w][c].p = nullptr; best[w][c].len = 0; best[w][c].valid = 0; }
+  uint32_t ncomp = 0;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < E.n; j += gridDim.x * blockDim.x) {
+    const Desc d = E.kept[j];
+    if (!(d.flags & ENT_FIRST_OF_ROW)) continue;
+    const uint8_t* key = kept_rec(E, d, S);
+    const int ulen = static_cast<int>(d.klen) - 8;
+    if (ulen <= 0) continue;
+    const uint8_t t0 = key[0];
+    if (t0 == 6 || t0 == 7 || t0 == 8 || t0 == 'x') continue;          // IsMetaKeyType (dockv/value_type.h:252-273)
+    int pos = dockey_id_size(key, ulen);
+    if (pos < 0) continue;
+    if (pos < ulen && key[pos] == 'G') {                                 // hash code + hashed group: not reported
+      if (ulen - pos < 3) continue;
+      pos += 3;
+      const int k = consume_primitive_group(key + pos, ulen - pos);
+      if (k < 0) continue;
+      pos += k;
+    }
+    uint32_t c = 0;
+    while (pos < ulen && key[pos] != '!') {
+      if (is_special_key_entry_type(key[pos])) break;
+      const int k = key_entry_size(key + pos, ulen - pos);
+      if (k < 0) break;
+      if (c < BV_MAXC) { bv_take(&best[0][c], key + pos, k, 0); bv_take(&best[1][c], key + pos, k, 1); }
+      else out->overflow = 1;
+      pos += k; c++;
+    }
+    ncomp = max(ncomp, min(c, static_cast<uint32_t>(BV_MAXC)));
+  }
+  // CTA reduction, component by component (only as many as any thread of the CTA has seen)
+  __shared__ BvCand sh[2][8];
+  __shared__ uint32_t sh_nc;
+  if (threadIdx.x == 0) sh_nc = 0;
+  __syncthreads();
+  if (ncomp) atomicMax(&sh_nc, ncomp);
+  __syncthreads();
+  const uint32_t nc = sh_nc;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t c = 0; c < nc; c++) {
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      BvCand b = best[w][c];
+      for (int o = 16; o; o >>= 1) {
+        BvCand y;
+        y.p = reinterpret_cast<const uint8_t*>(__shfl_xor_sync(0xffffffffu, reinterpret_cast<unsigned long long>(b.p), o));
+        y.len = __shfl_xor_sync(0xffffffffu, b.len, o);
+        y.valid = __shfl_xor_sync(0xffffffffu, b.valid, o);
+        if (y.valid) bv_take(&b, y.p, y.len, w);
+      }
+      if (lane == 0) sh[w][wid] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const int w = threadIdx.x;
+      BvCand b = sh[w][0];
+      for (int q = 1; q < 8; q++) if (sh[w][q].valid) bv_take(&b, sh[w][q].p, sh[w][q].len, w);
+      cand[(static_cast<size_t>(blockIdx.x) * 2 + w) * BV_MAXC + c] = b;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && nc) atomicMax(&out->n_comps, nc);
+}
+
+// One CTA: the winners over all CTAs of k_boundary_values, copied out.
+__global__ void __launch_bounds__(64) k_boundary_values_finish(const BvCand* cand, uint32_t grid, BvOut* out) {
+  const uint32_t nc = out->n_comps;
+  const uint32_t t = threadIdx.x;                  // (which, component)
+  if (t >= 2 * BV_MAXC) return;
+  const int w = t / BV_MAXC; const uint32_t c = t % BV_MAXC;
+  if (c >= nc) { out->len[w][c] = 0; return; }
+  BvCand b; b.p = nullptr; b.len = 0; b.valid = 0;
+  for (uint32_t g = 0; g < grid; g++) {
+    const BvCand y = cand[(static_cast<size_t>(g) * 2 + w) * BV_MAXC + c];
+    if (y.valid) bv_take(&b, y.p, y.len, w);
+  }
+  if (!b.valid) { out->len[w][c] = 0; return; }
+  if (b.len > BV_MAXLEN) { out->overflow = 1; out->len[w][c] = 0; return; }
+  out->len[w][c] = b.len;
+  for (uint32_t i = 0; i < b.len; i++) out->val[w][c][i] = b.p[i];
 }
 
 }  // namespace ybgpu

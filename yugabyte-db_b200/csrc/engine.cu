@@ -44,6 +44,7 @@ struct RunView {
   uint32_t* blk_count;          // entries per block (K1), then exclusive prefix (blk_base)
   uint8_t* rec;                 // n_entries * S key records (K1')
   uint64_t* val_off;            // value offset inside `data` per entry
+  uint32_t* val_crc;            // RAW CRC32C (zero initial register, no complement) of every entry's value bytes
   uint32_t nb;
   uint32_t n_entries;
   uint32_t restart_interval;    // entries per restart interval in this file
@@ -63,6 +64,7 @@ struct JobDev {                 // device-global job state
   uint32_t n_rewrites;
   uint32_t n_tiles;
   uint32_t max_tile;            // largest tile of the current partition (k_tile_check)
+  int ingest_fallback;          // k_ingest met something it does not take: the host runs the general kernels
   unsigned long long digest;
 };
 
@@ -1096,6 +1098,19 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
       }
     }
   }
+  // first surviving entry of every row group: the one whose DocKey enters the file's user boundary values
+  // (the group-start mark is not needed any more; its bit now carries this)
+  if (prm->R.enabled) {
+    for (uint32_t g = threadIdx.x; g < sh_ngroups; g += blockDim.x) {
+      const uint32_t i0 = gstart[g], i1 = gstart[g + 1];
+      bool done = false;
+      for (uint32_t i = i0; i < i1; i++) {
+        uint8_t f = res[i] & static_cast<uint8_t>(~ENT_FIRST_OF_ROW);
+        if (!done && (f & ENT_KEEP)) { f |= ENT_FIRST_OF_ROW; done = true; }
+        res[i] = f;
+      }
+    }
+  }
   __syncthreads();
 
   // (e) descriptors in merged order
@@ -1111,7 +1126,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
     Desc d;
     d.gid = V.runs[r].gid_base + idx;
     d.klen = static_cast<uint16_t>(rec_ulen(e, S) + 8);
-    d.flags = f & static_cast<uint8_t>(~ENT_GROUP_START); d.run = static_cast<uint8_t>(r);
+    d.flags = prm->R.enabled ? f : (f & static_cast<uint8_t>(~ENT_GROUP_START)); d.run = static_cast<uint8_t>(r);
     d.rewrite_slot = rw_slot[i];
     uint32_t vout = rec_vlen(e, S);
     if (f & ENT_VAL_TOMBSTONE) vout = 1;
@@ -1330,6 +1345,7 @@ __global__ void __launch_bounds__(256) k_digest(const uint8_t* keys, const uint6
 
 }  // namespace ybgpu
 #include "encode_kernels.cuh"
+#include "ingest_kernels.cuh"
 namespace ybgpu {
 
 // =============================================================================================
@@ -1401,6 +1417,7 @@ struct Engine::Impl {
   // bloom filter blocks
   uint32_t n_filter_blocks = 0, filter_block_bytes = 0, filter_key_stride = 0;
   uint8_t* d_filters = nullptr; uint8_t* d_filter_keys = nullptr; uint32_t* d_filter_first = nullptr;
+  BvOut* d_bv = nullptr;               // user boundary values (options.compute_user_boundary_values)
 };
 
 // Small device->host reads between phases (error word, counts: <= 4 KB) do not use the copy engine:
@@ -1674,16 +1691,109 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     return cudaEventRecord(I.phase_ev[phase++], I.stream);
   };
 
-  // ---- K1: prepass + scan per file
+  // ---- K0/K1: one fused pass (k_ingest: TMA-staged blocks, checksum verification, value CRCs, entry counts,
+  // key records) when every input is shared-prefix encoded; otherwise, or when the fused kernel meets something
+  // it does not take, the general kernels: k_crc_blocks (verify), k_prepass, k_decode_all, k_value_crc.
   uint32_t* d_totals = nullptr;
   CUDA_TRY(DevAlloc(&I.allocs, &d_totals, static_cast<size_t>(k) + 1));
-  {
-    std::vector<uint32_t> blk_base(k + 1, 0);
-    for (int r = 0; r < k; r++) blk_base[r + 1] = blk_base[r] + I.runs[r].nb;
-    uint32_t* d_blk_base = nullptr;
-    CUDA_TRY(DevAlloc(&I.allocs, &d_blk_base, static_cast<size_t>(k) + 1));
-    CUDA_TRY(cudaMemcpyAsync(d_blk_base, blk_base.data(), 4 * (static_cast<size_t>(k) + 1), cudaMemcpyHostToDevice, I.stream));
-    CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+  std::vector<uint32_t> blk_base(k + 1, 0);
+  for (int r = 0; r < k; r++) blk_base[r + 1] = blk_base[r] + I.runs[r].nb;
+  uint32_t* d_blk_base = nullptr;
+  CUDA_TRY(DevAlloc(&I.allocs, &d_blk_base, static_cast<size_t>(k) + 1));
+  CUDA_TRY(cudaMemcpyAsync(d_blk_base, blk_base.data(), 4 * (static_cast<size_t>(k) + 1), cudaMemcpyHostToDevice, I.stream));
+  CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+  RangeDev* d_range = nullptr;
+  if (!range_lower_.empty() || !range_upper_.empty()) {
+    if (range_lower_.size() > 255 || range_upper_.size() > 255) return Fail(YBGPU_NOT_SUPPORTED, "range bounds longer than 255 bytes");
+    RangeDev hr{};
+    hr.lower_len = static_cast<uint32_t>(range_lower_.size()); memcpy(hr.lower, range_lower_.data(), range_lower_.size());
+    hr.upper_len = static_cast<uint32_t>(range_upper_.size()); memcpy(hr.upper, range_upper_.data(), range_upper_.size());
+    CUDA_TRY(DevAlloc(&I.allocs, &d_range, 1));
+    CUDA_TRY(cudaMemcpyAsync(d_range, &hr, sizeof(hr), cudaMemcpyHostToDevice, I.stream));
+  }
+  uint64_t N = 0;
+  uint32_t max_ikey = 0;
+  int Sfinal = 32;
+  bool ingested = false;
+  bool try_ingest = blk_base[k] > 0 && getenv("YBGPU_NO_INGEST") == nullptr;
+  for (int r = 0; r < k; r++) try_ingest = try_ingest && I.runs[r].key_encoding == 1;
+  if (try_ingest) {
+    unsigned long long* d_rsum = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_rsum, static_cast<size_t>(k)));
+    CUDA_TRY(cudaMemsetAsync(d_rsum, 0, 8 * static_cast<size_t>(k), I.stream));
+    k_restart_probe<<<GridFor(blk_base[k], 256, sms), 256, 0, I.stream>>>(I.dRuns, d_blk_base, k, d_rsum, I.dJ);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(end_phase());
+    if (ybgpu_status s = CheckDeviceError("block scan")) return s;
+    std::vector<unsigned long long> rsum(k, 0);
+    if (ybgpu_status s = ReadSmall(rsum.data(), d_rsum, 8 * static_cast<size_t>(k))) return s;
+    if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
+    // upper bound of the entries of a file: every restart interval holds at most `restart interval` entries
+    std::vector<uint32_t> cap(k, 0);
+    uint64_t cap_total = 0;
+    for (int r = 0; r < k; r++) {
+      const uint64_t ri = I.hJ.restart_interval[r] ? I.hJ.restart_interval[r] : static_cast<uint64_t>(ING_MAXE);
+      const uint64_t c = rsum[r] * ri;
+      cap_total += c;
+      if (cap_total >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "more than 2^32 entries in one job: shard the compaction");
+      cap[r] = static_cast<uint32_t>(c);
+    }
+    // record stride: user key + 16-byte trailer, from the longest key the probe's sample met; a longer key inside
+    // k_ingest costs one more attempt with the widest stride the kernel takes (64-byte internal keys)
+    const int S_widest = 16 * ING_NVI + 16;
+    const uint32_t sample_max = std::max<uint32_t>(I.hJ.max_ikey_len, 8);
+    Sfinal = std::min(S_widest, std::max(32, static_cast<int>(((sample_max - 8 + 16) + 15) & ~15u)));
+    IngestView iv{};
+    uint32_t* d_cap = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_cap, static_cast<size_t>(k)));
+    CUDA_TRY(DevAlloc(&I.allocs, &iv.status, static_cast<size_t>(blk_base[k])));
+    CUDA_TRY(DevAlloc(&I.allocs, &iv.ticket, 1));
+    CUDA_TRY(cudaMemcpyAsync(d_cap, cap.data(), 4 * static_cast<size_t>(k), cudaMemcpyHostToDevice, I.stream));
+    CUDA_TRY(cudaFuncSetAttribute(k_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ING_SMEM)));
+    for (int attempt = 0; attempt < 2; attempt++) {
+      for (int r = 0; r < k; r++) {
+        RunView& rv = I.runs[r];
+        CUDA_TRY(DevAlloc(&I.allocs, &rv.rec, static_cast<size_t>(cap[r]) * Sfinal + 16));
+        if (attempt == 0) {
+          CUDA_TRY(DevAlloc(&I.allocs, &rv.val_off, static_cast<size_t>(cap[r]) + 1));
+          CUDA_TRY(DevAlloc(&I.allocs, &rv.val_crc, static_cast<size_t>(cap[r]) + 1));
+        }
+      }
+      CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+      CUDA_TRY(cudaMemsetAsync(iv.status, 0, 8 * static_cast<size_t>(blk_base[k]), I.stream));
+      CUDA_TRY(cudaMemsetAsync(iv.ticket, 0, 4, I.stream));
+      CUDA_TRY(cudaMemsetAsync(d_totals, 0, 4 * (static_cast<size_t>(k) + 1), I.stream));
+      CUDA_TRY(cudaMemsetAsync(&I.dJ->ingest_fallback, 0, sizeof(int), I.stream));
+      iv.runs = I.dRuns; iv.blk_base = d_blk_base; iv.totals = d_totals; iv.cap = d_cap; iv.range = d_range;
+      iv.k = k; iv.S = Sfinal; iv.verify = opt_.verify_checksums ? 1 : 0;
+      const int grid = static_cast<int>(std::min<uint64_t>(blk_base[k], static_cast<uint64_t>(sms) * 3));
+      k_ingest<<<grid, ING_THREADS, ING_SMEM, I.stream>>>(iv, I.dJ);
+      launches++;
+      CUDA_TRY(cudaGetLastError());
+      if (ybgpu_status s = CheckDeviceError("ingest")) return s;
+      if (I.hJ.ingest_fallback != ING_FALLBACK_WIDER || Sfinal == S_widest) break;
+      Sfinal = S_widest;
+    }
+    CUDA_TRY(end_phase());
+    tick("ingest");
+    if (!I.hJ.ingest_fallback) {
+      std::vector<uint32_t> h_totals(k + 1, 0);
+      if (ybgpu_status s = ReadSmall(h_totals.data(), d_totals, 4 * static_cast<size_t>(k))) return s;
+      for (int r = 0; r < k; r++) {
+        I.runs[r].n_entries = h_totals[r];
+        I.runs[r].restart_interval = I.hJ.restart_interval[r];
+        I.runs[r].gid_base = static_cast<uint32_t>(N);
+        N += h_totals[r];
+      }
+      max_ikey = I.hJ.max_ikey_len;
+      ingested = true;
+    } else {
+      phase = 0;                           // the general path starts over
+    }
+  }
+  if (!ingested) {
+    // ---- general path. K1: prepass + scan per file
     if (opt_.verify_checksums) {
       // ReadBlock's checksum verification (table/format.cc:352-395) for every input block
       for (int r = 0; r < k; r++) {
@@ -1699,65 +1809,60 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       launches++;
     }
     if (k) { k_scan_blk_counts<<<k, 1024, 0, I.stream>>>(I.dRuns, d_totals); launches++; }
-  }
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(end_phase());
-  if (ybgpu_status s = CheckDeviceError("block scan")) return s;
-  tick("block scan");
-  if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
-  uint64_t N = 0;
-  std::vector<uint32_t> h_totals(k + 1, 0);
-  if (k) { if (ybgpu_status s = ReadSmall(h_totals.data(), d_totals, 4 * static_cast<size_t>(k))) return s; }
-  for (int r = 0; r < k; r++) {
-    const uint32_t n = h_totals[r];
-    I.runs[r].n_entries = n;
-    I.runs[r].restart_interval = I.hJ.restart_interval[r];
-    if (N + n >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "more than 2^32 entries in one job: shard the compaction");
-    I.runs[r].gid_base = static_cast<uint32_t>(N);
-    N += n;
-  }
-  const uint32_t max_ikey = I.hJ.max_ikey_len;
-  if (max_ikey > 1008 + 8) return Fail(YBGPU_NOT_SUPPORTED, "user keys longer than 1008 bytes are not supported");
-  const int S = N ? static_cast<int>(((max_ikey - 8 + 16) + 15) & ~15u) : 32;   // user key + 16-byte trailer
-  const int Sfinal = std::max(S, 32);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(end_phase());
+    if (ybgpu_status s = CheckDeviceError("block scan")) return s;
+    tick("block scan");
+    if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
+    std::vector<uint32_t> h_totals(k + 1, 0);
+    if (k) { if (ybgpu_status s = ReadSmall(h_totals.data(), d_totals, 4 * static_cast<size_t>(k))) return s; }
+    for (int r = 0; r < k; r++) {
+      const uint32_t n = h_totals[r];
+      I.runs[r].n_entries = n;
+      I.runs[r].restart_interval = I.hJ.restart_interval[r];
+      if (N + n >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "more than 2^32 entries in one job: shard the compaction");
+      I.runs[r].gid_base = static_cast<uint32_t>(N);
+      N += n;
+    }
+    max_ikey = I.hJ.max_ikey_len;
+    if (max_ikey > 1008 + 8) return Fail(YBGPU_NOT_SUPPORTED, "user keys longer than 1008 bytes are not supported");
+    const int S = N ? static_cast<int>(((max_ikey - 8 + 16) + 15) & ~15u) : 32;   // user key + 16-byte trailer
+    Sfinal = std::max(S, 32);
 
-  // ---- K1': decode
-  RangeDev* d_range = nullptr;
-  if (!range_lower_.empty() || !range_upper_.empty()) {
-    if (range_lower_.size() > 255 || range_upper_.size() > 255) return Fail(YBGPU_NOT_SUPPORTED, "range bounds longer than 255 bytes");
-    RangeDev hr{};
-    hr.lower_len = static_cast<uint32_t>(range_lower_.size()); memcpy(hr.lower, range_lower_.data(), range_lower_.size());
-    hr.upper_len = static_cast<uint32_t>(range_upper_.size()); memcpy(hr.upper, range_upper_.data(), range_upper_.size());
-    CUDA_TRY(DevAlloc(&I.allocs, &d_range, 1));
-    CUDA_TRY(cudaMemcpyAsync(d_range, &hr, sizeof(hr), cudaMemcpyHostToDevice, I.stream));
+    // ---- K1': decode
+    std::vector<uint32_t> group_base(k + 1, 0);
+    for (int r = 0; r < k; r++) {
+      RunView& rv = I.runs[r];
+      CUDA_TRY(DevAlloc(&I.allocs, &rv.rec, static_cast<size_t>(rv.n_entries) * Sfinal + 16));
+      CUDA_TRY(DevAlloc(&I.allocs, &rv.val_off, static_cast<size_t>(rv.n_entries) + 1));
+      CUDA_TRY(DevAlloc(&I.allocs, &rv.val_crc, static_cast<size_t>(rv.n_entries) + 1));
+      group_base[r + 1] = group_base[r] + (rv.nb + DEC_WB - 1) / DEC_WB;
+    }
+    CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+    if (group_base[k]) {
+      uint32_t* d_group_base = nullptr;
+      CUDA_TRY(DevAlloc(&I.allocs, &d_group_base, k + 1));
+      CUDA_TRY(cudaMemcpyAsync(d_group_base, group_base.data(), 4 * (k + 1), cudaMemcpyHostToDevice, I.stream));
+      const int grid = GridFor(static_cast<uint64_t>(group_base[k]) * 32, 128, sms);
+      // fast path: shared-prefix inputs, internal keys of at most 64 bytes, no HybridTime filter / key range
+      bool fast = d_range == nullptr && max_ikey <= 64;
+      for (int r = 0; r < k; r++) fast = fast && I.runs[r].key_encoding == 1 && I.runs[r].ht_filter == 0xfffffffffffffffeull;
+      if (fast && getenv("YBGPU_NO_FAST_DECODE") == nullptr) {
+        if (max_ikey <= 32) k_decode_fast<2><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
+        else if (max_ikey <= 48) k_decode_fast<3><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
+        else k_decode_fast<4><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
+      } else if (max_ikey <= 128) k_decode_all<128><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
+      else if (max_ikey <= 320) k_decode_all<320><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
+      else k_decode_all<1024><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
+      launches++;
+      // per-entry value CRCs for the block encoder (the fused path computes them while verifying)
+      CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+      k_value_crc<<<GridFor(N, 256, sms), 256, 0, I.stream>>>(I.dRuns, k, Sfinal);
+      launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(end_phase());
   }
-  std::vector<uint32_t> group_base(k + 1, 0);
-  for (int r = 0; r < k; r++) {
-    RunView& rv = I.runs[r];
-    CUDA_TRY(DevAlloc(&I.allocs, &rv.rec, static_cast<size_t>(rv.n_entries) * Sfinal + 16));
-    CUDA_TRY(DevAlloc(&I.allocs, &rv.val_off, static_cast<size_t>(rv.n_entries) + 1));
-    group_base[r + 1] = group_base[r] + (rv.nb + DEC_WB - 1) / DEC_WB;
-  }
-  CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
-  if (group_base[k]) {
-    uint32_t* d_group_base = nullptr;
-    CUDA_TRY(DevAlloc(&I.allocs, &d_group_base, k + 1));
-    CUDA_TRY(cudaMemcpyAsync(d_group_base, group_base.data(), 4 * (k + 1), cudaMemcpyHostToDevice, I.stream));
-    const int grid = GridFor(static_cast<uint64_t>(group_base[k]) * 32, 128, sms);
-    // fast path: shared-prefix inputs, internal keys of at most 64 bytes, no HybridTime filter / key range
-    bool fast = d_range == nullptr && max_ikey <= 64;
-    for (int r = 0; r < k; r++) fast = fast && I.runs[r].key_encoding == 1 && I.runs[r].ht_filter == 0xfffffffffffffffeull;
-    if (fast && getenv("YBGPU_NO_FAST_DECODE") == nullptr) {
-      if (max_ikey <= 32) k_decode_fast<2><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
-      else if (max_ikey <= 48) k_decode_fast<3><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
-      else k_decode_fast<4><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
-    } else if (max_ikey <= 128) k_decode_all<128><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
-    else if (max_ikey <= 320) k_decode_all<320><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
-    else k_decode_all<1024><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
-    launches++;
-  }
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(end_phase());
   CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
 
   // ---- job parameters
@@ -1977,7 +2082,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     {
       const size_t esm = ENC_SMEM_CAP + 32;
       const bool tsp = E.key_encoding == YBGPU_KEY_ENCODING_THREE_SHARED_PARTS;
-      auto smem_kernel = tsp ? k_encode_smem<2> : k_encode_smem<1>;
+      const bool v3 = getenv("YBGPU_ENC_V3") != nullptr;           // A/B: the image-CRC assembler of round 1
+      auto smem_kernel = v3 ? (tsp ? k_encode_smem<2> : k_encode_smem<1>) : (tsp ? k_encode_v4<2> : k_encode_v4<1>);
       auto fused_kernel = tsp ? k_encode_fused<2> : k_encode_fused<1>;
       CUDA_TRY(cudaFuncSetAttribute(smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esm)));
       CUDA_TRY(cudaEventRecord(I.enc_ev[0], I.stream));
@@ -2024,6 +2130,17 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       k_filter_finish<<<GridFor(static_cast<uint64_t>(nfb) * 2, 256, sms), 256, 0, I.stream>>>(E, Sfinal, d_new_entry, n_keys, g, nfb, I.d_filters,
                                                                                               I.d_filter_keys, I.filter_key_stride, I.d_filter_first);
       launches += 5 + (n_keys ? 1 : 0);
+    }
+    if (opt_.compute_user_boundary_values && opt_.retention_enabled) {
+      const int bgrid = static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, static_cast<uint64_t>(sms) * 2)));
+      BvCand* d_cand = nullptr;
+      CUDA_TRY(DevAlloc(&I.allocs, &d_cand, static_cast<size_t>(bgrid) * 2 * BV_MAXC));
+      CUDA_TRY(DevAlloc(&I.allocs, &I.d_bv, 1));
+      CUDA_TRY(cudaMemsetAsync(d_cand, 0, sizeof(BvCand) * static_cast<size_t>(bgrid) * 2 * BV_MAXC, I.stream));
+      CUDA_TRY(cudaMemsetAsync(I.d_bv, 0, sizeof(BvOut), I.stream));
+      k_boundary_values<<<bgrid, 256, 0, I.stream>>>(E, Sfinal, d_cand, I.d_bv);
+      k_boundary_values_finish<<<1, 64, 0, I.stream>>>(d_cand, static_cast<uint32_t>(bgrid), I.d_bv);
+      launches += 2;
     }
     I.boundary_stride = static_cast<uint32_t>((max_ikey + 2 + 7) & ~7u);
     // slot 2*nblocks (one past the per-block pairs): the first key of the file (FileMetaData::smallest)
@@ -2175,6 +2292,33 @@ ybgpu_status Engine::FetchFileBoundaries(uint8_t* smallest, uint8_t* largest) {
   CUDA_TRY(cudaMemcpyAsync(largest, I.d_boundary + static_cast<size_t>(I.n_blocks - 1) * 2 * I.boundary_stride, I.boundary_stride, cudaMemcpyDeviceToHost, I.stream));
   CUDA_TRY(cudaStreamSynchronize(I.stream));
   stats_.d2h_bytes += 2ull * I.boundary_stride;
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::FetchUserValues(ybgpu_user_value* smallest, ybgpu_user_value* largest, uint32_t cap, uint32_t* n) {
+  if (!ran_) return Fail(YBGPU_ILLEGAL_STATE, "job has not run");
+  if (!opt_.compute_user_boundary_values) return Fail(YBGPU_ILLEGAL_STATE, "options.compute_user_boundary_values was not set");
+  Impl& I = *impl_;
+  *n = 0;
+  if (!I.d_bv) return YBGPU_OK;                           // nothing survived / plain RocksDB mode
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  std::vector<uint8_t> buf(sizeof(BvOut));
+  CUDA_TRY(cudaMemcpyAsync(buf.data(), I.d_bv, sizeof(BvOut), cudaMemcpyDeviceToHost, I.stream));
+  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  stats_.d2h_bytes += sizeof(BvOut);
+  const BvOut& o = *reinterpret_cast<const BvOut*>(buf.data());
+  if (o.overflow) return Fail(YBGPU_NOT_SUPPORTED, "more than 16 range components or a component longer than 255 bytes: boundary values not computed");
+  uint32_t m = 0;
+  for (uint32_t c = 0; c < o.n_comps && c < BV_MAXC; c++) {
+    if (!o.len[0][c] && !o.len[1][c]) continue;
+    if (m >= cap) return Fail(YBGPU_INVALID_ARGUMENT, "user value buffers too small");
+    smallest[m].tag = largest[m].tag = 10 + c;           // TagForRangeComponent (doc_boundary_values_extractor.cc:108-110)
+    smallest[m].len = o.len[0][c]; largest[m].len = o.len[1][c];
+    memcpy(smallest[m].value, o.val[0][c], o.len[0][c]);
+    memcpy(largest[m].value, o.val[1][c], o.len[1][c]);
+    m++;
+  }
+  *n = m;
   return YBGPU_OK;
 }
 

@@ -36,6 +36,8 @@ class Engine {
   // filters: n*block_bytes; keys: per block [first key][last key] records ([u16 len][bytes], key_stride each);
   // first_entry[f]: output entry whose filter key opens block f; block_first[b]: first entry of data block b.
   ybgpu_status FetchFilter(uint8_t* filters, uint8_t* keys, uint32_t* first_entry, uint32_t* block_first);
+  // FileMetaData user boundary values (options.compute_user_boundary_values): per range component, min / max value
+  ybgpu_status FetchUserValues(ybgpu_user_value* smallest, ybgpu_user_value* largest, uint32_t cap, uint32_t* n);
   const ybgpu_job_options& options() const { return opt_; }
   ybgpu_job_stats& stats() { return stats_; }
   const std::string& error() const { return error_; }

@@ -569,6 +569,84 @@ static uint64_t PropVarint(const SstMeta& m, const char* name) {
   return v;
 }
 
+ConcatBuilder::ConcatBuilder(const TableOptions& o) : o_(o), w_(new MetaFileWriter(o)), mp_(new MetaProps()) {}
+ConcatBuilder::~ConcatBuilder() { delete w_; delete mp_; }
+void ConcatBuilder::Reserve(size_t bytes) { w_->Reserve(bytes); }
+
+std::string ConcatBuilder::AddPiece(const SstPiece& piece, const SstPiece* next, const SstMeta* parsed) {
+  try {
+    SstMeta local;
+    if (!parsed) {
+      std::string e = ParseSplitSstMeta(piece.meta, piece.meta_len, &local);
+      if (!e.empty()) return "piece " + std::to_string(n_pieces_) + ": " + e;
+      parsed = &local;
+    }
+    const SstMeta& m = *parsed;
+    const std::string tag = "piece " + std::to_string(n_pieces_);
+    if (m.data_blocks.empty()) return tag + " has no data blocks";
+    if (m.key_encoding != o_.key_encoding) return "pieces use a different data block key encoding than the output table options";
+    if ((o_.filter_policy != 0) != !m.filter_blocks.empty()) return "filter blocks of " + tag + " do not match the output table options";
+    if (o_.filter_policy && m.filter_policy_name != "DocKeyV3Filter") return "unknown filter policy " + m.filter_policy_name;
+    if (piece.smallest.size() < 8 || piece.largest.size() < 8 || (next && next->smallest.size() < 8)) return "piece boundary keys are missing";
+    if (n_pieces_ && CompareBytes(prev_largest_.substr(0, prev_largest_.size() - 8), piece.smallest.substr(0, piece.smallest.size() - 8)) >= 0)
+      return "pieces are not in ascending, disjoint key order";
+    if (next && CompareBytes(piece.largest.substr(0, piece.largest.size() - 8), next->smallest.substr(0, next->smallest.size() - 8)) >= 0)
+      return "pieces are not in ascending, disjoint key order";
+    const Handle& last = m.data_blocks.back();
+    if (last.offset + last.size + kTrailer > piece.data_len) return tag + ": data file shorter than its index says";
+    const bool last_piece = next == nullptr;
+    // filter blocks of this piece first: the order of blocks inside the metadata file is free, the handles
+    // in the filter index are what readers follow
+    for (size_t f = 0; f < m.filter_blocks.size(); f++) {
+      std::string key = m.filter_index_keys[f];
+      if (f + 1 == m.filter_blocks.size() && !last_piece) {
+        const std::string& lk = piece.largest; const std::string& nk = next->smallest;
+        const int fl = docdb_filter_prefix_len(reinterpret_cast<const uint8_t*>(lk.data()), static_cast<int>(lk.size() - 8));
+        const int fn = docdb_filter_prefix_len(reinterpret_cast<const uint8_t*>(nk.data()), static_cast<int>(nk.size() - 8));
+        if (fl <= 0 || fn <= 0) return "a piece boundary key has no bloom filter key (not a DocKey): cannot place the filter index entry";
+        key.assign(lk.data(), fl);
+        ShortenUserSeparator(&key, reinterpret_cast<const uint8_t*>(nk.data()), static_cast<size_t>(fn));
+      }
+      w_->AddFilterBlockRaw(piece.meta + m.filter_blocks[f].offset, m.filter_blocks[f].size, key);
+    }
+    for (size_t b = 0; b < m.data_blocks.size(); b++) {
+      const bool last_block = b + 1 == m.data_blocks.size();
+      Handle h = m.data_blocks[b];
+      h.offset += base_;
+      if (last_block && !last_piece) {
+        std::string key = piece.largest;
+        InternalSeparator(&key, reinterpret_cast<const uint8_t*>(next->smallest.data()), next->smallest.size());
+        w_->AddDataBlockRaw(key, true, h);
+      } else {
+        w_->AddDataBlockRaw(m.separators[b], !(last_block && last_piece), h);
+      }
+    }
+    base_ += piece.data_len;
+    mp_->raw_key_size += PropVarint(m, "rocksdb.raw.key.size");
+    mp_->raw_value_size += PropVarint(m, "rocksdb.raw.value.size");
+    mp_->num_entries += PropVarint(m, "rocksdb.num.entries");
+    mp_->num_data_blocks += PropVarint(m, "rocksdb.num.data.blocks");
+    mp_->deleted_keys += PropVarint(m, "rocksdb.deleted.keys");
+    prev_largest_ = piece.largest;
+    n_pieces_++;
+    return std::string();
+  } catch (const std::exception& ex) {
+    return ex.what();
+  }
+}
+
+std::string ConcatBuilder::Finish(std::string* meta_out) {
+  try {
+    if (!n_pieces_) return "no pieces";
+    mp_->data_size = base_;
+    w_->Finish(*mp_);
+    w_->TakeMetaFile(meta_out);
+    return std::string();
+  } catch (const std::exception& ex) {
+    return ex.what();
+  }
+}
+
 std::string ConcatSplitSstMeta(const TableOptions& o, const std::vector<SstPiece>& pieces, std::string* meta_out) {
   try {
     std::vector<SstMeta> metas(pieces.size());
@@ -583,64 +661,14 @@ std::string ConcatSplitSstMeta(const TableOptions& o, const std::vector<SstPiece
         if (!errs[i].empty()) return "piece " + std::to_string(i) + ": " + errs[i];
     }
     uint64_t total_meta = 0;
+    for (size_t i = 0; i < pieces.size(); i++) total_meta += pieces[i].meta_len;
+    ConcatBuilder cb(o);
+    cb.Reserve(total_meta + total_meta / 4 + 65536);
     for (size_t i = 0; i < pieces.size(); i++) {
-      total_meta += pieces[i].meta_len;
-      const SstMeta& m = metas[i];
-      if (m.data_blocks.empty()) return "piece " + std::to_string(i) + " has no data blocks";
-      if (m.key_encoding != o.key_encoding) return "pieces use a different data block key encoding than the output table options";
-      if ((o.filter_policy != 0) != !m.filter_blocks.empty()) return "filter blocks of piece " + std::to_string(i) + " do not match the output table options";
-      if (o.filter_policy && m.filter_policy_name != "DocKeyV3Filter") return "unknown filter policy " + m.filter_policy_name;
-      if (pieces[i].smallest.size() < 8 || pieces[i].largest.size() < 8) return "piece boundary keys are missing";
-      if (i && CompareBytes(pieces[i - 1].largest.substr(0, pieces[i - 1].largest.size() - 8),
-                            pieces[i].smallest.substr(0, pieces[i].smallest.size() - 8)) >= 0)
-        return "pieces are not in ascending, disjoint key order";
-      const Handle& last = m.data_blocks.back();
-      if (last.offset + last.size + kTrailer > pieces[i].data_len) return "piece " + std::to_string(i) + ": data file shorter than its index says";
+      std::string e = cb.AddPiece(pieces[i], i + 1 < pieces.size() ? &pieces[i + 1] : nullptr, &metas[i]);
+      if (!e.empty()) return e;
     }
-    MetaFileWriter w(o);
-    w.Reserve(total_meta + total_meta / 4 + 65536);
-    MetaProps mp;
-    uint64_t base = 0;
-    for (size_t i = 0; i < pieces.size(); i++) {
-      const SstMeta& m = metas[i];
-      const bool last_piece = i + 1 == pieces.size();
-      // filter blocks of this piece first: the order of blocks inside the metadata file is free, the handles
-      // in the filter index are what readers follow
-      for (size_t f = 0; f < m.filter_blocks.size(); f++) {
-        std::string key = m.filter_index_keys[f];
-        if (f + 1 == m.filter_blocks.size() && !last_piece) {
-          const std::string& lk = pieces[i].largest; const std::string& nk = pieces[i + 1].smallest;
-          const int fl = docdb_filter_prefix_len(reinterpret_cast<const uint8_t*>(lk.data()), static_cast<int>(lk.size() - 8));
-          const int fn = docdb_filter_prefix_len(reinterpret_cast<const uint8_t*>(nk.data()), static_cast<int>(nk.size() - 8));
-          if (fl <= 0 || fn <= 0) return "a piece boundary key has no bloom filter key (not a DocKey): cannot place the filter index entry";
-          key.assign(lk.data(), fl);
-          ShortenUserSeparator(&key, reinterpret_cast<const uint8_t*>(nk.data()), static_cast<size_t>(fn));
-        }
-        w.AddFilterBlockRaw(pieces[i].meta + m.filter_blocks[f].offset, m.filter_blocks[f].size, key);
-      }
-      for (size_t b = 0; b < m.data_blocks.size(); b++) {
-        const bool last_block = b + 1 == m.data_blocks.size();
-        Handle h = m.data_blocks[b];
-        h.offset += base;
-        if (last_block && !last_piece) {
-          std::string key = pieces[i].largest;
-          InternalSeparator(&key, reinterpret_cast<const uint8_t*>(pieces[i + 1].smallest.data()), pieces[i + 1].smallest.size());
-          w.AddDataBlockRaw(key, true, h);
-        } else {
-          w.AddDataBlockRaw(m.separators[b], !(last_block && last_piece), h);
-        }
-      }
-      base += pieces[i].data_len;
-      mp.raw_key_size += PropVarint(m, "rocksdb.raw.key.size");
-      mp.raw_value_size += PropVarint(m, "rocksdb.raw.value.size");
-      mp.num_entries += PropVarint(m, "rocksdb.num.entries");
-      mp.num_data_blocks += PropVarint(m, "rocksdb.num.data.blocks");
-      mp.deleted_keys += PropVarint(m, "rocksdb.deleted.keys");
-    }
-    mp.data_size = base;
-    w.Finish(mp);
-    w.TakeMetaFile(meta_out);
-    return std::string();
+    return cb.Finish(meta_out);
   } catch (const std::exception& ex) {
     return ex.what();
   }

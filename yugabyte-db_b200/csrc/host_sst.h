@@ -123,6 +123,28 @@ struct SstPiece {
 // properties. Nothing in the data files is re-encoded. Returns "" or an error message.
 std::string ConcatSplitSstMeta(const TableOptions& o, const std::vector<SstPiece>& pieces, std::string* meta_out);
 
+// The same assembly, piece by piece: a piece can be added as soon as its successor's smallest key is known (the
+// index entry of its last block and the filter index entry of its last filter block are separators against it),
+// so a pipelined compaction (ybgpu_compact_files_one_table) assembles the one table while later key ranges still
+// run. AddPiece / Finish return "" or an error message.
+class ConcatBuilder {
+ public:
+  explicit ConcatBuilder(const TableOptions& o);
+  ~ConcatBuilder();
+  void Reserve(size_t bytes);
+  // next == nullptr: this is the last piece. parsed (optional): the piece's metadata file already parsed.
+  std::string AddPiece(const SstPiece& piece, const SstPiece* next, const SstMeta* parsed = nullptr);
+  std::string Finish(std::string* meta_out);
+  uint64_t data_bytes() const { return base_; }
+ private:
+  TableOptions o_;
+  MetaFileWriter* w_;
+  MetaProps* mp_;
+  uint64_t base_ = 0;
+  size_t n_pieces_ = 0;
+  std::string prev_largest_;
+};
+
 // rocksdb::TableBuilder shape: Add / Finish / NumEntries / TotalFileSize / status.
 class SplitSstWriter {
  public:

@@ -11,6 +11,7 @@
 // Everything here is host orchestration above the C ABI; no compaction logic runs on the CPU.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
@@ -242,16 +243,29 @@ ybgpu_status ybgpu_plan_subcompactions(const ybgpu_input_file* files, uint32_t n
   return YBGPU_OK;
 }
 
-ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_input_file* files, uint32_t num_files,
-                                 uint32_t max_subcompactions, uint32_t max_in_flight,
-                                 uint8_t* data_arena, uint64_t data_arena_cap, uint8_t* meta_arena, uint64_t meta_arena_cap,
-                                 const volatile int32_t* shutting_down, ybgpu_sub_output* outputs, uint32_t* num_outputs,
-                                 ybgpu_job_stats* total, char* err, uint64_t err_cap) {
+}  // extern "C"
+
+namespace {
+
+// ONE output table: the range data files land back to back in the caller's buffer (a range's D2H target is known as
+// soon as every earlier range knows its size) and a ConcatBuilder consumes the ranges in key order as they complete.
+struct OneTable {
+  std::string meta;                     // result: the one metadata file
+  uint64_t data_len = 0;
+  uint32_t pieces = 0;
+  std::string smallest, largest;
+};
+
+ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_input_file* files, uint32_t num_files,
+                              uint32_t max_subcompactions, uint32_t max_in_flight,
+                              uint8_t* data_arena, uint64_t data_arena_cap, uint8_t* meta_arena, uint64_t meta_arena_cap,
+                              const volatile int32_t* shutting_down, ybgpu_sub_output* outputs, uint32_t* num_outputs,
+                              ybgpu_job_stats* total, char* err, uint64_t err_cap, OneTable* one) {
   auto fail = [&](ybgpu_status s, const std::string& msg) {
     if (err && err_cap) snprintf(err, err_cap, "%s", msg.c_str());
     return s;
   };
-  if (!options || !files || !outputs || !num_outputs || !data_arena || !meta_arena) return fail(YBGPU_INVALID_ARGUMENT, "null argument");
+  if (!options || !files || !outputs || !num_outputs || !data_arena || (!meta_arena && !one)) return fail(YBGPU_INVALID_ARGUMENT, "null argument");
   if (options->range_lower_len || options->range_upper_len) return fail(YBGPU_INVALID_ARGUMENT, "range bounds are set by the subcompaction planner");
   if (max_subcompactions == 0) max_subcompactions = 1;
   if (max_in_flight == 0) max_in_flight = 3;
@@ -291,9 +305,59 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
   std::mutex err_mu;
   ybgpu_status first_status = YBGPU_OK;
   std::string first_error;
+  // one-table mode: per-range progress (0 running, 1 output size known, 2 complete) and the assembler
+  std::mutex ot_mu;
+  std::condition_variable ot_cv;
+  std::vector<int> ot_state(one ? n_ranges : 0, 0);
+  std::vector<uint64_t> ot_dlen(one ? n_ranges : 0, 0);
+  std::vector<std::string> ot_meta(one ? n_ranges : 0);
+  uint32_t ot_next = 0;
+  std::unique_ptr<ybgpu::host::ConcatBuilder> ot_builder;
+  std::string ot_error;
   auto record_failure = [&](ybgpu_status s, const std::string& msg) {
-    std::lock_guard<std::mutex> lock(err_mu);
-    if (!failed.exchange(true)) { first_status = s; first_error = msg; }
+    {
+      std::lock_guard<std::mutex> lock(err_mu);
+      if (!failed.exchange(true)) { first_status = s; first_error = msg; }
+    }
+    if (one) { std::lock_guard<std::mutex> lock(ot_mu); ot_cv.notify_all(); }
+  };
+  ybgpu::host::TableOptions ot_topt;
+  if (one) {
+    ot_topt.block_size = options->block_size; ot_topt.block_restart_interval = options->block_restart_interval;
+    ot_topt.block_size_deviation = options->block_size_deviation; ot_topt.index_block_size = options->index_block_size;
+    ot_topt.min_keys_per_index_block = options->min_keys_per_index_block; ot_topt.key_encoding = options->output_key_encoding;
+    ot_topt.filter_policy = options->filter_policy; if (options->filter_block_size) ot_topt.filter_block_size = options->filter_block_size;
+    ot_builder.reset(new ybgpu::host::ConcatBuilder(ot_topt));
+    uint64_t in_meta = 0;
+    for (uint32_t f = 0; f < num_files; f++) in_meta += files[f].meta_file_len;
+    ot_builder->Reserve(in_meta + in_meta / 4 + 65536);
+  }
+  auto ot_piece = [&](uint32_t r) {
+    ybgpu::host::SstPiece p;
+    p.meta = reinterpret_cast<const uint8_t*>(ot_meta[r].data()); p.meta_len = ot_meta[r].size(); p.data_len = ot_dlen[r];
+    p.smallest.assign(reinterpret_cast<const char*>(outputs[r].smallest_key), outputs[r].smallest_key_len);
+    p.largest.assign(reinterpret_cast<const char*>(outputs[r].largest_key), outputs[r].largest_key_len);
+    return p;
+  };
+  // called with ot_mu held: feeds every piece whose successor is known to the builder, in key order
+  auto ot_advance = [&]() {
+    while (ot_error.empty()) {
+      uint32_t a = ot_next;
+      while (a < n_ranges && ot_state[a] == 2 && ot_dlen[a] == 0) a++;
+      if (a >= n_ranges) { ot_next = n_ranges; return; }
+      if (ot_state[a] != 2) return;
+      uint32_t nx = a + 1;
+      while (nx < n_ranges && ot_state[nx] == 2 && ot_dlen[nx] == 0) nx++;
+      if (nx < n_ranges && ot_state[nx] != 2) return;              // the successor's first key is not known yet
+      const ybgpu::host::SstPiece pa = ot_piece(a);
+      if (nx < n_ranges) { const ybgpu::host::SstPiece pn = ot_piece(nx); ot_error = ot_builder->AddPiece(pa, &pn); }
+      else ot_error = ot_builder->AddPiece(pa, nullptr);
+      if (one->pieces == 0) one->smallest = pa.smallest;
+      one->largest = pa.largest;
+      one->pieces++;
+      std::string().swap(ot_meta[a]);                               // the piece's own metadata file is no longer needed
+      ot_next = nx;
+    }
   };
 
   const bool trace = getenv("YBGPU_SUB_TRACE") != nullptr;      // per-range timeline on stderr (ms since the call)
@@ -376,12 +440,33 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
       s = ybgpu_job_output_sizes(job, &dl, &ml);
       if (s != YBGPU_OK) { job_fail(s, "output_sizes"); return; }
       t_sized = ms_now();
+      uint64_t doff = 0, moff = 0;
+      uint8_t* meta_dst = nullptr;
+      if (one) {
+        // this range's bytes follow those of every earlier range: wait until they all know their sizes
+        std::unique_lock<std::mutex> lock(ot_mu);
+        ot_dlen[r] = dl; ot_state[r] = 1;
+        ot_cv.notify_all();
+        ot_cv.wait(lock, [&] {
+          if (failed.load()) return true;
+          for (uint32_t q = 0; q < r; q++) if (ot_state[q] == 0) return false;
+          return true;
+        });
+        if (failed.load()) { lock.unlock(); ybgpu_job_destroy(job); return; }
+        for (uint32_t q = 0; q < r; q++) doff += ot_dlen[q];
+        ot_meta[r].resize(ml);
+        meta_dst = reinterpret_cast<uint8_t*>(&ot_meta[r][0]);
+      }
       if (dl) {
-        // 4 KB aligned slices of the caller's arenas, handed out in completion order
-        const uint64_t doff = data_used.fetch_add((dl + 4095) & ~4095ull);
-        const uint64_t moff = meta_used.fetch_add((ml + 4095) & ~4095ull);
-        if (doff + dl > data_arena_cap || moff + ml > meta_arena_cap) { job_fail(YBGPU_INVALID_ARGUMENT, "output arena too small"); return; }
-        s = ybgpu_job_fetch_output(job, data_arena + doff, dl, meta_arena + moff, ml);
+        if (!one) {
+          // 4 KB aligned slices of the caller's arenas, handed out in completion order
+          doff = data_used.fetch_add((dl + 4095) & ~4095ull);
+          moff = meta_used.fetch_add((ml + 4095) & ~4095ull);
+          if (moff + ml > meta_arena_cap) { job_fail(YBGPU_INVALID_ARGUMENT, "output arena too small"); return; }
+          meta_dst = meta_arena + moff;
+        }
+        if (doff + dl > data_arena_cap) { job_fail(YBGPU_INVALID_ARGUMENT, "output arena too small"); return; }
+        s = ybgpu_job_fetch_output(job, data_arena + doff, dl, meta_dst, ml);
         if (s != YBGPU_OK) { job_fail(s, "fetch_output"); return; }
         out.data_offset = doff; out.data_len = dl; out.meta_offset = moff; out.meta_len = ml;
         uint64_t sl = 0, ll = 0;
@@ -397,6 +482,12 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
       ybgpu_job_get_stats(job, &out.stats);
     }
     ybgpu_job_destroy(job);
+    if (one) {
+      std::lock_guard<std::mutex> lock(ot_mu);
+      ot_state[r] = 2;
+      ot_advance();
+      ot_cv.notify_all();
+    }
     if (trace)
       fprintf(stderr, "[ybgpu sub] range %2u: begin %7.1f  inputs queued %7.1f  run done %7.1f  meta built %7.1f  output fetched %7.1f  destroyed %7.1f  (gpu %.1f ms, %.2f GB in)\n",
               r, t_begin, t_added, t_ran, t_sized, t_fetched, ms_now(), out.stats.gpu_seconds * 1e3, out.stats.h2d_bytes / 1e9);
@@ -422,6 +513,17 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
     for (std::thread& t : pool) t.join();
   }
   if (failed.load()) return fail(first_status, first_error);
+  if (one) {
+    std::lock_guard<std::mutex> lock(ot_mu);
+    ot_advance();
+    if (!ot_error.empty()) return fail(YBGPU_INVALID_ARGUMENT, "one-table assembly: " + ot_error);
+    if (ot_next != n_ranges) return fail(YBGPU_RUNTIME_ERROR, "one-table assembly did not consume every range");
+    for (uint32_t r = 0; r < n_ranges; r++) one->data_len += ot_dlen[r];
+    if (one->pieces) {
+      const std::string e = ot_builder->Finish(&one->meta);
+      if (!e.empty()) return fail(YBGPU_INVALID_ARGUMENT, "one-table assembly: " + e);
+    }
+  }
   if (total) {
     memset(total, 0, sizeof(*total));
     bool first_output = true;
@@ -430,6 +532,47 @@ ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_i
       if (outputs[r].stats.num_output_records) first_output = false;
     }
   }
+  return YBGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+ybgpu_status ybgpu_compact_files(const ybgpu_job_options* options, const ybgpu_input_file* files, uint32_t num_files,
+                                 uint32_t max_subcompactions, uint32_t max_in_flight,
+                                 uint8_t* data_arena, uint64_t data_arena_cap, uint8_t* meta_arena, uint64_t meta_arena_cap,
+                                 const volatile int32_t* shutting_down, ybgpu_sub_output* outputs, uint32_t* num_outputs,
+                                 ybgpu_job_stats* total, char* err, uint64_t err_cap) {
+  return CompactFilesCore(options, files, num_files, max_subcompactions, max_in_flight, data_arena, data_arena_cap, meta_arena,
+                          meta_arena_cap, shutting_down, outputs, num_outputs, total, err, err_cap, nullptr);
+}
+
+ybgpu_status ybgpu_compact_files_one_table(const ybgpu_job_options* options, const ybgpu_input_file* files, uint32_t num_files,
+                                           uint32_t max_subcompactions, uint32_t max_in_flight,
+                                           uint8_t* data_out, uint64_t data_cap, uint8_t* meta_out, uint64_t meta_cap,
+                                           const volatile int32_t* shutting_down, ybgpu_one_table_result* result,
+                                           ybgpu_job_stats* total, char* err, uint64_t err_cap) {
+  if (!result || !data_out || !meta_out) { if (err && err_cap) snprintf(err, err_cap, "null argument"); return YBGPU_INVALID_ARGUMENT; }
+  memset(result, 0, sizeof(*result));
+  if (max_subcompactions == 0) max_subcompactions = 1;
+  std::vector<ybgpu_sub_output> outs(max_subcompactions);
+  uint32_t n = 0;
+  OneTable one;
+  ybgpu_job_stats tot;
+  ybgpu_status s = CompactFilesCore(options, files, num_files, max_subcompactions, max_in_flight, data_out, data_cap, nullptr, 0,
+                                    shutting_down, outs.data(), &n, &tot, err, err_cap, &one);
+  if (s != YBGPU_OK) return s;
+  if (one.meta.size() > meta_cap) { if (err && err_cap) snprintf(err, err_cap, "metadata buffer too small"); return YBGPU_INVALID_ARGUMENT; }
+  memcpy(meta_out, one.meta.data(), one.meta.size());
+  result->data_len = one.data_len; result->meta_len = one.meta.size();
+  result->num_ranges = n; result->num_pieces = one.pieces;
+  result->smallest_key_len = static_cast<uint32_t>(std::min<size_t>(one.smallest.size(), sizeof(result->smallest_key)));
+  result->largest_key_len = static_cast<uint32_t>(std::min<size_t>(one.largest.size(), sizeof(result->largest_key)));
+  memcpy(result->smallest_key, one.smallest.data(), result->smallest_key_len);
+  memcpy(result->largest_key, one.largest.data(), result->largest_key_len);
+  tot.output_data_file_size = one.data_len; tot.output_meta_file_size = one.meta.size();
+  if (total) *total = tot;
   return YBGPU_OK;
 }
 
