@@ -88,8 +88,20 @@ struct DocDBRetention {
   int64_t table_ttl_ns = YBGPU_TTL_MAX_NS;
   bool retain_delete_markers_in_major_compaction = false;
   uint64_t other_min_ht = YBGPU_HT_MAX;
+  // CompactionHybridTimeConstraints::input_min (docdb_compaction_context.h:178-196). DocDBCompactionFeed replaces the
+  // output's user boundary values only when could_change_key_range_ holds, i.e. when no other data can lie before the
+  // oldest input entry: !CanHaveOtherDataBefore(input_min) (docdb_compaction_context.cc:668,775-777). The default
+  // (unknown) leaves the union of the inputs' values in place.
+  uint64_t input_min_ht = YBGPU_HT_MAX;
   std::string key_bounds_lower, key_bounds_upper;
+  bool CouldChangeKeyRange() const {
+    const uint64_t min_other = retain_delete_markers_in_major_compaction ? YBGPU_HT_MIN : other_min_ht;
+    return enabled && input_min_ht < min_other;
+  }
 };
+
+// rocksdb::UserBoundaryValue (rocksdb/metadata.h): tag + encoded key component.
+struct UserBoundaryValue { uint32_t tag = 0; std::string value; };
 
 // One L0 input file, as VersionSet::MakeInputIterator sees it (db/version_set.cc:3788-3849).
 struct InputFile {
@@ -191,6 +203,7 @@ class GpuCompactionJob {
     o.min_keys_per_index_block = p_.min_keys_per_index_block; o.verify_checksums = p_.verify_checksums;
     o.output_key_encoding = p_.output_key_encoding; o.filter_policy = p_.filter_policy; o.filter_block_size = p_.filter_block_size;
     o.yield_fn = p_.yield_fn; o.yield_ctx = p_.yield_ctx;
+    o.compute_user_boundary_values = p_.retention.CouldChangeKeyRange() && p_.max_subcompactions <= 1;
     options_ = o;
     inputs_ = inputs;
     if (p_.max_subcompactions > 1) return Status::OK();      // every range creates its own job in Run()
@@ -327,7 +340,16 @@ class GpuCompactionJob {
 
   // REQUIRED: mutex held. In the reference this adds the output FileMetaData to a VersionEdit
   // (compaction_job.cc:1098-1141); here it hands the caller what that edit needs.
-  struct OutputMeta { std::string smallest_key, largest_key; uint64_t smallest_seqno = 0, largest_seqno = 0, num_entries = 0; };
+  struct OutputMeta {
+    std::string smallest_key, largest_key; uint64_t smallest_seqno = 0, largest_seqno = 0, num_entries = 0;
+    // DocDBCompactionContext::UpdateMeta (docdb_compaction_context.cc:684-689): when replace_user_values is set the
+    // caller assigns these to FileMetaData::smallest.user_values / largest.user_values; otherwise it keeps the union
+    // of the inputs' values it seeded the output with (compaction_job.cc:1188-1195). The user FRONTIERS are not
+    // derived from the KV stream at all: the caller keeps calling its DocDBCompactionContext::GetLargestUserFrontier
+    // (history cutoff, :1387-1391) and the inputs' frontier union exactly as before.
+    bool replace_user_values = false;
+    std::vector<UserBoundaryValue> smallest_user_values, largest_user_values;
+  };
   // Output seqno bounds the way the reference computes them: the union of the inputs' FileMetaData bounds
   // (UpdateBoundariesExceptKey, compaction_job.cc:1188-1195; db/version_edit.cc:133-152) extended by every
   // surviving entry's (possibly zeroed) sequence number (SubcompactionState::Feed, :156-169) — which is what the
@@ -355,6 +377,21 @@ class GpuCompactionJob {
     meta->largest_key.assign(reinterpret_cast<char*>(b), bl);
     SeqnoBounds(inputs_, stats_.smallest_seqno, stats_.largest_seqno, stats_.num_output_records, &meta->smallest_seqno, &meta->largest_seqno);
     meta->num_entries = stats_.num_output_records;
+    meta->replace_user_values = false;
+    if (options_.compute_user_boundary_values) {
+      std::vector<ybgpu_user_value> lo(32), hi(32);
+      uint32_t n = 0;
+      s = ybgpu_job_output_user_values(job_, lo.data(), hi.data(), 32, &n);
+      if (s == YBGPU_OK) {
+        meta->replace_user_values = true;
+        for (uint32_t i = 0; i < n; i++) {
+          meta->smallest_user_values.push_back({lo[i].tag, std::string(reinterpret_cast<const char*>(lo[i].value), lo[i].len)});
+          meta->largest_user_values.push_back({hi[i].tag, std::string(reinterpret_cast<const char*>(hi[i].value), hi[i].len)});
+        }
+      } else if (s != YBGPU_NOT_SUPPORTED) {
+        return ToStatus(s, ybgpu_job_error(job_));
+      }                                        // NotSupported: the inputs' union stays (a superset range, still correct)
+    }
     return Status::OK();
   }
 
