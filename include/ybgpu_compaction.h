@@ -309,6 +309,37 @@ ybgpu_status ybgpu_compact_files_one_table(const ybgpu_job_options* options, con
                                            const volatile int32_t* shutting_down, ybgpu_one_table_result* result,
                                            ybgpu_job_stats* total, char* err, uint64_t err_cap);
 
+/* --- one oversized compaction, key-range sharded across the GPUs of a box (BASELINE config 5) ----------
+ * Replaces, across devices, what CompactionJob::GenSubcompactionBoundaries + the subcompaction threads do inside one
+ * process (rocksdb/db/compaction_job.cc:409-519,532-552). One process per GPU; every rank holds some of the tablet's
+ * input files in host memory (any distribution). The ranks agree on world * rounds - 1 row-aligned splitter keys
+ * (sampled index separators, all-gathered), rank d owns the `rounds` consecutive key ranges starting at d * rounds, and
+ * per round every (file, destination) block slice travels once: host -> device staging in chunks of `chunk_bytes` ->
+ * grouped ncclSend / ncclRecv over NVLink -> the destination's HBM ("one NCCL all-to-all", counts first). Each rank
+ * then compacts its range on its GPU and returns ONE table (its rounds' outputs concatenated); the ranks' tables are
+ * key-disjoint and ascending by rank — the order the reference installs sub-outputs in (compaction_job.cc:1128-1131).
+ * rounds > 1 bounds HBM use to 1 / (world * rounds) of the compaction per GPU (inputs larger than the GPUs' memory).
+ * The communicator is created from an ncclUniqueId the caller distributes (ybgpu_range_comm_unique_id on one rank). */
+typedef struct ybgpu_range_comm ybgpu_range_comm;
+ybgpu_status ybgpu_range_comm_unique_id(uint8_t id[128]);
+ybgpu_status ybgpu_range_comm_create(const uint8_t id[128], int32_t rank, int32_t world, int32_t device, ybgpu_range_comm** comm);
+void ybgpu_range_comm_destroy(ybgpu_range_comm* comm);
+typedef struct ybgpu_range_shard_result {
+  uint64_t data_len, meta_len;                          /* this rank's table */
+  uint32_t num_ranges, num_pieces;                      /* key ranges of the whole compaction / outputs of this rank */
+  uint64_t sent_bytes, received_bytes;                  /* through the exchange, this rank (incl. its own slices) */
+  uint64_t sent_to_peers_bytes;                         /* the part that crossed NVLink */
+  double plan_seconds, exchange_seconds, total_seconds; /* exchange: CUDA events around the grouped send / recv rounds */
+  uint32_t range_lower_len, range_upper_len;            /* [lower, upper) user keys owned by this rank; len 0 = unbounded */
+  uint8_t range_lower[256], range_upper[256];
+  uint32_t smallest_key_len, largest_key_len;           /* FileMetaData::smallest / largest of this rank's table */
+  uint8_t smallest_key[1032], largest_key[1032];
+} ybgpu_range_shard_result;
+ybgpu_status ybgpu_compact_range_sharded(ybgpu_range_comm* comm, const ybgpu_job_options* options, const ybgpu_input_file* local_files,
+                                         uint32_t num_local_files, uint32_t rounds, uint64_t chunk_bytes,
+                                         uint8_t* data_out, uint64_t data_cap, uint8_t* meta_out, uint64_t meta_cap,
+                                         ybgpu_range_shard_result* result, ybgpu_job_stats* total, char* err, uint64_t err_cap);
+
 /* One table out of the range outputs. For layouts where a compaction must produce a single sorted run
  * (DocDB's single-level universal compaction, db/compaction.cc:593-604), the per-range SSTs of
  * ybgpu_compact_files — ascending, key-disjoint — concatenate into one split SST without re-encoding

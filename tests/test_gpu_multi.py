@@ -1,5 +1,5 @@
 """Multi-GPU paths on real GPUs (skipped on a 1-GPU box): key-range sharded compaction of one tablet
-with one NCCL all_to_all (BASELINE config 5, scaled), and the key-range filter on a single GPU."""
+through ybgpu_compact_range_sharded (BASELINE config 5, scaled), and the key-range filter on a single GPU."""
 import importlib
 import os
 import socket
@@ -11,54 +11,77 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _ranges_worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+def _ranges_worker(rank, world, uid, q, rounds, colocated):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
-    import numpy as np
-    import torch
-    import torch.distributed as dist
     import oracle_py as o
     pkg = importlib.import_module("yugabyte-db_b200")
-    rs = importlib.import_module("yugabyte-db_b200.range_sharded")
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    cfg = o.GenConfig(seed=31, num_rows=60000, cols=2, versions=3, num_files=8, value_len=120, tombstone_per_1024=40)
-    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=8192))
-    cutoff = o.ht_from_micros(cfg.base_micros + 1500)
-    all_last = max(s.read_all()[-1][0][:-8] for s in ssts)
+    comm = pkg.RangeComm(uid, rank, world, rank)
+    if colocated:
+        import workloads as w
+        runs = w.random_cotable_runs(77, n_runs=6, n_tables=3, rows_per_table=400, colocated=True)
+        ssts = [o.Sst.build(r, o.TableOptions(block_size=1024)) for r in runs if r]
+        kw = dict(bottommost=True, cutoff_ht=o.ht_from_micros(w.BASE_US + 75, 1), other_min_ht=o.HT_MAX)
+        bs = 1024
+    else:
+        cfg = o.GenConfig(seed=31, num_rows=60000, cols=2, versions=3, num_files=8, value_len=120, tombstone_per_1024=40)
+        ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=8192))
+        kw = dict(cutoff_ht=o.ht_from_micros(cfg.base_micros + 1500))
+        bs = 8192
     mine = [(s.meta_view().copy(), s.data_view().copy()) for f, s in enumerate(ssts) if f % world == rank]
-    job, my_range, info = rs.compact(mine, rank, world, rank, all_last, cutoff_ht=cutoff, block_size=8192)
-    piece = job.kv_list() if job is not None else []
-    pieces = [None] * world
-    dist.all_gather_object(pieces, piece)
-    stats = [None] * world
-    dist.all_gather_object(stats, (job.stats().num_input_records if job else 0, info["sent_bytes"], info["recv_bytes"]))
-    if rank == 0:
-        exp = o.compact(ssts, o.CompactionParams(cutoff_ht=cutoff), o.TableOptions(block_size=8192))
-        ok = [kv for p in pieces for kv in p] == exp.kv_list()
-        ok = ok and sum(s[0] for s in stats) == exp.stats.num_input_records
-        ok = ok and all(len(p) > 0 for p in pieces)
-        q.put((ok, [len(p) for p in pieces], stats))
-    dist.barrier()
-    dist.destroy_process_group()
+    data, meta, res, total = comm.compact(mine, rounds=rounds, chunk_bytes=1 << 20, block_size=bs, filter_policy=1, filter_block_size=4096,
+                                          out_bytes_hint=sum(len(s.data) for s in ssts) + (1 << 20), **kw)
+    piece = o.Sst.from_bytes(meta.tobytes(), data.tobytes()).read_all() if res.data_len else []
+    q.put((rank, piece, int(total.num_input_records), int(res.sent_to_peers_bytes), int(res.received_bytes), res.lower, res.upper,
+           res.smallest, res.largest, int(res.num_ranges)))
+    comm.close()
 
 
-def test_key_range_sharded_compaction_two_gpus():
+@pytest.mark.parametrize("rounds,colocated", [(1, False), (3, False), (2, True)])
+def test_key_range_sharded_compaction_two_gpus(rounds, colocated):
+    """BASELINE config 5 (scaled) through the PRODUCT path: ybgpu_compact_range_sharded — C++ over NCCL behind the C ABI,
+    splitters agreed through the communicator, block slices exchanged with chunked grouped ncclSend / ncclRecv, every
+    rank compacting its key range(s). The ranks' tables, in rank order, hold exactly the single-job KV stream; with
+    rounds > 1 a rank's table is assembled from several sequential sub-range jobs; ranges that start inside a
+    colocated table receive that table's tombstones."""
     pkg = importlib.import_module("yugabyte-db_b200")
     if pkg.device_count() < 2:                     # checked without importing torch (cold import is slow)
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    import torch.multiprocessing as mp
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import multiprocessing as mp
+    import oracle_py as o
+    world = 2
+    uid = pkg.range_comm_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    mp.spawn(_ranges_worker, args=(2, port, q), nprocs=2, join=True)
-    ok, lens, stats = q.get(timeout=10)
-    assert ok, (lens, stats)
+    procs = [ctx.Process(target=_ranges_worker, args=(r, world, uid, q, rounds, colocated)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    got = sorted(q.get(timeout=300) for _ in range(world))
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    if colocated:
+        import workloads as w
+        runs = w.random_cotable_runs(77, n_runs=6, n_tables=3, rows_per_table=400, colocated=True)
+        ssts = [o.Sst.build(r, o.TableOptions(block_size=1024)) for r in runs if r]
+        exp = o.compact(ssts, o.CompactionParams(bottommost=True, cutoff_ht=o.ht_from_micros(w.BASE_US + 75, 1), other_min_ht=o.HT_MAX),
+                        o.TableOptions(block_size=1024, filter_policy=1, filter_block_size=4096))
+    else:
+        cfg = o.GenConfig(seed=31, num_rows=60000, cols=2, versions=3, num_files=8, value_len=120, tombstone_per_1024=40)
+        ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=8192))
+        exp = o.compact(ssts, o.CompactionParams(cutoff_ht=o.ht_from_micros(cfg.base_micros + 1500)),
+                        o.TableOptions(block_size=8192, filter_policy=1, filter_block_size=4096))
+    ekv = exp.kv_list()
+    assert [kv for g in got for kv in g[1]] == ekv
+    assert sum(g[2] for g in got) == exp.stats.num_input_records
+    assert all(len(g[1]) > 0 for g in got) and all(g[3] > 0 for g in got)          # both ranks work, bytes crossed NVLink
+    assert got[0][5] == b"" and got[0][6] == got[1][5] and got[1][6] == b""           # [lower, upper) tile the key space
+    assert got[0][7] == ekv[0][0] and got[1][8] == ekv[-1][0]
+    assert got[0][9] == world * rounds
 
 
 def test_key_range_filter_single_gpu():

@@ -593,6 +593,83 @@ def compact_files_one_table(ssts, max_subcompactions=8, max_in_flight=3, data_ou
     return data_out[:res.data_len], meta_out[:res.meta_len], res, total
 
 
+class RangeShardResult(C.Structure):
+    _fields_ = [("data_len", C.c_uint64), ("meta_len", C.c_uint64), ("num_ranges", C.c_uint32), ("num_pieces", C.c_uint32),
+                ("sent_bytes", C.c_uint64), ("received_bytes", C.c_uint64), ("sent_to_peers_bytes", C.c_uint64),
+                ("plan_seconds", C.c_double), ("exchange_seconds", C.c_double), ("total_seconds", C.c_double),
+                ("range_lower_len", C.c_uint32), ("range_upper_len", C.c_uint32),
+                ("range_lower", C.c_uint8 * 256), ("range_upper", C.c_uint8 * 256),
+                ("smallest_key_len", C.c_uint32), ("largest_key_len", C.c_uint32),
+                ("smallest_key", C.c_uint8 * 1032), ("largest_key", C.c_uint8 * 1032)]
+
+    @property
+    def lower(self):
+        return bytes(self.range_lower[:self.range_lower_len])
+
+    @property
+    def upper(self):
+        return bytes(self.range_upper[:self.range_upper_len])
+
+    @property
+    def smallest(self):
+        return bytes(self.smallest_key[:self.smallest_key_len])
+
+    @property
+    def largest(self):
+        return bytes(self.largest_key[:self.largest_key_len])
+
+
+def range_comm_unique_id():
+    """ybgpu_range_comm_unique_id: 128 bytes to hand to every rank (one rank creates it)."""
+    buf = (C.c_uint8 * 128)()
+    st = lib().ybgpu_range_comm_unique_id(buf)
+    if st != 0:
+        raise YbGpuError(st, "range_comm_unique_id (is libnccl available?)")
+    return bytes(buf)
+
+
+class RangeComm:
+    """ybgpu_range_comm: the communicator of a key-range sharded compaction (one process per GPU)."""
+
+    def __init__(self, unique_id, rank, world, device):
+        L = lib()
+        L.ybgpu_range_comm_create.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.ybgpu_range_comm_destroy.argtypes = [C.c_void_p]
+        h = C.c_void_p()
+        st = L.ybgpu_range_comm_create(unique_id, rank, world, device, C.byref(h))
+        if st != 0:
+            raise YbGpuError(st, "range_comm_create")
+        self.h, self.rank, self.world, self.device = h, rank, world, device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ybgpu_range_comm_destroy(self.h)
+            self.h = None
+
+    def compact(self, ssts, rounds=1, chunk_bytes=64 << 20, data_out=None, meta_out=None, ht_filters=None, out_bytes_hint=None, **job_kwargs):
+        """ybgpu_compact_range_sharded over this rank's local files [(meta ndarray, data ndarray)]. Returns
+        (data view, meta view, RangeShardResult, JobStats) — this rank's table of the sharded compaction."""
+        L = lib()
+        L.ybgpu_compact_range_sharded.argtypes = [C.c_void_p, C.POINTER(JobOptions), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
+                                                  C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(RangeShardResult),
+                                                  C.POINTER(JobStats), C.c_char_p, C.c_uint64]
+        job_kwargs.setdefault("device", self.device)
+        o, keep_o = make_options(**job_kwargs)
+        arr, keep = _input_files(ssts, ht_filters) if ssts else (None, None)
+        if data_out is None:
+            n = out_bytes_hint if out_bytes_hint is not None else 2 * sum(int(d.size) for _, d in ssts) * self.world + (8 << 20)
+            data_out = np.empty(n, np.uint8)
+        if meta_out is None:
+            meta_out = np.empty((data_out.size >> 4) + (4 << 20), np.uint8)
+        res, total = RangeShardResult(), JobStats()
+        err = C.create_string_buffer(512)
+        st = L.ybgpu_compact_range_sharded(self.h, C.byref(o), arr, len(ssts), rounds, chunk_bytes, data_out.ctypes.data, data_out.size,
+                                           meta_out.ctypes.data, meta_out.size, C.byref(res), C.byref(total), err, 512)
+        if st != 0:
+            raise YbGpuError(st, err.value.decode(errors="replace"))
+        return data_out[:res.data_len], meta_out[:res.meta_len], res, total
+
+
 class SstPiece(C.Structure):
     _fields_ = [("meta_file", C.c_void_p), ("meta_file_len", C.c_uint64), ("data_file_len", C.c_uint64),
                 ("smallest_key", C.c_char_p), ("smallest_key_len", C.c_uint32),

@@ -6,9 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libybgpu.so")
-SOURCES = ["engine.cu", "abi.cc", "host_sst.cc", "host_gen.cc", "subcompaction.cc", "numa.cc"]
+SOURCES = ["engine.cu", "abi.cc", "host_sst.cc", "host_gen.cc", "subcompaction.cc", "numa.cc", "range_exchange.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-msse4.2,-Wall", "--shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC,-msse4.2,-Wall", "--shared", "-cudart", "shared", "-ldl"]
 
 
 def needs_build():

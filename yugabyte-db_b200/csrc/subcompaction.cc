@@ -24,15 +24,12 @@
 #include "../../include/ybgpu_compaction.h"
 #include "dev_logic.cuh"
 #include "host_sst.h"
+#include "range_plan.h"
 
-namespace {
+namespace ybgpu {
+namespace plan {
 
 using ybgpu::host::SstMeta;
-
-struct ParsedInput {
-  SstMeta meta;
-  std::vector<std::string> useps;      // user-key part of every block's index separator
-};
 
 std::string UserPart(const std::string& ikey) { return ikey.size() >= 8 ? ikey.substr(0, ikey.size() - 8) : ikey; }
 
@@ -73,32 +70,33 @@ bool ParseInputs(const ybgpu_input_file* files, uint32_t n, std::vector<ParsedIn
 //   * if it fails with a malformed key (FindShortestSeparator cut the separator inside a
 //     component), the separator does not start with any complete DocKey and is used whole;
 //   * if it stops at a key the engine does not take (vector-index metadata), the separator is skipped.
-std::vector<std::string> PlanSplitters(const std::vector<ParsedInput>& in, uint32_t n_ranges, bool docdb_keys) {
-  std::vector<std::string> out;
-  if (n_ranges <= 1) return out;
-  struct Sample { const std::string* key; uint64_t w; };
-  std::vector<Sample> samples;
-  uint64_t total = 0;
+void CollectSamples(const std::vector<ParsedInput>& in, uint32_t n_ranges, std::vector<Sample>* samples) {
   // every stride-th separator of a file stands for the bytes of the blocks since the previous sample
   // (about 2^11 samples per range are plenty; a 30 GB compaction has ~10^6 index entries)
   size_t n_blocks = 0;
   for (const ParsedInput& p : in) n_blocks += p.useps.size();
-  const size_t stride = std::max<size_t>(1, n_blocks / (static_cast<size_t>(n_ranges) << 11));
+  const size_t stride = std::max<size_t>(1, n_blocks / (static_cast<size_t>(std::max(1u, n_ranges)) << 11));
   for (const ParsedInput& p : in) {
     uint64_t w = 0;
     for (size_t i = 0; i < p.useps.size(); i++) {
       w += p.meta.data_blocks[i].size + 5;
-      if ((i + 1) % stride == 0 || i + 1 == p.useps.size()) { samples.push_back({&p.useps[i], w}); total += w; w = 0; }
+      if ((i + 1) % stride == 0 || i + 1 == p.useps.size()) { samples->push_back({p.useps[i], w}); w = 0; }
     }
   }
-  if (samples.empty()) return out;
-  std::sort(samples.begin(), samples.end(), [](const Sample& a, const Sample& b) { return *a.key < *b.key; });
+}
+
+std::vector<std::string> SplittersFromSamples(std::vector<Sample> samples, uint32_t n_ranges, bool docdb_keys) {
+  std::vector<std::string> out;
+  if (n_ranges <= 1 || samples.empty()) return out;
+  uint64_t total = 0;
+  for (const Sample& s : samples) total += s.w;
+  std::sort(samples.begin(), samples.end(), [](const Sample& a, const Sample& b) { return a.key < b.key; });
   const double target = static_cast<double>(total) / n_ranges;
   double acc = 0, next = target;
   for (const Sample& s : samples) {
     acc += static_cast<double>(s.w);
     if (acc < next || out.size() + 1 >= n_ranges) continue;
-    const std::string& k = *s.key;
+    const std::string& k = s.key;
     int plen = static_cast<int>(k.size());
     if (docdb_keys) {
       // group_prefix_len scans with aligned 8-byte loads: give it an aligned, padded copy
@@ -119,6 +117,13 @@ std::vector<std::string> PlanSplitters(const std::vector<ParsedInput>& in, uint3
   return out;
 }
 
+std::vector<std::string> PlanSplitters(const std::vector<ParsedInput>& in, uint32_t n_ranges, bool docdb_keys) {
+  if (n_ranges <= 1) return {};
+  std::vector<Sample> samples;
+  CollectSamples(in, n_ranges, &samples);
+  return SplittersFromSamples(std::move(samples), n_ranges, docdb_keys);
+}
+
 // Blocks [a, b) of one input that can hold user keys in [lo, hi): block i holds keys in
 // (sep[i-1], sep[i]] (the separator is >= the block's last key and < the next block's first key).
 void BlocksForRange(const std::vector<std::string>& useps, const std::string& lo, const std::string& hi, size_t* a, size_t* b) {
@@ -127,6 +132,33 @@ void BlocksForRange(const std::vector<std::string>& useps, const std::string& lo
   if (hi.empty()) { *b = nb; return; }
   const size_t c = static_cast<size_t>(std::lower_bound(useps.begin(), useps.end(), hi) - useps.begin());
   *b = std::max(*a, std::min(nb, c + 1));
+}
+
+void SpansForRange(const ParsedInput& in, const std::string& lo, const std::string& hi, bool retention_enabled, std::vector<Span>* out) {
+  out->clear();
+  size_t a, b;
+  BlocksForRange(in.useps, lo, hi, &a, &b);
+  // A range that starts inside a cotable / colocated table ('y' + uuid or '0' + colocation id): the table's
+  // tombstone entries `id ! # HT` sort before every row of the table, i.e. before this range, yet their
+  // overwrite time (slot 0 of DocDBCompactionFeed's overwrite stack, docdb_compaction_context.cc:999-1024)
+  // shadows the rows in it.
+  if (retention_enabled && !lo.empty() && (lo[0] == 'y' || lo[0] == '0')) {
+    const int id = ybgpu::dockey_id_size(reinterpret_cast<const uint8_t*>(lo.data()), static_cast<int>(lo.size()));
+    if (id > 0 && static_cast<size_t>(id) <= lo.size()) {
+      const std::string tomb_lo = lo.substr(0, id) + '!', tomb_hi = lo.substr(0, id) + '"';     // '!' + 1
+      if (tomb_lo < lo) {                              // else the range starts at the tombstones themselves
+        size_t ta, tb;
+        BlocksForRange(in.useps, tomb_lo, tomb_hi, &ta, &tb);
+        if (b <= a) { a = b = tb; }                    // no block of this file holds range keys
+        tb = std::min(tb, a);
+        if (tb > ta) {
+          if (tb == a && b > a) a = ta;                // contiguous with the range's blocks: one span
+          else out->push_back({ta, tb});
+        }
+      }
+    }
+  }
+  if (b > a) out->push_back({a, b});
 }
 
 // Last internal key of one data block (BlockIter::SeekToLast: from the last restart point forward;
@@ -192,6 +224,14 @@ bool LastKeyOfFile(const ybgpu_input_file& f, const SstMeta& m, std::string* key
   if (f.data_file[h.offset + h.size] != 0) return false;            // compressed block: not supported
   return LastKeyOfBlock(f.data_file + h.offset, h.size, m.key_encoding, key);
 }
+
+}  // namespace plan
+}  // namespace ybgpu
+
+namespace {
+
+using namespace ybgpu::plan;
+using ybgpu::host::SstMeta;
 
 void AddStats(ybgpu_job_stats* t, const ybgpu_job_stats& s, bool first_output) {
   t->num_input_records += s.num_input_records; t->num_output_records += s.num_output_records;
@@ -386,50 +426,21 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
     };
     uint32_t added = 0;
     std::vector<ybgpu_block_handle> h;
-    // A range that starts inside a cotable / colocated table ('y' + uuid or '0' + colocation id): the table's
-    // tombstone entries `id ! # HT` sort before every row of the table, i.e. before this range, yet their
-    // overwrite time (slot 0 of DocDBCompactionFeed's overwrite stack, docdb_compaction_context.cc:999-1024)
-    // shadows the rows in it. The blocks that hold them are loaded too; the engine keeps such out-of-range
-    // entries invisible (REC_F_OUT_OF_RANGE) except for seeding the table state.
-    std::string tomb_lo, tomb_hi;
-    if (options->retention_enabled && !lo.empty() && (lo[0] == 'y' || lo[0] == '0')) {
-      const int id = ybgpu::dockey_id_size(reinterpret_cast<const uint8_t*>(lo.data()), static_cast<int>(lo.size()));
-      if (id > 0 && static_cast<size_t>(id) <= lo.size()) {
-        tomb_lo = lo.substr(0, id) + '!';
-        tomb_hi = lo.substr(0, id) + '"';              // '!' + 1
-        if (!(tomb_lo < lo)) tomb_lo.clear();           // the range starts at the tombstones themselves
-      }
-    }
+    // the blocks of every input that can hold keys of the range, plus — for a range that starts inside a cotable —
+    // the blocks with that table's tombstones (SpansForRange); the last span of an input is its range span
+    std::vector<Span> spans;
     for (uint32_t f = 0; f < num_files; f++) {
-      size_t a, b;
-      BlocksForRange(in[f].useps, lo, hi, &a, &b);
+      SpansForRange(in[f], lo, hi, options->retention_enabled != 0, &spans);
       const auto& blocks = in[f].meta.data_blocks;
-      if (!tomb_lo.empty()) {
-        size_t ta, tb;
-        BlocksForRange(in[f].useps, tomb_lo, tomb_hi, &ta, &tb);
-        if (b <= a) { a = b = tb; }                     // no block of this file holds range keys
-        tb = std::min(tb, a);
-        if (tb > ta) {
-          if (tb == a && b > a) {
-            a = ta;                                     // contiguous with the range's blocks: one span
-          } else {
-            const uint64_t start = blocks[ta].offset;
-            const uint64_t end = blocks[tb - 1].offset + blocks[tb - 1].size + 5;
-            h.resize(tb - ta);
-            for (size_t i = ta; i < tb; i++) { h[i - ta].offset = blocks[i].offset - start; h[i - ta].size = blocks[i].size; }
-            s = ybgpu_job_add_input(job, files[f].data_file + start, end - start, h.data(), h.size(), in[f].meta.key_encoding, files[f].hybrid_time_filter);
-            if (s != YBGPU_OK) { job_fail(s, "add_input (table tombstones)"); return; }
-          }
-        }
+      for (const Span& sp : spans) {
+        const uint64_t start = blocks[sp.a].offset;
+        const uint64_t end = blocks[sp.b - 1].offset + blocks[sp.b - 1].size + 5;
+        h.resize(sp.b - sp.a);
+        for (size_t i = sp.a; i < sp.b; i++) { h[i - sp.a].offset = blocks[i].offset - start; h[i - sp.a].size = blocks[i].size; }
+        s = ybgpu_job_add_input(job, files[f].data_file + start, end - start, h.data(), h.size(), in[f].meta.key_encoding, files[f].hybrid_time_filter);
+        if (s != YBGPU_OK) { job_fail(s, "add_input"); return; }
+        added++;
       }
-      if (b <= a) continue;
-      const uint64_t start = blocks[a].offset;
-      const uint64_t end = blocks[b - 1].offset + blocks[b - 1].size + 5;
-      h.resize(b - a);
-      for (size_t i = a; i < b; i++) { h[i - a].offset = blocks[i].offset - start; h[i - a].size = blocks[i].size; }
-      s = ybgpu_job_add_input(job, files[f].data_file + start, end - start, h.data(), h.size(), in[f].meta.key_encoding, files[f].hybrid_time_filter);
-      if (s != YBGPU_OK) { job_fail(s, "add_input"); return; }
-      added++;
     }
     t_added = ms_now();
     if (added) {
