@@ -17,6 +17,7 @@ struct orc_table_options {
   uint32_t block_size; int32_t block_restart_interval; int32_t key_encoding; int32_t block_size_deviation;
   uint32_t index_block_size; uint32_t min_keys_per_index_block;
   int32_t filter_policy; uint32_t filter_block_size;
+  int32_t compression;
 };
 
 struct orc_compaction_params {
@@ -59,6 +60,7 @@ static TableOptions ToOpts(const orc_table_options* o) {
     if (o->key_encoding) t.key_encoding = o->key_encoding;
     if (o->block_size_deviation >= 0) t.block_size_deviation = o->block_size_deviation;
     if (o->index_block_size) t.index_block_size = o->index_block_size;
+    t.compression = o->compression;
     if (o->min_keys_per_index_block) t.min_keys_per_index_block = o->min_keys_per_index_block;
     t.filter_policy = o->filter_policy;
     if (o->filter_block_size) t.filter_block_size = o->filter_block_size;
@@ -159,7 +161,8 @@ orc_result* orc_sst_read_all(const orc_sst* s, int verify) {
     TableReader r; r.Open(Slice(s->meta), Slice(s->data), verify != 0);
     res->koff.push_back(0); res->voff.push_back(0);
     for (auto& h : r.data_blocks) {
-      BlockIter it(TableReader::ReadBlock(r.data, h, verify != 0), r.key_encoding);
+      std::string scratch;
+      BlockIter it(TableReader::ReadBlock(r.data, h, verify != 0, &scratch), r.key_encoding);
       for (it.SeekToFirst(); it.Valid(); it.Next()) {
         res->keys.append(reinterpret_cast<const char*>(it.key().p), it.key().n);
         res->vals.append(reinterpret_cast<const char*>(it.value().p), it.value().n);

@@ -17,6 +17,7 @@ struct SstIter : InputIter {
   TableReader r;
   size_t blk = 0;
   std::unique_ptr<BlockIter> it;
+  std::string scratch;                 // contents of the current block when it is stored compressed
   bool verify;
   uint64_t ht_filter;
   SstIter(const SstInput& in, bool verify_) : verify(verify_), ht_filter(in.hybrid_time_filter) {
@@ -28,7 +29,7 @@ struct SstIter : InputIter {
   void Load() {
     it.reset();
     while (blk < r.data_blocks.size()) {
-      it.reset(new BlockIter(TableReader::ReadBlock(r.data, r.data_blocks[blk], verify), r.key_encoding));
+      it.reset(new BlockIter(TableReader::ReadBlock(r.data, r.data_blocks[blk], verify, &scratch), r.key_encoding));
       it->SeekToFirst();
       if (it->Valid()) return;
       blk++;
@@ -441,7 +442,8 @@ void RunCompaction(const std::vector<SstInput>& inputs, const CompactionParams& 
     for (auto& in : inputs) {
       TableReader r; r.Open(in.meta, in.data, false);
       if (r.data_blocks.empty()) continue;
-      BlockIter it(TableReader::ReadBlock(r.data, r.data_blocks.back(), false), r.key_encoding);
+      std::string scratch;
+      BlockIter it(TableReader::ReadBlock(r.data, r.data_blocks.back(), false, &scratch), r.key_encoding);
       std::string last;
       for (it.SeekToFirst(); it.Valid(); it.Next()) last = it.key().str();
       if (last.size() < 8) continue;

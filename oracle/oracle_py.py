@@ -40,12 +40,12 @@ class TableOptions(C.Structure):
     _fields_ = [("block_size", C.c_uint32), ("block_restart_interval", C.c_int32),
                 ("key_encoding", C.c_int32), ("block_size_deviation", C.c_int32),
                 ("index_block_size", C.c_uint32), ("min_keys_per_index_block", C.c_uint32),
-                ("filter_policy", C.c_int32), ("filter_block_size", C.c_uint32)]
+                ("filter_policy", C.c_int32), ("filter_block_size", C.c_uint32), ("compression", C.c_int32)]
 
     def __init__(self, block_size=32768, restart=16, key_encoding=1, deviation=10,
-                 index_block_size=32768, min_keys_per_index_block=100, filter_policy=0, filter_block_size=65536):
+                 index_block_size=32768, min_keys_per_index_block=100, filter_policy=0, filter_block_size=65536, compression=0):
         super().__init__(block_size, restart, key_encoding, deviation, index_block_size,
-                         min_keys_per_index_block, filter_policy, filter_block_size)
+                         min_keys_per_index_block, filter_policy, filter_block_size, compression)
 
 
 class CompactionParams(C.Structure):

@@ -464,9 +464,14 @@ TableBuilder::TableBuilder(const TableOptions& o)
 TableBuilder::~TableBuilder() {}
 
 void TableBuilder::WriteRawBlock(Slice c, std::string* file, BlockHandle* h) {
+  uint8_t type = 0;   // kNoCompression
+  std::string compressed;
+  if (o_.compression == 1 && file == &data_) {          // CompressBlock (block_based_table_builder.cc:115-131) for data blocks
+    SnappyCompress(c, &compressed);
+    if (compressed.size() < c.n - (c.n / 8u)) { c = Slice(compressed); type = 1; }     // GoodCompressionRatio :109-112
+  }
   h->offset = file->size(); h->size = c.n;
   file->append(reinterpret_cast<const char*>(c.p), c.n);
-  uint8_t type = 0;   // kNoCompression
   uint32_t crc = Crc32cExtend(Crc32cValue(c.p, c.n), &type, 1);
   file->push_back(static_cast<char>(type));
   PutFixed32(file, Crc32cMask(crc));
@@ -599,16 +604,99 @@ void TableBuilder::Finish() {
 }
 
 // ---------------------------------------------------------------------------------------------
-Slice TableReader::ReadBlock(Slice file, BlockHandle h, bool verify) {
+Slice TableReader::ReadBlock(Slice file, BlockHandle h, bool verify, std::string* scratch) {
   if (h.offset + h.size + kBlockTrailerSize > file.n) throw Corruption("truncated block read");
   const uint8_t* p = file.p + h.offset;
-  if (p[h.size] != 0) throw NotSupported("compressed block: compression is not restated in the oracle");
-  if (verify) {
+  if (p[h.size] > 1 || (p[h.size] == 1 && !scratch)) throw NotSupported("compressed block: only Snappy data blocks are restated in the oracle");
+  if (verify) {      // the checksum covers the stored (compressed) bytes + the type byte (format.cc:352-395)
     uint32_t stored = Crc32cUnmask(DecodeFixed32(p + h.size + 1));
     uint32_t actual = Crc32cValue(p, h.size + 1);
     if (stored != actual) throw Corruption("block checksum mismatch");
   }
+  if (p[h.size] == 1) { SnappyUncompress(Slice(p, h.size), scratch); return Slice(*scratch); }
   return Slice(p, h.size);
+}
+
+// ---- Snappy raw format ------------------------------------------------------------------------
+void SnappyUncompress(Slice c, std::string* out) {
+  const uint8_t* p = c.p; const uint8_t* e = c.p + c.n;
+  uint32_t ulen = 0;
+  p = GetVarint32Ptr(p, e, &ulen);
+  if (!p) throw Corruption("snappy: bad length preamble");
+  out->clear(); out->reserve(ulen);
+  while (p < e) {
+    const uint8_t tag = *p++;
+    const uint32_t kind = tag & 3;
+    if (kind == 0) {
+      uint32_t len = tag >> 2;
+      if (len >= 60) {
+        const uint32_t nb = len - 59;
+        if (static_cast<size_t>(e - p) < nb) throw Corruption("snappy: truncated literal length");
+        len = 0;
+        for (uint32_t i = 0; i < nb; i++) len |= static_cast<uint32_t>(p[i]) << (8 * i);
+        p += nb;
+      }
+      len += 1;
+      if (static_cast<size_t>(e - p) < len) throw Corruption("snappy: truncated literal");
+      out->append(reinterpret_cast<const char*>(p), len);
+      p += len;
+    } else {
+      uint32_t len, off;
+      if (kind == 1) { if (p >= e) throw Corruption("snappy: truncated copy"); len = 4 + ((tag >> 2) & 7); off = (static_cast<uint32_t>(tag >> 5) << 8) | *p++; }
+      else if (kind == 2) { if (e - p < 2) throw Corruption("snappy: truncated copy"); len = 1 + (tag >> 2); off = p[0] | (p[1] << 8); p += 2; }
+      else { if (e - p < 4) throw Corruption("snappy: truncated copy"); len = 1 + (tag >> 2); off = DecodeFixed32(p); p += 4; }
+      if (off == 0 || off > out->size()) throw Corruption("snappy: copy offset out of range");
+      const size_t start = out->size() - off;
+      for (uint32_t i = 0; i < len; i++) out->push_back((*out)[start + i]);       // may overlap its own output
+    }
+    if (out->size() > ulen) throw Corruption("snappy: output longer than announced");
+  }
+  if (out->size() != ulen) throw Corruption("snappy: output shorter than announced");
+}
+
+void SnappyCompress(Slice raw, std::string* out) {
+  out->clear();
+  PutVarint32(out, static_cast<uint32_t>(raw.n));
+  const uint8_t* b = raw.p; const size_t n = raw.n;
+  auto emit_literal = [&](size_t from, size_t to) {
+    while (from < to) {
+      const size_t len = std::min<size_t>(to - from, 65536);
+      const size_t l1 = len - 1;
+      if (l1 < 60) out->push_back(static_cast<char>(l1 << 2));
+      else if (l1 < 256) { out->push_back(static_cast<char>(60 << 2)); out->push_back(static_cast<char>(l1)); }
+      else { out->push_back(static_cast<char>(61 << 2)); out->push_back(static_cast<char>(l1 & 0xff)); out->push_back(static_cast<char>(l1 >> 8)); }
+      out->append(reinterpret_cast<const char*>(b + from), len);
+      from += len;
+    }
+  };
+  std::vector<int32_t> table(1 << 14, -1);
+  size_t lit = 0, i = 0;
+  while (i + 4 <= n) {
+    uint32_t w; memcpy(&w, b + i, 4);
+    const uint32_t hsh = (w * 0x1e35a7bdu) >> 18;
+    const int32_t cand = table[hsh];
+    table[hsh] = static_cast<int32_t>(i);
+    uint32_t cw = 0;
+    if (cand >= 0) memcpy(&cw, b + cand, 4);
+    if (cand >= 0 && cw == w && i - cand <= 65535) {
+      size_t len = 4;
+      while (i + len < n && b[cand + len] == b[i + len]) len++;
+      emit_literal(lit, i);
+      const uint32_t off = static_cast<uint32_t>(i - cand);
+      size_t left = len;
+      while (left) {
+        size_t l = std::min<size_t>(left, 64);
+        if (left - l > 0 && left - l < 4) l = left - 4;                 // keep every piece >= 4 bytes... copy2 takes 1..64
+        if (l >= 4 && l <= 11 && off < 2048) { out->push_back(static_cast<char>(1 | ((l - 4) << 2) | ((off >> 8) << 5))); out->push_back(static_cast<char>(off & 0xff)); }
+        else { out->push_back(static_cast<char>(2 | ((l - 1) << 2))); out->push_back(static_cast<char>(off & 0xff)); out->push_back(static_cast<char>(off >> 8)); }
+        left -= l;
+      }
+      i += len; lit = i;
+    } else {
+      i++;
+    }
+  }
+  emit_literal(lit, n);
 }
 
 static BlockHandle DecodeHandle(Slice* s) {

@@ -51,7 +51,18 @@ struct TableOptions {
   // (docdb_rocksdb_util.cc:761-763, docdb_filter_policy.cc:103-108).
   int filter_policy = 0;
   uint32_t filter_block_size = 64 * 1024;   // db_filter_block_size_bytes (docdb_rocksdb_util.cc:132)
+  // rocksdb::CompressionType of the DATA blocks: 0 = kNoCompression, 1 = kSnappyCompression (the production default,
+  // docdb_rocksdb_util.cc:184). A block is stored compressed only when that saves at least 12.5 %
+  // (block_based_table_builder.cc:109-131). Test inputs only: the compressed BYTES are this file's own encoder's, not
+  // the snappy library's (parity unpinned for them); what is pinned is the format, i.e. that they decompress back.
+  int compression = 0;
 };
+
+// Snappy raw format (format_description.txt of the snappy library, third_party: yugabyte-db-thirdparty, not vendored):
+// varint32 uncompressed length, then literal / copy elements. Compress emits a valid (greedy, hash-based) encoding;
+// Uncompress accepts any valid stream and throws Corruption otherwise.
+void SnappyCompress(Slice raw, std::string* out);
+void SnappyUncompress(Slice compressed, std::string* out);
 
 // util/hash.cc:32-75 (the LevelDB hash) and util/hash.h:40-42.
 uint32_t LevelDbHash(const uint8_t* data, size_t n, uint32_t seed);
@@ -203,7 +214,9 @@ struct TableReader {
   std::vector<std::pair<std::string, BlockHandle>> filter_blocks;
   void Open(Slice meta_file, Slice data_file, bool verify_checksums = true);
   // Returns block contents (without trailer); verifies CRC if asked.
-  static Slice ReadBlock(Slice file, BlockHandle h, bool verify);
+  // scratch: receives the contents of a compressed block (format.cc:441-500 UncompressBlockContents); without it a
+  // compressed block is an error
+  static Slice ReadBlock(Slice file, BlockHandle h, bool verify, std::string* scratch = nullptr);
 };
 
 }  // namespace orc

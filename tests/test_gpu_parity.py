@@ -576,6 +576,34 @@ def test_user_boundary_values(pkg, seed):
         assert job.user_values() == exp.user_values()
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_snappy_compressed_inputs(pkg, seed):
+    """f2: Snappy-compressed input data blocks (DocDB's production default, docdb_rocksdb_util.cc:184). The stored bytes'
+    checksum is verified, the blocks are uncompressed on the GPU (table/format.cc:441-500) and the compaction proceeds as
+    for raw inputs: output files identical to the oracle's, which reads the same compressed inputs. Files mix compressed
+    and raw blocks (a block is stored compressed only if that saves 12.5 %, block_based_table_builder.cc:109-131)."""
+    if seed < 2:
+        runs = w.random_docdb_runs(600 + seed, n_runs=3, n_rows=150 + 100 * seed)
+        kws = [w.param_grid()[i] for i in (0, 2, 6)]
+    else:
+        cfg = o.GenConfig(seed=60 + seed, num_rows=4000, cols=2, versions=3, num_files=3, value_len=24 if seed == 2 else 200, tombstone_per_1024=50)
+        runs = [s.read_all() for s in o.Sst.generate_all(cfg, o.TableOptions(block_size=4096))]
+        kws = [dict(cutoff_ht=o.ht_from_micros(cfg.base_micros + 1500))]
+    ssts = [o.Sst.build(r, o.TableOptions(block_size=2048 if seed < 2 else 8192, compression=1)) for r in runs if r]
+    raw = sum(sum(len(k) + len(v) for k, v in r) for r in runs)
+    assert sum(len(s.data) for s in ssts) < raw                      # something was compressed
+    for kw in kws:
+        check(pkg, ssts, block_size=4096, filter_policy=1, filter_block_size=4096, **kw)
+    # a flipped bit in a compressed block is a checksum error, not garbage
+    bad = bytearray(ssts[0].data)
+    bad[len(bad) // 2] ^= 0x10
+    job = pkg.GpuCompactionJob(block_size=4096)
+    job.add_input_sst(ssts[0].meta_view(), np.frombuffer(bytes(bad), np.uint8))
+    with pytest.raises(pkg.YbGpuError) as e:
+        job.run()
+    assert e.value.status_name == "Corruption"
+
+
 def test_yield_points(pkg):
     """The scheduler's pause hook (PriorityThreadPoolSuspender::PauseIfNecessary in the reference) is honoured
     between kernel phases of a job and between the ranges of a compaction run as subcompactions."""

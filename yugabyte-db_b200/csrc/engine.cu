@@ -65,6 +65,7 @@ struct JobDev {                 // device-global job state
   uint32_t n_tiles;
   uint32_t max_tile;            // largest tile of the current partition (k_tile_check)
   int ingest_fallback;          // k_ingest met something it does not take: the host runs the general kernels
+  uint32_t n_compressed;        // Snappy-compressed input blocks seen by k_restart_probe
   unsigned long long digest;
 };
 
@@ -1346,6 +1347,7 @@ __global__ void __launch_bounds__(256) k_digest(const uint8_t* keys, const uint6
 }  // namespace ybgpu
 #include "encode_kernels.cuh"
 #include "ingest_kernels.cuh"
+#include "snappy_kernels.cuh"
 namespace ybgpu {
 
 // =============================================================================================
@@ -1355,7 +1357,7 @@ static const char* DevErrorName(int e) {
   switch (e) {
     case DEV_ERR_BAD_BLOCK: return "bad block contents";
     case DEV_ERR_BAD_ENTRY: return "bad entry in block";
-    case DEV_ERR_COMPRESSED: return "compressed block (only kNoCompression inputs are supported)";
+    case DEV_ERR_COMPRESSED: return "compressed block (only kNoCompression and kSnappyCompression inputs are supported)";
     case DEV_ERR_KEY_TOO_LONG: return "key longer than the engine limit";
     case DEV_ERR_IRREGULAR_RESTARTS: return "data block restart intervals are not uniform";
     case DEV_ERR_BAD_KEY: return "cannot decode DocKey/SubDocKey components";
@@ -1717,18 +1719,71 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   bool ingested = false;
   bool try_ingest = blk_base[k] > 0 && getenv("YBGPU_NO_INGEST") == nullptr;
   for (int r = 0; r < k; r++) try_ingest = try_ingest && I.runs[r].key_encoding == 1;
-  if (try_ingest) {
-    unsigned long long* d_rsum = nullptr;
+  // ---- probe: restart counts (entry upper bounds), restart interval, key length sample, compression types
+  unsigned long long* d_rsum = nullptr;
+  std::vector<unsigned long long> rsum(k, 0);
+  bool verify_pending = opt_.verify_checksums != 0;      // false once the stored blocks' checksums have been verified
+  if (blk_base[k] > 0) {
     CUDA_TRY(DevAlloc(&I.allocs, &d_rsum, static_cast<size_t>(k)));
-    CUDA_TRY(cudaMemsetAsync(d_rsum, 0, 8 * static_cast<size_t>(k), I.stream));
-    k_restart_probe<<<GridFor(blk_base[k], 256, sms), 256, 0, I.stream>>>(I.dRuns, d_blk_base, k, d_rsum, I.dJ);
-    launches++;
-    CUDA_TRY(cudaGetLastError());
+    for (int pass = 0; pass < 2; pass++) {
+      CUDA_TRY(cudaMemsetAsync(d_rsum, 0, 8 * static_cast<size_t>(k), I.stream));
+      k_restart_probe<<<GridFor(blk_base[k], 256, sms), 256, 0, I.stream>>>(I.dRuns, d_blk_base, k, d_rsum, I.dJ);
+      launches++;
+      CUDA_TRY(cudaGetLastError());
+      if (ybgpu_status s = CheckDeviceError("block scan")) return s;
+      if (!I.hJ.n_compressed) break;
+      if (pass == 1) return Fail(YBGPU_CORRUPTION, "compressed blocks after decompression");
+      // ---- Snappy-compressed data blocks (production default, docdb_rocksdb_util.cc:184): checksum of the STORED bytes
+      // first (format.cc:352-395), then one uncompressed image of all inputs (format.cc:441-500)
+      if (verify_pending) {
+        for (int r = 0; r < k; r++) {
+          RunView& rv = I.runs[r];
+          if (!rv.nb) continue;
+          k_crc_blocks<<<GridFor(static_cast<uint64_t>(rv.nb) * 32, 256, sms), 256, 0, I.stream>>>(
+              const_cast<uint8_t*>(rv.data), reinterpret_cast<const unsigned long long*>(rv.blk_off), rv.blk_size, nullptr, rv.nb, 1, I.dJ);
+          launches++;
+        }
+        verify_pending = false;
+      }
+      SnapView sv{};
+      sv.runs = I.dRuns; sv.blk_base = d_blk_base; sv.k = k;
+      CUDA_TRY(DevAlloc(&I.allocs, &sv.out_off, static_cast<size_t>(blk_base[k]) + 1));
+      CUDA_TRY(DevAlloc(&I.allocs, &sv.usize, static_cast<size_t>(blk_base[k])));
+      unsigned long long* d_img = nullptr;
+      CUDA_TRY(DevAlloc(&I.allocs, &d_img, 1));
+      k_snappy_sizes<<<GridFor(blk_base[k], 256, sms), 256, 0, I.stream>>>(sv, I.dJ);
+      k_scan_u64_single<<<1, 1024, 0, I.stream>>>(sv.out_off, blk_base[k], d_img);
+      launches += 2;
+      CUDA_TRY(cudaGetLastError());
+      if (ybgpu_status s = CheckDeviceError("uncompressed sizes")) return s;
+      unsigned long long img_bytes = 0;
+      if (ybgpu_status s = ReadSmall(&img_bytes, d_img, 8)) return s;
+      uint8_t* img = nullptr;
+      CUDA_TRY(DevAlloc(&I.allocs, &img, img_bytes + 96));
+      CUDA_TRY(cudaMemsetAsync(img, 0, 16, I.stream));
+      CUDA_TRY(cudaMemsetAsync(img + 16 + img_bytes, 0, 64, I.stream));
+      sv.out = img + 16;
+      k_snappy_decode<<<sms * 8, 128, 0, I.stream>>>(sv, I.dJ);
+      launches++;
+      CUDA_TRY(cudaGetLastError());
+      for (int r = 0; r < k; r++) {
+        RunView& rv = I.runs[r];
+        rv.data = img + 16;
+        rv.blk_off = reinterpret_cast<const uint64_t*>(sv.out_off) + blk_base[r];
+        rv.blk_size = sv.usize + blk_base[r];
+      }
+      CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+      // the probe starts over on the uncompressed image
+      CUDA_TRY(cudaMemsetAsync(&I.dJ->n_compressed, 0, sizeof(uint32_t), I.stream));
+      CUDA_TRY(cudaMemsetAsync(I.dJ->restart_interval, 0, sizeof(uint32_t) * MAX_RUNS, I.stream));
+      CUDA_TRY(cudaMemsetAsync(&I.dJ->max_ikey_len, 0, sizeof(uint32_t), I.stream));
+      tick("snappy");
+    }
     CUDA_TRY(end_phase());
-    if (ybgpu_status s = CheckDeviceError("block scan")) return s;
-    std::vector<unsigned long long> rsum(k, 0);
     if (ybgpu_status s = ReadSmall(rsum.data(), d_rsum, 8 * static_cast<size_t>(k))) return s;
     if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
+  }
+  if (try_ingest) {
     // upper bound of the entries of a file: every restart interval holds at most `restart interval` entries
     std::vector<uint32_t> cap(k, 0);
     uint64_t cap_total = 0;
@@ -1766,7 +1821,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       CUDA_TRY(cudaMemsetAsync(d_totals, 0, 4 * (static_cast<size_t>(k) + 1), I.stream));
       CUDA_TRY(cudaMemsetAsync(&I.dJ->ingest_fallback, 0, sizeof(int), I.stream));
       iv.runs = I.dRuns; iv.blk_base = d_blk_base; iv.totals = d_totals; iv.cap = d_cap; iv.range = d_range;
-      iv.k = k; iv.S = Sfinal; iv.verify = opt_.verify_checksums ? 1 : 0;
+      iv.k = k; iv.S = Sfinal; iv.verify = verify_pending ? 1 : 0;
       const int grid = static_cast<int>(std::min<uint64_t>(blk_base[k], static_cast<uint64_t>(sms) * 3));
       k_ingest<<<grid, ING_THREADS, ING_SMEM, I.stream>>>(iv, I.dJ);
       launches++;
@@ -1789,12 +1844,12 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       max_ikey = I.hJ.max_ikey_len;
       ingested = true;
     } else {
-      phase = 0;                           // the general path starts over
     }
   }
   if (!ingested) {
     // ---- general path. K1: prepass + scan per file
-    if (opt_.verify_checksums) {
+    phase = 0;                             // "block scan" = everything up to the end of the prepass (probe, a failed fused attempt)
+    if (verify_pending) {
       // ReadBlock's checksum verification (table/format.cc:352-395) for every input block
       for (int r = 0; r < k; r++) {
         RunView& rv = I.runs[r];
