@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   __shared__ uint32_t sh_ncot;
   __shared__ unsigned long long sh_stats[9];
   __shared__ const uint8_t* sh_pred;             // tile that starts inside a row group: the last visible record before it
+  __shared__ uint32_t sh_rb[2][MAX_RUNS + 2];    // run boundaries of the merge tree (ping-pong per level)
 
   const uint32_t tile = blockIdx.x;
   const bool cont = (V.tile_rank[tile] & TILE_CONT) != 0;
@@ -770,64 +771,72 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   }
   __syncthreads();
 
-  // (b) rank every record among the other segments (rank-based k-way merge) and parse its group.
-  // Two levels: every RANK_C-th record of a segment is ranked by a full binary search; the others
-  // only search between the ranks of their two coarse neighbours (ranks are monotone inside a
-  // segment), which cuts the probes by ~40 %.
-  const bool two_level = k <= RANK_KMAX;
-  auto search = [&](const uint8_t* e, unsigned long long pe, unsigned long long pe2, int r, int r2, uint32_t lo, uint32_t hi) {
-    const uint32_t b2 = seg_start[r2];
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      const unsigned long long pm = pfx[b2 + mid];
-      bool less;
-      if (pm != pe) less = pm < pe;
-      else if (pfx2[b2 + mid] != pe2) less = pfx2[b2 + mid] < pe2;
-      else {
-        const int c = cmp_records(recs + static_cast<size_t>(SS) * (b2 + mid), e, S);
-        less = (r2 < r) ? (c <= 0) : (c < 0);
+  // (b) k-way merge of the sorted segments: a binary tree of pairwise merges in shared memory. On every level
+  // each thread produces MT consecutive output positions of one pair of neighbouring runs: a merge-path search
+  // along its diagonal finds where the two runs are cut, then MT sequential merge steps follow. Only the u16
+  // permutation moves (ping-pong between `order` and the former coarse-rank area); comparisons go through the
+  // 16-byte sort prefixes and fall back to the full record compare on ties. Records of the lower-numbered run
+  // come first among equals (the order the reference's MergingIterator heap produces for equal internal keys is
+  // never observable: sequence numbers are unique across files — table/merger.cc:652-697).
+  // ~log2(k) x (log2(n) probes + MT steps) per MT records instead of (k - 1) binary searches per record.
+  {
+    constexpr int MT = 4;
+    uint16_t* bufs[2] = {order, reinterpret_cast<uint16_t*>(crank)};
+    // a <= b in merged order, a from the earlier run group
+    auto le = [&](uint32_t a, uint32_t b) -> bool {
+      const unsigned long long pa = pfx[a], pb = pfx[b];
+      if (pa != pb) return pa < pb;
+      const unsigned long long qa = pfx2[a], qb = pfx2[b];
+      if (qa != qb) return qa < qb;
+      return cmp_records(recs + static_cast<size_t>(SS) * a, recs + static_cast<size_t>(SS) * b, S) <= 0;
+    };
+    for (uint32_t li = threadIdx.x; li < T; li += blockDim.x) bufs[0][li] = static_cast<uint16_t>(li);
+    if (threadIdx.x <= static_cast<uint32_t>(k)) sh_rb[0][threadIdx.x] = seg_start[threadIdx.x];
+    __syncthreads();
+    int nruns = k, cur = 0;
+    while (nruns > 1) {
+      const uint16_t* src = bufs[cur]; uint16_t* dst = bufs[cur ^ 1];
+      const uint32_t* rb = sh_rb[cur];
+      const int npairs = (nruns + 1) >> 1;
+      for (uint32_t o0 = threadIdx.x * MT; o0 < T; o0 += blockDim.x * MT) {
+        int p = 0;
+        while (p + 1 < npairs && rb[2 * (p + 1)] <= o0) p++;
+        uint32_t a0 = rb[2 * p], a1 = rb[min(2 * p + 1, nruns)], b1 = rb[min(2 * p + 2, nruns)];
+        // merge path: how many of the first d outputs of this pair come from A = src[a0, a1) (B = src[a1, b1))
+        const uint32_t d = o0 - a0, la = a1 - a0, lb = b1 - a1;
+        uint32_t lo = d > lb ? d - lb : 0, hi = min(d, la);
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (le(src[a0 + mid], src[a1 + (d - 1 - mid)])) lo = mid + 1; else hi = mid;
+        }
+        uint32_t i = a0 + lo, j = a1 + (d - lo);
+        const uint32_t o_end = min(o0 + MT, T);
+        for (uint32_t o = o0; o < o_end; o++) {
+          while (o == b1 && p + 1 < npairs) {              // the chunk runs into the next (non-empty) pair
+            p++;
+            a0 = rb[2 * p]; a1 = rb[min(2 * p + 1, nruns)]; b1 = rb[min(2 * p + 2, nruns)];
+            i = a0; j = a1;
+          }
+          uint16_t pick;
+          if (i < a1 && (j >= b1 || le(src[i], src[j]))) pick = src[i++]; else pick = src[j++];
+          dst[o] = pick;
+        }
       }
-      if (less) lo = mid + 1; else hi = mid;
+      if (threadIdx.x <= static_cast<uint32_t>(npairs)) sh_rb[cur ^ 1][threadIdx.x] = rb[min(2 * static_cast<int>(threadIdx.x), nruns)];
+      __syncthreads();
+      nruns = npairs; cur ^= 1;
     }
-    return lo;
-  };
-  if (two_level) {
-    // coarse index of record p of segment r: cbase[r] + p / RANK_C
-    if (threadIdx.x == 0) { uint32_t acc = 0; for (int r = 0; r < k; r++) { cbase[r] = acc; acc += (seg_start[r + 1] - seg_start[r] + RANK_C - 1) / RANK_C; } cbase[k] = acc; }
-    __syncthreads();
-    const uint32_t ncoarse = cbase[k];
-    for (uint32_t t = threadIdx.x; t < ncoarse * k; t += blockDim.x) {
-      const uint32_t ci = t / k; const int r2 = static_cast<int>(t - ci * k);
-      int r = 0;
-      while (cbase[r + 1] <= ci) r++;
-      if (r2 == r) continue;
-      const uint32_t p = (ci - cbase[r]) * RANK_C;
-      const uint32_t li = seg_start[r] + p;
-      crank[ci * RANK_KMAX + r2] = static_cast<uint16_t>(search(recs + static_cast<size_t>(SS) * li, pfx[li], pfx2[li], r, r2, 0, seg_start[r2 + 1] - seg_start[r2]));
+    if (cur) {                                             // the permutation must end up in `order`
+      for (uint32_t li = threadIdx.x; li < T; li += blockDim.x) order[li] = bufs[1][li];
     }
-    __syncthreads();
   }
+  // per record: input order check, row-group prefix, bloom filter key length
   for (uint32_t li = threadIdx.x; li < T; li += blockDim.x) {
     int r = 0;
     while (seg_start[r + 1] <= li) r++;
     const uint32_t p = li - seg_start[r];
     const uint8_t* e = recs + static_cast<size_t>(SS) * li;
     if (p > 0 && cmp_records(e - SS, e, S) >= 0) dev_fail(J, DEV_ERR_UNSORTED, tile);
-    const unsigned long long pe = pfx[li], pe2 = pfx2[li];
-    uint32_t rank = p;
-    const uint32_t nseg = seg_start[r + 1] - seg_start[r];
-    const uint32_t ci = two_level ? cbase[r] + p / RANK_C : 0;
-    const bool is_coarse = two_level && (p % RANK_C) == 0;
-    const bool has_next_coarse = two_level && (p / RANK_C + 1) * RANK_C < nseg;
-    for (int r2 = 0; r2 < k; r2++) {
-      if (r2 == r) continue;
-      const uint32_t n2 = seg_start[r2 + 1] - seg_start[r2];
-      if (is_coarse) { rank += crank[ci * RANK_KMAX + r2]; continue; }
-      uint32_t lo = 0, hi = n2;
-      if (two_level) { lo = crank[ci * RANK_KMAX + r2]; if (has_next_coarse) hi = crank[(ci + 1) * RANK_KMAX + r2]; }
-      rank += search(e, pe, pe2, r, r2, lo, hi);
-    }
-    order[rank] = static_cast<uint16_t>(li);
     int fk = 0;
     const int g = group_prefix_len(e, rec_ulen(e, S), prm->R.enabled != 0, V.fk16 ? &fk : nullptr);
     if (g < 0) { dev_fail(J, -g, tile); glen[li] = 0; } else glen[li] = static_cast<uint16_t>(g);
