@@ -71,6 +71,9 @@ def parse_args():
     ap.add_argument("--c3-rows", type=int, default=10_000_000, help="configs[2]: entries per tablet")
     ap.add_argument("--c4-rows", type=int, default=200_000_000,
                     help="configs[3] (MVCC-heavy, 20 versions/key): entries resident on one GPU (the full 1 G entries = 310 GB do not fit HBM)")
+    ap.add_argument("--c5-rows-per-gpu", type=int, default=40_000_000,
+                    help="configs[4] (one oversized tablet, 32-way, key-range sharded over the GPUs with NCCL): entries per GPU")
+    ap.add_argument("--c5-timeout", type=float, default=240.0, help="configs[4]: give up (and still print the line) after this many seconds")
     ap.add_argument("--workload", default="config2", choices=["config2", "mvcc"],
                     help="config2 = BASELINE configs[1] (the bench line); mvcc = configs[3] shape (20 versions/key, "
                          "history cutoff drops 90 %), scaled to --rows entries, for profiles/ only")
@@ -695,9 +698,42 @@ def main():
             except Exception as ex:
                 extra["configs[3]"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
-    if rank != 0:
+    run_c5 = world > 1 and not args.no_extra_configs and args.workload == "config2"
+
+    def finish(line):
+        """Rank 0 prints the one JSON line — after the key-range sharded sub-result (configs[4], N > 1 only), which all
+        ranks run under a watchdog: a rank that fails or hangs inside the exchange must not cost the whole line."""
+        printed = threading.Event()
+
+        def emit_once(c5=None):
+            if rank == 0 and not printed.is_set():
+                printed.set()
+                if c5 is not None:
+                    line.setdefault("configs", {})["configs[4]"] = c5
+                emit_json_line(line)
+        if run_c5:
+            def bail():
+                emit_once({"error": "no result within %.0f s (watchdog)" % args.c5_timeout})
+                os._exit(0)
+            timer = threading.Timer(args.c5_timeout, bail)
+            timer.daemon = True
+            timer.start()
+            failed = False
+            try:
+                c5 = config5_sharded(args, pkg, torch, dist, rank, world, local_rank, job_kw, hbm_peak, barrier)
+            except Exception as ex:
+                c5, failed = {"error": "%s: %s" % (type(ex).__name__, ex)}, True
+            timer.cancel()
+            emit_once(c5)
+            if failed:
+                os._exit(0)                     # the other ranks may be stuck in a collective: do not wait for them
+        else:
+            emit_once()
         if world > 1:
             dist.destroy_process_group()
+
+    if rank != 0:
+        finish(None)
         return
 
     # dominant kernel = longest phase; its algorithmic bytes (DESIGN.md "Roofline accounting")
@@ -772,9 +808,82 @@ def main():
         base, parity = cpu_baseline(args, pkg, local_rank)
         line["cpu_baseline"] = base
         line["parity_check"] = parity
-    emit_json_line(line)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(line)
+
+
+def config5_sharded(args, pkg, torch, dist, rank, world, local_rank, job_kw, hbm_peak, barrier):
+    """BASELINE configs[4]: ONE oversized tablet, 32 input files, key-range sharded across the GPUs through
+    ybgpu_compact_range_sharded (C++ over NCCL: splitters all-gathered, block slices exchanged with chunked grouped
+    ncclSend / ncclRecv over NVLink, every rank compacting its key range). All ranks call this; returns the
+    sub-result on rank 0. Scaled: --c5-rows-per-gpu entries per GPU (the 1 TB of BASELINE does not fit 8 x 180 GB
+    together with the outputs; the `rounds` mechanism that bounds HBM use is exercised by the tests)."""
+    n_files = 32
+    total_rows = args.c5_rows_per_gpu * world
+    cfg = pkg.GenConfig(seed=5, num_rows=total_rows, cols=1, versions=1, num_files=n_files, value_len=VALUE_LEN)
+    mine = [f for f in range(n_files) if f % world == rank]
+    t0 = time.perf_counter()
+    ssts = pkg.generate_sst_files(cfg, mine, max_threads=len(mine))
+    gen_s = time.perf_counter() - t0
+    files = [(s_.meta_view(), s_.data_view()) for s_ in ssts]
+    local_in = sum(s_.raw_bytes for s_ in ssts)
+    local_entries = sum(s_.num_entries for s_ in ssts)
+    local_file_bytes = sum(int(d.size) for _, d in files)
+    cudart = torch.cuda.cudart()
+    pinned = [int(cudart.cudaHostRegister(d.ctypes.data, d.size, 0)) == 0 for _, d in files]
+    tot = torch.tensor([float(local_in), float(local_entries), float(local_file_bytes)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+    total_in, total_entries, total_file_bytes = (float(x) for x in tot.tolist())
+    out_cap = int(total_file_bytes / world * 1.5) + (256 << 20)
+    out_data = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True).numpy()
+    out_meta = torch.empty(max(64 << 20, out_cap // 50), dtype=torch.uint8, pin_memory=True).numpy()
+    uid = [pkg.range_comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    comm = pkg.RangeComm(uid[0], rank, world, local_rank)
+    results = []
+    steps = 2
+    dts = []
+    for it in range(1 + steps):                      # one warm-up (communicator set-up, allocator) + `steps` timed
+        barrier()
+        t0 = time.perf_counter()
+        data, meta, res, st = comm.compact(files, rounds=1, chunk_bytes=64 << 20, data_out=out_data, meta_out=out_meta,
+                                           verify_checksums=bool(args.verify), **job_kw)
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        if it:
+            dts.append(float(te.item()))
+            results.append((res, st))
+    res, st = results[-1]
+    mine_stats = torch.tensor([float(st.num_input_records), float(st.num_output_records), float(res.sent_to_peers_bytes),
+                               float(res.exchange_seconds), float(st.gpu_seconds), float(res.data_len)], dtype=torch.float64, device="cuda")
+    summed = mine_stats.clone()
+    dist.all_reduce(summed)
+    mx = mine_stats.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    comm.close()
+    for (_, d), ok in zip(files, pinned):
+        if ok:
+            cudart.cudaHostUnregister(d.ctypes.data)
+    if rank != 0:
+        return None
+    dt = sum(dts) / len(dts)
+    s_in, s_out, nvl, _, _, s_dlen = (float(x) for x in summed.tolist())
+    _, _, _, ex_max, gpu_max, _ = (float(x) for x in mx.tolist())
+    assert int(s_in) == int(total_entries), "the ranks' key ranges must cover every input entry exactly once"
+    return {
+        "workload": "single tablet, 32-way major compaction, key-range-sharded across %d GPUs with one NCCL exchange: %d entries "
+                    "(%.1f GB raw, %.1f GB of files) in total, %d per GPU; host files in, one host table per rank out" % (
+                        world, int(total_entries), total_in / 1e9, total_file_bytes / 1e9, args.c5_rows_per_gpu),
+        "value": round(total_in / dt / 1e9, 2), "unit": "GB/s", "mkeys_per_s": round(total_entries / dt / 1e6, 1),
+        "ms_per_step": round(dt * 1e3, 1), "steps": steps, "timing": "host wall clock between barriers, max over ranks (includes "
+        "host->device staging of the inputs and device->host copy of the outputs)",
+        "exchange": {"nvlink_bytes": int(nvl), "seconds_max_rank": round(ex_max, 4),
+                     "aggregate_gbs": round(nvl / ex_max / 1e9, 1) if ex_max > 0 else None,
+                     "mechanism": "ncclSend/ncclRecv grouped per 64 MB chunk, counts all-gathered first, staged from pinned host memory"},
+        "gpu_seconds_max_rank": round(gpu_max, 4), "output_entries": int(s_out), "output_data_bytes": int(s_dlen),
+        "ranges": int(res.num_ranges), "verify_checksums": bool(args.verify), "generate_s": round(gen_s, 1)}
 
 
 def read_handles(pkg, sst):

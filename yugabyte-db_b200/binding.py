@@ -420,6 +420,34 @@ def generate_ssts(cfg, block_size=32768, restart_interval=16, max_threads=None):
     return [GeneratedSst(arr[i]) for i in range(cfg.num_files)]
 
 
+def generate_sst_files(cfg, file_indices, block_size=32768, restart_interval=16, max_threads=None):
+    """Only the files `file_indices` of the synthetic tablet `cfg` (ybgpu_gen_sst per file, on threads): what one rank
+    of a key-range sharded compaction holds."""
+    import threading
+    L = lib()
+    o = JobOptions()
+    L.ybgpu_job_options_init(C.byref(o))
+    o.block_size, o.block_restart_interval = block_size, restart_interval
+    out = [None] * len(file_indices)
+    errs = []
+
+    def work(slot, f):
+        h = C.c_void_p()
+        st = L.ybgpu_gen_sst(C.byref(cfg), f, C.byref(o), C.byref(h))
+        if st != 0:
+            errs.append(st)
+        else:
+            out[slot] = GeneratedSst(h)
+    threads = [threading.Thread(target=work, args=(i, f)) for i, f in enumerate(file_indices)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        raise YbGpuError(errs[0], "synthetic SST generation failed")
+    return out
+
+
 def sst_block_handles(meta):
     """(offsets, sizes, key_encoding) of the data blocks of a split SST, from its metadata file."""
     L = lib()
