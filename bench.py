@@ -207,11 +207,19 @@ def all_cores_cpu(o, args, rows_each=1_000_000, min_seconds=4.0):
     ncpu = os.cpu_count() or 1
     worker = os.path.join(ROOT, "oracle", "cpu_worker.py")
     out = {}
+
+    def whole_machine():
+        # the bench process may be bound to its GPU's NUMA node (ybgpu_bind_thread_to_device): the CPU figure must not be
+        try:
+            os.sched_setaffinity(0, range(ncpu))
+            ctypes.CDLL(None, use_errno=True).syscall(238, 0, None, 0)       # set_mempolicy(MPOL_DEFAULT) on x86-64
+        except Exception:
+            pass
     for label, T in (("pool", max(1, int(ncpu * 3.5 / 8))), ("all_threads", ncpu)):
         start_at = time.time() + 3.0 + 0.02 * T          # interpreter start + sample generation of every worker
         procs = [subprocess.Popen([sys.executable, worker, "--rows", str(rows_each), "--seconds", str(min_seconds),
                                    "--start-at", "%.3f" % start_at, "--verify", str(int(bool(args.verify)))],
-                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(T)]
+                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, preexec_fn=whole_machine) for _ in range(T)]
         rate, done, late = 0.0, 0, 0
         for p_ in procs:
             txt, _ = p_.communicate(timeout=120 + 10 * min_seconds)

@@ -238,6 +238,9 @@ class GpuCompactionJob {
   struct OutputFile {
     std::string data_file, base_file;        // <n>.sst.sblock.0, <n>.sst
     std::string smallest_key, largest_key;   // FileMetaData::smallest / largest (internal keys)
+    // FileMetaData seqno bounds of THIS file: the union over the compaction's inputs (every output is seeded with it,
+    // compaction_job.cc:1188-1195) extended by the file's own survivors (:156-169)
+    uint64_t smallest_seqno = 0, largest_seqno = 0;
     ybgpu_job_stats stats;
   };
   Status RunSubcompactions() {
@@ -273,6 +276,7 @@ class GpuCompactionJob {
       f.smallest_key.assign(reinterpret_cast<const char*>(so.smallest_key), so.smallest_key_len);
       f.largest_key.assign(reinterpret_cast<const char*>(so.largest_key), so.largest_key_len);
       f.stats = so.stats;
+      SeqnoBounds(inputs_, so.stats.smallest_seqno, so.stats.largest_seqno, so.stats.num_output_records, &f.smallest_seqno, &f.largest_seqno);
       outputs_.push_back(std::move(f));
     }
     return Status::OK();
