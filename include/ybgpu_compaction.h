@@ -158,7 +158,17 @@ typedef struct ybgpu_job_stats {
    * 5 the block-assembler kernel alone (k_encode_smem, one launch; part of phase 4) */
   double phase_seconds[8];
   uint32_t phase_launches[8];
+  /* which kernels ran (diagnostics, tests): YBGPU_PATH_* bits; summed over the ranges of a pipelined compaction */
+  uint32_t path_flags;
+  uint32_t tiles_inside_rows;          /* merge tiles that started inside a row group larger than a tile */
 } ybgpu_job_stats;
+enum {
+  YBGPU_PATH_FUSED_INGEST = 1,         /* k_ingest: TMA-staged verify + value CRCs + decode in one pass */
+  YBGPU_PATH_GENERAL_DECODE = 2,       /* k_prepass / k_decode_* / k_value_crc (other encodings, long keys, huge blocks) */
+  YBGPU_PATH_SNAPPY = 4,               /* compressed input blocks were uncompressed on the GPU */
+  YBGPU_PATH_PARTITION_RETRY = 8,      /* the partition was repeated with a smaller sample stride */
+  YBGPU_PATH_ENCODER_V4 = 16           /* block assembler with checksums by CRC linearity */
+};
 
 typedef struct ybgpu_job ybgpu_job;
 

@@ -64,6 +64,7 @@ def check(pkg, ssts, block_size=4096, ht_filters=None, **kw):
         assert data.tobytes() == ref.data
         assert meta.tobytes() == ref.meta
     assert st.gpu_kernel_launches > 0
+    assert st.path_flags & (pkg.PATH_FUSED_INGEST | pkg.PATH_GENERAL_DECODE) and (st.path_flags & pkg.PATH_ENCODER_V4 or not ekv)
     return job, exp
 
 
@@ -153,6 +154,8 @@ def test_config2_shape_scaled_8way(pkg):
     ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=32768))
     job, exp = check(pkg, ssts, block_size=32768)
     assert job.stats().num_output_records == 200000
+    # the bench shape takes the fused pass (TMA-staged verify + value CRCs + decode) and the CRC-linearity block assembler
+    assert job.stats().path_flags & pkg.PATH_FUSED_INGEST and not job.stats().path_flags & pkg.PATH_GENERAL_DECODE
 
 
 def test_hybrid_time_filter(pkg):
@@ -244,7 +247,8 @@ def test_three_shared_parts_inputs(pkg):
     cfg = o.GenConfig(seed=19, num_rows=6000, cols=3, versions=4, num_files=4, value_len=48, tombstone_per_1024=50)
     ssts = [o.Sst.generate(cfg, f, o.TableOptions(block_size=2048, key_encoding=2 if f != 2 else 1)) for f in range(4)]
     assert [s.key_encoding for s in ssts] == [2, 2, 1, 2]
-    check(pkg, ssts, block_size=4096, cutoff_ht=o.ht_from_micros(cfg.base_micros + 2500))
+    job, _ = check(pkg, ssts, block_size=4096, cutoff_ht=o.ht_from_micros(cfg.base_micros + 2500))
+    assert job.stats().path_flags & pkg.PATH_GENERAL_DECODE      # three_shared_parts inputs: the general kernels
     runs = w.random_docdb_runs(4, n_runs=3, n_rows=200)
     ssts = [o.Sst.build(r, o.TableOptions(block_size=512, key_encoding=2)) for r in runs]
     for kw in w.param_grid()[:4]:
@@ -405,7 +409,8 @@ def test_rows_larger_than_a_merge_tile(pkg, seed, cols, versions, collection, co
     ssts = runs_to_ssts(runs, 4096)
     grid = w.param_grid()
     for kw in ([grid[i] for i in (0, 2, 3, 4, 6, 8, 9)] if seed < 2 else [grid[2], grid[4]]):
-        check(pkg, ssts, block_size=4096, **kw)
+        job, _ = check(pkg, ssts, block_size=4096, **kw)
+        assert job.stats().tiles_inside_rows > 0            # the rows really were cut across tiles
 
 
 def test_plain_mode_user_key_with_thousands_of_versions(pkg):
@@ -593,7 +598,8 @@ def test_snappy_compressed_inputs(pkg, seed):
     raw = sum(sum(len(k) + len(v) for k, v in r) for r in runs)
     assert sum(len(s.data) for s in ssts) < raw                      # something was compressed
     for kw in kws:
-        check(pkg, ssts, block_size=4096, filter_policy=1, filter_block_size=4096, **kw)
+        job, _ = check(pkg, ssts, block_size=4096, filter_policy=1, filter_block_size=4096, **kw)
+        assert job.stats().path_flags & pkg.PATH_SNAPPY
     # a flipped bit in a compressed block is a checksum error, not garbage
     bad = bytearray(ssts[0].data)
     bad[len(bad) // 2] ^= 0x10

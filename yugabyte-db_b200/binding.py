@@ -63,7 +63,8 @@ class JobStats(C.Structure):
         "total_output_raw_key_bytes", "total_output_raw_value_bytes", "num_output_data_blocks",
         "output_data_file_size", "output_meta_file_size", "smallest_seqno", "largest_seqno")] + [
         ("gpu_seconds", C.c_double), ("gpu_kernel_launches", C.c_uint32), ("h2d_bytes", C.c_uint64),
-        ("d2h_bytes", C.c_uint64), ("phase_seconds", C.c_double * 8), ("phase_launches", C.c_uint32 * 8)]
+        ("d2h_bytes", C.c_uint64), ("phase_seconds", C.c_double * 8), ("phase_launches", C.c_uint32 * 8),
+                ("path_flags", C.c_uint32), ("tiles_inside_rows", C.c_uint32)]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}
@@ -73,6 +74,7 @@ class JobStats(C.Structure):
 
 
 PHASE_NAMES = ["block_scan", "decode", "partition", "merge_filter", "encode"]
+PATH_FUSED_INGEST, PATH_GENERAL_DECODE, PATH_SNAPPY, PATH_PARTITION_RETRY, PATH_ENCODER_V4 = 1, 2, 4, 8, 16
 
 
 class GenConfig(C.Structure):

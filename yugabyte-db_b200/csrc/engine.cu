@@ -66,6 +66,7 @@ struct JobDev {                 // device-global job state
   uint32_t max_tile;            // largest tile of the current partition (k_tile_check)
   int ingest_fallback;          // k_ingest met something it does not take: the host runs the general kernels
   uint32_t n_compressed;        // Snappy-compressed input blocks seen by k_restart_probe
+  uint32_t n_cont_tiles;        // merge tiles that started inside a row group
   unsigned long long digest;
 };
 
@@ -709,6 +710,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   __syncthreads();
   const uint32_t T = sh_T;
   if (T == 0) return;
+  if (cont && threadIdx.x == 0) atomicAdd(&J->n_cont_tiles, 1u);
   if (T > cap) { if (threadIdx.x == 0) dev_fail(J, DEV_ERR_TILE_OVERFLOW, tile); return; }
 
   // (a) stage the k segments: contiguous 16-byte vector loads from HBM, re-strided to SS in smem
@@ -1786,6 +1788,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       CUDA_TRY(cudaMemsetAsync(&I.dJ->n_compressed, 0, sizeof(uint32_t), I.stream));
       CUDA_TRY(cudaMemsetAsync(I.dJ->restart_interval, 0, sizeof(uint32_t) * MAX_RUNS, I.stream));
       CUDA_TRY(cudaMemsetAsync(&I.dJ->max_ikey_len, 0, sizeof(uint32_t), I.stream));
+      stats_.path_flags |= YBGPU_PATH_SNAPPY;
       tick("snappy");
     }
     CUDA_TRY(end_phase());
@@ -1852,12 +1855,14 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       }
       max_ikey = I.hJ.max_ikey_len;
       ingested = true;
+      stats_.path_flags |= YBGPU_PATH_FUSED_INGEST;
     } else {
     }
   }
   if (!ingested) {
     // ---- general path. K1: prepass + scan per file
     phase = 0;                             // "block scan" = everything up to the end of the prepass (probe, a failed fused attempt)
+    stats_.path_flags |= YBGPU_PATH_GENERAL_DECODE;
     if (verify_pending) {
       // ReadBlock's checksum verification (table/format.cc:352-395) for every input block
       for (int r = 0; r < k; r++) {
@@ -2024,6 +2029,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     if (hp.M <= 1 || attempt >= 4)
       return Fail(YBGPU_NOT_SUPPORTED, "record stride and run count too large for a merge tile");
     hp.M = std::max(1u, hp.M / 2);
+    stats_.path_flags |= YBGPU_PATH_PARTITION_RETRY;
     CUDA_TRY(cudaMemcpyAsync(I.dP, &hp, sizeof(hp), cudaMemcpyHostToDevice, I.stream));
     CUDA_TRY(cudaMemsetAsync(&I.dJ->max_tile, 0, sizeof(uint32_t), I.stream));
   }
@@ -2147,6 +2153,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       const size_t esm = ENC_SMEM_CAP + 32;
       const bool tsp = E.key_encoding == YBGPU_KEY_ENCODING_THREE_SHARED_PARTS;
       const bool v3 = getenv("YBGPU_ENC_V3") != nullptr;           // A/B: the image-CRC assembler of round 1
+      if (!v3) stats_.path_flags |= YBGPU_PATH_ENCODER_V4;
       auto smem_kernel = v3 ? (tsp ? k_encode_smem<2> : k_encode_smem<1>) : (tsp ? k_encode_v4<2> : k_encode_v4<1>);
       auto fused_kernel = tsp ? k_encode_fused<2> : k_encode_fused<1>;
       CUDA_TRY(cudaFuncSetAttribute(smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esm)));
@@ -2231,6 +2238,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     stats_.phase_seconds[5] = ems / 1e3; stats_.phase_launches[5] = 1;
   }
 
+  stats_.tiles_inside_rows = I.hJ.n_cont_tiles;
   stats_.num_input_records = I.hJ.n_counted;
   stats_.num_output_records = I.hJ.n_kept;
   stats_.num_record_drop_hidden = I.hJ.n_hidden;

@@ -478,6 +478,7 @@ ybgpu_status ybgpu_compact_range_sharded(ybgpu_range_comm* c, const ybgpu_job_op
     tot.gpu_seconds += st.gpu_seconds; tot.gpu_kernel_launches += st.gpu_kernel_launches;
     tot.h2d_bytes += st.h2d_bytes; tot.d2h_bytes += st.d2h_bytes;
     for (int i = 0; i < 8; i++) { tot.phase_seconds[i] += st.phase_seconds[i]; tot.phase_launches[i] += st.phase_launches[i]; }
+    tot.path_flags |= st.path_flags; tot.tiles_inside_rows += st.tiles_inside_rows;
   }
 
   // ---- 4. this rank's table

@@ -248,6 +248,7 @@ void AddStats(ybgpu_job_stats* t, const ybgpu_job_stats& s, bool first_output) {
   t->gpu_seconds += s.gpu_seconds; t->gpu_kernel_launches += s.gpu_kernel_launches;
   t->h2d_bytes += s.h2d_bytes; t->d2h_bytes += s.d2h_bytes;
   for (int i = 0; i < 8; i++) { t->phase_seconds[i] += s.phase_seconds[i]; t->phase_launches[i] += s.phase_launches[i]; }
+  t->path_flags |= s.path_flags; t->tiles_inside_rows += s.tiles_inside_rows;
 }
 
 }  // namespace
