@@ -612,8 +612,8 @@ def main():
                    "single_job": single}
             del one_meta
             if isinstance(ceiling, dict) and "both" in ceiling and ceiling["both"]:
-                # the step moves in_bytes in and about as much out: bound = the slower direction of the duplex figure
-                e2e["frac_of_pcie_ceiling"] = round(e2e["value"] / (ceiling["both"] / 2.0), 3)
+                # the step moves in_bytes in and about as much out at once; "both" is the per-direction rate of exactly that
+                e2e["frac_of_pcie_ceiling"] = round(e2e["value"] / ceiling["both"], 3)
         for v, ok in pinned:
             if ok:
                 cudart.cudaHostUnregister(v.ctypes.data)

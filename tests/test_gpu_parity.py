@@ -593,13 +593,27 @@ def test_snappy_compressed_inputs(pkg, seed):
     else:
         cfg = o.GenConfig(seed=60 + seed, num_rows=4000, cols=2, versions=3, num_files=3, value_len=24 if seed == 2 else 200, tombstone_per_1024=50)
         runs = [s.read_all() for s in o.Sst.generate_all(cfg, o.TableOptions(block_size=4096))]
+        if seed == 3:
+            # random 200-byte strings do not compress; every other stretch of 150 entries gets a repetitive string, so
+            # the files hold compressed and raw blocks side by side
+            runs = [[(k, v[:1] + (k[-12:-8] * 50)[:len(v) - 1]) if v[:1] == b"S" and (i // 150) % 2 else (k, v) for i, (k, v) in enumerate(r)] for r in runs]
         kws = [dict(cutoff_ht=o.ht_from_micros(cfg.base_micros + 1500))]
     ssts = [o.Sst.build(r, o.TableOptions(block_size=2048 if seed < 2 else 8192, compression=1)) for r in runs if r]
     raw = sum(sum(len(k) + len(v) for k, v in r) for r in runs)
     assert sum(len(s.data) for s in ssts) < raw                      # something was compressed
+    def stored_compressed(s):                                       # any block whose trailer says kSnappyCompression
+        offs, sizes = s.block_handles()
+        d = bytes(s.data)
+        return any(d[int(off) + int(size)] == 1 for off, size in zip(offs, sizes))
+    def stored_raw(s):
+        offs, sizes = s.block_handles()
+        d = bytes(s.data)
+        return any(d[int(off) + int(size)] == 0 for off, size in zip(offs, sizes))
+    any_compressed = any(stored_compressed(s) for s in ssts)
+    assert any_compressed and (seed != 3 or all(stored_raw(s) for s in ssts))
     for kw in kws:
         job, _ = check(pkg, ssts, block_size=4096, filter_policy=1, filter_block_size=4096, **kw)
-        assert job.stats().path_flags & pkg.PATH_SNAPPY
+        assert bool(job.stats().path_flags & pkg.PATH_SNAPPY) == any_compressed
     # a flipped bit in a compressed block is a checksum error, not garbage
     bad = bytearray(ssts[0].data)
     bad[len(bad) // 2] ^= 0x10

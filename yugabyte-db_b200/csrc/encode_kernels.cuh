@@ -447,6 +447,34 @@ __device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {
   }
   return p;
 }
+// The same product without the bit-serial loop. In the reflected representation (bit 31 = x^0) the carry-less
+// product of two registers, shifted left by one, holds the 63-coefficient product with x^0..x^31 in its HIGH word
+// and x^32..x^62 in its LOW word; (low word) * x^32 mod P is the ordinary four-byte zero step of the CRC, so
+//   a * b mod P = step32(lo(z << 1)) ^ hi(z << 1),   z = clmul(a, b).
+// The carry-less multiplication itself uses integer multipliers: with the operands split into four classes of bit
+// positions (mod 4), every product bit sums at most eight partial products — the carries stay inside the 4-bit
+// group and the group's lowest bit is the XOR. Reduction is linear: products are XOR-accumulated unreduced
+// (crc_clmul) and reduced once (crc_clmul_reduce).
+__device__ __forceinline__ unsigned long long crc_clmul(uint32_t x, uint32_t y) {
+  const uint32_t x0 = x & 0x11111111u, x1 = x & 0x22222222u, x2 = x & 0x44444444u, x3 = x & 0x88888888u;
+  const uint32_t y0 = y & 0x11111111u, y1 = y & 0x22222222u, y2 = y & 0x44444444u, y3 = y & 0x88888888u;
+#define YB_M64(a, b) (static_cast<unsigned long long>(a) * (b))
+  const unsigned long long z0 = YB_M64(x0, y0) ^ YB_M64(x1, y3) ^ YB_M64(x2, y2) ^ YB_M64(x3, y1);
+  const unsigned long long z1 = YB_M64(x0, y1) ^ YB_M64(x1, y0) ^ YB_M64(x2, y3) ^ YB_M64(x3, y2);
+  const unsigned long long z2 = YB_M64(x0, y2) ^ YB_M64(x1, y1) ^ YB_M64(x2, y0) ^ YB_M64(x3, y3);
+  const unsigned long long z3 = YB_M64(x0, y3) ^ YB_M64(x1, y2) ^ YB_M64(x2, y1) ^ YB_M64(x3, y0);
+#undef YB_M64
+  return (z0 & 0x1111111111111111ull) | (z1 & 0x2222222222222222ull) | (z2 & 0x4444444444444444ull) | (z3 & 0x8888888888888888ull);
+}
+// tab(b) = g_crc_tab[0][b] from wherever the caller keeps the byte table
+template <class Tab>
+__device__ __forceinline__ uint32_t crc_clmul_reduce(unsigned long long z, Tab tab) {
+  z <<= 1;
+  uint32_t c = static_cast<uint32_t>(z);
+#pragma unroll
+  for (int i = 0; i < 4; i++) c = tab(c & 0xff) ^ (c >> 8);
+  return c ^ static_cast<uint32_t>(z >> 32);
+}
 // x^(8 * nbytes) mod P
 __device__ __forceinline__ uint32_t crc_xpow_bytes(uint64_t nbytes, const uint32_t* x2n) {
   uint32_t p = 1u << 31;                         // x^0
@@ -1180,7 +1208,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_v4(EncView E, int S, 
     };
     __syncthreads();
 
-    uint32_t acc = 0;
+    unsigned long long acc = 0;                  // XOR of unreduced carry-less products
     for (uint32_t p0 = s; p0 < e; p0 += ENC_EM_S) {
       const uint32_t pn = min(static_cast<uint32_t>(ENC_EM_S), e - p0);
       // ---- phase A: one thread per entry: header + key delta into the image, value copy job into the table
@@ -1296,9 +1324,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_v4(EncView E, int S, 
         const uint32_t gap_end = len ? d0 : eend;
         uint32_t gc = 0;
         for (uint32_t x = est; x < gap_end; x++) gc = tab0[((gc ^ img_raw[x]) & 0xff) * ENC4_REP + copy] ^ (gc >> 8);
-        uint32_t Ee = (gc && len) ? crc_mulmod(__ldg(&g_crc_xpow8[len]), gc) : gc;
-        Ee ^= t_vcrc[q];
-        if (Ee) acc ^= crc_mulmod(__ldg(&g_crc_xpow8[(mis + L) - eend]), Ee);
+        // gap * x^(8 (bytes behind the gap)) + value * x^(8 (bytes behind the value)), unreduced
+        acc ^= crc_clmul(gc, __ldg(&g_crc_xpow8[(mis + L) - gap_end]));
+        if (len) acc ^= crc_clmul(t_vcrc[q], __ldg(&g_crc_xpow8[(mis + L) - eend]));
         // chunks: from the one the entry starts in up to the first full value chunk (or the end of the entry)
         const uint32_t c_lo = est >> 4, c_hi = full ? (fa >> 4) : ((eend + 15) >> 4);
         for (uint32_t c = c_lo; c < c_hi; c++) store_chunk(c);
@@ -1313,8 +1341,11 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_v4(EncView E, int S, 
       q[0] = static_cast<uint8_t>(nres); q[1] = static_cast<uint8_t>(nres >> 8); q[2] = static_cast<uint8_t>(nres >> 16); q[3] = static_cast<uint8_t>(nres >> 24);
       q[4] = 0;   // kNoCompression
     }
-    acc = __reduce_xor_sync(0xffffffffu, acc);
-    if (lane == 0 && acc) atomicXor(&sh_acc, acc);
+    {
+      uint32_t a32 = crc_clmul_reduce(acc, [&](uint32_t x) { return tab0[x * ENC4_REP + copy]; });
+      a32 = __reduce_xor_sync(0xffffffffu, a32);
+      if (lane == 0 && a32) atomicXor(&sh_acc, a32);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t r = sh_acc, tc = 0;

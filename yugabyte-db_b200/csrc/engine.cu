@@ -1731,14 +1731,10 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   bool try_ingest = blk_base[k] > 0 && getenv("YBGPU_NO_INGEST") == nullptr;
   for (int r = 0; r < k; r++) try_ingest = try_ingest && I.runs[r].key_encoding == 1;
   // ---- probe: restart counts (entry upper bounds), restart interval, key length sample, compression types
-  unsigned long long* d_rsum = nullptr;
-  std::vector<unsigned long long> rsum(k, 0);
   bool verify_pending = opt_.verify_checksums != 0;      // false once the stored blocks' checksums have been verified
   if (blk_base[k] > 0) {
-    CUDA_TRY(DevAlloc(&I.allocs, &d_rsum, static_cast<size_t>(k)));
     for (int pass = 0; pass < 2; pass++) {
-      CUDA_TRY(cudaMemsetAsync(d_rsum, 0, 8 * static_cast<size_t>(k), I.stream));
-      k_restart_probe<<<GridFor(blk_base[k], 256, sms), 256, 0, I.stream>>>(I.dRuns, d_blk_base, k, d_rsum, I.dJ);
+      k_restart_probe<<<GridFor(blk_base[k], 256, sms), 256, 0, I.stream>>>(I.dRuns, d_blk_base, k, I.dJ);
       launches++;
       CUDA_TRY(cudaGetLastError());
       if (ybgpu_status s = CheckDeviceError("block scan")) return s;
@@ -1792,19 +1788,20 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       tick("snappy");
     }
     CUDA_TRY(end_phase());
-    if (ybgpu_status s = ReadSmall(rsum.data(), d_rsum, 8 * static_cast<size_t>(k))) return s;
     if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
   }
   if (try_ingest) {
-    // upper bound of the entries of a file: every restart interval holds at most `restart interval` entries
-    std::vector<uint32_t> cap(k, 0);
-    uint64_t cap_total = 0;
-    for (int r = 0; r < k; r++) {
-      const uint64_t ri = I.hJ.restart_interval[r] ? I.hJ.restart_interval[r] : static_cast<uint64_t>(ING_MAXE);
-      const uint64_t c = rsum[r] * ri;
-      cap_total += c;
+    // exact entry counts: (restarts - 1) x restart interval + the last interval (probe), scanned per file
+    k_block_counts<<<GridFor(blk_base[k], 256, sms), 256, 0, I.stream>>>(I.dRuns, d_blk_base, k, I.dJ);
+    k_scan_blk_counts<<<k, 1024, 0, I.stream>>>(I.dRuns, d_totals);
+    launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<uint32_t> cap(k + 1, 0);
+    if (ybgpu_status s = ReadSmall(cap.data(), d_totals, 4 * static_cast<size_t>(k))) return s;
+    {
+      uint64_t cap_total = 0;
+      for (int r = 0; r < k; r++) cap_total += cap[r];
       if (cap_total >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "more than 2^32 entries in one job: shard the compaction");
-      cap[r] = static_cast<uint32_t>(c);
     }
     // record stride: user key + 16-byte trailer, from the longest key the probe's sample met; a longer key inside
     // k_ingest costs one more attempt with the widest stride the kernel takes (64-byte internal keys)
@@ -1812,11 +1809,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     const uint32_t sample_max = std::max<uint32_t>(I.hJ.max_ikey_len, 8);
     Sfinal = std::min(S_widest, std::max(32, static_cast<int>(((sample_max - 8 + 16) + 15) & ~15u)));
     IngestView iv{};
-    uint32_t* d_cap = nullptr;
-    CUDA_TRY(DevAlloc(&I.allocs, &d_cap, static_cast<size_t>(k)));
-    CUDA_TRY(DevAlloc(&I.allocs, &iv.status, static_cast<size_t>(blk_base[k])));
     CUDA_TRY(DevAlloc(&I.allocs, &iv.ticket, 1));
-    CUDA_TRY(cudaMemcpyAsync(d_cap, cap.data(), 4 * static_cast<size_t>(k), cudaMemcpyHostToDevice, I.stream));
     CUDA_TRY(cudaFuncSetAttribute(k_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ING_SMEM)));
     for (int attempt = 0; attempt < 2; attempt++) {
       for (int r = 0; r < k; r++) {
@@ -1828,13 +1821,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
         }
       }
       CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
-      CUDA_TRY(cudaMemsetAsync(iv.status, 0, 8 * static_cast<size_t>(blk_base[k]), I.stream));
       CUDA_TRY(cudaMemsetAsync(iv.ticket, 0, 4, I.stream));
-      CUDA_TRY(cudaMemsetAsync(d_totals, 0, 4 * (static_cast<size_t>(k) + 1), I.stream));
       CUDA_TRY(cudaMemsetAsync(&I.dJ->ingest_fallback, 0, sizeof(int), I.stream));
-      iv.runs = I.dRuns; iv.blk_base = d_blk_base; iv.totals = d_totals; iv.cap = d_cap; iv.range = d_range;
+      iv.runs = I.dRuns; iv.blk_base = d_blk_base; iv.totals = d_totals; iv.range = d_range;
       iv.k = k; iv.S = Sfinal; iv.verify = verify_pending ? 1 : 0;
-      const int grid = static_cast<int>(std::min<uint64_t>(blk_base[k], static_cast<uint64_t>(sms) * 3));
+      const int grid = static_cast<int>(std::min<uint64_t>((blk_base[k] + ING_BATCH - 1) / ING_BATCH, static_cast<uint64_t>(sms) * 2));
       k_ingest<<<grid, ING_THREADS, ING_SMEM, I.stream>>>(iv, I.dJ);
       launches++;
       CUDA_TRY(cudaGetLastError());
@@ -1845,8 +1836,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(end_phase());
     tick("ingest");
     if (!I.hJ.ingest_fallback) {
-      std::vector<uint32_t> h_totals(k + 1, 0);
-      if (ybgpu_status s = ReadSmall(h_totals.data(), d_totals, 4 * static_cast<size_t>(k))) return s;
+      const std::vector<uint32_t>& h_totals = cap;
       for (int r = 0; r < k; r++) {
         I.runs[r].n_entries = h_totals[r];
         I.runs[r].restart_interval = I.hJ.restart_interval[r];

@@ -15,8 +15,10 @@
 //     stored trailer; the per-entry VALUE CRCs are kept (4 B per entry): the block encoder derives the
 //     output blocks' checksums from them without ever looking at value bytes again (values are copied
 //     verbatim from input to output, so their CRC contribution only needs shifting);
-//   * the entry base of the block inside its file comes from a decoupled look-back over per-block counts
-//     (blocks are claimed through an atomic ticket, so every predecessor of a claimed block is running);
+//   * the entry base of the block inside its file is known beforehand: the probe kernel counts a block's entries as
+//     (restarts - 1) x restart interval + the entries of its last interval (only that interval's headers are walked,
+//     ~1/7 of the block's sectors), a per-file scan turns the counts into bases (a decoupled look-back inside this
+//     kernel was tried first: with ~450 blocks in flight every block ended up summing all in-flight predecessors);
 //   * lanes walk their intervals a second time, rebuild the internal keys in registers and write records.
 //
 // CRC table look-ups dominate the shared-memory pipe; the four 256-entry slicing tables are replicated
@@ -37,17 +39,16 @@ constexpr uint32_t ING_BUF = 36 * 1024;       // staged bytes per block: content
 constexpr int ING_MAXE = 512;                 // entries per block
 constexpr int ING_REP = 8;                    // replication of the CRC tables
 constexpr int ING_NVI = 4;                    // internal keys up to 64 bytes
+constexpr int ING_BATCH = 4;                  // blocks claimed per ticket
 constexpr int ING_FALLBACK_WIDER = 1;         // a key does not fit the guessed record stride: once more with the widest
 constexpr int ING_FALLBACK_GENERAL = 2;       // not for this kernel: general path
-constexpr size_t ING_SMEM = ING_BUF + 32 + 4 * 256 * ING_REP * 4 + ING_MAXE * 8 + ING_MAXE * 4;
+constexpr size_t ING_SMEM = 2 * (ING_BUF + 32) + 4 * 256 * ING_REP * 4 + ING_MAXE * 12;
 
 struct IngestView {
   const RunView* runs;
   const uint32_t* blk_base;        // [k+1] first global block index of every run
-  unsigned long long* status;      // [total blocks] look-back word: flag << 32 | entries
   uint32_t* ticket;
-  uint32_t* totals;                // [k] exact entries per run
-  const uint32_t* cap;             // [k] record capacity per run (upper bound the arrays were sized by)
+  const uint32_t* totals;          // [k] entries per run (the blocks' bases are run.blk_count[], an exclusive prefix)
   const RangeDev* range;           // nullptr = no key range
   int k, S, verify;
 };
@@ -80,9 +81,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-// Per run: sum of the blocks' restart counts (-> an upper bound of the entries: every interval holds at most
-// `restart interval` entries) and the restart interval itself, read off the first block that has two intervals.
-__global__ void __launch_bounds__(256) k_restart_probe(const RunView* runs, const uint32_t* blk_base, int k, unsigned long long* restart_sum, JobDev* J) {
+// Per block: its entry count (in two parts, see below) and compression type; per run: the restart interval, read off
+// the first block that has two intervals; a sample of key lengths.
+__global__ void __launch_bounds__(256) k_restart_probe(const RunView* runs, const uint32_t* blk_base, int k, JobDev* J) {
   const uint32_t total = blk_base[k];
   for (uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x; gb < total; gb += gridDim.x * blockDim.x) {
     int ri_ = 0;
@@ -98,16 +99,33 @@ __global__ void __launch_bounds__(256) k_restart_probe(const RunView* runs, cons
       if (type == 1) atomicAdd(&J->n_compressed, 1u); else dev_fail(J, DEV_ERR_COMPRESSED, b);
       nres = 0;
     } else if (nres == 0 || static_cast<uint64_t>(nres) * 4 + 4 > size) { dev_fail(J, DEV_ERR_BAD_BLOCK, b); nres = 0; }
-    {
-      // one atomic per (warp, run): consecutive blocks almost always belong to the same file
-      const uint32_t active = __activemask();
-      const uint32_t peers = __match_any_sync(active, ri_);
-      const uint32_t sum = __reduce_add_sync(peers, nres);
-      if (lane_id() == __ffs(peers) - 1 && sum) atomicAdd(&restart_sum[ri_], static_cast<unsigned long long>(sum));
-    }
     if (nres == 0) continue;
-    // The first interval of every 16th block is walked as well: the longest key met is the host's guess for the
-    // record stride (a longer key inside k_ingest only costs a second attempt with the widest stride).
+    // entries of the block = (restarts - 1) full intervals + the last interval, whose headers are walked here
+    {
+      const uint32_t restarts_off = size - 4 - 4 * nres;
+      uint32_t p = ldg_u32_unaligned(blk + restarts_off + 4 * (nres - 1));
+      const uint32_t end = restarts_off;
+      uint32_t n = 0, klen = 0;
+      bool ok = p <= end;
+      while (ok && p < end) {
+        if (run.key_encoding == 2) {
+          TspHeader th; uint32_t nk, ms, ml;
+          const int h = parse_entry_header_tsp(blk + p, end - p, &th);
+          ok = h && tsp_key_layout(th, klen, &nk, &ms, &ml);
+          if (ok) { klen = nk; p += h + th.ns1 + th.ns2 + th.vlen; n++; }
+        } else {
+          uint32_t shared, non_shared, vlen;
+          const int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
+          ok = h != 0;
+          if (ok) { p += h + non_shared + vlen; n++; }
+        }
+      }
+      if (!ok || p != end || n == 0 || n > 0xffff || nres - 1 > 0xffff) { dev_fail(J, DEV_ERR_BAD_ENTRY, b); n = 0; }
+      run.blk_count[b] = ((nres - 1) << 16) | n;          // resolved by k_block_counts once the restart interval is known
+    }
+    // The first interval of a block with two intervals gives the restart interval; that of every 16th block is walked
+    // as well: the longest key met is the host's guess for the record stride (a longer key inside k_ingest only costs a
+    // second attempt with the widest stride).
     if ((nres >= 2 && __ldcg(&J->restart_interval[ri_]) == 0) || (nres >= 2 && (b & 15) == 0)) {
       // walk the first interval's headers (either encoding is delimited by the second restart offset)
       const uint32_t restarts_off = size - 4 - 4 * nres;
@@ -137,7 +155,19 @@ __global__ void __launch_bounds__(256) k_restart_probe(const RunView* runs, cons
   }
 }
 
-struct IngEntry { uint16_t estart, vstart; uint32_t vlen; };    // offsets inside the block
+// blk_count[b] = full intervals x restart interval + entries of the last interval (then scanned per file)
+__global__ void __launch_bounds__(256) k_block_counts(const RunView* runs, const uint32_t* blk_base, int k, JobDev* J) {
+  const uint32_t total = blk_base[k];
+  for (uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x; gb < total; gb += gridDim.x * blockDim.x) {
+    int r = 0;
+    while (blk_base[r + 1] <= gb) r++;
+    const uint32_t b = gb - blk_base[r];
+    const uint32_t v = runs[r].blk_count[b];
+    runs[r].blk_count[b] = (v >> 16) * J->restart_interval[r] + (v & 0xffff);
+  }
+}
+
+struct IngEntry { uint16_t estart, kstart, vstart, vlen, shared, klen; };    // offsets inside the block (a block is at most ING_BUF bytes), key delta geometry
 
 // raw CRC32C step functions over the lane's private copy of the tables: tabs[(t * 256 + e) * ING_REP + copy]
 #define ING_TAB(t, e) tabs[(((t) << 8) + (e)) * ING_REP + copy]
@@ -167,14 +197,21 @@ __device__ __forceinline__ uint32_t ing_crc_span(const uint32_t* tabs, uint32_t 
 }
 #undef ING_TAB
 
-__global__ void __launch_bounds__(ING_THREADS, 3) k_ingest(IngestView V, JobDev* J) {
+// What the producer thread prepares for a block before its bytes are requested.
+struct IngBlk { unsigned long long boff; uint32_t gb, run, b, size, mis, span, valid; };
+
+__global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev* J) {
   extern __shared__ __align__(16) uint8_t ing_smem[];
-  uint8_t* buf = ing_smem + 16;                                               // 16 B front pad (walk 2 reads up to 12 B in front of the block), ING_BUF, 16 B back pad
-  uint32_t* tabs = reinterpret_cast<uint32_t*>(ing_smem + ING_BUF + 32);      // 4 * 256 * ING_REP words
-  IngEntry* etab = reinterpret_cast<IngEntry*>(tabs + 4 * 256 * ING_REP);     // ING_MAXE
-  uint32_t* ecrc = reinterpret_cast<uint32_t*>(etab + ING_MAXE);              // ING_MAXE value CRCs
-  __shared__ __align__(8) unsigned long long bar;
-  __shared__ uint32_t sh_gb, sh_n, sh_base, sh_bad, sh_crc_acc;
+  // two staging buffers (16 B front pad: walk 2 reads up to 12 B in front of a block; 16 B back pad), the CRC tables,
+  // the entry table of the block being processed
+  uint8_t* bufs[2] = {ing_smem + 16, ing_smem + 16 + ING_BUF + 32};
+  uint32_t* tabs = reinterpret_cast<uint32_t*>(ing_smem + 2 * (ING_BUF + 32));        // 4 * 256 * ING_REP words
+  IngEntry* etab = reinterpret_cast<IngEntry*>(tabs + 4 * 256 * ING_REP);             // ING_MAXE
+  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ IngBlk sh_blk[2];                   // per stage: the block whose bytes are (being) staged there
+  __shared__ IngBlk sh_batch[ING_BATCH];         // claimed, not yet requested
+  __shared__ uint32_t sh_batch_pos, sh_batch_n;
+  __shared__ uint32_t sh_bad, sh_crc_acc;
   __shared__ int sh_fb;
   __shared__ uint32_t sh_wsum[ING_THREADS / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -184,53 +221,77 @@ __global__ void __launch_bounds__(ING_THREADS, 3) k_ingest(IngestView V, JobDev*
 #pragma unroll
     for (int c = 0; c < ING_REP; c++) tabs[i * ING_REP + c] = v;
   }
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
   const uint32_t total_blocks = V.blk_base[V.k];
   const int S = V.S;
-  uint32_t parity = 0;
-
-  for (;;) {
-    if (threadIdx.x == 0) {
-      sh_gb = atomicAdd(V.ticket, 1u);
-      sh_bad = 0; sh_crc_acc = 0; sh_fb = 0;
-    }
-    __syncthreads();
-    const uint32_t gb = sh_gb;
-    if (gb >= total_blocks) break;
-    int run_idx = 0;
-    while (V.blk_base[run_idx + 1] <= gb) run_idx++;
-    const RunView& run = V.runs[run_idx];
-    const uint32_t run_first = V.blk_base[run_idx];
-    const uint32_t b = gb - run_first;
-    const uint64_t boff = run.blk_off[b];
-    const uint32_t size = run.blk_size[b];
-    const uint8_t* gsrc = run.data + boff;
-    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gsrc) & 15);
-    const uint32_t span = (mis + size + 5 + 15) & ~15u;
-    // not for this kernel: the host switches to the general path
-    const bool unfit = span > ING_BUF || run.key_encoding != 1;
-    if (unfit) {
-      // results are discarded once the fallback flag is up; the look-back chain only has to stay alive
-      if (threadIdx.x == 0) {
-        atomicMax(&J->ingest_fallback, ING_FALLBACK_GENERAL);
-        *reinterpret_cast<volatile unsigned long long*>(&V.status[gb]) = 2ull << 32;
+  // The producer (the last thread: it has walk or CRC work only in blocks with >= 128 intervals / entries) keeps one
+  // block ahead: it claims ING_BATCH consecutive blocks per atomic, resolves their handles, and requests the bytes of
+  // the next block into the other staging buffer while the CTA works on the current one — the ticket, the handle
+  // loads and the HBM round trip of the bulk copy all hide behind compute.
+  const bool producer = threadIdx.x == blockDim.x - 1;
+  auto request_next = [&](int stage) {           // producer only
+    IngBlk nb; nb.valid = 0;
+    for (;;) {
+      if (sh_batch_pos == sh_batch_n) {
+        const uint32_t g0 = atomicAdd(V.ticket, static_cast<uint32_t>(ING_BATCH));
+        uint32_t n = 0;
+        for (; n < ING_BATCH && g0 + n < total_blocks; n++) {
+          const uint32_t gb = g0 + n;
+          int r = 0;
+          while (V.blk_base[r + 1] <= gb) r++;
+          const RunView& run = V.runs[r];
+          IngBlk x;
+          x.gb = gb; x.run = static_cast<uint32_t>(r); x.b = gb - V.blk_base[r];
+          x.boff = run.blk_off[x.b]; x.size = run.blk_size[x.b];
+          const uint8_t* gsrc = run.data + x.boff;
+          x.mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gsrc) & 15);
+          x.span = (x.mis + x.size + 5 + 15) & ~15u;
+          x.valid = 1;
+          sh_batch[n] = x;
+        }
+        sh_batch_pos = 0; sh_batch_n = n;
+        if (n == 0) break;                         // nothing left
       }
-      __syncthreads();
-      continue;
+      nb = sh_batch[sh_batch_pos++];
+      // not for this kernel (the host switches to the general path): nothing to stage, take the next one
+      if (nb.span > ING_BUF || V.runs[nb.run].key_encoding != 1) { atomicMax(&J->ingest_fallback, ING_FALLBACK_GENERAL); nb.valid = 0; continue; }
+      break;
     }
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(&bar, span);
-      bulk_g2s(buf, gsrc - mis, span, &bar);
+    sh_blk[stage] = nb;
+    if (nb.valid) {
+      mbar_expect_tx(&bars[stage], nb.span);
+      bulk_g2s(bufs[stage], V.runs[nb.run].data + nb.boff - nb.mis, nb.span, &bars[stage]);
     }
-    mbar_wait(&bar, parity);
-    parity ^= 1;
-    const uint8_t* blk = buf + mis;
+  };
+  if (producer) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sh_batch_pos = 0; sh_batch_n = 0;
+    request_next(0);
+  }
+  __syncthreads();
+  uint32_t phases = 0;                           // bit s: the parity of staging buffer s's next mbarrier phase
 
-    // ---- walk 1: lanes own restart intervals; entry table, counts, validation
+  for (int stage = 0;; stage ^= 1) {
+    if (threadIdx.x == 0) { sh_bad = 0; sh_crc_acc = 0; sh_fb = 0; }
+    // the other buffer was released by the barrier that ended the previous iteration
+    if (producer) request_next(stage ^ 1);
+    const IngBlk cur = sh_blk[stage];              // written before the previous barrier (or the prologue)
+    if (!cur.valid) break;
+    mbar_wait(&bars[stage], (phases >> stage) & 1);
+    phases ^= 1u << stage;
+    const uint32_t gb = cur.gb;
+    const int run_idx = static_cast<int>(cur.run);
+    const RunView& run = V.runs[run_idx];
+    const uint32_t b = cur.b;
+    const uint64_t boff = cur.boff;
+    const uint32_t size = cur.size;
+    const uint32_t mis = cur.mis;
+    const uint8_t* blk = bufs[stage] + mis;
+    (void)gb;
+    __syncthreads();                               // per-block shared words are reset, sh_blk[stage ^ 1] is published
+
+    // ---- walk: threads own restart intervals and parse the entry headers (the only serial part of a block: an
+    // entry's position depends on its predecessors' lengths); entry table, counts, validation
     const uint32_t nres = ld_u32_unaligned(blk + size - 4);
     const uint32_t ri = J->restart_interval[run_idx] ? J->restart_interval[run_idx] : 0xffffffffu;   // 0: every block has one interval
     uint32_t bad = 0;
@@ -254,8 +315,10 @@ __global__ void __launch_bounds__(ING_THREADS, 3) k_ingest(IngestView V, JobDev*
           if (klen < 8) { bad = DEV_ERR_SHORT_KEY; break; }
           my_maxk = max(my_maxk, klen);
           const uint64_t slot = slot0 + n;
-          if (slot >= ING_MAXE) { fallback = ING_FALLBACK_GENERAL; break; }
-          IngEntry e; e.estart = static_cast<uint16_t>(p); e.vstart = static_cast<uint16_t>(p + h + non_shared); e.vlen = vlen;
+          if (slot >= ING_MAXE || klen > 16 * ING_NVI) { fallback = ING_FALLBACK_GENERAL; break; }
+          IngEntry e;
+          e.estart = static_cast<uint16_t>(p); e.kstart = static_cast<uint16_t>(p + h); e.vstart = static_cast<uint16_t>(p + h + non_shared);
+          e.vlen = static_cast<uint16_t>(vlen); e.shared = static_cast<uint16_t>(shared); e.klen = static_cast<uint16_t>(klen);
           etab[slot] = e;
           p += h + non_shared + vlen;
           n++;
@@ -267,8 +330,7 @@ __global__ void __launch_bounds__(ING_THREADS, 3) k_ingest(IngestView V, JobDev*
         my_n += n;
       }
     }
-    if (my_maxk > 16 * ING_NVI) fallback = ING_FALLBACK_GENERAL;
-    else if (my_maxk > static_cast<uint32_t>(S) - 8) fallback = max(fallback, ING_FALLBACK_WIDER);      // user key longer than S - 16
+    if (!fallback && my_maxk > static_cast<uint32_t>(S) - 8) fallback = ING_FALLBACK_WIDER;      // user key longer than S - 16
     if (bad) atomicMax(&sh_bad, bad);
     if (fallback) { atomicMax(&J->ingest_fallback, fallback); atomicMax(&sh_fb, fallback); }
     // a flag raised by another CTA: this block's results are discarded anyway (one uniform decision per CTA)
@@ -282,159 +344,119 @@ __global__ void __launch_bounds__(ING_THREADS, 3) k_ingest(IngestView V, JobDev*
 #pragma unroll
     for (int q = 0; q < ING_THREADS / 32; q++) n_ent += sh_wsum[q];
     if (sh_bad || sh_fb) n_ent = 0;
-    // ---- publish this block's count, so that successors can look back while the CRCs are computed
-    if (threadIdx.x == 0) {
-      const unsigned long long flag = gb == run_first ? 2ull : 1ull;
-      *reinterpret_cast<volatile unsigned long long*>(&V.status[gb]) = (flag << 32) | n_ent;
-    }
+    // the block's entry base and count were fixed by the probe + scan; they must agree with what the walk found
+    const uint32_t base = run.blk_count[b];
+    const uint32_t expect = ((b + 1 < run.nb) ? run.blk_count[b + 1] : V.totals[run_idx]) - base;
+    if (n_ent != expect && !sh_bad && !sh_fb) { if (threadIdx.x == 0) dev_fail(J, DEV_ERR_IRREGULAR_RESTARTS, b); n_ent = 0; }
 
-    // ---- CRCs: one thread per entry
+    // ---- one thread per entry: the internal key (own delta + the prefix bytes inherited from earlier entries of
+    // the interval), the record, the value's CRC and the entry's share of the block checksum
     const uint32_t L = size + 1;                       // contents + type byte
-    uint32_t acc = 0;
+    const bool filtered = run.ht_filter != 0xfffffffffffffffeull || V.range;
+    unsigned long long acc = 0;                        // XOR of unreduced carry-less products
     for (uint32_t e = threadIdx.x; e < n_ent; e += blockDim.x) {
       const IngEntry en = etab[e];
-      const uint32_t vc = ing_crc_span(tabs, copy, 0u, blk + en.vstart, en.vlen);
-      ecrc[e] = vc;
+      uint4 kv[ING_NVI];
+#pragma unroll
+      for (int w = 0; w < ING_NVI; w++) kv[w] = make_uint4(0, 0, 0, 0);
+      // key bytes [a, z) come from the delta of an entry whose delta starts at key offset a (its `shared`)
+      auto take = [&](uint32_t kstart, uint32_t a, uint32_t z) {
+#pragma unroll
+        for (int w = 0; w < ING_NVI; w++) {
+          const int lo = 16 * w;
+          if (lo + 16 <= static_cast<int>(a) || lo >= static_cast<int>(z)) continue;
+          // 16 delta bytes starting at blk + kstart + lo - a (any alignment, shared memory; up to 15 bytes in front of the delta)
+          const uint8_t* src = blk + kstart + lo - static_cast<int>(a);
+          const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3);
+          const uint32_t* sa = reinterpret_cast<const uint32_t*>(src - sh);
+          const uint32_t w0 = sa[0], w1 = sa[1], w2 = sa[2], w3 = sa[3], w4 = sa[4];
+          const uint32_t bits = sh * 8;
+          const uint4 nw = make_uint4(__funnelshift_r(w0, w1, bits), __funnelshift_r(w1, w2, bits), __funnelshift_r(w2, w3, bits), __funnelshift_r(w3, w4, bits));
+          const uint4 below = low_bytes_mask16(static_cast<int>(a) - lo), upto = low_bytes_mask16(static_cast<int>(z) - lo);
+          kv[w].x |= nw.x & upto.x & ~below.x;
+          kv[w].y |= nw.y & upto.y & ~below.y;
+          kv[w].z |= nw.z & upto.z & ~below.z;
+          kv[w].w |= nw.w & upto.w & ~below.w;
+        }
+      };
+      take(en.kstart, en.shared, en.klen);
+      // inherited bytes [0, shared): walking back, an entry contributes the bytes between its own `shared` and the
+      // lowest `shared` met so far (the restart entry has shared = 0 and ends the walk; the walk validated all that)
+      {
+        uint32_t need = en.shared;
+        for (uint32_t j = e; need; ) {
+          j--;
+          const uint32_t sj = etab[j].shared;
+          if (sj < need) { take(etab[j].kstart, sj, need); need = sj; }
+        }
+      }
+      const uint32_t klen = en.klen, ulen = klen - 8, vlen = en.vlen;
+      // suffix = internal-key bytes [ulen, ulen + 8)
+      uint4 va = kv[0], vb = kv[1];
+#pragma unroll
+      for (int w = 1; w < ING_NVI; w++) if (static_cast<int>(ulen >> 4) == w) { va = kv[w]; vb = (w + 1 < ING_NVI) ? kv[w + 1] : make_uint4(0, 0, 0, 0); }
+      uint32_t s0, s1;
+      {
+        uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w, w4 = vb.x, w5 = vb.y;
+        const uint32_t sh = ulen & 15, qq = sh >> 2, bits = (sh & 3) * 8;
+        if (qq & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+        if (qq & 2) { w0 = w2; w1 = w3; w2 = w4; }
+        s0 = __funnelshift_r(w0, w1, bits); s1 = __funnelshift_r(w1, w2, bits);
+      }
+      uint8_t flags = 0;
+      if (filtered) {
+        // rare: per-file HybridTime filter / key range of a subcompaction — the user key as bytes
+        __align__(16) uint8_t kb[16 * ING_NVI];
+#pragma unroll
+        for (int w = 0; w < ING_NVI; w++) reinterpret_cast<uint4*>(kb)[w] = kv[w];
+        if (run.ht_filter != 0xfffffffffffffffeull) {
+          const uint32_t htl = doc_ht_len_from_end(kb, ulen);
+          uint64_t ht;
+          if (htl && doc_ht_decode(kb + ulen - htl, htl, &ht) && ht > run.ht_filter) flags |= REC_F_HT_FILTERED;
+        }
+        if (V.range) {
+          if (V.range->lower_len && cmp_raw(kb, ulen, V.range->lower, V.range->lower_len) < 0) flags |= REC_F_OUT_OF_RANGE;
+          if (V.range->upper_len && cmp_raw(kb, ulen, V.range->upper, V.range->upper_len) >= 0) flags |= REC_F_OUT_OF_RANGE;
+        }
+      }
+      uint8_t* rec = run.rec + static_cast<size_t>(base + e) * S;
+      const int key_vecs = (S - 16) >> 4;
+#pragma unroll
+      for (int w = 0; w < ING_NVI; w++) {
+        if (w < key_vecs) {
+          const uint4 m = low_bytes_mask16(static_cast<int>(ulen) - 16 * w);
+          reinterpret_cast<uint4*>(rec)[w] = make_uint4(kv[w].x & m.x, kv[w].y & m.y, kv[w].z & m.z, kv[w].w & m.w);
+        }
+      }
+      const uint8_t vfirst = vlen ? blk[en.vstart] : 0;
+      uint4 tr;
+      tr.x = s0; tr.y = s1;
+      tr.z = ulen | (static_cast<uint32_t>(vfirst) << 16) | (static_cast<uint32_t>(flags) << 24);
+      tr.w = vlen;
+      *reinterpret_cast<uint4*>(rec + S - 16) = tr;
+      // CRCs
+      const uint32_t vc = ing_crc_span(tabs, copy, 0u, blk + en.vstart, vlen);
+      run.val_off[base + e] = boff + en.vstart;
+      run.val_crc[base + e] = vc;
       if (V.verify) {
         const uint32_t gc = ing_crc_span(tabs, copy, 0u, blk + en.estart, en.vstart - en.estart);
-        const uint32_t vend = en.vstart + en.vlen;
-        uint32_t E = gc ? crc_mulmod(__ldg(&g_crc_xpow8[en.vlen]), gc) : 0u;      // en.vlen < 64 K: inside the table
-        E ^= vc;
-        if (E) acc ^= crc_mulmod(__ldg(&g_crc_xpow8[L - vend]), E);
+        // gap * x^(8 (bytes behind the gap)) + value * x^(8 (bytes behind the value)), unreduced (L < 64 K: inside the table)
+        acc ^= crc_clmul(gc, __ldg(&g_crc_xpow8[L - en.vstart])) ^ crc_clmul(vc, __ldg(&g_crc_xpow8[L - en.vstart - vlen]));
       }
     }
     if (V.verify && n_ent) {
-      acc = __reduce_xor_sync(0xffffffffu, acc);
-      if (lane == 0 && acc) atomicXor(&sh_crc_acc, acc);
+      uint32_t a32 = crc_clmul_reduce(acc, [&](uint32_t x) { return tabs[x * ING_REP + copy]; });
+      a32 = __reduce_xor_sync(0xffffffffu, a32);
+      if (lane == 0 && a32) atomicXor(&sh_crc_acc, a32);
       __syncthreads();
       if (threadIdx.x == 0) {
         // tail: restart array, restart count, type byte; then the 0xffffffff initial register and the final complement
         const IngEntry last = etab[n_ent - 1];
-        const uint32_t tail0 = last.vstart + last.vlen;
+        const uint32_t tail0 = static_cast<uint32_t>(last.vstart) + last.vlen;
         uint32_t r = sh_crc_acc ^ ing_crc_span(tabs, copy, 0u, blk + tail0, L - tail0);
         r ^= crc_mulmod(L <= CRC_XPOW_TABLE ? g_crc_xpow8[L] : crc_xpow_bytes(L, g_crc_x2n), 0xffffffffu);
         const uint32_t crc = crc_mask(~r);
         if (crc != ld_u32_unaligned(blk + size + 1)) dev_fail(J, DEV_ERR_BAD_CRC, b);
-      }
-    }
-
-    // ---- look-back: entries of this file in front of the block
-    if (wid == 0) {
-      unsigned long long excl = 0;
-      if (gb != run_first) {
-        long long hi = static_cast<long long>(gb) - 1;
-        for (;;) {
-          const long long idx = hi - lane;
-          unsigned long long s = (2ull << 32);                                   // in front of the run: prefix 0
-          if (idx >= static_cast<long long>(run_first)) s = *reinterpret_cast<volatile unsigned long long*>(&V.status[idx]);
-          const uint32_t flag = static_cast<uint32_t>(s >> 32);
-          const uint32_t ballot_x = __ballot_sync(0xffffffffu, flag == 0);
-          const uint32_t ballot_p = __ballot_sync(0xffffffffu, flag == 2);
-          const int first_p = ballot_p ? __ffs(ballot_p) - 1 : 32;
-          const uint32_t upto = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
-          if (ballot_x & upto) continue;                                        // a needed predecessor has not published yet
-          const uint32_t contrib = lane <= first_p ? static_cast<uint32_t>(s) : 0u;
-          excl += __reduce_add_sync(0xffffffffu, contrib);
-          if (first_p < 32) break;
-          hi -= 32;
-        }
-        if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&V.status[gb]) = (2ull << 32) | ((excl + n_ent) & 0xffffffffull);
-      }
-      if (lane == 0) {
-        sh_base = static_cast<uint32_t>(excl);
-        if (gb + 1 == V.blk_base[run_idx + 1]) V.totals[run_idx] = static_cast<uint32_t>(excl + n_ent);
-        if (excl + n_ent > V.cap[run_idx]) { dev_fail(J, DEV_ERR_BAD_BLOCK, b); sh_n = 0; } else sh_n = n_ent;
-      }
-    }
-    __syncthreads();
-    const uint32_t base = sh_base;
-    const uint32_t n_out = sh_n;
-    // value offsets and value CRCs: coalesced
-    for (uint32_t e = threadIdx.x; e < n_out; e += blockDim.x) {
-      run.val_off[base + e] = boff + etab[e].vstart;
-      run.val_crc[base + e] = ecrc[e];
-    }
-    // ---- walk 2: rebuild the internal keys in registers, write the records
-    if (n_out) {
-      for (uint32_t r = threadIdx.x; r < nres; r += blockDim.x) {
-        uint32_t p = ld_u32_unaligned(blk + restarts_off + 4 * r);
-        const uint32_t end = (r + 1 < nres) ? ld_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
-        uint32_t idx = base + r * (ri == 0xffffffffu ? 0u : ri);
-        uint4 kv[ING_NVI];
-#pragma unroll
-        for (int w = 0; w < ING_NVI; w++) kv[w] = make_uint4(0, 0, 0, 0);
-        while (p < end) {
-          uint32_t shared, non_shared, vlen;
-          const int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
-          p += h;
-          const uint32_t klen = shared + non_shared;
-          const uint32_t ulen = klen - 8;
-#pragma unroll
-          for (int w = 0; w < ING_NVI; w++) {
-            const int lo = 16 * w;
-            if (lo + 16 <= static_cast<int>(shared)) continue;
-            if (lo >= static_cast<int>(klen)) { kv[w] = make_uint4(0, 0, 0, 0); continue; }
-            // 16 key-delta bytes starting at blk + p + lo - shared (any alignment, shared memory)
-            const uint8_t* src = blk + p + lo - static_cast<int>(shared);
-            const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3);
-            const uint32_t* sa = reinterpret_cast<const uint32_t*>(src - sh);
-            const uint32_t w0 = sa[0], w1 = sa[1], w2 = sa[2], w3 = sa[3], w4 = sa[4];
-            const uint32_t bits = sh * 8;
-            const uint4 nw = make_uint4(__funnelshift_r(w0, w1, bits), __funnelshift_r(w1, w2, bits), __funnelshift_r(w2, w3, bits), __funnelshift_r(w3, w4, bits));
-            const uint4 keep = low_bytes_mask16(static_cast<int>(shared) - lo);
-            const uint4 valid = low_bytes_mask16(static_cast<int>(klen) - lo);
-            kv[w].x = (kv[w].x & keep.x) | (nw.x & ~keep.x & valid.x);
-            kv[w].y = (kv[w].y & keep.y) | (nw.y & ~keep.y & valid.y);
-            kv[w].z = (kv[w].z & keep.z) | (nw.z & ~keep.z & valid.z);
-            kv[w].w = (kv[w].w & keep.w) | (nw.w & ~keep.w & valid.w);
-          }
-          p += non_shared;
-          // suffix = internal-key bytes [ulen, ulen + 8)
-          uint4 va = kv[0], vb = kv[1];
-#pragma unroll
-          for (int w = 1; w < ING_NVI; w++) if (static_cast<int>(ulen >> 4) == w) { va = kv[w]; vb = (w + 1 < ING_NVI) ? kv[w + 1] : make_uint4(0, 0, 0, 0); }
-          uint32_t s0, s1;
-          {
-            uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w, w4 = vb.x, w5 = vb.y;
-            const uint32_t sh = ulen & 15, qq = sh >> 2, bits = (sh & 3) * 8;
-            if (qq & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
-            if (qq & 2) { w0 = w2; w1 = w3; w2 = w4; }
-            s0 = __funnelshift_r(w0, w1, bits); s1 = __funnelshift_r(w1, w2, bits);
-          }
-          uint8_t flags = 0;
-          if (run.ht_filter != 0xfffffffffffffffeull || V.range) {
-            // rare: per-file HybridTime filter / key range of a subcompaction — the user key as bytes
-            __align__(16) uint8_t kb[16 * ING_NVI];
-#pragma unroll
-            for (int w = 0; w < ING_NVI; w++) reinterpret_cast<uint4*>(kb)[w] = kv[w];
-            if (run.ht_filter != 0xfffffffffffffffeull) {
-              const uint32_t htl = doc_ht_len_from_end(kb, ulen);
-              uint64_t ht;
-              if (htl && doc_ht_decode(kb + ulen - htl, htl, &ht) && ht > run.ht_filter) flags |= REC_F_HT_FILTERED;
-            }
-            if (V.range) {
-              if (V.range->lower_len && cmp_raw(kb, ulen, V.range->lower, V.range->lower_len) < 0) flags |= REC_F_OUT_OF_RANGE;
-              if (V.range->upper_len && cmp_raw(kb, ulen, V.range->upper, V.range->upper_len) >= 0) flags |= REC_F_OUT_OF_RANGE;
-            }
-          }
-          uint8_t* rec = run.rec + static_cast<size_t>(idx) * S;
-          const int key_vecs = (S - 16) >> 4;
-#pragma unroll
-          for (int w = 0; w < ING_NVI; w++) {
-            if (w < key_vecs) {
-              const uint4 m = low_bytes_mask16(static_cast<int>(ulen) - 16 * w);
-              reinterpret_cast<uint4*>(rec)[w] = make_uint4(kv[w].x & m.x, kv[w].y & m.y, kv[w].z & m.z, kv[w].w & m.w);
-            }
-          }
-          const uint8_t vfirst = vlen ? blk[p] : 0;
-          uint4 tr;
-          tr.x = s0; tr.y = s1;
-          tr.z = ulen | (static_cast<uint32_t>(vfirst) << 16) | (static_cast<uint32_t>(flags) << 24);
-          tr.w = vlen;
-          *reinterpret_cast<uint4*>(rec + S - 16) = tr;
-          p += vlen;
-          idx++;
-        }
       }
     }
     __syncthreads();        // every read of the staging buffer is done before the next bulk copy lands in it
