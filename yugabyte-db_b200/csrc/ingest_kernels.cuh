@@ -34,15 +34,16 @@
 
 namespace ybgpu {
 
-constexpr int ING_THREADS = 128;
-constexpr uint32_t ING_BUF = 36 * 1024;       // staged bytes per block: contents + trailer + alignment slack
+constexpr int ING_CONSUMERS = 128;            // warps 0-3: one thread per entry
+constexpr int ING_THREADS = 192;              // + warp 4: walker (entry headers), warp 5: producer (tickets, handles, bulk copies)
+constexpr uint32_t ING_BUF = 34304;           // staged bytes per block (33.5 KB): contents + trailer + alignment slack
 constexpr int ING_MAXE = 512;                 // entries per block
 constexpr int ING_REP = 8;                    // replication of the CRC tables
 constexpr int ING_NVI = 4;                    // internal keys up to 64 bytes
-constexpr int ING_BATCH = 4;                  // blocks claimed per ticket
+constexpr int ING_BATCH = 8;                  // blocks claimed per ticket
 constexpr int ING_FALLBACK_WIDER = 1;         // a key does not fit the guessed record stride: once more with the widest
 constexpr int ING_FALLBACK_GENERAL = 2;       // not for this kernel: general path
-constexpr size_t ING_SMEM = 2 * (ING_BUF + 32) + 4 * 256 * ING_REP * 4 + ING_MAXE * 12;
+constexpr size_t ING_SMEM = 2 * (ING_BUF + 32) + 4 * 256 * ING_REP * 4 + 2 * ING_MAXE * 12;
 
 struct IngestView {
   const RunView* runs;
@@ -59,6 +60,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 1-D TMA bulk copy global -> shared; dst, src 16-byte aligned, bytes a multiple of 16
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
@@ -197,23 +201,61 @@ __device__ __forceinline__ uint32_t ing_crc_span(const uint32_t* tabs, uint32_t 
 }
 #undef ING_TAB
 
-// What the producer thread prepares for a block before its bytes are requested.
-struct IngBlk { unsigned long long boff; uint32_t gb, run, b, size, mis, span, valid; };
+// What the producer resolves for a block before it requests the block's bytes.
+struct IngBlk {
+  const uint8_t* gsrc;             // 16-byte aligned start of the bulk copy (mis bytes in front of the block)
+  unsigned long long boff;         // block offset inside the data file
+  uint8_t* rec; uint64_t* val_off; uint32_t* val_crc;
+  unsigned long long ht_filter;
+  uint32_t run, b, size, mis, span;
+  uint32_t base, expect;           // first entry of the block inside its file, entries in the block (probe + scan)
+  uint32_t ri;                     // restart interval of the file (0xffffffff: every block has one interval)
+  uint32_t valid;                  // 0: past the end, 1: staged, 2: not for this kernel (skipped)
+};
 
+// raw CRC of smem bytes [p, p + n) with two independent chains over the two halves of a long span (the look-up
+// latency of one chain no longer bounds a thread), joined by one multiplication
+__device__ __forceinline__ uint32_t ing_crc_span2(const uint32_t* tabs, uint32_t copy, const uint8_t* p, uint32_t n) {
+  if (n < 96) return ing_crc_span(tabs, copy, 0u, p, n);
+  uint32_t c = 0;
+  while (reinterpret_cast<uintptr_t>(p) & 3) { c = ing_crc_byte(tabs, copy, c, *p++); n--; }
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+  const uint32_t nw = n >> 2, h = nw >> 1, h2 = nw - h;      // h <= h2 <= h + 1
+  uint32_t d = 0;
+  for (uint32_t i = 0; i < h; i++) {
+    const uint32_t x = w[i], y = w[h + i];
+    c = ing_crc_word(tabs, copy, c, x);
+    d = ing_crc_word(tabs, copy, d, y);
+  }
+  if (h2 > h) d = ing_crc_word(tabs, copy, d, w[nw - 1]);
+  c = crc_clmul_reduce(crc_clmul(c, __ldg(&g_crc_xpow8[4 * h2])), [&](uint32_t x) { return tabs[x * ING_REP + copy]; }) ^ d;
+  p = reinterpret_cast<const uint8_t*>(w + nw);
+  for (uint32_t i = 0; i < (n & 3); i++) c = ing_crc_byte(tabs, copy, c, p[i]);
+  return c;
+}
+
+// Warp-specialised: nothing a block needs from global memory is fetched by the threads that work on it.
+//   warp 5 (producer): claims ING_BATCH consecutive blocks per atomic, resolves their handles, entry bases and output
+//     pointers (lanes in parallel), and issues one bulk copy per block into a free staging buffer;
+//   warp 4 (walker): parses the entry headers of a staged block — the only serial part, an entry's position
+//     depends on its predecessors' lengths; lanes own restart intervals — into the entry table, validates, and
+//     computes the CRC of the block's tail;
+//   warps 0-3 (consumers): one thread per entry — internal key (own delta + inherited prefix bytes), record, value
+//     CRC, the entry's share of the block checksum.
+// Stages hand over through mbarriers (full -> walked -> empty), so the walker works on block i + 1 and the bulk
+// copy of block i + 2 is in flight while the consumers are on block i; the consumers never meet a CTA-wide barrier.
 __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev* J) {
   extern __shared__ __align__(16) uint8_t ing_smem[];
-  // two staging buffers (16 B front pad: walk 2 reads up to 12 B in front of a block; 16 B back pad), the CRC tables,
-  // the entry table of the block being processed
-  uint8_t* bufs[2] = {ing_smem + 16, ing_smem + 16 + ING_BUF + 32};
+  // two staging buffers (16 B front pad: key deltas are fetched with up to 15 + 3 bytes in front; 16 B back pad),
+  // the CRC tables, two entry tables
+  uint8_t* const buf0 = ing_smem + 16;
   uint32_t* tabs = reinterpret_cast<uint32_t*>(ing_smem + 2 * (ING_BUF + 32));        // 4 * 256 * ING_REP words
-  IngEntry* etab = reinterpret_cast<IngEntry*>(tabs + 4 * 256 * ING_REP);             // ING_MAXE
-  __shared__ __align__(8) unsigned long long bars[2];
-  __shared__ IngBlk sh_blk[2];                   // per stage: the block whose bytes are (being) staged there
+  IngEntry* const etab0 = reinterpret_cast<IngEntry*>(tabs + 4 * 256 * ING_REP);      // 2 * ING_MAXE
+  __shared__ __align__(8) unsigned long long full_bar[2], walked_bar[2], empty_bar[2];
+  __shared__ IngBlk sh_blk[2];                   // per stage: the block staged there
   __shared__ IngBlk sh_batch[ING_BATCH];         // claimed, not yet requested
-  __shared__ uint32_t sh_batch_pos, sh_batch_n;
-  __shared__ uint32_t sh_bad, sh_crc_acc;
-  __shared__ int sh_fb;
-  __shared__ uint32_t sh_wsum[ING_THREADS / 32];
+  __shared__ uint32_t sh_nent[2], sh_tail[2], sh_acc[2], sh_cnt[2];
+  __shared__ uint4 sh_upto[17];                  // sh_upto[n]: 0xff in the first n bytes of a 16-byte vector
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t copy = threadIdx.x & (ING_REP - 1);
   for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
@@ -221,173 +263,219 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
 #pragma unroll
     for (int c = 0; c < ING_REP; c++) tabs[i * ING_REP + c] = v;
   }
+  if (threadIdx.x < 17) sh_upto[threadIdx.x] = low_bytes_mask16(static_cast<int>(threadIdx.x));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&full_bar[s], 1); mbar_init(&walked_bar[s], 1); mbar_init(&empty_bar[s], ING_CONSUMERS / 32);
+      sh_acc[s] = 0; sh_cnt[s] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   const uint32_t total_blocks = V.blk_base[V.k];
   const int S = V.S;
-  // The producer (the last thread: it has walk or CRC work only in blocks with >= 128 intervals / entries) keeps one
-  // block ahead: it claims ING_BATCH consecutive blocks per atomic, resolves their handles, and requests the bytes of
-  // the next block into the other staging buffer while the CTA works on the current one — the ticket, the handle
-  // loads and the HBM round trip of the bulk copy all hide behind compute.
-  const bool producer = threadIdx.x == blockDim.x - 1;
-  auto request_next = [&](int stage) {           // producer only
-    IngBlk nb; nb.valid = 0;
-    for (;;) {
-      if (sh_batch_pos == sh_batch_n) {
-        const uint32_t g0 = atomicAdd(V.ticket, static_cast<uint32_t>(ING_BATCH));
-        uint32_t n = 0;
-        for (; n < ING_BATCH && g0 + n < total_blocks; n++) {
-          const uint32_t gb = g0 + n;
+
+  if (wid == 5) {
+    // ---------------- producer
+    uint32_t uses[2] = {0, 0};
+    int stage = 0;
+    bool more = true;
+    while (more) {
+      uint32_t g0 = 0;
+      if (lane == 0) g0 = atomicAdd(V.ticket, static_cast<uint32_t>(ING_BATCH));
+      g0 = __shfl_sync(0xffffffffu, g0, 0);
+      if (lane < ING_BATCH) {
+        IngBlk x;
+        x.valid = 0;
+        const uint32_t gb = g0 + lane;
+        if (gb < total_blocks) {
           int r = 0;
           while (V.blk_base[r + 1] <= gb) r++;
           const RunView& run = V.runs[r];
-          IngBlk x;
-          x.gb = gb; x.run = static_cast<uint32_t>(r); x.b = gb - V.blk_base[r];
+          x.run = static_cast<uint32_t>(r); x.b = gb - V.blk_base[r];
           x.boff = run.blk_off[x.b]; x.size = run.blk_size[x.b];
-          const uint8_t* gsrc = run.data + x.boff;
-          x.mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gsrc) & 15);
+          const uint8_t* g = run.data + x.boff;
+          x.mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 15);
+          x.gsrc = g - x.mis;
           x.span = (x.mis + x.size + 5 + 15) & ~15u;
+          x.rec = run.rec; x.val_off = run.val_off; x.val_crc = run.val_crc; x.ht_filter = run.ht_filter;
+          x.base = run.blk_count[x.b];
+          x.expect = ((x.b + 1 < run.nb) ? run.blk_count[x.b + 1] : V.totals[r]) - x.base;
+          const uint32_t ri = J->restart_interval[r];
+          x.ri = ri ? ri : 0xffffffffu;
           x.valid = 1;
-          sh_batch[n] = x;
+          // not for this kernel (the host switches to the general path): nothing to stage
+          if (x.span > ING_BUF || run.key_encoding != 1) { atomicMax(&J->ingest_fallback, ING_FALLBACK_GENERAL); x.valid = 2; }
         }
-        sh_batch_pos = 0; sh_batch_n = n;
-        if (n == 0) break;                         // nothing left
+        sh_batch[lane] = x;
       }
-      nb = sh_batch[sh_batch_pos++];
-      // not for this kernel (the host switches to the general path): nothing to stage, take the next one
-      if (nb.span > ING_BUF || V.runs[nb.run].key_encoding != 1) { atomicMax(&J->ingest_fallback, ING_FALLBACK_GENERAL); nb.valid = 0; continue; }
-      break;
+      __syncwarp();
+      if (lane == 0) {
+        for (int n = 0; n < ING_BATCH; n++) {
+          const uint32_t v = sh_batch[n].valid;
+          if (v == 0) { more = false; break; }
+          if (v == 2) continue;
+          if (uses[stage]) mbar_wait(&empty_bar[stage], (uses[stage] - 1) & 1);      // the consumers are done with its previous block
+          uses[stage]++;
+          sh_blk[stage] = sh_batch[n];
+          mbar_expect_tx(&full_bar[stage], sh_batch[n].span);
+          bulk_g2s(buf0 + stage * (ING_BUF + 32), sh_batch[n].gsrc, sh_batch[n].span, &full_bar[stage]);
+          stage ^= 1;
+        }
+        if (g0 + ING_BATCH >= total_blocks) more = false;
+      }
+      more = __shfl_sync(0xffffffffu, more ? 1 : 0, 0) != 0;
+      stage = __shfl_sync(0xffffffffu, stage, 0);
     }
-    sh_blk[stage] = nb;
-    if (nb.valid) {
-      mbar_expect_tx(&bars[stage], nb.span);
-      bulk_g2s(bufs[stage], V.runs[nb.run].data + nb.boff - nb.mis, nb.span, &bars[stage]);
+    if (lane == 0) {                               // end marker for the walker and, through it, the consumers
+      if (uses[stage]) mbar_wait(&empty_bar[stage], (uses[stage] - 1) & 1);
+      sh_blk[stage].valid = 0;
+      mbar_arrive(&full_bar[stage]);
     }
-  };
-  if (producer) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    sh_batch_pos = 0; sh_batch_n = 0;
-    request_next(0);
+    return;
   }
-  __syncthreads();
-  uint32_t phases = 0;                           // bit s: the parity of staging buffer s's next mbarrier phase
 
-  for (int stage = 0;; stage ^= 1) {
-    if (threadIdx.x == 0) { sh_bad = 0; sh_crc_acc = 0; sh_fb = 0; }
-    // the other buffer was released by the barrier that ended the previous iteration
-    if (producer) request_next(stage ^ 1);
-    const IngBlk cur = sh_blk[stage];              // written before the previous barrier (or the prologue)
-    if (!cur.valid) break;
-    mbar_wait(&bars[stage], (phases >> stage) & 1);
-    phases ^= 1u << stage;
-    const uint32_t gb = cur.gb;
-    const int run_idx = static_cast<int>(cur.run);
-    const RunView& run = V.runs[run_idx];
-    const uint32_t b = cur.b;
-    const uint64_t boff = cur.boff;
-    const uint32_t size = cur.size;
-    const uint32_t mis = cur.mis;
-    const uint8_t* blk = bufs[stage] + mis;
-    (void)gb;
-    __syncthreads();                               // per-block shared words are reset, sh_blk[stage ^ 1] is published
-
-    // ---- walk: threads own restart intervals and parse the entry headers (the only serial part of a block: an
-    // entry's position depends on its predecessors' lengths); entry table, counts, validation
-    const uint32_t nres = ld_u32_unaligned(blk + size - 4);
-    const uint32_t ri = J->restart_interval[run_idx] ? J->restart_interval[run_idx] : 0xffffffffu;   // 0: every block has one interval
-    uint32_t bad = 0;
-    if (nres == 0 || static_cast<uint64_t>(nres) * 4 + 4 > size) bad = DEV_ERR_BAD_BLOCK;
-    else if (blk[size] != 0) bad = DEV_ERR_COMPRESSED;
-    const uint32_t restarts_off = bad ? 0 : size - 4 - 4 * nres;
-    uint32_t my_n = 0, my_maxk = 0;
-    int fallback = 0;
-    if (!bad) {
-      for (uint32_t r = threadIdx.x; r < nres; r += blockDim.x) {
-        uint32_t p = ld_u32_unaligned(blk + restarts_off + 4 * r);
-        const uint32_t end = (r + 1 < nres) ? ld_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
-        if (p > end || end > restarts_off) { bad = DEV_ERR_BAD_BLOCK; break; }
-        uint32_t n = 0, klen = 0;
-        const uint64_t slot0 = static_cast<uint64_t>(r) * (ri == 0xffffffffu ? 0u : ri);
-        while (p < end) {
-          uint32_t shared, non_shared, vlen;
-          const int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
-          if (!h || shared > klen || (n == 0 && shared != 0) || static_cast<uint64_t>(p) + h + non_shared + vlen > end) { bad = DEV_ERR_BAD_ENTRY; break; }
-          klen = shared + non_shared;
-          if (klen < 8) { bad = DEV_ERR_SHORT_KEY; break; }
-          my_maxk = max(my_maxk, klen);
-          const uint64_t slot = slot0 + n;
-          if (slot >= ING_MAXE || klen > 16 * ING_NVI) { fallback = ING_FALLBACK_GENERAL; break; }
-          IngEntry e;
-          e.estart = static_cast<uint16_t>(p); e.kstart = static_cast<uint16_t>(p + h); e.vstart = static_cast<uint16_t>(p + h + non_shared);
-          e.vlen = static_cast<uint16_t>(vlen); e.shared = static_cast<uint16_t>(shared); e.klen = static_cast<uint16_t>(klen);
-          etab[slot] = e;
-          p += h + non_shared + vlen;
-          n++;
-        }
-        if (bad || fallback) break;
-        // every interval but the last of a block is full (BlockBuilder restarts every block_restart_interval entries)
-        if (r + 1 < nres) { if (n != ri) { bad = DEV_ERR_IRREGULAR_RESTARTS; break; } }
-        else if (n > ri || n == 0) { bad = n ? DEV_ERR_IRREGULAR_RESTARTS : DEV_ERR_BAD_ENTRY; break; }
-        my_n += n;
+  if (wid == 4) {
+    // ---------------- walker
+    uint32_t maxk = 0;
+    for (uint32_t it = 0;; it++) {
+      const int stage = it & 1;
+      mbar_wait(&full_bar[stage], (it >> 1) & 1);
+      const uint32_t valid = sh_blk[stage].valid;
+      if (!valid) {
+        if (lane == 0) { sh_nent[stage] = 0xffffffffu; mbar_arrive(&walked_bar[stage]); }
+        break;
       }
+      const uint32_t size = sh_blk[stage].size, b = sh_blk[stage].b, ri = sh_blk[stage].ri, expect = sh_blk[stage].expect;
+      const uint8_t* blk = buf0 + stage * (ING_BUF + 32) + sh_blk[stage].mis;
+      IngEntry* etab = etab0 + stage * ING_MAXE;
+      const uint32_t nres = ld_u32_unaligned(blk + size - 4);
+      uint32_t bad = 0;
+      if (nres == 0 || static_cast<uint64_t>(nres) * 4 + 4 > size) bad = DEV_ERR_BAD_BLOCK;
+      else if (blk[size] != 0) bad = DEV_ERR_COMPRESSED;
+      const uint32_t restarts_off = bad ? 0 : size - 4 - 4 * nres;
+      uint32_t my_n = 0;
+      int fallback = 0;
+      if (!bad) {
+        for (uint32_t r = lane; r < nres; r += 32) {
+          uint32_t p = ld_u32_unaligned(blk + restarts_off + 4 * r);
+          const uint32_t end = (r + 1 < nres) ? ld_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
+          if (p > end || end > restarts_off) { bad = DEV_ERR_BAD_BLOCK; break; }
+          uint32_t n = 0, klen = 0;
+          const uint64_t slot0 = static_cast<uint64_t>(r) * (ri == 0xffffffffu ? 0u : ri);
+          while (p < end) {
+            uint32_t shared, non_shared, vlen;
+            const int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
+            if (!h || shared > klen || (n == 0 && shared != 0) || static_cast<uint64_t>(p) + h + non_shared + vlen > end) { bad = DEV_ERR_BAD_ENTRY; break; }
+            klen = shared + non_shared;
+            if (klen < 8) { bad = DEV_ERR_SHORT_KEY; break; }
+            maxk = max(maxk, klen);
+            const uint64_t slot = slot0 + n;
+            if (slot >= ING_MAXE || klen > 16 * ING_NVI) { fallback = ING_FALLBACK_GENERAL; break; }
+            if (klen > static_cast<uint32_t>(S) - 8) fallback = ING_FALLBACK_WIDER;      // user key longer than S - 16: the walk goes on (longest key)
+            IngEntry e;
+            e.estart = static_cast<uint16_t>(p); e.kstart = static_cast<uint16_t>(p + h); e.vstart = static_cast<uint16_t>(p + h + non_shared);
+            e.vlen = static_cast<uint16_t>(vlen); e.shared = static_cast<uint16_t>(shared); e.klen = static_cast<uint16_t>(klen);
+            etab[slot] = e;
+            p += h + non_shared + vlen;
+            n++;
+          }
+          if (bad || fallback == ING_FALLBACK_GENERAL) break;
+          // every interval but the last of a block is full (BlockBuilder restarts every block_restart_interval entries)
+          if (r + 1 < nres) { if (n != ri) { bad = DEV_ERR_IRREGULAR_RESTARTS; break; } }
+          else if (n > ri || n == 0) { bad = n ? DEV_ERR_IRREGULAR_RESTARTS : DEV_ERR_BAD_ENTRY; break; }
+          my_n += n;
+        }
+      }
+      bad = __reduce_max_sync(0xffffffffu, bad);
+      fallback = static_cast<int>(__reduce_max_sync(0xffffffffu, static_cast<uint32_t>(fallback)));
+      uint32_t n_ent = __reduce_add_sync(0xffffffffu, my_n);
+      uint32_t tail = 0;
+      if (lane == 0) {
+        if (bad) dev_fail(J, bad, b);
+        if (fallback) atomicMax(&J->ingest_fallback, fallback);
+        if (bad || fallback) n_ent = 0;
+        // the block's entry count was fixed by the probe + scan; it must agree with what the walk found
+        else if (n_ent != expect) { dev_fail(J, DEV_ERR_IRREGULAR_RESTARTS, b); n_ent = 0; }
+        if (V.verify && n_ent) {
+          // tail: restart array, restart count, type byte; and the 0xffffffff initial register's share
+          const uint32_t L = size + 1;
+          tail = ing_crc_span(tabs, copy, 0u, blk + restarts_off, L - restarts_off);
+          tail ^= crc_clmul_reduce(crc_clmul(L <= CRC_XPOW_TABLE ? __ldg(&g_crc_xpow8[L]) : crc_xpow_bytes(L, g_crc_x2n), 0xffffffffu),
+                                   [&](uint32_t x) { return tabs[x * ING_REP + copy]; });
+        }
+        sh_nent[stage] = n_ent; sh_tail[stage] = tail;
+      }
+      __syncwarp();                                // the lanes' entry table writes are ordered before lane 0's arrive
+      if (lane == 0) mbar_arrive(&walked_bar[stage]);
     }
-    if (!fallback && my_maxk > static_cast<uint32_t>(S) - 8) fallback = ING_FALLBACK_WIDER;      // user key longer than S - 16
-    if (bad) atomicMax(&sh_bad, bad);
-    if (fallback) { atomicMax(&J->ingest_fallback, fallback); atomicMax(&sh_fb, fallback); }
-    // a flag raised by another CTA: this block's results are discarded anyway (one uniform decision per CTA)
-    if (threadIdx.x == 0) { const int g = *reinterpret_cast<volatile int*>(&J->ingest_fallback); if (g) atomicMax(&sh_fb, g); }
-    uint32_t wn = __reduce_add_sync(0xffffffffu, my_n);
-    const uint32_t wk = __reduce_max_sync(0xffffffffu, my_maxk);
-    if (lane == 0) { sh_wsum[wid] = wn; if (wk > __ldcg(&J->max_ikey_len)) atomicMax(&J->max_ikey_len, wk); }
-    __syncthreads();
-    if (sh_bad) { if (threadIdx.x == 0) dev_fail(J, sh_bad, b); }
-    uint32_t n_ent = 0;
-#pragma unroll
-    for (int q = 0; q < ING_THREADS / 32; q++) n_ent += sh_wsum[q];
-    if (sh_bad || sh_fb) n_ent = 0;
-    // the block's entry base and count were fixed by the probe + scan; they must agree with what the walk found
-    const uint32_t base = run.blk_count[b];
-    const uint32_t expect = ((b + 1 < run.nb) ? run.blk_count[b + 1] : V.totals[run_idx]) - base;
-    if (n_ent != expect && !sh_bad && !sh_fb) { if (threadIdx.x == 0) dev_fail(J, DEV_ERR_IRREGULAR_RESTARTS, b); n_ent = 0; }
+    maxk = __reduce_max_sync(0xffffffffu, maxk);
+    if (lane == 0 && maxk > __ldcg(&J->max_ikey_len)) atomicMax(&J->max_ikey_len, maxk);
+    return;
+  }
 
-    // ---- one thread per entry: the internal key (own delta + the prefix bytes inherited from earlier entries of
-    // the interval), the record, the value's CRC and the entry's share of the block checksum
+  // ---------------- consumers
+  const bool ranged = V.range != nullptr;
+  for (uint32_t it = 0;; it++) {
+    const int stage = it & 1;
+    mbar_wait(&walked_bar[stage], (it >> 1) & 1);
+    const uint32_t n_ent = sh_nent[stage];
+    if (n_ent == 0xffffffffu) break;
+    const IngBlk& cur = sh_blk[stage];
+    const uint32_t size = cur.size, base = cur.base;
+    const uint64_t boff = cur.boff;
+    const unsigned long long ht_filter = cur.ht_filter;
+    uint8_t* const rec0 = cur.rec;
+    uint64_t* const val_off = cur.val_off;
+    uint32_t* const val_crc = cur.val_crc;
+    const uint8_t* blk = buf0 + stage * (ING_BUF + 32) + cur.mis;
+    const IngEntry* etab = etab0 + stage * ING_MAXE;
     const uint32_t L = size + 1;                       // contents + type byte
-    const bool filtered = run.ht_filter != 0xfffffffffffffffeull || V.range;
+    const bool filtered = ht_filter != 0xfffffffffffffffeull || ranged;
     unsigned long long acc = 0;                        // XOR of unreduced carry-less products
-    for (uint32_t e = threadIdx.x; e < n_ent; e += blockDim.x) {
+    for (uint32_t e = threadIdx.x; e < n_ent; e += ING_CONSUMERS) {
       const IngEntry en = etab[e];
       uint4 kv[ING_NVI];
 #pragma unroll
       for (int w = 0; w < ING_NVI; w++) kv[w] = make_uint4(0, 0, 0, 0);
-      // key bytes [a, z) come from the delta of an entry whose delta starts at key offset a (its `shared`)
-      auto take = [&](uint32_t kstart, uint32_t a, uint32_t z) {
-#pragma unroll
-        for (int w = 0; w < ING_NVI; w++) {
-          const int lo = 16 * w;
-          if (lo + 16 <= static_cast<int>(a) || lo >= static_cast<int>(z)) continue;
-          // 16 delta bytes starting at blk + kstart + lo - a (any alignment, shared memory; up to 15 bytes in front of the delta)
-          const uint8_t* src = blk + kstart + lo - static_cast<int>(a);
-          const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3);
-          const uint32_t* sa = reinterpret_cast<const uint32_t*>(src - sh);
-          const uint32_t w0 = sa[0], w1 = sa[1], w2 = sa[2], w3 = sa[3], w4 = sa[4];
-          const uint32_t bits = sh * 8;
-          const uint4 nw = make_uint4(__funnelshift_r(w0, w1, bits), __funnelshift_r(w1, w2, bits), __funnelshift_r(w2, w3, bits), __funnelshift_r(w3, w4, bits));
-          const uint4 below = low_bytes_mask16(static_cast<int>(a) - lo), upto = low_bytes_mask16(static_cast<int>(z) - lo);
-          kv[w].x |= nw.x & upto.x & ~below.x;
-          kv[w].y |= nw.y & upto.y & ~below.y;
-          kv[w].z |= nw.z & upto.z & ~below.z;
-          kv[w].w |= nw.w & upto.w & ~below.w;
-        }
+      // 16 delta bytes for key offsets [16 w, 16 w + 16) of an entry whose delta starts at key offset a (its `shared`):
+      // any alignment, shared memory; up to 15 + 3 bytes in front of the delta are touched
+      auto fetch = [&](uint32_t kstart, uint32_t a, int w) {
+        const uint8_t* src = blk + kstart + 16 * w - static_cast<int>(a);
+        const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3);
+        const uint32_t* sa = reinterpret_cast<const uint32_t*>(src - sh);
+        const uint32_t w0 = sa[0], w1 = sa[1], w2 = sa[2], w3 = sa[3], w4 = sa[4];
+        const uint32_t bits = sh * 8;
+        return make_uint4(__funnelshift_r(w0, w1, bits), __funnelshift_r(w1, w2, bits), __funnelshift_r(w2, w3, bits), __funnelshift_r(w3, w4, bits));
       };
-      take(en.kstart, en.shared, en.klen);
+      // own delta: key bytes [shared, klen). Bytes in front of `shared` inside its first window are overwritten below,
+      // bytes behind klen are never looked at (the record write masks by the key length)
+#pragma unroll
+      for (int w = 0; w < ING_NVI; w++)
+        if (16 * w + 16 > static_cast<int>(en.shared) && 16 * w < static_cast<int>(en.klen)) kv[w] = fetch(en.kstart, en.shared, w);
       // inherited bytes [0, shared): walking back, an entry contributes the bytes between its own `shared` and the
-      // lowest `shared` met so far (the restart entry has shared = 0 and ends the walk; the walk validated all that)
+      // lowest `shared` met so far (the restart entry has shared = 0 and ends the walk; the walker validated all
+      // that). A contribution overwrites everything below `need` in its windows: what it writes below its own
+      // `shared` is overwritten in turn by the entries further back.
       {
         uint32_t need = en.shared;
         for (uint32_t j = e; need; ) {
           j--;
           const uint32_t sj = etab[j].shared;
-          if (sj < need) { take(etab[j].kstart, sj, need); need = sj; }
+          if (sj < need) {
+            const uint32_t kstart = etab[j].kstart;
+#pragma unroll
+            for (int w = 0; w < ING_NVI; w++) {
+              if (16 * w + 16 <= static_cast<int>(sj) || 16 * w >= static_cast<int>(need)) continue;
+              const uint4 nw = fetch(kstart, sj, w);
+              const uint4 m = sh_upto[min(need - 16 * w, 16u)];
+              kv[w].x = (nw.x & m.x) | (kv[w].x & ~m.x);
+              kv[w].y = (nw.y & m.y) | (kv[w].y & ~m.y);
+              kv[w].z = (nw.z & m.z) | (kv[w].z & ~m.z);
+              kv[w].w = (nw.w & m.w) | (kv[w].w & ~m.w);
+            }
+            need = sj;
+          }
         }
       }
       const uint32_t klen = en.klen, ulen = klen - 8, vlen = en.vlen;
@@ -409,17 +497,17 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
         __align__(16) uint8_t kb[16 * ING_NVI];
 #pragma unroll
         for (int w = 0; w < ING_NVI; w++) reinterpret_cast<uint4*>(kb)[w] = kv[w];
-        if (run.ht_filter != 0xfffffffffffffffeull) {
+        if (ht_filter != 0xfffffffffffffffeull) {
           const uint32_t htl = doc_ht_len_from_end(kb, ulen);
           uint64_t ht;
-          if (htl && doc_ht_decode(kb + ulen - htl, htl, &ht) && ht > run.ht_filter) flags |= REC_F_HT_FILTERED;
+          if (htl && doc_ht_decode(kb + ulen - htl, htl, &ht) && ht > ht_filter) flags |= REC_F_HT_FILTERED;
         }
-        if (V.range) {
+        if (ranged) {
           if (V.range->lower_len && cmp_raw(kb, ulen, V.range->lower, V.range->lower_len) < 0) flags |= REC_F_OUT_OF_RANGE;
           if (V.range->upper_len && cmp_raw(kb, ulen, V.range->upper, V.range->upper_len) >= 0) flags |= REC_F_OUT_OF_RANGE;
         }
       }
-      uint8_t* rec = run.rec + static_cast<size_t>(base + e) * S;
+      uint8_t* rec = rec0 + static_cast<size_t>(base + e) * S;
       const int key_vecs = (S - 16) >> 4;
 #pragma unroll
       for (int w = 0; w < ING_NVI; w++) {
@@ -435,9 +523,9 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
       tr.w = vlen;
       *reinterpret_cast<uint4*>(rec + S - 16) = tr;
       // CRCs
-      const uint32_t vc = ing_crc_span(tabs, copy, 0u, blk + en.vstart, vlen);
-      run.val_off[base + e] = boff + en.vstart;
-      run.val_crc[base + e] = vc;
+      const uint32_t vc = ing_crc_span2(tabs, copy, blk + en.vstart, vlen);
+      val_off[base + e] = boff + en.vstart;
+      val_crc[base + e] = vc;
       if (V.verify) {
         const uint32_t gc = ing_crc_span(tabs, copy, 0u, blk + en.estart, en.vstart - en.estart);
         // gap * x^(8 (bytes behind the gap)) + value * x^(8 (bytes behind the value)), unreduced (L < 64 K: inside the table)
@@ -447,19 +535,20 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
     if (V.verify && n_ent) {
       uint32_t a32 = crc_clmul_reduce(acc, [&](uint32_t x) { return tabs[x * ING_REP + copy]; });
       a32 = __reduce_xor_sync(0xffffffffu, a32);
-      if (lane == 0 && a32) atomicXor(&sh_crc_acc, a32);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        // tail: restart array, restart count, type byte; then the 0xffffffff initial register and the final complement
-        const IngEntry last = etab[n_ent - 1];
-        const uint32_t tail0 = static_cast<uint32_t>(last.vstart) + last.vlen;
-        uint32_t r = sh_crc_acc ^ ing_crc_span(tabs, copy, 0u, blk + tail0, L - tail0);
-        r ^= crc_mulmod(L <= CRC_XPOW_TABLE ? g_crc_xpow8[L] : crc_xpow_bytes(L, g_crc_x2n), 0xffffffffu);
-        const uint32_t crc = crc_mask(~r);
-        if (crc != ld_u32_unaligned(blk + size + 1)) dev_fail(J, DEV_ERR_BAD_CRC, b);
+      if (lane == 0) {
+        if (a32) atomicXor(&sh_acc[stage], a32);
+        __threadfence_block();
+        if (atomicAdd(&sh_cnt[stage], 1u) == ING_CONSUMERS / 32 - 1) {
+          // the last warp of the block: entries + tail + initial register, final complement, against the trailer
+          __threadfence_block();
+          const uint32_t r = atomicExch(&sh_acc[stage], 0u) ^ sh_tail[stage];
+          sh_cnt[stage] = 0;
+          if (crc_mask(~r) != ld_u32_unaligned(blk + size + 1)) dev_fail(J, DEV_ERR_BAD_CRC, cur.b);
+        }
       }
     }
-    __syncthreads();        // every read of the staging buffer is done before the next bulk copy lands in it
+    __syncwarp();                                  // every lane's reads of the stage are done before lane 0 releases it
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
   }
 }
 
