@@ -75,12 +75,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"      // suspended until the phase completes or the hint (ns) expires
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(100000u)
       : "memory");
 }
 
