@@ -167,7 +167,8 @@ enum {
   YBGPU_PATH_GENERAL_DECODE = 2,       /* k_prepass / k_decode_* / k_value_crc (other encodings, long keys, huge blocks) */
   YBGPU_PATH_SNAPPY = 4,               /* compressed input blocks were uncompressed on the GPU */
   YBGPU_PATH_PARTITION_RETRY = 8,      /* the partition was repeated with a smaller sample stride */
-  YBGPU_PATH_ENCODER_V4 = 16           /* block assembler with checksums by CRC linearity */
+  YBGPU_PATH_ENCODER_V4 = 16,          /* block assembler with checksums by CRC linearity */
+  YBGPU_PATH_ENCODER_V5 = 32           /* ... warp per block, no block image (k_encode_v5) */
 };
 
 typedef struct ybgpu_job ybgpu_job;

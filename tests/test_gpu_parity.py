@@ -636,3 +636,26 @@ def test_yield_points(pkg):
     res = pkg.compact_files([(s.meta_view(), s.data_view()) for s in ssts], max_subcompactions=4, max_in_flight=2,
                             block_size=4096, yield_fn=lambda: calls.append(1))
     assert len(calls) >= len(res.outputs) and res.total.num_input_records == 12000
+
+
+@pytest.mark.parametrize("assembler", ["v5", "v4"])
+def test_block_assemblers(pkg, assembler, monkeypatch):
+    """Both block assemblers produce the oracle's bytes: k_encode_v5 (warp per block, the default) and k_encode_v4
+    (CTA per block with a shared-memory image; what runs when a scratch row per lane does not fit, and the A/B switch
+    YBGPU_ENC_V4) — TTL rewrites and tombstoned values (the entries whose bytes are not copied from the inputs), both
+    key encodings, tiny and large blocks, empty values."""
+    if assembler == "v4":
+        monkeypatch.setenv("YBGPU_ENC_V4", "1")
+    want = pkg.PATH_ENCODER_V5 if assembler == "v5" else 0
+    runs = w.random_docdb_runs(77, n_runs=4, n_rows=400)
+    ssts = runs_to_ssts(runs, 1024)
+    for kw in w.param_grid():
+        for enc in (1, 2):
+            job, _ = check(pkg, ssts, block_size=512 if enc == 1 else 8192, output_key_encoding=enc, **kw)
+            assert (job.stats().path_flags & pkg.PATH_ENCODER_V5) == want
+    cfg = o.GenConfig(seed=5, num_rows=4000, cols=2, versions=3, num_files=3, value_len=700, tombstone_per_1024=100)
+    ssts = o.Sst.generate_all(cfg, o.TableOptions(block_size=8192))
+    for bs in (300, 4096, 65536, 1 << 20):
+        check(pkg, ssts, block_size=bs, cutoff_ht=o.ht_from_micros(cfg.base_micros + 1500), filter_policy=1)
+    cfg = o.GenConfig(seed=6, num_rows=3000, cols=1, versions=2, num_files=2, value_len=0)
+    check(pkg, o.Sst.generate_all(cfg, o.TableOptions(block_size=2048)), block_size=2048)

@@ -74,7 +74,7 @@ class JobStats(C.Structure):
 
 
 PHASE_NAMES = ["block_scan", "decode", "partition", "merge_filter", "encode"]
-PATH_FUSED_INGEST, PATH_GENERAL_DECODE, PATH_SNAPPY, PATH_PARTITION_RETRY, PATH_ENCODER_V4 = 1, 2, 4, 8, 16
+PATH_FUSED_INGEST, PATH_GENERAL_DECODE, PATH_SNAPPY, PATH_PARTITION_RETRY, PATH_ENCODER_V4, PATH_ENCODER_V5 = 1, 2, 4, 8, 16, 32
 
 
 class GenConfig(C.Structure):

@@ -1365,6 +1365,146 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_encode_v4(EncView E, int S, 
   }
 }
 
+// ---- warp-per-block assembler (v5) ---------------------------------------------------------------
+// One WARP builds one output block; nothing in the kernel waits on a CTA-wide barrier and there is no block image:
+//   * a lane owns an entry: it writes the bytes that exist nowhere else — header + key delta, a tombstone's 'X', the
+//     prefix of a rewritten value (the entry's "gap") — into its private scratch row, END-aligned to a word (its
+//     length is known beforehand from nr / D) behind zero padding: the gap's raw CRC is then a handful of whole-word
+//     table steps (leading zeros do not move a zero register);
+//   * the warp then walks the round's entries two at a time, one per half-warp: the gap goes scratch -> HBM, the value
+//     HBM -> registers -> HBM as destination-aligned 16-byte chunks (one per lane, two aligned source vectors funnel-
+//     shifted into place), the <= 15 bytes in front of the first / behind the last full chunk as one byte per lane;
+//   * the block checksum is the same GF(2)-linear combination as in v4 — every gap, value and restart-array word
+//     enters as (raw CRC) * x^(8 * bytes behind it), XOR-accumulated unreduced per lane — so no byte of the block is
+//     read back.
+// Shared memory per CTA: the four slicing tables (4 KB) + one scratch row per lane, which leaves the occupancy to the
+// register file (v4: one 36 KB image per CTA, four CTAs per SM, seven CTA barriers per block). Blocks of any size.
+constexpr int ENC5_THREADS = 256;
+__device__ __forceinline__ uint32_t enc5_crc_word(const uint32_t (*tab)[256], uint32_t c, uint32_t w) {
+  c ^= w;
+  return tab[3][c & 0xff] ^ tab[2][(c >> 8) & 0xff] ^ tab[1][(c >> 16) & 0xff] ^ tab[0][c >> 24];
+}
+__device__ __forceinline__ uint32_t enc5_xpow(unsigned long long nbytes) {
+  return nbytes <= CRC_XPOW_TABLE ? __ldg(&g_crc_xpow8[nbytes]) : crc_xpow_bytes(nbytes, g_crc_x2n);
+}
+__device__ __forceinline__ void enc5_store_u32(uint8_t* p, uint32_t v) {
+  p[0] = static_cast<uint8_t>(v); p[1] = static_cast<uint8_t>(v >> 8); p[2] = static_cast<uint8_t>(v >> 16); p[3] = static_cast<uint8_t>(v >> 24);
+}
+
+template <int ENC>
+__global__ void __launch_bounds__(ENC5_THREADS) k_encode_v5(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
+                                                          const unsigned long long* block_off, uint8_t* out, uint32_t G) {
+  extern __shared__ __align__(16) uint8_t v5_smem[];      // tab[4][256], then ENC5_THREADS scratch rows of G bytes
+  uint32_t (*tab)[256] = reinterpret_cast<uint32_t (*)[256]>(v5_smem);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, hl = lane & 15, half = lane >> 4;
+  uint8_t* const wsc = v5_smem + 4096 + static_cast<size_t>(wid) * 32 * G;
+  uint8_t* const sc = wsc + static_cast<size_t>(lane) * G;
+  const uint32_t nwarps = gridDim.x * (ENC5_THREADS / 32);
+  for (uint32_t b = blockIdx.x * (ENC5_THREADS / 32) + wid; b < nblocks; b += nwarps) {
+    const unsigned long long boff = block_off[b];
+    const unsigned long long L = block_off[b + 1] - boff - 4;          // contents + type byte
+    const uint32_t s = block_first[b], e = (b + 1 < nblocks) ? block_first[b + 1] : E.n;
+    const unsigned long long Ps = E.P[s];
+    const unsigned long long Qs = E.QQ[s] - static_cast<unsigned long long>(static_cast<long long>(E.D[s]));
+    const uint32_t tl = (e - 1 - s) >> E.ri_shift;
+    const unsigned long long body = (E.P[e] - Ps) + (E.QQ[s + (tl << E.ri_shift)] - Qs);
+    uint8_t* const blk = out + boff;
+    unsigned long long acc = 0;                  // XOR of unreduced carry-less products
+    for (uint32_t r0 = s; r0 < e; r0 += 32) {
+      const uint32_t j = r0 + lane;
+      unsigned long long eoff = 0, srcp = 0;
+      uint32_t gap_len = 0, copy_len = 0;
+      if (j < e) {
+        const bool restart = ((j - s) & (E.ri - 1)) == 0;
+        eoff = E.P[j] - Ps;
+        if (j > s) { const uint32_t tp = (j - 1 - s) >> E.ri_shift; eoff += E.QQ[s + (tp << E.ri_shift)] - Qs; }
+        const Desc d = E.kept[j];
+        const uint8_t* rec = kept_rec(E, d, S);
+        const RunView& run = E.runs[d.run];
+        const uint32_t idx = d.gid - run.gid_base;
+        const uint8_t* vs = run.data + run.val_off[idx];
+        const uint32_t vlen = d.vlen_out;
+        uint32_t esize = E.nr[j];
+        if (restart) esize += static_cast<uint32_t>(static_cast<int32_t>(E.D[j]));
+        const ValueRewrite* rw = nullptr;
+        copy_len = vlen;
+        if (d.flags & ENT_VAL_TOMBSTONE) copy_len = 0;
+        else if (d.flags & ENT_VAL_REENCODE) { rw = &E.rewrites[d.rewrite_slot]; copy_len = vlen - rw->prefix_len; vs += rw->skip; }
+        gap_len = esize - copy_len;
+        const uint32_t pad = (4u - (gap_len & 3u)) & 3u;
+        *reinterpret_cast<uint32_t*>(sc) = 0;
+        uint8_t* p = emit_entry_key<ENC>(E, S, j, d, rec, kept_suffix(rec, d, S), restart, sc + pad);
+        if (d.flags & ENT_VAL_TOMBSTONE) *p++ = 'X';
+        else if (rw) for (uint32_t i = 0; i < rw->prefix_len; i++) *p++ = rw->prefix[i];
+        uint32_t vcrc = 0;
+        if (copy_len) {
+          if (rw) { for (uint32_t i = 0; i < copy_len; i++) vcrc = tab[0][(vcrc ^ __ldg(vs + i)) & 0xff] ^ (vcrc >> 8); }
+          else vcrc = run.val_crc[idx];
+        }
+        uint32_t gc = 0;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(sc);
+        const uint32_t nw = (pad + gap_len) >> 2;
+        for (uint32_t i = 0; i < nw; i++) gc = enc5_crc_word(tab, gc, w[i]);
+        const unsigned long long gap_end = eoff + gap_len;
+        acc ^= crc_clmul(gc, enc5_xpow(L - gap_end));
+        if (copy_len) acc ^= crc_clmul(vcrc, enc5_xpow(L - gap_end - copy_len));
+        srcp = reinterpret_cast<unsigned long long>(vs);
+        if (restart) {
+          const uint32_t t = (j - s) >> E.ri_shift;
+          const uint32_t o32 = static_cast<uint32_t>(eoff);
+          enc5_store_u32(blk + body + 4ull * t, o32);
+          acc ^= crc_clmul(enc5_crc_word(tab, 0u, o32), enc5_xpow(L - (body + 4ull * t + 4)));
+        }
+      }
+      __syncwarp();
+      const uint32_t nact = min(32u, e - r0);
+#pragma unroll 2
+      for (uint32_t q0 = 0; q0 < nact; q0 += 2) {
+        const uint32_t q = q0 + half;
+        const unsigned long long eoff_q = __shfl_sync(0xffffffffu, eoff, q & 31);
+        const unsigned long long src_q = __shfl_sync(0xffffffffu, srcp, q & 31);
+        const uint32_t gap_q = __shfl_sync(0xffffffffu, gap_len, q & 31);
+        const uint32_t len_q = __shfl_sync(0xffffffffu, copy_len, q & 31);
+        if (q >= nact) continue;
+        uint8_t* gdst = blk + eoff_q;
+        {
+          const uint8_t* scq = wsc + static_cast<size_t>(q) * G + ((4u - (gap_q & 3u)) & 3u);
+          for (uint32_t i = hl; i < gap_q; i += 16) gdst[i] = scq[i];
+        }
+        if (len_q) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(src_q);
+          uint8_t* vd = gdst + gap_q;
+          const uintptr_t d0 = reinterpret_cast<uintptr_t>(vd), d1 = d0 + len_q;
+          const uintptr_t fa = (d0 + 15) & ~static_cast<uintptr_t>(15), fb = d1 & ~static_cast<uintptr_t>(15);
+          if (fb > fa) {
+            if (d0 + hl < fa) vd[hl] = __ldg(src + hl);
+            if (fb + hl < d1) *reinterpret_cast<uint8_t*>(fb + hl) = __ldg(src + (fb - d0) + hl);
+            for (uintptr_t A = fa + 16u * hl; A < fb; A += 256) copy_chunk16(reinterpret_cast<uint8_t*>(A), src + (A - d0));
+          } else {
+            for (uint32_t i = hl; i < len_q; i += 16) vd[i] = __ldg(src + i);
+          }
+        }
+      }
+      __syncwarp();                                // the scratch rows are rewritten by the next round
+    }
+    // restart count + type byte, the 0xffffffff initial register's share, trailer
+    uint32_t a32 = crc_clmul_reduce(acc, [&](uint32_t x) { return tab[0][x]; });
+    a32 = __reduce_xor_sync(0xffffffffu, a32);
+    if (lane == 0) {
+      const uint32_t nres = tl + 1;
+      uint8_t* q = blk + body + 4ull * nres;
+      enc5_store_u32(q, nres);
+      q[4] = 0;   // kNoCompression
+      uint32_t tc = enc5_crc_word(tab, 0u, nres);
+      tc = tab[0][tc & 0xff] ^ (tc >> 8);                                // the type byte (0)
+      const uint32_t r = a32 ^ tc ^ crc_clmul_reduce(crc_clmul(enc5_xpow(L), 0xffffffffu), [&](uint32_t x) { return tab[0][x]; });
+      enc5_store_u32(blk + L, crc_mask(~r));
+    }
+  }
+}
+
 // ---- bloom filter blocks (block_based_table_builder.cc:514-528,594-620; util/bloom.cc:43-61,384-455) ----
 // is_new[j] = the entry's filter key is non-empty and differs from the last non-empty filter key
 // before it ("no need to insert duplicate keys"). Equal keys are adjacent, so the previous entry

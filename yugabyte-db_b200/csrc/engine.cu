@@ -2143,20 +2143,39 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       const size_t esm = ENC_SMEM_CAP + 32;
       const bool tsp = E.key_encoding == YBGPU_KEY_ENCODING_THREE_SHARED_PARTS;
       const bool v3 = getenv("YBGPU_ENC_V3") != nullptr;           // A/B: the image-CRC assembler of round 1
+      // v5 (warp per block, no block image): one scratch row per lane for header + key delta + rewritten value prefix
+      const uint32_t G = (4u + 28u + static_cast<uint32_t>(Sfinal) + 32u + 15u) & ~15u;
+      const size_t v5_smem = 4096 + static_cast<size_t>(ENC5_THREADS) * G;
+      const bool v5 = !v3 && getenv("YBGPU_ENC_V4") == nullptr && v5_smem <= 96 * 1024;
       if (!v3) stats_.path_flags |= YBGPU_PATH_ENCODER_V4;
-      auto smem_kernel = v3 ? (tsp ? k_encode_smem<2> : k_encode_smem<1>) : (tsp ? k_encode_v4<2> : k_encode_v4<1>);
-      auto fused_kernel = tsp ? k_encode_fused<2> : k_encode_fused<1>;
-      CUDA_TRY(cudaFuncSetAttribute(smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esm)));
       CUDA_TRY(cudaEventRecord(I.enc_ev[0], I.stream));
-      smem_kernel<<<std::min<uint32_t>(nblocks, sms * 8), ENC_THREADS, esm, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
+      if (v5) {
+        stats_.path_flags |= YBGPU_PATH_ENCODER_V5;
+        auto kern = tsp ? k_encode_v5<2> : k_encode_v5<1>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(v5_smem)));
+        static int occ_cache[2][64] = {};
+        int& occ = occ_cache[tsp ? 1 : 0][(Sfinal >> 4) & 63];
+        if (!occ) {
+          CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ENC5_THREADS, v5_smem));
+          if (occ < 1) occ = 1;
+        }
+        const uint32_t grid = std::min<uint32_t>((nblocks + ENC5_THREADS / 32 - 1) / (ENC5_THREADS / 32), static_cast<uint32_t>(sms) * occ);
+        kern<<<grid, ENC5_THREADS, v5_smem, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file, G);
+        launches++;
+      } else {
+        auto smem_kernel = v3 ? (tsp ? k_encode_smem<2> : k_encode_smem<1>) : (tsp ? k_encode_v4<2> : k_encode_v4<1>);
+        auto fused_kernel = tsp ? k_encode_fused<2> : k_encode_fused<1>;
+        CUDA_TRY(cudaFuncSetAttribute(smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esm)));
+        smem_kernel<<<std::min<uint32_t>(nblocks, sms * 8), ENC_THREADS, esm, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file);
+        launches++;
+        // blocks whose image does not fit shared memory (huge values)
+        if (total_and_max[1] > ENC_SMEM_CAP) {
+          fused_kernel<<<std::min<uint32_t>(nblocks, sms * 4), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file, ENC_SMEM_CAP);
+          launches++;
+        }
+      }
       CUDA_TRY(cudaEventRecord(I.enc_ev[1], I.stream));
       I.enc_timed = true;
-      launches++;
-      // blocks whose image does not fit shared memory (huge values)
-      if (total_and_max[1] > ENC_SMEM_CAP) {
-        fused_kernel<<<std::min<uint32_t>(nblocks, sms * 4), ENC_THREADS, 0, I.stream>>>(E, Sfinal, I.d_block_first, nblocks, I.d_block_off, I.out_file, ENC_SMEM_CAP);
-        launches++;
-      }
     }
     if (E.fk_len) {
       // ---- bloom filter blocks: distinct filter keys -> ordinals -> 64 KB blocks of max_keys keys each
