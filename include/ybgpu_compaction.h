@@ -190,6 +190,11 @@ ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint6
                                  const ybgpu_block_handle* handles, uint64_t num_handles,
                                  int32_t key_encoding, uint64_t hybrid_time_filter);
 
+/* Blocks until every host->device copy queued by ybgpu_job_add_input has completed (the input buffers may then be
+ * reused). Optional: ybgpu_job_run orders itself behind the copies anyway. The subcompaction pipeline uses it to keep
+ * the copy engine on ONE range's inputs at a time instead of interleaving the chunks of all ranges in flight. */
+ybgpu_status ybgpu_job_wait_inputs(ybgpu_job* job);
+
 /* Same, but `data_file_dev` already lives in device memory of the job's device (used by the
  * bench's HBM-resident measurement and by callers that stage files themselves). Not copied, not
  * owned; must stay valid until destroy. The kernels fetch 16-byte vectors around entry boundaries:

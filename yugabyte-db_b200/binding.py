@@ -112,6 +112,7 @@ def lib():
     L.ybgpu_job_add_input.argtypes = [vp, vp, u64, vp, u64, C.c_int32, u64]
     L.ybgpu_job_add_input_device.argtypes = [vp, vp, u64, vp, u64, C.c_int32, u64]
     L.ybgpu_job_add_input_sst.argtypes = [vp, vp, u64, vp, u64, u64]
+    L.ybgpu_job_wait_inputs.argtypes = [vp]
     L.ybgpu_job_run.argtypes = [vp, vp]
     L.ybgpu_job_get_stats.argtypes = [vp, C.POINTER(JobStats)]
     L.ybgpu_job_kv_stream_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -248,6 +249,10 @@ class GpuCompactionJob:
         hs[:, 0] = offsets
         hs[:, 1] = sizes
         self._check(lib().ybgpu_job_add_input_device(self.h, dev_ptr, length, _np_ptr(hs), len(offsets), key_encoding, ht_filter))
+
+    def wait_inputs(self):
+        """Blocks until the queued host->device copies of the inputs have completed."""
+        self._check(lib().ybgpu_job_wait_inputs(self.h))
 
     def add_input_sst(self, meta, data, ht_filter=HT_INVALID):
         meta = np.ascontiguousarray(meta, dtype=np.uint8)

@@ -88,6 +88,11 @@ ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint6
   return Sync(job, job->engine->AddInput(data_file, data_file_len, handles, num_handles, key_encoding, hybrid_time_filter, false));
 }
 
+ybgpu_status ybgpu_job_wait_inputs(ybgpu_job* job) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  return Sync(job, job->engine->WaitInputs());
+}
+
 ybgpu_status ybgpu_job_add_input_device(ybgpu_job* job, const uint8_t* data_file_dev, uint64_t data_file_len,
                                         const ybgpu_block_handle* handles, uint64_t num_handles, int32_t key_encoding,
                                         uint64_t hybrid_time_filter) {

@@ -1399,8 +1399,8 @@ __global__ void __launch_bounds__(ENC5_THREADS) k_encode_v5(EncView E, int S, co
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&tab[0][0])[i] = (&g_crc_tab[0][0])[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, hl = lane & 15, half = lane >> 4;
-  uint8_t* const wsc = v5_smem + 4096 + static_cast<size_t>(wid) * 32 * G;
-  uint8_t* const sc = wsc + static_cast<size_t>(lane) * G;
+  uint8_t* const wsc = v5_smem + 4096 + static_cast<uint32_t>(wid) * 32u * G;
+  uint8_t* const sc = wsc + static_cast<uint32_t>(lane) * G;      // G = an odd number of words: the lanes' rows start in different banks
   const uint32_t nwarps = gridDim.x * (ENC5_THREADS / 32);
   for (uint32_t b = blockIdx.x * (ENC5_THREADS / 32) + wid; b < nblocks; b += nwarps) {
     const unsigned long long boff = block_off[b];
@@ -1470,8 +1470,10 @@ __global__ void __launch_bounds__(ENC5_THREADS) k_encode_v5(EncView E, int S, co
         if (q >= nact) continue;
         uint8_t* gdst = blk + eoff_q;
         {
-          const uint8_t* scq = wsc + static_cast<size_t>(q) * G + ((4u - (gap_q & 3u)) & 3u);
-          for (uint32_t i = hl; i < gap_q; i += 16) gdst[i] = scq[i];
+          const uint8_t* scq = wsc + q * G + ((4u - (gap_q & 3u)) & 3u);
+          if (hl < gap_q) gdst[hl] = scq[hl];
+          if (hl + 16 < gap_q) gdst[hl + 16] = scq[hl + 16];
+          for (uint32_t i = hl + 32; i < gap_q; i += 16) gdst[i] = scq[i];
         }
         if (len_q) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(src_q);

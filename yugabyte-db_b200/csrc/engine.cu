@@ -1616,6 +1616,12 @@ ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_blo
   return YBGPU_OK;
 }
 
+ybgpu_status Engine::WaitInputs() {
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  CUDA_TRY(cudaStreamSynchronize(impl_->stream));
+  return YBGPU_OK;
+}
+
 static int GridFor(uint64_t work_items, int threads, int sms) {
   uint64_t blocks = (work_items + threads - 1) / threads;
   uint64_t cap = static_cast<uint64_t>(sms) * 16;
@@ -2144,7 +2150,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       const bool tsp = E.key_encoding == YBGPU_KEY_ENCODING_THREE_SHARED_PARTS;
       const bool v3 = getenv("YBGPU_ENC_V3") != nullptr;           // A/B: the image-CRC assembler of round 1
       // v5 (warp per block, no block image): one scratch row per lane for header + key delta + rewritten value prefix
-      const uint32_t G = (4u + 28u + static_cast<uint32_t>(Sfinal) + 32u + 15u) & ~15u;
+      const uint32_t G = ((4u + 28u + static_cast<uint32_t>(Sfinal) + 32u + 7u) & ~7u) + 4u;   // bytes; an odd number of words (bank spread)
       const size_t v5_smem = 4096 + static_cast<size_t>(ENC5_THREADS) * G;
       const bool v5 = !v3 && getenv("YBGPU_ENC_V4") == nullptr && v5_smem <= 96 * 1024;
       if (!v3) stats_.path_flags |= YBGPU_PATH_ENCODER_V4;

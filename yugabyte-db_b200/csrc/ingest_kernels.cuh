@@ -173,33 +173,93 @@ __global__ void __launch_bounds__(256) k_block_counts(const RunView* runs, const
 
 struct IngEntry { uint16_t estart, kstart, vstart, vlen, shared, klen; };    // offsets inside the block (a block is at most ING_BUF bytes), key delta geometry
 
-// raw CRC32C step functions over the lane's private copy of the tables: tabs[(t * 256 + e) * ING_REP + copy]
-#define ING_TAB(t, e) tabs[(((t) << 8) + (e)) * ING_REP + copy]
-__device__ __forceinline__ uint32_t ing_crc_byte(const uint32_t* tabs, uint32_t copy, uint32_t c, uint32_t byte) {
-  return ING_TAB(0, (c ^ byte) & 0xff) ^ (c >> 8);
-}
-__device__ __forceinline__ uint32_t ing_crc_word(const uint32_t* tabs, uint32_t copy, uint32_t c, uint32_t w) {
-  c ^= w;
-  return ING_TAB(3, c & 0xff) ^ ING_TAB(2, (c >> 8) & 0xff) ^ ING_TAB(1, (c >> 16) & 0xff) ^ ING_TAB(0, c >> 24);
-}
-// raw CRC (register starts at `c`) of smem bytes [p, p + n)
-__device__ __forceinline__ uint32_t ing_crc_span(const uint32_t* tabs, uint32_t copy, uint32_t c, const uint8_t* p, uint32_t n) {
-  while (n && (reinterpret_cast<uintptr_t>(p) & 3)) { c = ing_crc_byte(tabs, copy, c, *p++); n--; }
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
-  uint32_t nw = n >> 2;
-  // two words in flight: the loads do not depend on the register
-  while (nw >= 2) {
-    const uint32_t a = w[0], b = w[1];
-    c = ing_crc_word(tabs, copy, c, a);
-    c = ing_crc_word(tabs, copy, c, b);
-    w += 2; nw -= 2;
+// The four slicing tables, ING_REP = 8 copies, laid out so that the TABLE index is part of the bank number:
+//   word address of T_t[e], copy c  =  e * 32 + t * 8 + c        (bank = t * 8 + c, independent of e)
+// A lane uses copy (lane & 7) and looks the four bytes of a word step up in ROTATED order: in its k-th look-up it
+// addresses table t = (k + (lane >> 3)) & 3. The 32 lanes of a warp then hit 32 different banks in every one of the
+// four look-up instructions, whatever the data: no bank conflicts with 32 KB of tables (the plain interleaved layout
+// with 8 copies measured 2.4 wavefronts per look-up, ncu r02_ncu_full_100m_v1).
+struct IngTab {
+  const uint32_t* base;            // table words in shared memory
+  uint32_t sel[4];                 // PRMT selector extracting the byte table t_k consumes (T3 <-> byte 0 ... T0 <-> byte 3)
+  uint32_t off[4];                 // t_k * 8 + copy
+  uint32_t copy;
+};
+__device__ __forceinline__ IngTab ing_tab_init(const uint32_t* base, uint32_t lane) {
+  IngTab T;
+  T.base = base; T.copy = lane & 7u;
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++) {
+    const uint32_t t = (k + (lane >> 3)) & 3u;
+    T.sel[k] = 0x4440u + (3u - t);
+    T.off[k] = t * 8u + T.copy;
   }
-  if (nw) { c = ing_crc_word(tabs, copy, c, *w++); }
-  p = reinterpret_cast<const uint8_t*>(w);
-  for (uint32_t i = 0; i < (n & 3); i++) c = ing_crc_byte(tabs, copy, c, p[i]);
+  return T;
+}
+// T0[x] (single byte steps: the lanes that share a copy collide — rare paths only)
+__device__ __forceinline__ uint32_t ing_t0(const IngTab& T, uint32_t x) { return T.base[x * 32u + T.copy]; }
+__device__ __forceinline__ uint32_t ing_crc_byte(const IngTab& T, uint32_t c, uint32_t byte) { return ing_t0(T, (c ^ byte) & 0xff) ^ (c >> 8); }
+__device__ __forceinline__ uint32_t ing_crc_word(const IngTab& T, uint32_t c, uint32_t w) {
+  c ^= w;
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) r ^= T.base[__byte_perm(c, 0u, T.sel[k]) * 32u + T.off[k]];
+  return r;
+}
+// c * x^32 mod P (four zero bytes): what crc_clmul_reduce needs, as one conflict-free word step
+__device__ __forceinline__ uint32_t ing_clmul_reduce(const IngTab& T, unsigned long long z) {
+  z <<= 1;
+  return ing_crc_word(T, static_cast<uint32_t>(z), 0u) ^ static_cast<uint32_t>(z >> 32);
+}
+// Raw CRC (zero initial register) of the shared-memory bytes [p, p + n). The word grid is aligned to the END of the
+// span: the first word may reach up to 3 bytes in front of p, which are masked to zero (leading zeros do not move a
+// zero register) — so there are only whole-word steps, no byte steps at either end. Every word is one aligned load
+// plus a funnel shift with its predecessor. Touches up to 6 bytes in front of p and 3 behind the span.
+// `c_in` = register to continue from (only zero keeps the leading-zero argument: callers pass 0 for a fresh span).
+__device__ __forceinline__ uint32_t ing_crc_words(const IngTab& T, const uint32_t* wb, uint32_t bits, uint32_t nw, uint32_t first_mask) {
+  uint32_t c = 0;
+  uint32_t prev = wb[0];
+  for (uint32_t i = 0; i < nw; i++) {
+    const uint32_t cur = wb[i + 1];
+    uint32_t w = __funnelshift_r(prev, cur, bits);
+    if (i == 0) w &= first_mask;
+    c = ing_crc_word(T, c, w);
+    prev = cur;
+  }
   return c;
 }
-#undef ING_TAB
+__device__ __forceinline__ uint32_t ing_crc_span(const IngTab& T, const uint8_t* p, uint32_t n) {
+  if (n == 0) return 0;
+  const uint8_t* end = p + n;
+  const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(end) & 3);
+  const uint32_t nw = (n + 3) >> 2, lead = 4 * nw - n;
+  const uint32_t* wb = reinterpret_cast<const uint32_t*>(end - 4 * nw - a);
+  return ing_crc_words(T, wb, 8 * a, nw, 0xffffffffu << (8 * lead));
+}
+// The same with two independent chains over the two halves of a long span (the look-up latency of one chain no longer
+// bounds a thread), joined by one multiplication.
+__device__ __forceinline__ uint32_t ing_crc_span2(const IngTab& T, const uint8_t* p, uint32_t n) {
+  if (n < 96) return ing_crc_span(T, p, n);
+  const uint8_t* end = p + n;
+  const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(end) & 3), bits = 8 * a;
+  const uint32_t nw = (n + 3) >> 2, lead = 4 * nw - n;
+  const uint32_t* wb = reinterpret_cast<const uint32_t*>(end - 4 * nw - a);
+  const uint32_t h = nw >> 1, h2 = nw - h;          // first chain: words [0, h), second: [h, nw); h <= h2 <= h + 1
+  uint32_t c = 0, d = 0;
+  uint32_t pc = wb[0], pd = wb[h];
+  const uint32_t first_mask = 0xffffffffu << (8 * lead);
+  for (uint32_t i = 0; i < h; i++) {
+    const uint32_t cc = wb[i + 1], cd = wb[h + i + 1];
+    uint32_t x = __funnelshift_r(pc, cc, bits);
+    const uint32_t y = __funnelshift_r(pd, cd, bits);
+    if (i == 0) x &= first_mask;
+    c = ing_crc_word(T, c, x);
+    d = ing_crc_word(T, d, y);
+    pc = cc; pd = cd;
+  }
+  if (h2 > h) d = ing_crc_word(T, d, __funnelshift_r(pd, wb[nw], bits));
+  return ing_clmul_reduce(T, crc_clmul(c, __ldg(&g_crc_xpow8[4 * h2]))) ^ d;
+}
 
 // What the producer resolves for a block before it requests the block's bytes.
 struct IngBlk {
@@ -212,27 +272,6 @@ struct IngBlk {
   uint32_t ri;                     // restart interval of the file (0xffffffff: every block has one interval)
   uint32_t valid;                  // 0: past the end, 1: staged, 2: not for this kernel (skipped)
 };
-
-// raw CRC of smem bytes [p, p + n) with two independent chains over the two halves of a long span (the look-up
-// latency of one chain no longer bounds a thread), joined by one multiplication
-__device__ __forceinline__ uint32_t ing_crc_span2(const uint32_t* tabs, uint32_t copy, const uint8_t* p, uint32_t n) {
-  if (n < 96) return ing_crc_span(tabs, copy, 0u, p, n);
-  uint32_t c = 0;
-  while (reinterpret_cast<uintptr_t>(p) & 3) { c = ing_crc_byte(tabs, copy, c, *p++); n--; }
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
-  const uint32_t nw = n >> 2, h = nw >> 1, h2 = nw - h;      // h <= h2 <= h + 1
-  uint32_t d = 0;
-  for (uint32_t i = 0; i < h; i++) {
-    const uint32_t x = w[i], y = w[h + i];
-    c = ing_crc_word(tabs, copy, c, x);
-    d = ing_crc_word(tabs, copy, d, y);
-  }
-  if (h2 > h) d = ing_crc_word(tabs, copy, d, w[nw - 1]);
-  c = crc_clmul_reduce(crc_clmul(c, __ldg(&g_crc_xpow8[4 * h2])), [&](uint32_t x) { return tabs[x * ING_REP + copy]; }) ^ d;
-  p = reinterpret_cast<const uint8_t*>(w + nw);
-  for (uint32_t i = 0; i < (n & 3); i++) c = ing_crc_byte(tabs, copy, c, p[i]);
-  return c;
-}
 
 // Warp-specialised: nothing a block needs from global memory is fetched by the threads that work on it.
 //   warp 5 (producer): claims ING_BATCH consecutive blocks per atomic, resolves their handles, entry bases and output
@@ -257,12 +296,13 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
   __shared__ uint32_t sh_nent[2], sh_tail[2], sh_acc[2], sh_cnt[2];
   __shared__ uint4 sh_upto[17];                  // sh_upto[n]: 0xff in the first n bytes of a 16-byte vector
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t copy = threadIdx.x & (ING_REP - 1);
   for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
-    const uint32_t v = (&g_crc_tab[0][0])[i];
+    const uint32_t v = (&g_crc_tab[0][0])[i];        // i = t * 256 + e
+    const uint32_t t = static_cast<uint32_t>(i) >> 8, e = static_cast<uint32_t>(i) & 255u;
 #pragma unroll
-    for (int c = 0; c < ING_REP; c++) tabs[i * ING_REP + c] = v;
+    for (int c = 0; c < ING_REP; c++) tabs[e * 32u + t * 8u + c] = v;
   }
+  const IngTab T = ing_tab_init(tabs, static_cast<uint32_t>(lane));
   if (threadIdx.x < 17) sh_upto[threadIdx.x] = low_bytes_mask16(static_cast<int>(threadIdx.x));
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; s++) {
@@ -400,9 +440,8 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
         if (V.verify && n_ent) {
           // tail: restart array, restart count, type byte; and the 0xffffffff initial register's share
           const uint32_t L = size + 1;
-          tail = ing_crc_span(tabs, copy, 0u, blk + restarts_off, L - restarts_off);
-          tail ^= crc_clmul_reduce(crc_clmul(L <= CRC_XPOW_TABLE ? __ldg(&g_crc_xpow8[L]) : crc_xpow_bytes(L, g_crc_x2n), 0xffffffffu),
-                                   [&](uint32_t x) { return tabs[x * ING_REP + copy]; });
+          tail = ing_crc_span(T, blk + restarts_off, L - restarts_off);
+          tail ^= ing_clmul_reduce(T, crc_clmul(L <= CRC_XPOW_TABLE ? __ldg(&g_crc_xpow8[L]) : crc_xpow_bytes(L, g_crc_x2n), 0xffffffffu));
         }
         sh_nent[stage] = n_ent; sh_tail[stage] = tail;
       }
@@ -523,17 +562,17 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
       tr.w = vlen;
       *reinterpret_cast<uint4*>(rec + S - 16) = tr;
       // CRCs
-      const uint32_t vc = ing_crc_span2(tabs, copy, blk + en.vstart, vlen);
+      const uint32_t vc = ing_crc_span2(T, blk + en.vstart, vlen);
       val_off[base + e] = boff + en.vstart;
       val_crc[base + e] = vc;
       if (V.verify) {
-        const uint32_t gc = ing_crc_span(tabs, copy, 0u, blk + en.estart, en.vstart - en.estart);
+        const uint32_t gc = ing_crc_span(T, blk + en.estart, en.vstart - en.estart);
         // gap * x^(8 (bytes behind the gap)) + value * x^(8 (bytes behind the value)), unreduced (L < 64 K: inside the table)
         acc ^= crc_clmul(gc, __ldg(&g_crc_xpow8[L - en.vstart])) ^ crc_clmul(vc, __ldg(&g_crc_xpow8[L - en.vstart - vlen]));
       }
     }
     if (V.verify && n_ent) {
-      uint32_t a32 = crc_clmul_reduce(acc, [&](uint32_t x) { return tabs[x * ING_REP + copy]; });
+      uint32_t a32 = ing_clmul_reduce(T, acc);
       a32 = __reduce_xor_sync(0xffffffffu, a32);
       if (lane == 0) {
         if (a32) atomicXor(&sh_acc[stage], a32);

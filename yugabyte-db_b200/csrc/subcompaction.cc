@@ -406,8 +406,49 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
   auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
   if (trace) fprintf(stderr, "[ybgpu sub] planned %u ranges at %.1f ms\n", n_ranges, ms_now());
 
+  // Copy slots. A copy engine serves the streams that have copies pending chunk by chunk in turn: with every range in
+  // flight queueing its inputs at once, all of them receive their data at the same (late) time, compute together and
+  // copy out together — the pipeline moves in convoys and each direction idles while the other ramps. Instead at most
+  // `h2d_slots` ranges have inputs in transit (taken in range order) and at most `d2h_slots` copy out, so the first
+  // range computes after ONE range's worth of DMA and both directions stay busy from then on.
+  struct Slots {
+    std::mutex mu; std::condition_variable cv; uint32_t free_slots;
+    explicit Slots(uint32_t n) : free_slots(n) {}
+    void Acquire() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return free_slots > 0; }); free_slots--; }
+    void Release() { { std::lock_guard<std::mutex> l(mu); free_slots++; } cv.notify_one(); }
+  };
+  struct SlotGuard {
+    Slots* s = nullptr;
+    void Take(Slots* x) { x->Acquire(); s = x; }
+    void Drop() { if (s) { s->Release(); s = nullptr; } }
+    ~SlotGuard() { Drop(); }
+  };
+  auto env_u32 = [](const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const long x = atol(v);
+    return x <= 0 ? 0u : static_cast<uint32_t>(x);
+  };
+  const uint32_t h2d_slots = env_u32("YBGPU_H2D_SLOTS", 2), d2h_slots = env_u32("YBGPU_D2H_SLOTS", 2);   // 0 = ungated
+  Slots h2d_gate(h2d_slots ? h2d_slots : 1u << 30), d2h_gate(d2h_slots ? d2h_slots : 1u << 30);
+  // ranges take their input slot in range order (a later range must not overtake: its output offset waits on the
+  // earlier ones in one-table mode)
+  std::mutex order_mu; std::condition_variable order_cv; uint32_t h2d_next = 0;
+
   auto run_range = [&](uint32_t r) {
     ybgpu_sub_output& out = outputs[r];
+    // input slot, in range order; every range that was handed out passes here, so nobody waits for a range that gave up
+    SlotGuard in_slot, out_slot;
+    {
+      std::unique_lock<std::mutex> lock(order_mu);
+      order_cv.wait(lock, [&] { return h2d_next == r; });
+    }
+    in_slot.Take(&h2d_gate);
+    {
+      std::lock_guard<std::mutex> lock(order_mu);
+      h2d_next = r + 1;
+    }
+    order_cv.notify_all();
     double t_begin = ms_now(), t_added = 0, t_ran = 0, t_sized = 0, t_fetched = 0;
     const std::string lo(reinterpret_cast<const char*>(out.range_lower), out.range_lower_len);
     const std::string hi(reinterpret_cast<const char*>(out.range_upper), out.range_upper_len);
@@ -427,6 +468,7 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
     };
     uint32_t added = 0;
     std::vector<ybgpu_block_handle> h;
+
     // the blocks of every input that can hold keys of the range, plus — for a range that starts inside a cotable —
     // the blocks with that table's tombstones (SpansForRange); the last span of an input is its range span
     std::vector<Span> spans;
@@ -443,6 +485,11 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
         added++;
       }
     }
+    if (added && h2d_slots) {
+      s = ybgpu_job_wait_inputs(job);
+      if (s != YBGPU_OK) { job_fail(s, "wait_inputs"); return; }
+    }
+    in_slot.Drop();
     t_added = ms_now();
     if (added) {
       s = ybgpu_job_run(job, shutting_down);
@@ -478,7 +525,9 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
           meta_dst = meta_arena + moff;
         }
         if (doff + dl > data_arena_cap) { job_fail(YBGPU_INVALID_ARGUMENT, "output arena too small"); return; }
+        out_slot.Take(&d2h_gate);
         s = ybgpu_job_fetch_output(job, data_arena + doff, dl, meta_dst, ml);
+        out_slot.Drop();
         if (s != YBGPU_OK) { job_fail(s, "fetch_output"); return; }
         out.data_offset = doff; out.data_len = dl; out.meta_offset = moff; out.meta_len = ml;
         uint64_t sl = 0, ll = 0;
