@@ -1401,6 +1401,7 @@ struct Engine::Impl {
   bool owns_stream = false;            // cuda_stream == YBGPU_STREAM_PRIVATE: created in Init, destroyed with the job
   uint8_t* status_host = nullptr; uint8_t* status_dev = nullptr;   // host-mapped page for small read-backs (may be null)
   uint32_t readback_launches = 0;
+  size_t upload_off = 0;                             // ring position of the next small upload inside the page
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t phase_ev[8] = {};
   cudaEvent_t enc_ev[2] = {};          // around the block-assembler launch (the dominant kernel of the encode phase)
@@ -1441,7 +1442,8 @@ __global__ void k_readback(uint8_t* dst_mapped, const uint8_t* src, uint32_t n) 
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst_mapped[i] = src[i];
   __threadfence_system();
 }
-constexpr size_t STATUS_PAGE_BYTES = 4096;
+constexpr size_t STATUS_READ_BYTES = 4096;             // [0, 4096): read-backs; the rest: a ring of small parameter uploads
+constexpr size_t STATUS_PAGE_BYTES = 65536;
 struct StatusPage { uint8_t* host = nullptr; uint8_t* dev = nullptr; };
 static std::mutex g_status_mu;
 static std::vector<StatusPage> g_status_free;          // process-wide: cudaHostAlloc costs ~1 ms
@@ -1631,7 +1633,7 @@ static int GridFor(uint64_t work_items, int threads, int sms) {
 // Device -> host read of a few words followed by a stream synchronisation (see k_readback).
 ybgpu_status Engine::ReadSmall(void* host_dst, const void* dev_src, size_t n) {
   Impl& I = *impl_;
-  if (I.status_host && n <= STATUS_PAGE_BYTES) {
+  if (I.status_host && n <= STATUS_READ_BYTES) {
     k_readback<<<1, 128, 0, I.stream>>>(I.status_dev, static_cast<const uint8_t*>(dev_src), static_cast<uint32_t>(n));
     I.readback_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1641,6 +1643,30 @@ ybgpu_status Engine::ReadSmall(void* host_dst, const void* dev_src, size_t n) {
   }
   CUDA_TRY(cudaMemcpyAsync(host_dst, dev_src, n, cudaMemcpyDeviceToHost, I.stream));
   CUDA_TRY(cudaStreamSynchronize(I.stream));
+  return YBGPU_OK;
+}
+
+// Small host -> device parameter blocks (run table, job parameters, prefix tables: ~a dozen per job, < 8 KB each) go
+// through the host-mapped page as well: a host -> device DMA would queue on the copy engine behind the bulk input
+// copies of the jobs running beside this one (tens of milliseconds each in a pipelined compaction), and every one of
+// them sits on the job's critical path. The bytes are staged in a ring inside the page and copied by one small CTA.
+ybgpu_status Engine::UploadSmall(void* dev_dst, const void* host_src, size_t n) {
+  Impl& I = *impl_;
+  const size_t need = (n + 15) & ~static_cast<size_t>(15);
+  if (!I.status_host || need > STATUS_PAGE_BYTES - STATUS_READ_BYTES) {
+    CUDA_TRY(cudaMemcpyAsync(dev_dst, host_src, n, cudaMemcpyHostToDevice, I.stream));
+    return YBGPU_OK;
+  }
+  if (I.upload_off < STATUS_READ_BYTES) I.upload_off = STATUS_READ_BYTES;
+  if (I.upload_off + need > STATUS_PAGE_BYTES) {
+    CUDA_TRY(cudaStreamSynchronize(I.stream));           // every earlier upload has been consumed
+    I.upload_off = STATUS_READ_BYTES;
+  }
+  memcpy(I.status_host + I.upload_off, host_src, n);
+  k_readback<<<1, 128, 0, I.stream>>>(static_cast<uint8_t*>(dev_dst), I.status_dev + I.upload_off, static_cast<uint32_t>(n));
+  I.readback_launches++;
+  CUDA_TRY(cudaGetLastError());
+  I.upload_off += need;
   return YBGPU_OK;
 }
 
@@ -1692,7 +1718,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   CUDA_TRY(cudaMemsetAsync(I.dJ, 0, sizeof(JobDev), I.stream));
   {
     JobDev init{}; init.min_seq = ~0ull;
-    CUDA_TRY(cudaMemcpyAsync(I.dJ, &init, sizeof(init), cudaMemcpyHostToDevice, I.stream));
+    if (ybgpu_status us = UploadSmall(I.dJ, &init, sizeof(init))) return us;
   }
   CUDA_TRY(cudaEventRecord(I.ev0, I.stream));
   uint32_t phase_launch_mark[8] = {};
@@ -1719,8 +1745,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   for (int r = 0; r < k; r++) blk_base[r + 1] = blk_base[r] + I.runs[r].nb;
   uint32_t* d_blk_base = nullptr;
   CUDA_TRY(DevAlloc(&I.allocs, &d_blk_base, static_cast<size_t>(k) + 1));
-  CUDA_TRY(cudaMemcpyAsync(d_blk_base, blk_base.data(), 4 * (static_cast<size_t>(k) + 1), cudaMemcpyHostToDevice, I.stream));
-  CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+  if (ybgpu_status us = UploadSmall(d_blk_base, blk_base.data(), 4 * (static_cast<size_t>(k) + 1))) return us;
+  if (ybgpu_status us = UploadSmall(I.dRuns, I.runs.data(), sizeof(RunView) * k)) return us;
   RangeDev* d_range = nullptr;
   if (!range_lower_.empty() || !range_upper_.empty()) {
     if (range_lower_.size() > 255 || range_upper_.size() > 255) return Fail(YBGPU_NOT_SUPPORTED, "range bounds longer than 255 bytes");
@@ -1728,7 +1754,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     hr.lower_len = static_cast<uint32_t>(range_lower_.size()); memcpy(hr.lower, range_lower_.data(), range_lower_.size());
     hr.upper_len = static_cast<uint32_t>(range_upper_.size()); memcpy(hr.upper, range_upper_.data(), range_upper_.size());
     CUDA_TRY(DevAlloc(&I.allocs, &d_range, 1));
-    CUDA_TRY(cudaMemcpyAsync(d_range, &hr, sizeof(hr), cudaMemcpyHostToDevice, I.stream));
+    if (ybgpu_status us = UploadSmall(d_range, &hr, sizeof(hr))) return us;
   }
   uint64_t N = 0;
   uint32_t max_ikey = 0;
@@ -1785,7 +1811,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
         rv.blk_off = reinterpret_cast<const uint64_t*>(sv.out_off) + blk_base[r];
         rv.blk_size = sv.usize + blk_base[r];
       }
-      CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+      if (ybgpu_status us = UploadSmall(I.dRuns, I.runs.data(), sizeof(RunView) * k)) return us;
       // the probe starts over on the uncompressed image
       CUDA_TRY(cudaMemsetAsync(&I.dJ->n_compressed, 0, sizeof(uint32_t), I.stream));
       CUDA_TRY(cudaMemsetAsync(I.dJ->restart_interval, 0, sizeof(uint32_t) * MAX_RUNS, I.stream));
@@ -1826,7 +1852,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
           CUDA_TRY(DevAlloc(&I.allocs, &rv.val_crc, static_cast<size_t>(cap[r]) + 1));
         }
       }
-      CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+      if (ybgpu_status us = UploadSmall(I.dRuns, I.runs.data(), sizeof(RunView) * k)) return us;
       CUDA_TRY(cudaMemsetAsync(iv.ticket, 0, 4, I.stream));
       CUDA_TRY(cudaMemsetAsync(&I.dJ->ingest_fallback, 0, sizeof(int), I.stream));
       iv.runs = I.dRuns; iv.blk_base = d_blk_base; iv.totals = d_totals; iv.range = d_range;
@@ -1903,11 +1929,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       CUDA_TRY(DevAlloc(&I.allocs, &rv.val_crc, static_cast<size_t>(rv.n_entries) + 1));
       group_base[r + 1] = group_base[r] + (rv.nb + DEC_WB - 1) / DEC_WB;
     }
-    CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+    if (ybgpu_status us = UploadSmall(I.dRuns, I.runs.data(), sizeof(RunView) * k)) return us;
     if (group_base[k]) {
       uint32_t* d_group_base = nullptr;
       CUDA_TRY(DevAlloc(&I.allocs, &d_group_base, k + 1));
-      CUDA_TRY(cudaMemcpyAsync(d_group_base, group_base.data(), 4 * (k + 1), cudaMemcpyHostToDevice, I.stream));
+      if (ybgpu_status us = UploadSmall(d_group_base, group_base.data(), 4 * (k + 1))) return us;
       const int grid = GridFor(static_cast<uint64_t>(group_base[k]) * 32, 128, sms);
       // fast path: shared-prefix inputs, internal keys of at most 64 bytes, no HybridTime filter / key range
       bool fast = d_range == nullptr && max_ikey <= 64;
@@ -1921,14 +1947,14 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       else k_decode_all<1024><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, d_range, I.dJ);
       launches++;
       // per-entry value CRCs for the block encoder (the fused path computes them while verifying)
-      CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+      if (ybgpu_status us = UploadSmall(I.dRuns, I.runs.data(), sizeof(RunView) * k)) return us;
       k_value_crc<<<GridFor(N, 256, sms), 256, 0, I.stream>>>(I.dRuns, k, Sfinal);
       launches++;
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(end_phase());
   }
-  CUDA_TRY(cudaMemcpyAsync(I.dRuns, I.runs.data(), sizeof(RunView) * k, cudaMemcpyHostToDevice, I.stream));
+  if (ybgpu_status us = UploadSmall(I.dRuns, I.runs.data(), sizeof(RunView) * k)) return us;
 
   // ---- job parameters
   JobParams hp{};
@@ -1938,8 +1964,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   cap = std::min(cap, 4096u) & ~15u;
   if (cap < 16) return Fail(YBGPU_NOT_SUPPORTED, "record stride too large for a merge tile");
   hp.tile_cap = cap;
-  hp.H = std::max(1u, cap / 2);
-  hp.M = std::max(1u, hp.H / std::max(1, k));
+  // Target tile size H: the samples of one run are M records apart, so a tile of ordinary data holds about H + M records;
+  // only adversarial inputs approach the bound H + 2kM, and the partition is then repeated with a smaller M (below).
+  static const uint32_t h_pct = [] { const char* v = getenv("YBGPU_TILE_H_PCT"); const int x = v ? atoi(v) : 0; return static_cast<uint32_t>(x >= 25 && x <= 90 ? x : 50); }();
+  hp.H = std::max(1u, cap * h_pct / 100);
+  hp.M = std::max(1u, (cap / 2) / std::max(1, k));
   hp.R.enabled = opt_.retention_enabled;
   hp.R.cutoff_ht = opt_.history_cutoff_ht;
   hp.R.table_ttl_ns = opt_.table_ttl_ns;
@@ -1976,7 +2005,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   if (largest_.size() > sizeof(hp.largest)) return Fail(YBGPU_NOT_SUPPORTED, "largest user key too long");
   hp.largest_len = static_cast<uint32_t>(largest_.size());
   memcpy(hp.largest, largest_.data(), largest_.size());
-  CUDA_TRY(cudaMemcpyAsync(I.dP, &hp, sizeof(hp), cudaMemcpyHostToDevice, I.stream));
+  if (ybgpu_status us = UploadSmall(I.dP, &hp, sizeof(hp))) return us;
   if (ybgpu_status s = CheckDeviceError("decode")) return s;
   tick("decode");
   if (shutdown()) return Fail(YBGPU_SHUTDOWN_IN_PROGRESS, "Database shutdown or Column family drop during compaction");
@@ -2004,7 +2033,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(DevAlloc(&I.allocs, &pv.bucket_min, n_buckets));
     CUDA_TRY(DevAlloc(&I.allocs, &d_tile_lo, static_cast<size_t>(n_buckets + 1) * k));
     CUDA_TRY(DevAlloc(&I.allocs, &d_tile_rank, n_buckets + 1));
-    CUDA_TRY(cudaMemcpyAsync(d_sample_base, sample_base.data(), 4 * (k + 1), cudaMemcpyHostToDevice, I.stream));
+    if (ybgpu_status us = UploadSmall(d_sample_base, sample_base.data(), 4 * (k + 1))) return us;
     CUDA_TRY(cudaMemsetAsync(pv.bucket_min, 0xff, static_cast<size_t>(n_buckets) * 8, I.stream));
     pv.runs = I.dRuns; pv.sample_base = d_sample_base; pv.n_samples = n_samples; pv.n_buckets = n_buckets;
     k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ);
@@ -2026,7 +2055,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       return Fail(YBGPU_NOT_SUPPORTED, "record stride and run count too large for a merge tile");
     hp.M = std::max(1u, hp.M / 2);
     stats_.path_flags |= YBGPU_PATH_PARTITION_RETRY;
-    CUDA_TRY(cudaMemcpyAsync(I.dP, &hp, sizeof(hp), cudaMemcpyHostToDevice, I.stream));
+    if (ybgpu_status us = UploadSmall(I.dP, &hp, sizeof(hp))) return us;
     CUDA_TRY(cudaMemsetAsync(&I.dJ->max_tile, 0, sizeof(uint32_t), I.stream));
   }
   CUDA_TRY(end_phase());
@@ -2142,7 +2171,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     unsigned long long total_and_max[2] = {0, 0};
     if (ybgpu_status s = ReadSmall(total_and_max, d_total, 16)) return s;
     const unsigned long long total = total_and_max[0];
-    CUDA_TRY(cudaMemcpyAsync(I.d_block_off + nblocks, &total, 8, cudaMemcpyHostToDevice, I.stream));
+    if (ybgpu_status us = UploadSmall(I.d_block_off + nblocks, &total, 8)) return us;
     I.out_file_len = total;
     CUDA_TRY(DevAlloc(&I.allocs, &I.out_file, total + 64));
     {

@@ -50,6 +50,7 @@ class Engine {
  private:
   ybgpu_status CheckDeviceError(const char* phase);
   ybgpu_status ReadSmall(void* host_dst, const void* dev_src, size_t n);
+  ybgpu_status UploadSmall(void* dev_dst, const void* host_src, size_t n);
   ybgpu_status EnsureKvStream();
   struct Impl;
   ybgpu_job_options opt_;
