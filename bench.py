@@ -65,7 +65,7 @@ def parse_args():
     ap.add_argument("--verify", type=int, default=1, help="verify input block checksums (reference default: on)")
     ap.add_argument("--subcompactions", type=int, default=32,
                     help="e2e arm: key-range subcompactions per job (DBOptions::max_subcompactions; 1 = one job, one output file)")
-    ap.add_argument("--in-flight", type=int, default=6, help="e2e arm: subcompactions in flight (host threads / private streams)")
+    ap.add_argument("--in-flight", type=int, default=12, help="e2e arm: subcompactions in flight (host threads / private streams)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE configs[2] / configs[3] sub-results")
     ap.add_argument("--c3-tablets", type=int, default=8, help="configs[2]: tablets per GPU (64 tablets / 8 GPUs)")
     ap.add_argument("--c3-rows", type=int, default=10_000_000, help="configs[2]: entries per tablet")

@@ -182,6 +182,39 @@ __global__ void __launch_bounds__(1024) k_scan_u64_single(unsigned long long* a,
   }
   if (threadIdx.x == 0 && total) *total = carry;
 }
+// Exclusive scan of a long u64 array in place (block sizes -> file offsets): chunk sums, one-CTA scan of the chunk sums
+// (k_scan_u64_single), then every chunk scans itself from its base. (One CTA walking 10^6 elements took 0.9 ms.)
+__global__ void __launch_bounds__(256) k_u64_chunk_sums(const unsigned long long* a, uint32_t n, unsigned long long* partial) {
+  __shared__ unsigned long long sh;
+  if (threadIdx.x == 0) sh = 0;
+  __syncthreads();
+  unsigned long long s = 0;
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_CHUNK;
+  for (uint32_t j = threadIdx.x; j < SCAN_CHUNK; j += 256) { const uint64_t i = base + j; if (i < n) s += a[i]; }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sh, s);
+  __syncthreads();
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh;
+}
+__global__ void __launch_bounds__(256) k_u64_chunk_final(unsigned long long* a, uint32_t n, const unsigned long long* partial) {
+  __shared__ unsigned long long ws[8];
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_CHUNK;
+  constexpr int PER = SCAN_CHUNK / 256;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long v[PER], s = 0;
+  for (int j = 0; j < PER; j++) { const uint64_t i = base + threadIdx.x * PER + j; v[j] = i < n ? a[i] : 0; s += v[j]; }
+  unsigned long long x = s;
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) ws[wid] = x;
+  __syncthreads();
+  unsigned long long run = partial[blockIdx.x] + x - s;
+  for (int w = 0; w < wid; w++) run += ws[w];
+  for (int j = 0; j < PER; j++) {
+    const uint64_t i = base + threadIdx.x * PER + j;
+    if (i < n) a[i] = run;
+    run += v[j];
+  }
+}
 __global__ void __launch_bounds__(256) k_p_final(const uint32_t* nr, uint32_t n, const unsigned long long* partial, unsigned long long* P) {
   __shared__ uint32_t warp_sums[32];
   const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_CHUNK;

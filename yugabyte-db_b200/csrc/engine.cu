@@ -473,7 +473,12 @@ struct PartView {
 // (dev_logic.cuh replay_ancestors). Candidates of one run are then < 2M records apart in that run, which bounds
 // a tile by H + 2kM records (the host halves M and repeats the partition in the rare case that exceeds a tile).
 constexpr unsigned long long TILE_CONT = 1ull << 63;   // tile_rank flag: the tile starts inside a row group
-__global__ void __launch_bounds__(256) k_sample_pos(PartView P, const JobParams* prm, JobDev* J) {
+// Two passes: every SAMPLE_COARSE-th sample of a run searches the whole of every run (pass 0); the samples between two
+// coarse ones then search only between the positions those found (pass 1) — positions are monotone in the sample index
+// of a run, whichever of the two splitter kinds neighbouring samples use: ~10 probes instead of ~24, and the probes of
+// neighbouring threads stay close together.
+constexpr uint32_t SAMPLE_COARSE = 32;
+__global__ void __launch_bounds__(256) k_sample_pos(PartView P, const JobParams* prm, JobDev* J, int pass) {
   const int S = prm->S, k = prm->k;
   const uint64_t total = static_cast<uint64_t>(P.n_samples) * k;
   for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < total;
@@ -482,7 +487,9 @@ __global__ void __launch_bounds__(256) k_sample_pos(PartView P, const JobParams*
     // which run owns sample s
     int r = 0;
     while (r + 1 < k && P.sample_base[r + 1] <= s) r++;
-    const uint32_t idx = (s - P.sample_base[r]) * prm->M;
+    const uint32_t s_local = s - P.sample_base[r];
+    if (((s_local % SAMPLE_COARSE) == 0) != (pass == 0)) continue;
+    const uint32_t idx = s_local * prm->M;
     const uint8_t* srec = P.runs[r].rec + static_cast<size_t>(idx) * S;
     const int g = group_prefix_len(srec, rec_ulen(srec, S), prm->R.enabled != 0);
     if (g < 0) { dev_fail(J, -g, s); continue; }
@@ -495,6 +502,11 @@ __global__ void __launch_bounds__(256) k_sample_pos(PartView P, const JobParams*
     if (r2 == 0) P.smode[s] = inside ? 1 : 0;
     const RunView& q = P.runs[r2];
     uint32_t lo = 0, hi = q.n_entries;
+    if (pass == 1) {
+      const uint32_t c0 = s_local - s_local % SAMPLE_COARSE, c1 = c0 + SAMPLE_COARSE;
+      lo = P.pos[static_cast<size_t>(P.sample_base[r] + c0) * k + r2];
+      if (P.sample_base[r] + c1 < P.sample_base[r + 1]) hi = P.pos[static_cast<size_t>(P.sample_base[r] + c1) * k + r2];
+    }
     if (inside) {
       if (r2 == static_cast<uint32_t>(r)) lo = hi = idx;
       while (lo < hi) {
@@ -1401,6 +1413,7 @@ struct Engine::Impl {
   bool owns_stream = false;            // cuda_stream == YBGPU_STREAM_PRIVATE: created in Init, destroyed with the job
   uint8_t* status_host = nullptr; uint8_t* status_dev = nullptr;   // host-mapped page for small read-backs (may be null)
   uint32_t readback_launches = 0;
+  uint8_t* staging_host = nullptr; uint8_t* staging_dev = nullptr;   // host-mapped staging for metadata-sized read-backs
   size_t upload_off = 0;                             // ring position of the next small upload inside the page
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t phase_ev[8] = {};
@@ -1465,6 +1478,48 @@ static void ReleaseStatusPage(const StatusPage& p) {
   std::lock_guard<std::mutex> lock(g_status_mu);
   g_status_free.push_back(p);
 }
+// Metadata-sized device -> host reads (block offsets, boundary keys, bloom filter blocks: megabytes per job) bypass the
+// copy engine as well: in a pipelined compaction the D2H engine is busy with the neighbours' output files for tens of
+// milliseconds at a stretch, and a job cannot size / place its own output before it has these arrays. A kernel stores
+// them into host-mapped pinned staging memory (posted PCIe writes from the SMs), the host copies them out of there.
+constexpr size_t STAGING_BYTES = 8u << 20;
+struct Staging { uint8_t* host = nullptr; uint8_t* dev = nullptr; };
+static std::vector<Staging> g_staging_free;            // process-wide, guarded by g_status_mu
+static cudaError_t AcquireStaging(Staging* p) {
+  {
+    std::lock_guard<std::mutex> lock(g_status_mu);
+    if (!g_staging_free.empty()) { *p = g_staging_free.back(); g_staging_free.pop_back(); return cudaSuccess; }
+  }
+  void* h = nullptr; void* d = nullptr;
+  cudaError_t e = cudaHostAlloc(&h, STAGING_BYTES, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e != cudaSuccess) return e;
+  e = cudaHostGetDevicePointer(&d, h, 0);
+  if (e != cudaSuccess) { cudaFreeHost(h); return e; }
+  p->host = static_cast<uint8_t*>(h); p->dev = static_cast<uint8_t*>(d);
+  return cudaSuccess;
+}
+static void ReleaseStaging(const Staging& p) {
+  if (!p.host) return;
+  std::lock_guard<std::mutex> lock(g_status_mu);
+  g_staging_free.push_back(p);
+}
+// rows of `row_bytes` bytes, `src_pitch` apart in device memory, packed back to back in the destination
+__global__ void __launch_bounds__(256) k_copy_out(uint8_t* dst_mapped, const uint8_t* src, size_t row_bytes, size_t src_pitch, size_t rows) {
+  const size_t total = row_bytes * rows;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  if (src_pitch == row_bytes && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst_mapped)) & 15) == 0) {
+    const size_t nv = total >> 4;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nv; i += stride)
+      reinterpret_cast<uint4*>(dst_mapped)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = (nv << 4) + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += stride) dst_mapped[i] = src[i];
+  } else {
+    // pitched rows (bloom filter blocks): a CTA walks whole rows, no division per byte
+    for (size_t r = blockIdx.x; r < rows; r += gridDim.x)
+      for (size_t c = threadIdx.x; c < row_bytes; c += blockDim.x) dst_mapped[r * row_bytes + c] = src[r * src_pitch + c];
+  }
+  __threadfence_system();
+}
+
 static bool ZeroCopyStatusEnabled() {
   const char* e = getenv("YBGPU_ZC_STATUS");
   return e ? atoi(e) != 0 : true;
@@ -1494,6 +1549,7 @@ Engine::~Engine() {
     if (impl_->copy_ev) cudaEventDestroy(impl_->copy_ev);
     for (auto& e : impl_->enc_ev) if (e) cudaEventDestroy(e);
     for (auto& e : impl_->phase_ev) if (e) cudaEventDestroy(e);
+    if (impl_->staging_host) { Staging st; st.host = impl_->staging_host; st.dev = impl_->staging_dev; ReleaseStaging(st); }   // every read through it was synchronous
     if (impl_->status_host) {
       cudaStreamSynchronize(impl_->stream);              // no read-back kernel may still target the page
       StatusPage pg; pg.host = impl_->status_host; pg.dev = impl_->status_dev;
@@ -1557,6 +1613,12 @@ ybgpu_status Engine::Init() {
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, opt_.device));
     uint64_t thr = ~0ull;
     CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    // Never satisfy an allocation with memory whose free is still pending on ANOTHER stream: the pool would make this
+    // job's stream wait for that stream's queued work — in a pipelined compaction that is a neighbour's multi-GB output
+    // copy, and this job's kernels would sit behind it (seen as 50-80 ms "run" phases of 5 ms jobs). Memory whose free
+    // has completed is still reused; otherwise the pool grows.
+    int off = 0;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
   }
   if (ZeroCopyStatusEnabled()) {
     StatusPage pg;
@@ -1667,6 +1729,34 @@ ybgpu_status Engine::UploadSmall(void* dev_dst, const void* host_src, size_t n) 
   I.readback_launches++;
   CUDA_TRY(cudaGetLastError());
   I.upload_off += need;
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::ReadViaMapped(void* host_dst, const void* dev_src, size_t row_bytes, size_t src_pitch, size_t rows) {
+  Impl& I = *impl_;
+  if (!row_bytes || !rows) return YBGPU_OK;
+  if (!I.status_host || row_bytes > STAGING_BYTES) {      // zero-copy reads disabled (A/B switch): the copy engine
+    if (src_pitch == row_bytes) CUDA_TRY(cudaMemcpyAsync(host_dst, dev_src, row_bytes * rows, cudaMemcpyDeviceToHost, I.stream));
+    else CUDA_TRY(cudaMemcpy2DAsync(host_dst, row_bytes, dev_src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost, I.stream));
+    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    return YBGPU_OK;
+  }
+  if (!I.staging_host) {
+    Staging st;
+    CUDA_TRY(AcquireStaging(&st));
+    I.staging_host = st.host; I.staging_dev = st.dev;
+  }
+  const size_t rows_per = std::max<size_t>(1, STAGING_BYTES / row_bytes);
+  for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
+    const size_t nr = std::min(rows_per, rows - r0);
+    const size_t bytes = nr * row_bytes;
+    const int grid = src_pitch == row_bytes ? static_cast<int>(std::min<size_t>(64, (bytes + 65535) / 65536)) : static_cast<int>(std::min<size_t>(64, nr));
+    k_copy_out<<<std::max(grid, 1), 256, 0, I.stream>>>(I.staging_dev, static_cast<const uint8_t*>(dev_src) + r0 * src_pitch, row_bytes, src_pitch, nr);
+    I.readback_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(I.stream));
+    memcpy(static_cast<uint8_t*>(host_dst) + r0 * row_bytes, I.staging_host, bytes);
+  }
   return YBGPU_OK;
 }
 
@@ -1966,7 +2056,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   hp.tile_cap = cap;
   // Target tile size H: the samples of one run are M records apart, so a tile of ordinary data holds about H + M records;
   // only adversarial inputs approach the bound H + 2kM, and the partition is then repeated with a smaller M (below).
-  static const uint32_t h_pct = [] { const char* v = getenv("YBGPU_TILE_H_PCT"); const int x = v ? atoi(v) : 0; return static_cast<uint32_t>(x >= 25 && x <= 90 ? x : 50); }();
+  static const uint32_t h_pct = [] { const char* v = getenv("YBGPU_TILE_H_PCT"); const int x = v ? atoi(v) : 0; return static_cast<uint32_t>(x >= 25 && x <= 90 ? x : 65); }();
   hp.H = std::max(1u, cap * h_pct / 100);
   hp.M = std::max(1u, (cap / 2) / std::max(1, k));
   hp.R.enabled = opt_.retention_enabled;
@@ -2036,7 +2126,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     if (ybgpu_status us = UploadSmall(d_sample_base, sample_base.data(), 4 * (k + 1))) return us;
     CUDA_TRY(cudaMemsetAsync(pv.bucket_min, 0xff, static_cast<size_t>(n_buckets) * 8, I.stream));
     pv.runs = I.dRuns; pv.sample_base = d_sample_base; pv.n_samples = n_samples; pv.n_buckets = n_buckets;
-    k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ);
+    k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ, 0);
+    k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ, 1);
     k_sample_bucket<<<GridFor(n_samples, 256, sms), 256, 0, I.stream>>>(pv, I.dP);
     {
       const uint32_t tchunks = (n_buckets + TILE_CHUNK - 1) / TILE_CHUNK;
@@ -2047,7 +2138,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       k_build_tiles<<<tchunks, 256, 0, I.stream>>>(pv, I.dP, d_tpart, d_ttotal, d_tile_lo, d_tile_rank, I.dJ);
       k_tile_check<<<GridFor(n_buckets + 1, 256, sms), 256, 0, I.stream>>>(I.dRuns, d_tile_lo, k, I.dJ);
     }
-    launches += 6;
+    launches += 7;
     CUDA_TRY(cudaGetLastError());
     if (ybgpu_status s = CheckDeviceError("partition")) return s;
     if (I.hJ.max_tile <= cap) break;
@@ -2167,7 +2258,15 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(cudaMemsetAsync(d_total, 0, 16, I.stream));
     k_block_first<<<pc, 256, 0, I.stream>>>(d_is_start, n, d_spart, I.d_block_first);
     k_block_sizes<<<GridFor(nblocks, 256, sms), 256, 0, I.stream>>>(E, I.d_block_first, nblocks, I.d_block_off, d_total + 1);
-    k_scan_u64_single<<<1, 1024, 0, I.stream>>>(I.d_block_off, nblocks, d_total);
+    {
+      const uint32_t bc = (nblocks + SCAN_CHUNK - 1) / SCAN_CHUNK;
+      unsigned long long* d_bpart = nullptr;
+      CUDA_TRY(DevAlloc(&I.allocs, &d_bpart, static_cast<size_t>(bc) + 1));
+      k_u64_chunk_sums<<<bc, 256, 0, I.stream>>>(I.d_block_off, nblocks, d_bpart);
+      k_scan_u64_single<<<1, 1024, 0, I.stream>>>(d_bpart, bc, d_total);
+      k_u64_chunk_final<<<bc, 256, 0, I.stream>>>(I.d_block_off, nblocks, d_bpart);
+      launches += 2;
+    }
     unsigned long long total_and_max[2] = {0, 0};
     if (ybgpu_status s = ReadSmall(total_and_max, d_total, 16)) return s;
     const unsigned long long total = total_and_max[0];
@@ -2360,8 +2459,8 @@ ybgpu_status Engine::FetchOutput(uint8_t* data_file, uint64_t* block_off /*n_blo
   CUDA_TRY(cudaSetDevice(opt_.device));
   if (I.out_file_len && data_file) CUDA_TRY(cudaMemcpyAsync(data_file, I.out_file, I.out_file_len, cudaMemcpyDeviceToHost, I.stream));
   if (I.n_blocks) {
-    if (block_off) CUDA_TRY(cudaMemcpyAsync(block_off, I.d_block_off, (static_cast<size_t>(I.n_blocks) + 1) * 8, cudaMemcpyDeviceToHost, I.stream));
-    if (boundary) CUDA_TRY(cudaMemcpyAsync(boundary, I.d_boundary, static_cast<size_t>(I.n_blocks) * 2 * I.boundary_stride, cudaMemcpyDeviceToHost, I.stream));
+    if (block_off) { const size_t nb8 = (static_cast<size_t>(I.n_blocks) + 1) * 8; if (ybgpu_status rs = ReadViaMapped(block_off, I.d_block_off, nb8, nb8, 1)) return rs; }
+    if (boundary) { const size_t bb = static_cast<size_t>(I.boundary_stride) * 2; if (ybgpu_status rs = ReadViaMapped(boundary, I.d_boundary, bb, bb, I.n_blocks)) return rs; }
   }
   CUDA_TRY(cudaStreamSynchronize(I.stream));
   stats_.d2h_bytes += (data_file ? I.out_file_len : 0) + (block_off ? (static_cast<size_t>(I.n_blocks) + 1) * 8 : 0) +
@@ -2404,9 +2503,8 @@ ybgpu_status Engine::FetchFileBoundaries(uint8_t* smallest, uint8_t* largest) {
   smallest[0] = smallest[1] = 0; largest[0] = largest[1] = 0;
   if (!I.n_blocks) return YBGPU_OK;
   CUDA_TRY(cudaSetDevice(opt_.device));
-  CUDA_TRY(cudaMemcpyAsync(smallest, I.d_boundary + static_cast<size_t>(I.n_blocks) * 2 * I.boundary_stride, I.boundary_stride, cudaMemcpyDeviceToHost, I.stream));
-  CUDA_TRY(cudaMemcpyAsync(largest, I.d_boundary + static_cast<size_t>(I.n_blocks - 1) * 2 * I.boundary_stride, I.boundary_stride, cudaMemcpyDeviceToHost, I.stream));
-  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  if (ybgpu_status rs = ReadViaMapped(smallest, I.d_boundary + static_cast<size_t>(I.n_blocks) * 2 * I.boundary_stride, I.boundary_stride, I.boundary_stride, 1)) return rs;
+  if (ybgpu_status rs = ReadViaMapped(largest, I.d_boundary + static_cast<size_t>(I.n_blocks - 1) * 2 * I.boundary_stride, I.boundary_stride, I.boundary_stride, 1)) return rs;
   stats_.d2h_bytes += 2ull * I.boundary_stride;
   return YBGPU_OK;
 }
@@ -2419,8 +2517,7 @@ ybgpu_status Engine::FetchUserValues(ybgpu_user_value* smallest, ybgpu_user_valu
   if (!I.d_bv) return YBGPU_OK;                           // nothing survived / plain RocksDB mode
   CUDA_TRY(cudaSetDevice(opt_.device));
   std::vector<uint8_t> buf(sizeof(BvOut));
-  CUDA_TRY(cudaMemcpyAsync(buf.data(), I.d_bv, sizeof(BvOut), cudaMemcpyDeviceToHost, I.stream));
-  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  if (ybgpu_status rs = ReadViaMapped(buf.data(), I.d_bv, sizeof(BvOut), sizeof(BvOut), 1)) return rs;
   stats_.d2h_bytes += sizeof(BvOut);
   const BvOut& o = *reinterpret_cast<const BvOut*>(buf.data());
   if (o.overflow) return Fail(YBGPU_NOT_SUPPORTED, "more than 16 range components or a component longer than 255 bytes: boundary values not computed");
@@ -2450,13 +2547,12 @@ ybgpu_status Engine::FetchFilter(uint8_t* filters, uint8_t* keys, uint32_t* firs
   CUDA_TRY(cudaSetDevice(opt_.device));
   const size_t fb = static_cast<size_t>(I.n_filter_blocks) * I.filter_block_bytes, kb = static_cast<size_t>(I.n_filter_blocks) * 2 * I.filter_key_stride;
   if (I.n_filter_blocks) {
-    CUDA_TRY(cudaMemcpy2DAsync(filters, I.filter_block_bytes, I.d_filters, (I.filter_block_bytes + 7u) & ~7u, I.filter_block_bytes, I.n_filter_blocks,
-                               cudaMemcpyDeviceToHost, I.stream));
-    CUDA_TRY(cudaMemcpyAsync(keys, I.d_filter_keys, kb, cudaMemcpyDeviceToHost, I.stream));
-    CUDA_TRY(cudaMemcpyAsync(first_entry, I.d_filter_first, static_cast<size_t>(I.n_filter_blocks) * 4, cudaMemcpyDeviceToHost, I.stream));
+    if (ybgpu_status rs = ReadViaMapped(filters, I.d_filters, I.filter_block_bytes, (I.filter_block_bytes + 7u) & ~7u, I.n_filter_blocks)) return rs;
+    if (ybgpu_status rs = ReadViaMapped(keys, I.d_filter_keys, kb, kb, 1)) return rs;
+    const size_t fe = static_cast<size_t>(I.n_filter_blocks) * 4;
+    if (ybgpu_status rs = ReadViaMapped(first_entry, I.d_filter_first, fe, fe, 1)) return rs;
   }
-  if (I.n_blocks) CUDA_TRY(cudaMemcpyAsync(block_first, I.d_block_first, static_cast<size_t>(I.n_blocks) * 4, cudaMemcpyDeviceToHost, I.stream));
-  CUDA_TRY(cudaStreamSynchronize(I.stream));
+  if (I.n_blocks) { const size_t bf = static_cast<size_t>(I.n_blocks) * 4; if (ybgpu_status rs = ReadViaMapped(block_first, I.d_block_first, bf, bf, 1)) return rs; }
   stats_.d2h_bytes += fb + kb + static_cast<size_t>(I.n_filter_blocks) * 4 + static_cast<size_t>(I.n_blocks) * 4;
   return YBGPU_OK;
 }

@@ -51,6 +51,7 @@ class Engine {
   ybgpu_status CheckDeviceError(const char* phase);
   ybgpu_status ReadSmall(void* host_dst, const void* dev_src, size_t n);
   ybgpu_status UploadSmall(void* dev_dst, const void* host_src, size_t n);
+  ybgpu_status ReadViaMapped(void* host_dst, const void* dev_src, size_t row_bytes, size_t src_pitch, size_t rows);
   ybgpu_status EnsureKvStream();
   struct Impl;
   ybgpu_job_options opt_;

@@ -380,25 +380,36 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
     p.largest.assign(reinterpret_cast<const char*>(outputs[r].largest_key), outputs[r].largest_key_len);
     return p;
   };
-  // called with ot_mu held: feeds every piece whose successor is known to the builder, in key order
-  auto ot_advance = [&]() {
+  // Called with ot_mu held (through `lock`): feeds every piece whose successor is known to the builder, in key order.
+  // The assembly itself (index keys rebased, separators recomputed: milliseconds per piece) runs WITHOUT ot_mu — the
+  // other ranges publish their sizes and learn their offsets under that mutex — by whichever thread finds no assembler
+  // active; that thread keeps going until no further piece is ready.
+  bool ot_building = false;
+  auto ot_advance = [&](std::unique_lock<std::mutex>& lock) {
+    if (ot_building) return;
+    ot_building = true;
     while (ot_error.empty()) {
       uint32_t a = ot_next;
       while (a < n_ranges && ot_state[a] == 2 && ot_dlen[a] == 0) a++;
-      if (a >= n_ranges) { ot_next = n_ranges; return; }
-      if (ot_state[a] != 2) return;
+      if (a >= n_ranges) { ot_next = n_ranges; break; }
+      if (ot_state[a] != 2) break;
       uint32_t nx = a + 1;
       while (nx < n_ranges && ot_state[nx] == 2 && ot_dlen[nx] == 0) nx++;
-      if (nx < n_ranges && ot_state[nx] != 2) return;              // the successor's first key is not known yet
+      if (nx < n_ranges && ot_state[nx] != 2) break;               // the successor's first key is not known yet
       const ybgpu::host::SstPiece pa = ot_piece(a);
-      if (nx < n_ranges) { const ybgpu::host::SstPiece pn = ot_piece(nx); ot_error = ot_builder->AddPiece(pa, &pn); }
-      else ot_error = ot_builder->AddPiece(pa, nullptr);
+      ybgpu::host::SstPiece pn;
+      if (nx < n_ranges) pn = ot_piece(nx);
+      lock.unlock();
+      std::string e = ot_builder->AddPiece(pa, nx < n_ranges ? &pn : nullptr);
+      lock.lock();
+      ot_error = e;
       if (one->pieces == 0) one->smallest = pa.smallest;
       one->largest = pa.largest;
       one->pieces++;
       std::string().swap(ot_meta[a]);                               // the piece's own metadata file is no longer needed
       ot_next = nx;
     }
+    ot_building = false;
   };
 
   const bool trace = getenv("YBGPU_SUB_TRACE") != nullptr;      // per-range timeline on stderr (ms since the call)
@@ -449,7 +460,7 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
       h2d_next = r + 1;
     }
     order_cv.notify_all();
-    double t_begin = ms_now(), t_added = 0, t_ran = 0, t_sized = 0, t_fetched = 0;
+    double t_begin = ms_now(), t_added = 0, t_ran = 0, t_sized = 0, t_d2h = 0, t_fetched = 0;
     const std::string lo(reinterpret_cast<const char*>(out.range_lower), out.range_lower_len);
     const std::string hi(reinterpret_cast<const char*>(out.range_upper), out.range_upper_len);
     ybgpu_job_options o = *options;
@@ -526,6 +537,7 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
         }
         if (doff + dl > data_arena_cap) { job_fail(YBGPU_INVALID_ARGUMENT, "output arena too small"); return; }
         out_slot.Take(&d2h_gate);
+        t_d2h = ms_now();
         s = ybgpu_job_fetch_output(job, data_arena + doff, dl, meta_dst, ml);
         out_slot.Drop();
         if (s != YBGPU_OK) { job_fail(s, "fetch_output"); return; }
@@ -543,15 +555,16 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
       ybgpu_job_get_stats(job, &out.stats);
     }
     ybgpu_job_destroy(job);
+    const double t_destroyed = ms_now();
     if (one) {
-      std::lock_guard<std::mutex> lock(ot_mu);
+      std::unique_lock<std::mutex> lock(ot_mu);
       ot_state[r] = 2;
-      ot_advance();
       ot_cv.notify_all();
+      ot_advance(lock);
     }
     if (trace)
-      fprintf(stderr, "[ybgpu sub] range %2u: begin %7.1f  inputs queued %7.1f  run done %7.1f  meta built %7.1f  output fetched %7.1f  destroyed %7.1f  (gpu %.1f ms, %.2f GB in)\n",
-              r, t_begin, t_added, t_ran, t_sized, t_fetched, ms_now(), out.stats.gpu_seconds * 1e3, out.stats.h2d_bytes / 1e9);
+      fprintf(stderr, "[ybgpu sub] range %2u: begin %7.1f  inputs in %7.1f  run done %7.1f  meta built %7.1f  d2h start %7.1f  output fetched %7.1f  destroyed %7.1f  assembled %7.1f  (gpu %.1f ms, %.2f GB in)\n",
+              r, t_begin, t_added, t_ran, t_sized, t_d2h, t_fetched, t_destroyed, ms_now(), out.stats.gpu_seconds * 1e3, out.stats.h2d_bytes / 1e9);
   };
 
   auto worker = [&](bool pool_thread) {
@@ -575,8 +588,8 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
   }
   if (failed.load()) return fail(first_status, first_error);
   if (one) {
-    std::lock_guard<std::mutex> lock(ot_mu);
-    ot_advance();
+    std::unique_lock<std::mutex> lock(ot_mu);
+    ot_advance(lock);
     if (!ot_error.empty()) return fail(YBGPU_INVALID_ARGUMENT, "one-table assembly: " + ot_error);
     if (ot_next != n_ranges) return fail(YBGPU_RUNTIME_ERROR, "one-table assembly did not consume every range");
     for (uint32_t r = 0; r < n_ranges; r++) one->data_len += ot_dlen[r];
