@@ -2231,7 +2231,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     k_qq_final<<<(qthreads + 255) / 256, 256, 0, I.stream>>>(E.D, n, ri, d_qp, qchunks, E.QQ);
     launches += 8;
     // block cuts
-    k_next<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E);
+    k_next<<<static_cast<uint32_t>(std::min<uint64_t>((static_cast<uint64_t>(n) + NEXT_TILE - 1) / NEXT_TILE, static_cast<uint64_t>(sms) * 16)), 256, 0, I.stream>>>(E);
     const uint32_t nsegs = (n + SEG - 1) / SEG;
     const uint32_t ngroups = (nsegs + GROUP_SEGS - 1) / GROUP_SEGS;
     uint32_t *d_gexit = nullptr, *d_group_first = nullptr, *d_seg_first = nullptr, *d_spart = nullptr, *d_nblocks = nullptr;
