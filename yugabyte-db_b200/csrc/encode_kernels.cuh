@@ -91,8 +91,18 @@ __device__ __forceinline__ uint64_t kept_suffix(const uint8_t* rec, const Desc& 
 __global__ void __launch_bounds__(256) k_entry_sizes(EncView E, int S) {
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < E.n; j += gridDim.x * blockDim.x) {
     const Desc d = E.kept[j];
-    const uint8_t* rec = kept_rec(E, d, S);
     const uint32_t klen = d.klen, ulen = klen - 8u;
+    // the merge kernel has usually compared the key with the previous survivor's already (see its phase (e))
+    if (E.key_encoding != 2 && j > 0 && !(d.flags & ENT_VAL_REENCODE) && (d.rewrite_slot & 0xffffu) != 0xffffu) {
+      const uint32_t shared = d.rewrite_slot & 0xffffu, vlen = d.vlen_out;
+      const uint32_t nr = varint_len(shared) + varint_len(klen - shared) + varint_len(vlen) + (klen - shared) + vlen;
+      const uint32_t rs = 1 + varint_len(klen) + varint_len(vlen) + klen + vlen;
+      if (E.fk_len) E.fk_len[j] = E.fk_src ? E.fk_src[d.gid] : static_cast<uint16_t>(docdb_filter_prefix_len(kept_rec(E, d, S), static_cast<int>(ulen)));
+      E.nr[j] = nr; E.shared[j] = static_cast<uint16_t>(shared);
+      E.D[j] = static_cast<int16_t>(static_cast<int32_t>(rs) - static_cast<int32_t>(nr));
+      continue;
+    }
+    const uint8_t* rec = kept_rec(E, d, S);
     uint32_t shared = 0;
     if (j > 0) {
       const Desc pd = E.kept[j - 1];
@@ -264,76 +274,46 @@ __device__ __forceinline__ unsigned long long blk_cur(const EncView& E, uint32_t
 // next[s]: first entry of the block after the one starting at s (flush_block_policy.cc:45-76).
 // (A two-level variant — every 32nd start searched fully, the others guided by their neighbour's block
 // length — measured slower on B200 than this single pass from a static guess and was dropped.)
-// A CTA owns NEXT_TILE consecutive starts; every probe of their searches falls into the next few hundred entries, so the
-// window [tile start, + NEXT_WIN] of P, QQ and of the per-entry size estimate terms is staged in shared memory once and
-// the ~10 probes per start read it from there (probes beyond the window — blocks of thousands of entries — go to HBM).
-constexpr int NEXT_TILE = 1024;
-constexpr int NEXT_WIN = 2304;
+// (Staging the P / QQ window of 1024 consecutive starts in shared memory measured slower, 4.5 vs 4.1 ms at 10^8 entries:
+// the probes hit L2 anyway and the staging halves the occupancy.)
 __global__ void __launch_bounds__(256) k_next(EncView E) {
-  __shared__ unsigned long long sP[NEXT_WIN + 1];
-  __shared__ unsigned long long sQ[NEXT_WIN];
-  __shared__ uint32_t sAdd[NEXT_WIN];            // klen + vlen + their varint lengths + 4 of entry m (the estimate of Add(m))
   const unsigned long long BS = E.block_size;
   const unsigned long long thresh = BS * (100 - E.deviation);       // cur*100 > thresh
-  for (uint64_t base64 = static_cast<uint64_t>(blockIdx.x) * NEXT_TILE; base64 < E.n; base64 += static_cast<uint64_t>(gridDim.x) * NEXT_TILE) {
-    const uint32_t base = static_cast<uint32_t>(base64);
-    const uint32_t win = static_cast<uint32_t>(umin64(NEXT_WIN, E.n - base64));       // entries [base, base + win) are staged; P up to base + win
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= win; i += blockDim.x) sP[i] = E.P[base + i];
-    for (uint32_t i = threadIdx.x; i < win; i += blockDim.x) {
-      sQ[i] = E.QQ[base + i];
-      const Desc d = E.kept[base + i];
-      sAdd[i] = d.klen + d.vlen_out + 4u + varint_len(d.klen) + varint_len(d.vlen_out);
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < E.n; s += gridDim.x * blockDim.x) {
+    // smallest m in (s, n] such that the block [s, m) satisfies cur*100 > thresh (or m == n)
+    uint32_t lo = s + 1, hi = E.n;
+    if (E.deviation == 0) {
+      // only rule 1 (cur >= BS)
+      while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (blk_cur(E, s, mid - 1) >= BS) hi = mid; else lo = mid + 1; }
+      E.next[s] = lo;
+      continue;
     }
-    __syncthreads();
-    const uint32_t tile_end = static_cast<uint32_t>(umin64(base64 + NEXT_TILE, E.n));
-    for (uint32_t s = base + threadIdx.x; s < tile_end; s += blockDim.x) {
-      const unsigned long long Ps = sP[s - base];
-      const unsigned long long Qs = sQ[s - base] - static_cast<unsigned long long>(static_cast<long long>(E.D[s]));
-      // BlockBuilder::CurrentSizeEstimate after entries s..j of a block that started at s (blk_cur)
-      auto cur_of = [&](uint32_t j) -> unsigned long long {
-        const uint32_t t = (j - s) >> E.ri_shift;
-        const uint32_t qi = s + (t << E.ri_shift);
-        const unsigned long long Pj = (j + 1 - base <= win) ? sP[j + 1 - base] : E.P[j + 1];
-        const unsigned long long Qt = (qi - base < win) ? sQ[qi - base] : E.QQ[qi];
-        return (Pj - Ps) + (Qt - Qs) + 4ull * (t + 1) + 4ull;
-      };
-      // smallest m in (s, n] such that the block [s, m) satisfies cur*100 > thresh (or m == n)
-      uint32_t lo = s + 1, hi = E.n;
-      if (E.deviation == 0) {
-        // only rule 1 (cur >= BS)
-        while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (cur_of(mid - 1) >= BS) hi = mid; else lo = mid + 1; }
-        E.next[s] = lo;
-        continue;
+    {
+      // gallop: the answer is almost always within [guess, 2*guess] entries of s
+      uint32_t step = E.guess;
+      uint32_t probe = s + step < hi ? s + step : hi;
+      while (probe < hi && !(blk_cur(E, s, probe - 1) * 100 > thresh)) {
+        lo = probe + 1;
+        step <<= 1;
+        probe = (hi - probe > step) ? probe + step : hi;
       }
-      {
-        // gallop: the answer is almost always within [guess, 2*guess] entries of s
-        uint32_t step = E.guess;
-        uint32_t probe = s + step < hi ? s + step : hi;
-        while (probe < hi && !(cur_of(probe - 1) * 100 > thresh)) {
-          lo = probe + 1;
-          step <<= 1;
-          probe = (hi - probe > step) ? probe + step : hi;
-        }
-        if (probe < hi) hi = probe;
-      }
-      while (lo < hi) {
-        uint32_t mid = lo + ((hi - lo) >> 1);
-        if (cur_of(mid - 1) * 100 > thresh) hi = mid; else lo = mid + 1;
-      }
-      uint32_t m = lo;
-      while (m < E.n) {
-        const unsigned long long cur = cur_of(m - 1);
-        if (cur >= BS) break;
-        uint32_t add;
-        if (m - base < win) add = sAdd[m - base];
-        else { const Desc d = E.kept[m]; add = d.klen + d.vlen_out + 4u + varint_len(d.klen) + varint_len(d.vlen_out); }
-        const unsigned long long est = cur + add + ((((m - s) & (E.ri - 1)) == 0) ? 4 : 0);
-        if (est > BS && cur * 100 > thresh) break;
-        m++;
-      }
-      E.next[s] = m;
+      if (probe < hi) hi = probe;
     }
+    while (lo < hi) {
+      uint32_t mid = lo + ((hi - lo) >> 1);
+      if (blk_cur(E, s, mid - 1) * 100 > thresh) hi = mid; else lo = mid + 1;
+    }
+    uint32_t m = lo;
+    while (m < E.n) {
+      const unsigned long long cur = blk_cur(E, s, m - 1);
+      if (cur >= BS) break;
+      const Desc d = E.kept[m];
+      const unsigned long long est = cur + d.klen + d.vlen_out + ((((m - s) & (E.ri - 1)) == 0) ? 4 : 0) + 4 +
+                                     varint_len(d.klen) + varint_len(d.vlen_out);
+      if (est > BS && cur * 100 > thresh) break;
+      m++;
+    }
+    E.next[s] = m;
   }
 }
 

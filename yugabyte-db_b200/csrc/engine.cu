@@ -480,10 +480,9 @@ constexpr unsigned long long TILE_CONT = 1ull << 63;   // tile_rank flag: the ti
 constexpr uint32_t SAMPLE_COARSE = 32;
 __global__ void __launch_bounds__(256) k_sample_pos(PartView P, const JobParams* prm, JobDev* J, int pass) {
   const int S = prm->S, k = prm->k;
-  const uint64_t total = static_cast<uint64_t>(P.n_samples) * k;
-  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < total;
-       t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    const uint32_t s = static_cast<uint32_t>(t / k), r2 = static_cast<uint32_t>(t % k);
+  // one thread per sample: the splitter (row-group prefix, "inside a group" test against the previous sample) is worked
+  // out once, then searched in every run
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_samples; s += gridDim.x * blockDim.x) {
     // which run owns sample s
     int r = 0;
     while (r + 1 < k && P.sample_base[r + 1] <= s) r++;
@@ -499,31 +498,34 @@ __global__ void __launch_bounds__(256) k_sample_pos(PartView P, const JobParams*
       inside = rec_ulen(prec, S) >= static_cast<uint32_t>(g) && common_prefix_len(srec, g, prec, g) >= static_cast<uint32_t>(g) &&
                group_prefix_len(prec, rec_ulen(prec, S), prm->R.enabled != 0) == g;
     }
-    if (r2 == 0) P.smode[s] = inside ? 1 : 0;
-    const RunView& q = P.runs[r2];
-    uint32_t lo = 0, hi = q.n_entries;
-    if (pass == 1) {
-      const uint32_t c0 = s_local - s_local % SAMPLE_COARSE, c1 = c0 + SAMPLE_COARSE;
-      lo = P.pos[static_cast<size_t>(P.sample_base[r] + c0) * k + r2];
-      if (P.sample_base[r] + c1 < P.sample_base[r + 1]) hi = P.pos[static_cast<size_t>(P.sample_base[r] + c1) * k + r2];
-    }
-    if (inside) {
-      if (r2 == static_cast<uint32_t>(r)) lo = hi = idx;
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        const int c = cmp_records(q.rec + static_cast<size_t>(mid) * S, srec, S);
-        // merged order breaks ties by run index: equal records of lower runs come first
-        if (r2 < static_cast<uint32_t>(r) ? c <= 0 : c < 0) lo = mid + 1; else hi = mid;
+    P.smode[s] = inside ? 1 : 0;
+    const uint32_t c0 = s_local - s_local % SAMPLE_COARSE, c1 = c0 + SAMPLE_COARSE;
+    const bool have_c1 = P.sample_base[r] + c1 < P.sample_base[r + 1];
+    for (uint32_t r2 = 0; r2 < static_cast<uint32_t>(k); r2++) {
+      const RunView& q = P.runs[r2];
+      uint32_t lo = 0, hi = q.n_entries;
+      if (pass == 1) {
+        lo = P.pos[static_cast<size_t>(P.sample_base[r] + c0) * k + r2];
+        if (have_c1) hi = P.pos[static_cast<size_t>(P.sample_base[r] + c1) * k + r2];
       }
-    } else {
-      while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        const uint8_t* c = q.rec + static_cast<size_t>(mid) * S;
-        // first record whose user key >= prefix
-        if (cmp_prefix_vs_key(srec, g, c, rec_ulen(c, S)) > 0) lo = mid + 1; else hi = mid;
+      if (inside) {
+        if (r2 == static_cast<uint32_t>(r)) lo = hi = idx;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          const int c = cmp_records(q.rec + static_cast<size_t>(mid) * S, srec, S);
+          // merged order breaks ties by run index: equal records of lower runs come first
+          if (r2 < static_cast<uint32_t>(r) ? c <= 0 : c < 0) lo = mid + 1; else hi = mid;
+        }
+      } else {
+        while (lo < hi) {
+          uint32_t mid = (lo + hi) >> 1;
+          const uint8_t* c = q.rec + static_cast<size_t>(mid) * S;
+          // first record whose user key >= prefix
+          if (cmp_prefix_vs_key(srec, g, c, rec_ulen(c, S)) > 0) lo = mid + 1; else hi = mid;
+        }
       }
+      P.pos[static_cast<size_t>(s) * k + r2] = lo;
     }
-    P.pos[static_cast<size_t>(s) * k + r2] = lo;
   }
 }
 
@@ -1156,6 +1158,22 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
     if (f & ENT_VAL_TOMBSTONE) vout = 1;
     else if (f & ENT_VAL_REENCODE) { const ValueRewrite& rw = V.rewrites[rw_slot[i]]; vout = vout - rw.skip + rw.prefix_len; }
     d.vlen_out = vout;
+    if ((f & ENT_KEEP) && !(f & ENT_VAL_REENCODE)) {
+      // For the block encoder: bytes shared with the previous SURVIVOR's key (BlockBuilder::Add, block_builder.cc:363-365),
+      // found here while both records sit in shared memory; it rides in the unused rewrite slot. 0xffff = not known (first
+      // survivor of the tile, a long run of dropped entries in between, one user key a prefix of the other): k_entry_sizes
+      // computes those few from the records.
+      uint32_t sh = 0xffffu;
+      int j = static_cast<int>(i) - 1;
+      for (int steps = 0; j >= 0 && !(res[j] & ENT_KEEP) && steps < 24; steps++) j--;
+      if (j >= 0 && (res[j] & ENT_KEEP)) {
+        const uint8_t* p = recs + static_cast<size_t>(SS) * order[j];
+        const uint32_t m = min(rec_ulen(e, S), rec_ulen(p, S));
+        const uint32_t c = common_prefix_len(e, m, p, m);
+        if (c < m) sh = c;
+      }
+      d.rewrite_slot = sh;
+    }
     V.desc[rank0 + i] = d;
     if (f & ENT_KEEP) {
       st_kept++; st_kbytes += d.klen; st_vbytes += vout;
@@ -2058,7 +2076,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   // only adversarial inputs approach the bound H + 2kM, and the partition is then repeated with a smaller M (below).
   static const uint32_t h_pct = [] { const char* v = getenv("YBGPU_TILE_H_PCT"); const int x = v ? atoi(v) : 0; return static_cast<uint32_t>(x >= 25 && x <= 90 ? x : 65); }();
   hp.H = std::max(1u, cap * h_pct / 100);
-  hp.M = std::max(1u, (cap / 2) / std::max(1, k));
+  // between two consecutive candidates lie fewer than M records of every run, so a tile of small rows holds at most H + kM
+  hp.M = std::max(1u, std::min(cap / 2, cap - hp.H) / std::max(1, k));
   hp.R.enabled = opt_.retention_enabled;
   hp.R.cutoff_ht = opt_.history_cutoff_ht;
   hp.R.table_ttl_ns = opt_.table_ttl_ns;
@@ -2126,8 +2145,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     if (ybgpu_status us = UploadSmall(d_sample_base, sample_base.data(), 4 * (k + 1))) return us;
     CUDA_TRY(cudaMemsetAsync(pv.bucket_min, 0xff, static_cast<size_t>(n_buckets) * 8, I.stream));
     pv.runs = I.dRuns; pv.sample_base = d_sample_base; pv.n_samples = n_samples; pv.n_buckets = n_buckets;
-    k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ, 0);
-    k_sample_pos<<<GridFor(static_cast<uint64_t>(n_samples) * k, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ, 1);
+    k_sample_pos<<<GridFor(n_samples, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ, 0);
+    k_sample_pos<<<GridFor(n_samples, 256, sms), 256, 0, I.stream>>>(pv, I.dP, I.dJ, 1);
     k_sample_bucket<<<GridFor(n_samples, 256, sms), 256, 0, I.stream>>>(pv, I.dP);
     {
       const uint32_t tchunks = (n_buckets + TILE_CHUNK - 1) / TILE_CHUNK;
@@ -2231,7 +2250,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     k_qq_final<<<(qthreads + 255) / 256, 256, 0, I.stream>>>(E.D, n, ri, d_qp, qchunks, E.QQ);
     launches += 8;
     // block cuts
-    k_next<<<static_cast<uint32_t>(std::min<uint64_t>((static_cast<uint64_t>(n) + NEXT_TILE - 1) / NEXT_TILE, static_cast<uint64_t>(sms) * 16)), 256, 0, I.stream>>>(E);
+    k_next<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E);
     const uint32_t nsegs = (n + SEG - 1) / SEG;
     const uint32_t ngroups = (nsegs + GROUP_SEGS - 1) / GROUP_SEGS;
     uint32_t *d_gexit = nullptr, *d_group_first = nullptr, *d_seg_first = nullptr, *d_spart = nullptr, *d_nblocks = nullptr;
