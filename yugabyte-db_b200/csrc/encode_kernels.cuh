@@ -1432,12 +1432,13 @@ __device__ __forceinline__ uint32_t enc5_crc_word(const uint32_t (*tab)[256], ui
 __device__ __forceinline__ uint32_t enc5_xpow(unsigned long long nbytes) {
   return nbytes <= CRC_XPOW_TABLE ? __ldg(&g_crc_xpow8[nbytes]) : crc_xpow_bytes(nbytes, g_crc_x2n);
 }
+__device__ __forceinline__ void enc5_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void enc5_store_u32(uint8_t* p, uint32_t v) {
   p[0] = static_cast<uint8_t>(v); p[1] = static_cast<uint8_t>(v >> 8); p[2] = static_cast<uint8_t>(v >> 16); p[3] = static_cast<uint8_t>(v >> 24);
 }
 
 template <int ENC>
-__global__ void __launch_bounds__(ENC5_THREADS) k_encode_v5(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
+__global__ void __launch_bounds__(ENC5_THREADS, ENC == 1 ? 4 : 2) k_encode_v5(EncView E, int S, const uint32_t* block_first, uint32_t nblocks,
                                                           const unsigned long long* block_off, uint8_t* out, uint32_t G) {
   extern __shared__ __align__(16) uint8_t v5_smem[];      // tab[4][256], then ENC5_THREADS scratch rows of G bytes
   uint32_t (*tab)[256] = reinterpret_cast<uint32_t (*)[256]>(v5_smem);
@@ -1457,15 +1458,23 @@ __global__ void __launch_bounds__(ENC5_THREADS) k_encode_v5(EncView E, int S, co
     const unsigned long long body = (E.P[e] - Ps) + (E.QQ[s + (tl << E.ri_shift)] - Qs);
     uint8_t* const blk = out + boff;
     unsigned long long acc = 0;                  // XOR of unreduced carry-less products
+    // The kernel is bound by memory latency (a round's loads form a chain: descriptor -> record / value offset -> value
+    // bytes), so the next round's chain is started ahead: its descriptors are loaded while this round's entries are
+    // assembled, its record and value lines are requested into L2 while this round's values are copied.
+    Desc d_cur{};
+    if (s + lane < e) d_cur = E.kept[s + lane];
     for (uint32_t r0 = s; r0 < e; r0 += 32) {
       const uint32_t j = r0 + lane;
+      const uint32_t jn = j + 32;
+      Desc d_next{};
+      if (jn < e) d_next = E.kept[jn];
       unsigned long long eoff = 0, srcp = 0;
       uint32_t gap_len = 0, copy_len = 0;
       if (j < e) {
         const bool restart = ((j - s) & (E.ri - 1)) == 0;
         eoff = E.P[j] - Ps;
         if (j > s) { const uint32_t tp = (j - 1 - s) >> E.ri_shift; eoff += E.QQ[s + (tp << E.ri_shift)] - Qs; }
-        const Desc d = E.kept[j];
+        const Desc d = d_cur;
         const uint8_t* rec = kept_rec(E, d, S);
         const RunView& run = E.runs[d.run];
         const uint32_t idx = d.gid - run.gid_base;
@@ -1504,6 +1513,13 @@ __global__ void __launch_bounds__(ENC5_THREADS) k_encode_v5(EncView E, int S, co
         }
       }
       __syncwarp();
+      const uint8_t* next_val = nullptr;
+      if (jn < e) {
+        const RunView& rn = E.runs[d_next.run];
+        const uint32_t idxn = d_next.gid - rn.gid_base;
+        enc5_prefetch_l2(rn.rec + static_cast<size_t>(idxn) * S);
+        next_val = rn.data + rn.val_off[idxn];
+      }
       const uint32_t nact = min(32u, e - r0);
 #pragma unroll 2
       for (uint32_t q0 = 0; q0 < nact; q0 += 2) {
@@ -1534,6 +1550,12 @@ __global__ void __launch_bounds__(ENC5_THREADS) k_encode_v5(EncView E, int S, co
           }
         }
       }
+      if (next_val) {
+        const uint32_t vl = d_next.vlen_out;
+        for (uint32_t o = 0; o < vl; o += 128) enc5_prefetch_l2(next_val + o);
+        if (vl) enc5_prefetch_l2(next_val + vl - 1);
+      }
+      d_cur = d_next;
       __syncwarp();                                // the scratch rows are rewritten by the next round
     }
     // restart count + type byte, the 0xffffffff initial register's share, trailer

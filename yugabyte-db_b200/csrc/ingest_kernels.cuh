@@ -34,8 +34,9 @@
 
 namespace ybgpu {
 
-constexpr int ING_CONSUMERS = 128;            // warps 0-3: one thread per entry
-constexpr int ING_THREADS = 192;              // + warp 4: walker (entry headers), warp 5: producer (tickets, handles, bulk copies)
+constexpr int ING_CONSUMERS = 128;            // threads per consumer role: warps 0-3 rebuild keys and write records, warps 4-7 compute the CRCs
+constexpr int ING_WALKER = 8, ING_PRODUCER = 9;   // warp 8: walker (entry headers), warp 9: producer (tickets, handles, bulk copies)
+constexpr int ING_THREADS = 320;
 constexpr uint32_t ING_BUF = 34304;           // staged bytes per block (33.5 KB): contents + trailer + alignment slack
 constexpr int ING_MAXE = 512;                 // entries per block
 constexpr int ING_REP = 8;                    // replication of the CRC tables
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
   if (threadIdx.x < 17) sh_upto[threadIdx.x] = low_bytes_mask16(static_cast<int>(threadIdx.x));
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; s++) {
-      mbar_init(&full_bar[s], 1); mbar_init(&walked_bar[s], 1); mbar_init(&empty_bar[s], ING_CONSUMERS / 32);
+      mbar_init(&full_bar[s], 1); mbar_init(&walked_bar[s], 1); mbar_init(&empty_bar[s], 2 * ING_CONSUMERS / 32);
       sh_acc[s] = 0; sh_cnt[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
   const uint32_t total_blocks = V.blk_base[V.k];
   const int S = V.S;
 
-  if (wid == 5) {
+  if (wid == ING_PRODUCER) {
     // ---------------- producer
     uint32_t uses[2] = {0, 0};
     int stage = 0;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
     return;
   }
 
-  if (wid == 4) {
+  if (wid == ING_WALKER) {
     // ---------------- walker
     uint32_t maxk = 0;
     for (uint32_t it = 0;; it++) {
@@ -471,8 +472,10 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
     const IngEntry* etab = etab0 + stage * ING_MAXE;
     const uint32_t L = size + 1;                       // contents + type byte
     const bool filtered = ht_filter != 0xfffffffffffffffeull || ranged;
-    unsigned long long acc = 0;                        // XOR of unreduced carry-less products
-    for (uint32_t e = threadIdx.x; e < n_ent; e += ING_CONSUMERS) {
+    unsigned long long acc = 0;                        // XOR of unreduced carry-less products (CRC warps)
+    const uint32_t rt = threadIdx.x & (ING_CONSUMERS - 1);   // thread index inside its role
+    if (wid < ING_CONSUMERS / 32) {
+    for (uint32_t e = rt; e < n_ent; e += ING_CONSUMERS) {
       const IngEntry en = etab[e];
       uint4 kv[ING_NVI];
 #pragma unroll
@@ -561,9 +564,14 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
       tr.z = ulen | (static_cast<uint32_t>(vfirst) << 16) | (static_cast<uint32_t>(flags) << 24);
       tr.w = vlen;
       *reinterpret_cast<uint4*>(rec + S - 16) = tr;
+      val_off[base + e] = boff + en.vstart;
+    }
+    } else {
+    for (uint32_t e = rt; e < n_ent; e += ING_CONSUMERS) {
+      const IngEntry en = etab[e];
+      const uint32_t vlen = en.vlen;
       // CRCs
       const uint32_t vc = ing_crc_span2(T, blk + en.vstart, vlen);
-      val_off[base + e] = boff + en.vstart;
       val_crc[base + e] = vc;
       if (V.verify) {
         const uint32_t gc = ing_crc_span(T, blk + en.estart, en.vstart - en.estart);
@@ -571,7 +579,8 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
         acc ^= crc_clmul(gc, __ldg(&g_crc_xpow8[L - en.vstart])) ^ crc_clmul(vc, __ldg(&g_crc_xpow8[L - en.vstart - vlen]));
       }
     }
-    if (V.verify && n_ent) {
+    }
+    if (wid >= ING_CONSUMERS / 32 && V.verify && n_ent) {
       uint32_t a32 = ing_clmul_reduce(T, acc);
       a32 = __reduce_xor_sync(0xffffffffu, a32);
       if (lane == 0) {
