@@ -289,15 +289,29 @@ __global__ void __launch_bounds__(256) k_next(EncView E) {
       continue;
     }
     {
-      // gallop: the answer is almost always within [guess, 2*guess] entries of s
-      uint32_t step = E.guess;
-      uint32_t probe = s + step < hi ? s + step : hi;
-      while (probe < hi && !(blk_cur(E, s, probe - 1) * 100 > thresh)) {
-        lo = probe + 1;
-        step <<= 1;
-        probe = (hi - probe > step) ? probe + step : hi;
+      // interpolation: entries of one block have similar sizes, so "bytes still missing / bytes per entry so far" lands
+      // within an entry or two of the answer; every probe tightens [lo, hi) (the predicate is monotone), the binary
+      // search below finishes whatever is left (a probe costs two or three L2 round trips — this is what the kernel
+      // is made of: ~4 probes per start instead of ~10 with galloping + bisection)
+      uint32_t m = s + E.guess + (E.guess >> 3);
+      for (int it = 0; it < 3 && lo < hi; it++) {
+        if (m < lo) m = lo;
+        if (m > hi) m = hi;
+        const unsigned long long cur = blk_cur(E, s, m - 1);
+        const unsigned long long have = cur * 100;
+        const unsigned long long bpe = cur / (m - s) + 1;                      // bytes per entry so far (>= 1)
+        if (have > thresh) {
+          hi = m;
+          const unsigned long long over = (have - thresh) / 100;
+          const unsigned long long back = over / bpe + 1;
+          m = back >= m - s ? s + 1 : m - static_cast<uint32_t>(back);
+        } else {
+          lo = m < E.n ? m + 1 : E.n;
+          const unsigned long long miss = (thresh - have) / 100;
+          const unsigned long long fwd = miss / bpe + 1;
+          m = fwd >= E.n - m ? E.n : m + static_cast<uint32_t>(fwd);
+        }
       }
-      if (probe < hi) hi = probe;
     }
     while (lo < hi) {
       uint32_t mid = lo + ((hi - lo) >> 1);
@@ -1619,10 +1633,21 @@ __global__ void __launch_bounds__(256) k_filter_build(EncView E, int S, const ui
   }
 }
 
+// Hashes of the distinct filter keys, one thread per key at full occupancy (the chain ordinal -> survivor -> record is
+// three dependent loads; the block builder below then streams the hashes instead of walking that chain with a
+// thousand threads per filter block).
+__global__ void __launch_bounds__(256) k_filter_hash(EncView E, int S, const uint32_t* new_entry, uint32_t n_keys, uint32_t* hashes) {
+  for (uint32_t ord = blockIdx.x * blockDim.x + threadIdx.x; ord < n_keys; ord += gridDim.x * blockDim.x) {
+    const uint32_t j = new_entry[ord];
+    const Desc d = E.kept[j];
+    hashes[ord] = leveldb_hash(kept_rec(E, d, S), E.fk_len[j], kBloomSeed);
+  }
+}
+
 // Same, one CTA per filter block with the bits assembled in shared memory (a 64 KB block fits):
 // shared-memory atomics instead of ~6 scattered global atomics per key, then one coalesced write.
 constexpr uint32_t FILTER_SMEM_MAX = 96 * 1024;
-__global__ void __launch_bounds__(1024) k_filter_build_smem(EncView E, int S, const uint32_t* new_entry, uint32_t n_keys, BloomGeometry g, uint32_t nfb,
+__global__ void __launch_bounds__(1024) k_filter_build_smem(const uint32_t* hashes, uint32_t n_keys, BloomGeometry g, uint32_t nfb,
                                                             uint32_t parts, uint8_t* filters) {
   // `parts` CTAs share one filter block (each takes a slice of its keys); the zero-initialised
   // global block receives the non-zero words of every partial image by atomicOr.
@@ -1636,10 +1661,7 @@ __global__ void __launch_bounds__(1024) k_filter_build_smem(EncView E, int S, co
     const uint32_t per = (hi - lo + parts - 1) / parts;
     const uint32_t plo = min(hi, lo + part * per), phi = min(hi, plo + per);
     for (uint32_t ord = plo + threadIdx.x; ord < phi; ord += blockDim.x) {
-      const uint32_t j = new_entry[ord];
-      const Desc d = E.kept[j];
-      const uint8_t* rec = kept_rec(E, d, S);
-      uint32_t h = leveldb_hash(rec, E.fk_len[j], kBloomSeed);
+      uint32_t h = hashes[ord];
       const uint32_t delta = (h >> 17) | (h << 15);
       uint32_t* line = fbits + (h % g.num_lines) * (kBloomLineBits / 32);
       for (uint32_t i = 0; i < g.num_probes; i++) {

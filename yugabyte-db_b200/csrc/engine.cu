@@ -2355,7 +2355,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
         CUDA_TRY(cudaFuncSetAttribute(k_filter_build_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.dev_stride)));
         const uint32_t resident = std::max<uint32_t>(1, std::min<uint32_t>(2, (200u * 1024u) / (g.dev_stride + 1024u))) * sms;   // CTAs that fit at once
         const uint32_t parts = std::max<uint32_t>(1, std::min<uint32_t>(8, resident / nfb));
-        k_filter_build_smem<<<std::min<uint32_t>(nfb * parts, resident * 4), 1024, g.dev_stride, I.stream>>>(E, Sfinal, d_new_entry, n_keys, g, nfb, parts, I.d_filters);
+        uint32_t* d_hash = nullptr;
+        CUDA_TRY(DevAlloc(&I.allocs, &d_hash, n_keys));
+        k_filter_hash<<<GridFor(n_keys, 256, sms), 256, 0, I.stream>>>(E, Sfinal, d_new_entry, n_keys, d_hash);
+        k_filter_build_smem<<<std::min<uint32_t>(nfb * parts, resident * 4), 1024, g.dev_stride, I.stream>>>(d_hash, n_keys, g, nfb, parts, I.d_filters);
+        launches++;
       } else if (n_keys) {
         k_filter_build<<<GridFor(n_keys, 256, sms), 256, 0, I.stream>>>(E, Sfinal, d_new_entry, n_keys, g, I.d_filters);
       }
