@@ -17,6 +17,8 @@ out = {}
 ki = H.index('Kernel Name')
 for r in rows[2:]:
     name = r[ki].split('(')[0]
+    if name.startswith('void '):
+        name = name[5:]
     d = {}
     for w in want:
         if w in H:
@@ -30,4 +32,5 @@ for r in rows[2:]:
     for k, v in d.items():
         print('  ', k, v if k == "top_stalls_per_issue" else (v["value"], v["unit"]))
 if len(sys.argv) > 2:
-    json.dump(out, open(sys.argv[2], 'w'), indent=1)
+    src = sys.argv[3] if len(sys.argv) > 3 else "ncu --set full --clock-control none, bench.py default workload (config 2, 100 M entries, 1 GPU), one launch per kernel"
+    json.dump({"source": src, "kernels": out}, open(sys.argv[2], 'w'), indent=1)

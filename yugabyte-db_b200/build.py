@@ -23,11 +23,17 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    tmp = OUT + ".tmp%d" % os.getpid()          # written beside the target, then renamed: a snapshot of the tree never sees half a library
+    cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
-    subprocess.check_call(cmd)
+    try:
+        subprocess.check_call(cmd)
+        os.replace(tmp, OUT)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return OUT
 
 

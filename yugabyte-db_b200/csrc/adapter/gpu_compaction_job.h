@@ -103,6 +103,22 @@ struct DocDBRetention {
 // rocksdb::UserBoundaryValue (rocksdb/metadata.h): tag + encoded key component.
 struct UserBoundaryValue { uint32_t tag = 0; std::string value; };
 
+// FdWithBoundaries::user_filter_data (db/version_set.cc:3824) -> the engine's per-file HybridTime filter. Empty: no
+// filter. 8 bytes: the global filter (docdb/consensus_frontier.cc:245-253; invisible above it,
+// docdb_rocksdb_util.cc:534-537). Longer: per-database cotable filters follow (master sys catalog after a restore,
+// docdb_rocksdb_util.cc:503-509,541-563) — the engine does not apply those, the caller keeps the CPU job.
+inline Status HybridTimeFilterFromUserFilterData(const Slice& user_filter_data, uint64_t* hybrid_time_filter) {
+  *hybrid_time_filter = YBGPU_HT_INVALID;
+  if (user_filter_data.empty()) return Status();
+  if (user_filter_data.size() < 8) return Status(Status::kCorruption, "user_filter_data shorter than a HybridTime");
+  if (user_filter_data.size() > 8)
+    return Status(Status::kNotSupported, "per-database cotable HybridTime filters are not applied by the GPU engine");
+  uint64_t ht;
+  memcpy(&ht, user_filter_data.data(), 8);
+  *hybrid_time_filter = ht;
+  return Status();
+}
+
 // One L0 input file, as VersionSet::MakeInputIterator sees it (db/version_set.cc:3788-3849).
 struct InputFile {
   Slice base_file;            // <n>.sst (metadata file) bytes

@@ -2210,8 +2210,12 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       return Fail(YBGPU_NOT_SUPPORTED, "block_restart_interval must be a power of two <= 64 for the GPU block encoder");
     if (opt_.output_key_encoding != YBGPU_KEY_ENCODING_SHARED_PREFIX && opt_.output_key_encoding != YBGPU_KEY_ENCODING_THREE_SHARED_PARTS)
       return Fail(YBGPU_INVALID_ARGUMENT, "unknown output_key_encoding");
-    CUDA_TRY(DevAlloc(&I.allocs, &I.d_kept, n));
-    k_compact_desc<<<n_chunks, EMIT_THREADS, 0, I.stream>>>(d_desc, N, d_partial, I.d_kept);
+    if (static_cast<uint64_t>(n) == N) {
+      I.d_kept = d_desc;                                  // nothing was dropped: the merged-order list IS the survivor list
+    } else {
+      CUDA_TRY(DevAlloc(&I.allocs, &I.d_kept, n));
+      k_compact_desc<<<n_chunks, EMIT_THREADS, 0, I.stream>>>(d_desc, N, d_partial, I.d_kept);
+    }
     EncView& E = I.enc;
     E.runs = I.dRuns; E.kept = I.d_kept; E.rewrites = d_rw; E.n = n; E.ri = ri;
     E.ri_shift = 0; while ((1u << E.ri_shift) < ri) E.ri_shift++;
