@@ -587,6 +587,20 @@ YB_HD int parse_entry_header(const uint8_t* p, uint32_t avail, uint32_t* shared,
   if (avail < 3) return 0;
   uint32_t a = p[0], b = p[1], c = p[2];
   if ((a | b | c) < 128) { *shared = a; *non_shared = b; *vlen = c; return 3; }
+  if (avail >= 6) {
+    // fields of at most two bytes (values below 16384: every key, most values): straight-line, no byte loop
+    const uint32_t d = p[3], e = p[4], f = p[5];
+    uint32_t i = 1, v0 = a, v1, v2;
+    bool ok = true;
+    if (a & 128) { ok = !(b & 128); v0 = (a & 127) | (b << 7); i = 2; }
+    const uint32_t q0 = i == 1 ? b : c, q1 = i == 1 ? c : d;
+    v1 = q0; uint32_t i1 = i + 1;
+    if (q0 & 128) { ok = ok && !(q1 & 128); v1 = (q0 & 127) | (q1 << 7); i1 = i + 2; }
+    const uint32_t r0 = i1 == 2 ? c : (i1 == 3 ? d : e), r1 = i1 == 2 ? d : (i1 == 3 ? e : f);
+    v2 = r0; uint32_t i2 = i1 + 1;
+    if (r0 & 128) { ok = ok && !(r1 & 128); v2 = (r0 & 127) | (r1 << 7); i2 = i1 + 2; }
+    if (ok) { *shared = v0; *non_shared = v1; *vlen = v2; return static_cast<int>(i2); }
+  }
   uint32_t out[3]; uint32_t i = 0;
   for (int f = 0; f < 3; f++) {
     uint32_t r = 0; int shift = 0; bool done = false;

@@ -172,10 +172,7 @@ __global__ void __launch_bounds__(256) k_block_counts(const RunView* runs, const
   }
 }
 
-// offsets inside the block (a block is at most ING_BUF bytes), key delta geometry (key length = shared + vstart - kstart),
-// `prev` = the latest earlier entry of the restart interval whose `shared` is smaller (where the inherited bytes below
-// this entry's `shared` continue; unused for the restart entry itself)
-struct IngEntry { uint16_t estart, kstart, vstart, vlen, shared, prev; };
+struct IngEntry { uint16_t estart, kstart, vstart, vlen, shared, klen; };    // offsets inside the block (a block is at most ING_BUF bytes), key delta geometry
 
 // The four slicing tables, ING_REP = 8 copies, laid out so that the TABLE index is part of the bank number:
 //   word address of T_t[e], copy c  =  e * 32 + t * 8 + c        (bank = t * 8 + c, independent of e)
@@ -419,13 +416,7 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
             if (klen > static_cast<uint32_t>(S) - 8) fallback = ING_FALLBACK_WIDER;      // user key longer than S - 16: the walk goes on (longest key)
             IngEntry e;
             e.estart = static_cast<uint16_t>(p); e.kstart = static_cast<uint16_t>(p + h); e.vstart = static_cast<uint16_t>(p + h + non_shared);
-            e.vlen = static_cast<uint16_t>(vlen); e.shared = static_cast<uint16_t>(shared);
-            {
-              // previous smaller `shared` (amortised O(1): follows the links of the entries it skips)
-              uint32_t pj = static_cast<uint32_t>(slot);
-              if (n && shared) { pj--; while (etab[pj].shared >= shared) pj = etab[pj].prev; }
-              e.prev = static_cast<uint16_t>(pj);
-            }
+            e.vlen = static_cast<uint16_t>(vlen); e.shared = static_cast<uint16_t>(shared); e.klen = static_cast<uint16_t>(klen);
             etab[slot] = e;
             p += h + non_shared + vlen;
             n++;
@@ -447,12 +438,8 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
         if (bad || fallback) n_ent = 0;
         // the block's entry count was fixed by the probe + scan; it must agree with what the walk found
         else if (n_ent != expect) { dev_fail(J, DEV_ERR_IRREGULAR_RESTARTS, b); n_ent = 0; }
-        if (V.verify && n_ent) {
-          // tail: restart array, restart count, type byte; and the 0xffffffff initial register's share
-          const uint32_t L = size + 1;
-          tail = ing_crc_span(T, blk + restarts_off, L - restarts_off);
-          tail ^= ing_clmul_reduce(T, crc_clmul(L <= CRC_XPOW_TABLE ? __ldg(&g_crc_xpow8[L]) : crc_xpow_bytes(L, g_crc_x2n), 0xffffffffu));
-        }
+        // (the CRC of the block's tail is left to the CRC warps: this warp is the serial stage of the pipeline — a lane
+        // parses its restart interval entry by entry — and everything it does beyond that lengthens the pipeline period)
         sh_nent[stage] = n_ent; sh_tail[stage] = tail;
       }
       __syncwarp();                                // the lanes' entry table writes are ordered before lane 0's arrive
@@ -486,7 +473,6 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
     if (wid < ING_CONSUMERS / 32) {
     for (uint32_t e = rt; e < n_ent; e += ING_CONSUMERS) {
       const IngEntry en = etab[e];
-      const uint32_t klen = static_cast<uint32_t>(en.shared) + en.vstart - en.kstart;
       uint4 kv[ING_NVI];
 #pragma unroll
       for (int w = 0; w < ING_NVI; w++) kv[w] = make_uint4(0, 0, 0, 0);
@@ -504,29 +490,33 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
       // bytes behind klen are never looked at (the record write masks by the key length)
 #pragma unroll
       for (int w = 0; w < ING_NVI; w++)
-        if (16 * w + 16 > static_cast<int>(en.shared) && 16 * w < static_cast<int>(klen)) kv[w] = fetch(en.kstart, en.shared, w);
-      // inherited bytes [0, shared): following the `prev` links (each points at the latest earlier entry with a smaller
-      // `shared`), an entry contributes the bytes between its own `shared` and the one it was reached from; the restart
-      // entry has shared = 0 and ends the walk (the walker validated all that and built the links). A contribution overwrites everything below `need` in its windows: what it writes below its own
+        if (16 * w + 16 > static_cast<int>(en.shared) && 16 * w < static_cast<int>(en.klen)) kv[w] = fetch(en.kstart, en.shared, w);
+      // inherited bytes [0, shared): walking back, an entry contributes the bytes between its own `shared` and the
+      // lowest `shared` met so far (the restart entry has shared = 0 and ends the walk; the walker validated all
+      // that). A contribution overwrites everything below `need` in its windows: what it writes below its own
       // `shared` is overwritten in turn by the entries further back.
       {
-        uint32_t need = en.shared, j = en.prev;
-        while (need) {
-          const uint32_t sj = etab[j].shared, kstart = etab[j].kstart, pj = etab[j].prev;      // sj < need: every link is a contribution
+        uint32_t need = en.shared;
+        for (uint32_t j = e; need; ) {
+          j--;
+          const uint32_t sj = etab[j].shared;
+          if (sj < need) {
+            const uint32_t kstart = etab[j].kstart;
 #pragma unroll
-          for (int w = 0; w < ING_NVI; w++) {
-            if (16 * w + 16 <= static_cast<int>(sj) || 16 * w >= static_cast<int>(need)) continue;
-            const uint4 nw = fetch(kstart, sj, w);
-            const uint4 m = sh_upto[min(need - 16 * w, 16u)];
-            kv[w].x = (nw.x & m.x) | (kv[w].x & ~m.x);
-            kv[w].y = (nw.y & m.y) | (kv[w].y & ~m.y);
-            kv[w].z = (nw.z & m.z) | (kv[w].z & ~m.z);
-            kv[w].w = (nw.w & m.w) | (kv[w].w & ~m.w);
+            for (int w = 0; w < ING_NVI; w++) {
+              if (16 * w + 16 <= static_cast<int>(sj) || 16 * w >= static_cast<int>(need)) continue;
+              const uint4 nw = fetch(kstart, sj, w);
+              const uint4 m = sh_upto[min(need - 16 * w, 16u)];
+              kv[w].x = (nw.x & m.x) | (kv[w].x & ~m.x);
+              kv[w].y = (nw.y & m.y) | (kv[w].y & ~m.y);
+              kv[w].z = (nw.z & m.z) | (kv[w].z & ~m.z);
+              kv[w].w = (nw.w & m.w) | (kv[w].w & ~m.w);
+            }
+            need = sj;
           }
-          need = sj; j = pj;
         }
       }
-      const uint32_t ulen = klen - 8, vlen = en.vlen;
+      const uint32_t klen = en.klen, ulen = klen - 8, vlen = en.vlen;
       // suffix = internal-key bytes [ulen, ulen + 8)
       uint4 va = kv[0], vb = kv[1];
 #pragma unroll
@@ -588,6 +578,12 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
     }
     if (wid >= ING_CONSUMERS / 32 && V.verify && n_ent) {
       uint32_t a32 = ing_clmul_reduce(T, acc);
+      if (rt == ING_CONSUMERS - 1) {
+        // tail: restart array, restart count, type byte; and the 0xffffffff initial register's share (L < 64 K)
+        const uint32_t nres = ld_u32_unaligned(blk + size - 4);
+        const uint32_t restarts_off = size - 4 - 4 * nres;
+        a32 ^= ing_crc_span(T, blk + restarts_off, L - restarts_off) ^ ing_clmul_reduce(T, crc_clmul(__ldg(&g_crc_xpow8[L]), 0xffffffffu));
+      }
       a32 = __reduce_xor_sync(0xffffffffu, a32);
       if (lane == 0) {
         if (a32) atomicXor(&sh_acc[stage], a32);
