@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
 
   if (wid == ING_WALKER) {
     // ---------------- walker
+    uint32_t maxk = 0;
     for (uint32_t it = 0;; it++) {
       const int stage = it & 1;
       mbar_wait(&full_bar[stage], (it >> 1) & 1);
@@ -401,19 +402,22 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
           uint32_t p = ld_u32_unaligned(blk + restarts_off + 4 * r);
           const uint32_t end = (r + 1 < nres) ? ld_u32_unaligned(blk + restarts_off + 4 * (r + 1)) : restarts_off;
           if (p > end || end > restarts_off) { bad = DEV_ERR_BAD_BLOCK; break; }
-          uint32_t n = 0;
+          uint32_t n = 0, klen = 0;
           const uint64_t slot0 = static_cast<uint64_t>(r) * (ri == 0xffffffffu ? 0u : ri);
-          // Only what is inherently serial happens here — where does the next entry start — because this loop IS the
-          // pipeline period: one warp, every instruction waiting for the one before (measured ~14 K cycles per block
-          // with validation and the entry table in it, against ~4 K for all eight consumer warps). The key warps parse
-          // the headers again, fill the rest of the entry table and validate.
           while (p < end) {
             uint32_t shared, non_shared, vlen;
             const int h = parse_entry_header(blk + p, end - p, &shared, &non_shared, &vlen);
-            if (!h || static_cast<uint64_t>(p) + h + non_shared + vlen > end) { bad = DEV_ERR_BAD_ENTRY; break; }
+            if (!h || shared > klen || (n == 0 && shared != 0) || static_cast<uint64_t>(p) + h + non_shared + vlen > end) { bad = DEV_ERR_BAD_ENTRY; break; }
+            klen = shared + non_shared;
+            if (klen < 8) { bad = DEV_ERR_SHORT_KEY; break; }
+            maxk = max(maxk, klen);
             const uint64_t slot = slot0 + n;
-            if (slot >= ING_MAXE) { fallback = ING_FALLBACK_GENERAL; break; }
-            etab[slot].estart = static_cast<uint16_t>(p);
+            if (slot >= ING_MAXE || klen > 16 * ING_NVI) { fallback = ING_FALLBACK_GENERAL; break; }
+            if (klen > static_cast<uint32_t>(S) - 8) fallback = ING_FALLBACK_WIDER;      // user key longer than S - 16: the walk goes on (longest key)
+            IngEntry e;
+            e.estart = static_cast<uint16_t>(p); e.kstart = static_cast<uint16_t>(p + h); e.vstart = static_cast<uint16_t>(p + h + non_shared);
+            e.vlen = static_cast<uint16_t>(vlen); e.shared = static_cast<uint16_t>(shared); e.klen = static_cast<uint16_t>(klen);
+            etab[slot] = e;
             p += h + non_shared + vlen;
             n++;
           }
@@ -435,18 +439,22 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
         // the block's entry count was fixed by the probe + scan; it must agree with what the walk found
         else if (n_ent != expect) { dev_fail(J, DEV_ERR_IRREGULAR_RESTARTS, b); n_ent = 0; }
         // (the CRC of the block's tail is left to the CRC warps: this warp is the serial stage of the pipeline — a lane
-        // parses its restart interval entry by entry — and everything it does beyond that lengthens the pipeline period)
+        // parses its restart interval entry by entry — and what it does beyond that lengthens the pipeline period. Measured:
+        // building previous-smaller links here cost 3.3 ms per 10^8 entries, moving the tail CRC out gained 2.3 ms; moving
+        // validation and the entry table to the consumer warps as well gained nothing — the consumers then re-parse every
+        // header and the kernel, at 62 % issue utilisation, is bound by its instruction count.)
         sh_nent[stage] = n_ent; sh_tail[stage] = tail;
       }
       __syncwarp();                                // the lanes' entry table writes are ordered before lane 0's arrive
       if (lane == 0) mbar_arrive(&walked_bar[stage]);
     }
+    maxk = __reduce_max_sync(0xffffffffu, maxk);
+    if (lane == 0 && maxk > __ldcg(&J->max_ikey_len)) atomicMax(&J->max_ikey_len, maxk);
     return;
   }
 
   // ---------------- consumers
   const bool ranged = V.range != nullptr;
-  uint32_t maxk = 0;                                 // longest internal key met (key warps)
   for (uint32_t it = 0;; it++) {
     const int stage = it & 1;
     mbar_wait(&walked_bar[stage], (it >> 1) & 1);
@@ -460,36 +468,14 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
     uint64_t* const val_off = cur.val_off;
     uint32_t* const val_crc = cur.val_crc;
     const uint8_t* blk = buf0 + stage * (ING_BUF + 32) + cur.mis;
-    IngEntry* etab = etab0 + stage * ING_MAXE;
+    const IngEntry* etab = etab0 + stage * ING_MAXE;
     const uint32_t L = size + 1;                       // contents + type byte
     const bool filtered = ht_filter != 0xfffffffffffffffeull || ranged;
     unsigned long long acc = 0;                        // XOR of unreduced carry-less products (CRC warps)
     const uint32_t rt = threadIdx.x & (ING_CONSUMERS - 1);   // thread index inside its role
-    const uint32_t restarts_off = size - 4 - 4 * ld_u32_unaligned(blk + size - 4);   // validated by the walker
     if (wid < ING_CONSUMERS / 32) {
-    // step 1: every entry's header once more (the walker only left the entry offsets), the entry table, validation
-    for (uint32_t e = rt; e < n_ent; e += ING_CONSUMERS) {
-      const uint32_t p0 = etab[e].estart;
-      uint32_t shared, non_shared, vlen;
-      const int h = parse_entry_header(blk + p0, restarts_off - p0, &shared, &non_shared, &vlen);
-      uint32_t klen = shared + non_shared;
-      if (klen < 8) { dev_fail(J, DEV_ERR_SHORT_KEY, cur.b); klen = 8; shared = 0; }
-      maxk = max(maxk, klen);
-      if (klen > 16 * ING_NVI) { atomicMax(&J->ingest_fallback, ING_FALLBACK_GENERAL); shared = 0; klen = 16 * ING_NVI; }   // not for this kernel; keep the walk below in bounds
-      else if (klen > static_cast<uint32_t>(S) - 8) atomicMax(&J->ingest_fallback, ING_FALLBACK_WIDER);   // user key longer than S - 16
-      IngEntry en;
-      en.estart = static_cast<uint16_t>(p0); en.kstart = static_cast<uint16_t>(p0 + h); en.vstart = static_cast<uint16_t>(p0 + h + non_shared);
-      en.vlen = static_cast<uint16_t>(vlen); en.shared = static_cast<uint16_t>(shared); en.klen = static_cast<uint16_t>(klen);
-      etab[e] = en;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(ING_CONSUMERS) : "memory");          // the key warps only
     for (uint32_t e = rt; e < n_ent; e += ING_CONSUMERS) {
       const IngEntry en = etab[e];
-      {
-        // a key shares at most the whole previous key; the first entry of a restart interval shares nothing
-        const bool first = cur.ri == 0xffffffffu ? e == 0 : (e % cur.ri) == 0;
-        if (first ? en.shared != 0 : en.shared > etab[e - 1].klen) dev_fail(J, DEV_ERR_BAD_ENTRY, cur.b);
-      }
       uint4 kv[ING_NVI];
 #pragma unroll
       for (int w = 0; w < ING_NVI; w++) kv[w] = make_uint4(0, 0, 0, 0);
@@ -581,19 +567,15 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
     }
     } else {
     for (uint32_t e = rt; e < n_ent; e += ING_CONSUMERS) {
-      // the walker left the entry's offset; the rest of the geometry comes from its header (the key warps fill the
-      // entry table concurrently: only `estart` may be read here)
-      const uint32_t p0 = etab[e].estart;
-      uint32_t shared, non_shared, vlen;
-      const int h = parse_entry_header(blk + p0, restarts_off - p0, &shared, &non_shared, &vlen);
-      const uint32_t vstart = p0 + h + non_shared;
+      const IngEntry en = etab[e];
+      const uint32_t vlen = en.vlen;
       // CRCs
-      const uint32_t vc = ing_crc_span2(T, blk + vstart, vlen);
+      const uint32_t vc = ing_crc_span2(T, blk + en.vstart, vlen);
       val_crc[base + e] = vc;
       if (V.verify) {
-        const uint32_t gc = ing_crc_span(T, blk + p0, vstart - p0);
+        const uint32_t gc = ing_crc_span(T, blk + en.estart, en.vstart - en.estart);
         // gap * x^(8 (bytes behind the gap)) + value * x^(8 (bytes behind the value)), unreduced (L < 64 K: inside the table)
-        acc ^= crc_clmul(gc, __ldg(&g_crc_xpow8[L - vstart])) ^ crc_clmul(vc, __ldg(&g_crc_xpow8[L - vstart - vlen]));
+        acc ^= crc_clmul(gc, __ldg(&g_crc_xpow8[L - en.vstart])) ^ crc_clmul(vc, __ldg(&g_crc_xpow8[L - en.vstart - vlen]));
       }
     }
     }
@@ -620,10 +602,6 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
     }
     __syncwarp();                                  // every lane's reads of the stage are done before lane 0 releases it
     if (lane == 0) mbar_arrive(&empty_bar[stage]);
-  }
-  if (wid < ING_CONSUMERS / 32) {
-    maxk = __reduce_max_sync(0xffffffffu, maxk);
-    if (lane == 0 && maxk > __ldcg(&J->max_ikey_len)) atomicMax(&J->max_ikey_len, maxk);
   }
 }
 
