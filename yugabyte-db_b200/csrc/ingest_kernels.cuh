@@ -184,6 +184,7 @@ struct IngTab {
   const uint32_t* base;            // table words in shared memory
   uint32_t sel[4];                 // PRMT selector extracting the byte table t_k consumes (T3 <-> byte 0 ... T0 <-> byte 3)
   uint32_t off[4];                 // t_k * 8 + copy
+  uint32_t addr[4];                // shared-space byte address of word off[k] (a look-up is idx * 128 + addr[k]: one multiply-add)
   uint32_t copy;
 };
 __device__ __forceinline__ IngTab ing_tab_init(const uint32_t* base, uint32_t lane) {
@@ -194,6 +195,7 @@ __device__ __forceinline__ IngTab ing_tab_init(const uint32_t* base, uint32_t la
     const uint32_t t = (k + (lane >> 3)) & 3u;
     T.sel[k] = 0x4440u + (3u - t);
     T.off[k] = t * 8u + T.copy;
+    T.addr[k] = static_cast<uint32_t>(__cvta_generic_to_shared(base)) + 4u * T.off[k];
   }
   return T;
 }
@@ -204,7 +206,12 @@ __device__ __forceinline__ uint32_t ing_crc_word(const IngTab& T, uint32_t c, ui
   c ^= w;
   uint32_t r = 0;
 #pragma unroll
-  for (int k = 0; k < 4; k++) r ^= T.base[__byte_perm(c, 0u, T.sel[k]) * 32u + T.off[k]];
+  for (int k = 0; k < 4; k++) {
+    // address arithmetic in the shared window (the generic-pointer form costs an extra add of the window base per look-up)
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(__byte_perm(c, 0u, T.sel[k]) * 128u + T.addr[k]));
+    r ^= v;
+  }
   return r;
 }
 // c * x^32 mod P (four zero bytes): what crc_clmul_reduce needs, as one conflict-free word step
@@ -553,7 +560,7 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
 #pragma unroll
       for (int w = 0; w < ING_NVI; w++) {
         if (w < key_vecs) {
-          const uint4 m = low_bytes_mask16(static_cast<int>(ulen) - 16 * w);
+          const uint4 m = sh_upto[min(max(static_cast<int>(ulen) - 16 * w, 0), 16)];
           reinterpret_cast<uint4*>(rec)[w] = make_uint4(kv[w].x & m.x, kv[w].y & m.y, kv[w].z & m.z, kv[w].w & m.w);
         }
       }
