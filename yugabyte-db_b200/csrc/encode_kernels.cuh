@@ -39,6 +39,7 @@ struct EncView {
   int key_encoding;                // 1 = shared_prefix, 2 = three_shared_parts (rocksdb/types.h:50-56)
   uint16_t* fk_len;                // [n] bloom filter key length of the entry (0 = none), nullptr = no filter policy
   const uint16_t* fk_src;          // [N] the same by input entry id, written by the merge kernel's DocKey walk
+  uint32_t* max_add;               // [1] largest size-estimate increment of one entry (FlushBlockBySizePolicy's `estimated size after`)
 };
 
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
@@ -89,6 +90,7 @@ __device__ __forceinline__ uint64_t kept_suffix(const uint8_t* rec, const Desc& 
 
 // Per survivor: shared prefix with the previous survivor's internal key, encoded sizes.
 __global__ void __launch_bounds__(256) k_entry_sizes(EncView E, int S) {
+  uint32_t my_add = 0;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < E.n; j += gridDim.x * blockDim.x) {
     const Desc d = E.kept[j];
     const uint32_t klen = d.klen, ulen = klen - 8u;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(256) k_entry_sizes(EncView E, int S) {
       if (E.fk_len) E.fk_len[j] = E.fk_src ? E.fk_src[d.gid] : static_cast<uint16_t>(docdb_filter_prefix_len(kept_rec(E, d, S), static_cast<int>(ulen)));
       E.nr[j] = nr; E.shared[j] = static_cast<uint16_t>(shared);
       E.D[j] = static_cast<int16_t>(static_cast<int32_t>(rs) - static_cast<int32_t>(nr));
+      my_add = max(my_add, klen + vlen + 8u + varint_len(klen) + varint_len(vlen));
       continue;
     }
     const uint8_t* rec = kept_rec(E, d, S);
@@ -148,7 +151,11 @@ __global__ void __launch_bounds__(256) k_entry_sizes(EncView E, int S) {
     if (E.fk_len) E.fk_len[j] = E.fk_src ? E.fk_src[d.gid] : static_cast<uint16_t>(docdb_filter_prefix_len(rec, static_cast<int>(ulen)));
     E.nr[j] = nr; E.shared[j] = static_cast<uint16_t>(shared);
     E.D[j] = static_cast<int16_t>(static_cast<int32_t>(rs) - static_cast<int32_t>(nr));
+    my_add = max(my_add, klen + vlen + 8u + varint_len(klen) + varint_len(vlen));
   }
+  // the most one entry can add to FlushBlockBySizePolicy's estimate (k_next skips ahead with it)
+  my_add = __reduce_max_sync(0xffffffffu, my_add);
+  if ((threadIdx.x & 31) == 0 && my_add) atomicMax(E.max_add, my_add);
 }
 
 // ---- scans: P = exclusive prefix of nr (u64); QQ = per-residue-class inclusive prefix of D ------
@@ -279,6 +286,7 @@ __device__ __forceinline__ unsigned long long blk_cur(const EncView& E, uint32_t
 __global__ void __launch_bounds__(256) k_next(EncView E) {
   const unsigned long long BS = E.block_size;
   const unsigned long long thresh = BS * (100 - E.deviation);       // cur*100 > thresh
+  const unsigned long long madd = *E.max_add;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < E.n; s += gridDim.x * blockDim.x) {
     // smallest m in (s, n] such that the block [s, m) satisfies cur*100 > thresh (or m == n)
     uint32_t lo = s + 1, hi = E.n;
@@ -318,6 +326,33 @@ __global__ void __launch_bounds__(256) k_next(EncView E) {
       if (blk_cur(E, s, mid - 1) * 100 > thresh) hi = mid; else lo = mid + 1;
     }
     uint32_t m = lo;
+    if (m < E.n && BS > madd) {
+      // The scan below ends at the first m with cur(m - 1) >= BS or cur(m - 1) + add(m) > BS; no entry adds more than
+      // `madd`, so every m with cur(m - 1) <= BS - madd can be skipped — cur is monotone: interpolate to that point
+      // (the walk from 90 % to 100 % of a block is ~10 entries, each a round of dependent loads).
+      const unsigned long long lim = BS - madd;
+      uint32_t a = m, b = E.n, g = m;
+      for (int it = 0; it < 3 && a < b; it++) {
+        if (g < a) g = a;
+        if (g > b) g = b;
+        const unsigned long long c = blk_cur(E, s, g - 1);
+        const unsigned long long bpe = c / (g - s) + 1;
+        if (c > lim) {
+          b = g;
+          const unsigned long long back = (c - lim) / bpe + 1;
+          g = back >= g - a ? a : g - static_cast<uint32_t>(back);
+        } else {
+          a = g < E.n ? g + 1 : E.n;
+          const unsigned long long fwd = (lim - c) / bpe + 1;
+          g = fwd >= E.n - g ? E.n : g + static_cast<uint32_t>(fwd);
+        }
+      }
+      while (a < b) {
+        const uint32_t mid = a + ((b - a) >> 1);
+        if (blk_cur(E, s, mid - 1) > lim) b = mid; else a = mid + 1;
+      }
+      m = a;
+    }
     while (m < E.n) {
       const unsigned long long cur = blk_cur(E, s, m - 1);
       if (cur >= BS) break;

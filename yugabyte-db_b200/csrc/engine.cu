@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   // never observable: sequence numbers are unique across files — table/merger.cc:652-697).
   // ~log2(k) x (log2(n) probes + MT steps) per MT records instead of (k - 1) binary searches per record.
   {
-    constexpr int MT = 4;
+    constexpr int MT = 2;
     uint16_t* bufs[2] = {order, reinterpret_cast<uint16_t*>(crank)};
     // a <= b in merged order, a from the earlier run group
     auto le = [&](uint32_t a, uint32_t b) -> bool {
@@ -2234,6 +2234,8 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       CUDA_TRY(DevAlloc(&I.allocs, &E.fk_len, n));
       E.fk_src = d_fk16;
     }
+    CUDA_TRY(DevAlloc(&I.allocs, &E.max_add, 1));
+    CUDA_TRY(cudaMemsetAsync(E.max_add, 0, 4, I.stream));
     k_entry_sizes<<<GridFor(n, 256, sms), 256, 0, I.stream>>>(E, Sfinal);
     // P
     const uint32_t pc = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
