@@ -659,3 +659,16 @@ def test_block_assemblers(pkg, assembler, monkeypatch):
         check(pkg, ssts, block_size=bs, cutoff_ht=o.ht_from_micros(cfg.base_micros + 1500), filter_policy=1)
     cfg = o.GenConfig(seed=6, num_rows=3000, cols=1, versions=2, num_files=2, value_len=0)
     check(pkg, o.Sst.generate_all(cfg, o.TableOptions(block_size=2048)), block_size=2048)
+
+
+def test_small_upload_ring_wraps(pkg, monkeypatch):
+    """Parameter uploads go through a ring inside the job's host-mapped page (no DMA on the critical path); with a
+    tiny ring every few uploads wrap (stream synchronise, start over) — many input files make the run table the
+    largest upload."""
+    monkeypatch.setenv("YBGPU_UPLOAD_RING_BYTES", "2048")
+    runs = w.random_docdb_runs(5, n_runs=6, n_rows=300)
+    ssts = runs_to_ssts(runs, 1024)
+    for kw in w.param_grid()[:3]:
+        check(pkg, ssts, block_size=1024, filter_policy=1, filter_block_size=2048, **kw)
+    cfg = o.GenConfig(seed=9, num_rows=5000, cols=2, versions=2, num_files=24, value_len=60)
+    check(pkg, o.Sst.generate_all(cfg, o.TableOptions(block_size=2048)), block_size=4096)

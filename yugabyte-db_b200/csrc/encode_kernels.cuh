@@ -39,6 +39,7 @@ struct EncView {
   int key_encoding;                // 1 = shared_prefix, 2 = three_shared_parts (rocksdb/types.h:50-56)
   uint16_t* fk_len;                // [n] bloom filter key length of the entry (0 = none), nullptr = no filter policy
   const uint16_t* fk_src;          // [N] the same by input entry id, written by the merge kernel's DocKey walk
+  const uint32_t* fkh_src;         // [N] bloom hash of the filter key by input entry id (merge kernel), or nullptr
   uint32_t* max_add;               // [1] largest size-estimate increment of one entry (FlushBlockBySizePolicy's `estimated size after`)
 };
 
@@ -1678,7 +1679,7 @@ __global__ void __launch_bounds__(256) k_filter_hash(EncView E, int S, const uin
   for (uint32_t ord = blockIdx.x * blockDim.x + threadIdx.x; ord < n_keys; ord += gridDim.x * blockDim.x) {
     const uint32_t j = new_entry[ord];
     const Desc d = E.kept[j];
-    hashes[ord] = leveldb_hash(kept_rec(E, d, S), E.fk_len[j], kBloomSeed);
+    hashes[ord] = E.fkh_src ? E.fkh_src[d.gid] : leveldb_hash(kept_rec(E, d, S), E.fk_len[j], kBloomSeed);
   }
 }
 

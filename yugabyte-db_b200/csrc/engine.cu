@@ -624,6 +624,8 @@ struct MergeView {
   uint32_t rewrite_cap;
   uint32_t n_tiles;
   uint16_t* fk16;                 // [N] by input entry id: bloom filter key length (nullptr = no filter policy)
+  uint32_t* fkh;                  // [N] by input entry id: bloom hash of that filter key (the record is in shared memory here;
+                                  //     the filter builder would have to gather it from HBM again); nullptr = not wanted
   int32_t S, k;                   // record stride / number of runs / tile capacity: kernel-parameter constants
   uint32_t cap;
 };
@@ -708,16 +710,30 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   const uint32_t tile = blockIdx.x;
   const bool cont = (V.tile_rank[tile] & TILE_CONT) != 0;
   if (threadIdx.x < 9) sh_stats[threadIdx.x] = 0;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // segment bounds: one lane per run (k <= MAX_RUNS), prefix sum by shuffles; the job's error word rides along so
+    // that no thread has to fetch it from HBM in the middle of the tile
+    static_assert(MAX_RUNS <= 64, "two rounds of 32 lanes cover the runs");
     uint32_t acc = 0;
-    for (int r = 0; r < k; r++) {
-      uint32_t lo = V.tile_lo[static_cast<size_t>(tile) * k + r];
-      uint32_t hi = (tile + 1 < V.n_tiles) ? V.tile_lo[static_cast<size_t>(tile + 1) * k + r] : V.runs[r].n_entries;
-      seg_lo[r] = lo; seg_start[r] = acc; acc += hi - lo;
+    for (int r0 = 0; r0 < k; r0 += 32) {
+      const int r = r0 + static_cast<int>(threadIdx.x);
+      uint32_t lo = 0, n = 0;
+      if (r < k) {
+        lo = V.tile_lo[static_cast<size_t>(tile) * k + r];
+        const uint32_t hi = (tile + 1 < V.n_tiles) ? V.tile_lo[static_cast<size_t>(tile + 1) * k + r] : V.runs[r].n_entries;
+        n = hi - lo;
+      }
+      uint32_t x = n;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (static_cast<int>(threadIdx.x) >= o) x += y; }
+      if (r < k) { seg_lo[r] = lo; seg_start[r] = acc + x - n; }
+      acc += __shfl_sync(0xffffffffu, x, 31);
     }
-    seg_start[k] = acc;
-    sh_T = acc;
-    sh_any_filtered = 0;
+    if (threadIdx.x == 0) {
+      seg_start[k] = acc;
+      sh_T = acc;
+      sh_any_filtered = 0;
+      sh_err = *reinterpret_cast<volatile int*>(&J->error);
+    }
   }
   __syncthreads();
   const uint32_t T = sh_T;
@@ -725,38 +741,47 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
   if (cont && threadIdx.x == 0) atomicAdd(&J->n_cont_tiles, 1u);
   if (T > cap) { if (threadIdx.x == 0) dev_fail(J, DEV_ERR_TILE_OVERFLOW, tile); return; }
 
-  // (a) stage the k segments: contiguous 16-byte vector loads from HBM, re-strided to SS in smem
-  for (int r = 0; r < k; r++) {
-    const uint32_t n = seg_start[r + 1] - seg_start[r];
-    const uint4* src = reinterpret_cast<const uint4*>(V.runs[r].rec + static_cast<size_t>(seg_lo[r]) * S);
-    uint8_t* dst = recs + static_cast<size_t>(SS) * seg_start[r];
+  // (a) stage the k segments: 16-byte vector loads from HBM, re-strided to SS in smem. ONE flat loop over all the
+  // tile's vectors (a thread's ~8 loads are independent and in flight together); a loop per segment had every segment
+  // wait for the previous one's loads — 8 round trips to HBM per tile, a fifth of the tile's time.
+  {
     const uint32_t vpr = S >> 4;                      // 16-byte vectors per record
-    const uint32_t nvec = n * vpr;
+    const uint32_t nvec = T * vpr;
     const bool vpr_pow2 = (vpr & (vpr - 1)) == 0;
     const uint32_t vpr_shift = 31 - __clz(vpr);
+#pragma unroll 4
     for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-      const uint4 v = __ldg(src + i);
-      const uint32_t rec_i = vpr_pow2 ? i >> vpr_shift : i / vpr, q = i - rec_i * vpr;
-      uint2* d = reinterpret_cast<uint2*>(dst + static_cast<size_t>(rec_i) * SS + 16 * q);
+      const uint32_t li = vpr_pow2 ? i >> vpr_shift : i / vpr, q = i - li * vpr;
+      int r = 0;
+      while (seg_start[r + 1] <= li) r++;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(V.runs[r].rec + static_cast<size_t>(seg_lo[r] + (li - seg_start[r])) * S) + q);
+      uint2* d = reinterpret_cast<uint2*>(recs + static_cast<size_t>(li) * SS + 16 * q);
       d[0] = make_uint2(v.x, v.y); d[1] = make_uint2(v.z, v.w);
     }
   }
   __syncthreads();
 
   // tile-common key prefix -> 8-byte sort prefixes (most comparisons are decided by one u64)
-  if (threadIdx.x == 0) {
-    const uint8_t* mn = nullptr; const uint8_t* mx = nullptr;
-    for (int r = 0; r < k; r++) {
+  if (threadIdx.x < 32) {
+    // The prefix common to every key of the tile = min over the segments' first and last keys of their common prefix
+    // with any one key of the tile (the segments are sorted): one lane per segment instead of a serial min / max search
+    // by one thread while the CTA waits.
+    const uint8_t* ref = recs;                         // local record 0 (T > 0)
+    const uint32_t ref_len = rec_ulen(ref, S);
+    uint32_t c = 0xffffffffu;
+    for (int r = static_cast<int>(threadIdx.x); r < k; r += 32) {
       const uint32_t n = seg_start[r + 1] - seg_start[r];
       if (!n) continue;
       const uint8_t* f = recs + static_cast<size_t>(SS) * seg_start[r];
       const uint8_t* l = recs + static_cast<size_t>(SS) * (seg_start[r + 1] - 1);
-      if (!mn || cmp_user_keys(f, rec_ulen(f, S), mn, rec_ulen(mn, S)) < 0) mn = f;
-      if (!mx || cmp_user_keys(l, rec_ulen(l, S), mx, rec_ulen(mx, S)) > 0) mx = l;
+      c = min(c, min(common_prefix_len(ref, ref_len, f, rec_ulen(f, S)), common_prefix_len(ref, ref_len, l, rec_ulen(l, S))));
     }
-    uint32_t c = common_prefix_len(mn, rec_ulen(mn, S), mx, rec_ulen(mx, S)) & ~7u;
+    c = __reduce_min_sync(0xffffffffu, c);
+    c = min(c, ref_len) & ~7u;
     if (c + 16 > static_cast<uint32_t>(S - 16)) c = (S - 16 >= 16) ? static_cast<uint32_t>(S - 32) & ~7u : 0;
-    sh_c0 = c;
+    if (threadIdx.x == 0) sh_c0 = c;
+  }
+  if (threadIdx.x == 0) {
     // A tile that starts inside a row group needs the record that precedes it in merged order (rule A compares
     // with the previous visible user key): the largest visible record below the tile's start over all runs.
     const uint8_t* pred = nullptr;
@@ -850,16 +875,19 @@ __global__ void __launch_bounds__(MERGE_THREADS, 3) k_merge_filter(MergeView V, 
     while (seg_start[r + 1] <= li) r++;
     const uint32_t p = li - seg_start[r];
     const uint8_t* e = recs + static_cast<size_t>(SS) * li;
-    if (p > 0 && cmp_records(e - SS, e, S) >= 0) dev_fail(J, DEV_ERR_UNSORTED, tile);
+    if (p > 0 && cmp_records(e - SS, e, S) >= 0) { dev_fail(J, DEV_ERR_UNSORTED, tile); sh_err = 1; }
     int fk = 0;
     const int g = group_prefix_len(e, rec_ulen(e, S), prm->R.enabled != 0, V.fk16 ? &fk : nullptr);
-    if (g < 0) { dev_fail(J, -g, tile); glen[li] = 0; } else glen[li] = static_cast<uint16_t>(g);
-    if (V.fk16) V.fk16[V.runs[r].gid_base + seg_lo[r] + p] = static_cast<uint16_t>(g < 0 ? 0 : fk);
+    if (g < 0) { dev_fail(J, -g, tile); sh_err = 1; glen[li] = 0; } else glen[li] = static_cast<uint16_t>(g);
+    if (V.fk16) {
+      const uint32_t gid = V.runs[r].gid_base + seg_lo[r] + p;
+      V.fk16[gid] = static_cast<uint16_t>(g < 0 ? 0 : fk);
+      if (V.fkh) V.fkh[gid] = (g < 0 || fk <= 0) ? 0u : leveldb_hash(e, static_cast<uint32_t>(fk), kBloomSeed);
+    }
     if (rec_flags(e, S) & REC_F_INVISIBLE) sh_any_filtered = 1;
   }
-  if (threadIdx.x == 0) sh_err = *reinterpret_cast<volatile int*>(&J->error);
   __syncthreads();
-  if (sh_err) return;
+  if (sh_err) return;                              // the job had failed already, or this tile's records are bad
 
   // previous-visible map (identity - 1 unless HybridTime-filtered entries exist)
   if (sh_any_filtered) {
@@ -1736,7 +1764,12 @@ ybgpu_status Engine::UploadSmall(void* dev_dst, const void* host_src, size_t n) 
     return YBGPU_OK;
   }
   if (I.upload_off < STATUS_READ_BYTES) I.upload_off = STATUS_READ_BYTES;
-  if (I.upload_off + need > STATUS_PAGE_BYTES) {
+  size_t ring_end = STATUS_PAGE_BYTES;
+  if (const char* e = getenv("YBGPU_UPLOAD_RING_BYTES")) {         // tests: a small ring wraps after a few uploads
+    const long v = atol(e);
+    if (v > 0) ring_end = std::min<size_t>(STATUS_PAGE_BYTES, STATUS_READ_BYTES + std::max<size_t>(static_cast<size_t>(v), need));
+  }
+  if (I.upload_off + need > ring_end) {
     CUDA_TRY(cudaStreamSynchronize(I.stream));           // every earlier upload has been consumed
     I.upload_off = STATUS_READ_BYTES;
   }
@@ -2182,6 +2215,9 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   uint16_t* d_fk16 = nullptr;
   if (opt_.filter_policy != YBGPU_FILTER_NONE && getenv("YBGPU_NO_FK16") == nullptr) CUDA_TRY(DevAlloc(&I.allocs, &d_fk16, N));
   mv.fk16 = d_fk16;
+  uint32_t* d_fkh = nullptr;
+  if (d_fk16) CUDA_TRY(DevAlloc(&I.allocs, &d_fkh, N));
+  mv.fkh = d_fkh;
   mv.S = Sfinal; mv.k = k; mv.cap = cap;
   const size_t smem = tile_layout::bytes(Sfinal, cap);
   CUDA_TRY(cudaFuncSetAttribute(k_merge_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -2228,11 +2264,12 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(DevAlloc(&I.allocs, &E.nr, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.shared, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.D, n));
     CUDA_TRY(DevAlloc(&I.allocs, &E.P, static_cast<size_t>(n) + 1)); CUDA_TRY(DevAlloc(&I.allocs, &E.QQ, n));
     CUDA_TRY(DevAlloc(&I.allocs, &E.next, n)); CUDA_TRY(DevAlloc(&I.allocs, &E.exit1, n));
-    E.fk_len = nullptr; E.fk_src = nullptr;
+    E.fk_len = nullptr; E.fk_src = nullptr; E.fkh_src = nullptr;
     if (opt_.filter_policy != YBGPU_FILTER_NONE) {
       if (opt_.filter_policy != YBGPU_FILTER_DOCKEY_V3) return Fail(YBGPU_INVALID_ARGUMENT, "unknown filter_policy");
       CUDA_TRY(DevAlloc(&I.allocs, &E.fk_len, n));
       E.fk_src = d_fk16;
+      E.fkh_src = d_fkh;
     }
     CUDA_TRY(DevAlloc(&I.allocs, &E.max_add, 1));
     CUDA_TRY(cudaMemsetAsync(E.max_add, 0, 4, I.stream));
