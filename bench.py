@@ -16,11 +16,11 @@ entries, as rocksdb.raw.key.size + rocksdb.raw.value.size count them).
             value_no_verify: the same without verification (informational).
   e2e       same compaction through the C ABI with HOST (pinned) input files and ONE HOST output table:
             H2D of every input file and D2H of the result inside the timed region. The compaction runs
-            as --subcompactions key ranges pipelined on private streams (ybgpu_compact_files) so that H2D /
-            kernels / D2H of different ranges overlap, and ybgpu_sst_concat_meta assembles the range
-            outputs into ONE table (data pieces appended in range order, one rebased index / filter
-            index) inside the timed region — the shape DocDB's single-level universal layout (and the
-            reference arm) writes. e2e.range_files = the same without the assembly (one SST per range);
+            as --subcompactions key ranges pipelined on private streams (ybgpu_compact_files_one_table, --in-flight
+            host threads, copy slots) so that H2D / kernels / D2H of different ranges overlap; every range's data
+            lands at its final offset and the ONE metadata file (rebased index / filter index) is assembled while
+            later ranges run — the shape DocDB's single-level universal layout (and the reference arm) writes.
+            e2e.range_files = the same with one SST per range (ybgpu_compact_files);
             e2e.single_job = one job, H2D / run / D2H back to back. e2e.pcie_ceiling_gbs = concurrent
             bidirectional copies of the same pinned buffers, measured in this run.
   roofline  dominant kernel, algorithmic bytes / its CUDA-event time; roofline.traffic is

@@ -21,9 +21,9 @@
 //     kernel was tried first: with ~450 blocks in flight every block ended up summing all in-flight predecessors);
 //   * lanes walk their intervals a second time, rebuild the internal keys in registers and write records.
 //
-// CRC table look-ups dominate the shared-memory pipe; the four 256-entry slicing tables are replicated
-// ING_REP times, lane l using copy l % ING_REP, which cuts the expected bank conflict degree of a look-up
-// from ~3.5 to ~2.1.
+// CRC table look-ups dominate the kernel's instruction count (one per byte: there is no CRC / carry-less multiply
+// instruction); the four 256-entry slicing tables are stored ING_REP = 8 times with the table index in the bank number,
+// lane l uses copy l % 8 and rotates its look-up order by l / 8: no bank conflicts whatever the data (IngTab below).
 //
 // Anything this kernel does not take — other key encodings, keys longer than 64 bytes, blocks larger than the
 // staging buffer, more than ING_MAXE entries in a block — raises J->ingest_fallback (not an error) and the host
