@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--trace", action="store_true")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--grid", default="", help="settings to run instead of the built-in grid: 'ranges,in_flight,h2d_slots,d2h_slots;...'")
     args = ap.parse_args()
     import torch
     pkg = importlib.import_module("yugabyte-db_b200")
@@ -73,6 +74,8 @@ def main():
             (64, 12, 2, 2), (64, 16, 2, 2), (16, 8, 2, 2), (48, 12, 2, 2)]
     if args.quick:
         grid = grid[:5]
+    if args.grid:
+        grid = [tuple(int(x) for x in g.split(',')) for g in args.grid.split(';')]
     for g in grid:
         run(*g, steps=args.steps)
     if args.trace:

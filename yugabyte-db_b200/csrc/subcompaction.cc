@@ -420,8 +420,9 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
   // Copy slots. A copy engine serves the streams that have copies pending chunk by chunk in turn: with every range in
   // flight queueing its inputs at once, all of them receive their data at the same (late) time, compute together and
   // copy out together — the pipeline moves in convoys and each direction idles while the other ramps. Instead at most
-  // `h2d_slots` ranges have inputs in transit (taken in range order) and at most `d2h_slots` copy out, so the first
-  // range computes after ONE range's worth of DMA and both directions stay busy from then on.
+  // `h2d_slots` ranges have inputs in transit (taken in range order; default 1: a range's inputs arrive at the full
+  // link rate) and at most `d2h_slots` copy out (default 2), so the first range computes after ONE range's worth of DMA
+  // and both directions stay busy from then on (profiles/r02_e2e_sweep_100m*.jsonl).
   struct Slots {
     std::mutex mu; std::condition_variable cv; uint32_t free_slots;
     explicit Slots(uint32_t n) : free_slots(n) {}
@@ -440,7 +441,7 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
     const long x = atol(v);
     return x <= 0 ? 0u : static_cast<uint32_t>(x);
   };
-  const uint32_t h2d_slots = env_u32("YBGPU_H2D_SLOTS", 2), d2h_slots = env_u32("YBGPU_D2H_SLOTS", 2);   // 0 = ungated
+  const uint32_t h2d_slots = env_u32("YBGPU_H2D_SLOTS", 1), d2h_slots = env_u32("YBGPU_D2H_SLOTS", 2);   // 0 = ungated
   Slots h2d_gate(h2d_slots ? h2d_slots : 1u << 30), d2h_gate(d2h_slots ? d2h_slots : 1u << 30);
   // ranges take their input slot in range order (a later range must not overtake: its output offset waits on the
   // earlier ones in one-table mode)
