@@ -190,6 +190,13 @@ ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint6
                                  const ybgpu_block_handle* handles, uint64_t num_handles,
                                  int32_t key_encoding, uint64_t hybrid_time_filter);
 
+/* Per-database cotable HybridTime filters of the input added LAST — the tail of FdWithBoundaries::user_filter_data
+ * behind the 8-byte global filter (docdb/docdb_rocksdb_util.cc:503-509; written for the master's sys catalog by a
+ * restore): `n` strictly increasing database oids with a hybrid time each. An entry of a cotable ('y' + uuid, the
+ * uuid's last four bytes = the database oid) whose DocHybridTime is above its database's filter is invisible to the
+ * compaction, like an entry above the global filter (HybridTimeFilteringIterator::Satisfied, :525-565). Copied. */
+ybgpu_status ybgpu_job_set_cotable_filters(ybgpu_job* job, const uint32_t* db_oids, const uint64_t* hybrid_times, uint32_t n);
+
 /* Blocks until every host->device copy queued by ybgpu_job_add_input has completed (the input buffers may then be
  * reused). Optional: ybgpu_job_run orders itself behind the copies anyway. The subcompaction pipeline uses it to keep
  * the copy engine on ONE range's inputs at a time instead of interleaving the chunks of all ranges in flight. */
@@ -270,6 +277,9 @@ typedef struct ybgpu_input_file {
   const uint8_t* meta_file; uint64_t meta_file_len;     /* <n>.sst */
   const uint8_t* data_file; uint64_t data_file_len;     /* <n>.sst.sblock.0 (host memory; pinned = async DMA) */
   uint64_t hybrid_time_filter;                          /* YBGPU_HT_INVALID = none */
+  const uint32_t* cotable_db_oids;                      /* per-database cotable filters (ybgpu_job_set_cotable_filters), or NULL */
+  const uint64_t* cotable_hybrid_times;
+  uint64_t num_cotable_filters;
 } ybgpu_input_file;
 
 #define YBGPU_MAX_SPLITTER_LEN 255

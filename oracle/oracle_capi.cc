@@ -210,15 +210,24 @@ static void FillStats(orc_result* res, const CompactionStats& st, uint64_t hash,
 
 // mode bit0: collect KV stream; bit1: build output SST; bit2: hash_kv==0 -> skip hashing (baseline
 // timing should not pay for the test hash): when set, the FNV hash is skipped.
+struct orc_cotable_filters { const uint32_t* db_oids; const uint64_t* hybrid_times; uint64_t n; };
+orc_result* orc_compact2(int n_inputs, const orc_sst* const* inputs, const uint64_t* ht_filters, const orc_cotable_filters* cotable_filters,
+                         const orc_compaction_params* params, const orc_table_options* topts, int mode, int verify_checksums);
 orc_result* orc_compact(int n_inputs, const orc_sst* const* inputs, const uint64_t* ht_filters,
                         const orc_compaction_params* params, const orc_table_options* topts, int mode,
                         int verify_checksums) {
+  return orc_compact2(n_inputs, inputs, ht_filters, nullptr, params, topts, mode, verify_checksums);
+}
+orc_result* orc_compact2(int n_inputs, const orc_sst* const* inputs, const uint64_t* ht_filters, const orc_cotable_filters* cotable_filters,
+                         const orc_compaction_params* params, const orc_table_options* topts, int mode, int verify_checksums) {
   auto* res = new orc_result;
   try {
     std::vector<SstInput> in;
     for (int i = 0; i < n_inputs; i++) {
       SstInput s; s.meta = Slice(inputs[i]->meta); s.data = Slice(inputs[i]->data);
       s.hybrid_time_filter = ht_filters ? ht_filters[i] : kHtInvalid;
+      if (cotable_filters)
+        for (uint64_t q = 0; q < cotable_filters[i].n; q++) s.cotable_filters.emplace_back(cotable_filters[i].db_oids[q], cotable_filters[i].hybrid_times[q]);
       in.push_back(s);
     }
     CompactionParams p = ToParams(params);

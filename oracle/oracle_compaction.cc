@@ -20,7 +20,8 @@ struct SstIter : InputIter {
   std::string scratch;                 // contents of the current block when it is stored compressed
   bool verify;
   uint64_t ht_filter;
-  SstIter(const SstInput& in, bool verify_) : verify(verify_), ht_filter(in.hybrid_time_filter) {
+  std::vector<std::pair<uint32_t, uint64_t>> cotable_filters;
+  SstIter(const SstInput& in, bool verify_) : verify(verify_), ht_filter(in.hybrid_time_filter), cotable_filters(in.cotable_filters) {
     r.Open(in.meta, in.data, verify);
     blk = 0;
     Load();
@@ -40,20 +41,33 @@ struct SstIter : InputIter {
     it->Next();
     if (!it->Valid()) { blk++; Load(); }
   }
-  // docdb/docdb_rocksdb_util.cc:525-540 HybridTimeFilteringIterator::Satisfied (global filter).
+  // docdb/docdb_rocksdb_util.cc:525-565 HybridTimeFilteringIterator::Satisfied: the logical AND of the file's global
+  // filter and, for keys of a cotable, the filter of the cotable's database (the database oid is bytes 12..15 of the
+  // table uuid, little endian, :548-551; Uuid::FromComparable leaves that half of the uuid in place, util/uuid.cc:162-178).
+  bool Satisfied(Slice uk) const {
+    uint64_t ht; uint32_t wid;
+    size_t sz;
+    try {
+      sz = DocHtEncodedSizeFromEnd(uk);
+      DecodeDocHt(Slice(uk.p + uk.n - sz, sz), &ht, &wid);
+    } catch (const Corruption&) { return true; }
+    if (ht_filter != kHtInvalid && ht > ht_filter) return false;
+    if (cotable_filters.empty()) return true;
+    const size_t key_len = uk.n - sz;                    // user key without the DocHybridTime
+    if (key_len < 1 || uk.p[0] != 'y') return true;      // kTableId
+    if (key_len < 17) return true;
+    const uint8_t* u = reinterpret_cast<const uint8_t*>(uk.p) + 1;
+    const uint32_t db_oid = static_cast<uint32_t>(u[12]) | (static_cast<uint32_t>(u[13]) << 8) | (static_cast<uint32_t>(u[14]) << 16) |
+                            (static_cast<uint32_t>(u[15]) << 24);
+    for (const auto& f : cotable_filters)
+      if (f.first == db_oid) return ht <= f.second;
+    return true;
+  }
   void SkipFiltered() {
-    if (ht_filter == kHtInvalid) return;
+    if (ht_filter == kHtInvalid && cotable_filters.empty()) return;
     while (it) {
       Slice k = it->key();
-      Slice uk(k.p, k.n - 8);
-      bool ok = true;
-      try {
-        size_t sz = DocHtEncodedSizeFromEnd(uk);
-        uint64_t ht; uint32_t wid;
-        DecodeDocHt(Slice(uk.p + uk.n - sz, sz), &ht, &wid);
-        if (ht > ht_filter) ok = false;
-      } catch (const Corruption&) { ok = true; }
-      if (ok) return;
+      if (Satisfied(Slice(k.p, k.n - 8))) return;
       Advance();
     }
   }

@@ -4,6 +4,8 @@
 // CompactionIterator (rule A + seqno zeroing) -> DocDBCompactionFeed (MVCC retention) ->
 // TableBuilder. One thread per compaction, like the reference (rocksdb/util/options.cc:258).
 #pragma once
+#include <utility>
+#include <vector>
 #include "oracle_sst.h"
 #include <functional>
 
@@ -48,7 +50,13 @@ struct CompactionFeed {
   virtual void Flush() = 0;
 };
 
-struct SstInput { Slice meta, data; uint64_t hybrid_time_filter = kHtInvalid; };
+// hybrid_time_filter: the file's global filter; cotable_filters: (database oid, hybrid time) sorted by oid — the tail of
+// FdWithBoundaries::user_filter_data (docdb/docdb_rocksdb_util.cc:503-509).
+struct SstInput {
+  Slice meta, data;
+  uint64_t hybrid_time_filter = kHtInvalid;
+  std::vector<std::pair<uint32_t, uint64_t>> cotable_filters;
+};
 
 // Runs the whole loop (rocksdb/db/compaction_job.cc:664-895). `sink` receives every surviving
 // (internal key, value) in output order.

@@ -415,14 +415,34 @@ BUILD_SST = 2
 NO_HASH = 4
 
 
-def compact(ssts, params=None, opts=None, mode=COLLECT_KV | BUILD_SST, verify=True, ht_filters=None):
+class _CotableFilters(C.Structure):
+    _fields_ = [("db_oids", C.c_void_p), ("hybrid_times", C.c_void_p), ("n", C.c_uint64)]
+
+
+def compact(ssts, params=None, opts=None, mode=COLLECT_KV | BUILD_SST, verify=True, ht_filters=None, cotable_filters=None):
+    """cotable_filters: per input None or (sorted database oids, hybrid times) — the per-database part of
+    user_filter_data (docdb_rocksdb_util.cc:503-509)."""
     params = params or CompactionParams()
     opts = opts or TableOptions()
     arr = (C.c_void_p * len(ssts))(*[s.h for s in ssts])
     filt = None
     if ht_filters is not None:
         filt = (C.c_uint64 * len(ssts))(*ht_filters)
-    return Result(lib().orc_compact(len(ssts), arr, filt, C.byref(params), C.byref(opts), mode, int(verify)))
+    if cotable_filters is None:
+        return Result(lib().orc_compact(len(ssts), arr, filt, C.byref(params), C.byref(opts), mode, int(verify)))
+    cf = (_CotableFilters * len(ssts))()
+    keep = []
+    for i, f in enumerate(cotable_filters):
+        if not f:
+            continue
+        oids = np.ascontiguousarray(f[0], dtype=np.uint32)
+        hts = np.ascontiguousarray(f[1], dtype=np.uint64)
+        keep += [oids, hts]
+        cf[i] = _CotableFilters(oids.ctypes.data, hts.ctypes.data, oids.size)
+    L = lib()
+    L.orc_compact2.restype = C.c_void_p
+    L.orc_compact2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    return Result(L.orc_compact2(len(ssts), arr, filt, cf, C.byref(params), C.byref(opts), mode, int(verify)))
 
 
 def compact_runs(runs, params=None):

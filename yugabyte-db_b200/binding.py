@@ -113,6 +113,7 @@ def lib():
     L.ybgpu_job_add_input_device.argtypes = [vp, vp, u64, vp, u64, C.c_int32, u64]
     L.ybgpu_job_add_input_sst.argtypes = [vp, vp, u64, vp, u64, u64]
     L.ybgpu_job_wait_inputs.argtypes = [vp]
+    L.ybgpu_job_set_cotable_filters.argtypes = [vp, vp, vp, C.c_uint32]
     L.ybgpu_job_run.argtypes = [vp, vp]
     L.ybgpu_job_get_stats.argtypes = [vp, C.POINTER(JobStats)]
     L.ybgpu_job_kv_stream_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -249,6 +250,13 @@ class GpuCompactionJob:
         hs[:, 0] = offsets
         hs[:, 1] = sizes
         self._check(lib().ybgpu_job_add_input_device(self.h, dev_ptr, length, _np_ptr(hs), len(offsets), key_encoding, ht_filter))
+
+    def set_cotable_filters(self, db_oids, hybrid_times):
+        """Per-database cotable HybridTime filters of the input added last (sorted database oids, a hybrid time each)."""
+        oids = np.ascontiguousarray(db_oids, dtype=np.uint32)
+        hts = np.ascontiguousarray(hybrid_times, dtype=np.uint64)
+        assert oids.size == hts.size
+        self._check(lib().ybgpu_job_set_cotable_filters(self.h, _np_ptr(oids), _np_ptr(hts), oids.size))
 
     def wait_inputs(self):
         """Blocks until the queued host->device copies of the inputs have completed."""
@@ -487,7 +495,8 @@ def sst_separators(meta):
 
 class InputFile(C.Structure):
     _fields_ = [("meta_file", C.c_void_p), ("meta_file_len", C.c_uint64), ("data_file", C.c_void_p),
-                ("data_file_len", C.c_uint64), ("hybrid_time_filter", C.c_uint64)]
+                ("data_file_len", C.c_uint64), ("hybrid_time_filter", C.c_uint64),
+                ("cotable_db_oids", C.c_void_p), ("cotable_hybrid_times", C.c_void_p), ("num_cotable_filters", C.c_uint64)]
 
 
 class SubOutput(C.Structure):
@@ -514,16 +523,23 @@ class SubOutput(C.Structure):
         return bytes(self.largest_key[:self.largest_key_len])
 
 
-def _input_files(ssts, ht_filters=None):
-    """ssts: list of (meta ndarray, data ndarray). Returns (ctypes array, keepalive)."""
+def _input_files(ssts, ht_filters=None, cotable_filters=None):
+    """ssts: list of (meta ndarray, data ndarray); cotable_filters: per file None or (sorted database oids, hybrid
+    times). Returns (ctypes array, keepalive)."""
     arr = (InputFile * len(ssts))()
     keep = []
     for i, (meta, data) in enumerate(ssts):
         meta = np.ascontiguousarray(meta, dtype=np.uint8)
         data = np.ascontiguousarray(data, dtype=np.uint8)
         keep += [meta, data]
+        oid_p, ht_p, ncf = None, None, 0
+        if cotable_filters and cotable_filters[i]:
+            oids = np.ascontiguousarray(cotable_filters[i][0], dtype=np.uint32)
+            hts = np.ascontiguousarray(cotable_filters[i][1], dtype=np.uint64)
+            keep += [oids, hts]
+            oid_p, ht_p, ncf = oids.ctypes.data, hts.ctypes.data, oids.size
         arr[i] = InputFile(meta.ctypes.data, meta.size, data.ctypes.data, data.size,
-                           ht_filters[i] if ht_filters else HT_INVALID)
+                           ht_filters[i] if ht_filters else HT_INVALID, oid_p, ht_p, ncf)
     return arr, keep
 
 
@@ -565,7 +581,7 @@ class SubcompactionResult:
                 for o in self.outputs if o.data_len]
 
 
-def compact_files(ssts, max_subcompactions=8, max_in_flight=3, data_arena=None, meta_arena=None, ht_filters=None, **job_kwargs):
+def compact_files(ssts, max_subcompactions=8, max_in_flight=3, data_arena=None, meta_arena=None, ht_filters=None, cotable_filters=None, **job_kwargs):
     """ybgpu_compact_files: one compaction as pipelined key-range subcompactions (one output SST per
     range, in range order). ssts: list of (meta ndarray, data ndarray) in host memory."""
     L = lib()
@@ -573,7 +589,7 @@ def compact_files(ssts, max_subcompactions=8, max_in_flight=3, data_arena=None, 
                                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(JobStats),
                                       C.c_char_p, C.c_uint64]
     o, keep_o = make_options(**job_kwargs)
-    arr, keep = _input_files(ssts, ht_filters)
+    arr, keep = _input_files(ssts, ht_filters, cotable_filters)
     in_bytes = sum(int(d.size) for _, d in ssts)
     if data_arena is None:
         data_arena = np.empty(in_bytes + (in_bytes >> 4) + (1 << 20) + 4096 * max_subcompactions, np.uint8)
@@ -604,7 +620,7 @@ class OneTableResult(C.Structure):
         return bytes(self.largest_key[:self.largest_key_len])
 
 
-def compact_files_one_table(ssts, max_subcompactions=8, max_in_flight=3, data_out=None, meta_out=None, ht_filters=None, **job_kwargs):
+def compact_files_one_table(ssts, max_subcompactions=8, max_in_flight=3, data_out=None, meta_out=None, ht_filters=None, cotable_filters=None, **job_kwargs):
     """ybgpu_compact_files_one_table: the pipelined compaction with ONE output table. Returns
     (data view, meta view, OneTableResult, total JobStats)."""
     L = lib()
@@ -612,7 +628,7 @@ def compact_files_one_table(ssts, max_subcompactions=8, max_in_flight=3, data_ou
                                                 C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(OneTableResult), C.POINTER(JobStats),
                                                 C.c_char_p, C.c_uint64]
     o, keep_o = make_options(**job_kwargs)
-    arr, keep = _input_files(ssts, ht_filters)
+    arr, keep = _input_files(ssts, ht_filters, cotable_filters)
     in_bytes = sum(int(d.size) for _, d in ssts)
     if data_out is None:
         data_out = np.empty(in_bytes + (in_bytes >> 4) + (1 << 20), np.uint8)

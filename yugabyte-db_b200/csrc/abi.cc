@@ -88,6 +88,11 @@ ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint6
   return Sync(job, job->engine->AddInput(data_file, data_file_len, handles, num_handles, key_encoding, hybrid_time_filter, false));
 }
 
+ybgpu_status ybgpu_job_set_cotable_filters(ybgpu_job* job, const uint32_t* db_oids, const uint64_t* hybrid_times, uint32_t n) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  return Sync(job, job->engine->SetCotableFilters(db_oids, hybrid_times, n));
+}
+
 ybgpu_status ybgpu_job_wait_inputs(ybgpu_job* job) {
   if (!job) return YBGPU_INVALID_ARGUMENT;
   return Sync(job, job->engine->WaitInputs());

@@ -103,19 +103,25 @@ struct DocDBRetention {
 // rocksdb::UserBoundaryValue (rocksdb/metadata.h): tag + encoded key component.
 struct UserBoundaryValue { uint32_t tag = 0; std::string value; };
 
-// FdWithBoundaries::user_filter_data (db/version_set.cc:3824) -> the engine's per-file HybridTime filter. Empty: no
-// filter. 8 bytes: the global filter (docdb/consensus_frontier.cc:245-253; invisible above it,
-// docdb_rocksdb_util.cc:534-537). Longer: per-database cotable filters follow (master sys catalog after a restore,
-// docdb_rocksdb_util.cc:503-509,541-563) — the engine does not apply those, the caller keeps the CPU job.
-inline Status HybridTimeFilterFromUserFilterData(const Slice& user_filter_data, uint64_t* hybrid_time_filter) {
+// FdWithBoundaries::user_filter_data (db/version_set.cc:3824) -> the engine's per-file HybridTime filters. Empty: no
+// filter. First 8 bytes: the global filter (docdb/consensus_frontier.cc:245-253; invisible above it,
+// docdb_rocksdb_util.cc:534-537). Behind it, n 4-byte database oids followed by n 8-byte hybrid times: the per-database
+// cotable filters of the master's sys catalog after a restore (docdb_rocksdb_util.cc:503-509,541-563).
+inline Status ParseUserFilterData(const Slice& user_filter_data, uint64_t* hybrid_time_filter,
+                                  std::vector<uint32_t>* cotable_db_oids, std::vector<uint64_t>* cotable_hybrid_times) {
   *hybrid_time_filter = YBGPU_HT_INVALID;
+  cotable_db_oids->clear(); cotable_hybrid_times->clear();
   if (user_filter_data.empty()) return Status();
   if (user_filter_data.size() < 8) return Status(Status::kCorruption, "user_filter_data shorter than a HybridTime");
-  if (user_filter_data.size() > 8)
-    return Status(Status::kNotSupported, "per-database cotable HybridTime filters are not applied by the GPU engine");
-  uint64_t ht;
-  memcpy(&ht, user_filter_data.data(), 8);
-  *hybrid_time_filter = ht;
+  memcpy(hybrid_time_filter, user_filter_data.data(), 8);
+  const size_t rest = user_filter_data.size() - 8;
+  if (rest % 12) return Status(Status::kCorruption, "cotable filters are 12 bytes per database");
+  const size_t n = rest / 12;
+  cotable_db_oids->resize(n); cotable_hybrid_times->resize(n);
+  if (n) {
+    memcpy(cotable_db_oids->data(), user_filter_data.data() + 8, 4 * n);
+    memcpy(cotable_hybrid_times->data(), user_filter_data.data() + 8 + 4 * n, 8 * n);
+  }
   return Status();
 }
 
@@ -123,7 +129,9 @@ inline Status HybridTimeFilterFromUserFilterData(const Slice& user_filter_data, 
 struct InputFile {
   Slice base_file;            // <n>.sst (metadata file) bytes
   Slice data_file;            // <n>.sst.sblock.0 bytes
-  uint64_t hybrid_time_filter = YBGPU_HT_INVALID;   // FdWithBoundaries::user_filter_data (:3824)
+  uint64_t hybrid_time_filter = YBGPU_HT_INVALID;   // FdWithBoundaries::user_filter_data (:3824), see ParseUserFilterData
+  std::vector<uint32_t> cotable_db_oids;            // per-database cotable filters (sorted oids, a hybrid time each)
+  std::vector<uint64_t> cotable_hybrid_times;
   // FileMetaData::smallest.seqno / largest.seqno of the input (db/version_edit.h:101-165). The reference seeds
   // every output file's seqno bounds with the union over the inputs (compaction_job.cc:1188-1195) before the
   // surviving entries extend them; leave the defaults when the caller does not track them.
@@ -235,6 +243,8 @@ class GpuCompactionJob {
     for (const InputFile& f : inputs_) {
       ybgpu_status s = ybgpu_job_add_input_sst(job_, f.base_file.data(), f.base_file.size(), f.data_file.data(),
                                                f.data_file.size(), f.hybrid_time_filter);
+      if (s == YBGPU_OK && !f.cotable_db_oids.empty())
+        s = ybgpu_job_set_cotable_filters(job_, f.cotable_db_oids.data(), f.cotable_hybrid_times.data(), static_cast<uint32_t>(f.cotable_db_oids.size()));
       if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
     }
     ybgpu_status s = ybgpu_job_run(job_, p_.shutting_down);
@@ -267,7 +277,8 @@ class GpuCompactionJob {
     std::vector<ybgpu_input_file> files;
     uint64_t in_bytes = 0;
     for (const InputFile& f : inputs_) {
-      files.push_back({f.base_file.data(), f.base_file.size(), f.data_file.data(), f.data_file.size(), f.hybrid_time_filter});
+      files.push_back({f.base_file.data(), f.base_file.size(), f.data_file.data(), f.data_file.size(), f.hybrid_time_filter,
+                       f.cotable_db_oids.data(), f.cotable_hybrid_times.data(), f.cotable_db_oids.size()});
       in_bytes += f.data_file.size();
     }
     // the output of a compaction is never larger than its input plus per-file metadata
@@ -342,6 +353,8 @@ class GpuCompactionJob {
     for (const InputFile& f : inputs_) {
       ybgpu_status s = ybgpu_job_add_input_sst(job_, f.base_file.data(), f.base_file.size(), f.data_file.data(),
                                                f.data_file.size(), f.hybrid_time_filter);
+      if (s == YBGPU_OK && !f.cotable_db_oids.empty())
+        s = ybgpu_job_set_cotable_filters(job_, f.cotable_db_oids.data(), f.cotable_hybrid_times.data(), static_cast<uint32_t>(f.cotable_db_oids.size()));
       if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
     }
     ybgpu_status s = ybgpu_job_run(job_, p_.shutting_down);

@@ -579,6 +579,27 @@ YB_HD int decode_control_fields(const uint8_t* v, int n, ControlFields* cf) {
   return i;
 }
 
+// HybridTimeFilteringIterator::Satisfied (docdb/docdb_rocksdb_util.cc:525-565), negated: is this entry hidden by its
+// input file's HybridTime filters? `global` = the file's global filter (HT_FILTER_NONE = none): hidden above it. Then the
+// per-database cotable filters (master sys catalog after a restore: `n` sorted database oids with a hybrid time each,
+// the tail of user_filter_data, :503-509): a key of a cotable ('y' + 16-byte comparable uuid, whose last four bytes are
+// the database oid — the low half of the uuid is stored verbatim, util/uuid.cc:66-74,162-178) is hidden above the
+// filter of its database; keys of other tables and databases without a filter stay visible. A key whose DocHybridTime
+// does not decode is visible (:527-531).
+constexpr uint64_t HT_FILTER_NONE = 0xfffffffffffffffeull;
+YB_HD bool hidden_by_ht_filters(const uint8_t* key, uint32_t ulen, uint64_t global, const uint32_t* oids, const uint64_t* hts, uint32_t n) {
+  const uint32_t htl = doc_ht_len_from_end(key, ulen);
+  uint64_t ht;
+  if (!htl || !doc_ht_decode(key + ulen - htl, htl, &ht)) return false;
+  if (global != HT_FILTER_NONE && ht > global) return true;
+  if (!n || ulen - htl < 17 || key[0] != 'y') return false;
+  const uint32_t oid = static_cast<uint32_t>(key[13]) | (static_cast<uint32_t>(key[14]) << 8) | (static_cast<uint32_t>(key[15]) << 16) |
+                       (static_cast<uint32_t>(key[16]) << 24);
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (oids[mid] < oid) lo = mid + 1; else hi = mid; }
+  return lo < n && oids[lo] == oid && ht > hts[lo];
+}
+
 YB_HD bool has_control_fields(uint8_t first) { return first == 'k' || first == '#' || first == 't' || first == 'u'; }
 
 // rocksdb/table/block.cc:65-87 DecodeEntry for kKeyDeltaEncodingSharedPrefix: parses the three

@@ -51,6 +51,9 @@ struct RunView {
   uint32_t gid_base;            // global entry id of entry 0
   uint32_t key_encoding;        // rocksdb::KeyValueEncodingFormat of this file's data blocks
   uint64_t ht_filter;
+  const uint32_t* cf_oid;       // per-database cotable HybridTime filters of the file: sorted database oids,
+  const uint64_t* cf_ht;        //   their hybrid times (device arrays), and how many (0 = none)
+  uint32_t cf_n;
 };
 
 struct JobDev {                 // device-global job state
@@ -309,11 +312,8 @@ __global__ void __launch_bounds__(128) k_decode_all(const RunView* runs, const u
         uint64_t suffix = 0;
         for (int i = 7; i >= 0; i--) suffix = (suffix << 8) | keybuf[ulen + i];
         uint8_t flags = 0;
-        if (run.ht_filter != 0xfffffffffffffffeull) {
-          uint32_t htl = doc_ht_len_from_end(keybuf, ulen);
-          uint64_t ht;
-          if (htl && doc_ht_decode(keybuf + ulen - htl, htl, &ht) && ht > run.ht_filter) flags |= REC_F_HT_FILTERED;
-        }
+        if ((run.ht_filter != HT_FILTER_NONE || run.cf_n) && hidden_by_ht_filters(keybuf, ulen, run.ht_filter, run.cf_oid, run.cf_ht, run.cf_n))
+          flags |= REC_F_HT_FILTERED;
         if (range && (range->lower_len | range->upper_len)) {
           if (range->lower_len && cmp_raw(keybuf, ulen, range->lower, range->lower_len) < 0) flags |= REC_F_OUT_OF_RANGE;
           if (range->upper_len && cmp_raw(keybuf, ulen, range->upper, range->upper_len) >= 0) flags |= REC_F_OUT_OF_RANGE;
@@ -1457,6 +1457,8 @@ struct Engine::Impl {
   bool owns_stream = false;            // cuda_stream == YBGPU_STREAM_PRIVATE: created in Init, destroyed with the job
   uint8_t* status_host = nullptr; uint8_t* status_dev = nullptr;   // host-mapped page for small read-backs (may be null)
   uint32_t readback_launches = 0;
+  std::vector<std::vector<uint32_t>> cf_oids;         // per input: cotable HybridTime filters (host copies until Run)
+  std::vector<std::vector<uint64_t>> cf_hts;
   uint8_t* staging_host = nullptr; uint8_t* staging_dev = nullptr;   // host-mapped staging for metadata-sized read-backs
   size_t upload_off = 0;                             // ring position of the next small upload inside the page
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1721,6 +1723,18 @@ ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_blo
   rv.ht_filter = ht_filter;
   rv.key_encoding = static_cast<uint32_t>(key_encoding);
   impl_->runs.push_back(rv);
+  impl_->cf_oids.emplace_back(); impl_->cf_hts.emplace_back();
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::SetCotableFilters(const uint32_t* db_oids, const uint64_t* hybrid_times, uint32_t n) {
+  if (ran_) return Fail(YBGPU_ILLEGAL_STATE, "set_cotable_filters after run");
+  if (impl_->runs.empty()) return Fail(YBGPU_ILLEGAL_STATE, "set_cotable_filters before any input");
+  if (n && (!db_oids || !hybrid_times)) return Fail(YBGPU_INVALID_ARGUMENT, "null cotable filter arrays");
+  for (uint32_t i = 1; i < n; i++)
+    if (db_oids[i - 1] >= db_oids[i]) return Fail(YBGPU_INVALID_ARGUMENT, "cotable filter database oids must be strictly increasing");
+  impl_->cf_oids.back().assign(db_oids, db_oids + n);
+  impl_->cf_hts.back().assign(hybrid_times, hybrid_times + n);
   return YBGPU_OK;
 }
 
@@ -1884,6 +1898,15 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   for (int r = 0; r < k; r++) blk_base[r + 1] = blk_base[r] + I.runs[r].nb;
   uint32_t* d_blk_base = nullptr;
   CUDA_TRY(DevAlloc(&I.allocs, &d_blk_base, static_cast<size_t>(k) + 1));
+  for (int r = 0; r < k; r++) {
+    const size_t n = I.cf_oids[r].size();
+    if (!n || I.runs[r].cf_n) continue;
+    uint32_t* d_oid = nullptr; uint64_t* d_ht = nullptr;
+    CUDA_TRY(DevAlloc(&I.allocs, &d_oid, n)); CUDA_TRY(DevAlloc(&I.allocs, &d_ht, n));
+    if (ybgpu_status us = UploadSmall(d_oid, I.cf_oids[r].data(), 4 * n)) return us;
+    if (ybgpu_status us = UploadSmall(d_ht, I.cf_hts[r].data(), 8 * n)) return us;
+    I.runs[r].cf_oid = d_oid; I.runs[r].cf_ht = d_ht; I.runs[r].cf_n = static_cast<uint32_t>(n);
+  }
   if (ybgpu_status us = UploadSmall(d_blk_base, blk_base.data(), 4 * (static_cast<size_t>(k) + 1))) return us;
   if (ybgpu_status us = UploadSmall(I.dRuns, I.runs.data(), sizeof(RunView) * k)) return us;
   RangeDev* d_range = nullptr;
@@ -2076,7 +2099,7 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       const int grid = GridFor(static_cast<uint64_t>(group_base[k]) * 32, 128, sms);
       // fast path: shared-prefix inputs, internal keys of at most 64 bytes, no HybridTime filter / key range
       bool fast = d_range == nullptr && max_ikey <= 64;
-      for (int r = 0; r < k; r++) fast = fast && I.runs[r].key_encoding == 1 && I.runs[r].ht_filter == 0xfffffffffffffffeull;
+      for (int r = 0; r < k; r++) fast = fast && I.runs[r].key_encoding == 1 && I.runs[r].ht_filter == 0xfffffffffffffffeull && I.runs[r].cf_n == 0;
       if (fast && getenv("YBGPU_NO_FAST_DECODE") == nullptr) {
         if (max_ikey <= 32) k_decode_fast<2><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);
         else if (max_ikey <= 48) k_decode_fast<3><<<grid, 128, 0, I.stream>>>(I.dRuns, d_group_base, k, Sfinal, I.dJ);

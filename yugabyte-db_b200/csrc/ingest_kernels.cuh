@@ -477,7 +477,9 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
     const uint8_t* blk = buf0 + stage * (ING_BUF + 32) + cur.mis;
     const IngEntry* etab = etab0 + stage * ING_MAXE;
     const uint32_t L = size + 1;                       // contents + type byte
-    const bool filtered = ht_filter != 0xfffffffffffffffeull || ranged;
+    const RunView& crun = V.runs[cur.run];
+    const uint32_t cf_n = crun.cf_n;
+    const bool filtered = ht_filter != 0xfffffffffffffffeull || ranged || cf_n != 0;
     unsigned long long acc = 0;                        // XOR of unreduced carry-less products (CRC warps)
     const uint32_t rt = threadIdx.x & (ING_CONSUMERS - 1);   // thread index inside its role
     if (wid < ING_CONSUMERS / 32) {
@@ -545,11 +547,7 @@ __global__ void __launch_bounds__(ING_THREADS, 2) k_ingest(IngestView V, JobDev*
         __align__(16) uint8_t kb[16 * ING_NVI];
 #pragma unroll
         for (int w = 0; w < ING_NVI; w++) reinterpret_cast<uint4*>(kb)[w] = kv[w];
-        if (ht_filter != 0xfffffffffffffffeull) {
-          const uint32_t htl = doc_ht_len_from_end(kb, ulen);
-          uint64_t ht;
-          if (htl && doc_ht_decode(kb + ulen - htl, htl, &ht) && ht > ht_filter) flags |= REC_F_HT_FILTERED;
-        }
+        if ((ht_filter != HT_FILTER_NONE || cf_n) && hidden_by_ht_filters(kb, ulen, ht_filter, crun.cf_oid, crun.cf_ht, cf_n)) flags |= REC_F_HT_FILTERED;
         if (ranged) {
           if (V.range->lower_len && cmp_raw(kb, ulen, V.range->lower, V.range->lower_len) < 0) flags |= REC_F_OUT_OF_RANGE;
           if (V.range->upper_len && cmp_raw(kb, ulen, V.range->upper, V.range->upper_len) >= 0) flags |= REC_F_OUT_OF_RANGE;

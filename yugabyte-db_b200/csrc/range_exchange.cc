@@ -216,6 +216,8 @@ ybgpu_status ybgpu_compact_range_sharded(ybgpu_range_comm* c, const ybgpu_job_op
   if (!N) return fail(YBGPU_RUNTIME_ERROR, nerr);
   if (!c || !options || (!files && num_files) || !data_out || !meta_out || !result) return fail(YBGPU_INVALID_ARGUMENT, "null argument");
   if (options->range_lower_len || options->range_upper_len) return fail(YBGPU_INVALID_ARGUMENT, "range bounds are set by the planner");
+  for (uint32_t f = 0; f < num_files; f++)
+    if (files[f].num_cotable_filters) return fail(YBGPU_NOT_SUPPORTED, "per-database cotable HybridTime filters do not travel with the exchanged block slices");
   if (rounds == 0) rounds = 1;
   if (chunk_bytes == 0) chunk_bytes = 64ull << 20;
   chunk_bytes = (chunk_bytes + 15) & ~15ull;

@@ -260,7 +260,7 @@ ybgpu_status ybgpu_sst_last_key(const uint8_t* meta_file, uint64_t meta_file_len
   if (!meta_file || !data_file || !key || !key_len) return YBGPU_INVALID_ARGUMENT;
   SstMeta m;
   if (!ybgpu::host::ParseSplitSstMeta(meta_file, meta_file_len, &m).empty()) return YBGPU_CORRUPTION;
-  ybgpu_input_file f{meta_file, meta_file_len, data_file, data_file_len, YBGPU_HT_INVALID};
+  ybgpu_input_file f{meta_file, meta_file_len, data_file, data_file_len, YBGPU_HT_INVALID, nullptr, nullptr, 0};
   std::string k;
   if (!LastKeyOfFile(f, m, &k) || k.size() > 1032) return YBGPU_CORRUPTION;
   memcpy(key, k.data(), k.size());
@@ -494,6 +494,10 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
         for (size_t i = sp.a; i < sp.b; i++) { h[i - sp.a].offset = blocks[i].offset - start; h[i - sp.a].size = blocks[i].size; }
         s = ybgpu_job_add_input(job, files[f].data_file + start, end - start, h.data(), h.size(), in[f].meta.key_encoding, files[f].hybrid_time_filter);
         if (s != YBGPU_OK) { job_fail(s, "add_input"); return; }
+        if (files[f].num_cotable_filters) {
+          s = ybgpu_job_set_cotable_filters(job, files[f].cotable_db_oids, files[f].cotable_hybrid_times, static_cast<uint32_t>(files[f].num_cotable_filters));
+          if (s != YBGPU_OK) { job_fail(s, "set_cotable_filters"); return; }
+        }
         added++;
       }
     }
