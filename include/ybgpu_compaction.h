@@ -168,7 +168,8 @@ enum {
   YBGPU_PATH_SNAPPY = 4,               /* compressed input blocks were uncompressed on the GPU */
   YBGPU_PATH_PARTITION_RETRY = 8,      /* the partition was repeated with a smaller sample stride */
   YBGPU_PATH_ENCODER_V4 = 16,          /* block assembler with checksums by CRC linearity */
-  YBGPU_PATH_ENCODER_V5 = 32           /* ... warp per block, no block image (k_encode_v5) */
+  YBGPU_PATH_ENCODER_V5 = 32,          /* ... warp per block, no block image (k_encode_v5) */
+  YBGPU_PATH_KV_INPUT = 64             /* the inputs were KV streams (ybgpu_job_add_input_kv), not table files */
 };
 
 typedef struct ybgpu_job ybgpu_job;
@@ -189,6 +190,16 @@ const char* ybgpu_last_error(void);                      /* for failures of crea
 ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint64_t data_file_len,
                                  const ybgpu_block_handle* handles, uint64_t num_handles,
                                  int32_t key_encoding, uint64_t hybrid_time_filter);
+
+/* A sorted run the caller holds in MEMORY instead of a table file — the flush path's input: BuildTable
+ * (rocksdb/db/builder.cc:119-318) walks the memtable iterator through the same CompactionIterator / TableBuilder chain a
+ * compaction uses, so a job fed with the memtable's entries (and retention_enabled = 0, or the DocDB rules if the
+ * caller wants them applied at flush time) writes the L0 table the reference would. `keys` = n internal keys (user key +
+ * 8-byte suffix) back to back, key i at [key_offsets[i], key_offsets[i+1]); values likewise; entries in internal-key
+ * order (checked: YBGPU_CORRUPTION otherwise). Host memory, copied (queued like ybgpu_job_add_input). KV-stream inputs
+ * and table-file inputs cannot be mixed in one job. */
+ybgpu_status ybgpu_job_add_input_kv(ybgpu_job* job, const uint8_t* keys, const uint64_t* key_offsets,
+                                    const uint8_t* values, const uint64_t* value_offsets, uint64_t n);
 
 /* Per-database cotable HybridTime filters of the input added LAST — the tail of FdWithBoundaries::user_filter_data
  * behind the 8-byte global filter (docdb/docdb_rocksdb_util.cc:503-509; written for the master's sys catalog by a

@@ -672,3 +672,45 @@ def test_small_upload_ring_wraps(pkg, monkeypatch):
         check(pkg, ssts, block_size=1024, filter_policy=1, filter_block_size=2048, **kw)
     cfg = o.GenConfig(seed=9, num_rows=5000, cols=2, versions=2, num_files=24, value_len=60)
     check(pkg, o.Sst.generate_all(cfg, o.TableOptions(block_size=2048)), block_size=4096)
+
+
+def test_kv_stream_inputs_flush_path(pkg):
+    """ybgpu_job_add_input_kv: sorted runs held in memory instead of table files — the flush path's shape (BuildTable,
+    rocksdb/db/builder.cc:119-318: memtable iterator -> CompactionIterator -> TableBuilder). The job must write exactly
+    what a compaction of table files with the same entries writes: KV stream, counters, both output files."""
+    topt = dict(block_size=2048, filter_policy=1, filter_block_size=2048)
+    runs = [r for r in w.random_docdb_runs(12, n_runs=3, n_rows=300) if r]
+    ssts = runs_to_ssts(runs, 1024)
+    for kw in (dict(retention=False, bottommost=False), dict(retention=False, bottommost=True, last_sequence=o.MAX_SEQ), w.param_grid()[1], w.param_grid()[4]):
+        exp = o.compact(ssts, o.CompactionParams(**kw), o.TableOptions(**topt))
+        job = pkg.GpuCompactionJob(**topt, **kw)
+        for r in runs:
+            job.add_input_kv(r)
+        job.run()
+        st = job.stats()
+        assert st.path_flags & pkg.PATH_KV_INPUT and not st.path_flags & (pkg.PATH_FUSED_INGEST | pkg.PATH_GENERAL_DECODE)
+        assert job.kv_list() == exp.kv_list()
+        assert (st.num_input_records, st.num_output_records) == (exp.stats.num_input_records, exp.stats.num_output_records)
+        assert job.digest() == exp.stats.kv_hash
+        data, meta = job.fetch_output()
+        ref = exp.sst()
+        assert (data.tobytes(), meta.tobytes()) == ((ref.data, ref.meta) if ref is not None else (b"", b""))
+    # a flush proper: ONE memtable -> one L0 table, plain RocksDB rules (duplicates of a user key: the newest wins)
+    mem = w.sort_run([(o.ikey(b"k%05d" % (i // 3), (1 << 50) + i), b"v%d" % i) for i in range(6000)])
+    exp = o.compact([o.Sst.build(mem, o.TableOptions(block_size=4096))], o.CompactionParams(retention=False, bottommost=False), o.TableOptions(block_size=4096))
+    job = pkg.GpuCompactionJob(block_size=4096, retention=False, bottommost=False)
+    job.add_input_kv(mem)
+    job.run()
+    assert job.kv_list() == exp.kv_list() and len(job.kv_list()) == 2000
+    data, meta = job.fetch_output()
+    assert data.tobytes() == exp.sst().data and meta.tobytes() == exp.sst().meta
+    # empty and single-entry inputs; mixing with table files is refused
+    job = pkg.GpuCompactionJob(block_size=4096, retention=False)
+    job.add_input_kv([])
+    job.add_input_kv(mem[:1])
+    job.run()
+    assert [v for _, v in job.kv_list()] == [mem[0][1]]
+    job = pkg.GpuCompactionJob(block_size=4096)
+    job.add_input_kv(mem[:10])
+    with pytest.raises(pkg.YbGpuError):
+        job.add_input_sst(ssts[0].meta_view(), ssts[0].data_view())

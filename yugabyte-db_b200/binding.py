@@ -74,7 +74,7 @@ class JobStats(C.Structure):
 
 
 PHASE_NAMES = ["block_scan", "decode", "partition", "merge_filter", "encode"]
-PATH_FUSED_INGEST, PATH_GENERAL_DECODE, PATH_SNAPPY, PATH_PARTITION_RETRY, PATH_ENCODER_V4, PATH_ENCODER_V5 = 1, 2, 4, 8, 16, 32
+PATH_FUSED_INGEST, PATH_GENERAL_DECODE, PATH_SNAPPY, PATH_PARTITION_RETRY, PATH_ENCODER_V4, PATH_ENCODER_V5, PATH_KV_INPUT = 1, 2, 4, 8, 16, 32, 64
 
 
 class GenConfig(C.Structure):
@@ -114,6 +114,7 @@ def lib():
     L.ybgpu_job_add_input_sst.argtypes = [vp, vp, u64, vp, u64, u64]
     L.ybgpu_job_wait_inputs.argtypes = [vp]
     L.ybgpu_job_set_cotable_filters.argtypes = [vp, vp, vp, C.c_uint32]
+    L.ybgpu_job_add_input_kv.argtypes = [vp, vp, vp, vp, vp, u64]
     L.ybgpu_job_run.argtypes = [vp, vp]
     L.ybgpu_job_get_stats.argtypes = [vp, C.POINTER(JobStats)]
     L.ybgpu_job_kv_stream_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -250,6 +251,19 @@ class GpuCompactionJob:
         hs[:, 0] = offsets
         hs[:, 1] = sizes
         self._check(lib().ybgpu_job_add_input_device(self.h, dev_ptr, length, _np_ptr(hs), len(offsets), key_encoding, ht_filter))
+
+    def add_input_kv(self, kvs):
+        """A sorted run held in memory (the flush path's input): kvs = [(internal key, value)] in internal-key order."""
+        keys = np.frombuffer(b"".join(k for k, _ in kvs), dtype=np.uint8) if kvs else np.zeros(0, np.uint8)
+        vals = np.frombuffer(b"".join(v for _, v in kvs), dtype=np.uint8) if kvs else np.zeros(0, np.uint8)
+        koff = np.zeros(len(kvs) + 1, np.uint64)
+        voff = np.zeros(len(kvs) + 1, np.uint64)
+        if kvs:
+            koff[1:] = np.cumsum([len(k) for k, _ in kvs])
+            voff[1:] = np.cumsum([len(v) for _, v in kvs])
+        self._inputs.append((keys, vals, koff, voff))
+        self._check(lib().ybgpu_job_add_input_kv(self.h, _np_ptr(keys) if keys.size else None, _np_ptr(koff), _np_ptr(vals) if vals.size else None,
+                                                 _np_ptr(voff), len(kvs)))
 
     def set_cotable_filters(self, db_oids, hybrid_times):
         """Per-database cotable HybridTime filters of the input added last (sorted database oids, a hybrid time each)."""

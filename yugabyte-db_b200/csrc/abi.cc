@@ -88,6 +88,12 @@ ybgpu_status ybgpu_job_add_input(ybgpu_job* job, const uint8_t* data_file, uint6
   return Sync(job, job->engine->AddInput(data_file, data_file_len, handles, num_handles, key_encoding, hybrid_time_filter, false));
 }
 
+ybgpu_status ybgpu_job_add_input_kv(ybgpu_job* job, const uint8_t* keys, const uint64_t* key_offsets,
+                                    const uint8_t* values, const uint64_t* value_offsets, uint64_t n) {
+  if (!job) return YBGPU_INVALID_ARGUMENT;
+  return Sync(job, job->engine->AddInputKv(keys, key_offsets, values, value_offsets, n));
+}
+
 ybgpu_status ybgpu_job_set_cotable_filters(ybgpu_job* job, const uint32_t* db_oids, const uint64_t* hybrid_times, uint32_t n) {
   if (!job) return YBGPU_INVALID_ARGUMENT;
   return Sync(job, job->engine->SetCotableFilters(db_oids, hybrid_times, n));

@@ -1457,6 +1457,9 @@ struct Engine::Impl {
   bool owns_stream = false;            // cuda_stream == YBGPU_STREAM_PRIVATE: created in Init, destroyed with the job
   uint8_t* status_host = nullptr; uint8_t* status_dev = nullptr;   // host-mapped page for small read-backs (may be null)
   uint32_t readback_launches = 0;
+  // KV-stream inputs (add_input_kv): device copies of the key bytes / offset arrays per input, entries, longest key
+  struct KvInput { const uint8_t* keys; const unsigned long long* koff; const unsigned long long* voff; uint32_t n; uint32_t max_klen; std::string last_user_key; };
+  std::vector<KvInput> kv;
   std::vector<std::vector<uint32_t>> cf_oids;         // per input: cotable HybridTime filters (host copies until Run)
   std::vector<std::vector<uint64_t>> cf_hts;
   uint8_t* staging_host = nullptr; uint8_t* staging_dev = nullptr;   // host-mapped staging for metadata-sized read-backs
@@ -1497,6 +1500,34 @@ struct Engine::Impl {
 // a one-CTA kernel stores the words into a host-mapped pinned page (a posted PCIe write from the SM)
 // and the host reads the page after the stream synchronises. Next to other jobs' multi-GB output
 // copies a DMA read-back would queue behind them on the device->host engine.
+// KV-stream inputs (ybgpu_job_add_input_kv: the contents of a memtable for a flush, rocksdb/db/builder.cc:119-318, or any
+// sorted run a caller holds in memory): internal keys back to back with an offset array, values likewise. One thread per
+// entry writes the fixed-stride key record the rest of the pipeline works on; the values stay where they are.
+__global__ void __launch_bounds__(256) k_records_from_kv(const uint8_t* keys, const unsigned long long* koff, const unsigned long long* voff,
+                                                         const uint8_t* vals, uint32_t n, int S, uint8_t* rec, uint64_t* val_off, JobDev* J) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long k0 = koff[i], k1 = koff[i + 1], v0 = voff[i], v1 = voff[i + 1];
+    uint8_t* r = rec + static_cast<size_t>(i) * S;
+    if (k1 < k0 + 8 || k1 - k0 - 8 > static_cast<unsigned long long>(S - 16) || v1 < v0 || v1 - v0 >= (1ull << 32)) {
+      dev_fail(J, k1 < k0 + 8 ? DEV_ERR_SHORT_KEY : DEV_ERR_BAD_ENTRY, i);
+      for (int b = 0; b < S; b++) r[b] = 0;
+      val_off[i] = 0;
+      continue;
+    }
+    const uint32_t ulen = static_cast<uint32_t>(k1 - k0 - 8), vlen = static_cast<uint32_t>(v1 - v0);
+    const uint8_t* kp = keys + k0;
+    for (int b = 0; b < S - 16; b++) r[b] = static_cast<uint32_t>(b) < ulen ? kp[b] : 0;
+    uint64_t suffix = 0;
+    for (int b = 7; b >= 0; b--) suffix = (suffix << 8) | kp[ulen + b];
+    uint4 tr;
+    tr.x = static_cast<uint32_t>(suffix); tr.y = static_cast<uint32_t>(suffix >> 32);
+    tr.z = ulen | (static_cast<uint32_t>(vlen ? vals[v0] : 0) << 16);
+    tr.w = vlen;
+    *reinterpret_cast<uint4*>(r + S - 16) = tr;
+    val_off[i] = v0;
+  }
+}
+
 __global__ void k_readback(uint8_t* dst_mapped, const uint8_t* src, uint32_t n) {
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst_mapped[i] = src[i];
   __threadfence_system();
@@ -1685,6 +1716,7 @@ ybgpu_status Engine::AddInput(const uint8_t* data, uint64_t len, const ybgpu_blo
                               int key_encoding, uint64_t ht_filter, bool on_device) {
   if (ran_) return Fail(YBGPU_ILLEGAL_STATE, "add_input after run");
   if (impl_->runs.size() >= MAX_RUNS) return Fail(YBGPU_NOT_SUPPORTED, "too many input files");
+  if (!impl_->kv.empty()) return Fail(YBGPU_NOT_SUPPORTED, "KV-stream inputs and table-file inputs cannot be mixed in one job");
   if (key_encoding != YBGPU_KEY_ENCODING_SHARED_PREFIX && key_encoding != YBGPU_KEY_ENCODING_THREE_SHARED_PARTS)
     return Fail(YBGPU_INVALID_ARGUMENT, "unknown data block key encoding");
   if (nh >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "too many data blocks in one file");
@@ -1735,6 +1767,44 @@ ybgpu_status Engine::SetCotableFilters(const uint32_t* db_oids, const uint64_t* 
     if (db_oids[i - 1] >= db_oids[i]) return Fail(YBGPU_INVALID_ARGUMENT, "cotable filter database oids must be strictly increasing");
   impl_->cf_oids.back().assign(db_oids, db_oids + n);
   impl_->cf_hts.back().assign(hybrid_times, hybrid_times + n);
+  return YBGPU_OK;
+}
+
+ybgpu_status Engine::AddInputKv(const uint8_t* keys, const uint64_t* key_offsets, const uint8_t* values, const uint64_t* value_offsets, uint64_t n) {
+  Impl& I = *impl_;
+  if (ran_) return Fail(YBGPU_ILLEGAL_STATE, "add_input after run");
+  if (I.runs.size() >= MAX_RUNS) return Fail(YBGPU_NOT_SUPPORTED, "too many input files");
+  if (I.kv.size() != I.runs.size()) return Fail(YBGPU_NOT_SUPPORTED, "KV-stream inputs and table-file inputs cannot be mixed in one job");
+  if (n >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "more than 2^32 entries in one input");
+  if (n && (!keys || !key_offsets || !value_offsets)) return Fail(YBGPU_INVALID_ARGUMENT, "null argument");
+  CUDA_TRY(cudaSetDevice(opt_.device));
+  g_alloc_stream = I.stream;
+  const uint64_t kbytes = n ? key_offsets[n] : 0, vbytes = n ? value_offsets[n] : 0;
+  uint32_t max_klen = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    if (key_offsets[i + 1] < key_offsets[i] + 8 || value_offsets[i + 1] < value_offsets[i]) return Fail(YBGPU_INVALID_ARGUMENT, "bad key / value offsets");
+    max_klen = std::max<uint32_t>(max_klen, static_cast<uint32_t>(std::min<uint64_t>(key_offsets[i + 1] - key_offsets[i], 0xffffffffu)));
+  }
+  uint8_t* dk = nullptr; uint8_t* dv = nullptr; unsigned long long* dko = nullptr; unsigned long long* dvo = nullptr; uint32_t* dcnt = nullptr;
+  CUDA_TRY(DevAlloc(&I.allocs, &dk, kbytes + 16));
+  CUDA_TRY(DevAlloc(&I.allocs, &dv, vbytes + 64));
+  CUDA_TRY(DevAlloc(&I.allocs, &dko, n + 1)); CUDA_TRY(DevAlloc(&I.allocs, &dvo, n + 1)); CUDA_TRY(DevAlloc(&I.allocs, &dcnt, 1));
+  CUDA_TRY(cudaMemsetAsync(dv, 0, 16, I.stream));
+  if (kbytes) CUDA_TRY(ChunkedCopyAsync(dk, keys, kbytes, cudaMemcpyHostToDevice, I.stream));
+  if (vbytes) CUDA_TRY(ChunkedCopyAsync(dv + 16, values, vbytes, cudaMemcpyHostToDevice, I.stream));
+  CUDA_TRY(cudaMemsetAsync(dv + 16 + vbytes, 0, 16, I.stream));
+  static const uint64_t zero_off[1] = {0};
+  CUDA_TRY(ChunkedCopyAsync(dko, n ? key_offsets : zero_off, (n + 1) * 8, cudaMemcpyHostToDevice, I.stream));
+  CUDA_TRY(ChunkedCopyAsync(dvo, n ? value_offsets : zero_off, (n + 1) * 8, cudaMemcpyHostToDevice, I.stream));
+  stats_.h2d_bytes += kbytes + vbytes + 16 * (n + 1);
+  RunView rv{};
+  rv.data = dv + 16; rv.blk_off = nullptr; rv.blk_size = nullptr; rv.blk_count = dcnt; rv.nb = 0;
+  rv.ht_filter = HT_FILTER_NONE; rv.key_encoding = YBGPU_KEY_ENCODING_SHARED_PREFIX;
+  I.runs.push_back(rv);
+  I.cf_oids.emplace_back(); I.cf_hts.emplace_back();
+  Impl::KvInput ki{dk, dko, dvo, static_cast<uint32_t>(n), max_klen, std::string()};
+  if (n) ki.last_user_key.assign(reinterpret_cast<const char*>(keys + key_offsets[n - 1]), key_offsets[n] - key_offsets[n - 1] - 8);
+  I.kv.push_back(ki);
   return YBGPU_OK;
 }
 
@@ -1924,6 +1994,39 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
   bool ingested = false;
   bool try_ingest = blk_base[k] > 0 && getenv("YBGPU_NO_INGEST") == nullptr;
   for (int r = 0; r < k; r++) try_ingest = try_ingest && I.runs[r].key_encoding == 1;
+  if (!I.kv.empty()) {
+    // ---- KV-stream inputs: no blocks to verify or decode; records straight from the key arrays, value CRCs for the
+    // block encoder from the value arrays
+    try_ingest = false;
+    for (int r = 0; r < k; r++) {
+      I.runs[r].n_entries = I.kv[r].n;
+      I.runs[r].gid_base = static_cast<uint32_t>(N);
+      N += I.kv[r].n;
+      max_ikey = std::max(max_ikey, I.kv[r].max_klen);
+    }
+    if (N >= (1ull << 32)) return Fail(YBGPU_NOT_SUPPORTED, "more than 2^32 entries in one job: shard the compaction");
+    if (max_ikey > 1008 + 8) return Fail(YBGPU_NOT_SUPPORTED, "user keys longer than 1008 bytes are not supported");
+    Sfinal = std::max(32, N ? static_cast<int>(((std::max<uint32_t>(max_ikey, 8) - 8 + 16) + 15) & ~15u) : 32);
+    CUDA_TRY(end_phase());
+    for (int r = 0; r < k; r++) {
+      RunView& rv = I.runs[r];
+      CUDA_TRY(DevAlloc(&I.allocs, &rv.rec, static_cast<size_t>(rv.n_entries) * Sfinal + 16));
+      CUDA_TRY(DevAlloc(&I.allocs, &rv.val_off, static_cast<size_t>(rv.n_entries) + 1));
+      CUDA_TRY(DevAlloc(&I.allocs, &rv.val_crc, static_cast<size_t>(rv.n_entries) + 1));
+      if (rv.n_entries) {
+        k_records_from_kv<<<GridFor(rv.n_entries, 256, sms), 256, 0, I.stream>>>(I.kv[r].keys, I.kv[r].koff, I.kv[r].voff, rv.data, rv.n_entries, Sfinal,
+                                                                             rv.rec, rv.val_off, I.dJ);
+        launches++;
+      }
+    }
+    if (ybgpu_status us = UploadSmall(I.dRuns, I.runs.data(), sizeof(RunView) * k)) return us;
+    if (N) { k_value_crc<<<GridFor(N, 256, sms), 256, 0, I.stream>>>(I.dRuns, k, Sfinal); launches++; }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(end_phase());
+    if (ybgpu_status s = CheckDeviceError("kv inputs")) return s;
+    ingested = true;
+    stats_.path_flags |= YBGPU_PATH_KV_INPUT;
+  }
   // ---- probe: restart counts (entry upper bounds), restart interval, key length sample, compression types
   bool verify_pending = opt_.verify_checksums != 0;      // false once the stored blocks' checksums have been verified
   if (blk_base[k] > 0) {

@@ -17,6 +17,7 @@ class Engine {
   ybgpu_status Init();
   ybgpu_status AddInput(const uint8_t* data, uint64_t len, const ybgpu_block_handle* handles, uint64_t nh,
                         int key_encoding, uint64_t ht_filter, bool on_device);
+  ybgpu_status AddInputKv(const uint8_t* keys, const uint64_t* key_offsets, const uint8_t* values, const uint64_t* value_offsets, uint64_t n);
   ybgpu_status SetCotableFilters(const uint32_t* db_oids, const uint64_t* hybrid_times, uint32_t n);
   ybgpu_status WaitInputs();
   ybgpu_status Run(const volatile int32_t* shutting_down);
