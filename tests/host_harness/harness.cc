@@ -160,6 +160,11 @@ const uint8_t* hh_vals() { return reinterpret_cast<const uint8_t*>(g_out->vals.d
 const uint64_t* hh_koff() { return g_out->koff.data(); }
 const uint64_t* hh_voff() { return g_out->voff.data(); }
 
+// hidden_by_ht_filters (HybridTimeFilteringIterator::Satisfied, negated)
+int hh_hidden_by_ht_filters(const uint8_t* key, uint32_t ulen, uint64_t global, const uint32_t* oids, const uint64_t* hts, uint32_t n) {
+  return hidden_by_ht_filters(key, ulen, global, oids, hts, n) ? 1 : 0;
+}
+
 int hh_group_prefix_len(const uint8_t* key, int ulen, int retention) {
   std::vector<uint8_t> buf(ulen + 32, 0); uint8_t* p = buf.data(); p += (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
   memcpy(p, key, ulen);

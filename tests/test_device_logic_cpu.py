@@ -153,3 +153,73 @@ def test_state_rebuilt_by_ancestor_replay_inside_groups(cut):
                 getattr(t, name)()
     finally:
         L.hh_set_cut_every(0)
+
+
+def test_entry_header_parser_all_paths():
+    """parse_entry_header has three paths: three one-byte varints, fields of at most two bytes decoded in straight-line
+    code (every real key, most values), and the general byte loop. All three against an independent LEB128 encoder, with
+    short `avail` and truncated headers."""
+    import ctypes as C
+    import random
+    L = hh.lib()
+    L.hh_parse_entry_header.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+
+    def leb(v):
+        out = bytearray()
+        while v >= 128:
+            out.append((v & 127) | 128)
+            v >>= 7
+        out.append(v)
+        return bytes(out)
+    rng = random.Random(3)
+    pools = [[0, 1, 5, 127], [128, 129, 300, 16383], [16384, 70000, (1 << 28) - 1, (1 << 32) - 1]]
+    cases = [(a, b, c) for pa in pools for pb in pools for pc in pools for a in pa[:2] for b in pb[-2:] for c in (pc[0], pc[-1])]
+    cases += [tuple(rng.choice(rng.choice(pools)) for _ in range(3)) for _ in range(400)]
+    oa, ob, oc = C.c_uint32(), C.c_uint32(), C.c_uint32()
+
+    def parse(buf, avail):
+        return L.hh_parse_entry_header(buf, avail, C.byref(oa), C.byref(ob), C.byref(oc))
+    for a, b, c in cases:
+        hdr = leb(a) + leb(b) + leb(c)
+        for pad in (0, 1, 9):
+            buf = hdr + bytes(rng.randrange(256) for _ in range(pad))
+            n = parse(buf + b"\0" * 8, len(buf))
+            if len(buf) < 3:
+                assert n == 0                      # DecodeEntry needs three bytes (block.cc:70-73)
+                continue
+            assert n == len(hdr) and (oa.value, ob.value, oc.value) == (a, b, c), (a, b, c, pad)
+        if len(hdr) > 3:
+            assert parse(hdr + b"\0" * 8, len(hdr) - 1) == 0      # truncated inside a varint
+    assert parse(bytes([0x80] * 6 + [1]) + b"\0" * 8, 7) == 0      # a varint32 longer than 5 bytes
+
+
+def test_hybrid_time_filter_predicate():
+    """hidden_by_ht_filters (the device side of HybridTimeFilteringIterator::Satisfied, docdb_rocksdb_util.cc:525-565)
+    against the rule written out in Python: global filter, per-database cotable filters (database oid = uuid bytes
+    12..15, little endian), keys of other tables, undecodable hybrid times."""
+    import ctypes as C
+    import struct
+    import numpy as np
+    L = hh.lib()
+    L.hh_hidden_by_ht_filters.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+    none = (1 << 64) - 2
+    oids = np.array([7, 1000, 70000, 0x01020304], np.uint32)
+    hts = np.array([o.ht_from_micros(o.YB_EPOCH_US + t) for t in (50, 20, 90, 10)], np.uint64)
+
+    def key(prefix, micros, logical=0):
+        return prefix + b"Srow\x00\x00!" + b"K\x81" + b"#" + o.encode_doc_ht(o.YB_EPOCH_US + micros, logical)
+    for oid in (7, 8, 1000, 70000, 0x01020304, 0xffffffff):
+        uuid = bytes(range(1, 13)) + struct.pack("<I", oid)
+        for prefix in (b"y" + uuid, b"0" + struct.pack(">I", oid), b""):
+            for micros in (5, 10, 11, 20, 21, 50, 51, 90, 91):
+                for glob in (none, o.ht_from_micros(o.YB_EPOCH_US + 30)):
+                    k = key(prefix, micros)
+                    ht = o.ht_from_micros(o.YB_EPOCH_US + micros)
+                    want = glob != none and ht > glob
+                    if not want and prefix[:1] == b"y" and oid in oids.tolist():
+                        want = ht > int(hts[oids.tolist().index(oid)])
+                    got = L.hh_hidden_by_ht_filters(k, len(k), glob, oids.ctypes.data, hts.ctypes.data, len(oids))
+                    assert bool(got) == want, (oid, prefix[:1], micros, glob)
+                    assert not L.hh_hidden_by_ht_filters(k, len(k), none, None, None, 0)
+    bad = b"y" + bytes(16) + b"Sx\x00\x00!" + b"#\x00"          # a DocHybridTime that does not decode: visible
+    assert not L.hh_hidden_by_ht_filters(bad, len(bad), 0, oids.ctypes.data, hts.ctypes.data, len(oids))
