@@ -45,7 +45,7 @@ enum DevError : int {
   DEV_ERR_IRREGULAR_RESTARTS = 5, // restart intervals of different sizes inside one file
   DEV_ERR_BAD_KEY = 6,            // DocKey / SubDocKey component decode failed
   DEV_ERR_UNSUPPORTED_KEY = 7,    // vector-index metadata keys, frozen containers nested deeper than 4
-  DEV_ERR_TILE_OVERFLOW = 8,      // one DocKey group larger than a merge tile
+  DEV_ERR_TILE_OVERFLOW = 8,      // internal: a merge tile larger than its capacity (the host repartitions before this can happen)
   DEV_ERR_BAD_HT = 9,             // DocHybridTime at the end of a key is malformed
   DEV_ERR_BAD_VALUE = 10,         // value control fields malformed
   DEV_ERR_STACK_DEPTH = 11,       // more subkey levels than DEV_MAX_DEPTH
