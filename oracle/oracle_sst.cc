@@ -463,10 +463,12 @@ TableBuilder::TableBuilder(const TableOptions& o)
 }
 TableBuilder::~TableBuilder() {}
 
-void TableBuilder::WriteRawBlock(Slice c, std::string* file, BlockHandle* h) {
+void TableBuilder::WriteRawBlock(Slice c, std::string* file, BlockHandle* h, bool compressible) {
   uint8_t type = 0;   // kNoCompression
   std::string compressed;
-  if (o_.compression == 1 && file == &data_) {          // CompressBlock (block_based_table_builder.cc:115-131) for data blocks
+  // CompressBlock (block_based_table_builder.cc:115-131) for what goes through WriteBlock: data blocks, index blocks and
+  // the filter index (:550,586,790,823,869); filter blocks, properties and the metaindex are written raw (:600,849,864)
+  if (o_.compression == 1 && (file == &data_ || compressible)) {
     SnappyCompress(c, &compressed);
     if (compressed.size() < c.n - (c.n / 8u)) { c = Slice(compressed); type = 1; }     // GoodCompressionRatio :109-112
   }
@@ -525,7 +527,7 @@ void TableBuilder::FlushDataBlock(Slice next_first_key, bool has_next) {
     std::string contents;
     bool r = index_->FlushNextBlock(&contents, last_index_handle_, last_index_handle_set_);
     if (!r) throw std::runtime_error("index flush returned false");
-    WriteRawBlock(Slice(contents), &meta_, &last_index_handle_);
+    WriteRawBlock(Slice(contents), &meta_, &last_index_handle_, true);
     last_index_handle_set_ = true;
     ++props_.num_data_index_blocks;
   }
@@ -568,7 +570,7 @@ void TableBuilder::Finish() {
   BlockHandle filter_index_handle;
   if (filter_) {
     Slice fi = filter_index_->Finish();
-    WriteRawBlock(fi, &meta_, &filter_index_handle);
+    WriteRawBlock(fi, &meta_, &filter_index_handle, true);
     props_.filter_index_size = filter_index_->CurrentSizeEstimate() + kBlockTrailerSize;
     p["rocksdb.filter.index.size"].clear(); PutVarint64(&p["rocksdb.filter.index.size"], props_.filter_index_size);
     p["rocksdb.filter.policy"] = "DocKeyV3Filter";
@@ -589,7 +591,7 @@ void TableBuilder::Finish() {
     mb.Add(Slice(std::string("rocksdb.properties")), Slice(enc)); }
   BlockHandle metaindex_handle;
   WriteRawBlock(mb.Finish(), &meta_, &metaindex_handle);
-  if (have_top) { WriteRawBlock(Slice(top_index), &meta_, &last_index_handle_); last_index_handle_set_ = true; }
+  if (have_top) { WriteRawBlock(Slice(top_index), &meta_, &last_index_handle_, true); last_index_handle_set_ = true; }
 
   // Footer (format.cc:118-153), version 2, checksum type kCRC32c = 1.
   std::string f;
@@ -730,7 +732,8 @@ void TableReader::Open(Slice meta_file, Slice data_file, bool verify) {
       } else if (it.key().str().rfind("fixedsizefilter.", 0) == 0) {
         Slice v = it.value();
         BlockHandle fh = DecodeHandle(&v);
-        BlockIter fit(ReadBlock(meta, fh, verify), kSharedPrefix);
+        std::string fscratch;
+        BlockIter fit(ReadBlock(meta, fh, verify, &fscratch), kSharedPrefix);
         for (fit.SeekToFirst(); fit.Valid(); fit.Next()) { Slice hv = fit.value(); filter_blocks.emplace_back(fit.key().str(), DecodeHandle(&hv)); }
       }
     }
@@ -745,7 +748,8 @@ void TableReader::Open(Slice meta_file, Slice data_file, bool verify) {
   for (int l = 0; l < num_index_levels; l++) {
     std::vector<BlockHandle> next;
     for (auto& h : level) {
-      BlockIter it(ReadBlock(meta, h, verify), kSharedPrefix);
+      std::string iscratch;                  // index blocks are stored compressed when the table's blocks are
+      BlockIter it(ReadBlock(meta, h, verify, &iscratch), kSharedPrefix);
       for (it.SeekToFirst(); it.Valid(); it.Next()) { Slice v = it.value(); next.push_back(DecodeHandle(&v)); }
     }
     level.swap(next);

@@ -182,7 +182,7 @@ class TableBuilder {
   const std::vector<BlockHandle>& data_block_handles() const { return data_handles_; }
  private:
   void FlushDataBlock(Slice next_first_key, bool has_next);
-  void WriteRawBlock(Slice contents, std::string* file, BlockHandle* h);
+  void WriteRawBlock(Slice contents, std::string* file, BlockHandle* h, bool compressible = false);
   TableOptions o_;
   BlockBuilder data_block_;
   FlushBySize policy_;

@@ -319,3 +319,35 @@ def test_sst_verify_blocks_detects_corruption(pkg):
     assert pkg.sst_verify_blocks(sst.meta_view(), bad) == (nb, 1)
     assert pkg.sst_verify_blocks(sst.meta_view(), bad, stride=2) == ((nb + 1) // 2, 0)      # block 3 is not sampled
     assert pkg.sst_verify_blocks(sst.meta_view(), sst.data_view()[:int(off[-1])].copy())[1] == 1   # truncated data file: last block missing
+
+
+def test_meta_reader_snappy_compressed_index_blocks(pkg):
+    """Production tables are Snappy-compressed (docdb_rocksdb_util.cc:184) and index blocks go through WriteBlock like data
+    blocks (block_based_table_builder.cc:586,790,823,869): the host-side reader of the metadata file must uncompress the
+    multi-level index and the filter index. Same handles and separators as for the uncompressed twin of the table."""
+    cfg = o.GenConfig(seed=16, num_rows=6000, cols=2, versions=2, num_files=1, value_len=40)
+    kw = dict(block_size=1024, index_block_size=700, min_keys_per_index_block=4, filter_policy=1, filter_block_size=1024)
+    plain = o.Sst.generate(cfg, 0, o.TableOptions(**kw))
+    comp = o.Sst.build(plain.read_all(), o.TableOptions(compression=1, **kw))
+    meta = comp.meta_view().tobytes()
+    # the twin's index really is stored compressed: some block trailer of the metadata file carries type 1
+    off, sz, enc = pkg.sst_block_handles(comp.meta_view())
+    eo, es = comp.block_handles()
+    assert list(off) == list(eo) and list(sz) == list(es) and len(off) > 50
+    assert pkg.sst_separators(comp.meta_view()) == pkg.sst_separators(plain.meta_view())
+    assert comp.read_all() == plain.read_all()
+    assert len(meta) < len(plain.meta_view().tobytes())          # the index blocks shrank
+    # planner and last-key helper work on it (the planner parses the metadata file; the last-key helper uncompresses the
+    # last data block on the host)
+    sp = pkg.plan_subcompactions([(comp.meta_view(), comp.data_view())], 4)
+    assert 1 <= len(sp) <= 3 and sp == sorted(sp)
+    kvs = plain.read_all()
+    assert pkg.sst_last_key(comp.meta_view(), comp.data_view()) == kvs[-1][0]
+    for cut in range(0, 60):                                       # a table whose LAST data block is stored compressed
+        t = o.Sst.build(kvs[:len(kvs) - cut], o.TableOptions(compression=1, **kw))
+        toff, tsz = t.block_handles()
+        if bytes(t.data_view())[int(toff[-1]) + int(tsz[-1])] == 1:
+            assert pkg.sst_last_key(t.meta_view(), t.data_view()) == kvs[len(kvs) - cut - 1][0]
+            break
+    else:
+        raise AssertionError("no variant with a compressed last block")

@@ -614,6 +614,14 @@ def test_snappy_compressed_inputs(pkg, seed):
     for kw in kws:
         job, _ = check(pkg, ssts, block_size=4096, filter_policy=1, filter_block_size=4096, **kw)
         assert bool(job.stats().path_flags & pkg.PATH_SNAPPY) == any_compressed
+    # pipelined key ranges over the same production-shaped inputs (compressed index blocks are read by the host planner, the
+    # last data block by the last-key helper): the ranges' tables hold the single job's KV stream
+    exp = o.compact(ssts, o.CompactionParams(**kws[0]), o.TableOptions(block_size=4096))
+    res = pkg.compact_files([(s.meta_view(), s.data_view()) for s in ssts], max_subcompactions=3, max_in_flight=2, block_size=4096, **kws[0])
+    got = []
+    for data, meta in res.files():
+        got += o.Sst.from_bytes(meta.tobytes(), data.tobytes()).read_all()
+    assert got == exp.kv_list()
     # a flipped bit in a compressed block is a checksum error, not garbage
     bad = bytearray(ssts[0].data)
     bad[len(bad) // 2] ^= 0x10

@@ -74,6 +74,65 @@ struct BlockCursor {
   }
 };
 
+// Snappy raw format (the block compression of production tables, docdb_rocksdb_util.cc:184; UncompressBlockContents,
+// table/format.cc:441-500): varint32 uncompressed length, then elements — tag & 3 == 0: literal of (tag >> 2) + 1 bytes
+// (60..63: the length - 1 follows in 1..4 little-endian bytes); 1: copy, length 4 + ((tag >> 2) & 7), offset = (tag >> 5)
+// << 8 | next byte; 2 / 3: copy, length (tag >> 2) + 1, offset in the next 2 / 4 bytes. Copies may overlap their output.
+// Index blocks of the metadata file go through WriteBlock like data blocks (block_based_table_builder.cc:586,790,823,869)
+// and so are stored compressed in production files; data blocks are uncompressed on the GPU (snappy_kernels.cuh).
+void SnappyUncompress(const uint8_t* in, size_t n, std::string* out) {
+  const uint8_t* p = in; const uint8_t* end = in + n;
+  uint64_t ulen = 0;
+  if (!ReadVarint(&p, end, &ulen) || ulen > (1ull << 32)) throw std::runtime_error("bad compressed block (length)");
+  out->clear();
+  out->reserve(ulen);
+  while (p < end) {
+    const uint32_t tag = *p++;
+    uint64_t len, off = 0;
+    if ((tag & 3) == 0) {
+      len = (tag >> 2) + 1;
+      if (len > 60) {
+        const uint32_t nb = static_cast<uint32_t>(len - 60);
+        if (static_cast<size_t>(end - p) < nb) throw std::runtime_error("bad compressed block (literal length)");
+        len = 0;
+        for (uint32_t i = 0; i < nb; i++) len |= static_cast<uint64_t>(p[i]) << (8 * i);
+        len += 1; p += nb;
+      }
+      if (static_cast<uint64_t>(end - p) < len || out->size() + len > ulen) throw std::runtime_error("bad compressed block (literal)");
+      out->append(reinterpret_cast<const char*>(p), len);
+      p += len;
+      continue;
+    }
+    if ((tag & 3) == 1) {
+      if (p >= end) throw std::runtime_error("bad compressed block (copy)");
+      len = 4 + ((tag >> 2) & 7); off = (static_cast<uint64_t>(tag >> 5) << 8) | *p++;
+    } else {
+      const uint32_t nb = (tag & 3) == 2 ? 2 : 4;
+      if (static_cast<size_t>(end - p) < nb) throw std::runtime_error("bad compressed block (copy)");
+      len = (tag >> 2) + 1;
+      for (uint32_t i = 0; i < nb; i++) off |= static_cast<uint64_t>(p[i]) << (8 * i);
+      p += nb;
+    }
+    if (off == 0 || off > out->size() || out->size() + len > ulen) throw std::runtime_error("bad compressed block (copy offset)");
+    const size_t from = out->size() - off;
+    for (uint64_t i = 0; i < len; i++) out->push_back((*out)[from + i]);
+  }
+  if (out->size() != ulen) throw std::runtime_error("bad compressed block (short)");
+}
+
+// A block of the metadata file, uncompressed if it is stored compressed.
+struct LoadedBlock {
+  const uint8_t* data = nullptr; size_t size = 0;
+  std::string scratch;
+};
+void LoadBlock(const uint8_t* file, uint64_t len, const Handle& h, LoadedBlock* b) {
+  if (h.offset + h.size + kTrailer > len) throw std::runtime_error("block handle outside file");
+  const uint8_t type = file[h.offset + h.size];
+  if (type == 0) { b->data = file + h.offset; b->size = h.size; return; }
+  if (type != 1) throw std::runtime_error("metadata block compressed with an unsupported codec (only Snappy)");
+  SnappyUncompress(file + h.offset, h.size, &b->scratch);
+  b->data = reinterpret_cast<const uint8_t*>(b->scratch.data()); b->size = b->scratch.size();
+}
 const uint8_t* BlockAt(const uint8_t* file, uint64_t len, const Handle& h) {
   if (h.offset + h.size + kTrailer > len) throw std::runtime_error("block handle outside file");
   if (file[h.offset + h.size] != 0) throw std::runtime_error("compressed meta block not supported");
@@ -87,6 +146,10 @@ Handle ReadHandle(const uint8_t** p, const uint8_t* end) {
 }
 
 }  // namespace
+
+bool SnappyUncompressBlock(const uint8_t* stored, size_t n, std::string* out) {
+  try { SnappyUncompress(stored, n, out); return true; } catch (const std::exception&) { return false; }
+}
 
 uint32_t Crc32c(const uint8_t* p, size_t n, uint32_t init) {
   uint32_t c = ~init;
@@ -116,7 +179,9 @@ std::string ParseSplitSstMeta(const uint8_t* meta, uint64_t len, SstMeta* out) {
         out->filter_policy_name = mi.key.substr(16);
         const uint8_t* vp = mi.val;
         Handle fh = ReadHandle(&vp, mi.val + mi.vlen);
-        BlockCursor fi(BlockAt(meta, len, fh), fh.size);
+        LoadedBlock fib;
+        LoadBlock(meta, len, fh, &fib);                  // the filter index is an index block: compressed in production files
+        BlockCursor fi(fib.data, fib.size);
         while (fi.Next()) {
           const uint8_t* hp = fi.val;
           Handle bh = ReadHandle(&hp, fi.val + fi.vlen);
@@ -142,7 +207,9 @@ std::string ParseSplitSstMeta(const uint8_t* meta, uint64_t len, SstMeta* out) {
       std::vector<Handle> next;
       const bool last_level = lv + 1 == out->index_levels;
       for (const Handle& h : level) {
-        BlockCursor c(BlockAt(meta, len, h), h.size);
+        LoadedBlock ib;
+        LoadBlock(meta, len, h, &ib);
+        BlockCursor c(ib.data, ib.size);
         while (c.Next()) {
           const uint8_t* vp = c.val; next.push_back(ReadHandle(&vp, c.val + c.vlen));
           if (last_level) out->separators.push_back(c.key);

@@ -20,6 +20,8 @@ namespace host {
 
 struct Handle { uint64_t offset = 0, size = 0; };
 
+// Contents of a block stored Snappy-compressed (trailer type 1; table/format.cc:441-500). False on a malformed stream.
+bool SnappyUncompressBlock(const uint8_t* stored, size_t n, std::string* out);
 uint32_t Crc32c(const uint8_t* p, size_t n, uint32_t init = 0);   // rocksdb/util/crc32c.h Extend
 inline uint32_t Crc32cMask(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xa282ead8u; }
 

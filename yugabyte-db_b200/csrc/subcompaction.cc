@@ -221,7 +221,13 @@ bool LastKeyOfFile(const ybgpu_input_file& f, const SstMeta& m, std::string* key
   if (m.data_blocks.empty()) { key->clear(); return true; }
   const auto& h = m.data_blocks.back();
   if (h.offset + h.size + 5 > f.data_file_len) return false;
-  if (f.data_file[h.offset + h.size] != 0) return false;            // compressed block: not supported
+  const uint8_t type = f.data_file[h.offset + h.size];
+  if (type == 1) {                                                  // Snappy (the production default): uncompress on the host
+    std::string raw;
+    if (!ybgpu::host::SnappyUncompressBlock(f.data_file + h.offset, h.size, &raw)) return false;
+    return LastKeyOfBlock(reinterpret_cast<const uint8_t*>(raw.data()), raw.size(), m.key_encoding, key);
+  }
+  if (type != 0) return false;                                      // other codecs: not supported
   return LastKeyOfBlock(f.data_file + h.offset, h.size, m.key_encoding, key);
 }
 
