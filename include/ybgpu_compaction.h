@@ -48,6 +48,7 @@ typedef enum ybgpu_status {
  * property kDataBlockKeyValueEncodingFormat (block_based_table_reader.cc:759-765). */
 enum { YBGPU_KEY_ENCODING_SHARED_PREFIX = 1, YBGPU_KEY_ENCODING_THREE_SHARED_PARTS = 2 };
 enum { YBGPU_FILTER_NONE = 0, YBGPU_FILTER_DOCKEY_V3 = 1 };
+enum { YBGPU_COMPRESSION_NONE = 0, YBGPU_COMPRESSION_SNAPPY = 1 };   /* rocksdb::CompressionType (options.h:92-101) */
 
 #define YBGPU_HT_MIN      0ull
 #define YBGPU_HT_MAX      0xffffffffffffffffull
@@ -122,6 +123,15 @@ typedef struct ybgpu_job_options {
    * (input_min has no other data before it, docdb_compaction_context.cc:668): only then does UpdateMeta replace
    * the union of the inputs' values. */
   int32_t compute_user_boundary_values;
+
+  /* --- compression of the output (rocksdb::Options::compression; DocDB sets kSnappyCompression unless
+   * enable_ondisk_compression is off, docdb_rocksdb_util.cc:176-202) --- YBGPU_COMPRESSION_SNAPPY: every data block
+   * is run through a Snappy-format encoder on the GPU after it was assembled and is stored compressed (trailer type 1,
+   * checksum over the compressed bytes) when that saves at least 12.5 % — BlockBasedTableBuilder::WriteBlock /
+   * CompressBlock / GoodCompressionRatio (block_based_table_builder.cc:109-131,630-655); index blocks and the filter
+   * index of the metadata file likewise (host). The compressed BYTES are this engine's encoder's, not the snappy
+   * library's: any Snappy reader decodes them (tests: pyarrow's libsnappy), the block CONTENTS are the reference's. */
+  int32_t output_compression;        /* YBGPU_COMPRESSION_* ; default none */
 } ybgpu_job_options;
 
 void ybgpu_job_options_init(ybgpu_job_options* o);   /* reference defaults */
@@ -169,7 +179,8 @@ enum {
   YBGPU_PATH_PARTITION_RETRY = 8,      /* the partition was repeated with a smaller sample stride */
   YBGPU_PATH_ENCODER_V4 = 16,          /* block assembler with checksums by CRC linearity */
   YBGPU_PATH_ENCODER_V5 = 32,          /* ... warp per block, no block image (k_encode_v5) */
-  YBGPU_PATH_KV_INPUT = 64             /* the inputs were KV streams (ybgpu_job_add_input_kv), not table files */
+  YBGPU_PATH_KV_INPUT = 64,            /* the inputs were KV streams (ybgpu_job_add_input_kv), not table files */
+  YBGPU_PATH_SNAPPY_OUTPUT = 128       /* output data blocks went through the GPU Snappy encoder (k_snappy_compress) */
 };
 
 typedef struct ybgpu_job ybgpu_job;

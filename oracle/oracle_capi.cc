@@ -112,6 +112,20 @@ int orc_shortest_separator(const uint8_t* start, uint64_t sn, const uint8_t* lim
   return static_cast<int>(s.size());
 }
 
+// Snappy raw format (oracle_sst.h): sizes first (out == NULL), then the bytes. -1 = malformed stream.
+int64_t orc_snappy_compress(const uint8_t* p, uint64_t n, uint8_t* out, uint64_t cap) {
+  std::string c; SnappyCompress(Slice(p, n), &c);
+  if (out) { if (c.size() > cap) return -1; memcpy(out, c.data(), c.size()); }
+  return static_cast<int64_t>(c.size());
+}
+int64_t orc_snappy_uncompress(const uint8_t* p, uint64_t n, uint8_t* out, uint64_t cap) {
+  try {
+    std::string u; SnappyUncompress(Slice(p, n), &u);
+    if (out) { if (u.size() > cap) return -1; memcpy(out, u.data(), u.size()); }
+    return static_cast<int64_t>(u.size());
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // ---- SST build / read ------------------------------------------------------------------------
 orc_sst* orc_sst_build(uint64_t n, const uint8_t* keys, const uint64_t* koff, const uint8_t* vals,
                        const uint64_t* voff, const orc_table_options* o) {

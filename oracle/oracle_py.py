@@ -445,6 +445,29 @@ def compact(ssts, params=None, opts=None, mode=COLLECT_KV | BUILD_SST, verify=Tr
     return Result(L.orc_compact2(len(ssts), arr, filt, cf, C.byref(params), C.byref(opts), mode, int(verify)))
 
 
+def snappy_compress(raw: bytes) -> bytes:
+    """The repository's Snappy-format encoder (oracle_sst.cc SnappyCompress)."""
+    L = lib()
+    L.orc_snappy_compress.restype = C.c_int64
+    L.orc_snappy_compress.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    n = L.orc_snappy_compress(raw, len(raw), None, 0)
+    buf = C.create_string_buffer(max(1, n))
+    assert L.orc_snappy_compress(raw, len(raw), buf, n) == n
+    return buf.raw[:n]
+
+
+def snappy_uncompress(comp: bytes) -> bytes:
+    L = lib()
+    L.orc_snappy_uncompress.restype = C.c_int64
+    L.orc_snappy_uncompress.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    n = L.orc_snappy_uncompress(comp, len(comp), None, 0)
+    if n < 0:
+        raise ValueError("snappy: malformed stream")
+    buf = C.create_string_buffer(max(1, n))
+    assert L.orc_snappy_uncompress(comp, len(comp), buf, n) == n
+    return buf.raw[:n]
+
+
 def compact_runs(runs, params=None):
     """runs: list of sorted lists of (internal_key, value)."""
     params = params or CompactionParams()

@@ -656,49 +656,58 @@ void SnappyUncompress(Slice c, std::string* out) {
   if (out->size() != ulen) throw Corruption("snappy: output shorter than announced");
 }
 
+// The encoder every writer of this repository shares (this oracle, the engine's host writer and its GPU kernel), so
+// that whole files can be compared byte for byte: the input is cut into 64 KB fragments like the snappy library does
+// (a match never crosses a fragment); inside a fragment the classic greedy scan — hash the four bytes at every visited
+// position into a table of 2^12 fragment-relative positions (zero-initialised; a stale or empty slot only costs a
+// failed comparison), take the slot's previous occupant as the candidate, and on a four-byte match extend it as far
+// as it goes; positions covered by a match are not visited. It is NOT the library's encoder (different table size and
+// no skipping heuristic): compressed bytes are unpinned, the format is pinned by SnappyUncompress.
 void SnappyCompress(Slice raw, std::string* out) {
   out->clear();
   PutVarint32(out, static_cast<uint32_t>(raw.n));
-  const uint8_t* b = raw.p; const size_t n = raw.n;
-  auto emit_literal = [&](size_t from, size_t to) {
-    while (from < to) {
-      const size_t len = std::min<size_t>(to - from, 65536);
-      const size_t l1 = len - 1;
+  constexpr size_t kFragment = 65536;
+  constexpr uint32_t kHashBits = 12;
+  std::vector<uint16_t> table(1u << kHashBits);
+  for (size_t fs = 0; fs < raw.n; fs += kFragment) {
+    const uint8_t* b = raw.p + fs; const size_t n = std::min(kFragment, raw.n - fs);
+    auto emit_literal = [&](size_t from, size_t to) {
+      if (from >= to) return;
+      const size_t len = to - from, l1 = len - 1;                       // <= 65536
       if (l1 < 60) out->push_back(static_cast<char>(l1 << 2));
       else if (l1 < 256) { out->push_back(static_cast<char>(60 << 2)); out->push_back(static_cast<char>(l1)); }
       else { out->push_back(static_cast<char>(61 << 2)); out->push_back(static_cast<char>(l1 & 0xff)); out->push_back(static_cast<char>(l1 >> 8)); }
       out->append(reinterpret_cast<const char*>(b + from), len);
-      from += len;
-    }
-  };
-  std::vector<int32_t> table(1 << 14, -1);
-  size_t lit = 0, i = 0;
-  while (i + 4 <= n) {
-    uint32_t w; memcpy(&w, b + i, 4);
-    const uint32_t hsh = (w * 0x1e35a7bdu) >> 18;
-    const int32_t cand = table[hsh];
-    table[hsh] = static_cast<int32_t>(i);
-    uint32_t cw = 0;
-    if (cand >= 0) memcpy(&cw, b + cand, 4);
-    if (cand >= 0 && cw == w && i - cand <= 65535) {
-      size_t len = 4;
-      while (i + len < n && b[cand + len] == b[i + len]) len++;
-      emit_literal(lit, i);
-      const uint32_t off = static_cast<uint32_t>(i - cand);
-      size_t left = len;
-      while (left) {
-        size_t l = std::min<size_t>(left, 64);
-        if (left - l > 0 && left - l < 4) l = left - 4;                 // keep every piece >= 4 bytes... copy2 takes 1..64
-        if (l >= 4 && l <= 11 && off < 2048) { out->push_back(static_cast<char>(1 | ((l - 4) << 2) | ((off >> 8) << 5))); out->push_back(static_cast<char>(off & 0xff)); }
-        else { out->push_back(static_cast<char>(2 | ((l - 1) << 2))); out->push_back(static_cast<char>(off & 0xff)); out->push_back(static_cast<char>(off >> 8)); }
-        left -= l;
+    };
+    std::fill(table.begin(), table.end(), 0);
+    size_t lit = 0, i = 0;
+    while (i + 4 <= n) {
+      uint32_t w; memcpy(&w, b + i, 4);
+      const uint32_t hsh = (w * 0x1e35a7bdu) >> (32 - kHashBits);
+      const size_t cand = table[hsh];
+      table[hsh] = static_cast<uint16_t>(i);
+      uint32_t cw = 0;
+      if (cand < i) memcpy(&cw, b + cand, 4);
+      if (cand < i && cw == w) {
+        size_t len = 4;
+        while (i + len < n && b[cand + len] == b[i + len]) len++;
+        emit_literal(lit, i);
+        const uint32_t off = static_cast<uint32_t>(i - cand);
+        size_t left = len;
+        while (left) {
+          size_t l = std::min<size_t>(left, 64);
+          if (left - l > 0 && left - l < 4) l = left - 4;                 // every piece is at least 4 bytes long
+          if (l >= 4 && l <= 11 && off < 2048) { out->push_back(static_cast<char>(1 | ((l - 4) << 2) | ((off >> 8) << 5))); out->push_back(static_cast<char>(off & 0xff)); }
+          else { out->push_back(static_cast<char>(2 | ((l - 1) << 2))); out->push_back(static_cast<char>(off & 0xff)); out->push_back(static_cast<char>(off >> 8)); }
+          left -= l;
+        }
+        i += len; lit = i;
+      } else {
+        i++;
       }
-      i += len; lit = i;
-    } else {
-      i++;
     }
+    emit_literal(lit, n);
   }
-  emit_literal(lit, n);
 }
 
 static BlockHandle DecodeHandle(Slice* s) {

@@ -351,3 +351,39 @@ def test_meta_reader_snappy_compressed_index_blocks(pkg):
             break
     else:
         raise AssertionError("no variant with a compressed last block")
+
+
+def _compressible_kvs(seed, n, vmax=200):
+    """Rows whose values repeat phrases (compressible), mixed with stretches of random values (blocks that stay raw)."""
+    rng = random.Random(seed)
+    words = [bytes(rng.randrange(32, 127) for _ in range(rng.randrange(3, 24))) for _ in range(40)]
+    kvs = []
+    for i in range(n):
+        if (i // 500) % 4 == 3:
+            v = bytes(rng.randrange(256) for _ in range(rng.randrange(1, vmax)))
+        else:
+            v = b" ".join(rng.choice(words) for _ in range(rng.randrange(0, vmax // 10)))
+        kvs.append((o.ikey(b"user%08d/col%d" % (i // 3, i % 3), 500 + i), v))
+    return kvs
+
+
+@pytest.mark.parametrize("enc,filt,bs", [(1, 0, 4096), (2, 1, 2048), (1, 1, 32768)])
+def test_host_table_builder_snappy_output(pkg, enc, filt, bs):
+    """CompressBlock with kSnappyCompression (block_based_table_builder.cc:115-131): data blocks, index blocks and
+    the filter index are stored compressed when that saves 12.5 %; the host writer and the oracle share one encoder, so
+    the files are byte-identical; the oracle's reader (and so any Snappy reader) gets the same entries back."""
+    kvs = _compressible_kvs(21 + enc, 6000)
+    topt = dict(block_size=bs, index_block_size=1024, min_keys_per_index_block=8, key_encoding=enc, filter_policy=filt, filter_block_size=4096)
+    ref = o.Sst.build(kvs, o.TableOptions(compression=1, **topt))
+    plain = o.Sst.build(kvs, o.TableOptions(**topt))
+    assert len(ref.data) < len(plain.data) * 0.8                   # most blocks were worth compressing ...
+    b = pkg.HostTableBuilder(compression=1, **topt)
+    for k, v in kvs:
+        b.add(k, v)
+    data, meta = b.finish()
+    assert data == ref.data
+    assert meta == ref.meta
+    assert o.Sst.from_bytes(meta, data).read_all() == kvs
+    off, sz, _ = pkg.sst_block_handles(np.frombuffer(meta, np.uint8))
+    types = {data[int(a) + int(b)] for a, b in zip(off, sz)}
+    assert types == {0, 1}                                          # ... and the random stretches stayed raw

@@ -34,12 +34,14 @@ def okw(kw):
     m.pop("output_key_encoding", None)
     m.pop("filter_policy", None)
     m.pop("filter_block_size", None)
+    m.pop("output_compression", None)
     return m
 
 
 def check(pkg, ssts, block_size=4096, ht_filters=None, **kw):
     topt = o.TableOptions(block_size=block_size, key_encoding=kw.get("output_key_encoding", 1),
-                          filter_policy=kw.get("filter_policy", 0), filter_block_size=kw.get("filter_block_size", 65536))
+                          filter_policy=kw.get("filter_policy", 0), filter_block_size=kw.get("filter_block_size", 65536),
+                          compression=kw.get("output_compression", 0))
     exp = o.compact(ssts, o.CompactionParams(**okw(kw)), topt, ht_filters=ht_filters)
     job = gpu_compact(pkg, ssts, ht_filters=ht_filters, block_size=block_size, **kw)
     st = job.stats()
@@ -630,6 +632,101 @@ def test_snappy_compressed_inputs(pkg, seed):
     with pytest.raises(pkg.YbGpuError) as e:
         job.run()
     assert e.value.status_name == "Corruption"
+
+
+def _phrase_runs(seed, n_runs, n_rows, vmax=160, random_every=None):
+    """DocDB-shaped runs whose values are made of recurring phrases (compressible); with random_every, every other
+    stretch of that many rows carries random bytes instead, so that tables hold blocks worth compressing next to
+    blocks that are not."""
+    import random as _random
+    rng = _random.Random(seed)
+    runs = w.random_docdb_runs(seed, n_runs=n_runs, n_rows=n_rows)
+    words = [bytes(rng.randrange(32, 127) for _ in range(rng.randrange(2, 20))) for _ in range(30)]
+    out = []
+    for r in runs:
+        rr = []
+        for i, (k, v) in enumerate(r):
+            if v[:1] == b"S":                                      # string values only: control fields / tombstones keep their bytes
+                if random_every and (i // random_every) % 2:
+                    v = b"S" + bytes(rng.randrange(256) for _ in range(rng.randrange(vmax)))
+                else:
+                    v = b"S" + b" ".join(rng.choice(words) for _ in range(rng.randrange(vmax // 8)))
+            rr.append((k, v))
+        out.append(rr)
+    return out
+
+
+def _stored_types(data, meta, pkg):
+    off, sz, _ = pkg.sst_block_handles(np.frombuffer(meta, np.uint8))
+    return [data[int(a) + int(b)] for a, b in zip(off, sz)], off, sz
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_snappy_compressed_output(pkg, seed):
+    """a17: BlockBasedTableBuilder::WriteBlock -> CompressBlock with kSnappyCompression, DocDB's production setting
+    (block_based_table_builder.cc:109-131,630-655; docdb_rocksdb_util.cc:184). Every assembled data block goes through
+    the GPU encoder (k_snappy_compress) and is stored compressed when that saves 12.5 %, its checksum then covers the
+    compressed bytes; index blocks and the filter index likewise (host). The oracle's builder uses the same encoder, so
+    whole files are compared byte for byte; the block CONTENTS are pinned independently: each stored block, decoded by
+    the real snappy library (pyarrow) when it is there and by the oracle's decoder otherwise, is the block the
+    uncompressed twin of the table holds at that index."""
+    if seed == 0:
+        runs, bs, enc, kws = _phrase_runs(900, 3, 300), 1024, 1, [w.param_grid()[i] for i in (0, 2, 6)]
+    elif seed == 1:
+        runs, bs, enc, kws = _phrase_runs(901, 4, 1500, random_every=120), 4096, 2, [w.param_grid()[0]]
+    elif seed == 2:
+        runs, bs, enc, kws = _phrase_runs(902, 3, 4000, vmax=400, random_every=700), 32768, 1, [w.param_grid()[2]]
+    else:
+        # values beyond a fragment (64 KB): blocks of several fragments, long runs (copy elements of 64 bytes), tiny blocks
+        runs = _phrase_runs(903, 2, 60)
+        big = [(k, b"S" + (bytes(range(256)) * 700)[:150000 + 7 * i] if i % 9 == 4 and v[:1] == b"S" else
+                (b"S" + b"\0" * (3000 + i) if i % 9 == 7 and v[:1] == b"S" else v)) for i, (k, v) in enumerate(runs[0])]
+        runs, bs, enc, kws = [big, runs[1]], 2048, 1, [w.param_grid()[0]]
+    # production shape on both sides: the inputs are Snappy tables too
+    ssts = [o.Sst.build(r, o.TableOptions(block_size=bs, compression=1)) for r in runs if r]
+    try:
+        import pyarrow as pa
+        lib_ok = pa.Codec.is_available("snappy")
+    except ImportError:
+        lib_ok = False
+    for kw in kws:
+        job, exp = check(pkg, ssts, block_size=bs, output_key_encoding=enc, filter_policy=1, filter_block_size=4096, output_compression=1, **kw)
+        assert job.stats().path_flags & pkg.PATH_SNAPPY_OUTPUT
+        data, meta = job.fetch_output()
+        data, meta = data.tobytes(), meta.tobytes()
+        types, off, sz = _stored_types(data, meta, pkg)
+        plain = gpu_compact(pkg, ssts, block_size=bs, output_key_encoding=enc, filter_policy=1, filter_block_size=4096, **kw)
+        assert not plain.stats().path_flags & pkg.PATH_SNAPPY_OUTPUT
+        pdata, pmeta = plain.fetch_output()
+        pdata, pmeta = pdata.tobytes(), pmeta.tobytes()
+        ptypes, poff, psz = _stored_types(pdata, pmeta, pkg)
+        assert len(types) == len(ptypes) and set(ptypes) == {0} and 1 in types
+        assert len(data) < len(pdata)
+        if seed in (1, 2):
+            assert 0 in types                                      # the random stretches were not worth it
+        for t, a, b, pa_, pb in zip(types, off, sz, poff, psz):
+            stored = data[int(a):int(a) + int(b)]
+            want = pdata[int(pa_):int(pa_) + int(pb)]
+            if t == 0:
+                assert stored == want
+            else:
+                assert len(stored) < len(want) - len(want) // 8
+                assert o.snappy_uncompress(stored) == want
+                if lib_ok:
+                    assert pa.decompress(stored, decompressed_size=len(want), codec="snappy").to_pybytes() == want
+        assert pkg.sst_verify_blocks(np.frombuffer(meta, np.uint8), np.frombuffer(data, np.uint8)) == (len(types), 0)
+    # the compressed table is a valid input of the next compaction, and pipelined key ranges write compressed pieces that
+    # assemble into one table with the single job's entries
+    kw = kws[0]
+    exp = o.compact(ssts, o.CompactionParams(**okw(kw)), o.TableOptions(block_size=bs, key_encoding=enc))
+    again = gpu_compact(pkg, [o.Sst.from_bytes(meta, data)], block_size=bs, **kw)
+    assert again.kv_list() == o.compact([o.Sst.from_bytes(meta, data)], o.CompactionParams(**okw(kw)), o.TableOptions(block_size=bs)).kv_list()
+    files = [(s.meta_view(), s.data_view()) for s in ssts]
+    d1, m1, res, total = pkg.compact_files_one_table(files, max_subcompactions=4, max_in_flight=2, block_size=bs, output_key_encoding=enc,
+                                                     filter_policy=1, filter_block_size=4096, output_compression=1, **kw)
+    whole = o.Sst.from_bytes(m1.tobytes(), d1.tobytes())
+    assert whole.read_all() == exp.kv_list()
+    assert total.path_flags & pkg.PATH_SNAPPY_OUTPUT and 1 in _stored_types(d1.tobytes(), m1.tobytes(), pkg)[0]
 
 
 def test_yield_points(pkg):

@@ -1,7 +1,10 @@
 """Pins the oracle's codecs against the reference's own golden vectors."""
 import random
 
+import pytest
+
 import dockv_util as dk
+import oracle_py as o
 
 EPOCH = 1500000000 * 1000000
 MAXW = 4294967295
@@ -170,3 +173,65 @@ def test_varint_and_decimal_key_components(oracle):
         ends = oracle.subdockey_ends(key)
         # [cotable-id end, DocKey end, subkey ends...] (SubDocKey::DecodeDocKeyAndSubKeyEnds, doc_key.cc:963-996)
         assert ends[:4] == [0, len(d), len(d) + 2, len(d) + 2 + len(c)], c
+
+
+def _snappy_inputs():
+    import os as _os
+    import random as _random
+    rng = _random.Random(5)
+
+    def gen(n, mode):
+        if mode == 0:
+            return bytes(rng.randrange(256) for _ in range(n))
+        if mode == 1:
+            return bytes(n)
+        if mode == 2:
+            words = [bytes(rng.randrange(256) for _ in range(rng.randint(1, 40))) for _ in range(rng.randint(2, 30))]
+            b = bytearray()
+            while len(b) < n:
+                b += rng.choice(words)
+            return bytes(b[:n])
+        if mode == 3:
+            b = bytearray()
+            while len(b) < n:
+                b += bytes(rng.randrange(256) for _ in range(rng.randint(1, 300))) if rng.random() < 0.5 else bytes([rng.randrange(256)]) * rng.randint(1, 400)
+            return bytes(b[:n])
+        return bytes(rng.choice(b"ab" if mode == 4 else b"abcdefgh") for _ in range(n))       # many collisions, short matches
+    for n in list(range(0, 140, 3)) + [255, 256, 257, 1000, 4096, 5000, 32768, 65535, 65536, 65537, 65540, 70000, 140000]:
+        for mode in range(6):
+            yield n, mode, gen(n, mode)
+
+
+def test_snappy_format_round_trip_and_library_cross_check():
+    """Snappy is the one third-party codec on the path: the library is not in the tree, so the FORMAT is
+    what is pinned — every stream the repository's encoder emits decodes back, the real library (pyarrow bundles
+    libsnappy) decodes it to the same bytes, and the oracle's decoder reads the library's own streams."""
+    pa = None
+    try:
+        import pyarrow as pa_mod
+        if pa_mod.Codec.is_available("snappy"):
+            pa = pa_mod
+    except ImportError:
+        pass
+    for n, mode, raw in _snappy_inputs():
+        c = o.snappy_compress(raw)
+        assert o.snappy_uncompress(c) == raw, (n, mode)
+        if pa is not None and n:
+            assert pa.decompress(c, decompressed_size=n, codec="snappy").to_pybytes() == raw, (n, mode)
+            assert o.snappy_uncompress(pa.compress(raw, codec="snappy", asbytes=True)) == raw, (n, mode)
+    for bad in (b"", b"\x05\x00a", b"\x04\x0cabcd\x01", b"\x08\x0cabcd\x05\x09"):      # empty, short literal, trailing junk, offset beyond the output
+        with pytest.raises(ValueError):
+            o.snappy_uncompress(bad)
+
+
+def test_snappy_warp_model_is_the_scalar_encoder():
+    """The GPU encoder tries 32 positions per step (snappy_warp_model.py mirrors the kernel statement for statement);
+    its element stream must be the scalar encoder's, including the decision to give a block up."""
+    from snappy_warp_model import warp_compress
+    kept = 0
+    for n, mode, raw in _snappy_inputs():
+        c = o.snappy_compress(raw)
+        want = c if len(c) < n - n // 8 else None
+        assert warp_compress(raw) == want, (n, mode)
+        kept += want is not None
+    assert kept > 100

@@ -42,6 +42,7 @@ class JobOptions(C.Structure):
         ("filter_policy", C.c_int32), ("filter_block_size", C.c_uint32),
         ("yield_fn", C.c_void_p), ("yield_ctx", C.c_void_p),
         ("compute_user_boundary_values", C.c_int32),
+        ("output_compression", C.c_int32),
     ]
 
 
@@ -75,6 +76,7 @@ class JobStats(C.Structure):
 
 PHASE_NAMES = ["block_scan", "decode", "partition", "merge_filter", "encode"]
 PATH_FUSED_INGEST, PATH_GENERAL_DECODE, PATH_SNAPPY, PATH_PARTITION_RETRY, PATH_ENCODER_V4, PATH_ENCODER_V5, PATH_KV_INPUT = 1, 2, 4, 8, 16, 32, 64
+PATH_SNAPPY_OUTPUT = 128
 
 
 class GenConfig(C.Structure):
@@ -166,7 +168,8 @@ def make_options(device=0, bottommost=True, last_sequence=MAX_SEQUENCE, largest_
                  retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
                  restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
                  min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b"",
-                 filter_policy=0, filter_block_size=65536, yield_fn=None, user_boundary_values=False):
+                 filter_policy=0, filter_block_size=65536, yield_fn=None, user_boundary_values=False,
+                 output_compression=0):
     """ybgpu_job_options from keyword arguments; returns (options, objects to keep alive). yield_fn: a Python
     callable() invoked at the engine's yield points (PauseIfNecessary)."""
     L = lib()
@@ -194,6 +197,7 @@ def make_options(device=0, bottommost=True, last_sequence=MAX_SEQUENCE, largest_
     o.range_lower, o.range_lower_len = range_lower, len(range_lower)
     o.range_upper, o.range_upper_len = range_upper, len(range_upper)
     o.compute_user_boundary_values = int(bool(user_boundary_values))
+    o.output_compression = int(output_compression)
     cb = None
     if yield_fn is not None:
         cb = YIELD_FN(lambda _ctx: yield_fn())
@@ -209,13 +213,13 @@ class GpuCompactionJob:
                  retain_delete_markers=False, other_min_ht=HT_MAX, lower=b"", upper=b"", block_size=32768,
                  restart_interval=16, deviation=10, output_key_encoding=1, index_block_size=32768,
                  min_keys_per_index_block=100, verify_checksums=True, cuda_stream=None, range_lower=b"", range_upper=b"",
-                 filter_policy=0, filter_block_size=65536, yield_fn=None, user_boundary_values=False):
+                 filter_policy=0, filter_block_size=65536, yield_fn=None, user_boundary_values=False, output_compression=0):
         L = lib()
         o, self._keep = make_options(device, bottommost, last_sequence, largest_user_key, retention, cutoff_ht,
                                      cotables_cutoff_ht, table_ttl_ns, retain_delete_markers, other_min_ht, lower, upper,
                                      block_size, restart_interval, deviation, output_key_encoding, index_block_size,
                                      min_keys_per_index_block, verify_checksums, cuda_stream, range_lower, range_upper,
-                                     filter_policy, filter_block_size, yield_fn, user_boundary_values)
+                                     filter_policy, filter_block_size, yield_fn, user_boundary_values, output_compression)
         h = C.c_void_p()
         st = L.ybgpu_job_create(C.byref(o), C.byref(h))
         if st != 0:
@@ -364,7 +368,7 @@ class HostTableBuilder:
     """rocksdb::TableBuilder-shaped host writer (ybgpu_table_builder_*)."""
 
     def __init__(self, block_size=32768, restart_interval=16, deviation=10, index_block_size=32768,
-                 min_keys_per_index_block=100, key_encoding=1, filter_policy=0, filter_block_size=65536):
+                 min_keys_per_index_block=100, key_encoding=1, filter_policy=0, filter_block_size=65536, compression=0):
         L = lib()
         L.ybgpu_table_builder_create.argtypes = [C.POINTER(JobOptions), C.POINTER(C.c_void_p)]
         L.ybgpu_table_builder_add.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
@@ -379,6 +383,7 @@ class HostTableBuilder:
         o.block_size, o.block_restart_interval, o.block_size_deviation = block_size, restart_interval, deviation
         o.index_block_size, o.min_keys_per_index_block, o.output_key_encoding = index_block_size, min_keys_per_index_block, key_encoding
         o.filter_policy, o.filter_block_size = filter_policy, filter_block_size
+        o.output_compression = compression
         self.h = C.c_void_p()
         st = L.ybgpu_table_builder_create(C.byref(o), C.byref(self.h))
         if st != 0:

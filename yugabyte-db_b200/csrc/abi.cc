@@ -219,7 +219,7 @@ static ybgpu_status EnsureSst(ybgpu_job* job) {
       t.block_size = o.block_size; t.block_restart_interval = o.block_restart_interval;
       t.block_size_deviation = o.block_size_deviation; t.index_block_size = o.index_block_size;
       t.min_keys_per_index_block = o.min_keys_per_index_block; t.key_encoding = o.output_key_encoding;
-      t.filter_policy = o.filter_policy; if (o.filter_block_size) t.filter_block_size = o.filter_block_size;
+      t.filter_policy = o.filter_policy; if (o.filter_block_size) t.filter_block_size = o.filter_block_size; t.compression = o.output_compression;
       ybgpu::host::MetaFileWriter w(t);
       // Filter blocks come finished from the GPU too. In the metadata file they are interleaved with
       // the index blocks in the order BlockBasedTableBuilder::Add produces them: filter block f is
@@ -337,7 +337,7 @@ ybgpu_status ybgpu_table_builder_create(const ybgpu_job_options* o, ybgpu_table_
     t.block_size = o->block_size; t.block_restart_interval = o->block_restart_interval;
     t.block_size_deviation = o->block_size_deviation; t.index_block_size = o->index_block_size;
     t.min_keys_per_index_block = o->min_keys_per_index_block; t.key_encoding = o->output_key_encoding;
-    t.filter_policy = o->filter_policy; if (o->filter_block_size) t.filter_block_size = o->filter_block_size;
+    t.filter_policy = o->filter_policy; if (o->filter_block_size) t.filter_block_size = o->filter_block_size; t.compression = o->output_compression;
     std::unique_ptr<ybgpu_table_builder> tb(new ybgpu_table_builder);
     tb->w.reset(new ybgpu::host::SplitSstWriter(t));
     *b = tb.release();
@@ -413,7 +413,7 @@ ybgpu_status ybgpu_sst_concat_meta(const ybgpu_job_options* o, const ybgpu_sst_p
   t.block_size = o->block_size; t.block_restart_interval = o->block_restart_interval;
   t.block_size_deviation = o->block_size_deviation; t.index_block_size = o->index_block_size;
   t.min_keys_per_index_block = o->min_keys_per_index_block; t.key_encoding = o->output_key_encoding;
-  t.filter_policy = o->filter_policy; if (o->filter_block_size) t.filter_block_size = o->filter_block_size;
+  t.filter_policy = o->filter_policy; if (o->filter_block_size) t.filter_block_size = o->filter_block_size; t.compression = o->output_compression;
   std::vector<ybgpu::host::SstPiece> ps(n);
   for (uint32_t i = 0; i < n; i++) {
     ps[i].meta = pieces[i].meta_file; ps[i].meta_len = pieces[i].meta_file_len; ps[i].data_len = pieces[i].data_file_len;
@@ -443,7 +443,7 @@ ybgpu_status ybgpu_sst_verify_blocks(const uint8_t* meta, uint64_t meta_len, con
     if (h.offset + h.size + 5 > data_len) { (*bad)++; continue; }
     const uint8_t* p = data + h.offset;
     uint32_t stored; memcpy(&stored, p + h.size + 1, 4);
-    if (p[h.size] != 0 || ybgpu::host::Crc32cMask(ybgpu::host::Crc32c(p, h.size + 1)) != stored) (*bad)++;
+    if (p[h.size] > 1 /* kNoCompression / kSnappyCompression: the checksum covers the stored bytes */ || ybgpu::host::Crc32cMask(ybgpu::host::Crc32c(p, h.size + 1)) != stored) (*bad)++;
   }
   if (*bad) { g_last_error = "block checksum mismatch"; return YBGPU_CORRUPTION; }
   return YBGPU_OK;

@@ -184,6 +184,7 @@ class GpuCompactionJob {
     int output_key_encoding = YBGPU_KEY_ENCODING_SHARED_PREFIX;   // data_block_key_value_encoding_format
     int filter_policy = YBGPU_FILTER_NONE;     // YBGPU_FILTER_DOCKEY_V3 for DocDB tables (docdb_rocksdb_util.cc:761-763)
     uint32_t filter_block_size = 64 * 1024;    // db_filter_block_size_bytes
+    int output_compression = YBGPU_COMPRESSION_NONE;   // Options::compression: YBGPU_COMPRESSION_SNAPPY in production (docdb_rocksdb_util.cc:184)
     bool verify_checksums = true;
     const volatile int32_t* shutting_down = nullptr;   // std::atomic<bool>* shutting_down_ in the reference
     // DBOptions::max_subcompactions (rocksdb/options.h:1029; default 1, util/options.cc:258). > 1: the
@@ -226,6 +227,7 @@ class GpuCompactionJob {
     o.block_size_deviation = p_.block_size_deviation; o.index_block_size = p_.index_block_size;
     o.min_keys_per_index_block = p_.min_keys_per_index_block; o.verify_checksums = p_.verify_checksums;
     o.output_key_encoding = p_.output_key_encoding; o.filter_policy = p_.filter_policy; o.filter_block_size = p_.filter_block_size;
+    o.output_compression = p_.output_compression;
     o.yield_fn = p_.yield_fn; o.yield_ctx = p_.yield_ctx;
     o.compute_user_boundary_values = p_.retention.CouldChangeKeyRange() && p_.max_subcompactions <= 1;
     options_ = o;

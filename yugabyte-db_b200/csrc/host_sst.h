@@ -50,6 +50,7 @@ struct TableOptions {
   int key_encoding = 1;
   int filter_policy = 0;             // 1 = DocKeyV3Filter fixed-size bloom blocks (docdb_filter_policy.h:71-80)
   uint32_t filter_block_size = 64 * 1024;
+  int compression = 0;               // rocksdb::CompressionType of the output: 0 = kNoCompression, 1 = kSnappyCompression
 };
 
 // FixedSizeFilterBitsBuilder geometry (util/bloom.cc:389-422) for filter blocks of `block_bytes`.
@@ -102,7 +103,7 @@ class MetaFileWriter {
   void Reserve(size_t bytes) { meta_.reserve(bytes); }
   void TakeMetaFile(std::string* out) { out->swap(meta_); }
  private:
-  void AppendBlock(const std::string& contents, Handle* h);
+  void AppendBlock(const std::string& contents, Handle* h, bool compressible = false);
   TableOptions o_;
   std::unique_ptr<BlockEncoder> filter_index_;
   uint64_t filter_size_ = 0, num_filter_blocks_ = 0;

@@ -273,7 +273,7 @@ ybgpu_status ybgpu_compact_range_sharded(ybgpu_range_comm* c, const ybgpu_job_op
   topt.block_size = options->block_size; topt.block_restart_interval = options->block_restart_interval;
   topt.block_size_deviation = options->block_size_deviation; topt.index_block_size = options->index_block_size;
   topt.min_keys_per_index_block = options->min_keys_per_index_block; topt.key_encoding = options->output_key_encoding;
-  topt.filter_policy = options->filter_policy; if (options->filter_block_size) topt.filter_block_size = options->filter_block_size;
+  topt.filter_policy = options->filter_policy; if (options->filter_block_size) topt.filter_block_size = options->filter_block_size; topt.compression = options->output_compression;
   struct Piece { std::string meta, smallest, largest; uint64_t data_len = 0; };
   std::vector<Piece> pieces;
   ybgpu_job_stats tot; memset(&tot, 0, sizeof(tot));

@@ -132,4 +132,189 @@ __global__ void __launch_bounds__(128) k_snappy_decode(SnapView V, JobDev* J) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Snappy-compressed OUTPUT data blocks (BlockBasedTableBuilder::WriteBlock -> CompressBlock,
+// block_based_table_builder.cc:115-131,630-655). The block assembler writes the table uncompressed (contents +
+// trailer, back to back); k_snappy_compress then encodes every block into a scratch image at the same offsets and
+// decides per block whether the compressed form is kept (GoodCompressionRatio, :109-112: shorter than 7/8 of the
+// contents — an encoding that reaches that bound is abandoned on the spot, so the scratch never overflows a block's
+// slot); the kept sizes are prefix-summed into the final block offsets and k_snappy_gather moves each block's stored
+// form (compressed + type 1 + checksum of the compressed bytes, or the raw block with the trailer it already has).
+//
+// Encoder (one warp per block; identical element for element to host_sst.cc SnappyCompress, which writes the index
+// blocks of the same table): 64 KB fragments; a table of 2^12 fragment-relative positions per warp in shared memory,
+// keyed by a multiplicative hash of the four bytes at a position. The scalar algorithm visits positions one by one:
+// the slot's previous occupant is the match candidate, the position takes the slot. Here 32 consecutive positions are
+// tried at once: a lane's candidate is the nearest lower lane with the same hash (__match_any_sync) or else the
+// slot's occupant; the lowest lane that finds a four-byte match wins, lanes up to and including it take their slots
+// (the highest lane of every hash group), the lanes behind it are covered by the match and do not count as visited —
+// exactly the scalar order of events. The match is extended 32 bytes per step; literal bytes are moved with
+// word-wide copies.
+constexpr int SNAPC_WARPS = 4;
+constexpr uint32_t SNAPC_HASH_BITS = 12;
+constexpr uint32_t SNAPC_FRAGMENT = 65536;
+
+struct SnapCompView {
+  const uint8_t* raw;                  // assembled table: block b at raw_off[b], contents + 5-byte trailer
+  const unsigned long long* raw_off;   // [nblocks + 1]
+  uint8_t* comp;                       // scratch image, same offsets
+  uint32_t* csize;                     // [nblocks] compressed contents size; 0 = the block stays raw
+  unsigned long long* fsize;           // [nblocks + 1] stored size incl. trailer -> exclusive prefix sum -> final offsets
+  uint8_t* out;                        // final table (k_snappy_gather)
+  uint32_t nblocks;
+};
+
+__device__ __forceinline__ uint32_t snapc_literal_header(uint32_t len, uint32_t* nbytes) {
+  const uint32_t l1 = len - 1;
+  if (l1 < 60) { *nbytes = 1; return l1 << 2; }
+  if (l1 < 256) { *nbytes = 2; return (60u << 2) | (l1 << 8); }
+  *nbytes = 3; return (61u << 2) | (l1 << 8);            // l1 <= 65535: a literal never crosses a fragment
+}
+
+__global__ void __launch_bounds__(SNAPC_WARPS * 32) k_snappy_compress(SnapCompView V) {
+  __shared__ uint16_t s_table[SNAPC_WARPS][1u << SNAPC_HASH_BITS];
+  const int lane = threadIdx.x & 31;
+  uint16_t* T = s_table[threadIdx.x >> 5];
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t FULL = 0xffffffffu;
+  for (uint32_t b = warp; b < V.nblocks; b += nwarps) {
+    const unsigned long long o = V.raw_off[b];
+    const unsigned long long n64 = V.raw_off[b + 1] - o - 5;
+    const uint8_t* in = V.raw + o;
+    uint8_t* out = V.comp + o;
+    const uint32_t n = static_cast<uint32_t>(n64);
+    const uint32_t limit = n - n / 8u;                    // kept only if the stream is SHORTER than this
+    bool give_up = n64 >= 0x7fffffffull;                  // kCompressionSizeLimit (:642)
+    uint32_t op = 0;
+    if (!give_up) {                                       // varint32 preamble: the uncompressed length
+      uint32_t v = n;
+      while (v >= 128) { if (lane == 0) out[op] = static_cast<uint8_t>(v | 128); v >>= 7; op++; }
+      if (lane == 0) out[op] = static_cast<uint8_t>(v);
+      op++;
+      if (op >= limit) give_up = true;
+    }
+    for (uint32_t fs = 0; fs < n && !give_up; fs += SNAPC_FRAGMENT) {
+      const uint8_t* f = in + fs;
+      const uint32_t m = min(n - fs, SNAPC_FRAGMENT);
+      __syncwarp();
+      for (uint32_t i = lane; i < (1u << SNAPC_HASH_BITS) / 2; i += 32) reinterpret_cast<uint32_t*>(T)[i] = 0;
+      __syncwarp();
+      uint32_t lit = 0, i = 0;
+      while (i + 4 <= m) {
+        const uint32_t pos = i + lane;
+        const bool act = pos + 4 <= m;
+        uint32_t w = 0, h = 0x10000u + lane;              // idle lanes: a hash group of their own
+        if (act) { w = ldg_u32_unaligned(f + pos); h = (w * 0x1e35a7bdu) >> (32 - SNAPC_HASH_BITS); }
+        const uint32_t grp = __match_any_sync(FULL, h);
+        const uint32_t lower = grp & ((1u << lane) - 1u);
+        uint32_t cand = 0;
+        bool hit = false;
+        if (act) {
+          cand = lower ? i + (31 - __clz(lower)) : T[h];
+          hit = cand < pos && ldg_u32_unaligned(f + cand) == w;
+        }
+        const uint32_t hits = __ballot_sync(FULL, hit);
+        const uint32_t upto = hits ? static_cast<uint32_t>(__ffs(hits) - 1) : 31u;     // lanes <= upto are visited
+        __syncwarp();
+        if (act && static_cast<uint32_t>(lane) <= upto) {
+          const uint32_t g = grp & (0xffffffffu >> (31 - upto));
+          if (31 - __clz(g) == lane) T[h] = static_cast<uint16_t>(pos);
+        }
+        __syncwarp();
+        if (!hits) { i += 32; continue; }
+        const uint32_t mpos = i + upto;
+        const uint32_t c = __shfl_sync(FULL, cand, upto);
+        uint32_t len = 4;
+        for (;;) {                                        // extend: 32 bytes per step
+          const uint32_t q = mpos + len + lane;
+          const bool same = q < m && f[c + len + lane] == f[q];
+          const uint32_t differ = __ballot_sync(FULL, !same);
+          if (differ) { len += __ffs(differ) - 1; break; }
+          len += 32;
+        }
+        // ---- the literal in front of the match
+        if (mpos > lit) {
+          const uint32_t L = mpos - lit;
+          uint32_t hb; const uint32_t hdr = snapc_literal_header(L, &hb);
+          if (op + hb + L >= limit) { give_up = true; break; }
+          if (lane < static_cast<int>(hb)) out[op + lane] = static_cast<uint8_t>(hdr >> (8 * lane));
+          warp_copy(out + op + hb, f + lit, L, lane);
+          op += hb + L;
+        }
+        // ---- the copy: pieces of 64 bytes while at least 4 remain behind them, then one or two closing pieces
+        const uint32_t off = mpos - c;
+        const uint32_t nfull = len >= 68 ? (len - 68) / 64 + 1 : 0;
+        uint32_t left = len - 64 * nfull;                 // 4..67
+        unsigned long long closing = 0; uint32_t cb = 0;  // the closing pieces' bytes, packed
+        while (left) {
+          uint32_t l = min(left, 64u);
+          if (left > l && left - l < 4) l = left - 4;
+          if (l <= 11 && off < 2048) {
+            closing |= static_cast<unsigned long long>(1u | ((l - 4) << 2) | ((off >> 8) << 5) | ((off & 0xff) << 8)) << (8 * cb);
+            cb += 2;
+          } else {
+            closing |= static_cast<unsigned long long>(2u | ((l - 1) << 2) | (off << 8)) << (8 * cb);
+            cb += 3;
+          }
+          left -= l;
+        }
+        if (op + 3 * nfull + cb >= limit) { give_up = true; break; }
+        for (uint32_t j = lane; j < nfull; j += 32) {
+          uint8_t* e = out + op + 3 * j;
+          e[0] = static_cast<uint8_t>(2u | (63u << 2)); e[1] = static_cast<uint8_t>(off); e[2] = static_cast<uint8_t>(off >> 8);
+        }
+        op += 3 * nfull;
+        if (lane < static_cast<int>(cb)) out[op + lane] = static_cast<uint8_t>(closing >> (8 * lane));
+        op += cb;
+        i = mpos + len; lit = i;
+      }
+      if (!give_up && m > lit) {                          // the fragment's closing literal
+        const uint32_t L = m - lit;
+        uint32_t hb; const uint32_t hdr = snapc_literal_header(L, &hb);
+        if (op + hb + L >= limit) { give_up = true; break; }
+        if (lane < static_cast<int>(hb)) out[op + lane] = static_cast<uint8_t>(hdr >> (8 * lane));
+        warp_copy(out + op + hb, f + lit, L, lane);
+        op += hb + L;
+      }
+    }
+    const bool keep = !give_up && op < limit;
+    if (lane == 0) {
+      if (keep) out[op] = 1;                              // the trailer's type byte: kSnappyCompression
+      V.csize[b] = keep ? op : 0u;
+      V.fsize[b] = (keep ? static_cast<unsigned long long>(op) : n64) + 5ull;
+    }
+  }
+}
+
+// Moves every block's stored form to its final place; compressed blocks get their checksum here (over the
+// compressed bytes and the type byte, masked: WriteRawBlock, block_based_table_builder.cc:684-689).
+__global__ void __launch_bounds__(256) k_snappy_gather(SnapCompView V) {
+  __shared__ uint32_t tab0[256];
+  __shared__ uint32_t s32[4][256];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&s32[0][0])[i] = (&g_crc_s32[0][0])[i];
+  tab0[threadIdx.x] = g_crc_tab[0][threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t kc = g_crc_xpow8[4 * (lane + 1)];
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t b = warp; b < V.nblocks; b += nwarps) {
+    const unsigned long long o = V.raw_off[b];
+    const uint32_t cs = V.csize[b];
+    uint8_t* dst = V.out + V.fsize[b];
+    if (!cs) {
+      const unsigned long long len = V.raw_off[b + 1] - o;      // contents + trailer
+      const uint8_t* src = V.raw + o;
+      for (unsigned long long done = 0; done < len; done += 1u << 30) {
+        const uint32_t part = static_cast<uint32_t>(len - done < (1ull << 30) ? len - done : (1ull << 30));
+        warp_copy(dst + done, src + done, part, lane);
+      }
+    } else {
+      const uint8_t* src = V.comp + o;
+      warp_copy(dst, src, cs + 1, lane);
+      const uint32_t crc = crc_mask(warp_crc32c_strided(src, static_cast<uint64_t>(cs) + 1, lane, tab0, s32, kc));
+      if (lane < 4) dst[cs + 1 + lane] = static_cast<uint8_t>(crc >> (8 * lane));
+    }
+  }
+}
+
 }  // namespace ybgpu

@@ -373,7 +373,7 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
     ot_topt.block_size = options->block_size; ot_topt.block_restart_interval = options->block_restart_interval;
     ot_topt.block_size_deviation = options->block_size_deviation; ot_topt.index_block_size = options->index_block_size;
     ot_topt.min_keys_per_index_block = options->min_keys_per_index_block; ot_topt.key_encoding = options->output_key_encoding;
-    ot_topt.filter_policy = options->filter_policy; if (options->filter_block_size) ot_topt.filter_block_size = options->filter_block_size;
+    ot_topt.filter_policy = options->filter_policy; if (options->filter_block_size) ot_topt.filter_block_size = options->filter_block_size; ot_topt.compression = options->output_compression;
     ot_builder.reset(new ybgpu::host::ConcatBuilder(ot_topt));
     uint64_t in_meta = 0;
     for (uint32_t f = 0; f < num_files; f++) in_meta += files[f].meta_file_len;
