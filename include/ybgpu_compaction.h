@@ -165,7 +165,8 @@ typedef struct ybgpu_job_stats {
   /* device time per phase (CUDA events on the job's stream), seconds:
    * 0 checksum verify + block scan (K1), 1 decode (K1'), 2 partition (K2), 3 merge+filter (K3),
    * 4 survivor scan + block encode + CRC + bloom filter blocks (K4/K5/K6),
-   * 5 the block-assembler kernel alone (k_encode_smem, one launch; part of phase 4) */
+   * 5 the block-assembler kernel alone (k_encode_smem, one launch; part of phase 4),
+   * 6 / 7 the Snappy encoder / the move of the stored blocks (output_compression; one launch each; part of phase 4) */
   double phase_seconds[8];
   uint32_t phase_launches[8];
   /* which kernels ran (diagnostics, tests): YBGPU_PATH_* bits; summed over the ranges of a pipelined compaction */

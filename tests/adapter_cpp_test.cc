@@ -2,6 +2,7 @@
 // argv[1] = "cpu": only checks that creation fails loudly without a GPU and the host TableBuilder works.
 // argv[1] = "gpu": runs a small compaction read from files given as argv[2..] pairs (base, data).
 // argv[1] = "gpusub": the same with max_subcompactions = 4 (one output file per key range).
+// argv[1] = "gpusnappy": the same as "gpu" with kSnappyCompression output.
 #include <cstdio>
 #include <fstream>
 #include <iterator>
@@ -76,6 +77,7 @@ int main(int argc, char** argv) {
   for (size_t i = 0; i + 1 < bufs.size(); i += 2) { InputFile f; f.base_file = Slice(bufs[i]); f.data_file = Slice(bufs[i + 1]); in.push_back(f); }
   GpuCompactionJob::Params p;
   if (mode == "gpusub") p.max_subcompactions = 4;
+  if (mode == "gpusnappy") p.output_compression = YBGPU_COMPRESSION_SNAPPY;   // Options::compression as DocDB sets it (docdb_rocksdb_util.cc:184)
   if (mode == "gpufeed") {
     // RunIntoFeed: the surviving stream goes entry by entry through a host CompactionFeed (compaction_context.h:25-35)
     // into the host TableBuilder; a second job's feed fails at entry `abort_at` and the status must come back

@@ -31,23 +31,30 @@ def warp_compress(raw, hash_bits=12, fragment=65536):
     while fs < n and not give_up:
         f = raw[fs:fs + fragment]; m = len(f)
         T = [0] * (1 << hash_bits)
+        G = [0] * (1 << hash_bits)                       # eight more bits of the occupant's hash product
         lit = 0; i = 0
         broke = False
         while i + 4 <= m:
             pos = [i + l for l in range(32)]
             act = [p + 4 <= m for p in pos]
-            w = [0] * 32; h = [0x10000 + l for l in range(32)]
+            w = [0] * 32; h = [0x10000 + l for l in range(32)]; tag = [0] * 32
             for l in range(32):
                 if act[l]:
                     w[l] = struct.unpack_from("<I", f, pos[l])[0]
-                    h[l] = ((w[l] * 0x1e35a7bd) & 0xffffffff) >> (32 - hash_bits)
+                    prod = (w[l] * 0x1e35a7bd) & 0xffffffff
+                    h[l] = prod >> (32 - hash_bits); tag[l] = (prod >> (24 - hash_bits)) & 0xff
             grp = [sum(1 << k for k in range(32) if h[k] == h[l]) for l in range(32)]
             cand = [0] * 32; hit = [False] * 32
             for l in range(32):
                 lower = grp[l] & ((1 << l) - 1)
+                nearest = 31 - clz32(lower) if lower else l
+                w_nearest = w[nearest]
                 if act[l]:
-                    cand[l] = i + (31 - clz32(lower)) if lower else T[h[l]]
-                    hit[l] = cand[l] < pos[l] and struct.unpack_from("<I", f, cand[l])[0] == w[l]
+                    if lower:
+                        cand[l] = i + nearest; hit[l] = w_nearest == w[l]
+                    else:
+                        cand[l] = T[h[l]]
+                        hit[l] = cand[l] < pos[l] and G[h[l]] == tag[l] and struct.unpack_from("<I", f, cand[l])[0] == w[l]
             hits = sum(1 << l for l in range(32) if hit[l])
             upto = ffs(hits) - 1 if hits else 31
             writes = {}
@@ -56,8 +63,8 @@ def warp_compress(raw, hash_bits=12, fragment=65536):
                     g = grp[l] & (0xffffffff >> (31 - upto))
                     if 31 - clz32(g) == l:
                         assert h[l] not in writes
-                        writes[h[l]] = pos[l] & 0xffff
-            for k, v in writes.items(): T[k] = v
+                        writes[h[l]] = (pos[l] & 0xffff, tag[l])
+            for k, v in writes.items(): T[k], G[k] = v
             if not hits:
                 i += 32; continue
             mpos = i + upto; c = cand[upto]

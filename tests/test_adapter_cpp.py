@@ -44,6 +44,30 @@ def test_adapter_runs_compaction(tmp_path):
 
 
 @pytest.mark.gpu
+def test_adapter_snappy_in_snappy_out(tmp_path):
+    """The production configuration end to end through the C++ adapter: Snappy-compressed input tables, Snappy-compressed
+    output (Options::compression = kSnappyCompression, docdb_rocksdb_util.cc:184); files equal the oracle's."""
+    import oracle_py as o
+    import test_gpu_parity as T
+    build_bin()
+    runs = T._phrase_runs(77, 3, 800, random_every=150)
+    ssts = [o.Sst.build(r, o.TableOptions(block_size=4096, compression=1)) for r in runs]
+    args = [BIN, "gpusnappy"]
+    for i, s in enumerate(ssts):
+        b, d = tmp_path / ("%d.sst" % i), tmp_path / ("%d.sst.sblock.0" % i)
+        b.write_bytes(bytes(s.meta))
+        d.write_bytes(bytes(s.data))
+        args += [str(b), str(d)]
+    out = subprocess.check_output(args, text=True)
+    assert "OK in=%d" % sum(len(r) for r in runs) in out
+    exp = o.compact(ssts, o.CompactionParams(), o.TableOptions(compression=1))
+    plain = o.compact(ssts, o.CompactionParams(), o.TableOptions())
+    assert (tmp_path / "0.sst.out.data").read_bytes() == bytes(exp.sst().data)
+    assert (tmp_path / "0.sst.out.base").read_bytes() == bytes(exp.sst().meta)
+    assert len(exp.sst().data) < 0.9 * len(plain.sst().data)
+
+
+@pytest.mark.gpu
 def test_adapter_runs_subcompactions(tmp_path):
     """GpuCompactionJob with max_subcompactions = 4: one output file per key range, in range order;
     together they hold exactly the single-job KV stream."""

@@ -1468,6 +1468,8 @@ struct Engine::Impl {
   cudaEvent_t phase_ev[8] = {};
   cudaEvent_t enc_ev[2] = {};          // around the block-assembler launch (the dominant kernel of the encode phase)
   bool enc_timed = false;
+  cudaEvent_t snap_ev[4] = {};         // around the Snappy encoder and the gather of the stored blocks (output compression)
+  bool snap_timed = false;
   std::vector<void*> allocs;
   JobDev* dJ = nullptr;
   JobParams* dP = nullptr;
@@ -1625,6 +1627,7 @@ Engine::~Engine() {
     if (impl_->copy_stream) cudaStreamDestroy(impl_->copy_stream);
     if (impl_->copy_ev) cudaEventDestroy(impl_->copy_ev);
     for (auto& e : impl_->enc_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : impl_->snap_ev) if (e) cudaEventDestroy(e);
     for (auto& e : impl_->phase_ev) if (e) cudaEventDestroy(e);
     if (impl_->staging_host) { Staging st; st.host = impl_->staging_host; st.dev = impl_->staging_dev; ReleaseStaging(st); }   // every read through it was synchronous
     if (impl_->status_host) {
@@ -2511,8 +2514,28 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       CUDA_TRY(DevAlloc(&I.allocs, &d_ftotal, 1));
       CUDA_TRY(DevAlloc(&I.allocs, &d_fpart, static_cast<size_t>(bc) + 1));
       C.fsize = d_foff;
-      const uint32_t cgrid = std::min<uint32_t>((nblocks + SNAPC_WARPS - 1) / SNAPC_WARPS, static_cast<uint32_t>(sms) * 6);
-      k_snappy_compress<<<cgrid, SNAPC_WARPS * 32, 0, I.stream>>>(C);
+      const uint32_t cgrid = std::min<uint32_t>((nblocks + SNAPC_WARPS - 1) / SNAPC_WARPS, static_cast<uint32_t>(sms) * 4);
+      // A/B switch (same binary): how the encoder forms the hash groups of a batch, see snapc_prepare
+      const char* sv = getenv("YBGPU_SNAPC_VARIANT");
+      const int variant = sv ? atoi(sv) : 0;
+      for (auto& e : I.snap_ev) if (!e) CUDA_TRY(cudaEventCreate(&e));
+      {
+        // 48 KB of static tables per CTA: ask for the largest shared-memory carve-out so that four CTAs share an SM (a hint;
+        // without it the driver may settle for a carve-out that holds one)
+        static bool hinted = false;
+        if (!hinted) {
+          hinted = true;
+          (void)cudaFuncSetAttribute(k_snappy_compress<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          (void)cudaFuncSetAttribute(k_snappy_compress<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          (void)cudaFuncSetAttribute(k_snappy_compress<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          (void)cudaGetLastError();
+        }
+      }
+      CUDA_TRY(cudaEventRecord(I.snap_ev[0], I.stream));
+      if (variant == 2) k_snappy_compress<2><<<cgrid, SNAPC_WARPS * 32, 0, I.stream>>>(C);
+      else if (variant == 1) k_snappy_compress<1><<<cgrid, SNAPC_WARPS * 32, 0, I.stream>>>(C);
+      else k_snappy_compress<0><<<cgrid, SNAPC_WARPS * 32, 0, I.stream>>>(C);
+      CUDA_TRY(cudaEventRecord(I.snap_ev[1], I.stream));
       k_u64_chunk_sums<<<bc, 256, 0, I.stream>>>(d_foff, nblocks, d_fpart);
       k_scan_u64_single<<<1, 1024, 0, I.stream>>>(d_fpart, bc, d_ftotal);
       k_u64_chunk_final<<<bc, 256, 0, I.stream>>>(d_foff, nblocks, d_fpart);
@@ -2520,7 +2543,10 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       if (ybgpu_status s = ReadSmall(&ftotal, d_ftotal, 8)) return s;
       if (ybgpu_status us = UploadSmall(d_foff + nblocks, &ftotal, 8)) return us;
       CUDA_TRY(DevAlloc(&I.allocs, &C.out, ftotal + 64));
+      CUDA_TRY(cudaEventRecord(I.snap_ev[2], I.stream));
       k_snappy_gather<<<GridFor(static_cast<uint64_t>(nblocks) * 32, 256, sms), 256, 0, I.stream>>>(C);
+      CUDA_TRY(cudaEventRecord(I.snap_ev[3], I.stream));
+      I.snap_timed = true;
       launches += 5;
       stats_.path_flags |= YBGPU_PATH_SNAPPY_OUTPUT;
       I.out_file = C.out; I.out_file_len = ftotal; I.d_block_off = d_foff;
@@ -2592,6 +2618,13 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
     CUDA_TRY(cudaEventElapsedTime(&pms, ph ? I.phase_ev[ph - 1] : I.ev0, I.phase_ev[ph]));
     stats_.phase_seconds[ph] = pms / 1e3;
     stats_.phase_launches[ph] = phase_launch_mark[ph] - (ph ? phase_launch_mark[ph - 1] : 0);
+  }
+  if (I.snap_timed) {                                    // slots 6, 7: k_snappy_compress, k_snappy_gather (one launch each)
+    float cms = 0, gms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&cms, I.snap_ev[0], I.snap_ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&gms, I.snap_ev[2], I.snap_ev[3]));
+    stats_.phase_seconds[6] = cms / 1e3; stats_.phase_launches[6] = 1;
+    stats_.phase_seconds[7] = gms / 1e3; stats_.phase_launches[7] = 1;
   }
   if (I.enc_timed) {                                     // slot 5: k_encode_smem alone (one launch)
     float ems = 0;

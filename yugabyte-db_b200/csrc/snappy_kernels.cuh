@@ -171,10 +171,61 @@ __device__ __forceinline__ uint32_t snapc_literal_header(uint32_t len, uint32_t*
   *nbytes = 3; return (61u << 2) | (l1 << 8);            // l1 <= 65535: a literal never crosses a fragment
 }
 
+// Four bytes at any address: the two aligned words around them (reads at most 7 bytes past p, inside the block's
+// trailer or the buffer's padding).
+__device__ __forceinline__ uint32_t snapc_load32(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  return __funnelshift_r(__ldg(q), __ldg(q + 1), static_cast<uint32_t>(a & 3) * 8);   // the assembled table is read-only here
+}
+
+// What a lane knows about its position of a batch before the table is consulted.
+struct SnapcBatch {
+  uint32_t w, h, tag, grp;
+  bool act;
+};
+
+// VARIANT 0: hash groups by __match_any_sync. 1: by one ballot per hash bit (twelve independent votes). 2: as 1, and the
+// NEXT batch (its bytes, hashes and groups, none of which depend on the table) is prepared before the current one is
+// resolved, so that the loads and votes of one batch overlap the table round trip of the other; a match discards it.
+template <int VARIANT>
+__device__ __forceinline__ SnapcBatch snapc_prepare(const uint8_t* f, uint32_t i, uint32_t m, int lane) {
+  const uint32_t FULL = 0xffffffffu;
+  SnapcBatch B;
+  const uint32_t pos = i + lane;
+  B.act = pos + 4 <= m && pos >= i;
+  B.w = 0; B.h = 0x10000u + lane; B.tag = 0;            // idle lanes: a hash group of their own
+  if (B.act) {
+    B.w = snapc_load32(f + pos);
+    const uint32_t prod = B.w * 0x1e35a7bdu;
+    B.h = prod >> (32 - SNAPC_HASH_BITS); B.tag = (prod >> (24 - SNAPC_HASH_BITS)) & 0xffu;
+  }
+  if (VARIANT == 0) {
+    B.grp = __match_any_sync(FULL, B.h);
+  } else {
+    if (lane == 0 && i + 288 < m) asm volatile("prefetch.global.L2 [%0];" :: "l"(f + i + 256));
+    uint32_t g = __ballot_sync(FULL, B.act);
+#pragma unroll
+    for (uint32_t bit = 0; bit < SNAPC_HASH_BITS; bit++) {
+      const bool one = (B.h >> bit) & 1u;
+      const uint32_t v = __ballot_sync(FULL, one);
+      g &= one ? v : ~v;
+    }
+    B.grp = B.act ? g : (1u << lane);
+  }
+  return B;
+}
+
+template <int VARIANT>
 __global__ void __launch_bounds__(SNAPC_WARPS * 32) k_snappy_compress(SnapCompView V) {
-  __shared__ uint16_t s_table[SNAPC_WARPS][1u << SNAPC_HASH_BITS];
+  // per warp: the slot's position and eight more bits of the occupant's hash product. A candidate whose tag differs
+  // cannot hold the same four bytes, so its bytes (a scattered read of the block: 32 lanes, 32 sectors) are fetched
+  // only when the tag agrees — with nothing to find that is one batch in eight instead of every batch.
+  __shared__ uint16_t s_pos[SNAPC_WARPS][1u << SNAPC_HASH_BITS];
+  __shared__ uint8_t s_tag[SNAPC_WARPS][1u << SNAPC_HASH_BITS];
   const int lane = threadIdx.x & 31;
-  uint16_t* T = s_table[threadIdx.x >> 5];
+  uint16_t* T = s_pos[threadIdx.x >> 5];
+  uint8_t* G = s_tag[threadIdx.x >> 5];
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t FULL = 0xffffffffu;
   for (uint32_t b = warp; b < V.nblocks; b += nwarps) {
@@ -198,30 +249,38 @@ __global__ void __launch_bounds__(SNAPC_WARPS * 32) k_snappy_compress(SnapCompVi
       const uint32_t m = min(n - fs, SNAPC_FRAGMENT);
       __syncwarp();
       for (uint32_t i = lane; i < (1u << SNAPC_HASH_BITS) / 2; i += 32) reinterpret_cast<uint32_t*>(T)[i] = 0;
+      for (uint32_t i = lane; i < (1u << SNAPC_HASH_BITS) / 4; i += 32) reinterpret_cast<uint32_t*>(G)[i] = 0;
       __syncwarp();
       uint32_t lit = 0, i = 0;
+      SnapcBatch cur = snapc_prepare<VARIANT>(f, 0, m, lane);
       while (i + 4 <= m) {
+        SnapcBatch nxt;
+        if (VARIANT == 2) nxt = snapc_prepare<VARIANT>(f, i + 32, m, lane);
         const uint32_t pos = i + lane;
-        const bool act = pos + 4 <= m;
-        uint32_t w = 0, h = 0x10000u + lane;              // idle lanes: a hash group of their own
-        if (act) { w = ldg_u32_unaligned(f + pos); h = (w * 0x1e35a7bdu) >> (32 - SNAPC_HASH_BITS); }
-        const uint32_t grp = __match_any_sync(FULL, h);
+        const bool act = cur.act;
+        const uint32_t w = cur.w, h = cur.h, tag = cur.tag, grp = cur.grp;
         const uint32_t lower = grp & ((1u << lane) - 1u);
+        const int nearest = lower ? 31 - __clz(lower) : lane;                          // the nearest lower lane of the group
+        const uint32_t w_nearest = __shfl_sync(FULL, w, nearest);
         uint32_t cand = 0;
         bool hit = false;
         if (act) {
-          cand = lower ? i + (31 - __clz(lower)) : T[h];
-          hit = cand < pos && ldg_u32_unaligned(f + cand) == w;
+          if (lower) { cand = i + nearest; hit = w_nearest == w; }
+          else { cand = T[h]; hit = cand < pos && G[h] == tag && snapc_load32(f + cand) == w; }
         }
         const uint32_t hits = __ballot_sync(FULL, hit);
         const uint32_t upto = hits ? static_cast<uint32_t>(__ffs(hits) - 1) : 31u;     // lanes <= upto are visited
         __syncwarp();
         if (act && static_cast<uint32_t>(lane) <= upto) {
           const uint32_t g = grp & (0xffffffffu >> (31 - upto));
-          if (31 - __clz(g) == lane) T[h] = static_cast<uint16_t>(pos);
+          if (31 - __clz(g) == lane) { T[h] = static_cast<uint16_t>(pos); G[h] = static_cast<uint8_t>(tag); }
         }
         __syncwarp();
-        if (!hits) { i += 32; continue; }
+        if (!hits) {
+          i += 32;
+          if (VARIANT == 2) cur = nxt; else cur = snapc_prepare<VARIANT>(f, i, m, lane);
+          continue;
+        }
         const uint32_t mpos = i + upto;
         const uint32_t c = __shfl_sync(FULL, cand, upto);
         uint32_t len = 4;
@@ -267,6 +326,7 @@ __global__ void __launch_bounds__(SNAPC_WARPS * 32) k_snappy_compress(SnapCompVi
         if (lane < static_cast<int>(cb)) out[op + lane] = static_cast<uint8_t>(closing >> (8 * lane));
         op += cb;
         i = mpos + len; lit = i;
+        cur = snapc_prepare<VARIANT>(f, i, m, lane);
       }
       if (!give_up && m > lit) {                          // the fragment's closing literal
         const uint32_t L = m - lit;
