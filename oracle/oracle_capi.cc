@@ -126,6 +126,20 @@ int64_t orc_snappy_uncompress(const uint8_t* p, uint64_t n, uint8_t* out, uint64
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// ---- whole-file TTL expiration (docdb/compaction_file_filter.cc) ------------------------------
+int orc_ttl_is_expired(uint64_t ttl_expiration_ht, uint64_t created_ht, int64_t table_ttl_ns, uint64_t now, int mode) {
+  return TtlIsExpired(ExpirationTime{ttl_expiration_ht, created_ht}, table_ttl_ns, now, static_cast<ExpiryMode>(mode)) ? 1 : 0;
+}
+// frontier fields per file: created[i] = ConsensusFrontier::hybrid_time, value_ttl[i] = max_value_level_ttl_expiration_time
+// (kHtInvalid = not set); has_frontier[i] = 0: the file has no largest user frontier. discard[i] = 1: kDiscard.
+void orc_file_filter(uint64_t n, const uint8_t* has_frontier, const uint64_t* created, const uint64_t* value_ttl, int64_t table_ttl_ns,
+                     uint64_t primary_cutoff_ht, uint64_t cotables_cutoff_ht, uint64_t now, int mode, uint8_t* discard) {
+  std::vector<ExpirationTime> files;
+  for (uint64_t i = 0; i < n; i++) files.push_back(ExtractExpirationTime(has_frontier[i] != 0, created[i], value_ttl[i]));
+  std::vector<bool> d = FileFilterDecisions(files, table_ttl_ns, primary_cutoff_ht, cotables_cutoff_ht, now, static_cast<ExpiryMode>(mode));
+  for (uint64_t i = 0; i < n; i++) discard[i] = d[i] ? 1 : 0;
+}
+
 // ---- SST build / read ------------------------------------------------------------------------
 orc_sst* orc_sst_build(uint64_t n, const uint8_t* keys, const uint64_t* koff, const uint8_t* vals,
                        const uint64_t* voff, const orc_table_options* o) {

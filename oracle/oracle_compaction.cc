@@ -492,4 +492,59 @@ void RunCompactionOnRuns(const std::vector<KvRun>& runs, const CompactionParams&
   CompactionLoop(&merged, p, &cs, stats);
 }
 
+// ---------------------------------------------------------------------------------------------
+// docdb/compaction_file_filter.cc, dockv/doc_ttl_util.cc:42-47,81-129, common/hybrid_time.h:150-165,185-194.
+static bool HtIsSpecial(uint64_t v) { return v == kHtMin || v == kHtMax || v == kHtInvalid; }
+static uint64_t HtAddDelta(uint64_t ht, int64_t delta_ns) {            // AddDelta -> AddMicroseconds(delta.ToMicroseconds())
+  if (HtIsSpecial(ht)) return ht;
+  const uint64_t micros = static_cast<uint64_t>(delta_ns / 1000);
+  return ht + (micros << 12);
+}
+ExpirationTime ExtractExpirationTime(bool has_frontier, uint64_t frontier_ht, uint64_t max_value_level_ttl_expiration_ht) {
+  if (!has_frontier) return ExpirationTime{};
+  ExpirationTime e;
+  e.ttl_expiration_ht = max_value_level_ttl_expiration_ht != kHtInvalid ? max_value_level_ttl_expiration_ht : kNoExpiration;   // GetValueOr
+  e.created_ht = frontier_ht;
+  return e;
+}
+uint64_t ComputeExpiration(uint64_t ht, int64_t ttl_ns) {
+  const uint64_t expiry = HtAddDelta(ht, ttl_ns);
+  return CompareHybridTimesToDelta(ht, expiry, ttl_ns) == 0 ? expiry : kNoExpiration;     // overflow check
+}
+uint64_t MaxExpirationFromValueAndTableTTL(uint64_t key_ht, int64_t table_ttl_ns, uint64_t value_expiry) {
+  if (value_expiry == kNoExpiration || HtIsSpecial(key_ht)) return kNoExpiration;
+  if (table_ttl_ns == kMaxTtlNs) return value_expiry == kUseDefaultTTL ? kNoExpiration : value_expiry;
+  const uint64_t table_expiry = ComputeExpiration(key_ht, table_ttl_ns);
+  if (table_expiry == kNoExpiration) return kNoExpiration;
+  return value_expiry >= table_expiry ? value_expiry : table_expiry;
+}
+bool HasExpiredTTL(uint64_t expiration_ht, uint64_t read_ht) {
+  if (expiration_ht == kNoExpiration || expiration_ht == kUseDefaultTTL) return false;
+  return expiration_ht < read_ht;
+}
+bool TtlIsExpired(ExpirationTime expiry, int64_t table_ttl_ns, uint64_t now, ExpiryMode mode) {
+  const uint64_t ttl_expiry_ht = mode == EXP_TABLE_ONLY ? kUseDefaultTTL : expiry.ttl_expiration_ht;
+  if (mode == EXP_TRUST_VALUE && ttl_expiry_ht != kHtInvalid && ttl_expiry_ht != kUseDefaultTTL) return HasExpiredTTL(ttl_expiry_ht, now);
+  return HasExpiredTTL(MaxExpirationFromValueAndTableTTL(expiry.created_ht, table_ttl_ns, ttl_expiry_ht), now);
+}
+std::vector<bool> FileFilterDecisions(const std::vector<ExpirationTime>& files, int64_t table_ttl_ns, uint64_t primary_cutoff_ht,
+                                      uint64_t cotables_cutoff_ht, uint64_t now, ExpiryMode mode) {
+  // the factory (:196-243): the history cutoff is the smaller valid one; min_kept_ht = the smallest creation time among the
+  // files that are NOT expired or still inside the history retention window
+  uint64_t history_cutoff = kHtMax;
+  if (cotables_cutoff_ht != kHtInvalid) history_cutoff = std::min(history_cutoff, cotables_cutoff_ht);
+  if (primary_cutoff_ht != kHtInvalid) history_cutoff = std::min(history_cutoff, primary_cutoff_ht);
+  uint64_t min_kept_ht = kHtMax;
+  for (const ExpirationTime& e : files)
+    if (!TtlIsExpired(e, table_ttl_ns, now, mode) || !(e.created_ht < history_cutoff)) min_kept_ht = std::min(min_kept_ht, e.created_ht);
+  // the filter (:150-188): files created before min_kept_ht go, with both sanity checks repeated
+  std::vector<bool> discard;
+  for (const ExpirationTime& e : files) {
+    bool d = false;
+    if (e.created_ht < min_kept_ht) d = e.created_ht < history_cutoff && TtlIsExpired(e, table_ttl_ns, now, mode);
+    discard.push_back(d);
+  }
+  return discard;
+}
+
 }  // namespace orc

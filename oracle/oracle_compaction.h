@@ -69,4 +69,25 @@ struct KvRun { std::vector<std::pair<std::string, std::string>> kv; };
 void RunCompactionOnRuns(const std::vector<KvRun>& runs, const CompactionParams& params,
                          CompactionFeed* sink, CompactionStats* stats);
 
+// ---- docdb/compaction_file_filter.{h,cc}: whole-file expiration by TTL (CompactionFileFilterFactory; the picker marks
+// the files it discards delete_after_compaction, compaction_picker.cc:476-492, and MakeInputIterator leaves them out,
+// db/version_set.cc:3812-3820). HybridTimes are reprs; kNoExpiration = kMax, kUseDefaultTTL = kInitial
+// (dockv/doc_ttl_util.h:65-73).
+enum ExpiryMode { EXP_NORMAL = 0, EXP_TABLE_ONLY = 1, EXP_TRUST_VALUE = 2 };     // compaction_file_filter.h:26-30
+constexpr uint64_t kNoExpiration = kHtMax, kUseDefaultTTL = kHtMin + 1;
+struct ExpirationTime {                                                         // compaction_file_filter.h:32-43
+  uint64_t ttl_expiration_ht = kNoExpiration;   // the largest frontier's max_value_level_ttl_expiration_time
+  uint64_t created_ht = kHtMax;                 // the largest frontier's hybrid_time
+};
+// ExtractExpirationTime (:70-85) from the two frontier fields; `has_frontier` false = no largest user frontier.
+ExpirationTime ExtractExpirationTime(bool has_frontier, uint64_t frontier_ht, uint64_t max_value_level_ttl_expiration_ht);
+uint64_t ComputeExpiration(uint64_t ht, int64_t ttl_ns);                                        // doc_ttl_util.cc:81-87
+uint64_t MaxExpirationFromValueAndTableTTL(uint64_t key_ht, int64_t table_ttl_ns, uint64_t value_expiry);   // :107-129
+bool HasExpiredTTL(uint64_t expiration_ht, uint64_t read_ht);                                   // :42-47
+bool TtlIsExpired(ExpirationTime expiry, int64_t table_ttl_ns, uint64_t now, ExpiryMode mode);  // compaction_file_filter.cc:126-144
+// DocDBCompactionFileFilterFactory::CreateCompactionFileFilter over all input files, then ::Filter of each (:150-243):
+// true = kDiscard.
+std::vector<bool> FileFilterDecisions(const std::vector<ExpirationTime>& files, int64_t table_ttl_ns, uint64_t primary_cutoff_ht,
+                                      uint64_t cotables_cutoff_ht, uint64_t now, ExpiryMode mode);
+
 }  // namespace orc

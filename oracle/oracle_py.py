@@ -445,6 +445,33 @@ def compact(ssts, params=None, opts=None, mode=COLLECT_KV | BUILD_SST, verify=Tr
     return Result(L.orc_compact2(len(ssts), arr, filt, cf, C.byref(params), C.byref(opts), mode, int(verify)))
 
 
+EXP_NORMAL, EXP_TABLE_ONLY, EXP_TRUST_VALUE = 0, 1, 2
+NO_EXPIRATION, USE_DEFAULT_TTL = HT_MAX, HT_MIN + 1      # dockv/doc_ttl_util.h:65-73
+
+
+def ttl_is_expired(ttl_expiration_ht, created_ht, table_ttl_ns, now, mode=EXP_NORMAL):
+    """docdb::TtlIsExpired (compaction_file_filter.cc:126-144)."""
+    L = lib()
+    L.orc_ttl_is_expired.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_uint64, C.c_int]
+    return bool(L.orc_ttl_is_expired(ttl_expiration_ht, created_ht, table_ttl_ns, now, mode))
+
+
+def file_filter(frontiers, table_ttl_ns, now, primary_cutoff_ht=HT_MAX, cotables_cutoff_ht=HT_INVALID, mode=EXP_NORMAL):
+    """DocDBCompactionFileFilterFactory::CreateCompactionFileFilter over the files + Filter of each
+    (compaction_file_filter.cc:150-243). frontiers: per file None (no largest user frontier) or (hybrid_time,
+    max_value_level_ttl_expiration_time or HT_INVALID). Returns a list of booleans, True = kDiscard."""
+    n = len(frontiers)
+    has = np.array([f is not None for f in frontiers], np.uint8)
+    created = np.array([f[0] if f is not None else 0 for f in frontiers], np.uint64)
+    vttl = np.array([f[1] if f is not None else HT_INVALID for f in frontiers], np.uint64)
+    out = np.zeros(max(n, 1), np.uint8)
+    L = lib()
+    L.orc_file_filter.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    L.orc_file_filter.restype = None
+    L.orc_file_filter(n, has.ctypes.data, created.ctypes.data, vttl.ctypes.data, table_ttl_ns, primary_cutoff_ht, cotables_cutoff_ht, now, mode, out.ctypes.data)
+    return [bool(x) for x in out[:n]]
+
+
 def snappy_compress(raw: bytes) -> bytes:
     """The repository's Snappy-format encoder (oracle_sst.cc SnappyCompress)."""
     L = lib()

@@ -3,6 +3,7 @@
 // argv[1] = "gpu": runs a small compaction read from files given as argv[2..] pairs (base, data).
 // argv[1] = "gpusub": the same with max_subcompactions = 4 (one output file per key range).
 // argv[1] = "gpusnappy": the same as "gpu" with kSnappyCompression output.
+#include <cstdlib>
 #include <cstdio>
 #include <fstream>
 #include <iterator>
@@ -60,6 +61,34 @@ int main(int argc, char** argv) {
     ybgpu_sst_meta_handles(reinterpret_cast<const uint8_t*>(base.data()), base.size(), h.data(), n, &n, &enc);
     if (n != blocks || data.size() != total || h.back().offset + h.back().size + 5 != total) { printf("concat layout\n"); return 1; }
     for (uint64_t i = 1; i < n; i++) if (h[i].offset != h[i - 1].offset + h[i - 1].size + 5) { printf("concat handles\n"); return 1; }
+  }
+  if (mode == "filefilter") {
+    // argv: filefilter <table_ttl_ns> <primary_cutoff> <cotables_cutoff> <now> <expiry mode> then per file:
+    // <has frontier 0/1> <frontier hybrid time> <max value-level TTL expiration time>. Prints one K / D per file
+    // (DocDBCompactionFileFilterFactory + Filter as the adapter restates them), then the TtlIsExpired verdict per file.
+    if (argc < 7 || (argc - 7) % 3) { printf("usage\n"); return 2; }
+    DocDBRetention r;
+    r.table_ttl_ns = strtoll(argv[2], nullptr, 10);
+    r.primary_cutoff_ht = strtoull(argv[3], nullptr, 10); r.cotables_cutoff_ht = strtoull(argv[4], nullptr, 10);
+    const uint64_t now = strtoull(argv[5], nullptr, 10);
+    const ExpiryMode em = static_cast<ExpiryMode>(atoi(argv[6]));
+    std::vector<InputFile> files;
+    for (int i = 7; i + 2 < argc; i += 3) {
+      InputFile f;
+      f.has_largest_frontier = atoi(argv[i]) != 0;
+      f.frontier_hybrid_time = strtoull(argv[i + 1], nullptr, 10);
+      f.max_value_level_ttl_expiration_time = strtoull(argv[i + 2], nullptr, 10);
+      files.push_back(f);
+    }
+    std::vector<InputFile> marked = files;
+    const size_t n = MarkExpiredFiles(&marked, r, now, em);
+    size_t seen = 0;
+    for (const InputFile& f : marked) { printf("%c", f.delete_after_compaction ? 'D' : 'K'); seen += f.delete_after_compaction; }
+    if (seen != n) { printf(" count\n"); return 1; }
+    printf(" ");
+    for (const InputFile& f : files) printf("%c", TtlIsExpired(ExtractExpirationTime(&f), r.table_ttl_ns, now, em) ? 'E' : 'L');
+    printf("\n");
+    return 0;
   }
   if (mode == "cpu") {
     if (ybgpu_device_count() == 0) {

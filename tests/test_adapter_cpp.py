@@ -24,6 +24,51 @@ def test_adapter_compiles_and_fails_loudly_without_gpu():
     assert out.strip().endswith("OK")
 
 
+def _adapter_file_filter(frontiers, table_ttl_ns, now, primary=2**64 - 1, cotables=2**64 - 2, mode=0):
+    args = [BIN, "filefilter", str(table_ttl_ns), str(primary), str(cotables), str(now), str(mode)]
+    for f in frontiers:
+        args += ["0", "0", str(2**64 - 2)] if f is None else ["1", str(f[0]), str(f[1])]
+    marks, expired = subprocess.check_output(args, text=True).rstrip("\n").split(" ")
+    return [c == "D" for c in marks], [c == "E" for c in expired]
+
+
+def test_adapter_file_filter_reference_known_answers():
+    """f4: whole-file TTL expiration as the C++ adapter restates it (DocDBCompactionFileFilter + factory, MarkExpiredFiles)
+    against the reference's own known answers (docdb/compaction_file_filter-test.cc:321-484, the table in
+    tests/test_oracle_file_filter.py) and, on random frontiers / TTLs / cutoffs / modes, against the oracle."""
+    import random
+    import oracle_py as o
+    import test_oracle_file_filter as K
+    build_bin()
+    for name, ttl, mode, frontiers, want in K.FILTER_CASES:
+        got, _ = _adapter_file_filter(frontiers, ttl, K.NOW, mode=mode)
+        assert got == want, name
+    rng = random.Random(11)
+    specials = [o.NO_EXPIRATION, o.USE_DEFAULT_TTL, o.HT_INVALID]
+    for _ in range(150):
+        now = K.NOW + rng.randrange(-10**6, 10**6)
+        n = rng.randrange(0, 7)
+        fr = []
+        for _ in range(n):
+            if rng.random() < 0.1:
+                fr.append(None)
+                continue
+            created = K.ht_add_seconds(now, rng.choice([-10000, -100, -50, -2, -1, 0, 1, 30, 10000])) + rng.randrange(3)
+            if rng.random() < 0.05:
+                created = rng.choice([o.HT_MIN, o.HT_MAX, o.HT_INVALID])
+            vttl = rng.choice(specials) if rng.random() < 0.5 else K.ht_add_seconds(now, rng.choice([-10000, -100, -10, -1, 0, 1, 10, 10000]))
+            fr.append((created, vttl))
+        ttl = rng.choice([o.MAX_TTL_NS, 0, 1, 10**9, 20 * 10**9, 1000 * 10**9, 2**62])
+        primary = rng.choice([o.HT_MAX, o.HT_INVALID, o.HT_MIN, K.ht_add_seconds(now, rng.choice([-200, -60, -1, 5]))])
+        cot = rng.choice([o.HT_INVALID, o.HT_MAX, K.ht_add_seconds(now, rng.choice([-200, -60, 5]))])
+        mode = rng.randrange(3)
+        got, expired = _adapter_file_filter(fr, ttl, now, primary, cot, mode)
+        assert got == o.file_filter(fr, ttl, now, primary, cot, mode), (fr, ttl, now, primary, cot, mode)
+        for f, e in zip(fr, expired):
+            vt, cr = (o.NO_EXPIRATION, o.HT_MAX) if f is None else (f[1] if f[1] != o.HT_INVALID else o.NO_EXPIRATION, f[0])
+            assert e == o.ttl_is_expired(vt, cr, ttl, now, mode)
+
+
 @pytest.mark.gpu
 def test_adapter_runs_compaction(tmp_path):
     import oracle_py as o

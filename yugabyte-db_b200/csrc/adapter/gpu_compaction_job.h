@@ -136,7 +136,119 @@ struct InputFile {
   // every output file's seqno bounds with the union over the inputs (compaction_job.cc:1188-1195) before the
   // surviving entries extend them; leave the defaults when the caller does not track them.
   uint64_t smallest_seqno = YBGPU_MAX_SEQUENCE, largest_seqno = 0;
+  // FileMetaData::delete_after_compaction(): set by the picker for files the CompactionFileFilter discards
+  // (db/compaction_picker.cc:476-492); MakeInputIterator leaves such a file out of the merge (db/version_set.cc:3812-3820)
+  // while it stays an input of the compaction (it is deleted afterwards; its seqno bounds still seed the outputs').
+  bool delete_after_compaction = false;
+  // The largest user frontier of the file, as far as whole-file TTL expiration reads it (docdb/compaction_file_filter.cc:
+  // 70-85): ConsensusFrontier::hybrid_time and ::max_value_level_ttl_expiration_time (YBGPU_HT_INVALID = not set).
+  bool has_largest_frontier = false;
+  uint64_t frontier_hybrid_time = YBGPU_HT_MAX;
+  uint64_t max_value_level_ttl_expiration_time = YBGPU_HT_INVALID;
 };
+
+// ---- whole-file TTL expiration: docdb::DocDBCompactionFileFilter(Factory) (docdb/compaction_file_filter.{h,cc}) ----------
+// The reference's picker asks the factory for a filter over the compaction's input files and marks the files it discards;
+// the compaction then skips them. Host logic on FileMetaData frontiers, no GPU work: it lives here so that the GPU job
+// honours the same marks (Prepare) and a caller without the reference's picker can produce them (MarkExpiredFiles).
+enum ExpiryMode { EXP_NORMAL = 0, EXP_TABLE_ONLY = 1, EXP_TRUST_VALUE = 2 };    // compaction_file_filter.h:26-30; flags :34-49
+enum class FilterDecision { kKeep, kDiscard };                                   // rocksdb/compaction_filter.h
+constexpr uint64_t kNoExpiration = YBGPU_HT_MAX;           // dockv/doc_ttl_util.h:73  HybridTime::kMax
+constexpr uint64_t kUseDefaultTTL = YBGPU_HT_MIN + 1;      // :69                      HybridTime::kInitial
+struct ExpirationTime {                                    // compaction_file_filter.h:32-43
+  uint64_t ttl_expiration_ht = kNoExpiration;
+  uint64_t created_ht = YBGPU_HT_MAX;
+};
+inline ExpirationTime ExtractExpirationTime(const InputFile* file) {             // :70-85
+  ExpirationTime e;
+  if (!file || !file->has_largest_frontier) return e;
+  e.ttl_expiration_ht = file->max_value_level_ttl_expiration_time != YBGPU_HT_INVALID ? file->max_value_level_ttl_expiration_time : kNoExpiration;
+  e.created_ht = file->frontier_hybrid_time;
+  return e;
+}
+namespace ttl_detail {
+inline bool IsSpecial(uint64_t ht) { return ht == YBGPU_HT_MIN || ht == YBGPU_HT_MAX || ht == YBGPU_HT_INVALID; }   // hybrid_time.h:185-194
+// CompareHybridTimesToDelta (common/hybrid_time.cc:172-195): physical parts in nanoseconds against the delta, ties by the
+// logical parts
+inline int CompareToDelta(uint64_t begin, uint64_t end, int64_t delta_ns) {
+  if (end < begin) return -1;
+  const uint64_t bn = (begin >> 12) * 1000, en = (end >> 12) * 1000, dn = static_cast<uint64_t>(delta_ns);
+  if (en - bn > dn) return 1;
+  if (en - bn < dn) return -1;
+  const uint64_t bl = begin & 0xfff, el = end & 0xfff;
+  return el > bl ? 1 : (el < bl ? -1 : 0);
+}
+// dockv::ComputeExpiration (doc_ttl_util.cc:81-87): ht + ttl, kNoExpiration when the sum overflowed
+inline uint64_t ComputeExpiration(uint64_t ht, int64_t ttl_ns) {
+  const uint64_t expiry = IsSpecial(ht) ? ht : ht + (static_cast<uint64_t>(ttl_ns / 1000) << 12);
+  return CompareToDelta(ht, expiry, ttl_ns) == 0 ? expiry : kNoExpiration;
+}
+// dockv::MaxExpirationFromValueAndTableTTL (:107-129)
+inline uint64_t MaxExpiration(uint64_t key_ht, int64_t table_ttl_ns, uint64_t value_expiry) {
+  if (value_expiry == kNoExpiration || IsSpecial(key_ht)) return kNoExpiration;
+  if (table_ttl_ns == YBGPU_TTL_MAX_NS) return value_expiry == kUseDefaultTTL ? kNoExpiration : value_expiry;
+  const uint64_t table_expiry = ComputeExpiration(key_ht, table_ttl_ns);
+  if (table_expiry == kNoExpiration) return kNoExpiration;
+  return value_expiry >= table_expiry ? value_expiry : table_expiry;
+}
+inline bool HasExpired(uint64_t expiration_ht, uint64_t read_ht) {               // dockv::HasExpiredTTL (:42-47)
+  return expiration_ht != kNoExpiration && expiration_ht != kUseDefaultTTL && expiration_ht < read_ht;
+}
+}  // namespace ttl_detail
+inline bool TtlIsExpired(const ExpirationTime expiry, int64_t table_ttl_ns, uint64_t now, ExpiryMode mode = EXP_NORMAL) {   // :126-144
+  const uint64_t ttl_expiry_ht = mode == EXP_TABLE_ONLY ? kUseDefaultTTL : expiry.ttl_expiration_ht;
+  if (mode == EXP_TRUST_VALUE && ttl_expiry_ht != YBGPU_HT_INVALID && ttl_expiry_ht != kUseDefaultTTL)
+    return ttl_detail::HasExpired(ttl_expiry_ht, now);
+  return ttl_detail::HasExpired(ttl_detail::MaxExpiration(expiry.created_ht, table_ttl_ns, ttl_expiry_ht), now);
+}
+inline bool IsLastKeyCreatedBeforeHistoryCutoff(ExpirationTime expiry, uint64_t history_cutoff) { return expiry.created_ht < history_cutoff; }
+
+class DocDBCompactionFileFilter {                          // compaction_file_filter.h:69-97, .cc:150-188
+ public:
+  DocDBCompactionFileFilter(int64_t table_ttl_ns, uint64_t history_cutoff, uint64_t max_ht_to_expire, uint64_t filter_ht, ExpiryMode mode)
+      : table_ttl_ns_(table_ttl_ns), history_cutoff_(history_cutoff), max_ht_to_expire_(max_ht_to_expire), filter_ht_(filter_ht), mode_(mode) {}
+  // Files are expired from the oldest on: a file goes only if it was created before every file that stays
+  // (max_ht_to_expire_); the two conditions the factory already applied are checked again (the reference logs DFATAL and keeps).
+  FilterDecision Filter(const InputFile* file) const {
+    const ExpirationTime expiry = ExtractExpirationTime(file);
+    if (!(expiry.created_ht < max_ht_to_expire_)) return FilterDecision::kKeep;
+    if (!IsLastKeyCreatedBeforeHistoryCutoff(expiry, history_cutoff_)) return FilterDecision::kKeep;
+    if (!TtlIsExpired(expiry, table_ttl_ns_, filter_ht_, mode_)) return FilterDecision::kKeep;
+    return FilterDecision::kDiscard;
+  }
+  const char* Name() const { return "DocDBCompactionFileFilter"; }
+  uint64_t max_ht_to_expire() const { return max_ht_to_expire_; }
+ private:
+  const int64_t table_ttl_ns_;
+  const uint64_t history_cutoff_, max_ht_to_expire_, filter_ht_;
+  const ExpiryMode mode_;
+};
+
+// DocDBCompactionFileFilterFactory::CreateCompactionFileFilter (:196-243): `now` = clock_->Now(), the retention directive
+// as DocDBRetention carries it. The history cutoff is the smaller of the valid cutoffs; the smallest creation time among
+// the files that have NOT expired, or still hold keys inside the history retention window, bounds what may be expired.
+inline DocDBCompactionFileFilter CreateCompactionFileFilter(const std::vector<InputFile>& input_files, const DocDBRetention& retention,
+                                                            uint64_t now, ExpiryMode mode = EXP_NORMAL) {
+  uint64_t history_cutoff = YBGPU_HT_MAX;
+  if (retention.cotables_cutoff_ht != YBGPU_HT_INVALID && retention.cotables_cutoff_ht < history_cutoff) history_cutoff = retention.cotables_cutoff_ht;
+  if (retention.primary_cutoff_ht != YBGPU_HT_INVALID && retention.primary_cutoff_ht < history_cutoff) history_cutoff = retention.primary_cutoff_ht;
+  uint64_t min_kept_ht = YBGPU_HT_MAX;
+  for (const InputFile& f : input_files) {
+    const ExpirationTime expiry = ExtractExpirationTime(&f);
+    if (!TtlIsExpired(expiry, retention.table_ttl_ns, now, mode) || !IsLastKeyCreatedBeforeHistoryCutoff(expiry, history_cutoff))
+      if (expiry.created_ht < min_kept_ht) min_kept_ht = expiry.created_ht;
+  }
+  return DocDBCompactionFileFilter(retention.table_ttl_ns, history_cutoff, min_kept_ht, now, mode);
+}
+
+// What the picker does with the filter (db/compaction_picker.cc:476-492): marks the discarded files. Returns how many.
+inline size_t MarkExpiredFiles(std::vector<InputFile>* input_files, const DocDBRetention& retention, uint64_t now, ExpiryMode mode = EXP_NORMAL) {
+  const DocDBCompactionFileFilter filter = CreateCompactionFileFilter(*input_files, retention, now, mode);
+  size_t n = 0;
+  for (InputFile& f : *input_files)
+    if (filter.Filter(&f) == FilterDecision::kDiscard) { f.delete_after_compaction = true; n++; }
+  return n;
+}
 
 // TableBuilder over the product's host writer (what TableFactory::NewTableBuilder returns when the
 // KV stream is consumed by a host-side CompactionFeed chain).
@@ -241,8 +353,13 @@ class GpuCompactionJob {
   // REQUIRED: mutex NOT held. Replaces ProcessKeyValueCompaction; on success the output files are
   // available through output_data_file()/output_base_file() and stats().
   Status Run() {
+    if (NumReadInputs() == 0) {   // every input was expired as a whole (or there were none): nothing to merge, no output file
+      data_.clear(); base_.clear(); outputs_.clear(); stats_ = ybgpu_job_stats{};
+      return Status::OK();
+    }
     if (p_.max_subcompactions > 1) return RunSubcompactions();
     for (const InputFile& f : inputs_) {
+      if (f.delete_after_compaction) continue;             // db/version_set.cc:3812-3820
       ybgpu_status s = ybgpu_job_add_input_sst(job_, f.base_file.data(), f.base_file.size(), f.data_file.data(),
                                                f.data_file.size(), f.hybrid_time_filter);
       if (s == YBGPU_OK && !f.cotable_db_oids.empty())
@@ -279,6 +396,7 @@ class GpuCompactionJob {
     std::vector<ybgpu_input_file> files;
     uint64_t in_bytes = 0;
     for (const InputFile& f : inputs_) {
+      if (f.delete_after_compaction) continue;             // db/version_set.cc:3812-3820
       files.push_back({f.base_file.data(), f.base_file.size(), f.data_file.data(), f.data_file.size(), f.hybrid_time_filter,
                        f.cotable_db_oids.data(), f.cotable_hybrid_times.data(), f.cotable_db_oids.size()});
       in_bytes += f.data_file.size();
@@ -311,6 +429,10 @@ class GpuCompactionJob {
     return Status::OK();
   }
   const std::vector<OutputFile>& outputs() const { return outputs_; }
+  // Inputs that take part in the merge: all but the files marked delete_after_compaction (COMPACTION_FILES_NOT_FILTERED /
+  // COMPACTION_FILES_FILTERED tickers, db/version_set.cc:3817-3820).
+  size_t NumReadInputs() const { size_t n = 0; for (const InputFile& f : inputs_) n += !f.delete_after_compaction; return n; }
+  size_t NumFilteredInputs() const { return inputs_.size() - NumReadInputs(); }
 
   // The range outputs as ONE table, for layouts where a compaction must leave a single sorted run (DocDB's
   // single-level universal compaction never forms subcompactions, db/compaction.cc:593-604): the data file
@@ -353,6 +475,7 @@ class GpuCompactionJob {
     if (p_.max_subcompactions > 1 || !job_)
       return Status(Status::kNotSupported, "RunIntoFeed needs max_subcompactions == 1 (the host feed consumes one ordered stream)");
     for (const InputFile& f : inputs_) {
+      if (f.delete_after_compaction) continue;             // db/version_set.cc:3812-3820
       ybgpu_status s = ybgpu_job_add_input_sst(job_, f.base_file.data(), f.base_file.size(), f.data_file.data(),
                                                f.data_file.size(), f.hybrid_time_filter);
       if (s == YBGPU_OK && !f.cotable_db_oids.empty())
@@ -405,6 +528,7 @@ class GpuCompactionJob {
       meta->num_entries = stats_.num_output_records;
       return Status::OK();
     }
+    if (NumReadInputs() == 0) { *meta = OutputMeta(); return Status::OK(); }     // nothing was merged: no output file
     uint8_t a[4096], b[4096]; uint64_t al = 0, bl = 0;
     ybgpu_status s = ybgpu_job_output_boundaries(job_, a, &al, b, &bl);
     if (s != YBGPU_OK) return ToStatus(s, ybgpu_job_error(job_));
