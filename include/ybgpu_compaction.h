@@ -408,7 +408,8 @@ ybgpu_status ybgpu_sst_concat_meta(const ybgpu_job_options* table_options, const
                                    uint32_t num_pieces, uint8_t* meta_out, uint64_t meta_cap, uint64_t* meta_len);
 
 /* Host-side integrity check of a split SST: walks the index of `meta_file` and verifies the trailer of every
- * `stride`-th data block (type byte kNoCompression + masked CRC32C over contents and type, format.cc:352-395) in
+ * `stride`-th data block (type byte kNoCompression or kSnappyCompression + masked CRC32C over the stored bytes and the type,
+ * format.cc:352-395) in
  * `data_file`; stride 1 = every block. Used by bench.py on the full-size outputs it cannot compare with the
  * oracle. *bad_blocks > 0 => YBGPU_CORRUPTION. */
 ybgpu_status ybgpu_sst_verify_blocks(const uint8_t* meta_file, uint64_t meta_file_len, const uint8_t* data_file,
