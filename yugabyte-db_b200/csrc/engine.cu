@@ -2549,6 +2549,12 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       I.snap_timed = true;
       launches += 5;
       stats_.path_flags |= YBGPU_PATH_SNAPPY_OUTPUT;
+      // the uncompressed table and the scratch image are done with once the gather has run (stream-ordered frees): the job's
+      // footprint stays at one output table for the later phases and for the jobs running beside this one
+      for (void* dead : {static_cast<void*>(I.out_file), static_cast<void*>(C.comp)}) {
+        auto it = std::find(I.allocs.begin(), I.allocs.end(), dead);
+        if (it != I.allocs.end()) { I.allocs.erase(it); CUDA_TRY(cudaFreeAsync(dead, I.stream)); }
+      }
       I.out_file = C.out; I.out_file_len = ftotal; I.d_block_off = d_foff;
     }
     if (E.fk_len) {
