@@ -90,6 +90,15 @@ int main(int argc, char** argv) {
     printf("\n");
     return 0;
   }
+  if (mode == "checkfile") {
+    // argv: checkfile <base file> <data file> <num entries> <paranoid 0/1> <tail zeros>: prints the status code of
+    // GpuCompactionJob::CheckOutputFile.
+    if (argc != 7) { printf("usage\n"); return 2; }
+    const std::string base = ReadFile(argv[2]), data = ReadFile(argv[3]);
+    Status s = GpuCompactionJob::CheckOutputFile(Slice(data), Slice(base), strtoull(argv[4], nullptr, 10), atoi(argv[5]) != 0, strtoull(argv[6], nullptr, 10));
+    printf("%d\n", static_cast<int>(s.code()));
+    return 0;
+  }
   if (mode == "cpu") {
     if (ybgpu_device_count() == 0) {
       GpuCompactionJob job(GpuCompactionJob::Params{});

@@ -69,6 +69,38 @@ def test_adapter_file_filter_reference_known_answers():
             assert e == o.ttl_is_expired(vt, cr, ttl, now, mode)
 
 
+def test_adapter_check_output_file(tmp_path):
+    """CompactionJob::CheckOutputFile (compaction_job.cc:932-971) as the adapter offers it: the table must open; with
+    paranoid_file_checks every stored block must match its trailer; the tail-of-zeros check of the data file."""
+    import oracle_py as o
+    build_bin()
+    cfg = o.GenConfig(seed=19, num_rows=2000, cols=2, versions=2, num_files=1, value_len=60)
+    kvs = o.Sst.generate(cfg, 0, o.TableOptions(block_size=2048)).read_all()
+
+    def check(meta, data, n=len(kvs), paranoid=1, tail=0):
+        b, d = tmp_path / "t.sst", tmp_path / "t.sst.sblock.0"
+        b.write_bytes(bytes(meta))
+        d.write_bytes(bytes(data))
+        return int(subprocess.check_output([BIN, "checkfile", str(b), str(d), str(n), str(paranoid), str(tail)], text=True))
+
+    for comp in (0, 1):
+        t = o.Sst.build(kvs, o.TableOptions(block_size=2048, index_block_size=512, min_keys_per_index_block=4, filter_policy=1,
+                                            filter_block_size=1024, compression=comp))
+        meta, data = bytes(t.meta), bytes(t.data)
+        assert check(meta, data) == 0 and check(meta, data, paranoid=0) == 0 and check(meta, data, tail=64) == 0
+        bad = bytearray(data)
+        bad[len(bad) // 2] ^= 1                                    # a flipped bit in the middle of the data file
+        assert check(meta, bad) == 2                               # Corruption
+        assert check(meta, bad, paranoid=0) == 0                   # the quick check only opens the table (first block)
+        bad = bytearray(data)
+        bad[3] ^= 1
+        assert check(meta, bad, paranoid=0) == 2
+        assert check(meta[:-1], data) == 2 and check(meta[:40], data) == 2          # truncated metadata file
+        assert check(meta, data[:len(data) // 2]) == 2                               # truncated data file
+        assert check(meta, data + bytes(100), tail=64) == 2 and check(meta, data + bytes(100), tail=0) == 0
+        assert check(b"", b"", n=0) == 0                            # nothing survived: no file, nothing to check (:950-952)
+
+
 @pytest.mark.gpu
 def test_adapter_runs_compaction(tmp_path):
     import oracle_py as o

@@ -554,6 +554,40 @@ class GpuCompactionJob {
     return Status::OK();
   }
 
+  // CompactionJob::CheckOutputFile (compaction_job.cc:932-971) on bytes instead of file names: the table must open —
+  // footer, metaindex, properties, every level of the index (the host reader that also reads input tables, Snappy index
+  // blocks included) and its first data block's checksum; with paranoid_file_checks (DBOptions::paranoid_file_checks, the
+  // reference then iterates the whole table) every data block's stored bytes are checked against its trailer. A non-zero
+  // `check_tail_for_zeros` is FLAGS_rocksdb_check_sst_file_tail_for_zeros: that many trailing bytes of the data file must
+  // not all be zero (CheckSstTailForZeros, :940-948). The caller still runs the reference's own check on the files it
+  // writes; this one catches a bad table before anything touches the disk.
+  static Status CheckOutputFile(const Slice& data_file, const Slice& base_file, uint64_t num_entries, bool paranoid_file_checks,
+                                uint64_t check_tail_for_zeros = 0) {
+    if (check_tail_for_zeros > 0 && data_file.size() > 0) {
+      const uint64_t n = check_tail_for_zeros < data_file.size() ? check_tail_for_zeros : data_file.size();
+      bool all_zero = true;
+      for (uint64_t i = 0; i < n && all_zero; i++) all_zero = data_file.data()[data_file.size() - 1 - i] == 0;
+      if (all_zero) return Status(Status::kCorruption, "the tail of the data file is all zeros");
+    }
+    if (num_entries == 0) return Status::OK();                     // :950-952
+    uint64_t checked = 0, bad = 0;
+    const uint32_t stride = paranoid_file_checks ? 1u : 0xffffffffu;   // stride beyond the block count: the first block only
+    ybgpu_status s = ybgpu_sst_verify_blocks(base_file.data(), base_file.size(), data_file.data(), data_file.size(), stride, &checked, &bad);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_last_error());
+    if (checked == 0) return Status(Status::kCorruption, "the output table has entries but no data blocks");
+    return Status::OK();
+  }
+  Status CheckOutputFile(bool paranoid_file_checks, uint64_t check_tail_for_zeros = 0) const {
+    if (p_.max_subcompactions > 1) {
+      for (const OutputFile& f : outputs_) {
+        Status s = CheckOutputFile(Slice(f.data_file), Slice(f.base_file), f.stats.num_output_records, paranoid_file_checks, check_tail_for_zeros);
+        if (!s.ok()) return s;
+      }
+      return Status::OK();
+    }
+    return CheckOutputFile(Slice(data_), Slice(base_), stats_.num_output_records, paranoid_file_checks, check_tail_for_zeros);
+  }
+
   const std::string& output_data_file() const { return data_; }    // <n>.sst.sblock.0
   const std::string& output_base_file() const { return base_; }    // <n>.sst
   const ybgpu_job_stats& stats() const { return stats_; }
