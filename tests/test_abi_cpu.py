@@ -387,3 +387,41 @@ def test_host_table_builder_snappy_output(pkg, enc, filt, bs):
     off, sz, _ = pkg.sst_block_handles(np.frombuffer(meta, np.uint8))
     types = {data[int(a) + int(b)] for a, b in zip(off, sz)}
     assert types == {0, 1}                                          # ... and the random stretches stayed raw
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_host_table_builder_snappy_random_tables(pkg, seed):
+    """The host writer's encoder against the oracle's over random table options and value shapes: tiny and huge blocks,
+    values longer than a 64 KB fragment, long runs (chains of 64-byte copy elements), incompressible stretches."""
+    rng = random.Random(1000 + seed)
+    words = [bytes(rng.randrange(256) for _ in range(rng.randrange(1, 30))) for _ in range(rng.randrange(2, 40))]
+    kvs = []
+    for i in range(rng.randrange(50, 900)):
+        shape = rng.randrange(6)
+        if shape == 0:
+            v = bytes(rng.randrange(256) for _ in range(rng.randrange(0, 300)))
+        elif shape == 1:
+            v = bytes([rng.randrange(256)]) * rng.randrange(0, 5000)
+        elif shape == 2:
+            v = b"".join(rng.choice(words) for _ in range(rng.randrange(0, 60)))
+        elif shape == 3 and i % 40 == 0:
+            v = (rng.choice(words) * 9000)[:rng.randrange(66000, 200000)]
+        elif shape == 4:
+            v = b""
+        else:
+            v = bytes(rng.choice(b"ab") for _ in range(rng.randrange(0, 400)))
+        kvs.append((o.ikey(b"k%06d" % i + bytes(rng.randrange(97, 100) for _ in range(rng.randrange(0, 5))), 9000 - i), v))
+    kvs.sort(key=lambda kv: (kv[0][:-8], -int.from_bytes(kv[0][-8:], "little")))
+    kvs = [kv for j, kv in enumerate(kvs) if j == 0 or kvs[j - 1][0][:-8] != kv[0][:-8]]
+    topt = dict(block_size=rng.choice([256, 1024, 4096, 32768, 70000]), restart_interval=rng.choice([1, 4, 16]),
+                index_block_size=rng.choice([256, 4096]), min_keys_per_index_block=rng.choice([2, 100]),
+                key_encoding=rng.choice([1, 2]), filter_policy=rng.randrange(2), filter_block_size=1024)
+    otopt = dict(topt)
+    otopt["restart"] = otopt.pop("restart_interval")
+    ref = o.Sst.build(kvs, o.TableOptions(compression=1, **otopt))
+    b = pkg.HostTableBuilder(compression=1, **topt)
+    for k, v in kvs:
+        b.add(k, v)
+    data, meta = b.finish()
+    assert data == ref.data and meta == ref.meta
+    assert o.Sst.from_bytes(meta, data).read_all() == kvs
