@@ -2522,14 +2522,13 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
       {
         // 48 KB of static tables per CTA: ask for the largest shared-memory carve-out so that four CTAs share an SM (a hint;
         // without it the driver may settle for a carve-out that holds one)
-        static bool hinted = false;
-        if (!hinted) {
-          hinted = true;
+        static std::once_flag hinted;                      // ranges of a pipelined compaction run on several host threads
+        std::call_once(hinted, [] {
           (void)cudaFuncSetAttribute(k_snappy_compress<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
           (void)cudaFuncSetAttribute(k_snappy_compress<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
           (void)cudaFuncSetAttribute(k_snappy_compress<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
           (void)cudaGetLastError();
-        }
+        });
       }
       CUDA_TRY(cudaEventRecord(I.snap_ev[0], I.stream));
       if (variant == 2) k_snappy_compress<2><<<cgrid, SNAPC_WARPS * 32, 0, I.stream>>>(C);
