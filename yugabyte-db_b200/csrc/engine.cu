@@ -2530,6 +2530,11 @@ ybgpu_status Engine::Run(const volatile int32_t* shutting_down) {
           (void)cudaGetLastError();
         });
       }
+      if (trace) {                                         // what the runtime expects to keep resident (4 = the tables' limit)
+        int occ = -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_snappy_compress<0>, SNAPC_WARPS * 32, 0) != cudaSuccess) (void)cudaGetLastError();
+        fprintf(stderr, "[ybgpu trace] snappy encoder: %u blocks, grid %u x %d threads, variant %d, resident CTAs per SM %d\n", nblocks, cgrid, SNAPC_WARPS * 32, variant, occ);
+      }
       CUDA_TRY(cudaEventRecord(I.snap_ev[0], I.stream));
       if (variant == 2) k_snappy_compress<2><<<cgrid, SNAPC_WARPS * 32, 0, I.stream>>>(C);
       else if (variant == 1) k_snappy_compress<1><<<cgrid, SNAPC_WARPS * 32, 0, I.stream>>>(C);
