@@ -420,6 +420,17 @@ ybgpu_status ybgpu_sst_verify_blocks(const uint8_t* meta_file, uint64_t meta_fil
 ybgpu_status ybgpu_sst_last_key(const uint8_t* meta_file, uint64_t meta_file_len, const uint8_t* data_file,
                                 uint64_t data_file_len, uint8_t* key, uint32_t* key_len);
 
+/* Routing pre-check for one input table, on the host, before any byte is copied to the GPU: walks the index of
+ * `meta_file` and reads the trailer type byte of every data block of `data_file` (one byte per block). YBGPU_OK: the engine
+ * takes the table (data blocks stored raw or Snappy-compressed, a key-value encoding it decodes, handles inside the file).
+ * YBGPU_NOT_SUPPORTED: it would refuse it at run time (zlib / LZ4 / ZSTD blocks, an unknown encoding) — the caller keeps the
+ * stock CPU CompactionJob for this compaction (routing by job type) without paying the upload;
+ * YBGPU_CORRUPTION: the metadata file does not parse or a handle points outside the data file. Packed-row VALUES are not
+ * visible from the trailers: the engine still reports those at run time. counts (may be NULL) = blocks stored with
+ * CompressionType 0..7 (rocksdb/options.h:92-101). */
+ybgpu_status ybgpu_sst_check_supported(const uint8_t* meta_file, uint64_t meta_file_len, const uint8_t* data_file,
+                                       uint64_t data_file_len, uint64_t counts[8]);
+
 /* Device-side checksum of the surviving KV stream: order-sensitive 64-bit hash over
  * (key_len, key, value_len, value) per entry, combined per entry position. Used by the parity
  * tests at sizes where copying the stream back is pointless. */

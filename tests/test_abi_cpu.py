@@ -425,3 +425,31 @@ def test_host_table_builder_snappy_random_tables(pkg, seed):
     data, meta = b.finish()
     assert data == ref.data and meta == ref.meta
     assert o.Sst.from_bytes(meta, data).read_all() == kvs
+
+
+def test_sst_check_supported_routing_precheck(pkg):
+    """Routing by job type before any upload: raw and Snappy tables are taken; a table with blocks of another
+    CompressionType (here: trailers re-labelled LZ4 / ZSTD / zlib) is NotSupported with the count of such blocks; a
+    handle outside the data file or an unreadable metadata file is Corruption."""
+    cfg = o.GenConfig(seed=23, num_rows=3000, cols=2, versions=2, num_files=1, value_len=40)
+    kvs = o.Sst.generate(cfg, 0, o.TableOptions(block_size=2048)).read_all()
+    plain = o.Sst.build(kvs, o.TableOptions(block_size=2048))
+    snap = o.Sst.build(kvs, o.TableOptions(block_size=2048, compression=1))
+    tsp = o.Sst.build(kvs, o.TableOptions(block_size=2048, key_encoding=2))
+    nb = len(plain.block_handles()[0])
+    assert pkg.sst_check_supported(plain.meta_view(), plain.data_view()) == ("OK", [nb, 0, 0, 0, 0, 0, 0, 0])
+    st, counts = pkg.sst_check_supported(snap.meta_view(), snap.data_view())
+    assert st == "OK" and counts[1] > 0 and counts[0] + counts[1] == nb and sum(counts[2:]) == 0
+    assert pkg.sst_check_supported(tsp.meta_view(), tsp.data_view())[0] == "OK"
+    off, sz = plain.block_handles()
+    for ctype in (2, 4, 7):                                           # kZlibCompression, kLZ4Compression, kZSTD (options.h:92-101)
+        d = bytearray(plain.data)
+        for b in (3, 5):
+            d[int(off[b]) + int(sz[b])] = ctype
+        st, counts = pkg.sst_check_supported(plain.meta_view(), bytes(d))
+        assert st == "NotSupported" and counts[ctype] == 2 and counts[0] == nb - 2
+    d = bytearray(plain.data)
+    d[int(off[1]) + int(sz[1])] = 9
+    assert pkg.sst_check_supported(plain.meta_view(), bytes(d))[0] == "Corruption"
+    assert pkg.sst_check_supported(plain.meta_view(), bytes(plain.data)[:int(off[-1]) + 3])[0] == "Corruption"
+    assert pkg.sst_check_supported(bytes(plain.meta)[:-7], plain.data_view())[0] == "Corruption"

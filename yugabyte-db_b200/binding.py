@@ -770,6 +770,17 @@ def sst_concat_meta(pieces, out=None, **table_kwargs):
     return buf[:n.value] if out is not None else buf[:n.value].tobytes()
 
 
+def sst_check_supported(meta, data):
+    """ybgpu_sst_check_supported: (status name, [blocks per CompressionType 0..7]) — host-side routing pre-check of one table."""
+    L = lib()
+    L.ybgpu_sst_check_supported.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64 * 8)]
+    meta = np.ascontiguousarray(np.frombuffer(meta, np.uint8) if isinstance(meta, (bytes, bytearray)) else meta, dtype=np.uint8)
+    data = np.ascontiguousarray(np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+    counts = (C.c_uint64 * 8)()
+    st = L.ybgpu_sst_check_supported(meta.ctypes.data, meta.size, data.ctypes.data if data.size else None, data.size, C.byref(counts))
+    return STATUS_NAMES.get(st, str(st)), list(counts)
+
+
 def sst_verify_blocks(meta, data, stride=1):
     """ybgpu_sst_verify_blocks: (blocks checked, bad blocks) — host-side CRC32C check of every stride-th data block."""
     L = lib()

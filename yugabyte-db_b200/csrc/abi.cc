@@ -429,6 +429,33 @@ ybgpu_status ybgpu_sst_concat_meta(const ybgpu_job_options* o, const ybgpu_sst_p
   return YBGPU_OK;
 }
 
+ybgpu_status ybgpu_sst_check_supported(const uint8_t* meta, uint64_t meta_len, const uint8_t* data, uint64_t data_len, uint64_t counts[8]) {
+  if (!meta || (!data && data_len)) { g_last_error = "null argument"; return YBGPU_INVALID_ARGUMENT; }
+  ybgpu::host::SstMeta m;
+  std::string err = ybgpu::host::ParseSplitSstMeta(meta, meta_len, &m);
+  if (!err.empty()) { g_last_error = err; return YBGPU_CORRUPTION; }
+  uint64_t local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (const ybgpu::host::Handle& h : m.data_blocks) {
+    if (h.offset > data_len || h.size > data_len - h.offset || data_len - h.offset - h.size < 5) {
+      g_last_error = "a data block handle points outside the data file"; return YBGPU_CORRUPTION;
+    }
+    const uint8_t type = data[h.offset + h.size];
+    if (type > 7) { g_last_error = "unknown block compression type " + std::to_string(type); return YBGPU_CORRUPTION; }
+    local[type]++;
+  }
+  if (counts) memcpy(counts, local, sizeof(local));
+  if (m.key_encoding != YBGPU_KEY_ENCODING_SHARED_PREFIX && m.key_encoding != YBGPU_KEY_ENCODING_THREE_SHARED_PARTS) {
+    g_last_error = "data block key-value encoding format " + std::to_string(m.key_encoding) + " is not decoded by the engine"; return YBGPU_NOT_SUPPORTED;
+  }
+  for (int t = 2; t < 8; t++)
+    if (local[t]) {
+      static const char* const kNames[8] = {"none", "snappy", "zlib", "bzip2", "lz4", "lz4hc", "xpress", "zstd"};
+      g_last_error = std::to_string(local[t]) + " data blocks are stored with " + kNames[t] + " compression: only raw and Snappy blocks are decoded on the GPU";
+      return YBGPU_NOT_SUPPORTED;
+    }
+  return YBGPU_OK;
+}
+
 ybgpu_status ybgpu_sst_verify_blocks(const uint8_t* meta, uint64_t meta_len, const uint8_t* data, uint64_t data_len, uint32_t stride,
                                      uint64_t* checked, uint64_t* bad) {
   if (!meta || !data || !checked || !bad) return YBGPU_INVALID_ARGUMENT;

@@ -250,6 +250,18 @@ inline size_t MarkExpiredFiles(std::vector<InputFile>* input_files, const DocDBR
   return n;
 }
 
+// Routing ("ShouldOffload"): whether the engine takes these input tables, decided on the host from
+// the metadata files and one trailer byte per data block, before any upload. NotSupported = keep the stock CompactionJob
+// for this compaction; files marked delete_after_compaction are not read and so not looked at.
+inline Status CheckInputsSupported(const std::vector<InputFile>& inputs) {
+  for (const InputFile& f : inputs) {
+    if (f.delete_after_compaction) continue;
+    ybgpu_status s = ybgpu_sst_check_supported(f.base_file.data(), f.base_file.size(), f.data_file.data(), f.data_file.size(), nullptr);
+    if (s != YBGPU_OK) return ToStatus(s, ybgpu_last_error());
+  }
+  return Status::OK();
+}
+
 // TableBuilder over the product's host writer (what TableFactory::NewTableBuilder returns when the
 // KV stream is consumed by a host-side CompactionFeed chain).
 class GpuSideTableBuilder : public TableBuilder {
