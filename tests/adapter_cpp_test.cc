@@ -106,6 +106,23 @@ int main(int argc, char** argv) {
       if (s.ok()) { printf("expected failure without a GPU\n"); return 1; }
       printf("no-gpu status: %s\n", s.ToString().c_str());
     }
+    {
+      // CompactionJobStats mapping (compaction_job.cc:851-861,897-920,1337-1371) on synthetic engine stats
+      ybgpu_job_stats st{};
+      st.num_input_records = 100; st.num_output_records = 60; st.num_record_drop_hidden = 25; st.num_record_drop_obsolete = 5;
+      st.total_input_raw_key_bytes = 4000; st.total_input_raw_value_bytes = 9000;
+      std::string b1(300, 'b'), d1(5000, 'd'), b2(200, 'b'), d2(7000, 'd');
+      std::vector<InputFile> in(2);
+      in[0].base_file = Slice(b1); in[0].data_file = Slice(d1); in[1].base_file = Slice(b2); in[1].data_file = Slice(d2); in[1].delete_after_compaction = true;
+      GpuCompactionJob::CompactionJobStats js;
+      GpuCompactionJob::FillCompactionJobStats(st, in, 8123, 1, std::string("abcdefghijkl") + std::string(8, '\1'), std::string("zz") + std::string(8, '\0'), &js);
+      if (js.num_input_records != 100 || js.num_output_records != 60 || js.num_records_replaced != 25 || js.num_expired_deletion_records != 5 ||
+          js.num_input_files != 2 || js.total_input_bytes != 12500 || js.total_output_bytes != 8123 || js.num_output_files != 1 ||
+          js.total_input_raw_key_bytes != 4000 || js.total_input_raw_value_bytes != 9000 || js.smallest_output_key_prefix != "abcdefgh" ||
+          js.largest_output_key_prefix != "zz") { printf("job stats mapping\n"); return 1; }
+      GpuCompactionJob::FillCompactionJobStats(st, in, 0, 0, "", "", &js);
+      if (js.num_output_files != 0) { printf("job stats (no output)\n"); return 1; }
+    }
     printf("OK\n");
     return 0;
   }

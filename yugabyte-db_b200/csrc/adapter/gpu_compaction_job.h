@@ -520,6 +520,57 @@ class GpuCompactionJob {
     bool replace_user_values = false;
     std::vector<UserBoundaryValue> smallest_user_values, largest_user_values;
   };
+  // rocksdb::CompactionJobStats (rocksdb/compaction_job_stats.h:35-99) as UpdateCompactionJobStats / RecordDroppedKeys /
+  // ProcessKeyValueCompaction fill it (compaction_job.cc:851-861,897-920,1337-1371). Timing members stay with the caller
+  // (it measures its own wall clock and file IO); num_input_deletion_records is not reported by the engine (0).
+  struct CompactionJobStats {
+    uint64_t elapsed_micros = 0;
+    uint64_t num_input_records = 0, num_input_files = 0, num_input_files_at_output_level = 0;
+    uint64_t num_output_records = 0, num_output_files = 0;
+    bool is_manual_compaction = false;
+    uint64_t total_input_bytes = 0, total_output_bytes = 0;
+    uint64_t num_records_replaced = 0;               // += CompactionIteratorStats::num_record_drop_hidden (:904-911)
+    uint64_t total_input_raw_key_bytes = 0, total_input_raw_value_bytes = 0;
+    uint64_t num_input_deletion_records = 0;
+    uint64_t num_expired_deletion_records = 0;       // += num_record_drop_obsolete (:912-919)
+    uint64_t num_corrupt_keys = 0;
+    static constexpr size_t kMaxPrefixLength = 8;
+    std::string smallest_output_key_prefix, largest_output_key_prefix;   // user keys, cut to kMaxPrefixLength (:1359-1368)
+  };
+  static void FillCompactionJobStats(const ybgpu_job_stats& st, const std::vector<InputFile>& inputs, uint64_t output_bytes,
+                                     uint64_t num_output_files, const std::string& smallest_internal_key,
+                                     const std::string& largest_internal_key, CompactionJobStats* out) {
+    out->num_input_records = st.num_input_records;
+    out->num_input_files = inputs.size();            // marked-for-deletion files are inputs of the compaction too (:1318-1334)
+    out->num_input_files_at_output_level = 0;        // universal compactions of level-0 files into level 0 count them all as inputs
+    out->total_input_bytes = 0;
+    for (const InputFile& f : inputs) out->total_input_bytes += f.base_file.size() + f.data_file.size();   // fd.GetTotalFileSize()
+    out->num_output_records = st.num_output_records;
+    out->num_output_files = num_output_files;
+    out->total_output_bytes = output_bytes;
+    out->num_records_replaced = st.num_record_drop_hidden;
+    out->num_expired_deletion_records = st.num_record_drop_obsolete;
+    out->total_input_raw_key_bytes = st.total_input_raw_key_bytes;
+    out->total_input_raw_value_bytes = st.total_input_raw_value_bytes;
+    out->num_corrupt_keys = 0;                       // a corrupt key aborts the job with Corruption instead of being counted
+    auto prefix = [](const std::string& ikey) {
+      const size_t ulen = ikey.size() >= 8 ? ikey.size() - 8 : 0;
+      return ikey.substr(0, ulen < CompactionJobStats::kMaxPrefixLength ? ulen : CompactionJobStats::kMaxPrefixLength);
+    };
+    if (num_output_files > 0) { out->smallest_output_key_prefix = prefix(smallest_internal_key); out->largest_output_key_prefix = prefix(largest_internal_key); }
+  }
+  // After Install(): the job's CompactionJobStats.
+  Status UpdateCompactionJobStats(CompactionJobStats* out) {
+    OutputMeta m;
+    Status s = Install(&m);
+    if (!s.ok()) return s;
+    uint64_t bytes = 0, files = 0;
+    if (p_.max_subcompactions > 1) { for (const OutputFile& f : outputs_) { bytes += f.data_file.size() + f.base_file.size(); files++; } }
+    else if (!data_.empty()) { bytes = data_.size() + base_.size(); files = 1; }
+    FillCompactionJobStats(stats_, inputs_, bytes, files, m.smallest_key, m.largest_key, out);
+    return Status::OK();
+  }
+
   // Output seqno bounds the way the reference computes them: the union of the inputs' FileMetaData bounds
   // (UpdateBoundariesExceptKey, compaction_job.cc:1188-1195; db/version_edit.cc:133-152) extended by every
   // surviving entry's (possibly zeroed) sequence number (SubcompactionState::Feed, :156-169) — which is what the
