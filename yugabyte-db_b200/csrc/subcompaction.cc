@@ -220,7 +220,14 @@ bool LastKeyOfBlock(const uint8_t* blk, uint64_t size, int key_encoding, std::st
 bool LastKeyOfFile(const ybgpu_input_file& f, const SstMeta& m, std::string* key) {
   if (m.data_blocks.empty()) { key->clear(); return true; }
   const auto& h = m.data_blocks.back();
-  if (h.offset + h.size + 5 > f.data_file_len) return false;
+  if (h.offset > f.data_file_len || h.size > f.data_file_len - h.offset || f.data_file_len - h.offset - h.size < 5) return false;
+  {
+    // ReadBlock verifies the stored bytes + type byte against the trailer before anything is decoded (table/format.cc:352-395)
+    const uint8_t* p = f.data_file + h.offset;
+    uint32_t stored;
+    memcpy(&stored, p + h.size + 1, 4);
+    if (ybgpu::host::Crc32cMask(ybgpu::host::Crc32c(p, h.size + 1)) != stored) return false;
+  }
   const uint8_t type = f.data_file[h.offset + h.size];
   if (type == 1) {                                                  // Snappy (the production default): uncompress on the host
     std::string raw;
