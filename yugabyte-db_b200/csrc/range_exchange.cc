@@ -237,7 +237,7 @@ ybgpu_status ybgpu_compact_range_sharded(ybgpu_range_comm* c, const ybgpu_job_op
     std::string largest_local; bool have = false;
     for (uint32_t f = 0; f < num_files; f++) {
       std::string k;
-      if (!LastKeyOfFile(files[f], in[f].meta, &k)) return fail(YBGPU_CORRUPTION, "cannot read the last key of input " + std::to_string(f));
+      if (!LastKeyOfFile(files[f], in[f].meta, &k, options->verify_checksums != 0)) return fail(YBGPU_CORRUPTION, "cannot read the last key of input " + std::to_string(f));
       if (k.empty()) continue;
       const std::string u = UserPart(k);
       if (!have || largest_local < u) { largest_local = u; have = true; }

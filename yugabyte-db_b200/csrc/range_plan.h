@@ -31,7 +31,7 @@ void BlocksForRange(const std::vector<std::string>& useps, const std::string& lo
 // Spans are disjoint and ascending; adjacent ones are merged.
 void SpansForRange(const ParsedInput& in, const std::string& lo, const std::string& hi, bool retention_enabled, std::vector<Span>* out);
 bool LastKeyOfBlock(const uint8_t* blk, uint64_t size, int key_encoding, std::string* key);
-bool LastKeyOfFile(const ybgpu_input_file& f, const host::SstMeta& m, std::string* key);
+bool LastKeyOfFile(const ybgpu_input_file& f, const host::SstMeta& m, std::string* key, bool verify_checksum = true);
 
 }  // namespace plan
 }  // namespace ybgpu

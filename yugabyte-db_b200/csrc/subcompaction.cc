@@ -217,12 +217,13 @@ bool LastKeyOfBlock(const uint8_t* blk, uint64_t size, int key_encoding, std::st
   return true;
 }
 
-bool LastKeyOfFile(const ybgpu_input_file& f, const SstMeta& m, std::string* key) {
+bool LastKeyOfFile(const ybgpu_input_file& f, const SstMeta& m, std::string* key, bool verify_checksum) {
   if (m.data_blocks.empty()) { key->clear(); return true; }
   const auto& h = m.data_blocks.back();
   if (h.offset > f.data_file_len || h.size > f.data_file_len - h.offset || f.data_file_len - h.offset - h.size < 5) return false;
-  {
-    // ReadBlock verifies the stored bytes + type byte against the trailer before anything is decoded (table/format.cc:352-395)
+  if (verify_checksum) {
+    // ReadBlock verifies the stored bytes + type byte against the trailer before anything is decoded (table/format.cc:352-395;
+    // ReadOptions::verify_checksums, which a compaction takes from verify_checksums_in_compaction)
     const uint8_t* p = f.data_file + h.offset;
     uint32_t stored;
     memcpy(&stored, p + h.size + 1, 4);
@@ -336,7 +337,7 @@ ybgpu_status CompactFilesCore(const ybgpu_job_options* options, const ybgpu_inpu
   } else {
     for (uint32_t f = 0; f < num_files; f++) {
       std::string k;
-      if (!LastKeyOfFile(files[f], in[f].meta, &k)) return fail(YBGPU_CORRUPTION, "cannot read the last key of input " + std::to_string(f));
+      if (!LastKeyOfFile(files[f], in[f].meta, &k, options->verify_checksums != 0)) return fail(YBGPU_CORRUPTION, "cannot read the last key of input " + std::to_string(f));
       if (k.empty()) continue;
       std::string u = UserPart(k);
       if (!have_largest || largest_user < u) { largest_user = u; have_largest = true; }
