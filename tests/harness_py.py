@@ -58,3 +58,46 @@ def compact_runs(runs, params):
     keys = arr(L.hh_keys(), int(koff[-1]), np.uint8).tobytes()
     vals = arr(L.hh_vals(), int(voff[-1]), np.uint8).tobytes()
     return [(keys[int(koff[i]):int(koff[i + 1])], vals[int(voff[i]):int(voff[i + 1])]) for i in range(n)]
+
+
+# ---- the Snappy kernels' source on emulated warps (tests/host_harness/warp_emu.cc) -------------------------------------
+_WARP = None
+
+
+def warp_lib():
+    global _WARP
+    if _WARP is None:
+        subprocess.check_call(["make", "-s", "-C", _DIR], stderr=subprocess.DEVNULL)
+        L = C.CDLL(os.path.join(_DIR, "libwarpemu.so"))
+        L.we_compress_table.restype = C.c_uint64
+        L.we_compress_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        L.we_uncompress_table.restype = C.c_uint64
+        L.we_uncompress_table.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        _WARP = L
+    return _WARP
+
+
+def warp_compress_table(data_file: bytes, offsets, variant=0):
+    """k_snappy_compress<variant> + k_snappy_gather over an uncompressed data file (blocks + trailers back to back;
+    offsets = the blocks' start offsets): (compressed data file, final block offsets incl. the end)."""
+    raw = np.frombuffer(data_file, np.uint8)
+    off = np.array(list(offsets) + [len(data_file)], np.uint64)
+    out = np.zeros(len(data_file) + 64, np.uint8)
+    foff = np.zeros(len(off), np.uint64)
+    n = warp_lib().we_compress_table(raw.ctypes.data, off.ctypes.data, len(off) - 1, variant, out.ctypes.data, foff.ctypes.data)
+    return out[:n].tobytes(), [int(x) for x in foff]
+
+
+def warp_uncompress_table(data_file: bytes, offsets, sizes):
+    """k_snappy_sizes + k_snappy_decode: (uncompressed image, its block offsets incl. the end); RuntimeError(device error code)
+    when the kernels flag a block."""
+    raw = np.frombuffer(data_file, np.uint8)
+    off = np.array(list(offsets), np.uint64)
+    sz = np.array(list(sizes), np.uint32)
+    cap = 64 + sum(int(s) for s in sz) * 40 + 5 * len(sz)
+    out = np.zeros(cap, np.uint8)
+    ooff = np.zeros(len(off) + 1, np.uint64)
+    n = warp_lib().we_uncompress_table(raw.ctypes.data, raw.size, off.ctypes.data, sz.ctypes.data, len(off), out.ctypes.data, cap, ooff.ctypes.data)
+    if n > 2**63:
+        raise RuntimeError(2**64 - 1 - n)
+    return out[:n].tobytes(), [int(x) for x in ooff]

@@ -203,7 +203,9 @@ __device__ __forceinline__ SnapcBatch snapc_prepare(const uint8_t* f, uint32_t i
   if (VARIANT == 0) {
     B.grp = __match_any_sync(FULL, B.h);
   } else {
+#if defined(__CUDA_ARCH__)                                // (the kernel source is also compiled for the CPU by tests/host_harness/warp_emu.cc)
     if (lane == 0 && i + 288 < m) asm volatile("prefetch.global.L2 [%0];" :: "l"(f + i + 256));
+#endif
     uint32_t g = __ballot_sync(FULL, B.act);
 #pragma unroll
     for (uint32_t bit = 0; bit < SNAPC_HASH_BITS; bit++) {
