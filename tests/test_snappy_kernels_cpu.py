@@ -83,3 +83,52 @@ def test_decode_kernels_rebuild_the_uncompressed_table():
         assert e.args[0] == 3                                   # DEV_ERR_BAD_BLOCK
     else:
         assert got != img                                       # (a flipped literal byte is the checksum's to catch, not the decoder's)
+
+
+def test_decode_kernel_every_element_kind():
+    """Hand-made streams with what neither this repository's encoder nor libsnappy emits but the format allows: literal
+    lengths in 1..4 trailing bytes, copies with 4-byte offsets, overlapping copies at every offset around a warp's width
+    (1, 2, 3, 5, 31, 32, 33, ...) — k_snappy_decode against the oracle's decoder."""
+    import struct
+    rng = random.Random(9)
+
+    def varint(n):
+        out = b""
+        while n >= 128:
+            out += bytes([(n & 127) | 128])
+            n >>= 7
+        return out + bytes([n])
+
+    def lit(data, nb):
+        l1 = len(data) - 1
+        return bytes([l1 << 2]) + data if nb == 0 else bytes([(59 + nb) << 2]) + l1.to_bytes(nb, "little") + data
+
+    blob, offs, sizes, raws = b"", [], [], []
+    for _ in range(300):
+        out, stream = bytearray(), b""
+        for _ in range(rng.randrange(1, 30)):
+            k = rng.randrange(5)
+            if k == 0 or not out:
+                d = bytes(rng.randrange(256) for _ in range(rng.choice([1, 2, 59, 60, 61, 255, 256, 257, 1000])))
+                need = 0 if len(d) - 1 < 60 else (1 if len(d) - 1 < 256 else 2)
+                stream += lit(d, rng.choice([need] + [nb for nb in (1, 2, 3, 4) if nb >= max(need, 1)]))
+                out += d
+            else:
+                off = min(rng.choice([1, 2, 3, 5, 31, 32, 33, 64, 100, 2047, 2048, 5000]), len(out))
+                ln = rng.randrange(4, 12) if k == 1 else rng.randrange(1, 65)
+                if k == 1 and off < 2048:
+                    stream += bytes([1 | ((ln - 4) << 2) | ((off >> 8) << 5), off & 0xff])
+                elif k == 3:
+                    stream += bytes([3 | ((ln - 1) << 2)]) + struct.pack("<I", off)
+                else:
+                    stream += bytes([2 | ((ln - 1) << 2)]) + struct.pack("<H", off)
+                for _ in range(ln):
+                    out.append(out[len(out) - off])
+        c = varint(len(out)) + stream
+        assert o.snappy_uncompress(c) == bytes(out)
+        offs.append(len(blob))
+        sizes.append(len(c))
+        raws.append(bytes(out))
+        blob += c + b"\x01" + bytes(4)
+    img, _ = h.warp_uncompress_table(blob, offs, sizes)
+    assert img == b"".join(r + bytes(5) for r in raws)
